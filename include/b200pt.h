@@ -1,0 +1,271 @@
+/* b200pt.h -- C ABI of the B200-native path-tracing hot path.
+ *
+ * This is the drop-in boundary for ONE path of pbrt-v3(-distributed): the
+ * per-tile SamplerIntegrator::Render loop (core/integrator.cpp:228-339) with
+ * PathIntegrator::Li (integrators/path.cpp:64-188), BVHAccel::Intersect /
+ * IntersectP (accelerators/bvh.cpp:662-738), Triangle::Intersect
+ * (shapes/triangle.cpp:188-425), the Sobol' sampler (samplers/sobol.cpp:42-59),
+ * the perspective camera (cameras/perspective.cpp:95-144), the four materials
+ * matte/plastic/metal/glass, diffuse area lights with MIS direct lighting
+ * (core/integrator.cpp:85-215) and the box-filtered film
+ * (core/film.h:121-161, core/film.cpp:117-130).
+ *
+ * The reference has no FFI: its "plugins" are C++ subclasses picked by name in
+ * RenderOptions::MakeIntegrator (core/api.cpp:1666-1718).  A host integrator
+ * (pbrt-v3-distributed_b200/host/gpupath.cpp, class GpuPathIntegrator :
+ * public Integrator, integrator.h:53-58) flattens the parsed Scene into the
+ * plain-old-data descriptors below and calls these entry points; see
+ * INTEGRATION.md for the binding.  Everything is `extern "C"`, plain pointers
+ * and sizes; no torch / CUDA types appear in any signature (device pointers
+ * travel as uint64_t).
+ *
+ * Conventions: every function returns 0 on success and a negative
+ * b200pt_status on failure; b200pt_last_error() gives the message (thread
+ * local).  The caller owns all host arrays passed to b200pt_scene_create for
+ * the duration of the call; the library copies what it needs to the device and
+ * owns all device memory behind a handle.  There is NO CPU fallback: if no
+ * CUDA device is usable every compute entry point fails with
+ * B200PT_ERR_NO_DEVICE.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_ABI_VERSION 1
+
+typedef enum b200pt_status {
+    B200PT_OK = 0,
+    B200PT_ERR_INVALID = -1,     /* bad argument / unsupported feature        */
+    B200PT_ERR_NO_DEVICE = -2,   /* no usable CUDA device (no CPU fallback)   */
+    B200PT_ERR_CUDA = -3,        /* a CUDA runtime call failed                */
+    B200PT_ERR_OOM = -4          /* device or host allocation failed          */
+} b200pt_status;
+
+/* ---- materials: materials/{matte,plastic,metal,glass}.cpp ---------------- */
+typedef enum b200pt_material_type {
+    B200PT_MAT_MATTE = 0,   /* LambertianReflection(Kd)        matte.cpp:45-62   (sigma must be 0) */
+    B200PT_MAT_PLASTIC = 1, /* Lambertian(Kd)+MicrofacetReflection(Ks,TR(a,a),FrDielectric(1.5,1)) plastic.cpp:45-70 */
+    B200PT_MAT_METAL = 2,   /* MicrofacetReflection(1,TR(ax,ay),FrConductor(1,eta,k))   metal.cpp:59-80 */
+    B200PT_MAT_GLASS = 3,   /* FresnelSpecular(R,T,1,index) -- smooth glass, glass.cpp:62-64 */
+    B200PT_MAT_NONE = 4     /* null material: GetMaterial()==nullptr is NOT supported; reserved */
+} b200pt_material_type;
+
+/* Textures are constant (textures/constant.h); the host evaluates them and
+ * applies TrowbridgeReitzDistribution::RoughnessToAlpha (microfacet.h:123-128)
+ * itself, so alpha_x/alpha_y below are the final alphas. Spectra are RGB
+ * (core/spectrum.h:429), already Clamp()ed like the materials do. */
+typedef struct b200pt_material {
+    int32_t type;        /* b200pt_material_type */
+    float kd[3];         /* matte Kd, plastic Kd                      */
+    float ks[3];         /* plastic Ks, glass Kr (R)                  */
+    float kt[3];         /* glass Kt (T)                              */
+    float eta[3];        /* metal eta (RGB)                           */
+    float k[3];          /* metal k   (RGB)                           */
+    float alpha_x;       /* TR alpha (plastic: ax==ay)                */
+    float alpha_y;
+    float index;         /* glass index of refraction (BSDF::eta)     */
+} b200pt_material;
+
+/* ---- lights: one DiffuseAreaLight per emissive triangle (api.cpp:1357-1364,
+ * lights/diffuse.cpp:42-87).  Order == Scene::lights order. --------------- */
+typedef struct b200pt_area_light {
+    int32_t triangle;    /* index into the triangle arrays              */
+    float lemit[3];      /* Lemit (already multiplied by "scale")       */
+    int32_t two_sided;   /* "twosided" parameter                        */
+} b200pt_area_light;
+
+/* ---- scene: world-space triangle soup + per-triangle attributes ---------
+ * Triangle i is the i-th GeometricPrimitive handed to the accelerator
+ * (accelerators/bvh.cpp:183).  Vertices are the world-space TriangleMesh::p
+ * values (shapes/triangle.cpp:73-75) gathered through the index buffer:
+ * 9 floats per triangle (p0 p1 p2).  Meshes with per-vertex normals, tangents,
+ * uvs or alpha masks are outside this round's scope and must be rejected by
+ * the host. */
+typedef struct b200pt_scene_desc {
+    int64_t n_triangles;
+    const float *vertices;        /* [n_triangles][3][3]                              */
+    const int32_t *material_id;   /* [n_triangles] index into materials               */
+    const int32_t *light_id;      /* [n_triangles] index into lights or -1            */
+    const uint8_t *flip_normal;   /* [n_triangles] reverseOrientation ^ transformSwapsHandedness
+                                     (shapes/triangle.cpp:420-421); may be NULL (=0)  */
+    int32_t n_materials;
+    const b200pt_material *materials;
+    int32_t n_lights;
+    const b200pt_area_light *lights;
+} b200pt_scene_desc;
+
+/* ---- camera: PerspectiveCamera (cameras/perspective.cpp:45-144) ----------
+ * The two matrices are the host's own Transform::m values (row-major,
+ * core/transform.h:60-80): RasterToCamera (camera.h:104) and the static
+ * CameraToWorld.  Animated cameras are out of scope. */
+typedef struct b200pt_camera_desc {
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    float lens_radius;       /* > 0 enables the thin lens branch :104-116 */
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+} b200pt_camera_desc;
+
+/* ---- film: Film with the default BoxFilter (core/film.cpp:44-130) -------- */
+typedef struct b200pt_film_desc {
+    int32_t full_resolution[2];
+    int32_t cropped_bounds[4];     /* croppedPixelBounds x0 y0 x1 y1 (film.cpp:54-58) */
+    float filter_radius[2];        /* BoxFilter radius, default 0.5 0.5 (box.cpp:41-47)*/
+    float scale;                   /* Film::scale                                     */
+    float max_sample_luminance;    /* Film::maxSampleLuminance (INFINITY = off)       */
+} b200pt_film_desc;
+
+/* ---- sampler: SobolSampler (samplers/sobol.h:45-69) ----------------------
+ * The generator matrices stay the host's data (core/sobolmatrices.cpp): the
+ * host passes SobolMatrices32 and the two rows VdCSobolMatrices[log2res-1],
+ * VdCSobolMatricesInv[log2res-1] it already owns. */
+typedef struct b200pt_sampler_desc {
+    int32_t samples_per_pixel;     /* already rounded up to a power of two (sobol.h:52) */
+    int32_t sample_bounds[4];      /* Film::GetSampleBounds() x0 y0 x1 y1             */
+    int32_t n_dimensions;          /* rows provided in matrices32 (<=1024)            */
+    const uint32_t *matrices32;    /* [n_dimensions][52]  SobolMatrices32             */
+    const uint64_t *vdc;           /* [52] VdCSobolMatrices[log2Resolution-1]         */
+    const uint64_t *vdc_inv;       /* [52] VdCSobolMatricesInv[log2Resolution-1]      */
+} b200pt_sampler_desc;
+
+/* ---- integrator: PathIntegrator parameters (integrators/path.cpp:190-213) */
+typedef enum b200pt_light_strategy {
+    B200PT_LIGHTS_UNIFORM = 0,     /* UniformLightDistribution  lightdistrib.cpp:68-75 */
+    B200PT_LIGHTS_POWER = 1        /* PowerLightDistribution    lightdistrib.cpp:77-82 */
+    /* "spatial" (lightdistrib.cpp:96-300) is a SURVEY 8(f) next row */
+} b200pt_light_strategy;
+
+typedef struct b200pt_integrator_desc {
+    int32_t max_depth;             /* "maxdepth", default 5          */
+    float rr_threshold;            /* "rrthreshold", default 1       */
+    int32_t light_strategy;        /* b200pt_light_strategy          */
+    int32_t pixel_bounds[4];       /* "pixelbounds" ∩ sample bounds, x0 y0 x1 y1 (path.cpp:195-207) */
+} b200pt_integrator_desc;
+
+/* ---- per-ray records for the kernel-level entry points ------------------ */
+typedef struct b200pt_ray {
+    float o[3];
+    float t_max;
+    float d[3];
+    float pad;
+} b200pt_ray;                      /* 32 B */
+
+typedef struct b200pt_hit {
+    int32_t triangle;              /* -1 = miss                                       */
+    float t;                       /* Triangle::Intersect tHit                        */
+    float b0, b1;                  /* barycentrics (b2 recomputed as in :268)         */
+} b200pt_hit;                      /* 16 B */
+
+/* ---- counters mirroring the reference's STAT_COUNTERs ------------------- */
+typedef struct b200pt_stats {
+    uint64_t camera_rays;          /* "Integrator/Camera rays traced"   integrator.cpp:48  */
+    uint64_t regular_rays;         /* "Intersections/Regular ray intersection tests" scene.cpp:40 */
+    uint64_t shadow_rays;          /* "Intersections/Shadow ray intersection tests"  scene.cpp:41 */
+    uint64_t nodes_visited;        /* wide-BVH nodes fetched by the traversal kernels */
+    uint64_t tris_tested;          /* ray-triangle tests in the traversal kernels     */
+    double closest_ms;             /* device time in closest-hit traversal launches   */
+    double any_ms;                 /* device time in any-hit traversal launches       */
+    double shade_ms;               /* device time in all other launches               */
+    uint64_t launches;             /* kernels launched by the library                 */
+} b200pt_stats;
+
+typedef struct b200pt_ctx b200pt_ctx;      /* device + stream                          */
+typedef struct b200pt_scene b200pt_scene;  /* device-resident triangles + wide BVH     */
+typedef struct b200pt_render b200pt_render;/* camera+film+sampler+integrator + film buffers */
+
+/* ---- library ------------------------------------------------------------ */
+int b200pt_abi_version(void);
+const char *b200pt_last_error(void);
+
+/* Binds to CUDA device `device` (cudaSetDevice) and creates the stream all
+ * work of this context runs on. */
+int b200pt_ctx_create(int device, b200pt_ctx **out);
+void b200pt_ctx_destroy(b200pt_ctx *ctx);
+int b200pt_ctx_synchronize(b200pt_ctx *ctx);
+/* cudaStream_t of the context as an integer (for CUDA-event timing by the caller). */
+uint64_t b200pt_ctx_stream(b200pt_ctx *ctx);
+
+/* ---- scene: replaces CreateBVHAccelerator (accelerators/bvh.cpp:740-760) --
+ * Builds the 8-wide compressed BVH on the host (SAH) and uploads it. */
+int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *desc, b200pt_scene **out);
+void b200pt_scene_destroy(b200pt_scene *scene);
+/* bytes of device memory held by nodes / triangles, node count */
+int b200pt_scene_info(const b200pt_scene *scene, uint64_t *node_bytes, uint64_t *tri_bytes,
+                      uint64_t *n_nodes);
+
+/* ---- kernel-level entry points (parity tests, traversal benchmarks) -------
+ * Replace Scene::Intersect / Scene::IntersectP (core/scene.cpp:45-55) on
+ * batches of rays.  `*_dev` variants take device pointers (rays already in
+ * HBM); the plain variants copy host buffers in and out. */
+int b200pt_trace_closest(b200pt_scene *scene, const b200pt_ray *rays, b200pt_hit *hits, int64_t n);
+int b200pt_trace_any(b200pt_scene *scene, const b200pt_ray *rays, uint8_t *occluded, int64_t n);
+int b200pt_trace_closest_dev(b200pt_scene *scene, uint64_t rays_dev, uint64_t hits_dev, int64_t n);
+int b200pt_trace_any_dev(b200pt_scene *scene, uint64_t rays_dev, uint64_t occluded_dev, int64_t n);
+
+/* ---- render: replaces SamplerIntegrator::Render (integrator.cpp:228-339) -- */
+int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *camera,
+                         const b200pt_film_desc *film, const b200pt_sampler_desc *sampler,
+                         const b200pt_integrator_desc *integrator, b200pt_render **out);
+void b200pt_render_destroy(b200pt_render *r);
+
+/* Number of 16x16 tiles in x and y (integrator.cpp:235-237). */
+int b200pt_render_tile_counts(const b200pt_render *r, int32_t *nx, int32_t *ny);
+
+/* Film::Clear (film.cpp:108-115) on the device film. */
+int b200pt_film_clear(b200pt_render *r);
+
+/* Renders the given tiles (tile index = y*nx + x, the reference's `seed`,
+ * integrator.cpp:247) with ALL samples per pixel and merges them into the
+ * device film (raw XYZ sums + filter weight sums, film.cpp:117-130).
+ * tiles == NULL renders tiles [0, n_tiles) in order.  Asynchronous on the
+ * context's stream. */
+int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles);
+
+/* Device address and size of the film accumulation buffer: float4 per cropped
+ * pixel = (X, Y, Z, filterWeightSum), row-major over cropped_bounds.  This is
+ * the buffer a multi-GPU caller reduces (sum) across ranks before read-back. */
+int b200pt_film_device_buffer(b200pt_render *r, uint64_t *dev_ptr, uint64_t *n_floats);
+
+/* Copies the raw film (X,Y,Z,weight per pixel) to the host (synchronises). */
+int b200pt_film_read_raw(b200pt_render *r, float *xyzw);
+/* Film::WriteImage's pixel pipeline (film.cpp:174-203): XYZ->RGB, divide by
+ * weight, clamp >=0, *scale; rgb is [h][w][3] over the cropped bounds. */
+int b200pt_film_read_rgb(b200pt_render *r, float *rgb);
+
+/* Diagnostics for parity tests: the Sobol' sample values the device generates
+ * for (pixel, sample index, dimension range) -- GlobalSampler::Get1D stream,
+ * sampler.cpp:181-195 -- and the camera rays of the first `n` samples of a
+ * pixel (RayDifferential main ray only). */
+int b200pt_debug_sobol(b200pt_render *r, int32_t px, int32_t py, int64_t sample, int32_t dim0,
+                       int32_t n_dims, float *out);
+int b200pt_debug_camera_rays(b200pt_render *r, int32_t px, int32_t py, int32_t n_samples,
+                             b200pt_ray *out);
+/* Per-sample radiance (after the NaN / negative / infinite guards of
+ * integrator.cpp:294-315) of one pixel: out is [samples_per_pixel][3]. */
+int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *out_rgb);
+
+int b200pt_get_stats(b200pt_render *r, b200pt_stats *out);
+int b200pt_reset_stats(b200pt_render *r);
+
+/* ---- host helpers (no device work) ---------------------------------------
+ * Mirror of the host-side math a caller outside pbrt needs to fill the
+ * descriptors exactly like the reference would:
+ *  - camera matrices from LookAt + Perspective(fov, 1e-2, 1000) + screen
+ *    window, as ProjectiveCamera does (core/camera.h:84-115,
+ *    core/transform.cpp:203-249,303-318, cameras/perspective.cpp:227-273);
+ *  - TrowbridgeReitzDistribution::RoughnessToAlpha (microfacet.h:123-128). */
+int b200pt_host_perspective_camera(const float eye[3], const float look[3], const float up[3],
+                                   float fov_degrees, int32_t xres, int32_t yres,
+                                   b200pt_camera_desc *out);
+float b200pt_host_roughness_to_alpha(float roughness);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

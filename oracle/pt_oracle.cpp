@@ -1,0 +1,1648 @@
+// oracle/pt_oracle.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// CPU restatement (scalar C++, float32 exactly as the reference with
+// Float=float, Spectrum=RGBSpectrum) of the reference's hot path:
+//   SamplerIntegrator::Render        core/integrator.cpp:228-339
+//   PathIntegrator::Li               integrators/path.cpp:64-188
+//   UniformSampleOneLight/EstimateDirect  core/integrator.cpp:85-215
+//   BVHAccel::Intersect/IntersectP   accelerators/bvh.cpp:662-738
+//   Triangle::Intersect/IntersectP/Sample/Area  shapes/triangle.cpp:188-608
+//   Sobol' sampler, perspective camera, matte/plastic/metal/glass BSDFs,
+//   DiffuseAreaLight, box-filter Film.
+// Every function cites the reference lines it follows.  Expression order and
+// float/double promotions are kept so that results are bit-identical to the
+// reference binary built from the same sources (oracle/_ref/pbrt_ref); that
+// is what tests/test_oracle_vs_reference.py pins.  The BVH *topology* is not
+// part of the contract (closest hits are topology independent except for
+// exact-t ties), so the build here is a plain median split; traversal and
+// slab test follow the reference.
+//
+// PARITY PIN: checked against oracle/_ref (the unmodified reference compiled
+// from /root/reference) and the golden fixtures in tests/golden/.
+#include "pt_oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------- constants
+// core/pbrt.h:195-206
+const float MachineEpsilon = std::numeric_limits<float>::epsilon() * 0.5;
+const float ShadowEpsilon = 0.0001f;
+const float Pi = 3.14159265358979323846;
+const float InvPi = 0.31830988618379067154;
+const float PiOver2 = 1.57079632679489661923;
+const float PiOver4 = 0.78539816339744830961;
+const float Infinity = std::numeric_limits<float>::infinity();
+const float OneMinusEpsilon = 0x1.fffffep-1;  // core/rng.h FloatOneMinusEpsilon
+
+// core/pbrt.h:285-287
+inline float gamma_(int n) { return (n * MachineEpsilon) / (1 - n * MachineEpsilon); }
+
+inline uint32_t FloatToBits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+inline float BitsToFloat(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+// core/pbrt.h:237-261
+inline float NextFloatUp(float v) {
+    if (std::isinf(v) && v > 0.) return v;
+    if (v == -0.f) v = 0.f;
+    uint32_t ui = FloatToBits(v);
+    if (v >= 0)
+        ++ui;
+    else
+        --ui;
+    return BitsToFloat(ui);
+}
+inline float NextFloatDown(float v) {
+    if (std::isinf(v) && v < 0.) return v;
+    if (v == 0.f) v = -0.f;
+    uint32_t ui = FloatToBits(v);
+    if (v > 0)
+        --ui;
+    else
+        ++ui;
+    return BitsToFloat(ui);
+}
+// core/pbrt.h:300-308
+inline float Clamp(float val, float low, float high) {
+    if (val < low)
+        return low;
+    else if (val > high)
+        return high;
+    else
+        return val;
+}
+
+// ------------------------------------------------------------------ vectors
+struct V3 {
+    float x, y, z;
+    V3() : x(0), y(0), z(0) {}
+    V3(float x, float y, float z) : x(x), y(y), z(z) {}
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    float &operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 operator+(const V3 &a, const V3 &b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(const V3 &a, const V3 &b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(const V3 &a) { return V3(-a.x, -a.y, -a.z); }
+inline V3 operator*(float s, const V3 &v) { return V3(s * v.x, s * v.y, s * v.z); }
+inline V3 operator*(const V3 &v, float s) { return V3(s * v.x, s * v.y, s * v.z); }
+inline float Dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float AbsDot(const V3 &a, const V3 &b) { return std::abs(Dot(a, b)); }
+inline float LengthSquared(const V3 &v) { return v.x * v.x + v.y * v.y + v.z * v.z; }
+inline float Length(const V3 &v) { return std::sqrt(LengthSquared(v)); }
+// geometry.h:243-248 : division multiplies by the reciprocal
+inline V3 Div(const V3 &v, float f) {
+    float inv = (float)1 / f;
+    return V3(v.x * inv, v.y * inv, v.z * inv);
+}
+inline V3 Normalize(const V3 &v) { return Div(v, Length(v)); }
+inline V3 Abs(const V3 &v) { return V3(std::abs(v.x), std::abs(v.y), std::abs(v.z)); }
+// geometry.h:957-963 : cross product evaluated in double
+inline V3 Cross(const V3 &v1, const V3 &v2) {
+    double v1x = v1.x, v1y = v1.y, v1z = v1.z;
+    double v2x = v2.x, v2y = v2.y, v2z = v2.z;
+    return V3((float)((v1y * v2z) - (v1z * v2y)), (float)((v1z * v2x) - (v1x * v2z)),
+              (float)((v1x * v2y) - (v1y * v2x)));
+}
+inline float MaxComponent(const V3 &v) { return std::max(v.x, std::max(v.y, v.z)); }
+// geometry.h:998-1000
+inline int MaxDimension(const V3 &v) {
+    return (v.x > v.y) ? ((v.x > v.z) ? 0 : 2) : ((v.y > v.z) ? 1 : 2);
+}
+inline V3 Permute(const V3 &v, int x, int y, int z) { return V3(v[x], v[y], v[z]); }
+// geometry.h:1020-1027
+inline void CoordinateSystem(const V3 &v1, V3 *v2, V3 *v3) {
+    if (std::abs(v1.x) > std::abs(v1.y))
+        *v2 = Div(V3(-v1.z, 0, v1.x), std::sqrt(v1.x * v1.x + v1.z * v1.z));
+    else
+        *v2 = Div(V3(0, v1.z, -v1.y), std::sqrt(v1.y * v1.y + v1.z * v1.z));
+    *v3 = Cross(v1, *v2);
+}
+
+// ----------------------------------------------------------------- spectrum
+struct S3 {
+    float c[3];
+    S3(float v = 0.f) { c[0] = c[1] = c[2] = v; }
+    S3(float r, float g, float b) {
+        c[0] = r;
+        c[1] = g;
+        c[2] = b;
+    }
+    bool IsBlack() const { return c[0] == 0. && c[1] == 0. && c[2] == 0.; }
+    // spectrum.h:462-465
+    float y() const {
+        const float YWeight[3] = {0.212671f, 0.715160f, 0.072169f};
+        return YWeight[0] * c[0] + YWeight[1] * c[1] + YWeight[2] * c[2];
+    }
+    float MaxComponentValue() const {
+        float m = c[0];
+        for (int i = 1; i < 3; ++i) m = std::max(m, c[i]);
+        return m;
+    }
+    bool HasNaNs() const { return std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]); }
+};
+inline S3 SP(const float *p) { return S3(p[0], p[1], p[2]); }
+inline S3 operator+(const S3 &a, const S3 &b) { return S3(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+inline S3 operator-(const S3 &a, const S3 &b) { return S3(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
+inline S3 operator*(const S3 &a, const S3 &b) { return S3(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
+inline S3 operator/(const S3 &a, const S3 &b) { return S3(a.c[0] / b.c[0], a.c[1] / b.c[1], a.c[2] / b.c[2]); }
+inline S3 operator*(const S3 &a, float s) { return S3(a.c[0] * s, a.c[1] * s, a.c[2] * s); }
+inline S3 operator*(float s, const S3 &a) { return a * s; }
+inline S3 operator/(const S3 &a, float s) { return S3(a.c[0] / s, a.c[1] / s, a.c[2] / s); }  // spectrum.h:181-188
+inline S3 Sqrt(const S3 &a) { return S3(std::sqrt(a.c[0]), std::sqrt(a.c[1]), std::sqrt(a.c[2])); }
+inline S3 &operator+=(S3 &a, const S3 &b) {
+    a = a + b;
+    return a;
+}
+
+// ------------------------------------------------------------------- Sobol'
+// core/lowdiscrepancy.h:229-249
+inline uint64_t SobolIntervalToIndex(const b200pt_sampler_desc &sd, uint32_t m, uint64_t frame, int px,
+                                     int py) {
+    if (m == 0) return 0;
+    const uint32_t m2 = m << 1;
+    uint64_t index = uint64_t(frame) << m2;
+    uint64_t delta = 0;
+    for (int c = 0; frame; frame >>= 1, ++c)
+        if (frame & 1) delta ^= sd.vdc[c];
+    uint64_t b = (((uint64_t)((uint32_t)px) << m) | ((uint32_t)py)) ^ delta;
+    for (int c = 0; b; b >>= 1, ++c)
+        if (b & 1) index ^= sd.vdc_inv[c];
+    return index;
+}
+// core/lowdiscrepancy.h:259-274
+inline float SobolSampleFloat(const b200pt_sampler_desc &sd, int64_t a, int dimension) {
+    if (dimension >= sd.n_dimensions) {
+        fprintf(stderr, "oracle: Sobol dimension %d exceeds provided table (%d)\n", dimension,
+                sd.n_dimensions);
+        abort();
+    }
+    uint32_t v = 0;
+    for (int i = dimension * 52; a != 0; a >>= 1, i++)
+        if (a & 1) v ^= sd.matrices32[i];
+    return std::min(v * 0x1p-32f, OneMinusEpsilon);
+}
+
+inline int RoundUpPow2(int v) {
+    v--;
+    v |= v >> 1;
+    v |= v >> 2;
+    v |= v >> 4;
+    v |= v >> 8;
+    v |= v >> 16;
+    return v + 1;
+}
+inline int Log2Int(uint32_t v) { return 31 - __builtin_clz(v); }
+
+// samplers/sobol.h:45-69 + core/sampler.cpp:136-195 (GlobalSampler)
+struct Sobol {
+    const b200pt_sampler_desc *sd;
+    int resolution, log2Resolution;
+    int px, py;
+    int64_t intervalSampleIndex;
+    int dimension;
+    explicit Sobol(const b200pt_sampler_desc *sd) : sd(sd) {
+        int dx = sd->sample_bounds[2] - sd->sample_bounds[0];
+        int dy = sd->sample_bounds[3] - sd->sample_bounds[1];
+        resolution = RoundUpPow2(std::max(dx, dy));
+        log2Resolution = Log2Int(resolution);
+        px = py = 0;
+        intervalSampleIndex = 0;
+        dimension = 0;
+    }
+    // sobol.cpp:42-45
+    int64_t GetIndexForSample(int64_t sampleNum) const {
+        return SobolIntervalToIndex(*sd, log2Resolution, sampleNum, px - sd->sample_bounds[0],
+                                    py - sd->sample_bounds[1]);
+    }
+    // sobol.cpp:47-59
+    float SampleDimension(int64_t index, int dim) const {
+        float s = SobolSampleFloat(*sd, index, dim);
+        if (dim == 0 || dim == 1) {
+            s = s * resolution + sd->sample_bounds[dim];
+            s = Clamp(s - (dim == 0 ? px : py), (float)0, OneMinusEpsilon);
+        }
+        return s;
+    }
+    void StartPixelSample(int x, int y, int64_t sampleNum) {
+        px = x;
+        py = y;
+        dimension = 0;
+        intervalSampleIndex = GetIndexForSample(sampleNum);
+    }
+    float Get1D() { return SampleDimension(intervalSampleIndex, dimension++); }
+    void Get2D(float u[2]) {
+        u[0] = SampleDimension(intervalSampleIndex, dimension);
+        u[1] = SampleDimension(intervalSampleIndex, dimension + 1);
+        dimension += 2;
+    }
+};
+
+// ------------------------------------------------------------------- camera
+struct Ray {
+    V3 o, d;
+    float tMax;
+};
+// core/transform.h:221-233
+inline V3 XformPoint(const float *m, const V3 &p) {
+    float x = p.x, y = p.y, z = p.z;
+    float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    if (wp == 1) return V3(xp, yp, zp);
+    float inv = (float)1 / wp;  // Point3::operator/ geometry.h:499-503
+    return V3(inv * xp, inv * yp, inv * zp);
+}
+// core/transform.h:278-303
+inline V3 XformPointErr(const float *m, const V3 &p, V3 *pError) {
+    float x = p.x, y = p.y, z = p.z;
+    float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    float xAbsSum = (std::abs(m[0] * x) + std::abs(m[1] * y) + std::abs(m[2] * z) + std::abs(m[3]));
+    float yAbsSum = (std::abs(m[4] * x) + std::abs(m[5] * y) + std::abs(m[6] * z) + std::abs(m[7]));
+    float zAbsSum = (std::abs(m[8] * x) + std::abs(m[9] * y) + std::abs(m[10] * z) + std::abs(m[11]));
+    *pError = gamma_(3) * V3(xAbsSum, yAbsSum, zAbsSum);
+    if (wp == 1) return V3(xp, yp, zp);
+    float inv = (float)1 / wp;
+    return V3(inv * xp, inv * yp, inv * zp);
+}
+// core/transform.h:235-241
+inline V3 XformVector(const float *m, const V3 &v) {
+    float x = v.x, y = v.y, z = v.z;
+    return V3(m[0] * x + m[1] * y + m[2] * z, m[4] * x + m[5] * y + m[6] * z,
+              m[8] * x + m[9] * y + m[10] * z);
+}
+
+// core/sampling.cpp:113-130
+inline void ConcentricSampleDisk(const float u[2], float out[2]) {
+    float ux = 2.f * u[0] - 1, uy = 2.f * u[1] - 1;
+    if (ux == 0 && uy == 0) {
+        out[0] = out[1] = 0;
+        return;
+    }
+    float theta, r;
+    if (std::abs(ux) > std::abs(uy)) {
+        r = ux;
+        theta = PiOver4 * (uy / ux);
+    } else {
+        r = uy;
+        theta = PiOver2 - PiOver4 * (ux / uy);
+    }
+    out[0] = r * std::cos(theta);
+    out[1] = r * std::sin(theta);
+}
+
+// cameras/perspective.cpp:95-144 (main ray only; differentials only feed
+// texture filtering, dead for constant textures) + transform.h:251-264
+inline Ray GenerateCameraRay(const b200pt_camera_desc &cam, const float pFilm[2], const float pLensU[2]) {
+    V3 pCamera = XformPoint(cam.raster_to_camera, V3(pFilm[0], pFilm[1], 0));
+    Ray ray;
+    ray.o = V3(0, 0, 0);
+    ray.d = Normalize(V3(pCamera.x, pCamera.y, pCamera.z));
+    ray.tMax = Infinity;
+    if (cam.lens_radius > 0) {
+        float d2[2];
+        ConcentricSampleDisk(pLensU, d2);
+        float lx = cam.lens_radius * d2[0], ly = cam.lens_radius * d2[1];
+        float ft = cam.focal_distance / ray.d.z;
+        V3 pFocus = ray.o + ray.d * ft;
+        ray.o = V3(lx, ly, 0);
+        ray.d = Normalize(pFocus - ray.o);
+    }
+    // CameraToWorld(ray)
+    V3 oError;
+    V3 o = XformPointErr(cam.camera_to_world, ray.o, &oError);
+    V3 d = XformVector(cam.camera_to_world, ray.d);
+    float lengthSquared = LengthSquared(d);
+    float tMax = ray.tMax;
+    if (lengthSquared > 0) {
+        float dt = Dot(Abs(d), oError) / lengthSquared;
+        o = o + d * dt;
+        tMax -= dt;
+    }
+    Ray out;
+    out.o = o;
+    out.d = d;
+    out.tMax = tMax;
+    return out;
+}
+
+// ----------------------------------------------------------------- triangle
+struct TriHit {
+    float t, b0, b1, b2;
+};
+
+// shapes/triangle.cpp:188-291 (Intersect) == :427-517 (IntersectP): the
+// watertight test up to and including the t > deltaT check.
+inline bool TriangleTest(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &ro, const V3 &rd,
+                         float rayTMax, TriHit *h) {
+    V3 p0t = p0 - ro, p1t = p1 - ro, p2t = p2 - ro;
+    int kz = MaxDimension(Abs(rd));
+    int kx = kz + 1;
+    if (kx == 3) kx = 0;
+    int ky = kx + 1;
+    if (ky == 3) ky = 0;
+    V3 d = Permute(rd, kx, ky, kz);
+    p0t = Permute(p0t, kx, ky, kz);
+    p1t = Permute(p1t, kx, ky, kz);
+    p2t = Permute(p2t, kx, ky, kz);
+    float Sx = -d.x / d.z;
+    float Sy = -d.y / d.z;
+    float Sz = 1.f / d.z;
+    p0t.x += Sx * p0t.z;
+    p0t.y += Sy * p0t.z;
+    p1t.x += Sx * p1t.z;
+    p1t.y += Sy * p1t.z;
+    p2t.x += Sx * p2t.z;
+    p2t.y += Sy * p2t.z;
+    float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+    float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+    float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+        double p2txp1ty = (double)p2t.x * (double)p1t.y;
+        double p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y;
+        double p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y;
+        double p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0t.z *= Sz;
+    p1t.z *= Sz;
+    p2t.z *= Sz;
+    float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0 && (tScaled >= 0 || tScaled < rayTMax * det))
+        return false;
+    else if (det > 0 && (tScaled <= 0 || tScaled > rayTMax * det))
+        return false;
+    float invDet = 1 / det;
+    float b0 = e0 * invDet;
+    float b1 = e1 * invDet;
+    float b2 = e2 * invDet;
+    float t = tScaled * invDet;
+    float maxZt = MaxComponent(Abs(V3(p0t.z, p1t.z, p2t.z)));
+    float deltaZ = gamma_(3) * maxZt;
+    float maxXt = MaxComponent(Abs(V3(p0t.x, p1t.x, p2t.x)));
+    float maxYt = MaxComponent(Abs(V3(p0t.y, p1t.y, p2t.y)));
+    float deltaX = gamma_(5) * (maxXt + maxZt);
+    float deltaY = gamma_(5) * (maxYt + maxZt);
+    float deltaE = 2 * (gamma_(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = MaxComponent(Abs(V3(e0, e1, e2)));
+    float deltaT =
+        3 * (gamma_(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * std::abs(invDet);
+    if (t <= deltaT) return false;
+    h->t = t;
+    h->b0 = b0;
+    h->b1 = b1;
+    h->b2 = b2;
+    return true;
+}
+
+// shapes/triangle.cpp:293-318: partial derivatives with the default uvs of
+// GetUVs (triangle.h:116-126) -- (0,0),(1,0),(1,1) -- returns false for a
+// degenerate triangle (the "intersection is bogus" exit).
+inline bool TrianglePartials(const V3 &p0, const V3 &p1, const V3 &p2, V3 *dpdu, V3 *dpdv) {
+    const float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};
+    float duv02[2] = {uv[0][0] - uv[2][0], uv[0][1] - uv[2][1]};
+    float duv12[2] = {uv[1][0] - uv[2][0], uv[1][1] - uv[2][1]};
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02[0] * duv12[1] - duv02[1] * duv12[0];
+    bool degenerateUV = std::abs(determinant) < 1e-8;
+    if (!degenerateUV) {
+        float invdet = 1 / determinant;
+        *dpdu = (duv12[1] * dp02 - duv02[1] * dp12) * invdet;
+        *dpdv = (-duv12[0] * dp02 + duv02[0] * dp12) * invdet;
+    }
+    if (degenerateUV || LengthSquared(Cross(*dpdu, *dpdv)) == 0) {
+        V3 ng = Cross(p2 - p0, p1 - p0);
+        if (LengthSquared(ng) == 0) return false;
+        CoordinateSystem(Normalize(ng), dpdu, dpdv);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- the scene
+struct BVHNode {  // accelerators/bvh.cpp:95-104 (LinearBVHNode)
+    float bmin[3], bmax[3];
+    int offset;  // primitivesOffset or secondChildOffset
+    uint16_t nPrimitives;
+    uint8_t axis;
+    uint8_t pad;
+};
+
+struct Distribution1D {  // core/sampling.h:55-109
+    std::vector<float> func, cdf;
+    float funcInt;
+    void Init(const float *f, int n) {
+        func.assign(f, f + n);
+        cdf.resize(n + 1);
+        cdf[0] = 0;
+        for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+        funcInt = cdf[n];
+        if (funcInt == 0) {
+            for (int i = 1; i < n + 1; ++i) cdf[i] = float(i) / float(n);
+        } else {
+            for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+        }
+    }
+    int Count() const { return (int)func.size(); }
+    // pbrt.h:353-368 FindInterval + sampling.h:90-100
+    int SampleDiscrete(float u, float *pdf) const {
+        int size = (int)cdf.size();
+        int first = 0, len = size;
+        while (len > 0) {
+            int half = len >> 1, middle = first + half;
+            if (cdf[middle] <= u) {
+                first = middle + 1;
+                len -= half + 1;
+            } else
+                len = half;
+        }
+        int offset = std::min(std::max(first - 1, 0), size - 2);
+        if (pdf) *pdf = (funcInt > 0) ? func[offset] / (funcInt * Count()) : 0;
+        return offset;
+    }
+};
+
+}  // namespace
+
+struct oracle_scene {
+    int64_t nTris;
+    std::vector<V3> p;  // 3 per triangle
+    std::vector<int32_t> materialId, lightId;
+    std::vector<uint8_t> flip;
+    std::vector<uint8_t> degenerate;
+    std::vector<b200pt_material> materials;
+    std::vector<b200pt_area_light> lights;
+    std::vector<float> lightArea;
+    std::vector<BVHNode> nodes;
+    std::vector<int32_t> orderedPrims;
+};
+
+namespace {
+
+// shapes/triangle.cpp:575-581
+inline float TriangleArea(const oracle_scene &s, int tri) {
+    const V3 &p0 = s.p[3 * tri], &p1 = s.p[3 * tri + 1], &p2 = s.p[3 * tri + 2];
+    return 0.5 * Length(Cross(p1 - p0, p2 - p0));
+}
+
+// -------------------------------------------------------------------- BVH
+struct BuildPrim {
+    int32_t id;
+    float bmin[3], bmax[3], c[3];
+};
+
+int BuildRecursive(oracle_scene &s, std::vector<BuildPrim> &prims, int start, int end) {
+    int nodeIdx = (int)s.nodes.size();
+    s.nodes.push_back(BVHNode());
+    float bmin[3] = {Infinity, Infinity, Infinity}, bmax[3] = {-Infinity, -Infinity, -Infinity};
+    float cmin[3] = {Infinity, Infinity, Infinity}, cmax[3] = {-Infinity, -Infinity, -Infinity};
+    for (int i = start; i < end; ++i)
+        for (int a = 0; a < 3; ++a) {
+            bmin[a] = std::min(bmin[a], prims[i].bmin[a]);
+            bmax[a] = std::max(bmax[a], prims[i].bmax[a]);
+            cmin[a] = std::min(cmin[a], prims[i].c[a]);
+            cmax[a] = std::max(cmax[a], prims[i].c[a]);
+        }
+    int n = end - start;
+    int axis = 0;
+    for (int a = 1; a < 3; ++a)
+        if (cmax[a] - cmin[a] > cmax[axis] - cmin[axis]) axis = a;
+    BVHNode node;
+    memcpy(node.bmin, bmin, 12);
+    memcpy(node.bmax, bmax, 12);
+    node.pad = 0;
+    if (n <= 2 || cmax[axis] == cmin[axis]) {
+        node.offset = (int)s.orderedPrims.size();
+        node.nPrimitives = (uint16_t)n;
+        node.axis = 0;
+        for (int i = start; i < end; ++i) s.orderedPrims.push_back(prims[i].id);
+        if (n > 65535) {
+            fprintf(stderr, "oracle: too many coincident primitives\n");
+            abort();
+        }
+        s.nodes[nodeIdx] = node;
+        return nodeIdx;
+    }
+    int mid = (start + end) / 2;
+    std::nth_element(prims.begin() + start, prims.begin() + mid, prims.begin() + end,
+                     [axis](const BuildPrim &a, const BuildPrim &b) { return a.c[axis] < b.c[axis]; });
+    node.nPrimitives = 0;
+    node.axis = (uint8_t)axis;
+    BuildRecursive(s, prims, start, mid);
+    node.offset = BuildRecursive(s, prims, mid, end);
+    s.nodes[nodeIdx] = node;
+    return nodeIdx;
+}
+
+// core/geometry.h:1411-1438
+inline bool BoundsIntersectP(const BVHNode &b, const V3 &ro, float rayTMax, const V3 &invDir,
+                             const int dirIsNeg[3]) {
+    const float *bounds[2] = {b.bmin, b.bmax};
+    float tMin = (bounds[dirIsNeg[0]][0] - ro.x) * invDir.x;
+    float tMax = (bounds[1 - dirIsNeg[0]][0] - ro.x) * invDir.x;
+    float tyMin = (bounds[dirIsNeg[1]][1] - ro.y) * invDir.y;
+    float tyMax = (bounds[1 - dirIsNeg[1]][1] - ro.y) * invDir.y;
+    tMax *= 1 + 2 * gamma_(3);
+    tyMax *= 1 + 2 * gamma_(3);
+    if (tMin > tyMax || tyMin > tMax) return false;
+    if (tyMin > tMin) tMin = tyMin;
+    if (tyMax < tMax) tMax = tyMax;
+    float tzMin = (bounds[dirIsNeg[2]][2] - ro.z) * invDir.z;
+    float tzMax = (bounds[1 - dirIsNeg[2]][2] - ro.z) * invDir.z;
+    tzMax *= 1 + 2 * gamma_(3);
+    if (tMin > tzMax || tzMin > tMax) return false;
+    if (tzMin > tMin) tMin = tzMin;
+    if (tzMax < tMax) tMax = tzMax;
+    return (tMin < rayTMax) && (tMax > 0);
+}
+
+// accelerators/bvh.cpp:662-700.  Returns triangle index or -1; ray.tMax
+// shrinks on every accepted hit (primitive.cpp:120).
+int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut) {
+    if (s.nodes.empty()) return -1;
+    int hitTri = -1;
+    V3 invDir(1 / rd.x, 1 / rd.y, 1 / rd.z);
+    int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    int toVisitOffset = 0, currentNodeIndex = 0;
+    int nodesToVisit[128];
+    while (true) {
+        const BVHNode *node = &s.nodes[currentNodeIndex];
+        if (BoundsIntersectP(*node, ro, rayTMax, invDir, dirIsNeg)) {
+            if (node->nPrimitives > 0) {
+                for (int i = 0; i < node->nPrimitives; ++i) {
+                    int tri = s.orderedPrims[node->offset + i];
+                    if (s.degenerate[tri]) continue;
+                    TriHit h;
+                    if (TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, rd, rayTMax,
+                                     &h)) {
+                        rayTMax = h.t;
+                        *hitOut = h;
+                        hitTri = tri;
+                    }
+                }
+                if (toVisitOffset == 0) break;
+                currentNodeIndex = nodesToVisit[--toVisitOffset];
+            } else {
+                if (dirIsNeg[node->axis]) {
+                    nodesToVisit[toVisitOffset++] = currentNodeIndex + 1;
+                    currentNodeIndex = node->offset;
+                } else {
+                    nodesToVisit[toVisitOffset++] = node->offset;
+                    currentNodeIndex = currentNodeIndex + 1;
+                }
+            }
+        } else {
+            if (toVisitOffset == 0) break;
+            currentNodeIndex = nodesToVisit[--toVisitOffset];
+        }
+    }
+    return hitTri;
+}
+
+// accelerators/bvh.cpp:702-738
+bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
+    if (s.nodes.empty()) return false;
+    V3 invDir(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
+    int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    int nodesToVisit[128];
+    int toVisitOffset = 0, currentNodeIndex = 0;
+    while (true) {
+        const BVHNode *node = &s.nodes[currentNodeIndex];
+        if (BoundsIntersectP(*node, ro, rayTMax, invDir, dirIsNeg)) {
+            if (node->nPrimitives > 0) {
+                for (int i = 0; i < node->nPrimitives; ++i) {
+                    int tri = s.orderedPrims[node->offset + i];
+                    if (s.degenerate[tri]) continue;
+                    TriHit h;
+                    if (TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, rd, rayTMax,
+                                     &h))
+                        return true;
+                }
+                if (toVisitOffset == 0) break;
+                currentNodeIndex = nodesToVisit[--toVisitOffset];
+            } else {
+                if (dirIsNeg[node->axis]) {
+                    nodesToVisit[toVisitOffset++] = currentNodeIndex + 1;
+                    currentNodeIndex = node->offset;
+                } else {
+                    nodesToVisit[toVisitOffset++] = node->offset;
+                    currentNodeIndex = currentNodeIndex + 1;
+                }
+            }
+        } else {
+            if (toVisitOffset == 0) break;
+            currentNodeIndex = nodesToVisit[--toVisitOffset];
+        }
+    }
+    return false;
+}
+
+// ----------------------------------------------------- surface interaction
+struct Isect {
+    V3 p, pError, n, wo;  // Interaction: n = geometric normal after orientation
+    V3 dpdu;              // shading.dpdu == dpdu (no per-vertex shading data)
+    int tri;
+};
+
+// shapes/triangle.cpp:319-425 for a mesh without n/s/uv + interaction.cpp:44-71
+inline void FillIsect(const oracle_scene &s, int tri, const TriHit &h, const V3 &rayD, Isect *is) {
+    const V3 &p0 = s.p[3 * tri], &p1 = s.p[3 * tri + 1], &p2 = s.p[3 * tri + 2];
+    V3 dpdu, dpdv;
+    TrianglePartials(p0, p1, p2, &dpdu, &dpdv);
+    float xAbsSum = (std::abs(h.b0 * p0.x) + std::abs(h.b1 * p1.x) + std::abs(h.b2 * p2.x));
+    float yAbsSum = (std::abs(h.b0 * p0.y) + std::abs(h.b1 * p1.y) + std::abs(h.b2 * p2.y));
+    float zAbsSum = (std::abs(h.b0 * p0.z) + std::abs(h.b1 * p1.z) + std::abs(h.b2 * p2.z));
+    is->pError = gamma_(7) * V3(xAbsSum, yAbsSum, zAbsSum);
+    is->p = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
+    is->wo = Normalize(-rayD);  // Interaction ctor, interaction.h:62
+    is->dpdu = dpdu;
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    is->n = Normalize(Cross(dp02, dp12));
+    if (s.flip[tri]) is->n = -is->n;
+    is->tri = tri;
+}
+
+// core/geometry.h:1440-1460
+inline V3 OffsetRayOrigin(const V3 &p, const V3 &pError, const V3 &n, const V3 &w) {
+    float d = Dot(Abs(n), pError);
+    V3 offset = d * n;
+    if (Dot(w, n) < 0) offset = -offset;
+    V3 po = p + offset;
+    for (int i = 0; i < 3; ++i) {
+        if (offset[i] > 0)
+            po[i] = NextFloatUp(po[i]);
+        else if (offset[i] < 0)
+            po[i] = NextFloatDown(po[i]);
+    }
+    return po;
+}
+
+// ------------------------------------------------------------------- BSDFs
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+enum BxKind { BX_LAMBERT, BX_MICROFACET, BX_FRESNEL_SPECULAR };
+enum FrKind { FR_DIELECTRIC, FR_CONDUCTOR };
+
+struct BxDF {
+    BxKind kind;
+    int type;
+    S3 R, T;
+    // microfacet
+    float alphax, alphay;
+    FrKind fr;
+    float frEtaI, frEtaT;  // dielectric
+    S3 cEtaI, cEtaT, cK;   // conductor
+    // fresnel specular
+    float etaA, etaB;
+    bool MatchesFlags(int t) const { return (type & t) == type; }
+};
+
+inline float CosTheta(const V3 &w) { return w.z; }
+inline float Cos2Theta(const V3 &w) { return w.z * w.z; }
+inline float AbsCosTheta(const V3 &w) { return std::abs(w.z); }
+inline float Sin2Theta(const V3 &w) { return std::max((float)0, (float)1 - Cos2Theta(w)); }
+inline float SinTheta(const V3 &w) { return std::sqrt(Sin2Theta(w)); }
+inline float TanTheta(const V3 &w) { return SinTheta(w) / CosTheta(w); }
+inline float Tan2Theta(const V3 &w) { return Sin2Theta(w) / Cos2Theta(w); }
+inline float CosPhi(const V3 &w) {
+    float sinTheta = SinTheta(w);
+    return (sinTheta == 0) ? 1 : Clamp(w.x / sinTheta, -1, 1);
+}
+inline float SinPhi(const V3 &w) {
+    float sinTheta = SinTheta(w);
+    return (sinTheta == 0) ? 0 : Clamp(w.y / sinTheta, -1, 1);
+}
+inline float Cos2Phi(const V3 &w) { return CosPhi(w) * CosPhi(w); }
+inline float Sin2Phi(const V3 &w) { return SinPhi(w) * SinPhi(w); }
+inline bool SameHemisphere(const V3 &w, const V3 &wp) { return w.z * wp.z > 0; }
+inline V3 Reflect(const V3 &wo, const V3 &n) { return -wo + 2 * Dot(wo, n) * n; }
+// reflection.h:101-114
+inline bool Refract(const V3 &wi, const V3 &n, float eta, V3 *wt) {
+    float cosThetaI = Dot(n, wi);
+    float sin2ThetaI = std::max(float(0), float(1 - cosThetaI * cosThetaI));
+    float sin2ThetaT = eta * eta * sin2ThetaI;
+    if (sin2ThetaT >= 1) return false;
+    float cosThetaT = std::sqrt(1 - sin2ThetaT);
+    *wt = eta * -wi + (eta * cosThetaI - cosThetaT) * n;
+    return true;
+}
+
+// reflection.cpp:47-68
+float FrDielectric(float cosThetaI, float etaI, float etaT) {
+    cosThetaI = Clamp(cosThetaI, -1, 1);
+    bool entering = cosThetaI > 0.f;
+    if (!entering) {
+        std::swap(etaI, etaT);
+        cosThetaI = std::abs(cosThetaI);
+    }
+    float sinThetaI = std::sqrt(std::max((float)0, 1 - cosThetaI * cosThetaI));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    if (sinThetaT >= 1) return 1;
+    float cosThetaT = std::sqrt(std::max((float)0, 1 - sinThetaT * sinThetaT));
+    float Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+    float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+    return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+// reflection.cpp:71-94
+S3 FrConductor(float cosThetaI, const S3 &etai, const S3 &etat, const S3 &k) {
+    cosThetaI = Clamp(cosThetaI, -1, 1);
+    S3 eta = etat / etai;
+    S3 etak = k / etai;
+    float cosThetaI2 = cosThetaI * cosThetaI;
+    float sinThetaI2 = 1. - cosThetaI2;
+    S3 eta2 = eta * eta;
+    S3 etak2 = etak * etak;
+    S3 t0 = eta2 - etak2 - S3(sinThetaI2);
+    S3 a2plusb2 = Sqrt(t0 * t0 + 4 * eta2 * etak2);
+    S3 t1 = a2plusb2 + S3(cosThetaI2);
+    S3 a = Sqrt(0.5f * (a2plusb2 + t0));
+    S3 t2 = (float)2 * cosThetaI * a;
+    S3 Rs = (t1 - t2) / (t1 + t2);
+    S3 t3 = cosThetaI2 * a2plusb2 + S3(sinThetaI2 * sinThetaI2);
+    S3 t4 = t2 * sinThetaI2;
+    S3 Rp = Rs * (t3 - t4) / (t3 + t4);
+    return 0.5 * (Rp + Rs);
+}
+inline S3 FresnelEvaluate(const BxDF &b, float cosThetaI) {
+    if (b.fr == FR_DIELECTRIC) return S3(FrDielectric(cosThetaI, b.frEtaI, b.frEtaT));  // reflection.cpp:128-130
+    return FrConductor(std::abs(cosThetaI), b.cEtaI, b.cEtaT, b.cK);                       // reflection.cpp:117-119
+}
+
+// microfacet.cpp:155-163
+float TR_D(const BxDF &b, const V3 &wh) {
+    float tan2Theta = Tan2Theta(wh);
+    if (std::isinf(tan2Theta)) return 0.;
+    const float cos4Theta = Cos2Theta(wh) * Cos2Theta(wh);
+    float e = (Cos2Phi(wh) / (b.alphax * b.alphax) + Sin2Phi(wh) / (b.alphay * b.alphay)) * tan2Theta;
+    return 1 / (Pi * b.alphax * b.alphay * cos4Theta * (1 + e) * (1 + e));
+}
+// microfacet.cpp:176-184
+float TR_Lambda(const BxDF &b, const V3 &w) {
+    float absTanTheta = std::abs(TanTheta(w));
+    if (std::isinf(absTanTheta)) return 0.;
+    float alpha = std::sqrt(Cos2Phi(w) * b.alphax * b.alphax + Sin2Phi(w) * b.alphay * b.alphay);
+    float alpha2Tan2Theta = (alpha * absTanTheta) * (alpha * absTanTheta);
+    return (-1 + std::sqrt(1.f + alpha2Tan2Theta)) / 2;
+}
+inline float TR_G1(const BxDF &b, const V3 &w) { return 1 / (1 + TR_Lambda(b, w)); }
+inline float TR_G(const BxDF &b, const V3 &wo, const V3 &wi) { return 1 / (1 + TR_Lambda(b, wo) + TR_Lambda(b, wi)); }
+// microfacet.cpp:338-344 (sampleVisibleArea == true, the materials' default)
+inline float TR_Pdf(const BxDF &b, const V3 &wo, const V3 &wh) {
+    return TR_D(b, wh) * TR_G1(b, wo) * AbsDot(wo, wh) / AbsCosTheta(wo);
+}
+// microfacet.cpp:238-283
+void TrowbridgeReitzSample11(float cosTheta, float U1, float U2, float *slope_x, float *slope_y) {
+    if (cosTheta > .9999) {
+        float r = sqrt(U1 / (1 - U1));
+        float phi = 6.28318530718 * U2;
+        *slope_x = r * cos((double)phi);  // unqualified cos/sin on a float promote to double in the reference
+        *slope_y = r * sin((double)phi);
+        return;
+    }
+    float sinTheta = std::sqrt(std::max((float)0, (float)1 - cosTheta * cosTheta));
+    float tanTheta = sinTheta / cosTheta;
+    float a = 1 / tanTheta;
+    float G1 = 2 / (1 + std::sqrt(1.f + 1.f / (a * a)));
+    float A = 2 * U1 / G1 - 1;
+    float tmp = 1.f / (A * A - 1.f);
+    if (tmp > 1e10) tmp = 1e10;
+    float B = tanTheta;
+    float D = std::sqrt(std::max(float(B * B * tmp * tmp - (A * A - B * B) * tmp), float(0)));
+    float slope_x_1 = B * tmp - D;
+    float slope_x_2 = B * tmp + D;
+    *slope_x = (A < 0 || slope_x_2 > 1.f / tanTheta) ? slope_x_1 : slope_x_2;
+    float S;
+    if (U2 > 0.5f) {
+        S = 1.f;
+        U2 = 2.f * (U2 - .5f);
+    } else {
+        S = -1.f;
+        U2 = 2.f * (.5f - U2);
+    }
+    float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) /
+              (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+    *slope_y = S * z * std::sqrt(1.f + *slope_x * *slope_x);
+}
+// microfacet.cpp:285-305
+V3 TrowbridgeReitzSample(const V3 &wi, float alpha_x, float alpha_y, float U1, float U2) {
+    V3 wiStretched = Normalize(V3(alpha_x * wi.x, alpha_y * wi.y, wi.z));
+    float slope_x, slope_y;
+    TrowbridgeReitzSample11(CosTheta(wiStretched), U1, U2, &slope_x, &slope_y);
+    float tmp = CosPhi(wiStretched) * slope_x - SinPhi(wiStretched) * slope_y;
+    slope_y = SinPhi(wiStretched) * slope_x + CosPhi(wiStretched) * slope_y;
+    slope_x = tmp;
+    slope_x = alpha_x * slope_x;
+    slope_y = alpha_y * slope_y;
+    return Normalize(V3(-slope_x, -slope_y, 1.));
+}
+// microfacet.cpp:307-336 (visible-area branch)
+inline V3 TR_Sample_wh(const BxDF &b, const V3 &wo, const float u[2]) {
+    bool flip = wo.z < 0;
+    V3 wh = TrowbridgeReitzSample(flip ? -wo : wo, b.alphax, b.alphay, u[0], u[1]);
+    if (flip) wh = -wh;
+    return wh;
+}
+
+// sampling.h:159-163
+inline V3 CosineSampleHemisphere(const float u[2]) {
+    float d[2];
+    ConcentricSampleDisk(u, d);
+    float z = std::sqrt(std::max((float)0, 1 - d[0] * d[0] - d[1] * d[1]));
+    return V3(d[0], d[1], z);
+}
+
+// BxDF::f
+S3 Bx_f(const BxDF &b, const V3 &wo, const V3 &wi) {
+    switch (b.kind) {
+    case BX_LAMBERT:
+        return b.R * InvPi;  // reflection.cpp:178-180
+    case BX_MICROFACET: {    // reflection.cpp:226-236
+        float cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+        V3 wh = wi + wo;
+        if (cosThetaI == 0 || cosThetaO == 0) return S3(0.);
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return S3(0.);
+        wh = Normalize(wh);
+        S3 F = FresnelEvaluate(b, Dot(wi, wh));
+        return b.R * TR_D(b, wh) * TR_G(b, wo, wi) * F / (4 * cosThetaI * cosThetaO);
+    }
+    case BX_FRESNEL_SPECULAR:
+        return S3(0.f);  // reflection.h:363-365
+    }
+    return S3(0.f);
+}
+// BxDF::Pdf
+float Bx_Pdf(const BxDF &b, const V3 &wo, const V3 &wi) {
+    switch (b.kind) {
+    case BX_LAMBERT:
+        return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * InvPi : 0;  // reflection.cpp:387-389
+    case BX_MICROFACET: {                                             // reflection.cpp:419-423
+        if (!SameHemisphere(wo, wi)) return 0;
+        V3 wh = Normalize(wo + wi);
+        return TR_Pdf(b, wo, wh) / (4 * Dot(wo, wh));
+    }
+    case BX_FRESNEL_SPECULAR:
+        return 0;  // reflection.h:368
+    }
+    return 0;
+}
+// BxDF::Sample_f.  *pdfSet tells whether the callee wrote *pdf (the
+// reference leaves it untouched on some early returns).
+S3 Bx_Sample_f(const BxDF &b, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
+    switch (b.kind) {
+    case BX_LAMBERT: {  // reflection.cpp:378-385
+        *wi = CosineSampleHemisphere(u);
+        if (wo.z < 0) wi->z *= -1;
+        *pdf = Bx_Pdf(b, wo, *wi);
+        return Bx_f(b, wo, *wi);
+    }
+    case BX_MICROFACET: {  // reflection.cpp:405-417
+        if (wo.z == 0) return S3(0.);
+        V3 wh = TR_Sample_wh(b, wo, u);
+        *wi = Reflect(wo, wh);
+        if (!SameHemisphere(wo, *wi)) return S3(0.f);
+        *pdf = TR_Pdf(b, wo, wh) / (4 * Dot(wo, wh));
+        return Bx_f(b, wo, *wi);
+    }
+    case BX_FRESNEL_SPECULAR: {  // reflection.cpp:477-511 (TransportMode::Radiance)
+        float F = FrDielectric(CosTheta(wo), b.etaA, b.etaB);
+        if (u[0] < F) {
+            *wi = V3(-wo.x, -wo.y, wo.z);
+            if (sampledType) *sampledType = BSDF_SPECULAR | BSDF_REFLECTION;
+            *pdf = F;
+            return F * b.R / AbsCosTheta(*wi);
+        } else {
+            bool entering = CosTheta(wo) > 0;
+            float etaI = entering ? b.etaA : b.etaB;
+            float etaT = entering ? b.etaB : b.etaA;
+            V3 nn(0, 0, 1);
+            if (Dot(nn, wo) < 0.f) nn = -nn;  // Faceforward, geometry.h:1213-1216
+            if (!Refract(wo, nn, etaI / etaT, wi)) return S3(0.f);
+            S3 ft = b.T * (1 - F);
+            ft = ft * ((etaI * etaI) / (etaT * etaT));
+            if (sampledType) *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
+            *pdf = 1 - F;
+            return ft / AbsCosTheta(*wi);
+        }
+    }
+    }
+    return S3(0.f);
+}
+
+struct BSDF {  // reflection.h:153-202
+    float eta;
+    V3 ns, ng, ss, ts;
+    int nBxDFs;
+    BxDF bxdfs[2];
+    V3 WorldToLocal(const V3 &v) const { return V3(Dot(v, ss), Dot(v, ts), Dot(v, ns)); }
+    V3 LocalToWorld(const V3 &v) const {
+        return V3(ss.x * v.x + ts.x * v.y + ns.x * v.z, ss.y * v.x + ts.y * v.y + ns.y * v.z,
+                  ss.z * v.x + ts.z * v.y + ns.z * v.z);
+    }
+    int NumComponents(int flags) const {
+        int num = 0;
+        for (int i = 0; i < nBxDFs; ++i)
+            if (bxdfs[i].MatchesFlags(flags)) ++num;
+        return num;
+    }
+    // reflection.cpp:670-683
+    S3 f(const V3 &woW, const V3 &wiW, int flags) const {
+        V3 wi = WorldToLocal(wiW), wo = WorldToLocal(woW);
+        if (wo.z == 0) return S3(0.);
+        bool reflect = Dot(wiW, ng) * Dot(woW, ng) > 0;
+        S3 f(0.f);
+        for (int i = 0; i < nBxDFs; ++i)
+            if (bxdfs[i].MatchesFlags(flags) && ((reflect && (bxdfs[i].type & BSDF_REFLECTION)) ||
+                                                 (!reflect && (bxdfs[i].type & BSDF_TRANSMISSION))))
+                f += Bx_f(bxdfs[i], wo, wi);
+        return f;
+    }
+    // reflection.cpp:770-785
+    float Pdf(const V3 &woWorld, const V3 &wiWorld, int flags) const {
+        if (nBxDFs == 0.f) return 0.f;
+        V3 wo = WorldToLocal(woWorld), wi = WorldToLocal(wiWorld);
+        if (wo.z == 0) return 0.;
+        float pdf = 0.f;
+        int matchingComps = 0;
+        for (int i = 0; i < nBxDFs; ++i)
+            if (bxdfs[i].MatchesFlags(flags)) {
+                ++matchingComps;
+                pdf += Bx_Pdf(bxdfs[i], wo, wi);
+            }
+        float v = matchingComps > 0 ? pdf / matchingComps : 0.f;
+        return v;
+    }
+    // reflection.cpp:703-768.  *pdf is left untouched where the reference
+    // leaves it untouched.
+    S3 Sample_f(const V3 &woWorld, V3 *wiWorld, const float u[2], float *pdf, int type,
+                int *sampledType) const {
+        int matchingComps = NumComponents(type);
+        if (matchingComps == 0) {
+            *pdf = 0;
+            if (sampledType) *sampledType = 0;
+            return S3(0.f);
+        }
+        int comp = std::min((int)std::floor(u[0] * matchingComps), matchingComps - 1);
+        const BxDF *bxdf = nullptr;
+        int count = comp;
+        for (int i = 0; i < nBxDFs; ++i)
+            if (bxdfs[i].MatchesFlags(type) && count-- == 0) {
+                bxdf = &bxdfs[i];
+                break;
+            }
+        float uRemapped[2] = {std::min(u[0] * matchingComps - comp, OneMinusEpsilon), u[1]};
+        V3 wi, wo = WorldToLocal(woWorld);
+        if (wo.z == 0) return S3(0.);
+        *pdf = 0;
+        if (sampledType) *sampledType = bxdf->type;
+        S3 f = Bx_Sample_f(*bxdf, wo, &wi, uRemapped, pdf, sampledType);
+        if (*pdf == 0) {
+            if (sampledType) *sampledType = 0;
+            return S3(0.f);
+        }
+        *wiWorld = LocalToWorld(wi);
+        if (!(bxdf->type & BSDF_SPECULAR) && matchingComps > 1)
+            for (int i = 0; i < nBxDFs; ++i)
+                if (&bxdfs[i] != bxdf && bxdfs[i].MatchesFlags(type)) *pdf += Bx_Pdf(bxdfs[i], wo, wi);
+        if (matchingComps > 1) *pdf /= matchingComps;
+        if (!(bxdf->type & BSDF_SPECULAR)) {
+            bool reflect = Dot(*wiWorld, ng) * Dot(woWorld, ng) > 0;
+            f = S3(0.);
+            for (int i = 0; i < nBxDFs; ++i)
+                if (bxdfs[i].MatchesFlags(type) && ((reflect && (bxdfs[i].type & BSDF_REFLECTION)) ||
+                                                    (!reflect && (bxdfs[i].type & BSDF_TRANSMISSION))))
+                    f += Bx_f(bxdfs[i], wo, wi);
+        }
+        return f;
+    }
+};
+
+// materials/*.cpp ComputeScatteringFunctions with constant textures
+// (allowMultipleLobes = true, TransportMode::Radiance; path.cpp:107)
+void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
+    const b200pt_material &m = s.materials[s.materialId[is.tri]];
+    bsdf->eta = 1;
+    bsdf->ns = is.n;  // shading.n == n for meshes without shading normals
+    bsdf->ng = is.n;
+    bsdf->ss = Normalize(is.dpdu);
+    bsdf->ts = Cross(bsdf->ns, bsdf->ss);
+    bsdf->nBxDFs = 0;
+    auto lambert = [&](const float *kd) {
+        BxDF b;
+        b.kind = BX_LAMBERT;
+        b.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+        b.R = SP(kd);
+        bsdf->bxdfs[bsdf->nBxDFs++] = b;
+    };
+    switch (m.type) {
+    case B200PT_MAT_MATTE:  // matte.cpp:45-62
+        if (!SP(m.kd).IsBlack()) lambert(m.kd);
+        break;
+    case B200PT_MAT_PLASTIC: {  // plastic.cpp:45-70
+        if (!SP(m.kd).IsBlack()) lambert(m.kd);
+        if (!SP(m.ks).IsBlack()) {
+            BxDF b;
+            b.kind = BX_MICROFACET;
+            b.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            b.R = SP(m.ks);
+            b.alphax = m.alpha_x;
+            b.alphay = m.alpha_x;
+            b.fr = FR_DIELECTRIC;
+            b.frEtaI = 1.5f;
+            b.frEtaT = 1.f;
+            bsdf->bxdfs[bsdf->nBxDFs++] = b;
+        }
+        break;
+    }
+    case B200PT_MAT_METAL: {  // metal.cpp:59-80
+        BxDF b;
+        b.kind = BX_MICROFACET;
+        b.type = BSDF_REFLECTION | BSDF_GLOSSY;
+        b.R = S3(1.);
+        b.alphax = m.alpha_x;
+        b.alphay = m.alpha_y;
+        b.fr = FR_CONDUCTOR;
+        b.cEtaI = S3(1.);
+        b.cEtaT = SP(m.eta);
+        b.cK = SP(m.k);
+        bsdf->bxdfs[bsdf->nBxDFs++] = b;
+        break;
+    }
+    case B200PT_MAT_GLASS: {  // glass.cpp:45-64 (smooth + allowMultipleLobes)
+        bsdf->eta = m.index;
+        S3 R = SP(m.ks), T = SP(m.kt);
+        if (R.IsBlack() && T.IsBlack()) break;
+        BxDF b;
+        b.kind = BX_FRESNEL_SPECULAR;
+        b.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+        b.R = R;
+        b.T = T;
+        b.etaA = 1.f;
+        b.etaB = m.index;
+        bsdf->bxdfs[bsdf->nBxDFs++] = b;
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+// ------------------------------------------------------------------ lights
+// lights/diffuse.h:56-58
+inline S3 AreaLightL(const b200pt_area_light &l, const V3 &n, const V3 &w) {
+    return (l.two_sided || Dot(n, w) > 0) ? SP(l.lemit) : S3(0.f);
+}
+// interaction.cpp:151-154
+inline S3 IsectLe(const oracle_scene &s, const Isect &is, const V3 &w) {
+    int lid = s.lightId[is.tri];
+    return lid >= 0 ? AreaLightL(s.lights[lid], is.n, w) : S3(0.f);
+}
+
+struct LightSample {
+    V3 p, n, pError;
+};
+// shapes/triangle.cpp:583-608 (mesh without normals)
+inline LightSample TriangleSample(const oracle_scene &s, int tri, const float u[2], float *pdf) {
+    float su0 = std::sqrt(u[0]);  // sampling.cpp:154-157
+    float b[2] = {1 - su0, u[1] * su0};
+    const V3 &p0 = s.p[3 * tri], &p1 = s.p[3 * tri + 1], &p2 = s.p[3 * tri + 2];
+    LightSample it;
+    it.p = b[0] * p0 + b[1] * p1 + (1 - b[0] - b[1]) * p2;
+    it.n = Normalize(Cross(p1 - p0, p2 - p0));
+    if (s.flip[tri]) it.n = it.n * -1.f;
+    V3 pAbsSum = Abs(b[0] * p0) + Abs(b[1] * p1) + Abs((1 - b[0] - b[1]) * p2);
+    it.pError = gamma_(6) * V3(pAbsSum.x, pAbsSum.y, pAbsSum.z);
+    *pdf = 1 / TriangleArea(s, tri);
+    return it;
+}
+
+struct RenderCtx {
+    const oracle_scene *s;
+    const b200pt_camera_desc *cam;
+    const b200pt_film_desc *film;
+    const b200pt_sampler_desc *sd;
+    const b200pt_integrator_desc *integ;
+    Distribution1D lightDistrib;
+    uint64_t cameraRays, regularRays, shadowRays;
+};
+
+// core/integrator.cpp:108-215 (handleMedia = false, specular = false)
+S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float uScattering[2], int lightNum,
+                  const float uLight[2]) {
+    const oracle_scene &s = *rc.s;
+    const b200pt_area_light &light = s.lights[lightNum];
+    int bsdfFlags = BSDF_ALL & ~BSDF_SPECULAR;
+    S3 Ld(0.f);
+    V3 wi;
+    float lightPdf = 0, scatteringPdf = 0;
+    // light.Sample_Li: lights/diffuse.cpp:68-81, shape.cpp:56-70
+    S3 Li(0.f);
+    LightSample pShape = TriangleSample(s, light.triangle, uLight, &lightPdf);
+    {
+        V3 w = pShape.p - it.p;
+        if (LengthSquared(w) == 0)
+            lightPdf = 0;
+        else {
+            w = Normalize(w);
+            lightPdf *= LengthSquared(it.p - pShape.p) / AbsDot(pShape.n, -w);
+            if (std::isinf(lightPdf)) lightPdf = 0.f;
+        }
+    }
+    if (lightPdf == 0 || LengthSquared(pShape.p - it.p) == 0) {
+        lightPdf = 0;
+        Li = S3(0.f);
+    } else {
+        wi = Normalize(pShape.p - it.p);
+        Li = AreaLightL(light, pShape.n, -wi);
+    }
+    if (lightPdf > 0 && !Li.IsBlack()) {
+        S3 f = bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
+        scatteringPdf = bsdf.Pdf(it.wo, wi, bsdfFlags);
+        if (!f.IsBlack()) {
+            // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
+            V3 origin = OffsetRayOrigin(it.p, it.pError, it.n, pShape.p - it.p);
+            V3 target = OffsetRayOrigin(pShape.p, pShape.pError, pShape.n, origin - pShape.p);
+            V3 d = target - origin;
+            ++rc.shadowRays;
+            if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
+            if (!Li.IsBlack()) {
+                float weight = (lightPdf * lightPdf) / (lightPdf * lightPdf + scatteringPdf * scatteringPdf);
+                Ld += f * Li * weight / lightPdf;
+            }
+        }
+    }
+    // BSDF sampling with MIS
+    {
+        S3 f;
+        bool sampledSpecular = false;
+        int sampledType = 0;
+        f = bsdf.Sample_f(it.wo, &wi, uScattering, &scatteringPdf, bsdfFlags, &sampledType);
+        f = f * AbsDot(wi, bsdf.ns);
+        sampledSpecular = (sampledType & BSDF_SPECULAR) != 0;
+        if (!f.IsBlack() && scatteringPdf > 0) {
+            float weight = 1;
+            if (!sampledSpecular) {
+                // light.Pdf_Li -> Shape::Pdf, shape.cpp:72-87
+                V3 ro = OffsetRayOrigin(it.p, it.pError, it.n, wi);
+                TriHit h;
+                int tri = light.triangle;
+                lightPdf = 0;
+                if (!s.degenerate[tri] &&
+                    TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, wi, Infinity, &h)) {
+                    Isect li;
+                    FillIsect(s, tri, h, wi, &li);
+                    lightPdf = LengthSquared(it.p - li.p) / (AbsDot(li.n, -wi) * TriangleArea(s, tri));
+                    if (std::isinf(lightPdf)) lightPdf = 0.f;
+                }
+                if (lightPdf == 0) return Ld;
+                float fw = scatteringPdf, gw = lightPdf;
+                weight = (fw * fw) / (fw * fw + gw * gw);
+            }
+            V3 ro = OffsetRayOrigin(it.p, it.pError, it.n, wi);
+            TriHit h;
+            ++rc.regularRays;
+            int hitTri = SceneIntersect(s, ro, wi, Infinity, &h);
+            S3 Li2(0.f);
+            if (hitTri >= 0) {
+                if (s.lightId[hitTri] == lightNum) {
+                    Isect li;
+                    FillIsect(s, hitTri, h, wi, &li);
+                    Li2 = IsectLe(s, li, -wi);
+                }
+            }
+            if (!Li2.IsBlack()) Ld += f * Li2 * S3(1.f) * weight / scatteringPdf;
+        }
+    }
+    return Ld;
+}
+
+// integrators/path.cpp:64-188
+S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
+    const oracle_scene &s = *rc.s;
+    const int maxDepth = rc.integ->max_depth;
+    const float rrThreshold = rc.integ->rr_threshold;
+    S3 L(0.f), beta(1.f);
+    bool specularBounce = false;
+    int bounces;
+    float etaScale = 1;
+    for (bounces = 0;; ++bounces) {
+        TriHit h;
+        ++rc.regularRays;
+        int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h);
+        bool foundIntersection = tri >= 0;
+        Isect isect;
+        if (foundIntersection) FillIsect(s, tri, h, ray.d, &isect);
+        if (bounces == 0 || specularBounce) {
+            if (foundIntersection) L += beta * IsectLe(s, isect, -ray.d);
+        }
+        if (!foundIntersection || bounces >= maxDepth) break;
+        BSDF bsdf;
+        MakeBSDF(s, isect, &bsdf);
+        if (bsdf.NumComponents(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
+            // UniformSampleOneLight, integrator.cpp:85-106
+            S3 Ld(0.f);
+            int nLights = (int)s.lights.size();
+            if (nLights > 0) {
+                float lightPdf;
+                int lightNum = rc.lightDistrib.SampleDiscrete(sampler.Get1D(), &lightPdf);
+                if (lightPdf != 0) {
+                    float uLight[2], uScattering[2];
+                    sampler.Get2D(uLight);
+                    sampler.Get2D(uScattering);
+                    Ld = EstimateDirect(rc, isect, bsdf, uScattering, lightNum, uLight) / lightPdf;
+                }
+            }
+            Ld = beta * Ld;
+            L += Ld;
+        }
+        V3 wo = -ray.d, wi;
+        float pdf = 0;  // uninitialised in the reference; only read when f is non-black
+        int flags = 0;
+        float u2[2];
+        sampler.Get2D(u2);
+        S3 f = bsdf.Sample_f(wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+        if (f.IsBlack() || pdf == 0.f) break;
+        beta = beta * (f * AbsDot(wi, bsdf.ns) / pdf);
+        specularBounce = (flags & BSDF_SPECULAR) != 0;
+        if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+            float eta = bsdf.eta;
+            etaScale *= (Dot(wo, isect.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+        }
+        ray.o = OffsetRayOrigin(isect.p, isect.pError, isect.n, wi);  // SpawnRay
+        ray.d = wi;
+        ray.tMax = Infinity;
+        S3 rrBeta = beta * etaScale;
+        if (rrBeta.MaxComponentValue() < rrThreshold && bounces > 3) {
+            float q = std::max((float).05, 1 - rrBeta.MaxComponentValue());
+            if (sampler.Get1D() < q) break;
+            beta = beta / (1 - q);
+        }
+    }
+    return L;
+}
+
+// One camera sample: integrator.cpp:276-316.  Returns guarded L and pFilm.
+S3 RenderSample(RenderCtx &rc, Sobol &sampler, int px, int py, int64_t sampleNum, float pFilm[2]) {
+    sampler.StartPixelSample(px, py, sampleNum);
+    float u[2];
+    sampler.Get2D(u);  // sampler.cpp:46-52
+    pFilm[0] = (float)px + u[0];
+    pFilm[1] = (float)py + u[1];
+    (void)sampler.Get1D();  // time
+    float pLens[2];
+    sampler.Get2D(pLens);
+    Ray ray = GenerateCameraRay(*rc.cam, pFilm, pLens);
+    ++rc.cameraRays;
+    S3 L = PathLi(rc, ray, sampler);
+    if (L.HasNaNs())
+        L = S3(0.f);
+    else if (L.y() < -1e-5)
+        L = S3(0.f);
+    else if (std::isinf(L.y()))
+        L = S3(0.f);
+    return L;
+}
+
+struct FilmTilePixel {
+    S3 contribSum;
+    float filterWeightSum;
+    FilmTilePixel() : contribSum(0.f), filterWeightSum(0.f) {}
+};
+
+void InitLightDistribution(RenderCtx &rc) {
+    const oracle_scene &s = *rc.s;
+    int n = (int)s.lights.size();
+    if (n == 0) return;
+    std::vector<float> prob(n, 1.f);
+    // lightdistrib.cpp:48-58: a single light always gets the uniform distribution
+    if (rc.integ->light_strategy == B200PT_LIGHTS_POWER && n != 1) {
+        // integrator.cpp:216-224 + diffuse.cpp:64-66
+        for (int i = 0; i < n; ++i) {
+            const b200pt_area_light &l = s.lights[i];
+            S3 power = (l.two_sided ? 2 : 1) * SP(l.lemit) * s.lightArea[i] * Pi;
+            prob[i] = power.y();
+        }
+    }
+    rc.lightDistrib.Init(prob.data(), n);
+}
+
+inline void RGBToXYZ(const float rgb[3], float xyz[3]) {  // spectrum.h:62-66
+    xyz[0] = 0.412453f * rgb[0] + 0.357580f * rgb[1] + 0.180423f * rgb[2];
+    xyz[1] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+    xyz[2] = 0.019334f * rgb[0] + 0.119193f * rgb[1] + 0.950227f * rgb[2];
+}
+inline void XYZToRGB(const float xyz[3], float rgb[3]) {  // spectrum.h:56-60
+    rgb[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
+    rgb[1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+    rgb[2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
+}
+
+// One 16x16 tile: integrator.cpp:241-331 with film.h:121-161 / film.cpp:95-130.
+void RenderTile(RenderCtx &rc, int tileIdx, int nTilesX, float *filmXYZW, std::mutex &filmMutex) {
+    const b200pt_film_desc &fd = *rc.film;
+    const int *sb = rc.sd->sample_bounds;
+    const int tileSize = 16;
+    int tx = tileIdx % nTilesX, ty = tileIdx / nTilesX;
+    int x0 = sb[0] + tx * tileSize, x1 = std::min(x0 + tileSize, sb[2]);
+    int y0 = sb[1] + ty * tileSize, y1 = std::min(y0 + tileSize, sb[3]);
+    // Film::GetFilmTile, film.cpp:95-106
+    float rx = fd.filter_radius[0], ry = fd.filter_radius[1];
+    int p0x = (int)std::ceil((float)x0 - 0.5f - rx), p0y = (int)std::ceil((float)y0 - 0.5f - ry);
+    int p1x = (int)std::floor((float)x1 - 0.5f + rx) + 1, p1y = (int)std::floor((float)y1 - 0.5f + ry) + 1;
+    int bx0 = std::max(p0x, fd.cropped_bounds[0]), by0 = std::max(p0y, fd.cropped_bounds[1]);
+    int bx1 = std::min(p1x, fd.cropped_bounds[2]), by1 = std::min(p1y, fd.cropped_bounds[3]);
+    int tw = std::max(0, bx1 - bx0), th = std::max(0, by1 - by0);
+    std::vector<FilmTilePixel> pixels((size_t)tw * th);
+    const float invRx = 1 / rx, invRy = 1 / ry;
+    const int filterTableSize = 16;  // film.h:99 filterTableWidth; box filter table is all ones
+    Sobol sampler(rc.sd);
+    const int *pb = rc.integ->pixel_bounds;
+    for (int py = y0; py < y1; ++py)
+        for (int px = x0; px < x1; ++px) {
+            if (!(px >= pb[0] && px < pb[2] && py >= pb[1] && py < pb[3])) continue;  // integrator.cpp:273
+            for (int64_t sIdx = 0; sIdx < rc.sd->samples_per_pixel; ++sIdx) {
+                float pFilm[2];
+                S3 L = RenderSample(rc, sampler, px, py, sIdx, pFilm);
+                // FilmTile::AddSample, film.h:121-161 (sampleWeight = rayWeight = 1)
+                if (L.y() > fd.max_sample_luminance) L = L * (fd.max_sample_luminance / L.y());
+                float dx = pFilm[0] - 0.5f, dy = pFilm[1] - 0.5f;
+                int q0x = (int)std::ceil(dx - rx), q0y = (int)std::ceil(dy - ry);
+                int q1x = (int)std::floor(dx + rx) + 1, q1y = (int)std::floor(dy + ry) + 1;
+                q0x = std::max(q0x, bx0);
+                q0y = std::max(q0y, by0);
+                q1x = std::min(q1x, bx1);
+                q1y = std::min(q1y, by1);
+                for (int y = q0y; y < q1y; ++y)
+                    for (int x = q0x; x < q1x; ++x) {
+                        // box filter: every table entry is 1 (filters/box.cpp:41-43); the
+                        // index arithmetic of film.h:135-146 cannot change the weight
+                        (void)invRx;
+                        (void)invRy;
+                        (void)filterTableSize;
+                        float filterWeight = 1.f;
+                        FilmTilePixel &pixel = pixels[(size_t)(y - by0) * tw + (x - bx0)];
+                        pixel.contribSum += L * 1.f * filterWeight;
+                        pixel.filterWeightSum += filterWeight;
+                    }
+            }
+        }
+    // Film::MergeFilmTile, film.cpp:117-130
+    std::lock_guard<std::mutex> lock(filmMutex);
+    int fw = fd.cropped_bounds[2] - fd.cropped_bounds[0];
+    for (int y = by0; y < by1; ++y)
+        for (int x = bx0; x < bx1; ++x) {
+            const FilmTilePixel &tp = pixels[(size_t)(y - by0) * tw + (x - bx0)];
+            float xyz[3];
+            RGBToXYZ(tp.contribSum.c, xyz);
+            float *mp = filmXYZW + 4 * ((size_t)(y - fd.cropped_bounds[1]) * fw + (x - fd.cropped_bounds[0]));
+            for (int i = 0; i < 3; ++i) mp[i] += xyz[i];
+            mp[3] += tp.filterWeightSum;
+        }
+}
+
+}  // namespace
+
+// =============================================================== C interface
+extern "C" {
+
+oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
+    oracle_scene *s = new oracle_scene;
+    s->nTris = d->n_triangles;
+    s->p.resize(3 * (size_t)d->n_triangles);
+    for (int64_t i = 0; i < 3 * d->n_triangles; ++i)
+        s->p[i] = V3(d->vertices[3 * i], d->vertices[3 * i + 1], d->vertices[3 * i + 2]);
+    s->materialId.assign(d->material_id, d->material_id + d->n_triangles);
+    if (d->light_id)
+        s->lightId.assign(d->light_id, d->light_id + d->n_triangles);
+    else
+        s->lightId.assign(d->n_triangles, -1);
+    if (d->flip_normal)
+        s->flip.assign(d->flip_normal, d->flip_normal + d->n_triangles);
+    else
+        s->flip.assign(d->n_triangles, 0);
+    s->materials.assign(d->materials, d->materials + d->n_materials);
+    s->lights.assign(d->lights, d->lights + d->n_lights);
+    s->lightArea.resize(d->n_lights);
+    for (int i = 0; i < d->n_lights; ++i) s->lightArea[i] = TriangleArea(*s, s->lights[i].triangle);
+    s->degenerate.resize(d->n_triangles);
+    std::vector<BuildPrim> prims;
+    prims.reserve(d->n_triangles);
+    for (int64_t i = 0; i < d->n_triangles; ++i) {
+        V3 dpdu, dpdv;
+        s->degenerate[i] = !TrianglePartials(s->p[3 * i], s->p[3 * i + 1], s->p[3 * i + 2], &dpdu, &dpdv);
+        BuildPrim bp;
+        bp.id = (int32_t)i;
+        for (int a = 0; a < 3; ++a) {
+            float v0 = s->p[3 * i][a], v1 = s->p[3 * i + 1][a], v2 = s->p[3 * i + 2][a];
+            bp.bmin[a] = std::min(v0, std::min(v1, v2));
+            bp.bmax[a] = std::max(v0, std::max(v1, v2));
+            bp.c[a] = .5f * bp.bmin[a] + .5f * bp.bmax[a];
+        }
+        prims.push_back(bp);
+    }
+    if (!prims.empty()) {
+        s->nodes.reserve(2 * prims.size());
+        BuildRecursive(*s, prims, 0, (int)prims.size());
+    }
+    return s;
+}
+
+void oracle_scene_destroy(oracle_scene *s) { delete s; }
+
+int oracle_trace_closest(const oracle_scene *s, const b200pt_ray *rays, b200pt_hit *hits, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        TriHit h;
+        V3 o(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        int tri = SceneIntersect(*s, o, d, rays[i].t_max, &h);
+        hits[i].triangle = tri;
+        hits[i].t = tri >= 0 ? h.t : 0;
+        hits[i].b0 = tri >= 0 ? h.b0 : 0;
+        hits[i].b1 = tri >= 0 ? h.b1 : 0;
+    }
+    return 0;
+}
+
+int oracle_trace_any(const oracle_scene *s, const b200pt_ray *rays, uint8_t *occluded, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        V3 o(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        occluded[i] = SceneIntersectP(*s, o, d, rays[i].t_max) ? 1 : 0;
+    }
+    return 0;
+}
+
+int oracle_trace_closest_brute(const oracle_scene *s, const b200pt_ray *rays, b200pt_hit *hits, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        V3 o(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        float tMax = rays[i].t_max;
+        int best = -1;
+        TriHit bh = {0, 0, 0, 0};
+        for (int64_t t = 0; t < s->nTris; ++t) {
+            if (s->degenerate[t]) continue;
+            TriHit h;
+            if (TriangleTest(s->p[3 * t], s->p[3 * t + 1], s->p[3 * t + 2], o, d, tMax, &h)) {
+                tMax = h.t;
+                bh = h;
+                best = (int)t;
+            }
+        }
+        hits[i].triangle = best;
+        hits[i].t = bh.t;
+        hits[i].b0 = bh.b0;
+        hits[i].b1 = bh.b1;
+    }
+    return 0;
+}
+
+int oracle_render(const oracle_scene *s, const b200pt_camera_desc *camera, const b200pt_film_desc *film,
+                  const b200pt_sampler_desc *sampler, const b200pt_integrator_desc *integrator,
+                  const int32_t *tiles, int64_t n_tiles, int n_threads, float *film_xyzw,
+                  b200pt_stats *stats) {
+    const int *sb = sampler->sample_bounds;
+    int nTilesX = (sb[2] - sb[0] + 15) / 16, nTilesY = (sb[3] - sb[1] + 15) / 16;
+    if (!tiles) n_tiles = std::min<int64_t>(n_tiles < 0 ? (int64_t)nTilesX * nTilesY : n_tiles,
+                                           (int64_t)nTilesX * nTilesY);
+    std::mutex filmMutex;
+    std::atomic<int64_t> next(0);
+    std::atomic<uint64_t> cam(0), reg(0), shad(0);
+    auto worker = [&]() {
+        RenderCtx rc;
+        rc.s = s;
+        rc.cam = camera;
+        rc.film = film;
+        rc.sd = sampler;
+        rc.integ = integrator;
+        rc.cameraRays = rc.regularRays = rc.shadowRays = 0;
+        InitLightDistribution(rc);
+        for (;;) {
+            int64_t i = next.fetch_add(1);
+            if (i >= n_tiles) break;
+            int tile = tiles ? tiles[i] : (int)i;
+            RenderTile(rc, tile, nTilesX, film_xyzw, filmMutex);
+        }
+        cam += rc.cameraRays;
+        reg += rc.regularRays;
+        shad += rc.shadowRays;
+    };
+    n_threads = std::max(1, n_threads);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->camera_rays = cam;
+        stats->regular_rays = reg;
+        stats->shadow_rays = shad;
+    }
+    return 0;
+}
+
+// core/film.cpp:174-203
+int oracle_film_rgb(const b200pt_film_desc *film, const float *xyzw, float *rgb) {
+    int w = film->cropped_bounds[2] - film->cropped_bounds[0];
+    int h = film->cropped_bounds[3] - film->cropped_bounds[1];
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        float xyz[3] = {xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 2]};
+        float *o = rgb + 3 * i;
+        XYZToRGB(xyz, o);
+        float filterWeightSum = xyzw[4 * i + 3];
+        if (filterWeightSum != 0) {
+            float invWt = (float)1 / filterWeightSum;
+            o[0] = std::max((float)0, o[0] * invWt);
+            o[1] = std::max((float)0, o[1] * invWt);
+            o[2] = std::max((float)0, o[2] * invWt);
+        }
+        // splats are always zero on this path: rgb += splatScale * 0
+        float zero[3] = {0, 0, 0}, splatRGB[3];
+        XYZToRGB(zero, splatRGB);
+        o[0] += 1.f * splatRGB[0];
+        o[1] += 1.f * splatRGB[1];
+        o[2] += 1.f * splatRGB[2];
+        o[0] *= film->scale;
+        o[1] *= film->scale;
+        o[2] *= film->scale;
+    }
+    return 0;
+}
+
+int oracle_sobol(const b200pt_sampler_desc *sampler, int32_t px, int32_t py, int64_t sample, int32_t dim0,
+                 int32_t n_dims, float *out) {
+    Sobol sob(sampler);
+    sob.StartPixelSample(px, py, sample);
+    for (int i = 0; i < n_dims; ++i) out[i] = sob.SampleDimension(sob.intervalSampleIndex, dim0 + i);
+    return 0;
+}
+
+int oracle_camera_rays(const b200pt_camera_desc *camera, const b200pt_sampler_desc *sampler, int32_t px,
+                       int32_t py, int32_t n_samples, b200pt_ray *out) {
+    Sobol sob(sampler);
+    for (int i = 0; i < n_samples; ++i) {
+        sob.StartPixelSample(px, py, i);
+        float u[2], pLens[2];
+        sob.Get2D(u);
+        float pFilm[2] = {(float)px + u[0], (float)py + u[1]};
+        (void)sob.Get1D();
+        sob.Get2D(pLens);
+        Ray r = GenerateCameraRay(*camera, pFilm, pLens);
+        out[i].o[0] = r.o.x;
+        out[i].o[1] = r.o.y;
+        out[i].o[2] = r.o.z;
+        out[i].d[0] = r.d.x;
+        out[i].d[1] = r.d.y;
+        out[i].d[2] = r.d.z;
+        out[i].t_max = r.tMax;
+        out[i].pad = 0;
+    }
+    return 0;
+}
+
+int oracle_pixel_samples(const oracle_scene *s, const b200pt_camera_desc *camera, const b200pt_film_desc *film,
+                         const b200pt_sampler_desc *sampler, const b200pt_integrator_desc *integrator,
+                         int32_t px, int32_t py, float *out_rgb) {
+    RenderCtx rc;
+    rc.s = s;
+    rc.cam = camera;
+    rc.film = film;
+    rc.sd = sampler;
+    rc.integ = integrator;
+    rc.cameraRays = rc.regularRays = rc.shadowRays = 0;
+    InitLightDistribution(rc);
+    Sobol sob(sampler);
+    for (int64_t i = 0; i < sampler->samples_per_pixel; ++i) {
+        float pFilm[2];
+        S3 L = RenderSample(rc, sob, px, py, i, pFilm);
+        out_rgb[3 * i] = L.c[0];
+        out_rgb[3 * i + 1] = L.c[1];
+        out_rgb[3 * i + 2] = L.c[2];
+    }
+    return 0;
+}
+
+float oracle_libm_sinf(float x) { return std::sin(x); }
+float oracle_libm_cosf(float x) { return std::cos(x); }
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""Synthetic workloads of BASELINE.json (`configs`) as plain arrays + descriptors.
+
+The triangle soup is SURVEY.md Appendix A.3 verbatim (numpy default_rng(1234),
+centres U[-1,1]^3, offsets U[-s,s]^3, unshared vertices).  `version` 0 is the
+soup the CPU probes in BASELINE.md were timed on (s = N^-1/3, one emissive quad
+at y=+3); version 1 (s = 0.5 N^-1/3, five inward-facing emissive quads) is the
+better-lit variant SURVEY.md section 6 asks for before taking parity numbers.
+Everything here is host-side description; nothing touches the device.
+
+The same description can be written out as `.pbrt` + binary PLY
+(`write_pbrt`) so the unmodified reference renders the identical scene.
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+from . import abi
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# default copper spectrum of MetalMaterial converted to RGB by the reference
+# (materials/metal.cpp:82-118; values dumped by oracle/probe `consts`).
+COPPER_ETA = [float.fromhex("0x1.9994b8p-3"), float.fromhex("0x1.d81b7ap-1"), float.fromhex("0x1.199178p+0")]
+COPPER_K = [float.fromhex("0x1.f3cb18p+1"), float.fromhex("0x1.394c0cp+1"), float.fromhex("0x1.119e9ap+1")]
+
+
+def soup_vertices(n, seed=1234, version=0):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    k = 1.0 if version == 0 else 0.5
+    s = np.float32(k * n ** (-1 / 3))
+    v = (c + rng.uniform(-s, s, (n, 3, 3)).astype(np.float32)).astype(np.float32)
+    return np.ascontiguousarray(v)
+
+
+def quad(p0, p1, p2, p3):
+    """Two triangles (0 1 2) (0 2 3) as in the `trianglemesh` of Appendix A.4."""
+    q = np.array([p0, p1, p2, p3], dtype=np.float32)
+    return np.stack([q[[0, 1, 2]], q[[0, 2, 3]]])
+
+
+def light_quads(version, n_lights=None):
+    """Emissive quads, each wound so that Cross(p0-p2, p1-p2) faces the soup."""
+    top = quad([-1.5, 3, -1.5], [1.5, 3, -1.5], [1.5, 3, 1.5], [-1.5, 3, 1.5])
+    if n_lights is not None:  # Cfg 4: n_lights/2 1x1 quads on a grid at y=+3
+        quads = []
+        nq = n_lights // 2
+        cols = 4
+        for i in range(nq):
+            cx = -2.25 + 1.5 * (i % cols)
+            cz = -0.75 + 1.5 * (i // cols)
+            quads.append(quad([cx - .5, 3, cz - .5], [cx + .5, 3, cz - .5], [cx + .5, 3, cz + .5],
+                              [cx - .5, 3, cz + .5]))
+        return quads
+    if version == 0:
+        return [top]
+    bottom = quad([-1.5, -3, -1.5], [-1.5, -3, 1.5], [1.5, -3, 1.5], [1.5, -3, -1.5])
+    left = quad([-3, -1.5, -1.5], [-3, 1.5, -1.5], [-3, 1.5, 1.5], [-3, -1.5, 1.5])
+    right = quad([3, -1.5, -1.5], [3, -1.5, 1.5], [3, 1.5, 1.5], [3, 1.5, -1.5])
+    back = quad([-1.5, -1.5, 3], [-1.5, 1.5, 3], [1.5, 1.5, 3], [1.5, -1.5, 3])
+    return [top, bottom, left, right, back]
+
+
+def default_materials(which):
+    """Material table: matte Kd .5 / glass / metal(copper, roughness .01) /
+    plastic(Kd=Ks=.25, roughness .1) with the factories' defaults
+    (glass.cpp:94-110, metal.cpp:115-134, plastic.cpp:72-83)."""
+    from . import host_roughness_to_alpha  # C-ABI host helper (same libm as the reference)
+    mats = []
+    for w in which:
+        m = abi.Material()
+        if w == "matte":
+            m.type = abi.MAT_MATTE
+            m.kd[:] = [0.5, 0.5, 0.5]
+        elif w == "black":
+            m.type = abi.MAT_MATTE
+            m.kd[:] = [0, 0, 0]
+        elif w == "glass":
+            m.type = abi.MAT_GLASS
+            m.ks[:] = [1, 1, 1]
+            m.kt[:] = [1, 1, 1]
+            m.index = 1.5
+        elif w == "metal":
+            m.type = abi.MAT_METAL
+            m.eta[:] = COPPER_ETA
+            m.k[:] = COPPER_K
+            a = host_roughness_to_alpha(0.01)
+            m.alpha_x = a
+            m.alpha_y = a
+        elif w == "plastic":
+            m.type = abi.MAT_PLASTIC
+            m.kd[:] = [0.25, 0.25, 0.25]
+            m.ks[:] = [0.25, 0.25, 0.25]
+            a = host_roughness_to_alpha(0.1)
+            m.alpha_x = a
+            m.alpha_y = a
+        else:
+            raise ValueError(w)
+        mats.append(m)
+    return mats
+
+
+PBRT_MATERIAL = {
+    "matte": 'Material "matte" "rgb Kd" [0.5 0.5 0.5]',
+    "black": 'Material "matte" "rgb Kd" [0 0 0]',
+    "glass": 'Material "glass"',
+    "metal": 'Material "metal"',
+    "plastic": 'Material "plastic"',
+}
+
+
+class SceneArrays:
+    """Flattened scene in the layout b200pt_scene_desc wants."""
+
+    def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
+                 n_lights=None, two_sided=False):
+        self.material_names = list(materials) + ["black"]
+        soup = soup_vertices(n_tris, seed, soup_version)
+        quads = light_quads(soup_version, n_lights)
+        light_tris = np.concatenate(quads) if quads else np.zeros((0, 3, 3), np.float32)
+        nl = len(light_tris)
+        # primitive order == .pbrt order (write_pbrt): lights first, then one
+        # plymesh per material holding triangles m::len(materials)
+        nm = len(materials)
+        parts, mids = [light_tris], [np.full(nl, nm, np.int32)]
+        self.ply_parts = []
+        for m in range(nm):
+            part = np.ascontiguousarray(soup[m::nm])
+            parts.append(part)
+            mids.append(np.full(len(part), m, np.int32))
+            self.ply_parts.append(part)
+        self.vertices = np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
+        self.material_id = np.ascontiguousarray(np.concatenate(mids))
+        self.light_id = np.full(len(self.vertices), -1, np.int32)
+        self.light_id[:nl] = np.arange(nl, dtype=np.int32)
+        self.flip = np.zeros(len(self.vertices), np.uint8)
+        self.light_quads = quads
+        self.light_L = float(light_L)
+        self.two_sided = bool(two_sided)
+        self._materials = None
+        self._lights = (abi.AreaLight * max(nl, 1))()
+        for i in range(nl):
+            self._lights[i].triangle = i
+            self._lights[i].lemit[:] = [light_L] * 3
+            self._lights[i].two_sided = int(two_sided)
+        self.n_lights = nl
+
+    @property
+    def n_triangles(self):
+        return len(self.vertices)
+
+    def desc(self):
+        if self._materials is None:
+            mats = default_materials(self.material_names)
+            self._materials = (abi.Material * len(mats))(*mats)
+        d = abi.SceneDesc()
+        d.n_triangles = self.n_triangles
+        d.vertices = abi.ptr(self.vertices)
+        d.material_id = abi.ptr(self.material_id)
+        d.light_id = abi.ptr(self.light_id)
+        d.flip_normal = abi.ptr(self.flip)
+        d.n_materials = len(self._materials)
+        d.materials = C.cast(self._materials, C.POINTER(abi.Material))
+        d.n_lights = self.n_lights
+        d.lights = C.cast(self._lights, C.POINTER(abi.AreaLight))
+        return d
+
+
+def write_ply(path, tris):
+    n = len(tris)
+    with open(path, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\n"
+                 "property float y\nproperty float z\nelement face %d\n"
+                 "property list uchar int vertex_indices\nend_header\n" % (3 * n, n)).encode())
+        f.write(np.ascontiguousarray(tris, dtype="<f4").tobytes())
+        rec = np.zeros(n, dtype=[("c", "u1"), ("i", "<i4", 3)])
+        rec["c"] = 3
+        rec["i"] = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+        f.write(rec.tobytes())
+
+
+def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
+               eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0):
+    """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
+    os.makedirs(dirname, exist_ok=True)
+    lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
+             'Camera "perspective" "float fov" [%g]' % fov,
+             'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "%s.pfm"'
+             % (xres, yres, name),
+             'Sampler "sobol" "integer pixelsamples" [%d]' % spp]
+    integ = 'Integrator "path" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (max_depth, strategy)
+    if pixel_bounds is not None:
+        integ += ' "integer pixelbounds" [%d %d %d %d]' % (pixel_bounds[0], pixel_bounds[2], pixel_bounds[1],
+                                                          pixel_bounds[3])
+    lines += [integ, "WorldBegin"]
+    for q in scene.light_quads:
+        # quad() stores (p0 p1 p2)(p0 p2 p3); recover the 4 corners
+        pts = [q[0][0], q[0][1], q[0][2], q[1][2]]
+        flat = " ".join("%.9g" % v for p in pts for v in p)
+        lines += ["AttributeBegin",
+                  '  AreaLightSource "diffuse" "rgb L" [%g %g %g]%s' %
+                  (scene.light_L, scene.light_L, scene.light_L,
+                   ' "bool twosided" "true"' if scene.two_sided else ""),
+                  '  Material "matte" "rgb Kd" [0 0 0]',
+                  '  Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [%s]' % flat,
+                  "AttributeEnd"]
+    for m, part in enumerate(scene.ply_parts):
+        ply = "%s_m%d.ply" % (name, m)
+        write_ply(os.path.join(dirname, ply), part)
+        lines += [PBRT_MATERIAL[scene.material_names[m]], 'Shape "plymesh" "string filename" "%s"' % ply]
+    lines.append("WorldEnd")
+    path = os.path.join(dirname, name + ".pbrt")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        tag = f.readline().strip()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        nc = 3 if tag == b"PF" else 1
+        data = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, nc)
+    return np.ascontiguousarray(data[::-1]).astype(np.float32)
+
+
+def write_pfm(path, rgb):
+    h, w, _ = rgb.shape
+    with open(path, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.000000\n" % (w, h))
+        f.write(np.ascontiguousarray(rgb[::-1], dtype="<f4").tobytes())
+
+
+class SobolTables:
+    """tests/golden/sobol_tables.bin: the Joe-Kuo generator matrices pbrt uses
+    (first 256 of its 1024 dimensions) + the (0,2)-net index maps, dumped from
+    the reference's own tables by oracle/probe `tables`.  A pbrt host passes
+    its in-memory tables instead."""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(GOLDEN_DIR, "sobol_tables.bin")
+        raw = open(path, "rb").read()
+        magic, nd, msize, nrows = struct.unpack_from("<4I", raw, 0)
+        assert magic == 0x32424F53 and msize == 52
+        off = 16
+        self.n_dims = nd
+        self.matrices32 = np.frombuffer(raw, "<u4", nd * 52, off).copy()
+        off += nd * 52 * 4
+        self.vdc = np.frombuffer(raw, "<u8", nrows * 52, off).reshape(nrows, 52).copy()
+        off += nrows * 52 * 8
+        self.vdc_inv = np.frombuffer(raw, "<u8", nrows * 52, off).reshape(nrows, 52).copy()
+
+
+def round_up_pow2(v):
+    return 1 << (int(v) - 1).bit_length()
+
+
+class RenderSetup:
+    """camera + film + sampler + integrator descriptors for a full-film render
+    with the default box filter (sample bounds == cropped pixel bounds)."""
+
+    def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
+                 eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None):
+        from . import host_perspective_camera
+        self.xres, self.yres = xres, yres
+        self.tables = tables or SobolTables()
+        self.camera = camera if camera is not None else host_perspective_camera(eye, look, up, fov, xres, yres)
+        self.film = abi.FilmDesc()
+        self.film.full_resolution[:] = [xres, yres]
+        self.film.cropped_bounds[:] = [0, 0, xres, yres]
+        self.film.filter_radius[:] = [0.5, 0.5]
+        self.film.scale = 1.0
+        self.film.max_sample_luminance = float("inf")
+        self.sampler = abi.SamplerDesc()
+        self.sampler.samples_per_pixel = round_up_pow2(spp)
+        self.sampler.sample_bounds[:] = [0, 0, xres, yres]
+        self.sampler.n_dimensions = self.tables.n_dims
+        res = round_up_pow2(max(xres, yres))
+        m = res.bit_length() - 1
+        self._vdc = np.ascontiguousarray(self.tables.vdc[max(m - 1, 0)])
+        self._vdc_inv = np.ascontiguousarray(self.tables.vdc_inv[max(m - 1, 0)])
+        self.sampler.matrices32 = abi.ptr(self.tables.matrices32)
+        self.sampler.vdc = abi.ptr(self._vdc)
+        self.sampler.vdc_inv = abi.ptr(self._vdc_inv)
+        self.integrator = abi.IntegratorDesc()
+        self.integrator.max_depth = max_depth
+        self.integrator.rr_threshold = 1.0
+        self.integrator.light_strategy = strategy
+        self.integrator.pixel_bounds[:] = pixel_bounds or [0, 0, xres, yres]
+
+    @property
+    def n_tiles(self):
+        return ((self.xres + 15) // 16) * ((self.yres + 15) // 16)

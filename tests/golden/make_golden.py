@@ -1,0 +1,99 @@
+"""Regenerates tests/golden/* from the UNMODIFIED reference (oracle/_ref/).
+
+Run here (the container that has /root/reference):  python tests/golden/make_golden.py
+Fixtures:
+  sobol_tables.bin   generator matrices dumped from core/sobolmatrices.cpp (first 256 dims)
+  probe.json         camera matrices, Sobol' sample streams, camera rays, material constants
+                     (hex floats) from PerspectiveCamera / SobolSampler / MetalMaterial
+  isect_*.npy        rays + BVHAccel::Intersect / IntersectP answers on a 3000-triangle soup
+  render_*.pfm       pbrt_ref renders of small soup scenes (all four materials, uniform/power)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+pkg = g.load_package()
+ob = g.load_oracle()
+from pbrt_v3_distributed_b200 import abi, scenes  # noqa: E402
+
+CAMERAS = [(64, 64), (96, 64), (48, 80), (1024, 1024), (1920, 1080), (3840, 2160)]
+RENDERS = {
+    # name: (n_tris, materials, xres, yres, spp, maxdepth, strategy, n_lights)
+    "matte": (3000, ("matte",), 40, 32, 8, 5, "uniform", None),
+    "four": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "uniform", None),
+    "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
+}
+
+
+def main():
+    ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
+    out = {"cameras": {}, "sobol": [], "camrays": []}
+    cam_args = [0, 0, -4.5, 0, 0, 0, 0, 1, 0, 35]
+    for (w, h) in CAMERAS:
+        txt = ob.probe("camera", *cam_args, w, h).splitlines()
+        rec = {}
+        for line in txt:
+            k, *v = line.split()
+            rec[k] = v
+        out["cameras"]["%dx%d" % (w, h)] = rec
+    for (bounds, spp, px, py, sample, dim0, n) in [((0, 0, 64, 64), 16, 3, 5, 2, 0, 48),
+                                                   ((0, 0, 1024, 1024), 256, 1023, 517, 255, 0, 48),
+                                                   ((0, 0, 1920, 1080), 1024, 1919, 1079, 1023, 0, 140),
+                                                   ((0, 0, 1920, 1080), 1024, 0, 0, 0, 0, 16),
+                                                   ((0, 0, 3840, 2160), 4096, 2000, 1000, 4095, 100, 40)]:
+        vals = ob.probe("sobol", *bounds, spp, px, py, sample, dim0, n).split()
+        out["sobol"].append({"bounds": bounds, "spp": spp, "px": px, "py": py, "sample": sample, "dim0": dim0,
+                             "values": vals})
+    for (w, h, spp, px, py, n) in [(64, 64, 16, 3, 5, 16), (1920, 1080, 1024, 1900, 1000, 8)]:
+        lines = ob.probe("camrays", *cam_args, w, h, spp, px, py, n).splitlines()
+        out["camrays"].append({"res": [w, h], "spp": spp, "px": px, "py": py, "rays": [l.split() for l in lines]})
+    consts = {}
+    for line in ob.probe("consts").splitlines():
+        k, *v = line.split()
+        consts.setdefault(k, []).append(v)
+    out["consts"] = consts
+    json.dump(out, open(os.path.join(HERE, "probe.json"), "w"), indent=1)
+
+    # ray/triangle + BVH answers from the real BVHAccel
+    arr = scenes.SceneArrays(3000, materials=("matte",), soup_version=1, seed=99)
+    rng = np.random.default_rng(5)
+    n = 6000
+    rays = np.zeros(n, dtype=abi.RAY_DTYPE)
+    rays["o"] = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[: n // 2] /= np.linalg.norm(d[: n // 2], axis=1, keepdims=True)  # half unit, half unnormalised
+    rays["d"] = d
+    rays["t_max"] = np.inf
+    rays["t_max"][n // 3: n // 2] = rng.uniform(0.05, 1.0, n // 2 - n // 3).astype(np.float32)
+    # axis-aligned directions exercise the zero-component paths of the slab and watertight tests
+    rays["d"][:30] = np.tile(np.eye(3, dtype=np.float32), (10, 1))
+    tmp = "/tmp/golden_isect"
+    os.makedirs(tmp, exist_ok=True)
+    arr.vertices.tofile(os.path.join(tmp, "tris.f32"))
+    rays.tofile(os.path.join(tmp, "rays.bin"))
+    ob.probe("intersect", os.path.join(tmp, "tris.f32"), os.path.join(tmp, "rays.bin"), os.path.join(tmp, "out.bin"))
+    res = np.fromfile(os.path.join(tmp, "out.bin"),
+                      dtype=[("tri", "<i4"), ("t", "<f4"), ("p", "<f4", 3), ("n", "<f4", 3), ("perr", "<f4", 3),
+                             ("occluded", "<i4")])
+    np.save(os.path.join(HERE, "isect_rays.npy"), rays)
+    np.save(os.path.join(HERE, "isect_ref.npy"), res)
+
+    for name, (nt, mats, w, h, spp, depth, strat, nl) in RENDERS.items():
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+        path = scenes.write_pbrt("/tmp/golden_render", "render_" + name, arr, w, h, spp, max_depth=depth,
+                                 strategy=strat)
+        ob.run_pbrt_ref(path)
+        os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % name),
+                   os.path.join(HERE, "render_%s.pfm" % name))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""CPU tests: the oracle restatement against golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py) -- bit-exact everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bits, golden_camera, hexf
+
+RENDERS = {
+    "matte": (3000, ("matte",), 40, 32, 8, 5, "uniform", None),
+    "four": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "uniform", None),
+    "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
+}
+
+
+def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
+    lib = ob.load(abi)
+    for rec in probe_json["sobol"]:
+        b = rec["bounds"]
+        setup = scenes.RenderSetup(b[2], b[3], rec["spp"], camera=abi.CameraDesc())
+        n = len(rec["values"])
+        out = np.zeros(n, np.float32)
+        import ctypes as C
+        lib.oracle_sobol(C.byref(setup.sampler), rec["px"], rec["py"], rec["sample"], rec["dim0"], n, abi.ptr(out))
+        assert np.array_equal(bits(out), bits(hexf(rec["values"])))
+
+
+def test_camera_rays_match_reference(abi, scenes, ob, probe_json):
+    lib = ob.load(abi)
+    import ctypes as C
+    for rec in probe_json["camrays"]:
+        w, h = rec["res"]
+        cam = golden_camera(abi, probe_json, w, h)
+        setup = scenes.RenderSetup(w, h, rec["spp"], camera=cam)
+        n = len(rec["rays"])
+        out = np.zeros(n, dtype=abi.RAY_DTYPE)
+        lib.oracle_camera_rays(C.byref(cam), C.byref(setup.sampler), rec["px"], rec["py"], n, abi.ptr(out))
+        want = np.array([hexf(r) for r in rec["rays"]])
+        assert np.array_equal(bits(out["o"]), bits(want[:, 0:3]))
+        assert np.array_equal(bits(out["d"]), bits(want[:, 3:6]))
+        assert np.array_equal(bits(out["t_max"]), bits(want[:, 6]))
+
+
+def test_host_camera_matches_reference(pkg, abi, probe_json):
+    for key, rec in probe_json["cameras"].items():
+        w, h = map(int, key.split("x"))
+        cam = pkg.host_perspective_camera((0, 0, -4.5), (0, 0, 0), (0, 1, 0), 35.0, w, h)
+        assert np.array_equal(bits(np.array(cam.raster_to_camera[:])), bits(hexf(rec["raster_to_camera"]))), key
+        assert np.array_equal(bits(np.array(cam.camera_to_world[:])), bits(hexf(rec["camera_to_world"]))), key
+
+
+def test_host_roughness_and_copper_constants(pkg, scenes, probe_json):
+    for r, a in probe_json["consts"]["roughness_to_alpha"]:
+        got = np.float32(pkg.host_roughness_to_alpha(float.fromhex(r)))
+        assert bits(got) == bits(hexf([a]))[0]
+    assert np.array_equal(bits(np.array(scenes.COPPER_ETA)), bits(hexf(probe_json["consts"]["copper_eta"][0])))
+    assert np.array_equal(bits(np.array(scenes.COPPER_K)), bits(hexf(probe_json["consts"]["copper_k"][0])))
+
+
+def test_intersections_match_reference_bvhaccel(abi, scenes, ob):
+    rays = np.load(os.path.join(GOLDEN, "isect_rays.npy"))
+    ref = np.load(os.path.join(GOLDEN, "isect_ref.npy"))
+    arr = scenes.SceneArrays(3000, materials=("matte",), soup_version=1, seed=99)
+    o = ob.Oracle(abi, arr)
+    for brute in (False, True):
+        hits = o.trace_closest(rays, brute=brute)
+        assert np.array_equal(hits["triangle"], ref["tri"])
+        m = ref["tri"] >= 0
+        assert m.sum() > 500
+        assert np.array_equal(bits(hits["t"][m]), bits(ref["t"][m]))
+    occ = o.trace_any(rays)
+    assert np.array_equal(occ.astype(np.int32), ref["occluded"])
+    o.close()
+
+
+def test_triangle_badcase_misses(abi, scenes, ob):
+    # reference tests/shapes.cpp:544-559 (Triangle.BadCases): this ray must NOT hit this triangle
+    arr = scenes.SceneArrays(1, materials=("matte",), soup_version=0)
+    arr.vertices = np.array([[[-1113.45459, -79.049614, -56.2431908], [-1113.45459, -87.0922699, -56.2431908],
+                              [-1113.45459, -79.2090149, -56.2431908]]], np.float32)
+    arr.material_id = np.zeros(1, np.int32)
+    arr.light_id = np.full(1, -1, np.int32)
+    arr.flip = np.zeros(1, np.uint8)
+    arr.n_lights = 0
+    arr.ply_parts = []
+    rays = np.zeros(1, dtype=abi.RAY_DTYPE)
+    rays["o"] = [[-1081.47925, 99.9999542, 87.7701111]]
+    rays["d"] = [[-32.1072998, -183.355865, -144.607635]]
+    rays["t_max"] = 0.9999
+    o = ob.Oracle(abi, arr)
+    assert o.trace_closest(rays, brute=True)["triangle"][0] == -1
+    assert o.trace_closest(rays)["triangle"][0] == -1
+    o.close()
+
+
+@pytest.mark.parametrize("name", sorted(RENDERS))
+def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM)
+    o = ob.Oracle(abi, arr)
+    film, stats = o.render(setup, threads=4)
+    rgb = o.film_rgb(setup, film)
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % name))
+    assert ref.shape == rgb.shape
+    assert np.array_equal(bits(rgb), bits(ref)), "oracle render is not bit-identical to the reference PFM"
+    assert stats["camera_rays"] == w * h * spp
+    o.close()
+
+
+def test_pixelbounds_shards_equal_full_render(abi, scenes, ob):
+    # tile shards with the full-film sampler are bit-identical to the full render
+    arr = scenes.SceneArrays(2000, materials=("matte", "plastic"), soup_version=1)
+    setup = scenes.RenderSetup(48, 32, 4)
+    o = ob.Oracle(abi, arr)
+    full, _ = o.render(setup, threads=2)
+    tiles = np.arange(setup.n_tiles)
+    a, _ = o.render(setup, tiles=tiles[0::2], threads=2)
+    b, _ = o.render(setup, tiles=tiles[1::2], threads=2)
+    assert np.array_equal(bits(a + b), bits(full))
+    o.close()
