@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg4|small] [--impl reference]
+
+One "step" = one complete pass of the hot path over the workload: every 16x16
+tile of the film rendered with all its samples per pixel (SamplerIntegrator::
+Render), film tiles sharded over the ranks (tile i -> rank i mod N) and the raw
+film sums reduced to rank 0 (one NCCL reduce) when N > 1.
+Metric: Mrays/s = (Scene::Intersect + Scene::IntersectP calls of all ranks) / time,
+the reference's own ray counters (core/scene.cpp:40-52).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_tris, materials, xres, yres, spp, max_depth, n_lights, description)
+    "cfg2": (1000000, ("matte",), 1024, 1024, 256, 5, None,
+             "synthetic 1M random triangles (soup v1), single diffuse BSDF, 256spp, 1024x1024"),
+    "cfg3": (10000000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 1024, 5, None,
+             "synthetic 10M triangles, 4 BSDF types, 1024spp, 1920x1080"),
+    "cfg4": (10000000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 1024, 5, 16,
+             "synthetic 10M triangles + 16 area lights (MIS), 1024spp, 1920x1080, tile-sharded"),
+    "small": (100000, ("matte", "glass", "metal", "plastic"), 256, 256, 16, 5, None,
+              "smoke-sized: 100k triangles, 4 BSDF types, 16spp, 256x256"),
+}
+
+
+def rank_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def write_reference_scene(scenes, arr, wl, spp, tmp):
+    n_tris, mats, xres, yres, _, depth, n_lights, _ = wl
+    return scenes.write_pbrt(tmp, "bench", arr, xres, yres, spp, max_depth=depth, strategy="uniform")
+
+
+def parse_pbrt_output(out):
+    def num(pat):
+        m = re.search(pat, out)
+        return float(m.group(1)) if m else 0.0
+    secs = [float(x) for x in re.findall(r"\((\d+\.\d+)s\)", out)]
+    return {"render_s": secs[-1] if secs else None,
+            "camera": num(r"Camera rays traced\s+(\d+)"),
+            "regular": num(r"Regular ray intersection tests\s+(\d+)"),
+            "shadow": num(r"Shadow ray intersection tests\s+(\d+)")}
+
+
+def reference_step(ob, scenes, abi, arr, wl, setup_small, sample_spp, tmp, pbrt_path):
+    """One bounded sample of the workload on the host cores: the unmodified
+    reference when oracle/_ref exists (kind 'reference'), else the oracle port."""
+    cores = os.cpu_count() or 1
+    if ob.have_reference():
+        t0 = time.time()
+        out = ob.run_pbrt_ref(pbrt_path, threads=cores)
+        wall = time.time() - t0
+        st = parse_pbrt_output(out)
+        secs = st["render_s"] or wall
+        return {"kind": "reference", "cores": cores, "rays": st["regular"] + st["shadow"], "samples": st["camera"],
+                "seconds": secs}
+    o = ob.Oracle(abi, arr)
+    t0 = time.time()
+    _, st = o.render(setup_small, threads=cores)
+    secs = time.time() - t0
+    o.close()
+    return {"kind": "port", "cores": cores, "rays": st["regular_rays"] + st["shadow_rays"],
+            "samples": st["camera_rays"], "seconds": secs}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-spp", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = rank_env()
+    wl = WORKLOADS[args.workload]
+    n_tris, mats, xres, yres, spp, depth, n_lights, desc = wl
+
+    pkg = graft.load_package()
+    from pbrt_v3_distributed_b200 import abi, scenes
+    config = {"workload": "%s: %s, maxdepth %d, Sobol, box filter, lightsamplestrategy uniform" %
+              (args.workload, desc, depth),
+              "n_triangles": n_tris, "resolution": [xres, yres], "spp": spp,
+              "scene": "soup v1 (s=0.5*N^-1/3, seed 1234) + %s" %
+                       ("%d emissive triangles at y=+3" % n_lights if n_lights else "5 inward emissive quads (10 lights), L=40"),
+              "parallelism": "tiles i mod %d over %d GPU(s), one film reduce" % (world, world) if world > 1 else "1 GPU",
+              "l2_policy": "inputs larger than L2 (BVH+triangles %s MB, path state > 0.5 GB); no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ob = graft.load_oracle()
+        arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
+        setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
+        tmp = tempfile.mkdtemp(prefix="b200pt_ref_")
+        pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if ob.have_reference() else None
+        rays = secs = samples = 0.0
+        last = None
+        for i in range(args.warmup + args.steps):
+            last = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path)
+            if i >= args.warmup:
+                rays += last["rays"]
+                secs += last["seconds"]
+                samples += last["samples"]
+        value = rays / secs / 1e6
+        sample = "%dx%d film, %d spp of %d, all tiles, per step" % (xres, yres, args.cpu_sample_spp, spp)
+        config["l2_policy"] = "n/a (CPU)"
+        print(json.dumps({
+            "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "msamples_per_s": samples / secs / 1e6,
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"],
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this benchmark has no CPU fallback"}))
+        return 2
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
+    setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth)
+    ctx = pkg.Context(local_rank)
+    t0 = time.time()
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    build_s = time.time() - t0
+    info = scene.info()
+    config["l2_policy"] = config["l2_policy"] % ("%.0f" % ((info["node_bytes"] + info["tri_bytes"]) / 1e6))
+    config["bvh"] = {"nodes": info["n_nodes"], "node_bytes": info["node_bytes"], "tri_bytes": info["tri_bytes"],
+                     "host_build_s": round(build_s, 2)}
+    render = pkg.Render(scene, setup)
+    my_tiles = np.arange(render.n_tiles, dtype=np.int32)[rank::world]
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    film_ptr, film_n = render.film_device_buffer()
+
+    class _Film:
+        __cuda_array_interface__ = {"shape": (film_n,), "typestr": "<f4", "data": (film_ptr, False), "version": 2}
+    film_t = torch.as_tensor(_Film(), device=torch.device("cuda", local_rank))
+    host_rgb = torch.empty((render.height, render.width, 3), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e):
+        h2d = 0
+        if e2e:
+            h2d = scene.upload()                      # pinned host -> device: BVH nodes + triangle records
+        render.clear()
+        render.render_tiles(my_tiles)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+        if e2e and rank == 0:
+            pkg._check(pkg.lib.b200pt_film_read_rgb(render.h, host_rgb.data_ptr()))
+        return h2d
+
+    # instrumented pass (untimed): BVH nodes fetched / triangles tested per ray -> algorithmic bytes
+    render.set_option("instrument", 1)
+    step(False)
+    ctx.synchronize()
+    st_i = render.stats()
+    render.set_option("instrument", 0)
+    render.reset_stats()
+
+    def timed(e2e, steps, warmup):
+        for _ in range(warmup):
+            step(e2e)
+        barrier()
+        render.reset_stats()
+        render.set_option("profile", 1)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record()
+        h2d = 0
+        for _ in range(steps):
+            h2d = step(e2e)
+        with torch.cuda.stream(stream):
+            ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.summary()
+        st = render.stats()
+        render.set_option("profile", 0)
+        t = torch.tensor([ms, float(st["regular_rays"] + st["shadow_rays"]), float(st["camera_rays"])],
+                         dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms = float(mx[0])
+        return ms, float(t[1]), float(t[2]), st, clocks, h2d
+
+    ms, rays, samples, st, clocks, _ = timed(False, args.steps, args.warmup)
+    ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, args.steps, 1)
+
+    out = None
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        value = rays / (ms * 1e-3) / 1e6
+        # roofline of the dominant kernel: closest-hit traversal (k_trace<false,...>)
+        n_reg = st_i["regular_rays"]
+        bytes_per_closest_ray = 32 + 4 + (st_i["nodes_visited"] * 80.0 + st_i["tris_tested"] * 48.0) / max(n_reg, 1)
+        closest_bytes = bytes_per_closest_ray * st["regular_rays"]
+        achieved = closest_bytes / (st["closest_ms"] * 1e-3) / 1e9 if st["closest_ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload)
+        cpu = None
+        if not args.no_cpu_baseline:
+            ob = graft.load_oracle()
+            tmp = tempfile.mkdtemp(prefix="b200pt_cpu_")
+            setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
+            pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if ob.have_reference() else None
+            c = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path)
+            cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"],
+                   "sample": "%dx%d film, %d spp of %d, all tiles (%.1f s render)" %
+                             (xres, yres, args.cpu_sample_spp, spp, c["seconds"]),
+                   "msamples_per_s": c["samples"] / c["seconds"] / 1e6}
+        out = {
+            "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "msamples_per_s": samples / (ms * 1e-3) / 1e6,
+            "rays_per_sample": rays / max(samples, 1),
+            "roofline": {"bound": "hbm", "kernel": "k_trace<closest-hit> (8-wide BVH traversal)",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": traffic,
+                         "algorithmic_bytes_per_ray": bytes_per_closest_ray,
+                         "nodes_per_ray": st_i["nodes_visited"] / max(n_reg, 1),
+                         "tris_per_ray": st_i["tris_tested"] / max(n_reg, 1),
+                         "avg_launch_ms": st["closest_ms"] / max(st["closest_launches"], 1),
+                         "launches": st["closest_launches"],
+                         "share_of_step": st["closest_ms"] / ms if ms > 0 else None},
+            "kernel_ms_per_step": {"closest_hit": st["closest_ms"] / args.steps, "any_hit": st["any_ms"] / args.steps,
+                                   "shade_raygen_film": st["shade_ms"] / args.steps},
+            "cpu_baseline": cpu,
+            "e2e": {"value": rays_e / (ms_e * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(st["launches"]),
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    render.close()
+    scene.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,12 +167,16 @@ typedef struct b200pt_stats {
     uint64_t camera_rays;          /* "Integrator/Camera rays traced"   integrator.cpp:48  */
     uint64_t regular_rays;         /* "Intersections/Regular ray intersection tests" scene.cpp:40 */
     uint64_t shadow_rays;          /* "Intersections/Shadow ray intersection tests"  scene.cpp:41 */
-    uint64_t nodes_visited;        /* wide-BVH nodes fetched by the traversal kernels */
-    uint64_t tris_tested;          /* ray-triangle tests in the traversal kernels     */
+    uint64_t nodes_visited;        /* wide-BVH nodes fetched by closest-hit launches ("instrument") */
+    uint64_t tris_tested;          /* ray-triangle tests in closest-hit launches                    */
+    uint64_t any_nodes_visited;    /* same for the any-hit (shadow) launches                        */
+    uint64_t any_tris_tested;
     double closest_ms;             /* device time in closest-hit traversal launches   */
     double any_ms;                 /* device time in any-hit traversal launches       */
     double shade_ms;               /* device time in all other launches               */
     uint64_t launches;             /* kernels launched by the library                 */
+    uint64_t closest_launches;     /* of which closest-hit traversal                  */
+    uint64_t any_launches;         /* of which any-hit traversal                      */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;      /* device + stream                          */
@@ -195,6 +199,10 @@ uint64_t b200pt_ctx_stream(b200pt_ctx *ctx);
  * Builds the 8-wide compressed BVH on the host (SAH) and uploads it. */
 int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *desc, b200pt_scene **out);
 void b200pt_scene_destroy(b200pt_scene *scene);
+/* Re-uploads the scene's nodes, triangle records and materials from the
+ * library's pinned host copies (asynchronous on the context's stream).  This is
+ * the host->device traffic of one end-to-end render; returns the bytes copied. */
+int b200pt_scene_upload(b200pt_scene *scene, uint64_t *bytes);
 /* bytes of device memory held by nodes / triangles, node count */
 int b200pt_scene_info(const b200pt_scene *scene, uint64_t *node_bytes, uint64_t *tri_bytes,
                       uint64_t *n_nodes);
@@ -249,6 +257,12 @@ int b200pt_debug_camera_rays(b200pt_render *r, int32_t px, int32_t py, int32_t n
 /* Per-sample radiance (after the NaN / negative / infinite guards of
  * integrator.cpp:294-315) of one pixel: out is [samples_per_pixel][3]. */
 int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *out_rgb);
+
+/* Options: "instrument" (count BVH nodes fetched / triangles tested in the
+ * traversal kernels -- the algorithmic-bytes figure of the roofline) and
+ * "profile" (bracket every launch with CUDA events on the context's stream so
+ * b200pt_get_stats reports device time per kernel class). Both default to 0. */
+int b200pt_render_set_option(b200pt_render *r, const char *name, int value);
 
 int b200pt_get_stats(b200pt_render *r, b200pt_stats *out);
 int b200pt_reset_stats(b200pt_render *r);

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b200pt_ctx_stream": (_u64, [_vp]),
     "b200pt_scene_create": (C.c_int, [_vp, C.POINTER(abi.SceneDesc), C.POINTER(_vp)]),
     "b200pt_scene_destroy": (None, [_vp]),
+    "b200pt_scene_upload": (C.c_int, [_vp, C.POINTER(_u64)]),
     "b200pt_scene_info": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "b200pt_trace_closest": (C.c_int, [_vp, _vp, _vp, _i64]),
     "b200pt_trace_any": (C.c_int, [_vp, _vp, _vp, _i64]),
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "b200pt_debug_sobol": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _i32, _vp]),
     "b200pt_debug_camera_rays": (C.c_int, [_vp, _i32, _i32, _i32, _vp]),
     "b200pt_debug_pixel_samples": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "b200pt_render_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "b200pt_get_stats": (C.c_int, [_vp, C.POINTER(abi.Stats)]),
     "b200pt_reset_stats": (C.c_int, [_vp]),
     "b200pt_host_perspective_camera": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float),
@@ -125,6 +127,11 @@ class Scene:
         self._keep = keepalive
         self.h = _vp()
         _check(lib.b200pt_scene_create(ctx.h, C.byref(desc), C.byref(self.h)))
+
+    def upload(self):
+        n = _u64()
+        _check(lib.b200pt_scene_upload(self.h, C.byref(n)))
+        return n.value
 
     def info(self):
         a, b, c = _u64(), _u64(), _u64()
@@ -213,6 +220,9 @@ class Render:
         out = np.zeros((self.setup.sampler.samples_per_pixel, 3), np.float32)
         _check(lib.b200pt_debug_pixel_samples(self.h, px, py, abi.ptr(out)))
         return out
+
+    def set_option(self, name, value):
+        _check(lib.b200pt_render_set_option(self.h, name.encode(), int(value)))
 
     def stats(self):
         s = abi.Stats()

@@ -53,8 +53,10 @@ class IntegratorDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("regular_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("closest_ms", C.c_double),
-                ("any_ms", C.c_double), ("shade_ms", C.c_double), ("launches", C.c_uint64)]
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("any_nodes_visited", C.c_uint64),
+                ("any_tris_tested", C.c_uint64), ("closest_ms", C.c_double),
+                ("any_ms", C.c_double), ("shade_ms", C.c_double), ("launches", C.c_uint64),
+                ("closest_launches", C.c_uint64), ("any_launches", C.c_uint64)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("t_max", np.float32), ("d", np.float32, 3),

@@ -1,0 +1,808 @@
+// api.cu -- implementation of the C ABI (include/b200pt.h): contexts, scene
+// upload (+ host BVH build), the wavefront batch driver and film read-back.
+// Host code only orchestrates; all arithmetic of the path runs in kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "b200pt_internal.h"
+#include "bvh8.h"
+#include "kernels.cuh"
+
+using namespace b200pt;
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return b200pt_fail(e_ == cudaErrorMemoryAllocation ? B200PT_ERR_OOM : B200PT_ERR_CUDA,       \
+                               "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct b200pt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+};
+
+struct b200pt_scene {
+    b200pt_ctx *ctx = nullptr;
+    U4 *d_nodes = nullptr;
+    F4 *d_tris = nullptr;
+    b200pt_material *d_materials = nullptr;
+    uint64_t n_nodes = 0, n_tris = 0;
+    std::vector<b200pt_material> materials;
+    std::vector<b200pt_area_light> lights;  // host copy, triangle = original index
+    std::vector<uint32_t> prim_to_tri;
+    std::vector<float> light_area;
+    uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
+    void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
+};
+
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int category;  // 0 closest, 1 any, 2 other
+};
+
+struct b200pt_render {
+    b200pt_scene *scene = nullptr;
+    RenderDev host;           // host copy of the device parameter block
+    RenderDev *d_dev = nullptr;
+    std::vector<void *> allocs;
+    b200pt_film_desc film;
+    int spp = 0;
+    uint32_t tiles_per_batch = 1;
+    int32_t *d_tile_list = nullptr;
+    size_t tile_list_capacity = 0;
+    int grid_trace = 0, grid_shade = 0;
+    bool instrumented = false, profiling = false;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double ms[3] = {0, 0, 0};
+    uint64_t launches = 0, launches_cat[3] = {0, 0, 0};
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------- context
+int b200pt_ctx_create(int device, b200pt_ctx **out) {
+    if (!out) return b200pt_fail(B200PT_ERR_INVALID, "ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return b200pt_fail(B200PT_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                           e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return b200pt_fail(B200PT_ERR_INVALID, "ctx_create: device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return b200pt_fail(B200PT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                           prop.major, prop.minor);
+    b200pt_ctx *c = new b200pt_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return B200PT_OK;
+}
+
+void b200pt_ctx_destroy(b200pt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200pt_ctx_synchronize(b200pt_ctx *ctx) {
+    if (!ctx) return b200pt_fail(B200PT_ERR_INVALID, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200PT_OK;
+}
+
+uint64_t b200pt_ctx_stream(b200pt_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+// --------------------------------------------------------------------- scene
+int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scene **out) {
+    if (!ctx || !d || !out) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: NULL argument");
+    if (d->n_triangles < 0 || (d->n_triangles > 0 && (!d->vertices || !d->material_id)))
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: vertices / material_id missing");
+    if (d->n_triangles >= (1ll << 31)) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: too many triangles");
+    if (d->n_materials <= 0 || !d->materials) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: no materials");
+    if (d->n_materials > 65535) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: more than 65535 materials");
+    for (int i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].type < 0 || d->materials[i].type > B200PT_MAT_GLASS)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: material %d has unsupported type %d", i,
+                               d->materials[i].type);
+    for (int64_t i = 0; i < d->n_triangles; ++i) {
+        if (d->material_id[i] < 0 || d->material_id[i] >= d->n_materials)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: triangle %lld has material %d", (long long)i,
+                               d->material_id[i]);
+        if (d->light_id && (d->light_id[i] < -1 || d->light_id[i] >= d->n_lights))
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: triangle %lld has light %d", (long long)i,
+                               d->light_id[i]);
+    }
+    for (int i = 0; i < d->n_lights; ++i) {
+        int t = d->lights[i].triangle;
+        if (t < 0 || t >= d->n_triangles || !d->light_id || d->light_id[t] != i)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: light %d and light_id[] disagree", i);
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+
+    // triangles the reference can never hit (shapes/triangle.cpp:304-312)
+    std::vector<uint8_t> degenerate((size_t)d->n_triangles);
+    for (int64_t i = 0; i < d->n_triangles; ++i) {
+        const float *v = d->vertices + 9 * i;
+        V3 dpdu, dpdv;
+        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), &dpdu, &dpdv);
+    }
+    Bvh8 bvh;
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("B200PT_BUILD_THREADS")) threads = atoi(e);
+    build_bvh8(d->vertices, d->n_triangles, d->material_id, d->light_id, d->flip_normal, degenerate.data(),
+               std::max(1, threads), &bvh);
+    if (bvh.max_depth > B200PT_STACK - 4)
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d exceeds the traversal stack", bvh.max_depth);
+    int64_t bad = validate_bvh8(bvh);
+    if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
+
+    b200pt_scene *s = new b200pt_scene;
+    s->ctx = ctx;
+    s->n_nodes = bvh.nodes.size();
+    s->n_tris = bvh.tris.size();
+    s->materials.assign(d->materials, d->materials + d->n_materials);
+    s->lights.assign(d->lights, d->lights + d->n_lights);
+    s->prim_to_tri = std::move(bvh.prim_to_tri);
+    s->light_area.resize(d->n_lights);
+    for (int i = 0; i < d->n_lights; ++i) {
+        const float *v = d->vertices + 9 * (int64_t)d->lights[i].triangle;
+        s->light_area[i] = triangle_area(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(Bvh8Node))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(TriRecord))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
+        b200pt_scene_destroy(s);
+        return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMallocHost(&s->h_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(Bvh8Node))) != cudaSuccess ||
+        (e = cudaMallocHost(&s->h_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(TriRecord))) != cudaSuccess) {
+        b200pt_scene_destroy(s);
+        return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMallocHost failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
+    memcpy(s->h_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord));
+    int rc = b200pt_scene_upload(s, nullptr);
+    if (rc != B200PT_OK) {
+        b200pt_scene_destroy(s);
+        return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return B200PT_OK;
+}
+
+int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
+    if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    const size_t nb = s->n_nodes * sizeof(Bvh8Node), tb = s->n_tris * sizeof(TriRecord),
+                 mb = s->materials.size() * sizeof(b200pt_material);
+    CUDA_TRY(cudaMemcpyAsync(s->d_nodes, s->h_nodes, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_tris, s->h_tris, tb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_materials, s->materials.data(), mb, cudaMemcpyHostToDevice, st));
+    if (bytes) *bytes = nb + tb + mb;
+    return B200PT_OK;
+}
+
+void b200pt_scene_destroy(b200pt_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_nodes);
+    cudaFree(s->d_tris);
+    cudaFree(s->d_materials);
+    cudaFree(s->d_work);
+    cudaFreeHost(s->h_nodes);
+    cudaFreeHost(s->h_tris);
+    delete s;
+}
+
+int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri_bytes, uint64_t *n_nodes) {
+    if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
+    if (node_bytes) *node_bytes = s->n_nodes * sizeof(Bvh8Node);
+    if (tri_bytes) *tri_bytes = s->n_tris * sizeof(TriRecord);
+    if (n_nodes) *n_nodes = s->n_nodes;
+    return B200PT_OK;
+}
+
+// ------------------------------------------------- ray-batch entry points
+static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * 8; }
+
+static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64_t n, bool any_hit) {
+    if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
+    if (n < 0 || n >= (1ll << 32)) return b200pt_fail(B200PT_ERR_INVALID, "trace: bad ray count");
+    if (n == 0) return B200PT_OK;
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    uint32_t hdr[2] = {0u, (uint32_t)n};  // work counter, ray count
+    CUDA_TRY(cudaMemcpyAsync(s->d_work, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    TraceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nodes = s->d_nodes;
+    a.tris = s->d_tris;
+    a.ray_o = reinterpret_cast<const float4 *>(rays_dev);
+    a.ray_d = reinterpret_cast<const float4 *>(rays_dev) + 1;
+    a.stride = 2;
+    a.t_max_from_w = 1;
+    a.count = s->d_work + 1;
+    a.work = s->d_work;
+    a.materials = s->d_materials;
+    if (any_hit)
+        a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
+    else
+        a.full_out = reinterpret_cast<b200pt_hit *>(out_dev);
+    launch_trace(a, any_hit, false, false, trace_grid(s->ctx), st);
+    CUDA_TRY(cudaGetLastError());
+    return B200PT_OK;
+}
+
+int b200pt_trace_closest_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t hits_dev, int64_t n) {
+    return trace_dev(s, rays_dev, hits_dev, n, false);
+}
+int b200pt_trace_any_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t occluded_dev, int64_t n) {
+    return trace_dev(s, rays_dev, occluded_dev, n, true);
+}
+
+static int trace_host(b200pt_scene *s, const b200pt_ray *rays, void *out, size_t out_elem, int64_t n, bool any_hit) {
+    if (!s || (n > 0 && (!rays || !out))) return b200pt_fail(B200PT_ERR_INVALID, "trace: NULL argument");
+    if (n <= 0) return n == 0 ? B200PT_OK : b200pt_fail(B200PT_ERR_INVALID, "trace: negative count");
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    void *d_rays = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rays, (size_t)n * sizeof(b200pt_ray)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * out_elem);
+    if (e != cudaSuccess) {
+        cudaFree(d_rays);
+        return b200pt_fail(B200PT_ERR_OOM, "trace: cudaMalloc failed");
+    }
+    int rc = B200PT_OK;
+    if (cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(b200pt_ray), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = b200pt_fail(B200PT_ERR_CUDA, "trace: H2D copy failed");
+    if (rc == B200PT_OK) rc = trace_dev(s, (uint64_t)(uintptr_t)d_rays, (uint64_t)(uintptr_t)d_out, n, any_hit);
+    if (rc == B200PT_OK && (cudaMemcpyAsync(out, d_out, (size_t)n * out_elem, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                            cudaStreamSynchronize(st) != cudaSuccess))
+        rc = b200pt_fail(B200PT_ERR_CUDA, "trace: kernel or D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_rays);
+    cudaFree(d_out);
+    return rc;
+}
+
+int b200pt_trace_closest(b200pt_scene *s, const b200pt_ray *rays, b200pt_hit *hits, int64_t n) {
+    return trace_host(s, rays, hits, sizeof(b200pt_hit), n, false);
+}
+int b200pt_trace_any(b200pt_scene *s, const b200pt_ray *rays, uint8_t *occluded, int64_t n) {
+    return trace_host(s, rays, occluded, 1, n, true);
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------- render
+template <typename T>
+static cudaError_t dev_alloc(b200pt_render *r, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        r->allocs.push_back(q);
+        *p = static_cast<T *>(q);
+    }
+    return e;
+}
+
+extern "C" {
+
+int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, const b200pt_film_desc *film,
+                         const b200pt_sampler_desc *smp, const b200pt_integrator_desc *integ, b200pt_render **out) {
+    if (!scene || !cam || !film || !smp || !integ || !out) return b200pt_fail(B200PT_ERR_INVALID, "render_create: NULL argument");
+    if (film->filter_radius[0] != 0.5f || film->filter_radius[1] != 0.5f)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: only the default box filter (radius 0.5) is supported");
+    if (smp->samples_per_pixel <= 0 || (smp->samples_per_pixel & (smp->samples_per_pixel - 1)))
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: samples_per_pixel must be a power of two (sobol.h:52)");
+    if (!smp->matrices32 || !smp->vdc || !smp->vdc_inv || smp->n_dimensions < 5)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: Sobol' tables missing");
+    if (integ->max_depth < 0 || integ->max_depth > 200) return b200pt_fail(B200PT_ERR_INVALID, "render_create: bad max_depth");
+    // 5 camera dims + per bounce: light pick 1 + uLight 2 + uScattering 2 + BSDF 2 + roulette 1
+    if (5 + 8 * integ->max_depth > smp->n_dimensions)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d Sobol' dimensions, %d provided",
+                           integ->max_depth, 5 + 8 * integ->max_depth, smp->n_dimensions);
+    if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: unsupported light sample strategy");
+    const int sbw = smp->sample_bounds[2] - smp->sample_bounds[0], sbh = smp->sample_bounds[3] - smp->sample_bounds[1];
+    if (sbw <= 0 || sbh <= 0) return b200pt_fail(B200PT_ERR_INVALID, "render_create: empty sample bounds");
+    const int cw = film->cropped_bounds[2] - film->cropped_bounds[0], chh = film->cropped_bounds[3] - film->cropped_bounds[1];
+    if (cw <= 0 || chh <= 0) return b200pt_fail(B200PT_ERR_INVALID, "render_create: empty film");
+
+    b200pt_ctx *ctx = scene->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    b200pt_render *r = new b200pt_render;
+    r->scene = scene;
+    r->film = *film;
+    r->spp = smp->samples_per_pixel;
+    RenderDev &H = r->host;
+    memset(&H, 0, sizeof(H));
+    H.scene.nodes = scene->d_nodes;
+    H.scene.tris = scene->d_tris;
+    H.scene.materials = scene->d_materials;
+    H.scene.n_nodes = (uint32_t)scene->n_nodes;
+    H.scene.n_tris = (uint32_t)scene->n_tris;
+    // sampler (samplers/sobol.h:49-62)
+    H.sampler.spp = smp->samples_per_pixel;
+    memcpy(H.sampler.sb, smp->sample_bounds, sizeof(int) * 4);
+    int res = 1;
+    while (res < std::max(sbw, sbh)) res <<= 1;
+    H.sampler.resolution = res;
+    int lg = 0;
+    while ((1 << lg) < res) ++lg;
+    H.sampler.log2res = lg;
+    H.sampler.n_dims = smp->n_dimensions;
+    memcpy(H.sampler.vdc, smp->vdc, sizeof(uint64_t) * 52);
+    memcpy(H.sampler.vdc_inv, smp->vdc_inv, sizeof(uint64_t) * 52);
+    memcpy(H.camera.r2c, cam->raster_to_camera, sizeof(float) * 16);
+    memcpy(H.camera.c2w, cam->camera_to_world, sizeof(float) * 16);
+    H.camera.lens_radius = cam->lens_radius;
+    H.camera.focal_distance = cam->focal_distance;
+    memcpy(H.crop, film->cropped_bounds, sizeof(int) * 4);
+    memcpy(H.pixel_bounds, integ->pixel_bounds, sizeof(int) * 4);
+    H.max_sample_luminance = film->max_sample_luminance;
+    H.max_depth = integ->max_depth;
+    H.rr_threshold = integ->rr_threshold;
+    H.tiles_x = (sbw + 15) / 16;
+    H.tiles_y = (sbh + 15) / 16;
+
+    // light distribution (lightdistrib.cpp:48-82, sampling.h:57-71)
+    const int nl = (int)scene->lights.size();
+    std::vector<DevLight> dl(nl);
+    std::vector<float> func(std::max(nl, 1), 1.f), cdf(nl + 1, 0.f);
+    for (int i = 0; i < nl; ++i) {
+        dl[i].tri = scene->prim_to_tri[scene->lights[i].triangle];
+        memcpy(dl[i].lemit, scene->lights[i].lemit, sizeof(float) * 3);
+        dl[i].two_sided = scene->lights[i].two_sided;
+        dl[i].area = scene->light_area[i];
+        if (integ->light_strategy == B200PT_LIGHTS_POWER && nl != 1) {
+            // DiffuseAreaLight::Power().y(), diffuse.cpp:64-66 + integrator.cpp:216-224
+            const float k = dl[i].two_sided ? 2.f : 1.f;
+            RGB p = k * rgbp(dl[i].lemit) * dl[i].area * PT_PI;
+            func[i] = lum(p);
+        }
+    }
+    float funcInt = 0.f;
+    if (nl > 0) {
+        for (int i = 1; i < nl + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / nl;
+        funcInt = cdf[nl];
+        if (funcInt == 0) {
+            for (int i = 1; i < nl + 1; ++i) cdf[i] = float(i) / float(nl);
+        } else {
+            for (int i = 1; i < nl + 1; ++i) cdf[i] /= funcInt;
+        }
+    }
+    H.n_lights = nl;
+    H.light_func_int = funcInt;
+
+    // batch sizing: whole tiles, about B200PT_BATCH_PATHS path slots
+    size_t target = 4u << 20;
+    if (const char *e = getenv("B200PT_BATCH_PATHS")) target = (size_t)atoll(e);
+    const size_t per_tile = 256u * (size_t)r->spp;
+    r->tiles_per_batch = (uint32_t)std::max<size_t>(1, target / per_tile);
+    r->tiles_per_batch = std::min<uint32_t>(r->tiles_per_batch, (uint32_t)(H.tiles_x * H.tiles_y));
+    const size_t cap = (size_t)r->tiles_per_batch * per_tile;
+    if (cap >= (1ull << 31)) {
+        delete r;
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: one tile needs %zu path slots (too many samples)", per_tile);
+    }
+    H.capacity = (uint32_t)cap;
+
+    cudaError_t e = cudaSuccess;
+    uint32_t *mat32 = nullptr;
+    DevLight *d_lights = nullptr;
+    float *d_cdf = nullptr, *d_func = nullptr;
+#define ALLOC(ptr, count) \
+    if (e == cudaSuccess) e = dev_alloc(r, &(ptr), (count))
+    ALLOC(mat32, (size_t)smp->n_dimensions * 52);
+    ALLOC(d_lights, (size_t)nl);
+    ALLOC(d_cdf, (size_t)nl + 1);
+    ALLOC(d_func, (size_t)std::max(nl, 1));
+    ALLOC(H.film, (size_t)cw * chh);
+    ALLOC(H.ray_o, cap);
+    ALLOC(H.ray_d, cap);
+    ALLOC(H.beta, cap);
+    ALLOC(H.L, cap);
+    ALLOC(H.sobol, cap);
+    ALLOC(H.hit, cap);
+    ALLOC(H.sh_o, cap);
+    ALLOC(H.sh_d, cap);
+    ALLOC(H.A, cap);
+    ALLOC(H.mi_o, cap);
+    ALLOC(H.mi_d, cap);
+    ALLOC(H.B, cap);
+    ALLOC(H.beta_ld, cap);
+    ALLOC(H.occluded, cap);
+    ALLOC(H.mis_hit, cap);
+    ALLOC(H.pix_bleed, (size_t)r->tiles_per_batch * 256);
+    ALLOC(H.q_path[0], cap);
+    ALLOC(H.q_path[1], cap);
+    for (int m = 0; m < 4; ++m) ALLOC(H.q_mat[m], cap);
+    ALLOC(H.q_shadow, cap);
+    ALLOC(H.q_mis, cap);
+    ALLOC(H.qcount, (size_t)(H.max_depth + 2) * Q_PER_BOUNCE);
+    ALLOC(H.work, (size_t)(H.max_depth + 2) * 16);
+    ALLOC(H.stats, 8);
+    ALLOC(r->d_dev, 1);
+#undef ALLOC
+    if (e != cudaSuccess) {
+        b200pt_render_destroy(r);
+        return b200pt_fail(B200PT_ERR_OOM, "render_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    H.sampler.mat32 = mat32;
+    H.lights = d_lights;
+    H.light_cdf = d_cdf;
+    H.light_func = d_func;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(mat32, smp->matrices32, (size_t)smp->n_dimensions * 52 * 4, cudaMemcpyHostToDevice, st));
+    if (nl) CUDA_TRY(cudaMemcpyAsync(d_lights, dl.data(), nl * sizeof(DevLight), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cdf, cdf.data(), (nl + 1) * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_func, func.data(), std::max(nl, 1) * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(H.film, 0, (size_t)cw * chh * sizeof(float4), st));
+    CUDA_TRY(cudaMemsetAsync(H.stats, 0, 8 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemcpyAsync(r->d_dev, &H, sizeof(H), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    r->grid_trace = ctx->sm_count * 8;
+    r->grid_shade = ctx->sm_count * 8;
+    if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
+    if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
+    *out = r;
+    return B200PT_OK;
+}
+
+void b200pt_render_destroy(b200pt_render *r) {
+    if (!r) return;
+    cudaSetDevice(r->scene->ctx->device);
+    cudaStreamSynchronize(r->scene->ctx->stream);
+    for (void *p : r->allocs) cudaFree(p);
+    cudaFree(r->d_tile_list);
+    for (auto &t : r->timed) {
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    for (auto ev : r->event_pool) cudaEventDestroy(ev);
+    delete r;
+}
+
+int b200pt_render_tile_counts(const b200pt_render *r, int32_t *nx, int32_t *ny) {
+    if (!r) return b200pt_fail(B200PT_ERR_INVALID, "render is NULL");
+    if (nx) *nx = r->host.tiles_x;
+    if (ny) *ny = r->host.tiles_y;
+    return B200PT_OK;
+}
+
+int b200pt_film_clear(b200pt_render *r) {
+    if (!r) return b200pt_fail(B200PT_ERR_INVALID, "render is NULL");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    const size_t n = (size_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
+    CUDA_TRY(cudaMemsetAsync(r->host.film, 0, n * sizeof(float4), r->scene->ctx->stream));
+    return B200PT_OK;
+}
+
+static cudaEvent_t take_event(b200pt_render *r) {
+    if (!r->event_pool.empty()) {
+        cudaEvent_t e = r->event_pool.back();
+        r->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchTimer {
+    b200pt_render *r;
+    cudaStream_t st;
+    TimedLaunch t;
+    bool on;
+    LaunchTimer(b200pt_render *r, cudaStream_t st, int category) : r(r), st(st), on(r->profiling) {
+        r->launches++;
+        r->launches_cat[category]++;
+        if (on) {
+            t.category = category;
+            t.a = take_event(r);
+            t.b = take_event(r);
+            cudaEventRecord(t.a, st);
+        }
+    }
+    ~LaunchTimer() {
+        if (on) {
+            cudaEventRecord(t.b, st);
+            r->timed.push_back(t);
+        }
+    }
+};
+
+static void drain_timers(b200pt_render *r) {
+    for (auto &t : r->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) r->ms[t.category] += ms;
+        r->event_pool.push_back(t.a);
+        r->event_pool.push_back(t.b);
+    }
+    r->timed.clear();
+}
+
+int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles) {
+    if (!r) return b200pt_fail(B200PT_ERR_INVALID, "render is NULL");
+    const int64_t total = (int64_t)r->host.tiles_x * r->host.tiles_y;
+    if (n_tiles < 0 || n_tiles > (1 << 30)) return b200pt_fail(B200PT_ERR_INVALID, "render_tiles: bad tile count");
+    if (!tiles && n_tiles > total) return b200pt_fail(B200PT_ERR_INVALID, "render_tiles: more tiles than the film has");
+    if (n_tiles == 0) return B200PT_OK;
+    b200pt_ctx *ctx = r->scene->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> list((size_t)n_tiles);
+    for (int64_t i = 0; i < n_tiles; ++i) {
+        list[i] = tiles ? tiles[i] : (int32_t)i;
+        if (list[i] < 0 || list[i] >= total) return b200pt_fail(B200PT_ERR_INVALID, "render_tiles: tile %d out of range", list[i]);
+    }
+    if ((size_t)n_tiles > r->tile_list_capacity) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(r->d_tile_list);
+        r->d_tile_list = nullptr;
+        CUDA_TRY(cudaMalloc(&r->d_tile_list, (size_t)n_tiles * sizeof(int32_t)));
+        r->tile_list_capacity = (size_t)n_tiles;
+    }
+    // the list is consumed asynchronously: copy from a pageable vector is staged by the driver before returning
+    CUDA_TRY(cudaMemcpyAsync(r->d_tile_list, list.data(), (size_t)n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (r->host.tile_list != r->d_tile_list) {
+        r->host.tile_list = r->d_tile_list;
+        CUDA_TRY(cudaMemcpyAsync(r->d_dev, &r->host, sizeof(RenderDev), cudaMemcpyHostToDevice, st));
+    }
+    const RenderDev &H = r->host;
+    const int maxDepth = H.max_depth;
+    const size_t qbytes = (size_t)(maxDepth + 2) * Q_PER_BOUNCE * sizeof(uint32_t);
+    const size_t wbytes = (size_t)(maxDepth + 2) * 16 * sizeof(uint32_t);
+    bool families[4] = {false, false, false, false};
+    for (const auto &m : r->scene->materials) families[m.type] = true;
+
+    for (int64_t first = 0; first < n_tiles; first += r->tiles_per_batch) {
+        const uint32_t nb = (uint32_t)std::min<int64_t>(r->tiles_per_batch, n_tiles - first);
+        const uint32_t n_slots = nb * 256u * (uint32_t)r->spp;
+        CUDA_TRY(cudaMemsetAsync(H.qcount, 0, qbytes, st));
+        CUDA_TRY(cudaMemsetAsync(H.work, 0, wbytes, st));
+        CUDA_TRY(cudaMemsetAsync(H.pix_bleed, 0, (size_t)nb * 256, st));
+        {
+            LaunchTimer lt(r, st, 2);
+            launch_raygen(r->d_dev, (uint32_t)first, nb, n_slots, st);
+        }
+        for (int b = 0; b <= maxDepth; ++b) {
+            uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
+            uint32_t *wk = H.work + (size_t)b * 16;
+            TraceArgs a;
+            memset(&a, 0, sizeof(a));
+            a.nodes = H.scene.nodes;
+            a.tris = H.scene.tris;
+            a.materials = H.scene.materials;
+            a.stats = H.stats;
+            a.stride = 1;
+            // closest hit of the path rays + classification by BSDF family
+            a.ray_o = H.ray_o;
+            a.ray_d = H.ray_d;
+            a.queue = H.q_path[b & 1];
+            a.count = qc + Q_PATH;
+            a.work = wk + 0;
+            a.fixed_t_max = INFINITY;
+            a.hit_out = H.hit;
+            for (int m = 0; m < 4; ++m) a.q_mat[m] = H.q_mat[m];
+            a.qcount_mat = qc + Q_MAT0;
+            {
+                LaunchTimer lt(r, st, 0);
+                launch_trace(a, false, true, r->instrumented, r->grid_trace, st);
+            }
+            for (int m = 0; m < 4; ++m)
+                if (families[m]) {
+                    LaunchTimer lt(r, st, 2);
+                    launch_shade(r->d_dev, m, b, wk + 1 + m, r->grid_shade, st);
+                }
+            if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
+                // shadow rays (any hit), tMax = 1 - ShadowEpsilon
+                a.ray_o = H.sh_o;
+                a.ray_d = H.sh_d;
+                a.queue = H.q_shadow;
+                a.count = qc + Q_SHADOW;
+                a.work = wk + 5;
+                a.fixed_t_max = PT_SHADOW_TMAX;
+                a.hit_out = nullptr;
+                a.occ_out = H.occluded;
+                {
+                    LaunchTimer lt(r, st, 1);
+                    launch_trace(a, true, false, r->instrumented, r->grid_trace, st);
+                }
+                // BSDF-sampled MIS rays (closest hit)
+                a.ray_o = H.mi_o;
+                a.ray_d = H.mi_d;
+                a.queue = H.q_mis;
+                a.count = qc + Q_MIS;
+                a.work = wk + 6;
+                a.fixed_t_max = INFINITY;
+                a.hit_out = H.mis_hit;
+                a.occ_out = nullptr;
+                {
+                    LaunchTimer lt(r, st, 0);
+                    launch_trace(a, false, false, r->instrumented, r->grid_trace, st);
+                }
+                {
+                    LaunchTimer lt(r, st, 2);
+                    launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
+                }
+            }
+        }
+        {
+            LaunchTimer lt(r, st, 2);
+            launch_film(r->d_dev, (uint32_t)first, nb, st);
+        }
+        launch_accumulate_stats(r->d_dev, 0, st);
+        r->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return B200PT_OK;
+}
+
+int b200pt_film_device_buffer(b200pt_render *r, uint64_t *dev_ptr, uint64_t *n_floats) {
+    if (!r) return b200pt_fail(B200PT_ERR_INVALID, "render is NULL");
+    if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)r->host.film;
+    if (n_floats) *n_floats = 4ull * (uint64_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
+    return B200PT_OK;
+}
+
+int b200pt_film_read_raw(b200pt_render *r, float *xyzw) {
+    if (!r || !xyzw) return b200pt_fail(B200PT_ERR_INVALID, "film_read_raw: NULL argument");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    const size_t n = (size_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
+    cudaStream_t st = r->scene->ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(xyzw, r->host.film, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200PT_OK;
+}
+
+int b200pt_film_read_rgb(b200pt_render *r, float *rgb_out) {
+    if (!r || !rgb_out) return b200pt_fail(B200PT_ERR_INVALID, "film_read_rgb: NULL argument");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    const size_t n = (size_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
+    cudaStream_t st = r->scene->ctx->stream;
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * 3 * sizeof(float)));
+    launch_film_rgb(r->host.film, d, (int)n, r->film.scale, st);
+    cudaError_t e = cudaMemcpyAsync(rgb_out, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return b200pt_fail(B200PT_ERR_CUDA, "film_read_rgb: %s", cudaGetErrorString(e));
+    return B200PT_OK;
+}
+
+int b200pt_debug_sobol(b200pt_render *r, int32_t px, int32_t py, int64_t sample, int32_t dim0, int32_t n, float *out) {
+    if (!r || !out || n <= 0 || dim0 < 0 || dim0 + n > r->host.sampler.n_dims)
+        return b200pt_fail(B200PT_ERR_INVALID, "debug_sobol: bad argument");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    cudaStream_t st = r->scene->ctx->stream;
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(float)));
+    launch_debug_sobol(r->d_dev, px, py, sample, dim0, n, d, st);
+    cudaError_t e = cudaMemcpyAsync(out, d, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return b200pt_fail(B200PT_ERR_CUDA, "debug_sobol: %s", cudaGetErrorString(e));
+    return B200PT_OK;
+}
+
+int b200pt_debug_camera_rays(b200pt_render *r, int32_t px, int32_t py, int32_t n, b200pt_ray *out) {
+    if (!r || !out || n <= 0) return b200pt_fail(B200PT_ERR_INVALID, "debug_camera_rays: bad argument");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    cudaStream_t st = r->scene->ctx->stream;
+    b200pt_ray *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(b200pt_ray)));
+    launch_debug_camera(r->d_dev, px, py, n, d, st);
+    cudaError_t e = cudaMemcpyAsync(out, d, n * sizeof(b200pt_ray), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return b200pt_fail(B200PT_ERR_CUDA, "debug_camera_rays: %s", cudaGetErrorString(e));
+    return B200PT_OK;
+}
+
+// Renders the pixel's tile into the per-slot radiance buffer and returns the
+// guarded per-sample values (film accumulation is undone by saving/restoring the film).
+int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *out_rgb) {
+    if (!r || !out_rgb) return b200pt_fail(B200PT_ERR_INVALID, "debug_pixel_samples: NULL argument");
+    const RenderDev &H = r->host;
+    if (px < H.sampler.sb[0] || px >= H.sampler.sb[2] || py < H.sampler.sb[1] || py >= H.sampler.sb[3])
+        return b200pt_fail(B200PT_ERR_INVALID, "debug_pixel_samples: pixel outside the sample bounds");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    cudaStream_t st = r->scene->ctx->stream;
+    const size_t npx = (size_t)(H.crop[2] - H.crop[0]) * (H.crop[3] - H.crop[1]);
+    float4 *saved = nullptr;
+    CUDA_TRY(cudaMalloc(&saved, npx * sizeof(float4)));
+    CUDA_TRY(cudaMemcpyAsync(saved, H.film, npx * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    const int tx = (px - H.sampler.sb[0]) / 16, ty = (py - H.sampler.sb[1]) / 16;
+    int32_t tile = ty * H.tiles_x + tx;
+    int rc = b200pt_render_tiles(r, &tile, 1);
+    if (rc == B200PT_OK) {
+        const uint32_t pix = (uint32_t)((py - (H.sampler.sb[1] + ty * 16)) * 16 + (px - (H.sampler.sb[0] + tx * 16)));
+        std::vector<float4> tmp((size_t)r->spp);
+        cudaError_t e = cudaMemcpyAsync(tmp.data(), H.L + (size_t)pix * r->spp, (size_t)r->spp * sizeof(float4),
+                                        cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(H.film, saved, npx * sizeof(float4), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = b200pt_fail(B200PT_ERR_CUDA, "debug_pixel_samples: %s", cudaGetErrorString(e));
+        for (int i = 0; i < r->spp && rc == B200PT_OK; ++i) {
+            RGB L = rgb(tmp[i].x, tmp[i].y, tmp[i].z);
+            if (has_nans(L) || lum(L) < -1e-5f || pt_isinf(lum(L))) L = rgb1(0.f);  // integrator.cpp:294-315
+            out_rgb[3 * i] = L.r;
+            out_rgb[3 * i + 1] = L.g;
+            out_rgb[3 * i + 2] = L.b;
+        }
+    }
+    cudaFree(saved);
+    return rc;
+}
+
+int b200pt_get_stats(b200pt_render *r, b200pt_stats *out) {
+    if (!r || !out) return b200pt_fail(B200PT_ERR_INVALID, "get_stats: NULL argument");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    cudaStream_t st = r->scene->ctx->stream;
+    unsigned long long h[8];
+    CUDA_TRY(cudaMemcpyAsync(h, r->host.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    drain_timers(r);
+    memset(out, 0, sizeof(*out));
+    out->camera_rays = h[0];
+    out->regular_rays = h[1];
+    out->shadow_rays = h[2];
+    out->nodes_visited = h[3];
+    out->tris_tested = h[4];
+    out->any_nodes_visited = h[5];
+    out->any_tris_tested = h[6];
+    out->closest_launches = r->launches_cat[0];
+    out->any_launches = r->launches_cat[1];
+    out->closest_ms = r->ms[0];
+    out->any_ms = r->ms[1];
+    out->shade_ms = r->ms[2];
+    out->launches = r->launches;
+    return B200PT_OK;
+}
+
+int b200pt_reset_stats(b200pt_render *r) {
+    if (!r) return b200pt_fail(B200PT_ERR_INVALID, "render is NULL");
+    CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
+    cudaStream_t st = r->scene->ctx->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    drain_timers(r);
+    CUDA_TRY(cudaMemsetAsync(r->host.stats, 0, 8 * sizeof(unsigned long long), st));
+    r->ms[0] = r->ms[1] = r->ms[2] = 0;
+    r->launches = 0;
+    r->launches_cat[0] = r->launches_cat[1] = r->launches_cat[2] = 0;
+    return B200PT_OK;
+}
+
+int b200pt_render_set_option(b200pt_render *r, const char *name, int value) {
+    if (!r || !name) return b200pt_fail(B200PT_ERR_INVALID, "set_option: NULL argument");
+    if (!strcmp(name, "instrument"))
+        r->instrumented = value != 0;
+    else if (!strcmp(name, "profile"))
+        r->profiling = value != 0;
+    else
+        return b200pt_fail(B200PT_ERR_INVALID, "set_option: unknown option %s", name);
+    return B200PT_OK;
+}
+
+}  // extern "C"

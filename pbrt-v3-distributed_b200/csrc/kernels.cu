@@ -1,0 +1,609 @@
+// kernels.cu -- the sm_100a kernels of the wavefront path tracer.
+//
+//   k_raygen   K1  Sobol' camera samples -> camera rays (GetCameraSample + GenerateRayDifferential)
+//   k_trace    K2/K3  persistent-thread closest-hit / any-hit traversal of the 8-wide BVH; the
+//              closest-hit epilogue classifies hits into per-material-family queues
+//              (warp-ballot aggregated appends)
+//   k_shade<M> K4  one kernel per BSDF family: surface reconstruction, emission, light
+//              sampling + MIS bookkeeping (EstimateDirect), BSDF sampling, Russian roulette
+//   k_resolve      adds the direct-lighting estimate once shadow / MIS rays are traced
+//   k_film     K6  FilmTile::AddSample + MergeFilmTile in the reference's summation order
+// All kernels of a batch run back to back on one stream with device-side queue
+// counters; the host never synchronises inside a batch.
+#include <cstdio>
+
+#include "kernels.cuh"
+
+namespace b200pt {
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ V3 v3(const float4 &f) { return mk(f.x, f.y, f.z); }
+__device__ __forceinline__ V3 v3(const F4 &f) { return mk(f.x, f.y, f.z); }
+__device__ __forceinline__ float4 f4(const V3 &v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ float4 f4(const RGB &c, float w) { return make_float4(c.r, c.g, c.b, w); }
+__device__ __forceinline__ RGB rgb3(const float4 &f) { return rgb(f.x, f.y, f.z); }
+
+// Warp-aggregated append: every lane of the warp must call it (converged);
+// lanes with pred get consecutive positions behind one atomicAdd.
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+    const uint32_t mask = __ballot_sync(FULL_MASK, pred);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// Persistent-thread fetch of 32 work items per warp.
+__device__ __forceinline__ bool warp_fetch(uint32_t *work, uint32_t n, uint32_t *item) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work, 32u);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (base >= n) return false;
+    *item = base + (uint32_t)lane;
+    return true;
+}
+
+// ------------------------------------------------------------------ tile maths
+struct TileRect {
+    int x0, y0, x1, y1;  // sample-space rectangle of the tile (integrator.cpp:251-255)
+};
+__device__ __forceinline__ TileRect tile_rect(const RenderDev *R, int tile) {
+    TileRect t;
+    const int tx = tile % R->tiles_x, ty = tile / R->tiles_x;
+    t.x0 = R->sampler.sb[0] + tx * 16;
+    t.x1 = min(t.x0 + 16, R->sampler.sb[2]);
+    t.y0 = R->sampler.sb[1] + ty * 16;
+    t.y1 = min(t.y0 + 16, R->sampler.sb[3]);
+    return t;
+}
+// a pixel of the tile is rendered iff it lies in the tile and in "pixelbounds" (integrator.cpp:273)
+__device__ __forceinline__ bool pixel_rendered(const RenderDev *R, const TileRect &t, int px, int py) {
+    return px >= t.x0 && px < t.x1 && py >= t.y0 && py < t.y1 && px >= R->pixel_bounds[0] &&
+           px < R->pixel_bounds[2] && py >= R->pixel_bounds[1] && py < R->pixel_bounds[3];
+}
+
+// ---------------------------------------------------------------------- raygen
+__global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t first_tile, uint32_t n_slots) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    if (slot < n_slots) {
+        const uint32_t spp = (uint32_t)R->sampler.spp;
+        const uint32_t sample = slot % spp;
+        const uint32_t pix = (slot / spp) & 255u;
+        const uint32_t tb = slot / (spp * 256u);
+        const int tile = R->tile_list[first_tile + tb];
+        const TileRect t = tile_rect(R, tile);
+        const int px = t.x0 + (int)(pix & 15u), py = t.y0 + (int)(pix >> 4);
+        if (pixel_rendered(R, t, px, py)) {
+            valid = true;
+            const SamplerParams &sp = R->sampler;
+            SobolStream st;
+            st.index = sobol_interval_to_index(sp, sample, px - sp.sb[0], py - sp.sb[1]);  // sobol.cpp:42-45
+            st.dim = 0;
+            st.px = px;
+            st.py = py;
+            float u[2], ul[2];
+            get2d(sp, st, u);  // sampler.cpp:46-52
+            float pFilm[2] = {(float)px + u[0], (float)py + u[1]};
+            (void)get1d(sp, st);  // time
+            get2d(sp, st, ul);
+            V3 o, d;
+            float tMax;
+            generate_camera_ray(R->camera, pFilm, ul, &o, &d, &tMax);
+            // box-filter footprint of the sample (film.h:126-132, radius 0.5)
+            const float dx = pFilm[0] - 0.5f, dy = pFilm[1] - 0.5f;
+            uint32_t code = 0;
+            if ((int)ceilf(dx - 0.5f) < px) code |= 1u;
+            if ((int)floorf(dx + 0.5f) + 1 > px + 1) code |= 2u;
+            if ((int)ceilf(dy - 0.5f) < py) code |= 4u;
+            if ((int)floorf(dy + 0.5f) + 1 > py + 1) code |= 8u;
+            if (code) R->pix_bleed[tb * 256u + pix] = 1;
+            R->sobol[slot] = st.index;
+            R->ray_o[slot] = f4(o, 1.f);                                // etaScale = 1
+            R->ray_d[slot] = f4(d, __uint_as_float((uint32_t)st.dim));  // dim = 5, bounces = 0, flags = 0
+            R->beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+            R->L[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(code));
+            R->sh_d[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const uint32_t pos = warp_append(&R->qcount[Q_PATH], valid);
+    if (valid) R->q_path[0][pos] = slot;
+}
+
+// ----------------------------------------------------------------------- trace
+template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
+__global__ void __launch_bounds__(128, 4) k_trace(const TraceArgs a) {
+    const uint32_t n = *a.count;
+    TraceCounters ctr;
+    ctr.nodes = ctr.tris = 0;
+    uint32_t i;
+    while (warp_fetch(a.work, n, &i)) {
+        const bool active = i < n;
+        uint32_t slot = 0, tri = B200PT_MISS;
+        int family = -1;
+        if (active) {
+            slot = a.queue ? a.queue[i] : i;
+            const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+            const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+            const float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
+            TriHit h;
+            h.t = h.b0 = h.b1 = h.b2 = 0.f;
+            tri = traverse_bvh8<ANY_HIT, COUNT>(a.nodes, a.tris, v3(o4), v3(d4), tmax, &h, &ctr);
+            if (ANY_HIT) {
+                a.occ_out[slot] = tri != B200PT_MISS ? 1 : 0;
+            } else {
+                if (a.hit_out) a.hit_out[slot] = tri;
+                if (a.full_out) {
+                    b200pt_hit r;
+                    r.triangle = tri != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)tri * 3).w) : -1;
+                    r.t = h.t;
+                    r.b0 = h.b0;
+                    r.b1 = h.b1;
+                    a.full_out[slot] = r;
+                }
+                if (CLASSIFY && tri != B200PT_MISS) {
+                    const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)tri * 3 + 1).w);
+                    family = a.materials[mf & 0xffffu].type;
+                }
+            }
+        }
+        if (CLASSIFY) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const bool mine = family == m;
+                const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
+                if (mine) a.q_mat[m][pos] = slot;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&a.stats[ANY_HIT ? 5 : 3], (unsigned long long)ctr.nodes);
+        atomicAdd(&a.stats[ANY_HIT ? 6 : 4], (unsigned long long)ctr.tris);
+    }
+}
+
+// ----------------------------------------------------------------------- shade
+struct DirectOut {
+    uint32_t pend;
+    V3 sh_o, sh_d, mi_o, mi_d;
+    RGB A, B;
+};
+
+// EstimateDirect (core/integrator.cpp:108-215), handleMedia = false,
+// specular = false, for a DiffuseAreaLight on one triangle.  The two rays it
+// needs are not traced here: the shadow ray and the BSDF-sampled ("MIS") ray
+// are queued with the terms they gate (A and B).
+__device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
+                                int lightNum, const float uLight[2], DirectOut *out) {
+    const DevLight light = R->lights[lightNum];
+    const F4 *tp = R->scene.tris + (size_t)light.tri * 3;
+    const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+    const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
+    const uint32_t lflags = __float_as_uint(t1.w);
+    const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
+    const RGB lemit = rgbp(light.lemit);
+    const int flagsNS = BSDF_ALL & ~BSDF_SPECULAR;
+    out->pend = 0;
+    out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
+    out->A = out->B = rgb1(0.f);
+    V3 wi = mk(0.f, 0.f, 0.f);
+    float lightPdf = 0.f, scatteringPdf = 0.f;
+    // light.Sample_Li: diffuse.cpp:68-81, shape.cpp:56-70
+    RGB Li = rgb1(0.f);
+    LightSample ps = triangle_sample(p0, p1, p2, lflip, uLight, &lightPdf);
+    {
+        V3 w = ps.p - is.p;
+        if (len2(w) == 0)
+            lightPdf = 0;
+        else {
+            w = normalize(w);
+            lightPdf *= len2(is.p - ps.p) / absdot(ps.n, -w);
+            if (pt_isinf(lightPdf)) lightPdf = 0.f;
+        }
+    }
+    if (lightPdf == 0 || len2(ps.p - is.p) == 0) {
+        lightPdf = 0;
+    } else {
+        wi = normalize(ps.p - is.p);
+        Li = (light.two_sided || dot(ps.n, -wi) > 0) ? lemit : rgb1(0.f);  // diffuse.h:56-58
+    }
+    if (lightPdf > 0 && !is_black(Li)) {
+        RGB f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
+        scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+        if (!is_black(f)) {
+            // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
+            const V3 origin = offset_ray_origin(is.p, is.pError, is.n, ps.p - is.p);
+            const V3 target = offset_ray_origin(ps.p, ps.pError, ps.n, origin - ps.p);
+            out->sh_o = origin;
+            out->sh_d = target - origin;
+            const float weight = power_heuristic(lightPdf, scatteringPdf);
+            out->A = f * Li * weight / lightPdf;
+            out->pend |= PEND_LIGHT;
+        }
+    }
+    // BSDF sampling with MIS (integrator.cpp:166-213)
+    int sampledType = 0;
+    RGB f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+    f = f * absdot(wi, bsdf.ns);
+    if (!is_black(f) && scatteringPdf > 0) {
+        // light.Pdf_Li -> Shape::Pdf (shape.cpp:72-87): intersect the light's own triangle
+        const V3 ro = offset_ray_origin(is.p, is.pError, is.n, wi);
+        float lpdf = 0.f;
+        V3 ln = mk(0.f, 0.f, 0.f);
+        TriHit h;
+        if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
+            const V3 lp = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
+            ln = normalize(cross(p0 - p2, p1 - p2));
+            if (lflip) ln = -ln;
+            lpdf = len2(is.p - lp) / (absdot(ln, -wi) * light.area);
+            if (pt_isinf(lpdf)) lpdf = 0.f;
+        }
+        if (lpdf != 0) {
+            const float weight = power_heuristic(scatteringPdf, lpdf);
+            // lightIsect.Le(-wi) if the closest hit along the ray is this light (integrator.cpp:205-209)
+            const RGB Le = (light.two_sided || dot(ln, -wi) > 0) ? lemit : rgb1(0.f);
+            out->B = is_black(Le) ? rgb1(0.f) : f * Le * 1.f * weight / scatteringPdf;
+            out->mi_o = ro;
+            out->mi_d = wi;
+            out->pend |= PEND_BSDF;
+        }
+    }
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(128) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
+    const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
+    const uint32_t *queue = R->q_mat[MAT];
+    uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
+    uint32_t *qc_shadow = &R->qcount[bounce * Q_PER_BOUNCE + Q_SHADOW];
+    uint32_t *qc_mis = &R->qcount[bounce * Q_PER_BOUNCE + Q_MIS];
+    uint32_t *q_next = R->q_path[(bounce + 1) & 1];
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        const bool active = i < n;
+        bool cont = false;
+        uint32_t pend = 0, slot = 0;
+        if (active) {
+            slot = queue[i];
+            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot], b4 = R->beta[slot];
+            float4 L4 = R->L[slot];
+            const V3 ro = v3(o4), rd = v3(d4);
+            float etaScale = o4.w;
+            const uint32_t meta = __float_as_uint(d4.w);
+            const int bounces = (int)((meta >> 16) & 0xffu);
+            const bool specularBounce = ((meta >> 24) & PF_SPECULAR) != 0;
+            RGB beta = rgb3(b4), L = rgb3(L4);
+            const uint32_t ti = R->hit[slot];
+            const F4 *tp = R->scene.tris + (size_t)ti * 3;
+            const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+            const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
+            const uint32_t mflags = __float_as_uint(t1.w);
+            const int lightId = (int)__float_as_uint(t2.w);
+            // re-derive (t, b0, b1, b2) of the accepted hit: Triangle::Intersect's values do not depend on tMax
+            TriHit h;
+            if (triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h)) {
+                Isect is;
+                fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, h, rd, &is);
+                // path.cpp:91-101: emitted light at the first vertex or after a specular bounce
+                if (bounces == 0 || specularBounce) {
+                    if (lightId >= 0) {
+                        const DevLight lt = R->lights[lightId];
+                        const RGB Le = (lt.two_sided || dot(is.n, -rd) > 0) ? rgbp(lt.lemit) : rgb1(0.f);
+                        L = L + beta * Le;
+                    }
+                }
+                if (bounces < R->max_depth) {  // path.cpp:104
+                    Bsdf bsdf;
+                    make_bsdf<MAT>(R->scene.materials[mflags & 0xffffu], is, &bsdf);
+                    SobolStream st;
+                    st.index = R->sobol[slot];
+                    st.dim = (int)(meta & 0xffffu);
+                    st.px = st.py = 0;  // only dimensions 0/1 depend on the pixel
+                    const SamplerParams &sp = R->sampler;
+                    // path.cpp:119-128 -> UniformSampleOneLight (integrator.cpp:85-106)
+                    if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && R->n_lights > 0) {
+                        float pickPdf;
+                        const int lightNum = sample_discrete(R->light_cdf, R->light_func, R->light_func_int,
+                                                             R->n_lights, get1d(sp, st), &pickPdf);
+                        if (pickPdf != 0) {
+                            float uLight[2], uScattering[2];
+                            get2d(sp, st, uLight);
+                            get2d(sp, st, uScattering);
+                            DirectOut dout;
+                            estimate_direct(R, is, bsdf, uScattering, lightNum, uLight, &dout);
+                            pend = dout.pend;
+                            if (pend) {
+                                R->beta_ld[slot] = f4(beta, pickPdf);
+                                R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
+                                if (pend & PEND_LIGHT) R->A[slot] = f4(dout.A, 0.f);
+                                if (pend & PEND_BSDF) {
+                                    R->mi_o[slot] = f4(dout.mi_o, 0.f);
+                                    R->mi_d[slot] = f4(dout.mi_d, 0.f);
+                                    R->B[slot] = f4(dout.B, 0.f);
+                                }
+                            }
+                            R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
+                        }
+                    }
+                    // path.cpp:131-150: sample the BSDF for the next direction
+                    const V3 wo = -rd;
+                    V3 wi = mk(0.f, 0.f, 0.f);
+                    float pdf = 0.f;
+                    int flags = 0;
+                    float u2[2];
+                    get2d(sp, st, u2);
+                    const RGB f = bsdf_sample_f(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+                    if (!(is_black(f) || pdf == 0.f)) {
+                        beta = beta * (f * absdot(wi, bsdf.ns) / pdf);
+                        const bool spec = (flags & BSDF_SPECULAR) != 0;
+                        if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+                            const float eta = bsdf.eta;
+                            etaScale *= (dot(wo, is.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+                        }
+                        const V3 no = offset_ray_origin(is.p, is.pError, is.n, wi);  // isect.SpawnRay(wi)
+                        cont = true;
+                        // path.cpp:176-184: Russian roulette
+                        const RGB rrBeta = beta * etaScale;
+                        if (max_comp(rrBeta) < R->rr_threshold && bounces > 3) {
+                            const float q = pt_max(.05f, 1 - max_comp(rrBeta));
+                            if (get1d(sp, st) < q)
+                                cont = false;
+                            else
+                                beta = beta / (1 - q);
+                        }
+                        if (cont) {
+                            const uint32_t nmeta = ((uint32_t)st.dim & 0xffffu) | ((uint32_t)(bounces + 1) << 16) |
+                                                   ((spec ? (uint32_t)PF_SPECULAR : 0u) << 24);
+                            R->ray_o[slot] = f4(no, etaScale);
+                            R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
+                            R->beta[slot] = f4(beta, 0.f);
+                        }
+                    }
+                }
+                R->L[slot] = f4(L, L4.w);
+            }
+        }
+        const uint32_t ps = warp_append(qc_shadow, (pend & PEND_LIGHT) != 0);
+        if (pend & PEND_LIGHT) R->q_shadow[ps] = slot;
+        const uint32_t pm = warp_append(qc_mis, (pend & PEND_BSDF) != 0);
+        if (pend & PEND_BSDF) R->q_mis[pm] = slot;
+        const uint32_t pn = warp_append(qc_next, cont);
+        if (cont) q_next[pn] = slot;
+    }
+}
+
+// L += beta * (EstimateDirect(...) / lightPdf)   (path.cpp:122-127, integrator.cpp:104-105)
+__global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce, uint32_t *work) {
+    const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_PATH];
+    const uint32_t *queue = R->q_path[bounce & 1];
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        if (i >= n) continue;
+        const uint32_t slot = queue[i];
+        const float4 sd = R->sh_d[slot];
+        const uint32_t pend = __float_as_uint(sd.w);
+        if (!pend) continue;
+        RGB Ld = rgb1(0.f);
+        bool any = false;
+        if ((pend & PEND_LIGHT) && !R->occluded[slot]) {
+            Ld = Ld + rgb3(R->A[slot]);
+            any = true;
+        }
+        if (pend & PEND_BSDF) {
+            const uint32_t lightNum = __float_as_uint(R->sh_o[slot].w);
+            const RGB B = rgb3(R->B[slot]);
+            if (R->mis_hit[slot] == R->lights[lightNum].tri && !is_black(B)) {
+                Ld = Ld + B;
+                any = true;
+            }
+        }
+        if (any) {
+            const float4 bl = R->beta_ld[slot];
+            float4 L4 = R->L[slot];
+            const RGB L = rgb3(L4) + rgb3(bl) * (Ld / bl.w);
+            R->L[slot] = f4(L, L4.w);
+        }
+        R->sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------ film
+// One block per tile, one thread per pixel of the tile's FilmTile (the tile
+// plus a one-pixel apron, film.cpp:95-106).  A thread re-creates the
+// reference's accumulation order for its pixel: source pixels in row-major
+// order within the tile, samples in order (integrator.cpp:263-325), each
+// sample added to every pixel of its box-filter footprint (film.h:121-161),
+// then one RGB->XYZ conversion and add into the film (film.cpp:117-130).
+__global__ void __launch_bounds__(18 * 18) k_film(const RenderDev *R, uint32_t first_tile) {
+    const uint32_t tb = blockIdx.x;
+    const int tile = R->tile_list[first_tile + tb];
+    const TileRect t = tile_rect(R, tile);
+    const int X = t.x0 - 1 + (int)threadIdx.x, Y = t.y0 - 1 + (int)threadIdx.y;
+    // FilmTile pixel bounds: [x0-1, x1+1) x [y0-1, y1+1) clipped to the cropped film
+    if (X >= t.x1 + 1 || Y >= t.y1 + 1) return;
+    if (X < R->crop[0] || X >= R->crop[2] || Y < R->crop[1] || Y >= R->crop[3]) return;
+    const uint32_t spp = (uint32_t)R->sampler.spp;
+    const float maxLum = R->max_sample_luminance;
+    RGB sum = rgb1(0.f);
+    float wsum = 0.f;
+    for (int sy = Y - 1; sy <= Y + 1; ++sy)
+        for (int sx = X - 1; sx <= X + 1; ++sx) {
+            if (!pixel_rendered(R, t, sx, sy)) continue;
+            const uint32_t pix = (uint32_t)((sy - t.y0) * 16 + (sx - t.x0));
+            const bool own = (sx == X && sy == Y);
+            if (!own && !R->pix_bleed[tb * 256u + pix]) continue;
+            const float4 *Ls = R->L + ((size_t)tb * 256u + pix) * spp;
+            for (uint32_t s = 0; s < spp; ++s) {
+                const float4 v = Ls[s];
+                if (!own) {
+                    const uint32_t code = __float_as_uint(v.w);
+                    const bool cx = (X == sx) || (X == sx - 1 && (code & 1u)) || (X == sx + 1 && (code & 2u));
+                    const bool cy = (Y == sy) || (Y == sy - 1 && (code & 4u)) || (Y == sy + 1 && (code & 8u));
+                    if (!(cx && cy)) continue;
+                }
+                RGB Lv = rgb(v.x, v.y, v.z);
+                // integrator.cpp:294-315
+                if (has_nans(Lv))
+                    Lv = rgb1(0.f);
+                else if (lum(Lv) < -1e-5f)
+                    Lv = rgb1(0.f);
+                else if (pt_isinf(lum(Lv)))
+                    Lv = rgb1(0.f);
+                if (lum(Lv) > maxLum) Lv = Lv * (maxLum / lum(Lv));  // film.h:124-125
+                sum = sum + Lv * 1.f * 1.f;                           // L * sampleWeight * filterWeight
+                wsum += 1.f;
+            }
+        }
+    if (wsum != 0.f) {
+        float xyz[3];
+        rgb_to_xyz(sum, xyz);
+        float *fp = reinterpret_cast<float *>(R->film + (size_t)(Y - R->crop[1]) * (R->crop[2] - R->crop[0]) +
+                                              (X - R->crop[0]));
+        atomicAdd(fp + 0, xyz[0]);
+        atomicAdd(fp + 1, xyz[1]);
+        atomicAdd(fp + 2, xyz[2]);
+        atomicAdd(fp + 3, wsum);
+    }
+}
+
+__global__ void k_accumulate_stats(const RenderDev *R) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long regular = 0, shadow = 0;
+    for (int b = 0; b <= R->max_depth; ++b) {
+        regular += R->qcount[b * Q_PER_BOUNCE + Q_PATH] + R->qcount[b * Q_PER_BOUNCE + Q_MIS];
+        shadow += R->qcount[b * Q_PER_BOUNCE + Q_SHADOW];
+    }
+    R->stats[0] += R->qcount[Q_PATH];
+    R->stats[1] += regular;
+    R->stats[2] += shadow;
+}
+
+// Film::WriteImage pixel pipeline (film.cpp:174-203); splats are always zero here.
+__global__ void k_film_rgb(const float4 *film, float *out, int n, float scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = film[i];
+    float xyz[3] = {p.x, p.y, p.z}, c[3];
+    xyz_to_rgb(xyz, c);
+    if (p.w != 0) {
+        const float invWt = 1.0f / p.w;
+        c[0] = pt_max(0.f, c[0] * invWt);
+        c[1] = pt_max(0.f, c[1] * invWt);
+        c[2] = pt_max(0.f, c[2] * invWt);
+    }
+    float zero[3] = {0.f, 0.f, 0.f}, splat[3];
+    xyz_to_rgb(zero, splat);
+    for (int k = 0; k < 3; ++k) {
+        c[k] += 1.f * splat[k];
+        c[k] *= scale;
+        out[3 * i + k] = c[k];
+    }
+}
+
+__global__ void k_debug_sobol(const RenderDev *R, int px, int py, long long sample, int dim0, int n, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SamplerParams &sp = R->sampler;
+    const uint64_t idx = sobol_interval_to_index(sp, (uint64_t)sample, px - sp.sb[0], py - sp.sb[1]);
+    out[i] = sobol_sample(sp, idx, dim0 + i, px, py);
+}
+
+__global__ void k_debug_camera(const RenderDev *R, int px, int py, int n, b200pt_ray *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SamplerParams &sp = R->sampler;
+    SobolStream st;
+    st.index = sobol_interval_to_index(sp, (uint64_t)i, px - sp.sb[0], py - sp.sb[1]);
+    st.dim = 0;
+    st.px = px;
+    st.py = py;
+    float u[2], ul[2];
+    get2d(sp, st, u);
+    float pFilm[2] = {(float)px + u[0], (float)py + u[1]};
+    (void)get1d(sp, st);
+    get2d(sp, st, ul);
+    V3 o, d;
+    float tMax;
+    generate_camera_ray(R->camera, pFilm, ul, &o, &d, &tMax);
+    b200pt_ray r;
+    r.o[0] = o.x;
+    r.o[1] = o.y;
+    r.o[2] = o.z;
+    r.t_max = tMax;
+    r.d[0] = d.x;
+    r.d[1] = d.y;
+    r.d[2] = d.z;
+    r.pad = 0.f;
+    out[i] = r;
+}
+
+// -------------------------------------------------------------------- launchers
+void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
+                   cudaStream_t s) {
+    (void)n_batch_tiles;
+    k_raygen<<<(n_slots + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_slots);
+}
+
+void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s) {
+    if (any_hit) {
+        if (count)
+            k_trace<true, false, true><<<grid, 128, 0, s>>>(a);
+        else
+            k_trace<true, false, false><<<grid, 128, 0, s>>>(a);
+    } else if (classify) {
+        if (count)
+            k_trace<false, true, true><<<grid, 128, 0, s>>>(a);
+        else
+            k_trace<false, true, false><<<grid, 128, 0, s>>>(a);
+    } else {
+        if (count)
+            k_trace<false, false, true><<<grid, 128, 0, s>>>(a);
+        else
+            k_trace<false, false, false><<<grid, 128, 0, s>>>(a);
+    }
+}
+
+void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work, int grid, cudaStream_t s) {
+    switch (material) {
+    case B200PT_MAT_MATTE:
+        k_shade<B200PT_MAT_MATTE><<<grid, 128, 0, s>>>(dev, bounce, work);
+        break;
+    case B200PT_MAT_PLASTIC:
+        k_shade<B200PT_MAT_PLASTIC><<<grid, 128, 0, s>>>(dev, bounce, work);
+        break;
+    case B200PT_MAT_METAL:
+        k_shade<B200PT_MAT_METAL><<<grid, 128, 0, s>>>(dev, bounce, work);
+        break;
+    case B200PT_MAT_GLASS:
+        k_shade<B200PT_MAT_GLASS><<<grid, 128, 0, s>>>(dev, bounce, work);
+        break;
+    }
+}
+
+void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
+    k_resolve<<<grid, 256, 0, s>>>(dev, bounce, work);
+}
+
+void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s) {
+    k_film<<<n_batch_tiles, dim3(18, 18), 0, s>>>(dev, batch_first_tile);
+}
+
+void launch_accumulate_stats(const RenderDev *dev, uint32_t, cudaStream_t s) { k_accumulate_stats<<<1, 32, 0, s>>>(dev); }
+
+void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
+                        cudaStream_t s) {
+    k_debug_sobol<<<(n + 63) / 64, 64, 0, s>>>(dev, px, py, sample, dim0, n, out);
+}
+void launch_debug_camera(const RenderDev *dev, int px, int py, int n, b200pt_ray *out, cudaStream_t s) {
+    k_debug_camera<<<(n + 63) / 64, 64, 0, s>>>(dev, px, py, n, out);
+}
+void launch_film_rgb(const float4 *film, float *rgb, int n_pixels, float scale, cudaStream_t s) {
+    k_film_rgb<<<(n_pixels + 255) / 256, 256, 0, s>>>(film, rgb, n_pixels, scale);
+}
+
+}  // namespace b200pt

@@ -1,0 +1,125 @@
+// kernels.cuh -- device-side data layout shared by kernels.cu and api.cu.
+//
+// Wavefront organisation of SamplerIntegrator::Render (integrator.cpp:228-339):
+// a *batch* is a set of 16x16 film tiles rendered with all their samples at
+// once.  Path slot = ((tile_in_batch * 256 + pixel_in_tile) * spp + sample),
+// i.e. the reference's loop nest tile -> pixel (row-major) -> sample flattened,
+// so a warp holds 32 consecutive samples of one pixel (coherent camera rays)
+// and the film kernel can re-create the reference's per-tile summation order.
+// Per-slot state lives in float4-packed SoA arrays (one coalesced 16-byte
+// access per thread); queues of slot indices connect the stages.
+#ifndef B200PT_KERNELS_CUH
+#define B200PT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "bvh8_traverse.cuh"
+#include "pt_core.cuh"
+
+namespace b200pt {
+
+struct DevLight {
+    uint32_t tri;  // leaf-order triangle index
+    float lemit[3];
+    int two_sided;
+    float area;  // Triangle::Area(), computed on the host
+};
+
+struct DevScene {
+    const U4 *nodes;
+    const F4 *tris;
+    const b200pt_material *materials;
+    uint32_t n_nodes, n_tris;
+};
+
+// queue ids inside one bounce's counter block
+enum { Q_PATH = 0, Q_MAT0 = 1, Q_SHADOW = 5, Q_MIS = 6, Q_NEXT = 7, Q_PER_BOUNCE = 8 };
+// meta word of a path: dim (16 bits) | bounces (8) | flags (8)
+enum { PF_SPECULAR = 1 };
+// pending direct-lighting flags
+enum { PEND_LIGHT = 1, PEND_BSDF = 2 };
+
+struct RenderDev {
+    DevScene scene;
+    SamplerParams sampler;
+    CameraParams camera;
+    // film
+    int crop[4];            // cropped pixel bounds
+    int pixel_bounds[4];    // integrator "pixelbounds"
+    float max_sample_luminance;
+    float4 *film;           // [h][w] (X, Y, Z, weight) raw sums
+    // integrator
+    int max_depth;
+    float rr_threshold;
+    // lights + Distribution1D of the chosen strategy
+    const DevLight *lights;
+    int n_lights;
+    const float *light_cdf;   // [n_lights + 1]
+    const float *light_func;  // [n_lights]
+    float light_func_int;
+    // batch
+    int tiles_x, tiles_y;
+    const int32_t *tile_list;  // tile ids of the whole render_tiles call
+    uint32_t capacity;         // path slots per batch
+    // per-slot state (float4-packed)
+    float4 *ray_o;     // o.xyz, etaScale
+    float4 *ray_d;     // d.xyz, meta (bits)
+    float4 *beta;      // beta.rgb, light pick pdf
+    float4 *L;         // L.rgb, bleed code (bits)
+    uint64_t *sobol;   // Sobol' index of (pixel, sample)
+    uint32_t *hit;     // closest-hit triangle (leaf order) of the path ray
+    float4 *sh_o;      // shadow ray origin, light number (bits)
+    float4 *sh_d;      // shadow ray direction, pending flags (bits)
+    float4 *A;         // light-sampling term  f*Li*w/lightPdf
+    float4 *mi_o;      // MIS (BSDF-sampled) ray origin
+    float4 *mi_d;      // MIS ray direction
+    float4 *B;         // BSDF-sampling term f*Le*w/scatteringPdf, valid if the MIS ray reaches the light
+    float4 *beta_ld;   // beta at the time of the direct-lighting estimate
+    uint8_t *occluded; // any-hit result of the shadow ray
+    uint32_t *mis_hit; // closest-hit triangle of the MIS ray
+    uint8_t *pix_bleed;  // [tiles_per_batch*256] pixel has a sample whose box-filter footprint leaves the pixel
+    // queues (slot indices) and their counters
+    uint32_t *q_path[2];       // ping-pong
+    uint32_t *q_mat[4];
+    uint32_t *q_shadow;
+    uint32_t *q_mis;
+    uint32_t *qcount;          // [(max_depth + 2) * Q_PER_BOUNCE]
+    uint32_t *work;            // persistent-fetch counters, one per launch of a batch
+    unsigned long long *stats; // camera, regular, shadow, nodes, tris
+};
+
+struct TraceArgs {
+    const U4 *nodes;
+    const F4 *tris;
+    const float4 *ray_o;   // o.xyz (+ t_max in .w when t_max_from_w)
+    const float4 *ray_d;
+    const uint32_t *queue; // slot indices or nullptr for identity
+    const uint32_t *count; // device-side number of rays
+    uint32_t *work;        // persistent fetch counter (zeroed)
+    float fixed_t_max;     // used unless t_max_from_w
+    int t_max_from_w;
+    int stride;            // ray_o/ray_d element stride in float4 (1 for SoA state, 2 for b200pt_ray)
+    uint32_t *hit_out;     // closest: triangle per slot
+    b200pt_hit *full_out;  // closest: optional full record (prim id, t, b0, b1)
+    uint8_t *occ_out;      // any-hit result per slot
+    // classification of closest hits by material family
+    uint32_t *q_mat[4];
+    uint32_t *qcount_mat;  // &qcount[bounce*Q_PER_BOUNCE + Q_MAT0]
+    const b200pt_material *materials;
+    unsigned long long *stats;  // nodes/tris counters when instrumented
+};
+
+void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
+                   cudaStream_t s);
+void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s);
+void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
+void launch_accumulate_stats(const RenderDev *dev, uint32_t n_camera, cudaStream_t s);
+void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
+                        cudaStream_t s);
+void launch_debug_camera(const RenderDev *dev, int px, int py, int n, b200pt_ray *out, cudaStream_t s);
+void launch_film_rgb(const float4 *film, float *rgb, int n_pixels, float scale, cudaStream_t s);
+
+}  // namespace b200pt
+#endif

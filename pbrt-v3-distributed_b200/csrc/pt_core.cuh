@@ -1,0 +1,885 @@
+// pt_core.cuh -- device arithmetic of the path: Sobol' sampler, perspective
+// camera, watertight triangle test, surface reconstruction, BSDF families,
+// area-light sampling.
+//
+// Numerics contract: every function rounds exactly like the reference's
+// scalar float code (Float=float, compiled without FMA contraction), so the
+// kernels are built with -fmad=false and this header never uses fast-math
+// intrinsics.  Each function cites the reference lines whose operation order
+// it keeps.  The header is also compilable as plain C++ so that
+// tests/host_preflight.cpp can check it on the CPU against the oracle before
+// GPU time is spent (that test binary is never part of libb200pt.so).
+#ifndef B200PT_CORE_CUH
+#define B200PT_CORE_CUH
+
+#include "../../include/b200pt.h"
+#include "pt_platform.h"
+#include "pt_sincos.cuh"
+
+namespace b200pt {
+
+// ------------------------------------------------------------------ constants
+#define PT_MACHINE_EPS 5.9604644775390625e-08f /* 2^-24, pbrt.h:195-199 */
+#define PT_PI ((float)3.14159265358979323846)
+#define PT_INV_PI ((float)0.31830988618379067154)
+#define PT_PI_OVER2 ((float)1.57079632679489661923)
+#define PT_PI_OVER4 ((float)0.78539816339744830961)
+#define PT_ONE_MINUS_EPS 0x1.fffffep-1f
+#define PT_SHADOW_TMAX (1.f - 0.0001f) /* 1 - ShadowEpsilon in float, interaction.h:76 */
+
+B200_HD float pt_inf() { return uint_as_float(0x7f800000u); }
+// pbrt.h:285-287
+B200_HD float pt_gamma(int n) { return (n * PT_MACHINE_EPS) / (1 - n * PT_MACHINE_EPS); }
+B200_HD float pt_abs(float x) { return fabsf(x); }
+// std::min / std::max semantics (second argument wins only when strictly better)
+B200_HD float pt_min(float a, float b) { return (b < a) ? b : a; }
+B200_HD float pt_max(float a, float b) { return (a < b) ? b : a; }
+B200_HD int pt_mini(int a, int b) { return (b < a) ? b : a; }
+B200_HD int pt_maxi(int a, int b) { return (a < b) ? b : a; }
+B200_HD bool pt_isinf(float x) { return (float_as_uint(x) & 0x7fffffffu) == 0x7f800000u; }
+B200_HD bool pt_isnan(float x) { return (float_as_uint(x) & 0x7fffffffu) > 0x7f800000u; }
+// pbrt.h:300-308
+B200_HD float pt_clamp(float v, float lo, float hi) {
+    if (v < lo)
+        return lo;
+    else if (v > hi)
+        return hi;
+    else
+        return v;
+}
+// pbrt.h:237-261
+B200_HD float next_float_up(float v) {
+    if (pt_isinf(v) && v > 0.f) return v;
+    if (v == -0.f) v = 0.f;
+    uint32_t ui = float_as_uint(v);
+    if (v >= 0)
+        ++ui;
+    else
+        --ui;
+    return uint_as_float(ui);
+}
+B200_HD float next_float_down(float v) {
+    if (pt_isinf(v) && v < 0.f) return v;
+    if (v == 0.f) v = -0.f;
+    uint32_t ui = float_as_uint(v);
+    if (v > 0)
+        --ui;
+    else
+        ++ui;
+    return uint_as_float(ui);
+}
+
+// -------------------------------------------------------------------- vectors
+struct V3 {
+    float x, y, z;
+};
+B200_HD V3 mk(float x, float y, float z) {
+    V3 v;
+    v.x = x;
+    v.y = y;
+    v.z = z;
+    return v;
+}
+B200_HD float comp(const V3 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+B200_HD V3 operator+(const V3 &a, const V3 &b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+B200_HD V3 operator-(const V3 &a, const V3 &b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+B200_HD V3 operator-(const V3 &a) { return mk(-a.x, -a.y, -a.z); }
+B200_HD V3 operator*(float s, const V3 &v) { return mk(s * v.x, s * v.y, s * v.z); }
+B200_HD V3 operator*(const V3 &v, float s) { return mk(s * v.x, s * v.y, s * v.z); }
+B200_HD float dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+B200_HD float absdot(const V3 &a, const V3 &b) { return pt_abs(dot(a, b)); }
+B200_HD float len2(const V3 &v) { return v.x * v.x + v.y * v.y + v.z * v.z; }
+B200_HD float len(const V3 &v) { return sqrtf(len2(v)); }
+// geometry.h:243-248 (division = multiplication by the rounded reciprocal)
+B200_HD V3 vdiv(const V3 &v, float f) {
+    float inv = 1.0f / f;
+    return mk(v.x * inv, v.y * inv, v.z * inv);
+}
+B200_HD V3 normalize(const V3 &v) { return vdiv(v, len(v)); }
+B200_HD V3 vabs(const V3 &v) { return mk(pt_abs(v.x), pt_abs(v.y), pt_abs(v.z)); }
+// geometry.h:957-963: products and differences in double, one rounding to float
+B200_HD V3 cross(const V3 &a, const V3 &b) {
+    double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z;
+    return mk((float)((ay * bz) - (az * by)), (float)((az * bx) - (ax * bz)), (float)((ax * by) - (ay * bx)));
+}
+B200_HD float max3(float a, float b, float c) { return pt_max(a, pt_max(b, c)); }
+// geometry.h:1020-1027
+B200_HD void coordinate_system(const V3 &v1, V3 *v2, V3 *v3) {
+    if (pt_abs(v1.x) > pt_abs(v1.y))
+        *v2 = vdiv(mk(-v1.z, 0.f, v1.x), sqrtf(v1.x * v1.x + v1.z * v1.z));
+    else
+        *v2 = vdiv(mk(0.f, v1.z, -v1.y), sqrtf(v1.y * v1.y + v1.z * v1.z));
+    *v3 = cross(v1, *v2);
+}
+
+// ------------------------------------------------------------------- spectrum
+struct RGB {
+    float r, g, b;
+};
+B200_HD RGB rgb(float r, float g, float b) {
+    RGB c;
+    c.r = r;
+    c.g = g;
+    c.b = b;
+    return c;
+}
+B200_HD RGB rgb1(float v) { return rgb(v, v, v); }
+B200_HD RGB rgbp(const float *p) { return rgb(p[0], p[1], p[2]); }
+B200_HD RGB operator+(const RGB &a, const RGB &b) { return rgb(a.r + b.r, a.g + b.g, a.b + b.b); }
+B200_HD RGB operator-(const RGB &a, const RGB &b) { return rgb(a.r - b.r, a.g - b.g, a.b - b.b); }
+B200_HD RGB operator*(const RGB &a, const RGB &b) { return rgb(a.r * b.r, a.g * b.g, a.b * b.b); }
+B200_HD RGB operator/(const RGB &a, const RGB &b) { return rgb(a.r / b.r, a.g / b.g, a.b / b.b); }
+B200_HD RGB operator*(const RGB &a, float s) { return rgb(a.r * s, a.g * s, a.b * s); }
+B200_HD RGB operator*(float s, const RGB &a) { return rgb(a.r * s, a.g * s, a.b * s); }
+B200_HD RGB operator/(const RGB &a, float s) { return rgb(a.r / s, a.g / s, a.b / s); }  // spectrum.h:181-188
+B200_HD RGB rgb_sqrt(const RGB &a) { return rgb(sqrtf(a.r), sqrtf(a.g), sqrtf(a.b)); }
+B200_HD bool is_black(const RGB &a) { return a.r == 0.f && a.g == 0.f && a.b == 0.f; }
+// spectrum.h:462-465
+B200_HD float lum(const RGB &a) { return 0.212671f * a.r + 0.715160f * a.g + 0.072169f * a.b; }
+B200_HD float max_comp(const RGB &a) { return pt_max(pt_max(a.r, a.g), a.b); }
+B200_HD bool has_nans(const RGB &a) { return pt_isnan(a.r) || pt_isnan(a.g) || pt_isnan(a.b); }
+
+// ---------------------------------------------------------------------- Sobol'
+struct SamplerParams {          // samplers/sobol.h:45-69
+    int spp;
+    int sb[4];                  // sample bounds x0 y0 x1 y1
+    int resolution, log2res;
+    int n_dims;
+    const uint32_t *mat32;      // [n_dims][52]
+    uint64_t vdc[52];
+    uint64_t vdc_inv[52];
+};
+
+// core/lowdiscrepancy.h:229-249
+B200_HD uint64_t sobol_interval_to_index(const SamplerParams &sp, uint64_t frame, int px, int py) {
+    const uint32_t m = (uint32_t)sp.log2res;
+    if (m == 0) return 0;
+    const uint32_t m2 = m << 1;
+    uint64_t index = frame << m2;
+    uint64_t delta = 0;
+    for (int c = 0; frame; frame >>= 1, ++c)
+        if (frame & 1) delta ^= sp.vdc[c];
+    uint64_t b = (((uint64_t)((uint32_t)px) << m) | ((uint32_t)py)) ^ delta;
+    for (int c = 0; b; b >>= 1, ++c)
+        if (b & 1) index ^= sp.vdc_inv[c];
+    return index;
+}
+// core/lowdiscrepancy.h:259-274 (+ sobol.cpp:47-59 for the two pixel dimensions)
+B200_HD float sobol_sample(const SamplerParams &sp, uint64_t a, int dim, int px, int py) {
+    uint32_t v = 0;
+    const uint32_t *m = sp.mat32 + dim * 52;
+    for (; a != 0; a >>= 1, ++m)
+        if (a & 1) v ^= *m;
+    float s = pt_min((float)v * 0x1p-32f, PT_ONE_MINUS_EPS);
+    if (dim == 0 || dim == 1) {
+        s = s * (float)sp.resolution + (float)sp.sb[dim];
+        s = pt_clamp(s - (float)(dim == 0 ? px : py), 0.f, PT_ONE_MINUS_EPS);
+    }
+    return s;
+}
+
+// GlobalSampler stream state of one path (sampler.cpp:136-195): the Sobol'
+// index of (pixel, sample) and the dimension cursor.
+struct SobolStream {
+    uint64_t index;
+    int dim;
+    int px, py;
+};
+B200_HD float get1d(const SamplerParams &sp, SobolStream &s) {
+    float v = sobol_sample(sp, s.index, s.dim, s.px, s.py);
+    s.dim += 1;
+    return v;
+}
+B200_HD void get2d(const SamplerParams &sp, SobolStream &s, float u[2]) {
+    u[0] = sobol_sample(sp, s.index, s.dim, s.px, s.py);
+    u[1] = sobol_sample(sp, s.index, s.dim + 1, s.px, s.py);
+    s.dim += 2;
+}
+
+// --------------------------------------------------------------------- camera
+struct CameraParams {
+    float r2c[16];
+    float c2w[16];
+    float lens_radius, focal_distance;
+};
+// core/transform.h:221-233
+B200_HD V3 xform_point(const float *m, const V3 &p) {
+    float x = p.x, y = p.y, z = p.z;
+    float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    if (wp == 1.f) return mk(xp, yp, zp);
+    float inv = 1.0f / wp;
+    return mk(inv * xp, inv * yp, inv * zp);
+}
+// core/transform.h:278-303
+B200_HD V3 xform_point_err(const float *m, const V3 &p, V3 *err) {
+    float x = p.x, y = p.y, z = p.z;
+    float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    float xs = (pt_abs(m[0] * x) + pt_abs(m[1] * y) + pt_abs(m[2] * z) + pt_abs(m[3]));
+    float ys = (pt_abs(m[4] * x) + pt_abs(m[5] * y) + pt_abs(m[6] * z) + pt_abs(m[7]));
+    float zs = (pt_abs(m[8] * x) + pt_abs(m[9] * y) + pt_abs(m[10] * z) + pt_abs(m[11]));
+    *err = pt_gamma(3) * mk(xs, ys, zs);
+    if (wp == 1.f) return mk(xp, yp, zp);
+    float inv = 1.0f / wp;
+    return mk(inv * xp, inv * yp, inv * zp);
+}
+// core/transform.h:235-241
+B200_HD V3 xform_vector(const float *m, const V3 &v) {
+    float x = v.x, y = v.y, z = v.z;
+    return mk(m[0] * x + m[1] * y + m[2] * z, m[4] * x + m[5] * y + m[6] * z, m[8] * x + m[9] * y + m[10] * z);
+}
+
+// core/sampling.cpp:113-130
+B200_HD void concentric_sample_disk(const float u[2], float out[2]) {
+    float ux = 2.f * u[0] - 1.f, uy = 2.f * u[1] - 1.f;
+    if (ux == 0.f && uy == 0.f) {
+        out[0] = out[1] = 0.f;
+        return;
+    }
+    float theta, r;
+    if (pt_abs(ux) > pt_abs(uy)) {
+        r = ux;
+        theta = PT_PI_OVER4 * (uy / ux);
+    } else {
+        r = uy;
+        theta = PT_PI_OVER2 - PT_PI_OVER4 * (ux / uy);
+    }
+    out[0] = r * pt_cosf(theta);
+    out[1] = r * pt_sinf(theta);
+}
+
+// cameras/perspective.cpp:95-144 (main ray) + transform.h:251-264.  The ray
+// differentials only feed texture filtering (interaction.cpp:103-149), which
+// is dead for constant textures, so they are not generated.
+B200_HD void generate_camera_ray(const CameraParams &cam, const float pFilm[2], const float uLens[2], V3 *o,
+                                 V3 *d, float *tMax) {
+    V3 pc = xform_point(cam.r2c, mk(pFilm[0], pFilm[1], 0.f));
+    V3 ro = mk(0.f, 0.f, 0.f);
+    V3 rd = normalize(pc);
+    if (cam.lens_radius > 0.f) {
+        float dd[2];
+        concentric_sample_disk(uLens, dd);
+        float lx = cam.lens_radius * dd[0], ly = cam.lens_radius * dd[1];
+        float ft = cam.focal_distance / rd.z;
+        V3 pFocus = ro + rd * ft;
+        ro = mk(lx, ly, 0.f);
+        rd = normalize(pFocus - ro);
+    }
+    V3 oErr;
+    V3 wo = xform_point_err(cam.c2w, ro, &oErr);
+    V3 wd = xform_vector(cam.c2w, rd);
+    float l2 = len2(wd);
+    float tm = pt_inf();
+    if (l2 > 0.f) {
+        float dt = dot(vabs(wd), oErr) / l2;
+        wo = wo + wd * dt;
+        tm -= dt;
+    }
+    *o = wo;
+    *d = wd;
+    *tMax = tm;
+}
+
+// ------------------------------------------------------------------- triangle
+// Per-ray constants of the watertight test (shapes/triangle.cpp:207-219): the
+// dimension permutation and the shear.  The reference recomputes them for
+// every triangle; they depend on the ray only.
+struct RayShear {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+B200_HD RayShear make_shear(const V3 &d) {
+    RayShear s;
+    V3 a = vabs(d);
+    s.kz = (a.x > a.y) ? ((a.x > a.z) ? 0 : 2) : ((a.y > a.z) ? 1 : 2);  // geometry.h:998-1000
+    s.kx = s.kz + 1;
+    if (s.kx == 3) s.kx = 0;
+    s.ky = s.kx + 1;
+    if (s.ky == 3) s.ky = 0;
+    float dx = comp(d, s.kx), dy = comp(d, s.ky), dz = comp(d, s.kz);
+    s.Sx = -dx / dz;
+    s.Sy = -dy / dz;
+    s.Sz = 1.f / dz;
+    return s;
+}
+
+struct TriHit {
+    float t, b0, b1, b2;
+};
+
+// shapes/triangle.cpp:188-291 (== IntersectP :427-517): translate, permute,
+// shear, edge functions with the fp64 fallback on an exact zero, scaled-t
+// range test against ray.tMax, then the conservative t > deltaT check.
+B200_HD bool triangle_test(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &ro, const RayShear &sh,
+                           float rayTMax, TriHit *h) {
+    V3 q0 = p0 - ro, q1 = p1 - ro, q2 = p2 - ro;
+    float p0x = comp(q0, sh.kx), p0y = comp(q0, sh.ky), p0z = comp(q0, sh.kz);
+    float p1x = comp(q1, sh.kx), p1y = comp(q1, sh.ky), p1z = comp(q1, sh.kz);
+    float p2x = comp(q2, sh.kx), p2y = comp(q2, sh.ky), p2z = comp(q2, sh.kz);
+    p0x += sh.Sx * p0z;
+    p0y += sh.Sy * p0z;
+    p1x += sh.Sx * p1z;
+    p1y += sh.Sy * p1z;
+    p2x += sh.Sx * p2z;
+    p2y += sh.Sy * p2z;
+    float e0 = p1x * p2y - p1y * p2x;
+    float e1 = p2x * p0y - p2y * p0x;
+    float e2 = p0x * p1y - p0y * p1x;
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+        double p2txp1ty = (double)p2x * (double)p1y;
+        double p2typ1tx = (double)p2y * (double)p1x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0x * (double)p2y;
+        double p0typ2tx = (double)p0y * (double)p2x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1x * (double)p0y;
+        double p1typ0tx = (double)p1y * (double)p0x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0z *= sh.Sz;
+    p1z *= sh.Sz;
+    p2z *= sh.Sz;
+    float tScaled = e0 * p0z + e1 * p1z + e2 * p2z;
+    if (det < 0 && (tScaled >= 0 || tScaled < rayTMax * det))
+        return false;
+    else if (det > 0 && (tScaled <= 0 || tScaled > rayTMax * det))
+        return false;
+    float invDet = 1 / det;
+    float b0 = e0 * invDet;
+    float b1 = e1 * invDet;
+    float b2 = e2 * invDet;
+    float t = tScaled * invDet;
+    float maxZt = max3(pt_abs(p0z), pt_abs(p1z), pt_abs(p2z));
+    float deltaZ = pt_gamma(3) * maxZt;
+    float maxXt = max3(pt_abs(p0x), pt_abs(p1x), pt_abs(p2x));
+    float maxYt = max3(pt_abs(p0y), pt_abs(p1y), pt_abs(p2y));
+    float deltaX = pt_gamma(5) * (maxXt + maxZt);
+    float deltaY = pt_gamma(5) * (maxYt + maxZt);
+    float deltaE = 2 * (pt_gamma(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = max3(pt_abs(e0), pt_abs(e1), pt_abs(e2));
+    float deltaT = 3 * (pt_gamma(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * pt_abs(invDet);
+    if (t <= deltaT) return false;
+    h->t = t;
+    h->b0 = b0;
+    h->b1 = b1;
+    h->b2 = b2;
+    return true;
+}
+
+// shapes/triangle.cpp:293-318 with the default uvs (0,0),(1,0),(1,1) of
+// Triangle::GetUVs (triangle.h:116-126).  false = degenerate triangle (the
+// reference then reports no intersection at all).
+B200_HD bool triangle_partials(const V3 &p0, const V3 &p1, const V3 &p2, V3 *dpdu, V3 *dpdv) {
+    const float uv0x = 0.f, uv0y = 0.f, uv1x = 1.f, uv1y = 0.f, uv2x = 1.f, uv2y = 1.f;
+    float duv02x = uv0x - uv2x, duv02y = uv0y - uv2y;
+    float duv12x = uv1x - uv2x, duv12y = uv1y - uv2y;
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerateUV = pt_abs(determinant) < 1e-8f;
+    if (!degenerateUV) {
+        float invdet = 1 / determinant;
+        *dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        *dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+    }
+    if (degenerateUV || len2(cross(*dpdu, *dpdv)) == 0) {
+        V3 ng = cross(p2 - p0, p1 - p0);
+        if (len2(ng) == 0) return false;
+        coordinate_system(normalize(ng), dpdu, dpdv);
+    }
+    return true;
+}
+
+// shapes/triangle.cpp:575-581
+B200_HD float triangle_area(const V3 &p0, const V3 &p1, const V3 &p2) {
+    return (float)(0.5 * (double)len(cross(p1 - p0, p2 - p0)));
+}
+
+// SurfaceInteraction of a triangle hit on a mesh without per-vertex n/s/uv:
+// triangle.cpp:319-341, 415-421 and interaction.cpp:44-71.
+struct Isect {
+    V3 p, pError, n, wo, dpdu;
+};
+B200_HD void fill_isect(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const TriHit &h, const V3 &rayD,
+                        Isect *is) {
+    V3 dpdu, dpdv;
+    triangle_partials(p0, p1, p2, &dpdu, &dpdv);
+    float xs = (pt_abs(h.b0 * p0.x) + pt_abs(h.b1 * p1.x) + pt_abs(h.b2 * p2.x));
+    float ys = (pt_abs(h.b0 * p0.y) + pt_abs(h.b1 * p1.y) + pt_abs(h.b2 * p2.y));
+    float zs = (pt_abs(h.b0 * p0.z) + pt_abs(h.b1 * p1.z) + pt_abs(h.b2 * p2.z));
+    is->pError = pt_gamma(7) * mk(xs, ys, zs);
+    is->p = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
+    is->wo = normalize(-rayD);
+    is->dpdu = dpdu;
+    V3 n = normalize(cross(p0 - p2, p1 - p2));
+    is->n = flip ? -n : n;
+}
+
+// core/geometry.h:1440-1460
+B200_HD V3 offset_ray_origin(const V3 &p, const V3 &pError, const V3 &n, const V3 &w) {
+    float d = dot(vabs(n), pError);
+    V3 offset = d * n;
+    if (dot(w, n) < 0) offset = -offset;
+    V3 po = p + offset;
+    if (offset.x > 0)
+        po.x = next_float_up(po.x);
+    else if (offset.x < 0)
+        po.x = next_float_down(po.x);
+    if (offset.y > 0)
+        po.y = next_float_up(po.y);
+    else if (offset.y < 0)
+        po.y = next_float_down(po.y);
+    if (offset.z > 0)
+        po.z = next_float_up(po.z);
+    else if (offset.z < 0)
+        po.z = next_float_down(po.z);
+    return po;
+}
+
+// ---------------------------------------------------------------------- BSDFs
+enum {
+    BSDF_REFLECTION = 1,
+    BSDF_TRANSMISSION = 2,
+    BSDF_DIFFUSE = 4,
+    BSDF_GLOSSY = 8,
+    BSDF_SPECULAR = 16,
+    BSDF_ALL = 31
+};
+
+B200_HD float cos_theta(const V3 &w) { return w.z; }
+B200_HD float cos2_theta(const V3 &w) { return w.z * w.z; }
+B200_HD float abs_cos_theta(const V3 &w) { return pt_abs(w.z); }
+B200_HD float sin2_theta(const V3 &w) { return pt_max(0.f, 1.f - cos2_theta(w)); }
+B200_HD float sin_theta(const V3 &w) { return sqrtf(sin2_theta(w)); }
+B200_HD float tan_theta(const V3 &w) { return sin_theta(w) / cos_theta(w); }
+B200_HD float tan2_theta(const V3 &w) { return sin2_theta(w) / cos2_theta(w); }
+B200_HD float cos_phi(const V3 &w) {
+    float st = sin_theta(w);
+    return (st == 0) ? 1.f : pt_clamp(w.x / st, -1.f, 1.f);
+}
+B200_HD float sin_phi(const V3 &w) {
+    float st = sin_theta(w);
+    return (st == 0) ? 0.f : pt_clamp(w.y / st, -1.f, 1.f);
+}
+B200_HD float cos2_phi(const V3 &w) { return cos_phi(w) * cos_phi(w); }
+B200_HD float sin2_phi(const V3 &w) { return sin_phi(w) * sin_phi(w); }
+B200_HD bool same_hemisphere(const V3 &w, const V3 &wp) { return w.z * wp.z > 0; }
+B200_HD V3 reflect(const V3 &wo, const V3 &n) { return -wo + 2 * dot(wo, n) * n; }  // reflection.h:97-99
+// reflection.h:101-114
+B200_HD bool refract(const V3 &wi, const V3 &n, float eta, V3 *wt) {
+    float cosThetaI = dot(n, wi);
+    float sin2ThetaI = pt_max(0.f, 1 - cosThetaI * cosThetaI);
+    float sin2ThetaT = eta * eta * sin2ThetaI;
+    if (sin2ThetaT >= 1) return false;
+    float cosThetaT = sqrtf(1 - sin2ThetaT);
+    *wt = eta * -wi + (eta * cosThetaI - cosThetaT) * n;
+    return true;
+}
+// reflection.cpp:47-68
+B200_HD float fr_dielectric(float cosThetaI, float etaI, float etaT) {
+    cosThetaI = pt_clamp(cosThetaI, -1.f, 1.f);
+    bool entering = cosThetaI > 0.f;
+    if (!entering) {
+        float t = etaI;
+        etaI = etaT;
+        etaT = t;
+        cosThetaI = pt_abs(cosThetaI);
+    }
+    float sinThetaI = sqrtf(pt_max(0.f, 1 - cosThetaI * cosThetaI));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    if (sinThetaT >= 1) return 1;
+    float cosThetaT = sqrtf(pt_max(0.f, 1 - sinThetaT * sinThetaT));
+    float Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+    float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+    return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+// reflection.cpp:71-94
+B200_HD RGB fr_conductor(float cosThetaI, const RGB &etai, const RGB &etat, const RGB &k) {
+    cosThetaI = pt_clamp(cosThetaI, -1.f, 1.f);
+    RGB eta = etat / etai;
+    RGB etak = k / etai;
+    float cosThetaI2 = cosThetaI * cosThetaI;
+    float sinThetaI2 = (float)(1. - (double)cosThetaI2);
+    RGB eta2 = eta * eta;
+    RGB etak2 = etak * etak;
+    RGB t0 = eta2 - etak2 - rgb1(sinThetaI2);
+    RGB a2plusb2 = rgb_sqrt(t0 * t0 + 4.f * eta2 * etak2);
+    RGB t1 = a2plusb2 + rgb1(cosThetaI2);
+    RGB a = rgb_sqrt(0.5f * (a2plusb2 + t0));
+    RGB t2 = (2.f * cosThetaI) * a;
+    RGB Rs = (t1 - t2) / (t1 + t2);
+    RGB t3 = cosThetaI2 * a2plusb2 + rgb1(sinThetaI2 * sinThetaI2);
+    RGB t4 = t2 * sinThetaI2;
+    RGB Rp = Rs * (t3 - t4) / (t3 + t4);
+    return 0.5f * (Rp + Rs);
+}
+
+// TrowbridgeReitzDistribution with sampleVisibleArea = true (the materials' default)
+struct TRDist {
+    float ax, ay;
+};
+// microfacet.cpp:155-163
+B200_HD float tr_D(const TRDist &d, const V3 &wh) {
+    float tan2Theta = tan2_theta(wh);
+    if (pt_isinf(tan2Theta)) return 0.f;
+    const float cos4Theta = cos2_theta(wh) * cos2_theta(wh);
+    float e = (cos2_phi(wh) / (d.ax * d.ax) + sin2_phi(wh) / (d.ay * d.ay)) * tan2Theta;
+    return 1 / (PT_PI * d.ax * d.ay * cos4Theta * (1 + e) * (1 + e));
+}
+// microfacet.cpp:176-184
+B200_HD float tr_lambda(const TRDist &d, const V3 &w) {
+    float absTanTheta = pt_abs(tan_theta(w));
+    if (pt_isinf(absTanTheta)) return 0.f;
+    float alpha = sqrtf(cos2_phi(w) * d.ax * d.ax + sin2_phi(w) * d.ay * d.ay);
+    float alpha2Tan2Theta = (alpha * absTanTheta) * (alpha * absTanTheta);
+    return (-1 + sqrtf(1.f + alpha2Tan2Theta)) / 2;
+}
+B200_HD float tr_G1(const TRDist &d, const V3 &w) { return 1 / (1 + tr_lambda(d, w)); }            // microfacet.h:54-57
+B200_HD float tr_G(const TRDist &d, const V3 &wo, const V3 &wi) { return 1 / (1 + tr_lambda(d, wo) + tr_lambda(d, wi)); }
+// microfacet.cpp:338-344
+B200_HD float tr_pdf(const TRDist &d, const V3 &wo, const V3 &wh) {
+    return tr_D(d, wh) * tr_G1(d, wo) * absdot(wo, wh) / abs_cos_theta(wo);
+}
+// microfacet.cpp:238-283.  The normal-incidence branch calls the C `cos`/`sin`
+// on a float (promoted to double) and multiplies in double.
+B200_HD void tr_sample11(float cosTheta, float U1, float U2, float *slope_x, float *slope_y) {
+    if ((double)cosTheta > .9999) {
+        float r = sqrtf(U1 / (1 - U1));
+        float phi = (float)(6.28318530718 * (double)U2);
+        *slope_x = (float)((double)r * cos((double)phi));
+        *slope_y = (float)((double)r * sin((double)phi));
+        return;
+    }
+    float sinTheta = sqrtf(pt_max(0.f, 1.f - cosTheta * cosTheta));
+    float tanTheta = sinTheta / cosTheta;
+    float a = 1 / tanTheta;
+    float G1 = 2 / (1 + sqrtf(1.f + 1.f / (a * a)));
+    float A = 2 * U1 / G1 - 1;
+    float tmp = 1.f / (A * A - 1.f);
+    if (tmp > 1e10f) tmp = 1e10f;
+    float B = tanTheta;
+    float D = sqrtf(pt_max(B * B * tmp * tmp - (A * A - B * B) * tmp, 0.f));
+    float slope_x_1 = B * tmp - D;
+    float slope_x_2 = B * tmp + D;
+    *slope_x = (A < 0 || slope_x_2 > 1.f / tanTheta) ? slope_x_1 : slope_x_2;
+    float S;
+    if (U2 > 0.5f) {
+        S = 1.f;
+        U2 = 2.f * (U2 - .5f);
+    } else {
+        S = -1.f;
+        U2 = 2.f * (.5f - U2);
+    }
+    float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) /
+              (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+    *slope_y = S * z * sqrtf(1.f + *slope_x * *slope_x);
+}
+// microfacet.cpp:285-305
+B200_HD V3 tr_sample(const V3 &wi, float ax, float ay, float U1, float U2) {
+    V3 ws = normalize(mk(ax * wi.x, ay * wi.y, wi.z));
+    float sx, sy;
+    tr_sample11(cos_theta(ws), U1, U2, &sx, &sy);
+    float tmp = cos_phi(ws) * sx - sin_phi(ws) * sy;
+    sy = sin_phi(ws) * sx + cos_phi(ws) * sy;
+    sx = tmp;
+    sx = ax * sx;
+    sy = ay * sy;
+    return normalize(mk(-sx, -sy, 1.f));
+}
+// microfacet.cpp:307-336 (visible-area branch)
+B200_HD V3 tr_sample_wh(const TRDist &d, const V3 &wo, const float u[2]) {
+    bool flip = wo.z < 0;
+    V3 wh = tr_sample(flip ? -wo : wo, d.ax, d.ay, u[0], u[1]);
+    if (flip) wh = -wh;
+    return wh;
+}
+// sampling.h:159-163
+B200_HD V3 cosine_sample_hemisphere(const float u[2]) {
+    float d[2];
+    concentric_sample_disk(u, d);
+    float z = sqrtf(pt_max(0.f, 1 - d[0] * d[0] - d[1] * d[1]));
+    return mk(d[0], d[1], z);
+}
+
+// One BxDF lobe.  kind: 0 Lambertian, 1 MicrofacetReflection (TR), 2 FresnelSpecular
+enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2 };
+struct Lobe {
+    int kind, type;
+    RGB R, T;
+    TRDist dist;
+    int conductor;      // Fresnel of the microfacet lobe: 0 dielectric(etaI, etaT), 1 conductor(1, cEta, cK)
+    float frEtaI, frEtaT;
+    RGB cEta, cK;
+    float etaA, etaB;   // FresnelSpecular
+};
+B200_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
+B200_HD RGB lobe_fresnel(const Lobe &l, float cosThetaI) {
+    if (!l.conductor) return rgb1(fr_dielectric(cosThetaI, l.frEtaI, l.frEtaT));  // reflection.cpp:128-130
+    return fr_conductor(pt_abs(cosThetaI), rgb1(1.f), l.cEta, l.cK);               // reflection.cpp:117-119
+}
+B200_HD RGB lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+    if (l.kind == BX_LAMBERT) return l.R * PT_INV_PI;  // reflection.cpp:178-180
+    if (l.kind == BX_MICROFACET) {                     // reflection.cpp:226-236
+        float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
+        V3 wh = wi + wo;
+        if (cosThetaI == 0 || cosThetaO == 0) return rgb1(0.f);
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return rgb1(0.f);
+        wh = normalize(wh);
+        RGB F = lobe_fresnel(l, dot(wi, wh));
+        return l.R * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
+    }
+    return rgb1(0.f);  // FresnelSpecular::f, reflection.h:363-365
+}
+B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+    if (l.kind == BX_LAMBERT) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PT_INV_PI : 0.f;  // reflection.cpp:387-389
+    if (l.kind == BX_MICROFACET) {                                                                   // reflection.cpp:419-423
+        if (!same_hemisphere(wo, wi)) return 0.f;
+        V3 wh = normalize(wo + wi);
+        return tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
+    }
+    return 0.f;
+}
+// BxDF::Sample_f; *pdf is written only where the reference writes it.
+B200_HD RGB lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
+    if (l.kind == BX_LAMBERT) {  // reflection.cpp:378-385
+        *wi = cosine_sample_hemisphere(u);
+        if (wo.z < 0) wi->z *= -1;
+        *pdf = lobe_pdf(l, wo, *wi);
+        return lobe_f(l, wo, *wi);
+    }
+    if (l.kind == BX_MICROFACET) {  // reflection.cpp:405-417
+        if (wo.z == 0) return rgb1(0.f);
+        V3 wh = tr_sample_wh(l.dist, wo, u);
+        *wi = reflect(wo, wh);
+        if (!same_hemisphere(wo, *wi)) return rgb1(0.f);
+        *pdf = tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
+        return lobe_f(l, wo, *wi);
+    }
+    // FresnelSpecular::Sample_f, reflection.cpp:477-511 (TransportMode::Radiance)
+    float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
+    if (u[0] < F) {
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *sampledType = BSDF_SPECULAR | BSDF_REFLECTION;
+        *pdf = F;
+        return F * l.R / abs_cos_theta(*wi);
+    }
+    bool entering = cos_theta(wo) > 0;
+    float etaI = entering ? l.etaA : l.etaB;
+    float etaT = entering ? l.etaB : l.etaA;
+    V3 nn = mk(0.f, 0.f, 1.f);
+    if (dot(nn, wo) < 0.f) nn = -nn;  // Faceforward, geometry.h:1213-1216
+    if (!refract(wo, nn, etaI / etaT, wi)) return rgb1(0.f);
+    RGB ft = l.T * (1 - F);
+    ft = ft * ((etaI * etaI) / (etaT * etaT));
+    *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
+    *pdf = 1 - F;
+    return ft / abs_cos_theta(*wi);
+}
+
+// BSDF (reflection.h:153-202) with at most two lobes
+struct Bsdf {
+    float eta;
+    V3 ns, ng, ss, ts;
+    int n;
+    Lobe lobes[2];
+};
+B200_HD V3 world_to_local(const Bsdf &b, const V3 &v) { return mk(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+B200_HD V3 local_to_world(const Bsdf &b, const V3 &v) {
+    return mk(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
+              b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+B200_HD int bsdf_num_components(const Bsdf &b, int flags) {
+    int num = 0;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags)) ++num;
+    return num;
+}
+// reflection.cpp:670-683
+B200_HD RGB bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+    V3 wi = world_to_local(b, wiW), wo = world_to_local(b, woW);
+    if (wo.z == 0) return rgb1(0.f);
+    bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    RGB f = rgb1(0.f);
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
+                                                (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
+            f = f + lobe_f(b.lobes[i], wo, wi);
+    return f;
+}
+// reflection.cpp:770-785
+B200_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+    if (b.n == 0) return 0.f;
+    V3 wo = world_to_local(b, woW), wi = world_to_local(b, wiW);
+    if (wo.z == 0) return 0.f;
+    float pdf = 0.f;
+    int matching = 0;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags)) {
+            ++matching;
+            pdf += lobe_pdf(b.lobes[i], wo, wi);
+        }
+    return matching > 0 ? pdf / matching : 0.f;
+}
+// reflection.cpp:703-768
+B200_HD RGB bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type,
+                          int *sampledType) {
+    int matching = bsdf_num_components(b, type);
+    if (matching == 0) {
+        *pdf = 0;
+        *sampledType = 0;
+        return rgb1(0.f);
+    }
+    int comp_ = pt_mini((int)floorf(u[0] * matching), matching - 1);
+    int which = 0, count = comp_;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], type) && count-- == 0) {
+            which = i;
+            break;
+        }
+    const Lobe &lobe = b.lobes[which];
+    float ur[2] = {pt_min(u[0] * matching - comp_, PT_ONE_MINUS_EPS), u[1]};
+    V3 wi = mk(0.f, 0.f, 0.f), wo = world_to_local(b, woW);
+    if (wo.z == 0) return rgb1(0.f);
+    *pdf = 0;
+    *sampledType = lobe.type;
+    RGB f = lobe_sample_f(lobe, wo, &wi, ur, pdf, sampledType);
+    if (*pdf == 0) {
+        *sampledType = 0;
+        return rgb1(0.f);
+    }
+    *wiW = local_to_world(b, wi);
+    if (!(lobe.type & BSDF_SPECULAR) && matching > 1)
+        for (int i = 0; i < b.n; ++i)
+            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    if (matching > 1) *pdf /= matching;
+    if (!(lobe.type & BSDF_SPECULAR)) {
+        bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        f = rgb1(0.f);
+        for (int i = 0; i < b.n; ++i)
+            if (lobe_matches(b.lobes[i], type) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
+                                                   (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
+                f = f + lobe_f(b.lobes[i], wo, wi);
+    }
+    return f;
+}
+
+B200_HD void add_lambert(Bsdf *b, const float *kd) {
+    Lobe &l = b->lobes[b->n++];
+    l.kind = BX_LAMBERT;
+    l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+    l.R = rgbp(kd);
+}
+// Material::ComputeScatteringFunctions with constant textures
+// (allowMultipleLobes = true, TransportMode::Radiance; path.cpp:107).
+// MATERIAL is a b200pt_material_type known at compile time in the per-family
+// shading kernels, or -1 for a run-time switch.
+template <int MATERIAL>
+B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
+    b->eta = 1.f;
+    b->ns = is.n;  // shading.n == n without per-vertex shading normals
+    b->ng = is.n;
+    b->ss = normalize(is.dpdu);   // reflection.h:159
+    b->ts = cross(b->ns, b->ss);  // reflection.h:160
+    b->n = 0;
+    const int type = MATERIAL >= 0 ? MATERIAL : m.type;
+    if (type == B200PT_MAT_MATTE) {  // matte.cpp:45-62
+        if (!is_black(rgbp(m.kd))) add_lambert(b, m.kd);
+    } else if (type == B200PT_MAT_PLASTIC) {  // plastic.cpp:45-70
+        if (!is_black(rgbp(m.kd))) add_lambert(b, m.kd);
+        if (!is_black(rgbp(m.ks))) {
+            Lobe &l = b->lobes[b->n++];
+            l.kind = BX_MICROFACET;
+            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            l.R = rgbp(m.ks);
+            l.dist.ax = m.alpha_x;
+            l.dist.ay = m.alpha_x;
+            l.conductor = 0;
+            l.frEtaI = 1.5f;
+            l.frEtaT = 1.f;
+        }
+    } else if (type == B200PT_MAT_METAL) {  // metal.cpp:59-80
+        Lobe &l = b->lobes[b->n++];
+        l.kind = BX_MICROFACET;
+        l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+        l.R = rgb1(1.f);
+        l.dist.ax = m.alpha_x;
+        l.dist.ay = m.alpha_y;
+        l.conductor = 1;
+        l.cEta = rgbp(m.eta);
+        l.cK = rgbp(m.k);
+    } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
+        b->eta = m.index;
+        RGB R = rgbp(m.ks), T = rgbp(m.kt);
+        if (!(is_black(R) && is_black(T))) {
+            Lobe &l = b->lobes[b->n++];
+            l.kind = BX_FRESNEL_SPECULAR;
+            l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+            l.R = R;
+            l.T = T;
+            l.etaA = 1.f;
+            l.etaB = m.index;
+        }
+    }
+}
+
+// --------------------------------------------------------------------- lights
+struct LightSample {
+    V3 p, n, pError;
+};
+// shapes/triangle.cpp:583-608 + sampling.cpp:154-157
+B200_HD LightSample triangle_sample(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const float u[2],
+                                    float *pdf) {
+    float su0 = sqrtf(u[0]);
+    float b0 = 1 - su0, b1 = u[1] * su0;
+    LightSample it;
+    it.p = b0 * p0 + b1 * p1 + (1 - b0 - b1) * p2;
+    it.n = normalize(cross(p1 - p0, p2 - p0));
+    if (flip) it.n = it.n * -1.f;
+    V3 s = vabs(b0 * p0) + vabs(b1 * p1) + vabs((1 - b0 - b1) * p2);
+    it.pError = pt_gamma(6) * mk(s.x, s.y, s.z);
+    *pdf = 1 / triangle_area(p0, p1, p2);
+    return it;
+}
+// sampling.h:171-174
+B200_HD float power_heuristic(float fPdf, float gPdf) {
+    float f = fPdf, g = gPdf;
+    return (f * f) / (f * f + g * g);
+}
+// pbrt.h:353-368 FindInterval over cdf[0..n] + sampling.h:90-100
+B200_HD int sample_discrete(const float *cdf, const float *func, float funcInt, int n, float u, float *pdf) {
+    int size = n + 1;
+    int first = 0, l = size;
+    while (l > 0) {
+        int half = l >> 1, middle = first + half;
+        if (cdf[middle] <= u) {
+            first = middle + 1;
+            l -= half + 1;
+        } else
+            l = half;
+    }
+    int offset = pt_mini(pt_maxi(first - 1, 0), size - 2);
+    *pdf = (funcInt > 0) ? func[offset] / (funcInt * n) : 0.f;
+    return offset;
+}
+
+// ----------------------------------------------------------------------- film
+B200_HD void rgb_to_xyz(const RGB &c, float xyz[3]) {  // spectrum.h:62-66
+    xyz[0] = 0.412453f * c.r + 0.357580f * c.g + 0.180423f * c.b;
+    xyz[1] = 0.212671f * c.r + 0.715160f * c.g + 0.072169f * c.b;
+    xyz[2] = 0.019334f * c.r + 0.119193f * c.g + 0.950227f * c.b;
+}
+B200_HD void xyz_to_rgb(const float xyz[3], float rgbv[3]) {  // spectrum.h:56-60
+    rgbv[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
+    rgbv[1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+    rgbv[2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
+}
+
+}  // namespace b200pt
+#endif

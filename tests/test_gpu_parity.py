@@ -1,0 +1,263 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the
+C ABI against (1) golden vectors produced by the unmodified reference and
+(2) the oracle restatement on the same seeded inputs.  Integer / index results
+and float results are compared bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bits, golden_camera, hexf
+
+pytestmark = pytest.mark.gpu
+
+RENDERS = {
+    "matte": (3000, ("matte",), 40, 32, 8, 5, "uniform", None),
+    "four": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "uniform", None),
+    "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
+}
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def make(pkg, abi, scenes, ctx, nt, mats, w, h, spp, depth=5, strat="uniform", nl=None, seed=1234, **kw):
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, seed=seed)
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM, **kw)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    return arr, setup, scene
+
+
+def test_sobol_stream_vs_reference(pkg, abi, scenes, ctx, probe_json):
+    arr = scenes.SceneArrays(10, materials=("matte",), soup_version=1)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    for rec in probe_json["sobol"]:
+        b = rec["bounds"]
+        setup = scenes.RenderSetup(b[2], b[3], rec["spp"], max_depth=16)
+        r = pkg.Render(scene, setup)
+        got = r.debug_sobol(rec["px"], rec["py"], rec["sample"], rec["dim0"], len(rec["values"]))
+        assert np.array_equal(bits(got), bits(hexf(rec["values"])))
+        r.close()
+    scene.close()
+
+
+def test_camera_rays_vs_reference(pkg, abi, scenes, ctx, probe_json):
+    arr = scenes.SceneArrays(10, materials=("matte",), soup_version=1)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    for rec in probe_json["camrays"]:
+        w, h = rec["res"]
+        setup = scenes.RenderSetup(w, h, rec["spp"], camera=golden_camera(abi, probe_json, w, h))
+        r = pkg.Render(scene, setup)
+        got = r.debug_camera_rays(rec["px"], rec["py"], len(rec["rays"]))
+        want = np.array([hexf(x) for x in rec["rays"]])
+        assert np.array_equal(bits(got["o"]), bits(want[:, 0:3]))
+        assert np.array_equal(bits(got["d"]), bits(want[:, 3:6]))
+        assert np.array_equal(bits(got["t_max"]), bits(want[:, 6]))
+        r.close()
+    scene.close()
+
+
+def test_intersections_vs_reference_bvhaccel(pkg, abi, scenes, ctx):
+    rays = np.load(os.path.join(GOLDEN, "isect_rays.npy"))
+    ref = np.load(os.path.join(GOLDEN, "isect_ref.npy"))
+    arr = scenes.SceneArrays(3000, materials=("matte",), soup_version=1, seed=99)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    hits = scene.trace_closest(rays)
+    assert np.array_equal(hits["triangle"], ref["tri"])
+    m = ref["tri"] >= 0
+    assert np.array_equal(bits(hits["t"][m]), bits(ref["t"][m]))
+    assert np.array_equal(scene.trace_any(rays).astype(np.int32), ref["occluded"])
+    scene.close()
+
+
+@pytest.mark.parametrize("n_tris,n_rays", [(1, 2000), (37, 20000), (20000, 200000), (400000, 400000)])
+def test_trace_vs_oracle(pkg, abi, scenes, ob, ctx, n_tris, n_rays):
+    arr = scenes.SceneArrays(n_tris, materials=("matte",), soup_version=1, seed=n_tris)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    o = ob.Oracle(abi, arr)
+    rng = np.random.default_rng(n_rays)
+    rays = np.zeros(n_rays, dtype=abi.RAY_DTYPE)
+    rays["o"] = rng.uniform(-1.5, 1.5, (n_rays, 3)).astype(np.float32)
+    rays["d"] = rng.normal(size=(n_rays, 3)).astype(np.float32)
+    rays["t_max"] = np.inf
+    rays["t_max"][::3] = rng.uniform(0.05, 2.0, len(rays[::3])).astype(np.float32)
+    rays["d"][::17, 0] = 0.0                      # axis-parallel components
+    rays["d"][5::101] = [0.0, 0.0, 1.0]           # axis-aligned rays
+    tgt = arr.vertices[rng.integers(0, arr.n_triangles, len(rays[7::31])), 0]
+    rays["d"][7::31] = tgt - rays["o"][7::31]     # aimed exactly at vertices
+    got, want = scene.trace_closest(rays), o.trace_closest(rays)
+    same = got["triangle"] == want["triangle"]
+    # an exact-t tie may pick the other of two triangles; everything else must be identical
+    tie = ~same & (got["triangle"] >= 0) & (want["triangle"] >= 0) & (bits(got["t"]) == bits(want["t"]))
+    assert (same | tie).all(), "%d rays disagree" % (~(same | tie)).sum()
+    assert tie.sum() <= 2
+    hit = same & (want["triangle"] >= 0)
+    assert hit.sum() > 0
+    for k in ("t", "b0", "b1"):
+        assert np.array_equal(bits(got[k][hit]), bits(want[k][hit])), k
+    assert np.array_equal(scene.trace_any(rays), o.trace_any(rays))
+    o.close()
+    scene.close()
+
+
+def test_empty_and_ragged_inputs(pkg, abi, scenes, ctx):
+    arr = scenes.SceneArrays(500, materials=("matte",), soup_version=1)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    assert len(scene.trace_closest(np.zeros(0, dtype=abi.RAY_DTYPE))) == 0
+    rays = np.zeros(33, dtype=abi.RAY_DTYPE)        # not a multiple of the warp size
+    rays["o"] = [0, 0, -4.5]
+    rays["d"] = [0, 0, 1]
+    rays["t_max"] = np.inf
+    h = scene.trace_closest(rays)
+    assert (h["triangle"] == h["triangle"][0]).all()
+    setup = scenes.RenderSetup(17, 9, 2)            # partial tiles in x and y
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    raw = r.read_raw()
+    assert raw.shape == (9, 17, 4) and np.all(raw[..., 3] >= 2)
+    r.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("name", sorted(RENDERS))
+def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    arr, setup, scene = make(pkg, abi, scenes, ctx, nt, mats, w, h, spp, depth, strat, nl)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    rgb = r.read_rgb()
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % name))
+    nbad = int((bits(rgb) != bits(ref)).sum())
+    if nbad:
+        o = ob.Oracle(abi, arr)
+        ys, xs, _ = np.nonzero(bits(rgb) != bits(ref))
+        y, x = int(ys[0]), int(xs[0])
+        print("first differing pixel", x, y, rgb[y, x], ref[y, x])
+        print("gpu samples", r.debug_pixel_samples(x, y))
+        print("oracle samples", o.pixel_samples(setup, x, y))
+    assert nbad == 0, "%d of %d components differ from the reference render" % (nbad, rgb.size)
+    st = r.stats()
+    assert st["camera_rays"] == w * h * spp
+    r.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("mats,depth,strat", [(("matte",), 5, "uniform"), (("glass",), 8, "uniform"),
+                                             (("metal",), 5, "power"), (("plastic",), 5, "uniform"),
+                                             (("matte", "glass", "metal", "plastic"), 16, "power")])
+def test_render_and_counters_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat):
+    arr, setup, scene = make(pkg, abi, scenes, ctx, 60000, mats, 96, 64, 16, depth, strat)
+    o = ob.Oracle(abi, arr)
+    film, ostats = o.render(setup)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    raw = r.read_raw()
+    nbad = int((bits(raw) != bits(film)).sum())
+    if nbad:
+        ys, xs, _ = np.nonzero(bits(raw) != bits(film))
+        y, x = int(ys[0]), int(xs[0])
+        print("first differing pixel", x, y, raw[y, x], film[y, x])
+        g, w_ = r.debug_pixel_samples(x, y), o.pixel_samples(setup, x, y)
+        print("differing samples", np.nonzero((bits(g) != bits(w_)).any(axis=1))[0], g[:4], w_[:4])
+    assert nbad == 0, "%d of %d raw film values differ from the oracle" % (nbad, raw.size)
+    st = r.stats()
+    for k in ("camera_rays", "regular_rays", "shadow_rays"):
+        assert st[k] == ostats[k], (k, st[k], ostats[k])
+    assert np.array_equal(bits(r.read_rgb()), bits(o.film_rgb(setup, film)))
+    o.close()
+    r.close()
+    scene.close()
+
+
+def test_pixel_samples_vs_oracle(pkg, abi, scenes, ob, ctx):
+    arr, setup, scene = make(pkg, abi, scenes, ctx, 30000, ("matte", "glass", "metal", "plastic"), 64, 64, 64, 8)
+    o = ob.Oracle(abi, arr)
+    r = pkg.Render(scene, setup)
+    for (x, y) in [(0, 0), (31, 17), (63, 63), (40, 5)]:
+        assert np.array_equal(bits(r.debug_pixel_samples(x, y)), bits(o.pixel_samples(setup, x, y)))
+    o.close()
+    r.close()
+    scene.close()
+
+
+def test_tile_shards_sum_to_full_render(pkg, abi, scenes, ctx):
+    """disjoint tile sets rendered with the full-film sampler add up to the full film."""
+    arr, setup, scene = make(pkg, abi, scenes, ctx, 20000, ("matte", "plastic"), 80, 48, 8)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    full = r.read_raw()
+    parts = []
+    for k in range(3):
+        r.clear()
+        r.render_tiles(np.arange(r.n_tiles)[k::3])
+        parts.append(r.read_raw())
+    assert np.array_equal(bits(parts[0] + parts[1] + parts[2]), bits(full))
+    # pixelbounds sharding (path.cpp:195-207): left/right halves
+    halves = []
+    for pb in ([0, 0, 40, 48], [40, 0, 80, 48]):
+        s2 = scenes.RenderSetup(80, 48, 8, pixel_bounds=pb)
+        r2 = pkg.Render(scene, s2)
+        r2.render_tiles()
+        halves.append(r2.read_raw())
+        r2.close()
+    assert np.array_equal(bits(halves[0] + halves[1]), bits(full))
+    r.close()
+    scene.close()
+
+
+def test_render_is_deterministic_and_batch_independent(pkg, abi, scenes, ctx, monkeypatch):
+    arr, setup, scene = make(pkg, abi, scenes, ctx, 20000, ("matte", "glass"), 64, 64, 16)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    a = r.read_raw()
+    r.clear()
+    r.render_tiles()
+    assert np.array_equal(bits(a), bits(r.read_raw()))
+    r.close()
+    monkeypatch.setenv("B200PT_BATCH_PATHS", str(256 * 16 * 3))  # 3 tiles per batch
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    assert np.array_equal(bits(a), bits(r.read_raw()))
+    r.close()
+    scene.close()
+
+
+def test_large_scene_properties(pkg, abi, scenes, ctx):
+    """BASELINE-size scene (1M triangles): properties that need no CPU oracle at full size."""
+    arr, setup, scene = make(pkg, abi, scenes, ctx, 1000000, ("matte",), 256, 256, 4)
+    rng = np.random.default_rng(3)
+    n = 300000
+    rays = np.zeros(n, dtype=abi.RAY_DTYPE)
+    rays["o"] = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    rays["d"] = rng.normal(size=(n, 3)).astype(np.float32)
+    rays["t_max"] = np.inf
+    h = scene.trace_closest(rays)
+    hit = h["triangle"] >= 0
+    assert 0.3 < hit.mean() < 1.0
+    # a hit found with t_max = inf must also be found with t_max slightly above t, and be occluding
+    r2 = rays[hit].copy()
+    r2["t_max"] = np.nextafter(h["t"][hit], np.float32(np.inf))
+    h2 = scene.trace_closest(r2)
+    assert np.array_equal(h2["triangle"], h["triangle"][hit]) and np.array_equal(bits(h2["t"]), bits(h["t"][hit]))
+    assert scene.trace_any(r2).all()
+    # and nothing is hit strictly before it
+    r3 = rays[hit].copy()
+    r3["t_max"] = np.nextafter(h["t"][hit], np.float32(0))
+    assert not (scene.trace_closest(r3)["triangle"] == h["triangle"][hit]).any()
+    # reconstruct the hit point from the barycentrics: must lie on the ray
+    v = arr.vertices[h["triangle"][hit]]
+    b0, b1 = h["b0"][hit, None], h["b1"][hit, None]
+    p = b0 * v[:, 0] + b1 * v[:, 1] + (1 - b0 - b1) * v[:, 2]
+    q = rays["o"][hit] + h["t"][hit, None] * rays["d"][hit]
+    assert np.abs(p - q).max() < 1e-3
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    raw = r.read_raw()
+    assert np.isfinite(raw).all() and (raw[..., 3] >= 4).all() and raw[..., 1].mean() > 0
+    r.close()
+    scene.close()
