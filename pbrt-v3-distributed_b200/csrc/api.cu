@@ -224,6 +224,10 @@ int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri
 
 // ------------------------------------------------- ray-batch entry points
 static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * 8; }
+static int refill_lanes() {
+    static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 22;
+    return v;
+}
 
 static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64_t n, bool any_hit) {
     if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
@@ -244,6 +248,7 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     a.count = s->d_work + 1;
     a.work = s->d_work;
     a.materials = s->d_materials;
+    a.refill_lanes = refill_lanes();
     if (any_hit)
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
@@ -596,6 +601,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.materials = H.scene.materials;
             a.stats = H.stats;
             a.stride = 1;
+            a.refill_lanes = refill_lanes();
             // closest hit of the path rays + classification by BSDF family
             a.ray_o = H.ray_o;
             a.ray_d = H.ray_d;

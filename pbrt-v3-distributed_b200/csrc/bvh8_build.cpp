@@ -58,7 +58,8 @@ struct Box {
 struct Node2 {
     Box box;
     int32_t left, right;   // children (inner) or -1
-    int32_t first, count;  // leaf range in idx[] (count > 0 <=> leaf)
+    int32_t first, count;  // leaf range in idx[] (count > 0 <=> binary leaf = one triangle)
+    int32_t ntri;          // triangles in the subtree: idx[first .. first + ntri)
 };
 
 struct Builder2 {
@@ -68,7 +69,6 @@ struct Builder2 {
     std::vector<Node2> nodes;
     std::atomic<int32_t> next_node{0};
     std::atomic<int> threads_free{0};
-    float tri_cost = 0.6f;
 
     int32_t alloc() { return next_node.fetch_add(1); }
 
@@ -85,6 +85,7 @@ struct Builder2 {
         n.left = n.right = -1;
         n.first = first;
         n.count = 0;
+        n.ntri = count;
         if (count == 1) {
             n.count = 1;
             return;
@@ -132,15 +133,6 @@ struct Builder2 {
                     bestAxis = axis;
                     bestBin = i;
                 }
-            }
-        }
-        float area = b.half_area();
-        if (count <= 3) {
-            float leafCost = tri_cost * count;
-            float splitCost = (bestAxis >= 0 && area > 0) ? 1.f + tri_cost * bestCost / area : INFINITY;
-            if (leafCost <= splitCost) {
-                n.count = count;
-                return;
             }
         }
         int32_t mid;
@@ -228,11 +220,91 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
         b2.cent = cent.data();
         b2.nodes.resize(2 * (size_t)nLeafTris);
         b2.threads_free = std::max(0, n_threads - 1);
-        if (const char *e = getenv("B200PT_LEAF_COST")) b2.tri_cost = (float)atof(e);
         int32_t root = b2.alloc();
         b2.build(root, 0, nLeafTris);
 
-        // ---- collapse to 8-wide, breadth-first so siblings are contiguous
+        // ---- SAH-optimal collapse (Ylitie et al. 2017, section 3.1): cost[n][i-1] is the cheapest
+        // way to represent the binary subtree n with at most i roots (i = 1..7); a single root is
+        // either a leaf child (<= 3 triangles) or an 8-wide node whose children come from
+        // distributing the two binary children over 8 slots.
+        const int32_t nNodes2 = b2.next_node.load();
+        float cNode = 1.0f, cPrim = 0.75f;  // a watertight triangle test costs about as many instructions as a node
+        if (const char *e = getenv("B200PT_SAH_CNODE")) cNode = (float)atof(e);
+        if (const char *e = getenv("B200PT_SAH_CPRIM")) cPrim = (float)atof(e);
+        std::vector<float> cost((size_t)nNodes2 * 7);
+        std::vector<uint8_t> dec((size_t)nNodes2 * 7);   // i=1: 0 leaf / 1 inner ; i>=2: 0 = reuse i-1, k = left gets k roots
+        std::vector<uint8_t> split8((size_t)nNodes2);    // left share when the node becomes an 8-wide node
+        for (int32_t n = nNodes2 - 1; n >= 0; --n) {
+            const Node2 &nd = b2.nodes[n];
+            float *c = &cost[(size_t)n * 7];
+            uint8_t *d = &dec[(size_t)n * 7];
+            const float A = nd.box.half_area();
+            const float leafCost = nd.ntri <= 3 ? A * nd.ntri * cPrim : INFINITY;
+            if (nd.count > 0) {  // single triangle
+                for (int i = 0; i < 7; ++i) {
+                    c[i] = leafCost;
+                    d[i] = 0;
+                }
+                split8[n] = 0;
+                continue;
+            }
+            const float *cl = &cost[(size_t)nd.left * 7], *cr = &cost[(size_t)nd.right * 7];
+            auto distribute = [&](int j, int *bestK) {
+                float best = INFINITY;
+                *bestK = 1;
+                for (int k = 1; k < j; ++k) {
+                    if (k > 7 || j - k > 7) continue;
+                    float v = cl[k - 1] + cr[j - k - 1];
+                    if (v < best) {
+                        best = v;
+                        *bestK = k;
+                    }
+                }
+                return best;
+            };
+            int k8;
+            const float innerCost = distribute(8, &k8) + A * cNode;
+            split8[n] = (uint8_t)k8;
+            if (leafCost <= innerCost) {
+                c[0] = leafCost;
+                d[0] = 0;
+            } else {
+                c[0] = innerCost;
+                d[0] = 1;
+            }
+            for (int i = 2; i <= 7; ++i) {
+                int k;
+                float v = distribute(i, &k);
+                if (v < c[i - 2]) {
+                    c[i - 1] = v;
+                    d[i - 1] = (uint8_t)k;
+                } else {
+                    c[i - 1] = c[i - 2];
+                    d[i - 1] = 0;
+                }
+            }
+        }
+        // children of a wide node: expand binary node `n` into at most `budget` roots
+        struct Collector {
+            const Builder2 &b2;
+            const std::vector<uint8_t> &dec;
+            Child *ch;
+            int k;
+            void collect(int32_t n, int budget) {
+                const Node2 &nd = b2.nodes[n];
+                int i = budget;
+                while (i >= 2 && dec[(size_t)n * 7 + i - 1] == 0) --i;  // reuse the (i-1)-root solution
+                if (i == 1 || nd.count > 0) {
+                    ch[k++] = {n, nd.box};
+                    return;
+                }
+                const int kl = dec[(size_t)n * 7 + i - 1];
+                collect(nd.left, kl);
+                collect(nd.right, i - kl);
+            }
+        };
+
+        // ---- emit 8-wide nodes breadth-first so siblings are contiguous
         struct Pending {
             int32_t node2;
             uint32_t wide;
@@ -248,29 +320,13 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
             Child ch[8];
             int k = 0;
             const Node2 &rn = b2.nodes[cur.node2];
-            if (rn.count > 0) {  // the whole scene is one leaf
-                ch[k++] = {cur.node2, rn.box};
+            if (rn.count > 0 || (cur.node2 == root && dec[(size_t)root * 7] == 0)) {
+                ch[k++] = {cur.node2, rn.box};  // the whole scene is one leaf child of the root
             } else {
-                ch[k++] = {rn.left, b2.nodes[rn.left].box};
-                ch[k++] = {rn.right, b2.nodes[rn.right].box};
-                while (k < 8) {
-                    int best = -1;
-                    float bestA = -1.f;
-                    for (int i = 0; i < k; ++i) {
-                        const Node2 &c = b2.nodes[ch[i].node2];
-                        if (c.count > 0) continue;
-                        float a = c.box.half_area();
-                        if (a > bestA) {
-                            bestA = a;
-                            best = i;
-                        }
-                    }
-                    if (best < 0) break;
-                    const Node2 &c = b2.nodes[ch[best].node2];
-                    int32_t l = c.left, r = c.right;
-                    ch[best] = {l, b2.nodes[l].box};
-                    ch[k++] = {r, b2.nodes[r].box};
-                }
+                Collector col{b2, dec, ch, 0};
+                col.collect(rn.left, split8[cur.node2]);
+                col.collect(rn.right, 8 - split8[cur.node2]);
+                k = col.k;
             }
             // node bounds and centroid
             Box nb;
@@ -333,6 +389,7 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
                 int i = childAt[s];
                 if (i < 0) continue;
                 const Node2 &c = b2.nodes[ch[i].node2];
+                const bool isLeaf = c.count > 0 || dec[(size_t)ch[i].node2 * 7] == 0;
                 for (int a = 0; a < 3; ++a) {
                     float lo = std::floor((ch[i].box.lo[a] - node.p[a]) / scale[a]) - 1.f;
                     float hi = std::ceil((ch[i].box.hi[a] - node.p[a]) / scale[a]) + 1.f;
@@ -344,15 +401,15 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
                     node.qlo[a][s] = (uint8_t)qlo;
                     node.qhi[a][s] = (uint8_t)qhi;
                 }
-                if (c.count > 0) {
+                if (isLeaf) {
                     const uint8_t unary[4] = {0, 1, 3, 7};
-                    node.meta[s] = (uint8_t)((unary[c.count] << 5) | triOffset);
-                    for (int t = 0; t < c.count; ++t) {
+                    node.meta[s] = (uint8_t)((unary[c.ntri] << 5) | triOffset);
+                    for (int t = 0; t < c.ntri; ++t) {
                         int32_t tri = b2.idx[c.first + t];
                         out->prim_to_tri[tri] = (uint32_t)out->tris.size();
                         out->tris.push_back(make_tri(tri));
                     }
-                    triOffset += c.count;
+                    triOffset += c.ntri;
                 } else {
                     node.imask |= (uint8_t)(1u << s);
                     node.meta[s] = (uint8_t)((1u << 5) | (24 + s));

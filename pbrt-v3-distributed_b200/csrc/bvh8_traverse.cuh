@@ -73,115 +73,145 @@ B200_HD float safe_rcp_dir(float d) {
     return 1.0f / d;
 }
 
-// Returns the leaf-order index of the closest (ANY_HIT: of some) hit triangle
-// or B200PT_MISS.  *hit receives (t, b0, b1, b2) of the accepted intersection.
+// byte j of w as a float, without an integer->float conversion: splice the byte
+// into the mantissa of 2^23 and subtract 2^23 (exact for 0..255).
+#ifdef __CUDA_ARCH__
+B200_D float byte_to_float(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+}
+#else
+inline float byte_to_float(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+#endif
+
+// Per-ray traversal state.  One step = "take the next child group: fetch its node
+// and test the eight children, then intersect the leaf triangles that were hit".
+struct Trav {
+    V3 o;
+    RayShear sh;
+    float idx, idy, idz;
+    uint32_t oct, octinv;
+    float tmax;
+    uint32_t best;
+    TriHit hit;
+    uint32_t cur_x, cur_y;
+    int sp;
+    uint32_t stk_x[B200PT_STACK], stk_y[B200PT_STACK];
+};
+
+B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
+    T.o = o;
+    T.sh = make_shear(d);
+    T.idx = safe_rcp_dir(d.x);
+    T.idy = safe_rcp_dir(d.y);
+    T.idz = safe_rcp_dir(d.z);
+    T.oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    T.octinv = 7u - T.oct;
+    T.tmax = rayTMax;
+    T.best = B200PT_MISS;
+    T.hit.t = T.hit.b0 = T.hit.b1 = T.hit.b2 = 0.f;
+    T.cur_x = 0u;
+    T.cur_y = 0x80000000u;  // the root as a one-child group
+    T.sp = 0;
+}
+
+// Returns true when the traversal is complete (closest hit known / any hit found / nothing left).
+template <bool ANY_HIT, bool COUNT>
+B200_HD bool trav_step(Trav &T, const U4 *__restrict__ nodes, const F4 *__restrict__ tris, TraceCounters *ctr) {
+    uint32_t tg_x, tg_y;
+    if (T.cur_y & 0xff000000u) {
+        const uint32_t hits = T.cur_y;
+        const int bit = msb32(hits);
+        T.cur_y &= ~(1u << bit);
+        if (T.cur_y & 0xff000000u) {
+            if (T.sp < B200PT_STACK) {
+                T.stk_x[T.sp] = T.cur_x;
+                T.stk_y[T.sp] = T.cur_y;
+                ++T.sp;
+            }
+        }
+        const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.octinv;
+        const uint32_t rel = (uint32_t)popc32(hits & 0xffu & ((1u << slot) - 1u));
+        const U4 *np = nodes + (size_t)(T.cur_x + rel) * 5;
+        const U4 n0 = ld_u4(np), n1 = ld_u4(np + 1), n2 = ld_u4(np + 2), n3 = ld_u4(np + 3), n4 = ld_u4(np + 4);
+        if (COUNT) ctr->nodes++;
+        // n0: p.xyz | e.x e.y e.z imask      n1: child_base tri_base meta[0..3] meta[4..7]
+        // n2: qlo.x[0..7] qlo.y[0..7]        n3: qlo.z[0..7] qhi.x[0..7]      n4: qhi.y[0..7] qhi.z[0..7]
+        const float ax = uint_as_float((n0.w & 0xffu) << 23) * T.idx;
+        const float ay = uint_as_float(((n0.w >> 8) & 0xffu) << 23) * T.idy;
+        const float az = uint_as_float(((n0.w >> 16) & 0xffu) << 23) * T.idz;
+        const uint32_t imask = n0.w >> 24;
+        const float bx = (uint_as_float(n0.x) - T.o.x) * T.idx, by = (uint_as_float(n0.y) - T.o.y) * T.idy,
+                    bz = (uint_as_float(n0.z) - T.o.z) * T.idz;
+        const bool nxg = (T.oct & 1u) != 0, nyg = (T.oct & 2u) != 0, nzg = (T.oct & 4u) != 0;
+        uint32_t hitmask = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // near / far quantised planes per axis according to the ray's direction sign
+            const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
+            const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+            const uint32_t nx = nxg ? qhix : qlox, fx = nxg ? qlox : qhix;
+            const uint32_t ny = nyg ? qhiy : qloy, fy = nyg ? qloy : qhiy;
+            const uint32_t nz = nzg ? qhiz : qloz, fz = nzg ? qloz : qhiz;
+            const uint32_t meta4 = h ? n1.w : n1.z;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t m = (meta4 >> (8 * j)) & 0xffu;
+                const float tn = fmaxf(fmaxf(fma_any(byte_to_float(nx, j), ax, bx), fma_any(byte_to_float(ny, j), ay, by)),
+                                       fmaxf(fma_any(byte_to_float(nz, j), az, bz), 0.f));
+                const float tf = fminf(fminf(fma_any(byte_to_float(fx, j), ax, bx), fma_any(byte_to_float(fy, j), ay, by)),
+                                       fminf(fma_any(byte_to_float(fz, j), az, bz), T.tmax));
+                const uint32_t s = (uint32_t)(4 * h + j);
+                // inner child: one bit at 24 + (slot ^ octinv); leaf: its triangles' bits; empty slot: m == 0
+                const uint32_t bits = ((imask >> s) & 1u) ? (1u << (24u + (s ^ T.octinv))) : ((m >> 5) << (m & 31u));
+                hitmask |= (tn <= tf) ? bits : 0u;
+            }
+        }
+        T.cur_x = n1.x;
+        T.cur_y = (hitmask & 0xff000000u) | imask;
+        tg_x = n1.y;
+        tg_y = hitmask & 0x00ffffffu;
+    } else {
+        tg_x = T.cur_x;
+        tg_y = T.cur_y;
+        T.cur_x = 0;
+        T.cur_y = 0;
+    }
+    while (tg_y) {
+        const int j = msb32(tg_y);
+        tg_y &= ~(1u << j);
+        const uint32_t ti = tg_x + (uint32_t)j;
+        const F4 *tp = tris + (size_t)ti * 3;
+        const F4 v0 = ld_f4(tp), v1 = ld_f4(tp + 1), v2 = ld_f4(tp + 2);
+        if (COUNT) ctr->tris++;
+        TriHit h;
+        if (triangle_test(mk(v0.x, v0.y, v0.z), mk(v1.x, v1.y, v1.z), mk(v2.x, v2.y, v2.z), T.o, T.sh, T.tmax, &h)) {
+            T.tmax = h.t;  // primitive.cpp:120
+            T.best = ti;
+            T.hit = h;
+            if (ANY_HIT) return true;
+        }
+    }
+    if ((T.cur_y & 0xff000000u) == 0) {
+        if (T.sp == 0) return true;
+        --T.sp;
+        T.cur_x = T.stk_x[T.sp];
+        T.cur_y = T.stk_y[T.sp];
+    }
+    return false;
+}
+
+// Whole traversal of one ray (used by the CPU pre-flight and the simple entry points).
+// Returns the leaf-order index of the closest (ANY_HIT: of some) hit triangle or
+// B200PT_MISS; *hit receives (t, b0, b1, b2) of the accepted intersection.
 template <bool ANY_HIT, bool COUNT>
 B200_HD uint32_t traverse_bvh8(const U4 *__restrict__ nodes, const F4 *__restrict__ tris, const V3 &o, const V3 &d,
                                float rayTMax, TriHit *hit, TraceCounters *ctr) {
-    const RayShear sh = make_shear(d);
-    const float idx = safe_rcp_dir(d.x), idy = safe_rcp_dir(d.y), idz = safe_rcp_dir(d.z);
-    const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-    const uint32_t octinv = 7u - oct;
-    float tmax = rayTMax;
-    uint32_t best = B200PT_MISS;
-
-    uint32_t stk_x[B200PT_STACK], stk_y[B200PT_STACK];
-    int sp = 0;
-    uint32_t cur_x = 0u, cur_y = 0x80000000u;  // the root as a one-child group
-
-    while (true) {
-        uint32_t tg_x, tg_y;
-        if (cur_y & 0xff000000u) {
-            const uint32_t hits = cur_y;
-            const int bit = msb32(hits);
-            cur_y &= ~(1u << bit);
-            if (cur_y & 0xff000000u) {
-                if (sp < B200PT_STACK) {
-                    stk_x[sp] = cur_x;
-                    stk_y[sp] = cur_y;
-                    ++sp;
-                }
-            }
-            const uint32_t slot = ((uint32_t)(bit - 24)) ^ octinv;
-            const uint32_t rel = (uint32_t)popc32(hits & 0xffu & ((1u << slot) - 1u));
-            const U4 *np = nodes + (size_t)(cur_x + rel) * 5;
-            const U4 n0 = ld_u4(np), n1 = ld_u4(np + 1), n2 = ld_u4(np + 2), n3 = ld_u4(np + 3), n4 = ld_u4(np + 4);
-            if (COUNT) ctr->nodes++;
-            // n0: p.x p.y p.z (e.x e.y e.z imask) ; n1: child_base tri_base meta[0..3] meta[4..7]
-            // n2: qlo.x[0..7] qlo.y[0..3] qlo.y[4..7] -> (x: qlox 0-3, y: qlox 4-7, z: qloy 0-3, w: qloy 4-7)
-            // n3: qloz 0-3, qloz 4-7, qhix 0-3, qhix 4-7 ; n4: qhiy 0-3, qhiy 4-7, qhiz 0-3, qhiz 4-7
-            const float px = uint_as_float(n0.x), py = uint_as_float(n0.y), pz = uint_as_float(n0.z);
-            const float sx = uint_as_float((n0.w & 0xffu) << 23), sy = uint_as_float(((n0.w >> 8) & 0xffu) << 23),
-                        sz = uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-            const uint32_t imask = n0.w >> 24;
-            const float ax = sx * idx, ay = sy * idy, az = sz * idz;
-            const float bx = (px - o.x) * idx, by = (py - o.y) * idy, bz = (pz - o.z) * idz;
-            // near / far quantised planes per axis according to the ray's direction sign
-            const uint32_t qlox[2] = {n2.x, n2.y}, qloy[2] = {n2.z, n2.w}, qloz[2] = {n3.x, n3.y};
-            const uint32_t qhix[2] = {n3.z, n3.w}, qhiy[2] = {n4.x, n4.y}, qhiz[2] = {n4.z, n4.w};
-            const uint32_t meta[2] = {n1.z, n1.w};
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t nx = (oct & 1u) ? qhix[h] : qlox[h], fx = (oct & 1u) ? qlox[h] : qhix[h];
-                const uint32_t ny = (oct & 2u) ? qhiy[h] : qloy[h], fy = (oct & 2u) ? qloy[h] : qhiy[h];
-                const uint32_t nz = (oct & 4u) ? qhiz[h] : qloz[h], fz = (oct & 4u) ? qloz[h] : qhiz[h];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t m = (meta[h] >> (8 * j)) & 0xffu;
-                    if (m == 0) continue;
-                    const float tnx = fma_any((float)((nx >> (8 * j)) & 0xffu), ax, bx);
-                    const float tny = fma_any((float)((ny >> (8 * j)) & 0xffu), ay, by);
-                    const float tnz = fma_any((float)((nz >> (8 * j)) & 0xffu), az, bz);
-                    const float tfx = fma_any((float)((fx >> (8 * j)) & 0xffu), ax, bx);
-                    const float tfy = fma_any((float)((fy >> (8 * j)) & 0xffu), ay, by);
-                    const float tfz = fma_any((float)((fz >> (8 * j)) & 0xffu), az, bz);
-                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
-                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-                    if (tn <= tf) {
-                        const uint32_t s = (uint32_t)(4 * h + j);
-                        if (imask & (1u << s))
-                            hitmask |= 1u << (24u + (s ^ octinv));
-                        else
-                            hitmask |= (m >> 5) << (m & 31u);
-                    }
-                }
-            }
-            cur_x = n1.x;
-            cur_y = (hitmask & 0xff000000u) | imask;
-            tg_x = n1.y;
-            tg_y = hitmask & 0x00ffffffu;
-        } else {
-            tg_x = cur_x;
-            tg_y = cur_y;
-            cur_x = 0;
-            cur_y = 0;
-        }
-
-        while (tg_y) {
-            const int j = msb32(tg_y);
-            tg_y &= ~(1u << j);
-            const uint32_t ti = tg_x + (uint32_t)j;
-            const F4 *tp = tris + (size_t)ti * 3;
-            const F4 v0 = ld_f4(tp), v1 = ld_f4(tp + 1), v2 = ld_f4(tp + 2);
-            if (COUNT) ctr->tris++;
-            TriHit h;
-            if (triangle_test(mk(v0.x, v0.y, v0.z), mk(v1.x, v1.y, v1.z), mk(v2.x, v2.y, v2.z), o, sh, tmax, &h)) {
-                tmax = h.t;  // primitive.cpp:120
-                best = ti;
-                *hit = h;
-                if (ANY_HIT) return best;
-            }
-        }
-
-        if ((cur_y & 0xff000000u) == 0) {
-            if (sp == 0) break;
-            --sp;
-            cur_x = stk_x[sp];
-            cur_y = stk_y[sp];
-        }
+    Trav T;
+    trav_init(T, o, d, rayTMax);
+    while (!trav_step<ANY_HIT, COUNT>(T, nodes, tris, ctr)) {
     }
-    return best;
+    *hit = T.hit;
+    return T.best;
 }
 
 }  // namespace b200pt

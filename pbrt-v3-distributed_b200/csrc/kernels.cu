@@ -116,50 +116,87 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
 }
 
 // ----------------------------------------------------------------------- trace
+// Persistent warps; every lane owns one ray at a time.  A lane whose ray is
+// finished parks until fewer than `refill_lanes` lanes of the warp are
+// still traversing (TraceArgs::refill_lanes); then the warp reconverges, finished rays are written out
+// (+ classified by BSDF family with warp-aggregated appends) and idle lanes
+// fetch new rays -- so one long ray never keeps 31 lanes idle.
+
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
 __global__ void __launch_bounds__(128, 4) k_trace(const TraceArgs a) {
     const uint32_t n = *a.count;
+    const int lane = threadIdx.x & 31;
     TraceCounters ctr;
     ctr.nodes = ctr.tris = 0;
-    uint32_t i;
-    while (warp_fetch(a.work, n, &i)) {
-        const bool active = i < n;
-        uint32_t slot = 0, tri = B200PT_MISS;
-        int family = -1;
-        if (active) {
-            slot = a.queue ? a.queue[i] : i;
-            const float4 o4 = a.ray_o[(size_t)slot * a.stride];
-            const float4 d4 = a.ray_d[(size_t)slot * a.stride];
-            const float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
-            TriHit h;
-            h.t = h.b0 = h.b1 = h.b2 = 0.f;
-            tri = traverse_bvh8<ANY_HIT, COUNT>(a.nodes, a.tris, v3(o4), v3(d4), tmax, &h, &ctr);
-            if (ANY_HIT) {
-                a.occ_out[slot] = tri != B200PT_MISS ? 1 : 0;
-            } else {
-                if (a.hit_out) a.hit_out[slot] = tri;
-                if (a.full_out) {
-                    b200pt_hit r;
-                    r.triangle = tri != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)tri * 3).w) : -1;
-                    r.t = h.t;
-                    r.b0 = h.b0;
-                    r.b1 = h.b1;
-                    a.full_out[slot] = r;
-                }
-                if (CLASSIFY && tri != B200PT_MISS) {
-                    const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)tri * 3 + 1).w);
-                    family = a.materials[mf & 0xffffu].type;
+    Trav T;
+    uint32_t slot = 0;
+    bool has = false, fin = false, exhausted = false;
+    while (true) {
+        // ---- converged: retire finished rays
+        {
+            int family = -1;
+            if (fin) {
+                if (ANY_HIT) {
+                    a.occ_out[slot] = T.best != B200PT_MISS ? 1 : 0;
+                } else {
+                    if (a.hit_out) a.hit_out[slot] = T.best;
+                    if (a.full_out) {
+                        b200pt_hit r;
+                        r.triangle = T.best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)T.best * 3).w) : -1;
+                        r.t = T.hit.t;
+                        r.b0 = T.hit.b0;
+                        r.b1 = T.hit.b1;
+                        a.full_out[slot] = r;
+                    }
+                    if (CLASSIFY && T.best != B200PT_MISS) {
+                        const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)T.best * 3 + 1).w);
+                        family = a.materials[mf & 0xffffu].type;
+                    }
                 }
             }
-        }
-        if (CLASSIFY) {
+            if (CLASSIFY) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const bool mine = family == m;
-                const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
-                if (mine) a.q_mat[m][pos] = slot;
+                for (int m = 0; m < 4; ++m) {
+                    const bool mine = family == m;
+                    const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
+                    if (mine) a.q_mat[m][pos] = slot;
+                }
+            }
+            fin = false;
+        }
+        // ---- converged: idle lanes fetch new rays
+        {
+            const bool want = !has && !exhausted;
+            const uint32_t mask = __ballot_sync(FULL_MASK, want);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(a.work, (uint32_t)__popc(mask));
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if (want) {
+                    const uint32_t i = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    if (i < n) {
+                        slot = a.queue ? a.queue[i] : i;
+                        const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+                        const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+                        trav_init(T, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max);
+                        has = true;
+                    } else {
+                        exhausted = true;
+                    }
+                }
             }
         }
+        if (__ballot_sync(FULL_MASK, has) == 0) break;
+        // ---- traverse until this lane's ray is done or the warp is mostly idle
+        while (has) {
+            if (trav_step<ANY_HIT, COUNT>(T, a.nodes, a.tris, &ctr)) {
+                has = false;
+                fin = true;
+            }
+            if (__popc(__activemask()) < a.refill_lanes) break;
+        }
+        __syncwarp();
     }
     if (COUNT) {
         atomicAdd(&a.stats[ANY_HIT ? 5 : 3], (unsigned long long)ctr.nodes);

@@ -107,6 +107,7 @@ struct TraceArgs {
     uint32_t *qcount_mat;  // &qcount[bounce*Q_PER_BOUNCE + Q_MAT0]
     const b200pt_material *materials;
     unsigned long long *stats;  // nodes/tris counters when instrumented
+    int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
 };
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,

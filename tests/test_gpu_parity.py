@@ -95,7 +95,9 @@ def test_trace_vs_oracle(pkg, abi, scenes, ob, ctx, n_tris, n_rays):
     # an exact-t tie may pick the other of two triangles; everything else must be identical
     tie = ~same & (got["triangle"] >= 0) & (want["triangle"] >= 0) & (bits(got["t"]) == bits(want["t"]))
     assert (same | tie).all(), "%d rays disagree" % (~(same | tie)).sum()
-    assert tie.sum() <= 2
+    aimed = np.zeros(len(rays), bool)
+    aimed[7::31] = True  # rays aimed at a vertex shared by the two triangles of a light quad tie by design
+    assert not (tie & ~aimed).any()
     hit = same & (want["triangle"] >= 0)
     assert hit.sum() > 0
     for k in ("t", "b0", "b1"):
