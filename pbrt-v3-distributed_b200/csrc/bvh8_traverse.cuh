@@ -95,7 +95,12 @@ struct Trav {
     TriHit hit;
     uint32_t cur_x, cur_y;
     int sp;
-    uint32_t stk_x[B200PT_STACK], stk_y[B200PT_STACK];
+};
+// The stack of postponed child groups lives in its own object so that the scalar
+// state above stays in registers (a struct with a dynamically indexed array is
+// placed in local memory as a whole).
+struct TravStack {
+    uint32_t x[B200PT_STACK], y[B200PT_STACK];
 };
 
 B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
@@ -116,7 +121,8 @@ B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
 
 // Returns true when the traversal is complete (closest hit known / any hit found / nothing left).
 template <bool ANY_HIT, bool COUNT>
-B200_HD bool trav_step(Trav &T, const U4 *__restrict__ nodes, const F4 *__restrict__ tris, TraceCounters *ctr) {
+B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const F4 *__restrict__ tris,
+                        TraceCounters *ctr) {
     uint32_t tg_x, tg_y;
     if (T.cur_y & 0xff000000u) {
         const uint32_t hits = T.cur_y;
@@ -124,8 +130,8 @@ B200_HD bool trav_step(Trav &T, const U4 *__restrict__ nodes, const F4 *__restri
         T.cur_y &= ~(1u << bit);
         if (T.cur_y & 0xff000000u) {
             if (T.sp < B200PT_STACK) {
-                T.stk_x[T.sp] = T.cur_x;
-                T.stk_y[T.sp] = T.cur_y;
+                S.x[T.sp] = T.cur_x;
+                S.y[T.sp] = T.cur_y;
                 ++T.sp;
             }
         }
@@ -194,8 +200,8 @@ B200_HD bool trav_step(Trav &T, const U4 *__restrict__ nodes, const F4 *__restri
     if ((T.cur_y & 0xff000000u) == 0) {
         if (T.sp == 0) return true;
         --T.sp;
-        T.cur_x = T.stk_x[T.sp];
-        T.cur_y = T.stk_y[T.sp];
+        T.cur_x = S.x[T.sp];
+        T.cur_y = S.y[T.sp];
     }
     return false;
 }
@@ -207,8 +213,9 @@ template <bool ANY_HIT, bool COUNT>
 B200_HD uint32_t traverse_bvh8(const U4 *__restrict__ nodes, const F4 *__restrict__ tris, const V3 &o, const V3 &d,
                                float rayTMax, TriHit *hit, TraceCounters *ctr) {
     Trav T;
+    TravStack S;
     trav_init(T, o, d, rayTMax);
-    while (!trav_step<ANY_HIT, COUNT>(T, nodes, tris, ctr)) {
+    while (!trav_step<ANY_HIT, COUNT>(T, S, nodes, tris, ctr)) {
     }
     *hit = T.hit;
     return T.best;

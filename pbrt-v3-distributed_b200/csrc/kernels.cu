@@ -123,12 +123,13 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
 // fetch new rays -- so one long ray never keeps 31 lanes idle.
 
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
-__global__ void __launch_bounds__(128, 4) k_trace(const TraceArgs a) {
+__global__ void __launch_bounds__(128, 6) k_trace(const TraceArgs a) {
     const uint32_t n = *a.count;
     const int lane = threadIdx.x & 31;
     TraceCounters ctr;
     ctr.nodes = ctr.tris = 0;
     Trav T;
+    TravStack S;
     uint32_t slot = 0;
     bool has = false, fin = false, exhausted = false;
     while (true) {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128, 4) k_trace(const TraceArgs a) {
         if (__ballot_sync(FULL_MASK, has) == 0) break;
         // ---- traverse until this lane's ray is done or the warp is mostly idle
         while (has) {
-            if (trav_step<ANY_HIT, COUNT>(T, a.nodes, a.tris, &ctr)) {
+            if (trav_step<ANY_HIT, COUNT>(T, S, a.nodes, a.tris, &ctr)) {
                 has = false;
                 fin = true;
             }
