@@ -202,7 +202,7 @@ def main():
     config["bvh"] = {"nodes": info["n_nodes"], "node_bytes": info["node_bytes"], "tri_bytes": info["tri_bytes"],
                      "host_build_s": round(build_s, 2)}
     render = pkg.Render(scene, setup)
-    my_tiles = np.arange(render.n_tiles, dtype=np.int32)[rank::world]
+    my_tiles = scenes.rank_tiles(render.n_tiles, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     film_ptr, film_n = render.film_device_buffer()
 

@@ -1,0 +1,395 @@
+// gpupath.cpp -- host side of the drop-in: a pbrt Integrator that renders on
+// the B200 through the C ABI (include/b200pt.h).
+//
+//   class GpuPathIntegrator : public PathIntegrator      (integrators/path.h:48-66)
+//       void Render(const Scene &) override               (core/integrator.h:53-58, replaces
+//                                                          SamplerIntegrator::Render, integrator.cpp:228-339)
+//   PathIntegrator *CreatePathIntegrator(const ParamSet&, shared_ptr<Sampler>, shared_ptr<const Camera>)
+//                                                         (integrators/path.cpp:190-213; same signature, same
+//                                                          parameters: maxdepth, pixelbounds, rrthreshold,
+//                                                          lightsamplestrategy)
+//
+// pbrt has no plugin ABI: integrators are chosen by name in
+// RenderOptions::MakeIntegrator (core/api.cpp:1686-1687).  This translation
+// unit DEFINES pbrt::CreatePathIntegrator, so linking it in place of the
+// reference's definition makes every `Integrator "path"` of an unmodified
+// .pbrt file render on the GPU while parser, scene construction, Film and image
+// output stay the reference's own code (see INTEGRATION.md for the link recipe
+// and for the in-tree alternative of adding a "gpupath" branch to api.cpp).
+//
+// Render() flattens the already-built Scene into the POD descriptors of the C
+// ABI.  The reference keeps the needed members private (Scene::aggregate,
+// BVHAccel::primitives, GeometricPrimitive::shape/material/areaLight,
+// Triangle::mesh/v, the materials' textures, Film::pixels ...); an in-tree
+// integration would add `friend class GpuPathIntegrator;` to those classes.
+// Out of tree, this file widens access for its own includes only -- it reads
+// those members, never changes layout or behaviour.
+//
+// Error conventions follow the reference: unsupported scene features call
+// Error() (core/error.h:54) and return without rendering, like a failed
+// factory in pbrtWorldEnd (api.cpp:1623); there is NO CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <glog/logging.h>
+
+#define private public
+#define protected public
+#include "accelerators/bvh.h"
+#include "cameras/perspective.h"
+#include "core/film.h"
+#include "core/integrator.h"
+#include "core/light.h"
+#include "core/paramset.h"
+#include "core/primitive.h"
+#include "core/progressreporter.h"
+#include "core/sampler.h"
+#include "core/scene.h"
+#include "core/sobolmatrices.h"
+#include "core/stats.h"
+#include "core/texture.h"
+#include "filters/box.h"
+#include "integrators/path.h"
+#include "lights/diffuse.h"
+#include "materials/glass.h"
+#include "materials/matte.h"
+#include "materials/metal.h"
+#include "materials/plastic.h"
+#include "samplers/sobol.h"
+#include "shapes/triangle.h"
+#include "textures/constant.h"
+#undef private
+#undef protected
+
+#include "../../include/b200pt.h"
+
+namespace pbrt {
+
+STAT_COUNTER("Integrator/Camera rays traced (GPU)", nGpuCameraRays);
+STAT_COUNTER("Intersections/Regular ray intersection tests (GPU)", nGpuRegular);
+STAT_COUNTER("Intersections/Shadow ray intersection tests (GPU)", nGpuShadow);
+
+namespace {
+
+template <typename T>
+bool ConstantValue(const std::shared_ptr<Texture<T>> &tex, T *out) {
+    auto c = dynamic_cast<const ConstantTexture<T> *>(tex.get());
+    if (!c) return false;
+    *out = c->value;
+    return true;
+}
+
+void ToRGB(const Spectrum &s, float out[3]) {
+    Float rgb[3];
+    s.ToRGB(rgb);
+    out[0] = rgb[0];
+    out[1] = rgb[1];
+    out[2] = rgb[2];
+}
+
+struct Flattened {
+    std::vector<float> vertices;
+    std::vector<int32_t> materialId, lightId;
+    std::vector<uint8_t> flip;
+    std::vector<b200pt_material> materials;
+    std::vector<b200pt_area_light> lights;
+};
+
+// materials/{matte,plastic,metal,glass}.cpp ComputeScatteringFunctions with constant textures
+bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) {
+    memset(out, 0, sizeof(*out));
+    Spectrum sv;
+    Float fv;
+    if (auto mm = dynamic_cast<const MatteMaterial *>(m)) {
+        if (mm->bumpMap) return *why = "bump maps", false;
+        if (!ConstantValue(mm->Kd, &sv) || !ConstantValue(mm->sigma, &fv)) return *why = "non-constant textures", false;
+        if (Clamp(fv, 0, 90) != 0) return *why = "matte sigma != 0 (OrenNayar)", false;
+        out->type = B200PT_MAT_MATTE;
+        ToRGB(sv.Clamp(), out->kd);
+        return true;
+    }
+    if (auto pm = dynamic_cast<const PlasticMaterial *>(m)) {
+        if (pm->bumpMap) return *why = "bump maps", false;
+        Spectrum kd, ks;
+        if (!ConstantValue(pm->Kd, &kd) || !ConstantValue(pm->Ks, &ks) || !ConstantValue(pm->roughness, &fv))
+            return *why = "non-constant textures", false;
+        out->type = B200PT_MAT_PLASTIC;
+        ToRGB(kd.Clamp(), out->kd);
+        ToRGB(ks.Clamp(), out->ks);
+        Float rough = fv;
+        if (pm->remapRoughness) rough = TrowbridgeReitzDistribution::RoughnessToAlpha(rough);
+        out->alpha_x = out->alpha_y = rough;
+        return true;
+    }
+    if (auto me = dynamic_cast<const MetalMaterial *>(m)) {
+        if (me->bumpMap) return *why = "bump maps", false;
+        Spectrum eta, k;
+        Float ur, vr;
+        if (!ConstantValue(me->eta, &eta) || !ConstantValue(me->k, &k)) return *why = "non-constant textures", false;
+        if (!ConstantValue(me->uRoughness ? me->uRoughness : me->roughness, &ur) ||
+            !ConstantValue(me->vRoughness ? me->vRoughness : me->roughness, &vr))
+            return *why = "non-constant textures", false;
+        if (me->remapRoughness) {
+            ur = TrowbridgeReitzDistribution::RoughnessToAlpha(ur);
+            vr = TrowbridgeReitzDistribution::RoughnessToAlpha(vr);
+        }
+        out->type = B200PT_MAT_METAL;
+        ToRGB(eta, out->eta);
+        ToRGB(k, out->k);
+        out->alpha_x = ur;
+        out->alpha_y = vr;
+        return true;
+    }
+    if (auto gm = dynamic_cast<const GlassMaterial *>(m)) {
+        if (gm->bumpMap) return *why = "bump maps", false;
+        Spectrum R, T;
+        Float ur, vr, index;
+        if (!ConstantValue(gm->Kr, &R) || !ConstantValue(gm->Kt, &T) || !ConstantValue(gm->uRoughness, &ur) ||
+            !ConstantValue(gm->vRoughness, &vr) || !ConstantValue(gm->index, &index))
+            return *why = "non-constant textures", false;
+        if (ur != 0 || vr != 0) return *why = "rough glass (MicrofacetTransmission)", false;
+        out->type = B200PT_MAT_GLASS;
+        ToRGB(R.Clamp(), out->ks);
+        ToRGB(T.Clamp(), out->kt);
+        out->index = index;
+        return true;
+    }
+    *why = "a material other than matte / plastic / metal / glass";
+    return false;
+}
+
+bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
+    auto bvh = dynamic_cast<const BVHAccel *>(scene.aggregate.get());
+    if (!bvh) return *why = "an aggregate other than BVHAccel", false;
+    // BVHAccel reorders its vector (orderedPrims, bvh.cpp:208); any order works as long as it is
+    // used consistently -- triangle ids only name primitives
+    const auto &prims = bvh->primitives;
+    std::unordered_map<const Material *, int> matIndex;
+    std::unordered_map<const Shape *, int> triOfShape;
+    f->vertices.reserve(prims.size() * 9);
+    for (size_t i = 0; i < prims.size(); ++i) {
+        auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
+        if (!gp) return *why = "a primitive other than GeometricPrimitive (instancing / animation)", false;
+        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
+        auto tri = dynamic_cast<const Triangle *>(gp->shape.get());
+        if (!tri) return *why = "a shape other than Triangle", false;
+        const TriangleMesh &mesh = *tri->mesh;
+        if (mesh.n || mesh.s || mesh.uv || mesh.alphaMask || mesh.shadowAlphaMask)
+            return *why = "meshes with per-vertex normals / tangents / uvs / alpha masks", false;
+        for (int v = 0; v < 3; ++v) {
+            const Point3f &p = mesh.p[tri->v[v]];
+            f->vertices.push_back(p.x);
+            f->vertices.push_back(p.y);
+            f->vertices.push_back(p.z);
+        }
+        f->flip.push_back((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0);
+        const Material *m = gp->material.get();
+        if (!m) return *why = "primitives without a material (medium boundaries)", false;
+        auto it = matIndex.find(m);
+        if (it == matIndex.end()) {
+            b200pt_material bm;
+            if (!ConvertMaterial(m, &bm, why)) return false;
+            it = matIndex.emplace(m, (int)f->materials.size()).first;
+            f->materials.push_back(bm);
+        }
+        f->materialId.push_back(it->second);
+        f->lightId.push_back(-1);
+        triOfShape[gp->shape.get()] = (int)i;
+    }
+    if (!scene.infiniteLights.empty()) return *why = "infinite area lights", false;
+    for (size_t l = 0; l < scene.lights.size(); ++l) {
+        auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
+        if (!dl) return *why = "a light other than a diffuse area light", false;
+        auto it = triOfShape.find(dl->shape.get());
+        if (it == triOfShape.end()) return *why = "an area light on a shape that is not in the scene", false;
+        b200pt_area_light bl;
+        bl.triangle = it->second;
+        ToRGB(dl->Lemit, bl.lemit);
+        bl.two_sided = dl->twoSided ? 1 : 0;
+        f->lightId[it->second] = (int)l;
+        f->lights.push_back(bl);
+    }
+    return true;
+}
+
+}  // namespace
+
+class GpuPathIntegrator : public PathIntegrator {
+  public:
+    GpuPathIntegrator(int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler,
+                      const Bounds2i &pixelBounds, Float rrThreshold, const std::string &lightSampleStrategy)
+        : PathIntegrator(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightSampleStrategy),
+          cam(camera),
+          smp(sampler),
+          bounds(pixelBounds) {}
+
+    void Render(const Scene &scene) override {
+#define B200_CHECK(call)                                                            \
+    do {                                                                            \
+        if ((call) != B200PT_OK) {                                                  \
+            Error("gpupath: %s failed: %s", #call, b200pt_last_error());            \
+            return;                                                                 \
+        }                                                                           \
+    } while (0)
+        std::string why;
+        auto pcam = dynamic_cast<const PerspectiveCamera *>(cam.get());
+        if (!pcam) return Error("gpupath: only the perspective camera is supported");
+        if (pcam->CameraToWorld.actuallyAnimated) return Error("gpupath: animated cameras are not supported");
+        auto sobol = dynamic_cast<const SobolSampler *>(smp.get());
+        if (!sobol) return Error("gpupath: only Sampler \"sobol\" is supported");
+        Film *film = cam->film;
+        if (!dynamic_cast<const BoxFilter *>(film->filter.get()) || film->filter->radius.x != 0.5f ||
+            film->filter->radius.y != 0.5f)
+            return Error("gpupath: only the default box filter (radius 0.5) is supported");
+        int strategy;
+        if (lightSampleStrategy == "uniform" || scene.lights.size() == 1)
+            strategy = B200PT_LIGHTS_UNIFORM;
+        else if (lightSampleStrategy == "power")
+            strategy = B200PT_LIGHTS_POWER;
+        else
+            return Error("gpupath: lightsamplestrategy \"%s\" is not supported (use \"uniform\" or \"power\")",
+                         lightSampleStrategy.c_str());
+        Flattened flat;
+        if (!FlattenScene(scene, &flat, &why)) return Error("gpupath: the scene uses %s", why.c_str());
+
+        b200pt_scene_desc sd;
+        memset(&sd, 0, sizeof(sd));
+        sd.n_triangles = (int64_t)flat.materialId.size();
+        sd.vertices = flat.vertices.data();
+        sd.material_id = flat.materialId.data();
+        sd.light_id = flat.lightId.data();
+        sd.flip_normal = flat.flip.data();
+        sd.n_materials = (int)flat.materials.size();
+        sd.materials = flat.materials.data();
+        sd.n_lights = (int)flat.lights.size();
+        sd.lights = flat.lights.data();
+
+        b200pt_camera_desc cd;
+        memcpy(cd.raster_to_camera, pcam->RasterToCamera.m.m, sizeof(float) * 16);
+        memcpy(cd.camera_to_world, pcam->CameraToWorld.startTransform->m.m, sizeof(float) * 16);
+        cd.lens_radius = pcam->lensRadius;
+        cd.focal_distance = pcam->focalDistance;
+        cd.shutter_open = pcam->shutterOpen;
+        cd.shutter_close = pcam->shutterClose;
+
+        b200pt_film_desc fd;
+        fd.full_resolution[0] = film->fullResolution.x;
+        fd.full_resolution[1] = film->fullResolution.y;
+        const Bounds2i cb = film->croppedPixelBounds;
+        fd.cropped_bounds[0] = cb.pMin.x;
+        fd.cropped_bounds[1] = cb.pMin.y;
+        fd.cropped_bounds[2] = cb.pMax.x;
+        fd.cropped_bounds[3] = cb.pMax.y;
+        fd.filter_radius[0] = film->filter->radius.x;
+        fd.filter_radius[1] = film->filter->radius.y;
+        fd.scale = film->scale;
+        fd.max_sample_luminance = film->maxSampleLuminance;
+
+        b200pt_sampler_desc smpd;
+        smpd.samples_per_pixel = (int32_t)sobol->samplesPerPixel;
+        const Bounds2i sb = sobol->sampleBounds;
+        smpd.sample_bounds[0] = sb.pMin.x;
+        smpd.sample_bounds[1] = sb.pMin.y;
+        smpd.sample_bounds[2] = sb.pMax.x;
+        smpd.sample_bounds[3] = sb.pMax.y;
+        smpd.n_dimensions = NumSobolDimensions;
+        smpd.matrices32 = SobolMatrices32;
+        const int row = std::max(sobol->log2Resolution - 1, 0);
+        smpd.vdc = VdCSobolMatrices[row];
+        smpd.vdc_inv = VdCSobolMatricesInv[row];
+
+        b200pt_integrator_desc id;
+        id.max_depth = maxDepth;
+        id.rr_threshold = rrThreshold;
+        id.light_strategy = strategy;
+        id.pixel_bounds[0] = bounds.pMin.x;
+        id.pixel_bounds[1] = bounds.pMin.y;
+        id.pixel_bounds[2] = bounds.pMax.x;
+        id.pixel_bounds[3] = bounds.pMax.y;
+
+        const int device = getenv("B200PT_DEVICE") ? atoi(getenv("B200PT_DEVICE")) : 0;
+        b200pt_ctx *ctx = nullptr;
+        b200pt_scene *gscene = nullptr;
+        b200pt_render *render = nullptr;
+        B200_CHECK(b200pt_ctx_create(device, &ctx));
+        B200_CHECK(b200pt_scene_create(ctx, &sd, &gscene));
+        B200_CHECK(b200pt_render_create(gscene, &cd, &fd, &smpd, &id, &render));
+        int32_t nx = 0, ny = 0;
+        B200_CHECK(b200pt_render_tile_counts(render, &nx, &ny));
+        // image-space sharding across processes (one per GPU): rank r renders tiles r, r+N, ...
+        const int rank = getenv("B200PT_RANK") ? atoi(getenv("B200PT_RANK")) : 0;
+        const int world = getenv("B200PT_WORLD_SIZE") ? std::max(1, atoi(getenv("B200PT_WORLD_SIZE"))) : 1;
+        std::vector<int32_t> tiles;
+        for (int32_t t = rank; t < nx * ny; t += world) tiles.push_back(t);
+        {
+            ProgressReporter reporter(1, "Rendering (B200)");
+            B200_CHECK(b200pt_render_tiles(render, tiles.data(), (int64_t)tiles.size()));
+            B200_CHECK(b200pt_ctx_synchronize(ctx));
+            reporter.Update();
+            reporter.Done();
+        }
+        // raw film sums -> Film::pixels (film.h:83-89), then the reference's own WriteImage
+        const int w = cb.pMax.x - cb.pMin.x, h = cb.pMax.y - cb.pMin.y;
+        std::vector<float> raw((size_t)w * h * 4);
+        B200_CHECK(b200pt_film_read_raw(render, raw.data()));
+        for (size_t i = 0; i < (size_t)w * h; ++i) {
+            Film::Pixel &p = film->pixels[i];
+            p.xyz[0] = raw[4 * i];
+            p.xyz[1] = raw[4 * i + 1];
+            p.xyz[2] = raw[4 * i + 2];
+            p.filterWeightSum = raw[4 * i + 3];
+        }
+        b200pt_stats st;
+        if (b200pt_get_stats(render, &st) == B200PT_OK) {
+            nGpuCameraRays += st.camera_rays;
+            nGpuRegular += st.regular_rays;
+            nGpuShadow += st.shadow_rays;
+        }
+        b200pt_render_destroy(render);
+        b200pt_scene_destroy(gscene);
+        b200pt_ctx_destroy(ctx);
+        film->WriteImage();
+#undef B200_CHECK
+    }
+
+  private:
+    std::shared_ptr<const Camera> cam;
+    std::shared_ptr<Sampler> smp;
+    const Bounds2i bounds;
+};
+
+// integrators/path.cpp:190-213 -- same parameters, same defaults.
+PathIntegrator *CreatePathIntegrator(const ParamSet &params, std::shared_ptr<Sampler> sampler,
+                                     std::shared_ptr<const Camera> camera) {
+    int maxDepth = params.FindOneInt("maxdepth", 5);
+    int np;
+    const int *pb = params.FindInt("pixelbounds", &np);
+    Bounds2i pixelBounds = camera->film->GetSampleBounds();
+    if (pb) {
+        if (np != 4)
+            Error("Expected four values for \"pixelbounds\" parameter. Got %d.", np);
+        else {
+            pixelBounds = Intersect(pixelBounds, Bounds2i{{pb[0], pb[2]}, {pb[1], pb[3]}});
+            if (pixelBounds.Area() == 0) Error("Degenerate \"pixelbounds\" specified.");
+        }
+    }
+    Float rrThreshold = params.FindOneFloat("rrthreshold", 1.);
+    std::string lightStrategy = params.FindOneString("lightsamplestrategy", "spatial");
+    return new GpuPathIntegrator(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightStrategy);
+}
+
+}  // namespace pbrt

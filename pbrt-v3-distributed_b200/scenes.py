@@ -254,6 +254,13 @@ class SobolTables:
         self.vdc_inv = np.frombuffer(raw, "<u8", nrows * 52, off).reshape(nrows, 52).copy()
 
 
+def rank_tiles(n_tiles, rank, world):
+    """Image-space decomposition used for multi-GPU runs: tile i -> rank i mod N.
+    Interleaving balances sky / geometry tiles; every rank keeps the FULL-film sampler so the
+    union of the shards is sample-identical to a single-GPU render."""
+    return np.arange(n_tiles, dtype=np.int32)[rank::world]
+
+
 def round_up_pow2(v):
     return 1 << (int(v) - 1).bit_length()
 

@@ -1,0 +1,41 @@
+"""The drop-in boundary: pbrt_b200 = the reference's own CLI / parser / Film linked with
+pbrt-v3-distributed_b200/host/gpupath.cpp (GpuPathIntegrator).  CPU: it must fail loudly
+without a GPU (no CPU fallback).  GPU: an unmodified .pbrt file renders bit-identically to the
+reference's PFM."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, bits
+
+PLUGIN = os.path.join(ROOT, "pbrt-v3-distributed_b200", "_plugin", "pbrt_b200")
+needs_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN), reason="pbrt_b200 is built where /root/reference exists")
+
+
+def _scene(scenes, tmp_path, name="four"):
+    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1)
+    return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, 8, max_depth=5, strategy="uniform")
+
+
+@needs_plugin
+def test_plugin_fails_loudly_without_gpu(scenes, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    path = _scene(scenes, tmp_path)
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert "no usable CUDA device" in (r.stdout + r.stderr)
+    assert not os.path.exists(os.path.join(str(tmp_path), "render_four.pfm")), "no image may be produced without a GPU"
+
+
+@needs_plugin
+@pytest.mark.gpu
+def test_dropin_binary_matches_reference(scenes, tmp_path):
+    path = _scene(scenes, tmp_path)
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_four.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_four.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render differs from the reference PFM"
