@@ -40,6 +40,7 @@ struct b200pt_scene {
     std::vector<b200pt_area_light> lights;  // host copy, triangle = original index
     std::vector<uint32_t> prim_to_tri;
     std::vector<float> light_area;
+    float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
     void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
 };
@@ -61,6 +62,7 @@ struct b200pt_render {
     size_t tile_list_capacity = 0;
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
+    int sort_from_bounce = 1;  // coherence-sort the path / shadow queues from this bounce on (<0: never)
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     double ms[3] = {0, 0, 0};
@@ -159,6 +161,18 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->prim_to_tri = std::move(bvh.prim_to_tri);
+    for (int a = 0; a < 3; ++a) {
+        s->bounds_lo[a] = INFINITY;
+        s->bounds_hi[a] = -INFINITY;
+    }
+    for (int64_t i = 0; i < 3 * d->n_triangles; ++i)
+        for (int a = 0; a < 3; ++a) {
+            const float v = d->vertices[3 * i + a];
+            if (std::isfinite(v)) {
+                s->bounds_lo[a] = std::min(s->bounds_lo[a], v);
+                s->bounds_hi[a] = std::max(s->bounds_hi[a], v);
+            }
+        }
     s->light_area.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
         const float *v = d->vertices + 9 * (int64_t)d->lights[i].triangle;
@@ -398,6 +412,11 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     }
     H.n_lights = nl;
     H.light_func_int = funcInt;
+    for (int a = 0; a < 3; ++a) {
+        const float ext = scene->bounds_hi[a] - scene->bounds_lo[a];
+        H.sort_lo[a] = scene->bounds_lo[a];
+        H.sort_inv[a] = ext > 0 ? 32.f / ext : 0.f;
+    }
 
     // batch sizing: whole tiles, about B200PT_BATCH_PATHS path slots
     size_t target = 4u << 20;
@@ -443,6 +462,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.q_path[1], cap);
     for (int m = 0; m < 4; ++m) ALLOC(H.q_mat[m], cap);
     ALLOC(H.q_shadow, cap);
+    ALLOC(H.q_sorted, cap);
+    ALLOC(H.sort_keys, cap);
+    ALLOC(H.sort_hist, (size_t)SORT_BUCKETS);
     ALLOC(H.q_mis, cap);
     ALLOC(H.qcount, (size_t)(H.max_depth + 2) * Q_PER_BOUNCE);
     ALLOC(H.work, (size_t)(H.max_depth + 2) * 16);
@@ -470,6 +492,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     r->grid_shade = ctx->sm_count * 8;
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
+    if (getenv("B200PT_SORT_FROM")) r->sort_from_bounce = atoi(getenv("B200PT_SORT_FROM"));
     *out = r;
     return B200PT_OK;
 }
@@ -603,9 +626,14 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.stride = 1;
             a.refill_lanes = refill_lanes();
             // closest hit of the path rays + classification by BSDF family
+            const bool sorted = r->sort_from_bounce >= 0 && b >= r->sort_from_bounce;
+            if (sorted) {
+                LaunchTimer lt(r, st, 2);
+                launch_sort_queue(r->d_dev, H, H.q_path[b & 1], qc + Q_PATH, H.ray_o, H.ray_d, r->grid_shade, st);
+            }
             a.ray_o = H.ray_o;
             a.ray_d = H.ray_d;
-            a.queue = H.q_path[b & 1];
+            a.queue = sorted ? H.q_sorted : H.q_path[b & 1];
             a.count = qc + Q_PATH;
             a.work = wk + 0;
             a.fixed_t_max = INFINITY;
@@ -623,9 +651,14 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
                 // shadow rays (any hit), tMax = 1 - ShadowEpsilon
+                const bool sorted_sh = r->sort_from_bounce >= 0;
+                if (sorted_sh) {
+                    LaunchTimer lt(r, st, 2);
+                    launch_sort_queue(r->d_dev, H, H.q_shadow, qc + Q_SHADOW, H.sh_o, H.sh_d, r->grid_shade, st);
+                }
                 a.ray_o = H.sh_o;
                 a.ray_d = H.sh_d;
-                a.queue = H.q_shadow;
+                a.queue = sorted_sh ? H.q_sorted : H.q_shadow;
                 a.count = qc + Q_SHADOW;
                 a.work = wk + 5;
                 a.fixed_t_max = PT_SHADOW_TMAX;

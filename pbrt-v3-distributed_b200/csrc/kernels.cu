@@ -450,6 +450,64 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
     }
 }
 
+// ------------------------------------------------------------------------ sort
+// Coherence sort between bounces: rays that start in the same cell of a 32^3 grid and travel into
+// the same octant become neighbours in the queue, so the lanes of a warp walk the same top of the
+// tree and touch the same cache lines.  Three small kernels: histogram of keys, exclusive scan,
+// scatter.  Pure integer work on 4-byte records, bound by HBM/L2 bandwidth.
+__device__ __forceinline__ uint32_t spread5(uint32_t v) {  // 5 bits -> every third bit
+    v &= 0x1fu;
+    v = (v | (v << 8)) & 0x100fu;
+    v = (v | (v << 4)) & 0x10c3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t coherence_key(const RenderDev *R, const float4 &o, const float4 &d) {
+    const int cx = min(31, max(0, (int)((o.x - R->sort_lo[0]) * R->sort_inv[0])));
+    const int cy = min(31, max(0, (int)((o.y - R->sort_lo[1]) * R->sort_inv[1])));
+    const int cz = min(31, max(0, (int)((o.z - R->sort_lo[2]) * R->sort_inv[2])));
+    const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    return (oct << 15) | spread5((uint32_t)cx) | (spread5((uint32_t)cy) << 1) | (spread5((uint32_t)cz) << 2);
+}
+__global__ void __launch_bounds__(256) k_sort_hist(const RenderDev *R, const uint32_t *queue, const uint32_t *count,
+                                                   const float4 *ray_o, const float4 *ray_d) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        const uint32_t key = coherence_key(R, ray_o[slot], ray_d[slot]);
+        R->sort_keys[i] = key;
+        atomicAdd(&R->sort_hist[key], 1u);
+    }
+}
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *hist) {
+    __shared__ uint32_t partial[1024];
+    const uint32_t per = SORT_BUCKETS / 1024u;
+    uint32_t *mine = hist + threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; ++i) sum += mine[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) {  // Hillis-Steele inclusive scan
+        uint32_t v = threadIdx.x >= off ? partial[threadIdx.x - off] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[threadIdx.x] - sum;  // exclusive prefix of this thread's segment
+    for (uint32_t i = 0; i < per; ++i) {
+        const uint32_t c = mine[i];
+        mine[i] = run;
+        run += c;
+    }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const RenderDev *R, const uint32_t *queue, const uint32_t *count) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pos = atomicAdd(&R->sort_hist[R->sort_keys[i]], 1u);
+        R->q_sorted[pos] = queue[i];
+    }
+}
+
 // ------------------------------------------------------------------------ film
 // One block per tile, one thread per pixel of the tile's FilmTile (the tile
 // plus a one-pixel apron, film.cpp:95-106).  A thread re-creates the
@@ -625,6 +683,14 @@ void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work
 
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
     k_resolve<<<grid, 256, 0, s>>>(dev, bounce, work);
+}
+
+void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
+                       const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s) {
+    cudaMemsetAsync(host.sort_hist, 0, SORT_BUCKETS * sizeof(uint32_t), s);
+    k_sort_hist<<<grid, 256, 0, s>>>(dev, queue, count, ray_o, ray_d);
+    k_sort_scan<<<1, 1024, 0, s>>>(host.sort_hist);
+    k_sort_scatter<<<grid, 256, 0, s>>>(dev, queue, count);
 }
 
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s) {

@@ -83,6 +83,10 @@ struct RenderDev {
     uint32_t *q_mat[4];
     uint32_t *q_shadow;
     uint32_t *q_mis;
+    uint32_t *q_sorted;        // queue re-ordered by (ray octant, Morton cell of the origin)
+    uint32_t *sort_keys;       // key per queue entry
+    uint32_t *sort_hist;       // [SORT_BUCKETS] counting-sort histogram / cursors
+    float sort_lo[3], sort_inv[3];  // origin -> 32^3 grid over the scene bounds
     uint32_t *qcount;          // [(max_depth + 2) * Q_PER_BOUNCE]
     uint32_t *work;            // persistent-fetch counters, one per launch of a batch
     unsigned long long *stats; // camera, regular, shadow, nodes, tris
@@ -115,6 +119,11 @@ void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_b
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s);
 void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work, int grid, cudaStream_t s);
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+#define SORT_BUCKETS (1u << 18)  // 3 octant bits + 15 Morton bits
+// Counting sort of a queue of slots by the coherence key of the rays they refer to; `out` receives
+// the permuted queue (order inside a bucket is arbitrary -- it never affects a path's arithmetic).
+void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
+                       const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s);
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
 void launch_accumulate_stats(const RenderDev *dev, uint32_t n_camera, cudaStream_t s);
 void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
