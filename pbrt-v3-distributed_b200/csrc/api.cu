@@ -62,7 +62,7 @@ struct b200pt_render {
     size_t tile_list_capacity = 0;
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
-    int sort_from_bounce = 1;  // coherence-sort the path / shadow queues from this bounce on (<0: never)
+    int sort_from_bounce = -1;  // coherence-sort the path / shadow queues from this bounce on (<0: never; measured: no gain on the soups)
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     double ms[3] = {0, 0, 0};

@@ -15,7 +15,8 @@
 //      (slot XOR ray octant) approximates front-to-back order;
 //   4. child boxes quantised to 8 bits per coordinate on a power-of-two grid
 //      anchored one cell below the node's min corner, rounded outward by one
-//      extra cell on every side.
+//      extra cell on every side (the traversal kernel's fused slab arithmetic may be
+//      off by up to half a cell; a second cell of slack costs 7 % more node visits).
 #include <algorithm>
 #include <atomic>
 #include <cmath>

@@ -73,14 +73,14 @@ B200_HD float safe_rcp_dir(float d) {
     return 1.0f / d;
 }
 
-// byte j of w as a float, without an integer->float conversion: splice the byte
-// into the mantissa of 2^23 and subtract 2^23 (exact for 0..255).
+// Byte j of w spliced into the mantissa of 2^23: the float 2^23 + byte, exactly, with one PRMT and
+// no integer->float conversion.  The node test folds the "- 2^23" into the FMA's addend.
 #ifdef __CUDA_ARCH__
-B200_D float byte_to_float(uint32_t w, int j) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+B200_D float byte_plus_2p23(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j));
 }
 #else
-inline float byte_to_float(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+inline float byte_plus_2p23(uint32_t w, int j) { return 8388608.0f + (float)((w >> (8 * j)) & 0xffu); }
 #endif
 
 // Per-ray traversal state.  One step = "take the next child group: fetch its node
@@ -142,13 +142,18 @@ B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, cons
         if (COUNT) ctr->nodes++;
         // n0: p.xyz | e.x e.y e.z imask      n1: child_base tri_base meta[0..3] meta[4..7]
         // n2: qlo.x[0..7] qlo.y[0..7]        n3: qlo.z[0..7] qhi.x[0..7]      n4: qhi.y[0..7] qhi.z[0..7]
+        // t(q) = (p + q*scale - o) / d = q*a + b with a = scale/d, b = (p - o)/d.  The byte arrives as
+        // 2^23 + q, so the FMA uses the addend c = b - 2^23*a; the product is exact inside the FMA and
+        // the only extra rounding (in c) is below half a grid cell -- the builder leaves one full cell of slack.
         const float ax = uint_as_float((n0.w & 0xffu) << 23) * T.idx;
         const float ay = uint_as_float(((n0.w >> 8) & 0xffu) << 23) * T.idy;
         const float az = uint_as_float(((n0.w >> 16) & 0xffu) << 23) * T.idz;
+        const float cx = fma_any(-8388608.0f, ax, (uint_as_float(n0.x) - T.o.x) * T.idx);
+        const float cy = fma_any(-8388608.0f, ay, (uint_as_float(n0.y) - T.o.y) * T.idy);
+        const float cz = fma_any(-8388608.0f, az, (uint_as_float(n0.z) - T.o.z) * T.idz);
         const uint32_t imask = n0.w >> 24;
-        const float bx = (uint_as_float(n0.x) - T.o.x) * T.idx, by = (uint_as_float(n0.y) - T.o.y) * T.idy,
-                    bz = (uint_as_float(n0.z) - T.o.z) * T.idz;
         const bool nxg = (T.oct & 1u) != 0, nyg = (T.oct & 2u) != 0, nzg = (T.oct & 4u) != 0;
+        const uint32_t octinv4 = T.octinv * 0x01010101u;
         uint32_t hitmask = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -158,17 +163,20 @@ B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, cons
             const uint32_t nx = nxg ? qhix : qlox, fx = nxg ? qlox : qhix;
             const uint32_t ny = nyg ? qhiy : qloy, fy = nyg ? qloy : qhiy;
             const uint32_t nz = nzg ? qhiz : qloz, fz = nzg ? qloz : qhiz;
+            // four children at a time (Ylitie et al.): inner children (meta = 001sssss, sssss = 24 + slot)
+            // get the bit 24 + (slot ^ octinv); leaves get their unary triangle count at their offset
             const uint32_t meta4 = h ? n1.w : n1.z;
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+            const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t m = (meta4 >> (8 * j)) & 0xffu;
-                const float tn = fmaxf(fmaxf(fma_any(byte_to_float(nx, j), ax, bx), fma_any(byte_to_float(ny, j), ay, by)),
-                                       fmaxf(fma_any(byte_to_float(nz, j), az, bz), 0.f));
-                const float tf = fminf(fminf(fma_any(byte_to_float(fx, j), ax, bx), fma_any(byte_to_float(fy, j), ay, by)),
-                                       fminf(fma_any(byte_to_float(fz, j), az, bz), T.tmax));
-                const uint32_t s = (uint32_t)(4 * h + j);
-                // inner child: one bit at 24 + (slot ^ octinv); leaf: its triangles' bits; empty slot: m == 0
-                const uint32_t bits = ((imask >> s) & 1u) ? (1u << (24u + (s ^ T.octinv))) : ((m >> 5) << (m & 31u));
+                const float tn = fmaxf(fmaxf(fma_any(byte_plus_2p23(nx, j), ax, cx), fma_any(byte_plus_2p23(ny, j), ay, cy)),
+                                       fmaxf(fma_any(byte_plus_2p23(nz, j), az, cz), 0.f));
+                const float tf = fminf(fminf(fma_any(byte_plus_2p23(fx, j), ax, cx), fma_any(byte_plus_2p23(fy, j), ay, cy)),
+                                       fminf(fma_any(byte_plus_2p23(fz, j), az, cz), T.tmax));
+                const uint32_t bits = ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
                 hitmask |= (tn <= tf) ? bits : 0u;
             }
         }
