@@ -238,6 +238,10 @@ int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri
 
 // ------------------------------------------------- ray-batch entry points
 static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * 8; }
+static int postpone_pct() {
+    static int v = getenv("B200PT_POSTPONE_PCT") ? atoi(getenv("B200PT_POSTPONE_PCT")) : 25;
+    return v;
+}
 static int refill_lanes() {
     static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 22;
     return v;
@@ -263,6 +267,7 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     a.work = s->d_work;
     a.materials = s->d_materials;
     a.refill_lanes = refill_lanes();
+    a.postpone_pct = postpone_pct();
     if (any_hit)
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
@@ -625,6 +630,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.stats = H.stats;
             a.stride = 1;
             a.refill_lanes = refill_lanes();
+            a.postpone_pct = postpone_pct();
             // closest hit of the path rays + classification by BSDF family
             const bool sorted = r->sort_from_bounce >= 0 && b >= r->sort_from_bounce;
             if (sorted) {

@@ -119,12 +119,12 @@ B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
     T.sp = 0;
 }
 
-// Returns true when the traversal is complete (closest hit known / any hit found / nothing left).
-template <bool ANY_HIT, bool COUNT>
-B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const F4 *__restrict__ tris,
-                        TraceCounters *ctr) {
-    uint32_t tg_x, tg_y;
-    if (T.cur_y & 0xff000000u) {
+// Node phase: take the next inner child of the current group, fetch its node, test the eight
+// children.  Leaves the hit inner children in T.cur and returns the hit leaf triangles as a
+// triangle group (*tg_x = first triangle, *tg_y = bit per triangle).  Requires T.cur to be a node group.
+template <bool COUNT>
+B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes, uint32_t *tg_x, uint32_t *tg_y,
+                             TraceCounters *ctr) {
         const uint32_t hits = T.cur_y;
         const int bit = msb32(hits);
         T.cur_y &= ~(1u << bit);
@@ -182,14 +182,13 @@ B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, cons
         }
         T.cur_x = n1.x;
         T.cur_y = (hitmask & 0xff000000u) | imask;
-        tg_x = n1.y;
-        tg_y = hitmask & 0x00ffffffu;
-    } else {
-        tg_x = T.cur_x;
-        tg_y = T.cur_y;
-        T.cur_x = 0;
-        T.cur_y = 0;
-    }
+        *tg_x = n1.y;
+        *tg_y = hitmask & 0x00ffffffu;
+}
+
+// Triangle phase: exact watertight tests of a triangle group.  Returns true if ANY_HIT found a hit.
+template <bool ANY_HIT, bool COUNT>
+B200_HD bool trav_tri_phase(Trav &T, const F4 *__restrict__ tris, uint32_t tg_x, uint32_t tg_y, TraceCounters *ctr) {
     while (tg_y) {
         const int j = msb32(tg_y);
         tg_y &= ~(1u << j);
@@ -205,13 +204,29 @@ B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, cons
             if (ANY_HIT) return true;
         }
     }
+    return false;
+}
+
+// Pops the next node group if the current one is exhausted; false when nothing is left.
+B200_HD bool trav_next_group(Trav &T, TravStack &S) {
     if ((T.cur_y & 0xff000000u) == 0) {
-        if (T.sp == 0) return true;
+        if (T.sp == 0) return false;
         --T.sp;
         T.cur_x = S.x[T.sp];
         T.cur_y = S.y[T.sp];
     }
-    return false;
+    return true;
+}
+
+// One complete step (node phase, then its triangles at once).  Returns true when the traversal
+// is complete (closest hit known / any hit found / nothing left).
+template <bool ANY_HIT, bool COUNT>
+B200_HD bool trav_step(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const F4 *__restrict__ tris,
+                        TraceCounters *ctr) {
+    uint32_t tg_x = 0, tg_y = 0;
+    if (T.cur_y & 0xff000000u) trav_node_phase<COUNT>(T, S, nodes, &tg_x, &tg_y, ctr);
+    if (trav_tri_phase<ANY_HIT, COUNT>(T, tris, tg_x, tg_y, ctr)) return true;
+    return !trav_next_group(T, S);
 }
 
 // Whole traversal of one ray (used by the CPU pre-flight and the simple entry points).

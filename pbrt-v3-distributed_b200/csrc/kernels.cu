@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128, 6) k_trace(const TraceArgs a) {
     ctr.nodes = ctr.tris = 0;
     Trav T;
     TravStack S;
-    uint32_t slot = 0;
+    uint32_t slot = 0, pend_x = 0, pend_y = 0;
     bool has = false, fin = false, exhausted = false;
     while (true) {
         // ---- converged: retire finished rays
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(128, 6) k_trace(const TraceArgs a) {
                         const float4 o4 = a.ray_o[(size_t)slot * a.stride];
                         const float4 d4 = a.ray_d[(size_t)slot * a.stride];
                         trav_init(T, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max);
+                        pend_y = 0;
                         has = true;
                     } else {
                         exhausted = true;
@@ -189,9 +190,45 @@ __global__ void __launch_bounds__(128, 6) k_trace(const TraceArgs a) {
             }
         }
         if (__ballot_sync(FULL_MASK, has) == 0) break;
-        // ---- traverse until this lane's ray is done or the warp is mostly idle
+        // ---- traverse until this lane's ray is done or the warp is mostly idle.
+        // Leaf triangles are not intersected the moment a node step finds them: the watertight test is
+        // long and typically only two or three lanes have triangles after a given step.  Each lane
+        // parks its triangle group in (pend_x, pend_y); the lanes converged here run the triangle phase
+        // together once enough of them have work (a.postpone_pct % of the converged lanes), or when a
+        // lane needs it now (it found a second group, or has nothing else left to do).
         while (has) {
-            if (trav_step<ANY_HIT, COUNT>(T, S, a.nodes, a.tris, &ctr)) {
+            uint32_t ng_x = 0, ng_y = 0;
+            const bool node_work = (T.cur_y & 0xff000000u) != 0;
+            if (node_work) trav_node_phase<COUNT>(T, S, a.nodes, &ng_x, &ng_y, &ctr);
+            bool must = false;
+            if (ng_y) {
+                if (pend_y) {
+                    must = true;  // two groups: flush the parked one now, park the new one after
+                } else {
+                    pend_x = ng_x;
+                    pend_y = ng_y;
+                    ng_y = 0;
+                }
+            }
+            const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0 && T.sp == 0;
+            const unsigned act = __activemask();
+            const unsigned parked = __ballot_sync(act, pend_y != 0);
+            const unsigned urgent = __ballot_sync(act, must || (out_of_nodes && pend_y != 0 && a.postpone_pct <= 0));
+            const unsigned starving = __ballot_sync(act, out_of_nodes && pend_y != 0);
+            // run the triangle phase if someone must, if enough lanes parked work, or if so many lanes are
+            // only waiting for it that the node phase itself would run half empty
+            if (urgent || __popc(parked) * 100 >= __popc(act) * a.postpone_pct || __popc(starving) * 4 >= __popc(act)) {
+                bool done = false;
+                if (pend_y) done = trav_tri_phase<ANY_HIT, COUNT>(T, a.tris, pend_x, pend_y, &ctr);
+                pend_x = ng_x;
+                pend_y = ng_y;
+                if (done) {
+                    has = false;
+                    fin = true;
+                    pend_y = 0;
+                }
+            }
+            if (has && !trav_next_group(T, S) && pend_y == 0) {
                 has = false;
                 fin = true;
             }

@@ -112,6 +112,7 @@ struct TraceArgs {
     const b200pt_material *materials;
     unsigned long long *stats;  // nodes/tris counters when instrumented
     int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
+    int postpone_pct;           // triangle postponing threshold (% of converged lanes), 0 = off
 };
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,

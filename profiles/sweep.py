@@ -37,8 +37,8 @@ ctx.synchronize()
 wall = time.time() - t0
 st = r.stats()
 rays = st["regular_rays"] + st["shadow_rays"]
-print("%s refill=%s batch=%s cprim=%s: build %.1fs; %.1f Mrays/s wall (%.1f ms); closest %.1f ms, any %.1f ms, other %.1f ms; "
+print("%s refill=%s batch=%s postpone=%s: build %.1fs; %.1f Mrays/s wall (%.1f ms); closest %.1f ms, any %.1f ms, other %.1f ms; "
       "closest-only %.1f Mrays/s" % (name, os.environ.get("B200PT_REFILL_LANES", "-"), os.environ.get("B200PT_BATCH_PATHS", "-"),
-                                    os.environ.get("B200PT_SAH_CPRIM", "-"), build_s, rays / wall / 1e6, wall * 1e3,
+                                    os.environ.get("B200PT_POSTPONE_PCT", "-"), build_s, rays / wall / 1e6, wall * 1e3,
                                     st["closest_ms"], st["any_ms"], st["shade_ms"],
                                     st["regular_rays"] / max(st["closest_ms"], 1e-9) / 1e3))
