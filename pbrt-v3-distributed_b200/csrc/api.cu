@@ -239,11 +239,11 @@ int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri
 // ------------------------------------------------- ray-batch entry points
 static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * 8; }
 static int postpone_pct() {
-    static int v = getenv("B200PT_POSTPONE_PCT") ? atoi(getenv("B200PT_POSTPONE_PCT")) : 25;
+    static int v = getenv("B200PT_POSTPONE_PCT") ? atoi(getenv("B200PT_POSTPONE_PCT")) : 40;
     return v;
 }
 static int refill_lanes() {
-    static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 22;
+    static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 26;
     return v;
 }
 
@@ -424,7 +424,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     }
 
     // batch sizing: whole tiles, about B200PT_BATCH_PATHS path slots
-    size_t target = 4u << 20;
+    size_t target = 16u << 20;  // path slots per batch (~200 B each)
     if (const char *e = getenv("B200PT_BATCH_PATHS")) target = (size_t)atoll(e);
     const size_t per_tile = 256u * (size_t)r->spp;
     r->tiles_per_batch = (uint32_t)std::max<size_t>(1, target / per_tile);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
 // fetch new rays -- so one long ray never keeps 31 lanes idle.
 
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
-__global__ void __launch_bounds__(128, 6) k_trace(const TraceArgs a) {
+__global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
     const uint32_t n = *a.count;
     const int lane = threadIdx.x & 31;
     TraceCounters ctr;

@@ -26,7 +26,7 @@ setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth)
 ctx = pkg.Context(0)
 scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
 r = pkg.Render(scene, setup)
-per_batch = max(1, (4 << 20) // (256 * spp))
+per_batch = max(1, int(os.environ.get('B200PT_BATCH_PATHS', 16 << 20)) // (256 * spp))
 # tiles from the middle of the film (the soup, not the background)
 mid = (r.tiles_y // 2) * r.tiles_x + r.tiles_x // 4
 tiles = (mid + np.arange(per_batch * n_batches)) % r.n_tiles

@@ -24,7 +24,7 @@ t0 = time.time()
 scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
 build_s = time.time() - t0
 r = pkg.Render(scene, setup)
-per_batch = max(1, int(os.environ.get("B200PT_BATCH_PATHS", 4 << 20)) // (256 * spp))
+per_batch = max(1, int(os.environ.get("B200PT_BATCH_PATHS", 16 << 20)) // (256 * spp))
 mid = (r.tiles_y // 2) * r.tiles_x + r.tiles_x // 4
 tiles = (mid + np.arange(per_batch * n_batches)) % r.n_tiles
 r.render_tiles(tiles[:per_batch])  # warm-up
