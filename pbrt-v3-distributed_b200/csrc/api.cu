@@ -268,6 +268,7 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     a.materials = s->d_materials;
     a.refill_lanes = refill_lanes();
     a.postpone_pct = postpone_pct();
+    a.magic = 0x4B000000u;
     if (any_hit)
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
@@ -631,6 +632,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.stride = 1;
             a.refill_lanes = refill_lanes();
             a.postpone_pct = postpone_pct();
+            a.magic = 0x4B000000u;
             // closest hit of the path rays + classification by BSDF family
             const bool sorted = r->sort_from_bounce >= 0 && b >= r->sort_from_bounce;
             if (sorted) {

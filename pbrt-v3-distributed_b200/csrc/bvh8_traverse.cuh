@@ -75,12 +75,19 @@ B200_HD float safe_rcp_dir(float d) {
 
 // Byte j of w spliced into the mantissa of 2^23: the float 2^23 + byte, exactly, with one PRMT and
 // no integer->float conversion.  The node test folds the "- 2^23" into the FMA's addend.
+// `magic` must hold 0x4B000000 in a REGISTER (the kernel passes it as a run-time argument): PRMT takes
+// one immediate, and it should be the byte selector -- otherwise the compiler re-materialises a
+// selector register for every one of the 48 extractions of a node.
 #ifdef __CUDA_ARCH__
-B200_D float byte_plus_2p23(uint32_t w, int j) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j));
+template <int J>
+B200_D float byte_plus_2p23(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7650 | J));
+    return __uint_as_float(r);
 }
 #else
-inline float byte_plus_2p23(uint32_t w, int j) { return 8388608.0f + (float)((w >> (8 * j)) & 0xffu); }
+template <int J>
+inline float byte_plus_2p23(uint32_t w, uint32_t) { return 8388608.0f + (float)((w >> (8 * J)) & 0xffu); }
 #endif
 
 // Per-ray traversal state.  One step = "take the next child group: fetch its node
@@ -95,6 +102,7 @@ struct Trav {
     TriHit hit;
     uint32_t cur_x, cur_y;
     int sp;
+    uint32_t magic;  // 0x4B000000 kept in a register, see byte_plus_2p23
 };
 // The stack of postponed child groups lives in its own object so that the scalar
 // state above stays in registers (a struct with a dynamically indexed array is
@@ -117,6 +125,7 @@ B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
     T.cur_x = 0u;
     T.cur_y = 0x80000000u;  // the root as a one-child group
     T.sp = 0;
+    T.magic = 0x4B000000u;
 }
 
 // Node phase: take the next inner child of the current group, fetch its node, test the eight
@@ -170,15 +179,22 @@ B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes
             const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
             const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
             const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float tn = fmaxf(fmaxf(fma_any(byte_plus_2p23(nx, j), ax, cx), fma_any(byte_plus_2p23(ny, j), ay, cy)),
-                                       fmaxf(fma_any(byte_plus_2p23(nz, j), az, cz), 0.f));
-                const float tf = fminf(fminf(fma_any(byte_plus_2p23(fx, j), ax, cx), fma_any(byte_plus_2p23(fy, j), ay, cy)),
-                                       fminf(fma_any(byte_plus_2p23(fz, j), az, cz), T.tmax));
-                const uint32_t bits = ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
-                hitmask |= (tn <= tf) ? bits : 0u;
-            }
+#define B200PT_CHILD(J)                                                                                              \
+    {                                                                                                                \
+        const float tn = fmaxf(fmaxf(fma_any(byte_plus_2p23<J>(nx, T.magic), ax, cx),                                \
+                                     fma_any(byte_plus_2p23<J>(ny, T.magic), ay, cy)),                               \
+                               fmaxf(fma_any(byte_plus_2p23<J>(nz, T.magic), az, cz), 0.f));                         \
+        const float tf = fminf(fminf(fma_any(byte_plus_2p23<J>(fx, T.magic), ax, cx),                                \
+                                     fma_any(byte_plus_2p23<J>(fy, T.magic), ay, cy)),                               \
+                               fminf(fma_any(byte_plus_2p23<J>(fz, T.magic), az, cz), T.tmax));                      \
+        const uint32_t bits = ((child_bits4 >> (8 * J)) & 0xffu) << ((bit_index4 >> (8 * J)) & 0xffu);               \
+        hitmask |= (tn <= tf) ? bits : 0u;                                                                           \
+    }
+            B200PT_CHILD(0)
+            B200PT_CHILD(1)
+            B200PT_CHILD(2)
+            B200PT_CHILD(3)
+#undef B200PT_CHILD
         }
         T.cur_x = n1.x;
         T.cur_y = (hitmask & 0xff000000u) | imask;

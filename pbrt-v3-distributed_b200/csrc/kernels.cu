@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
                         const float4 d4 = a.ray_d[(size_t)slot * a.stride];
                         trav_init(T, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max);
                         pend_y = 0;
+                        T.magic = a.magic;
                         has = true;
                     } else {
                         exhausted = true;

@@ -113,6 +113,7 @@ struct TraceArgs {
     unsigned long long *stats;  // nodes/tris counters when instrumented
     int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
     int postpone_pct;           // triangle postponing threshold (% of converged lanes), 0 = off
+    uint32_t magic;             // 0x4B000000 as a run-time value (see byte_plus_2p23)
 };
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
