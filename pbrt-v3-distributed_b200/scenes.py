@@ -115,7 +115,7 @@ class SceneArrays:
     """Flattened scene in the layout b200pt_scene_desc wants."""
 
     def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
-                 n_lights=None, two_sided=False):
+                 n_lights=None, two_sided=False, reverse_orientation=()):
         self.material_names = list(materials) + ["black"]
         soup = soup_vertices(n_tris, seed, soup_version)
         quads = light_quads(soup_version, n_lights)
@@ -136,6 +136,10 @@ class SceneArrays:
         self.light_id = np.full(len(self.vertices), -1, np.int32)
         self.light_id[:nl] = np.arange(nl, dtype=np.int32)
         self.flip = np.zeros(len(self.vertices), np.uint8)
+        # "ReverseOrientation" on the plymesh of material m (identity CTM: no handedness swap)
+        self.reverse_orientation = tuple(reverse_orientation)
+        for m in self.reverse_orientation:
+            self.flip[self.material_id == m] = 1
         self.light_quads = quads
         self.light_L = float(light_L)
         self.two_sided = bool(two_sided)
@@ -182,11 +186,13 @@ def write_ply(path, tris):
 
 
 def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
-               eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0):
+               eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6):
     """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
     os.makedirs(dirname, exist_ok=True)
     lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
-             'Camera "perspective" "float fov" [%g]' % fov,
+             'Camera "perspective" "float fov" [%g]' % fov +
+             (' "float lensradius" [%.9g] "float focaldistance" [%.9g]' % (lens_radius, focal_distance)
+              if lens_radius > 0 else ""),
              'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "%s.pfm"'
              % (xres, yres, name),
              'Sampler "sobol" "integer pixelsamples" [%d]' % spp]
@@ -209,7 +215,11 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
     for m, part in enumerate(scene.ply_parts):
         ply = "%s_m%d.ply" % (name, m)
         write_ply(os.path.join(dirname, ply), part)
+        if m in scene.reverse_orientation:
+            lines += ["AttributeBegin", "ReverseOrientation"]
         lines += [PBRT_MATERIAL[scene.material_names[m]], 'Shape "plymesh" "string filename" "%s"' % ply]
+        if m in scene.reverse_orientation:
+            lines += ["AttributeEnd"]
     lines.append("WorldEnd")
     path = os.path.join(dirname, name + ".pbrt")
     with open(path, "w") as f:
@@ -270,11 +280,15 @@ class RenderSetup:
     with the default box filter (sample bounds == cropped pixel bounds)."""
 
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
-                 eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None):
+                 eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
+                 lens_radius=0.0, focal_distance=1e6):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.tables = tables or SobolTables()
         self.camera = camera if camera is not None else host_perspective_camera(eye, look, up, fov, xres, yres)
+        if lens_radius > 0:
+            self.camera.lens_radius = lens_radius
+            self.camera.focal_distance = focal_distance
         self.film = abi.FilmDesc()
         self.film.full_resolution[:] = [xres, yres]
         self.film.cropped_bounds[:] = [0, 0, xres, yres]

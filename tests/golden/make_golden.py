@@ -29,7 +29,11 @@ RENDERS = {
     "matte": (3000, ("matte",), 40, 32, 8, 5, "uniform", None),
     "four": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "uniform", None),
     "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
+    # thin-lens camera, two-sided lights, ReverseOrientation on the glass and plastic meshes
+    "lens_flip": (3000, ("matte", "glass", "metal", "plastic"), 36, 24, 8, 6, "uniform", None),
 }
+EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
+                           camera=dict(lens_radius=0.05, focal_distance=4.5))}
 
 
 def main():
@@ -86,9 +90,10 @@ def main():
     np.save(os.path.join(HERE, "isect_ref.npy"), res)
 
     for name, (nt, mats, w, h, spp, depth, strat, nl) in RENDERS.items():
-        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+        ex = EXTRA.get(name, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
         path = scenes.write_pbrt("/tmp/golden_render", "render_" + name, arr, w, h, spp, max_depth=depth,
-                                 strategy=strat)
+                                 strategy=strat, **ex.get("camera", {}))
         ob.run_pbrt_ref(path)
         os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % name),
                    os.path.join(HERE, "render_%s.pfm" % name))

@@ -11,7 +11,11 @@ RENDERS = {
     "matte": (3000, ("matte",), 40, 32, 8, 5, "uniform", None),
     "four": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "uniform", None),
     "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
+    # thin-lens camera, two-sided lights, ReverseOrientation on the glass and plastic meshes
+    "lens_flip": (3000, ("matte", "glass", "metal", "plastic"), 36, 24, 8, 6, "uniform", None),
 }
+EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
+                           camera=dict(lens_radius=0.05, focal_distance=4.5))}
 
 
 def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
@@ -97,9 +101,11 @@ def test_triangle_badcase_misses(abi, scenes, ob):
 @pytest.mark.parametrize("name", sorted(RENDERS))
 def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
     nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
-    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+    ex = EXTRA.get(name, {})
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
     setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
-                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM)
+                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM,
+                               **ex.get("camera", {}))
     o = ob.Oracle(abi, arr)
     film, stats = o.render(setup, threads=4)
     rgb = o.film_rgb(setup, film)
