@@ -229,7 +229,7 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
         // either a leaf child (<= 3 triangles) or an 8-wide node whose children come from
         // distributing the two binary children over 8 slots.
         const int32_t nNodes2 = b2.next_node.load();
-        float cNode = 1.0f, cPrim = 0.75f;  // a watertight triangle test costs about as many instructions as a node
+        float cNode = 1.0f, cPrim = 1.0f;  // a watertight triangle test costs about as many instructions as a node
         if (const char *e = getenv("B200PT_SAH_CNODE")) cNode = (float)atof(e);
         if (const char *e = getenv("B200PT_SAH_CPRIM")) cPrim = (float)atof(e);
         std::vector<float> cost((size_t)nNodes2 * 7);
