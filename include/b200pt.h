@@ -137,8 +137,10 @@ typedef struct b200pt_sampler_desc {
 /* ---- integrator: PathIntegrator parameters (integrators/path.cpp:190-213) */
 typedef enum b200pt_light_strategy {
     B200PT_LIGHTS_UNIFORM = 0,     /* UniformLightDistribution  lightdistrib.cpp:68-75 */
-    B200PT_LIGHTS_POWER = 1        /* PowerLightDistribution    lightdistrib.cpp:77-82 */
-    /* "spatial" (lightdistrib.cpp:96-300) is a SURVEY 8(f) next row */
+    B200PT_LIGHTS_POWER = 1,       /* PowerLightDistribution    lightdistrib.cpp:77-82 */
+    B200PT_LIGHTS_SPATIAL = 2      /* SpatialLightDistribution  lightdistrib.cpp:96-300 (pbrt's default): every
+                                      voxel's distribution is a pure function of the voxel, so all of them are
+                                      computed up front on the device instead of lazily */
 } b200pt_light_strategy;
 
 typedef struct b200pt_integrator_desc {

@@ -30,6 +30,7 @@
 #include <limits>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -501,6 +502,7 @@ struct oracle_scene {
     std::vector<float> lightArea;
     std::vector<BVHNode> nodes;
     std::vector<int32_t> orderedPrims;
+    float wbMin[3], wbMax[3];  // Scene::WorldBound()
 };
 
 namespace {
@@ -1147,8 +1149,118 @@ struct RenderCtx {
     const b200pt_sampler_desc *sd;
     const b200pt_integrator_desc *integ;
     Distribution1D lightDistrib;
+    // SpatialLightDistribution (lightdistrib.cpp:96-300): per-voxel distributions, created on first use
+    bool spatial;
+    int nVoxels[3];
+    std::unordered_map<uint64_t, Distribution1D> voxelDistrib;
     uint64_t cameraRays, regularRays, shadowRays;
 };
+
+// core/lowdiscrepancy.cpp:389-403, 427-444 (bases 2, 3, 5, 7, 11)
+inline uint32_t ReverseBits32(uint32_t n) {
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+    n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+    n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+    n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+    return n;
+}
+inline float RadicalInverseBase(int base, uint64_t a) {
+    const float invBase = (float)1 / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    while (a) {
+        uint64_t next = a / base;
+        uint64_t digit = a - next * base;
+        reversedDigits = reversedDigits * base + digit;
+        invBaseN *= invBase;
+        a = next;
+    }
+    return std::min(reversedDigits * invBaseN, OneMinusEpsilon);
+}
+inline float RadicalInverse(int baseIndex, uint64_t a) {
+    static const int primes[5] = {2, 3, 5, 7, 11};
+    if (baseIndex == 0) {
+        uint64_t n0 = ReverseBits32((uint32_t)a), n1 = ReverseBits32((uint32_t)(a >> 32));
+        return (float)(((n0 << 32) | n1) * 0x1p-64);
+    }
+    return RadicalInverseBase(primes[baseIndex], a);
+}
+inline float LerpF(float t, float v1, float v2) { return (1 - t) * v1 + t * v2; }  // pbrt.h:413
+
+// SpatialLightDistribution ctor, lightdistrib.cpp:96-112 (maxVoxels = 64)
+void SpatialVoxelCounts(const oracle_scene &s, int nVoxels[3]) {
+    float diag[3] = {s.wbMax[0] - s.wbMin[0], s.wbMax[1] - s.wbMin[1], s.wbMax[2] - s.wbMin[2]};
+    int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);  // geometry.h:787-795
+    float bmax = diag[me];
+    for (int i = 0; i < 3; ++i) nVoxels[i] = std::max(1, int(std::round(diag[i] / bmax * 64)));
+}
+
+// SpatialLightDistribution::ComputeDistribution, lightdistrib.cpp:230-300
+void ComputeVoxelDistribution(const oracle_scene &s, const int nVoxels[3], const int pi[3], Distribution1D *out) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        float t0 = float(pi[a]) / float(nVoxels[a]), t1 = float(pi[a] + 1) / float(nVoxels[a]);
+        float b0 = LerpF(t0, s.wbMin[a], s.wbMax[a]), b1 = LerpF(t1, s.wbMin[a], s.wbMax[a]);
+        lo[a] = std::min(b0, b1);
+        hi[a] = std::max(b0, b1);
+    }
+    const int nSamples = 128;
+    std::vector<float> lightContrib(s.lights.size(), 0.f);
+    for (int i = 0; i < nSamples; ++i) {
+        V3 po(LerpF(RadicalInverse(0, i), lo[0], hi[0]), LerpF(RadicalInverse(1, i), lo[1], hi[1]),
+              LerpF(RadicalInverse(2, i), lo[2], hi[2]));
+        float u[2] = {RadicalInverse(3, i), RadicalInverse(4, i)};
+        for (size_t j = 0; j < s.lights.size(); ++j) {
+            // DiffuseAreaLight::Sample_Li for a reference point without a surface (diffuse.cpp:68-81)
+            const b200pt_area_light &light = s.lights[j];
+            float pdf;
+            LightSample ps = TriangleSample(s, light.triangle, u, &pdf);
+            V3 w = ps.p - po;
+            if (LengthSquared(w) == 0)
+                pdf = 0;
+            else {
+                w = Normalize(w);
+                pdf *= LengthSquared(po - ps.p) / AbsDot(ps.n, -w);
+                if (std::isinf(pdf)) pdf = 0.f;
+            }
+            S3 Li(0.f);
+            if (pdf == 0 || LengthSquared(ps.p - po) == 0) {
+                pdf = 0;
+            } else {
+                V3 wi = Normalize(ps.p - po);
+                Li = AreaLightL(light, ps.n, -wi);
+            }
+            if (pdf > 0) lightContrib[j] += Li.y() / pdf;
+        }
+    }
+    float sumContrib = 0;
+    for (float c : lightContrib) sumContrib = sumContrib + c;  // std::accumulate with a Float init
+    float avgContrib = sumContrib / (nSamples * lightContrib.size());
+    float minContrib = (avgContrib > 0) ? .001 * avgContrib : 1;
+    for (size_t i = 0; i < lightContrib.size(); ++i) lightContrib[i] = std::max(lightContrib[i], minContrib);
+    out->Init(lightContrib.data(), (int)lightContrib.size());
+}
+
+// SpatialLightDistribution::Lookup, lightdistrib.cpp:135-162 (the hash table is only a cache)
+const Distribution1D *LookupLightDistribution(RenderCtx &rc, const V3 &p) {
+    if (!rc.spatial) return &rc.lightDistrib;
+    const oracle_scene &s = *rc.s;
+    int pi[3];
+    for (int a = 0; a < 3; ++a) {
+        float o = p[a] - s.wbMin[a];
+        if (s.wbMax[a] > s.wbMin[a]) o /= s.wbMax[a] - s.wbMin[a];
+        int v = int(o * rc.nVoxels[a]);
+        pi[a] = v < 0 ? 0 : (v > rc.nVoxels[a] - 1 ? rc.nVoxels[a] - 1 : v);
+    }
+    uint64_t packedPos = (uint64_t(pi[0]) << 40) | (uint64_t(pi[1]) << 20) | (uint64_t)pi[2];
+    auto it = rc.voxelDistrib.find(packedPos);
+    if (it == rc.voxelDistrib.end()) {
+        it = rc.voxelDistrib.emplace(packedPos, Distribution1D()).first;
+        ComputeVoxelDistribution(s, rc.nVoxels, pi, &it->second);
+    }
+    return &it->second;
+}
 
 // core/integrator.cpp:108-215 (handleMedia = false, specular = false)
 S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float uScattering[2], int lightNum,
@@ -1268,7 +1380,8 @@ S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
             int nLights = (int)s.lights.size();
             if (nLights > 0) {
                 float lightPdf;
-                int lightNum = rc.lightDistrib.SampleDiscrete(sampler.Get1D(), &lightPdf);
+                const Distribution1D *distrib = LookupLightDistribution(rc, isect.p);  // path.cpp:115
+                int lightNum = distrib->SampleDiscrete(sampler.Get1D(), &lightPdf);
                 if (lightPdf != 0) {
                     float uLight[2], uScattering[2];
                     sampler.Get2D(uLight);
@@ -1336,7 +1449,12 @@ struct FilmTilePixel {
 void InitLightDistribution(RenderCtx &rc) {
     const oracle_scene &s = *rc.s;
     int n = (int)s.lights.size();
+    rc.spatial = false;
     if (n == 0) return;
+    if (rc.integ->light_strategy == B200PT_LIGHTS_SPATIAL && n != 1) {
+        rc.spatial = true;
+        SpatialVoxelCounts(s, rc.nVoxels);
+    }
     std::vector<float> prob(n, 1.f);
     // lightdistrib.cpp:48-58: a single light always gets the uniform distribution
     if (rc.integ->light_strategy == B200PT_LIGHTS_POWER && n != 1) {
@@ -1448,6 +1566,15 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->lightArea.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) s->lightArea[i] = TriangleArea(*s, s->lights[i].triangle);
+    for (int a = 0; a < 3; ++a) {
+        s->wbMin[a] = Infinity;
+        s->wbMax[a] = -Infinity;
+    }
+    for (size_t i = 0; i < s->p.size(); ++i)
+        for (int a = 0; a < 3; ++a) {
+            s->wbMin[a] = std::min(s->wbMin[a], s->p[i][a]);
+            s->wbMax[a] = std::max(s->wbMax[a], s->p[i][a]);
+        }
     s->degenerate.resize(d->n_triangles);
     std::vector<BuildPrim> prims;
     prims.reserve(d->n_triangles);

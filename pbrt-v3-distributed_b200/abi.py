@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_GLASS = 0, 1, 2, 3
-LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 
 
 class Material(C.Structure):

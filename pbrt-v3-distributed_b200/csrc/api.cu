@@ -346,7 +346,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     if (5 + 8 * integ->max_depth > smp->n_dimensions)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d Sobol' dimensions, %d provided",
                            integ->max_depth, 5 + 8 * integ->max_depth, smp->n_dimensions);
-    if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER)
+    if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER &&
+        integ->light_strategy != B200PT_LIGHTS_SPATIAL)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: unsupported light sample strategy");
     const int sbw = smp->sample_bounds[2] - smp->sample_bounds[0], sbh = smp->sample_bounds[3] - smp->sample_bounds[1];
     if (sbw <= 0 || sbh <= 0) return b200pt_fail(B200PT_ERR_INVALID, "render_create: empty sample bounds");
@@ -418,6 +419,28 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     }
     H.n_lights = nl;
     H.light_func_int = funcInt;
+    // SpatialLightDistribution grid (lightdistrib.cpp:96-112, maxVoxels = 64); a single light always
+    // gets the uniform distribution (lightdistrib.cpp:50)
+    long long nvox = 0;
+    if (integ->light_strategy == B200PT_LIGHTS_SPATIAL && nl > 1) {
+        float diag[3];
+        for (int a = 0; a < 3; ++a) diag[a] = scene->bounds_hi[a] - scene->bounds_lo[a];
+        const int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+        const float bmax = diag[me];
+        H.grid.enabled = 1;
+        for (int a = 0; a < 3; ++a) {
+            H.grid.nv[a] = std::max(1, int(std::round(diag[a] / bmax * 64)));
+            H.grid.wb_min[a] = scene->bounds_lo[a];
+            H.grid.wb_max[a] = scene->bounds_hi[a];
+        }
+        nvox = (long long)H.grid.nv[0] * H.grid.nv[1] * H.grid.nv[2];
+        if (nvox * (2ll * nl + 2) * 4 > (8ll << 30)) {
+            delete r;
+            return b200pt_fail(B200PT_ERR_INVALID,
+                               "render_create: spatial light distribution needs %lld voxels x %d lights; use \"uniform\" or \"power\"",
+                               nvox, nl);
+        }
+    }
     for (int a = 0; a < 3; ++a) {
         const float ext = scene->bounds_hi[a] - scene->bounds_lo[a];
         H.sort_lo[a] = scene->bounds_lo[a];
@@ -447,6 +470,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(d_lights, (size_t)nl);
     ALLOC(d_cdf, (size_t)nl + 1);
     ALLOC(d_func, (size_t)std::max(nl, 1));
+    ALLOC(H.sp_func, (size_t)nvox * nl);
+    ALLOC(H.sp_cdf, (size_t)nvox * (nl + 1));
+    ALLOC(H.sp_func_int, (size_t)nvox);
     ALLOC(H.film, (size_t)cw * chh);
     ALLOC(H.ray_o, cap);
     ALLOC(H.ray_d, cap);
@@ -493,6 +519,10 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     CUDA_TRY(cudaMemsetAsync(H.film, 0, (size_t)cw * chh * sizeof(float4), st));
     CUDA_TRY(cudaMemsetAsync(H.stats, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemcpyAsync(r->d_dev, &H, sizeof(H), cudaMemcpyHostToDevice, st));
+    if (H.grid.enabled) {
+        launch_spatial_build(r->d_dev, H, st);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     r->grid_trace = ctx->sm_count * 8;
     r->grid_shade = ctx->sm_count * 8;

@@ -384,8 +384,15 @@ __global__ void __launch_bounds__(128) k_shade(const RenderDev *R, int bounce, u
                     // path.cpp:119-128 -> UniformSampleOneLight (integrator.cpp:85-106)
                     if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && R->n_lights > 0) {
                         float pickPdf;
-                        const int lightNum = sample_discrete(R->light_cdf, R->light_func, R->light_func_int,
-                                                             R->n_lights, get1d(sp, st), &pickPdf);
+                        const float *cdf = R->light_cdf, *func = R->light_func;
+                        float funcInt = R->light_func_int;
+                        if (R->grid.enabled) {  // lightDistribution->Lookup(isect.p), path.cpp:115
+                            const int vox = spatial_voxel(R->grid, is.p);
+                            cdf = R->sp_cdf + (size_t)vox * (R->n_lights + 1);
+                            func = R->sp_func + (size_t)vox * R->n_lights;
+                            funcInt = R->sp_func_int[vox];
+                        }
+                        const int lightNum = sample_discrete(cdf, func, funcInt, R->n_lights, get1d(sp, st), &pickPdf);
                         if (pickPdf != 0) {
                             float uLight[2], uScattering[2];
                             get2d(sp, st, uLight);
@@ -486,6 +493,50 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
         }
         R->sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
     }
+}
+
+// --------------------------------------------------- spatial light distribution
+// SpatialLightDistribution::ComputeDistribution for every voxel (the reference fills its hash table
+// lazily; a voxel's distribution is a pure function of the voxel).  One thread per (voxel, light)
+// accumulates the 128 Halton terms in order, then one thread per voxel builds the Distribution1D.
+__global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
+    const SpatialGrid &g = R->grid;
+    const long long nvox = (long long)g.nv[0] * g.nv[1] * g.nv[2];
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nvox * R->n_lights) return;
+    const int j = (int)(id % R->n_lights);
+    const long long vox = id / R->n_lights;
+    const int vx = (int)(vox % g.nv[0]), vy = (int)((vox / g.nv[0]) % g.nv[1]), vz = (int)(vox / ((long long)g.nv[0] * g.nv[1]));
+    const DevLight light = R->lights[j];
+    const F4 *tp = R->scene.tris + (size_t)light.tri * 3;
+    const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+    const bool flip = (__float_as_uint(t1.w) & 0x10000u) != 0;
+    R->sp_func[vox * R->n_lights + j] =
+        spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), flip, rgbp(light.lemit), light.two_sided != 0);
+}
+__global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
+    const SpatialGrid &g = R->grid;
+    const long long nvox = (long long)g.nv[0] * g.nv[1] * g.nv[2];
+    const long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vox >= nvox) return;
+    const int n = R->n_lights;
+    float *func = R->sp_func + vox * n, *cdf = R->sp_cdf + vox * (n + 1);
+    // lightdistrib.cpp:277-299
+    float sumContrib = 0.f;
+    for (int i = 0; i < n; ++i) sumContrib = sumContrib + func[i];
+    const float avgContrib = sumContrib / (float)(128ull * (unsigned long long)n);
+    const float minContrib = (avgContrib > 0) ? (float)(.001 * (double)avgContrib) : 1.f;
+    for (int i = 0; i < n; ++i) func[i] = pt_max(func[i], minContrib);
+    // Distribution1D, sampling.h:57-71
+    cdf[0] = 0;
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+    const float funcInt = cdf[n];
+    if (funcInt == 0) {
+        for (int i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+    } else {
+        for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    }
+    R->sp_func_int[vox] = funcInt;
 }
 
 // ------------------------------------------------------------------------ sort
@@ -721,6 +772,13 @@ void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work
 
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
     k_resolve<<<grid, 256, 0, s>>>(dev, bounce, work);
+}
+
+void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s) {
+    const long long nvox = (long long)host.grid.nv[0] * host.grid.nv[1] * host.grid.nv[2];
+    const long long n1 = nvox * host.n_lights;
+    k_spatial_contrib<<<(unsigned)((n1 + 127) / 128), 128, 0, s>>>(dev);
+    k_spatial_cdf<<<(unsigned)((nvox + 127) / 128), 128, 0, s>>>(dev);
 }
 
 void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,

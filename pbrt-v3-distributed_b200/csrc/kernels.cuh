@@ -57,6 +57,9 @@ struct RenderDev {
     const float *light_cdf;   // [n_lights + 1]
     const float *light_func;  // [n_lights]
     float light_func_int;
+    // SpatialLightDistribution: per-voxel func [n_lights], cdf [n_lights+1], funcInt
+    SpatialGrid grid;
+    float *sp_func, *sp_cdf, *sp_func_int;
     // batch
     int tiles_x, tiles_y;
     const int32_t *tile_list;  // tile ids of the whole render_tiles call
@@ -126,6 +129,8 @@ void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, 
 // the permuted queue (order inside a bucket is arbitrary -- it never affects a path's arithmetic).
 void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
                        const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s);
+// Fills the per-voxel light distributions (all voxels, once per render object).
+void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s);
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
 void launch_accumulate_stats(const RenderDev *dev, uint32_t n_camera, cudaStream_t s);
 void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,

@@ -869,6 +869,92 @@ B200_HD int sample_discrete(const float *cdf, const float *func, float funcInt, 
     return offset;
 }
 
+// ------------------------------------------------ spatial light distribution
+// core/lowdiscrepancy.cpp:389-403, 427-444 (RadicalInverse for bases 2, 3, 5, 7, 11)
+B200_HD uint32_t reverse_bits32(uint32_t n) {
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
+    n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
+    n = ((n & 0x33333333u) << 2) | ((n & 0xccccccccu) >> 2);
+    n = ((n & 0x55555555u) << 1) | ((n & 0xaaaaaaaau) >> 1);
+    return n;
+}
+B200_HD float radical_inverse(int baseIndex, uint64_t a) {
+    if (baseIndex == 0) {
+        const uint64_t n0 = reverse_bits32((uint32_t)a), n1 = reverse_bits32((uint32_t)(a >> 32));
+        return (float)((double)((n0 << 32) | n1) * 0x1p-64);
+    }
+    const int base = baseIndex == 1 ? 3 : (baseIndex == 2 ? 5 : (baseIndex == 3 ? 7 : 11));
+    const float invBase = 1.0f / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    while (a) {
+        const uint64_t next = a / (uint64_t)base;
+        const uint64_t digit = a - next * (uint64_t)base;
+        reversedDigits = reversedDigits * (uint64_t)base + digit;
+        invBaseN *= invBase;
+        a = next;
+    }
+    return pt_min((float)reversedDigits * invBaseN, PT_ONE_MINUS_EPS);
+}
+B200_HD float lerpf(float t, float v1, float v2) { return (1 - t) * v1 + t * v2; }  // pbrt.h:413
+
+struct SpatialGrid {        // SpatialLightDistribution, lightdistrib.cpp:96-124
+    int enabled;
+    int nv[3];
+    float wb_min[3], wb_max[3];  // Scene::WorldBound()
+};
+// SpatialLightDistribution::Lookup, lightdistrib.cpp:139-148: voxel of a point
+B200_HD int spatial_voxel(const SpatialGrid &g, const V3 &p) {
+    int pi[3];
+    const float pc[3] = {p.x, p.y, p.z};
+    for (int a = 0; a < 3; ++a) {
+        float o = pc[a] - g.wb_min[a];
+        if (g.wb_max[a] > g.wb_min[a]) o /= g.wb_max[a] - g.wb_min[a];
+        const int v = (int)(o * (float)g.nv[a]);
+        pi[a] = v < 0 ? 0 : (v > g.nv[a] - 1 ? g.nv[a] - 1 : v);
+    }
+    return (pi[2] * g.nv[1] + pi[1]) * g.nv[0] + pi[0];
+}
+// One (voxel, light) term of SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:230-275):
+// sum over 128 Halton points of Li.y()/pdf for a DiffuseAreaLight on the triangle (p0,p1,p2).
+B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
+                                    const V3 &p2, bool flip, const RGB &lemit, bool twoSided) {
+    const int pi[3] = {vx, vy, vz};
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        const float t0 = (float)pi[a] / (float)g.nv[a], t1 = (float)(pi[a] + 1) / (float)g.nv[a];
+        const float b0 = lerpf(t0, g.wb_min[a], g.wb_max[a]), b1 = lerpf(t1, g.wb_min[a], g.wb_max[a]);
+        lo[a] = pt_min(b0, b1);
+        hi[a] = pt_max(b0, b1);
+    }
+    float contrib = 0.f;
+    for (int i = 0; i < 128; ++i) {
+        const V3 po = mk(lerpf(radical_inverse(0, i), lo[0], hi[0]), lerpf(radical_inverse(1, i), lo[1], hi[1]),
+                         lerpf(radical_inverse(2, i), lo[2], hi[2]));
+        const float u[2] = {radical_inverse(3, i), radical_inverse(4, i)};
+        float pdf;
+        const LightSample ps = triangle_sample(p0, p1, p2, flip, u, &pdf);
+        V3 w = ps.p - po;
+        if (len2(w) == 0)
+            pdf = 0;
+        else {
+            w = normalize(w);
+            pdf *= len2(po - ps.p) / absdot(ps.n, -w);
+            if (pt_isinf(pdf)) pdf = 0.f;
+        }
+        RGB Li = rgb1(0.f);
+        if (pdf == 0 || len2(ps.p - po) == 0) {
+            pdf = 0;
+        } else {
+            const V3 wi = normalize(ps.p - po);
+            Li = (twoSided || dot(ps.n, -wi) > 0) ? lemit : rgb1(0.f);
+        }
+        if (pdf > 0) contrib += lum(Li) / pdf;
+    }
+    return contrib;
+}
+
 // ----------------------------------------------------------------------- film
 B200_HD void rgb_to_xyz(const RGB &c, float xyz[3]) {  // spectrum.h:62-66
     xyz[0] = 0.412453f * c.r + 0.357580f * c.g + 0.180423f * c.b;

@@ -260,9 +260,8 @@ class GpuPathIntegrator : public PathIntegrator {
             strategy = B200PT_LIGHTS_UNIFORM;
         else if (lightSampleStrategy == "power")
             strategy = B200PT_LIGHTS_POWER;
-        else
-            return Error("gpupath: lightsamplestrategy \"%s\" is not supported (use \"uniform\" or \"power\")",
-                         lightSampleStrategy.c_str());
+        else  // "spatial" and, like the reference (lightdistrib.cpp:59-65), any unknown name
+            strategy = B200PT_LIGHTS_SPATIAL;
         Flattened flat;
         if (!FlattenScene(scene, &flat, &why)) return Error("gpupath: the scene uses %s", why.c_str());
 

@@ -31,6 +31,9 @@ RENDERS = {
     "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
     # thin-lens camera, two-sided lights, ReverseOrientation on the glass and plastic meshes
     "lens_flip": (3000, ("matte", "glass", "metal", "plastic"), 36, 24, 8, 6, "uniform", None),
+    # pbrt's default light sample strategy (SpatialLightDistribution), 10 and 16 lights
+    "spatial": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "spatial", None),
+    "spatial16": (3000, ("matte", "plastic"), 32, 32, 4, 8, "spatial", 16),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5))}

@@ -17,6 +17,9 @@ RENDERS = {
     "power16": (3000, ("matte", "glass", "metal", "plastic"), 32, 32, 4, 16, "power", 16),
     # thin-lens camera, two-sided lights, ReverseOrientation on the glass and plastic meshes
     "lens_flip": (3000, ("matte", "glass", "metal", "plastic"), 36, 24, 8, 6, "uniform", None),
+    # pbrt's default light sample strategy (SpatialLightDistribution), 10 and 16 lights
+    "spatial": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "spatial", None),
+    "spatial16": (3000, ("matte", "plastic"), 32, 32, 4, 8, "spatial", 16),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5))}
@@ -32,7 +35,7 @@ def ctx(pkg):
 def make(pkg, abi, scenes, ctx, nt, mats, w, h, spp, depth=5, strat="uniform", nl=None, seed=1234, **kw):
     arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, seed=seed)
     setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
-                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM, **kw)
+                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat], **kw)
     scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
     return arr, setup, scene
 
@@ -136,7 +139,7 @@ def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
     ex = EXTRA.get(name, {})
     arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
     setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
-                               strategy=abi.LIGHTS_POWER if strat == "power" else abi.LIGHTS_UNIFORM,
+                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
                                **ex.get("camera", {}))
     scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
     r = pkg.Render(scene, setup)
@@ -159,8 +162,9 @@ def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
 
 
 @pytest.mark.parametrize("mats,depth,strat", [(("matte",), 5, "uniform"), (("glass",), 8, "uniform"),
-                                             (("metal",), 5, "power"), (("plastic",), 5, "uniform"),
-                                             (("matte", "glass", "metal", "plastic"), 16, "power")])
+                                             (("metal",), 5, "power"), (("plastic",), 5, "spatial"),
+                                             (("matte", "glass", "metal", "plastic"), 16, "power"),
+                                             (("matte", "glass", "metal", "plastic"), 5, "spatial")])
 def test_render_and_counters_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat):
     arr, setup, scene = make(pkg, abi, scenes, ctx, 60000, mats, 96, 64, 16, depth, strat)
     o = ob.Oracle(abi, arr)
