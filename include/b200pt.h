@@ -83,9 +83,10 @@ typedef struct b200pt_area_light {
  * Triangle i is the i-th GeometricPrimitive handed to the accelerator
  * (accelerators/bvh.cpp:183).  Vertices are the world-space TriangleMesh::p
  * values (shapes/triangle.cpp:73-75) gathered through the index buffer:
- * 9 floats per triangle (p0 p1 p2).  Meshes with per-vertex normals, tangents,
- * uvs or alpha masks are outside this round's scope and must be rejected by
- * the host. */
+ * 9 floats per triangle (p0 p1 p2).  Per-vertex shading normals (TriangleMesh::n,
+ * world space) and uvs (TriangleMesh::uv) are optional, gathered the same way;
+ * per-vertex tangents (s) and alpha masks are out of scope and must be rejected
+ * by the host. */
 typedef struct b200pt_scene_desc {
     int64_t n_triangles;
     const float *vertices;        /* [n_triangles][3][3]                              */
@@ -97,6 +98,11 @@ typedef struct b200pt_scene_desc {
     const b200pt_material *materials;
     int32_t n_lights;
     const b200pt_area_light *lights;
+    /* optional per-vertex shading data (shapes/triangle.cpp:293-425); NULL = none */
+    const float *normals;         /* [n_triangles][3][3] world-space n of the three vertices  */
+    const float *uvs;             /* [n_triangles][3][2]                                      */
+    const uint8_t *vertex_flags;  /* [n_triangles] bit0: triangle's mesh has normals, bit1: has uvs;
+                                     NULL = every triangle has whatever arrays are non-NULL   */
 } b200pt_scene_desc;
 
 /* ---- camera: PerspectiveCamera (cameras/perspective.cpp:45-144) ----------

@@ -426,8 +426,9 @@ inline bool TriangleTest(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &ro,
 // shapes/triangle.cpp:293-318: partial derivatives with the default uvs of
 // GetUVs (triangle.h:116-126) -- (0,0),(1,0),(1,1) -- returns false for a
 // degenerate triangle (the "intersection is bogus" exit).
-inline bool TrianglePartials(const V3 &p0, const V3 &p1, const V3 &p2, V3 *dpdu, V3 *dpdv) {
-    const float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};
+static const float kDefaultUV[3][2] = {{0, 0}, {1, 0}, {1, 1}};  // Triangle::GetUVs, triangle.h:116-126
+inline bool TrianglePartials(const V3 &p0, const V3 &p1, const V3 &p2, V3 *dpdu, V3 *dpdv,
+                             const float (*uv)[2] = kDefaultUV) {
     float duv02[2] = {uv[0][0] - uv[2][0], uv[0][1] - uv[2][1]};
     float duv12[2] = {uv[1][0] - uv[2][0], uv[1][1] - uv[2][1]};
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
@@ -503,6 +504,12 @@ struct oracle_scene {
     std::vector<BVHNode> nodes;
     std::vector<int32_t> orderedPrims;
     float wbMin[3], wbMax[3];  // Scene::WorldBound()
+    std::vector<V3> nrm;       // 3 per triangle (TriangleMesh::n) when hasN[tri]
+    std::vector<float> uv;     // 6 per triangle (TriangleMesh::uv) when hasUV[tri]
+    std::vector<uint8_t> hasN, hasUV;
+    const float (*UV(int tri) const)[2] {
+        return hasUV[tri] ? reinterpret_cast<const float (*)[2]>(&uv[6 * (size_t)tri]) : kDefaultUV;
+    }
 };
 
 namespace {
@@ -668,26 +675,53 @@ bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float ra
 // ----------------------------------------------------- surface interaction
 struct Isect {
     V3 p, pError, n, wo;  // Interaction: n = geometric normal after orientation
-    V3 dpdu;              // shading.dpdu == dpdu (no per-vertex shading data)
+    V3 ns;                // shading.n
+    V3 sdpdu;             // shading.dpdu
     int tri;
 };
 
-// shapes/triangle.cpp:319-425 for a mesh without n/s/uv + interaction.cpp:44-71
+// shapes/triangle.cpp:293-425 (meshes without per-vertex tangents) + interaction.cpp:44-86
 inline void FillIsect(const oracle_scene &s, int tri, const TriHit &h, const V3 &rayD, Isect *is) {
     const V3 &p0 = s.p[3 * tri], &p1 = s.p[3 * tri + 1], &p2 = s.p[3 * tri + 2];
     V3 dpdu, dpdv;
-    TrianglePartials(p0, p1, p2, &dpdu, &dpdv);
+    TrianglePartials(p0, p1, p2, &dpdu, &dpdv, s.UV(tri));
     float xAbsSum = (std::abs(h.b0 * p0.x) + std::abs(h.b1 * p1.x) + std::abs(h.b2 * p2.x));
     float yAbsSum = (std::abs(h.b0 * p0.y) + std::abs(h.b1 * p1.y) + std::abs(h.b2 * p2.y));
     float zAbsSum = (std::abs(h.b0 * p0.z) + std::abs(h.b1 * p1.z) + std::abs(h.b2 * p2.z));
     is->pError = gamma_(7) * V3(xAbsSum, yAbsSum, zAbsSum);
     is->p = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
     is->wo = Normalize(-rayD);  // Interaction ctor, interaction.h:62
-    is->dpdu = dpdu;
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
-    is->n = Normalize(Cross(dp02, dp12));
-    if (s.flip[tri]) is->n = -is->n;
+    is->n = Normalize(Cross(dp02, dp12));  // triangle.cpp:341
+    is->ns = is->n;
+    is->sdpdu = dpdu;
     is->tri = tri;
+    const bool flip = s.flip[tri] != 0;
+    if (s.hasN[tri]) {
+        // triangle.cpp:342-413: shading normal, tangent from dpdu, SetShadingGeometry(ss, ts, ..., true)
+        const V3 &n0 = s.nrm[3 * tri], &n1 = s.nrm[3 * tri + 1], &n2 = s.nrm[3 * tri + 2];
+        V3 ns = (h.b0 * n0 + h.b1 * n1 + h.b2 * n2);
+        if (LengthSquared(ns) > 0)
+            ns = Normalize(ns);
+        else
+            ns = is->n;
+        V3 ss = Normalize(dpdu);
+        V3 ts = Cross(ss, ns);
+        if (LengthSquared(ts) > 0.f) {
+            ts = Normalize(ts);
+            ss = Cross(ts, ns);
+        } else
+            CoordinateSystem(ns, &ss, &ts);
+        // interaction.cpp:73-92
+        V3 sn = Normalize(Cross(ss, ts));
+        if (flip) sn = -sn;
+        is->n = (Dot(is->n, sn) < 0.f) ? -is->n : is->n;  // Faceforward(n, shading.n)
+        is->ns = sn;
+        is->sdpdu = ss;
+        is->n = (Dot(is->n, is->ns) < 0.f) ? -is->n : is->n;  // triangle.cpp:418-419
+    } else if (flip) {
+        is->n = is->ns = -is->n;  // triangle.cpp:420-421
+    }
 }
 
 // core/geometry.h:1440-1460
@@ -1048,9 +1082,9 @@ struct BSDF {  // reflection.h:153-202
 void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
     const b200pt_material &m = s.materials[s.materialId[is.tri]];
     bsdf->eta = 1;
-    bsdf->ns = is.n;  // shading.n == n for meshes without shading normals
+    bsdf->ns = is.ns;  // reflection.h:157-160
     bsdf->ng = is.n;
-    bsdf->ss = Normalize(is.dpdu);
+    bsdf->ss = Normalize(is.sdpdu);
     bsdf->ts = Cross(bsdf->ns, bsdf->ss);
     bsdf->nBxDFs = 0;
     auto lambert = [&](const float *kd) {
@@ -1135,7 +1169,12 @@ inline LightSample TriangleSample(const oracle_scene &s, int tri, const float u[
     LightSample it;
     it.p = b[0] * p0 + b[1] * p1 + (1 - b[0] - b[1]) * p2;
     it.n = Normalize(Cross(p1 - p0, p2 - p0));
-    if (s.flip[tri]) it.n = it.n * -1.f;
+    if (s.hasN[tri]) {
+        const V3 &n0 = s.nrm[3 * tri], &n1 = s.nrm[3 * tri + 1], &n2 = s.nrm[3 * tri + 2];
+        V3 ns(b[0] * n0 + b[1] * n1 + (1 - b[0] - b[1]) * n2);
+        it.n = (Dot(it.n, ns) < 0.f) ? -it.n : it.n;  // Faceforward, triangle.cpp:596-600
+    } else if (s.flip[tri])
+        it.n = it.n * -1.f;
     V3 pAbsSum = Abs(b[0] * p0) + Abs(b[1] * p1) + Abs((1 - b[0] - b[1]) * p2);
     it.pError = gamma_(6) * V3(pAbsSum.x, pAbsSum.y, pAbsSum.z);
     *pdf = 1 / TriangleArea(s, tri);
@@ -1575,12 +1614,25 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
             s->wbMin[a] = std::min(s->wbMin[a], s->p[i][a]);
             s->wbMax[a] = std::max(s->wbMax[a], s->p[i][a]);
         }
+    s->hasN.assign(d->n_triangles, 0);
+    s->hasUV.assign(d->n_triangles, 0);
+    for (int64_t i = 0; i < d->n_triangles; ++i) {
+        uint8_t f = d->vertex_flags ? d->vertex_flags[i] : 3;
+        s->hasN[i] = d->normals && (f & 1);
+        s->hasUV[i] = d->uvs && (f & 2);
+    }
+    if (d->normals) {
+        s->nrm.resize(3 * (size_t)d->n_triangles);
+        for (int64_t i = 0; i < 3 * d->n_triangles; ++i)
+            s->nrm[i] = V3(d->normals[3 * i], d->normals[3 * i + 1], d->normals[3 * i + 2]);
+    }
+    if (d->uvs) s->uv.assign(d->uvs, d->uvs + 6 * d->n_triangles);
     s->degenerate.resize(d->n_triangles);
     std::vector<BuildPrim> prims;
     prims.reserve(d->n_triangles);
     for (int64_t i = 0; i < d->n_triangles; ++i) {
         V3 dpdu, dpdv;
-        s->degenerate[i] = !TrianglePartials(s->p[3 * i], s->p[3 * i + 1], s->p[3 * i + 2], &dpdu, &dpdv);
+        s->degenerate[i] = !TrianglePartials(s->p[3 * i], s->p[3 * i + 1], s->p[3 * i + 2], &dpdu, &dpdv, s->UV((int)i));
         BuildPrim bp;
         bp.id = (int32_t)i;
         for (int a = 0; a < 3; ++a) {

@@ -25,7 +25,8 @@ class SceneDesc(C.Structure):
     _fields_ = [("n_triangles", C.c_int64), ("vertices", C.c_void_p), ("material_id", C.c_void_p),
                 ("light_id", C.c_void_p), ("flip_normal", C.c_void_p), ("n_materials", C.c_int32),
                 ("materials", C.POINTER(Material)), ("n_lights", C.c_int32),
-                ("lights", C.POINTER(AreaLight))]
+                ("lights", C.POINTER(AreaLight)), ("normals", C.c_void_p), ("uvs", C.c_void_p),
+                ("vertex_flags", C.c_void_p)]
 
 
 class CameraDesc(C.Structure):

@@ -35,6 +35,7 @@ struct b200pt_scene {
     U4 *d_nodes = nullptr;
     F4 *d_tris = nullptr;
     b200pt_material *d_materials = nullptr;
+    F4 *d_tri_n = nullptr, *d_tri_uv = nullptr;
     uint64_t n_nodes = 0, n_tris = 0;
     std::vector<b200pt_material> materials;
     std::vector<b200pt_area_light> lights;  // host copy, triangle = original index
@@ -142,7 +143,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     for (int64_t i = 0; i < d->n_triangles; ++i) {
         const float *v = d->vertices + 9 * i;
         V3 dpdu, dpdv;
-        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), &dpdu, &dpdv);
+        TriShading sh;
+        default_shading(&sh);
+        const uint8_t vf = d->vertex_flags ? d->vertex_flags[i] : 3;
+        if (d->uvs && (vf & 2)) memcpy(sh.uv, d->uvs + 6 * i, sizeof(float) * 6);
+        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), sh.uv, &dpdu, &dpdv);
     }
     Bvh8 bvh;
     int threads = (int)std::thread::hardware_concurrency();
@@ -151,6 +156,25 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
                std::max(1, threads), &bvh);
     if (bvh.max_depth > B200PT_STACK - 4)
         return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d exceeds the traversal stack", bvh.max_depth);
+    // per-vertex shading data in leaf order + flags (bit 18 normals, bit 19 uvs) in the triangle records
+    std::vector<F4> tri_n, tri_uv;
+    if (d->normals) tri_n.assign(bvh.tris.size() * 3, F4{0, 0, 0, 0});
+    if (d->uvs) tri_uv.assign(bvh.tris.size() * 2, F4{0, 0, 0, 0});
+    for (int64_t i = 0; i < d->n_triangles; ++i) {
+        const uint8_t vf = d->vertex_flags ? d->vertex_flags[i] : 3;
+        const uint32_t ti = bvh.prim_to_tri[i];
+        if (d->normals && (vf & 1)) {
+            const float *n = d->normals + 9 * i;
+            for (int k = 0; k < 3; ++k) tri_n[(size_t)ti * 3 + k] = F4{n[3 * k], n[3 * k + 1], n[3 * k + 2], 0.f};
+            bvh.tris[ti].mat_flags |= 0x40000u;
+        }
+        if (d->uvs && (vf & 2)) {
+            const float *u = d->uvs + 6 * i;
+            tri_uv[(size_t)ti * 2] = F4{u[0], u[1], u[2], u[3]};
+            tri_uv[(size_t)ti * 2 + 1] = F4{u[4], u[5], 0.f, 0.f};
+            bvh.tris[ti].mat_flags |= 0x80000u;
+        }
+    }
     int64_t bad = validate_bvh8(bvh);
     if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
 
@@ -191,6 +215,20 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMallocHost failed: %s", cudaGetErrorString(e));
     }
+    if (!tri_n.empty()) {
+        if ((e = cudaMalloc(&s->d_tri_n, tri_n.size() * sizeof(F4))) != cudaSuccess ||
+            (e = cudaMemcpy(s->d_tri_n, tri_n.data(), tri_n.size() * sizeof(F4), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            b200pt_scene_destroy(s);
+            return b200pt_fail(B200PT_ERR_OOM, "scene_create: shading normals upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (!tri_uv.empty()) {
+        if ((e = cudaMalloc(&s->d_tri_uv, tri_uv.size() * sizeof(F4))) != cudaSuccess ||
+            (e = cudaMemcpy(s->d_tri_uv, tri_uv.data(), tri_uv.size() * sizeof(F4), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            b200pt_scene_destroy(s);
+            return b200pt_fail(B200PT_ERR_OOM, "scene_create: uv upload failed: %s", cudaGetErrorString(e));
+        }
+    }
     memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
     memcpy(s->h_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord));
     int rc = b200pt_scene_upload(s, nullptr);
@@ -222,6 +260,8 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     cudaFree(s->d_nodes);
     cudaFree(s->d_tris);
     cudaFree(s->d_materials);
+    cudaFree(s->d_tri_n);
+    cudaFree(s->d_tri_uv);
     cudaFree(s->d_work);
     cudaFreeHost(s->h_nodes);
     cudaFreeHost(s->h_tris);
@@ -367,6 +407,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.scene.materials = scene->d_materials;
     H.scene.n_nodes = (uint32_t)scene->n_nodes;
     H.scene.n_tris = (uint32_t)scene->n_tris;
+    H.scene.tri_n = scene->d_tri_n;
+    H.scene.tri_uv = scene->d_tri_uv;
     // sampler (samplers/sobol.h:49-62)
     H.sampler.spp = smp->samples_per_pixel;
     memcpy(H.sampler.sb, smp->sample_bounds, sizeof(int) * 4);

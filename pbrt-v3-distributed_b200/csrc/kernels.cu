@@ -48,6 +48,27 @@ __device__ __forceinline__ bool warp_fetch(uint32_t *work, uint32_t n, uint32_t 
     return true;
 }
 
+// per-vertex shading data of triangle `ti` (flags: bit 18 = normals, bit 19 = uvs)
+__device__ __forceinline__ void load_shading(const DevScene &sc, uint32_t ti, uint32_t mflags, TriShading *t) {
+    default_shading(t);
+    if (mflags & 0x40000u) {
+        const F4 *np = sc.tri_n + (size_t)ti * 3;
+        t->has_n = 1;
+        t->n0 = v3(ld_f4(np));
+        t->n1 = v3(ld_f4(np + 1));
+        t->n2 = v3(ld_f4(np + 2));
+    }
+    if (mflags & 0x80000u) {
+        const F4 a = ld_f4(sc.tri_uv + (size_t)ti * 2), b = ld_f4(sc.tri_uv + (size_t)ti * 2 + 1);
+        t->uv[0] = a.x;
+        t->uv[1] = a.y;
+        t->uv[2] = a.z;
+        t->uv[3] = a.w;
+        t->uv[4] = b.x;
+        t->uv[5] = b.y;
+    }
+}
+
 // ------------------------------------------------------------------ tile maths
 struct TileRect {
     int x0, y0, x1, y1;  // sample-space rectangle of the tile (integrator.cpp:251-255)
@@ -262,6 +283,8 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
     const uint32_t lflags = __float_as_uint(t1.w);
     const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
+    TriShading lsh;
+    load_shading(R->scene, light.tri, lflags, &lsh);
     const RGB lemit = rgbp(light.lemit);
     const int flagsNS = BSDF_ALL & ~BSDF_SPECULAR;
     out->pend = 0;
@@ -271,7 +294,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     float lightPdf = 0.f, scatteringPdf = 0.f;
     // light.Sample_Li: diffuse.cpp:68-81, shape.cpp:56-70
     RGB Li = rgb1(0.f);
-    LightSample ps = triangle_sample(p0, p1, p2, lflip, uLight, &lightPdf);
+    LightSample ps = triangle_sample(p0, p1, p2, lflip, lsh, uLight, &lightPdf);
     {
         V3 w = ps.p - is.p;
         if (len2(w) == 0)
@@ -313,10 +336,10 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         V3 ln = mk(0.f, 0.f, 0.f);
         TriHit h;
         if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
-            const V3 lp = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
-            ln = normalize(cross(p0 - p2, p1 - p2));
-            if (lflip) ln = -ln;
-            lpdf = len2(is.p - lp) / (absdot(ln, -wi) * light.area);
+            Isect li;
+            fill_isect(p0, p1, p2, lflip, lsh, h, wi, &li);
+            ln = li.n;
+            lpdf = len2(is.p - li.p) / (absdot(ln, -wi) * light.area);
             if (pt_isinf(lpdf)) lpdf = 0.f;
         }
         if (lpdf != 0) {
@@ -364,7 +387,9 @@ __global__ void __launch_bounds__(128) k_shade(const RenderDev *R, int bounce, u
             TriHit h;
             if (triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h)) {
                 Isect is;
-                fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, h, rd, &is);
+                TriShading tsh;
+                load_shading(R->scene, ti, mflags, &tsh);
+                fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
                 // path.cpp:91-101: emitted light at the first vertex or after a specular bounce
                 if (bounces == 0 || specularBounce) {
                     if (lightId >= 0) {
@@ -510,9 +535,11 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     const DevLight light = R->lights[j];
     const F4 *tp = R->scene.tris + (size_t)light.tri * 3;
     const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
-    const bool flip = (__float_as_uint(t1.w) & 0x10000u) != 0;
-    R->sp_func[vox * R->n_lights + j] =
-        spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), flip, rgbp(light.lemit), light.two_sided != 0);
+    const uint32_t lflags = __float_as_uint(t1.w);
+    TriShading lsh;
+    load_shading(R->scene, light.tri, lflags, &lsh);
+    R->sp_func[vox * R->n_lights + j] = spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0,
+                                                              lsh, rgbp(light.lemit), light.two_sided != 0);
 }
 __global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
     const SpatialGrid &g = R->grid;

@@ -30,6 +30,8 @@ struct DevScene {
     const F4 *tris;
     const b200pt_material *materials;
     uint32_t n_nodes, n_tris;
+    const F4 *tri_n;   // optional per-vertex shading normals, 3 x float4 per triangle (leaf order)
+    const F4 *tri_uv;  // optional uvs, 2 x float4 per triangle: (u0 v0 u1 v1) (u2 v2 - -)
 };
 
 // queue ids inside one bounce's counter block

@@ -374,11 +374,25 @@ B200_HD bool triangle_test(const V3 &p0, const V3 &p1, const V3 &p2, const V3 &r
     return true;
 }
 
-// shapes/triangle.cpp:293-318 with the default uvs (0,0),(1,0),(1,1) of
-// Triangle::GetUVs (triangle.h:116-126).  false = degenerate triangle (the
-// reference then reports no intersection at all).
-B200_HD bool triangle_partials(const V3 &p0, const V3 &p1, const V3 &p2, V3 *dpdu, V3 *dpdv) {
-    const float uv0x = 0.f, uv0y = 0.f, uv1x = 1.f, uv1y = 0.f, uv2x = 1.f, uv2y = 1.f;
+// shapes/triangle.cpp:293-318.  false = degenerate triangle (the reference then
+// reports no intersection at all).
+// Per-vertex shading data of a triangle: TriangleMesh::n and ::uv gathered through the index buffer.
+struct TriShading {
+    int has_n;
+    V3 n0, n1, n2;
+    float uv[6];  // (u,v) of the three vertices; Triangle::GetUVs defaults (0,0),(1,0),(1,1) without mesh uvs
+};
+B200_HD void default_shading(TriShading *t) {
+    t->has_n = 0;
+    t->uv[0] = 0.f;
+    t->uv[1] = 0.f;
+    t->uv[2] = 1.f;
+    t->uv[3] = 0.f;
+    t->uv[4] = 1.f;
+    t->uv[5] = 1.f;
+}
+B200_HD bool triangle_partials(const V3 &p0, const V3 &p1, const V3 &p2, const float *uv, V3 *dpdu, V3 *dpdv) {
+    const float uv0x = uv[0], uv0y = uv[1], uv1x = uv[2], uv1y = uv[3], uv2x = uv[4], uv2y = uv[5];
     float duv02x = uv0x - uv2x, duv02y = uv0y - uv2y;
     float duv12x = uv1x - uv2x, duv12y = uv1y - uv2y;
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
@@ -402,24 +416,51 @@ B200_HD float triangle_area(const V3 &p0, const V3 &p1, const V3 &p2) {
     return (float)(0.5 * (double)len(cross(p1 - p0, p2 - p0)));
 }
 
-// SurfaceInteraction of a triangle hit on a mesh without per-vertex n/s/uv:
-// triangle.cpp:319-341, 415-421 and interaction.cpp:44-71.
+// SurfaceInteraction of a triangle hit (meshes without per-vertex tangents):
+// triangle.cpp:293-425 and interaction.cpp:44-92.
 struct Isect {
-    V3 p, pError, n, wo, dpdu;
+    V3 p, pError, n, wo;  // n = geometric normal after orientation
+    V3 ns;                // shading.n
+    V3 sdpdu;             // shading.dpdu
 };
-B200_HD void fill_isect(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const TriHit &h, const V3 &rayD,
-                        Isect *is) {
+B200_HD void fill_isect(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const TriShading &sh, const TriHit &h,
+                        const V3 &rayD, Isect *is) {
     V3 dpdu, dpdv;
-    triangle_partials(p0, p1, p2, &dpdu, &dpdv);
+    triangle_partials(p0, p1, p2, sh.uv, &dpdu, &dpdv);
     float xs = (pt_abs(h.b0 * p0.x) + pt_abs(h.b1 * p1.x) + pt_abs(h.b2 * p2.x));
     float ys = (pt_abs(h.b0 * p0.y) + pt_abs(h.b1 * p1.y) + pt_abs(h.b2 * p2.y));
     float zs = (pt_abs(h.b0 * p0.z) + pt_abs(h.b1 * p1.z) + pt_abs(h.b2 * p2.z));
     is->pError = pt_gamma(7) * mk(xs, ys, zs);
     is->p = h.b0 * p0 + h.b1 * p1 + h.b2 * p2;
     is->wo = normalize(-rayD);
-    is->dpdu = dpdu;
-    V3 n = normalize(cross(p0 - p2, p1 - p2));
-    is->n = flip ? -n : n;
+    V3 n = normalize(cross(p0 - p2, p1 - p2));  // triangle.cpp:341
+    is->ns = n;
+    is->sdpdu = dpdu;
+    if (sh.has_n) {
+        // triangle.cpp:342-413 + SetShadingGeometry(ss, ts, ..., true), interaction.cpp:73-92
+        V3 ns = (h.b0 * sh.n0 + h.b1 * sh.n1 + h.b2 * sh.n2);
+        if (len2(ns) > 0)
+            ns = normalize(ns);
+        else
+            ns = n;
+        V3 ss = normalize(dpdu);
+        V3 ts = cross(ss, ns);
+        if (len2(ts) > 0.f) {
+            ts = normalize(ts);
+            ss = cross(ts, ns);
+        } else
+            coordinate_system(ns, &ss, &ts);
+        V3 sn = normalize(cross(ss, ts));
+        if (flip) sn = -sn;
+        n = (dot(n, sn) < 0.f) ? -n : n;   // Faceforward(n, shading.n)
+        is->ns = sn;
+        is->sdpdu = ss;
+        n = (dot(n, is->ns) < 0.f) ? -n : n;  // triangle.cpp:418-419
+    } else if (flip) {
+        n = -n;  // triangle.cpp:420-421
+        is->ns = n;
+    }
+    is->n = n;
 }
 
 // core/geometry.h:1440-1460
@@ -783,9 +824,9 @@ B200_HD void add_lambert(Bsdf *b, const float *kd) {
 template <int MATERIAL>
 B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
     b->eta = 1.f;
-    b->ns = is.n;  // shading.n == n without per-vertex shading normals
+    b->ns = is.ns;  // reflection.h:157
     b->ng = is.n;
-    b->ss = normalize(is.dpdu);   // reflection.h:159
+    b->ss = normalize(is.sdpdu);  // reflection.h:159
     b->ts = cross(b->ns, b->ss);  // reflection.h:160
     b->n = 0;
     const int type = MATERIAL >= 0 ? MATERIAL : m.type;
@@ -834,14 +875,18 @@ struct LightSample {
     V3 p, n, pError;
 };
 // shapes/triangle.cpp:583-608 + sampling.cpp:154-157
-B200_HD LightSample triangle_sample(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const float u[2],
-                                    float *pdf) {
+B200_HD LightSample triangle_sample(const V3 &p0, const V3 &p1, const V3 &p2, bool flip, const TriShading &sh,
+                                    const float u[2], float *pdf) {
     float su0 = sqrtf(u[0]);
     float b0 = 1 - su0, b1 = u[1] * su0;
     LightSample it;
     it.p = b0 * p0 + b1 * p1 + (1 - b0 - b1) * p2;
     it.n = normalize(cross(p1 - p0, p2 - p0));
-    if (flip) it.n = it.n * -1.f;
+    if (sh.has_n) {
+        const V3 ns = b0 * sh.n0 + b1 * sh.n1 + (1 - b0 - b1) * sh.n2;
+        it.n = (dot(it.n, ns) < 0.f) ? -it.n : it.n;  // Faceforward, triangle.cpp:596-600
+    } else if (flip)
+        it.n = it.n * -1.f;
     V3 s = vabs(b0 * p0) + vabs(b1 * p1) + vabs((1 - b0 - b1) * p2);
     it.pError = pt_gamma(6) * mk(s.x, s.y, s.z);
     *pdf = 1 / triangle_area(p0, p1, p2);
@@ -919,7 +964,7 @@ B200_HD int spatial_voxel(const SpatialGrid &g, const V3 &p) {
 // One (voxel, light) term of SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:230-275):
 // sum over 128 Halton points of Li.y()/pdf for a DiffuseAreaLight on the triangle (p0,p1,p2).
 B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
-                                    const V3 &p2, bool flip, const RGB &lemit, bool twoSided) {
+                                    const V3 &p2, bool flip, const TriShading &sh, const RGB &lemit, bool twoSided) {
     const int pi[3] = {vx, vy, vz};
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
@@ -934,7 +979,7 @@ B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz
                          lerpf(radical_inverse(2, i), lo[2], hi[2]));
         const float u[2] = {radical_inverse(3, i), radical_inverse(4, i)};
         float pdf;
-        const LightSample ps = triangle_sample(p0, p1, p2, flip, u, &pdf);
+        const LightSample ps = triangle_sample(p0, p1, p2, flip, sh, u, &pdf);
         V3 w = ps.p - po;
         if (len2(w) == 0)
             pdf = 0;

@@ -102,7 +102,9 @@ void ToRGB(const Spectrum &s, float out[3]) {
 }
 
 struct Flattened {
-    std::vector<float> vertices;
+    std::vector<float> vertices, normals, uvs;
+    std::vector<uint8_t> vertexFlags;
+    bool anyNormals = false, anyUVs = false;
     std::vector<int32_t> materialId, lightId;
     std::vector<uint8_t> flip;
     std::vector<b200pt_material> materials;
@@ -188,14 +190,24 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         auto tri = dynamic_cast<const Triangle *>(gp->shape.get());
         if (!tri) return *why = "a shape other than Triangle", false;
         const TriangleMesh &mesh = *tri->mesh;
-        if (mesh.n || mesh.s || mesh.uv || mesh.alphaMask || mesh.shadowAlphaMask)
-            return *why = "meshes with per-vertex normals / tangents / uvs / alpha masks", false;
+        if (mesh.s || mesh.alphaMask || mesh.shadowAlphaMask)
+            return *why = "meshes with per-vertex tangents / alpha masks", false;
         for (int v = 0; v < 3; ++v) {
             const Point3f &p = mesh.p[tri->v[v]];
             f->vertices.push_back(p.x);
             f->vertices.push_back(p.y);
             f->vertices.push_back(p.z);
+            Normal3f n = mesh.n ? mesh.n[tri->v[v]] : Normal3f(0, 0, 0);
+            f->normals.push_back(n.x);
+            f->normals.push_back(n.y);
+            f->normals.push_back(n.z);
+            Point2f uv = mesh.uv ? mesh.uv[tri->v[v]] : Point2f(0, 0);
+            f->uvs.push_back(uv.x);
+            f->uvs.push_back(uv.y);
         }
+        f->vertexFlags.push_back((mesh.n ? 1 : 0) | (mesh.uv ? 2 : 0));
+        f->anyNormals |= mesh.n != nullptr;
+        f->anyUVs |= mesh.uv != nullptr;
         f->flip.push_back((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0);
         const Material *m = gp->material.get();
         if (!m) return *why = "primitives without a material (medium boundaries)", false;
@@ -276,6 +288,9 @@ class GpuPathIntegrator : public PathIntegrator {
         sd.materials = flat.materials.data();
         sd.n_lights = (int)flat.lights.size();
         sd.lights = flat.lights.data();
+        sd.normals = flat.anyNormals ? flat.normals.data() : nullptr;
+        sd.uvs = flat.anyUVs ? flat.uvs.data() : nullptr;
+        sd.vertex_flags = flat.vertexFlags.data();
 
         b200pt_camera_desc cd;
         memcpy(cd.raster_to_camera, pcam->RasterToCamera.m.m, sizeof(float) * 16);

@@ -115,7 +115,7 @@ class SceneArrays:
     """Flattened scene in the layout b200pt_scene_desc wants."""
 
     def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
-                 n_lights=None, two_sided=False, reverse_orientation=()):
+                 n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=()):
         self.material_names = list(materials) + ["black"]
         soup = soup_vertices(n_tris, seed, soup_version)
         quads = light_quads(soup_version, n_lights)
@@ -140,6 +140,22 @@ class SceneArrays:
         self.reverse_orientation = tuple(reverse_orientation)
         for m in self.reverse_orientation:
             self.flip[self.material_id == m] = 1
+        # optional per-vertex shading normals / uvs on the plymesh of material m (deterministic, seed + 7):
+        # un-normalised perturbed face normals and random uvs, to exercise triangle.cpp:293-413
+        self.shading_normals, self.uv_meshes = tuple(shading_normals), tuple(uvs)
+        self.normals = self.uvs = self.vertex_flags = None
+        if self.shading_normals or self.uv_meshes:
+            r2 = np.random.default_rng(seed + 7)
+            v = self.vertices
+            fn = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+            fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-20)
+            self.normals = np.ascontiguousarray((fn[:, None, :] + r2.uniform(-0.4, 0.4, v.shape)).astype(np.float32))
+            self.uvs = np.ascontiguousarray(r2.uniform(0, 1, (len(v), 3, 2)).astype(np.float32))
+            self.vertex_flags = np.zeros(len(v), np.uint8)
+            for m in self.shading_normals:
+                self.vertex_flags[self.material_id == m] |= 1
+            for m in self.uv_meshes:
+                self.vertex_flags[self.material_id == m] |= 2
         self.light_quads = quads
         self.light_L = float(light_L)
         self.two_sided = bool(two_sided)
@@ -169,16 +185,26 @@ class SceneArrays:
         d.materials = C.cast(self._materials, C.POINTER(abi.Material))
         d.n_lights = self.n_lights
         d.lights = C.cast(self._lights, C.POINTER(abi.AreaLight))
+        d.normals = abi.ptr(self.normals)
+        d.uvs = abi.ptr(self.uvs)
+        d.vertex_flags = abi.ptr(self.vertex_flags)
         return d
 
 
-def write_ply(path, tris):
+def write_ply(path, tris, normals=None, uvs=None):
     n = len(tris)
+    cols = [np.asarray(tris, np.float32).reshape(3 * n, 3)]
+    props = "property float x\nproperty float y\nproperty float z\n"
+    if normals is not None:
+        cols.append(np.asarray(normals, np.float32).reshape(3 * n, 3))
+        props += "property float nx\nproperty float ny\nproperty float nz\n"
+    if uvs is not None:
+        cols.append(np.asarray(uvs, np.float32).reshape(3 * n, 2))
+        props += "property float u\nproperty float v\n"
     with open(path, "wb") as f:
-        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\n"
-                 "property float y\nproperty float z\nelement face %d\n"
-                 "property list uchar int vertex_indices\nend_header\n" % (3 * n, n)).encode())
-        f.write(np.ascontiguousarray(tris, dtype="<f4").tobytes())
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n%selement face %d\n"
+                 "property list uchar int vertex_indices\nend_header\n" % (3 * n, props, n)).encode())
+        f.write(np.ascontiguousarray(np.concatenate(cols, axis=1), dtype="<f4").tobytes())
         rec = np.zeros(n, dtype=[("c", "u1"), ("i", "<i4", 3)])
         rec["c"] = 3
         rec["i"] = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
@@ -214,7 +240,10 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
                   "AttributeEnd"]
     for m, part in enumerate(scene.ply_parts):
         ply = "%s_m%d.ply" % (name, m)
-        write_ply(os.path.join(dirname, ply), part)
+        sel = scene.material_id == m
+        write_ply(os.path.join(dirname, ply), part,
+                  scene.normals[sel] if m in scene.shading_normals else None,
+                  scene.uvs[sel] if m in scene.uv_meshes else None)
         if m in scene.reverse_orientation:
             lines += ["AttributeBegin", "ReverseOrientation"]
         lines += [PBRT_MATERIAL[scene.material_names[m]], 'Shape "plymesh" "string filename" "%s"' % ply]

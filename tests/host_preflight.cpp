@@ -63,7 +63,9 @@ int main(int argc, char **argv) {
     for (int64_t i = 0; i < nTris; ++i) {
         const float *v = &verts[9 * i];
         V3 a, b;
-        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), &a, &b);
+        TriShading sh;
+        default_shading(&sh);
+        degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), sh.uv, &a, &b);
     }
     Bvh8 bvh;
     build_bvh8(verts.data(), nTris, mat.data(), light.data(), nullptr, degenerate.data(), 8, &bvh);

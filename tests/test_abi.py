@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(abi):
     assert C.sizeof(abi.FilmDesc) == 40
     assert C.sizeof(abi.SamplerDesc) == 48
     assert C.sizeof(abi.IntegratorDesc) == 28
-    assert C.sizeof(abi.SceneDesc) == 72
+    assert C.sizeof(abi.SceneDesc) == 96
     assert abi.RAY_DTYPE.itemsize == 32 and abi.HIT_DTYPE.itemsize == 16
 
 

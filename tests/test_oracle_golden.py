@@ -16,9 +16,12 @@ RENDERS = {
     # pbrt's default light sample strategy (SpatialLightDistribution), 10 and 16 lights
     "spatial": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "spatial", None),
     "spatial16": (3000, ("matte", "plastic"), 32, 32, 4, 8, "spatial", 16),
+    # per-vertex shading normals (matte + metal meshes) and uvs (matte + plastic meshes), flipped plastic
+    "normals_uv": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 6, "spatial", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
-                           camera=dict(lens_radius=0.05, focal_distance=4.5))}
+                           camera=dict(lens_radius=0.05, focal_distance=4.5)),
+         "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,)))}
 
 
 def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
