@@ -14,9 +14,9 @@ PLUGIN = os.path.join(ROOT, "pbrt-v3-distributed_b200", "_plugin", "pbrt_b200")
 needs_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN), reason="pbrt_b200 is built where /root/reference exists")
 
 
-def _scene(scenes, tmp_path, name="four", strategy="uniform"):
-    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1)
-    return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, 8, max_depth=5, strategy=strategy)
+def _scene(scenes, tmp_path, name="four", strategy="uniform", depth=5, **scene_kw):
+    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1, **scene_kw)
+    return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, 8, max_depth=depth, strategy=strategy)
 
 
 @needs_plugin
@@ -46,3 +46,11 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spatial.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spatial.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (spatial light distribution) differs from the reference"
+    # meshes with per-vertex shading normals / uvs and ReverseOrientation, read from PLY by the reference's own loader
+    path = _scene(scenes, tmp_path, "normals_uv", "spatial", depth=6, shading_normals=(0, 2), uvs=(0, 3),
+                  reverse_orientation=(3,))
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_normals_uv.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_normals_uv.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (shading normals / uvs) differs from the reference"
