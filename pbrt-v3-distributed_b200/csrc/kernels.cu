@@ -233,13 +233,16 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
                 }
             }
             const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0 && T.sp == 0;
+            // one warp reduction instead of three votes: byte 0 counts parked lanes, byte 1 urgent, byte 2 starving
             const unsigned act = __activemask();
-            const unsigned parked = __ballot_sync(act, pend_y != 0);
-            const unsigned urgent = __ballot_sync(act, must || (out_of_nodes && pend_y != 0 && a.postpone_pct <= 0));
-            const unsigned starving = __ballot_sync(act, out_of_nodes && pend_y != 0);
+            const bool starving_me = out_of_nodes && pend_y != 0;
+            const unsigned counts = __reduce_add_sync(
+                act, (pend_y != 0 ? 1u : 0u) | ((must || (starving_me && a.postpone_pct <= 0)) ? 0x100u : 0u) |
+                         (starving_me ? 0x10000u : 0u));
+            const int n_act = __popc(act), n_parked = (int)(counts & 0xffu), n_starving = (int)((counts >> 16) & 0xffu);
             // run the triangle phase if someone must, if enough lanes parked work, or if so many lanes are
             // only waiting for it that the node phase itself would run half empty
-            if (urgent || __popc(parked) * 100 >= __popc(act) * a.postpone_pct || __popc(starving) * 4 >= __popc(act)) {
+            if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_starving * 4 >= n_act) {
                 bool done = false;
                 if (pend_y) done = trav_tri_phase<ANY_HIT, COUNT>(T, a.tris, pend_x, pend_y, &ctr);
                 pend_x = ng_x;
@@ -355,7 +358,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
 }
 
 template <int MAT>
-__global__ void __launch_bounds__(128) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
+__global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
     const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
     const uint32_t *queue = R->q_mat[MAT];
     uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
