@@ -503,12 +503,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.capacity = (uint32_t)cap;
 
     cudaError_t e = cudaSuccess;
-    uint32_t *mat32 = nullptr;
+    uint32_t *mat32 = nullptr, *sobol_table = nullptr;
     DevLight *d_lights = nullptr;
     float *d_cdf = nullptr, *d_func = nullptr;
 #define ALLOC(ptr, count) \
     if (e == cudaSuccess) e = dev_alloc(r, &(ptr), (count))
     ALLOC(mat32, (size_t)smp->n_dimensions * 52);
+    ALLOC(sobol_table, (size_t)smp->n_dimensions * 5 * 256);
     ALLOC(d_lights, (size_t)nl);
     ALLOC(d_cdf, (size_t)nl + 1);
     ALLOC(d_func, (size_t)std::max(nl, 1));
@@ -550,11 +551,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         return b200pt_fail(B200PT_ERR_OOM, "render_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
     H.sampler.mat32 = mat32;
+    H.sampler.table = getenv("B200PT_NO_SOBOL_TABLE") ? nullptr : sobol_table;
     H.lights = d_lights;
     H.light_cdf = d_cdf;
     H.light_func = d_func;
     cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaMemcpyAsync(mat32, smp->matrices32, (size_t)smp->n_dimensions * 52 * 4, cudaMemcpyHostToDevice, st));
+    launch_sobol_table(mat32, sobol_table, smp->n_dimensions, st);
     if (nl) CUDA_TRY(cudaMemcpyAsync(d_lights, dl.data(), nl * sizeof(DevLight), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_cdf, cdf.data(), (nl + 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_func, func.data(), std::max(nl, 1) * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -727,7 +730,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
-                    launch_shade(r->d_dev, m, b, wk + 1 + m, r->grid_shade, st);
+                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr, b, wk + 1 + m, r->grid_shade, st);
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
                 // shadow rays (any hit), tMax = 1 - ShadowEpsilon

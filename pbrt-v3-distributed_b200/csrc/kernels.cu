@@ -49,8 +49,11 @@ __device__ __forceinline__ bool warp_fetch(uint32_t *work, uint32_t n, uint32_t 
 }
 
 // per-vertex shading data of triangle `ti` (flags: bit 18 = normals, bit 19 = uvs)
+// VTX = false is the variant for scenes without any per-vertex data: the defaults fold to constants.
+template <bool VTX>
 __device__ __forceinline__ void load_shading(const DevScene &sc, uint32_t ti, uint32_t mflags, TriShading *t) {
     default_shading(t);
+    if (!VTX) return;
     if (mflags & 0x40000u) {
         const F4 *np = sc.tri_n + (size_t)ti * 3;
         t->has_n = 1;
@@ -278,6 +281,7 @@ struct DirectOut {
 // specular = false, for a DiffuseAreaLight on one triangle.  The two rays it
 // needs are not traced here: the shadow ray and the BSDF-sampled ("MIS") ray
 // are queued with the terms they gate (A and B).
+template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                 int lightNum, const float uLight[2], DirectOut *out) {
     const DevLight light = R->lights[lightNum];
@@ -287,7 +291,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     const uint32_t lflags = __float_as_uint(t1.w);
     const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
     TriShading lsh;
-    load_shading(R->scene, light.tri, lflags, &lsh);
+    load_shading<VTX>(R->scene, light.tri, lflags, &lsh);
     const RGB lemit = rgbp(light.lemit);
     const int flagsNS = BSDF_ALL & ~BSDF_SPECULAR;
     out->pend = 0;
@@ -357,7 +361,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     }
 }
 
-template <int MAT>
+template <int MAT, bool VTX>
 __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
     const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
     const uint32_t *queue = R->q_mat[MAT];
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
             if (triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h)) {
                 Isect is;
                 TriShading tsh;
-                load_shading(R->scene, ti, mflags, &tsh);
+                load_shading<VTX>(R->scene, ti, mflags, &tsh);
                 fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
                 // path.cpp:91-101: emitted light at the first vertex or after a specular bounce
                 if (bounces == 0 || specularBounce) {
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                             get2d(sp, st, uLight);
                             get2d(sp, st, uScattering);
                             DirectOut dout;
-                            estimate_direct(R, is, bsdf, uScattering, lightNum, uLight, &dout);
+                            estimate_direct<VTX>(R, is, bsdf, uScattering, lightNum, uLight, &dout);
                             pend = dout.pend;
                             if (pend) {
                                 R->beta_ld[slot] = f4(beta, pickPdf);
@@ -523,6 +527,21 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
     }
 }
 
+// Sobol' byte tables: table[dim][k][b] = XOR of SobolMatrices32[dim*52 + 8k + i] over the set bits i of b.
+__global__ void k_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_dims * 5 * 256) return;
+    const int b = id & 255, k = (id >> 8) % 5, dim = id / (5 * 256);
+    uint32_t v = 0;
+    for (int i = 0; i < 8; ++i)
+        if (((b >> i) & 1) && 8 * k + i < 52) v ^= mat32[dim * 52 + 8 * k + i];
+    table[id] = v;
+}
+void launch_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims, cudaStream_t s) {
+    const int n = n_dims * 5 * 256;
+    k_sobol_table<<<(n + 255) / 256, 256, 0, s>>>(mat32, table, n_dims);
+}
+
 // --------------------------------------------------- spatial light distribution
 // SpatialLightDistribution::ComputeDistribution for every voxel (the reference fills its hash table
 // lazily; a voxel's distribution is a pure function of the voxel).  One thread per (voxel, light)
@@ -540,7 +559,7 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
     const uint32_t lflags = __float_as_uint(t1.w);
     TriShading lsh;
-    load_shading(R->scene, light.tri, lflags, &lsh);
+    load_shading<true>(R->scene, light.tri, lflags, &lsh);
     R->sp_func[vox * R->n_lights + j] = spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0,
                                                               lsh, rgbp(light.lemit), light.two_sided != 0);
 }
@@ -783,21 +802,22 @@ void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, i
     }
 }
 
-void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work, int grid, cudaStream_t s) {
+void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
+                  cudaStream_t s) {
+#define B200PT_SHADE(M)                                               \
+    case M:                                                           \
+        if (vertex_data)                                              \
+            k_shade<M, true><<<grid, 128, 0, s>>>(dev, bounce, work); \
+        else                                                          \
+            k_shade<M, false><<<grid, 128, 0, s>>>(dev, bounce, work); \
+        break;
     switch (material) {
-    case B200PT_MAT_MATTE:
-        k_shade<B200PT_MAT_MATTE><<<grid, 128, 0, s>>>(dev, bounce, work);
-        break;
-    case B200PT_MAT_PLASTIC:
-        k_shade<B200PT_MAT_PLASTIC><<<grid, 128, 0, s>>>(dev, bounce, work);
-        break;
-    case B200PT_MAT_METAL:
-        k_shade<B200PT_MAT_METAL><<<grid, 128, 0, s>>>(dev, bounce, work);
-        break;
-    case B200PT_MAT_GLASS:
-        k_shade<B200PT_MAT_GLASS><<<grid, 128, 0, s>>>(dev, bounce, work);
-        break;
+        B200PT_SHADE(B200PT_MAT_MATTE)
+        B200PT_SHADE(B200PT_MAT_PLASTIC)
+        B200PT_SHADE(B200PT_MAT_METAL)
+        B200PT_SHADE(B200PT_MAT_GLASS)
     }
+#undef B200PT_SHADE
 }
 
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {

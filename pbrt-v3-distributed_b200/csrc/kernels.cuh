@@ -124,13 +124,15 @@ struct TraceArgs {
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
                    cudaStream_t s);
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s);
-void launch_shade(const RenderDev *dev, int material, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
+                  cudaStream_t s);
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
 #define SORT_BUCKETS (1u << 18)  // 3 octant bits + 15 Morton bits
 // Counting sort of a queue of slots by the coherence key of the rays they refer to; `out` receives
 // the permuted queue (order inside a bucket is arbitrary -- it never affects a path's arithmetic).
 void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
                        const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s);
+void launch_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims, cudaStream_t s);
 // Fills the per-voxel light distributions (all voxels, once per render object).
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s);
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);

@@ -146,6 +146,7 @@ struct SamplerParams {          // samplers/sobol.h:45-69
     int resolution, log2res;
     int n_dims;
     const uint32_t *mat32;      // [n_dims][52]
+    const uint32_t *table;      // device only: [n_dims][5][256] XOR of the columns selected by one index byte
     uint64_t vdc[52];
     uint64_t vdc_inv[52];
 };
@@ -168,6 +169,19 @@ B200_HD uint64_t sobol_interval_to_index(const SamplerParams &sp, uint64_t frame
 B200_HD float sobol_sample(const SamplerParams &sp, uint64_t a, int dim, int px, int py) {
     uint32_t v = 0;
     const uint32_t *m = sp.mat32 + dim * 52;
+#ifdef __CUDA_ARCH__
+    // the XOR over the index bits is linear: combine five byte-indexed partial results (40 index bits)
+    // instead of walking the bits one by one; any higher bits fall through to the bit loop below
+    if (sp.table) {
+        const uint32_t *t = sp.table + (size_t)dim * (5 * 256);
+        const uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+        v = __ldg(t + (lo & 0xffu)) ^ __ldg(t + 256 + ((lo >> 8) & 0xffu)) ^ __ldg(t + 512 + ((lo >> 16) & 0xffu)) ^
+            __ldg(t + 768 + (lo >> 24));
+        if (hi) v ^= __ldg(t + 1024 + (hi & 0xffu));
+        a >>= 40;
+        m += 40;
+    }
+#endif
     for (; a != 0; a >>= 1, ++m)
         if (a & 1) v ^= *m;
     float s = pt_min((float)v * 0x1p-32f, PT_ONE_MINUS_EPS);
