@@ -212,7 +212,8 @@ def write_ply(path, tris, normals=None, uvs=None):
 
 
 def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
-               eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6):
+               eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6,
+               crop_window=None, film_scale=1.0, max_sample_luminance=None):
     """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
     os.makedirs(dirname, exist_ok=True)
     lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
@@ -220,7 +221,10 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
              (' "float lensradius" [%.9g] "float focaldistance" [%.9g]' % (lens_radius, focal_distance)
               if lens_radius > 0 else ""),
              'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "%s.pfm"'
-             % (xres, yres, name),
+             % (xres, yres, name) +
+             (' "float cropwindow" [%.9g %.9g %.9g %.9g]' % tuple(crop_window) if crop_window else "") +
+             (' "float scale" [%.9g]' % film_scale if film_scale != 1.0 else "") +
+             (' "float maxsampleluminance" [%.9g]' % max_sample_luminance if max_sample_luminance else ""),
              'Sampler "sobol" "integer pixelsamples" [%d]' % spp]
     integ = 'Integrator "path" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (max_depth, strategy)
     if pixel_bounds is not None:
@@ -310,7 +314,7 @@ class RenderSetup:
 
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
-                 lens_radius=0.0, focal_distance=1e6):
+                 lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.tables = tables or SobolTables()
@@ -320,15 +324,23 @@ class RenderSetup:
             self.camera.focal_distance = focal_distance
         self.film = abi.FilmDesc()
         self.film.full_resolution[:] = [xres, yres]
-        self.film.cropped_bounds[:] = [0, 0, xres, yres]
+        cb = [0, 0, xres, yres]
+        if crop_window:  # Film ctor, film.cpp:54-58: ceil(res * crop) in float
+            f32 = np.float32
+            cw = [f32(c) for c in crop_window]  # x0 x1 y0 y1
+            cb = [int(np.ceil(f32(xres) * cw[0])), int(np.ceil(f32(yres) * cw[2])),
+                  int(np.ceil(f32(xres) * cw[1])), int(np.ceil(f32(yres) * cw[3]))]
+        self.crop = cb
+        self.film.cropped_bounds[:] = cb
         self.film.filter_radius[:] = [0.5, 0.5]
-        self.film.scale = 1.0
-        self.film.max_sample_luminance = float("inf")
+        self.film.scale = film_scale
+        self.film.max_sample_luminance = max_sample_luminance if max_sample_luminance else float("inf")
         self.sampler = abi.SamplerDesc()
         self.sampler.samples_per_pixel = round_up_pow2(spp)
-        self.sampler.sample_bounds[:] = [0, 0, xres, yres]
+        # Film::GetSampleBounds with the box filter of radius 0.5 == the cropped pixel bounds (film.cpp:80-86)
+        self.sampler.sample_bounds[:] = cb
         self.sampler.n_dimensions = self.tables.n_dims
-        res = round_up_pow2(max(xres, yres))
+        res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))
         m = res.bit_length() - 1
         self._vdc = np.ascontiguousarray(self.tables.vdc[max(m - 1, 0)])
         self._vdc_inv = np.ascontiguousarray(self.tables.vdc_inv[max(m - 1, 0)])
@@ -339,8 +351,8 @@ class RenderSetup:
         self.integrator.max_depth = max_depth
         self.integrator.rr_threshold = 1.0
         self.integrator.light_strategy = strategy
-        self.integrator.pixel_bounds[:] = pixel_bounds or [0, 0, xres, yres]
+        self.integrator.pixel_bounds[:] = pixel_bounds or cb
 
     @property
     def n_tiles(self):
-        return ((self.xres + 15) // 16) * ((self.yres + 15) // 16)
+        return ((self.crop[2] - self.crop[0] + 15) // 16) * ((self.crop[3] - self.crop[1] + 15) // 16)

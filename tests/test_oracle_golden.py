@@ -18,10 +18,13 @@ RENDERS = {
     "spatial16": (3000, ("matte", "plastic"), 32, 32, 4, 8, "spatial", 16),
     # per-vertex shading normals (matte + metal meshes) and uvs (matte + plastic meshes), flipped plastic
     "normals_uv": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 6, "spatial", None),
+    # film crop window (sampler built from the cropped sample bounds), film scale, maxsampleluminance
+    "crop": (3000, ("matte", "glass", "metal", "plastic"), 70, 50, 4, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
-         "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,)))}
+         "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,))),
+         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0))}
 
 
 def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
@@ -118,7 +121,8 @@ def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % name))
     assert ref.shape == rgb.shape
     assert np.array_equal(bits(rgb), bits(ref)), "oracle render is not bit-identical to the reference PFM"
-    assert stats["camera_rays"] == w * h * spp
+    cb = setup.crop
+    assert stats["camera_rays"] == (cb[2] - cb[0]) * (cb[3] - cb[1]) * spp
     o.close()
 
 
