@@ -27,6 +27,8 @@ using namespace b200pt;
 struct b200pt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_aux = nullptr;   // shadow / MIS rays of bounce b overlap the path rays of bounce b+1
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 0;
 };
 
@@ -63,6 +65,7 @@ struct b200pt_render {
     size_t tile_list_capacity = 0;
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
+    bool overlap = true;  // run shadow/MIS rays of bounce b concurrently with the path rays of bounce b+1
     int sort_from_bounce = -1;  // coherence-sort the path / shadow queues from this bounce on (<0: never; measured: no gain on the soups)
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -91,6 +94,9 @@ int b200pt_ctx_create(int device, b200pt_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return B200PT_OK;
 }
@@ -99,6 +105,9 @@ void b200pt_ctx_destroy(b200pt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -574,6 +583,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
     if (getenv("B200PT_SORT_FROM")) r->sort_from_bounce = atoi(getenv("B200PT_SORT_FROM"));
+    if (getenv("B200PT_OVERLAP")) r->overlap = atoi(getenv("B200PT_OVERLAP")) != 0;
     *out = r;
     return B200PT_OK;
 }
@@ -695,7 +705,13 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             LaunchTimer lt(r, st, 2);
             launch_raygen(r->d_dev, (uint32_t)first, nb, n_slots, st);
         }
-        for (int b = 0; b <= maxDepth; ++b) {
+        // Launch order per bounce b (path.cpp:81-188):
+        //   closest(b) -> shade(b) -> { any(b), MIS-closest(b) } || closest(b+1) -> resolve(b) -> shade(b+1) ...
+        // The shadow / MIS rays of bounce b and the path rays of bounce b+1 are independent, so they run on
+        // two streams: as the persistent CTAs of one launch drain, the other launch fills the freed SMs.
+        const bool overlap = r->overlap && r->sort_from_bounce < 0;
+        cudaStream_t st2 = overlap ? ctx->stream_aux : st;
+        auto trace_path = [&](int b) {
             uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
             uint32_t *wk = H.work + (size_t)b * 16;
             TraceArgs a;
@@ -723,51 +739,71 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.hit_out = H.hit;
             for (int m = 0; m < 4; ++m) a.q_mat[m] = H.q_mat[m];
             a.qcount_mat = qc + Q_MAT0;
-            {
-                LaunchTimer lt(r, st, 0);
-                launch_trace(a, false, true, r->instrumented, r->grid_trace, st);
+            LaunchTimer lt(r, st, 0);
+            launch_trace(a, false, true, r->instrumented, r->grid_trace, st);
+        };
+        auto trace_direct = [&](int b) {
+            uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
+            uint32_t *wk = H.work + (size_t)b * 16;
+            TraceArgs a;
+            memset(&a, 0, sizeof(a));
+            a.nodes = H.scene.nodes;
+            a.tris = H.scene.tris;
+            a.materials = H.scene.materials;
+            a.stats = H.stats;
+            a.stride = 1;
+            a.refill_lanes = refill_lanes();
+            a.postpone_pct = postpone_pct();
+            a.magic = 0x4B000000u;
+            // shadow rays (any hit), tMax = 1 - ShadowEpsilon
+            const bool sorted_sh = r->sort_from_bounce >= 0;
+            if (sorted_sh) {
+                LaunchTimer lt(r, st2, 2);
+                launch_sort_queue(r->d_dev, H, H.q_shadow, qc + Q_SHADOW, H.sh_o, H.sh_d, r->grid_shade, st2);
             }
+            a.ray_o = H.sh_o;
+            a.ray_d = H.sh_d;
+            a.queue = sorted_sh ? H.q_sorted : H.q_shadow;
+            a.count = qc + Q_SHADOW;
+            a.work = wk + 5;
+            a.fixed_t_max = PT_SHADOW_TMAX;
+            a.occ_out = H.occluded;
+            {
+                LaunchTimer lt(r, st2, 1);
+                launch_trace(a, true, false, r->instrumented, r->grid_trace, st2);
+            }
+            // BSDF-sampled MIS rays (closest hit)
+            a.ray_o = H.mi_o;
+            a.ray_d = H.mi_d;
+            a.queue = H.q_mis;
+            a.count = qc + Q_MIS;
+            a.work = wk + 6;
+            a.fixed_t_max = INFINITY;
+            a.hit_out = H.mis_hit;
+            a.occ_out = nullptr;
+            LaunchTimer lt(r, st2, 0);
+            launch_trace(a, false, false, r->instrumented, r->grid_trace, st2);
+        };
+        trace_path(0);
+        for (int b = 0; b <= maxDepth; ++b) {
+            uint32_t *wk = H.work + (size_t)b * 16;
             for (int m = 0; m < 4; ++m)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
-                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr, b, wk + 1 + m, r->grid_shade, st);
+                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr, b, wk + 1 + m,
+                                 r->grid_shade, st);
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
-                // shadow rays (any hit), tMax = 1 - ShadowEpsilon
-                const bool sorted_sh = r->sort_from_bounce >= 0;
-                if (sorted_sh) {
-                    LaunchTimer lt(r, st, 2);
-                    launch_sort_queue(r->d_dev, H, H.q_shadow, qc + Q_SHADOW, H.sh_o, H.sh_d, r->grid_shade, st);
+                if (overlap) {
+                    CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+                    CUDA_TRY(cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
                 }
-                a.ray_o = H.sh_o;
-                a.ray_d = H.sh_d;
-                a.queue = sorted_sh ? H.q_sorted : H.q_shadow;
-                a.count = qc + Q_SHADOW;
-                a.work = wk + 5;
-                a.fixed_t_max = PT_SHADOW_TMAX;
-                a.hit_out = nullptr;
-                a.occ_out = H.occluded;
-                {
-                    LaunchTimer lt(r, st, 1);
-                    launch_trace(a, true, false, r->instrumented, r->grid_trace, st);
-                }
-                // BSDF-sampled MIS rays (closest hit)
-                a.ray_o = H.mi_o;
-                a.ray_d = H.mi_d;
-                a.queue = H.q_mis;
-                a.count = qc + Q_MIS;
-                a.work = wk + 6;
-                a.fixed_t_max = INFINITY;
-                a.hit_out = H.mis_hit;
-                a.occ_out = nullptr;
-                {
-                    LaunchTimer lt(r, st, 0);
-                    launch_trace(a, false, false, r->instrumented, r->grid_trace, st);
-                }
-                {
-                    LaunchTimer lt(r, st, 2);
-                    launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
-                }
+                trace_direct(b);
+                if (overlap) CUDA_TRY(cudaEventRecord(ctx->ev_join, st2));
+                trace_path(b + 1);
+                if (overlap) CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                LaunchTimer lt(r, st, 2);
+                launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
             }
         }
         {
