@@ -48,10 +48,12 @@ typedef enum b200pt_status {
 
 /* ---- materials: materials/{matte,plastic,metal,glass}.cpp ---------------- */
 typedef enum b200pt_material_type {
-    B200PT_MAT_MATTE = 0,   /* LambertianReflection(Kd)        matte.cpp:45-62   (sigma must be 0) */
+    B200PT_MAT_MATTE = 0,   /* LambertianReflection(Kd) or, variant 1, OrenNayar(Kd, sigma)   matte.cpp:45-62 */
     B200PT_MAT_PLASTIC = 1, /* Lambertian(Kd)+MicrofacetReflection(Ks,TR(a,a),FrDielectric(1.5,1)) plastic.cpp:45-70 */
     B200PT_MAT_METAL = 2,   /* MicrofacetReflection(1,TR(ax,ay),FrConductor(1,eta,k))   metal.cpp:59-80 */
-    B200PT_MAT_GLASS = 3,   /* FresnelSpecular(R,T,1,index) -- smooth glass, glass.cpp:62-64 */
+    B200PT_MAT_GLASS = 3,   /* FresnelSpecular(R,T,1,index) (smooth, glass.cpp:62-64) or, variant 1, rough glass:
+                               MicrofacetReflection(R,TR,FrDielectric(1,index)) + MicrofacetTransmission(T,TR,1,index)
+                               glass.cpp:65-90 */
     B200PT_MAT_NONE = 4     /* null material: GetMaterial()==nullptr is NOT supported; reserved */
 } b200pt_material_type;
 
@@ -66,9 +68,10 @@ typedef struct b200pt_material {
     float kt[3];         /* glass Kt (T)                              */
     float eta[3];        /* metal eta (RGB)                           */
     float k[3];          /* metal k   (RGB)                           */
-    float alpha_x;       /* TR alpha (plastic: ax==ay)                */
-    float alpha_y;
+    float alpha_x;       /* TR alpha (plastic: ax==ay); matte variant 1: OrenNayar A (reflection.h:416-419) */
+    float alpha_y;       /*                               matte variant 1: OrenNayar B                      */
     float index;         /* glass index of refraction (BSDF::eta)     */
+    int32_t variant;     /* 0 = default lobe set, 1 = see the material types above */
 } b200pt_material;
 
 /* ---- lights: one DiffuseAreaLight per emissive triangle (api.cpp:1357-1364,
@@ -286,6 +289,8 @@ int b200pt_host_perspective_camera(const float eye[3], const float look[3], cons
                                    float fov_degrees, int32_t xres, int32_t yres,
                                    b200pt_camera_desc *out);
 float b200pt_host_roughness_to_alpha(float roughness);
+/* OrenNayar's A and B from sigma in degrees (reflection.h:414-420), clamped like matte.cpp:54 */
+void b200pt_host_oren_nayar(float sigma_degrees, float *A, float *B);
 
 #ifdef __cplusplus
 }

@@ -741,7 +741,7 @@ inline V3 OffsetRayOrigin(const V3 &p, const V3 &pError, const V3 &n, const V3 &
 
 // ------------------------------------------------------------------- BSDFs
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
-enum BxKind { BX_LAMBERT, BX_MICROFACET, BX_FRESNEL_SPECULAR };
+enum BxKind { BX_LAMBERT, BX_MICROFACET, BX_FRESNEL_SPECULAR, BX_OREN_NAYAR, BX_MICROFACET_TRANS };
 enum FrKind { FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDF {
@@ -753,8 +753,10 @@ struct BxDF {
     FrKind fr;
     float frEtaI, frEtaT;  // dielectric
     S3 cEtaI, cEtaT, cK;   // conductor
-    // fresnel specular
+    // fresnel specular, microfacet transmission
     float etaA, etaB;
+    // oren-nayar
+    float onA, onB;
     bool MatchesFlags(int t) const { return (type & t) == type; }
 };
 
@@ -928,6 +930,41 @@ S3 Bx_f(const BxDF &b, const V3 &wo, const V3 &wi) {
     }
     case BX_FRESNEL_SPECULAR:
         return S3(0.f);  // reflection.h:363-365
+    case BX_OREN_NAYAR: {  // reflection.cpp:197-219
+        float sinThetaI = SinTheta(wi);
+        float sinThetaO = SinTheta(wo);
+        float maxCos = 0;
+        if (sinThetaI > 1e-4 && sinThetaO > 1e-4) {
+            float sinPhiI = SinPhi(wi), cosPhiI = CosPhi(wi);
+            float sinPhiO = SinPhi(wo), cosPhiO = CosPhi(wo);
+            float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+            maxCos = std::max((float)0, dCos);
+        }
+        float sinAlpha, tanBeta;
+        if (AbsCosTheta(wi) > AbsCosTheta(wo)) {
+            sinAlpha = sinThetaO;
+            tanBeta = sinThetaI / AbsCosTheta(wi);
+        } else {
+            sinAlpha = sinThetaI;
+            tanBeta = sinThetaO / AbsCosTheta(wo);
+        }
+        return b.R * InvPi * (b.onA + b.onB * maxCos * sinAlpha * tanBeta);
+    }
+    case BX_MICROFACET_TRANS: {  // reflection.cpp:244-266 (TransportMode::Radiance)
+        if (SameHemisphere(wo, wi)) return S3(0.f);
+        float cosThetaO = CosTheta(wo);
+        float cosThetaI = CosTheta(wi);
+        if (cosThetaI == 0 || cosThetaO == 0) return S3(0.f);
+        float eta = CosTheta(wo) > 0 ? (b.etaB / b.etaA) : (b.etaA / b.etaB);
+        V3 wh = Normalize(wo + wi * eta);
+        if (wh.z < 0) wh = -wh;
+        S3 F(FrDielectric(Dot(wo, wh), b.etaA, b.etaB));
+        float sqrtDenom = Dot(wo, wh) + eta * Dot(wi, wh);
+        float factor = 1 / eta;
+        return (S3(1.f) - F) * b.T *
+               std::abs(TR_D(b, wh) * TR_G(b, wo, wi) * eta * eta * AbsDot(wi, wh) * AbsDot(wo, wh) * factor *
+                        factor / (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
+    }
     }
     return S3(0.f);
 }
@@ -943,6 +980,16 @@ float Bx_Pdf(const BxDF &b, const V3 &wo, const V3 &wi) {
     }
     case BX_FRESNEL_SPECULAR:
         return 0;  // reflection.h:368
+    case BX_OREN_NAYAR:
+        return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * InvPi : 0;  // BxDF::Pdf, reflection.cpp:387-389
+    case BX_MICROFACET_TRANS: {                                       // reflection.cpp:436-448
+        if (SameHemisphere(wo, wi)) return 0;
+        float eta = CosTheta(wo) > 0 ? (b.etaB / b.etaA) : (b.etaA / b.etaB);
+        V3 wh = Normalize(wo + wi * eta);
+        float sqrtDenom = Dot(wo, wh) + eta * Dot(wi, wh);
+        float dwh_dwi = std::abs((eta * eta * Dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+        return TR_Pdf(b, wo, wh) * dwh_dwi;
+    }
     }
     return 0;
 }
@@ -950,7 +997,16 @@ float Bx_Pdf(const BxDF &b, const V3 &wo, const V3 &wi) {
 // reference leaves it untouched on some early returns).
 S3 Bx_Sample_f(const BxDF &b, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
     switch (b.kind) {
-    case BX_LAMBERT: {  // reflection.cpp:378-385
+    case BX_MICROFACET_TRANS: {  // reflection.cpp:425-434
+        if (wo.z == 0) return S3(0.);
+        V3 wh = TR_Sample_wh(b, wo, u);
+        float eta = CosTheta(wo) > 0 ? (b.etaA / b.etaB) : (b.etaB / b.etaA);
+        if (!Refract(wo, wh, eta, wi)) return S3(0.f);
+        *pdf = Bx_Pdf(b, wo, *wi);
+        return Bx_f(b, wo, *wi);
+    }
+    case BX_OREN_NAYAR:  // BxDF::Sample_f, reflection.cpp:378-385
+    case BX_LAMBERT: {   // reflection.cpp:378-385
         *wi = CosineSampleHemisphere(u);
         if (wo.z < 0) wi->z *= -1;
         *pdf = Bx_Pdf(b, wo, *wi);
@@ -1096,7 +1152,15 @@ void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
     };
     switch (m.type) {
     case B200PT_MAT_MATTE:  // matte.cpp:45-62
-        if (!SP(m.kd).IsBlack()) lambert(m.kd);
+        if (!SP(m.kd).IsBlack()) {
+            lambert(m.kd);
+            if (m.variant == 1) {  // sigma != 0: OrenNayar
+                BxDF &b = bsdf->bxdfs[bsdf->nBxDFs - 1];
+                b.kind = BX_OREN_NAYAR;
+                b.onA = m.alpha_x;
+                b.onB = m.alpha_y;
+            }
+        }
         break;
     case B200PT_MAT_PLASTIC: {  // plastic.cpp:45-70
         if (!SP(m.kd).IsBlack()) lambert(m.kd);
@@ -1132,6 +1196,32 @@ void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
         bsdf->eta = m.index;
         S3 R = SP(m.ks), T = SP(m.kt);
         if (R.IsBlack() && T.IsBlack()) break;
+        if (m.variant == 1) {  // rough glass, glass.cpp:65-90
+            if (!R.IsBlack()) {
+                BxDF b;
+                b.kind = BX_MICROFACET;
+                b.type = BSDF_REFLECTION | BSDF_GLOSSY;
+                b.R = R;
+                b.alphax = m.alpha_x;
+                b.alphay = m.alpha_y;
+                b.fr = FR_DIELECTRIC;
+                b.frEtaI = 1.f;
+                b.frEtaT = m.index;
+                bsdf->bxdfs[bsdf->nBxDFs++] = b;
+            }
+            if (!T.IsBlack()) {
+                BxDF b;
+                b.kind = BX_MICROFACET_TRANS;
+                b.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
+                b.T = T;
+                b.alphax = m.alpha_x;
+                b.alphay = m.alpha_y;
+                b.etaA = 1.f;
+                b.etaB = m.index;
+                bsdf->bxdfs[bsdf->nBxDFs++] = b;
+            }
+            break;
+        }
         BxDF b;
         b.kind = BX_FRESNEL_SPECULAR;
         b.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;

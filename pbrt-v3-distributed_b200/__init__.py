@@ -61,6 +61,7 @@ _SIGNATURES = {
                                                  C.POINTER(C.c_float), C.c_float, _i32, _i32,
                                                  C.POINTER(abi.CameraDesc)]),
     "b200pt_host_roughness_to_alpha": (C.c_float, [C.c_float]),
+    "b200pt_host_oren_nayar": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 
@@ -99,6 +100,12 @@ def host_perspective_camera(eye, look, up, fov, xres, yres):
 
 def host_roughness_to_alpha(r):
     return float(lib.b200pt_host_roughness_to_alpha(r))
+
+
+def host_oren_nayar(sigma_degrees):
+    a, b = C.c_float(), C.c_float()
+    lib.b200pt_host_oren_nayar(sigma_degrees, C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 class Context:

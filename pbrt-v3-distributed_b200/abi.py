@@ -14,7 +14,7 @@ LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3),
                 ("kt", C.c_float * 3), ("eta", C.c_float * 3), ("k", C.c_float * 3),
-                ("alpha_x", C.c_float), ("alpha_y", C.c_float), ("index", C.c_float)]
+                ("alpha_x", C.c_float), ("alpha_y", C.c_float), ("index", C.c_float), ("variant", C.c_int32)]
 
 
 class AreaLight(C.Structure):

@@ -218,3 +218,13 @@ extern "C" float b200pt_host_roughness_to_alpha(float roughness) {
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x +
            0.000640711f * x * x * x * x;
 }
+
+// OrenNayar::OrenNayar, reflection.h:414-420, after matte.cpp:54's Clamp(sigma, 0, 90)
+extern "C" void b200pt_host_oren_nayar(float sigma, float *A, float *B) {
+    sigma = sigma < 0 ? 0.f : (sigma > 90 ? 90.f : sigma);
+    const float PiF = 3.14159265358979323846;
+    sigma = (PiF / 180) * sigma;  // Radians
+    float sigma2 = sigma * sigma;
+    *A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+    *B = 0.45f * sigma2 / (sigma2 + 0.09f);
+}

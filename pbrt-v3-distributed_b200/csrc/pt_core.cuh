@@ -663,8 +663,9 @@ B200_HD V3 cosine_sample_hemisphere(const float u[2]) {
     return mk(d[0], d[1], z);
 }
 
-// One BxDF lobe.  kind: 0 Lambertian, 1 MicrofacetReflection (TR), 2 FresnelSpecular
-enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2 };
+// One BxDF lobe.  kind: 0 Lambertian, 1 MicrofacetReflection (TR), 2 FresnelSpecular, 3 OrenNayar,
+// 4 MicrofacetTransmission (TR)
+enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR = 3, BX_MICROFACET_TRANS = 4 };
 struct Lobe {
     int kind, type;
     RGB R, T;
@@ -672,7 +673,8 @@ struct Lobe {
     int conductor;      // Fresnel of the microfacet lobe: 0 dielectric(etaI, etaT), 1 conductor(1, cEta, cK)
     float frEtaI, frEtaT;
     RGB cEta, cK;
-    float etaA, etaB;   // FresnelSpecular
+    float etaA, etaB;   // FresnelSpecular, MicrofacetTransmission
+    float onA, onB;     // OrenNayar
 };
 B200_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
 B200_HD RGB lobe_fresnel(const Lobe &l, float cosThetaI) {
@@ -690,10 +692,54 @@ B200_HD RGB lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         RGB F = lobe_fresnel(l, dot(wi, wh));
         return l.R * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
+    if (l.kind == BX_OREN_NAYAR) {  // reflection.cpp:197-219
+        float sinThetaI = sin_theta(wi);
+        float sinThetaO = sin_theta(wo);
+        float maxCos = 0;
+        if ((double)sinThetaI > 1e-4 && (double)sinThetaO > 1e-4) {
+            float sinPhiI = sin_phi(wi), cosPhiI = cos_phi(wi);
+            float sinPhiO = sin_phi(wo), cosPhiO = cos_phi(wo);
+            float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+            maxCos = pt_max(0.f, dCos);
+        }
+        float sinAlpha, tanBeta;
+        if (abs_cos_theta(wi) > abs_cos_theta(wo)) {
+            sinAlpha = sinThetaO;
+            tanBeta = sinThetaI / abs_cos_theta(wi);
+        } else {
+            sinAlpha = sinThetaI;
+            tanBeta = sinThetaO / abs_cos_theta(wo);
+        }
+        return l.R * PT_INV_PI * (l.onA + l.onB * maxCos * sinAlpha * tanBeta);
+    }
+    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:244-266 (TransportMode::Radiance)
+        if (same_hemisphere(wo, wi)) return rgb1(0.f);
+        float cosThetaO = cos_theta(wo);
+        float cosThetaI = cos_theta(wi);
+        if (cosThetaI == 0 || cosThetaO == 0) return rgb1(0.f);
+        float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3 wh = normalize(wo + wi * eta);
+        if (wh.z < 0) wh = -wh;
+        RGB F = rgb1(fr_dielectric(dot(wo, wh), l.etaA, l.etaB));
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float factor = 1 / eta;
+        return (rgb1(1.f) - F) * l.T *
+               pt_abs(tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor *
+                      factor / (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
+    }
     return rgb1(0.f);  // FresnelSpecular::f, reflection.h:363-365
 }
 B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
-    if (l.kind == BX_LAMBERT) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PT_INV_PI : 0.f;  // reflection.cpp:387-389
+    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR)
+        return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PT_INV_PI : 0.f;  // reflection.cpp:387-389
+    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:436-448
+        if (same_hemisphere(wo, wi)) return 0.f;
+        float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3 wh = normalize(wo + wi * eta);
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float dwh_dwi = pt_abs((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+        return tr_pdf(l.dist, wo, wh) * dwh_dwi;
+    }
     if (l.kind == BX_MICROFACET) {                                                                   // reflection.cpp:419-423
         if (!same_hemisphere(wo, wi)) return 0.f;
         V3 wh = normalize(wo + wi);
@@ -703,7 +749,15 @@ B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
 }
 // BxDF::Sample_f; *pdf is written only where the reference writes it.
 B200_HD RGB lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
-    if (l.kind == BX_LAMBERT) {  // reflection.cpp:378-385
+    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:425-434
+        if (wo.z == 0) return rgb1(0.f);
+        V3 wh = tr_sample_wh(l.dist, wo, u);
+        float eta = cos_theta(wo) > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
+        if (!refract(wo, wh, eta, wi)) return rgb1(0.f);
+        *pdf = lobe_pdf(l, wo, *wi);
+        return lobe_f(l, wo, *wi);
+    }
+    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR) {  // BxDF::Sample_f, reflection.cpp:378-385
         *wi = cosine_sample_hemisphere(u);
         if (wo.z < 0) wi->z *= -1;
         *pdf = lobe_pdf(l, wo, *wi);
@@ -845,7 +899,15 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
     b->n = 0;
     const int type = MATERIAL >= 0 ? MATERIAL : m.type;
     if (type == B200PT_MAT_MATTE) {  // matte.cpp:45-62
-        if (!is_black(rgbp(m.kd))) add_lambert(b, m.kd);
+        if (!is_black(rgbp(m.kd))) {
+            add_lambert(b, m.kd);
+            if (m.variant == 1) {  // sigma != 0: OrenNayar(r, sig)
+                Lobe &l = b->lobes[b->n - 1];
+                l.kind = BX_OREN_NAYAR;
+                l.onA = m.alpha_x;
+                l.onB = m.alpha_y;
+            }
+        }
     } else if (type == B200PT_MAT_PLASTIC) {  // plastic.cpp:45-70
         if (!is_black(rgbp(m.kd))) add_lambert(b, m.kd);
         if (!is_black(rgbp(m.ks))) {
@@ -872,7 +934,30 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
     } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
         b->eta = m.index;
         RGB R = rgbp(m.ks), T = rgbp(m.kt);
-        if (!(is_black(R) && is_black(T))) {
+        if (is_black(R) && is_black(T)) {
+        } else if (m.variant == 1) {  // rough glass, glass.cpp:65-90
+            if (!is_black(R)) {
+                Lobe &l = b->lobes[b->n++];
+                l.kind = BX_MICROFACET;
+                l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+                l.R = R;
+                l.dist.ax = m.alpha_x;
+                l.dist.ay = m.alpha_y;
+                l.conductor = 0;
+                l.frEtaI = 1.f;
+                l.frEtaT = m.index;
+            }
+            if (!is_black(T)) {
+                Lobe &l = b->lobes[b->n++];
+                l.kind = BX_MICROFACET_TRANS;
+                l.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
+                l.T = T;
+                l.dist.ax = m.alpha_x;
+                l.dist.ay = m.alpha_y;
+                l.etaA = 1.f;
+                l.etaB = m.index;
+            }
+        } else {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_FRESNEL_SPECULAR;
             l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;

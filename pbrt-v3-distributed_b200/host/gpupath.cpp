@@ -119,9 +119,12 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
     if (auto mm = dynamic_cast<const MatteMaterial *>(m)) {
         if (mm->bumpMap) return *why = "bump maps", false;
         if (!ConstantValue(mm->Kd, &sv) || !ConstantValue(mm->sigma, &fv)) return *why = "non-constant textures", false;
-        if (Clamp(fv, 0, 90) != 0) return *why = "matte sigma != 0 (OrenNayar)", false;
         out->type = B200PT_MAT_MATTE;
         ToRGB(sv.Clamp(), out->kd);
+        if (Clamp(fv, 0, 90) != 0) {  // OrenNayar(r, sig), matte.cpp:59
+            out->variant = 1;
+            b200pt_host_oren_nayar(fv, &out->alpha_x, &out->alpha_y);
+        }
         return true;
     }
     if (auto pm = dynamic_cast<const PlasticMaterial *>(m)) {
@@ -163,11 +166,19 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
         if (!ConstantValue(gm->Kr, &R) || !ConstantValue(gm->Kt, &T) || !ConstantValue(gm->uRoughness, &ur) ||
             !ConstantValue(gm->vRoughness, &vr) || !ConstantValue(gm->index, &index))
             return *why = "non-constant textures", false;
-        if (ur != 0 || vr != 0) return *why = "rough glass (MicrofacetTransmission)", false;
         out->type = B200PT_MAT_GLASS;
         ToRGB(R.Clamp(), out->ks);
         ToRGB(T.Clamp(), out->kt);
         out->index = index;
+        if (ur != 0 || vr != 0) {  // glass.cpp:65-90
+            out->variant = 1;
+            if (gm->remapRoughness) {
+                ur = TrowbridgeReitzDistribution::RoughnessToAlpha(ur);
+                vr = TrowbridgeReitzDistribution::RoughnessToAlpha(vr);
+            }
+            out->alpha_x = ur;
+            out->alpha_y = vr;
+        }
         return true;
     }
     *why = "a material other than matte / plastic / metal / glass";

@@ -67,13 +67,26 @@ def default_materials(which):
     """Material table: matte Kd .5 / glass / metal(copper, roughness .01) /
     plastic(Kd=Ks=.25, roughness .1) with the factories' defaults
     (glass.cpp:94-110, metal.cpp:115-134, plastic.cpp:72-83)."""
-    from . import host_roughness_to_alpha  # C-ABI host helper (same libm as the reference)
+    from . import host_oren_nayar, host_roughness_to_alpha  # C-ABI host helpers (same libm as the reference)
     mats = []
     for w in which:
         m = abi.Material()
         if w == "matte":
             m.type = abi.MAT_MATTE
             m.kd[:] = [0.5, 0.5, 0.5]
+        elif w == "matte_rough":  # sigma = 30 degrees -> OrenNayar
+            m.type = abi.MAT_MATTE
+            m.kd[:] = [0.5, 0.5, 0.5]
+            m.alpha_x, m.alpha_y = host_oren_nayar(30.0)
+            m.variant = 1
+        elif w == "glass_rough":  # uroughness .2, vroughness .1, remapped -> microfacet reflection + transmission
+            m.type = abi.MAT_GLASS
+            m.ks[:] = [1, 1, 1]
+            m.kt[:] = [1, 1, 1]
+            m.index = 1.5
+            m.alpha_x = host_roughness_to_alpha(0.2)
+            m.alpha_y = host_roughness_to_alpha(0.1)
+            m.variant = 1
         elif w == "black":
             m.type = abi.MAT_MATTE
             m.kd[:] = [0, 0, 0]
@@ -106,6 +119,8 @@ PBRT_MATERIAL = {
     "matte": 'Material "matte" "rgb Kd" [0.5 0.5 0.5]',
     "black": 'Material "matte" "rgb Kd" [0 0 0]',
     "glass": 'Material "glass"',
+    "matte_rough": 'Material "matte" "rgb Kd" [0.5 0.5 0.5] "float sigma" [30]',
+    "glass_rough": 'Material "glass" "float uroughness" [0.2] "float vroughness" [0.1]',
     "metal": 'Material "metal"',
     "plastic": 'Material "plastic"',
 }

@@ -38,6 +38,9 @@ RENDERS = {
     "normals_uv": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 6, "spatial", None),
     # film crop window (sampler built from the cropped sample bounds), film scale, maxsampleluminance
     "crop": (3000, ("matte", "glass", "metal", "plastic"), 70, 50, 4, 5, "uniform", None),
+    # non-default lobes of the four materials: OrenNayar matte (sigma 30), rough glass (microfacet reflection +
+    # transmission)
+    "rough": (3000, ("matte_rough", "glass_rough", "metal", "plastic"), 40, 32, 8, 8, "spatial", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),

@@ -14,8 +14,9 @@ PLUGIN = os.path.join(ROOT, "pbrt-v3-distributed_b200", "_plugin", "pbrt_b200")
 needs_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN), reason="pbrt_b200 is built where /root/reference exists")
 
 
-def _scene(scenes, tmp_path, name="four", strategy="uniform", depth=5, **scene_kw):
-    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1, **scene_kw)
+def _scene(scenes, tmp_path, name="four", strategy="uniform", depth=5, materials=("matte", "glass", "metal", "plastic"),
+           **scene_kw):
+    arr = scenes.SceneArrays(3000, materials=materials, soup_version=1, **scene_kw)
     return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, 8, max_depth=depth, strategy=strategy)
 
 
@@ -54,3 +55,10 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_normals_uv.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_normals_uv.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (shading normals / uvs) differs from the reference"
+    # OrenNayar matte and rough glass parsed from the .pbrt file by the reference's own material factories
+    path = _scene(scenes, tmp_path, "rough", "spatial", depth=8, materials=("matte_rough", "glass_rough", "metal", "plastic"))
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_rough.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_rough.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (OrenNayar / rough glass) differs from the reference"

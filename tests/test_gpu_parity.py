@@ -24,6 +24,9 @@ RENDERS = {
     "normals_uv": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 6, "spatial", None),
     # film crop window (sampler built from the cropped sample bounds), film scale, maxsampleluminance
     "crop": (3000, ("matte", "glass", "metal", "plastic"), 70, 50, 4, 5, "uniform", None),
+    # non-default lobes of the four materials: OrenNayar matte (sigma 30), rough glass (microfacet reflection +
+    # transmission)
+    "rough": (3000, ("matte_rough", "glass_rough", "metal", "plastic"), 40, 32, 8, 8, "spatial", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
@@ -171,7 +174,8 @@ def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
 @pytest.mark.parametrize("mats,depth,strat", [(("matte",), 5, "uniform"), (("glass",), 8, "uniform"),
                                              (("metal",), 5, "power"), (("plastic",), 5, "spatial"),
                                              (("matte", "glass", "metal", "plastic"), 16, "power"),
-                                             (("matte", "glass", "metal", "plastic"), 5, "spatial")])
+                                             (("matte", "glass", "metal", "plastic"), 5, "spatial"),
+                                             (("matte_rough", "glass_rough"), 8, "uniform")])
 def test_render_and_counters_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat):
     arr, setup, scene = make(pkg, abi, scenes, ctx, 60000, mats, 96, 64, 16, depth, strat)
     o = ob.Oracle(abi, arr)
