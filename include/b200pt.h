@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 1
+#define B200PT_ABI_VERSION 2
 
 typedef enum b200pt_status {
     B200PT_OK = 0,
@@ -130,17 +130,28 @@ typedef struct b200pt_film_desc {
     float max_sample_luminance;    /* Film::maxSampleLuminance (INFINITY = off)       */
 } b200pt_film_desc;
 
-/* ---- sampler: SobolSampler (samplers/sobol.h:45-69) ----------------------
- * The generator matrices stay the host's data (core/sobolmatrices.cpp): the
- * host passes SobolMatrices32 and the two rows VdCSobolMatrices[log2res-1],
- * VdCSobolMatricesInv[log2res-1] it already owns. */
+/* ---- sampler: SobolSampler (samplers/sobol.h:45-69) or HaltonSampler
+ * (samplers/halton.h:48-83), both GlobalSamplers (core/sampler.cpp:136-195).
+ * The tables stay the host's data.  Sobol': the host passes SobolMatrices32 and
+ * the two rows VdCSobolMatrices[log2res-1], VdCSobolMatricesInv[log2res-1] it
+ * already owns (core/sobolmatrices.cpp).  Halton: the host passes
+ * HaltonSampler::radicalInversePermutations (halton.cpp:69-72, built by
+ * ComputeRadicalInversePermutations, lowdiscrepancy.cpp:2490-2504): the digit
+ * permutation of base Primes[d] starts at PrimeSums[d]; only the first
+ * n_dimensions bases are read.  baseScales / baseExponents / sampleStride /
+ * multInverse (halton.cpp:74-92) are recomputed by the library from
+ * sample_bounds. */
+enum { B200PT_SAMPLER_SOBOL = 0, B200PT_SAMPLER_HALTON = 1 };
 typedef struct b200pt_sampler_desc {
-    int32_t samples_per_pixel;     /* already rounded up to a power of two (sobol.h:52) */
+    int32_t samples_per_pixel;     /* Sobol': already rounded up to a power of two (sobol.h:52) */
     int32_t sample_bounds[4];      /* Film::GetSampleBounds() x0 y0 x1 y1             */
-    int32_t n_dimensions;          /* rows provided in matrices32 (<=1024)            */
+    int32_t n_dimensions;          /* Sobol': rows in matrices32 (<=1024); Halton: bases covered (<=1000) */
     const uint32_t *matrices32;    /* [n_dimensions][52]  SobolMatrices32             */
     const uint64_t *vdc;           /* [52] VdCSobolMatrices[log2Resolution-1]         */
     const uint64_t *vdc_inv;       /* [52] VdCSobolMatricesInv[log2Resolution-1]      */
+    int32_t type;                  /* B200PT_SAMPLER_*                                */
+    int32_t reserved;
+    const uint16_t *halton_permutations; /* [PrimeSums[n_dimensions]] (Halton only)   */
 } b200pt_sampler_desc;
 
 /* ---- integrator: PathIntegrator parameters (integrators/path.cpp:190-213) */

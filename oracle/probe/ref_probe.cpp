@@ -12,6 +12,8 @@
 //   camera ex ey ez lx ly lz ux uy uz fov xres yres
 //                                 RasterToCamera and CameraToWorld of the PerspectiveCamera pbrt builds
 //   sobol x0 y0 x1 y1 spp px py sample dim0 n    SobolSampler::SampleDimension stream
+//   halton x0 y0 x1 y1 spp px py sample dim0 n   HaltonSampler::SampleDimension stream (first line: the index)
+//   haltonperms <out.bin> <nbases>                HaltonSampler::radicalInversePermutations[0:PrimeSums[nbases]]
 //   camrays <camera args> spp px py n             GetCameraSample + GenerateRayDifferential main rays
 //   intersect <tris.f32> <rays.bin> <out.bin>     BVHAccel (SAH, maxnodeprims 4) Intersect + IntersectP
 //   consts                                        default copper eta/k RGB, RoughnessToAlpha samples
@@ -51,6 +53,7 @@
 #include "filters/box.h"
 #include "materials/matte.h"
 #include "materials/metal.h"
+#include "samplers/halton.h"
 #include "samplers/sobol.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
@@ -156,6 +159,26 @@ int main(int argc, char **argv) {
         s.StartPixel(p);
         s.SetSampleNumber(sample);
         for (int i = 0; i < n; ++i) printf("%a\n", (double)s.SampleDimension(s.intervalSampleIndex, dim0 + i));
+    } else if (cmd == "halton") {
+        Bounds2i sb(Point2i(atoi(argv[2]), atoi(argv[3])), Point2i(atoi(argv[4]), atoi(argv[5])));
+        HaltonSampler s(atoi(argv[6]), sb);
+        Point2i p(atoi(argv[7]), atoi(argv[8]));
+        int64_t sample = atoll(argv[9]);
+        int dim0 = atoi(argv[10]), n = atoi(argv[11]);
+        s.StartPixel(p);
+        s.SetSampleNumber(sample);
+        printf("%lld\n", (long long)s.intervalSampleIndex);
+        for (int i = 0; i < n; ++i) printf("%a\n", (double)s.SampleDimension(s.intervalSampleIndex, dim0 + i));
+    } else if (cmd == "haltonperms") {
+        int nb = atoi(argv[3]);
+        HaltonSampler s(1, Bounds2i(Point2i(0, 0), Point2i(16, 16)));  // the ctor fills the static table
+        FILE *f = fopen(argv[2], "wb");
+        if (!f) die("cannot open output");
+        uint32_t count = nb < PrimeTableSize ? (uint32_t)PrimeSums[nb] : (uint32_t)HaltonSampler::radicalInversePermutations.size();
+        uint32_t hdr[4] = {0x544c4148u /* "HALT" */, (uint32_t)nb, count, 0};
+        fwrite(hdr, 4, 4, f);
+        fwrite(HaltonSampler::radicalInversePermutations.data(), 2, count, f);
+        fclose(f);
     } else if (cmd == "camrays") {
         auto cam = makeCamera(argv + 2);
         int spp = atoi(argv[14]);

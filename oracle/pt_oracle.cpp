@@ -211,16 +211,168 @@ inline int RoundUpPow2(int v) {
 }
 inline int Log2Int(uint32_t v) { return 31 - __builtin_clz(v); }
 
-// samplers/sobol.h:45-69 + core/sampler.cpp:136-195 (GlobalSampler)
+
+// ------------------------------------------------------------------- Halton
+// core/lowdiscrepancy.cpp:45-... (Primes / PrimeSums): the first n primes and their prefix sums
+struct PrimeTable {
+    std::vector<int> primes, sums;
+    explicit PrimeTable(int n) {
+        int sum = 0;
+        for (int c = 2; (int)primes.size() < n; ++c) {
+            bool isPrime = true;
+            for (int d = 2; d * d <= c; ++d)
+                if (c % d == 0) {
+                    isPrime = false;
+                    break;
+                }
+            if (isPrime) {
+                sums.push_back(sum);
+                primes.push_back(c);
+                sum += c;
+            }
+        }
+        sums.push_back(sum);
+    }
+};
+inline const PrimeTable &Primes1000() {
+    static PrimeTable t(1000);
+    return t;
+}
+// core/rng.h:63-131 (PCG32 with the default state / stream)
+struct PcgRng {
+    uint64_t state = 0x853c49e6748fea9bULL, inc = 0xda3e39cb94b95bdbULL;
+    uint32_t UniformUInt32() {
+        uint64_t oldstate = state;
+        state = oldstate * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((oldstate >> 18u) ^ oldstate) >> 27u);
+        uint32_t rot = (uint32_t)(oldstate >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    uint32_t UniformUInt32(uint32_t b) {
+        uint32_t threshold = (~b + 1u) % b;
+        while (true) {
+            uint32_t r = UniformUInt32();
+            if (r >= threshold) return r % b;
+        }
+    }
+};
+// lowdiscrepancy.cpp:2490-2504 + sampling.h:150-157 (Shuffle with nDimensions = 1)
+inline void ComputeRadicalInversePermutations(int nBases, std::vector<uint16_t> *perms) {
+    const PrimeTable &pt = Primes1000();
+    PcgRng rng;
+    perms->resize((size_t)pt.sums[nBases]);
+    uint16_t *p = perms->data();
+    for (int i = 0; i < nBases; ++i) {
+        const int count = pt.primes[i];
+        for (int j = 0; j < count; ++j) p[j] = (uint16_t)j;
+        for (int j = 0; j < count; ++j) {
+            int other = j + (int)rng.UniformUInt32((uint32_t)(count - j));
+            std::swap(p[j], p[other]);
+        }
+        p += count;
+    }
+}
+inline uint64_t ReverseBits64(uint64_t n) {  // lowdiscrepancy.h:68-80
+    auto rev32 = [](uint32_t v) {
+        v = (v << 16) | (v >> 16);
+        v = ((v & 0x00ff00ff) << 8) | ((v & 0xff00ff00) >> 8);
+        v = ((v & 0x0f0f0f0f) << 4) | ((v & 0xf0f0f0f0) >> 4);
+        v = ((v & 0x33333333) << 2) | ((v & 0xcccccccc) >> 2);
+        v = ((v & 0x55555555) << 1) | ((v & 0xaaaaaaaa) >> 1);
+        return v;
+    };
+    uint64_t n0 = rev32((uint32_t)n), n1 = rev32((uint32_t)(n >> 32));
+    return (n0 << 32) | n1;
+}
+// lowdiscrepancy.cpp:389-403 (the template argument is a run-time value here: integer division is exact)
+inline float RadicalInverseBase(uint64_t base, uint64_t a) {
+    const float invBase = (float)1 / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    while (a) {
+        uint64_t next = a / base;
+        uint64_t digit = a - next * base;
+        reversedDigits = reversedDigits * base + digit;
+        invBaseN *= invBase;
+        a = next;
+    }
+    return std::min(reversedDigits * invBaseN, OneMinusEpsilon);
+}
+// lowdiscrepancy.cpp:405-424
+inline float ScrambledRadicalInverseBase(uint64_t base, const uint16_t *perm, uint64_t a) {
+    const float invBase = (float)1 / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    while (a) {
+        uint64_t next = a / base;
+        uint64_t digit = a - next * base;
+        reversedDigits = reversedDigits * base + perm[digit];
+        invBaseN *= invBase;
+        a = next;
+    }
+    return std::min(invBaseN * (reversedDigits + invBase * perm[0] / (1 - invBase)), OneMinusEpsilon);
+}
+inline int64_t ModI(int64_t a, int64_t b) {  // pbrt.h Mod
+    int64_t result = a - (a / b) * b;
+    return (int64_t)((result < 0) ? result + b : result);
+}
+inline void extendedGCD(uint64_t a, uint64_t b, int64_t *x, int64_t *y) {  // halton.cpp:52-63
+    if (b == 0) {
+        *x = 1;
+        *y = 0;
+        return;
+    }
+    int64_t d = a / b, xp, yp;
+    extendedGCD(b, a % b, &xp, &yp);
+    *x = yp;
+    *y = xp - (d * yp);
+}
+inline uint64_t multiplicativeInverse(int64_t a, int64_t n) {  // halton.cpp:46-50
+    int64_t x, y;
+    extendedGCD(a, n, &x, &y);
+    return ModI(x, n);
+}
+inline uint64_t InverseRadicalInverse(int base, uint64_t inverse, int nDigits) {  // lowdiscrepancy.h:82-91
+    uint64_t index = 0;
+    for (int i = 0; i < nDigits; ++i) {
+        uint64_t digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
+}
+
+// samplers/sobol.h:45-69 / samplers/halton.h:48-83 + core/sampler.cpp:136-195 (GlobalSampler).
+// (The struct keeps its first name; sd->type selects the sequence.)
 struct Sobol {
     const b200pt_sampler_desc *sd;
     int resolution, log2Resolution;
     int px, py;
     int64_t intervalSampleIndex;
     int dimension;
+    // HaltonSampler state (halton.h:60-70)
+    bool halton;
+    int baseScales[2], baseExponents[2], sampleStride, multInverse[2];
     explicit Sobol(const b200pt_sampler_desc *sd) : sd(sd) {
         int dx = sd->sample_bounds[2] - sd->sample_bounds[0];
         int dy = sd->sample_bounds[3] - sd->sample_bounds[1];
+        halton = sd->type == B200PT_SAMPLER_HALTON;
+        if (halton) {  // halton.cpp:74-92
+            const int res[2] = {dx, dy};
+            for (int i = 0; i < 2; ++i) {
+                int base = (i == 0) ? 2 : 3;
+                int scale = 1, exp = 0;
+                while (scale < std::min(res[i], 128)) {
+                    scale *= base;
+                    ++exp;
+                }
+                baseScales[i] = scale;
+                baseExponents[i] = exp;
+            }
+            sampleStride = baseScales[0] * baseScales[1];
+            multInverse[0] = (int)multiplicativeInverse(baseScales[1], baseScales[0]);
+            multInverse[1] = (int)multiplicativeInverse(baseScales[0], baseScales[1]);
+        }
         resolution = RoundUpPow2(std::max(dx, dy));
         log2Resolution = Log2Int(resolution);
         px = py = 0;
@@ -229,11 +381,35 @@ struct Sobol {
     }
     // sobol.cpp:42-45
     int64_t GetIndexForSample(int64_t sampleNum) const {
+        if (halton) {  // halton.cpp:95-116 (the cached offset is recomputed per call: same value)
+            int64_t offsetForCurrentPixel = 0;
+            if (sampleStride > 1) {
+                const int pm[2] = {(int)ModI(px, 128), (int)ModI(py, 128)};
+                for (int i = 0; i < 2; ++i) {
+                    uint64_t dimOffset = InverseRadicalInverse(i == 0 ? 2 : 3, pm[i], baseExponents[i]);
+                    offsetForCurrentPixel += dimOffset * (sampleStride / baseScales[i]) * multInverse[i];
+                }
+                offsetForCurrentPixel %= sampleStride;
+            }
+            return offsetForCurrentPixel + sampleNum * sampleStride;
+        }
         return SobolIntervalToIndex(*sd, log2Resolution, sampleNum, px - sd->sample_bounds[0],
                                     py - sd->sample_bounds[1]);
     }
     // sobol.cpp:47-59
     float SampleDimension(int64_t index, int dim) const {
+        if (halton) {  // halton.cpp:118-127, lowdiscrepancy.cpp:427-437 and :2506-...
+            if (dim == 0) return (float)(ReverseBits64((uint64_t)(index >> baseExponents[0])) * 0x1p-64);
+            if (dim == 1) return RadicalInverseBase(3, (uint64_t)(index / baseScales[1]));
+            if (dim >= sd->n_dimensions) {
+                fprintf(stderr, "oracle: Halton dimension %d exceeds provided permutations (%d)\n", dim,
+                        sd->n_dimensions);
+                abort();
+            }
+            const PrimeTable &pt = Primes1000();
+            return ScrambledRadicalInverseBase((uint64_t)pt.primes[dim], sd->halton_permutations + pt.sums[dim],
+                                               (uint64_t)index);
+        }
         float s = SobolSampleFloat(*sd, index, dim);
         if (dim == 0 || dim == 1) {
             s = s * resolution + sd->sample_bounds[dim];
@@ -1864,6 +2040,15 @@ int oracle_sobol(const b200pt_sampler_desc *sampler, int32_t px, int32_t py, int
     sob.StartPixelSample(px, py, sample);
     for (int i = 0; i < n_dims; ++i) out[i] = sob.SampleDimension(sob.intervalSampleIndex, dim0 + i);
     return 0;
+}
+
+int64_t oracle_halton_permutations(int32_t n_bases, uint16_t *out) {
+    if (n_bases < 0 || n_bases > 1000) return -1;
+    if (!out) return Primes1000().sums[n_bases];
+    std::vector<uint16_t> perms;
+    ComputeRadicalInversePermutations(n_bases, &perms);
+    memcpy(out, perms.data(), perms.size() * sizeof(uint16_t));
+    return (int64_t)perms.size();
 }
 
 int oracle_camera_rays(const b200pt_camera_desc *camera, const b200pt_sampler_desc *sampler, int32_t px,

@@ -42,6 +42,9 @@ int oracle_film_rgb(const b200pt_film_desc *film, const float *film_xyzw, float 
 
 int oracle_sobol(const b200pt_sampler_desc *sampler, int32_t px, int32_t py, int64_t sample,
                  int32_t dim0, int32_t n_dims, float *out);
+/* HaltonSampler::radicalInversePermutations for the first n_bases primes (lowdiscrepancy.cpp:2490-2504);
+ * returns the number of entries written (PrimeSums[n_bases]); out may be NULL to query the size. */
+int64_t oracle_halton_permutations(int32_t n_bases, uint16_t *out);
 int oracle_camera_rays(const b200pt_camera_desc *camera, const b200pt_sampler_desc *sampler,
                        int32_t px, int32_t py, int32_t n_samples, b200pt_ray *out);
 /* Per-sample radiance of one pixel after the guards of integrator.cpp:294-315. */

@@ -41,10 +41,14 @@ class FilmDesc(C.Structure):
                 ("max_sample_luminance", C.c_float)]
 
 
+SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
+
+
 class SamplerDesc(C.Structure):
     _fields_ = [("samples_per_pixel", C.c_int32), ("sample_bounds", C.c_int32 * 4),
                 ("n_dimensions", C.c_int32), ("matrices32", C.c_void_p), ("vdc", C.c_void_p),
-                ("vdc_inv", C.c_void_p)]
+                ("vdc_inv", C.c_void_p), ("type", C.c_int32), ("reserved", C.c_int32),
+                ("halton_permutations", C.c_void_p)]
 
 
 class IntegratorDesc(C.Structure):

@@ -386,14 +386,19 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     if (!scene || !cam || !film || !smp || !integ || !out) return b200pt_fail(B200PT_ERR_INVALID, "render_create: NULL argument");
     if (film->filter_radius[0] != 0.5f || film->filter_radius[1] != 0.5f)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: only the default box filter (radius 0.5) is supported");
-    if (smp->samples_per_pixel <= 0 || (smp->samples_per_pixel & (smp->samples_per_pixel - 1)))
+    const bool halton = smp->type == B200PT_SAMPLER_HALTON;
+    if (smp->type != B200PT_SAMPLER_SOBOL && !halton)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: unknown sampler type %d", smp->type);
+    if (smp->samples_per_pixel <= 0 || (!halton && (smp->samples_per_pixel & (smp->samples_per_pixel - 1))))
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: samples_per_pixel must be a power of two (sobol.h:52)");
-    if (!smp->matrices32 || !smp->vdc || !smp->vdc_inv || smp->n_dimensions < 5)
+    if (!halton && (!smp->matrices32 || !smp->vdc || !smp->vdc_inv || smp->n_dimensions < 5))
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: Sobol' tables missing");
+    if (halton && (!smp->halton_permutations || smp->n_dimensions < 5 || smp->n_dimensions > 1000))
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: Halton permutation table missing");
     if (integ->max_depth < 0 || integ->max_depth > 200) return b200pt_fail(B200PT_ERR_INVALID, "render_create: bad max_depth");
     // 5 camera dims + per bounce: light pick 1 + uLight 2 + uScattering 2 + BSDF 2 + roulette 1
     if (5 + 8 * integ->max_depth > smp->n_dimensions)
-        return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d Sobol' dimensions, %d provided",
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d sampler dimensions, %d provided",
                            integ->max_depth, 5 + 8 * integ->max_depth, smp->n_dimensions);
     if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER &&
         integ->light_strategy != B200PT_LIGHTS_SPATIAL)
@@ -428,8 +433,50 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     while ((1 << lg) < res) ++lg;
     H.sampler.log2res = lg;
     H.sampler.n_dims = smp->n_dimensions;
-    memcpy(H.sampler.vdc, smp->vdc, sizeof(uint64_t) * 52);
-    memcpy(H.sampler.vdc_inv, smp->vdc_inv, sizeof(uint64_t) * 52);
+    H.sampler.type = smp->type;
+    std::vector<uint32_t> primes, prime_sums;
+    if (halton) {
+        // halton.cpp:74-92: scales / exponents of bases 2 and 3 covering min(extent, kMaxResolution = 128)
+        const int ext[2] = {sbw, sbh};
+        for (int i = 0; i < 2; ++i) {
+            const int base = i == 0 ? 2 : 3;
+            int scale = 1, ex = 0;
+            while (scale < std::min(ext[i], 128)) {
+                scale *= base;
+                ++ex;
+            }
+            H.sampler.base_scale[i] = scale;
+            H.sampler.base_exp[i] = ex;
+        }
+        H.sampler.sample_stride = H.sampler.base_scale[0] * H.sampler.base_scale[1];
+        // multiplicativeInverse(a, n) (halton.cpp:46-63): the x in [0, n) with a*x = 1 (mod n); n <= 243 here
+        auto mul_inv = [](int a, int n) {
+            if (n == 1) return 0;
+            for (int x = 0; x < n; ++x)
+                if ((int)(((long long)a * x) % n) == 1) return x;
+            return 0;
+        };
+        H.sampler.mult_inverse[0] = mul_inv(H.sampler.base_scale[1], H.sampler.base_scale[0]);
+        H.sampler.mult_inverse[1] = mul_inv(H.sampler.base_scale[0], H.sampler.base_scale[1]);
+        // Primes / PrimeSums of the bases in use (lowdiscrepancy.cpp:45-...)
+        uint32_t sum = 0;
+        for (uint32_t c = 2; (int)primes.size() < smp->n_dimensions; ++c) {
+            bool is_prime = true;
+            for (uint32_t d = 2; d * d <= c; ++d)
+                if (c % d == 0) {
+                    is_prime = false;
+                    break;
+                }
+            if (!is_prime) continue;
+            primes.push_back(c);
+            prime_sums.push_back(sum);
+            sum += c;
+        }
+        prime_sums.push_back(sum);
+    } else {
+        memcpy(H.sampler.vdc, smp->vdc, sizeof(uint64_t) * 52);
+        memcpy(H.sampler.vdc_inv, smp->vdc_inv, sizeof(uint64_t) * 52);
+    }
     memcpy(H.camera.r2c, cam->raster_to_camera, sizeof(float) * 16);
     memcpy(H.camera.c2w, cam->camera_to_world, sizeof(float) * 16);
     H.camera.lens_radius = cam->lens_radius;
@@ -517,8 +564,16 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     float *d_cdf = nullptr, *d_func = nullptr;
 #define ALLOC(ptr, count) \
     if (e == cudaSuccess) e = dev_alloc(r, &(ptr), (count))
-    ALLOC(mat32, (size_t)smp->n_dimensions * 52);
-    ALLOC(sobol_table, (size_t)smp->n_dimensions * 5 * 256);
+    uint16_t *d_perms = nullptr;
+    uint32_t *d_primes = nullptr, *d_prime_sums = nullptr;
+    if (halton) {
+        ALLOC(d_perms, (size_t)prime_sums.back());
+        ALLOC(d_primes, primes.size());
+        ALLOC(d_prime_sums, prime_sums.size());
+    } else {
+        ALLOC(mat32, (size_t)smp->n_dimensions * 52);
+        ALLOC(sobol_table, (size_t)smp->n_dimensions * 5 * 256);
+    }
     ALLOC(d_lights, (size_t)nl);
     ALLOC(d_cdf, (size_t)nl + 1);
     ALLOC(d_func, (size_t)std::max(nl, 1));
@@ -565,8 +620,18 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.light_cdf = d_cdf;
     H.light_func = d_func;
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(cudaMemcpyAsync(mat32, smp->matrices32, (size_t)smp->n_dimensions * 52 * 4, cudaMemcpyHostToDevice, st));
-    launch_sobol_table(mat32, sobol_table, smp->n_dimensions, st);
+    if (halton) {
+        H.sampler.perms = d_perms;
+        H.sampler.primes = d_primes;
+        H.sampler.prime_sums = d_prime_sums;
+        CUDA_TRY(cudaMemcpyAsync(d_perms, smp->halton_permutations, (size_t)prime_sums.back() * 2, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_primes, primes.data(), primes.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_prime_sums, prime_sums.data(), prime_sums.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // the tables above are locals / caller memory
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(mat32, smp->matrices32, (size_t)smp->n_dimensions * 52 * 4, cudaMemcpyHostToDevice, st));
+        launch_sobol_table(mat32, sobol_table, smp->n_dimensions, st);
+    }
     if (nl) CUDA_TRY(cudaMemcpyAsync(d_lights, dl.data(), nl * sizeof(DevLight), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_cdf, cdf.data(), (nl + 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_func, func.data(), std::max(nl, 1) * sizeof(float), cudaMemcpyHostToDevice, st));

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
             valid = true;
             const SamplerParams &sp = R->sampler;
             SobolStream st;
-            st.index = sobol_interval_to_index(sp, sample, px - sp.sb[0], py - sp.sb[1]);  // sobol.cpp:42-45
+            st.index = sampler_index(sp, sample, px, py);
             st.dim = 0;
             st.px = px;
             st.py = py;
@@ -743,8 +743,8 @@ __global__ void k_debug_sobol(const RenderDev *R, int px, int py, long long samp
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const SamplerParams &sp = R->sampler;
-    const uint64_t idx = sobol_interval_to_index(sp, (uint64_t)sample, px - sp.sb[0], py - sp.sb[1]);
-    out[i] = sobol_sample(sp, idx, dim0 + i, px, py);
+    const uint64_t idx = sampler_index(sp, (uint64_t)sample, px, py);
+    out[i] = sampler_sample(sp, idx, dim0 + i, px, py);
 }
 
 __global__ void k_debug_camera(const RenderDev *R, int px, int py, int n, b200pt_ray *out) {
@@ -752,7 +752,7 @@ __global__ void k_debug_camera(const RenderDev *R, int px, int py, int n, b200pt
     if (i >= n) return;
     const SamplerParams &sp = R->sampler;
     SobolStream st;
-    st.index = sobol_interval_to_index(sp, (uint64_t)i, px - sp.sb[0], py - sp.sb[1]);
+    st.index = sampler_index(sp, (uint64_t)i, px, py);
     st.dim = 0;
     st.px = px;
     st.py = py;

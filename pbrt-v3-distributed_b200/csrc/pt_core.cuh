@@ -149,6 +149,12 @@ struct SamplerParams {          // samplers/sobol.h:45-69
     const uint32_t *table;      // device only: [n_dims][5][256] XOR of the columns selected by one index byte
     uint64_t vdc[52];
     uint64_t vdc_inv[52];
+    // HaltonSampler (samplers/halton.h:60-70); type selects the sequence
+    int type;                   // B200PT_SAMPLER_SOBOL / B200PT_SAMPLER_HALTON
+    int base_scale[2], base_exp[2], sample_stride, mult_inverse[2];
+    const uint16_t *perms;      // radicalInversePermutations
+    const uint32_t *primes;     // [n_dims] Primes[d]
+    const uint32_t *prime_sums; // [n_dims] PrimeSums[d]
 };
 
 // core/lowdiscrepancy.h:229-249
@@ -192,7 +198,81 @@ B200_HD float sobol_sample(const SamplerParams &sp, uint64_t a, int dim, int px,
     return s;
 }
 
-// GlobalSampler stream state of one path (sampler.cpp:136-195): the Sobol'
+// ---------------------------------------------------------------------- Halton
+// halton.cpp:95-116.  px, py are absolute pixel coordinates (currentPixel).
+B200_HD uint64_t halton_index_for_sample(const SamplerParams &sp, uint64_t sampleNum, int px, int py) {
+    int64_t offset = 0;
+    if (sp.sample_stride > 1) {
+        int pm[2] = {px % 128, py % 128};  // Mod(): non-negative remainder
+        if (pm[0] < 0) pm[0] += 128;
+        if (pm[1] < 0) pm[1] += 128;
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t base = i == 0 ? 2u : 3u;
+            uint32_t inverse = (uint32_t)pm[i];
+            uint64_t dimOffset = 0;  // InverseRadicalInverse<base>, lowdiscrepancy.h:82-91
+            for (int k = 0; k < sp.base_exp[i]; ++k) {
+                const uint32_t digit = inverse % base;
+                inverse /= base;
+                dimOffset = dimOffset * base + digit;
+            }
+            offset += (int64_t)(dimOffset * (uint64_t)(sp.sample_stride / sp.base_scale[i]) * (uint64_t)sp.mult_inverse[i]);
+        }
+        offset %= sp.sample_stride;
+    }
+    return (uint64_t)(offset + (int64_t)sampleNum * sp.sample_stride);
+}
+// lowdiscrepancy.cpp:389-424: digits of `a` in `base`, reversed (optionally through a permutation);
+// integer arithmetic is exact, so a run-time base gives the template's results.  32-bit division
+// while the remaining value fits.
+B200_HD float halton_radical_inverse(uint32_t base, const uint16_t *perm, uint64_t a) {
+    const float invBase = 1.f / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1.f;
+    while (a >> 32) {
+        const uint64_t next = a / base;
+        const uint32_t digit = (uint32_t)(a - next * base);
+        reversedDigits = reversedDigits * base + (perm ? (uint32_t)perm[digit] : digit);
+        invBaseN *= invBase;
+        a = next;
+    }
+    uint32_t a32 = (uint32_t)a;
+    while (a32) {
+        const uint32_t next = a32 / base;
+        const uint32_t digit = a32 - next * base;
+        reversedDigits = reversedDigits * base + (perm ? (uint32_t)perm[digit] : digit);
+        invBaseN *= invBase;
+        a32 = next;
+    }
+    if (!perm) return pt_min((float)reversedDigits * invBaseN, PT_ONE_MINUS_EPS);
+    return pt_min(invBaseN * ((float)reversedDigits + invBase * (float)perm[0] / (1.f - invBase)), PT_ONE_MINUS_EPS);
+}
+// halton.cpp:118-127
+B200_HD float halton_sample(const SamplerParams &sp, uint64_t index, int dim) {
+    if (dim == 0) {  // RadicalInverse(0, a) = ReverseBits64(a) * 0x1p-64 in double (lowdiscrepancy.cpp:430-435)
+        const uint64_t a = index >> sp.base_exp[0];
+#ifdef __CUDA_ARCH__
+        const uint64_t r = ((uint64_t)__brev((uint32_t)a) << 32) | (uint64_t)__brev((uint32_t)(a >> 32));
+#else
+        uint64_t r = 0;
+        for (int i = 0; i < 64; ++i) r |= ((a >> i) & 1ull) << (63 - i);
+#endif
+        return (float)((double)r * 0x1p-64);
+    }
+    if (dim == 1) return halton_radical_inverse(3u, nullptr, index / (uint64_t)sp.base_scale[1]);
+    return halton_radical_inverse(sp.primes[dim], sp.perms + sp.prime_sums[dim], index);
+}
+
+// Both sequences behind the GlobalSampler interface.
+B200_HD uint64_t sampler_index(const SamplerParams &sp, uint64_t sampleNum, int px, int py) {
+    if (sp.type == 1) return halton_index_for_sample(sp, sampleNum, px, py);
+    return sobol_interval_to_index(sp, sampleNum, px - sp.sb[0], py - sp.sb[1]);  // sobol.cpp:42-45
+}
+B200_HD float sampler_sample(const SamplerParams &sp, uint64_t index, int dim, int px, int py) {
+    if (sp.type == 1) return halton_sample(sp, index, dim);
+    return sobol_sample(sp, index, dim, px, py);
+}
+
+// GlobalSampler stream state of one path (sampler.cpp:136-195): the sequence
 // index of (pixel, sample) and the dimension cursor.
 struct SobolStream {
     uint64_t index;
@@ -200,13 +280,13 @@ struct SobolStream {
     int px, py;
 };
 B200_HD float get1d(const SamplerParams &sp, SobolStream &s) {
-    float v = sobol_sample(sp, s.index, s.dim, s.px, s.py);
+    float v = sampler_sample(sp, s.index, s.dim, s.px, s.py);
     s.dim += 1;
     return v;
 }
 B200_HD void get2d(const SamplerParams &sp, SobolStream &s, float u[2]) {
-    u[0] = sobol_sample(sp, s.index, s.dim, s.px, s.py);
-    u[1] = sobol_sample(sp, s.index, s.dim + 1, s.px, s.py);
+    u[0] = sampler_sample(sp, s.index, s.dim, s.px, s.py);
+    u[1] = sampler_sample(sp, s.index, s.dim + 1, s.px, s.py);
     s.dim += 2;
 }
 

@@ -69,6 +69,7 @@
 #include "materials/matte.h"
 #include "materials/metal.h"
 #include "materials/plastic.h"
+#include "samplers/halton.h"
 #include "samplers/sobol.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
@@ -273,7 +274,10 @@ class GpuPathIntegrator : public PathIntegrator {
         if (!pcam) return Error("gpupath: only the perspective camera is supported");
         if (pcam->CameraToWorld.actuallyAnimated) return Error("gpupath: animated cameras are not supported");
         auto sobol = dynamic_cast<const SobolSampler *>(smp.get());
-        if (!sobol) return Error("gpupath: only Sampler \"sobol\" is supported");
+        auto halton = dynamic_cast<const HaltonSampler *>(smp.get());
+        if (!sobol && !halton) return Error("gpupath: only Sampler \"sobol\" and \"halton\" are supported");
+        if (halton && halton->sampleAtPixelCenter)
+            return Error("gpupath: Sampler \"halton\" with samplepixelcenter is not supported");
         Film *film = cam->film;
         if (!dynamic_cast<const BoxFilter *>(film->filter.get()) || film->filter->radius.x != 0.5f ||
             film->filter->radius.y != 0.5f)
@@ -325,17 +329,27 @@ class GpuPathIntegrator : public PathIntegrator {
         fd.max_sample_luminance = film->maxSampleLuminance;
 
         b200pt_sampler_desc smpd;
-        smpd.samples_per_pixel = (int32_t)sobol->samplesPerPixel;
-        const Bounds2i sb = sobol->sampleBounds;
+        memset(&smpd, 0, sizeof(smpd));
+        smpd.samples_per_pixel = (int32_t)smp->samplesPerPixel;
+        // both samplers are constructed from Film::GetSampleBounds() (api.cpp:820-831); Halton keeps
+        // only what it derives from them
+        const Bounds2i sb = sobol ? sobol->sampleBounds : film->GetSampleBounds();
         smpd.sample_bounds[0] = sb.pMin.x;
         smpd.sample_bounds[1] = sb.pMin.y;
         smpd.sample_bounds[2] = sb.pMax.x;
         smpd.sample_bounds[3] = sb.pMax.y;
-        smpd.n_dimensions = NumSobolDimensions;
-        smpd.matrices32 = SobolMatrices32;
-        const int row = std::max(sobol->log2Resolution - 1, 0);
-        smpd.vdc = VdCSobolMatrices[row];
-        smpd.vdc_inv = VdCSobolMatricesInv[row];
+        if (sobol) {
+            smpd.type = B200PT_SAMPLER_SOBOL;
+            smpd.n_dimensions = NumSobolDimensions;
+            smpd.matrices32 = SobolMatrices32;
+            const int row = std::max(sobol->log2Resolution - 1, 0);
+            smpd.vdc = VdCSobolMatrices[row];
+            smpd.vdc_inv = VdCSobolMatricesInv[row];
+        } else {
+            smpd.type = B200PT_SAMPLER_HALTON;
+            smpd.n_dimensions = PrimeTableSize;
+            smpd.halton_permutations = HaltonSampler::radicalInversePermutations.data();
+        }
 
         b200pt_integrator_desc id;
         id.max_depth = maxDepth;

@@ -228,7 +228,7 @@ def write_ply(path, tris, normals=None, uvs=None):
 
 def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
                eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6,
-               crop_window=None, film_scale=1.0, max_sample_luminance=None):
+               crop_window=None, film_scale=1.0, max_sample_luminance=None, sampler="sobol"):
     """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
     os.makedirs(dirname, exist_ok=True)
     lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
@@ -240,7 +240,7 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
              (' "float cropwindow" [%.9g %.9g %.9g %.9g]' % tuple(crop_window) if crop_window else "") +
              (' "float scale" [%.9g]' % film_scale if film_scale != 1.0 else "") +
              (' "float maxsampleluminance" [%.9g]' % max_sample_luminance if max_sample_luminance else ""),
-             'Sampler "sobol" "integer pixelsamples" [%d]' % spp]
+             'Sampler "%s" "integer pixelsamples" [%d]' % (sampler, spp)]
     integ = 'Integrator "path" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (max_depth, strategy)
     if pixel_bounds is not None:
         integ += ' "integer pixelbounds" [%d %d %d %d]' % (pixel_bounds[0], pixel_bounds[2], pixel_bounds[1],
@@ -312,6 +312,20 @@ class SobolTables:
         self.vdc_inv = np.frombuffer(raw, "<u8", nrows * 52, off).reshape(nrows, 52).copy()
 
 
+class HaltonTables:
+    """tests/golden/halton_perms.bin: HaltonSampler::radicalInversePermutations for the first
+    n_dims prime bases, dumped from the reference by oracle/probe `haltonperms` (the table is the
+    output of pbrt's PCG32 shuffle with the default seed; a pbrt host passes its own copy)."""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(GOLDEN_DIR, "halton_perms.bin")
+        raw = open(path, "rb").read()
+        magic, nd, count, _ = struct.unpack_from("<4I", raw, 0)
+        assert magic == 0x544C4148
+        self.n_dims = nd
+        self.perms = np.frombuffer(raw, "<u2", count, 16).copy()
+
+
 def rank_tiles(n_tiles, rank, world):
     """Image-space decomposition used for multi-GPU runs: tile i -> rank i mod N.
     Interleaving balances sky / geometry tiles; every rank keeps the FULL-film sampler so the
@@ -329,10 +343,12 @@ class RenderSetup:
 
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
-                 lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None):
+                 lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None,
+                 sampler="sobol"):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
-        self.tables = tables or SobolTables()
+        self.sampler_name = sampler
+        self.tables = tables or (HaltonTables() if sampler == "halton" else SobolTables())
         self.camera = camera if camera is not None else host_perspective_camera(eye, look, up, fov, xres, yres)
         if lens_radius > 0:
             self.camera.lens_radius = lens_radius
@@ -351,10 +367,23 @@ class RenderSetup:
         self.film.scale = film_scale
         self.film.max_sample_luminance = max_sample_luminance if max_sample_luminance else float("inf")
         self.sampler = abi.SamplerDesc()
-        self.sampler.samples_per_pixel = round_up_pow2(spp)
         # Film::GetSampleBounds with the box filter of radius 0.5 == the cropped pixel bounds (film.cpp:80-86)
         self.sampler.sample_bounds[:] = cb
         self.sampler.n_dimensions = self.tables.n_dims
+        if sampler == "halton":  # halton.cpp:65-93: any sample count
+            self.sampler.type = abi.SAMPLER_HALTON
+            self.sampler.samples_per_pixel = spp
+            self.sampler.halton_permutations = abi.ptr(self.tables.perms)
+        else:
+            self.sampler.samples_per_pixel = round_up_pow2(spp)
+            self._sobol_tables(cb)
+        self.integrator = abi.IntegratorDesc()
+        self.integrator.max_depth = max_depth
+        self.integrator.rr_threshold = 1.0
+        self.integrator.light_strategy = strategy
+        self.integrator.pixel_bounds[:] = pixel_bounds or cb
+
+    def _sobol_tables(self, cb):
         res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))
         m = res.bit_length() - 1
         self._vdc = np.ascontiguousarray(self.tables.vdc[max(m - 1, 0)])
@@ -362,11 +391,6 @@ class RenderSetup:
         self.sampler.matrices32 = abi.ptr(self.tables.matrices32)
         self.sampler.vdc = abi.ptr(self._vdc)
         self.sampler.vdc_inv = abi.ptr(self._vdc_inv)
-        self.integrator = abi.IntegratorDesc()
-        self.integrator.max_depth = max_depth
-        self.integrator.rr_threshold = 1.0
-        self.integrator.light_strategy = strategy
-        self.integrator.pixel_bounds[:] = pixel_bounds or cb
 
     @property
     def n_tiles(self):

@@ -41,15 +41,37 @@ RENDERS = {
     # non-default lobes of the four materials: OrenNayar matte (sigma 30), rough glass (microfacet reflection +
     # transmission)
     "rough": (3000, ("matte_rough", "glass_rough", "metal", "plastic"), 40, 32, 8, 8, "spatial", None),
+    # HaltonSampler (pbrt's default sampler): non-power-of-two sample counts, cropped sample bounds
+    "halton": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 6, 5, "spatial", None),
+    "halton_crop": (3000, ("matte", "plastic"), 70, 50, 3, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
          "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,))),
-         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0))}
+         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0)),
+         "halton": dict(camera=dict(sampler="halton")),
+         "halton_crop": dict(camera=dict(sampler="halton", crop_window=(0.21, 0.83, 0.1, 0.74)))}
+
+
+HALTON_CASES = [((0, 0, 700, 700), 8, 345, 678, 5, 0, 100), ((0, 0, 64, 48), 16, 3, 47, 15, 0, 120),
+                ((0, 0, 1920, 1080), 1024, 1919, 1079, 1023, 0, 128), ((13, 7, 90, 50), 5, 13, 7, 0, 0, 64),
+                ((0, 0, 100, 100), 3, 99, 0, 2, 0, 64), ((0, 0, 1, 1), 4, 0, 0, 3, 0, 16)]
+
+
+def halton_fixtures():
+    """HaltonSampler: the digit permutations of the first 128 prime bases and sample streams."""
+    ob.probe("haltonperms", os.path.join(HERE, "halton_perms.bin"), 128)
+    out = []
+    for (bounds, spp, px, py, sample, dim0, n) in HALTON_CASES:
+        vals = ob.probe("halton", *bounds, spp, px, py, sample, dim0, n).split()
+        out.append({"bounds": bounds, "spp": spp, "px": px, "py": py, "sample": sample, "dim0": dim0,
+                    "index": int(vals[0]), "values": vals[1:]})
+    json.dump(out, open(os.path.join(HERE, "probe_halton.json"), "w"), indent=1)
 
 
 def main():
     ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
+    halton_fixtures()
     out = {"cameras": {}, "sobol": [], "camrays": []}
     cam_args = [0, 0, -4.5, 0, 0, 0, 0, 1, 0, 35]
     for (w, h) in CAMERAS:

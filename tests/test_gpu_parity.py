@@ -27,11 +27,16 @@ RENDERS = {
     # non-default lobes of the four materials: OrenNayar matte (sigma 30), rough glass (microfacet reflection +
     # transmission)
     "rough": (3000, ("matte_rough", "glass_rough", "metal", "plastic"), 40, 32, 8, 8, "spatial", None),
+    # HaltonSampler (pbrt's default sampler): non-power-of-two sample counts, cropped sample bounds
+    "halton": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 6, 5, "spatial", None),
+    "halton_crop": (3000, ("matte", "plastic"), 70, 50, 3, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
          "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,))),
-         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0))}
+         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0)),
+         "halton": dict(camera=dict(sampler="halton")),
+         "halton_crop": dict(camera=dict(sampler="halton", crop_window=(0.21, 0.83, 0.1, 0.74)))}
 
 
 @pytest.fixture(scope="module")
@@ -55,6 +60,24 @@ def test_sobol_stream_vs_reference(pkg, abi, scenes, ctx, probe_json):
     for rec in probe_json["sobol"]:
         b = rec["bounds"]
         setup = scenes.RenderSetup(b[2], b[3], rec["spp"], max_depth=16)
+        r = pkg.Render(scene, setup)
+        got = r.debug_sobol(rec["px"], rec["py"], rec["sample"], rec["dim0"], len(rec["values"]))
+        assert np.array_equal(bits(got), bits(hexf(rec["values"])))
+        r.close()
+    scene.close()
+
+
+def test_halton_stream_vs_reference(pkg, abi, scenes, ctx):
+    import json
+    import os
+    arr = scenes.SceneArrays(10, materials=("matte",), soup_version=1)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    for rec in json.load(open(os.path.join(scenes.GOLDEN_DIR, "probe_halton.json"))):
+        b = rec["bounds"]
+        setup = scenes.RenderSetup(b[2], b[3], rec["spp"], max_depth=10, sampler="halton")
+        setup.sampler.sample_bounds[:] = b
+        setup.film.cropped_bounds[:] = b
+        setup.integrator.pixel_bounds[:] = b
         r = pkg.Render(scene, setup)
         got = r.debug_sobol(rec["px"], rec["py"], rec["sample"], rec["dim0"], len(rec["values"]))
         assert np.array_equal(bits(got), bits(hexf(rec["values"])))

@@ -23,11 +23,16 @@ RENDERS = {
     # non-default lobes of the four materials: OrenNayar matte (sigma 30), rough glass (microfacet reflection +
     # transmission)
     "rough": (3000, ("matte_rough", "glass_rough", "metal", "plastic"), 40, 32, 8, 8, "spatial", None),
+    # HaltonSampler (pbrt's default sampler): non-power-of-two sample counts, cropped sample bounds
+    "halton": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 6, 5, "spatial", None),
+    "halton_crop": (3000, ("matte", "plastic"), 70, 50, 3, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
          "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,))),
-         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0))}
+         "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0)),
+         "halton": dict(camera=dict(sampler="halton")),
+         "halton_crop": dict(camera=dict(sampler="halton", crop_window=(0.21, 0.83, 0.1, 0.74)))}
 
 
 def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
@@ -39,6 +44,30 @@ def test_sobol_stream_matches_reference(abi, scenes, ob, probe_json):
         out = np.zeros(n, np.float32)
         import ctypes as C
         lib.oracle_sobol(C.byref(setup.sampler), rec["px"], rec["py"], rec["sample"], rec["dim0"], n, abi.ptr(out))
+        assert np.array_equal(bits(out), bits(hexf(rec["values"])))
+
+
+def test_halton_tables_and_stream_match_reference(abi, scenes, ob):
+    """HaltonSampler: PCG32-shuffled digit permutations and the sample stream (incl. a 1x1 film, stride 1)."""
+    import ctypes as C
+    import json
+    import os
+    lib = ob.load(abi)
+    tables = scenes.HaltonTables()
+    lib.oracle_halton_permutations.restype = C.c_int64
+    lib.oracle_halton_permutations.argtypes = [C.c_int32, C.c_void_p]
+    n = lib.oracle_halton_permutations(tables.n_dims, None)
+    assert n == tables.perms.size
+    mine = np.zeros(n, np.uint16)
+    lib.oracle_halton_permutations(tables.n_dims, abi.ptr(mine))
+    assert np.array_equal(mine, tables.perms)
+    for rec in json.load(open(os.path.join(scenes.GOLDEN_DIR, "probe_halton.json"))):
+        b = rec["bounds"]
+        setup = scenes.RenderSetup(b[2], b[3], rec["spp"], camera=abi.CameraDesc(), sampler="halton")
+        setup.sampler.sample_bounds[:] = b
+        nv = len(rec["values"])
+        out = np.zeros(nv, np.float32)
+        lib.oracle_sobol(C.byref(setup.sampler), rec["px"], rec["py"], rec["sample"], rec["dim0"], nv, abi.ptr(out))
         assert np.array_equal(bits(out), bits(hexf(rec["values"])))
 
 
