@@ -80,7 +80,25 @@ typedef struct b200pt_area_light {
     int32_t triangle;    /* index into the triangle arrays              */
     float lemit[3];      /* Lemit (already multiplied by "scale")       */
     int32_t two_sided;   /* "twosided" parameter                        */
+    int32_t sphere;      /* -1, or index into spheres[]: the light's shape is that sphere and
+                            `triangle` is ignored                       */
 } b200pt_area_light;
+
+/* ---- spheres: full Sphere shapes (shapes/sphere.cpp:49-306; zmin/zmax/phimax
+ * clipping is out of scope and must be rejected by the host).  A sphere keeps
+ * its object space like in the reference: both matrices are the host's own
+ * Transform::m / mInv (row-major).  Spheres are tested outside the triangle
+ * BVH (there are few of them: lights, a handful of objects). */
+typedef struct b200pt_sphere {
+    float object_to_world[16];          /* Shape::ObjectToWorld->m                      */
+    float world_to_object[16];          /* Shape::WorldToObject->m (== ObjectToWorld->mInv) */
+    float radius;
+    int32_t material_id;                /* index into materials                          */
+    int32_t light_id;                   /* index into lights or -1                       */
+    uint8_t reverse_orientation;        /* Shape::reverseOrientation                     */
+    uint8_t transform_swaps_handedness; /* Shape::transformSwapsHandedness               */
+    uint8_t pad[2];
+} b200pt_sphere;
 
 /* ---- scene: world-space triangle soup + per-triangle attributes ---------
  * Triangle i is the i-th GeometricPrimitive handed to the accelerator
@@ -106,6 +124,8 @@ typedef struct b200pt_scene_desc {
     const float *uvs;             /* [n_triangles][3][2]                                      */
     const uint8_t *vertex_flags;  /* [n_triangles] bit0: triangle's mesh has normals, bit1: has uvs;
                                      NULL = every triangle has whatever arrays are non-NULL   */
+    int32_t n_spheres;
+    const b200pt_sphere *spheres; /* [n_spheres]                                              */
 } b200pt_scene_desc;
 
 /* ---- camera: PerspectiveCamera (cameras/perspective.cpp:45-144) ----------

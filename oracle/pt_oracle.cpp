@@ -527,6 +527,13 @@ inline Ray GenerateCameraRay(const b200pt_camera_desc &cam, const float pFilm[2]
 struct TriHit {
     float t, b0, b1, b2;
 };
+// SurfaceInteraction members the path reads (interaction.h:98-145)
+struct Isect {
+    V3 p, pError, n, wo;  // Interaction: n = geometric normal after orientation
+    V3 ns;                // shading.n
+    V3 sdpdu;             // shading.dpdu
+    int tri;              // primitive: triangle index, or nTris + sphere index
+};
 
 // shapes/triangle.cpp:188-291 (Intersect) == :427-517 (IntersectP): the
 // watertight test up to and including the t > deltaT check.
@@ -683,6 +690,11 @@ struct oracle_scene {
     std::vector<V3> nrm;       // 3 per triangle (TriangleMesh::n) when hasN[tri]
     std::vector<float> uv;     // 6 per triangle (TriangleMesh::uv) when hasUV[tri]
     std::vector<uint8_t> hasN, hasUV;
+    std::vector<b200pt_sphere> spheres;  // primitive ids nTris .. nTris + spheres.size() - 1
+    int PrimMaterial(int prim) const {
+        return prim < nTris ? materialId[prim] : spheres[prim - nTris].material_id;
+    }
+    int PrimLight(int prim) const { return prim < nTris ? lightId[prim] : spheres[prim - nTris].light_id; }
     const float (*UV(int tri) const)[2] {
         return hasUV[tri] ? reinterpret_cast<const float (*)[2]>(&uv[6 * (size_t)tri]) : kDefaultUV;
     }
@@ -767,9 +779,181 @@ inline bool BoundsIntersectP(const BVHNode &b, const V3 &ro, float rayTMax, cons
     return (tMin < rayTMax) && (tMax > 0);
 }
 
+// ------------------------------------------------------------------ Sphere
+// core/efloat.h:47-214: a float with a conservative [low, high] interval
+struct EFloat {
+    float v, low, high;
+    EFloat() {}
+    EFloat(float v, float err = 0.f) : v(v) {
+        if (err == 0.)
+            low = high = v;
+        else {
+            low = NextFloatDown(v - err);
+            high = NextFloatUp(v + err);
+        }
+    }
+    EFloat operator+(EFloat ef) const {
+        EFloat r;
+        r.v = v + ef.v;
+        r.low = NextFloatDown(low + ef.low);
+        r.high = NextFloatUp(high + ef.high);
+        return r;
+    }
+    EFloat operator-(EFloat ef) const {
+        EFloat r;
+        r.v = v - ef.v;
+        r.low = NextFloatDown(low - ef.high);
+        r.high = NextFloatUp(high - ef.low);
+        return r;
+    }
+    EFloat operator*(EFloat ef) const {
+        EFloat r;
+        r.v = v * ef.v;
+        float prod[4] = {low * ef.low, high * ef.low, low * ef.high, high * ef.high};
+        r.low = NextFloatDown(std::min(std::min(prod[0], prod[1]), std::min(prod[2], prod[3])));
+        r.high = NextFloatUp(std::max(std::max(prod[0], prod[1]), std::max(prod[2], prod[3])));
+        return r;
+    }
+    EFloat operator/(EFloat ef) const {
+        EFloat r;
+        r.v = v / ef.v;
+        if (ef.low < 0 && ef.high > 0) {
+            r.low = -Infinity;
+            r.high = Infinity;
+        } else {
+            float div[4] = {low / ef.low, high / ef.low, low / ef.high, high / ef.high};
+            r.low = NextFloatDown(std::min(std::min(div[0], div[1]), std::min(div[2], div[3])));
+            r.high = NextFloatUp(std::max(std::max(div[0], div[1]), std::max(div[2], div[3])));
+        }
+        return r;
+    }
+};
+inline EFloat operator*(float f, EFloat fe) { return EFloat(f) * fe; }
+// efloat.h:265-285
+inline bool Quadratic(EFloat A, EFloat B, EFloat C, EFloat *t0, EFloat *t1) {
+    double discrim = (double)B.v * (double)B.v - 4. * (double)A.v * (double)C.v;
+    if (discrim < 0.) return false;
+    double rootDiscrim = std::sqrt(discrim);
+    EFloat floatRootDiscrim((float)rootDiscrim, (float)(MachineEpsilon * rootDiscrim));
+    EFloat q;
+    if (B.v < 0)
+        q = -.5f * (B - floatRootDiscrim);
+    else
+        q = -.5f * (B + floatRootDiscrim);
+    *t0 = q / A;
+    *t1 = C / q;
+    if (t0->v > t1->v) std::swap(*t0, *t1);
+    return true;
+}
+// core/transform.h:303-333
+inline V3 XformPointErrIn(const float *m, const V3 &pt, const V3 &ptError, V3 *absError) {
+    float x = pt.x, y = pt.y, z = pt.z;
+    float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    absError->x = (gamma_(3) + (float)1) * (std::abs(m[0]) * ptError.x + std::abs(m[1]) * ptError.y +
+                                            std::abs(m[2]) * ptError.z) +
+                  gamma_(3) * (std::abs(m[0] * x) + std::abs(m[1] * y) + std::abs(m[2] * z) + std::abs(m[3]));
+    absError->y = (gamma_(3) + (float)1) * (std::abs(m[4]) * ptError.x + std::abs(m[5]) * ptError.y +
+                                            std::abs(m[6]) * ptError.z) +
+                  gamma_(3) * (std::abs(m[4] * x) + std::abs(m[5] * y) + std::abs(m[6] * z) + std::abs(m[7]));
+    absError->z = (gamma_(3) + (float)1) * (std::abs(m[8]) * ptError.x + std::abs(m[9]) * ptError.y +
+                                            std::abs(m[10]) * ptError.z) +
+                  gamma_(3) * (std::abs(m[8] * x) + std::abs(m[9] * y) + std::abs(m[10] * z) + std::abs(m[11]));
+    if (wp == 1.) return V3(xp, yp, zp);
+    float inv = (float)1 / wp;
+    return V3(inv * xp, inv * yp, inv * zp);
+}
+// core/transform.h:335-351
+inline V3 XformVectorErr(const float *m, const V3 &v, V3 *absError) {
+    float x = v.x, y = v.y, z = v.z;
+    absError->x = gamma_(3) * (std::abs(m[0] * v.x) + std::abs(m[1] * v.y) + std::abs(m[2] * v.z));
+    absError->y = gamma_(3) * (std::abs(m[4] * v.x) + std::abs(m[5] * v.y) + std::abs(m[6] * v.z));
+    absError->z = gamma_(3) * (std::abs(m[8] * v.x) + std::abs(m[9] * v.y) + std::abs(m[10] * v.z));
+    return V3(m[0] * x + m[1] * y + m[2] * z, m[4] * x + m[5] * y + m[6] * z, m[8] * x + m[9] * y + m[10] * z);
+}
+// core/transform.h:243-249: normals go through the transpose of the inverse
+inline V3 XformNormal(const float *mInv, const V3 &n) {
+    float x = n.x, y = n.y, z = n.z;
+    return V3(mInv[0] * x + mInv[4] * y + mInv[8] * z, mInv[1] * x + mInv[5] * y + mInv[9] * z,
+              mInv[2] * x + mInv[6] * y + mInv[10] * z);
+}
+// Sphere constructor values for a full sphere (sphere.h:50-61): zMin = -r, zMax = r, phiMax = Radians(360)
+struct SphereConsts {
+    float radius, zMin, zMax, thetaMin, thetaMax, phiMax;
+    explicit SphereConsts(float r) {
+        radius = r;
+        zMin = Clamp(std::min(-r, r), -r, r);
+        zMax = Clamp(std::max(-r, r), -r, r);
+        thetaMin = std::acos(Clamp(std::min(zMin, zMax) / r, -1, 1));
+        thetaMax = std::acos(Clamp(std::max(zMin, zMax) / r, -1, 1));
+        phiMax = (Pi / 180) * Clamp(360.f, 0, 360);  // Radians()
+    }
+    float Area() const { return phiMax * radius * (zMax - zMin); }  // sphere.cpp:207
+};
+// shapes/sphere.cpp:49-158 (Intersect) and :160-212 (IntersectP); a full sphere is never clipped, so the
+// phi / z tests (and std::atan2, which only feeds them and the unused uv) drop out.
+// Returns false or fills *tHit (+ *is when is != nullptr).
+inline bool SphereIntersect(const b200pt_sphere &sp, const V3 &ro, const V3 &rd, float rayTMax, float *tHit,
+                            Isect *is) {
+    const SphereConsts c(sp.radius);
+    const float radius = c.radius;
+    // Transform::operator()(Ray, oError, dError), transform.h:372-384
+    V3 oErr, dErr;
+    V3 o = XformPointErr(sp.world_to_object, ro, &oErr);
+    V3 d = XformVectorErr(sp.world_to_object, rd, &dErr);
+    float lengthSquared = LengthSquared(d);
+    if (lengthSquared > 0) {
+        float dt = Dot(Abs(d), oErr) / lengthSquared;
+        o = o + d * dt;
+    }
+    EFloat ox(o.x, oErr.x), oy(o.y, oErr.y), oz(o.z, oErr.z);
+    EFloat dx(d.x, dErr.x), dy(d.y, dErr.y), dz(d.z, dErr.z);
+    EFloat a = dx * dx + dy * dy + dz * dz;
+    EFloat b = 2.f * (dx * ox + dy * oy + dz * oz);
+    EFloat cc = ox * ox + oy * oy + oz * oz - EFloat(radius) * EFloat(radius);
+    EFloat t0, t1;
+    if (!Quadratic(a, b, cc, &t0, &t1)) return false;
+    if (t0.high > rayTMax || t1.low <= 0) return false;
+    EFloat tShapeHit = t0;
+    if (tShapeHit.low <= 0) {
+        tShapeHit = t1;
+        if (tShapeHit.high > rayTMax) return false;
+    }
+    *tHit = tShapeHit.v;
+    if (!is) return true;
+    V3 pHit = o + d * tShapeHit.v;
+    pHit = pHit * (radius / Length(pHit));  // Distance(pHit, (0,0,0))
+    if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * radius;
+    float theta = std::acos(Clamp(pHit.z / radius, -1, 1));
+    float zRadius = std::sqrt(pHit.x * pHit.x + pHit.y * pHit.y);
+    float invZRadius = 1 / zRadius;
+    float cosPhi = pHit.x * invZRadius;
+    float sinPhi = pHit.y * invZRadius;
+    V3 dpdu(-c.phiMax * pHit.y, c.phiMax * pHit.x, 0);
+    V3 dpdv = (c.thetaMax - c.thetaMin) * V3(pHit.z * cosPhi, pHit.z * sinPhi, -radius * std::sin(theta));
+    V3 pError = gamma_(5) * Abs(pHit);
+    // SurfaceInteraction ctor, interaction.cpp:44-72
+    V3 n = Normalize(Cross(dpdu, dpdv));
+    if ((sp.reverse_orientation != 0) ^ (sp.transform_swaps_handedness != 0)) n = n * -1.f;
+    V3 wo = Normalize(-d);
+    // (*ObjectToWorld)(SurfaceInteraction), transform.cpp:262-297
+    is->p = XformPointErrIn(sp.object_to_world, pHit, pError, &is->pError);
+    is->n = Normalize(XformNormal(sp.world_to_object, n));
+    is->wo = Normalize(XformVector(sp.object_to_world, wo));
+    is->sdpdu = XformVector(sp.object_to_world, dpdu);
+    V3 sn = Normalize(XformNormal(sp.world_to_object, n));
+    is->ns = (Dot(sn, is->n) < 0.f) ? -sn : sn;  // Faceforward(shading.n, n)
+    return true;
+}
+inline V3 SphericalDirection(float sinTheta, float cosTheta, float phi, const V3 &x, const V3 &y, const V3 &z) {
+    return sinTheta * std::cos(phi) * x + sinTheta * std::sin(phi) * y + cosTheta * z;  // geometry.h:1488-1493
+}
+
 // accelerators/bvh.cpp:662-700.  Returns triangle index or -1; ray.tMax
 // shrinks on every accepted hit (primitive.cpp:120).
-int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut) {
+int BvhIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut) {
     if (s.nodes.empty()) return -1;
     int hitTri = -1;
     V3 invDir(1 / rd.x, 1 / rd.y, 1 / rd.z);
@@ -811,7 +995,7 @@ int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayT
 }
 
 // accelerators/bvh.cpp:702-738
-bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
+bool BvhIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
     if (s.nodes.empty()) return false;
     V3 invDir(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
@@ -848,13 +1032,38 @@ bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float ra
     return false;
 }
 
+// Scene::Intersect / IntersectP (scene.cpp:45-55) over the triangle BVH plus the spheres.  The reference keeps
+// spheres inside the same BVHAccel; testing them after the triangles gives the same closest hit except when a
+// triangle hit lies within the sphere root's error interval (order-dependent in the reference as well).
+// A sphere hit returns nTris + sphere index, hitOut->t and *sphereIs.
+int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut,
+                   Isect *sphereIs = nullptr) {
+    int hit = BvhIntersect(s, ro, rd, rayTMax, hitOut);
+    if (hit >= 0) rayTMax = hitOut->t;
+    for (size_t k = 0; k < s.spheres.size(); ++k) {
+        float tHit;
+        Isect tmp;
+        if (SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, &tmp)) {
+            rayTMax = tHit;
+            hit = (int)s.nTris + (int)k;
+            hitOut->t = tHit;
+            hitOut->b0 = hitOut->b1 = hitOut->b2 = 0;
+            tmp.tri = hit;
+            if (sphereIs) *sphereIs = tmp;
+        }
+    }
+    return hit;
+}
+bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
+    if (BvhIntersectP(s, ro, rd, rayTMax)) return true;
+    for (size_t k = 0; k < s.spheres.size(); ++k) {
+        float tHit;
+        if (SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, nullptr)) return true;
+    }
+    return false;
+}
+
 // ----------------------------------------------------- surface interaction
-struct Isect {
-    V3 p, pError, n, wo;  // Interaction: n = geometric normal after orientation
-    V3 ns;                // shading.n
-    V3 sdpdu;             // shading.dpdu
-    int tri;
-};
 
 // shapes/triangle.cpp:293-425 (meshes without per-vertex tangents) + interaction.cpp:44-86
 inline void FillIsect(const oracle_scene &s, int tri, const TriHit &h, const V3 &rayD, Isect *is) {
@@ -1312,7 +1521,7 @@ struct BSDF {  // reflection.h:153-202
 // materials/*.cpp ComputeScatteringFunctions with constant textures
 // (allowMultipleLobes = true, TransportMode::Radiance; path.cpp:107)
 void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
-    const b200pt_material &m = s.materials[s.materialId[is.tri]];
+    const b200pt_material &m = s.materials[s.PrimMaterial(is.tri)];
     bsdf->eta = 1;
     bsdf->ns = is.ns;  // reflection.h:157-160
     bsdf->ng = is.n;
@@ -1420,7 +1629,7 @@ inline S3 AreaLightL(const b200pt_area_light &l, const V3 &n, const V3 &w) {
 }
 // interaction.cpp:151-154
 inline S3 IsectLe(const oracle_scene &s, const Isect &is, const V3 &w) {
-    int lid = s.lightId[is.tri];
+    int lid = s.PrimLight(is.tri);
     return lid >= 0 ? AreaLightL(s.lights[lid], is.n, w) : S3(0.f);
 }
 
@@ -1445,6 +1654,83 @@ inline LightSample TriangleSample(const oracle_scene &s, int tri, const float u[
     it.pError = gamma_(6) * V3(pAbsSum.x, pAbsSum.y, pAbsSum.z);
     *pdf = 1 / TriangleArea(s, tri);
     return it;
+}
+
+// shapes/sphere.cpp:214-230: Sphere::Sample(u, pdf) (uniform over the area)
+inline LightSample SphereSampleArea(const b200pt_sphere &sp, const float u[2], float *pdf) {
+    const SphereConsts c(sp.radius);
+    // UniformSampleSphere, sampling.cpp:82-87
+    float z = 1 - 2 * u[0];
+    float r = std::sqrt(std::max((float)0, (float)1 - z * z));
+    float phi = 2 * Pi * u[1];
+    V3 pObj = c.radius * V3(r * std::cos(phi), r * std::sin(phi), z);  // Point3f(0,0,0) + radius * v
+    pObj = V3(0.f + pObj.x, 0.f + pObj.y, 0.f + pObj.z);
+    LightSample it;
+    it.n = Normalize(XformNormal(sp.world_to_object, pObj));
+    if (sp.reverse_orientation) it.n = it.n * -1.f;
+    pObj = pObj * (c.radius / Length(pObj));
+    V3 pObjError = gamma_(5) * Abs(pObj);
+    it.p = XformPointErrIn(sp.object_to_world, pObj, pObjError, &it.pError);
+    *pdf = 1 / c.Area();
+    return it;
+}
+// shapes/sphere.cpp:232-290: Sphere::Sample(ref, u, pdf) (cone sampling from outside)
+inline LightSample SphereSample(const b200pt_sphere &sp, const V3 &refP, const V3 &refPError, const V3 &refN,
+                                const float u[2], float *pdf) {
+    const float radius = sp.radius;
+    V3 pCenter = XformPoint(sp.object_to_world, V3(0, 0, 0));
+    V3 pOrigin = OffsetRayOrigin(refP, refPError, refN, pCenter - refP);
+    if (LengthSquared(pOrigin - pCenter) <= radius * radius) {
+        LightSample intr = SphereSampleArea(sp, u, pdf);
+        V3 wi = intr.p - refP;
+        if (LengthSquared(wi) == 0)
+            *pdf = 0;
+        else {
+            wi = Normalize(wi);
+            *pdf *= LengthSquared(refP - intr.p) / AbsDot(intr.n, -wi);
+        }
+        if (std::isinf(*pdf)) *pdf = 0.f;
+        return intr;
+    }
+    V3 wc = Normalize(pCenter - refP);
+    V3 wcX, wcY;
+    CoordinateSystem(wc, &wcX, &wcY);
+    float sinThetaMax2 = radius * radius / LengthSquared(refP - pCenter);
+    float cosThetaMax = std::sqrt(std::max((float)0, 1 - sinThetaMax2));
+    float cosTheta = (1 - u[0]) + u[0] * cosThetaMax;
+    float sinTheta = std::sqrt(std::max((float)0, 1 - cosTheta * cosTheta));
+    float phi = u[1] * 2 * Pi;
+    float dc = Length(refP - pCenter);
+    float ds = dc * cosTheta - std::sqrt(std::max((float)0, radius * radius - dc * dc * sinTheta * sinTheta));
+    float cosAlpha = (dc * dc + radius * radius - ds * ds) / (2 * dc * radius);
+    float sinAlpha = std::sqrt(std::max((float)0, 1 - cosAlpha * cosAlpha));
+    V3 nWorld = SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc);
+    V3 pWorld = pCenter + radius * V3(nWorld.x, nWorld.y, nWorld.z);
+    LightSample it;
+    it.p = pWorld;
+    it.pError = gamma_(5) * Abs(pWorld);
+    it.n = nWorld;
+    if (sp.reverse_orientation) it.n = it.n * -1.f;
+    *pdf = 1 / (2 * Pi * (1 - cosThetaMax));
+    return it;
+}
+// shapes/sphere.cpp:292-304 + shape.cpp:72-87: Sphere::Pdf(ref, wi)
+inline float SpherePdf(const b200pt_sphere &sp, const V3 &refP, const V3 &refPError, const V3 &refN, const V3 &wi) {
+    const float radius = sp.radius;
+    V3 pCenter = XformPoint(sp.object_to_world, V3(0, 0, 0));
+    V3 pOrigin = OffsetRayOrigin(refP, refPError, refN, pCenter - refP);
+    if (LengthSquared(pOrigin - pCenter) <= radius * radius) {
+        V3 ro = OffsetRayOrigin(refP, refPError, refN, wi);  // ref.SpawnRay(wi)
+        float tHit;
+        Isect li;
+        if (!SphereIntersect(sp, ro, wi, Infinity, &tHit, &li)) return 0;
+        float pdf = LengthSquared(refP - li.p) / (AbsDot(li.n, -wi) * SphereConsts(radius).Area());
+        if (std::isinf(pdf)) pdf = 0.f;
+        return pdf;
+    }
+    float sinThetaMax2 = radius * radius / LengthSquared(refP - pCenter);
+    float cosThetaMax = std::sqrt(std::max((float)0, 1 - sinThetaMax2));
+    return 1 / (2 * Pi * (1 - cosThetaMax));  // UniformConePdf, sampling.cpp:108-110
 }
 
 struct RenderCtx {
@@ -1520,9 +1806,15 @@ void ComputeVoxelDistribution(const oracle_scene &s, const int nVoxels[3], const
             // DiffuseAreaLight::Sample_Li for a reference point without a surface (diffuse.cpp:68-81)
             const b200pt_area_light &light = s.lights[j];
             float pdf;
-            LightSample ps = TriangleSample(s, light.triangle, u, &pdf);
+            LightSample ps;
+            if (light.sphere >= 0)  // Interaction(po, Normal3f(), Vector3f(), ...): no normal, no error
+                ps = SphereSample(s.spheres[light.sphere], po, V3(0, 0, 0), V3(0, 0, 0), u, &pdf);
+            else
+                ps = TriangleSample(s, light.triangle, u, &pdf);
             V3 w = ps.p - po;
-            if (LengthSquared(w) == 0)
+            if (light.sphere >= 0) {
+                // Sphere::Sample(ref, u, pdf) already returns a solid-angle density
+            } else if (LengthSquared(w) == 0)
                 pdf = 0;
             else {
                 w = Normalize(w);
@@ -1578,8 +1870,12 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
     float lightPdf = 0, scatteringPdf = 0;
     // light.Sample_Li: lights/diffuse.cpp:68-81, shape.cpp:56-70
     S3 Li(0.f);
-    LightSample pShape = TriangleSample(s, light.triangle, uLight, &lightPdf);
-    {
+    LightSample pShape;
+    if (light.sphere >= 0)
+        pShape = SphereSample(s.spheres[light.sphere], it.p, it.pError, it.n, uLight, &lightPdf);
+    else
+        pShape = TriangleSample(s, light.triangle, uLight, &lightPdf);
+    if (light.sphere < 0) {
         V3 w = pShape.p - it.p;
         if (LengthSquared(w) == 0)
             lightPdf = 0;
@@ -1628,7 +1924,9 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                 TriHit h;
                 int tri = light.triangle;
                 lightPdf = 0;
-                if (!s.degenerate[tri] &&
+                if (light.sphere >= 0)
+                    lightPdf = SpherePdf(s.spheres[light.sphere], it.p, it.pError, it.n, wi);
+                else if (!s.degenerate[tri] &&
                     TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, wi, Infinity, &h)) {
                     Isect li;
                     FillIsect(s, tri, h, wi, &li);
@@ -1642,12 +1940,12 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
             V3 ro = OffsetRayOrigin(it.p, it.pError, it.n, wi);
             TriHit h;
             ++rc.regularRays;
-            int hitTri = SceneIntersect(s, ro, wi, Infinity, &h);
+            Isect li;
+            int hitTri = SceneIntersect(s, ro, wi, Infinity, &h, &li);
             S3 Li2(0.f);
             if (hitTri >= 0) {
-                if (s.lightId[hitTri] == lightNum) {
-                    Isect li;
-                    FillIsect(s, hitTri, h, wi, &li);
+                if (s.PrimLight(hitTri) == lightNum) {
+                    if (hitTri < s.nTris) FillIsect(s, hitTri, h, wi, &li);
                     Li2 = IsectLe(s, li, -wi);
                 }
             }
@@ -1669,10 +1967,10 @@ S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
     for (bounces = 0;; ++bounces) {
         TriHit h;
         ++rc.regularRays;
-        int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h);
-        bool foundIntersection = tri >= 0;
         Isect isect;
-        if (foundIntersection) FillIsect(s, tri, h, ray.d, &isect);
+        int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h, &isect);
+        bool foundIntersection = tri >= 0;
+        if (foundIntersection && tri < s.nTris) FillIsect(s, tri, h, ray.d, &isect);
         if (bounces == 0 || specularBounce) {
             if (foundIntersection) L += beta * IsectLe(s, isect, -ray.d);
         }
@@ -1870,7 +2168,10 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->lightArea.resize(d->n_lights);
-    for (int i = 0; i < d->n_lights; ++i) s->lightArea[i] = TriangleArea(*s, s->lights[i].triangle);
+    if (d->n_spheres > 0) s->spheres.assign(d->spheres, d->spheres + d->n_spheres);
+    for (int i = 0; i < d->n_lights; ++i)
+        s->lightArea[i] = s->lights[i].sphere >= 0 ? SphereConsts(s->spheres[s->lights[i].sphere].radius).Area()
+                                                   : TriangleArea(*s, s->lights[i].triangle);
     for (int a = 0; a < 3; ++a) {
         s->wbMin[a] = Infinity;
         s->wbMax[a] = -Infinity;
@@ -1880,6 +2181,17 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
             s->wbMin[a] = std::min(s->wbMin[a], s->p[i][a]);
             s->wbMax[a] = std::max(s->wbMax[a], s->p[i][a]);
         }
+    for (const b200pt_sphere &sp : s->spheres) {
+        // Shape::WorldBound = (*ObjectToWorld)(ObjectBound()) (shape.cpp:52, transform.cpp:246-256)
+        const float r = sp.radius;
+        for (int c = 0; c < 8; ++c) {
+            V3 q = XformPoint(sp.object_to_world, V3((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
+            for (int a = 0; a < 3; ++a) {
+                s->wbMin[a] = std::min(s->wbMin[a], q[a]);
+                s->wbMax[a] = std::max(s->wbMax[a], q[a]);
+            }
+        }
+    }
     s->hasN.assign(d->n_triangles, 0);
     s->hasUV.assign(d->n_triangles, 0);
     for (int64_t i = 0; i < d->n_triangles; ++i) {

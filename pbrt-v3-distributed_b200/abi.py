@@ -18,7 +18,15 @@ class Material(C.Structure):
 
 
 class AreaLight(C.Structure):
-    _fields_ = [("triangle", C.c_int32), ("lemit", C.c_float * 3), ("two_sided", C.c_int32)]
+    _fields_ = [("triangle", C.c_int32), ("lemit", C.c_float * 3), ("two_sided", C.c_int32),
+                ("sphere", C.c_int32)]
+
+
+class Sphere(C.Structure):
+    _fields_ = [("object_to_world", C.c_float * 16), ("world_to_object", C.c_float * 16),
+                ("radius", C.c_float), ("material_id", C.c_int32), ("light_id", C.c_int32),
+                ("reverse_orientation", C.c_uint8), ("transform_swaps_handedness", C.c_uint8),
+                ("pad", C.c_uint8 * 2)]
 
 
 class SceneDesc(C.Structure):
@@ -26,7 +34,7 @@ class SceneDesc(C.Structure):
                 ("light_id", C.c_void_p), ("flip_normal", C.c_void_p), ("n_materials", C.c_int32),
                 ("materials", C.POINTER(Material)), ("n_lights", C.c_int32),
                 ("lights", C.POINTER(AreaLight)), ("normals", C.c_void_p), ("uvs", C.c_void_p),
-                ("vertex_flags", C.c_void_p)]
+                ("vertex_flags", C.c_void_p), ("n_spheres", C.c_int32), ("spheres", C.POINTER(Sphere))]
 
 
 class CameraDesc(C.Structure):

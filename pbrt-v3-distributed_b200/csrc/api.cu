@@ -44,6 +44,9 @@ struct b200pt_scene {
     std::vector<uint32_t> prim_to_tri;
     std::vector<float> light_area;
     float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
+    std::vector<DevSphere> spheres;  // Sphere shapes (tested outside the BVH)
+    DevSphere *d_spheres = nullptr;
+    uint64_t n_prims = 0;            // triangles of the descriptor (sphere k is reported as primitive n_prims + k)
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
     void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
 };
@@ -140,7 +143,21 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             return b200pt_fail(B200PT_ERR_INVALID, "scene_create: triangle %lld has light %d", (long long)i,
                                d->light_id[i]);
     }
+    if (d->n_spheres < 0 || (d->n_spheres > 0 && !d->spheres) || d->n_spheres > 4096)
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: bad sphere array (at most 4096 spheres; they are not in the BVH)");
+    for (int i = 0; i < d->n_spheres; ++i) {
+        const b200pt_sphere &sp = d->spheres[i];
+        if (!(sp.radius > 0.f) || sp.material_id < 0 || sp.material_id >= d->n_materials || sp.light_id < -1 ||
+            sp.light_id >= d->n_lights)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: sphere %d has a bad radius, material or light", i);
+    }
     for (int i = 0; i < d->n_lights; ++i) {
+        const int sph = d->lights[i].sphere;
+        if (sph >= 0) {
+            if (sph >= d->n_spheres || d->spheres[sph].light_id != i)
+                return b200pt_fail(B200PT_ERR_INVALID, "scene_create: light %d and spheres[].light_id disagree", i);
+            continue;
+        }
         int t = d->lights[i].triangle;
         if (t < 0 || t >= d->n_triangles || !d->light_id || d->light_id[t] != i)
             return b200pt_fail(B200PT_ERR_INVALID, "scene_create: light %d and light_id[] disagree", i);
@@ -206,8 +223,40 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
                 s->bounds_hi[a] = std::max(s->bounds_hi[a], v);
             }
         }
+    s->n_prims = (uint64_t)d->n_triangles;
+    s->spheres.resize((size_t)d->n_spheres);
+    for (int i = 0; i < d->n_spheres; ++i) {
+        const b200pt_sphere &in = d->spheres[i];
+        DevSphere &sp = s->spheres[i];
+        memcpy(sp.o2w, in.object_to_world, sizeof(sp.o2w));
+        memcpy(sp.w2o, in.world_to_object, sizeof(sp.w2o));
+        // Sphere ctor for a full sphere (sphere.h:50-61): zMin = -r, zMax = r, phiMax = Radians(360)
+        const float r = in.radius;
+        sp.radius = r;
+        const float zMin = pt_clamp(pt_min(-r, r), -r, r), zMax = pt_clamp(pt_max(-r, r), -r, r);
+        sp.theta_min = pt_acosf(pt_clamp(pt_min(zMin, zMax) / r, -1.f, 1.f));
+        sp.theta_max = pt_acosf(pt_clamp(pt_max(zMin, zMax) / r, -1.f, 1.f));
+        sp.phi_max = (PT_PI / 180) * pt_clamp(360.f, 0.f, 360.f);
+        sp.area = sp.phi_max * r * (zMax - zMin);
+        const bool flip = (in.reverse_orientation != 0) ^ (in.transform_swaps_handedness != 0);
+        sp.mat_flags = (uint32_t)in.material_id | (flip ? 0x10000u : 0u);
+        sp.light_id = in.light_id;
+        sp.reverse_orientation = in.reverse_orientation != 0;
+        // Shape::WorldBound (shape.cpp:52, transform.cpp:246-256) joins Scene::WorldBound()
+        for (int c = 0; c < 8; ++c) {
+            const V3 q = xform_point(sp.o2w, mk((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
+            for (int a = 0; a < 3; ++a) {
+                s->bounds_lo[a] = std::min(s->bounds_lo[a], comp(q, a));
+                s->bounds_hi[a] = std::max(s->bounds_hi[a], comp(q, a));
+            }
+        }
+    }
     s->light_area.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
+        if (d->lights[i].sphere >= 0) {
+            s->light_area[i] = s->spheres[d->lights[i].sphere].area;
+            continue;
+        }
         const float *v = d->vertices + 9 * (int64_t)d->lights[i].triangle;
         s->light_area[i] = triangle_area(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
     }
@@ -215,6 +264,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     if ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(Bvh8Node))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(TriRecord))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_spheres, std::max<size_t>(1, s->spheres.size()) * sizeof(DevSphere))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -259,7 +309,9 @@ int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
     CUDA_TRY(cudaMemcpyAsync(s->d_nodes, s->h_nodes, nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_tris, s->h_tris, tb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_materials, s->materials.data(), mb, cudaMemcpyHostToDevice, st));
-    if (bytes) *bytes = nb + tb + mb;
+    const size_t sb = s->spheres.size() * sizeof(DevSphere);
+    if (sb) CUDA_TRY(cudaMemcpyAsync(s->d_spheres, s->spheres.data(), sb, cudaMemcpyHostToDevice, st));
+    if (bytes) *bytes = nb + tb + mb + sb;
     return B200PT_OK;
 }
 
@@ -271,6 +323,7 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     cudaFree(s->d_materials);
     cudaFree(s->d_tri_n);
     cudaFree(s->d_tri_uv);
+    cudaFree(s->d_spheres);
     cudaFree(s->d_work);
     cudaFreeHost(s->h_nodes);
     cudaFreeHost(s->h_tris);
@@ -302,7 +355,7 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     if (n == 0) return B200PT_OK;
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
-    uint32_t hdr[2] = {0u, (uint32_t)n};  // work counter, ray count
+    uint32_t hdr[3] = {0u, (uint32_t)n, 0u};  // work counter, ray count, work counter of the sphere pass
     CUDA_TRY(cudaMemcpyAsync(s->d_work, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
     TraceArgs a;
     memset(&a, 0, sizeof(a));
@@ -323,6 +376,13 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     else
         a.full_out = reinterpret_cast<b200pt_hit *>(out_dev);
     launch_trace(a, any_hit, false, false, trace_grid(s->ctx), st);
+    if (!s->spheres.empty()) {
+        a.spheres = s->d_spheres;
+        a.n_spheres = (uint32_t)s->spheres.size();
+        a.n_tris = (uint32_t)s->n_prims;
+        a.sphere_work = s->d_work + 2;
+        launch_spheres(a, any_hit, false, trace_grid(s->ctx), st);
+    }
     CUDA_TRY(cudaGetLastError());
     return B200PT_OK;
 }
@@ -423,6 +483,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.scene.n_tris = (uint32_t)scene->n_tris;
     H.scene.tri_n = scene->d_tri_n;
     H.scene.tri_uv = scene->d_tri_uv;
+    H.scene.spheres = scene->d_spheres;
+    H.scene.n_spheres = (uint32_t)scene->spheres.size();
     // sampler (samplers/sobol.h:49-62)
     H.sampler.spp = smp->samples_per_pixel;
     memcpy(H.sampler.sb, smp->sample_bounds, sizeof(int) * 4);
@@ -494,7 +556,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     std::vector<DevLight> dl(nl);
     std::vector<float> func(std::max(nl, 1), 1.f), cdf(nl + 1, 0.f);
     for (int i = 0; i < nl; ++i) {
-        dl[i].tri = scene->prim_to_tri[scene->lights[i].triangle];
+        dl[i].tri = scene->lights[i].sphere >= 0 ? (SPHERE_HIT_BASE | (uint32_t)scene->lights[i].sphere)
+                                                 : scene->prim_to_tri[scene->lights[i].triangle];
         memcpy(dl[i].lemit, scene->lights[i].lemit, sizeof(float) * 3);
         dl[i].two_sided = scene->lights[i].two_sided;
         dl[i].area = scene->light_area[i];
@@ -776,6 +839,13 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         // two streams: as the persistent CTAs of one launch drain, the other launch fills the freed SMs.
         const bool overlap = r->overlap && r->sort_from_bounce < 0;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
+        const bool has_spheres = H.scene.n_spheres > 0;
+        auto sphere_args = [&](TraceArgs &a, uint32_t *work) {
+            a.spheres = H.scene.spheres;
+            a.n_spheres = H.scene.n_spheres;
+            a.n_tris = (uint32_t)r->scene->n_prims;
+            a.sphere_work = work;
+        };
         auto trace_path = [&](int b) {
             uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
             uint32_t *wk = H.work + (size_t)b * 16;
@@ -805,7 +875,13 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m) a.q_mat[m] = H.q_mat[m];
             a.qcount_mat = qc + Q_MAT0;
             LaunchTimer lt(r, st, 0);
-            launch_trace(a, false, true, r->instrumented, r->grid_trace, st);
+            // with spheres in the scene the sphere pass decides the final hit, so it does the classification
+            launch_trace(a, false, !has_spheres, r->instrumented, r->grid_trace, st);
+            if (has_spheres) {
+                sphere_args(a, wk + 8);
+                launch_spheres(a, false, true, r->grid_shade, st);
+                r->launches++;
+            }
         };
         auto trace_direct = [&](int b) {
             uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
@@ -836,6 +912,11 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             {
                 LaunchTimer lt(r, st2, 1);
                 launch_trace(a, true, false, r->instrumented, r->grid_trace, st2);
+                if (has_spheres) {
+                    sphere_args(a, wk + 9);
+                    launch_spheres(a, true, false, r->grid_shade, st2);
+                    r->launches++;
+                }
             }
             // BSDF-sampled MIS rays (closest hit)
             a.ray_o = H.mi_o;
@@ -848,6 +929,11 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.occ_out = nullptr;
             LaunchTimer lt(r, st2, 0);
             launch_trace(a, false, false, r->instrumented, r->grid_trace, st2);
+            if (has_spheres) {
+                sphere_args(a, wk + 10);
+                launch_spheres(a, false, false, r->grid_shade, st2);
+                r->launches++;
+            }
         };
         trace_path(0);
         for (int b = 0; b <= maxDepth; ++b) {
@@ -855,7 +941,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
-                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr, b, wk + 1 + m,
+                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr || has_spheres, b, wk + 1 + m,
                                  r->grid_shade, st);
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)

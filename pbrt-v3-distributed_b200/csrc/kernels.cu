@@ -270,6 +270,82 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------- spheres
+// Scene::Intersect / IntersectP for the Sphere shapes (not part of the BVH): one thread per ray of the
+// traversal launch that just finished.
+template <bool ANY_HIT, bool CLASSIFY>
+__global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
+    const uint32_t n = *a.count;
+    uint32_t i;
+    while (warp_fetch(a.sphere_work, n, &i)) {
+        int family = -1;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = a.queue ? a.queue[i] : i;
+            const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+            const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+            const V3 ro = v3(o4), rd = v3(d4);
+            float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
+            if (ANY_HIT) {
+                if (!a.occ_out[slot]) {
+                    for (uint32_t k = 0; k < a.n_spheres; ++k) {
+                        float t;
+                        if (sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                            a.occ_out[slot] = 1;
+                            break;
+                        }
+                    }
+                }
+            } else {
+                uint32_t best = B200PT_MISS;
+                if (a.hit_out) {
+                    best = a.hit_out[slot];
+                    if (best != B200PT_MISS) {  // ray.tMax after the triangle hit: Triangle::Intersect's t
+                        const F4 *tp = a.tris + (size_t)best * 3;
+                        TriHit h;
+                        if (triangle_test(v3(ld_f4(tp)), v3(ld_f4(tp + 1)), v3(ld_f4(tp + 2)), ro, make_shear(rd), pt_inf(), &h))
+                            tmax = h.t;
+                    }
+                } else if (a.full_out[slot].triangle >= 0) {
+                    tmax = a.full_out[slot].t;
+                }
+                uint32_t sph = B200PT_MISS;
+                for (uint32_t k = 0; k < a.n_spheres; ++k) {
+                    float t;
+                    if (sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                        tmax = t;
+                        sph = k;
+                    }
+                }
+                if (sph != B200PT_MISS) {
+                    best = SPHERE_HIT_BASE | sph;
+                    if (a.hit_out) a.hit_out[slot] = best;
+                    if (a.full_out) {
+                        b200pt_hit r;
+                        r.triangle = (int32_t)(a.n_tris + sph);
+                        r.t = tmax;
+                        r.b0 = r.b1 = 0.f;
+                        a.full_out[slot] = r;
+                    }
+                }
+                if (CLASSIFY && best != B200PT_MISS) {
+                    const uint32_t mf = is_sphere_hit(best) ? a.spheres[best & SPHERE_HIT_MASK].mat_flags
+                                                            : __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
+                    family = a.materials[mf & 0xffffu].type;
+                }
+            }
+        }
+        if (CLASSIFY) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const bool mine = family == m;
+                const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
+                if (mine) a.q_mat[m][pos] = slot;
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------- shade
 struct DirectOut {
     uint32_t pend;
@@ -285,8 +361,16 @@ template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                 int lightNum, const float uLight[2], DirectOut *out) {
     const DevLight light = R->lights[lightNum];
-    const F4 *tp = R->scene.tris + (size_t)light.tri * 3;
-    const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+    // a sphere light (scenes with spheres always run the VTX variant)
+    const bool onSphere = VTX && is_sphere_hit(light.tri);
+    const DevSphere *lsp = onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr;
+    const F4 *tp = R->scene.tris + (size_t)(onSphere ? 0u : light.tri) * 3;
+    F4 t0 = {0.f, 0.f, 0.f, 0.f}, t1 = t0, t2 = t0;
+    if (!onSphere) {
+        t0 = ld_f4(tp);
+        t1 = ld_f4(tp + 1);
+        t2 = ld_f4(tp + 2);
+    }
     const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
     const uint32_t lflags = __float_as_uint(t1.w);
     const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
@@ -301,8 +385,11 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     float lightPdf = 0.f, scatteringPdf = 0.f;
     // light.Sample_Li: diffuse.cpp:68-81, shape.cpp:56-70
     RGB Li = rgb1(0.f);
-    LightSample ps = triangle_sample(p0, p1, p2, lflip, lsh, uLight, &lightPdf);
-    {
+    LightSample ps;
+    if (onSphere) {
+        ps = sphere_sample(*lsp, is.p, is.pError, is.n, uLight, &lightPdf);  // already a solid-angle density
+    } else {
+        ps = triangle_sample(p0, p1, p2, lflip, lsh, uLight, &lightPdf);
         V3 w = ps.p - is.p;
         if (len2(w) == 0)
             lightPdf = 0;
@@ -342,7 +429,15 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         float lpdf = 0.f;
         V3 ln = mk(0.f, 0.f, 0.f);
         TriHit h;
-        if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
+        if (onSphere) {
+            // Sphere::Pdf (sphere.cpp:292-304); the ray can only return this light's radiance if it meets the sphere
+            float th;
+            Isect li;
+            if (sphere_intersect(*lsp, ro, wi, pt_inf(), &th, &li)) {
+                ln = li.n;
+                lpdf = sphere_pdf(*lsp, is.p, is.pError, is.n, wi);
+            }
+        } else if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
             Isect li;
             fill_isect(p0, p1, p2, lflip, lsh, h, wi, &li);
             ln = li.n;
@@ -385,18 +480,33 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
             const bool specularBounce = ((meta >> 24) & PF_SPECULAR) != 0;
             RGB beta = rgb3(b4), L = rgb3(L4);
             const uint32_t ti = R->hit[slot];
-            const F4 *tp = R->scene.tris + (size_t)ti * 3;
-            const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
-            const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
-            const uint32_t mflags = __float_as_uint(t1.w);
-            const int lightId = (int)__float_as_uint(t2.w);
-            // re-derive (t, b0, b1, b2) of the accepted hit: Triangle::Intersect's values do not depend on tMax
-            TriHit h;
-            if (triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h)) {
-                Isect is;
-                TriShading tsh;
-                load_shading<VTX>(R->scene, ti, mflags, &tsh);
-                fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
+            Isect is;
+            uint32_t mflags;
+            int lightId;
+            bool found;
+            if (VTX && is_sphere_hit(ti)) {
+                // the accepted root does not depend on tMax either (t0 unless its interval reaches 0, then t1)
+                const DevSphere *sp = R->scene.spheres + (ti & SPHERE_HIT_MASK);
+                float th;
+                found = sphere_intersect(*sp, ro, rd, pt_inf(), &th, &is);
+                mflags = sp->mat_flags;
+                lightId = sp->light_id;
+            } else {
+                const F4 *tp = R->scene.tris + (size_t)ti * 3;
+                const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+                const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
+                mflags = __float_as_uint(t1.w);
+                lightId = (int)__float_as_uint(t2.w);
+                // re-derive (t, b0, b1, b2) of the accepted hit: Triangle::Intersect's values do not depend on tMax
+                TriHit h;
+                found = triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h);
+                if (found) {
+                    TriShading tsh;
+                    load_shading<VTX>(R->scene, ti, mflags, &tsh);
+                    fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
+                }
+            }
+            if (found) {
                 // path.cpp:91-101: emitted light at the first vertex or after a specular bounce
                 if (bounces == 0 || specularBounce) {
                     if (lightId >= 0) {
@@ -555,13 +665,20 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     const long long vox = id / R->n_lights;
     const int vx = (int)(vox % g.nv[0]), vy = (int)((vox / g.nv[0]) % g.nv[1]), vz = (int)(vox / ((long long)g.nv[0] * g.nv[1]));
     const DevLight light = R->lights[j];
-    const F4 *tp = R->scene.tris + (size_t)light.tri * 3;
-    const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+    const bool onSphere = is_sphere_hit(light.tri);
+    const F4 *tp = R->scene.tris + (size_t)(onSphere ? 0u : light.tri) * 3;
+    F4 t0 = {0.f, 0.f, 0.f, 0.f}, t1 = t0, t2 = t0;
+    if (!onSphere) {
+        t0 = ld_f4(tp);
+        t1 = ld_f4(tp + 1);
+        t2 = ld_f4(tp + 2);
+    }
     const uint32_t lflags = __float_as_uint(t1.w);
     TriShading lsh;
     load_shading<true>(R->scene, light.tri, lflags, &lsh);
-    R->sp_func[vox * R->n_lights + j] = spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0,
-                                                              lsh, rgbp(light.lemit), light.two_sided != 0);
+    R->sp_func[vox * R->n_lights + j] =
+        spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0, lsh, rgbp(light.lemit),
+                              light.two_sided != 0, onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr);
 }
 __global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
     const SpatialGrid &g = R->grid;
@@ -800,6 +917,15 @@ void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, i
         else
             k_trace<false, false, false><<<grid, 128, 0, s>>>(a);
     }
+}
+
+void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, cudaStream_t s) {
+    if (any_hit)
+        k_spheres<true, false><<<grid, 128, 0, s>>>(a);
+    else if (classify)
+        k_spheres<false, true><<<grid, 128, 0, s>>>(a);
+    else
+        k_spheres<false, false><<<grid, 128, 0, s>>>(a);
 }
 
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,

@@ -15,11 +15,12 @@
 
 #include "bvh8_traverse.cuh"
 #include "pt_core.cuh"
+#include "pt_sphere.cuh"
 
 namespace b200pt {
 
 struct DevLight {
-    uint32_t tri;  // leaf-order triangle index
+    uint32_t tri;  // leaf-order triangle index, or SPHERE_HIT_BASE | sphere index (the id traversal reports)
     float lemit[3];
     int two_sided;
     float area;  // Triangle::Area(), computed on the host
@@ -32,6 +33,8 @@ struct DevScene {
     uint32_t n_nodes, n_tris;
     const F4 *tri_n;   // optional per-vertex shading normals, 3 x float4 per triangle (leaf order)
     const F4 *tri_uv;  // optional uvs, 2 x float4 per triangle: (u0 v0 u1 v1) (u2 v2 - -)
+    const DevSphere *spheres;  // Sphere shapes, tested outside the BVH (k_spheres)
+    uint32_t n_spheres;
 };
 
 // queue ids inside one bounce's counter block
@@ -119,11 +122,20 @@ struct TraceArgs {
     int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
     int postpone_pct;           // triangle postponing threshold (% of converged lanes), 0 = off
     uint32_t magic;             // 0x4B000000 as a run-time value (see byte_plus_2p23)
+    // sphere pass (launch_spheres): same rays, after the traversal launch
+    const DevSphere *spheres;
+    uint32_t n_spheres;
+    uint32_t n_tris;            // sphere k is reported as primitive n_tris + k in full_out
+    uint32_t *sphere_work;      // persistent fetch counter of the sphere pass (zeroed)
 };
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
                    cudaStream_t s);
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s);
+// Tests the spheres against the rays of a finished traversal launch (tMax shortened by the triangle hit),
+// updates hit_out / full_out / occ_out and, with `classify`, appends the slots to the BSDF-family queues
+// (the traversal launch then runs without classification).
+void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, cudaStream_t s);
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
                   cudaStream_t s);
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);

@@ -1142,42 +1142,7 @@ B200_HD int spatial_voxel(const SpatialGrid &g, const V3 &p) {
 }
 // One (voxel, light) term of SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:230-275):
 // sum over 128 Halton points of Li.y()/pdf for a DiffuseAreaLight on the triangle (p0,p1,p2).
-B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
-                                    const V3 &p2, bool flip, const TriShading &sh, const RGB &lemit, bool twoSided) {
-    const int pi[3] = {vx, vy, vz};
-    float lo[3], hi[3];
-    for (int a = 0; a < 3; ++a) {
-        const float t0 = (float)pi[a] / (float)g.nv[a], t1 = (float)(pi[a] + 1) / (float)g.nv[a];
-        const float b0 = lerpf(t0, g.wb_min[a], g.wb_max[a]), b1 = lerpf(t1, g.wb_min[a], g.wb_max[a]);
-        lo[a] = pt_min(b0, b1);
-        hi[a] = pt_max(b0, b1);
-    }
-    float contrib = 0.f;
-    for (int i = 0; i < 128; ++i) {
-        const V3 po = mk(lerpf(radical_inverse(0, i), lo[0], hi[0]), lerpf(radical_inverse(1, i), lo[1], hi[1]),
-                         lerpf(radical_inverse(2, i), lo[2], hi[2]));
-        const float u[2] = {radical_inverse(3, i), radical_inverse(4, i)};
-        float pdf;
-        const LightSample ps = triangle_sample(p0, p1, p2, flip, sh, u, &pdf);
-        V3 w = ps.p - po;
-        if (len2(w) == 0)
-            pdf = 0;
-        else {
-            w = normalize(w);
-            pdf *= len2(po - ps.p) / absdot(ps.n, -w);
-            if (pt_isinf(pdf)) pdf = 0.f;
-        }
-        RGB Li = rgb1(0.f);
-        if (pdf == 0 || len2(ps.p - po) == 0) {
-            pdf = 0;
-        } else {
-            const V3 wi = normalize(ps.p - po);
-            Li = (twoSided || dot(ps.n, -wi) > 0) ? lemit : rgb1(0.f);
-        }
-        if (pdf > 0) contrib += lum(Li) / pdf;
-    }
-    return contrib;
-}
+// spatial_light_contrib: see pt_sphere.cuh (it samples triangle and sphere lights)
 
 // ----------------------------------------------------------------------- film
 B200_HD void rgb_to_xyz(const RGB &c, float xyz[3]) {  // spectrum.h:62-66

@@ -71,6 +71,7 @@
 #include "materials/plastic.h"
 #include "samplers/halton.h"
 #include "samplers/sobol.h"
+#include "shapes/sphere.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
 #undef private
@@ -110,6 +111,7 @@ struct Flattened {
     std::vector<uint8_t> flip;
     std::vector<b200pt_material> materials;
     std::vector<b200pt_area_light> lights;
+    std::vector<b200pt_sphere> spheres;
 };
 
 // materials/{matte,plastic,metal,glass}.cpp ComputeScatteringFunctions with constant textures
@@ -193,14 +195,43 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
     // used consistently -- triangle ids only name primitives
     const auto &prims = bvh->primitives;
     std::unordered_map<const Material *, int> matIndex;
-    std::unordered_map<const Shape *, int> triOfShape;
+    std::unordered_map<const Shape *, int> triOfShape, sphereOfShape;
+    auto materialOf = [&](const Material *m, int *id) {
+        if (!m) return *why = "primitives without a material (medium boundaries)", false;
+        auto it = matIndex.find(m);
+        if (it == matIndex.end()) {
+            b200pt_material bm;
+            if (!ConvertMaterial(m, &bm, why)) return false;
+            it = matIndex.emplace(m, (int)f->materials.size()).first;
+            f->materials.push_back(bm);
+        }
+        *id = it->second;
+        return true;
+    };
     f->vertices.reserve(prims.size() * 9);
     for (size_t i = 0; i < prims.size(); ++i) {
         auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
         if (!gp) return *why = "a primitive other than GeometricPrimitive (instancing / animation)", false;
         if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
+        if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
+            // full spheres only (sphere.h:50-61): no zmin / zmax / phimax clipping
+            if (sph->zMin != -sph->radius || sph->zMax != sph->radius || sph->phiMax != Radians(360.f))
+                return *why = "partial spheres (zmin / zmax / phimax)", false;
+            b200pt_sphere bs;
+            memset(&bs, 0, sizeof(bs));
+            memcpy(bs.object_to_world, sph->ObjectToWorld->m.m, sizeof(float) * 16);
+            memcpy(bs.world_to_object, sph->WorldToObject->m.m, sizeof(float) * 16);
+            bs.radius = sph->radius;
+            if (!materialOf(gp->material.get(), &bs.material_id)) return false;
+            bs.light_id = -1;
+            bs.reverse_orientation = sph->reverseOrientation ? 1 : 0;
+            bs.transform_swaps_handedness = sph->transformSwapsHandedness ? 1 : 0;
+            sphereOfShape[gp->shape.get()] = (int)f->spheres.size();
+            f->spheres.push_back(bs);
+            continue;
+        }
         auto tri = dynamic_cast<const Triangle *>(gp->shape.get());
-        if (!tri) return *why = "a shape other than Triangle", false;
+        if (!tri) return *why = "a shape other than Triangle and Sphere", false;
         const TriangleMesh &mesh = *tri->mesh;
         if (mesh.s || mesh.alphaMask || mesh.shadowAlphaMask)
             return *why = "meshes with per-vertex tangents / alpha masks", false;
@@ -221,29 +252,31 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         f->anyNormals |= mesh.n != nullptr;
         f->anyUVs |= mesh.uv != nullptr;
         f->flip.push_back((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0);
-        const Material *m = gp->material.get();
-        if (!m) return *why = "primitives without a material (medium boundaries)", false;
-        auto it = matIndex.find(m);
-        if (it == matIndex.end()) {
-            b200pt_material bm;
-            if (!ConvertMaterial(m, &bm, why)) return false;
-            it = matIndex.emplace(m, (int)f->materials.size()).first;
-            f->materials.push_back(bm);
-        }
-        f->materialId.push_back(it->second);
+        int mid;
+        if (!materialOf(gp->material.get(), &mid)) return false;
+        triOfShape[gp->shape.get()] = (int)f->materialId.size();
+        f->materialId.push_back(mid);
         f->lightId.push_back(-1);
-        triOfShape[gp->shape.get()] = (int)i;
     }
     if (!scene.infiniteLights.empty()) return *why = "infinite area lights", false;
     for (size_t l = 0; l < scene.lights.size(); ++l) {
         auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
         if (!dl) return *why = "a light other than a diffuse area light", false;
-        auto it = triOfShape.find(dl->shape.get());
-        if (it == triOfShape.end()) return *why = "an area light on a shape that is not in the scene", false;
         b200pt_area_light bl;
-        bl.triangle = it->second;
         ToRGB(dl->Lemit, bl.lemit);
         bl.two_sided = dl->twoSided ? 1 : 0;
+        auto is = sphereOfShape.find(dl->shape.get());
+        if (is != sphereOfShape.end()) {
+            bl.triangle = -1;
+            bl.sphere = is->second;
+            f->spheres[is->second].light_id = (int)l;
+            f->lights.push_back(bl);
+            continue;
+        }
+        auto it = triOfShape.find(dl->shape.get());
+        if (it == triOfShape.end()) return *why = "an area light on a shape that is not in the scene", false;
+        bl.triangle = it->second;
+        bl.sphere = -1;
         f->lightId[it->second] = (int)l;
         f->lights.push_back(bl);
     }
@@ -306,6 +339,8 @@ class GpuPathIntegrator : public PathIntegrator {
         sd.normals = flat.anyNormals ? flat.normals.data() : nullptr;
         sd.uvs = flat.anyUVs ? flat.uvs.data() : nullptr;
         sd.vertex_flags = flat.vertexFlags.data();
+        sd.n_spheres = (int)flat.spheres.size();
+        sd.spheres = flat.spheres.data();
 
         b200pt_camera_desc cd;
         memcpy(cd.raster_to_camera, pcam->RasterToCamera.m.m, sizeof(float) * 16);

@@ -27,6 +27,8 @@ COPPER_K = [float.fromhex("0x1.f3cb18p+1"), float.fromhex("0x1.394c0cp+1"), floa
 
 
 def soup_vertices(n, seed=1234, version=0):
+    if n == 0:
+        return np.zeros((0, 3, 3), np.float32)
     rng = np.random.default_rng(seed)
     c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
     k = 1.0 if version == 0 else 0.5
@@ -130,7 +132,10 @@ class SceneArrays:
     """Flattened scene in the layout b200pt_scene_desc wants."""
 
     def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
-                 n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=()):
+                 n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=(), spheres=()):
+        """spheres: dicts {center, radius, material (a name in `materials` or "black"), emit (radiance or
+        None), scale (sx, sy, sz) or None, reverse_orientation} -- written as `Translate` + `Scale` +
+        `Shape "sphere"` by write_pbrt, after the meshes."""
         self.material_names = list(materials) + ["black"]
         soup = soup_vertices(n_tris, seed, soup_version)
         quads = light_quads(soup_version, n_lights)
@@ -175,11 +180,34 @@ class SceneArrays:
         self.light_L = float(light_L)
         self.two_sided = bool(two_sided)
         self._materials = None
-        self._lights = (abi.AreaLight * max(nl, 1))()
+        self.sphere_specs = [dict(s) for s in spheres]
+        n_sl = sum(1 for s in self.sphere_specs if s.get("emit"))
+        self._lights = (abi.AreaLight * max(nl + n_sl, 1))()
         for i in range(nl):
             self._lights[i].triangle = i
             self._lights[i].lemit[:] = [light_L] * 3
             self._lights[i].two_sided = int(two_sided)
+            self._lights[i].sphere = -1
+        self._spheres = (abi.Sphere * max(len(self.sphere_specs), 1))()
+        for k, sp in enumerate(self.sphere_specs):
+            m, minv = sphere_transform(sp["center"], sp.get("scale"))
+            rec = self._spheres[k]
+            rec.object_to_world[:] = m.reshape(-1).tolist()
+            rec.world_to_object[:] = minv.reshape(-1).tolist()
+            rec.radius = sp["radius"]
+            rec.material_id = self.material_names.index(sp.get("material", "black"))
+            rec.reverse_orientation = int(bool(sp.get("reverse_orientation")))
+            sc = sp.get("scale") or (1, 1, 1)
+            rec.transform_swaps_handedness = int(sc[0] * sc[1] * sc[2] < 0)  # Transform::SwapsHandedness
+            rec.light_id = -1
+            if sp.get("emit"):
+                li = nl
+                nl += 1
+                rec.light_id = li
+                self._lights[li].triangle = -1
+                self._lights[li].sphere = k
+                self._lights[li].lemit[:] = [sp["emit"]] * 3
+                self._lights[li].two_sided = int(bool(sp.get("two_sided")))
         self.n_lights = nl
 
     @property
@@ -203,7 +231,40 @@ class SceneArrays:
         d.normals = abi.ptr(self.normals)
         d.uvs = abi.ptr(self.uvs)
         d.vertex_flags = abi.ptr(self.vertex_flags)
+        d.n_spheres = len(self.sphere_specs)
+        d.spheres = C.cast(self._spheres, C.POINTER(abi.Sphere))
         return d
+
+
+def _mat_mul(a, b):
+    """Matrix4x4::Mul (transform.cpp:98-106): float sums in index order."""
+    f = np.float32
+    r = np.zeros((4, 4), f)
+    for i in range(4):
+        for j in range(4):
+            r[i, j] = f(f(f(a[i, 0] * b[0, j]) + f(a[i, 1] * b[1, j])) + f(a[i, 2] * b[2, j])) + f(a[i, 3] * b[3, j])
+    return r
+
+
+def sphere_transform(center, scale=None):
+    """CTM pbrt builds for `Translate c` [+ `Scale s`] inside an attribute block at identity
+    (api.cpp pbrtTranslate / pbrtScale: ctm = ctm * T; Transform::operator*, transform.cpp:222-225)."""
+    f = np.float32
+    m = np.eye(4, dtype=f)
+    minv = np.eye(4, dtype=f)
+    t = np.eye(4, dtype=f)
+    ti = np.eye(4, dtype=f)
+    t[:3, 3] = [f(c) for c in center]
+    ti[:3, 3] = [-f(c) for c in center]
+    m, minv = _mat_mul(m, t), _mat_mul(ti, minv)
+    if scale:
+        s_ = np.eye(4, dtype=f)
+        si = np.eye(4, dtype=f)
+        for a in range(3):
+            s_[a, a] = f(scale[a])
+            si[a, a] = f(1) / f(scale[a])
+        m, minv = _mat_mul(m, s_), _mat_mul(si, minv)
+    return m, minv
 
 
 def write_ply(path, tris, normals=None, uvs=None):
@@ -268,6 +329,20 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
         lines += [PBRT_MATERIAL[scene.material_names[m]], 'Shape "plymesh" "string filename" "%s"' % ply]
         if m in scene.reverse_orientation:
             lines += ["AttributeEnd"]
+    for sp in getattr(scene, "sphere_specs", ()):
+        lines.append("AttributeBegin")
+        if sp.get("emit"):
+            lines.append('  AreaLightSource "diffuse" "rgb L" [%g %g %g]%s' %
+                         (sp["emit"], sp["emit"], sp["emit"], ' "bool twosided" "true"' if sp.get("two_sided") else ""))
+        mat = sp.get("material", "black")
+        lines.append("  " + ('Material "matte" "rgb Kd" [0 0 0]' if mat == "black" else PBRT_MATERIAL[mat]))
+        lines.append("  Translate %.9g %.9g %.9g" % tuple(sp["center"]))
+        if sp.get("scale"):
+            lines.append("  Scale %.9g %.9g %.9g" % tuple(sp["scale"]))
+        if sp.get("reverse_orientation"):
+            lines.append("  ReverseOrientation")
+        lines.append('  Shape "sphere" "float radius" [%.9g]' % sp["radius"])
+        lines.append("AttributeEnd")
     lines.append("WorldEnd")
     path = os.path.join(dirname, name + ".pbrt")
     with open(path, "w") as f:

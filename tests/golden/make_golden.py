@@ -44,13 +44,32 @@ RENDERS = {
     # HaltonSampler (pbrt's default sampler): non-power-of-two sample counts, cropped sample bounds
     "halton": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 6, 5, "spatial", None),
     "halton_crop": (3000, ("matte", "plastic"), 70, 50, 3, 5, "uniform", None),
+    # Sphere shapes: two sphere area lights (one under a uniform scale) next to the 10 quad lights, a glass
+    # sphere, a plastic ellipsoid under a handedness-swapping scale, a matte sphere with ReverseOrientation
+    "spheres": (3000, ("matte", "glass", "metal", "plastic"), 48, 40, 8, 6, "spatial", None),
+    # the only light is a sphere (the situation of scenes/killeroo-simple.pbrt), Halton sampler
+    "sphere_light": (3000, ("matte", "plastic"), 40, 32, 6, 5, "spatial", 0),
+    "sphere_power": (3000, ("matte", "glass_rough"), 40, 32, 4, 7, "power", 4),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
          "normals_uv": dict(scene=dict(shading_normals=(0, 2), uvs=(0, 3), reverse_orientation=(3,))),
          "crop": dict(camera=dict(crop_window=(0.21, 0.83, 0.1, 0.74), film_scale=2.0, max_sample_luminance=9.0)),
          "halton": dict(camera=dict(sampler="halton")),
-         "halton_crop": dict(camera=dict(sampler="halton", crop_window=(0.21, 0.83, 0.1, 0.74)))}
+         "halton_crop": dict(camera=dict(sampler="halton", crop_window=(0.21, 0.83, 0.1, 0.74))),
+         "spheres": dict(scene=dict(spheres=(
+             dict(center=(1.2, 1.8, -1.5), radius=0.35, emit=60.0),
+             dict(center=(-2.0, 0.5, -2.5), radius=0.2, emit=90.0, scale=(1.5, 1.5, 1.5)),
+             dict(center=(0.1, 0.0, -2.2), radius=0.45, material="glass"),
+             dict(center=(-0.9, -0.6, -2.0), radius=0.4, material="plastic", scale=(1.3, 0.7, -1.1)),
+             dict(center=(0.9, -0.7, -1.9), radius=0.3, material="matte", reverse_orientation=True)))),
+         "sphere_light": dict(scene=dict(spheres=(dict(center=(0.5, 2.5, -2.0), radius=0.3, emit=400.0),
+                                                  dict(center=(-0.6, 0.2, -2.0), radius=0.5, material="plastic"))),
+                              camera=dict(sampler="halton")),
+         "sphere_power": dict(scene=dict(spheres=(dict(center=(0.0, 0.0, -2.4), radius=0.25, emit=150.0, two_sided=True),
+                                                  dict(center=(2.2, -1.0, 0.0), radius=0.6, emit=30.0,
+                                                       reverse_orientation=True),
+                                                  dict(center=(-0.7, 0.5, -1.9), radius=0.35, material="glass_rough"))))}
 
 
 HALTON_CASES = [((0, 0, 700, 700), 8, 345, 678, 5, 0, 100), ((0, 0, 64, 48), 16, 3, 47, 15, 0, 120),

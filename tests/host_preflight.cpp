@@ -5,6 +5,8 @@
 // (oracle/liboracle.so) BEFORE GPU time is spent:
 //   * 8-wide BVH build + traversal vs the oracle's closest / any hit answers (bit-exact t)
 //   * Sobol' sample stream and camera rays vs the oracle
+//   * Sphere::Intersect / IntersectP arithmetic (EFloat quadratic, error-tracking transforms) vs the oracle,
+//     and the restated acosf vs the host libm
 // This binary is test infrastructure: it is never linked into libb200pt.so and
 // the product has no CPU path.  Usage: host_preflight <n_tris> <n_rays> <seed>
 #include <cmath>
@@ -17,6 +19,7 @@
 #include "../oracle/pt_oracle.h"
 #include "../pbrt-v3-distributed_b200/csrc/bvh8.h"
 #include "../pbrt-v3-distributed_b200/csrc/bvh8_traverse.cuh"
+#include "../pbrt-v3-distributed_b200/csrc/pt_sphere.cuh"
 
 using namespace b200pt;
 
@@ -123,6 +126,82 @@ int main(int argc, char **argv) {
            (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
     fail |= (badTri || badT || badOcc);
     oracle_scene_destroy(os);
+
+    // ---- spheres: the device routine (compiled for the host) against the oracle's Scene::Intersect
+    {
+        const int nSph = 6;
+        std::vector<b200pt_sphere> sph(nSph);
+        std::vector<DevSphere> dev(nSph);
+        for (int k = 0; k < nSph; ++k) {
+            b200pt_sphere &sp = sph[k];
+            memset(&sp, 0, sizeof(sp));
+            const float c[3] = {U(rng), U(rng), U(rng)};
+            const float sc[3] = {k % 2 ? 0.6f + 0.5f * std::fabs(U(rng)) : 1.f, k % 2 ? 0.6f + 0.5f * std::fabs(U(rng)) : 1.f,
+                                 k % 3 == 2 ? -1.2f : 1.f};
+            for (int a = 0; a < 4; ++a) sp.object_to_world[5 * a] = sp.world_to_object[5 * a] = 1.f;
+            for (int a = 0; a < 3; ++a) {  // Translate(c) * Scale(sc): m = T S, mInv = S^-1 T^-1
+                sp.object_to_world[5 * a] = sc[a];
+                sp.object_to_world[4 * a + 3] = c[a];
+                sp.world_to_object[5 * a] = 1.f / sc[a];
+                sp.world_to_object[4 * a + 3] = (1.f / sc[a]) * -c[a];
+            }
+            sp.radius = 0.15f + 0.3f * std::fabs(U(rng));
+            sp.material_id = 0;
+            sp.light_id = -1;
+            sp.reverse_orientation = k == 1;
+            sp.transform_swaps_handedness = sc[2] < 0;
+            DevSphere &d = dev[k];
+            memcpy(d.o2w, sp.object_to_world, 64);
+            memcpy(d.w2o, sp.world_to_object, 64);
+            d.radius = sp.radius;
+            d.mat_flags = 0;
+        }
+        b200pt_scene_desc sd2;
+        memset(&sd2, 0, sizeof(sd2));
+        sd2.n_materials = 1;
+        sd2.materials = &m;
+        sd2.n_spheres = nSph;
+        sd2.spheres = sph.data();
+        oracle_scene *os2 = oracle_scene_create(&sd2);
+        std::vector<b200pt_hit> w2(nRays);
+        std::vector<uint8_t> o2(nRays);
+        for (int64_t i = 0; i < nRays; ++i)
+            if (i % 5 == 0)  // start some rays inside a sphere
+                for (int a = 0; a < 3; ++a) rays[i].o[a] = sph[i % nSph].object_to_world[4 * a + 3] + 0.05f * U(rng);
+        oracle_trace_closest(os2, rays.data(), w2.data(), nRays);
+        oracle_trace_any(os2, rays.data(), o2.data(), nRays);
+        int64_t nh = 0, badS = 0, badO = 0;
+        for (int64_t i = 0; i < nRays; ++i) {
+            V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+            float tmax = rays[i].t_max, t;
+            int best = -1;
+            bool occ = false;
+            for (int k = 0; k < nSph; ++k) {
+                if (sphere_intersect(dev[k], o, d, rays[i].t_max, &t, nullptr)) occ = true;
+                if (sphere_intersect(dev[k], o, d, tmax, &t, nullptr)) {
+                    tmax = t;
+                    best = k;
+                }
+            }
+            if (best >= 0) ++nh;
+            if (best != w2[i].triangle || (best >= 0 && bits(tmax) != bits(w2[i].t))) ++badS;
+            if (occ != (o2[i] != 0)) ++badO;
+        }
+        printf("spheres: %lld rays, %lld hits, wrong sphere/t %lld, wrong any-hit %lld\n", (long long)nRays, (long long)nh,
+               (long long)badS, (long long)badO);
+        fail |= (badS || badO);
+        oracle_scene_destroy(os2);
+        long badA = 0;
+        for (uint32_t u = 0; u <= 0x3f800000u; u += 3)
+            for (int sg = 0; sg < 2; ++sg) {
+                float x;
+                uint32_t ub = u | (sg ? 0x80000000u : 0u);
+                memcpy(&x, &ub, 4);
+                if (bits(std::acos(x)) != bits(pt_acosf(x))) ++badA;
+            }
+        printf("acosf: %ld mismatches against the host libm over [-1, 1] (every third float)\n", badA);
+        fail |= badA != 0;
+    }
     printf(fail ? "PREFLIGHT FAILED\n" : "PREFLIGHT OK\n");
     return fail;
 }

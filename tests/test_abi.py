@@ -28,12 +28,13 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_sizes_match_header(abi):
     # sizes implied by include/b200pt.h on LP64
     assert C.sizeof(abi.Material) == 4 + 15 * 4 + 12 + 4
-    assert C.sizeof(abi.AreaLight) == 20
+    assert C.sizeof(abi.AreaLight) == 24
+    assert C.sizeof(abi.Sphere) == 144
     assert C.sizeof(abi.CameraDesc) == 144
     assert C.sizeof(abi.FilmDesc) == 40
     assert C.sizeof(abi.SamplerDesc) == 64
     assert C.sizeof(abi.IntegratorDesc) == 28
-    assert C.sizeof(abi.SceneDesc) == 96
+    assert C.sizeof(abi.SceneDesc) == 112
     assert abi.RAY_DTYPE.itemsize == 32 and abi.HIT_DTYPE.itemsize == 16
 
 

@@ -15,9 +15,10 @@ needs_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN), reason="pbrt_b200 
 
 
 def _scene(scenes, tmp_path, name="four", strategy="uniform", depth=5, materials=("matte", "glass", "metal", "plastic"),
-           **scene_kw):
+           spp=8, sampler="sobol", **scene_kw):
     arr = scenes.SceneArrays(3000, materials=materials, soup_version=1, **scene_kw)
-    return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, 8, max_depth=depth, strategy=strategy)
+    return scenes.write_pbrt(str(tmp_path), "render_" + name, arr, 40, 32, spp, max_depth=depth, strategy=strategy,
+                             sampler=sampler)
 
 
 @needs_plugin
@@ -62,3 +63,20 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_rough.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_rough.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (OrenNayar / rough glass) differs from the reference"
+    # pbrt's default sampler (Halton) with a non-power-of-two sample count
+    path = _scene(scenes, tmp_path, "halton", "spatial", spp=6, sampler="halton")
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_halton.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_halton.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (Halton sampler) differs from the reference"
+    # Sphere shapes (two of them area lights) written as `Translate` / `Scale` / `Shape "sphere"`
+    from test_gpu_parity import EXTRA, RENDERS
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS["spheres"]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **EXTRA["spheres"]["scene"])
+    path = scenes.write_pbrt(str(tmp_path), "render_spheres", arr, w, h, spp, max_depth=depth, strategy=strat)
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spheres.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spheres.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (Sphere shapes) differs from the reference"
