@@ -20,8 +20,10 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 
 #include "bvh8.h"
@@ -222,7 +224,11 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
         b2.nodes.resize(2 * (size_t)nLeafTris);
         b2.threads_free = std::max(0, n_threads - 1);
         int32_t root = b2.alloc();
+        const bool trace = getenv("B200PT_BUILD_TRACE") != nullptr;
+        auto tnow = []() { return std::chrono::steady_clock::now(); };
+        auto tp0 = tnow();
         b2.build(root, 0, nLeafTris);
+        auto tp1 = tnow();
 
         // ---- SAH-optimal collapse (Ylitie et al. 2017, section 3.1): cost[n][i-1] is the cheapest
         // way to represent the binary subtree n with at most i roots (i = 1..7); a single root is
@@ -285,6 +291,7 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
                 }
             }
         }
+        auto tp2 = tnow();
         // children of a wide node: expand binary node `n` into at most `budget` roots
         struct Collector {
             const Builder2 &b2;
@@ -421,6 +428,10 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
             out->nodes[cur.wide] = node;
         }
         out->n_in_leaves = (uint32_t)out->tris.size();
+        if (trace)
+            fprintf(stderr, "bvh8 build: binary SAH %.3f s, collapse DP %.3f s, emit %.3f s\n",
+                    std::chrono::duration<double>(tp1 - tp0).count(), std::chrono::duration<double>(tp2 - tp1).count(),
+                    std::chrono::duration<double>(tnow() - tp2).count());
     } else {
         // empty scene: a root with no children
         Bvh8Node node;

@@ -29,6 +29,7 @@
 // Error() (core/error.h:54) and return without rendering, like a failed
 // factory in pbrtWorldEnd (api.cpp:1623); there is NO CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -399,9 +400,17 @@ class GpuPathIntegrator : public PathIntegrator {
         b200pt_ctx *ctx = nullptr;
         b200pt_scene *gscene = nullptr;
         b200pt_render *render = nullptr;
+        auto now = []() { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto t0 = now();
         B200_CHECK(b200pt_ctx_create(device, &ctx));
+        const auto t1 = now();
         B200_CHECK(b200pt_scene_create(ctx, &sd, &gscene));
         B200_CHECK(b200pt_render_create(gscene, &cd, &fd, &smpd, &id, &render));
+        B200_CHECK(b200pt_ctx_synchronize(ctx));
+        const auto t2 = now();
         int32_t nx = 0, ny = 0;
         B200_CHECK(b200pt_render_tile_counts(render, &nx, &ny));
         // image-space sharding across processes (one per GPU): rank r renders tiles r, r+N, ...
@@ -409,10 +418,20 @@ class GpuPathIntegrator : public PathIntegrator {
         const int world = getenv("B200PT_WORLD_SIZE") ? std::max(1, atoi(getenv("B200PT_WORLD_SIZE"))) : 1;
         std::vector<int32_t> tiles;
         for (int32_t t = rank; t < nx * ny; t += world) tiles.push_back(t);
+        // B200PT_REPEAT=n renders n times (film cleared in between) so that a launcher can time a warm render
+        const int repeat = getenv("B200PT_REPEAT") ? std::max(1, atoi(getenv("B200PT_REPEAT"))) : 1;
+        double renderMs = 0;
         {
             ProgressReporter reporter(1, "Rendering (B200)");
-            B200_CHECK(b200pt_render_tiles(render, tiles.data(), (int64_t)tiles.size()));
-            B200_CHECK(b200pt_ctx_synchronize(ctx));
+            for (int it = 0; it < repeat; ++it) {
+                if (it) B200_CHECK(b200pt_film_clear(render));
+                B200_CHECK(b200pt_reset_stats(render));
+                B200_CHECK(b200pt_ctx_synchronize(ctx));
+                const auto ta = now();
+                B200_CHECK(b200pt_render_tiles(render, tiles.data(), (int64_t)tiles.size()));
+                B200_CHECK(b200pt_ctx_synchronize(ctx));
+                renderMs = ms(ta, now());
+            }
             reporter.Update();
             reporter.Done();
         }
@@ -432,6 +451,19 @@ class GpuPathIntegrator : public PathIntegrator {
             nGpuCameraRays += st.camera_rays;
             nGpuRegular += st.regular_rays;
             nGpuShadow += st.shadow_rays;
+            // B200PT_REPORT=<file>: one JSON line with the timings of this render (bench.py --workload cfg1)
+            if (const char *rp = getenv("B200PT_REPORT")) {
+                if (FILE *rf = fopen(rp, "w")) {
+                    fprintf(rf,
+                            "{\"triangles\": %lld, \"spheres\": %d, \"lights\": %d, \"camera_rays\": %llu, "
+                            "\"regular_rays\": %llu, \"shadow_rays\": %llu, \"ctx_ms\": %.3f, \"scene_build_upload_ms\": %.3f, "
+                            "\"render_ms\": %.3f, \"launches\": %llu}\n",
+                            (long long)sd.n_triangles, sd.n_spheres, sd.n_lights, (unsigned long long)st.camera_rays,
+                            (unsigned long long)st.regular_rays, (unsigned long long)st.shadow_rays, ms(t0, t1), ms(t1, t2),
+                            renderMs, (unsigned long long)st.launches);
+                    fclose(rf);
+                }
+            }
         }
         b200pt_render_destroy(render);
         b200pt_scene_destroy(gscene);

@@ -87,22 +87,24 @@ KILLEROO_DIR = os.path.join(ROOT, "oracle", "_ref", "scenes")
 
 @needs_plugin
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(os.path.join(KILLEROO_DIR, "killeroo-simple-ref.pfm")),
+@pytest.mark.skipif(not os.path.exists(os.path.join(KILLEROO_DIR, "killeroo-cfg1-ref.pfm")),
                     reason="oracle/_ref/scenes is staged by `make -C oracle ref` where /root/reference exists")
-def test_killeroo_simple_as_shipped_matches_reference(scenes, tmp_path):
-    """BASELINE.json configs[0]: scenes/killeroo-simple.pbrt exactly as the reference ships it (Halton sampler,
-    loop-subdivision meshes with shading normals, plastic, a Sphere area light) through pbrt_b200 on the GPU vs
-    the image the unmodified reference rendered from the same file."""
+@pytest.mark.parametrize("name,res", [("simple", 700), ("cfg1", 400)])
+def test_killeroo_matches_reference(scenes, tmp_path, name, res):
+    """BASELINE.json configs[0]: scenes/killeroo-simple.pbrt exactly as the reference ships it (700x700, 8 spp) and
+    as BASELINE quotes it (400x400, 64 spp) -- Halton sampler, loop-subdivision meshes with shading normals,
+    plastic, a Sphere area light -- through pbrt_b200 on the GPU vs the image the unmodified reference rendered
+    from the same file."""
     import hashlib
-    ref_path = os.path.join(KILLEROO_DIR, "killeroo-simple-ref.pfm")
-    want = open(os.path.join(GOLDEN, "killeroo_simple.sha256")).read().split()[0]
+    ref_path = os.path.join(KILLEROO_DIR, "killeroo-%s-ref.pfm" % name)
+    want = open(os.path.join(GOLDEN, "killeroo_%s.sha256" % name)).read().split()[0]
     assert hashlib.sha256(open(ref_path, "rb").read()).hexdigest() == want, "staged reference image drifted"
     out = str(tmp_path / "killeroo-gpu.pfm")
-    r = subprocess.run([PLUGIN, "--quiet", "--outfile", out, "killeroo-simple.pbrt"], cwd=KILLEROO_DIR,
+    r = subprocess.run([PLUGIN, "--quiet", "--outfile", out, "killeroo-%s.pbrt" % name], cwd=KILLEROO_DIR,
                        capture_output=True, text=True)
     assert r.returncode == 0 and os.path.exists(out), r.stdout + r.stderr
     got, ref = scenes.read_pfm(out), scenes.read_pfm(ref_path)
-    assert got.shape == ref.shape == (700, 700, 3)
+    assert got.shape == ref.shape == (res, res, 3)
     diff = bits(got) != bits(ref)
     assert not diff.any(), "%d of %d components differ from the reference (max abs %.3g)" % (
         diff.sum(), diff.size, np.abs(got - ref).max())
