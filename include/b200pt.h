@@ -98,6 +98,12 @@ typedef struct b200pt_sphere {
     uint8_t reverse_orientation;        /* Shape::reverseOrientation                     */
     uint8_t transform_swaps_handedness; /* Shape::transformSwapsHandedness               */
     uint8_t pad[2];
+    /* Bounds (min xyz, max xyz) of the accelerator leaf that holds the sphere in the host's BVHAccel.  The
+     * reference only calls Sphere::Intersect(P) on rays that pass Bounds3::IntersectP on that leaf with the
+     * current ray.tMax (accelerators/bvh.cpp:676,713, core/geometry.h:1411-1438), and Sphere::Intersect's own
+     * root can be off by more than the box test's error, so the box test decides real cases (a shadow ray
+     * towards the limb of a distant sphere light).  All zeros = use the sphere's own Shape::WorldBound(). */
+    float leaf_bounds[6];
 } b200pt_sphere;
 
 /* ---- scene: world-space triangle soup + per-triangle attributes ---------

@@ -40,6 +40,7 @@
 #include "accelerators/bvh.h"
 #include "cameras/perspective.h"
 #include "core/api.h"
+#include "core/efloat.h"
 #include "core/film.h"
 #include "core/interaction.h"
 #include "core/lowdiscrepancy.h"
@@ -55,6 +56,7 @@
 #include "materials/metal.h"
 #include "samplers/halton.h"
 #include "samplers/sobol.h"
+#include "shapes/sphere.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
 #undef private
@@ -179,6 +181,49 @@ int main(int argc, char **argv) {
         fwrite(hdr, 4, 4, f);
         fwrite(HaltonSampler::radicalInversePermutations.data(), 2, count, f);
         fclose(f);
+    } else if (cmd == "sphere") {
+        // sphere cx cy cz radius ox oy oz dx dy dz tmax : Sphere under Translate(c): Intersect / IntersectP
+        Transform o2w = Translate(Vector3f(atof(argv[2]), atof(argv[3]), atof(argv[4])));
+        Transform w2o = Inverse(o2w);
+        float radius = atof(argv[5]);
+        Sphere sp(&o2w, &w2o, false, radius, -radius, radius, 360.f);
+        Ray r(Point3f(strtof(argv[6], 0), strtof(argv[7], 0), strtof(argv[8], 0)),
+              Vector3f(strtof(argv[9], 0), strtof(argv[10], 0), strtof(argv[11], 0)), strtof(argv[12], 0));
+        Float tHit = 0;
+        SurfaceInteraction is;
+        bool hp = sp.IntersectP(r, false);
+        bool h = sp.Intersect(r, &tHit, &is, false);
+        printf("IntersectP %d Intersect %d t %a\n", (int)hp, (int)h, (double)tHit);
+        // the EFloat roots
+        Vector3f oErr, dErr;
+        Ray ray = w2o(r, &oErr, &dErr);
+        EFloat ox(ray.o.x, oErr.x), oy(ray.o.y, oErr.y), oz(ray.o.z, oErr.z);
+        EFloat dx(ray.d.x, dErr.x), dy(ray.d.y, dErr.y), dz(ray.d.z, dErr.z);
+        EFloat a = dx * dx + dy * dy + dz * dz;
+        EFloat b = 2 * (dx * ox + dy * oy + dz * oz);
+        EFloat c = ox * ox + oy * oy + oz * oz - EFloat(radius) * EFloat(radius);
+        EFloat t0, t1;
+        bool q = Quadratic(a, b, c, &t0, &t1);
+        printf("o=(%a %a %a) oErr=(%a %a %a) dErr=(%a %a %a)\n", ray.o.x, ray.o.y, ray.o.z, oErr.x, oErr.y, oErr.z, dErr.x, dErr.y, dErr.z);
+        printf("a=[%a %a %a] b=[%a %a %a] c=[%a %a %a]\n", a.LowerBound(), (float)a, a.UpperBound(), b.LowerBound(), (float)b,
+               b.UpperBound(), c.LowerBound(), (float)c, c.UpperBound());
+        printf("quadratic %d t0=[%a %a %a] t1=[%a %a %a]\n", (int)q, t0.LowerBound(), (float)t0, t0.UpperBound(), t1.LowerBound(),
+               (float)t1, t1.UpperBound());
+    } else if (cmd == "spheresample") {
+        // spheresample cx cy cz radius  px py pz  ex ey ez  nx ny nz  u0 u1 : Sphere::Sample(ref, u, &pdf)
+        Transform o2w = Translate(Vector3f(atof(argv[2]), atof(argv[3]), atof(argv[4])));
+        Transform w2o = Inverse(o2w);
+        float radius = atof(argv[5]);
+        Sphere sp(&o2w, &w2o, false, radius, -radius, radius, 360.f);
+        Interaction ref;
+        ref.p = Point3f(strtof(argv[6], 0), strtof(argv[7], 0), strtof(argv[8], 0));
+        ref.pError = Vector3f(strtof(argv[9], 0), strtof(argv[10], 0), strtof(argv[11], 0));
+        ref.n = Normal3f(strtof(argv[12], 0), strtof(argv[13], 0), strtof(argv[14], 0));
+        Point2f u(strtof(argv[15], 0), strtof(argv[16], 0));
+        Float pdf = 0;
+        Interaction it = sp.Sample(ref, u, &pdf);
+        printf("p=(%a %a %a) n=(%a %a %a) pErr=(%a %a %a) pdf=%a\n", it.p.x, it.p.y, it.p.z, it.n.x, it.n.y, it.n.z,
+               it.pError.x, it.pError.y, it.pError.z, pdf);
     } else if (cmd == "camrays") {
         auto cam = makeCamera(argv + 2);
         int spp = atoi(argv[14]);

@@ -1036,6 +1036,16 @@ bool BvhIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayT
 // spheres inside the same BVHAccel; testing them after the triangles gives the same closest hit except when a
 // triangle hit lies within the sphere root's error interval (order-dependent in the reference as well).
 // A sphere hit returns nTris + sphere index, hitOut->t and *sphereIs.
+// The BVH leaf test that guards a sphere in the reference (bvh.cpp:676,713): Bounds3::IntersectP on the leaf's
+// bounds with the current ray.tMax.
+inline bool SphereLeafTest(const b200pt_sphere &sp, const V3 &ro, const V3 &rd, float rayTMax) {
+    BVHNode box;
+    memcpy(box.bmin, sp.leaf_bounds, 12);
+    memcpy(box.bmax, sp.leaf_bounds + 3, 12);
+    V3 invDir(1 / rd.x, 1 / rd.y, 1 / rd.z);
+    int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    return BoundsIntersectP(box, ro, rayTMax, invDir, dirIsNeg);
+}
 int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut,
                    Isect *sphereIs = nullptr) {
     int hit = BvhIntersect(s, ro, rd, rayTMax, hitOut);
@@ -1043,7 +1053,8 @@ int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayT
     for (size_t k = 0; k < s.spheres.size(); ++k) {
         float tHit;
         Isect tmp;
-        if (SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, &tmp)) {
+        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) &&
+            SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, &tmp)) {
             rayTMax = tHit;
             hit = (int)s.nTris + (int)k;
             hitOut->t = tHit;
@@ -1058,7 +1069,8 @@ bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float ra
     if (BvhIntersectP(s, ro, rd, rayTMax)) return true;
     for (size_t k = 0; k < s.spheres.size(); ++k) {
         float tHit;
-        if (SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, nullptr)) return true;
+        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) && SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, nullptr))
+            return true;
     }
     return false;
 }
@@ -1871,9 +1883,13 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
     // light.Sample_Li: lights/diffuse.cpp:68-81, shape.cpp:56-70
     S3 Li(0.f);
     LightSample pShape;
-    if (light.sphere >= 0)
+    if (light.sphere >= 0) {
         pShape = SphereSample(s.spheres[light.sphere], it.p, it.pError, it.n, uLight, &lightPdf);
-    else
+        if (getenv("ORACLE_TRACE"))
+            fprintf(stderr, "    spheresample ref p=(%a %a %a) pErr=(%a %a %a) n=(%a %a %a) u=(%a %a) -> p=(%a %a %a) n=(%a %a %a) pdf=%a\n",
+                    it.p.x, it.p.y, it.p.z, it.pError.x, it.pError.y, it.pError.z, it.n.x, it.n.y, it.n.z, uLight[0], uLight[1],
+                    pShape.p.x, pShape.p.y, pShape.p.z, pShape.n.x, pShape.n.y, pShape.n.z, lightPdf);
+    } else
         pShape = TriangleSample(s, light.triangle, uLight, &lightPdf);
     if (light.sphere < 0) {
         V3 w = pShape.p - it.p;
@@ -1901,6 +1917,14 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
             V3 target = OffsetRayOrigin(pShape.p, pShape.pError, pShape.n, origin - pShape.p);
             V3 d = target - origin;
             ++rc.shadowRays;
+            if (getenv("ORACLE_TRACE")) {
+                TriHit hh;
+                Isect ii;
+                int who = SceneIntersect(s, origin, d, 1 - ShadowEpsilon, &hh, &ii);
+                fprintf(stderr, "    shadow: pShape=(%a %a %a) n=(%g %g %g) lightPdf=%g Li=%g f=%g origin=(%a %a %a) d=(%a %a %a) closest prim=%d t=%a bvhP=%d\n",
+                        pShape.p.x, pShape.p.y, pShape.p.z, pShape.n.x, pShape.n.y, pShape.n.z, lightPdf, Li.c[0], f.c[0],
+                        origin.x, origin.y, origin.z, d.x, d.y, d.z, who, who >= 0 ? hh.t : 0.f, (int)BvhIntersectP(s, origin, d, 1 - ShadowEpsilon));
+            }
             if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
             if (!Li.IsBlack()) {
                 float weight = (lightPdf * lightPdf) / (lightPdf * lightPdf + scatteringPdf * scatteringPdf);
@@ -1971,6 +1995,12 @@ S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
         int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h, &isect);
         bool foundIntersection = tri >= 0;
         if (foundIntersection && tri < s.nTris) FillIsect(s, tri, h, ray.d, &isect);
+        static const bool traceOn = getenv("ORACLE_TRACE") != nullptr;
+        if (traceOn)
+            fprintf(stderr, "  bounce %d: o=(%a %a %a) d=(%a %a %a) prim=%d t=%a p=(%g %g %g) n=(%g %g %g) L=(%g %g %g) beta=(%g %g %g)\n",
+                    bounces, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, tri, foundIntersection ? h.t : 0.f,
+                    isect.p.x, isect.p.y, isect.p.z, isect.n.x, isect.n.y, isect.n.z, L.c[0], L.c[1], L.c[2], beta.c[0],
+                    beta.c[1], beta.c[2]);
         if (bounces == 0 || specularBounce) {
             if (foundIntersection) L += beta * IsectLe(s, isect, -ray.d);
         }
@@ -2181,15 +2211,24 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
             s->wbMin[a] = std::min(s->wbMin[a], s->p[i][a]);
             s->wbMax[a] = std::max(s->wbMax[a], s->p[i][a]);
         }
-    for (const b200pt_sphere &sp : s->spheres) {
+    for (b200pt_sphere &sp : s->spheres) {
         // Shape::WorldBound = (*ObjectToWorld)(ObjectBound()) (shape.cpp:52, transform.cpp:246-256)
         const float r = sp.radius;
+        float lo[3] = {Infinity, Infinity, Infinity}, hi[3] = {-Infinity, -Infinity, -Infinity};
         for (int c = 0; c < 8; ++c) {
             V3 q = XformPoint(sp.object_to_world, V3((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
             for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], q[a]);
+                hi[a] = std::max(hi[a], q[a]);
                 s->wbMin[a] = std::min(s->wbMin[a], q[a]);
                 s->wbMax[a] = std::max(s->wbMax[a], q[a]);
             }
+        }
+        bool unset = true;
+        for (int a = 0; a < 6; ++a) unset = unset && sp.leaf_bounds[a] == 0.f;
+        if (unset) {
+            memcpy(sp.leaf_bounds, lo, 12);
+            memcpy(sp.leaf_bounds + 3, hi, 12);
         }
     }
     s->hasN.assign(d->n_triangles, 0);

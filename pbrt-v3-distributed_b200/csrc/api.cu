@@ -243,12 +243,21 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         sp.light_id = in.light_id;
         sp.reverse_orientation = in.reverse_orientation != 0;
         // Shape::WorldBound (shape.cpp:52, transform.cpp:246-256) joins Scene::WorldBound()
+        float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int c = 0; c < 8; ++c) {
             const V3 q = xform_point(sp.o2w, mk((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
             for (int a = 0; a < 3; ++a) {
+                wlo[a] = std::min(wlo[a], comp(q, a));
+                whi[a] = std::max(whi[a], comp(q, a));
                 s->bounds_lo[a] = std::min(s->bounds_lo[a], comp(q, a));
                 s->bounds_hi[a] = std::max(s->bounds_hi[a], comp(q, a));
             }
+        }
+        bool unset = true;
+        for (int a = 0; a < 6; ++a) unset = unset && in.leaf_bounds[a] == 0.f;
+        for (int a = 0; a < 3; ++a) {
+            sp.leaf_lo[a] = unset ? wlo[a] : in.leaf_bounds[a];
+            sp.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
         }
     }
     s->light_area.resize(d->n_lights);

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                 if (!a.occ_out[slot]) {
                     for (uint32_t k = 0; k < a.n_spheres; ++k) {
                         float t;
-                        if (sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                        if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
                             a.occ_out[slot] = 1;
                             break;
                         }
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                 uint32_t sph = B200PT_MISS;
                 for (uint32_t k = 0; k < a.n_spheres; ++k) {
                     float t;
-                    if (sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                    if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
                         tmax = t;
                         sph = k;
                     }

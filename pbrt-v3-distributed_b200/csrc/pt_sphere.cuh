@@ -37,6 +37,7 @@ struct DevSphere {
     uint32_t mat_flags;      // material id | flip << 16 (reverseOrientation ^ transformSwapsHandedness)
     int light_id;
     int reverse_orientation;
+    float leaf_lo[3], leaf_hi[3];  // bounds of the host accelerator's leaf holding the sphere (b200pt_sphere::leaf_bounds)
 };
 
 // ---- glibc 2.3x acosf (sysdeps/ieee754/flt-32/e_acosf.c, fdlibm): float arithmetic only
@@ -181,6 +182,32 @@ B200_HD V3 xform_vector_err(const float *m, const V3 &v, V3 *absError) {
 B200_HD V3 xform_normal(const float *mInv, const V3 &n) {
     return mk(mInv[0] * n.x + mInv[4] * n.y + mInv[8] * n.z, mInv[1] * n.x + mInv[5] * n.y + mInv[9] * n.z,
               mInv[2] * n.x + mInv[6] * n.y + mInv[10] * n.z);
+}
+
+// ---- Bounds3::IntersectP(ray, invDir, dirIsNeg) (core/geometry.h:1411-1438) on the leaf that holds the sphere in
+// the host's BVHAccel: the reference reaches Sphere::Intersect(P) only through this test (bvh.cpp:676,713), and the
+// sphere's own root can be off by more than the box test's slack (a shadow ray aimed at the limb of a distant
+// sphere light is "hit" by Sphere::IntersectP at t < 1 - ShadowEpsilon but never enters the leaf's box before tMax).
+B200_HD bool sphere_leaf_test(const DevSphere &sp, const V3 &ro, const V3 &rd, float rayTMax) {
+    const float invDir[3] = {1 / rd.x, 1 / rd.y, 1 / rd.z};
+    const int neg[3] = {invDir[0] < 0, invDir[1] < 0, invDir[2] < 0};
+    const float g = 1 + 2 * pt_gamma(3);
+    float tMin = ((neg[0] ? sp.leaf_hi[0] : sp.leaf_lo[0]) - ro.x) * invDir[0];
+    float tMax = ((neg[0] ? sp.leaf_lo[0] : sp.leaf_hi[0]) - ro.x) * invDir[0];
+    const float tyMin = ((neg[1] ? sp.leaf_hi[1] : sp.leaf_lo[1]) - ro.y) * invDir[1];
+    float tyMax = ((neg[1] ? sp.leaf_lo[1] : sp.leaf_hi[1]) - ro.y) * invDir[1];
+    tMax *= g;
+    tyMax *= g;
+    if (tMin > tyMax || tyMin > tMax) return false;
+    if (tyMin > tMin) tMin = tyMin;
+    if (tyMax < tMax) tMax = tyMax;
+    const float tzMin = ((neg[2] ? sp.leaf_hi[2] : sp.leaf_lo[2]) - ro.z) * invDir[2];
+    float tzMax = ((neg[2] ? sp.leaf_lo[2] : sp.leaf_hi[2]) - ro.z) * invDir[2];
+    tzMax *= g;
+    if (tMin > tzMax || tzMin > tMax) return false;
+    if (tzMin > tMin) tMin = tzMin;
+    if (tzMax < tMax) tMax = tzMax;
+    return (tMin < rayTMax) && (tMax > 0);
 }
 
 // ---- Sphere::Intersect / IntersectP (sphere.cpp:49-212).  Returns false or *tHit (+ *is when is != nullptr).

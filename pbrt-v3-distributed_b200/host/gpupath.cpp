@@ -81,6 +81,22 @@
 #include "../../include/b200pt.h"
 
 namespace pbrt {
+// Layout of BVHAccel's flattened nodes: the reference defines this struct inside accelerators/bvh.cpp:95-104 (the
+// header only forward-declares it), so a host that reads the tree has to restate the 32-byte record.
+struct LinearBVHNode {
+    Bounds3f bounds;
+    union {
+        int primitivesOffset;   // leaf
+        int secondChildOffset;  // interior
+    };
+    uint16_t nPrimitives;  // 0 -> interior node
+    uint8_t axis;
+    uint8_t pad[1];
+};
+static_assert(sizeof(LinearBVHNode) == 32, "LinearBVHNode layout");
+}  // namespace pbrt
+
+namespace pbrt {
 
 STAT_COUNTER("Integrator/Camera rays traced (GPU)", nGpuCameraRays);
 STAT_COUNTER("Intersections/Regular ray intersection tests (GPU)", nGpuRegular);
@@ -259,6 +275,30 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         f->materialId.push_back(mid);
         f->lightId.push_back(-1);
     }
+    // the BVHAccel leaf of every sphere: its bounds gate Sphere::Intersect(P) in the reference (bvh.cpp:676,713)
+    if (!f->spheres.empty() && bvh->nodes) {
+        std::vector<int> stack(1, 0);
+        while (!stack.empty()) {
+            const int ni = stack.back();
+            stack.pop_back();
+            const LinearBVHNode &node = bvh->nodes[ni];
+            if (node.nPrimitives > 0) {
+                for (int i = 0; i < node.nPrimitives; ++i) {
+                    auto gp = dynamic_cast<const GeometricPrimitive *>(prims[node.primitivesOffset + i].get());
+                    auto it = gp ? sphereOfShape.find(gp->shape.get()) : sphereOfShape.end();
+                    if (it == sphereOfShape.end()) continue;
+                    float *lb = f->spheres[it->second].leaf_bounds;
+                    for (int a = 0; a < 3; ++a) {
+                        lb[a] = node.bounds.pMin[a];
+                        lb[3 + a] = node.bounds.pMax[a];
+                    }
+                }
+            } else {
+                stack.push_back(ni + 1);
+                stack.push_back(node.secondChildOffset);
+            }
+        }
+    }
     if (!scene.infiniteLights.empty()) return *why = "infinite area lights", false;
     for (size_t l = 0; l < scene.lights.size(); ++l) {
         auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
@@ -396,6 +436,32 @@ class GpuPathIntegrator : public PathIntegrator {
         id.pixel_bounds[2] = bounds.pMax.x;
         id.pixel_bounds[3] = bounds.pMax.y;
 
+        // B200PT_DUMP_SCENE=<file>: write the descriptors handed to the C ABI (debugging aid: the Python harness
+        // can replay exactly what this host passes, see tests/replay_dump.py)
+        if (const char *dp = getenv("B200PT_DUMP_SCENE")) {
+            if (FILE *df = fopen(dp, "wb")) {
+                const int64_t hdr[8] = {0x3154504d55443042ll, sd.n_triangles, sd.n_materials, sd.n_lights, sd.n_spheres,
+                                        sd.normals != nullptr, sd.uvs != nullptr, (int64_t)smpd.type};
+                fwrite(hdr, 8, 8, df);
+                fwrite(sd.vertices, 4, (size_t)sd.n_triangles * 9, df);
+                fwrite(sd.material_id, 4, (size_t)sd.n_triangles, df);
+                fwrite(sd.light_id, 4, (size_t)sd.n_triangles, df);
+                fwrite(sd.flip_normal, 1, (size_t)sd.n_triangles, df);
+                fwrite(sd.vertex_flags, 1, (size_t)sd.n_triangles, df);
+                if (sd.normals) fwrite(sd.normals, 4, (size_t)sd.n_triangles * 9, df);
+                if (sd.uvs) fwrite(sd.uvs, 4, (size_t)sd.n_triangles * 6, df);
+                fwrite(sd.materials, sizeof(b200pt_material), (size_t)sd.n_materials, df);
+                fwrite(sd.lights, sizeof(b200pt_area_light), (size_t)sd.n_lights, df);
+                fwrite(sd.spheres, sizeof(b200pt_sphere), (size_t)sd.n_spheres, df);
+                fwrite(&cd, sizeof(cd), 1, df);
+                fwrite(&fd, sizeof(fd), 1, df);
+                fwrite(&id, sizeof(id), 1, df);
+                const int32_t sm[6] = {smpd.samples_per_pixel, smpd.sample_bounds[0], smpd.sample_bounds[1],
+                                       smpd.sample_bounds[2], smpd.sample_bounds[3], smpd.n_dimensions};
+                fwrite(sm, 4, 6, df);
+                fclose(df);
+            }
+        }
         const int device = getenv("B200PT_DEVICE") ? atoi(getenv("B200PT_DEVICE")) : 0;
         b200pt_ctx *ctx = nullptr;
         b200pt_scene *gscene = nullptr;

@@ -155,6 +155,19 @@ int main(int argc, char **argv) {
             memcpy(d.w2o, sp.world_to_object, 64);
             d.radius = sp.radius;
             d.mat_flags = 0;
+            // Shape::WorldBound(): what the oracle and the library use when leaf_bounds is left zero
+            for (int a = 0; a < 3; ++a) {
+                d.leaf_lo[a] = INFINITY;
+                d.leaf_hi[a] = -INFINITY;
+            }
+            for (int cn = 0; cn < 8; ++cn) {
+                const float r = sp.radius;
+                const V3 q = xform_point(d.o2w, mk((cn & 1) ? r : -r, (cn & 2) ? r : -r, (cn & 4) ? r : -r));
+                for (int a = 0; a < 3; ++a) {
+                    d.leaf_lo[a] = std::min(d.leaf_lo[a], comp(q, a));
+                    d.leaf_hi[a] = std::max(d.leaf_hi[a], comp(q, a));
+                }
+            }
         }
         b200pt_scene_desc sd2;
         memset(&sd2, 0, sizeof(sd2));
@@ -177,8 +190,9 @@ int main(int argc, char **argv) {
             int best = -1;
             bool occ = false;
             for (int k = 0; k < nSph; ++k) {
-                if (sphere_intersect(dev[k], o, d, rays[i].t_max, &t, nullptr)) occ = true;
-                if (sphere_intersect(dev[k], o, d, tmax, &t, nullptr)) {
+                if (sphere_leaf_test(dev[k], o, d, rays[i].t_max) && sphere_intersect(dev[k], o, d, rays[i].t_max, &t, nullptr))
+                    occ = true;
+                if (sphere_leaf_test(dev[k], o, d, tmax) && sphere_intersect(dev[k], o, d, tmax, &t, nullptr)) {
                     tmax = t;
                     best = k;
                 }
