@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-spp", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh", default="host", choices=["host", "gpu"],
+                    help="acceleration structure builder: host SAH (default) or the on-device builder")
     args = ap.parse_args()
     rank, local_rank, world = rank_env()
     wl = WORKLOADS[args.workload]
@@ -194,13 +196,16 @@ def main():
     arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
     setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth)
     ctx = pkg.Context(local_rank)
+    if args.bvh == "gpu":
+        ctx.set_option("gpu_bvh_build", 1)
     t0 = time.time()
     scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
     build_s = time.time() - t0
     info = scene.info()
     config["l2_policy"] = config["l2_policy"] % ("%.0f" % ((info["node_bytes"] + info["tri_bytes"]) / 1e6))
     config["bvh"] = {"nodes": info["n_nodes"], "node_bytes": info["node_bytes"], "tri_bytes": info["tri_bytes"],
-                     "host_build_s": round(build_s, 2)}
+                     "host_build_s": round(build_s, 2),
+                     "builder": "device (Morton order -> radix tree -> 8-wide collapse)" if args.bvh == "gpu" else "host SAH"}
     render = pkg.Render(scene, setup)
     my_tiles = scenes.rank_tiles(render.n_tiles, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))

@@ -242,6 +242,12 @@ void b200pt_ctx_destroy(b200pt_ctx *ctx);
 int b200pt_ctx_synchronize(b200pt_ctx *ctx);
 /* cudaStream_t of the context as an integer (for CUDA-event timing by the caller). */
 uint64_t b200pt_ctx_stream(b200pt_ctx *ctx);
+/* Context options.  "gpu_bvh_build" (0/1, default 0; the environment variable B200PT_BVH_BUILD=gpu|host overrides
+ * it): build the acceleration structure on the device (Morton order -> binary radix tree -> 8-wide collapse) instead
+ * of the host SAH builder.  Both replace BVHAccel's constructor (accelerators/bvh.cpp:183-225); results are
+ * identical (hits are decided by the exact triangle test), the device build is faster to build and slightly slower
+ * to traverse on some scenes. */
+int b200pt_ctx_set_option(b200pt_ctx *ctx, const char *key, int64_t value);
 
 /* ---- scene: replaces CreateBVHAccelerator (accelerators/bvh.cpp:740-760) --
  * Builds the 8-wide compressed BVH on the host (SAH) and uploads it. */

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "b200pt_ctx_destroy": (None, [_vp]),
     "b200pt_ctx_synchronize": (C.c_int, [_vp]),
     "b200pt_ctx_stream": (_u64, [_vp]),
+    "b200pt_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "b200pt_scene_create": (C.c_int, [_vp, C.POINTER(abi.SceneDesc), C.POINTER(_vp)]),
     "b200pt_scene_destroy": (None, [_vp]),
     "b200pt_scene_upload": (C.c_int, [_vp, C.POINTER(_u64)]),
@@ -115,6 +116,9 @@ class Context:
 
     def synchronize(self):
         _check(lib.b200pt_ctx_synchronize(self.h))
+
+    def set_option(self, key, value):
+        _check(lib.b200pt_ctx_set_option(self.h, key.encode(), int(value)))
 
     @property
     def stream(self):

@@ -12,6 +12,7 @@
 
 #include "b200pt_internal.h"
 #include "bvh8.h"
+#include "bvh8_gpu.h"
 #include "kernels.cuh"
 
 using namespace b200pt;
@@ -30,6 +31,7 @@ struct b200pt_ctx {
     cudaStream_t stream_aux = nullptr;   // shadow / MIS rays of bounce b overlap the path rays of bounce b+1
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 0;
+    bool gpu_bvh_build = false;  // b200pt_ctx_set_option "gpu_bvh_build"
 };
 
 struct b200pt_scene {
@@ -123,6 +125,15 @@ int b200pt_ctx_synchronize(b200pt_ctx *ctx) {
 
 uint64_t b200pt_ctx_stream(b200pt_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 
+int b200pt_ctx_set_option(b200pt_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return b200pt_fail(B200PT_ERR_INVALID, "ctx_set_option: NULL argument");
+    if (!strcmp(key, "gpu_bvh_build")) {
+        ctx->gpu_bvh_build = value != 0;
+        return B200PT_OK;
+    }
+    return b200pt_fail(B200PT_ERR_INVALID, "ctx_set_option: unknown option '%s'", key);
+}
+
 // --------------------------------------------------------------------- scene
 int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scene **out) {
     if (!ctx || !d || !out) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: NULL argument");
@@ -164,6 +175,45 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
 
+    bool gpu_build = ctx->gpu_bvh_build;
+    if (const char *e = getenv("B200PT_BVH_BUILD")) gpu_build = !strcmp(e, "gpu");
+    Bvh8 bvh;
+    GpuBuildOutput gout;
+    if (gpu_build) {
+        // ---- on-device build (bvh8_gpu.cu): Morton order -> binary radix tree -> 8-wide collapse
+        GpuBuildInput gin;
+        gin.vertices = d->vertices;
+        gin.n_tris = d->n_triangles;
+        gin.material_id = d->material_id;
+        gin.light_id = d->light_id;
+        gin.flip = d->flip_normal;
+        gin.vertex_flags = d->vertex_flags;
+        gin.uvs = d->uvs;
+        gin.has_normals = d->normals != nullptr;
+        char msg[256] = "";
+        auto drop = [&]() {
+            cudaFree(gout.d_nodes);
+            cudaFree(gout.d_tris);
+            cudaFree(gout.d_prim_to_tri);
+        };
+        if (!build_bvh8_gpu(gin, ctx->stream, &gout, msg, sizeof(msg))) {
+            drop();
+            return b200pt_fail(B200PT_ERR_CUDA, "scene_create: device BVH build failed: %s", msg);
+        }
+        if (gout.max_depth > B200PT_STACK - 4) {
+            drop();
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: device-built BVH depth %d exceeds the traversal stack (use the host builder)",
+                               gout.max_depth);
+        }
+        bvh.prim_to_tri.resize((size_t)d->n_triangles);
+        cudaError_t ce = cudaMemcpy(bvh.prim_to_tri.data(), gout.d_prim_to_tri, (size_t)d->n_triangles * 4, cudaMemcpyDeviceToHost);
+        cudaFree(gout.d_prim_to_tri);
+        gout.d_prim_to_tri = nullptr;
+        if (ce != cudaSuccess) {
+            drop();
+            return b200pt_fail(B200PT_ERR_CUDA, "scene_create: prim_to_tri download failed: %s", cudaGetErrorString(ce));
+        }
+    } else {
     // triangles the reference can never hit (shapes/triangle.cpp:304-312)
     std::vector<uint8_t> degenerate((size_t)d->n_triangles);
     for (int64_t i = 0; i < d->n_triangles; ++i) {
@@ -175,39 +225,43 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         if (d->uvs && (vf & 2)) memcpy(sh.uv, d->uvs + 6 * i, sizeof(float) * 6);
         degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), sh.uv, &dpdu, &dpdv);
     }
-    Bvh8 bvh;
     int threads = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("B200PT_BUILD_THREADS")) threads = atoi(e);
     build_bvh8(d->vertices, d->n_triangles, d->material_id, d->light_id, d->flip_normal, degenerate.data(),
                std::max(1, threads), &bvh);
     if (bvh.max_depth > B200PT_STACK - 4)
         return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d exceeds the traversal stack", bvh.max_depth);
+    }
+    const size_t n_tri_records = gpu_build ? (size_t)gout.n_tris : bvh.tris.size();
+    const size_t n_node_records = gpu_build ? (size_t)gout.n_nodes : bvh.nodes.size();
     // per-vertex shading data in leaf order + flags (bit 18 normals, bit 19 uvs) in the triangle records
     std::vector<F4> tri_n, tri_uv;
-    if (d->normals) tri_n.assign(bvh.tris.size() * 3, F4{0, 0, 0, 0});
-    if (d->uvs) tri_uv.assign(bvh.tris.size() * 2, F4{0, 0, 0, 0});
+    if (d->normals) tri_n.assign(n_tri_records * 3, F4{0, 0, 0, 0});
+    if (d->uvs) tri_uv.assign(n_tri_records * 2, F4{0, 0, 0, 0});
     for (int64_t i = 0; i < d->n_triangles; ++i) {
         const uint8_t vf = d->vertex_flags ? d->vertex_flags[i] : 3;
         const uint32_t ti = bvh.prim_to_tri[i];
         if (d->normals && (vf & 1)) {
             const float *n = d->normals + 9 * i;
             for (int k = 0; k < 3; ++k) tri_n[(size_t)ti * 3 + k] = F4{n[3 * k], n[3 * k + 1], n[3 * k + 2], 0.f};
-            bvh.tris[ti].mat_flags |= 0x40000u;
+            if (!gpu_build) bvh.tris[ti].mat_flags |= 0x40000u;  // the device builder sets the flags itself
         }
         if (d->uvs && (vf & 2)) {
             const float *u = d->uvs + 6 * i;
             tri_uv[(size_t)ti * 2] = F4{u[0], u[1], u[2], u[3]};
             tri_uv[(size_t)ti * 2 + 1] = F4{u[4], u[5], 0.f, 0.f};
-            bvh.tris[ti].mat_flags |= 0x80000u;
+            if (!gpu_build) bvh.tris[ti].mat_flags |= 0x80000u;
         }
     }
-    int64_t bad = validate_bvh8(bvh);
-    if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
+    if (!gpu_build) {
+        int64_t bad = validate_bvh8(bvh);
+        if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
+    }
 
     b200pt_scene *s = new b200pt_scene;
     s->ctx = ctx;
-    s->n_nodes = bvh.nodes.size();
-    s->n_tris = bvh.tris.size();
+    s->n_nodes = n_node_records;
+    s->n_tris = n_tri_records;
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->prim_to_tri = std::move(bvh.prim_to_tri);
@@ -270,16 +324,20 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         s->light_area[i] = triangle_area(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
     }
     cudaError_t e;
-    if ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(Bvh8Node))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(TriRecord))) != cudaSuccess ||
+    if (gpu_build) {
+        s->d_nodes = static_cast<U4 *>(gout.d_nodes);
+        s->d_tris = static_cast<F4 *>(gout.d_tris);
+    }
+    if ((!gpu_build && ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_node_records) * sizeof(Bvh8Node))) != cudaSuccess ||
+                        (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess)) ||
         (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_spheres, std::max<size_t>(1, s->spheres.size()) * sizeof(DevSphere))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    if ((e = cudaMallocHost(&s->h_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(Bvh8Node))) != cudaSuccess ||
-        (e = cudaMallocHost(&s->h_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(TriRecord))) != cudaSuccess) {
+    if ((e = cudaMallocHost(&s->h_nodes, std::max<size_t>(1, n_node_records) * sizeof(Bvh8Node))) != cudaSuccess ||
+        (e = cudaMallocHost(&s->h_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMallocHost failed: %s", cudaGetErrorString(e));
     }
@@ -297,8 +355,30 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             return b200pt_fail(B200PT_ERR_OOM, "scene_create: uv upload failed: %s", cudaGetErrorString(e));
         }
     }
-    memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
-    memcpy(s->h_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord));
+    if (gpu_build) {
+        // keep host copies like the host path does (b200pt_scene_upload re-sends them; B200PT_VALIDATE_BVH checks them)
+        if ((e = cudaMemcpy(s->h_nodes, s->d_nodes, n_node_records * sizeof(Bvh8Node), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (e = cudaMemcpy(s->h_tris, s->d_tris, n_tri_records * sizeof(TriRecord), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            b200pt_scene_destroy(s);
+            return b200pt_fail(B200PT_ERR_CUDA, "scene_create: BVH download failed: %s", cudaGetErrorString(e));
+        }
+        if (getenv("B200PT_VALIDATE_BVH")) {
+            Bvh8 chk;
+            chk.nodes.assign(static_cast<Bvh8Node *>(s->h_nodes), static_cast<Bvh8Node *>(s->h_nodes) + n_node_records);
+            chk.tris.assign(static_cast<TriRecord *>(s->h_tris), static_cast<TriRecord *>(s->h_tris) + n_tri_records);
+            chk.prim_to_tri = s->prim_to_tri;
+            chk.n_in_leaves = gout.n_in_leaves;
+            chk.max_depth = gout.max_depth;
+            const int64_t bad = validate_bvh8(chk);
+            if (bad) {
+                b200pt_scene_destroy(s);
+                return b200pt_fail(B200PT_ERR_INVALID, "scene_create: device-built BVH failed validation (%lld violations)", (long long)bad);
+            }
+        }
+    } else {
+        memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
+        memcpy(s->h_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord));
+    }
     int rc = b200pt_scene_upload(s, nullptr);
     if (rc != B200PT_OK) {
         b200pt_scene_destroy(s);

@@ -5,6 +5,7 @@
 // (oracle/liboracle.so) BEFORE GPU time is spent:
 //   * 8-wide BVH build + traversal vs the oracle's closest / any hit answers (bit-exact t)
 //   * Sobol' sample stream and camera rays vs the oracle
+//   * the on-device BVH builder's per-element steps (lbvh.cuh) run sequentially: structure check + traversal vs the oracle
 //   * Sphere::Intersect / IntersectP arithmetic (EFloat quadratic, error-tracking transforms) vs the oracle,
 //     and the restated acosf vs the host libm
 // This binary is test infrastructure: it is never linked into libb200pt.so and
@@ -19,7 +20,11 @@
 #include "../oracle/pt_oracle.h"
 #include "../pbrt-v3-distributed_b200/csrc/bvh8.h"
 #include "../pbrt-v3-distributed_b200/csrc/bvh8_traverse.cuh"
+#include "../pbrt-v3-distributed_b200/csrc/lbvh.cuh"
 #include "../pbrt-v3-distributed_b200/csrc/pt_sphere.cuh"
+#include <algorithm>
+#include <climits>
+#include <numeric>
 
 using namespace b200pt;
 
@@ -125,6 +130,123 @@ int main(int argc, char **argv) {
            (long long)nRays, (long long)nHit, (long long)badTri, (long long)tieOk, (long long)badT, (long long)badOcc,
            (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
     fail |= (badTri || badT || badOcc);
+    // ---- the on-device builder (lbvh.cuh), emulated: same tree checks, same traversal answers
+    {
+        LbvhCtx c;
+        memset(&c, 0, sizeof(c));
+        c.vertices = verts.data();
+        c.material_id = mat.data();
+        c.light_id = light.data();
+        c.n = nTris;
+        std::vector<uint32_t> validIdx(nTris), sortedV(nTris), p2t(nTris);
+        std::vector<uint64_t> keys(nTris);
+        uint32_t counters[4] = {0, 1, 0, 0};
+        int32_t cb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        c.valid_idx = validIdx.data();
+        c.n_valid = &counters[0];
+        c.n_nodes = &counters[1];
+        c.n_tris = &counters[2];
+        c.q_out_count = &counters[3];
+        c.cbounds = cb;
+        c.keys = keys.data();
+        c.sorted = sortedV.data();
+        c.prim_to_tri = p2t.data();
+        Bvh8 g;
+        g.tris.resize(nTris);
+        c.tris = g.tris.data();
+        for (int64_t i = 0; i < nTris; ++i) lbvh_prep(c, i);
+        const int64_t m = counters[0];
+        c.m = m;
+        g.nodes.resize((size_t)(m * 3 / 4) + 16);
+        c.nodes = g.nodes.data();
+        c.node_cap = g.nodes.size();
+        for (int64_t k = 0; k < m; ++k) lbvh_key(c, k);
+        std::vector<uint32_t> order(m);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+        std::vector<uint64_t> k2(m);
+        std::vector<uint32_t> s2(m);
+        for (int64_t k = 0; k < m; ++k) {
+            k2[k] = keys[order[k]];
+            s2[k] = sortedV[order[k]];
+        }
+        keys.swap(k2);
+        sortedV.swap(s2);
+        c.keys = keys.data();
+        c.sorted = sortedV.data();
+        std::vector<int32_t> L(m), R(m), P(2 * m + 1), F(m), La(m);
+        std::vector<float> nbox(6 * (size_t)m + 6);
+        std::vector<uint32_t> arr(m + 1);
+        c.left = L.data();
+        c.right = R.data();
+        c.parent = P.data();
+        c.first = F.data();
+        c.last = La.data();
+        c.nbox = nbox.data();
+        c.arrivals = arr.data();
+        for (int64_t i = 0; i + 1 < m; ++i) lbvh_karras(c, i);
+        if (m > 1) {  // bottom-up fit in post-order
+            std::vector<std::pair<int32_t, int>> st;
+            st.push_back({0, 0});
+            while (!st.empty()) {
+                auto &top = st.back();
+                if (top.second == 0) {
+                    top.second = 1;
+                    const int32_t n0 = top.first;
+                    if (R[n0] >= 0) st.push_back({R[n0], 0});
+                    if (L[n0] >= 0) st.push_back({L[n0], 0});
+                } else {
+                    lb_fit_node(c, top.first);
+                    st.pop_back();
+                }
+            }
+        }
+        std::vector<LbvhItem> q0(m + 1), q1(m + 1);
+        q0[0].node2 = m > 1 ? 0 : ~0;
+        q0[0].wide = 0;
+        uint32_t nItems = m > 0 ? 1 : 0;
+        int depth = 1;
+        while (nItems) {
+            counters[3] = 0;
+            c.q_in = q0.data();
+            c.q_out = q1.data();
+            for (uint32_t i = 0; i < nItems; ++i) lbvh_collapse(c, q0[i]);
+            nItems = counters[3];
+            q0.swap(q1);
+            if (nItems) ++depth;
+        }
+        if (m == 0) {
+            memset(&g.nodes[0], 0, sizeof(Bvh8Node));
+            g.nodes[0].e[0] = g.nodes[0].e[1] = g.nodes[0].e[2] = 127;
+        }
+        g.n_in_leaves = counters[2];
+        for (int64_t i = 0; i < nTris; ++i) lbvh_leftover(c, i);
+        g.nodes.resize(counters[1]);
+        g.max_depth = depth;
+        g.prim_to_tri = p2t;
+        const int64_t badG = validate_bvh8(g);
+        const U4 *gn = reinterpret_cast<const U4 *>(g.nodes.data());
+        const F4 *gt = reinterpret_cast<const F4 *>(g.tris.data());
+        int64_t wrong = 0, wrongOcc = 0;
+        TraceCounters gc = {0, 0};
+        for (int64_t i = 0; i < nRays; ++i) {
+            V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+            TriHit h = {0, 0, 0, 0};
+            uint32_t ti = traverse_bvh8<false, true>(gn, gt, o, d, rays[i].t_max, &h, &gc);
+            int32_t prim = ti == B200PT_MISS ? -1 : (int32_t)g.tris[ti].prim;
+            const bool tie = prim >= 0 && want[i].triangle >= 0 && bits(h.t) == bits(want[i].t);
+            if (prim != want[i].triangle && !tie) ++wrong;
+            if (prim == want[i].triangle && prim >= 0 && bits(h.t) != bits(want[i].t)) ++wrong;
+            TriHit h2;
+            uint32_t occ = traverse_bvh8<true, false>(gn, gt, o, d, rays[i].t_max, &h2, &gc);
+            if ((occ != B200PT_MISS) != (wantOcc[i] != 0)) ++wrongOcc;
+        }
+        printf("lbvh builder (emulated): %lld of %lld triangles in the tree, %zu nodes, depth %d, violations %lld, wrong hits %lld, "
+               "wrong any-hit %lld, %.2f nodes/ray (host SAH tree: %.2f)\n",
+               (long long)m, (long long)nTris, g.nodes.size(), depth, (long long)badG, (long long)wrong, (long long)wrongOcc,
+               (double)gc.nodes / nRays, (double)ctr.nodes / nRays);
+        fail |= (badG || wrong || wrongOcc || depth > B200PT_STACK - 4);
+    }
     oracle_scene_destroy(os);
 
     // ---- spheres: the device routine (compiled for the host) against the oracle's Scene::Intersect
