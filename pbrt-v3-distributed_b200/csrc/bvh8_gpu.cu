@@ -124,8 +124,9 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
     GB_TRY(cudaStreamSynchronize(st));
     const int64_t m = m32;
     c.m = m;
-    // wide nodes: a node with an inner child always has 8 children, hence fewer than 0.65 m nodes (lbvh.cuh)
-    const size_t node_cap = (size_t)(m * 3 / 4) + 16;
+    // wide nodes: every node other than the root holds at least two triangles and a node with a large inner child
+    // always has 8 children, hence fewer than m nodes (lbvh.cuh)
+    const size_t node_cap = (size_t)m + 16;
     Bvh8Node *d_nodes_tmp = tmp.alloc<Bvh8Node>(node_cap);
     c.nodes = d_nodes_tmp;
     c.node_cap = node_cap;

@@ -30,6 +30,10 @@
 
 namespace b200pt {
 
+#ifndef LBVH_OPEN_SMALL
+#define LBVH_OPEN_SMALL 2  // also open subtrees of 2-3 triangles while the node has free slots (fewer triangle tests)
+#endif
+
 struct LbvhItem {
     int32_t node2;   // binary node to expand (internal id, or ~leaf for a single-triangle root)
     uint32_t wide;   // index of the 8-wide node to fill
@@ -259,8 +263,8 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
     int32_t ch[8];
     LbBox box[8];
     int k = 0;
-    if (it.node2 < 0 || lb_count(c, it.node2) <= 3) {
-        ch[k] = it.node2;  // the whole tree is one leaf child of the root
+    if (it.node2 < 0) {
+        ch[k] = it.node2;  // a single triangle: one leaf child of the root
         lb_child_box(c, it.node2, &box[k]);
         ++k;
     } else {
@@ -273,8 +277,16 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
             int best = -1;
             float bestArea = -1.f;
             for (int i = 0; i < k; ++i) {
-                if (ch[i] < 0 || lb_count(c, ch[i]) <= 3) continue;
-                const float area = lb_half_area(box[i]);
+                if (ch[i] < 0 || (LBVH_OPEN_SMALL == 0 && lb_count(c, ch[i]) <= 3)) continue;
+                float area = lb_half_area(box[i]);
+                if (LBVH_OPEN_SMALL == 2 && lb_count(c, ch[i]) <= 3) {
+                    // SAH gain of splitting a small leaf: A*n - (Al*nl + Ar*nr), in triangle-test units
+                    LbBox bl, br;
+                    lb_child_box(c, c.left[ch[i]], &bl);
+                    lb_child_box(c, c.right[ch[i]], &br);
+                    area = area * (float)lb_count(c, ch[i]) - (lb_half_area(bl) * (float)lb_count(c, c.left[ch[i]]) +
+                                                                lb_half_area(br) * (float)lb_count(c, c.right[ch[i]]));
+                }
                 if (area > bestArea) {
                     bestArea = area;
                     best = i;
@@ -331,14 +343,30 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
         slotUsed[bs] = true;
         childAt[bs] = bi;
     }
+    // A subtree of 2-3 triangles that found no free slots is either a leaf child (every ray entering its box tests
+    // all its triangles: A*n) or a small wide node of its own (A for the node + the triangles' own boxes).
+    bool isLeaf[8];
+    for (int i = 0; i < k; ++i) {
+        const int32_t cnt = lb_count(c, ch[i]);
+        isLeaf[i] = ch[i] < 0;
+        if (ch[i] >= 0 && cnt <= 3) {
+            float triAreas = 0.f;
+            for (int32_t t = 0; t < cnt; ++t) {
+                LbBox tb;
+                lb_tri_box(c.vertices + 9 * (int64_t)c.sorted[c.first[ch[i]] + t], &tb);
+                triAreas += lb_half_area(tb);
+            }
+            const float A = lb_half_area(box[i]);
+            isLeaf[i] = LBVH_OPEN_SMALL == 0 || A * (float)cnt <= A + triAreas;
+        }
+    }
     // allocation: inner children contiguous in slot order, leaf triangles contiguous in slot order
     uint32_t nInner = 0, nTri = 0;
     for (int s = 0; s < 8; ++s) {
         const int i = childAt[s];
         if (i < 0) continue;
-        const int32_t cnt = lb_count(c, ch[i]);
-        if (ch[i] < 0 || cnt <= 3)
-            nTri += (uint32_t)cnt;
+        if (isLeaf[i])
+            nTri += (uint32_t)lb_count(c, ch[i]);
         else
             ++nInner;
     }
@@ -382,7 +410,7 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
             node.qhi[a][s] = (uint8_t)qhi;
         }
         const int32_t cnt = lb_count(c, ch[i]);
-        if (ch[i] < 0 || cnt <= 3) {
+        if (isLeaf[i]) {
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             node.meta[s] = (uint8_t)((unary << 5) | triOffset);
             const int64_t f0 = ch[i] < 0 ? (int64_t)(~ch[i]) : (int64_t)c.first[ch[i]];

@@ -157,7 +157,7 @@ int main(int argc, char **argv) {
         for (int64_t i = 0; i < nTris; ++i) lbvh_prep(c, i);
         const int64_t m = counters[0];
         c.m = m;
-        g.nodes.resize((size_t)(m * 3 / 4) + 16);
+        g.nodes.resize((size_t)m + 16);
         c.nodes = g.nodes.data();
         c.node_cap = g.nodes.size();
         for (int64_t k = 0; k < m; ++k) lbvh_key(c, k);
@@ -242,9 +242,9 @@ int main(int argc, char **argv) {
             if ((occ != B200PT_MISS) != (wantOcc[i] != 0)) ++wrongOcc;
         }
         printf("lbvh builder (emulated): %lld of %lld triangles in the tree, %zu nodes, depth %d, violations %lld, wrong hits %lld, "
-               "wrong any-hit %lld, %.2f nodes/ray (host SAH tree: %.2f)\n",
+               "wrong any-hit %lld, %.2f nodes/ray %.2f tris/ray (host SAH tree: %.2f, %.2f)\n",
                (long long)m, (long long)nTris, g.nodes.size(), depth, (long long)badG, (long long)wrong, (long long)wrongOcc,
-               (double)gc.nodes / nRays, (double)ctr.nodes / nRays);
+               (double)gc.nodes / nRays, (double)gc.tris / nRays, (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
         fail |= (badG || wrong || wrongOcc || depth > B200PT_STACK - 4);
     }
     oracle_scene_destroy(os);
