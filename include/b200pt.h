@@ -147,13 +147,19 @@ typedef struct b200pt_camera_desc {
     float shutter_close;
 } b200pt_camera_desc;
 
-/* ---- film: Film with the default BoxFilter (core/film.cpp:44-130) -------- */
+/* ---- film: Film + pixel filter (core/film.cpp:44-130, core/film.h:121-161) --
+ * The filter is what Film keeps of it: its radius and the 16x16 table of
+ * weights Film's constructor evaluates (film.cpp:68-77) -- the host passes its
+ * own table, so every Filter subclass works and no filter function is
+ * evaluated here.  filter_table == NULL means the default BoxFilter (all
+ * weights 1, box.cpp:41-43), for which radius 0.5 takes a specialised path. */
 typedef struct b200pt_film_desc {
     int32_t full_resolution[2];
     int32_t cropped_bounds[4];     /* croppedPixelBounds x0 y0 x1 y1 (film.cpp:54-58) */
-    float filter_radius[2];        /* BoxFilter radius, default 0.5 0.5 (box.cpp:41-47)*/
+    float filter_radius[2];        /* Filter::radius (<= 8 pixels)                    */
     float scale;                   /* Film::scale                                     */
     float max_sample_luminance;    /* Film::maxSampleLuminance (INFINITY = off)       */
+    const float *filter_table;     /* [16][16] Film::filterTable, or NULL             */
 } b200pt_film_desc;
 
 /* ---- sampler: SobolSampler (samplers/sobol.h:45-69) or HaltonSampler

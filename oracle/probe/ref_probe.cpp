@@ -52,6 +52,10 @@
 #include "core/spectrum.h"
 #include "core/texture.h"
 #include "filters/box.h"
+#include "filters/triangle.h"
+#include "filters/sinc.h"
+#include "filters/mitchell.h"
+#include "filters/gaussian.h"
 #include "materials/matte.h"
 #include "materials/metal.h"
 #include "samplers/halton.h"
@@ -224,6 +228,35 @@ int main(int argc, char **argv) {
         Interaction it = sp.Sample(ref, u, &pdf);
         printf("p=(%a %a %a) n=(%a %a %a) pErr=(%a %a %a) pdf=%a\n", it.p.x, it.p.y, it.p.z, it.n.x, it.n.y, it.n.z,
                it.pError.x, it.pError.y, it.pError.z, pdf);
+    } else if (cmd == "filtertable") {
+        // filtertable name xwidth ywidth [p0 p1]: the Film's filterTable (film.cpp:68-77) for that PixelFilter
+        std::string name = argv[2];
+        ParamSet ps;
+        auto addf = [&](const char *n, float v) {
+            std::unique_ptr<Float[]> a(new Float[1]);
+            a[0] = v;
+            ps.AddFloat(n, std::move(a), 1);
+        };
+        addf("xwidth", atof(argv[3]));
+        addf("ywidth", atof(argv[4]));
+        if (name == "gaussian" && argc > 5) addf("alpha", atof(argv[5]));
+        if (name == "mitchell" && argc > 6) {
+            addf("B", atof(argv[5]));
+            addf("C", atof(argv[6]));
+        }
+        if (name == "sinc" && argc > 5) addf("tau", atof(argv[5]));
+        std::unique_ptr<Filter> filter;
+        if (name == "box") filter.reset(CreateBoxFilter(ps));
+        else if (name == "gaussian") filter.reset(CreateGaussianFilter(ps));
+        else if (name == "mitchell") filter.reset(CreateMitchellFilter(ps));
+        else if (name == "sinc") filter.reset(CreateSincFilter(ps));
+        else if (name == "triangle") filter.reset(CreateTriangleFilter(ps));
+        else die("unknown filter");
+        Film film(Point2i(16, 16), Bounds2f(Point2f(0, 0), Point2f(1, 1)), std::move(filter), 35.f, "probe.pfm", 1.f);
+        printf("radius %a %a\n", film.filter->radius.x, film.filter->radius.y);
+        for (int i = 0; i < 256; ++i) printf("%a\n", (double)film.filterTable[i]);
+        Bounds2i sb = film.GetSampleBounds();
+        printf("sample_bounds_16 %d %d %d %d\n", sb.pMin.x, sb.pMin.y, sb.pMax.x, sb.pMax.y);
     } else if (cmd == "camrays") {
         auto cam = makeCamera(argv + 2);
         int spp = atoi(argv[14]);

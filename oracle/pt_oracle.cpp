@@ -2113,7 +2113,11 @@ inline void XYZToRGB(const float xyz[3], float rgb[3]) {  // spectrum.h:56-60
 }
 
 // One 16x16 tile: integrator.cpp:241-331 with film.h:121-161 / film.cpp:95-130.
-void RenderTile(RenderCtx &rc, int tileIdx, int nTilesX, float *filmXYZW, std::mutex &filmMutex) {
+struct TileResult {  // a FilmTile (film.h:105-175) after its samples were added
+    int bx0 = 0, by0 = 0, tw = 0, th = 0;
+    std::vector<FilmTilePixel> pixels;
+};
+void RenderTile(RenderCtx &rc, int tileIdx, int nTilesX, TileResult *out) {
     const b200pt_film_desc &fd = *rc.film;
     const int *sb = rc.sd->sample_bounds;
     const int tileSize = 16;
@@ -2127,9 +2131,15 @@ void RenderTile(RenderCtx &rc, int tileIdx, int nTilesX, float *filmXYZW, std::m
     int bx0 = std::max(p0x, fd.cropped_bounds[0]), by0 = std::max(p0y, fd.cropped_bounds[1]);
     int bx1 = std::min(p1x, fd.cropped_bounds[2]), by1 = std::min(p1y, fd.cropped_bounds[3]);
     int tw = std::max(0, bx1 - bx0), th = std::max(0, by1 - by0);
-    std::vector<FilmTilePixel> pixels((size_t)tw * th);
+    std::vector<FilmTilePixel> &pixels = out->pixels;
+    pixels.assign((size_t)tw * th, FilmTilePixel());
+    out->bx0 = bx0;
+    out->by0 = by0;
+    out->tw = tw;
+    out->th = th;
     const float invRx = 1 / rx, invRy = 1 / ry;
-    const int filterTableSize = 16;  // film.h:99 filterTableWidth; box filter table is all ones
+    const int filterTableSize = 16;  // film.h:99 filterTableWidth
+    const float *filterTable = fd.filter_table;  // NULL: box filter, every entry is 1 (filters/box.cpp:41-43)
     Sobol sampler(rc.sd);
     const int *pb = rc.integ->pixel_bounds;
     for (int py = y0; py < y1; ++py)
@@ -2147,26 +2157,37 @@ void RenderTile(RenderCtx &rc, int tileIdx, int nTilesX, float *filmXYZW, std::m
                 q0y = std::max(q0y, by0);
                 q1x = std::min(q1x, bx1);
                 q1y = std::min(q1y, by1);
+                // film.h:134-146: offsets into the filter table
+                int ifx[40], ify[40];
+                for (int x = q0x; x < q1x; ++x) {
+                    float fx = std::abs((x - dx) * invRx * filterTableSize);
+                    ifx[x - q0x] = std::min((int)std::floor(fx), filterTableSize - 1);
+                }
+                for (int y = q0y; y < q1y; ++y) {
+                    float fy = std::abs((y - dy) * invRy * filterTableSize);
+                    ify[y - q0y] = std::min((int)std::floor(fy), filterTableSize - 1);
+                }
                 for (int y = q0y; y < q1y; ++y)
                     for (int x = q0x; x < q1x; ++x) {
-                        // box filter: every table entry is 1 (filters/box.cpp:41-43); the
-                        // index arithmetic of film.h:135-146 cannot change the weight
-                        (void)invRx;
-                        (void)invRy;
-                        (void)filterTableSize;
-                        float filterWeight = 1.f;
+                        int offset = ify[y - q0y] * filterTableSize + ifx[x - q0x];
+                        float filterWeight = filterTable ? filterTable[offset] : 1.f;
                         FilmTilePixel &pixel = pixels[(size_t)(y - by0) * tw + (x - bx0)];
                         pixel.contribSum += L * 1.f * filterWeight;
                         pixel.filterWeightSum += filterWeight;
                     }
             }
         }
-    // Film::MergeFilmTile, film.cpp:117-130
-    std::lock_guard<std::mutex> lock(filmMutex);
+}
+
+// Film::MergeFilmTile, film.cpp:117-130.  Tiles are merged in the order of the tile list, which is the order a
+// single-threaded reference run produces (ParallelFor2D without workers walks the tiles row-major); with more than
+// two tiles overlapping a pixel (filters wider than the box) the multi-threaded reference's own sums depend on the
+// order its threads finish in.
+void MergeTile(const b200pt_film_desc &fd, const TileResult &t, float *filmXYZW) {
     int fw = fd.cropped_bounds[2] - fd.cropped_bounds[0];
-    for (int y = by0; y < by1; ++y)
-        for (int x = bx0; x < bx1; ++x) {
-            const FilmTilePixel &tp = pixels[(size_t)(y - by0) * tw + (x - bx0)];
+    for (int y = t.by0; y < t.by0 + t.th; ++y)
+        for (int x = t.bx0; x < t.bx0 + t.tw; ++x) {
+            const FilmTilePixel &tp = t.pixels[(size_t)(y - t.by0) * t.tw + (x - t.bx0)];
             float xyz[3];
             RGBToXYZ(tp.contribSum.c, xyz);
             float *mp = filmXYZW + 4 * ((size_t)(y - fd.cropped_bounds[1]) * fw + (x - fd.cropped_bounds[0]));
@@ -2321,7 +2342,7 @@ int oracle_render(const oracle_scene *s, const b200pt_camera_desc *camera, const
     int nTilesX = (sb[2] - sb[0] + 15) / 16, nTilesY = (sb[3] - sb[1] + 15) / 16;
     if (!tiles) n_tiles = std::min<int64_t>(n_tiles < 0 ? (int64_t)nTilesX * nTilesY : n_tiles,
                                            (int64_t)nTilesX * nTilesY);
-    std::mutex filmMutex;
+    std::vector<TileResult> results((size_t)std::max<int64_t>(n_tiles, 0));
     std::atomic<int64_t> next(0);
     std::atomic<uint64_t> cam(0), reg(0), shad(0);
     auto worker = [&]() {
@@ -2337,7 +2358,7 @@ int oracle_render(const oracle_scene *s, const b200pt_camera_desc *camera, const
             int64_t i = next.fetch_add(1);
             if (i >= n_tiles) break;
             int tile = tiles ? tiles[i] : (int)i;
-            RenderTile(rc, tile, nTilesX, film_xyzw, filmMutex);
+            RenderTile(rc, tile, nTilesX, &results[(size_t)i]);
         }
         cam += rc.cameraRays;
         reg += rc.regularRays;
@@ -2348,6 +2369,7 @@ int oracle_render(const oracle_scene *s, const b200pt_camera_desc *camera, const
     for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
     worker();
     for (auto &t : th) t.join();
+    for (const TileResult &t : results) MergeTile(*film, t, film_xyzw);
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->camera_rays = cam;

@@ -46,7 +46,7 @@ class CameraDesc(C.Structure):
 class FilmDesc(C.Structure):
     _fields_ = [("full_resolution", C.c_int32 * 2), ("cropped_bounds", C.c_int32 * 4),
                 ("filter_radius", C.c_float * 2), ("scale", C.c_float),
-                ("max_sample_luminance", C.c_float)]
+                ("max_sample_luminance", C.c_float), ("filter_table", C.c_void_p)]
 
 
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1

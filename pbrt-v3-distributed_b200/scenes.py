@@ -289,7 +289,7 @@ def write_ply(path, tris, normals=None, uvs=None):
 
 def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
                eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6,
-               crop_window=None, film_scale=1.0, max_sample_luminance=None, sampler="sobol"):
+               crop_window=None, film_scale=1.0, max_sample_luminance=None, sampler="sobol", pixel_filter=None):
     """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
     os.makedirs(dirname, exist_ok=True)
     lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
@@ -302,6 +302,8 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
              (' "float scale" [%.9g]' % film_scale if film_scale != 1.0 else "") +
              (' "float maxsampleluminance" [%.9g]' % max_sample_luminance if max_sample_luminance else ""),
              'Sampler "%s" "integer pixelsamples" [%d]' % (sampler, spp)]
+    if pixel_filter:
+        lines.append(FilterTables().get(pixel_filter)[0])
     integ = 'Integrator "path" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (max_depth, strategy)
     if pixel_bounds is not None:
         integ += ' "integer pixelbounds" [%d %d %d %d]' % (pixel_bounds[0], pixel_bounds[2], pixel_bounds[1],
@@ -401,6 +403,22 @@ class HaltonTables:
         self.perms = np.frombuffer(raw, "<u2", count, 16).copy()
 
 
+class FilterTables:
+    """tests/golden/filter_tables.json: radius and Film::filterTable (16x16 weights, film.cpp:68-77) of a few
+    PixelFilter configurations, dumped from the reference by oracle/probe `filtertable`.  A pbrt host passes the
+    table of its own Film."""
+
+    def __init__(self, path=None):
+        import json
+        self.entries = json.load(open(path or os.path.join(GOLDEN_DIR, "filter_tables.json")))
+
+    def get(self, key):
+        e = self.entries[key]
+        radius = [float.fromhex(v) for v in e["radius"]]
+        table = np.array([float.fromhex(v) for v in e["table"]], np.float32)
+        return e["pbrt"], radius, table
+
+
 def rank_tiles(n_tiles, rank, world):
     """Image-space decomposition used for multi-GPU runs: tile i -> rank i mod N.
     Interleaving balances sky / geometry tiles; every rank keeps the FULL-film sampler so the
@@ -419,7 +437,7 @@ class RenderSetup:
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
                  lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None,
-                 sampler="sobol"):
+                 sampler="sobol", pixel_filter=None):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.sampler_name = sampler
@@ -439,11 +457,22 @@ class RenderSetup:
         self.crop = cb
         self.film.cropped_bounds[:] = cb
         self.film.filter_radius[:] = [0.5, 0.5]
+        self.pixel_filter = pixel_filter
+        sb = list(cb)
+        if pixel_filter:  # a key of tests/golden/filter_tables.json
+            _, radius, self._filter_table = FilterTables().get(pixel_filter)
+            self.film.filter_radius[:] = radius
+            self.film.filter_table = abi.ptr(self._filter_table)
+            # Film::GetSampleBounds, film.cpp:80-86
+            f32 = np.float32
+            sb = [int(np.floor(f32(cb[0]) + f32(0.5) - f32(radius[0]))), int(np.floor(f32(cb[1]) + f32(0.5) - f32(radius[1]))),
+                  int(np.ceil(f32(cb[2]) - f32(0.5) + f32(radius[0]))), int(np.ceil(f32(cb[3]) - f32(0.5) + f32(radius[1])))]
+        self.sample_bounds = sb
         self.film.scale = film_scale
         self.film.max_sample_luminance = max_sample_luminance if max_sample_luminance else float("inf")
         self.sampler = abi.SamplerDesc()
-        # Film::GetSampleBounds with the box filter of radius 0.5 == the cropped pixel bounds (film.cpp:80-86)
-        self.sampler.sample_bounds[:] = cb
+        # Film::GetSampleBounds; with the box filter of radius 0.5 == the cropped pixel bounds (film.cpp:80-86)
+        self.sampler.sample_bounds[:] = sb
         self.sampler.n_dimensions = self.tables.n_dims
         if sampler == "halton":  # halton.cpp:65-93: any sample count
             self.sampler.type = abi.SAMPLER_HALTON
@@ -451,12 +480,12 @@ class RenderSetup:
             self.sampler.halton_permutations = abi.ptr(self.tables.perms)
         else:
             self.sampler.samples_per_pixel = round_up_pow2(spp)
-            self._sobol_tables(cb)
+            self._sobol_tables(sb)
         self.integrator = abi.IntegratorDesc()
         self.integrator.max_depth = max_depth
         self.integrator.rr_threshold = 1.0
         self.integrator.light_strategy = strategy
-        self.integrator.pixel_bounds[:] = pixel_bounds or cb
+        self.integrator.pixel_bounds[:] = pixel_bounds or sb
 
     def _sobol_tables(self, cb):
         res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))
@@ -469,4 +498,5 @@ class RenderSetup:
 
     @property
     def n_tiles(self):
-        return ((self.crop[2] - self.crop[0] + 15) // 16) * ((self.crop[3] - self.crop[1] + 15) // 16)
+        sb = self.sample_bounds
+        return ((sb[2] - sb[0] + 15) // 16) * ((sb[3] - sb[1] + 15) // 16)

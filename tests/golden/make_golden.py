@@ -50,6 +50,14 @@ RENDERS = {
     # the only light is a sphere (the situation of scenes/killeroo-simple.pbrt), Halton sampler
     "sphere_light": (3000, ("matte", "plastic"), 40, 32, 6, 5, "spatial", 0),
     "sphere_power": (3000, ("matte", "glass_rough"), 40, 32, 4, 7, "power", 4),
+    # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
+    # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
+    "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
+    "filter_mitchell": (3000, ("matte", "plastic"), 37, 33, 4, 5, "uniform", None),
+    "filter_sinc": (3000, ("matte", "plastic"), 40, 32, 3, 5, "uniform", None),
+    "filter_aniso_crop": (3000, ("matte", "metal"), 70, 50, 4, 5, "uniform", None),
+    "filter_triangle": (3000, ("matte", "glass"), 33, 35, 4, 5, "power", None),
+    "filter_box1": (3000, ("matte", "plastic"), 40, 32, 4, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
@@ -63,6 +71,12 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              dict(center=(0.1, 0.0, -2.2), radius=0.45, material="glass"),
              dict(center=(-0.9, -0.6, -2.0), radius=0.4, material="plastic", scale=(1.3, 0.7, -1.1)),
              dict(center=(0.9, -0.7, -1.9), radius=0.3, material="matte", reverse_orientation=True)))),
+         "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
+         "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
+         "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),
+         "filter_aniso_crop": dict(camera=dict(pixel_filter="gaussian_aniso", crop_window=(0.21, 0.83, 0.1, 0.74))),
+         "filter_triangle": dict(camera=dict(pixel_filter="triangle", lens_radius=0.05, focal_distance=4.5)),
+         "filter_box1": dict(camera=dict(pixel_filter="box1")),
          "sphere_light": dict(scene=dict(spheres=(dict(center=(0.5, 2.5, -2.0), radius=0.3, emit=400.0),
                                                   dict(center=(-0.6, 0.2, -2.0), radius=0.5, material="plastic"))),
                               camera=dict(sampler="halton")),
@@ -88,8 +102,27 @@ def halton_fixtures():
     json.dump(out, open(os.path.join(HERE, "probe_halton.json"), "w"), indent=1)
 
 
+FILTERS = {  # key: (probe args, the PixelFilter line of the .pbrt twin)
+    "gaussian": (("gaussian", 2, 2, 2), 'PixelFilter "gaussian" "float xwidth" [2] "float ywidth" [2] "float alpha" [2]'),
+    "gaussian_aniso": (("gaussian", 1.5, 2.5, 1), 'PixelFilter "gaussian" "float xwidth" [1.5] "float ywidth" [2.5] "float alpha" [1]'),
+    "mitchell": (("mitchell", 2, 2), 'PixelFilter "mitchell" "float xwidth" [2] "float ywidth" [2]'),
+    "triangle": (("triangle", 2, 2), 'PixelFilter "triangle" "float xwidth" [2] "float ywidth" [2]'),
+    "sinc": (("sinc", 4, 4, 3), 'PixelFilter "sinc" "float xwidth" [4] "float ywidth" [4] "float tau" [3]'),
+    "box1": (("box", 1, 1), 'PixelFilter "box" "float xwidth" [1] "float ywidth" [1]'),
+}
+
+
+def filter_fixtures():
+    out = {}
+    for key, (args, line) in FILTERS.items():
+        txt = ob.probe("filtertable", *args).splitlines()
+        out[key] = {"pbrt": line, "radius": txt[0].split()[1:], "table": txt[1:257]}
+    json.dump(out, open(os.path.join(HERE, "filter_tables.json"), "w"), indent=0)
+
+
 def main():
     ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
+    filter_fixtures()
     halton_fixtures()
     out = {"cameras": {}, "sobol": [], "camrays": []}
     cam_args = [0, 0, -4.5, 0, 0, 0, 0, 1, 0, 35]
@@ -147,7 +180,7 @@ def main():
         arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
         path = scenes.write_pbrt("/tmp/golden_render", "render_" + name, arr, w, h, spp, max_depth=depth,
                                  strategy=strat, **ex.get("camera", {}))
-        ob.run_pbrt_ref(path)
+        ob.run_pbrt_ref(path, threads=1 if name.startswith("filter_") else None)
         os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % name),
                    os.path.join(HERE, "render_%s.pfm" % name))
     print("golden fixtures written to", HERE)

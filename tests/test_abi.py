@@ -31,7 +31,7 @@ def test_struct_sizes_match_header(abi):
     assert C.sizeof(abi.AreaLight) == 24
     assert C.sizeof(abi.Sphere) == 168
     assert C.sizeof(abi.CameraDesc) == 144
-    assert C.sizeof(abi.FilmDesc) == 40
+    assert C.sizeof(abi.FilmDesc) == 48
     assert C.sizeof(abi.SamplerDesc) == 64
     assert C.sizeof(abi.IntegratorDesc) == 28
     assert C.sizeof(abi.SceneDesc) == 112

@@ -36,6 +36,14 @@ RENDERS = {
     # the only light is a sphere (the situation of scenes/killeroo-simple.pbrt), Halton sampler
     "sphere_light": (3000, ("matte", "plastic"), 40, 32, 6, 5, "spatial", 0),
     "sphere_power": (3000, ("matte", "glass_rough"), 40, 32, 4, 7, "power", 4),
+    # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
+    # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
+    "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
+    "filter_mitchell": (3000, ("matte", "plastic"), 37, 33, 4, 5, "uniform", None),
+    "filter_sinc": (3000, ("matte", "plastic"), 40, 32, 3, 5, "uniform", None),
+    "filter_aniso_crop": (3000, ("matte", "metal"), 70, 50, 4, 5, "uniform", None),
+    "filter_triangle": (3000, ("matte", "glass"), 33, 35, 4, 5, "power", None),
+    "filter_box1": (3000, ("matte", "plastic"), 40, 32, 4, 5, "uniform", None),
 }
 EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)),
                            camera=dict(lens_radius=0.05, focal_distance=4.5)),
@@ -49,6 +57,12 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              dict(center=(0.1, 0.0, -2.2), radius=0.45, material="glass"),
              dict(center=(-0.9, -0.6, -2.0), radius=0.4, material="plastic", scale=(1.3, 0.7, -1.1)),
              dict(center=(0.9, -0.7, -1.9), radius=0.3, material="matte", reverse_orientation=True)))),
+         "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
+         "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
+         "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),
+         "filter_aniso_crop": dict(camera=dict(pixel_filter="gaussian_aniso", crop_window=(0.21, 0.83, 0.1, 0.74))),
+         "filter_triangle": dict(camera=dict(pixel_filter="triangle", lens_radius=0.05, focal_distance=4.5)),
+         "filter_box1": dict(camera=dict(pixel_filter="box1")),
          "sphere_light": dict(scene=dict(spheres=(dict(center=(0.5, 2.5, -2.0), radius=0.3, emit=400.0),
                                                   dict(center=(-0.6, 0.2, -2.0), radius=0.5, material="plastic"))),
                               camera=dict(sampler="halton")),
