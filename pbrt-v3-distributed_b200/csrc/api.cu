@@ -533,8 +533,10 @@ extern "C" {
 int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, const b200pt_film_desc *film,
                          const b200pt_sampler_desc *smp, const b200pt_integrator_desc *integ, b200pt_render **out) {
     if (!scene || !cam || !film || !smp || !integ || !out) return b200pt_fail(B200PT_ERR_INVALID, "render_create: NULL argument");
-    if (film->filter_radius[0] != 0.5f || film->filter_radius[1] != 0.5f)
-        return b200pt_fail(B200PT_ERR_INVALID, "render_create: only the default box filter (radius 0.5) is supported");
+    if (!(film->filter_radius[0] > 0.f) || !(film->filter_radius[1] > 0.f) || film->filter_radius[0] > 8.f ||
+        film->filter_radius[1] > 8.f)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: pixel filter radius must be in (0, 8]");
+    const bool filter_general = film->filter_table != nullptr || film->filter_radius[0] != 0.5f || film->filter_radius[1] != 0.5f;
     const bool halton = smp->type == B200PT_SAMPLER_HALTON;
     if (smp->type != B200PT_SAMPLER_SOBOL && !halton)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: unknown sampler type %d", smp->type);
@@ -633,6 +635,14 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.camera.lens_radius = cam->lens_radius;
     H.camera.focal_distance = cam->focal_distance;
     memcpy(H.crop, film->cropped_bounds, sizeof(int) * 4);
+    H.filter_general = filter_general ? 1 : 0;
+    for (int a = 0; a < 2; ++a) {
+        H.filter_radius[a] = film->filter_radius[a];
+        H.filter_inv_radius[a] = 1 / film->filter_radius[a];  // Filter::invRadius, filter.h:53-54
+        // Film::GetFilmTile (film.cpp:95-106): pixels [ceil(x0 - .5 - r), floor(x1 - .5 + r) + 1)
+        H.apron[a] = std::max((int)(0.f - std::ceil(0.f - 0.5f - film->filter_radius[a])),
+                              (int)std::floor(0.f - 0.5f + film->filter_radius[a]) + 1);
+    }
     memcpy(H.pixel_bounds, integ->pixel_bounds, sizeof(int) * 4);
     H.max_sample_luminance = film->max_sample_luminance;
     H.max_depth = integ->max_depth;
@@ -749,6 +759,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.occluded, cap);
     ALLOC(H.mis_hit, cap);
     ALLOC(H.pix_bleed, (size_t)r->tiles_per_batch * 256);
+    float *d_filter_table = nullptr;
+    if (filter_general) {
+        ALLOC(d_filter_table, 256);
+        ALLOC(H.pfilm, cap);
+        ALLOC(H.tile_film, (size_t)r->tiles_per_batch * (16 + 2 * H.apron[0]) * (16 + 2 * H.apron[1]));
+        ALLOC(H.tile_slot, (size_t)H.tiles_x * H.tiles_y);
+    }
     ALLOC(H.q_path[0], cap);
     ALLOC(H.q_path[1], cap);
     for (int m = 0; m < 4; ++m) ALLOC(H.q_mat[m], cap);
@@ -788,6 +805,14 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     CUDA_TRY(cudaMemcpyAsync(d_cdf, cdf.data(), (nl + 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_func, func.data(), std::max(nl, 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(H.film, 0, (size_t)cw * chh * sizeof(float4), st));
+    if (filter_general) {
+        float table[256];
+        for (int i = 0; i < 256; ++i) table[i] = film->filter_table ? film->filter_table[i] : 1.f;
+        H.filter_table = d_filter_table;
+        CUDA_TRY(cudaMemcpyAsync(d_filter_table, table, sizeof(table), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(H.tile_slot, 0xff, (size_t)H.tiles_x * H.tiles_y * sizeof(int32_t), st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // `table` is a local
+    }
     CUDA_TRY(cudaMemsetAsync(H.stats, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemcpyAsync(r->d_dev, &H, sizeof(H), cudaMemcpyHostToDevice, st));
     if (H.grid.enabled) {
@@ -1048,7 +1073,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         }
         {
             LaunchTimer lt(r, st, 2);
-            launch_film(r->d_dev, (uint32_t)first, nb, st);
+            if (H.filter_general)
+                launch_film_general(r->d_dev, H, (uint32_t)first, nb, st);
+            else
+                launch_film(r->d_dev, (uint32_t)first, nb, st);
         }
         launch_accumulate_stats(r->d_dev, 0, st);
         r->launches++;

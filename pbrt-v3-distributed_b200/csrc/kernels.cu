@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
             if ((int)ceilf(dy - 0.5f) < py) code |= 4u;
             if ((int)floorf(dy + 0.5f) + 1 > py + 1) code |= 8u;
             if (code) R->pix_bleed[tb * 256u + pix] = 1;
+            if (R->filter_general) R->pfilm[slot] = make_float2(pFilm[0], pFilm[1]);
             R->sobol[slot] = st.index;
             R->ray_o[slot] = f4(o, 1.f);                                // etaScale = 1
             R->ray_d[slot] = f4(d, __uint_as_float((uint32_t)st.dim));  // dim = 5, bounces = 0, flags = 0
@@ -822,6 +823,114 @@ __global__ void __launch_bounds__(18 * 18) k_film(const RenderDev *R, uint32_t f
     }
 }
 
+// ---- general pixel filter -------------------------------------------------------------------------------------
+// FilmTile pixel bounds of a tile (Film::GetFilmTile, film.cpp:95-106)
+struct TileFilm {
+    int bx0, by0, bx1, by1;
+};
+__device__ __forceinline__ TileFilm tile_film_bounds(const RenderDev *R, const TileRect &t) {
+    TileFilm f;
+    f.bx0 = max((int)ceilf((float)t.x0 - 0.5f - R->filter_radius[0]), R->crop[0]);
+    f.by0 = max((int)ceilf((float)t.y0 - 0.5f - R->filter_radius[1]), R->crop[1]);
+    f.bx1 = min((int)floorf((float)t.x1 - 0.5f + R->filter_radius[0]) + 1, R->crop[2]);
+    f.by1 = min((int)floorf((float)t.y1 - 0.5f + R->filter_radius[1]) + 1, R->crop[3]);
+    return f;
+}
+// One block per tile, one thread per FilmTile pixel: the thread replays FilmTile::AddSample (film.h:121-161) for its
+// pixel over the tile's samples in the reference's order (pixels row-major, samples in order) and stores what
+// MergeFilmTile would add to the film (film.cpp:117-130).
+__global__ void __launch_bounds__(1024) k_film_tile(const RenderDev *R, uint32_t first_tile) {
+    const uint32_t tb = blockIdx.x;
+    const int tile = R->tile_list[first_tile + tb];
+    const TileRect t = tile_rect(R, tile);
+    const TileFilm f = tile_film_bounds(R, t);
+    const int fw = 16 + 2 * R->apron[0], fh = 16 + 2 * R->apron[1];
+    const int lx = (int)threadIdx.x, ly = (int)threadIdx.y;
+    // local (lx, ly) <-> pixel: the tile's unclipped FilmTile window starts at (x0 - apron, y0 - apron)
+    const int X = t.x0 - R->apron[0] + lx, Y = t.y0 - R->apron[1] + ly;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (X >= f.bx0 && X < f.bx1 && Y >= f.by0 && Y < f.by1) {
+        const uint32_t spp = (uint32_t)R->sampler.spp;
+        const float maxLum = R->max_sample_luminance;
+        const float rx = R->filter_radius[0], ry = R->filter_radius[1];
+        RGB sum = rgb1(0.f);
+        float wsum = 0.f;
+        // source pixels whose samples can reach this pixel: |pFilm - 0.5 - X| <= r with pFilm in [sx, sx + 1)
+        const int sx0 = max(t.x0, (int)ceilf((float)X - 0.5f - rx) - 1), sx1 = min(t.x1 - 1, (int)floorf((float)X + 0.5f + rx) + 1);
+        const int sy0 = max(t.y0, (int)ceilf((float)Y - 0.5f - ry) - 1), sy1 = min(t.y1 - 1, (int)floorf((float)Y + 0.5f + ry) + 1);
+        for (int sy = sy0; sy <= sy1; ++sy)
+            for (int sx = sx0; sx <= sx1; ++sx) {
+                if (!pixel_rendered(R, t, sx, sy)) continue;
+                const uint32_t pix = (uint32_t)((sy - t.y0) * 16 + (sx - t.x0));
+                const size_t base = ((size_t)tb * 256u + pix) * spp;
+                for (uint32_t s = 0; s < spp; ++s) {
+                    const float2 pf = R->pfilm[base + s];
+                    const float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
+                    const int q0x = max((int)ceilf(dx - rx), f.bx0), q1x = min((int)floorf(dx + rx) + 1, f.bx1);
+                    const int q0y = max((int)ceilf(dy - ry), f.by0), q1y = min((int)floorf(dy + ry) + 1, f.by1);
+                    if (X < q0x || X >= q1x || Y < q0y || Y >= q1y) continue;
+                    const float fx = fabsf(((float)X - dx) * R->filter_inv_radius[0] * 16.f);
+                    const float fy = fabsf(((float)Y - dy) * R->filter_inv_radius[1] * 16.f);
+                    const int ifx = min((int)floorf(fx), 15), ify = min((int)floorf(fy), 15);
+                    const float w = R->filter_table[ify * 16 + ifx];
+                    const float4 v = R->L[base + s];
+                    RGB Lv = rgb(v.x, v.y, v.z);
+                    // integrator.cpp:294-315
+                    if (has_nans(Lv))
+                        Lv = rgb1(0.f);
+                    else if (lum(Lv) < -1e-5f)
+                        Lv = rgb1(0.f);
+                    else if (pt_isinf(lum(Lv)))
+                        Lv = rgb1(0.f);
+                    if (lum(Lv) > maxLum) Lv = Lv * (maxLum / lum(Lv));  // film.h:124-125
+                    sum = sum + Lv * 1.f * w;                             // L * sampleWeight * filterWeight
+                    wsum += w;
+                }
+            }
+        float xyz[3];
+        rgb_to_xyz(sum, xyz);
+        out = make_float4(xyz[0], xyz[1], xyz[2], wsum);
+    }
+    if (lx < fw && ly < fh) R->tile_film[((size_t)tb * fh + ly) * fw + lx] = out;
+}
+__global__ void k_film_tile_slots(const RenderDev *R, uint32_t first_tile, uint32_t n_batch_tiles) {
+    const uint32_t tb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tb < n_batch_tiles) R->tile_slot[R->tile_list[first_tile + tb]] = (int32_t)tb;
+}
+// One thread per film pixel: adds the FilmTile values of the batch's tiles that cover it, in ascending tile order.
+__global__ void k_film_merge(const RenderDev *R) {
+    const int w = R->crop[2] - R->crop[0], h = R->crop[3] - R->crop[1];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int X = R->crop[0] + i % w, Y = R->crop[1] + i / w;
+    const int fw = 16 + 2 * R->apron[0], fh = 16 + 2 * R->apron[1];
+    const int tx0 = max(0, (X - R->apron[0] - R->sampler.sb[0]) >> 4), tx1 = min(R->tiles_x - 1, (X + R->apron[0] - R->sampler.sb[0]) >> 4);
+    const int ty0 = max(0, (Y - R->apron[1] - R->sampler.sb[1]) >> 4), ty1 = min(R->tiles_y - 1, (Y + R->apron[1] - R->sampler.sb[1]) >> 4);
+    float4 acc = R->film[i];
+    bool touched = false;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int tile = ty * R->tiles_x + tx;
+            const int32_t tb = R->tile_slot[tile];
+            if (tb < 0) continue;
+            const TileRect t = tile_rect(R, tile);
+            const TileFilm f = tile_film_bounds(R, t);
+            if (X < f.bx0 || X >= f.bx1 || Y < f.by0 || Y >= f.by1) continue;
+            const int lx = X - (t.x0 - R->apron[0]), ly = Y - (t.y0 - R->apron[1]);
+            const float4 v = R->tile_film[((size_t)tb * fh + ly) * fw + lx];
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+            touched = true;
+        }
+    if (touched) R->film[i] = acc;
+}
+__global__ void k_film_tile_slots_reset(const RenderDev *R, uint32_t first_tile, uint32_t n_batch_tiles) {
+    const uint32_t tb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tb < n_batch_tiles) R->tile_slot[R->tile_list[first_tile + tb]] = -1;
+}
+
 __global__ void k_accumulate_stats(const RenderDev *R) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long regular = 0, shadow = 0;
@@ -967,6 +1076,16 @@ void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32
 
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s) {
     k_film<<<n_batch_tiles, dim3(18, 18), 0, s>>>(dev, batch_first_tile);
+}
+
+void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t batch_first_tile, uint32_t n_batch_tiles,
+                         cudaStream_t s) {
+    const dim3 block((unsigned)(16 + 2 * host.apron[0]), (unsigned)(16 + 2 * host.apron[1]));
+    k_film_tile_slots<<<(n_batch_tiles + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_batch_tiles);
+    k_film_tile<<<n_batch_tiles, block, 0, s>>>(dev, batch_first_tile);
+    const int npix = (host.crop[2] - host.crop[0]) * (host.crop[3] - host.crop[1]);
+    k_film_merge<<<(npix + 255) / 256, 256, 0, s>>>(dev);
+    k_film_tile_slots_reset<<<(n_batch_tiles + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_batch_tiles);
 }
 
 void launch_accumulate_stats(const RenderDev *dev, uint32_t, cudaStream_t s) { k_accumulate_stats<<<1, 32, 0, s>>>(dev); }

@@ -53,6 +53,14 @@ struct RenderDev {
     int pixel_bounds[4];    // integrator "pixelbounds"
     float max_sample_luminance;
     float4 *film;           // [h][w] (X, Y, Z, weight) raw sums
+    // general pixel filter (film.h:121-161); filter_general == 0 selects the box-radius-0.5 path
+    int filter_general;
+    float filter_radius[2], filter_inv_radius[2];
+    int apron[2];                   // FilmTile pixels beyond the 16x16 tile on each side (film.cpp:95-106)
+    const float *filter_table;      // [16][16] Film::filterTable
+    float2 *pfilm;                  // per slot: CameraSample::pFilm (general filter only)
+    float4 *tile_film;              // [tiles_per_batch][16 + 2 apron_y][16 + 2 apron_x] merged tile sums (XYZ, weight)
+    int32_t *tile_slot;             // [tiles_x * tiles_y] position of a tile in the current batch or -1
     // integrator
     int max_depth;
     float rr_threshold;
@@ -148,6 +156,10 @@ void launch_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims, cuda
 // Fills the per-voxel light distributions (all voxels, once per render object).
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s);
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
+// General pixel filter: per-tile FilmTile sums in the reference's sample order, then the tiles of the batch are
+// merged into the film in tile-list order (Film::MergeFilmTile order of a single-threaded reference run).
+void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t batch_first_tile, uint32_t n_batch_tiles,
+                         cudaStream_t s);
 void launch_accumulate_stats(const RenderDev *dev, uint32_t n_camera, cudaStream_t s);
 void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
                         cudaStream_t s);

@@ -353,9 +353,8 @@ class GpuPathIntegrator : public PathIntegrator {
         if (halton && halton->sampleAtPixelCenter)
             return Error("gpupath: Sampler \"halton\" with samplepixelcenter is not supported");
         Film *film = cam->film;
-        if (!dynamic_cast<const BoxFilter *>(film->filter.get()) || film->filter->radius.x != 0.5f ||
-            film->filter->radius.y != 0.5f)
-            return Error("gpupath: only the default box filter (radius 0.5) is supported");
+        if (film->filter->radius.x > 8 || film->filter->radius.y > 8)
+            return Error("gpupath: pixel filters wider than 8 pixels are not supported");
         int strategy;
         if (lightSampleStrategy == "uniform" || scene.lights.size() == 1)
             strategy = B200PT_LIGHTS_UNIFORM;
@@ -403,6 +402,10 @@ class GpuPathIntegrator : public PathIntegrator {
         fd.filter_radius[1] = film->filter->radius.y;
         fd.scale = film->scale;
         fd.max_sample_luminance = film->maxSampleLuminance;
+        // any Filter: Film already tabulated it (film.cpp:68-77); the default box filter keeps the specialised path
+        const bool defaultBox = dynamic_cast<const BoxFilter *>(film->filter.get()) && film->filter->radius.x == 0.5f &&
+                                film->filter->radius.y == 0.5f;
+        fd.filter_table = defaultBox ? nullptr : film->filterTable;
 
         b200pt_sampler_desc smpd;
         memset(&smpd, 0, sizeof(smpd));

@@ -80,6 +80,16 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spheres.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spheres.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (Sphere shapes) differs from the reference"
+    # a Gaussian pixel filter (samples outside the film, 2-pixel tile aprons); golden from the 1-thread reference
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS["filter_gaussian"]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+    path = scenes.write_pbrt(str(tmp_path), "render_filter_gaussian", arr, w, h, spp, max_depth=depth, strategy=strat,
+                             pixel_filter="gaussian")
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_filter_gaussian.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_filter_gaussian.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (Gaussian pixel filter) differs from the reference"
 
 
 KILLEROO_DIR = os.path.join(ROOT, "oracle", "_ref", "scenes")
