@@ -297,8 +297,8 @@ def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
         print("oracle samples", o.pixel_samples(setup, x, y))
     assert nbad == 0, "%d of %d components differ from the reference render" % (nbad, rgb.size)
     st = r.stats()
-    cb = setup.crop
-    assert st["camera_rays"] == (cb[2] - cb[0]) * (cb[3] - cb[1]) * spp
+    cb = setup.sample_bounds
+    assert st["camera_rays"] == (cb[2] - cb[0]) * (cb[3] - cb[1]) * setup.sampler.samples_per_pixel
     r.close()
     scene.close()
 
