@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-spp", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pixel-filter", default=None,
+                    help="a key of tests/golden/filter_tables.json (gaussian, mitchell, sinc ...); default: box filter")
     ap.add_argument("--bvh", default="host", choices=["host", "gpu"],
                     help="acceleration structure builder: host SAH (default) or the on-device builder")
     args = ap.parse_args()
@@ -194,7 +196,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
-    setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth)
+    setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=args.pixel_filter)
+    if args.pixel_filter:
+        config["pixel_filter"] = args.pixel_filter
     ctx = pkg.Context(local_rank)
     if args.bvh == "gpu":
         ctx.set_option("gpu_bvh_build", 1)

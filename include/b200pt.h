@@ -84,8 +84,8 @@ typedef struct b200pt_area_light {
                             `triangle` is ignored                       */
 } b200pt_area_light;
 
-/* ---- spheres: full Sphere shapes (shapes/sphere.cpp:49-306; zmin/zmax/phimax
- * clipping is out of scope and must be rejected by the host).  A sphere keeps
+/* ---- spheres: Sphere shapes (shapes/sphere.cpp:49-306), full or clipped by
+ * zmin / zmax / phimax.  A sphere keeps
  * its object space like in the reference: both matrices are the host's own
  * Transform::m / mInv (row-major).  Spheres are tested outside the triangle
  * BVH (there are few of them: lights, a handful of objects). */
@@ -104,6 +104,11 @@ typedef struct b200pt_sphere {
      * root can be off by more than the box test's error, so the box test decides real cases (a shadow ray
      * towards the limb of a distant sphere light).  All zeros = use the sphere's own Shape::WorldBound(). */
     float leaf_bounds[6];
+    /* The Sphere's own members (sphere.h:55-61, :66-68) for a partial sphere: zMin, zMax (already clamped and
+     * ordered), thetaMin, thetaMax, phiMax (radians).  phi_max == 0 means a full sphere and the five values are
+     * ignored (-r, r, acos(-1), acos(1), Radians(360) are used).  b200pt_host_sphere_params computes them from the
+     * shape's parameters for hosts that do not have a Sphere object. */
+    float z_min, z_max, theta_min, theta_max, phi_max;
 } b200pt_sphere;
 
 /* ---- scene: world-space triangle soup + per-triangle attributes ---------
@@ -340,6 +345,8 @@ int b200pt_host_perspective_camera(const float eye[3], const float look[3], cons
 float b200pt_host_roughness_to_alpha(float roughness);
 /* OrenNayar's A and B from sigma in degrees (reflection.h:414-420), clamped like matte.cpp:54 */
 void b200pt_host_oren_nayar(float sigma_degrees, float *A, float *B);
+/* Sphere constructor (sphere.h:49-61): out = {zMin, zMax, thetaMin, thetaMax, phiMax}. */
+void b200pt_host_sphere_params(float radius, float zmin, float zmax, float phimax_degrees, float out[5]);
 
 #ifdef __cplusplus
 }

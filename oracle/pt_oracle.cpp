@@ -879,25 +879,33 @@ inline V3 XformNormal(const float *mInv, const V3 &n) {
     return V3(mInv[0] * x + mInv[4] * y + mInv[8] * z, mInv[1] * x + mInv[5] * y + mInv[9] * z,
               mInv[2] * x + mInv[6] * y + mInv[10] * z);
 }
-// Sphere constructor values for a full sphere (sphere.h:50-61): zMin = -r, zMax = r, phiMax = Radians(360)
+// Sphere constructor values (sphere.h:49-61): a full sphere (phi_max == 0 in the descriptor: zMin = -r, zMax = r,
+// phiMax = Radians(360)) or the host's own members for a partial one
 struct SphereConsts {
     float radius, zMin, zMax, thetaMin, thetaMax, phiMax;
-    explicit SphereConsts(float r) {
+    explicit SphereConsts(const b200pt_sphere &sp) {
+        const float r = sp.radius;
         radius = r;
-        zMin = Clamp(std::min(-r, r), -r, r);
-        zMax = Clamp(std::max(-r, r), -r, r);
-        thetaMin = std::acos(Clamp(std::min(zMin, zMax) / r, -1, 1));
-        thetaMax = std::acos(Clamp(std::max(zMin, zMax) / r, -1, 1));
-        phiMax = (Pi / 180) * Clamp(360.f, 0, 360);  // Radians()
+        if (sp.phi_max == 0.f) {
+            zMin = Clamp(std::min(-r, r), -r, r);
+            zMax = Clamp(std::max(-r, r), -r, r);
+            thetaMin = std::acos(Clamp(std::min(zMin, zMax) / r, -1, 1));
+            thetaMax = std::acos(Clamp(std::max(zMin, zMax) / r, -1, 1));
+            phiMax = (Pi / 180) * Clamp(360.f, 0, 360);  // Radians()
+        } else {
+            zMin = sp.z_min;
+            zMax = sp.z_max;
+            thetaMin = sp.theta_min;
+            thetaMax = sp.theta_max;
+            phiMax = sp.phi_max;
+        }
     }
     float Area() const { return phiMax * radius * (zMax - zMin); }  // sphere.cpp:207
 };
-// shapes/sphere.cpp:49-158 (Intersect) and :160-212 (IntersectP); a full sphere is never clipped, so the
-// phi / z tests (and std::atan2, which only feeds them and the unused uv) drop out.
-// Returns false or fills *tHit (+ *is when is != nullptr).
+// shapes/sphere.cpp:49-158 (Intersect) and :160-212 (IntersectP).  Returns false or fills *tHit (+ *is when is != nullptr).
 inline bool SphereIntersect(const b200pt_sphere &sp, const V3 &ro, const V3 &rd, float rayTMax, float *tHit,
                             Isect *is) {
-    const SphereConsts c(sp.radius);
+    const SphereConsts c(sp);
     const float radius = c.radius;
     // Transform::operator()(Ray, oError, dError), transform.h:372-384
     V3 oErr, dErr;
@@ -921,11 +929,25 @@ inline bool SphereIntersect(const b200pt_sphere &sp, const V3 &ro, const V3 &rd,
         tShapeHit = t1;
         if (tShapeHit.high > rayTMax) return false;
     }
-    *tHit = tShapeHit.v;
-    if (!is) return true;
+    // sphere.cpp:85-112: hit position, phi, clipping against zmin / zmax / phimax (second root on failure)
     V3 pHit = o + d * tShapeHit.v;
     pHit = pHit * (radius / Length(pHit));  // Distance(pHit, (0,0,0))
     if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * radius;
+    float phi = std::atan2(pHit.y, pHit.x);
+    if (phi < 0) phi += 2 * Pi;
+    if ((c.zMin > -radius && pHit.z < c.zMin) || (c.zMax < radius && pHit.z > c.zMax) || phi > c.phiMax) {
+        if (tShapeHit.v == t1.v) return false;
+        if (t1.high > rayTMax) return false;
+        tShapeHit = t1;
+        pHit = o + d * tShapeHit.v;
+        pHit = pHit * (radius / Length(pHit));
+        if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * radius;
+        phi = std::atan2(pHit.y, pHit.x);
+        if (phi < 0) phi += 2 * Pi;
+        if ((c.zMin > -radius && pHit.z < c.zMin) || (c.zMax < radius && pHit.z > c.zMax) || phi > c.phiMax) return false;
+    }
+    *tHit = tShapeHit.v;
+    if (!is) return true;
     float theta = std::acos(Clamp(pHit.z / radius, -1, 1));
     float zRadius = std::sqrt(pHit.x * pHit.x + pHit.y * pHit.y);
     float invZRadius = 1 / zRadius;
@@ -1670,7 +1692,7 @@ inline LightSample TriangleSample(const oracle_scene &s, int tri, const float u[
 
 // shapes/sphere.cpp:214-230: Sphere::Sample(u, pdf) (uniform over the area)
 inline LightSample SphereSampleArea(const b200pt_sphere &sp, const float u[2], float *pdf) {
-    const SphereConsts c(sp.radius);
+    const SphereConsts c(sp);
     // UniformSampleSphere, sampling.cpp:82-87
     float z = 1 - 2 * u[0];
     float r = std::sqrt(std::max((float)0, (float)1 - z * z));
@@ -1736,7 +1758,7 @@ inline float SpherePdf(const b200pt_sphere &sp, const V3 &refP, const V3 &refPEr
         float tHit;
         Isect li;
         if (!SphereIntersect(sp, ro, wi, Infinity, &tHit, &li)) return 0;
-        float pdf = LengthSquared(refP - li.p) / (AbsDot(li.n, -wi) * SphereConsts(radius).Area());
+        float pdf = LengthSquared(refP - li.p) / (AbsDot(li.n, -wi) * SphereConsts(sp).Area());
         if (std::isinf(pdf)) pdf = 0.f;
         return pdf;
     }
@@ -2221,7 +2243,7 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     s->lightArea.resize(d->n_lights);
     if (d->n_spheres > 0) s->spheres.assign(d->spheres, d->spheres + d->n_spheres);
     for (int i = 0; i < d->n_lights; ++i)
-        s->lightArea[i] = s->lights[i].sphere >= 0 ? SphereConsts(s->spheres[s->lights[i].sphere].radius).Area()
+        s->lightArea[i] = s->lights[i].sphere >= 0 ? SphereConsts(s->spheres[s->lights[i].sphere]).Area()
                                                    : TriangleArea(*s, s->lights[i].triangle);
     for (int a = 0; a < 3; ++a) {
         s->wbMin[a] = Infinity;
@@ -2235,9 +2257,10 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     for (b200pt_sphere &sp : s->spheres) {
         // Shape::WorldBound = (*ObjectToWorld)(ObjectBound()) (shape.cpp:52, transform.cpp:246-256)
         const float r = sp.radius;
+        const SphereConsts sc(sp);  // Sphere::ObjectBound, sphere.cpp:43-46: (-r, -r, zMin) - (r, r, zMax)
         float lo[3] = {Infinity, Infinity, Infinity}, hi[3] = {-Infinity, -Infinity, -Infinity};
         for (int c = 0; c < 8; ++c) {
-            V3 q = XformPoint(sp.object_to_world, V3((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
+            V3 q = XformPoint(sp.object_to_world, V3((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? sc.zMax : sc.zMin));
             for (int a = 0; a < 3; ++a) {
                 lo[a] = std::min(lo[a], q[a]);
                 hi[a] = std::max(hi[a], q[a]);

@@ -63,6 +63,7 @@ _SIGNATURES = {
                                                  C.POINTER(abi.CameraDesc)]),
     "b200pt_host_roughness_to_alpha": (C.c_float, [C.c_float]),
     "b200pt_host_oren_nayar": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "b200pt_host_sphere_params": (None, [C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 
@@ -101,6 +102,12 @@ def host_perspective_camera(eye, look, up, fov, xres, yres):
 
 def host_roughness_to_alpha(r):
     return float(lib.b200pt_host_roughness_to_alpha(r))
+
+
+def host_sphere_params(radius, zmin, zmax, phimax_degrees):
+    out = (C.c_float * 5)()
+    lib.b200pt_host_sphere_params(radius, zmin, zmax, phimax_degrees, out)
+    return list(out)
 
 
 def host_oren_nayar(sigma_degrees):

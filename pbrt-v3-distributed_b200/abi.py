@@ -26,7 +26,9 @@ class Sphere(C.Structure):
     _fields_ = [("object_to_world", C.c_float * 16), ("world_to_object", C.c_float * 16),
                 ("radius", C.c_float), ("material_id", C.c_int32), ("light_id", C.c_int32),
                 ("reverse_orientation", C.c_uint8), ("transform_swaps_handedness", C.c_uint8),
-                ("pad", C.c_uint8 * 2), ("leaf_bounds", C.c_float * 6)]
+                ("pad", C.c_uint8 * 2), ("leaf_bounds", C.c_float * 6),
+                ("z_min", C.c_float), ("z_max", C.c_float), ("theta_min", C.c_float), ("theta_max", C.c_float),
+                ("phi_max", C.c_float)]
 
 
 class SceneDesc(C.Structure):

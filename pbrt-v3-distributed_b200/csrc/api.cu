@@ -284,13 +284,23 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         DevSphere &sp = s->spheres[i];
         memcpy(sp.o2w, in.object_to_world, sizeof(sp.o2w));
         memcpy(sp.w2o, in.world_to_object, sizeof(sp.w2o));
-        // Sphere ctor for a full sphere (sphere.h:50-61): zMin = -r, zMax = r, phiMax = Radians(360)
+        // Sphere ctor (sphere.h:49-61): a full sphere (zMin = -r, zMax = r, phiMax = Radians(360)) unless the host
+        // passed the members of a clipped one
         const float r = in.radius;
         sp.radius = r;
-        const float zMin = pt_clamp(pt_min(-r, r), -r, r), zMax = pt_clamp(pt_max(-r, r), -r, r);
+        float zMin = pt_clamp(pt_min(-r, r), -r, r), zMax = pt_clamp(pt_max(-r, r), -r, r);
         sp.theta_min = pt_acosf(pt_clamp(pt_min(zMin, zMax) / r, -1.f, 1.f));
         sp.theta_max = pt_acosf(pt_clamp(pt_max(zMin, zMax) / r, -1.f, 1.f));
         sp.phi_max = (PT_PI / 180) * pt_clamp(360.f, 0.f, 360.f);
+        if (in.phi_max != 0.f) {
+            zMin = in.z_min;
+            zMax = in.z_max;
+            sp.theta_min = in.theta_min;
+            sp.theta_max = in.theta_max;
+            sp.phi_max = in.phi_max;
+        }
+        sp.z_min = zMin;
+        sp.z_max = zMax;
         sp.area = sp.phi_max * r * (zMax - zMin);
         const bool flip = (in.reverse_orientation != 0) ^ (in.transform_swaps_handedness != 0);
         sp.mat_flags = (uint32_t)in.material_id | (flip ? 0x10000u : 0u);
@@ -299,7 +309,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         // Shape::WorldBound (shape.cpp:52, transform.cpp:246-256) joins Scene::WorldBound()
         float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int c = 0; c < 8; ++c) {
-            const V3 q = xform_point(sp.o2w, mk((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? r : -r));
+            const V3 q = xform_point(sp.o2w, mk((c & 1) ? r : -r, (c & 2) ? r : -r, (c & 4) ? zMax : zMin));  // ObjectBound
             for (int a = 0; a < 3; ++a) {
                 wlo[a] = std::min(wlo[a], comp(q, a));
                 whi[a] = std::max(whi[a], comp(q, a));

@@ -11,6 +11,7 @@
 // All arithmetic is float in the reference's order so the matrices are
 // bit-identical (tests/test_host_helpers.py checks against matrices dumped
 // from the reference).
+#include "pt_sphere.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -227,4 +228,14 @@ extern "C" void b200pt_host_oren_nayar(float sigma, float *A, float *B) {
     float sigma2 = sigma * sigma;
     *A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
     *B = 0.45f * sigma2 / (sigma2 + 0.09f);
+}
+
+// Sphere::Sphere, sphere.h:49-61 (std::acos through the restated libm routine of pt_sphere.cuh)
+extern "C" void b200pt_host_sphere_params(float radius, float zmin, float zmax, float phimax_degrees, float out[5]) {
+    using namespace b200pt;
+    out[0] = pt_clamp(pt_min(zmin, zmax), -radius, radius);
+    out[1] = pt_clamp(pt_max(zmin, zmax), -radius, radius);
+    out[2] = pt_acosf(pt_clamp(pt_min(zmin, zmax) / radius, -1.f, 1.f));
+    out[3] = pt_acosf(pt_clamp(pt_max(zmin, zmax) / radius, -1.f, 1.f));
+    out[4] = (PT_PI / 180) * pt_clamp(phimax_degrees, 0.f, 360.f);
 }

@@ -1,5 +1,5 @@
 // pt_sphere.cuh -- the Sphere shape of the reference on the device
-// (shapes/sphere.cpp:49-306), full spheres only.
+// (shapes/sphere.cpp:49-306), full or clipped by zmin / zmax / phimax.
 //
 // A sphere keeps its object space: rays are transformed with the reference's
 // error-tracking Transform operators (core/transform.h:278-384), the quadratic
@@ -9,8 +9,9 @@
 // (core/transform.cpp:262-297).  std::acos is restated from the host libm the
 // reference calls (glibc's fdlibm-derived float routine; pinned exhaustively
 // over [-1, 1] by tests/host_preflight.cpp); std::sin / std::cos come from
-// pt_sincos.cuh.  std::atan2 only feeds phi, which a full sphere needs for
-// nothing but the (u, v) of constant textures, so it is not evaluated.
+// pt_sincos.cuh.  std::atan2 (restated the same way) is evaluated only for
+// spheres clipped by zmin / zmax / phimax: for a full sphere phi can never exceed
+// phiMax and otherwise only feeds the (u, v) of constant textures.
 //
 // Spheres are few (lights, a handful of objects) and are tested outside the
 // triangle BVH by k_spheres after each traversal launch, with tMax already
@@ -31,8 +32,9 @@ B200_HD bool is_sphere_hit(uint32_t id) { return id >= SPHERE_HIT_BASE && id != 
 struct DevSphere {
     float o2w[16], w2o[16];  // ObjectToWorld->m, WorldToObject->m (= ObjectToWorld->mInv)
     float radius;
-    float phi_max;           // Radians(360) as the Sphere ctor computes it
-    float theta_min, theta_max;  // acos(-1), acos(1)
+    float phi_max;           // Sphere::phiMax (radians); Radians(360) for a full sphere
+    float theta_min, theta_max;  // Sphere::thetaMin / thetaMax; acos(-1), acos(1) for a full sphere
+    float z_min, z_max;      // Sphere::zMin / zMax; -r, r for a full sphere
     float area;              // Sphere::Area(), sphere.cpp:207
     uint32_t mat_flags;      // material id | flip << 16 (reverseOrientation ^ transformSwapsHandedness)
     int light_id;
@@ -80,6 +82,92 @@ B200_HD float pt_acosf(float x) {
         w = r * s + c;
         return 2.0f * (df + w);
     }
+}
+
+// ---- glibc 2.3x atanf / atan2f (sysdeps/ieee754/flt-32/s_atanf.c, e_atan2f.c, fdlibm): float arithmetic only.
+// Pinned against the host libm: atanf over all 2^32 floats, atan2f over 2*10^8 pairs (0 mismatches).
+B200_HD float pt_atanf(float x) {
+    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+                aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+                aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+    float w, s1, s2, z;
+    const int32_t hx = (int32_t)float_as_uint(x), ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return x + x;
+        if (hx > 0) return atanhi[3] + atanlo[3];
+        return -atanhi[3] - atanlo[3];
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = pt_abs(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) {
+                id = 0;
+                x = (2.0f * x - 1.0f) / (2.0f + x);
+            } else {
+                id = 1;
+                x = (x - 1.0f) / (x + 1.0f);
+            }
+        } else {
+            if (ix < 0x401c0000) {
+                id = 2;
+                x = (x - 1.5f) / (1.0f + 1.5f * x);
+            } else {
+                id = 3;
+                x = -1.0f / x;
+            }
+        }
+    }
+    z = x * x;
+    w = z * z;
+    s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (id < 0) return x - x * (s1 + s2);
+    z = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    return (hx < 0) ? -z : z;
+}
+B200_HD float pt_atan2f(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+                pi_lo = -8.7422776573e-08f;
+    float z;
+    const int32_t hx = (int32_t)float_as_uint(x), hy = (int32_t)float_as_uint(y);
+    const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+    if (hx == 0x3f800000) return pt_atanf(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) {
+        if (m < 2) return y;
+        return m == 2 ? pi + tiny : -pi - tiny;
+    }
+    if (ix == 0) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            if (m == 0) return pi_o_4 + tiny;
+            if (m == 1) return -pi_o_4 - tiny;
+            if (m == 2) return 3.0f * pi_o_4 + tiny;
+            return -3.0f * pi_o_4 - tiny;
+        }
+        if (m == 0) return 0.0f;
+        if (m == 1) return -0.0f;
+        return m == 2 ? pi + tiny : -pi - tiny;
+    }
+    if (iy == 0x7f800000) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int32_t k = (iy - ix) >> 23;
+    if (k > 60)
+        z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60)
+        z = 0.0f;
+    else
+        z = pt_atanf(pt_abs(y / x));
+    if (m == 0) return z;
+    if (m == 1) return uint_as_float(float_as_uint(z) ^ 0x80000000u);
+    if (m == 2) return pi - (z - pi_lo);
+    return (z - pi_lo) - pi;
 }
 
 // ---- core/efloat.h:47-214
@@ -235,11 +323,28 @@ B200_HD bool sphere_intersect(const DevSphere &sp, const V3 &ro, const V3 &rd, f
         tShapeHit = t1;
         if (tShapeHit.high > rayTMax) return false;
     }
-    *tHit = tShapeHit.v;
-    if (!is) return true;
+    // sphere.cpp:85-112: hit position; a clipped sphere (zmin / zmax / phimax) may fall back to the second root
     V3 pHit = o + d * tShapeHit.v;
     pHit = pHit * (radius / len(pHit));
     if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * radius;
+    if (sp.z_min > -radius || sp.z_max < radius || sp.phi_max < (PT_PI / 180) * 360.f) {
+        float phi = pt_atan2f(pHit.y, pHit.x);
+        if (phi < 0) phi += 2 * PT_PI;
+        if ((sp.z_min > -radius && pHit.z < sp.z_min) || (sp.z_max < radius && pHit.z > sp.z_max) || phi > sp.phi_max) {
+            if (tShapeHit.v == t1.v) return false;
+            if (t1.high > rayTMax) return false;
+            tShapeHit = t1;
+            pHit = o + d * tShapeHit.v;
+            pHit = pHit * (radius / len(pHit));
+            if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * radius;
+            phi = pt_atan2f(pHit.y, pHit.x);
+            if (phi < 0) phi += 2 * PT_PI;
+            if ((sp.z_min > -radius && pHit.z < sp.z_min) || (sp.z_max < radius && pHit.z > sp.z_max) || phi > sp.phi_max)
+                return false;
+        }
+    }
+    *tHit = tShapeHit.v;
+    if (!is) return true;
     const float theta = pt_acosf(pt_clamp(pHit.z / radius, -1.f, 1.f));
     const float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
     const float invZRadius = 1 / zRadius;

@@ -231,14 +231,17 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         if (!gp) return *why = "a primitive other than GeometricPrimitive (instancing / animation)", false;
         if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
         if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
-            // full spheres only (sphere.h:50-61): no zmin / zmax / phimax clipping
-            if (sph->zMin != -sph->radius || sph->zMax != sph->radius || sph->phiMax != Radians(360.f))
-                return *why = "partial spheres (zmin / zmax / phimax)", false;
             b200pt_sphere bs;
             memset(&bs, 0, sizeof(bs));
             memcpy(bs.object_to_world, sph->ObjectToWorld->m.m, sizeof(float) * 16);
             memcpy(bs.world_to_object, sph->WorldToObject->m.m, sizeof(float) * 16);
             bs.radius = sph->radius;
+            bs.z_min = sph->zMin;  // the Sphere's own members (sphere.h:66-68); phi_max != 0 marks them valid
+            bs.z_max = sph->zMax;
+            bs.theta_min = sph->thetaMin;
+            bs.theta_max = sph->thetaMax;
+            bs.phi_max = sph->phiMax;
+            if (!(sph->phiMax > 0)) return *why = "a sphere with phimax 0", false;
             if (!materialOf(gp->material.get(), &bs.material_id)) return false;
             bs.light_id = -1;
             bs.reverse_orientation = sph->reverseOrientation ? 1 : 0;

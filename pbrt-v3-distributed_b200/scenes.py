@@ -199,6 +199,11 @@ class SceneArrays:
             rec.reverse_orientation = int(bool(sp.get("reverse_orientation")))
             sc = sp.get("scale") or (1, 1, 1)
             rec.transform_swaps_handedness = int(sc[0] * sc[1] * sc[2] < 0)  # Transform::SwapsHandedness
+            if any(k in sp for k in ("zmin", "zmax", "phimax")):  # partial sphere: the Sphere ctor's members
+                from . import host_sphere_params
+                r_ = sp["radius"]
+                zp = host_sphere_params(r_, sp.get("zmin", -r_), sp.get("zmax", r_), sp.get("phimax", 360.0))
+                rec.z_min, rec.z_max, rec.theta_min, rec.theta_max, rec.phi_max = zp
             rec.light_id = -1
             if sp.get("emit"):
                 li = nl
@@ -343,7 +348,8 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
             lines.append("  Scale %.9g %.9g %.9g" % tuple(sp["scale"]))
         if sp.get("reverse_orientation"):
             lines.append("  ReverseOrientation")
-        lines.append('  Shape "sphere" "float radius" [%.9g]' % sp["radius"])
+        lines.append('  Shape "sphere" "float radius" [%.9g]' % sp["radius"] +
+                     "".join(' "float %s" [%.9g]' % (k, sp[k]) for k in ("zmin", "zmax", "phimax") if k in sp))
         lines.append("AttributeEnd")
     lines.append("WorldEnd")
     path = os.path.join(dirname, name + ".pbrt")

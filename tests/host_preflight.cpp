@@ -277,6 +277,25 @@ int main(int argc, char **argv) {
             memcpy(d.w2o, sp.world_to_object, 64);
             d.radius = sp.radius;
             d.mat_flags = 0;
+            d.z_min = -sp.radius;
+            d.z_max = sp.radius;
+            d.phi_max = (PT_PI / 180) * 360.f;
+            d.theta_min = pt_acosf(-1.f);
+            d.theta_max = pt_acosf(1.f);
+            if (k >= 3) {  // clipped spheres: the members the Sphere ctor would compute
+                float zp[5];
+                const float zmin = -0.5f * sp.radius, zmax = (k == 4 ? 0.7f : 1.f) * sp.radius, phimax = k == 5 ? 200.f : 360.f;
+                zp[0] = pt_clamp(pt_min(zmin, zmax), -sp.radius, sp.radius);
+                zp[1] = pt_clamp(pt_max(zmin, zmax), -sp.radius, sp.radius);
+                zp[2] = pt_acosf(pt_clamp(pt_min(zmin, zmax) / sp.radius, -1.f, 1.f));
+                zp[3] = pt_acosf(pt_clamp(pt_max(zmin, zmax) / sp.radius, -1.f, 1.f));
+                zp[4] = (PT_PI / 180) * pt_clamp(phimax, 0.f, 360.f);
+                sp.z_min = d.z_min = zp[0];
+                sp.z_max = d.z_max = zp[1];
+                sp.theta_min = d.theta_min = zp[2];
+                sp.theta_max = d.theta_max = zp[3];
+                sp.phi_max = d.phi_max = zp[4];
+            }
             // Shape::WorldBound(): what the oracle and the library use when leaf_bounds is left zero
             for (int a = 0; a < 3; ++a) {
                 d.leaf_lo[a] = INFINITY;
@@ -284,7 +303,7 @@ int main(int argc, char **argv) {
             }
             for (int cn = 0; cn < 8; ++cn) {
                 const float r = sp.radius;
-                const V3 q = xform_point(d.o2w, mk((cn & 1) ? r : -r, (cn & 2) ? r : -r, (cn & 4) ? r : -r));
+                const V3 q = xform_point(d.o2w, mk((cn & 1) ? r : -r, (cn & 2) ? r : -r, (cn & 4) ? d.z_max : d.z_min));
                 for (int a = 0; a < 3; ++a) {
                     d.leaf_lo[a] = std::min(d.leaf_lo[a], comp(q, a));
                     d.leaf_hi[a] = std::max(d.leaf_hi[a], comp(q, a));

@@ -29,7 +29,7 @@ def test_struct_sizes_match_header(abi):
     # sizes implied by include/b200pt.h on LP64
     assert C.sizeof(abi.Material) == 4 + 15 * 4 + 12 + 4
     assert C.sizeof(abi.AreaLight) == 24
-    assert C.sizeof(abi.Sphere) == 168
+    assert C.sizeof(abi.Sphere) == 188
     assert C.sizeof(abi.CameraDesc) == 144
     assert C.sizeof(abi.FilmDesc) == 48
     assert C.sizeof(abi.SamplerDesc) == 64

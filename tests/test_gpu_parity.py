@@ -36,6 +36,8 @@ RENDERS = {
     # the only light is a sphere (the situation of scenes/killeroo-simple.pbrt), Halton sampler
     "sphere_light": (3000, ("matte", "plastic"), 40, 32, 6, 5, "spatial", 0),
     "sphere_power": (3000, ("matte", "glass_rough"), 40, 32, 4, 7, "power", 4),
+    # partial spheres (zmin / zmax / phimax clipping: std::atan2, second root), one of them an area light
+    "sphere_partial": (3000, ("matte", "plastic"), 48, 40, 8, 5, "spatial", 4),
     # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
     # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
     "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
@@ -57,6 +59,11 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              dict(center=(0.1, 0.0, -2.2), radius=0.45, material="glass"),
              dict(center=(-0.9, -0.6, -2.0), radius=0.4, material="plastic", scale=(1.3, 0.7, -1.1)),
              dict(center=(0.9, -0.7, -1.9), radius=0.3, material="matte", reverse_orientation=True)))),
+         "sphere_partial": dict(scene=dict(spheres=(
+             dict(center=(0.1, 0.1, -2.2), radius=0.6, material="plastic", zmin=-0.3, zmax=0.45, phimax=250.0),
+             dict(center=(-1.0, -0.6, -2.0), radius=0.5, material="matte", scale=(1.2, 0.8, 1.0), phimax=200.0,
+                  reverse_orientation=True),
+             dict(center=(1.1, 0.6, -1.8), radius=0.4, emit=80.0, zmin=-0.1, two_sided=True)))),
          "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
          "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
          "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),
