@@ -277,7 +277,26 @@ def main():
         return ms, float(t[1]), float(t[2]), st, clocks, h2d
 
     ms, rays, samples, st, clocks, _ = timed(False, args.steps, args.warmup)
-    ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, args.steps, 1)
+    ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, args.steps, 2)
+    # one more end-to-end step with events between its three parts (reported, not part of any timed figure)
+    breakdown = None
+    if world == 1:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(stream):
+            evs[0].record()
+        scene.upload()
+        with torch.cuda.stream(stream):
+            evs[1].record()
+        render.clear()
+        render.render_tiles(my_tiles)
+        with torch.cuda.stream(stream):
+            evs[2].record()
+        pkg._check(pkg.lib.b200pt_film_read_rgb(render.h, host_rgb.data_ptr()))
+        with torch.cuda.stream(stream):
+            evs[3].record()
+        torch.cuda.synchronize()
+        breakdown = {"upload_ms": evs[0].elapsed_time(evs[1]), "render_ms": evs[1].elapsed_time(evs[2]),
+                     "readback_ms": evs[2].elapsed_time(evs[3])}
 
     out = None
     if rank == 0:
@@ -322,7 +341,8 @@ def main():
                                    "shade_raygen_film": st["shade_ms"] / args.steps},
             "cpu_baseline": cpu,
             "e2e": {"value": rays_e / (ms_e * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / args.steps},
+                    "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / args.steps,
+                    "breakdown_ms": breakdown},
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }

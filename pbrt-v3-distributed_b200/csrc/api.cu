@@ -68,6 +68,7 @@ struct b200pt_render {
     uint32_t tiles_per_batch = 1;
     int32_t *d_tile_list = nullptr;
     size_t tile_list_capacity = 0;
+    float *d_rgb = nullptr;  // b200pt_film_read_rgb staging (lazily allocated, freed with the render object)
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
     bool overlap = true;  // run shadow/MIS rays of bounce b concurrently with the path rays of bounce b+1
@@ -1117,12 +1118,13 @@ int b200pt_film_read_rgb(b200pt_render *r, float *rgb_out) {
     CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
     const size_t n = (size_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
     cudaStream_t st = r->scene->ctx->stream;
-    float *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * 3 * sizeof(float)));
-    launch_film_rgb(r->host.film, d, (int)n, r->film.scale, st);
-    cudaError_t e = cudaMemcpyAsync(rgb_out, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (!r->d_rgb) {  // staging buffer of the WriteImage pipeline, kept for the lifetime of the render object
+        cudaError_t ea = dev_alloc(r, &r->d_rgb, n * 3);
+        if (ea != cudaSuccess) return b200pt_fail(B200PT_ERR_OOM, "film_read_rgb: cudaMalloc failed: %s", cudaGetErrorString(ea));
+    }
+    launch_film_rgb(r->host.film, r->d_rgb, (int)n, r->film.scale, st);
+    cudaError_t e = cudaMemcpyAsync(rgb_out, r->d_rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d);
     if (e != cudaSuccess) return b200pt_fail(B200PT_ERR_CUDA, "film_read_rgb: %s", cudaGetErrorString(e));
     return B200PT_OK;
 }
