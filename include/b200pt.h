@@ -111,6 +111,27 @@ typedef struct b200pt_sphere {
     float z_min, z_max, theta_min, theta_max, phi_max;
 } b200pt_sphere;
 
+/* ---- object instances: TransformedPrimitive (core/primitive.cpp:70-98) over
+ * the triangles of an "ObjectBegin" block (api.cpp:1500-1592).  The object's
+ * triangles are a contiguous range of the scene's triangle arrays *behind* the
+ * n_toplevel_triangles ordinary ones, in the object's own space (what the
+ * reference keeps in its TriangleMesh); instances of the same object name the
+ * same range.  Rays are transformed into the object (Transform::operator()(Ray),
+ * transform.h:251-264), intersected there, and the hit is transformed back
+ * (transform.cpp:262-297) like the reference does.  Area lights cannot sit
+ * inside instances (api.cpp:1411-1413); animated instance transforms are out
+ * of scope. */
+typedef struct b200pt_instance {
+    int64_t first_triangle;        /* range of the object's triangles                       */
+    int64_t n_triangles;
+    float instance_to_world[16];   /* TransformedPrimitive::PrimitiveToWorld.startTransform->m */
+    float world_to_instance[16];   /* ... ->mInv                                             */
+    int32_t is_identity;           /* Transform::IsIdentity(): the hit is not transformed back (primitive.cpp:93-94) */
+    float leaf_bounds[6];          /* bounds of the top-level BVH leaf holding the instance (see b200pt_sphere);
+                                      all zeros = the instance's own WorldBound()            */
+    int32_t pad;
+} b200pt_instance;
+
 /* ---- scene: world-space triangle soup + per-triangle attributes ---------
  * Triangle i is the i-th GeometricPrimitive handed to the accelerator
  * (accelerators/bvh.cpp:183).  Vertices are the world-space TriangleMesh::p
@@ -137,6 +158,11 @@ typedef struct b200pt_scene_desc {
                                      NULL = every triangle has whatever arrays are non-NULL   */
     int32_t n_spheres;
     const b200pt_sphere *spheres; /* [n_spheres]                                              */
+    /* object instancing: triangles [n_toplevel_triangles, n_triangles) belong to objects (see b200pt_instance);
+     * with n_instances == 0 every triangle is a top-level one and n_toplevel_triangles is ignored */
+    int32_t n_instances;
+    const b200pt_instance *instances;
+    int64_t n_toplevel_triangles;
 } b200pt_scene_desc;
 
 /* ---- camera: PerspectiveCamera (cameras/perspective.cpp:45-144) ----------

@@ -675,6 +675,11 @@ struct Distribution1D {  // core/sampling.h:55-109
 
 }  // namespace
 
+struct OBvh {  // one BVHAccel: the top-level one or an object's (api.cpp:1570-1578)
+    std::vector<BVHNode> nodes;
+    std::vector<int32_t> orderedPrims;
+};
+
 struct oracle_scene {
     int64_t nTris;
     std::vector<V3> p;  // 3 per triangle
@@ -684,8 +689,11 @@ struct oracle_scene {
     std::vector<b200pt_material> materials;
     std::vector<b200pt_area_light> lights;
     std::vector<float> lightArea;
-    std::vector<BVHNode> nodes;
-    std::vector<int32_t> orderedPrims;
+    OBvh top;                        // over the top-level triangles [0, nTop)
+    std::vector<OBvh> objects;       // one per distinct instance range
+    std::vector<int> instanceObject; // instance -> objects[]
+    std::vector<b200pt_instance> instances;
+    int64_t nTop = 0;
     float wbMin[3], wbMax[3];  // Scene::WorldBound()
     std::vector<V3> nrm;       // 3 per triangle (TriangleMesh::n) when hasN[tri]
     std::vector<float> uv;     // 6 per triangle (TriangleMesh::uv) when hasUV[tri]
@@ -714,7 +722,7 @@ struct BuildPrim {
     float bmin[3], bmax[3], c[3];
 };
 
-int BuildRecursive(oracle_scene &s, std::vector<BuildPrim> &prims, int start, int end) {
+int BuildRecursive(OBvh &s, std::vector<BuildPrim> &prims, int start, int end) {
     int nodeIdx = (int)s.nodes.size();
     s.nodes.push_back(BVHNode());
     float bmin[3] = {Infinity, Infinity, Infinity}, bmax[3] = {-Infinity, -Infinity, -Infinity};
@@ -975,19 +983,19 @@ inline V3 SphericalDirection(float sinTheta, float cosTheta, float phi, const V3
 
 // accelerators/bvh.cpp:662-700.  Returns triangle index or -1; ray.tMax
 // shrinks on every accepted hit (primitive.cpp:120).
-int BvhIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut) {
-    if (s.nodes.empty()) return -1;
+int BvhIntersect(const oracle_scene &s, const OBvh &bvh, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut) {
+    if (bvh.nodes.empty()) return -1;
     int hitTri = -1;
     V3 invDir(1 / rd.x, 1 / rd.y, 1 / rd.z);
     int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     int toVisitOffset = 0, currentNodeIndex = 0;
     int nodesToVisit[128];
     while (true) {
-        const BVHNode *node = &s.nodes[currentNodeIndex];
+        const BVHNode *node = &bvh.nodes[currentNodeIndex];
         if (BoundsIntersectP(*node, ro, rayTMax, invDir, dirIsNeg)) {
             if (node->nPrimitives > 0) {
                 for (int i = 0; i < node->nPrimitives; ++i) {
-                    int tri = s.orderedPrims[node->offset + i];
+                    int tri = bvh.orderedPrims[node->offset + i];
                     if (s.degenerate[tri]) continue;
                     TriHit h;
                     if (TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, rd, rayTMax,
@@ -1017,18 +1025,18 @@ int BvhIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMa
 }
 
 // accelerators/bvh.cpp:702-738
-bool BvhIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
-    if (s.nodes.empty()) return false;
+bool BvhIntersectP(const oracle_scene &s, const OBvh &bvh, const V3 &ro, const V3 &rd, float rayTMax) {
+    if (bvh.nodes.empty()) return false;
     V3 invDir(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     int nodesToVisit[128];
     int toVisitOffset = 0, currentNodeIndex = 0;
     while (true) {
-        const BVHNode *node = &s.nodes[currentNodeIndex];
+        const BVHNode *node = &bvh.nodes[currentNodeIndex];
         if (BoundsIntersectP(*node, ro, rayTMax, invDir, dirIsNeg)) {
             if (node->nPrimitives > 0) {
                 for (int i = 0; i < node->nPrimitives; ++i) {
-                    int tri = s.orderedPrims[node->offset + i];
+                    int tri = bvh.orderedPrims[node->offset + i];
                     if (s.degenerate[tri]) continue;
                     TriHit h;
                     if (TriangleTest(s.p[3 * tri], s.p[3 * tri + 1], s.p[3 * tri + 2], ro, rd, rayTMax,
@@ -1068,35 +1076,6 @@ inline bool SphereLeafTest(const b200pt_sphere &sp, const V3 &ro, const V3 &rd, 
     int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
     return BoundsIntersectP(box, ro, rayTMax, invDir, dirIsNeg);
 }
-int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut,
-                   Isect *sphereIs = nullptr) {
-    int hit = BvhIntersect(s, ro, rd, rayTMax, hitOut);
-    if (hit >= 0) rayTMax = hitOut->t;
-    for (size_t k = 0; k < s.spheres.size(); ++k) {
-        float tHit;
-        Isect tmp;
-        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) &&
-            SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, &tmp)) {
-            rayTMax = tHit;
-            hit = (int)s.nTris + (int)k;
-            hitOut->t = tHit;
-            hitOut->b0 = hitOut->b1 = hitOut->b2 = 0;
-            tmp.tri = hit;
-            if (sphereIs) *sphereIs = tmp;
-        }
-    }
-    return hit;
-}
-bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
-    if (BvhIntersectP(s, ro, rd, rayTMax)) return true;
-    for (size_t k = 0; k < s.spheres.size(); ++k) {
-        float tHit;
-        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) && SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, nullptr))
-            return true;
-    }
-    return false;
-}
-
 // ----------------------------------------------------- surface interaction
 
 // shapes/triangle.cpp:293-425 (meshes without per-vertex tangents) + interaction.cpp:44-86
@@ -1141,6 +1120,108 @@ inline void FillIsect(const oracle_scene &s, int tri, const TriHit &h, const V3 
     } else if (flip) {
         is->n = is->ns = -is->n;  // triangle.cpp:420-421
     }
+}
+
+// Transform::operator()(const Ray &), transform.h:251-264, with the instance's WorldToInstance
+inline void InstanceRay(const b200pt_instance &in, const V3 &ro, const V3 &rd, float rayTMax, V3 *o2, V3 *d2, float *tMax2) {
+    V3 oError;
+    V3 o = XformPointErr(in.world_to_instance, ro, &oError);
+    V3 d = XformVector(in.world_to_instance, rd);
+    float lengthSquared = LengthSquared(d);
+    float tMax = rayTMax;
+    if (lengthSquared > 0) {
+        float dt = Dot(Abs(d), oError) / lengthSquared;
+        o = o + d * dt;
+        tMax -= dt;
+    }
+    *o2 = o;
+    *d2 = d;
+    *tMax2 = tMax;
+}
+inline bool InstanceLeafTest(const b200pt_instance &in, const V3 &ro, const V3 &rd, float rayTMax) {
+    BVHNode box;
+    memcpy(box.bmin, in.leaf_bounds, 12);
+    memcpy(box.bmax, in.leaf_bounds + 3, 12);
+    V3 invDir(1 / rd.x, 1 / rd.y, 1 / rd.z);
+    int dirIsNeg[3] = {invDir.x < 0, invDir.y < 0, invDir.z < 0};
+    return BoundsIntersectP(box, ro, rayTMax, invDir, dirIsNeg);
+}
+// InstanceToWorld(SurfaceInteraction), transform.cpp:262-297, applied by TransformedPrimitive::Intersect (primitive.cpp:93-94)
+inline void InstanceIsectToWorld(const b200pt_instance &in, Isect *is) {
+    if (in.is_identity) return;
+    Isect w = *is;
+    w.p = XformPointErrIn(in.instance_to_world, is->p, is->pError, &w.pError);
+    w.n = Normalize(XformNormal(in.world_to_instance, is->n));
+    w.wo = Normalize(XformVector(in.instance_to_world, is->wo));
+    w.sdpdu = XformVector(in.instance_to_world, is->sdpdu);
+    V3 sn = Normalize(XformNormal(in.world_to_instance, is->ns));
+    w.ns = (Dot(sn, w.n) < 0.f) ? -sn : sn;  // Faceforward(shading.n, n)
+    *is = w;
+}
+
+// Scene::Intersect / IntersectP (scene.cpp:45-55) over the top-level triangle BVH plus the spheres and the object
+// instances.  The reference keeps spheres and instances inside the same BVHAccel; testing them after the triangles
+// gives the same closest hit except when two hits lie within each other's error interval (order-dependent in the
+// reference as well).  Returns the primitive (triangle index, nTris + sphere, or an object triangle's index) and fills
+// *isOut with the world-space interaction when isOut != nullptr.
+int SceneIntersect(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax, TriHit *hitOut,
+                   Isect *isOut = nullptr, int *instOut = nullptr) {
+    int hit = BvhIntersect(s, s.top, ro, rd, rayTMax, hitOut);
+    int hitInst = -1;
+    if (hit >= 0) {
+        rayTMax = hitOut->t;
+        if (isOut) FillIsect(s, hit, *hitOut, rd, isOut);
+    }
+    for (size_t k = 0; k < s.spheres.size(); ++k) {
+        float tHit;
+        Isect tmp;
+        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) &&
+            SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, &tmp)) {
+            rayTMax = tHit;
+            hit = (int)s.nTris + (int)k;
+            hitOut->t = tHit;
+            hitOut->b0 = hitOut->b1 = hitOut->b2 = 0;
+            tmp.tri = hit;
+            if (isOut) *isOut = tmp;
+        }
+    }
+    for (size_t k = 0; k < s.instances.size(); ++k) {  // TransformedPrimitive::Intersect, primitive.cpp:76-98
+        const b200pt_instance &in = s.instances[k];
+        if (!InstanceLeafTest(in, ro, rd, rayTMax)) continue;
+        V3 o2, d2;
+        float tMax2;
+        InstanceRay(in, ro, rd, rayTMax, &o2, &d2, &tMax2);
+        TriHit h;
+        int tri = BvhIntersect(s, s.objects[s.instanceObject[k]], o2, d2, tMax2, &h);
+        if (tri < 0) continue;
+        rayTMax = h.t;  // r.tMax = ray.tMax
+        hit = tri;
+        hitInst = (int)k;
+        *hitOut = h;
+        if (isOut) {
+            FillIsect(s, tri, h, d2, isOut);
+            InstanceIsectToWorld(in, isOut);
+        }
+    }
+    if (instOut) *instOut = hitInst;
+    return hit;
+}
+bool SceneIntersectP(const oracle_scene &s, const V3 &ro, const V3 &rd, float rayTMax) {
+    if (BvhIntersectP(s, s.top, ro, rd, rayTMax)) return true;
+    for (size_t k = 0; k < s.spheres.size(); ++k) {
+        float tHit;
+        if (SphereLeafTest(s.spheres[k], ro, rd, rayTMax) && SphereIntersect(s.spheres[k], ro, rd, rayTMax, &tHit, nullptr))
+            return true;
+    }
+    for (size_t k = 0; k < s.instances.size(); ++k) {  // TransformedPrimitive::IntersectP
+        const b200pt_instance &in = s.instances[k];
+        if (!InstanceLeafTest(in, ro, rd, rayTMax)) continue;
+        V3 o2, d2;
+        float tMax2;
+        InstanceRay(in, ro, rd, rayTMax, &o2, &d2, &tMax2);
+        if (BvhIntersectP(s, s.objects[s.instanceObject[k]], o2, d2, tMax2)) return true;
+    }
+    return false;
 }
 
 // core/geometry.h:1440-1460
@@ -1945,7 +2026,7 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                 int who = SceneIntersect(s, origin, d, 1 - ShadowEpsilon, &hh, &ii);
                 fprintf(stderr, "    shadow: pShape=(%a %a %a) n=(%g %g %g) lightPdf=%g Li=%g f=%g origin=(%a %a %a) d=(%a %a %a) closest prim=%d t=%a bvhP=%d\n",
                         pShape.p.x, pShape.p.y, pShape.p.z, pShape.n.x, pShape.n.y, pShape.n.z, lightPdf, Li.c[0], f.c[0],
-                        origin.x, origin.y, origin.z, d.x, d.y, d.z, who, who >= 0 ? hh.t : 0.f, (int)BvhIntersectP(s, origin, d, 1 - ShadowEpsilon));
+                        origin.x, origin.y, origin.z, d.x, d.y, d.z, who, who >= 0 ? hh.t : 0.f, (int)BvhIntersectP(s, s.top, origin, d, 1 - ShadowEpsilon));
             }
             if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
             if (!Li.IsBlack()) {
@@ -1991,7 +2072,6 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
             S3 Li2(0.f);
             if (hitTri >= 0) {
                 if (s.PrimLight(hitTri) == lightNum) {
-                    if (hitTri < s.nTris) FillIsect(s, hitTri, h, wi, &li);
                     Li2 = IsectLe(s, li, -wi);
                 }
             }
@@ -2016,7 +2096,6 @@ S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
         Isect isect;
         int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h, &isect);
         bool foundIntersection = tri >= 0;
-        if (foundIntersection && tri < s.nTris) FillIsect(s, tri, h, ray.d, &isect);
         static const bool traceOn = getenv("ORACLE_TRACE") != nullptr;
         if (traceOn)
             fprintf(stderr, "  bounce %d: o=(%a %a %a) d=(%a %a %a) prim=%d t=%a p=(%g %g %g) n=(%g %g %g) L=(%g %g %g) beta=(%g %g %g)\n",
@@ -2249,7 +2328,8 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
         s->wbMin[a] = Infinity;
         s->wbMax[a] = -Infinity;
     }
-    for (size_t i = 0; i < s->p.size(); ++i)
+    const size_t nTopVerts = 3 * (size_t)(d->n_instances > 0 ? d->n_toplevel_triangles : d->n_triangles);
+    for (size_t i = 0; i < nTopVerts; ++i)  // object triangles enter through their instances' bounds below
         for (int a = 0; a < 3; ++a) {
             s->wbMin[a] = std::min(s->wbMin[a], s->p[i][a]);
             s->wbMax[a] = std::max(s->wbMax[a], s->p[i][a]);
@@ -2289,24 +2369,66 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     }
     if (d->uvs) s->uv.assign(d->uvs, d->uvs + 6 * d->n_triangles);
     s->degenerate.resize(d->n_triangles);
-    std::vector<BuildPrim> prims;
-    prims.reserve(d->n_triangles);
     for (int64_t i = 0; i < d->n_triangles; ++i) {
         V3 dpdu, dpdv;
         s->degenerate[i] = !TrianglePartials(s->p[3 * i], s->p[3 * i + 1], s->p[3 * i + 2], &dpdu, &dpdv, s->UV((int)i));
-        BuildPrim bp;
-        bp.id = (int32_t)i;
-        for (int a = 0; a < 3; ++a) {
-            float v0 = s->p[3 * i][a], v1 = s->p[3 * i + 1][a], v2 = s->p[3 * i + 2][a];
-            bp.bmin[a] = std::min(v0, std::min(v1, v2));
-            bp.bmax[a] = std::max(v0, std::max(v1, v2));
-            bp.c[a] = .5f * bp.bmin[a] + .5f * bp.bmax[a];
-        }
-        prims.push_back(bp);
     }
-    if (!prims.empty()) {
-        s->nodes.reserve(2 * prims.size());
-        BuildRecursive(*s, prims, 0, (int)prims.size());
+    auto buildRange = [&](int64_t first, int64_t count, OBvh *out) {
+        std::vector<BuildPrim> prims;
+        prims.reserve((size_t)count);
+        for (int64_t i = first; i < first + count; ++i) {
+            BuildPrim bp;
+            bp.id = (int32_t)i;
+            for (int a = 0; a < 3; ++a) {
+                float v0 = s->p[3 * i][a], v1 = s->p[3 * i + 1][a], v2 = s->p[3 * i + 2][a];
+                bp.bmin[a] = std::min(v0, std::min(v1, v2));
+                bp.bmax[a] = std::max(v0, std::max(v1, v2));
+                bp.c[a] = .5f * bp.bmin[a] + .5f * bp.bmax[a];
+            }
+            prims.push_back(bp);
+        }
+        if (!prims.empty()) {
+            out->nodes.reserve(2 * prims.size());
+            BuildRecursive(*out, prims, 0, (int)prims.size());
+        }
+    };
+    s->nTop = d->n_instances > 0 ? d->n_toplevel_triangles : d->n_triangles;
+    buildRange(0, s->nTop, &s->top);
+    // object instances (api.cpp:1550-1592): one BVH per distinct triangle range
+    if (d->n_instances > 0) s->instances.assign(d->instances, d->instances + d->n_instances);
+    std::vector<std::pair<int64_t, int64_t>> ranges;
+    for (b200pt_instance &in : s->instances) {
+        std::pair<int64_t, int64_t> r(in.first_triangle, in.n_triangles);
+        size_t oi = std::find(ranges.begin(), ranges.end(), r) - ranges.begin();
+        if (oi == ranges.size()) {
+            ranges.push_back(r);
+            s->objects.emplace_back();
+            buildRange(r.first, r.second, &s->objects.back());
+        }
+        s->instanceObject.push_back((int)oi);
+        // TransformedPrimitive::WorldBound (primitive.h:104-106): InstanceToWorld(object bound), 8 corners
+        float olo[3] = {Infinity, Infinity, Infinity}, ohi[3] = {-Infinity, -Infinity, -Infinity};
+        for (int64_t i = 3 * r.first; i < 3 * (r.first + r.second); ++i)
+            for (int a = 0; a < 3; ++a) {
+                olo[a] = std::min(olo[a], s->p[i][a]);
+                ohi[a] = std::max(ohi[a], s->p[i][a]);
+            }
+        float lo[3] = {Infinity, Infinity, Infinity}, hi[3] = {-Infinity, -Infinity, -Infinity};
+        for (int c = 0; c < 8; ++c) {
+            V3 q = XformPoint(in.instance_to_world, V3((c & 1) ? ohi[0] : olo[0], (c & 2) ? ohi[1] : olo[1], (c & 4) ? ohi[2] : olo[2]));
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], q[a]);
+                hi[a] = std::max(hi[a], q[a]);
+                s->wbMin[a] = std::min(s->wbMin[a], q[a]);
+                s->wbMax[a] = std::max(s->wbMax[a], q[a]);
+            }
+        }
+        bool unset = true;
+        for (int a = 0; a < 6; ++a) unset = unset && in.leaf_bounds[a] == 0.f;
+        if (unset) {
+            memcpy(in.leaf_bounds, lo, 12);
+            memcpy(in.leaf_bounds + 3, hi, 12);
+        }
     }
     return s;
 }

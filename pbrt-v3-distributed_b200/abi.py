@@ -31,12 +31,19 @@ class Sphere(C.Structure):
                 ("phi_max", C.c_float)]
 
 
+class Instance(C.Structure):
+    _fields_ = [("first_triangle", C.c_int64), ("n_triangles", C.c_int64), ("instance_to_world", C.c_float * 16),
+                ("world_to_instance", C.c_float * 16), ("is_identity", C.c_int32), ("leaf_bounds", C.c_float * 6),
+                ("pad", C.c_int32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("n_triangles", C.c_int64), ("vertices", C.c_void_p), ("material_id", C.c_void_p),
                 ("light_id", C.c_void_p), ("flip_normal", C.c_void_p), ("n_materials", C.c_int32),
                 ("materials", C.POINTER(Material)), ("n_lights", C.c_int32),
                 ("lights", C.POINTER(AreaLight)), ("normals", C.c_void_p), ("uvs", C.c_void_p),
-                ("vertex_flags", C.c_void_p), ("n_spheres", C.c_int32), ("spheres", C.POINTER(Sphere))]
+                ("vertex_flags", C.c_void_p), ("n_spheres", C.c_int32), ("spheres", C.POINTER(Sphere)),
+                ("n_instances", C.c_int32), ("instances", C.POINTER(Instance)), ("n_toplevel_triangles", C.c_int64)]
 
 
 class CameraDesc(C.Structure):

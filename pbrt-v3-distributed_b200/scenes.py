@@ -132,7 +132,8 @@ class SceneArrays:
     """Flattened scene in the layout b200pt_scene_desc wants."""
 
     def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
-                 n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=(), spheres=()):
+                 n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=(), spheres=(),
+                 objects=(), instances=()):
         """spheres: dicts {center, radius, material (a name in `materials` or "black"), emit (radiance or
         None), scale (sx, sy, sz) or None, reverse_orientation} -- written as `Translate` + `Scale` +
         `Shape "sphere"` by write_pbrt, after the meshes."""
@@ -180,6 +181,32 @@ class SceneArrays:
         self.light_L = float(light_L)
         self.two_sided = bool(two_sided)
         self._materials = None
+        # object instancing: objects = dicts {n_tris, seed, material, size}; each is a small soup in its own space
+        # (written as ObjectBegin/ObjectEnd at the identity CTM); instances = dicts {object, center, scale}
+        self.n_toplevel = len(self.vertices)
+        self.object_specs = [dict(o) for o in objects]
+        self.instance_specs = [dict(i) for i in instances]
+        self.object_ranges, self.object_parts = [], []
+        for o in self.object_specs:
+            part = np.ascontiguousarray(soup_vertices(o["n_tris"], o.get("seed", 5), 1) * np.float32(o.get("size", 0.3)))
+            self.object_ranges.append((len(self.vertices), len(part)))
+            self.object_parts.append(part)
+            mid = self.material_names.index(o.get("material", "matte"))
+            self.vertices = np.ascontiguousarray(np.concatenate([self.vertices, part]))
+            self.material_id = np.ascontiguousarray(np.concatenate([self.material_id, np.full(len(part), mid, np.int32)]))
+            self.light_id = np.ascontiguousarray(np.concatenate([self.light_id, np.full(len(part), -1, np.int32)]))
+            self.flip = np.ascontiguousarray(np.concatenate([self.flip, np.zeros(len(part), np.uint8)]))
+        assert not (self.object_specs and (self.shading_normals or self.uv_meshes)), "objects + per-vertex data: not wired"
+        self._instances = (abi.Instance * max(len(self.instance_specs), 1))()
+        for k, ins in enumerate(self.instance_specs):
+            first, count = self.object_ranges[ins["object"]]
+            rec = self._instances[k]
+            rec.first_triangle, rec.n_triangles = first, count
+            ident = tuple(ins.get("center", (0, 0, 0))) == (0, 0, 0) and not ins.get("scale")
+            m, minv = sphere_transform(ins.get("center", (0, 0, 0)), ins.get("scale"))
+            rec.instance_to_world[:] = m.reshape(-1).tolist()
+            rec.world_to_instance[:] = minv.reshape(-1).tolist()
+            rec.is_identity = int(ident)
         self.sphere_specs = [dict(s) for s in spheres]
         n_sl = sum(1 for s in self.sphere_specs if s.get("emit"))
         self._lights = (abi.AreaLight * max(nl + n_sl, 1))()
@@ -238,6 +265,10 @@ class SceneArrays:
         d.vertex_flags = abi.ptr(self.vertex_flags)
         d.n_spheres = len(self.sphere_specs)
         d.spheres = C.cast(self._spheres, C.POINTER(abi.Sphere))
+        d.n_instances = len(getattr(self, "instance_specs", ()))
+        if d.n_instances:
+            d.instances = C.cast(self._instances, C.POINTER(abi.Instance))
+            d.n_toplevel_triangles = self.n_toplevel
         return d
 
 
@@ -336,6 +367,19 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
         lines += [PBRT_MATERIAL[scene.material_names[m]], 'Shape "plymesh" "string filename" "%s"' % ply]
         if m in scene.reverse_orientation:
             lines += ["AttributeEnd"]
+    for k, (o, part) in enumerate(zip(getattr(scene, "object_specs", ()), getattr(scene, "object_parts", ()))):
+        ply = "%s_obj%d.ply" % (name, k)
+        write_ply(os.path.join(dirname, ply), part)
+        lines += ['ObjectBegin "obj%d"' % k, "  " + PBRT_MATERIAL[o.get("material", "matte")],
+                  '  Shape "plymesh" "string filename" "%s"' % ply, "ObjectEnd"]
+    for ins in getattr(scene, "instance_specs", ()):
+        lines.append("AttributeBegin")
+        c = ins.get("center", (0, 0, 0))
+        if tuple(c) != (0, 0, 0) or ins.get("scale"):
+            lines.append("  Translate %.9g %.9g %.9g" % tuple(c))
+        if ins.get("scale"):
+            lines.append("  Scale %.9g %.9g %.9g" % tuple(ins["scale"]))
+        lines += ['  ObjectInstance "obj%d"' % ins["object"], "AttributeEnd"]
     for sp in getattr(scene, "sphere_specs", ()):
         lines.append("AttributeBegin")
         if sp.get("emit"):

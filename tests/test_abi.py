@@ -34,7 +34,8 @@ def test_struct_sizes_match_header(abi):
     assert C.sizeof(abi.FilmDesc) == 48
     assert C.sizeof(abi.SamplerDesc) == 64
     assert C.sizeof(abi.IntegratorDesc) == 28
-    assert C.sizeof(abi.SceneDesc) == 112
+    assert C.sizeof(abi.SceneDesc) == 136
+    assert C.sizeof(abi.Instance) == 176
     assert abi.RAY_DTYPE.itemsize == 32 and abi.HIT_DTYPE.itemsize == 16
 
 

@@ -38,6 +38,8 @@ RENDERS = {
     "sphere_power": (3000, ("matte", "glass_rough"), 40, 32, 4, 7, "power", 4),
     # partial spheres (zmin / zmax / phimax clipping: std::atan2, second root), one of them an area light
     "sphere_partial": (3000, ("matte", "plastic"), 48, 40, 8, 5, "spatial", 4),
+    # object instancing (TransformedPrimitive): two objects, five instances (one at the identity, one mirrored)
+    "instances": (2000, ("matte", "glass", "metal", "plastic"), 48, 40, 8, 6, "spatial", None),
     # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
     # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
     "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
@@ -64,6 +66,11 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              dict(center=(-1.0, -0.6, -2.0), radius=0.5, material="matte", scale=(1.2, 0.8, 1.0), phimax=200.0,
                   reverse_orientation=True),
              dict(center=(1.1, 0.6, -1.8), radius=0.4, emit=80.0, zmin=-0.1, two_sided=True)))),
+         "instances": dict(scene=dict(
+             objects=(dict(n_tris=400, seed=5, material="plastic", size=0.35), dict(n_tris=150, seed=9, material="glass", size=0.5)),
+             instances=(dict(object=0, center=(0.0, 0.0, -2.4)), dict(object=0, center=(1.2, 0.8, -2.0), scale=(0.7, 1.4, 1.0)),
+                        dict(object=1, center=(-1.1, -0.7, -2.2), scale=(1.0, 1.0, -1.3)), dict(object=1),
+                        dict(object=0, center=(-1.3, 0.9, -1.9), scale=(1.5, 1.5, 1.5))))),
          "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
          "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
          "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),
