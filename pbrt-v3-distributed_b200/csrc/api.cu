@@ -48,6 +48,8 @@ struct b200pt_scene {
     float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
     std::vector<DevSphere> spheres;  // Sphere shapes (tested outside the BVH)
     DevSphere *d_spheres = nullptr;
+    std::vector<DevInstance> instances;  // object instances (tested by the same pass as the spheres)
+    DevInstance *d_instances = nullptr;
     uint64_t n_prims = 0;            // triangles of the descriptor (sphere k is reported as primitive n_prims + k)
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
     void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
@@ -178,6 +180,27 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
 
     bool gpu_build = ctx->gpu_bvh_build;
     if (const char *e = getenv("B200PT_BVH_BUILD")) gpu_build = !strcmp(e, "gpu");
+    if (d->n_instances > 0) gpu_build = false;  // object instances: the per-object trees come from the host builder
+    // object instancing (b200pt_instance): distinct triangle ranges = objects
+    if (d->n_instances < 0 || (d->n_instances > 0 && !d->instances) || d->n_instances > 65536)
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: bad instance array (at most 65536 instances)");
+    const int64_t n_top = d->n_instances > 0 ? d->n_toplevel_triangles : d->n_triangles;
+    if (n_top < 0 || n_top > d->n_triangles) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: bad n_toplevel_triangles");
+    std::vector<std::pair<int64_t, int64_t>> obj_ranges;
+    std::vector<int> inst_object((size_t)d->n_instances);
+    for (int i = 0; i < d->n_instances; ++i) {
+        const b200pt_instance &in = d->instances[i];
+        if (in.first_triangle < n_top || in.n_triangles <= 0 || in.first_triangle + in.n_triangles > d->n_triangles)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: instance %d names triangles outside the object range", i);
+        for (int64_t t = in.first_triangle; t < in.first_triangle + in.n_triangles; ++t)
+            if (d->light_id && d->light_id[t] >= 0)
+                return b200pt_fail(B200PT_ERR_INVALID, "scene_create: area lights cannot sit inside instances (api.cpp:1411-1413)");
+        const std::pair<int64_t, int64_t> rg(in.first_triangle, in.n_triangles);
+        size_t oi = std::find(obj_ranges.begin(), obj_ranges.end(), rg) - obj_ranges.begin();
+        if (oi == obj_ranges.size()) obj_ranges.push_back(rg);
+        inst_object[i] = (int)oi;
+    }
+    std::vector<uint32_t> obj_node_off(obj_ranges.size()), obj_tri_off(obj_ranges.size());
     Bvh8 bvh;
     GpuBuildOutput gout;
     if (gpu_build) {
@@ -228,10 +251,50 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     }
     int threads = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("B200PT_BUILD_THREADS")) threads = atoi(e);
-    build_bvh8(d->vertices, d->n_triangles, d->material_id, d->light_id, d->flip_normal, degenerate.data(),
-               std::max(1, threads), &bvh);
+    build_bvh8(d->vertices, n_top, d->material_id, d->light_id, d->flip_normal, degenerate.data(), std::max(1, threads), &bvh);
     if (bvh.max_depth > B200PT_STACK - 4)
         return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d exceeds the traversal stack", bvh.max_depth);
+    {
+        int64_t bad = validate_bvh8(bvh);
+        if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
+    }
+    // one tree per object, appended behind the top-level one; k_spheres traverses them through offset pointers,
+    // so their node / triangle indices stay relative to the object's own arrays
+    bvh.prim_to_tri.resize((size_t)d->n_triangles, 0xffffffffu);
+    for (size_t o = 0; o < obj_ranges.size(); ++o) {
+        const int64_t first = obj_ranges[o].first, count = obj_ranges[o].second;
+        Bvh8 ob;
+        build_bvh8(d->vertices + 9 * first, count, d->material_id + first, d->light_id ? d->light_id + first : nullptr,
+                   d->flip_normal ? d->flip_normal + first : nullptr, degenerate.data() + first, std::max(1, threads), &ob);
+        if (ob.max_depth > B200PT_STACK - 4)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d of an object exceeds the traversal stack", ob.max_depth);
+        const int64_t bad = validate_bvh8(ob);
+        if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: object BVH validation found %lld violations", (long long)bad);
+        obj_node_off[o] = (uint32_t)bvh.nodes.size();
+        obj_tri_off[o] = (uint32_t)bvh.tris.size();
+        bvh.nodes.insert(bvh.nodes.end(), ob.nodes.begin(), ob.nodes.end());
+        for (TriRecord t : ob.tris) {
+            t.prim += (uint32_t)first;      // back to the scene's triangle numbering
+            t.mat_flags |= 0x100000u;       // object-space triangle: shading goes through the instance transform
+            bvh.tris.push_back(t);
+        }
+        for (int64_t i = 0; i < count; ++i) bvh.prim_to_tri[(size_t)(first + i)] = obj_tri_off[o] + ob.prim_to_tri[(size_t)i];
+    }
+    // triangles of objects that no instance uses still need records (prim_to_tri must be total)
+    for (int64_t i = n_top; i < d->n_triangles; ++i)
+        if (bvh.prim_to_tri[(size_t)i] == 0xffffffffu) {
+            TriRecord t;
+            memset(&t, 0, sizeof(t));
+            const float *v = d->vertices + 9 * i;
+            memcpy(t.p0, v, 12);
+            memcpy(t.p1, v + 3, 12);
+            memcpy(t.p2, v + 6, 12);
+            t.prim = (uint32_t)i;
+            t.mat_flags = (uint32_t)d->material_id[i] | 0x20000u | 0x100000u;
+            t.light = -1;
+            bvh.prim_to_tri[(size_t)i] = (uint32_t)bvh.tris.size();
+            bvh.tris.push_back(t);
+        }
     }
     const size_t n_tri_records = gpu_build ? (size_t)gout.n_tris : bvh.tris.size();
     const size_t n_node_records = gpu_build ? (size_t)gout.n_nodes : bvh.nodes.size();
@@ -254,10 +317,6 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             if (!gpu_build) bvh.tris[ti].mat_flags |= 0x80000u;
         }
     }
-    if (!gpu_build) {
-        int64_t bad = validate_bvh8(bvh);
-        if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
-    }
 
     b200pt_scene *s = new b200pt_scene;
     s->ctx = ctx;
@@ -270,7 +329,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         s->bounds_lo[a] = INFINITY;
         s->bounds_hi[a] = -INFINITY;
     }
-    for (int64_t i = 0; i < 3 * d->n_triangles; ++i)
+    for (int64_t i = 0; i < 3 * n_top; ++i)  // object triangles enter through their instances' bounds
         for (int a = 0; a < 3; ++a) {
             const float v = d->vertices[3 * i + a];
             if (std::isfinite(v)) {
@@ -325,6 +384,39 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             sp.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
         }
     }
+    s->instances.resize((size_t)d->n_instances);
+    for (int i = 0; i < d->n_instances; ++i) {
+        const b200pt_instance &in = d->instances[i];
+        DevInstance &di = s->instances[i];
+        memcpy(di.i2w, in.instance_to_world, sizeof(di.i2w));
+        memcpy(di.w2i, in.world_to_instance, sizeof(di.w2i));
+        di.is_identity = in.is_identity != 0;
+        di.node_off = obj_node_off[inst_object[i]];
+        di.tri_off = obj_tri_off[inst_object[i]];
+        // TransformedPrimitive::WorldBound (primitive.h:104-106): InstanceToWorld(bounds of the object), 8 corners
+        float olo[3] = {INFINITY, INFINITY, INFINITY}, ohi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int64_t v = 3 * in.first_triangle; v < 3 * (in.first_triangle + in.n_triangles); ++v)
+            for (int a = 0; a < 3; ++a) {
+                olo[a] = std::min(olo[a], d->vertices[3 * v + a]);
+                ohi[a] = std::max(ohi[a], d->vertices[3 * v + a]);
+            }
+        float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 8; ++c) {
+            const V3 q = xform_point(di.i2w, mk((c & 1) ? ohi[0] : olo[0], (c & 2) ? ohi[1] : olo[1], (c & 4) ? ohi[2] : olo[2]));
+            for (int a = 0; a < 3; ++a) {
+                wlo[a] = std::min(wlo[a], comp(q, a));
+                whi[a] = std::max(whi[a], comp(q, a));
+                s->bounds_lo[a] = std::min(s->bounds_lo[a], comp(q, a));
+                s->bounds_hi[a] = std::max(s->bounds_hi[a], comp(q, a));
+            }
+        }
+        bool unset = true;
+        for (int a = 0; a < 6; ++a) unset = unset && in.leaf_bounds[a] == 0.f;
+        for (int a = 0; a < 3; ++a) {
+            di.leaf_lo[a] = unset ? wlo[a] : in.leaf_bounds[a];
+            di.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
+        }
+    }
     s->light_area.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
         if (d->lights[i].sphere >= 0) {
@@ -343,6 +435,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
                         (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess)) ||
         (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_spheres, std::max<size_t>(1, s->spheres.size()) * sizeof(DevSphere))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_instances, std::max<size_t>(1, s->instances.size()) * sizeof(DevInstance))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -411,7 +504,9 @@ int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
     CUDA_TRY(cudaMemcpyAsync(s->d_materials, s->materials.data(), mb, cudaMemcpyHostToDevice, st));
     const size_t sb = s->spheres.size() * sizeof(DevSphere);
     if (sb) CUDA_TRY(cudaMemcpyAsync(s->d_spheres, s->spheres.data(), sb, cudaMemcpyHostToDevice, st));
-    if (bytes) *bytes = nb + tb + mb + sb;
+    const size_t ib = s->instances.size() * sizeof(DevInstance);
+    if (ib) CUDA_TRY(cudaMemcpyAsync(s->d_instances, s->instances.data(), ib, cudaMemcpyHostToDevice, st));
+    if (bytes) *bytes = nb + tb + mb + sb + ib;
     return B200PT_OK;
 }
 
@@ -424,6 +519,7 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     cudaFree(s->d_tri_n);
     cudaFree(s->d_tri_uv);
     cudaFree(s->d_spheres);
+    cudaFree(s->d_instances);
     cudaFree(s->d_work);
     cudaFreeHost(s->h_nodes);
     cudaFreeHost(s->h_tris);
@@ -476,9 +572,11 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     else
         a.full_out = reinterpret_cast<b200pt_hit *>(out_dev);
     launch_trace(a, any_hit, false, false, trace_grid(s->ctx), st);
-    if (!s->spheres.empty()) {
+    if (!s->spheres.empty() || !s->instances.empty()) {
         a.spheres = s->d_spheres;
         a.n_spheres = (uint32_t)s->spheres.size();
+        a.instances = s->d_instances;
+        a.n_instances = (uint32_t)s->instances.size();
         a.n_tris = (uint32_t)s->n_prims;
         a.sphere_work = s->d_work + 2;
         launch_spheres(a, any_hit, false, trace_grid(s->ctx), st);
@@ -587,6 +685,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.scene.tri_uv = scene->d_tri_uv;
     H.scene.spheres = scene->d_spheres;
     H.scene.n_spheres = (uint32_t)scene->spheres.size();
+    H.scene.instances = scene->d_instances;
+    H.scene.n_instances = (uint32_t)scene->instances.size();
     // sampler (samplers/sobol.h:49-62)
     H.sampler.spp = smp->samples_per_pixel;
     memcpy(H.sampler.sb, smp->sample_bounds, sizeof(int) * 4);
@@ -760,6 +860,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.L, cap);
     ALLOC(H.sobol, cap);
     ALLOC(H.hit, cap);
+    if (!scene->instances.empty()) ALLOC(H.hit_inst, cap);
     ALLOC(H.sh_o, cap);
     ALLOC(H.sh_d, cap);
     ALLOC(H.A, cap);
@@ -964,10 +1065,13 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         // two streams: as the persistent CTAs of one launch drain, the other launch fills the freed SMs.
         const bool overlap = r->overlap && r->sort_from_bounce < 0;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
-        const bool has_spheres = H.scene.n_spheres > 0;
+        const bool has_spheres = H.scene.n_spheres > 0 || H.scene.n_instances > 0;  // "extra shapes" pass needed
         auto sphere_args = [&](TraceArgs &a, uint32_t *work) {
             a.spheres = H.scene.spheres;
             a.n_spheres = H.scene.n_spheres;
+            a.instances = H.scene.instances;
+            a.n_instances = H.scene.n_instances;
+            a.hit_inst_out = a.hit_out == H.hit ? H.hit_inst : nullptr;
             a.n_tris = (uint32_t)r->scene->n_prims;
             a.sphere_work = work;
         };

@@ -117,7 +117,9 @@ B200_HD void trav_init(Trav &T, const V3 &o, const V3 &d, float rayTMax) {
     T.idx = safe_rcp_dir(d.x);
     T.idy = safe_rcp_dir(d.y);
     T.idz = safe_rcp_dir(d.z);
-    T.oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    // the octant follows the sign BIT, like safe_rcp_dir does: a component of -0.0 (mirrored instances, reflections)
+    // must pick the same near / far planes as the sign of its reciprocal
+    T.oct = (float_as_uint(d.x) >> 31) | ((float_as_uint(d.y) >> 31) << 1) | ((float_as_uint(d.z) >> 31) << 2);
     T.octinv = 7u - T.oct;
     T.tmax = rayTMax;
     T.best = B200PT_MISS;

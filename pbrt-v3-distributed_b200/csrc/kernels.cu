@@ -297,6 +297,22 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                         }
                     }
                 }
+                if (!a.occ_out[slot]) {
+                    for (uint32_t k = 0; k < a.n_instances; ++k) {  // TransformedPrimitive::IntersectP
+                        const DevInstance &in = a.instances[k];
+                        if (!instance_leaf_test(in, ro, rd, tmax)) continue;
+                        V3 o2, d2;
+                        float tm2;
+                        instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
+                        TriHit h;
+                        TraceCounters ctr;
+                        if (traverse_bvh8<true, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3, o2, d2, tm2,
+                                                       &h, &ctr) != B200PT_MISS) {
+                            a.occ_out[slot] = 1;
+                            break;
+                        }
+                    }
+                }
             } else {
                 uint32_t best = B200PT_MISS;
                 if (a.hit_out) {
@@ -326,6 +342,30 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                         r.triangle = (int32_t)(a.n_tris + sph);
                         r.t = tmax;
                         r.b0 = r.b1 = 0.f;
+                        a.full_out[slot] = r;
+                    }
+                }
+                for (uint32_t k = 0; k < a.n_instances; ++k) {  // TransformedPrimitive::Intersect, primitive.cpp:76-98
+                    const DevInstance &in = a.instances[k];
+                    if (!instance_leaf_test(in, ro, rd, tmax)) continue;
+                    V3 o2, d2;
+                    float tm2;
+                    instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
+                    TriHit h;
+                    TraceCounters ctr;
+                    const uint32_t ti = traverse_bvh8<false, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3,
+                                                                    o2, d2, tm2, &h, &ctr);
+                    if (ti == B200PT_MISS) continue;
+                    tmax = h.t;  // r.tMax = ray.tMax
+                    best = in.tri_off + ti;
+                    if (a.hit_out) a.hit_out[slot] = best;
+                    if (a.hit_inst_out) a.hit_inst_out[slot] = k;
+                    if (a.full_out) {
+                        b200pt_hit r;
+                        r.triangle = (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w);
+                        r.t = h.t;
+                        r.b0 = h.b0;
+                        r.b1 = h.b1;
                         a.full_out[slot] = r;
                     }
                 }
@@ -500,11 +540,26 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                 lightId = (int)__float_as_uint(t2.w);
                 // re-derive (t, b0, b1, b2) of the accepted hit: Triangle::Intersect's values do not depend on tMax
                 TriHit h;
-                found = triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h);
-                if (found) {
-                    TriShading tsh;
-                    load_shading<VTX>(R->scene, ti, mflags, &tsh);
-                    fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
+                if (VTX && (mflags & 0x100000u)) {
+                    // a triangle of an instanced object: intersect in the object's space, bring the hit back
+                    const DevInstance *in = R->scene.instances + R->hit_inst[slot];
+                    V3 o2, d2;
+                    float tm2;
+                    instance_ray(*in, ro, rd, pt_inf(), &o2, &d2, &tm2);
+                    found = triangle_test(p0, p1, p2, o2, make_shear(d2), pt_inf(), &h);
+                    if (found) {
+                        TriShading tsh;
+                        load_shading<VTX>(R->scene, ti, mflags, &tsh);
+                        fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, d2, &is);
+                        instance_isect_to_world(*in, &is);
+                    }
+                } else {
+                    found = triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h);
+                    if (found) {
+                        TriShading tsh;
+                        load_shading<VTX>(R->scene, ti, mflags, &tsh);
+                        fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
+                    }
                 }
             }
             if (found) {

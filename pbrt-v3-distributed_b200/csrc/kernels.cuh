@@ -35,6 +35,8 @@ struct DevScene {
     const F4 *tri_uv;  // optional uvs, 2 x float4 per triangle: (u0 v0 u1 v1) (u2 v2 - -)
     const DevSphere *spheres;  // Sphere shapes, tested outside the BVH (k_spheres)
     uint32_t n_spheres;
+    const DevInstance *instances;  // object instances, tested by the same pass; their BVHs follow the top-level one
+    uint32_t n_instances;
 };
 
 // queue ids inside one bounce's counter block
@@ -84,6 +86,7 @@ struct RenderDev {
     float4 *L;         // L.rgb, bleed code (bits)
     uint64_t *sobol;   // Sobol' index of (pixel, sample)
     uint32_t *hit;     // closest-hit triangle (leaf order) of the path ray
+    uint32_t *hit_inst; // instance of that hit when the triangle belongs to an object (scenes with instances)
     float4 *sh_o;      // shadow ray origin, light number (bits)
     float4 *sh_d;      // shadow ray direction, pending flags (bits)
     float4 *A;         // light-sampling term  f*Li*w/lightPdf
@@ -135,6 +138,9 @@ struct TraceArgs {
     uint32_t n_spheres;
     uint32_t n_tris;            // sphere k is reported as primitive n_tris + k in full_out
     uint32_t *sphere_work;      // persistent fetch counter of the sphere pass (zeroed)
+    const DevInstance *instances;
+    uint32_t n_instances;
+    uint32_t *hit_inst_out;     // instance of an object-triangle hit (closest, render path)
 };
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,

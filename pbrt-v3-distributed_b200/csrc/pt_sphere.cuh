@@ -445,6 +445,51 @@ B200_HD float sphere_pdf(const DevSphere &sp, const V3 &refP, const V3 &refPErro
     return 1 / (2 * PT_PI * (1 - cosThetaMax));
 }
 
+// ---- object instances: TransformedPrimitive (core/primitive.cpp:70-98)
+struct DevInstance {
+    float w2i[16], i2w[16];        // WorldToInstance->m, InstanceToWorld->m
+    int is_identity;               // InstanceToWorld.IsIdentity(): the hit stays as it is (primitive.cpp:93-94)
+    float leaf_lo[3], leaf_hi[3];  // bounds of the host accelerator's leaf holding the instance
+    uint32_t node_off, tri_off;    // the object's BVH inside the scene's node / triangle arrays
+};
+// Transform::operator()(const Ray &) with WorldToInstance (transform.h:251-264): origin pushed to the edge of its
+// error bounds, tMax shortened by the same step
+B200_HD void instance_ray(const DevInstance &in, const V3 &ro, const V3 &rd, float rayTMax, V3 *o2, V3 *d2, float *tMax2) {
+    V3 oError;
+    V3 o = xform_point_err(in.w2i, ro, &oError);
+    const V3 d = xform_vector(in.w2i, rd);
+    const float lengthSquared = len2(d);
+    float tMax = rayTMax;
+    if (lengthSquared > 0) {
+        const float dt = dot(vabs(d), oError) / lengthSquared;
+        o = o + d * dt;
+        tMax -= dt;
+    }
+    *o2 = o;
+    *d2 = d;
+    *tMax2 = tMax;
+}
+B200_HD bool instance_leaf_test(const DevInstance &in, const V3 &ro, const V3 &rd, float rayTMax) {
+    DevSphere box;  // only the leaf bounds are read
+    for (int a = 0; a < 3; ++a) {
+        box.leaf_lo[a] = in.leaf_lo[a];
+        box.leaf_hi[a] = in.leaf_hi[a];
+    }
+    return sphere_leaf_test(box, ro, rd, rayTMax);
+}
+// InstanceToWorld(SurfaceInteraction), transform.cpp:262-297
+B200_HD void instance_isect_to_world(const DevInstance &in, Isect *is) {
+    if (in.is_identity) return;
+    Isect w = *is;
+    w.p = xform_point_err_in(in.i2w, is->p, is->pError, &w.pError);
+    w.n = normalize(xform_normal(in.w2i, is->n));
+    w.wo = normalize(xform_vector(in.i2w, is->wo));
+    w.sdpdu = xform_vector(in.i2w, is->sdpdu);
+    const V3 sn = normalize(xform_normal(in.w2i, is->ns));
+    w.ns = (dot(sn, w.n) < 0.f) ? -sn : sn;
+    *is = w;
+}
+
 // SpatialLightDistribution::ComputeDistribution, one (voxel, light) term (lightdistrib.cpp:196-275)
 B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
                                     const V3 &p2, bool flip, const TriShading &sh, const RGB &lemit, bool twoSided,

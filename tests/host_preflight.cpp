@@ -357,6 +357,125 @@ int main(int argc, char **argv) {
         printf("acosf: %ld mismatches against the host libm over [-1, 1] (every third float)\n", badA);
         fail |= badA != 0;
     }
+    // ---- object instances: the device routines (compiled for the host) against the oracle's TransformedPrimitive
+    if (nTris >= 50) {
+        const int64_t nObj = std::min<int64_t>(nTris, 3000);
+        std::vector<float> ov(verts.begin(), verts.begin() + 9 * nObj);
+        for (float &v : ov) v *= 0.3f;
+        Bvh8 ob;
+        std::vector<uint8_t> degO(degenerate.begin(), degenerate.begin() + nObj);
+        build_bvh8(ov.data(), nObj, mat.data(), light.data(), nullptr, degO.data(), 4, &ob);
+        const int nInst = 4;
+        std::vector<b200pt_instance> insts(nInst);
+        std::vector<DevInstance> dev(nInst);
+        for (int k = 0; k < nInst; ++k) {
+            b200pt_instance &in = insts[k];
+            memset(&in, 0, sizeof(in));
+            in.first_triangle = 0;
+            in.n_triangles = nObj;
+            const float c[3] = {k == 0 ? 0.f : U(rng), k == 0 ? 0.f : U(rng), k == 0 ? 0.f : U(rng)};
+            const float sc[3] = {k == 2 ? 1.4f : 1.f, k == 2 ? 0.7f : 1.f, k == 3 ? -1.2f : 1.f};
+            for (int a = 0; a < 4; ++a) in.instance_to_world[5 * a] = in.world_to_instance[5 * a] = 1.f;
+            for (int a = 0; a < 3; ++a) {
+                in.instance_to_world[5 * a] = sc[a];
+                in.instance_to_world[4 * a + 3] = c[a];
+                in.world_to_instance[5 * a] = 1.f / sc[a];
+                in.world_to_instance[4 * a + 3] = (1.f / sc[a]) * -c[a];
+            }
+            in.is_identity = k == 0;
+            DevInstance &d = dev[k];
+            memcpy(d.i2w, in.instance_to_world, 64);
+            memcpy(d.w2i, in.world_to_instance, 64);
+            d.is_identity = in.is_identity;
+            d.node_off = d.tri_off = 0;
+            // the instance's own WorldBound(): what the oracle and the library use when leaf_bounds is zero
+            float olo[3] = {INFINITY, INFINITY, INFINITY}, ohi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int64_t v = 0; v < 3 * nObj; ++v)
+                for (int a = 0; a < 3; ++a) {
+                    olo[a] = std::min(olo[a], ov[3 * v + a]);
+                    ohi[a] = std::max(ohi[a], ov[3 * v + a]);
+                }
+            for (int a = 0; a < 3; ++a) {
+                d.leaf_lo[a] = INFINITY;
+                d.leaf_hi[a] = -INFINITY;
+            }
+            for (int cn = 0; cn < 8; ++cn) {
+                const V3 q = xform_point(d.i2w, mk((cn & 1) ? ohi[0] : olo[0], (cn & 2) ? ohi[1] : olo[1], (cn & 4) ? ohi[2] : olo[2]));
+                for (int a = 0; a < 3; ++a) {
+                    d.leaf_lo[a] = std::min(d.leaf_lo[a], comp(q, a));
+                    d.leaf_hi[a] = std::max(d.leaf_hi[a], comp(q, a));
+                }
+            }
+        }
+        b200pt_scene_desc sd3;
+        memset(&sd3, 0, sizeof(sd3));
+        sd3.n_triangles = nObj;
+        sd3.vertices = ov.data();
+        sd3.material_id = mat.data();
+        sd3.light_id = light.data();
+        sd3.n_materials = 1;
+        sd3.materials = &m;
+        sd3.n_instances = nInst;
+        sd3.instances = insts.data();
+        sd3.n_toplevel_triangles = 0;
+        oracle_scene *os3 = oracle_scene_create(&sd3);
+        std::vector<b200pt_hit> w3(nRays);
+        std::vector<uint8_t> o3(nRays);
+        oracle_trace_closest(os3, rays.data(), w3.data(), nRays);
+        oracle_trace_any(os3, rays.data(), o3.data(), nRays);
+        const U4 *on = reinterpret_cast<const U4 *>(ob.nodes.data());
+        const F4 *ot = reinterpret_cast<const F4 *>(ob.tris.data());
+        int64_t nh = 0, badI = 0, badO = 0, ties = 0;
+        TraceCounters ic = {0, 0};
+        for (int64_t i = 0; i < nRays; ++i) {
+            V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+            float tmax = rays[i].t_max;
+            int32_t prim = -1;
+            float tBest = 0;
+            bool occ = false;
+            for (int k = 0; k < nInst; ++k) {
+                V3 o2, d2;
+                float tm2;
+                TriHit h;
+                if (instance_leaf_test(dev[k], o, d, rays[i].t_max)) {
+                    instance_ray(dev[k], o, d, rays[i].t_max, &o2, &d2, &tm2);
+                    if (traverse_bvh8<true, false>(on, ot, o2, d2, tm2, &h, &ic) != B200PT_MISS) occ = true;
+                }
+                if (getenv("PREFLIGHT_VERBOSE") && (i == 4505 || i == 15674)) {
+                    instance_ray(dev[k], o, d, tmax, &o2, &d2, &tm2);
+                    TriHit hb = {0, 0, 0, 0};
+                    uint32_t tb = traverse_bvh8<false, false>(on, ot, o2, d2, tm2, &hb, &ic);
+                    printf("   ray %lld inst %d: leaf %d o2=(%g %g %g) d2=(%g %g %g) tm2=%g hit %u t=%g\n", (long long)i, k,
+                           (int)instance_leaf_test(dev[k], o, d, tmax), o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, tm2, tb, hb.t);
+                }
+                if (!instance_leaf_test(dev[k], o, d, tmax)) continue;
+                instance_ray(dev[k], o, d, tmax, &o2, &d2, &tm2);
+                const uint32_t ti = traverse_bvh8<false, false>(on, ot, o2, d2, tm2, &h, &ic);
+                if (ti == B200PT_MISS) continue;
+                tmax = h.t;
+                tBest = h.t;
+                prim = (int32_t)ob.tris[ti].prim;
+            }
+            if (prim >= 0) ++nh;
+            if (prim != w3[i].triangle) {
+                if (prim >= 0 && w3[i].triangle >= 0 && bits(tBest) == bits(w3[i].t))
+                    ++ties;
+                else {
+                    ++badI;
+                    if (getenv("PREFLIGHT_VERBOSE")) printf("  ray %lld: prim %d t %a vs oracle %d t %a tmax %a\n", (long long)i, prim, tBest, w3[i].triangle, w3[i].t, rays[i].t_max);
+                }
+            } else if (prim >= 0 && bits(tBest) != bits(w3[i].t))
+                ++badI;
+            if (occ != (o3[i] != 0)) {
+                ++badO;
+                if (getenv("PREFLIGHT_VERBOSE")) printf("  ray %lld: occ %d vs oracle %d tmax %a\n", (long long)i, (int)occ, (int)o3[i], rays[i].t_max);
+            }
+        }
+        printf("instances: %lld rays, %lld hits, wrong triangle/t %lld (ties %lld), wrong any-hit %lld\n", (long long)nRays,
+               (long long)nh, (long long)badI, (long long)ties, (long long)badO);
+        fail |= (badI || badO);
+        oracle_scene_destroy(os3);
+    }
     printf(fail ? "PREFLIGHT FAILED\n" : "PREFLIGHT OK\n");
     return fail;
 }
