@@ -129,6 +129,8 @@ struct Flattened {
     std::vector<b200pt_material> materials;
     std::vector<b200pt_area_light> lights;
     std::vector<b200pt_sphere> spheres;
+    std::vector<b200pt_instance> instances;
+    int64_t nTopLevel = 0;
 };
 
 // materials/{matte,plastic,metal,glass}.cpp ComputeScatteringFunctions with constant textures
@@ -225,33 +227,10 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         *id = it->second;
         return true;
     };
-    f->vertices.reserve(prims.size() * 9);
-    for (size_t i = 0; i < prims.size(); ++i) {
-        auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
-        if (!gp) return *why = "a primitive other than GeometricPrimitive (instancing / animation)", false;
-        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
-        if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
-            b200pt_sphere bs;
-            memset(&bs, 0, sizeof(bs));
-            memcpy(bs.object_to_world, sph->ObjectToWorld->m.m, sizeof(float) * 16);
-            memcpy(bs.world_to_object, sph->WorldToObject->m.m, sizeof(float) * 16);
-            bs.radius = sph->radius;
-            bs.z_min = sph->zMin;  // the Sphere's own members (sphere.h:66-68); phi_max != 0 marks them valid
-            bs.z_max = sph->zMax;
-            bs.theta_min = sph->thetaMin;
-            bs.theta_max = sph->thetaMax;
-            bs.phi_max = sph->phiMax;
-            if (!(sph->phiMax > 0)) return *why = "a sphere with phimax 0", false;
-            if (!materialOf(gp->material.get(), &bs.material_id)) return false;
-            bs.light_id = -1;
-            bs.reverse_orientation = sph->reverseOrientation ? 1 : 0;
-            bs.transform_swaps_handedness = sph->transformSwapsHandedness ? 1 : 0;
-            sphereOfShape[gp->shape.get()] = (int)f->spheres.size();
-            f->spheres.push_back(bs);
-            continue;
-        }
+    auto appendTriangle = [&](const GeometricPrimitive *gp) {
         auto tri = dynamic_cast<const Triangle *>(gp->shape.get());
         if (!tri) return *why = "a shape other than Triangle and Sphere", false;
+        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
         const TriangleMesh &mesh = *tri->mesh;
         if (mesh.s || mesh.alphaMask || mesh.shadowAlphaMask)
             return *why = "meshes with per-vertex tangents / alpha masks", false;
@@ -277,9 +256,80 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         triOfShape[gp->shape.get()] = (int)f->materialId.size();
         f->materialId.push_back(mid);
         f->lightId.push_back(-1);
+        return true;
+    };
+    std::vector<const TransformedPrimitive *> transformed;
+    f->vertices.reserve(prims.size() * 9);
+    for (size_t i = 0; i < prims.size(); ++i) {
+        if (auto tp = dynamic_cast<const TransformedPrimitive *>(prims[i].get())) {
+            transformed.push_back(tp);
+            continue;
+        }
+        auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
+        if (!gp) return *why = "a primitive other than GeometricPrimitive / TransformedPrimitive", false;
+        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
+        if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
+            b200pt_sphere bs;
+            memset(&bs, 0, sizeof(bs));
+            memcpy(bs.object_to_world, sph->ObjectToWorld->m.m, sizeof(float) * 16);
+            memcpy(bs.world_to_object, sph->WorldToObject->m.m, sizeof(float) * 16);
+            bs.radius = sph->radius;
+            bs.z_min = sph->zMin;  // the Sphere's own members (sphere.h:66-68); phi_max != 0 marks them valid
+            bs.z_max = sph->zMax;
+            bs.theta_min = sph->thetaMin;
+            bs.theta_max = sph->thetaMax;
+            bs.phi_max = sph->phiMax;
+            if (!(sph->phiMax > 0)) return *why = "a sphere with phimax 0", false;
+            if (!materialOf(gp->material.get(), &bs.material_id)) return false;
+            bs.light_id = -1;
+            bs.reverse_orientation = sph->reverseOrientation ? 1 : 0;
+            bs.transform_swaps_handedness = sph->transformSwapsHandedness ? 1 : 0;
+            sphereOfShape[gp->shape.get()] = (int)f->spheres.size();
+            f->spheres.push_back(bs);
+            continue;
+        }
+        if (!appendTriangle(gp)) return false;
+    }
+    f->nTopLevel = (int64_t)f->materialId.size();
+    // object instances (TransformedPrimitive, primitive.cpp:70-98): the triangles of every distinct object are appended
+    // behind the top-level ones, in the object's own space
+    std::unordered_map<const Primitive *, std::pair<int64_t, int64_t>> objectRange;
+    std::unordered_map<const Primitive *, int> instanceOfPrim;
+    for (const TransformedPrimitive *tp : transformed) {
+        if (tp->PrimitiveToWorld.actuallyAnimated) return *why = "animated object instances", false;
+        const Primitive *inner = tp->primitive.get();
+        auto it = objectRange.find(inner);
+        if (it == objectRange.end()) {
+            const int64_t first = (int64_t)f->materialId.size();
+            if (auto ob = dynamic_cast<const BVHAccel *>(inner)) {
+                for (const auto &op : ob->primitives) {
+                    auto ogp = dynamic_cast<const GeometricPrimitive *>(op.get());
+                    if (!ogp) return *why = "nested instances", false;
+                    if (ogp->areaLight) return *why = "area lights inside object instances", false;
+                    if (!dynamic_cast<const Triangle *>(ogp->shape.get())) return *why = "non-triangle shapes inside object instances", false;
+                    if (!appendTriangle(ogp)) return false;
+                }
+            } else if (auto ogp = dynamic_cast<const GeometricPrimitive *>(inner)) {
+                if (!dynamic_cast<const Triangle *>(ogp->shape.get())) return *why = "non-triangle shapes inside object instances", false;
+                if (!appendTriangle(ogp)) return false;
+            } else {
+                return *why = "object instances over an aggregate other than BVHAccel", false;
+            }
+            it = objectRange.emplace(inner, std::make_pair(first, (int64_t)f->materialId.size() - first)).first;
+        }
+        b200pt_instance bi;
+        memset(&bi, 0, sizeof(bi));
+        bi.first_triangle = it->second.first;
+        bi.n_triangles = it->second.second;
+        const Transform *t2w = tp->PrimitiveToWorld.startTransform;
+        memcpy(bi.instance_to_world, t2w->m.m, sizeof(float) * 16);
+        memcpy(bi.world_to_instance, t2w->mInv.m, sizeof(float) * 16);
+        bi.is_identity = t2w->IsIdentity() ? 1 : 0;
+        instanceOfPrim[tp] = (int)f->instances.size();
+        f->instances.push_back(bi);
     }
     // the BVHAccel leaf of every sphere: its bounds gate Sphere::Intersect(P) in the reference (bvh.cpp:676,713)
-    if (!f->spheres.empty() && bvh->nodes) {
+    if ((!f->spheres.empty() || !f->instances.empty()) && bvh->nodes) {
         std::vector<int> stack(1, 0);
         while (!stack.empty()) {
             const int ni = stack.back();
@@ -287,6 +337,15 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
             const LinearBVHNode &node = bvh->nodes[ni];
             if (node.nPrimitives > 0) {
                 for (int i = 0; i < node.nPrimitives; ++i) {
+                    auto ii = instanceOfPrim.find(prims[node.primitivesOffset + i].get());
+                    if (ii != instanceOfPrim.end()) {
+                        float *lb = f->instances[ii->second].leaf_bounds;
+                        for (int a = 0; a < 3; ++a) {
+                            lb[a] = node.bounds.pMin[a];
+                            lb[3 + a] = node.bounds.pMax[a];
+                        }
+                        continue;
+                    }
                     auto gp = dynamic_cast<const GeometricPrimitive *>(prims[node.primitivesOffset + i].get());
                     auto it = gp ? sphereOfShape.find(gp->shape.get()) : sphereOfShape.end();
                     if (it == sphereOfShape.end()) continue;
@@ -384,6 +443,9 @@ class GpuPathIntegrator : public PathIntegrator {
         sd.vertex_flags = flat.vertexFlags.data();
         sd.n_spheres = (int)flat.spheres.size();
         sd.spheres = flat.spheres.data();
+        sd.n_instances = (int)flat.instances.size();
+        sd.instances = flat.instances.data();
+        sd.n_toplevel_triangles = flat.nTopLevel;
 
         b200pt_camera_desc cd;
         memcpy(cd.raster_to_camera, pcam->RasterToCamera.m.m, sizeof(float) * 16);

@@ -90,6 +90,15 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_filter_gaussian.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_filter_gaussian.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (Gaussian pixel filter) differs from the reference"
+    # object instancing: ObjectBegin / ObjectInstance blocks become TransformedPrimitives over per-object BVHAccels
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS["instances"]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **EXTRA["instances"]["scene"])
+    path = scenes.write_pbrt(str(tmp_path), "render_instances", arr, w, h, spp, max_depth=depth, strategy=strat)
+    r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_instances.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_instances.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "drop-in render (object instances) differs from the reference"
 
 
 KILLEROO_DIR = os.path.join(ROOT, "oracle", "_ref", "scenes")

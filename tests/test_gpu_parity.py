@@ -221,6 +221,38 @@ def test_trace_spheres_vs_oracle(pkg, abi, scenes, ob, ctx):
         scene.close()
 
 
+def test_trace_instances_vs_oracle(pkg, abi, scenes, ob, ctx):
+    """TransformedPrimitive::Intersect / IntersectP: rays are transformed into the object, the object's own tree is
+    traversed, the hit is reported with the object triangle's index and the object-space t, bit-exact."""
+    objects = (dict(n_tris=600, seed=5, material="matte", size=0.35), dict(n_tris=200, seed=9, material="matte", size=0.5))
+    instances = (dict(object=0, center=(0.0, 0.0, -0.4)), dict(object=0, center=(0.9, 0.6, 0.2), scale=(0.7, 1.4, 1.0)),
+                 dict(object=1, center=(-0.8, -0.5, 0.0), scale=(1.0, 1.0, -1.3)), dict(object=1),
+                 dict(object=0, center=(-0.9, 0.7, 0.4), scale=(1.5, 1.5, 1.5)))
+    for n_tris in (0, 3000):
+        arr = scenes.SceneArrays(n_tris, materials=("matte",), soup_version=1, seed=21, n_lights=0, objects=objects,
+                                 instances=instances)
+        scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+        o = ob.Oracle(abi, arr)
+        n_rays = 60000
+        rng = np.random.default_rng(6)
+        rays = np.zeros(n_rays, dtype=abi.RAY_DTYPE)
+        rays["o"] = rng.uniform(-1.5, 1.5, (n_rays, 3)).astype(np.float32)
+        rays["d"] = rng.normal(size=(n_rays, 3)).astype(np.float32)
+        rays["t_max"] = np.inf
+        rays["t_max"][::3] = rng.uniform(0.05, 2.0, len(rays[::3])).astype(np.float32)
+        rays["d"][::17, 2] = 0.0   # becomes -0.0 inside the mirrored instance
+        got, want = scene.trace_closest(rays), o.trace_closest(rays)
+        same = got["triangle"] == want["triangle"]
+        tie = ~same & (got["triangle"] >= 0) & (want["triangle"] >= 0) & (bits(got["t"]) == bits(want["t"]))
+        assert (same | tie).all(), "%d rays disagree" % (~(same | tie)).sum()
+        assert (want["triangle"] >= arr.n_toplevel).sum() > 1000
+        hit = same & (want["triangle"] >= 0)
+        assert np.array_equal(bits(got["t"][hit]), bits(want["t"][hit]))
+        assert np.array_equal(scene.trace_any(rays), o.trace_any(rays))
+        o.close()
+        scene.close()
+
+
 def test_device_bvh_build(pkg, abi, scenes, ob, monkeypatch):
     """the on-device builder (Morton order -> binary radix tree -> 8-wide collapse).  The tree passes
     the structural validation, traversal answers equal the oracle's (and the host-built tree's) bit for bit, and a
