@@ -34,9 +34,25 @@ WORKLOADS = {
              "synthetic 10M triangles, 4 BSDF types, 1024spp, 1920x1080"),
     "cfg4": (10000000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 1024, 5, 16,
              "synthetic 10M triangles + 16 area lights (MIS), 1024spp, 1920x1080, tile-sharded"),
+    # BASELINE configs[4] without its SampledSpectrum half and at a reduced film / sample count (the full
+    # 3840x2160 x 4096 spp job is sized for 8 GPUs): 50 M instanced triangles = 1000 instances of one 50k-triangle object
+    "cfg5rgb": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
+                "synthetic 50M triangles instanced (1000 x 50k, RGB spectrum), maxdepth 16, 64spp, 1920x1080"),
     "small": (100000, ("matte", "glass", "metal", "plastic"), 256, 256, 16, 5, None,
               "smoke-sized: 100k triangles, 4 BSDF types, 16spp, 256x256"),
 }
+
+
+def workload_scene_kwargs(name):
+    """Extra SceneArrays arguments of a workload (object instancing for cfg5rgb)."""
+    if name != "cfg5rgb":
+        return {}
+    inst = []
+    for k in range(1000):  # 10 x 10 x 10 lattice through the soup's volume, every third one mirrored / stretched
+        c = (-0.9 + 0.2 * (k % 10), -0.9 + 0.2 * ((k // 10) % 10), -0.9 + 0.2 * (k // 100))
+        sc = (1.0, 1.0, 1.0) if k % 3 == 0 else ((1.2, 0.8, 1.0) if k % 3 == 1 else (1.0, 1.0, -1.1))
+        inst.append(dict(object=0, center=c, scale=sc))
+    return dict(objects=(dict(n_tris=50000, seed=77, material="plastic", size=0.09),), instances=tuple(inst))
 
 
 def rank_env():
@@ -158,7 +174,7 @@ def main():
         if rank != 0:
             return 0
         ob = graft.load_oracle()
-        arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
+        arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **workload_scene_kwargs(args.workload))
         setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
         tmp = tempfile.mkdtemp(prefix="b200pt_ref_")
         pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if ob.have_reference() else None
@@ -195,7 +211,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
+    arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **workload_scene_kwargs(args.workload))
     setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=args.pixel_filter)
     if args.pixel_filter:
         config["pixel_filter"] = args.pixel_filter
