@@ -50,6 +50,7 @@ struct b200pt_scene {
     DevSphere *d_spheres = nullptr;
     std::vector<DevInstance> instances;  // object instances (tested by the same pass as the spheres)
     DevInstance *d_instances = nullptr;
+    uint32_t tlas_node_off = 0, tlas_tri_off = 0;  // tree over the instances' leaf boxes inside the node / triangle arrays
     uint64_t n_prims = 0;            // triangles of the descriptor (sphere k is reported as primitive n_prims + k)
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
     void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
@@ -296,6 +297,62 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             bvh.tris.push_back(t);
         }
     }
+    std::vector<DevInstance> dinst((size_t)d->n_instances);
+    for (int i = 0; i < d->n_instances; ++i) {
+        const b200pt_instance &in = d->instances[i];
+        DevInstance &di = dinst[i];
+        memcpy(di.i2w, in.instance_to_world, sizeof(di.i2w));
+        memcpy(di.w2i, in.world_to_instance, sizeof(di.w2i));
+        di.is_identity = in.is_identity != 0;
+        di.node_off = obj_node_off[inst_object[i]];
+        di.tri_off = obj_tri_off[inst_object[i]];
+        // TransformedPrimitive::WorldBound (primitive.h:104-106): InstanceToWorld(bounds of the object), 8 corners
+        float olo[3] = {INFINITY, INFINITY, INFINITY}, ohi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int64_t v = 3 * in.first_triangle; v < 3 * (in.first_triangle + in.n_triangles); ++v)
+            for (int a = 0; a < 3; ++a) {
+                olo[a] = std::min(olo[a], d->vertices[3 * v + a]);
+                ohi[a] = std::max(ohi[a], d->vertices[3 * v + a]);
+            }
+        float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 8; ++c) {
+            const V3 q = xform_point(di.i2w, mk((c & 1) ? ohi[0] : olo[0], (c & 2) ? ohi[1] : olo[1], (c & 4) ? ohi[2] : olo[2]));
+            for (int a = 0; a < 3; ++a) {
+                wlo[a] = std::min(wlo[a], comp(q, a));
+                whi[a] = std::max(whi[a], comp(q, a));
+            }
+        }
+        bool unset = true;
+        for (int a = 0; a < 6; ++a) unset = unset && in.leaf_bounds[a] == 0.f;
+        for (int a = 0; a < 3; ++a) {
+            di.leaf_lo[a] = unset ? wlo[a] : in.leaf_bounds[a];
+            di.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
+            di.world_lo[a] = wlo[a];
+            di.world_hi[a] = whi[a];
+        }
+    }
+    // a tree over the instances' leaf boxes (each box enters the builder as a triangle spanning it; the leaf
+    // "triangles" of this tree carry instance numbers and are only ever read by k_spheres): scenes with many instances
+    uint32_t tlas_node_off = 0, tlas_tri_off = 0;
+    if (d->n_instances > 8 && !gpu_build) {
+        std::vector<float> boxes((size_t)d->n_instances * 9);
+        std::vector<int32_t> zeros((size_t)d->n_instances, 0);
+        for (int i = 0; i < d->n_instances; ++i) {
+            const DevInstance &di = dinst[i];
+            float *v = boxes.data() + 9 * (size_t)i;
+            v[0] = di.leaf_lo[0], v[1] = di.leaf_lo[1], v[2] = di.leaf_lo[2];
+            v[3] = di.leaf_hi[0], v[4] = di.leaf_hi[1], v[5] = di.leaf_hi[2];
+            v[6] = di.leaf_lo[0], v[7] = di.leaf_hi[1], v[8] = di.leaf_lo[2];
+        }
+        Bvh8 tl;
+        build_bvh8(boxes.data(), d->n_instances, zeros.data(), nullptr, nullptr, nullptr, 1, &tl);
+        if (tl.max_depth <= B200PT_STACK - 4 && validate_bvh8(tl) == 0 && tl.n_in_leaves == (uint32_t)d->n_instances) {
+            tlas_node_off = (uint32_t)bvh.nodes.size();
+            tlas_tri_off = (uint32_t)bvh.tris.size();
+            bvh.nodes.insert(bvh.nodes.end(), tl.nodes.begin(), tl.nodes.end());
+            bvh.tris.insert(bvh.tris.end(), tl.tris.begin(), tl.tris.end());
+        }
+    }
+
     const size_t n_tri_records = gpu_build ? (size_t)gout.n_tris : bvh.tris.size();
     const size_t n_node_records = gpu_build ? (size_t)gout.n_nodes : bvh.nodes.size();
     // per-vertex shading data in leaf order + flags (bit 18 normals, bit 19 uvs) in the triangle records
@@ -384,39 +441,14 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             sp.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
         }
     }
-    s->instances.resize((size_t)d->n_instances);
-    for (int i = 0; i < d->n_instances; ++i) {
-        const b200pt_instance &in = d->instances[i];
-        DevInstance &di = s->instances[i];
-        memcpy(di.i2w, in.instance_to_world, sizeof(di.i2w));
-        memcpy(di.w2i, in.world_to_instance, sizeof(di.w2i));
-        di.is_identity = in.is_identity != 0;
-        di.node_off = obj_node_off[inst_object[i]];
-        di.tri_off = obj_tri_off[inst_object[i]];
-        // TransformedPrimitive::WorldBound (primitive.h:104-106): InstanceToWorld(bounds of the object), 8 corners
-        float olo[3] = {INFINITY, INFINITY, INFINITY}, ohi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int64_t v = 3 * in.first_triangle; v < 3 * (in.first_triangle + in.n_triangles); ++v)
-            for (int a = 0; a < 3; ++a) {
-                olo[a] = std::min(olo[a], d->vertices[3 * v + a]);
-                ohi[a] = std::max(ohi[a], d->vertices[3 * v + a]);
-            }
-        float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int c = 0; c < 8; ++c) {
-            const V3 q = xform_point(di.i2w, mk((c & 1) ? ohi[0] : olo[0], (c & 2) ? ohi[1] : olo[1], (c & 4) ? ohi[2] : olo[2]));
-            for (int a = 0; a < 3; ++a) {
-                wlo[a] = std::min(wlo[a], comp(q, a));
-                whi[a] = std::max(whi[a], comp(q, a));
-                s->bounds_lo[a] = std::min(s->bounds_lo[a], comp(q, a));
-                s->bounds_hi[a] = std::max(s->bounds_hi[a], comp(q, a));
-            }
-        }
-        bool unset = true;
-        for (int a = 0; a < 6; ++a) unset = unset && in.leaf_bounds[a] == 0.f;
+    s->instances = dinst;
+    s->tlas_node_off = tlas_node_off;
+    s->tlas_tri_off = tlas_tri_off;
+    for (const DevInstance &di : dinst)  // TransformedPrimitive::WorldBound joins Scene::WorldBound()
         for (int a = 0; a < 3; ++a) {
-            di.leaf_lo[a] = unset ? wlo[a] : in.leaf_bounds[a];
-            di.leaf_hi[a] = unset ? whi[a] : in.leaf_bounds[3 + a];
+            s->bounds_lo[a] = std::min(s->bounds_lo[a], di.world_lo[a]);
+            s->bounds_hi[a] = std::max(s->bounds_hi[a], di.world_hi[a]);
         }
-    }
     s->light_area.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
         if (d->lights[i].sphere >= 0) {
@@ -577,6 +609,8 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
         a.n_spheres = (uint32_t)s->spheres.size();
         a.instances = s->d_instances;
         a.n_instances = (uint32_t)s->instances.size();
+        a.tlas_node_off = s->tlas_node_off;
+        a.tlas_tri_off = s->tlas_tri_off;
         a.n_tris = (uint32_t)s->n_prims;
         a.sphere_work = s->d_work + 2;
         launch_spheres(a, any_hit, false, trace_grid(s->ctx), st);
@@ -687,6 +721,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.scene.n_spheres = (uint32_t)scene->spheres.size();
     H.scene.instances = scene->d_instances;
     H.scene.n_instances = (uint32_t)scene->instances.size();
+    H.scene.tlas_node_off = scene->tlas_node_off;
+    H.scene.tlas_tri_off = scene->tlas_tri_off;
     // sampler (samplers/sobol.h:49-62)
     H.sampler.spp = smp->samples_per_pixel;
     memcpy(H.sampler.sb, smp->sample_bounds, sizeof(int) * 4);
@@ -1071,6 +1107,8 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.n_spheres = H.scene.n_spheres;
             a.instances = H.scene.instances;
             a.n_instances = H.scene.n_instances;
+            a.tlas_node_off = H.scene.tlas_node_off;
+            a.tlas_tri_off = H.scene.tlas_tri_off;
             a.hit_inst_out = a.hit_out == H.hit ? H.hit_inst : nullptr;
             a.n_tris = (uint32_t)r->scene->n_prims;
             a.sphere_work = work;

@@ -271,6 +271,70 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------- instances
+// TransformedPrimitive::Intersect / IntersectP (primitive.cpp:76-106) for one instance with the current ray.tMax:
+// leaf-box gate, ray into the object's space, the object's own tree.  Closest: returns the triangle (index inside the
+// scene's leaf-order array) or B200PT_MISS and the hit; any-hit: B200PT_MISS or anything else.
+template <bool ANY_HIT>
+__device__ uint32_t instance_test(const TraceArgs &a, uint32_t k, const V3 &ro, const V3 &rd, float tmax, TriHit *h) {
+    const DevInstance &in = a.instances[k];
+    if (!instance_leaf_test(in, ro, rd, tmax)) return B200PT_MISS;
+    V3 o2, d2;
+    float tm2;
+    instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
+    TraceCounters ctr;
+    const uint32_t ti = traverse_bvh8<ANY_HIT, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3, o2, d2,
+                                                      tm2, h, &ctr);
+    return ti == B200PT_MISS ? B200PT_MISS : in.tri_off + ti;
+}
+// All instances against one ray: through the tree over their leaf boxes when there is one (its leaf "triangles" carry
+// instance numbers), else one by one.  Returns the closest object triangle (and *inst) or B200PT_MISS; *tmax is updated.
+template <bool ANY_HIT>
+__device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &rd, float *tmax, TriHit *hit, uint32_t *inst) {
+    uint32_t best = B200PT_MISS;
+    if (a.tlas_node_off == 0u) {
+        for (uint32_t k = 0; k < a.n_instances; ++k) {
+            TriHit h;
+            const uint32_t ti = instance_test<ANY_HIT>(a, k, ro, rd, *tmax, &h);
+            if (ti == B200PT_MISS) continue;
+            best = ti;
+            *inst = k;
+            *hit = h;
+            *tmax = h.t;  // r.tMax = ray.tMax
+            if (ANY_HIT) return best;
+        }
+        return best;
+    }
+    const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 5;
+    const F4 *tt = a.tris + (size_t)a.tlas_tri_off * 3;
+    Trav T;
+    TravStack S;
+    TraceCounters ctr;
+    trav_init(T, ro, rd, *tmax);
+    do {
+        uint32_t tg_x = 0, tg_y = 0;
+        if (T.cur_y & 0xff000000u) trav_node_phase<false>(T, S, tn, &tg_x, &tg_y, &ctr);
+        while (tg_y) {
+            const int j = msb32(tg_y);
+            tg_y &= ~(1u << j);
+            const uint32_t k = __float_as_uint(ld_f4(tt + (size_t)(tg_x + (uint32_t)j) * 3).w);  // TriRecord::prim
+            TriHit h;
+            const uint32_t ti = instance_test<ANY_HIT>(a, k, ro, rd, T.tmax, &h);
+            if (ti == B200PT_MISS) continue;
+            best = ti;
+            *inst = k;
+            *hit = h;
+            T.tmax = h.t;
+            if (ANY_HIT) {
+                *tmax = T.tmax;
+                return best;
+            }
+        }
+    } while (trav_next_group(T, S));
+    *tmax = T.tmax;
+    return best;
+}
+
 // ---------------------------------------------------------------------- spheres
 // Scene::Intersect / IntersectP for the Sphere shapes (not part of the BVH): one thread per ray of the
 // traversal launch that just finished.
@@ -297,21 +361,11 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                         }
                     }
                 }
-                if (!a.occ_out[slot]) {
-                    for (uint32_t k = 0; k < a.n_instances; ++k) {  // TransformedPrimitive::IntersectP
-                        const DevInstance &in = a.instances[k];
-                        if (!instance_leaf_test(in, ro, rd, tmax)) continue;
-                        V3 o2, d2;
-                        float tm2;
-                        instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
-                        TriHit h;
-                        TraceCounters ctr;
-                        if (traverse_bvh8<true, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3, o2, d2, tm2,
-                                                       &h, &ctr) != B200PT_MISS) {
-                            a.occ_out[slot] = 1;
-                            break;
-                        }
-                    }
+                if (!a.occ_out[slot] && a.n_instances) {
+                    TriHit h;
+                    uint32_t inst = 0;
+                    float tm = tmax;
+                    if (instances_test<true>(a, ro, rd, &tm, &h, &inst) != B200PT_MISS) a.occ_out[slot] = 1;
                 }
             } else {
                 uint32_t best = B200PT_MISS;
@@ -345,28 +399,22 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
                         a.full_out[slot] = r;
                     }
                 }
-                for (uint32_t k = 0; k < a.n_instances; ++k) {  // TransformedPrimitive::Intersect, primitive.cpp:76-98
-                    const DevInstance &in = a.instances[k];
-                    if (!instance_leaf_test(in, ro, rd, tmax)) continue;
-                    V3 o2, d2;
-                    float tm2;
-                    instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
+                if (a.n_instances) {
                     TriHit h;
-                    TraceCounters ctr;
-                    const uint32_t ti = traverse_bvh8<false, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3,
-                                                                    o2, d2, tm2, &h, &ctr);
-                    if (ti == B200PT_MISS) continue;
-                    tmax = h.t;  // r.tMax = ray.tMax
-                    best = in.tri_off + ti;
-                    if (a.hit_out) a.hit_out[slot] = best;
-                    if (a.hit_inst_out) a.hit_inst_out[slot] = k;
-                    if (a.full_out) {
-                        b200pt_hit r;
-                        r.triangle = (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w);
-                        r.t = h.t;
-                        r.b0 = h.b0;
-                        r.b1 = h.b1;
-                        a.full_out[slot] = r;
+                    uint32_t inst = 0;
+                    const uint32_t ti = instances_test<false>(a, ro, rd, &tmax, &h, &inst);
+                    if (ti != B200PT_MISS) {
+                        best = ti;
+                        if (a.hit_out) a.hit_out[slot] = best;
+                        if (a.hit_inst_out) a.hit_inst_out[slot] = inst;
+                        if (a.full_out) {
+                            b200pt_hit r;
+                            r.triangle = (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w);
+                            r.t = h.t;
+                            r.b0 = h.b0;
+                            r.b1 = h.b1;
+                            a.full_out[slot] = r;
+                        }
                     }
                 }
                 if (CLASSIFY && best != B200PT_MISS) {

@@ -37,6 +37,7 @@ struct DevScene {
     uint32_t n_spheres;
     const DevInstance *instances;  // object instances, tested by the same pass; their BVHs follow the top-level one
     uint32_t n_instances;
+    uint32_t tlas_node_off, tlas_tri_off;  // 8-wide tree over the instances' leaf boxes (its "triangles" name instances), 0 = none
 };
 
 // queue ids inside one bounce's counter block
@@ -140,6 +141,7 @@ struct TraceArgs {
     uint32_t *sphere_work;      // persistent fetch counter of the sphere pass (zeroed)
     const DevInstance *instances;
     uint32_t n_instances;
+    uint32_t tlas_node_off, tlas_tri_off;  // see DevScene
     uint32_t *hit_inst_out;     // instance of an object-triangle hit (closest, render path)
 };
 

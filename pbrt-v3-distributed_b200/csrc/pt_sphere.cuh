@@ -450,6 +450,7 @@ struct DevInstance {
     float w2i[16], i2w[16];        // WorldToInstance->m, InstanceToWorld->m
     int is_identity;               // InstanceToWorld.IsIdentity(): the hit stays as it is (primitive.cpp:93-94)
     float leaf_lo[3], leaf_hi[3];  // bounds of the host accelerator's leaf holding the instance
+    float world_lo[3], world_hi[3];  // TransformedPrimitive::WorldBound()
     uint32_t node_off, tri_off;    // the object's BVH inside the scene's node / triangle arrays
 };
 // Transform::operator()(const Ray &) with WorldToInstance (transform.h:251-264): origin pushed to the edge of its

@@ -228,7 +228,10 @@ def test_trace_instances_vs_oracle(pkg, abi, scenes, ob, ctx):
     instances = (dict(object=0, center=(0.0, 0.0, -0.4)), dict(object=0, center=(0.9, 0.6, 0.2), scale=(0.7, 1.4, 1.0)),
                  dict(object=1, center=(-0.8, -0.5, 0.0), scale=(1.0, 1.0, -1.3)), dict(object=1),
                  dict(object=0, center=(-0.9, 0.7, 0.4), scale=(1.5, 1.5, 1.5)))
-    for n_tris in (0, 3000):
+    # 5 instances are tested one by one; 40 go through the tree over their leaf boxes
+    lattice = tuple(dict(object=k % 2, center=(-0.9 + 0.45 * (k % 5), -0.7 + 0.45 * ((k // 5) % 4), -0.5 + 0.9 * (k // 20)),
+                         scale=(0.5, 0.5, -0.5 if k % 3 == 0 else 0.5)) for k in range(40))
+    for n_tris, instances in ((0, instances), (3000, instances), (3000, lattice)):
         arr = scenes.SceneArrays(n_tris, materials=("matte",), soup_version=1, seed=21, n_lights=0, objects=objects,
                                  instances=instances)
         scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
