@@ -21,9 +21,12 @@ pkg = graft.load_package()
 from pbrt_v3_distributed_b200 import scenes  # noqa: E402
 
 n_tris, mats, xres, yres, spp, depth, n_lights, _ = bench.WORKLOADS[name]
-arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights)
-setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth)
+arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **bench.workload_scene_kwargs(name))
+# PROFILE_PIXEL_FILTER=gaussian profiles the general film path, PROFILE_BVH=gpu the on-device builder
+setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=os.environ.get("PROFILE_PIXEL_FILTER"))
 ctx = pkg.Context(0)
+if os.environ.get("PROFILE_BVH") == "gpu":
+    ctx.set_option("gpu_bvh_build", 1)
 scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
 r = pkg.Render(scene, setup)
 per_batch = max(1, int(os.environ.get('B200PT_BATCH_PATHS', 16 << 20)) // (256 * spp))
