@@ -305,33 +305,63 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
         }
         return best;
     }
+    // Step-synchronous two-level traversal.  Each lane is a small state machine over its own ray -- walking the tree
+    // over the instances' boxes, picking the next candidate instance, or taking ONE step inside that instance's tree --
+    // so that the lanes of a warp meet again after every step instead of after whole nested traversals (measured with
+    // the nested loops: 2.4 of 32 lanes active per instruction).
     const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 5;
     const F4 *tt = a.tris + (size_t)a.tlas_tri_off * 3;
-    Trav T;
-    TravStack S;
+    Trav T1, T2;
+    TravStack S1, S2;
     TraceCounters ctr;
-    trav_init(T, ro, rd, *tmax);
-    do {
-        uint32_t tg_x = 0, tg_y = 0;
-        if (T.cur_y & 0xff000000u) trav_node_phase<false>(T, S, tn, &tg_x, &tg_y, &ctr);
-        while (tg_y) {
-            const int j = msb32(tg_y);
-            tg_y &= ~(1u << j);
-            const uint32_t k = __float_as_uint(ld_f4(tt + (size_t)(tg_x + (uint32_t)j) * 3).w);  // TriRecord::prim
-            TriHit h;
-            const uint32_t ti = instance_test<ANY_HIT>(a, k, ro, rd, T.tmax, &h);
-            if (ti == B200PT_MISS) continue;
-            best = ti;
-            *inst = k;
-            *hit = h;
-            T.tmax = h.t;
-            if (ANY_HIT) {
-                *tmax = T.tmax;
-                return best;
+    trav_init(T1, ro, rd, *tmax);
+    trav_init(T2, ro, rd, *tmax);
+    uint32_t pend_x = 0, pend_y = 0, cur_inst = 0, cur_tri_off = 0;
+    const U4 *bn = tn;
+    const F4 *bt = tt;
+    int state = 0;  // 0: instance tree, 1: next candidate, 2: inside an instance
+    while (true) {
+        if (state == 2) {
+            if (trav_step<ANY_HIT, false>(T2, S2, bn, bt, &ctr)) {
+                if (T2.best != B200PT_MISS) {
+                    best = cur_tri_off + T2.best;
+                    *inst = cur_inst;
+                    *hit = T2.hit;
+                    T1.tmax = T2.hit.t;  // r.tMax = ray.tMax
+                    if (ANY_HIT) break;
+                }
+                state = 1;
+            }
+        } else if (state == 1) {
+            if (pend_y) {
+                const int j = msb32(pend_y);
+                pend_y &= ~(1u << j);
+                const uint32_t k = __float_as_uint(ld_f4(tt + (size_t)(pend_x + (uint32_t)j) * 3).w);  // TriRecord::prim
+                const DevInstance &in = a.instances[k];
+                if (instance_leaf_test(in, ro, rd, T1.tmax)) {
+                    V3 o2, d2;
+                    float tm2;
+                    instance_ray(in, ro, rd, T1.tmax, &o2, &d2, &tm2);
+                    trav_init(T2, o2, d2, tm2);
+                    bn = a.nodes + (size_t)in.node_off * 5;
+                    bt = a.tris + (size_t)in.tri_off * 3;
+                    cur_inst = k;
+                    cur_tri_off = in.tri_off;
+                    state = 2;
+                }
+            } else {
+                state = 0;
+            }
+        } else {
+            if (T1.cur_y & 0xff000000u) {
+                trav_node_phase<false>(T1, S1, tn, &pend_x, &pend_y, &ctr);
+                state = 1;
+            } else if (!trav_next_group(T1, S1)) {
+                break;
             }
         }
-    } while (trav_next_group(T, S));
-    *tmax = T.tmax;
+    }
+    *tmax = T1.tmax;
     return best;
 }
 
