@@ -53,7 +53,8 @@ typedef enum b200pt_material_type {
     B200PT_MAT_METAL = 2,   /* MicrofacetReflection(1,TR(ax,ay),FrConductor(1,eta,k))   metal.cpp:59-80 */
     B200PT_MAT_GLASS = 3,   /* FresnelSpecular(R,T,1,index) (smooth, glass.cpp:62-64) or, variant 1, rough glass:
                                MicrofacetReflection(R,TR,FrDielectric(1,index)) + MicrofacetTransmission(T,TR,1,index)
-                               glass.cpp:65-90 */
+                               glass.cpp:65-90; variant 2 is MirrorMaterial (materials/mirror.cpp:45-56), which shares the
+                               specular family: SpecularReflection(ks, FresnelNoOp), BSDF eta 1 */
     B200PT_MAT_NONE = 4     /* null material: GetMaterial()==nullptr is NOT supported; reserved */
 } b200pt_material_type;
 
@@ -71,7 +72,7 @@ typedef struct b200pt_material {
     float alpha_x;       /* TR alpha (plastic: ax==ay); matte variant 1: OrenNayar A (reflection.h:416-419) */
     float alpha_y;       /*                               matte variant 1: OrenNayar B                      */
     float index;         /* glass index of refraction (BSDF::eta)     */
-    int32_t variant;     /* 0 = default lobe set, 1 = see the material types above */
+    int32_t variant;     /* 0 = default lobe set, 1 / 2 = see the material types above */
 } b200pt_material;
 
 /* ---- lights: one DiffuseAreaLight per emissive triangle (api.cpp:1357-1364,

@@ -1241,7 +1241,7 @@ inline V3 OffsetRayOrigin(const V3 &p, const V3 &pError, const V3 &n, const V3 &
 
 // ------------------------------------------------------------------- BSDFs
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
-enum BxKind { BX_LAMBERT, BX_MICROFACET, BX_FRESNEL_SPECULAR, BX_OREN_NAYAR, BX_MICROFACET_TRANS };
+enum BxKind { BX_LAMBERT, BX_MICROFACET, BX_FRESNEL_SPECULAR, BX_OREN_NAYAR, BX_MICROFACET_TRANS, BX_SPECULAR_REFLECTION };
 enum FrKind { FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDF {
@@ -1429,7 +1429,8 @@ S3 Bx_f(const BxDF &b, const V3 &wo, const V3 &wi) {
         return b.R * TR_D(b, wh) * TR_G(b, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
     case BX_FRESNEL_SPECULAR:
-        return S3(0.f);  // reflection.h:363-365
+    case BX_SPECULAR_REFLECTION:
+        return S3(0.f);  // reflection.h:363-365, :312-314
     case BX_OREN_NAYAR: {  // reflection.cpp:197-219
         float sinThetaI = SinTheta(wi);
         float sinThetaO = SinTheta(wo);
@@ -1479,7 +1480,8 @@ float Bx_Pdf(const BxDF &b, const V3 &wo, const V3 &wi) {
         return TR_Pdf(b, wo, wh) / (4 * Dot(wo, wh));
     }
     case BX_FRESNEL_SPECULAR:
-        return 0;  // reflection.h:368
+    case BX_SPECULAR_REFLECTION:
+        return 0;  // reflection.h:368, :317
     case BX_OREN_NAYAR:
         return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * InvPi : 0;  // BxDF::Pdf, reflection.cpp:387-389
     case BX_MICROFACET_TRANS: {                                       // reflection.cpp:436-448
@@ -1519,6 +1521,11 @@ S3 Bx_Sample_f(const BxDF &b, const V3 &wo, V3 *wi, const float u[2], float *pdf
         if (!SameHemisphere(wo, *wi)) return S3(0.f);
         *pdf = TR_Pdf(b, wo, wh) / (4 * Dot(wo, wh));
         return Bx_f(b, wo, *wi);
+    }
+    case BX_SPECULAR_REFLECTION: {  // reflection.cpp:136-143 with FresnelNoOp (reflection.h:297-301)
+        *wi = V3(-wo.x, -wo.y, wo.z);
+        *pdf = 1;
+        return S3(1.f) * b.R / AbsCosTheta(*wi);
     }
     case BX_FRESNEL_SPECULAR: {  // reflection.cpp:477-511 (TransportMode::Radiance)
         float F = FrDielectric(CosTheta(wo), b.etaA, b.etaB);
@@ -1693,6 +1700,17 @@ void MakeBSDF(const oracle_scene &s, const Isect &is, BSDF *bsdf) {
         break;
     }
     case B200PT_MAT_GLASS: {  // glass.cpp:45-64 (smooth + allowMultipleLobes)
+        if (m.variant == 2) {  // MirrorMaterial, materials/mirror.cpp:45-56: SpecularReflection(R, FresnelNoOp), eta = 1
+            S3 R = SP(m.ks);
+            if (!R.IsBlack()) {
+                BxDF b;
+                b.kind = BX_SPECULAR_REFLECTION;
+                b.type = BSDF_REFLECTION | BSDF_SPECULAR;
+                b.R = R;
+                bsdf->bxdfs[bsdf->nBxDFs++] = b;
+            }
+            break;
+        }
         bsdf->eta = m.index;
         S3 R = SP(m.ks), T = SP(m.kt);
         if (R.IsBlack() && T.IsBlack()) break;

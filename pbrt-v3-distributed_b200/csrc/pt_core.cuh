@@ -745,7 +745,8 @@ B200_HD V3 cosine_sample_hemisphere(const float u[2]) {
 
 // One BxDF lobe.  kind: 0 Lambertian, 1 MicrofacetReflection (TR), 2 FresnelSpecular, 3 OrenNayar,
 // 4 MicrofacetTransmission (TR)
-enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR = 3, BX_MICROFACET_TRANS = 4 };
+enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR = 3, BX_MICROFACET_TRANS = 4,
+       BX_SPECULAR_REFLECTION = 5 };
 struct Lobe {
     int kind, type;
     RGB R, T;
@@ -850,6 +851,11 @@ B200_HD RGB lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2],
         if (!same_hemisphere(wo, *wi)) return rgb1(0.f);
         *pdf = tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
         return lobe_f(l, wo, *wi);
+    }
+    if (l.kind == BX_SPECULAR_REFLECTION) {  // reflection.cpp:136-143 with FresnelNoOp (mirror.cpp:45-56)
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *pdf = 1.f;
+        return rgb1(1.f) * l.R / abs_cos_theta(*wi);
     }
     // FresnelSpecular::Sample_f, reflection.cpp:477-511 (TransportMode::Radiance)
     float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
@@ -1011,6 +1017,14 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
         l.conductor = 1;
         l.cEta = rgbp(m.eta);
         l.cK = rgbp(m.k);
+    } else if (type == B200PT_MAT_GLASS && m.variant == 2) {  // MirrorMaterial, mirror.cpp:45-56 (BSDF eta stays 1)
+        const RGB R = rgbp(m.ks);
+        if (!is_black(R)) {
+            Lobe &l = b->lobes[b->n++];
+            l.kind = BX_SPECULAR_REFLECTION;
+            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
+            l.R = R;
+        }
     } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
         b->eta = m.index;
         RGB R = rgbp(m.ks), T = rgbp(m.kt);

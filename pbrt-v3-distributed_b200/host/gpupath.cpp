@@ -69,6 +69,7 @@
 #include "materials/glass.h"
 #include "materials/matte.h"
 #include "materials/metal.h"
+#include "materials/mirror.h"
 #include "materials/plastic.h"
 #include "samplers/halton.h"
 #include "samplers/sobol.h"
@@ -203,7 +204,16 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
         }
         return true;
     }
-    *why = "a material other than matte / plastic / metal / glass";
+    if (auto mr = dynamic_cast<const MirrorMaterial *>(m)) {
+        if (mr->bumpMap) return *why = "bump maps", false;
+        if (!ConstantValue(mr->Kr, &sv)) return *why = "non-constant textures", false;
+        out->type = B200PT_MAT_GLASS;  // the specular family; variant 2 = SpecularReflection(Kr, FresnelNoOp), mirror.cpp:45-56
+        out->variant = 2;
+        ToRGB(sv.Clamp(), out->ks);
+        out->index = 1.f;
+        return true;
+    }
+    *why = "a material other than matte / plastic / metal / glass / mirror";
     return false;
 }
 

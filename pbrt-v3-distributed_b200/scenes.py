@@ -92,6 +92,11 @@ def default_materials(which):
         elif w == "black":
             m.type = abi.MAT_MATTE
             m.kd[:] = [0, 0, 0]
+        elif w == "mirror":  # MirrorMaterial, Kr 0.9 (mirror.cpp:58-64): the specular family's variant 2
+            m.type = abi.MAT_GLASS
+            m.ks[:] = [0.9, 0.9, 0.9]
+            m.index = 1.0
+            m.variant = 2
         elif w == "glass":
             m.type = abi.MAT_GLASS
             m.ks[:] = [1, 1, 1]
@@ -121,6 +126,7 @@ PBRT_MATERIAL = {
     "matte": 'Material "matte" "rgb Kd" [0.5 0.5 0.5]',
     "black": 'Material "matte" "rgb Kd" [0 0 0]',
     "glass": 'Material "glass"',
+    "mirror": 'Material "mirror"',
     "matte_rough": 'Material "matte" "rgb Kd" [0.5 0.5 0.5] "float sigma" [30]',
     "glass_rough": 'Material "glass" "float uroughness" [0.2] "float vroughness" [0.1]',
     "metal": 'Material "metal"',

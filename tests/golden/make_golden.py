@@ -54,6 +54,8 @@ RENDERS = {
     "sphere_partial": (3000, ("matte", "plastic"), 48, 40, 8, 5, "spatial", 4),
     # object instancing (TransformedPrimitive): two objects, five instances (one at the identity, one mirrored)
     "instances": (2000, ("matte", "glass", "metal", "plastic"), 48, 40, 8, 6, "spatial", None),
+    # MirrorMaterial (SpecularReflection + FresnelNoOp) next to glass: long specular chains
+    "mirror": (3000, ("matte", "mirror", "glass", "plastic"), 40, 32, 8, 8, "spatial", None),
     # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
     # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
     "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
