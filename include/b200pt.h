@@ -75,14 +75,24 @@ typedef struct b200pt_material {
     int32_t variant;     /* 0 = default lobe set, 1 / 2 = see the material types above */
 } b200pt_material;
 
-/* ---- lights: one DiffuseAreaLight per emissive triangle (api.cpp:1357-1364,
- * lights/diffuse.cpp:42-87).  Order == Scene::lights order. --------------- */
+/* ---- lights.  Order == Scene::lights order (it decides lightNum).  kind 0: one
+ * DiffuseAreaLight per emissive triangle or sphere (api.cpp:1357-1364,
+ * lights/diffuse.cpp:42-87).  kinds 1-3: the delta lights PointLight
+ * (lights/point.cpp:43-56), SpotLight (lights/spot.cpp:42-76) and DistantLight
+ * (lights/distant.cpp:43-66): no geometry, no BSDF-sampling branch in
+ * EstimateDirect (integrator.cpp:166). */
+enum { B200PT_LIGHT_AREA = 0, B200PT_LIGHT_POINT = 1, B200PT_LIGHT_SPOT = 2, B200PT_LIGHT_DISTANT = 3 };
 typedef struct b200pt_area_light {
-    int32_t triangle;    /* index into the triangle arrays              */
-    float lemit[3];      /* Lemit (already multiplied by "scale")       */
-    int32_t two_sided;   /* "twosided" parameter                        */
-    int32_t sphere;      /* -1, or index into spheres[]: the light's shape is that sphere and
-                            `triangle` is ignored                       */
+    int32_t triangle;    /* area light: index into the triangle arrays                */
+    float lemit[3];      /* area: Lemit; point / spot: I; distant: L (all already multiplied by "scale") */
+    int32_t two_sided;   /* area: "twosided" parameter                                */
+    int32_t sphere;      /* area: -1, or index into spheres[]: the light's shape is that sphere and
+                            `triangle` is ignored                                      */
+    int32_t kind;        /* B200PT_LIGHT_*                                             */
+    float position[3];   /* point / spot: pLight; distant: wLight (normalised, towards the light) */
+    float cos_total_width, cos_falloff_start;  /* spot (spot.cpp:50-51)                */
+    float world_to_light[16];                  /* spot: Light::WorldToLight.m           */
+    float world_radius;  /* distant: DistantLight::worldRadius (distant.h:54-58); 0 = computed from the scene bounds */
 } b200pt_area_light;
 
 /* ---- spheres: Sphere shapes (shapes/sphere.cpp:49-306), full or clipped by
@@ -372,6 +382,9 @@ int b200pt_host_perspective_camera(const float eye[3], const float look[3], cons
 float b200pt_host_roughness_to_alpha(float roughness);
 /* OrenNayar's A and B from sigma in degrees (reflection.h:414-420), clamped like matte.cpp:54 */
 void b200pt_host_oren_nayar(float sigma_degrees, float *A, float *B);
+/* CreateSpotLight (spot.cpp:104-124) at the identity CTM: fills kind, position, the cone cosines and world_to_light. */
+void b200pt_host_spot_light(const float from[3], const float to[3], float coneangle, float conedelta,
+                            b200pt_area_light *out);
 /* Sphere constructor (sphere.h:49-61): out = {zMin, zMax, thetaMin, thetaMax, phiMax}. */
 void b200pt_host_sphere_params(float radius, float zmin, float zmax, float phimax_degrees, float out[5]);
 

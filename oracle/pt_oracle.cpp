@@ -1866,6 +1866,51 @@ inline float SpherePdf(const b200pt_sphere &sp, const V3 &refP, const V3 &refPEr
     return 1 / (2 * Pi * (1 - cosThetaMax));  // UniformConePdf, sampling.cpp:108-110
 }
 
+// ---- delta lights: PointLight (point.cpp:43-56), SpotLight (spot.cpp:53-76), DistantLight (distant.cpp:49-60).
+// Sample_Li: *wi, pdf = 1, the point the VisibilityTester aims at (an Interaction without normal or error bounds).
+inline float DistantWorldRadius(const oracle_scene &s, const b200pt_area_light &l) {
+    if (l.world_radius != 0.f) return l.world_radius;
+    // Bounds3::BoundingSphere (geometry.h:808-811) of Scene::WorldBound(), DistantLight::Preprocess (distant.h:54-58)
+    V3 pMin(s.wbMin[0], s.wbMin[1], s.wbMin[2]), pMax(s.wbMax[0], s.wbMax[1], s.wbMax[2]);
+    V3 sum = pMin + pMax;
+    float inv = (float)1 / 2;
+    V3 c(inv * sum.x, inv * sum.y, inv * sum.z);
+    bool inside = c.x >= pMin.x && c.x <= pMax.x && c.y >= pMin.y && c.y <= pMax.y && c.z >= pMin.z && c.z <= pMax.z;
+    return inside ? Length(c - pMax) : 0;
+}
+inline S3 DeltaLightSample(const oracle_scene &s, const b200pt_area_light &l, const V3 &refP, V3 *wi, float *pdf, V3 *pTarget) {
+    *pdf = 1.f;
+    V3 pos(l.position[0], l.position[1], l.position[2]);
+    if (l.kind == B200PT_LIGHT_DISTANT) {
+        *wi = pos;  // wLight
+        *pTarget = refP + pos * (2 * DistantWorldRadius(s, l));
+        return SP(l.lemit);
+    }
+    *wi = Normalize(pos - refP);
+    *pTarget = pos;
+    float d2 = LengthSquared(pos - refP);  // DistanceSquared(pLight, ref.p)
+    if (l.kind == B200PT_LIGHT_POINT) return SP(l.lemit) / d2;
+    // SpotLight::Falloff(-wi), spot.cpp:64-74
+    V3 wl = Normalize(XformVector(l.world_to_light, -*wi));
+    float cosTheta = wl.z, falloff;
+    if (cosTheta < l.cos_total_width)
+        falloff = 0;
+    else if (cosTheta >= l.cos_falloff_start)
+        falloff = 1;
+    else {
+        float delta = (cosTheta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
+        falloff = (delta * delta) * (delta * delta);
+    }
+    return SP(l.lemit) * falloff / d2;
+}
+// Light::Power().y(): point.cpp:58, spot.cpp:78-80, distant.cpp:62-64
+inline S3 DeltaLightPower(const oracle_scene &s, const b200pt_area_light &l) {
+    if (l.kind == B200PT_LIGHT_POINT) return 4 * Pi * SP(l.lemit);
+    if (l.kind == B200PT_LIGHT_SPOT) return SP(l.lemit) * 2 * Pi * (1 - .5f * (l.cos_falloff_start + l.cos_total_width));
+    float r = DistantWorldRadius(s, l);
+    return SP(l.lemit) * Pi * r * r;
+}
+
 struct RenderCtx {
     const oracle_scene *s;
     const b200pt_camera_desc *cam;
@@ -1940,6 +1985,12 @@ void ComputeVoxelDistribution(const oracle_scene &s, const int nVoxels[3], const
             const b200pt_area_light &light = s.lights[j];
             float pdf;
             LightSample ps;
+            if (light.kind != B200PT_LIGHT_AREA) {
+                V3 wiD, pT;
+                S3 LiD = DeltaLightSample(s, light, po, &wiD, &pdf, &pT);
+                if (pdf > 0) lightContrib[j] += LiD.y() / pdf;
+                continue;
+            }
             if (light.sphere >= 0)  // Interaction(po, Normal3f(), Vector3f(), ...): no normal, no error
                 ps = SphereSample(s.spheres[light.sphere], po, V3(0, 0, 0), V3(0, 0, 0), u, &pdf);
             else
@@ -2001,6 +2052,23 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
     S3 Ld(0.f);
     V3 wi;
     float lightPdf = 0, scatteringPdf = 0;
+    if (light.kind != B200PT_LIGHT_AREA) {
+        // delta light: no MIS, no BSDF-sampling branch (integrator.cpp:147-148, :166)
+        V3 pTarget;
+        S3 Li = DeltaLightSample(s, light, it.p, &wi, &lightPdf, &pTarget);
+        if (lightPdf > 0 && !Li.IsBlack()) {
+            S3 f = bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
+            if (!f.IsBlack()) {
+                // SpawnRayTo(Interaction) with a target that has neither normal nor error bounds: target = its p
+                V3 origin = OffsetRayOrigin(it.p, it.pError, it.n, pTarget - it.p);
+                V3 d = pTarget - origin;
+                ++rc.shadowRays;
+                if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
+                if (!Li.IsBlack()) Ld += f * Li / lightPdf;
+            }
+        }
+        return Ld;
+    }
     // light.Sample_Li: lights/diffuse.cpp:68-81, shape.cpp:56-70
     S3 Li(0.f);
     LightSample pShape;
@@ -2213,7 +2281,7 @@ void InitLightDistribution(RenderCtx &rc) {
         // integrator.cpp:216-224 + diffuse.cpp:64-66
         for (int i = 0; i < n; ++i) {
             const b200pt_area_light &l = s.lights[i];
-            S3 power = (l.two_sided ? 2 : 1) * SP(l.lemit) * s.lightArea[i] * Pi;
+            S3 power = l.kind != B200PT_LIGHT_AREA ? DeltaLightPower(s, l) : (l.two_sided ? 2 : 1) * SP(l.lemit) * s.lightArea[i] * Pi;
             prob[i] = power.y();
         }
     }
@@ -2340,7 +2408,7 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
     s->lightArea.resize(d->n_lights);
     if (d->n_spheres > 0) s->spheres.assign(d->spheres, d->spheres + d->n_spheres);
     for (int i = 0; i < d->n_lights; ++i)
-        s->lightArea[i] = s->lights[i].sphere >= 0 ? SphereConsts(s->spheres[s->lights[i].sphere]).Area()
+        s->lightArea[i] = s->lights[i].kind != B200PT_LIGHT_AREA ? 0.f : s->lights[i].sphere >= 0 ? SphereConsts(s->spheres[s->lights[i].sphere]).Area()
                                                    : TriangleArea(*s, s->lights[i].triangle);
     for (int a = 0; a < 3; ++a) {
         s->wbMin[a] = Infinity;

@@ -63,6 +63,7 @@ _SIGNATURES = {
                                                  C.POINTER(abi.CameraDesc)]),
     "b200pt_host_roughness_to_alpha": (C.c_float, [C.c_float]),
     "b200pt_host_oren_nayar": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "b200pt_host_spot_light": (None, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, _vp]),
     "b200pt_host_sphere_params": (None, [C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
@@ -102,6 +103,13 @@ def host_perspective_camera(eye, look, up, fov, xres, yres):
 
 def host_roughness_to_alpha(r):
     return float(lib.b200pt_host_roughness_to_alpha(r))
+
+
+def host_spot_light(light, from_, to, coneangle, conedelta):
+    """Fills the spot-light fields of an abi.AreaLight like CreateSpotLight does."""
+    f = (C.c_float * 3)(*from_)
+    t = (C.c_float * 3)(*to)
+    lib.b200pt_host_spot_light(f, t, coneangle, conedelta, C.byref(light))
 
 
 def host_sphere_params(radius, zmin, zmax, phimax_degrees):

@@ -19,7 +19,9 @@ class Material(C.Structure):
 
 class AreaLight(C.Structure):
     _fields_ = [("triangle", C.c_int32), ("lemit", C.c_float * 3), ("two_sided", C.c_int32),
-                ("sphere", C.c_int32)]
+                ("sphere", C.c_int32), ("kind", C.c_int32), ("position", C.c_float * 3),
+                ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float), ("world_to_light", C.c_float * 16),
+                ("world_radius", C.c_float)]
 
 
 class Sphere(C.Structure):
@@ -59,6 +61,7 @@ class FilmDesc(C.Structure):
 
 
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
+LIGHT_AREA, LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 
 
 class SamplerDesc(C.Structure):

@@ -167,6 +167,10 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             return b200pt_fail(B200PT_ERR_INVALID, "scene_create: sphere %d has a bad radius, material or light", i);
     }
     for (int i = 0; i < d->n_lights; ++i) {
+        const int kind = d->lights[i].kind;
+        if (kind < B200PT_LIGHT_AREA || kind > B200PT_LIGHT_DISTANT)
+            return b200pt_fail(B200PT_ERR_INVALID, "scene_create: light %d has unknown kind %d", i, kind);
+        if (kind != B200PT_LIGHT_AREA) continue;  // delta lights have no geometry
         const int sph = d->lights[i].sphere;
         if (sph >= 0) {
             if (sph >= d->n_spheres || d->spheres[sph].light_id != i)
@@ -451,6 +455,10 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         }
     s->light_area.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
+        if (d->lights[i].kind != B200PT_LIGHT_AREA) {
+            s->light_area[i] = 0.f;
+            continue;
+        }
         if (d->lights[i].sphere >= 0) {
             s->light_area[i] = s->spheres[d->lights[i].sphere].area;
             continue;
@@ -801,11 +809,45 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     const int nl = (int)scene->lights.size();
     std::vector<DevLight> dl(nl);
     std::vector<float> func(std::max(nl, 1), 1.f), cdf(nl + 1, 0.f);
+    // DistantLight::Preprocess (distant.h:54-58): Bounds3::BoundingSphere of Scene::WorldBound() (geometry.h:808-811)
+    float world_radius = 0.f;
+    {
+        const float *lo = scene->bounds_lo, *hi = scene->bounds_hi;
+        const float inv = 1.f / 2;
+        const V3 c = mk(inv * (lo[0] + hi[0]), inv * (lo[1] + hi[1]), inv * (lo[2] + hi[2]));
+        const bool inside = c.x >= lo[0] && c.x <= hi[0] && c.y >= lo[1] && c.y <= hi[1] && c.z >= lo[2] && c.z <= hi[2];
+        world_radius = inside ? len(c - mk(hi[0], hi[1], hi[2])) : 0.f;
+    }
+    bool has_delta = false;
     for (int i = 0; i < nl; ++i) {
-        dl[i].tri = scene->lights[i].sphere >= 0 ? (SPHERE_HIT_BASE | (uint32_t)scene->lights[i].sphere)
-                                                 : scene->prim_to_tri[scene->lights[i].triangle];
-        memcpy(dl[i].lemit, scene->lights[i].lemit, sizeof(float) * 3);
-        dl[i].two_sided = scene->lights[i].two_sided;
+        const b200pt_area_light &sl = scene->lights[i];
+        memset(&dl[i], 0, sizeof(DevLight));
+        memcpy(dl[i].lemit, sl.lemit, sizeof(float) * 3);
+        dl[i].kind = sl.kind;
+        if (sl.kind != B200PT_LIGHT_AREA) {
+            has_delta = true;
+            dl[i].tri = B200PT_MISS;
+            memcpy(dl[i].position, sl.position, sizeof(float) * 3);
+            dl[i].cos_total_width = sl.cos_total_width;
+            dl[i].cos_falloff_start = sl.cos_falloff_start;
+            memcpy(dl[i].world_to_light, sl.world_to_light, sizeof(float) * 16);
+            const float wr = sl.world_radius != 0.f ? sl.world_radius : world_radius;
+            dl[i].two_world_radius = 2 * wr;
+            if (integ->light_strategy == B200PT_LIGHTS_POWER && nl != 1) {
+                // Light::Power().y(): point.cpp:58, spot.cpp:78-80, distant.cpp:62-64
+                RGB p;
+                if (sl.kind == B200PT_LIGHT_POINT)
+                    p = 4 * PT_PI * rgbp(sl.lemit);
+                else if (sl.kind == B200PT_LIGHT_SPOT)
+                    p = rgbp(sl.lemit) * 2 * PT_PI * (1 - .5f * (sl.cos_falloff_start + sl.cos_total_width));
+                else
+                    p = rgbp(sl.lemit) * PT_PI * wr * wr;
+                func[i] = lum(p);
+            }
+            continue;
+        }
+        dl[i].tri = sl.sphere >= 0 ? (SPHERE_HIT_BASE | (uint32_t)sl.sphere) : scene->prim_to_tri[sl.triangle];
+        dl[i].two_sided = sl.two_sided;
         dl[i].area = scene->light_area[i];
         if (integ->light_strategy == B200PT_LIGHTS_POWER && nl != 1) {
             // DiffuseAreaLight::Power().y(), diffuse.cpp:64-66 + integrator.cpp:216-224
@@ -934,6 +976,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.sampler.mat32 = mat32;
     H.sampler.table = getenv("B200PT_NO_SOBOL_TABLE") ? nullptr : sobol_table;
     H.lights = d_lights;
+    H.has_delta_lights = has_delta ? 1 : 0;
     H.light_cdf = d_cdf;
     H.light_func = d_func;
     cudaStream_t st = ctx->stream;
@@ -1102,6 +1145,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         const bool overlap = r->overlap && r->sort_from_bounce < 0;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
         const bool has_spheres = H.scene.n_spheres > 0 || H.scene.n_instances > 0;  // "extra shapes" pass needed
+        const bool full_shade = has_spheres || H.has_delta_lights || H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr;
         auto sphere_args = [&](TraceArgs &a, uint32_t *work) {
             a.spheres = H.scene.spheres;
             a.n_spheres = H.scene.n_spheres;
@@ -1208,7 +1252,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
-                    launch_shade(r->d_dev, m, H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr || has_spheres, b, wk + 1 + m,
+                    launch_shade(r->d_dev, m, full_shade, b, wk + 1 + m,
                                  r->grid_shade, st);
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)

@@ -239,3 +239,28 @@ extern "C" void b200pt_host_sphere_params(float radius, float zmin, float zmax, 
     out[3] = pt_acosf(pt_clamp(pt_max(zmin, zmax) / radius, -1.f, 1.f));
     out[4] = (PT_PI / 180) * pt_clamp(phimax_degrees, 0.f, 360.f);
 }
+
+// CreateSpotLight (lights/spot.cpp:104-124) at the identity CTM + SpotLight ctor (:42-51).
+// light2world = Translate(from) * Inverse(dirToZ), so WorldToLight.m = dirToZ.m * Translate(-from).m
+// (Transform::operator*, transform.cpp:222-225: no Gauss-Jordan inverse is involved on this side) and
+// pLight = LightToWorld(0,0,0) = from.
+extern "C" void b200pt_host_spot_light(const float from[3], const float to[3], float coneangle, float conedelta,
+                                       b200pt_area_light *out) {
+    using namespace b200pt;
+    const V3 dir = normalize(mk(to[0] - from[0], to[1] - from[1], to[2] - from[2]));
+    V3 du, dv;
+    coordinate_system(dir, &du, &dv);
+    const float dz[16] = {du.x, du.y, du.z, 0.f, dv.x, dv.y, dv.z, 0.f, dir.x, dir.y, dir.z, 0.f, 0.f, 0.f, 0.f, 1.f};
+    const float ti[16] = {1.f, 0.f, 0.f, -from[0], 0.f, 1.f, 0.f, -from[1], 0.f, 0.f, 1.f, -from[2], 0.f, 0.f, 0.f, 1.f};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)  // Matrix4x4::Mul, transform.cpp:98-106
+            out->world_to_light[4 * i + j] =
+                dz[4 * i] * ti[j] + dz[4 * i + 1] * ti[4 + j] + dz[4 * i + 2] * ti[8 + j] + dz[4 * i + 3] * ti[12 + j];
+    out->kind = B200PT_LIGHT_SPOT;
+    out->position[0] = from[0];
+    out->position[1] = from[1];
+    out->position[2] = from[2];
+    const float totalWidth = coneangle, falloffStart = coneangle - conedelta;
+    out->cos_total_width = pt_cosf((PT_PI / 180) * totalWidth);
+    out->cos_falloff_start = pt_cosf((PT_PI / 180) * falloffStart);
+}

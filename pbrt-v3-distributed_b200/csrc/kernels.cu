@@ -465,6 +465,18 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
     }
 }
 
+__device__ __forceinline__ DeltaLight delta_of(const DevLight &l) {
+    DeltaLight d;
+    d.kind = l.kind;
+    d.position = mk(l.position[0], l.position[1], l.position[2]);
+    d.intensity = rgbp(l.lemit);
+    d.cos_total_width = l.cos_total_width;
+    d.cos_falloff_start = l.cos_falloff_start;
+    d.world_to_light = l.world_to_light;
+    d.two_world_radius = l.two_world_radius;
+    return d;
+}
+
 // ----------------------------------------------------------------------- shade
 struct DirectOut {
     uint32_t pend;
@@ -479,7 +491,30 @@ struct DirectOut {
 template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                 int lightNum, const float uLight[2], DirectOut *out) {
-    const DevLight light = R->lights[lightNum];
+    const DevLight &lightRef = R->lights[lightNum];
+    if (VTX && lightRef.kind != 0) {
+        // delta light (scenes with delta lights always run the VTX variant): Sample_Li has pdf 1, there is no MIS weight
+        // and no BSDF-sampling branch (integrator.cpp:147-148, :166)
+        out->pend = 0;
+        out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
+        out->A = out->B = rgb1(0.f);
+        const DeltaLight dl = delta_of(lightRef);
+        V3 wiD, pTarget;
+        const RGB LiD = delta_light_sample(dl, is.p, &wiD, &pTarget);
+        if (!is_black(LiD)) {
+            const RGB fD = bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
+            if (!is_black(fD)) {
+                // SpawnRayTo(Interaction) towards a point without normal or error bounds (interaction.h:73-78)
+                const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
+                out->sh_o = origin;
+                out->sh_d = pTarget - origin;
+                out->A = fD * LiD / 1.f;
+                out->pend |= PEND_LIGHT;
+            }
+        }
+        return;
+    }
+    const DevLight light = lightRef;
     // a sphere light (scenes with spheres always run the VTX variant)
     const bool onSphere = VTX && is_sphere_hit(light.tri);
     const DevSphere *lsp = onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr;
@@ -799,20 +834,24 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     const long long vox = id / R->n_lights;
     const int vx = (int)(vox % g.nv[0]), vy = (int)((vox / g.nv[0]) % g.nv[1]), vz = (int)(vox / ((long long)g.nv[0] * g.nv[1]));
     const DevLight light = R->lights[j];
-    const bool onSphere = is_sphere_hit(light.tri);
-    const F4 *tp = R->scene.tris + (size_t)(onSphere ? 0u : light.tri) * 3;
+    const bool isDelta = light.kind != 0;
+    DeltaLight dl;
+    if (isDelta) dl = delta_of(R->lights[j]);
+    const bool onSphere = !isDelta && is_sphere_hit(light.tri);
+    const F4 *tp = R->scene.tris + (size_t)((onSphere || isDelta) ? 0u : light.tri) * 3;
     F4 t0 = {0.f, 0.f, 0.f, 0.f}, t1 = t0, t2 = t0;
-    if (!onSphere) {
+    if (!onSphere && !isDelta) {
         t0 = ld_f4(tp);
         t1 = ld_f4(tp + 1);
         t2 = ld_f4(tp + 2);
     }
     const uint32_t lflags = __float_as_uint(t1.w);
     TriShading lsh;
-    load_shading<true>(R->scene, light.tri, lflags, &lsh);
+    load_shading<true>(R->scene, isDelta ? 0u : light.tri, lflags, &lsh);
     R->sp_func[vox * R->n_lights + j] =
         spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0, lsh, rgbp(light.lemit),
-                              light.two_sided != 0, onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr);
+                              light.two_sided != 0, onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr,
+                              isDelta ? &dl : nullptr);
 }
 __global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
     const SpatialGrid &g = R->grid;

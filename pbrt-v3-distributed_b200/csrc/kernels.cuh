@@ -24,6 +24,13 @@ struct DevLight {
     float lemit[3];
     int two_sided;
     float area;  // Triangle::Area(), computed on the host
+    // delta lights (b200pt_area_light::kind != 0): position = pLight or wLight, the spot's cone and WorldToLight,
+    // the distant light's 2 * worldRadius
+    int kind;
+    float position[3];
+    float cos_total_width, cos_falloff_start;
+    float world_to_light[16];
+    float two_world_radius;
 };
 
 struct DevScene {
@@ -73,6 +80,7 @@ struct RenderDev {
     const float *light_cdf;   // [n_lights + 1]
     const float *light_func;  // [n_lights]
     float light_func_int;
+    int has_delta_lights;     // some light is a point / spot / distant light (handled by the full shading variant)
     // SpatialLightDistribution: per-voxel func [n_lights], cdf [n_lights+1], funcInt
     SpatialGrid grid;
     float *sp_func, *sp_cdf, *sp_func_int;

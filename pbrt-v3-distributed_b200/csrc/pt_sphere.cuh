@@ -491,10 +491,44 @@ B200_HD void instance_isect_to_world(const DevInstance &in, Isect *is) {
     *is = w;
 }
 
+// ---- delta lights: PointLight / SpotLight / DistantLight::Sample_Li (point.cpp:43-52, spot.cpp:53-76,
+// distant.cpp:49-60).  pdf is 1; *pTarget is the point the VisibilityTester aims at.
+struct DeltaLight {
+    int kind;  // B200PT_LIGHT_POINT / SPOT / DISTANT
+    V3 position;
+    RGB intensity;
+    float cos_total_width, cos_falloff_start;
+    const float *world_to_light;
+    float two_world_radius;
+};
+B200_HD RGB delta_light_sample(const DeltaLight &l, const V3 &refP, V3 *wi, V3 *pTarget) {
+    if (l.kind == 3) {
+        *wi = l.position;
+        *pTarget = refP + l.position * l.two_world_radius;
+        return l.intensity;
+    }
+    *wi = normalize(l.position - refP);
+    *pTarget = l.position;
+    const float d2 = len2(l.position - refP);
+    if (l.kind == 1) return l.intensity / d2;
+    const V3 wl = normalize(xform_vector(l.world_to_light, -*wi));  // SpotLight::Falloff, spot.cpp:64-74
+    const float cosTheta = wl.z;
+    float falloff;
+    if (cosTheta < l.cos_total_width)
+        falloff = 0.f;
+    else if (cosTheta >= l.cos_falloff_start)
+        falloff = 1.f;
+    else {
+        const float delta = (cosTheta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
+        falloff = (delta * delta) * (delta * delta);
+    }
+    return l.intensity * falloff / d2;
+}
+
 // SpatialLightDistribution::ComputeDistribution, one (voxel, light) term (lightdistrib.cpp:196-275)
 B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
                                     const V3 &p2, bool flip, const TriShading &sh, const RGB &lemit, bool twoSided,
-                                    const DevSphere *sphere) {
+                                    const DevSphere *sphere, const DeltaLight *delta) {
     const int pi[3] = {vx, vy, vz};
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
@@ -511,6 +545,12 @@ B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz
         float pdf;
         LightSample ps;
         V3 w;
+        if (delta) {  // Sample_Li of a delta light: pdf 1 (lightdistrib.cpp:230-236)
+            V3 wiD, pT;
+            const RGB LiD = delta_light_sample(*delta, po, &wiD, &pT);
+            contrib += lum(LiD) / 1.f;
+            continue;
+        }
         if (sphere) {
             // Interaction(po, Normal3f(), Vector3f(), ...) (lightdistrib.cpp:222-223): no normal, no error bounds;
             // Sphere::Sample(ref, u, pdf) already returns a solid-angle density

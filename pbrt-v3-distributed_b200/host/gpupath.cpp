@@ -66,6 +66,9 @@
 #include "filters/box.h"
 #include "integrators/path.h"
 #include "lights/diffuse.h"
+#include "lights/spot.h"
+#include "lights/point.h"
+#include "lights/distant.h"
 #include "materials/glass.h"
 #include "materials/matte.h"
 #include "materials/metal.h"
@@ -373,9 +376,37 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
     }
     if (!scene.infiniteLights.empty()) return *why = "infinite area lights", false;
     for (size_t l = 0; l < scene.lights.size(); ++l) {
-        auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
-        if (!dl) return *why = "a light other than a diffuse area light", false;
         b200pt_area_light bl;
+        memset(&bl, 0, sizeof(bl));
+        bl.triangle = bl.sphere = -1;
+        // delta lights (point.cpp:43-56, spot.cpp:42-76, distant.cpp:43-66): the lights' own members
+        if (auto pl = dynamic_cast<const PointLight *>(scene.lights[l].get())) {
+            bl.kind = B200PT_LIGHT_POINT;
+            ToRGB(pl->I, bl.lemit);
+            bl.position[0] = pl->pLight.x, bl.position[1] = pl->pLight.y, bl.position[2] = pl->pLight.z;
+            f->lights.push_back(bl);
+            continue;
+        }
+        if (auto sl = dynamic_cast<const SpotLight *>(scene.lights[l].get())) {
+            bl.kind = B200PT_LIGHT_SPOT;
+            ToRGB(sl->I, bl.lemit);
+            bl.position[0] = sl->pLight.x, bl.position[1] = sl->pLight.y, bl.position[2] = sl->pLight.z;
+            bl.cos_total_width = sl->cosTotalWidth;
+            bl.cos_falloff_start = sl->cosFalloffStart;
+            memcpy(bl.world_to_light, sl->WorldToLight.m.m, sizeof(float) * 16);
+            f->lights.push_back(bl);
+            continue;
+        }
+        if (auto tl = dynamic_cast<const DistantLight *>(scene.lights[l].get())) {
+            bl.kind = B200PT_LIGHT_DISTANT;
+            ToRGB(tl->L, bl.lemit);
+            bl.position[0] = tl->wLight.x, bl.position[1] = tl->wLight.y, bl.position[2] = tl->wLight.z;
+            bl.world_radius = tl->worldRadius;  // set by DistantLight::Preprocess in the Scene constructor
+            f->lights.push_back(bl);
+            continue;
+        }
+        auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
+        if (!dl) return *why = "a light other than diffuse area / point / spot / distant lights", false;
         ToRGB(dl->Lemit, bl.lemit);
         bl.two_sided = dl->twoSided ? 1 : 0;
         auto is = sphereOfShape.find(dl->shape.get());

@@ -139,7 +139,7 @@ class SceneArrays:
 
     def __init__(self, n_tris, materials=("matte",), soup_version=1, seed=1234, light_L=40.0,
                  n_lights=None, two_sided=False, reverse_orientation=(), shading_normals=(), uvs=(), spheres=(),
-                 objects=(), instances=()):
+                 objects=(), instances=(), delta_lights=()):
         """spheres: dicts {center, radius, material (a name in `materials` or "black"), emit (radiance or
         None), scale (sx, sy, sz) or None, reverse_orientation} -- written as `Translate` + `Scale` +
         `Shape "sphere"` by write_pbrt, after the meshes."""
@@ -215,12 +215,35 @@ class SceneArrays:
             rec.is_identity = int(ident)
         self.sphere_specs = [dict(s) for s in spheres]
         n_sl = sum(1 for s in self.sphere_specs if s.get("emit"))
-        self._lights = (abi.AreaLight * max(nl + n_sl, 1))()
+        # delta lights: dicts {kind: "point"|"spot"|"distant", from_, to, I or L, coneangle, conedelta}; they follow
+        # the emissive quads in the .pbrt file, hence in Scene::lights
+        self.delta_specs = [dict(x) for x in delta_lights]
+        self._lights = (abi.AreaLight * max(nl + len(self.delta_specs) + n_sl, 1))()
         for i in range(nl):
             self._lights[i].triangle = i
             self._lights[i].lemit[:] = [light_L] * 3
             self._lights[i].two_sided = int(two_sided)
             self._lights[i].sphere = -1
+        for dl in self.delta_specs:
+            from . import host_spot_light
+            rec = self._lights[nl]
+            nl += 1
+            rec.triangle, rec.sphere = -1, -1
+            val = dl.get("I", dl.get("L", 1.0))
+            rec.lemit[:] = [val] * 3 if np.isscalar(val) else list(val)
+            f_, t_ = dl.get("from_", (0, 0, 0)), dl.get("to", (0, 0, 1))
+            if dl["kind"] == "point":  # CreatePointLight, point.cpp:82-92
+                rec.kind = abi.LIGHT_POINT
+                rec.position[:] = [np.float32(v) for v in f_]
+            elif dl["kind"] == "spot":
+                host_spot_light(rec, f_, t_, dl.get("coneangle", 30.0), dl.get("conedelta", 5.0))
+            else:  # CreateDistantLight, distant.cpp:87-96: wLight = Normalize(from - to)
+                rec.kind = abi.LIGHT_DISTANT
+                f32 = np.float32
+                dvec = [f32(f32(a) - f32(b)) for a, b in zip(f_, t_)]
+                ln = np.sqrt(f32(f32(f32(dvec[0] * dvec[0]) + f32(dvec[1] * dvec[1])) + f32(dvec[2] * dvec[2])))
+                inv = f32(1) / f32(ln)  # Vector3::operator/ multiplies by the reciprocal (geometry.h:132-137)
+                rec.position[:] = [f32(v * inv) for v in dvec]
         self._spheres = (abi.Sphere * max(len(self.sphere_specs), 1))()
         for k, sp in enumerate(self.sphere_specs):
             m, minv = sphere_transform(sp["center"], sp.get("scale"))
@@ -362,6 +385,19 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
                   '  Material "matte" "rgb Kd" [0 0 0]',
                   '  Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [%s]' % flat,
                   "AttributeEnd"]
+    for dl in getattr(scene, "delta_specs", ()):
+        val = dl.get("I", dl.get("L", 1.0))
+        rgb = "%.9g %.9g %.9g" % ((val,) * 3 if np.isscalar(val) else tuple(val))
+        f_, t_ = dl.get("from_", (0, 0, 0)), dl.get("to", (0, 0, 1))
+        if dl["kind"] == "point":
+            lines.append('LightSource "point" "rgb I" [%s] "point from" [%.9g %.9g %.9g]' % ((rgb,) + tuple(f_)))
+        elif dl["kind"] == "spot":
+            lines.append('LightSource "spot" "rgb I" [%s] "point from" [%.9g %.9g %.9g] "point to" [%.9g %.9g %.9g] '
+                         '"float coneangle" [%.9g] "float conedeltaangle" [%.9g]'
+                         % ((rgb,) + tuple(f_) + tuple(t_) + (dl.get("coneangle", 30.0), dl.get("conedelta", 5.0))))
+        else:
+            lines.append('LightSource "distant" "rgb L" [%s] "point from" [%.9g %.9g %.9g] "point to" [%.9g %.9g %.9g]'
+                         % ((rgb,) + tuple(f_) + tuple(t_)))
     for m, part in enumerate(scene.ply_parts):
         ply = "%s_m%d.ply" % (name, m)
         sel = scene.material_id == m

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_sizes_match_header(abi):
     # sizes implied by include/b200pt.h on LP64
     assert C.sizeof(abi.Material) == 4 + 15 * 4 + 12 + 4
-    assert C.sizeof(abi.AreaLight) == 24
+    assert C.sizeof(abi.AreaLight) == 116
     assert C.sizeof(abi.Sphere) == 188
     assert C.sizeof(abi.CameraDesc) == 144
     assert C.sizeof(abi.FilmDesc) == 48

@@ -99,6 +99,16 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_instances.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_instances.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (object instances) differs from the reference"
+    # delta lights and the mirror material, parsed by the reference's own factories
+    for name in ("delta_lights", "mirror"):
+        nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **EXTRA.get(name, {}).get("scene", {}))
+        path = scenes.write_pbrt(str(tmp_path), "render_" + name, arr, w, h, spp, max_depth=depth, strategy=strat)
+        r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = scenes.read_pfm(os.path.join(str(tmp_path), "render_%s.pfm" % name))
+        ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % name))
+        assert np.array_equal(bits(got), bits(ref)), "drop-in render (%s) differs from the reference" % name
 
 
 KILLEROO_DIR = os.path.join(ROOT, "oracle", "_ref", "scenes")

@@ -42,6 +42,9 @@ RENDERS = {
     "instances": (2000, ("matte", "glass", "metal", "plastic"), 48, 40, 8, 6, "spatial", None),
     # MirrorMaterial (SpecularReflection + FresnelNoOp) next to glass: long specular chains
     "mirror": (3000, ("matte", "mirror", "glass", "plastic"), 40, 32, 8, 8, "spatial", None),
+    # delta lights (point, spot, distant) next to the area lights: no MIS branch, Light::Power / Sample_Li per kind
+    "delta_lights": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "spatial", 4),
+    "delta_power": (3000, ("matte", "plastic"), 40, 32, 4, 5, "power", 0),
     # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
     # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
     "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
@@ -73,6 +76,14 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              instances=(dict(object=0, center=(0.0, 0.0, -2.4)), dict(object=0, center=(1.2, 0.8, -2.0), scale=(0.7, 1.4, 1.0)),
                         dict(object=1, center=(-1.1, -0.7, -2.2), scale=(1.0, 1.0, -1.3)), dict(object=1),
                         dict(object=0, center=(-1.3, 0.9, -1.9), scale=(1.5, 1.5, 1.5))))),
+         "delta_lights": dict(scene=dict(delta_lights=(
+             dict(kind="point", from_=(0.5, 1.5, -2.5), I=6.0),
+             dict(kind="spot", from_=(-2.0, 2.0, -3.0), to=(0.0, 0.0, 0.0), I=(30.0, 24.0, 18.0), coneangle=25.0, conedelta=8.0),
+             dict(kind="distant", from_=(1.0, 2.0, -3.0), to=(0.0, 0.0, 0.0), L=0.8)))),
+         "delta_power": dict(scene=dict(delta_lights=(
+             dict(kind="point", from_=(-1.0, 0.5, -2.8), I=9.0),
+             dict(kind="spot", from_=(2.0, 2.5, -2.0), to=(0.2, -0.1, 0.0), I=40.0, coneangle=35.0, conedelta=35.0),
+             dict(kind="distant", from_=(0.0, 1.0, -1.0), to=(0.0, 0.0, 0.0), L=(1.0, 0.9, 0.8))))),
          "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
          "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
          "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),
