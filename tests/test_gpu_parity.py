@@ -453,6 +453,32 @@ def test_render_is_deterministic_and_batch_independent(pkg, abi, scenes, ctx, mo
     scene.close()
 
 
+def test_pixel_filter_many_batches_and_shards(pkg, abi, scenes, ctx, monkeypatch):
+    """Wide pixel filters with the film split over many wavefront batches (the tiles of a batch are merged in tile
+    order, batches follow each other in tile order) and over two tile shards: the first must stay bit-identical to
+    the single-threaded reference image, the shard sum must equal it up to the order of the float additions."""
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS["filter_gaussian"]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=abi.LIGHTS_SPATIAL, pixel_filter="gaussian")
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_filter_gaussian.pfm"))
+    monkeypatch.setenv("B200PT_BATCH_PATHS", str(256 * spp * 2))  # two tiles per batch
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    assert np.array_equal(bits(r.read_rgb()), bits(ref))
+    full = r.read_raw()
+    r.clear()
+    tiles = np.arange(r.n_tiles, dtype=np.int32)
+    r.render_tiles(tiles[0::2])
+    a = r.read_raw()
+    r.clear()
+    r.render_tiles(tiles[1::2])
+    b = r.read_raw()
+    np.testing.assert_allclose(a + b, full, rtol=2e-6, atol=1e-7)
+    r.close()
+    scene.close()
+
+
 def test_large_scene_properties(pkg, abi, scenes, ctx):
     """BASELINE-size scene (1M triangles): properties that need no CPU oracle at full size."""
     arr, setup, scene = make(pkg, abi, scenes, ctx, 1000000, ("matte",), 256, 256, 4)
