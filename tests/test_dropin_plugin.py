@@ -71,7 +71,7 @@ def test_dropin_binary_matches_reference(scenes, tmp_path):
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_halton.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "drop-in render (Halton sampler) differs from the reference"
     # Sphere shapes (two of them area lights) written as `Translate` / `Scale` / `Shape "sphere"`
-    from test_gpu_parity import EXTRA, RENDERS
+    from render_cases import EXTRA, RENDERS
     nt, mats, w, h, spp, depth, strat, nl = RENDERS["spheres"]
     arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **EXTRA["spheres"]["scene"])
     path = scenes.write_pbrt(str(tmp_path), "render_spheres", arr, w, h, spp, max_depth=depth, strategy=strat)
