@@ -2700,6 +2700,21 @@ int oracle_pixel_samples(const oracle_scene *s, const b200pt_camera_desc *camera
     return 0;
 }
 
+void oracle_sphere_sample(const b200pt_sphere *sphere, const float ref_p[3], const float ref_perr[3], const float ref_n[3],
+                          const float u[2], float out[10]) {
+    b200pt_sphere sp = *sphere;
+    float pdf = 0;
+    LightSample ls = SphereSample(sp, V3(ref_p[0], ref_p[1], ref_p[2]), V3(ref_perr[0], ref_perr[1], ref_perr[2]),
+                                  V3(ref_n[0], ref_n[1], ref_n[2]), u, &pdf);
+    const float v[10] = {ls.p.x, ls.p.y, ls.p.z, ls.n.x, ls.n.y, ls.n.z, ls.pError.x, ls.pError.y, ls.pError.z, pdf};
+    memcpy(out, v, sizeof(v));
+}
+float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const float ref_perr[3], const float ref_n[3],
+                        const float wi[3]) {
+    return SpherePdf(*sphere, V3(ref_p[0], ref_p[1], ref_p[2]), V3(ref_perr[0], ref_perr[1], ref_perr[2]),
+                     V3(ref_n[0], ref_n[1], ref_n[2]), V3(wi[0], wi[1], wi[2]));
+}
+
 float oracle_libm_sinf(float x) { return std::sin(x); }
 float oracle_libm_cosf(float x) { return std::cos(x); }
 

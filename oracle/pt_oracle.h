@@ -53,6 +53,13 @@ int oracle_pixel_samples(const oracle_scene *s, const b200pt_camera_desc *camera
                          const b200pt_integrator_desc *integrator, int32_t px, int32_t py,
                          float *out_rgb);
 
+/* Sphere::Sample(ref, u, pdf) and Sphere::Pdf(ref, wi) (sphere.cpp:232-304) for one sphere of a descriptor:
+ * out = {p.xyz, n.xyz, pError.xyz, pdf}.  Used by tests/host_preflight.cpp to check the device routines. */
+void oracle_sphere_sample(const b200pt_sphere *sphere, const float ref_p[3], const float ref_perr[3], const float ref_n[3],
+                          const float u[2], float out[10]);
+float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const float ref_perr[3], const float ref_n[3],
+                        const float wi[3]);
+
 /* The host libm's sinf/cosf (what the reference calls through std::sin/cos). */
 float oracle_libm_sinf(float x);
 float oracle_libm_cosf(float x);

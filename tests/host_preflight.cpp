@@ -345,6 +345,40 @@ int main(int argc, char **argv) {
         printf("spheres: %lld rays, %lld hits, wrong sphere/t %lld, wrong any-hit %lld\n", (long long)nRays, (long long)nh,
                (long long)badS, (long long)badO);
         fail |= (badS || badO);
+        // Sphere::Sample(ref, u) / Sphere::Pdf(ref, wi): reference points outside (cone sampling) and inside (area sampling,
+        // Shape::Pdf through Intersect) every sphere
+        int64_t badSample = 0, badPdf = 0, nInside = 0;
+        for (int64_t i = 0; i < 20000; ++i) {
+            const int k = (int)(i % nSph);
+            DevSphere d = dev[k];
+            d.area = d.phi_max * d.radius * (d.z_max - d.z_min);
+            d.reverse_orientation = sph[k].reverse_orientation;
+            const bool inside = (i % 3) == 0;
+            const float rr = inside ? 0.6f * sph[k].radius * std::fabs(U(rng)) : 2.f + 3.f * std::fabs(U(rng));
+            V3 dir = normalize(mk(U(rng), U(rng), U(rng) + 1e-3f));
+            const V3 ctr = mk(sph[k].object_to_world[3], sph[k].object_to_world[7], sph[k].object_to_world[11]);
+            const V3 refP = ctr + dir * rr, refN = normalize(mk(U(rng), U(rng), U(rng) + 1e-3f));
+            const V3 refE = mk(1e-6f * std::fabs(U(rng)), 1e-6f * std::fabs(U(rng)), 1e-6f * std::fabs(U(rng)));
+            const float u[2] = {0.5f * (U(rng) + 1.f) * 0.999f, 0.5f * (U(rng) + 1.f) * 0.999f};
+            float pdf = 0, want10[10];
+            const LightSample ls = sphere_sample(d, refP, refE, refN, u, &pdf);
+            const float rp[3] = {refP.x, refP.y, refP.z}, re[3] = {refE.x, refE.y, refE.z}, rn[3] = {refN.x, refN.y, refN.z};
+            oracle_sphere_sample(&sph[k], rp, re, rn, u, want10);
+            const float got10[10] = {ls.p.x, ls.p.y, ls.p.z, ls.n.x, ls.n.y, ls.n.z, ls.pError.x, ls.pError.y, ls.pError.z, pdf};
+            for (int a = 0; a < 10; ++a)
+                if (bits(got10[a]) != bits(want10[a]) && !(got10[a] != got10[a] && want10[a] != want10[a])) {
+                    ++badSample;
+                    break;
+                }
+            const V3 wi = normalize(ls.p - refP);
+            const float wv[3] = {wi.x, wi.y, wi.z};
+            const float pg = sphere_pdf(d, refP, refE, refN, wi), pw = oracle_sphere_pdf(&sph[k], rp, re, rn, wv);
+            if (bits(pg) != bits(pw) && !(pg != pg && pw != pw)) ++badPdf;
+            nInside += inside;
+        }
+        printf("sphere sampling: 20000 reference points (%lld inside), wrong samples %lld, wrong pdfs %lld\n", (long long)nInside,
+               (long long)badSample, (long long)badPdf);
+        fail |= (badSample || badPdf);
         oracle_scene_destroy(os2);
         long badA = 0;
         for (uint32_t u = 0; u <= 0x3f800000u; u += 3)

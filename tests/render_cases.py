@@ -37,6 +37,12 @@ RENDERS = {
     # delta lights (point, spot, distant) next to the area lights: no MIS branch, Light::Power / Sample_Li per kind
     "delta_lights": (3000, ("matte", "glass", "metal", "plastic"), 40, 32, 8, 5, "spatial", 4),
     "delta_power": (3000, ("matte", "plastic"), 40, 32, 4, 5, "power", 0),
+    # the reference's own known-answer scenes (src/tests/analytic_scenes.cpp:69-160): camera inside a unit sphere with
+    # Kd 0.5 (reverse orientation) lit by a point light of intensity pi at the centre, by four of pi/4, or emitting 0.5
+    # itself -- the radiance is 1 everywhere; PathIntegrator depth 8, 10x10 pixels, 256 samples, fov 45
+    "analytic_point": (0, ("matte",), 10, 10, 256, 8, "spatial", 0),
+    "analytic_4points": (0, ("matte",), 10, 10, 256, 8, "spatial", 0),
+    "analytic_area": (0, ("matte",), 10, 10, 256, 8, "spatial", 0),
     # pixel filters wider than the box (Film::filterTable weights, samples outside the film, tile aprons of 2-4
     # pixels); the reference image is rendered with --nthreads 1 so that its tile merge order is defined
     "filter_gaussian": (3000, ("matte", "glass", "metal", "plastic"), 40, 36, 4, 5, "spatial", None),
@@ -76,6 +82,16 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
              dict(kind="point", from_=(-1.0, 0.5, -2.8), I=9.0),
              dict(kind="spot", from_=(2.0, 2.5, -2.0), to=(0.2, -0.1, 0.0), I=40.0, coneangle=35.0, conedelta=35.0),
              dict(kind="distant", from_=(0.0, 1.0, -1.0), to=(0.0, 0.0, 0.0), L=(1.0, 0.9, 0.8))))),
+         "analytic_point": dict(scene=dict(spheres=(dict(center=(0, 0, 0), radius=1.0, material="matte", reverse_orientation=True),),
+                                           delta_lights=(dict(kind="point", from_=(0, 0, 0), I=3.14159265358979323846),)),
+                                camera=dict(eye=(0, 0, 0), look=(0, 0, 1), fov=45.0)),
+         "analytic_4points": dict(scene=dict(spheres=(dict(center=(0, 0, 0), radius=1.0, material="matte", reverse_orientation=True),),
+                                             delta_lights=tuple(dict(kind="point", from_=(0, 0, 0), I=3.14159265358979323846 / 4)
+                                                                for _ in range(4))),
+                                  camera=dict(eye=(0, 0, 0), look=(0, 0, 1), fov=45.0, sampler="halton")),
+         "analytic_area": dict(scene=dict(spheres=(dict(center=(0, 0, 0), radius=1.0, material="matte", reverse_orientation=True,
+                                                        emit=0.5),)),
+                               camera=dict(eye=(0, 0, 0), look=(0, 0, 1), fov=45.0)),
          "filter_gaussian": dict(camera=dict(pixel_filter="gaussian")),
          "filter_mitchell": dict(camera=dict(pixel_filter="mitchell", max_sample_luminance=20.0)),
          "filter_sinc": dict(camera=dict(pixel_filter="sinc", sampler="halton")),

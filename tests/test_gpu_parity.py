@@ -368,6 +368,22 @@ def test_render_is_deterministic_and_batch_independent(pkg, abi, scenes, ctx, mo
     scene.close()
 
 
+@pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
+def test_analytic_scenes_known_answer(pkg, abi, scenes, ctx, name):
+    """src/tests/analytic_scenes.cpp: camera inside a unit sphere of Kd 0.5 lit from its centre (or emitting 0.5):
+    the image mean is 1 +- 0.02 (CheckSceneAverage, :54-66)."""
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    ex = EXTRA[name]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex["scene"])
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=abi.LIGHTS_SPATIAL, **ex["camera"])
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    assert abs(float(r.read_rgb().mean()) - 1.0) < 0.02
+    r.close()
+    scene.close()
+
+
 def test_pixel_filter_many_batches_and_shards(pkg, abi, scenes, ctx, monkeypatch):
     """Wide pixel filters with the film split over many wavefront batches (the tiles of a batch are merged in tile
     order, batches follow each other in tile order) and over two tile shards: the first must stay bit-identical to

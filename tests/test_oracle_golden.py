@@ -133,6 +133,23 @@ def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
     o.close()
 
 
+@pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
+def test_analytic_scenes_known_answer(abi, scenes, ob, name):
+    """The reference's own known-answer test (src/tests/analytic_scenes.cpp:54-66, CheckSceneAverage): the mean of the
+    rendered image is 1 +- 0.02 -- for the reference's image and for the oracle's."""
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    ex = EXTRA[name]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex["scene"])
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=abi.LIGHTS_SPATIAL, **ex["camera"])
+    o = ob.Oracle(abi, arr)
+    film, _ = o.render(setup, threads=4)
+    rgb = o.film_rgb(setup, film)
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % name))
+    assert abs(float(ref.mean()) - 1.0) < 0.02
+    assert abs(float(rgb.mean()) - 1.0) < 0.02
+    o.close()
+
+
 def test_pixelbounds_shards_equal_full_render(abi, scenes, ob):
     # SURVEY 8(e): tile shards with the full-film sampler are bit-identical to the full render
     arr = scenes.SceneArrays(2000, materials=("matte", "plastic"), soup_version=1)
