@@ -20,9 +20,16 @@ def have_reference():
     return os.path.exists(PBRT_REF) and os.path.exists(REF_PROBE)
 
 
-def load(abi):
-    """abi = the product package's ctypes mirror of include/b200pt.h."""
-    lib = C.CDLL(LIB_PATH)
+LIB_SPECTRAL_PATH = os.path.join(_HERE, "liboracle_spectral.so")
+PBRT_REF_SPECTRAL = os.path.join(REF_DIR, "pbrt_ref_spectral")
+REF_PROBE_SPECTRAL = os.path.join(REF_DIR, "ref_probe_spectral")
+
+
+def load(abi, spectral=False):
+    """abi = the product package's ctypes mirror of include/b200pt.h.  spectral: the 60-bin SampledSpectrum build."""
+    lib = C.CDLL(LIB_SPECTRAL_PATH if spectral else LIB_PATH)
+    lib.oracle_spectral_register.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.oracle_spectral_set_cie.argtypes = [C.POINTER(C.c_float)] * 3
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.oracle_scene_create.restype = vp
     lib.oracle_scene_create.argtypes = [C.POINTER(abi.SceneDesc)]
@@ -45,9 +52,19 @@ def load(abi):
 
 
 class Oracle:
-    def __init__(self, abi, scene_arrays):
+    def __init__(self, abi, scene_arrays, spectral_tables=None):
+        """spectral_tables: dict from tests/golden/spectral_tables.json -> the SampledSpectrum build of the oracle."""
         self.abi = abi
-        self.lib = load(abi)
+        self.lib = load(abi, spectral=spectral_tables is not None)
+        if spectral_tables is not None:
+            f60 = C.c_float * 60
+
+            def arr(v):
+                return f60(*[float.fromhex(x) for x in v])
+            self.lib.oracle_spectral_set_cie(arr(spectral_tables["cie_x"]), arr(spectral_tables["cie_y"]),
+                                             arr(spectral_tables["cie_z"]))
+            for rgb, spec in spectral_tables["spectra"]:
+                self.lib.oracle_spectral_register((C.c_float * 3)(*[float.fromhex(x) for x in rgb]), arr(spec))
         self.arrays = scene_arrays
         d = scene_arrays.desc()
         self.h = self.lib.oracle_scene_create(C.byref(d))
@@ -103,17 +120,19 @@ class Oracle:
             self.h = None
 
 
-def run_pbrt_ref(pbrt_file, threads=None, quiet=True, timeout=3600):
-    """Runs the unmodified reference CLI; returns its stdout (stats + profile)."""
-    cmd = [PBRT_REF, "--nthreads", str(threads or os.cpu_count()), os.path.basename(pbrt_file)]
+def run_pbrt_ref(pbrt_file, threads=None, quiet=True, timeout=3600, spectral=False):
+    """Runs the unmodified reference CLI (spectral: its SampledSpectrum build); returns its stdout (stats + profile)."""
+    cmd = [PBRT_REF_SPECTRAL if spectral else PBRT_REF, "--nthreads", str(threads or os.cpu_count()),
+           os.path.basename(pbrt_file)]
     r = subprocess.run(cmd, cwd=os.path.dirname(pbrt_file), capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError("pbrt_ref failed: " + r.stderr[-2000:])
     return r.stdout + r.stderr
 
 
-def probe(*args):
-    r = subprocess.run([REF_PROBE] + [str(a) for a in args], capture_output=True, text=True)
+def probe(*args, spectral=False):
+    r = subprocess.run([REF_PROBE_SPECTRAL if spectral else REF_PROBE] + [str(a) for a in args], capture_output=True,
+                       text=True)
     if r.returncode != 0:
         raise RuntimeError("ref_probe failed: " + r.stderr[-2000:])
     return r.stdout

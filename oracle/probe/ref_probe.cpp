@@ -333,6 +333,34 @@ int main(int argc, char **argv) {
         for (float r : rough)
             printf("roughness_to_alpha %a %a\n", (double)r,
                    (double)TrowbridgeReitzDistribution::RoughnessToAlpha(r));
+#ifdef B200PT_PROBE_SPECTRAL
+    } else if (cmd == "spectral") {
+        // spectral <out.json-ish text>: everything liboracle_spectral needs from the SampledSpectrum build:
+        //   cie X|Y|Z <60 values>; rgb r g b <60 values> for every RGB triple given as r,g,b arguments (Spectrum::FromRGB,
+        //   what ParamSet::AddRGBSpectrum stores, paramset.cpp:110-120); const v <60 values>; copper eta / k
+        auto dump = [](const char *tag, const Spectrum &sp) {
+            printf("%s", tag);
+            for (int i = 0; i < nSpectralSamples; ++i) printf(" %a", (double)sp[i]);
+            printf("\n");
+        };
+        dump("cie_x", SampledSpectrum::X);
+        dump("cie_y", SampledSpectrum::Y);
+        dump("cie_z", SampledSpectrum::Z);
+        for (int a = 2; a + 2 < argc; a += 3) {
+            Float rgb[3] = {strtof(argv[a], 0), strtof(argv[a + 1], 0), strtof(argv[a + 2], 0)};
+            char tag[128];
+            snprintf(tag, sizeof(tag), "rgb %a %a %a", rgb[0], rgb[1], rgb[2]);
+            dump(tag, Spectrum::FromRGB(rgb));
+        }
+        ParamSet geom, mat;
+        std::map<std::string, std::shared_ptr<Texture<Float>>> ft;
+        std::map<std::string, std::shared_ptr<Texture<Spectrum>>> st;
+        TextureParams tp(geom, mat, ft, st);
+        std::unique_ptr<MetalMaterial> metal(CreateMetalMaterial(tp));
+        SurfaceInteraction si;
+        dump("copper_eta", metal->eta->Evaluate(si));
+        dump("copper_k", metal->k->Evaluate(si));
+#endif
     } else
         die("unknown command");
     return 0;

@@ -22,12 +22,14 @@
 #include "pt_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -137,40 +139,110 @@ inline void CoordinateSystem(const V3 &v1, V3 *v2, V3 *v3) {
 }
 
 // ----------------------------------------------------------------- spectrum
+// ORACLE_NSPEC == 3: RGBSpectrum (core/spectrum.h:429-560), the reference's default build.
+// ORACLE_NSPEC == 60: SampledSpectrum (spectrum.h:283-427), the reference compiled with PBRT_SAMPLED_SPECTRUM
+// (pbrt.h:124-125) -- liboracle_spectral.so, round-2 groundwork for BASELINE configs[4].  The spectra themselves
+// (Spectrum::FromRGB of a descriptor's RGB triple, the CIE matching curves resampled to the 60 bins) are data of
+// the reference: they are registered through oracle_spectral_register / oracle_spectral_set_cie from fixtures dumped
+// by the spectral probe, never computed here.
+#ifndef ORACLE_NSPEC
+#define ORACLE_NSPEC 3
+#endif
 struct S3 {
-    float c[3];
-    S3(float v = 0.f) { c[0] = c[1] = c[2] = v; }
+    float c[ORACLE_NSPEC];
+    S3(float v = 0.f) {
+        for (int i = 0; i < ORACLE_NSPEC; ++i) c[i] = v;
+    }
+#if ORACLE_NSPEC == 3
     S3(float r, float g, float b) {
         c[0] = r;
         c[1] = g;
         c[2] = b;
     }
-    bool IsBlack() const { return c[0] == 0. && c[1] == 0. && c[2] == 0.; }
-    // spectrum.h:462-465
-    float y() const {
-        const float YWeight[3] = {0.212671f, 0.715160f, 0.072169f};
-        return YWeight[0] * c[0] + YWeight[1] * c[1] + YWeight[2] * c[2];
+#endif
+    bool IsBlack() const {
+        for (int i = 0; i < ORACLE_NSPEC; ++i)
+            if (c[i] != 0.) return false;
+        return true;
     }
+    float y() const;
     float MaxComponentValue() const {
         float m = c[0];
-        for (int i = 1; i < 3; ++i) m = std::max(m, c[i]);
+        for (int i = 1; i < ORACLE_NSPEC; ++i) m = std::max(m, c[i]);
         return m;
     }
-    bool HasNaNs() const { return std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]); }
+    bool HasNaNs() const {
+        for (int i = 0; i < ORACLE_NSPEC; ++i)
+            if (std::isnan(c[i])) return true;
+        return false;
+    }
 };
-inline S3 SP(const float *p) { return S3(p[0], p[1], p[2]); }
-inline S3 operator+(const S3 &a, const S3 &b) { return S3(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
-inline S3 operator-(const S3 &a, const S3 &b) { return S3(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
-inline S3 operator*(const S3 &a, const S3 &b) { return S3(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
-inline S3 operator/(const S3 &a, const S3 &b) { return S3(a.c[0] / b.c[0], a.c[1] / b.c[1], a.c[2] / b.c[2]); }
-inline S3 operator*(const S3 &a, float s) { return S3(a.c[0] * s, a.c[1] * s, a.c[2] * s); }
+#define S3_BINOP(op)                                                  \
+    inline S3 operator op(const S3 &a, const S3 &b) {                 \
+        S3 r;                                                         \
+        for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = a.c[i] op b.c[i]; \
+        return r;                                                     \
+    }
+S3_BINOP(+)
+S3_BINOP(-)
+S3_BINOP(*)
+S3_BINOP(/)
+#undef S3_BINOP
+inline S3 operator*(const S3 &a, float s) {
+    S3 r;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = a.c[i] * s;
+    return r;
+}
 inline S3 operator*(float s, const S3 &a) { return a * s; }
-inline S3 operator/(const S3 &a, float s) { return S3(a.c[0] / s, a.c[1] / s, a.c[2] / s); }  // spectrum.h:181-188
-inline S3 Sqrt(const S3 &a) { return S3(std::sqrt(a.c[0]), std::sqrt(a.c[1]), std::sqrt(a.c[2])); }
+inline S3 operator/(const S3 &a, float s) {  // spectrum.h:181-188
+    S3 r;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = a.c[i] / s;
+    return r;
+}
+inline S3 Sqrt(const S3 &a) {
+    S3 r;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = std::sqrt(a.c[i]);
+    return r;
+}
 inline S3 &operator+=(S3 &a, const S3 &b) {
     a = a + b;
     return a;
 }
+#if ORACLE_NSPEC == 3
+inline S3 SP(const float *p) { return S3(p[0], p[1], p[2]); }
+// spectrum.h:462-465
+inline float S3::y() const {
+    const float YWeight[3] = {0.212671f, 0.715160f, 0.072169f};
+    return YWeight[0] * c[0] + YWeight[1] * c[1] + YWeight[2] * c[2];
+}
+#else
+struct SpectralTables {
+    std::map<std::array<uint32_t, 3>, S3> byRGB;  // descriptor RGB triple (bit patterns) -> the reference's spectrum
+    S3 X, Y, Z;                                   // SampledSpectrum::X / Y / Z (spectrum.cpp:80-100)
+    bool haveCIE = false;
+};
+inline SpectralTables &Spectral() {
+    static SpectralTables t;
+    return t;
+}
+inline S3 SP(const float *p) {
+    std::array<uint32_t, 3> key;
+    memcpy(key.data(), p, 12);
+    auto it = Spectral().byRGB.find(key);
+    if (it == Spectral().byRGB.end()) {
+        fprintf(stderr, "oracle (spectral): no spectrum registered for RGB (%g %g %g)\n", p[0], p[1], p[2]);
+        abort();
+    }
+    return it->second;
+}
+// spectrum.h:393-398
+inline float S3::y() const {
+    const S3 &Y = Spectral().Y;
+    float yy = 0.f;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) yy += Y.c[i] * c[i];
+    return yy * float(700 - 400) / float(106.856895f * ORACLE_NSPEC);
+}
+#endif
 
 // ------------------------------------------------------------------- Sobol'
 // core/lowdiscrepancy.h:229-249
@@ -2293,6 +2365,24 @@ inline void RGBToXYZ(const float rgb[3], float xyz[3]) {  // spectrum.h:62-66
     xyz[1] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
     xyz[2] = 0.019334f * rgb[0] + 0.119193f * rgb[1] + 0.950227f * rgb[2];
 }
+// Spectrum::ToXYZ: RGBSpectrum (spectrum.h:455) or SampledSpectrum (spectrum.h:380-392)
+inline void SpectrumToXYZ(const S3 &sp, float xyz[3]) {
+#if ORACLE_NSPEC == 3
+    RGBToXYZ(sp.c, xyz);
+#else
+    const SpectralTables &t = Spectral();
+    xyz[0] = xyz[1] = xyz[2] = 0.f;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) {
+        xyz[0] += t.X.c[i] * sp.c[i];
+        xyz[1] += t.Y.c[i] * sp.c[i];
+        xyz[2] += t.Z.c[i] * sp.c[i];
+    }
+    float scale = float(700 - 400) / float(106.856895f * ORACLE_NSPEC);
+    xyz[0] *= scale;
+    xyz[1] *= scale;
+    xyz[2] *= scale;
+#endif
+}
 inline void XYZToRGB(const float xyz[3], float rgb[3]) {  // spectrum.h:56-60
     rgb[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
     rgb[1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
@@ -2376,7 +2466,7 @@ void MergeTile(const b200pt_film_desc &fd, const TileResult &t, float *filmXYZW)
         for (int x = t.bx0; x < t.bx0 + t.tw; ++x) {
             const FilmTilePixel &tp = t.pixels[(size_t)(y - t.by0) * t.tw + (x - t.bx0)];
             float xyz[3];
-            RGBToXYZ(tp.contribSum.c, xyz);
+            SpectrumToXYZ(tp.contribSum, xyz);
             float *mp = filmXYZW + 4 * ((size_t)(y - fd.cropped_bounds[1]) * fw + (x - fd.cropped_bounds[0]));
             for (int i = 0; i < 3; ++i) mp[i] += xyz[i];
             mp[3] += tp.filterWeightSum;
@@ -2693,9 +2783,15 @@ int oracle_pixel_samples(const oracle_scene *s, const b200pt_camera_desc *camera
     for (int64_t i = 0; i < sampler->samples_per_pixel; ++i) {
         float pFilm[2];
         S3 L = RenderSample(rc, sob, px, py, i, pFilm);
+#if ORACLE_NSPEC == 3
         out_rgb[3 * i] = L.c[0];
         out_rgb[3 * i + 1] = L.c[1];
         out_rgb[3 * i + 2] = L.c[2];
+#else
+        float xyzL[3];
+        SpectrumToXYZ(L, xyzL);
+        XYZToRGB(xyzL, out_rgb + 3 * i);
+#endif
     }
     return 0;
 }
@@ -2713,6 +2809,34 @@ float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const
                         const float wi[3]) {
     return SpherePdf(*sphere, V3(ref_p[0], ref_p[1], ref_p[2]), V3(ref_perr[0], ref_perr[1], ref_perr[2]),
                      V3(ref_n[0], ref_n[1], ref_n[2]), V3(wi[0], wi[1], wi[2]));
+}
+
+int oracle_spectrum_samples(void) { return ORACLE_NSPEC; }
+int oracle_spectral_register(const float rgb[3], const float *spectrum) {
+#if ORACLE_NSPEC != 3
+    std::array<uint32_t, 3> key;
+    memcpy(key.data(), rgb, 12);
+    S3 v;
+    memcpy(v.c, spectrum, sizeof(v.c));
+    Spectral().byRGB[key] = v;
+#else
+    (void)rgb;
+    (void)spectrum;
+#endif
+    return ORACLE_NSPEC;
+}
+int oracle_spectral_set_cie(const float *X, const float *Y, const float *Z) {
+#if ORACLE_NSPEC != 3
+    memcpy(Spectral().X.c, X, sizeof(float) * ORACLE_NSPEC);
+    memcpy(Spectral().Y.c, Y, sizeof(float) * ORACLE_NSPEC);
+    memcpy(Spectral().Z.c, Z, sizeof(float) * ORACLE_NSPEC);
+    Spectral().haveCIE = true;
+#else
+    (void)X;
+    (void)Y;
+    (void)Z;
+#endif
+    return ORACLE_NSPEC;
 }
 
 float oracle_libm_sinf(float x) { return std::sin(x); }

@@ -60,6 +60,14 @@ void oracle_sphere_sample(const b200pt_sphere *sphere, const float ref_p[3], con
 float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const float ref_perr[3], const float ref_n[3],
                         const float wi[3]);
 
+/* liboracle_spectral.so only (ORACLE_NSPEC == 60): the reference's spectral data.  oracle_spectral_register maps a
+ * descriptor RGB triple to the 60-bin SampledSpectrum the reference derives for it (Spectrum::FromRGB for "rgb"
+ * parameters, a constant for float defaults, FromSampled for the metal's measured eta / k); oracle_spectral_set_cie
+ * passes SampledSpectrum::X, Y, Z.  Both come from fixtures dumped by the spectral probe.  Return the bin count. */
+int oracle_spectral_register(const float rgb[3], const float *spectrum);
+int oracle_spectral_set_cie(const float *X, const float *Y, const float *Z);
+int oracle_spectrum_samples(void);
+
 /* The host libm's sinf/cosf (what the reference calls through std::sin/cos). */
 float oracle_libm_sinf(float x);
 float oracle_libm_cosf(float x);

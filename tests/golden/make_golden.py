@@ -61,10 +61,50 @@ def filter_fixtures():
     json.dump(out, open(os.path.join(HERE, "filter_tables.json"), "w"), indent=0)
 
 
+SPECTRAL_RGB = [(0.5, 0.5, 0.5), (0.0, 0.0, 0.0), (40.0, 40.0, 40.0)]  # "rgb" parameters of the spectral golden scenes
+SPECTRAL_CONST = [0.25, 1.0, 0.9]                                      # float-default spectra (plastic, glass, mirror)
+SPECTRAL_RENDERS = {"spectral_four": "four", "spectral_rough": "rough"}  # rendered by the SampledSpectrum reference
+
+
+def spectral_fixtures():
+    """Round-2 groundwork: the data liboracle_spectral.so needs from the SampledSpectrum build of the reference, and
+    golden renders of that build (oracle/Makefile `ref_spectral`)."""
+    import numpy as np
+    f32 = np.float32
+
+    def hx(v):
+        return float(f32(v)).hex()
+    args = [c for rgb in SPECTRAL_RGB for c in rgb]
+    out = {"spectra": []}
+    for line in ob.probe("spectral", *args, spectral=True).splitlines():
+        tok = line.split()
+        if tok[0] in ("cie_x", "cie_y", "cie_z"):
+            out[tok[0]] = tok[1:]
+        elif tok[0] == "rgb":
+            out["spectra"].append([tok[1:4], tok[4:]])
+        elif tok[0] == "copper_eta":
+            out["spectra"].append([[hx(v) for v in scenes.COPPER_ETA], tok[1:]])
+        elif tok[0] == "copper_k":
+            out["spectra"].append([[hx(v) for v in scenes.COPPER_K], tok[1:]])
+    for v in SPECTRAL_CONST:  # Spectrum(v): every bin holds v (spectrum.h:62-65)
+        out["spectra"].append([[hx(v)] * 3, [hx(v)] * 60])
+    json.dump(out, open(os.path.join(HERE, "spectral_tables.json"), "w"), indent=0)
+    for gname, base in SPECTRAL_RENDERS.items():
+        nt, mats, w, h, spp, depth, strat, nl = RENDERS[base]
+        ex = EXTRA.get(base, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+        path = scenes.write_pbrt("/tmp/golden_render", "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
+                                 **ex.get("camera", {}))
+        ob.run_pbrt_ref(path, spectral=True)
+        os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
+
+
 def main():
     ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
     filter_fixtures()
     halton_fixtures()
+    if os.path.exists(ob.PBRT_REF_SPECTRAL):
+        spectral_fixtures()
     out = {"cameras": {}, "sobol": [], "camrays": []}
     cam_args = [0, 0, -4.5, 0, 0, 0, 0, 1, 0, 35]
     for (w, h) in CAMERAS:

@@ -133,6 +133,32 @@ def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
     o.close()
 
 
+@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
+def test_spectral_oracle_matches_sampled_spectrum_reference(abi, scenes, ob, gname, base):
+    """SURVEY 8(f) row 3, second half (groundwork for the device path): the oracle compiled with 60 spectral bins
+    (oracle/Makefile liboracle_spectral.so) against the reference compiled with `typedef SampledSpectrum Spectrum`
+    (core/pbrt.h:124-125; oracle/Makefile ref_spectral) -- bit-identical images.  The CIE curves and the FromRGB /
+    copper spectra come from that reference build (tests/golden/spectral_tables.json, make_golden.py)."""
+    import json
+    if not os.path.exists(ob.LIB_SPECTRAL_PATH):
+        pytest.skip("oracle/liboracle_spectral.so not built")
+    tables = json.load(open(os.path.join(GOLDEN, "spectral_tables.json")))
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[base]
+    ex = EXTRA.get(base, {})
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
+                               **ex.get("camera", {}))
+    o = ob.Oracle(abi, arr, spectral_tables=tables)
+    film, _ = o.render(setup, threads=4)
+    rgb = o.film_rgb(setup, film)
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+    assert np.array_equal(bits(rgb), bits(ref)), "spectral oracle is not bit-identical to the SampledSpectrum reference"
+    rgb_ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % base))
+    assert not np.array_equal(bits(ref), bits(rgb_ref))  # the two Spectrum types really give different images
+    o.close()
+
+
 @pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
 def test_analytic_scenes_known_answer(abi, scenes, ob, name):
     """The reference's own known-answer test (src/tests/analytic_scenes.cpp:54-66, CheckSceneAverage): the mean of the
