@@ -36,7 +36,9 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 2
+#define B200PT_ABI_VERSION 3
+#define B200PT_SPECTRUM_SAMPLES 60  /* nSpectralSamples, core/spectrum.h:52 */
+#define B200PT_MATERIAL_SPECTRA 5
 
 typedef enum b200pt_status {
     B200PT_OK = 0,
@@ -174,6 +176,14 @@ typedef struct b200pt_scene_desc {
     int32_t n_instances;
     const b200pt_instance *instances;
     int64_t n_toplevel_triangles;
+    /* Hosts built with `typedef SampledSpectrum Spectrum` (core/pbrt.h:124-125, core/spectrum.h:283-427) pass their
+     * spectra as they hold them: B200PT_SPECTRUM_SAMPLES bins each, and SampledSpectrum::X/Y/Z (spectrum.cpp:80-100)
+     * for y() and ToXYZ().  The RGB triples of materials and lights are then ignored.  0 = RGBSpectrum host. */
+    int32_t n_spectrum_samples;     /* 0 or B200PT_SPECTRUM_SAMPLES                                        */
+    int32_t reserved_spectral;
+    const float *material_spectra;  /* [n_materials][B200PT_MATERIAL_SPECTRA][60]: kd, ks, kt, eta, k        */
+    const float *light_spectra;     /* [n_lights][60]: Lemit / I / L, multiplied by "scale" like lemit      */
+    const float *cie_xyz;           /* [3][60]: SampledSpectrum::X, Y, Z                                    */
 } b200pt_scene_desc;
 
 /* ---- camera: PerspectiveCamera (cameras/perspective.cpp:45-144) ----------

@@ -55,7 +55,8 @@ class Oracle:
     def __init__(self, abi, scene_arrays, spectral_tables=None):
         """spectral_tables: dict from tests/golden/spectral_tables.json -> the SampledSpectrum build of the oracle."""
         self.abi = abi
-        self.lib = load(abi, spectral=spectral_tables is not None)
+        described = getattr(scene_arrays, "cie_xyz", None) is not None  # SceneArrays.attach_spectral(): tables in the descriptor
+        self.lib = load(abi, spectral=spectral_tables is not None or described)
         if spectral_tables is not None:
             f60 = C.c_float * 60
 

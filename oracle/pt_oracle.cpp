@@ -2495,6 +2495,34 @@ oracle_scene *oracle_scene_create(const b200pt_scene_desc *d) {
         s->flip.assign(d->n_triangles, 0);
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
+#if ORACLE_NSPEC != 3
+    // a descriptor written by a SampledSpectrum host (b200pt.h, n_spectrum_samples): its tables replace the registry
+    if (d->n_spectrum_samples == ORACLE_NSPEC) {
+        auto reg = [](const float *rgb, const float *spectrum) {
+            std::array<uint32_t, 3> key;
+            memcpy(key.data(), rgb, 12);
+            S3 v;
+            memcpy(v.c, spectrum, sizeof(v.c));
+            auto it = Spectral().byRGB.find(key);
+            if (it != Spectral().byRGB.end() && memcmp(it->second.c, v.c, sizeof(v.c)) != 0) {
+                fprintf(stderr, "oracle (spectral): two different spectra for RGB (%g %g %g)\n", rgb[0], rgb[1], rgb[2]);
+                abort();
+            }
+            Spectral().byRGB[key] = v;
+        };
+        for (int i = 0; i < d->n_materials; ++i) {
+            const b200pt_material &m = d->materials[i];
+            const float *rows = d->material_spectra + (size_t)i * B200PT_MATERIAL_SPECTRA * ORACLE_NSPEC;
+            const float *fields[B200PT_MATERIAL_SPECTRA] = {m.kd, m.ks, m.kt, m.eta, m.k};
+            const bool usedBy[4][B200PT_MATERIAL_SPECTRA] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {0, 0, 0, 1, 1}, {0, 1, 1, 0, 0}};
+            for (int f = 0; f < B200PT_MATERIAL_SPECTRA; ++f)
+                if (usedBy[m.type][f] && !(m.type == B200PT_MAT_GLASS && m.variant == 2 && f == 2))
+                    reg(fields[f], rows + (size_t)f * ORACLE_NSPEC);
+        }
+        for (int i = 0; i < d->n_lights; ++i) reg(d->lights[i].lemit, d->light_spectra + (size_t)i * ORACLE_NSPEC);
+        oracle_spectral_set_cie(d->cie_xyz, d->cie_xyz + ORACLE_NSPEC, d->cie_xyz + 2 * ORACLE_NSPEC);
+    }
+#endif
     s->lightArea.resize(d->n_lights);
     if (d->n_spheres > 0) s->spheres.assign(d->spheres, d->spheres + d->n_spheres);
     for (int i = 0; i < d->n_lights; ++i)

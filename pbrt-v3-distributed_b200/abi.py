@@ -45,7 +45,9 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(Material)), ("n_lights", C.c_int32),
                 ("lights", C.POINTER(AreaLight)), ("normals", C.c_void_p), ("uvs", C.c_void_p),
                 ("vertex_flags", C.c_void_p), ("n_spheres", C.c_int32), ("spheres", C.POINTER(Sphere)),
-                ("n_instances", C.c_int32), ("instances", C.POINTER(Instance)), ("n_toplevel_triangles", C.c_int64)]
+                ("n_instances", C.c_int32), ("instances", C.POINTER(Instance)), ("n_toplevel_triangles", C.c_int64),
+                ("n_spectrum_samples", C.c_int32), ("reserved_spectral", C.c_int32), ("material_spectra", C.c_void_p),
+                ("light_spectra", C.c_void_p), ("cie_xyz", C.c_void_p)]
 
 
 class CameraDesc(C.Structure):
@@ -61,6 +63,7 @@ class FilmDesc(C.Structure):
 
 
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
+SPECTRUM_SAMPLES, MATERIAL_SPECTRA = 60, 5  # B200PT_SPECTRUM_SAMPLES, B200PT_MATERIAL_SPECTRA
 LIGHT_AREA, LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2, 3
 
 

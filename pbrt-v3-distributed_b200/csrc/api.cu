@@ -34,6 +34,24 @@ struct b200pt_ctx {
     bool gpu_bvh_build = false;  // b200pt_ctx_set_option "gpu_bvh_build"
 };
 
+// Entry points of the SampledSpectrum translation unit (kernels.cu compiled with B200PT_NSPEC 60, see the Makefile).
+// Its RenderDev is the struct of kernels.cuh again -- no member depends on the spectrum type -- so this file hands
+// over its own RenderDev objects (render_dev_size() is checked once per render object).
+namespace b200pt_s60 {
+struct RenderDev;
+void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots, cudaStream_t s);
+void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s);
+void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
+void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t batch_first_tile, uint32_t n_batch_tiles,
+                         cudaStream_t s);
+void set_cie_xyz(const float *xyz, cudaStream_t s);
+size_t render_dev_size();
+}  // namespace b200pt_s60
+static inline const b200pt_s60::RenderDev *s60(const RenderDev *p) { return reinterpret_cast<const b200pt_s60::RenderDev *>(p); }
+static inline const b200pt_s60::RenderDev &s60(const RenderDev &p) { return reinterpret_cast<const b200pt_s60::RenderDev &>(p); }
+
 struct b200pt_scene {
     b200pt_ctx *ctx = nullptr;
     U4 *d_nodes = nullptr;
@@ -54,6 +72,10 @@ struct b200pt_scene {
     uint64_t n_prims = 0;            // triangles of the descriptor (sphere k is reported as primitive n_prims + k)
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
     void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
+    // SampledSpectrum hosts (b200pt_scene_desc::n_spectrum_samples == 60): host copies of the tables
+    int nspec = 0;
+    std::vector<float> material_spectra, light_spectra, cie_xyz;
+    float *d_material_spectra = nullptr;
 };
 
 struct TimedLaunch {
@@ -81,6 +103,21 @@ struct b200pt_render {
     double ms[3] = {0, 0, 0};
     uint64_t launches = 0, launches_cat[3] = {0, 0, 0};
 };
+
+// Host restatement of Spectrum::y() for the light-power distribution (Light::Power().y(), integrator.cpp:216-224):
+// RGBSpectrum (spectrum.h:462-465) or SampledSpectrum (spectrum.h:393-398) with the host's Y curve.
+static float host_spectrum_y(const b200pt_scene *sc, const std::vector<float> &c) {
+    if (!sc->nspec) return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2];
+    const float *Y = sc->cie_xyz.data() + sc->nspec;
+    float yy = 0.f;
+    for (int i = 0; i < sc->nspec; ++i) yy += Y[i] * c[i];
+    return yy * (float(700 - 400) / float(106.856895f * sc->nspec));
+}
+// Lemit / I / L of light i as the host holds it
+static std::vector<float> host_light_spectrum(const b200pt_scene *sc, int i) {
+    if (!sc->nspec) return std::vector<float>(sc->lights[i].lemit, sc->lights[i].lemit + 3);
+    return std::vector<float>(sc->light_spectra.begin() + (size_t)i * sc->nspec, sc->light_spectra.begin() + (size_t)(i + 1) * sc->nspec);
+}
 
 extern "C" {
 
@@ -146,6 +183,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     if (d->n_triangles >= (1ll << 31)) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: too many triangles");
     if (d->n_materials <= 0 || !d->materials) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: no materials");
     if (d->n_materials > 65535) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: more than 65535 materials");
+    if (d->n_spectrum_samples != 0 && d->n_spectrum_samples != B200PT_SPECTRUM_SAMPLES)
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: n_spectrum_samples is %d (0 = RGBSpectrum host, %d = SampledSpectrum host)",
+                           d->n_spectrum_samples, B200PT_SPECTRUM_SAMPLES);
+    if (d->n_spectrum_samples != 0 && (!d->material_spectra || !d->cie_xyz || (d->n_lights > 0 && !d->light_spectra)))
+        return b200pt_fail(B200PT_ERR_INVALID, "scene_create: a SampledSpectrum host must pass material_spectra, light_spectra and cie_xyz");
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type < 0 || d->materials[i].type > B200PT_MAT_GLASS)
             return b200pt_fail(B200PT_ERR_INVALID, "scene_create: material %d has unsupported type %d", i,
@@ -385,6 +427,13 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     s->n_tris = n_tri_records;
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
+    s->nspec = d->n_spectrum_samples;
+    if (s->nspec) {
+        const size_t ns = (size_t)s->nspec;
+        s->material_spectra.assign(d->material_spectra, d->material_spectra + (size_t)d->n_materials * B200PT_MATERIAL_SPECTRA * ns);
+        if (d->n_lights > 0) s->light_spectra.assign(d->light_spectra, d->light_spectra + (size_t)d->n_lights * ns);
+        s->cie_xyz.assign(d->cie_xyz, d->cie_xyz + 3 * ns);
+    }
     s->prim_to_tri = std::move(bvh.prim_to_tri);
     for (int a = 0; a < 3; ++a) {
         s->bounds_lo[a] = INFINITY;
@@ -474,6 +523,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     if ((!gpu_build && ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_node_records) * sizeof(Bvh8Node))) != cudaSuccess ||
                         (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess)) ||
         (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_material_spectra, std::max<size_t>(1, s->material_spectra.size()) * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_spheres, std::max<size_t>(1, s->spheres.size()) * sizeof(DevSphere))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_instances, std::max<size_t>(1, s->instances.size()) * sizeof(DevInstance))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
@@ -542,11 +592,13 @@ int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
     CUDA_TRY(cudaMemcpyAsync(s->d_nodes, s->h_nodes, nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_tris, s->h_tris, tb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_materials, s->materials.data(), mb, cudaMemcpyHostToDevice, st));
+    const size_t msb = s->material_spectra.size() * sizeof(float);
+    if (msb) CUDA_TRY(cudaMemcpyAsync(s->d_material_spectra, s->material_spectra.data(), msb, cudaMemcpyHostToDevice, st));
     const size_t sb = s->spheres.size() * sizeof(DevSphere);
     if (sb) CUDA_TRY(cudaMemcpyAsync(s->d_spheres, s->spheres.data(), sb, cudaMemcpyHostToDevice, st));
     const size_t ib = s->instances.size() * sizeof(DevInstance);
     if (ib) CUDA_TRY(cudaMemcpyAsync(s->d_instances, s->instances.data(), ib, cudaMemcpyHostToDevice, st));
-    if (bytes) *bytes = nb + tb + mb + sb + ib;
+    if (bytes) *bytes = nb + tb + mb + sb + ib + msb;
     return B200PT_OK;
 }
 
@@ -556,6 +608,7 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     cudaFree(s->d_nodes);
     cudaFree(s->d_tris);
     cudaFree(s->d_materials);
+    cudaFree(s->d_material_spectra);
     cudaFree(s->d_tri_n);
     cudaFree(s->d_tri_uv);
     cudaFree(s->d_spheres);
@@ -721,6 +774,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.scene.nodes = scene->d_nodes;
     H.scene.tris = scene->d_tris;
     H.scene.materials = scene->d_materials;
+    H.scene.material_spectra = scene->nspec ? scene->d_material_spectra : nullptr;
     H.scene.n_nodes = (uint32_t)scene->n_nodes;
     H.scene.n_tris = (uint32_t)scene->n_tris;
     H.scene.tri_n = scene->d_tri_n;
@@ -834,15 +888,17 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
             const float wr = sl.world_radius != 0.f ? sl.world_radius : world_radius;
             dl[i].two_world_radius = 2 * wr;
             if (integ->light_strategy == B200PT_LIGHTS_POWER && nl != 1) {
-                // Light::Power().y(): point.cpp:58, spot.cpp:78-80, distant.cpp:62-64
-                RGB p;
-                if (sl.kind == B200PT_LIGHT_POINT)
-                    p = 4 * PT_PI * rgbp(sl.lemit);
-                else if (sl.kind == B200PT_LIGHT_SPOT)
-                    p = rgbp(sl.lemit) * 2 * PT_PI * (1 - .5f * (sl.cos_falloff_start + sl.cos_total_width));
-                else
-                    p = rgbp(sl.lemit) * PT_PI * wr * wr;
-                func[i] = lum(p);
+                // Light::Power().y(): point.cpp:58, spot.cpp:78-80, distant.cpp:62-64 (per bin, then y())
+                std::vector<float> p = host_light_spectrum(scene, i);
+                for (float &c : p) {
+                    if (sl.kind == B200PT_LIGHT_POINT)
+                        c = (4 * PT_PI) * c;
+                    else if (sl.kind == B200PT_LIGHT_SPOT)
+                        c = c * 2 * PT_PI * (1 - .5f * (sl.cos_falloff_start + sl.cos_total_width));
+                    else
+                        c = c * PT_PI * wr * wr;
+                }
+                func[i] = host_spectrum_y(scene, p);
             }
             continue;
         }
@@ -852,8 +908,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         if (integ->light_strategy == B200PT_LIGHTS_POWER && nl != 1) {
             // DiffuseAreaLight::Power().y(), diffuse.cpp:64-66 + integrator.cpp:216-224
             const float k = dl[i].two_sided ? 2.f : 1.f;
-            RGB p = k * rgbp(dl[i].lemit) * dl[i].area * PT_PI;
-            func[i] = lum(p);
+            std::vector<float> p = host_light_spectrum(scene, i);
+            for (float &c : p) c = c * k * dl[i].area * PT_PI;
+            func[i] = host_spectrum_y(scene, p);
         }
     }
     float funcInt = 0.f;
@@ -897,7 +954,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     }
 
     // batch sizing: whole tiles, about B200PT_BATCH_PATHS path slots
-    size_t target = 16u << 20;  // path slots per batch (~200 B each)
+    // path slots per batch: ~200 B each, plus 5 x 60 floats with a SampledSpectrum host
+    size_t target = scene->nspec ? (4u << 20) : (16u << 20);
     if (const char *e = getenv("B200PT_BATCH_PATHS")) target = (size_t)atoll(e);
     const size_t per_tile = 256u * (size_t)r->spp;
     r->tiles_per_batch = (uint32_t)std::max<size_t>(1, target / per_tile);
@@ -949,6 +1007,16 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.occluded, cap);
     ALLOC(H.mis_hit, cap);
     ALLOC(H.pix_bleed, (size_t)r->tiles_per_batch * 256);
+    float *d_light_spectra = nullptr;
+    if (scene->nspec) {
+        const size_t planar = cap * (size_t)scene->nspec;
+        ALLOC(H.s_beta, planar);
+        ALLOC(H.s_L, planar);
+        ALLOC(H.s_A, planar);
+        ALLOC(H.s_B, planar);
+        ALLOC(H.s_beta_ld, planar);
+        ALLOC(d_light_spectra, std::max<size_t>(1, scene->light_spectra.size()));
+    }
     float *d_filter_table = nullptr;
     if (filter_general) {
         ALLOC(d_filter_table, 256);
@@ -976,6 +1044,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.sampler.mat32 = mat32;
     H.sampler.table = getenv("B200PT_NO_SOBOL_TABLE") ? nullptr : sobol_table;
     H.lights = d_lights;
+    H.light_spectra = d_light_spectra;
     H.has_delta_lights = has_delta ? 1 : 0;
     H.light_cdf = d_cdf;
     H.light_func = d_func;
@@ -993,6 +1062,16 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         launch_sobol_table(mat32, sobol_table, smp->n_dimensions, st);
     }
     if (nl) CUDA_TRY(cudaMemcpyAsync(d_lights, dl.data(), nl * sizeof(DevLight), cudaMemcpyHostToDevice, st));
+    if (scene->nspec) {
+        if (b200pt_s60::render_dev_size() != sizeof(RenderDev)) {
+            b200pt_render_destroy(r);
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: the SampledSpectrum kernels were built with another RenderDev layout");
+        }
+        if (!scene->light_spectra.empty())
+            CUDA_TRY(cudaMemcpyAsync(d_light_spectra, scene->light_spectra.data(), scene->light_spectra.size() * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        b200pt_s60::set_cie_xyz(scene->cie_xyz.data(), st);
+    }
     CUDA_TRY(cudaMemcpyAsync(d_cdf, cdf.data(), (nl + 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_func, func.data(), std::max(nl, 1) * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(H.film, 0, (size_t)cw * chh * sizeof(float4), st));
@@ -1007,7 +1086,10 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     CUDA_TRY(cudaMemsetAsync(H.stats, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemcpyAsync(r->d_dev, &H, sizeof(H), cudaMemcpyHostToDevice, st));
     if (H.grid.enabled) {
-        launch_spatial_build(r->d_dev, H, st);
+        if (scene->nspec)
+            b200pt_s60::launch_spatial_build(s60(r->d_dev), s60(H), st);
+        else
+            launch_spatial_build(r->d_dev, H, st);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1122,6 +1204,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         CUDA_TRY(cudaMemcpyAsync(r->d_dev, &r->host, sizeof(RenderDev), cudaMemcpyHostToDevice, st));
     }
     const RenderDev &H = r->host;
+    const bool spectral = r->scene->nspec != 0;
     const int maxDepth = H.max_depth;
     const size_t qbytes = (size_t)(maxDepth + 2) * Q_PER_BOUNCE * sizeof(uint32_t);
     const size_t wbytes = (size_t)(maxDepth + 2) * 16 * sizeof(uint32_t);
@@ -1136,7 +1219,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         CUDA_TRY(cudaMemsetAsync(H.pix_bleed, 0, (size_t)nb * 256, st));
         {
             LaunchTimer lt(r, st, 2);
-            launch_raygen(r->d_dev, (uint32_t)first, nb, n_slots, st);
+            if (spectral)
+                b200pt_s60::launch_raygen(s60(r->d_dev), (uint32_t)first, nb, n_slots, st);
+            else
+                launch_raygen(r->d_dev, (uint32_t)first, nb, n_slots, st);
         }
         // Launch order per bounce b (path.cpp:81-188):
         //   closest(b) -> shade(b) -> { any(b), MIS-closest(b) } || closest(b+1) -> resolve(b) -> shade(b+1) ...
@@ -1252,8 +1338,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
-                    launch_shade(r->d_dev, m, full_shade, b, wk + 1 + m,
-                                 r->grid_shade, st);
+                    if (spectral)
+                        b200pt_s60::launch_shade(s60(r->d_dev), m, full_shade, b, wk + 1 + m, r->grid_shade, st);
+                    else
+                        launch_shade(r->d_dev, m, full_shade, b, wk + 1 + m, r->grid_shade, st);
                 }
             if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
                 if (overlap) {
@@ -1265,13 +1353,20 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                 trace_path(b + 1);
                 if (overlap) CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
                 LaunchTimer lt(r, st, 2);
-                launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
+                if (spectral)
+                    b200pt_s60::launch_resolve(s60(r->d_dev), b, wk + 7, r->grid_shade, st);
+                else
+                    launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
             }
         }
         {
             LaunchTimer lt(r, st, 2);
-            if (H.filter_general)
+            if (H.filter_general && spectral)
+                b200pt_s60::launch_film_general(s60(r->d_dev), s60(H), (uint32_t)first, nb, st);
+            else if (H.filter_general)
                 launch_film_general(r->d_dev, H, (uint32_t)first, nb, st);
+            else if (spectral)
+                b200pt_s60::launch_film(s60(r->d_dev), (uint32_t)first, nb, st);
             else
                 launch_film(r->d_dev, (uint32_t)first, nb, st);
         }
@@ -1362,18 +1457,45 @@ int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *
     int rc = b200pt_render_tiles(r, &tile, 1);
     if (rc == B200PT_OK) {
         const uint32_t pix = (uint32_t)((py - (H.sampler.sb[1] + ty * 16)) * 16 + (px - (H.sampler.sb[0] + tx * 16)));
+        const int ns = r->scene->nspec;
         std::vector<float4> tmp((size_t)r->spp);
+        std::vector<float> bins((size_t)r->spp * (size_t)std::max(ns, 1));
         cudaError_t e = cudaMemcpyAsync(tmp.data(), H.L + (size_t)pix * r->spp, (size_t)r->spp * sizeof(float4),
                                         cudaMemcpyDeviceToHost, st);
+        for (int b = 0; b < ns && e == cudaSuccess; ++b)  // planar [bin][capacity]
+            e = cudaMemcpyAsync(bins.data() + (size_t)b * r->spp, H.s_L + (size_t)b * H.capacity + (size_t)pix * r->spp,
+                                (size_t)r->spp * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(H.film, saved, npx * sizeof(float4), cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = b200pt_fail(B200PT_ERR_CUDA, "debug_pixel_samples: %s", cudaGetErrorString(e));
         for (int i = 0; i < r->spp && rc == B200PT_OK; ++i) {
-            RGB L = rgb(tmp[i].x, tmp[i].y, tmp[i].z);
-            if (has_nans(L) || lum(L) < -1e-5f || pt_isinf(lum(L))) L = rgb1(0.f);  // integrator.cpp:294-315
-            out_rgb[3 * i] = L.r;
-            out_rgb[3 * i + 1] = L.g;
-            out_rgb[3 * i + 2] = L.b;
+            if (!ns) {
+                Spec L = rgb(tmp[i].x, tmp[i].y, tmp[i].z);
+                if (has_nans(L) || lum(L) < -1e-5f || pt_isinf(lum(L))) L = rgb1(0.f);  // integrator.cpp:294-315
+                out_rgb[3 * i] = L.c[0];
+                out_rgb[3 * i + 1] = L.c[1];
+                out_rgb[3 * i + 2] = L.c[2];
+                continue;
+            }
+            // SampledSpectrum host: the sample as ToXYZ -> XYZToRGB reports it (spectrum.h:380-392, :56-60)
+            std::vector<float> L((size_t)ns);
+            bool nan = false;
+            for (int b = 0; b < ns; ++b) {
+                L[b] = bins[(size_t)b * r->spp + i];
+                nan = nan || pt_isnan(L[b]);
+            }
+            const float y = host_spectrum_y(r->scene, L);
+            if (nan || y < -1e-5f || pt_isinf(y)) std::fill(L.begin(), L.end(), 0.f);
+            const float *cie = r->scene->cie_xyz.data();
+            float xyz[3] = {0.f, 0.f, 0.f};
+            for (int b = 0; b < ns; ++b) {
+                xyz[0] += cie[b] * L[b];
+                xyz[1] += cie[ns + b] * L[b];
+                xyz[2] += cie[2 * ns + b] * L[b];
+            }
+            const float scale = float(700 - 400) / float(106.856895f * ns);
+            for (int k = 0; k < 3; ++k) xyz[k] *= scale;
+            xyz_to_rgb(xyz, out_rgb + 3 * i);
         }
     }
     cudaFree(saved);

@@ -20,7 +20,7 @@
 
 #include "pt_core.cuh"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 struct U4 {
     uint32_t x, y, z, w;
@@ -262,5 +262,5 @@ B200_HD uint32_t traverse_bvh8(const U4 *__restrict__ nodes, const F4 *__restric
     return T.best;
 }
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

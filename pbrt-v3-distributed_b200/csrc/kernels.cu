@@ -14,15 +14,51 @@
 
 #include "kernels.cuh"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 #define FULL_MASK 0xffffffffu
 
 __device__ __forceinline__ V3 v3(const float4 &f) { return mk(f.x, f.y, f.z); }
 __device__ __forceinline__ V3 v3(const F4 &f) { return mk(f.x, f.y, f.z); }
 __device__ __forceinline__ float4 f4(const V3 &v, float w) { return make_float4(v.x, v.y, v.z, w); }
-__device__ __forceinline__ float4 f4(const RGB &c, float w) { return make_float4(c.r, c.g, c.b, w); }
-__device__ __forceinline__ RGB rgb3(const float4 &f) { return rgb(f.x, f.y, f.z); }
+// A per-slot spectrum travels with one packed scalar.  RGBSpectrum build: one float4 (r, g, b, w).  SampledSpectrum
+// build: the float4 keeps only w and the 60 bins live in a planar array [bin][capacity] (coalesced across slots).
+__device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *planar, uint32_t cap, uint32_t slot, float *w) {
+    const float4 f = a4[slot];
+    *w = f.w;
+#if B200PT_NSPEC == 3
+    (void)planar;
+    (void)cap;
+    return rgb(f.x, f.y, f.z);
+#else
+    Spec s;
+#pragma unroll
+    SPEC_FOR s.c[i_] = planar[(size_t)i_ * cap + slot];
+    return s;
+#endif
+}
+__device__ __forceinline__ void st_spec(float4 *a4, float *planar, uint32_t cap, uint32_t slot, const Spec &s, float w) {
+#if B200PT_NSPEC == 3
+    (void)planar;
+    (void)cap;
+    a4[slot] = make_float4(s.c[0], s.c[1], s.c[2], w);
+#else
+    a4[slot] = make_float4(0.f, 0.f, 0.f, w);
+#pragma unroll
+    SPEC_FOR planar[(size_t)i_ * cap + slot] = s.c[i_];
+#endif
+}
+// Lemit / I / L of light `lightNum` (b200pt_area_light::lemit, or its row of b200pt_scene_desc::light_spectra)
+__device__ __forceinline__ Spec light_emit(const RenderDev *R, int lightNum, const DevLight &l) {
+#if B200PT_NSPEC == 3
+    (void)R;
+    (void)lightNum;
+    return rgbp(l.lemit);
+#else
+    (void)l;
+    return rgbp(R->light_spectra + (size_t)lightNum * B200PT_NSPEC);
+#endif
+}
 
 // Warp-aggregated append: every lane of the warp must call it (converged);
 // lanes with pred get consecutive positions behind one atomicAdd.
@@ -131,8 +167,8 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
             R->sobol[slot] = st.index;
             R->ray_o[slot] = f4(o, 1.f);                                // etaScale = 1
             R->ray_d[slot] = f4(d, __uint_as_float((uint32_t)st.dim));  // dim = 5, bounces = 0, flags = 0
-            R->beta[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-            R->L[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(code));
+            st_spec(R->beta, R->s_beta, R->capacity, slot, rgb1(1.f), 0.f);
+            st_spec(R->L, R->s_L, R->capacity, slot, rgb1(0.f), __uint_as_float(code));
             R->sh_d[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -140,6 +176,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
     if (valid) R->q_path[0][pos] = slot;
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 // ----------------------------------------------------------------------- trace
 // Persistent warps; every lane owns one ray at a time.  A lane whose ray is
 // finished parks until fewer than `refill_lanes` lanes of the warp are
@@ -465,11 +502,12 @@ __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
     }
 }
 
-__device__ __forceinline__ DeltaLight delta_of(const DevLight &l) {
+#endif  // B200PT_NSPEC == 3
+__device__ __forceinline__ DeltaLight delta_of(const DevLight &l, const Spec &intensity) {
     DeltaLight d;
     d.kind = l.kind;
     d.position = mk(l.position[0], l.position[1], l.position[2]);
-    d.intensity = rgbp(l.lemit);
+    d.intensity = intensity;
     d.cos_total_width = l.cos_total_width;
     d.cos_falloff_start = l.cos_falloff_start;
     d.world_to_light = l.world_to_light;
@@ -481,7 +519,7 @@ __device__ __forceinline__ DeltaLight delta_of(const DevLight &l) {
 struct DirectOut {
     uint32_t pend;
     V3 sh_o, sh_d, mi_o, mi_d;
-    RGB A, B;
+    Spec A, B;
 };
 
 // EstimateDirect (core/integrator.cpp:108-215), handleMedia = false,
@@ -498,11 +536,11 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         out->pend = 0;
         out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
         out->A = out->B = rgb1(0.f);
-        const DeltaLight dl = delta_of(lightRef);
+        const DeltaLight dl = delta_of(lightRef, light_emit(R, lightNum, lightRef));
         V3 wiD, pTarget;
-        const RGB LiD = delta_light_sample(dl, is.p, &wiD, &pTarget);
+        const Spec LiD = delta_light_sample(dl, is.p, &wiD, &pTarget);
         if (!is_black(LiD)) {
-            const RGB fD = bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
+            const Spec fD = bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
             if (!is_black(fD)) {
                 // SpawnRayTo(Interaction) towards a point without normal or error bounds (interaction.h:73-78)
                 const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
@@ -530,7 +568,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
     TriShading lsh;
     load_shading<VTX>(R->scene, light.tri, lflags, &lsh);
-    const RGB lemit = rgbp(light.lemit);
+    const Spec lemit = light_emit(R, lightNum, light);
     const int flagsNS = BSDF_ALL & ~BSDF_SPECULAR;
     out->pend = 0;
     out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
@@ -538,7 +576,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     V3 wi = mk(0.f, 0.f, 0.f);
     float lightPdf = 0.f, scatteringPdf = 0.f;
     // light.Sample_Li: diffuse.cpp:68-81, shape.cpp:56-70
-    RGB Li = rgb1(0.f);
+    Spec Li = rgb1(0.f);
     LightSample ps;
     if (onSphere) {
         ps = sphere_sample(*lsp, is.p, is.pError, is.n, uLight, &lightPdf);  // already a solid-angle density
@@ -560,7 +598,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         Li = (light.two_sided || dot(ps.n, -wi) > 0) ? lemit : rgb1(0.f);  // diffuse.h:56-58
     }
     if (lightPdf > 0 && !is_black(Li)) {
-        RGB f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
+        Spec f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
         scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
         if (!is_black(f)) {
             // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
@@ -575,7 +613,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     }
     // BSDF sampling with MIS (integrator.cpp:166-213)
     int sampledType = 0;
-    RGB f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+    Spec f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
     f = f * absdot(wi, bsdf.ns);
     if (!is_black(f) && scatteringPdf > 0) {
         // light.Pdf_Li -> Shape::Pdf (shape.cpp:72-87): intersect the light's own triangle
@@ -601,7 +639,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         if (lpdf != 0) {
             const float weight = power_heuristic(scatteringPdf, lpdf);
             // lightIsect.Le(-wi) if the closest hit along the ray is this light (integrator.cpp:205-209)
-            const RGB Le = (light.two_sided || dot(ln, -wi) > 0) ? lemit : rgb1(0.f);
+            const Spec Le = (light.two_sided || dot(ln, -wi) > 0) ? lemit : rgb1(0.f);
             out->B = is_black(Le) ? rgb1(0.f) : f * Le * 1.f * weight / scatteringPdf;
             out->mi_o = ro;
             out->mi_d = wi;
@@ -625,14 +663,15 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
         uint32_t pend = 0, slot = 0;
         if (active) {
             slot = queue[i];
-            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot], b4 = R->beta[slot];
-            float4 L4 = R->L[slot];
+            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
+            float betaW, LW;
+            Spec beta = ld_spec(R->beta, R->s_beta, R->capacity, slot, &betaW);
+            Spec L = ld_spec(R->L, R->s_L, R->capacity, slot, &LW);
             const V3 ro = v3(o4), rd = v3(d4);
             float etaScale = o4.w;
             const uint32_t meta = __float_as_uint(d4.w);
             const int bounces = (int)((meta >> 16) & 0xffu);
             const bool specularBounce = ((meta >> 24) & PF_SPECULAR) != 0;
-            RGB beta = rgb3(b4), L = rgb3(L4);
             const uint32_t ti = R->hit[slot];
             Isect is;
             uint32_t mflags;
@@ -680,13 +719,14 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                 if (bounces == 0 || specularBounce) {
                     if (lightId >= 0) {
                         const DevLight lt = R->lights[lightId];
-                        const RGB Le = (lt.two_sided || dot(is.n, -rd) > 0) ? rgbp(lt.lemit) : rgb1(0.f);
+                        const Spec Le = (lt.two_sided || dot(is.n, -rd) > 0) ? light_emit(R, lightId, lt) : rgb1(0.f);
                         L = L + beta * Le;
                     }
                 }
                 if (bounces < R->max_depth) {  // path.cpp:104
                     Bsdf bsdf;
-                    make_bsdf<MAT>(R->scene.materials[mflags & 0xffffu], is, &bsdf);
+                    const uint32_t mi = mflags & 0xffffu;
+                    make_bsdf<MAT>(R->scene.materials[mi], R->scene.material_spectra + (size_t)mi * (5 * B200PT_NSPEC), is, &bsdf);
                     SobolStream st;
                     st.index = R->sobol[slot];
                     st.dim = (int)(meta & 0xffffu);
@@ -712,13 +752,13 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                             estimate_direct<VTX>(R, is, bsdf, uScattering, lightNum, uLight, &dout);
                             pend = dout.pend;
                             if (pend) {
-                                R->beta_ld[slot] = f4(beta, pickPdf);
+                                st_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, beta, pickPdf);
                                 R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
-                                if (pend & PEND_LIGHT) R->A[slot] = f4(dout.A, 0.f);
+                                if (pend & PEND_LIGHT) st_spec(R->A, R->s_A, R->capacity, slot, dout.A, 0.f);
                                 if (pend & PEND_BSDF) {
                                     R->mi_o[slot] = f4(dout.mi_o, 0.f);
                                     R->mi_d[slot] = f4(dout.mi_d, 0.f);
-                                    R->B[slot] = f4(dout.B, 0.f);
+                                    st_spec(R->B, R->s_B, R->capacity, slot, dout.B, 0.f);
                                 }
                             }
                             R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
@@ -731,7 +771,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                     int flags = 0;
                     float u2[2];
                     get2d(sp, st, u2);
-                    const RGB f = bsdf_sample_f(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+                    const Spec f = bsdf_sample_f(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
                     if (!(is_black(f) || pdf == 0.f)) {
                         beta = beta * (f * absdot(wi, bsdf.ns) / pdf);
                         const bool spec = (flags & BSDF_SPECULAR) != 0;
@@ -742,7 +782,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                         const V3 no = offset_ray_origin(is.p, is.pError, is.n, wi);  // isect.SpawnRay(wi)
                         cont = true;
                         // path.cpp:176-184: Russian roulette
-                        const RGB rrBeta = beta * etaScale;
+                        const Spec rrBeta = beta * etaScale;
                         if (max_comp(rrBeta) < R->rr_threshold && bounces > 3) {
                             const float q = pt_max(.05f, 1 - max_comp(rrBeta));
                             if (get1d(sp, st) < q)
@@ -755,11 +795,11 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                                                    ((spec ? (uint32_t)PF_SPECULAR : 0u) << 24);
                             R->ray_o[slot] = f4(no, etaScale);
                             R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
-                            R->beta[slot] = f4(beta, 0.f);
+                            st_spec(R->beta, R->s_beta, R->capacity, slot, beta, 0.f);
                         }
                     }
                 }
-                R->L[slot] = f4(L, L4.w);
+                st_spec(R->L, R->s_L, R->capacity, slot, L, LW);
             }
         }
         const uint32_t ps = warp_append(qc_shadow, (pend & PEND_LIGHT) != 0);
@@ -782,30 +822,33 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
         const float4 sd = R->sh_d[slot];
         const uint32_t pend = __float_as_uint(sd.w);
         if (!pend) continue;
-        RGB Ld = rgb1(0.f);
+        Spec Ld = rgb1(0.f);
         bool any = false;
         if ((pend & PEND_LIGHT) && !R->occluded[slot]) {
-            Ld = Ld + rgb3(R->A[slot]);
+            float w_;
+            Ld = Ld + ld_spec(R->A, R->s_A, R->capacity, slot, &w_);
             any = true;
         }
         if (pend & PEND_BSDF) {
             const uint32_t lightNum = __float_as_uint(R->sh_o[slot].w);
-            const RGB B = rgb3(R->B[slot]);
+            float w_;
+            const Spec B = ld_spec(R->B, R->s_B, R->capacity, slot, &w_);
             if (R->mis_hit[slot] == R->lights[lightNum].tri && !is_black(B)) {
                 Ld = Ld + B;
                 any = true;
             }
         }
         if (any) {
-            const float4 bl = R->beta_ld[slot];
-            float4 L4 = R->L[slot];
-            const RGB L = rgb3(L4) + rgb3(bl) * (Ld / bl.w);
-            R->L[slot] = f4(L, L4.w);
+            float pickPdf, LW;
+            const Spec betaLd = ld_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, &pickPdf);
+            const Spec L = ld_spec(R->L, R->s_L, R->capacity, slot, &LW) + betaLd * (Ld / pickPdf);
+            st_spec(R->L, R->s_L, R->capacity, slot, L, LW);
         }
         R->sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
     }
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 // Sobol' byte tables: table[dim][k][b] = XOR of SobolMatrices32[dim*52 + 8k + i] over the set bits i of b.
 __global__ void k_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -821,6 +864,7 @@ void launch_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims, cuda
     k_sobol_table<<<(n + 255) / 256, 256, 0, s>>>(mat32, table, n_dims);
 }
 
+#endif  // B200PT_NSPEC == 3
 // --------------------------------------------------- spatial light distribution
 // SpatialLightDistribution::ComputeDistribution for every voxel (the reference fills its hash table
 // lazily; a voxel's distribution is a pure function of the voxel).  One thread per (voxel, light)
@@ -835,8 +879,9 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     const int vx = (int)(vox % g.nv[0]), vy = (int)((vox / g.nv[0]) % g.nv[1]), vz = (int)(vox / ((long long)g.nv[0] * g.nv[1]));
     const DevLight light = R->lights[j];
     const bool isDelta = light.kind != 0;
+    const Spec lemit = light_emit(R, j, light);
     DeltaLight dl;
-    if (isDelta) dl = delta_of(R->lights[j]);
+    if (isDelta) dl = delta_of(R->lights[j], lemit);
     const bool onSphere = !isDelta && is_sphere_hit(light.tri);
     const F4 *tp = R->scene.tris + (size_t)((onSphere || isDelta) ? 0u : light.tri) * 3;
     F4 t0 = {0.f, 0.f, 0.f, 0.f}, t1 = t0, t2 = t0;
@@ -849,7 +894,7 @@ __global__ void __launch_bounds__(128) k_spatial_contrib(const RenderDev *R) {
     TriShading lsh;
     load_shading<true>(R->scene, isDelta ? 0u : light.tri, lflags, &lsh);
     R->sp_func[vox * R->n_lights + j] =
-        spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0, lsh, rgbp(light.lemit),
+        spatial_light_contrib(g, vx, vy, vz, v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0, lsh, lemit,
                               light.two_sided != 0, onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr,
                               isDelta ? &dl : nullptr);
 }
@@ -878,6 +923,7 @@ __global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
     R->sp_func_int[vox] = funcInt;
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 // ------------------------------------------------------------------------ sort
 // Coherence sort between bounces: rays that start in the same cell of a 32^3 grid and travel into
 // the same octant become neighbours in the queue, so the lanes of a warp walk the same top of the
@@ -936,6 +982,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const RenderDev *R, const 
     }
 }
 
+#endif  // B200PT_NSPEC == 3
 // ------------------------------------------------------------------------ film
 // One block per tile, one thread per pixel of the tile's FilmTile (the tile
 // plus a one-pixel apron, film.cpp:95-106).  A thread re-creates the
@@ -953,7 +1000,7 @@ __global__ void __launch_bounds__(18 * 18) k_film(const RenderDev *R, uint32_t f
     if (X < R->crop[0] || X >= R->crop[2] || Y < R->crop[1] || Y >= R->crop[3]) return;
     const uint32_t spp = (uint32_t)R->sampler.spp;
     const float maxLum = R->max_sample_luminance;
-    RGB sum = rgb1(0.f);
+    Spec sum = rgb1(0.f);
     float wsum = 0.f;
     for (int sy = Y - 1; sy <= Y + 1; ++sy)
         for (int sx = X - 1; sx <= X + 1; ++sx) {
@@ -961,16 +1008,16 @@ __global__ void __launch_bounds__(18 * 18) k_film(const RenderDev *R, uint32_t f
             const uint32_t pix = (uint32_t)((sy - t.y0) * 16 + (sx - t.x0));
             const bool own = (sx == X && sy == Y);
             if (!own && !R->pix_bleed[tb * 256u + pix]) continue;
-            const float4 *Ls = R->L + ((size_t)tb * 256u + pix) * spp;
+            const uint32_t base = (tb * 256u + pix) * spp;
             for (uint32_t s = 0; s < spp; ++s) {
-                const float4 v = Ls[s];
+                float vw;
+                Spec Lv = ld_spec(R->L, R->s_L, R->capacity, base + s, &vw);
                 if (!own) {
-                    const uint32_t code = __float_as_uint(v.w);
+                    const uint32_t code = __float_as_uint(vw);
                     const bool cx = (X == sx) || (X == sx - 1 && (code & 1u)) || (X == sx + 1 && (code & 2u));
                     const bool cy = (Y == sy) || (Y == sy - 1 && (code & 4u)) || (Y == sy + 1 && (code & 8u));
                     if (!(cx && cy)) continue;
                 }
-                RGB Lv = rgb(v.x, v.y, v.z);
                 // integrator.cpp:294-315
                 if (has_nans(Lv))
                     Lv = rgb1(0.f);
@@ -1025,7 +1072,7 @@ __global__ void __launch_bounds__(1024) k_film_tile(const RenderDev *R, uint32_t
         const uint32_t spp = (uint32_t)R->sampler.spp;
         const float maxLum = R->max_sample_luminance;
         const float rx = R->filter_radius[0], ry = R->filter_radius[1];
-        RGB sum = rgb1(0.f);
+        Spec sum = rgb1(0.f);
         float wsum = 0.f;
         // source pixels whose samples can reach this pixel: |pFilm - 0.5 - X| <= r with pFilm in [sx, sx + 1)
         const int sx0 = max(t.x0, (int)ceilf((float)X - 0.5f - rx) - 1), sx1 = min(t.x1 - 1, (int)floorf((float)X + 0.5f + rx) + 1);
@@ -1045,8 +1092,8 @@ __global__ void __launch_bounds__(1024) k_film_tile(const RenderDev *R, uint32_t
                     const float fy = fabsf(((float)Y - dy) * R->filter_inv_radius[1] * 16.f);
                     const int ifx = min((int)floorf(fx), 15), ify = min((int)floorf(fy), 15);
                     const float w = R->filter_table[ify * 16 + ifx];
-                    const float4 v = R->L[base + s];
-                    RGB Lv = rgb(v.x, v.y, v.z);
+                    float vw;
+                    Spec Lv = ld_spec(R->L, R->s_L, R->capacity, (uint32_t)(base + s), &vw);
                     // integrator.cpp:294-315
                     if (has_nans(Lv))
                         Lv = rgb1(0.f);
@@ -1103,6 +1150,7 @@ __global__ void k_film_tile_slots_reset(const RenderDev *R, uint32_t first_tile,
     if (tb < n_batch_tiles) R->tile_slot[R->tile_list[first_tile + tb]] = -1;
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 __global__ void k_accumulate_stats(const RenderDev *R) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long regular = 0, shadow = 0;
@@ -1174,6 +1222,7 @@ __global__ void k_debug_camera(const RenderDev *R, int px, int py, int n, b200pt
     out[i] = r;
 }
 
+#endif  // B200PT_NSPEC == 3
 // -------------------------------------------------------------------- launchers
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
                    cudaStream_t s) {
@@ -1181,6 +1230,7 @@ void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_b
     k_raygen<<<(n_slots + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_slots);
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s) {
     if (any_hit) {
         if (count)
@@ -1209,6 +1259,7 @@ void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, c
         k_spheres<false, false><<<grid, 128, 0, s>>>(a);
 }
 
+#endif  // B200PT_NSPEC == 3
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
                   cudaStream_t s) {
 #define B200PT_SHADE(M)                                               \
@@ -1238,6 +1289,7 @@ void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStrea
     k_spatial_cdf<<<(unsigned)((nvox + 127) / 128), 128, 0, s>>>(dev);
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
                        const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s) {
     cudaMemsetAsync(host.sort_hist, 0, SORT_BUCKETS * sizeof(uint32_t), s);
@@ -1246,6 +1298,7 @@ void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32
     k_sort_scatter<<<grid, 256, 0, s>>>(dev, queue, count);
 }
 
+#endif  // B200PT_NSPEC == 3
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s) {
     k_film<<<n_batch_tiles, dim3(18, 18), 0, s>>>(dev, batch_first_tile);
 }
@@ -1260,6 +1313,7 @@ void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t b
     k_film_tile_slots_reset<<<(n_batch_tiles + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_batch_tiles);
 }
 
+#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 void launch_accumulate_stats(const RenderDev *dev, uint32_t, cudaStream_t s) { k_accumulate_stats<<<1, 32, 0, s>>>(dev); }
 
 void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
@@ -1273,4 +1327,14 @@ void launch_film_rgb(const float4 *film, float *rgb, int n_pixels, float scale, 
     k_film_rgb<<<(n_pixels + 255) / 256, 256, 0, s>>>(film, rgb, n_pixels, scale);
 }
 
-}  // namespace b200pt
+#endif  // B200PT_NSPEC == 3
+#if B200PT_NSPEC != 3
+// SampledSpectrum::X / Y / Z of the host (b200pt_scene_desc::cie_xyz) into this translation unit's constant memory
+void set_cie_xyz(const float *xyz, cudaStream_t s) {
+    cudaMemcpyToSymbolAsync(c_cie_xyz, xyz, sizeof(float) * 3 * B200PT_NSPEC, 0, cudaMemcpyHostToDevice, s);
+}
+// api.cu is compiled with the RGBSpectrum structs; RenderDev must not depend on the spectrum type
+size_t render_dev_size() { return sizeof(RenderDev); }
+#endif
+
+}  // namespace B200PT_NS

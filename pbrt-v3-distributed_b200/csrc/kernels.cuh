@@ -17,7 +17,7 @@
 #include "pt_core.cuh"
 #include "pt_sphere.cuh"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 struct DevLight {
     uint32_t tri;  // leaf-order triangle index, or SPHERE_HIT_BASE | sphere index (the id traversal reports)
@@ -37,6 +37,7 @@ struct DevScene {
     const U4 *nodes;
     const F4 *tris;
     const b200pt_material *materials;
+    const float *material_spectra;  // SampledSpectrum build: [n_materials][5][60] (kd, ks, kt, eta, k), else nullptr
     uint32_t n_nodes, n_tris;
     const F4 *tri_n;   // optional per-vertex shading normals, 3 x float4 per triangle (leaf order)
     const F4 *tri_uv;  // optional uvs, 2 x float4 per triangle: (u0 v0 u1 v1) (u2 v2 - -)
@@ -105,6 +106,10 @@ struct RenderDev {
     float4 *beta_ld;   // beta at the time of the direct-lighting estimate
     uint8_t *occluded; // any-hit result of the shadow ray
     uint32_t *mis_hit; // closest-hit triangle of the MIS ray
+    // SampledSpectrum build only (nullptr otherwise): the bins of beta, L, A, B and beta_ld as planar arrays
+    // [60][capacity]; the float4 arrays above then keep just their fourth component
+    float *s_beta, *s_L, *s_A, *s_B, *s_beta_ld;
+    const float *light_spectra;  // [n_lights][60]: Lemit / I / L of each light
     uint8_t *pix_bleed;  // [tiles_per_batch*256] pixel has a sample whose box-filter footprint leaves the pixel
     // queues (slot indices) and their counters
     uint32_t *q_path[2];       // ping-pong
@@ -182,5 +187,5 @@ void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, 
 void launch_debug_camera(const RenderDev *dev, int px, int py, int n, b200pt_ray *out, cudaStream_t s);
 void launch_film_rgb(const float4 *film, float *rgb, int n_pixels, float scale, cudaStream_t s);
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

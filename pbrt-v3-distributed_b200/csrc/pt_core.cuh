@@ -16,7 +16,7 @@
 #include "pt_platform.h"
 #include "pt_sincos.cuh"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 // ------------------------------------------------------------------ constants
 #define PT_MACHINE_EPS 5.9604644775390625e-08f /* 2^-24, pbrt.h:195-199 */
@@ -113,31 +113,115 @@ B200_HD void coordinate_system(const V3 &v1, V3 *v2, V3 *v3) {
 }
 
 // ------------------------------------------------------------------- spectrum
-struct RGB {
-    float r, g, b;
+// B200PT_NSPEC == 3: RGBSpectrum (core/spectrum.h:429-560), the reference's default build.
+// B200PT_NSPEC == 60: SampledSpectrum (spectrum.h:283-427), the reference built with `typedef SampledSpectrum Spectrum`
+// (pbrt.h:124-125).  All arithmetic is per bin (CoefficientSpectrum, spectrum.h:59-280), in bin order.
+#ifdef __CUDACC__
+#define PT_UNROLL _Pragma("unroll")
+#else
+#define PT_UNROLL
+#endif
+#define SPEC_FOR for (int i_ = 0; i_ < B200PT_NSPEC; ++i_)
+struct Spec {
+    float c[B200PT_NSPEC];
 };
-B200_HD RGB rgb(float r, float g, float b) {
-    RGB c;
-    c.r = r;
-    c.g = g;
-    c.b = b;
+B200_HD Spec rgb1(float v) {
+    Spec s;
+    PT_UNROLL
+    SPEC_FOR s.c[i_] = v;
+    return s;
+}
+#if B200PT_NSPEC == 3
+B200_HD Spec rgb(float r, float g, float b) {
+    Spec c;
+    c.c[0] = r;
+    c.c[1] = g;
+    c.c[2] = b;
     return c;
 }
-B200_HD RGB rgb1(float v) { return rgb(v, v, v); }
-B200_HD RGB rgbp(const float *p) { return rgb(p[0], p[1], p[2]); }
-B200_HD RGB operator+(const RGB &a, const RGB &b) { return rgb(a.r + b.r, a.g + b.g, a.b + b.b); }
-B200_HD RGB operator-(const RGB &a, const RGB &b) { return rgb(a.r - b.r, a.g - b.g, a.b - b.b); }
-B200_HD RGB operator*(const RGB &a, const RGB &b) { return rgb(a.r * b.r, a.g * b.g, a.b * b.b); }
-B200_HD RGB operator/(const RGB &a, const RGB &b) { return rgb(a.r / b.r, a.g / b.g, a.b / b.b); }
-B200_HD RGB operator*(const RGB &a, float s) { return rgb(a.r * s, a.g * s, a.b * s); }
-B200_HD RGB operator*(float s, const RGB &a) { return rgb(a.r * s, a.g * s, a.b * s); }
-B200_HD RGB operator/(const RGB &a, float s) { return rgb(a.r / s, a.g / s, a.b / s); }  // spectrum.h:181-188
-B200_HD RGB rgb_sqrt(const RGB &a) { return rgb(sqrtf(a.r), sqrtf(a.g), sqrtf(a.b)); }
-B200_HD bool is_black(const RGB &a) { return a.r == 0.f && a.g == 0.f && a.b == 0.f; }
+#endif
+// spectrum stored contiguously (a descriptor's Spec triple, or one row of a 60-bin table)
+B200_HD Spec rgbp(const float *p) {
+    Spec s;
+    PT_UNROLL
+    SPEC_FOR s.c[i_] = p[i_];
+    return s;
+}
+#define SPEC_BINOP(op)                                          \
+    B200_HD Spec operator op(const Spec &a, const Spec &b) {    \
+        Spec r;                                                 \
+        PT_UNROLL SPEC_FOR r.c[i_] = a.c[i_] op b.c[i_]; \
+        return r;                                               \
+    }
+SPEC_BINOP(+)
+SPEC_BINOP(-)
+SPEC_BINOP(*)
+SPEC_BINOP(/)
+#undef SPEC_BINOP
+B200_HD Spec operator*(const Spec &a, float s) {
+    Spec r;
+    PT_UNROLL
+    SPEC_FOR r.c[i_] = a.c[i_] * s;
+    return r;
+}
+B200_HD Spec operator*(float s, const Spec &a) {
+    Spec r;
+    PT_UNROLL
+    SPEC_FOR r.c[i_] = a.c[i_] * s;
+    return r;
+}
+B200_HD Spec operator/(const Spec &a, float s) {  // spectrum.h:181-188
+    Spec r;
+    PT_UNROLL
+    SPEC_FOR r.c[i_] = a.c[i_] / s;
+    return r;
+}
+B200_HD Spec rgb_sqrt(const Spec &a) {
+    Spec r;
+    PT_UNROLL
+    SPEC_FOR r.c[i_] = sqrtf(a.c[i_]);
+    return r;
+}
+B200_HD bool is_black(const Spec &a) {
+    bool black = true;
+    PT_UNROLL
+    SPEC_FOR black = black && (a.c[i_] == 0.f);
+    return black;
+}
+B200_HD float max_comp(const Spec &a) {
+    float m = a.c[0];
+    PT_UNROLL
+    for (int i = 1; i < B200PT_NSPEC; ++i) m = pt_max(m, a.c[i]);
+    return m;
+}
+B200_HD bool has_nans(const Spec &a) {
+    bool nan = false;
+    PT_UNROLL
+    SPEC_FOR nan = nan || pt_isnan(a.c[i_]);
+    return nan;
+}
+#if B200PT_NSPEC == 3
 // spectrum.h:462-465
-B200_HD float lum(const RGB &a) { return 0.212671f * a.r + 0.715160f * a.g + 0.072169f * a.b; }
-B200_HD float max_comp(const RGB &a) { return pt_max(pt_max(a.r, a.g), a.b); }
-B200_HD bool has_nans(const RGB &a) { return pt_isnan(a.r) || pt_isnan(a.g) || pt_isnan(a.b); }
+B200_HD float lum(const Spec &a) { return 0.212671f * a.c[0] + 0.715160f * a.c[1] + 0.072169f * a.c[2]; }
+#else
+// SampledSpectrum::X / Y / Z (spectrum.cpp:80-100: the CIE curves averaged over the 60 bins), data of the host's
+// reference build, set once per context (b200pt_scene_desc::cie_xyz).
+#ifdef __CUDACC__
+__constant__ float c_cie_xyz[3][B200PT_NSPEC];
+#define PT_CIE(k, i) c_cie_xyz[k][i]
+#else
+static float h_cie_xyz[3][B200PT_NSPEC];
+#define PT_CIE(k, i) h_cie_xyz[k][i]
+#endif
+// CIE_Y_integral = 106.856895 and sampledLambdaStart / End = 400 / 700 (spectrum.h:49-53)
+#define PT_SPECTRAL_SCALE (float(700 - 400) / float(106.856895f * B200PT_NSPEC))
+// spectrum.h:393-398
+B200_HD float lum(const Spec &a) {
+    float yy = 0.f;
+    SPEC_FOR yy += PT_CIE(1, i_) * a.c[i_];
+    return yy * PT_SPECTRAL_SCALE;
+}
+#endif
 
 // ---------------------------------------------------------------------- Sobol'
 struct SamplerParams {          // samplers/sobol.h:45-69
@@ -636,23 +720,23 @@ B200_HD float fr_dielectric(float cosThetaI, float etaI, float etaT) {
     return (Rparl * Rparl + Rperp * Rperp) / 2;
 }
 // reflection.cpp:71-94
-B200_HD RGB fr_conductor(float cosThetaI, const RGB &etai, const RGB &etat, const RGB &k) {
+B200_HD Spec fr_conductor(float cosThetaI, const Spec &etai, const Spec &etat, const Spec &k) {
     cosThetaI = pt_clamp(cosThetaI, -1.f, 1.f);
-    RGB eta = etat / etai;
-    RGB etak = k / etai;
+    Spec eta = etat / etai;
+    Spec etak = k / etai;
     float cosThetaI2 = cosThetaI * cosThetaI;
     float sinThetaI2 = (float)(1. - (double)cosThetaI2);
-    RGB eta2 = eta * eta;
-    RGB etak2 = etak * etak;
-    RGB t0 = eta2 - etak2 - rgb1(sinThetaI2);
-    RGB a2plusb2 = rgb_sqrt(t0 * t0 + 4.f * eta2 * etak2);
-    RGB t1 = a2plusb2 + rgb1(cosThetaI2);
-    RGB a = rgb_sqrt(0.5f * (a2plusb2 + t0));
-    RGB t2 = (2.f * cosThetaI) * a;
-    RGB Rs = (t1 - t2) / (t1 + t2);
-    RGB t3 = cosThetaI2 * a2plusb2 + rgb1(sinThetaI2 * sinThetaI2);
-    RGB t4 = t2 * sinThetaI2;
-    RGB Rp = Rs * (t3 - t4) / (t3 + t4);
+    Spec eta2 = eta * eta;
+    Spec etak2 = etak * etak;
+    Spec t0 = eta2 - etak2 - rgb1(sinThetaI2);
+    Spec a2plusb2 = rgb_sqrt(t0 * t0 + 4.f * eta2 * etak2);
+    Spec t1 = a2plusb2 + rgb1(cosThetaI2);
+    Spec a = rgb_sqrt(0.5f * (a2plusb2 + t0));
+    Spec t2 = (2.f * cosThetaI) * a;
+    Spec Rs = (t1 - t2) / (t1 + t2);
+    Spec t3 = cosThetaI2 * a2plusb2 + rgb1(sinThetaI2 * sinThetaI2);
+    Spec t4 = t2 * sinThetaI2;
+    Spec Rp = Rs * (t3 - t4) / (t3 + t4);
     return 0.5f * (Rp + Rs);
 }
 
@@ -749,20 +833,20 @@ enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR
        BX_SPECULAR_REFLECTION = 5 };
 struct Lobe {
     int kind, type;
-    RGB R, T;
+    Spec R, T;
     TRDist dist;
     int conductor;      // Fresnel of the microfacet lobe: 0 dielectric(etaI, etaT), 1 conductor(1, cEta, cK)
     float frEtaI, frEtaT;
-    RGB cEta, cK;
+    Spec cEta, cK;
     float etaA, etaB;   // FresnelSpecular, MicrofacetTransmission
     float onA, onB;     // OrenNayar
 };
 B200_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
-B200_HD RGB lobe_fresnel(const Lobe &l, float cosThetaI) {
+B200_HD Spec lobe_fresnel(const Lobe &l, float cosThetaI) {
     if (!l.conductor) return rgb1(fr_dielectric(cosThetaI, l.frEtaI, l.frEtaT));  // reflection.cpp:128-130
     return fr_conductor(pt_abs(cosThetaI), rgb1(1.f), l.cEta, l.cK);               // reflection.cpp:117-119
 }
-B200_HD RGB lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
     if (l.kind == BX_LAMBERT) return l.R * PT_INV_PI;  // reflection.cpp:178-180
     if (l.kind == BX_MICROFACET) {                     // reflection.cpp:226-236
         float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
@@ -770,7 +854,7 @@ B200_HD RGB lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         if (cosThetaI == 0 || cosThetaO == 0) return rgb1(0.f);
         if (wh.x == 0 && wh.y == 0 && wh.z == 0) return rgb1(0.f);
         wh = normalize(wh);
-        RGB F = lobe_fresnel(l, dot(wi, wh));
+        Spec F = lobe_fresnel(l, dot(wi, wh));
         return l.R * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
     if (l.kind == BX_OREN_NAYAR) {  // reflection.cpp:197-219
@@ -801,7 +885,7 @@ B200_HD RGB lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
         V3 wh = normalize(wo + wi * eta);
         if (wh.z < 0) wh = -wh;
-        RGB F = rgb1(fr_dielectric(dot(wo, wh), l.etaA, l.etaB));
+        Spec F = rgb1(fr_dielectric(dot(wo, wh), l.etaA, l.etaB));
         float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
         float factor = 1 / eta;
         return (rgb1(1.f) - F) * l.T *
@@ -829,7 +913,7 @@ B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
     return 0.f;
 }
 // BxDF::Sample_f; *pdf is written only where the reference writes it.
-B200_HD RGB lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
+B200_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
     if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:425-434
         if (wo.z == 0) return rgb1(0.f);
         V3 wh = tr_sample_wh(l.dist, wo, u);
@@ -871,7 +955,7 @@ B200_HD RGB lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2],
     V3 nn = mk(0.f, 0.f, 1.f);
     if (dot(nn, wo) < 0.f) nn = -nn;  // Faceforward, geometry.h:1213-1216
     if (!refract(wo, nn, etaI / etaT, wi)) return rgb1(0.f);
-    RGB ft = l.T * (1 - F);
+    Spec ft = l.T * (1 - F);
     ft = ft * ((etaI * etaI) / (etaT * etaT));
     *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
     *pdf = 1 - F;
@@ -897,11 +981,11 @@ B200_HD int bsdf_num_components(const Bsdf &b, int flags) {
     return num;
 }
 // reflection.cpp:670-683
-B200_HD RGB bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+B200_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     V3 wi = world_to_local(b, wiW), wo = world_to_local(b, woW);
     if (wo.z == 0) return rgb1(0.f);
     bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
-    RGB f = rgb1(0.f);
+    Spec f = rgb1(0.f);
     for (int i = 0; i < b.n; ++i)
         if (lobe_matches(b.lobes[i], flags) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
                                                 (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
@@ -923,7 +1007,7 @@ B200_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     return matching > 0 ? pdf / matching : 0.f;
 }
 // reflection.cpp:703-768
-B200_HD RGB bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type,
+B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type,
                           int *sampledType) {
     int matching = bsdf_num_components(b, type);
     if (matching == 0) {
@@ -944,7 +1028,7 @@ B200_HD RGB bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2
     if (wo.z == 0) return rgb1(0.f);
     *pdf = 0;
     *sampledType = lobe.type;
-    RGB f = lobe_sample_f(lobe, wo, &wi, ur, pdf, sampledType);
+    Spec f = lobe_sample_f(lobe, wo, &wi, ur, pdf, sampledType);
     if (*pdf == 0) {
         *sampledType = 0;
         return rgb1(0.f);
@@ -975,8 +1059,32 @@ B200_HD void add_lambert(Bsdf *b, const float *kd) {
 // (allowMultipleLobes = true, TransportMode::Radiance; path.cpp:107).
 // MATERIAL is a b200pt_material_type known at compile time in the per-family
 // shading kernels, or -1 for a run-time switch.
+// The spectra of a material: the descriptor's RGB triples, or (SampledSpectrum build) the material's rows of
+// b200pt_scene_desc::material_spectra, B200PT_MATERIAL_SPECTRA rows of 60 bins in the order kd, ks, kt, eta, k.
+struct MatSpec {
+    const float *kd, *ks, *kt, *eta, *k;
+};
+B200_HD MatSpec mat_spec(const b200pt_material &m, const float *rows) {
+    MatSpec s;
+#if B200PT_NSPEC == 3
+    (void)rows;
+    s.kd = m.kd;
+    s.ks = m.ks;
+    s.kt = m.kt;
+    s.eta = m.eta;
+    s.k = m.k;
+#else
+    s.kd = rows;
+    s.ks = rows + B200PT_NSPEC;
+    s.kt = rows + 2 * B200PT_NSPEC;
+    s.eta = rows + 3 * B200PT_NSPEC;
+    s.k = rows + 4 * B200PT_NSPEC;
+#endif
+    return s;
+}
 template <int MATERIAL>
-B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
+B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, const Isect &is, Bsdf *b) {
+    const MatSpec ms = mat_spec(m, spectra_rows);
     b->eta = 1.f;
     b->ns = is.ns;  // reflection.h:157
     b->ng = is.n;
@@ -985,8 +1093,8 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
     b->n = 0;
     const int type = MATERIAL >= 0 ? MATERIAL : m.type;
     if (type == B200PT_MAT_MATTE) {  // matte.cpp:45-62
-        if (!is_black(rgbp(m.kd))) {
-            add_lambert(b, m.kd);
+        if (!is_black(rgbp(ms.kd))) {
+            add_lambert(b, ms.kd);
             if (m.variant == 1) {  // sigma != 0: OrenNayar(r, sig)
                 Lobe &l = b->lobes[b->n - 1];
                 l.kind = BX_OREN_NAYAR;
@@ -995,12 +1103,12 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
             }
         }
     } else if (type == B200PT_MAT_PLASTIC) {  // plastic.cpp:45-70
-        if (!is_black(rgbp(m.kd))) add_lambert(b, m.kd);
-        if (!is_black(rgbp(m.ks))) {
+        if (!is_black(rgbp(ms.kd))) add_lambert(b, ms.kd);
+        if (!is_black(rgbp(ms.ks))) {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_MICROFACET;
             l.type = BSDF_REFLECTION | BSDF_GLOSSY;
-            l.R = rgbp(m.ks);
+            l.R = rgbp(ms.ks);
             l.dist.ax = m.alpha_x;
             l.dist.ay = m.alpha_x;
             l.conductor = 0;
@@ -1015,10 +1123,10 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
         l.dist.ax = m.alpha_x;
         l.dist.ay = m.alpha_y;
         l.conductor = 1;
-        l.cEta = rgbp(m.eta);
-        l.cK = rgbp(m.k);
+        l.cEta = rgbp(ms.eta);
+        l.cK = rgbp(ms.k);
     } else if (type == B200PT_MAT_GLASS && m.variant == 2) {  // MirrorMaterial, mirror.cpp:45-56 (BSDF eta stays 1)
-        const RGB R = rgbp(m.ks);
+        const Spec R = rgbp(ms.ks);
         if (!is_black(R)) {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_SPECULAR_REFLECTION;
@@ -1027,7 +1135,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const Isect &is, Bsdf *b) {
         }
     } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
         b->eta = m.index;
-        RGB R = rgbp(m.ks), T = rgbp(m.kt);
+        Spec R = rgbp(ms.ks), T = rgbp(ms.kt);
         if (is_black(R) && is_black(T)) {
         } else if (m.variant == 1) {  // rough glass, glass.cpp:65-90
             if (!is_black(R)) {
@@ -1159,10 +1267,24 @@ B200_HD int spatial_voxel(const SpatialGrid &g, const V3 &p) {
 // spatial_light_contrib: see pt_sphere.cuh (it samples triangle and sphere lights)
 
 // ----------------------------------------------------------------------- film
-B200_HD void rgb_to_xyz(const RGB &c, float xyz[3]) {  // spectrum.h:62-66
-    xyz[0] = 0.412453f * c.r + 0.357580f * c.g + 0.180423f * c.b;
-    xyz[1] = 0.212671f * c.r + 0.715160f * c.g + 0.072169f * c.b;
-    xyz[2] = 0.019334f * c.r + 0.119193f * c.g + 0.950227f * c.b;
+// Spectrum::ToXYZ: RGBSpectrum (spectrum.h:455 -> :62-66) or SampledSpectrum (spectrum.h:380-392)
+B200_HD void rgb_to_xyz(const Spec &c, float xyz[3]) {
+#if B200PT_NSPEC == 3
+    xyz[0] = 0.412453f * c.c[0] + 0.357580f * c.c[1] + 0.180423f * c.c[2];
+    xyz[1] = 0.212671f * c.c[0] + 0.715160f * c.c[1] + 0.072169f * c.c[2];
+    xyz[2] = 0.019334f * c.c[0] + 0.119193f * c.c[1] + 0.950227f * c.c[2];
+#else
+    xyz[0] = xyz[1] = xyz[2] = 0.f;
+    SPEC_FOR {
+        xyz[0] += PT_CIE(0, i_) * c.c[i_];
+        xyz[1] += PT_CIE(1, i_) * c.c[i_];
+        xyz[2] += PT_CIE(2, i_) * c.c[i_];
+    }
+    const float scale = PT_SPECTRAL_SCALE;
+    xyz[0] *= scale;
+    xyz[1] *= scale;
+    xyz[2] *= scale;
+#endif
 }
 B200_HD void xyz_to_rgb(const float xyz[3], float rgbv[3]) {  // spectrum.h:56-60
     rgbv[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
@@ -1170,5 +1292,5 @@ B200_HD void xyz_to_rgb(const float xyz[3], float rgbv[3]) {  // spectrum.h:56-6
     rgbv[2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
 }
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

@@ -9,6 +9,15 @@
 #include <cstdint>
 #include <cstring>
 
+// The spectrum-dependent kernels are compiled twice: RGBSpectrum (B200PT_NSPEC 3, namespace b200pt) and
+// SampledSpectrum (B200PT_NSPEC 60, namespace b200pt_s60), see kernels.cu.
+#ifndef B200PT_NSPEC
+#define B200PT_NSPEC 3
+#endif
+#ifndef B200PT_NS
+#define B200PT_NS b200pt
+#endif
+
 #ifdef __CUDACC__
 #define B200_HD __host__ __device__ __forceinline__
 #define B200_D __device__ __forceinline__
@@ -17,7 +26,7 @@
 #define B200_D inline
 #endif
 
-namespace b200pt {
+namespace B200PT_NS {
 
 B200_HD uint32_t float_as_uint(float f) {
 #ifdef __CUDA_ARCH__
@@ -38,5 +47,5 @@ B200_HD float uint_as_float(uint32_t u) {
 #endif
 }
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

@@ -17,7 +17,7 @@
 
 #include "pt_platform.h"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 struct SinCosPoly {
     double sign[4];
@@ -106,5 +106,5 @@ B200_HD float pt_cosf(float y) {
     return sincos_poly(x * s, x * x, p, n ^ 1);
 }
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

@@ -22,7 +22,7 @@
 #include "pt_core.cuh"
 #include "pt_sincos.cuh"
 
-namespace b200pt {
+namespace B200PT_NS {
 
 // hit ids >= SPHERE_HIT_BASE (and != B200PT_MISS) name sphere (id & SPHERE_HIT_MASK)
 #define SPHERE_HIT_BASE 0xC0000000u
@@ -496,12 +496,12 @@ B200_HD void instance_isect_to_world(const DevInstance &in, Isect *is) {
 struct DeltaLight {
     int kind;  // B200PT_LIGHT_POINT / SPOT / DISTANT
     V3 position;
-    RGB intensity;
+    Spec intensity;
     float cos_total_width, cos_falloff_start;
     const float *world_to_light;
     float two_world_radius;
 };
-B200_HD RGB delta_light_sample(const DeltaLight &l, const V3 &refP, V3 *wi, V3 *pTarget) {
+B200_HD Spec delta_light_sample(const DeltaLight &l, const V3 &refP, V3 *wi, V3 *pTarget) {
     if (l.kind == 3) {
         *wi = l.position;
         *pTarget = refP + l.position * l.two_world_radius;
@@ -527,7 +527,7 @@ B200_HD RGB delta_light_sample(const DeltaLight &l, const V3 &refP, V3 *wi, V3 *
 
 // SpatialLightDistribution::ComputeDistribution, one (voxel, light) term (lightdistrib.cpp:196-275)
 B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz, const V3 &p0, const V3 &p1,
-                                    const V3 &p2, bool flip, const TriShading &sh, const RGB &lemit, bool twoSided,
+                                    const V3 &p2, bool flip, const TriShading &sh, const Spec &lemit, bool twoSided,
                                     const DevSphere *sphere, const DeltaLight *delta) {
     const int pi[3] = {vx, vy, vz};
     float lo[3], hi[3];
@@ -547,7 +547,7 @@ B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz
         V3 w;
         if (delta) {  // Sample_Li of a delta light: pdf 1 (lightdistrib.cpp:230-236)
             V3 wiD, pT;
-            const RGB LiD = delta_light_sample(*delta, po, &wiD, &pT);
+            const Spec LiD = delta_light_sample(*delta, po, &wiD, &pT);
             contrib += lum(LiD) / 1.f;
             continue;
         }
@@ -568,7 +568,7 @@ B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz
             pdf *= len2(po - ps.p) / absdot(ps.n, -w);
             if (pt_isinf(pdf)) pdf = 0.f;
         }
-        RGB Li = rgb1(0.f);
+        Spec Li = rgb1(0.f);
         if (pdf == 0 || len2(ps.p - po) == 0) {
             pdf = 0;
         } else {
@@ -580,5 +580,5 @@ B200_HD float spatial_light_contrib(const SpatialGrid &g, int vx, int vy, int vz
     return contrib;
 }
 
-}  // namespace b200pt
+}  // namespace B200PT_NS
 #endif

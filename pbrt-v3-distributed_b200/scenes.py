@@ -275,11 +275,49 @@ class SceneArrays:
     def n_triangles(self):
         return len(self.vertices)
 
+    def attach_spectral(self, tables):
+        """Describe the scene the way a SampledSpectrum build of the host would (b200pt_scene_desc::n_spectrum_samples
+        = 60).  `tables` is tests/golden/spectral_tables.json: the 60-bin spectra that build holds for the RGB triples /
+        constant spectra of this harness (dumped from the reference by oracle/probe, never computed here) and its
+        SampledSpectrum::X / Y / Z."""
+        f32 = np.float32
+        lut = {tuple(np.array([float.fromhex(x) for x in rgb], f32).view(np.uint32).tolist()):
+               np.array([float.fromhex(x) for x in spec], f32) for rgb, spec in tables["spectra"]}
+
+        def look(rgb, what):
+            key = tuple(np.array(list(rgb), f32).view(np.uint32).tolist())
+            if key not in lut:
+                raise KeyError("no SampledSpectrum fixture for %s = %s" % (what, list(rgb)))
+            return lut[key]
+        if self._materials is None:
+            mats = default_materials(self.material_names)
+            self._materials = (abi.Material * len(mats))(*mats)
+        used = {abi.MAT_MATTE: ("kd",), abi.MAT_PLASTIC: ("kd", "ks"), abi.MAT_METAL: ("eta", "k"), abi.MAT_GLASS: ("ks", "kt")}
+        order = ("kd", "ks", "kt", "eta", "k")
+        ms = np.zeros((len(self._materials), len(order), abi.SPECTRUM_SAMPLES), f32)
+        for i, m in enumerate(self._materials):
+            for name in used[m.type]:
+                if m.type == abi.MAT_GLASS and m.variant == 2 and name == "kt":
+                    continue  # MirrorMaterial has no Kt
+                ms[i, order.index(name)] = look(getattr(m, name), "material %d %s" % (i, name))
+        n = max(self.n_lights, 1)
+        ls = np.zeros((n, abi.SPECTRUM_SAMPLES), f32)
+        for i in range(self.n_lights):
+            ls[i] = look(self._lights[i].lemit, "light %d" % i)
+        self.material_spectra, self.light_spectra = ms, ls
+        self.cie_xyz = np.array([[float.fromhex(x) for x in tables[k]] for k in ("cie_x", "cie_y", "cie_z")], f32)
+        return self
+
     def desc(self):
         if self._materials is None:
             mats = default_materials(self.material_names)
             self._materials = (abi.Material * len(mats))(*mats)
         d = abi.SceneDesc()
+        if getattr(self, "cie_xyz", None) is not None:
+            d.n_spectrum_samples = abi.SPECTRUM_SAMPLES
+            d.material_spectra = abi.ptr(self.material_spectra)
+            d.light_spectra = abi.ptr(self.light_spectra)
+            d.cie_xyz = abi.ptr(self.cie_xyz)
         d.n_triangles = self.n_triangles
         d.vertices = abi.ptr(self.vertices)
         d.material_id = abi.ptr(self.material_id)

@@ -157,6 +157,14 @@ def test_spectral_oracle_matches_sampled_spectrum_reference(abi, scenes, ob, gna
     rgb_ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % base))
     assert not np.array_equal(bits(ref), bits(rgb_ref))  # the two Spectrum types really give different images
     o.close()
+    # the same scene described the way a SampledSpectrum host describes it to the library (b200pt_scene_desc::
+    # material_spectra / light_spectra / cie_xyz, filled by SceneArrays.attach_spectral): the oracle reads those tables
+    arr2 = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {})).attach_spectral(tables)
+    assert arr2.desc().n_spectrum_samples == abi.SPECTRUM_SAMPLES
+    o = ob.Oracle(abi, arr2)
+    film, _ = o.render(setup, threads=4)
+    assert np.array_equal(bits(o.film_rgb(setup, film)), bits(ref))
+    o.close()
 
 
 @pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
