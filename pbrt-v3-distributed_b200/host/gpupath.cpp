@@ -116,12 +116,26 @@ bool ConstantValue(const std::shared_ptr<Texture<T>> &tex, T *out) {
     return true;
 }
 
-void ToRGB(const Spectrum &s, float out[3]) {
+// A host built with `typedef SampledSpectrum Spectrum` (core/pbrt.h:124-125) also hands over the 60 bins of every
+// spectrum (b200pt_scene_desc::material_spectra / light_spectra) and its SampledSpectrum::X / Y / Z; the library then
+// computes per bin like that build does and the RGB triples are informational.
+constexpr bool kSampledHost = Spectrum::nSamples != 3;
+static_assert(!kSampledHost || Spectrum::nSamples == B200PT_SPECTRUM_SAMPLES, "SampledSpectrum with another bin count");
+
+void ToRGB(const Spectrum &s, float out[3], float *bins = nullptr) {
     Float rgb[3];
     s.ToRGB(rgb);
     out[0] = rgb[0];
     out[1] = rgb[1];
     out[2] = rgb[2];
+    if (kSampledHost && bins)
+        for (int i = 0; i < Spectrum::nSamples; ++i) bins[i] = s[i];
+}
+// one light's spectrum appended to Flattened::lightSpectra
+void ToRGB(const Spectrum &s, float out[3], std::vector<float> *lightSpectra) {
+    ToRGB(s, out);
+    if (kSampledHost)
+        for (int i = 0; i < Spectrum::nSamples; ++i) lightSpectra->push_back(s[i]);
 }
 
 struct Flattened {
@@ -135,18 +149,22 @@ struct Flattened {
     std::vector<b200pt_sphere> spheres;
     std::vector<b200pt_instance> instances;
     int64_t nTopLevel = 0;
+    std::vector<float> materialSpectra, lightSpectra;  // SampledSpectrum hosts: [material][5][60], [light][60]
 };
 
 // materials/{matte,plastic,metal,glass}.cpp ComputeScatteringFunctions with constant textures
-bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) {
+// `rows`: the material's B200PT_MATERIAL_SPECTRA x 60 block (kd, ks, kt, eta, k), zero-initialised by the caller
+bool ConvertMaterial(const Material *m, b200pt_material *out, float *rows, std::string *why) {
     memset(out, 0, sizeof(*out));
+    float *rowKd = rows, *rowKs = rows + B200PT_SPECTRUM_SAMPLES, *rowKt = rows + 2 * B200PT_SPECTRUM_SAMPLES,
+          *rowEta = rows + 3 * B200PT_SPECTRUM_SAMPLES, *rowK = rows + 4 * B200PT_SPECTRUM_SAMPLES;
     Spectrum sv;
     Float fv;
     if (auto mm = dynamic_cast<const MatteMaterial *>(m)) {
         if (mm->bumpMap) return *why = "bump maps", false;
         if (!ConstantValue(mm->Kd, &sv) || !ConstantValue(mm->sigma, &fv)) return *why = "non-constant textures", false;
         out->type = B200PT_MAT_MATTE;
-        ToRGB(sv.Clamp(), out->kd);
+        ToRGB(sv.Clamp(), out->kd, rowKd);
         if (Clamp(fv, 0, 90) != 0) {  // OrenNayar(r, sig), matte.cpp:59
             out->variant = 1;
             b200pt_host_oren_nayar(fv, &out->alpha_x, &out->alpha_y);
@@ -159,8 +177,8 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
         if (!ConstantValue(pm->Kd, &kd) || !ConstantValue(pm->Ks, &ks) || !ConstantValue(pm->roughness, &fv))
             return *why = "non-constant textures", false;
         out->type = B200PT_MAT_PLASTIC;
-        ToRGB(kd.Clamp(), out->kd);
-        ToRGB(ks.Clamp(), out->ks);
+        ToRGB(kd.Clamp(), out->kd, rowKd);
+        ToRGB(ks.Clamp(), out->ks, rowKs);
         Float rough = fv;
         if (pm->remapRoughness) rough = TrowbridgeReitzDistribution::RoughnessToAlpha(rough);
         out->alpha_x = out->alpha_y = rough;
@@ -179,8 +197,8 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
             vr = TrowbridgeReitzDistribution::RoughnessToAlpha(vr);
         }
         out->type = B200PT_MAT_METAL;
-        ToRGB(eta, out->eta);
-        ToRGB(k, out->k);
+        ToRGB(eta, out->eta, rowEta);
+        ToRGB(k, out->k, rowK);
         out->alpha_x = ur;
         out->alpha_y = vr;
         return true;
@@ -193,8 +211,8 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
             !ConstantValue(gm->vRoughness, &vr) || !ConstantValue(gm->index, &index))
             return *why = "non-constant textures", false;
         out->type = B200PT_MAT_GLASS;
-        ToRGB(R.Clamp(), out->ks);
-        ToRGB(T.Clamp(), out->kt);
+        ToRGB(R.Clamp(), out->ks, rowKs);
+        ToRGB(T.Clamp(), out->kt, rowKt);
         out->index = index;
         if (ur != 0 || vr != 0) {  // glass.cpp:65-90
             out->variant = 1;
@@ -212,7 +230,7 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, std::string *why) 
         if (!ConstantValue(mr->Kr, &sv)) return *why = "non-constant textures", false;
         out->type = B200PT_MAT_GLASS;  // the specular family; variant 2 = SpecularReflection(Kr, FresnelNoOp), mirror.cpp:45-56
         out->variant = 2;
-        ToRGB(sv.Clamp(), out->ks);
+        ToRGB(sv.Clamp(), out->ks, rowKs);
         out->index = 1.f;
         return true;
     }
@@ -233,9 +251,11 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         auto it = matIndex.find(m);
         if (it == matIndex.end()) {
             b200pt_material bm;
-            if (!ConvertMaterial(m, &bm, why)) return false;
+            std::vector<float> rows((size_t)B200PT_MATERIAL_SPECTRA * B200PT_SPECTRUM_SAMPLES, 0.f);
+            if (!ConvertMaterial(m, &bm, rows.data(), why)) return false;
             it = matIndex.emplace(m, (int)f->materials.size()).first;
             f->materials.push_back(bm);
+            if (kSampledHost) f->materialSpectra.insert(f->materialSpectra.end(), rows.begin(), rows.end());
         }
         *id = it->second;
         return true;
@@ -382,14 +402,14 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         // delta lights (point.cpp:43-56, spot.cpp:42-76, distant.cpp:43-66): the lights' own members
         if (auto pl = dynamic_cast<const PointLight *>(scene.lights[l].get())) {
             bl.kind = B200PT_LIGHT_POINT;
-            ToRGB(pl->I, bl.lemit);
+            ToRGB(pl->I, bl.lemit, &f->lightSpectra);
             bl.position[0] = pl->pLight.x, bl.position[1] = pl->pLight.y, bl.position[2] = pl->pLight.z;
             f->lights.push_back(bl);
             continue;
         }
         if (auto sl = dynamic_cast<const SpotLight *>(scene.lights[l].get())) {
             bl.kind = B200PT_LIGHT_SPOT;
-            ToRGB(sl->I, bl.lemit);
+            ToRGB(sl->I, bl.lemit, &f->lightSpectra);
             bl.position[0] = sl->pLight.x, bl.position[1] = sl->pLight.y, bl.position[2] = sl->pLight.z;
             bl.cos_total_width = sl->cosTotalWidth;
             bl.cos_falloff_start = sl->cosFalloffStart;
@@ -399,7 +419,7 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         }
         if (auto tl = dynamic_cast<const DistantLight *>(scene.lights[l].get())) {
             bl.kind = B200PT_LIGHT_DISTANT;
-            ToRGB(tl->L, bl.lemit);
+            ToRGB(tl->L, bl.lemit, &f->lightSpectra);
             bl.position[0] = tl->wLight.x, bl.position[1] = tl->wLight.y, bl.position[2] = tl->wLight.z;
             bl.world_radius = tl->worldRadius;  // set by DistantLight::Preprocess in the Scene constructor
             f->lights.push_back(bl);
@@ -407,7 +427,7 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         }
         auto dl = dynamic_cast<const DiffuseAreaLight *>(scene.lights[l].get());
         if (!dl) return *why = "a light other than diffuse area / point / spot / distant lights", false;
-        ToRGB(dl->Lemit, bl.lemit);
+        ToRGB(dl->Lemit, bl.lemit, &f->lightSpectra);
         bl.two_sided = dl->twoSided ? 1 : 0;
         auto is = sphereOfShape.find(dl->shape.get());
         if (is != sphereOfShape.end()) {
@@ -487,6 +507,15 @@ class GpuPathIntegrator : public PathIntegrator {
         sd.n_instances = (int)flat.instances.size();
         sd.instances = flat.instances.data();
         sd.n_toplevel_triangles = flat.nTopLevel;
+        std::vector<float> cie;
+        if (kSampledHost) {  // spectrum.cpp:80-100: the CIE matching curves averaged over the bins at SampledSpectrum::Init
+            for (const SampledSpectrum *c : {&SampledSpectrum::X, &SampledSpectrum::Y, &SampledSpectrum::Z})
+                for (int i = 0; i < SampledSpectrum::nSamples; ++i) cie.push_back((*c)[i]);
+            sd.n_spectrum_samples = Spectrum::nSamples;
+            sd.material_spectra = flat.materialSpectra.data();
+            sd.light_spectra = flat.lightSpectra.data();
+            sd.cie_xyz = cie.data();
+        }
 
         b200pt_camera_desc cd;
         memcpy(cd.raster_to_camera, pcam->RasterToCamera.m.m, sizeof(float) * 16);
@@ -568,6 +597,14 @@ class GpuPathIntegrator : public PathIntegrator {
                 const int32_t sm[6] = {smpd.samples_per_pixel, smpd.sample_bounds[0], smpd.sample_bounds[1],
                                        smpd.sample_bounds[2], smpd.sample_bounds[3], smpd.n_dimensions};
                 fwrite(sm, 4, 6, df);
+                // trailer of a SampledSpectrum host: bin count, then the three tables
+                const int32_t ns = sd.n_spectrum_samples;
+                fwrite(&ns, 4, 1, df);
+                if (ns) {
+                    fwrite(sd.material_spectra, 4, (size_t)sd.n_materials * B200PT_MATERIAL_SPECTRA * ns, df);
+                    fwrite(sd.light_spectra, 4, (size_t)sd.n_lights * ns, df);
+                    fwrite(sd.cie_xyz, 4, (size_t)3 * ns, df);
+                }
                 fclose(df);
             }
         }

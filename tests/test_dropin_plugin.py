@@ -137,3 +137,75 @@ def test_killeroo_matches_reference(scenes, tmp_path, name, res):
     diff = bits(got) != bits(ref)
     assert not diff.any(), "%d of %d components differ from the reference (max abs %.3g)" % (
         diff.sum(), diff.size, np.abs(got - ref).max())
+
+
+# ---- SampledSpectrum host: pbrt_b200_spectral = the same drop-in linked with the reference built with
+# `typedef SampledSpectrum Spectrum` (host/Makefile plugin_spectral, oracle/Makefile ref_spectral) ---------------------
+PLUGIN_SPECTRAL = os.path.join(ROOT, "pbrt-v3-distributed_b200", "_plugin", "pbrt_b200_spectral")
+needs_spectral_plugin = pytest.mark.skipif(not os.path.exists(PLUGIN_SPECTRAL),
+                                           reason="pbrt_b200_spectral is built where /root/reference exists")
+
+
+def _read_spectral_trailer(path, abi):
+    """The tables a SampledSpectrum host passes in b200pt_scene_desc, from a B200PT_DUMP_SCENE file (gpupath.cpp)."""
+    import ctypes as C
+    raw = open(path, "rb").read()
+    hdr = np.frombuffer(raw, np.int64, 8)
+    nt, nm, nl, nsph, has_n, has_uv = (int(x) for x in hdr[1:7])
+    off = 64 + nt * (36 + 4 + 4 + 1 + 1) + (nt * 36 if has_n else 0) + (nt * 24 if has_uv else 0)
+    mats = np.frombuffer(raw, np.uint8, nm * C.sizeof(abi.Material), off).reshape(nm, -1)
+    off += nm * C.sizeof(abi.Material) + nl * C.sizeof(abi.AreaLight) + nsph * C.sizeof(abi.Sphere)
+    off += C.sizeof(abi.CameraDesc) + 48 + C.sizeof(abi.IntegratorDesc) + 24  # film desc (48 B), six sampler ints
+    ns = int(np.frombuffer(raw, np.int32, 1, off)[0])
+    off += 4
+    ms = np.frombuffer(raw, np.float32, nm * 5 * ns, off).reshape(nm, 5, ns)
+    off += ms.nbytes
+    ls = np.frombuffer(raw, np.float32, nl * ns, off).reshape(nl, ns)
+    off += ls.nbytes
+    cie = np.frombuffer(raw, np.float32, 3 * ns, off).reshape(3, ns)
+    assert off + cie.nbytes == len(raw)
+    return ns, mats, ms, ls, cie
+
+
+@needs_spectral_plugin
+def test_spectral_plugin_hands_over_the_hosts_spectra(abi, scenes, tmp_path):
+    """CPU check of the host side: what gpupath.cpp (built against the SampledSpectrum reference) extracts from the
+    parsed scene -- 60 bins per material spectrum and light, SampledSpectrum::X/Y/Z -- equals what the harness builds
+    from the probe's fixtures (SceneArrays.attach_spectral), which the spectral oracle turns into the reference's image."""
+    import json
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the GPU test renders through this binary")
+    tables = json.load(open(os.path.join(GOLDEN, "spectral_tables.json")))
+    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1).attach_spectral(tables)
+    path = scenes.write_pbrt(str(tmp_path), "render_spectral_four", arr, 40, 32, 8, max_depth=5, strategy="uniform")
+    dump = os.path.join(str(tmp_path), "scene.dump")
+    r = subprocess.run([PLUGIN_SPECTRAL, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True,
+                       text=True, env=dict(os.environ, B200PT_DUMP_SCENE=dump))
+    assert "no usable CUDA device" in (r.stdout + r.stderr)
+    ns, mats, ms, ls, cie = _read_spectral_trailer(dump, abi)
+    assert ns == abi.SPECTRUM_SAMPLES
+    assert np.array_equal(bits(cie), bits(arr.cie_xyz))
+    assert len(ls) == arr.n_lights and all(np.array_equal(bits(row), bits(arr.light_spectra[0])) for row in ls)
+    # the host numbers materials in the order it meets them (one per light quad, too): every one of its materials
+    # must be one of the harness's, bin for bin, and every harness material must appear
+    mine = [(int(m.type), arr.material_spectra[i]) for i, m in enumerate(arr._materials)]
+    seen = set()
+    for i in range(len(mats)):
+        mtype = int(np.frombuffer(mats[i].tobytes(), np.int32, 1)[0])
+        hit = [k for k, (t, rows) in enumerate(mine) if t == mtype and np.array_equal(bits(ms[i]), bits(rows))]
+        assert hit, "host material %d (type %d) has spectra the fixtures do not hold" % (i, mtype)
+        seen.update(hit)
+    assert seen == set(range(len(mine)))
+
+
+@needs_spectral_plugin
+@pytest.mark.gpu
+def test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path):
+    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1)
+    path = scenes.write_pbrt(str(tmp_path), "render_spectral_four", arr, 40, 32, 8, max_depth=5, strategy="uniform")
+    r = subprocess.run([PLUGIN_SPECTRAL, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spectral_four.pfm"))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spectral_four.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "spectral drop-in render differs from the SampledSpectrum reference's PFM"
