@@ -60,6 +60,16 @@ __device__ __forceinline__ Spec light_emit(const RenderDev *R, int lightNum, con
 #endif
 }
 
+#ifdef B200PT_HOST_EMU
+// CPU check build (tests/emu): threads run one after the other, so a "warp" is one lane
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) { return pred ? atomicAdd(counter, 1u) : 0u; }
+__device__ __forceinline__ bool warp_fetch(uint32_t *work, uint32_t n, uint32_t *item) {
+    const uint32_t base = atomicAdd(work, 1u);
+    if (base >= n) return false;
+    *item = base;
+    return true;
+}
+#else
 // Warp-aggregated append: every lane of the warp must call it (converged);
 // lanes with pred get consecutive positions behind one atomicAdd.
 __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
@@ -83,6 +93,8 @@ __device__ __forceinline__ bool warp_fetch(uint32_t *work, uint32_t n, uint32_t 
     *item = base + (uint32_t)lane;
     return true;
 }
+
+#endif  // B200PT_HOST_EMU
 
 // per-vertex shading data of triangle `ti` (flags: bit 18 = normals, bit 19 = uvs)
 // VTX = false is the variant for scenes without any per-vertex data: the defaults fold to constants.
@@ -184,6 +196,48 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
 // (+ classified by BSDF family with warp-aggregated appends) and idle lanes
 // fetch new rays -- so one long ray never keeps 31 lanes idle.
 
+#ifdef B200PT_HOST_EMU
+// CPU check build: the warp-synchronous kernel below cannot run one lane at a time; every ray takes the per-ray
+// routine the kernel's lanes step through (traverse_bvh8 = trav_step until done) and retires like a lane does.
+template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
+void k_trace(const TraceArgs a) {
+    const uint32_t n = *a.count;
+    TraceCounters ctr;
+    ctr.nodes = ctr.tris = 0;
+    uint32_t i;
+    while (warp_fetch(a.work, n, &i)) {
+        const uint32_t slot = a.queue ? a.queue[i] : i;
+        const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+        const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+        TriHit hit;
+        hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
+        const uint32_t best = traverse_bvh8<ANY_HIT, COUNT>(a.nodes, a.tris, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max,
+                                                            &hit, &ctr);
+        if (ANY_HIT) {
+            a.occ_out[slot] = best != B200PT_MISS ? 1 : 0;
+            continue;
+        }
+        if (a.hit_out) a.hit_out[slot] = best;
+        if (a.full_out) {
+            b200pt_hit r;
+            r.triangle = best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w) : -1;
+            r.t = hit.t;
+            r.b0 = hit.b0;
+            r.b1 = hit.b1;
+            a.full_out[slot] = r;
+        }
+        if (CLASSIFY && best != B200PT_MISS) {
+            const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
+            const int family = a.materials[mf & 0xffffu].type;
+            a.q_mat[family][warp_append(&a.qcount_mat[family], true)] = slot;
+        }
+    }
+    if (COUNT) {
+        a.stats[ANY_HIT ? 5 : 3] += ctr.nodes;
+        a.stats[ANY_HIT ? 6 : 4] += ctr.tris;
+    }
+}
+#else
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
 __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
     const uint32_t n = *a.count;
@@ -307,6 +361,8 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
         atomicAdd(&a.stats[ANY_HIT ? 6 : 4], (unsigned long long)ctr.tris);
     }
 }
+
+#endif  // B200PT_HOST_EMU
 
 // ---------------------------------------------------------------------- instances
 // TransformedPrimitive::Intersect / IntersectP (primitive.cpp:76-106) for one instance with the current ray.tMax:
@@ -861,7 +917,7 @@ __global__ void k_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims
 }
 void launch_sobol_table(const uint32_t *mat32, uint32_t *table, int n_dims, cudaStream_t s) {
     const int n = n_dims * 5 * 256;
-    k_sobol_table<<<(n + 255) / 256, 256, 0, s>>>(mat32, table, n_dims);
+    B200PT_LAUNCH(B200PT_KERNEL(k_sobol_table), (n + 255) / 256, 256, s, mat32, table, n_dims);
 }
 
 #endif  // B200PT_NSPEC == 3
@@ -923,7 +979,7 @@ __global__ void __launch_bounds__(128) k_spatial_cdf(const RenderDev *R) {
     R->sp_func_int[vox] = funcInt;
 }
 
-#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
+#if B200PT_NSPEC == 3 && !defined(B200PT_HOST_EMU)  // spectrum-independent (block-synchronous: not in the CPU check build)
 // ------------------------------------------------------------------------ sort
 // Coherence sort between bounces: rays that start in the same cell of a 32^3 grid and travel into
 // the same octant become neighbours in the queue, so the lanes of a warp walk the same top of the
@@ -1227,36 +1283,36 @@ __global__ void k_debug_camera(const RenderDev *R, int px, int py, int n, b200pt
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
                    cudaStream_t s) {
     (void)n_batch_tiles;
-    k_raygen<<<(n_slots + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_slots);
+    B200PT_LAUNCH(B200PT_KERNEL(k_raygen), (n_slots + 255) / 256, 256, s, dev, batch_first_tile, n_slots);
 }
 
 #if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s) {
     if (any_hit) {
         if (count)
-            k_trace<true, false, true><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<true, false, true>), grid, 128, s, a);
         else
-            k_trace<true, false, false><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<true, false, false>), grid, 128, s, a);
     } else if (classify) {
         if (count)
-            k_trace<false, true, true><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<false, true, true>), grid, 128, s, a);
         else
-            k_trace<false, true, false><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<false, true, false>), grid, 128, s, a);
     } else {
         if (count)
-            k_trace<false, false, true><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<false, false, true>), grid, 128, s, a);
         else
-            k_trace<false, false, false><<<grid, 128, 0, s>>>(a);
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<false, false, false>), grid, 128, s, a);
     }
 }
 
 void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, cudaStream_t s) {
     if (any_hit)
-        k_spheres<true, false><<<grid, 128, 0, s>>>(a);
+        B200PT_LAUNCH(B200PT_KERNEL(k_spheres<true, false>), grid, 128, s, a);
     else if (classify)
-        k_spheres<false, true><<<grid, 128, 0, s>>>(a);
+        B200PT_LAUNCH(B200PT_KERNEL(k_spheres<false, true>), grid, 128, s, a);
     else
-        k_spheres<false, false><<<grid, 128, 0, s>>>(a);
+        B200PT_LAUNCH(B200PT_KERNEL(k_spheres<false, false>), grid, 128, s, a);
 }
 
 #endif  // B200PT_NSPEC == 3
@@ -1265,9 +1321,9 @@ void launch_shade(const RenderDev *dev, int material, bool vertex_data, int boun
 #define B200PT_SHADE(M)                                               \
     case M:                                                           \
         if (vertex_data)                                              \
-            k_shade<M, true><<<grid, 128, 0, s>>>(dev, bounce, work); \
+            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, true>), grid, 128, s, dev, bounce, work); \
         else                                                          \
-            k_shade<M, false><<<grid, 128, 0, s>>>(dev, bounce, work); \
+            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, false>), grid, 128, s, dev, bounce, work); \
         break;
     switch (material) {
         B200PT_SHADE(B200PT_MAT_MATTE)
@@ -1279,59 +1335,61 @@ void launch_shade(const RenderDev *dev, int material, bool vertex_data, int boun
 }
 
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
-    k_resolve<<<grid, 256, 0, s>>>(dev, bounce, work);
+    B200PT_LAUNCH(B200PT_KERNEL(k_resolve), grid, 256, s, dev, bounce, work);
 }
 
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s) {
     const long long nvox = (long long)host.grid.nv[0] * host.grid.nv[1] * host.grid.nv[2];
     const long long n1 = nvox * host.n_lights;
-    k_spatial_contrib<<<(unsigned)((n1 + 127) / 128), 128, 0, s>>>(dev);
-    k_spatial_cdf<<<(unsigned)((nvox + 127) / 128), 128, 0, s>>>(dev);
+    B200PT_LAUNCH(B200PT_KERNEL(k_spatial_contrib), (unsigned)((n1 + 127) / 128), 128, s, dev);
+    B200PT_LAUNCH(B200PT_KERNEL(k_spatial_cdf), (unsigned)((nvox + 127) / 128), 128, s, dev);
 }
 
-#if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
+#if B200PT_NSPEC == 3 && !defined(B200PT_HOST_EMU)
 void launch_sort_queue(const RenderDev *dev, const RenderDev &host, const uint32_t *queue, const uint32_t *count,
                        const float4 *ray_o, const float4 *ray_d, int grid, cudaStream_t s) {
     cudaMemsetAsync(host.sort_hist, 0, SORT_BUCKETS * sizeof(uint32_t), s);
-    k_sort_hist<<<grid, 256, 0, s>>>(dev, queue, count, ray_o, ray_d);
-    k_sort_scan<<<1, 1024, 0, s>>>(host.sort_hist);
-    k_sort_scatter<<<grid, 256, 0, s>>>(dev, queue, count);
+    B200PT_LAUNCH(B200PT_KERNEL(k_sort_hist), grid, 256, s, dev, queue, count, ray_o, ray_d);
+    B200PT_LAUNCH(B200PT_KERNEL(k_sort_scan), 1, 1024, s, host.sort_hist);
+    B200PT_LAUNCH(B200PT_KERNEL(k_sort_scatter), grid, 256, s, dev, queue, count);
 }
 
 #endif  // B200PT_NSPEC == 3
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s) {
-    k_film<<<n_batch_tiles, dim3(18, 18), 0, s>>>(dev, batch_first_tile);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film), n_batch_tiles, dim3(18, 18), s, dev, batch_first_tile);
 }
 
 void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t batch_first_tile, uint32_t n_batch_tiles,
                          cudaStream_t s) {
     const dim3 block((unsigned)(16 + 2 * host.apron[0]), (unsigned)(16 + 2 * host.apron[1]));
-    k_film_tile_slots<<<(n_batch_tiles + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_batch_tiles);
-    k_film_tile<<<n_batch_tiles, block, 0, s>>>(dev, batch_first_tile);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film_tile_slots), (n_batch_tiles + 255) / 256, 256, s, dev, batch_first_tile, n_batch_tiles);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film_tile), n_batch_tiles, block, s, dev, batch_first_tile);
     const int npix = (host.crop[2] - host.crop[0]) * (host.crop[3] - host.crop[1]);
-    k_film_merge<<<(npix + 255) / 256, 256, 0, s>>>(dev);
-    k_film_tile_slots_reset<<<(n_batch_tiles + 255) / 256, 256, 0, s>>>(dev, batch_first_tile, n_batch_tiles);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film_merge), (npix + 255) / 256, 256, s, dev);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film_tile_slots_reset), (n_batch_tiles + 255) / 256, 256, s, dev, batch_first_tile, n_batch_tiles);
 }
 
 #if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
-void launch_accumulate_stats(const RenderDev *dev, uint32_t, cudaStream_t s) { k_accumulate_stats<<<1, 32, 0, s>>>(dev); }
+void launch_accumulate_stats(const RenderDev *dev, uint32_t, cudaStream_t s) {
+    B200PT_LAUNCH(B200PT_KERNEL(k_accumulate_stats), 1, 32, s, dev);
+}
 
 void launch_debug_sobol(const RenderDev *dev, int px, int py, long long sample, int dim0, int n, float *out,
                         cudaStream_t s) {
-    k_debug_sobol<<<(n + 63) / 64, 64, 0, s>>>(dev, px, py, sample, dim0, n, out);
+    B200PT_LAUNCH(B200PT_KERNEL(k_debug_sobol), (n + 63) / 64, 64, s, dev, px, py, sample, dim0, n, out);
 }
 void launch_debug_camera(const RenderDev *dev, int px, int py, int n, b200pt_ray *out, cudaStream_t s) {
-    k_debug_camera<<<(n + 63) / 64, 64, 0, s>>>(dev, px, py, n, out);
+    B200PT_LAUNCH(B200PT_KERNEL(k_debug_camera), (n + 63) / 64, 64, s, dev, px, py, n, out);
 }
 void launch_film_rgb(const float4 *film, float *rgb, int n_pixels, float scale, cudaStream_t s) {
-    k_film_rgb<<<(n_pixels + 255) / 256, 256, 0, s>>>(film, rgb, n_pixels, scale);
+    B200PT_LAUNCH(B200PT_KERNEL(k_film_rgb), (n_pixels + 255) / 256, 256, s, film, rgb, n_pixels, scale);
 }
 
 #endif  // B200PT_NSPEC == 3
 #if B200PT_NSPEC != 3
 // SampledSpectrum::X / Y / Z of the host (b200pt_scene_desc::cie_xyz) into this translation unit's constant memory
 void set_cie_xyz(const float *xyz, cudaStream_t s) {
-    cudaMemcpyToSymbolAsync(c_cie_xyz, xyz, sizeof(float) * 3 * B200PT_NSPEC, 0, cudaMemcpyHostToDevice, s);
+    cudaMemcpyToSymbolAsync(PT_CIE_TABLE, xyz, sizeof(float) * 3 * B200PT_NSPEC, 0, cudaMemcpyHostToDevice, s);
 }
 // api.cu is compiled with the RGBSpectrum structs; RenderDev must not depend on the spectrum type
 size_t render_dev_size() { return sizeof(RenderDev); }

@@ -208,11 +208,12 @@ B200_HD float lum(const Spec &a) { return 0.212671f * a.c[0] + 0.715160f * a.c[1
 // reference build, set once per context (b200pt_scene_desc::cie_xyz).
 #ifdef __CUDACC__
 __constant__ float c_cie_xyz[3][B200PT_NSPEC];
-#define PT_CIE(k, i) c_cie_xyz[k][i]
+#define PT_CIE_TABLE c_cie_xyz
 #else
 static float h_cie_xyz[3][B200PT_NSPEC];
-#define PT_CIE(k, i) h_cie_xyz[k][i]
+#define PT_CIE_TABLE h_cie_xyz
 #endif
+#define PT_CIE(k, i) PT_CIE_TABLE[k][i]
 // CIE_Y_integral = 106.856895 and sampledLambdaStart / End = 400 / 700 (spectrum.h:49-53)
 #define PT_SPECTRAL_SCALE (float(700 - 400) / float(106.856895f * B200PT_NSPEC))
 // spectrum.h:393-398

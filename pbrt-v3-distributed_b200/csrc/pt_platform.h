@@ -18,6 +18,16 @@
 #define B200PT_NS b200pt
 #endif
 
+// Kernel launches go through one macro so that the CPU check build of the sources (tests/emu, -DB200PT_HOST_EMU:
+// test infrastructure, see tests/emu/cuda_runtime.h) can run a kernel function once per thread index.
+#define B200PT_KERNEL(...) __VA_ARGS__
+#ifdef B200PT_HOST_EMU
+#define B200PT_LAUNCH(kernel, grid, block, stream, ...) \
+    ::b200pt_emu::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
+#else
+#define B200PT_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
 #ifdef __CUDACC__
 #define B200_HD __host__ __device__ __forceinline__
 #define B200_D __device__ __forceinline__

@@ -61,3 +61,28 @@ def golden_camera(abi, probe_json, w, h):
     cam.shutter_open = 0.0
     cam.shutter_close = 1.0
     return cam
+
+
+HOSTCHECK_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="session")
+def hostcheck(pkg):
+    """The package's ctypes wrapper bound to tests/emu/libb200pt_hostcheck.so: the product's own api.cu / kernels.cu
+    compiled as plain C++ (tests/emu/cuda_runtime.h).  TEST INFRASTRUCTURE -- a CPU pre-flight of the sources, never
+    loaded by the package itself."""
+    import subprocess
+    import types
+    lib = os.path.join(HOSTCHECK_DIR, "libb200pt_hostcheck.so")
+    r = subprocess.run(["make", "-j", "8"], cwd=HOSTCHECK_DIR, capture_output=True, text=True)
+    if r.returncode != 0 or not os.path.exists(lib):
+        pytest.fail("tests/emu does not build:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    init = os.path.join(graft.PKG_DIR, "__init__.py")
+    src = open(init).read()
+    marker = 'LIB_PATH = os.path.join(_HERE, "libb200pt.so")'
+    assert marker in src
+    mod = types.ModuleType("pbrt_v3_distributed_b200_hostcheck")
+    mod.__file__ = init
+    mod.__package__ = graft.PKG_NAME
+    exec(compile(src.replace(marker, "LIB_PATH = %r" % lib), init, "exec"), mod.__dict__)
+    return mod

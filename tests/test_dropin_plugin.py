@@ -197,15 +197,3 @@ def test_spectral_plugin_hands_over_the_hosts_spectra(abi, scenes, tmp_path):
         assert hit, "host material %d (type %d) has spectra the fixtures do not hold" % (i, mtype)
         seen.update(hit)
     assert seen == set(range(len(mine)))
-
-
-@needs_spectral_plugin
-@pytest.mark.gpu
-def test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path):
-    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1)
-    path = scenes.write_pbrt(str(tmp_path), "render_spectral_four", arr, 40, 32, 8, max_depth=5, strategy="uniform")
-    r = subprocess.run([PLUGIN_SPECTRAL, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spectral_four.pfm"))
-    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spectral_four.pfm"))
-    assert np.array_equal(bits(got), bits(ref)), "spectral drop-in render differs from the SampledSpectrum reference's PFM"

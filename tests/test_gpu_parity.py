@@ -280,64 +280,6 @@ def test_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, name):
     scene.close()
 
 
-def _spectral_tables():
-    import json
-    return json.load(open(os.path.join(GOLDEN, "spectral_tables.json")))
-
-
-@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
-def test_spectral_render_vs_sampled_spectrum_reference(pkg, abi, scenes, ob, ctx, gname, base):
-    """a SampledSpectrum host (60-bin spectra in the descriptor) -- the image of the reference compiled
-    with `typedef SampledSpectrum Spectrum` (tests/golden/render_spectral_*.pfm), bit for bit."""
-    nt, mats, w, h, spp, depth, strat, nl = RENDERS[base]
-    ex = EXTRA.get(base, {})
-    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {})).attach_spectral(_spectral_tables())
-    setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
-                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
-                               **ex.get("camera", {}))
-    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
-    r = pkg.Render(scene, setup)
-    r.render_tiles()
-    rgb = r.read_rgb()
-    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
-    nbad = int((bits(rgb) != bits(ref)).sum())
-    if nbad:
-        o = ob.Oracle(abi, arr)
-        ys, xs, _ = np.nonzero(bits(rgb) != bits(ref))
-        y, x = int(ys[0]), int(xs[0])
-        print("first differing pixel", x, y, rgb[y, x], ref[y, x])
-        print("gpu samples", r.debug_pixel_samples(x, y))
-        print("oracle samples", o.pixel_samples(setup, x, y))
-    assert nbad == 0, "%d of %d components differ from the SampledSpectrum reference render" % (nbad, rgb.size)
-    r.close()
-    scene.close()
-
-
-@pytest.mark.parametrize("mats,depth,strat,pfilter", [(("matte", "glass", "metal", "plastic"), 8, "power", None),
-                                                     (("matte", "plastic"), 5, "spatial", None),
-                                                     (("matte", "metal"), 5, "uniform", "gaussian")])
-def test_spectral_render_and_counters_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat, pfilter):
-    """Larger SampledSpectrum renders against the 60-bin oracle: raw film sums and ray counters, every light
-    distribution, the general pixel-filter path, several batches."""
-    kw = {"pixel_filter": pfilter} if pfilter else {}
-    arr = scenes.SceneArrays(20000, materials=mats, soup_version=1).attach_spectral(_spectral_tables())
-    setup = scenes.RenderSetup(64, 48, 8, max_depth=depth,
-                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat], **kw)
-    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
-    o = ob.Oracle(abi, arr)
-    film, ostats = o.render(setup)
-    r = pkg.Render(scene, setup)
-    r.render_tiles()
-    raw = r.read_raw()
-    assert int((bits(raw) != bits(film)).sum()) == 0
-    st = r.stats()
-    for k in ("camera_rays", "regular_rays", "shadow_rays"):
-        assert st[k] == ostats[k], k
-    r.close()
-    scene.close()
-    o.close()
-
-
 @pytest.mark.parametrize("mats,depth,strat", [(("matte",), 5, "uniform"), (("glass",), 8, "uniform"),
                                              (("metal",), 5, "power"), (("plastic",), 5, "spatial"),
                                              (("matte", "glass", "metal", "plastic"), 16, "power"),

@@ -1,0 +1,87 @@
+"""CPU pre-flight of the product's sources (no GPU needed): tests/emu compiles api.cu and kernels.cu -- the files nvcc
+compiles into libb200pt.so -- as plain C++ against a stand-in <cuda_runtime.h> in which a kernel launch runs the kernel
+function once per thread index.  The GPU parity tests are then replayed against that library: the host logic (scene and
+render set-up, batching, wavefront sequencing, film read-back) and the scalar logic of every kernel except the
+warp-synchronous k_trace (its rays take traverse_bvh8, the per-ray routine the kernel's lanes step through) are checked
+against the reference's golden images and the oracle before any GPU time is spent.  What this cannot show -- nvcc's
+code generation, the real warp-level execution, performance -- is what the `-m gpu` run of the same tests is for."""
+import os
+
+import numpy as np
+import pytest
+
+import test_gpu_parity as G
+import test_zz_spectral_gpu as GS
+from conftest import GOLDEN, bits
+from render_cases import EXTRA, RENDERS
+
+
+@pytest.fixture(scope="module")
+def hctx(hostcheck):
+    c = hostcheck.Context(0)
+    yield c
+    c.close()
+
+
+def test_hostcheck_exports_the_abi(hostcheck, pkg):
+    assert hostcheck.lib._name.endswith("libb200pt_hostcheck.so") and pkg.lib._name.endswith("libb200pt.so")
+    assert hostcheck.MISSING_SYMBOLS == [] and hostcheck.lib.b200pt_abi_version() == pkg.lib.b200pt_abi_version()
+
+
+def test_streams_cameras_intersections(hostcheck, abi, scenes, hctx, probe_json):
+    G.test_sobol_stream_vs_reference(hostcheck, abi, scenes, hctx, probe_json)
+    G.test_halton_stream_vs_reference(hostcheck, abi, scenes, hctx)
+    G.test_camera_rays_vs_reference(hostcheck, abi, scenes, hctx, probe_json)
+    G.test_intersections_vs_reference_bvhaccel(hostcheck, abi, scenes, hctx)
+
+
+def test_trace_entry_points_vs_oracle(hostcheck, abi, scenes, ob, hctx):
+    G.test_trace_vs_oracle(hostcheck, abi, scenes, ob, hctx, 37, 20000)
+    G.test_trace_vs_oracle(hostcheck, abi, scenes, ob, hctx, 20000, 40000)
+    G.test_trace_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx)
+    G.test_trace_instances_vs_oracle(hostcheck, abi, scenes, ob, hctx)
+
+
+# every golden render of the reference whose light distribution is not the (slow to emulate) 64^3-voxel one, plus two
+# that are
+FAST = sorted(n for n in RENDERS if RENDERS[n][6] != "spatial") + ["spatial", "spheres"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, name):
+    G.test_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, name)
+
+
+@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
+def test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, base):
+    GS.test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, base)
+
+
+def test_spectral_counters_power_and_filter(hostcheck, abi, scenes, ob, hctx):
+    GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 8, "power", None)
+    GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "metal"), 5, "uniform", "gaussian")
+
+
+def test_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx):
+    G.test_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 16, "power")
+
+
+def test_pixel_samples_and_shards(hostcheck, abi, scenes, ob, hctx):
+    G.test_pixel_samples_vs_oracle(hostcheck, abi, scenes, ob, hctx)
+
+
+def test_host_logic_shards_batches_edges(hostcheck, abi, scenes, hctx, monkeypatch):
+    """Batching, tile shards, pixelbounds shards, partial tiles, empty ray batches, the ordered merge of FilmTiles."""
+    G.test_empty_and_ragged_inputs(hostcheck, abi, scenes, hctx)
+    G.test_tile_shards_sum_to_full_render(hostcheck, abi, scenes, hctx)
+    G.test_render_is_deterministic_and_batch_independent(hostcheck, abi, scenes, hctx, monkeypatch)
+
+
+def test_device_bvh_builder_is_refused(hostcheck, abi, scenes, hctx):
+    """The check build has no device BVH builder; asking for it must fail loudly, not fall back to the host builder."""
+    arr = scenes.SceneArrays(500, materials=("matte",), soup_version=1)
+    c = hostcheck.Context(0)
+    c.set_option("gpu_bvh_build", 1)
+    with pytest.raises(Exception):
+        hostcheck.Scene(c, arr.desc(), keepalive=arr)
+    c.close()
