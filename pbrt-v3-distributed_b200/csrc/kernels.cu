@@ -1318,13 +1318,23 @@ void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, c
 #endif  // B200PT_NSPEC == 3
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
                   cudaStream_t s) {
-#define B200PT_SHADE(M)                                               \
-    case M:                                                           \
-        if (vertex_data)                                              \
-            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, true>), grid, 128, s, dev, bounce, work); \
-        else                                                          \
-            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, false>), grid, 128, s, dev, bounce, work); \
+#if B200PT_NSPEC == 3
+#define B200PT_SHADE(M)                                                                         \
+    case M:                                                                                     \
+        if (vertex_data)                                                                        \
+            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, true>), grid, 128, s, dev, bounce, work);    \
+        else                                                                                    \
+            B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, false>), grid, 128, s, dev, bounce, work);   \
         break;
+#else
+    // the 60-bin build instantiates only the general variant (VTX = true handles every scene; the lean one is a
+    // register-pressure optimisation of the RGB build): half the compile time of that translation unit
+    (void)vertex_data;
+#define B200PT_SHADE(M)                                                                      \
+    case M:                                                                                  \
+        B200PT_LAUNCH(B200PT_KERNEL(k_shade<M, true>), grid, 128, s, dev, bounce, work);     \
+        break;
+#endif
     switch (material) {
         B200PT_SHADE(B200PT_MAT_MATTE)
         B200PT_SHADE(B200PT_MAT_PLASTIC)
