@@ -85,3 +85,42 @@ def test_device_bvh_builder_is_refused(hostcheck, abi, scenes, hctx):
     with pytest.raises(Exception):
         hostcheck.Scene(c, arr.desc(), keepalive=arr)
     c.close()
+
+
+# ---- the drop-in binaries linked against the check library: gpupath.cpp end to end on the CPU ---------------------------
+import test_dropin_plugin as P  # noqa: E402
+
+HC_PLUGIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "pbrt_b200_hostcheck")
+HC_PLUGIN_SPECTRAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "pbrt_b200_spectral_hostcheck")
+
+
+@pytest.fixture(scope="module")
+def hc_plugins(hostcheck):
+    import subprocess
+    if not (os.path.exists(P.PLUGIN) and os.path.exists(P.PLUGIN_SPECTRAL)):
+        pytest.skip("the drop-in's objects are built where /root/reference exists")
+    r = subprocess.run(["make", "plugins"], cwd=os.path.dirname(HC_PLUGIN), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    """pbrt's parser and scene construction -> gpupath.cpp's flattening -> C ABI -> the check build: unmodified .pbrt
+    files (all materials, PLY meshes with normals / uvs, Halton, spheres, instances, delta lights, a Gaussian filter)
+    render bit-identically to the reference."""
+    monkeypatch.setattr(P, "PLUGIN", HC_PLUGIN)
+    P.test_dropin_binary_matches_reference(scenes, tmp_path)
+
+
+def test_spectral_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    """The same through the SampledSpectrum host: the 60-bin tables gpupath.cpp extracts give the image of the reference
+    built with `typedef SampledSpectrum Spectrum`."""
+    monkeypatch.setattr(GS, "PLUGIN_SPECTRAL", HC_PLUGIN_SPECTRAL)
+    GS.test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(P.KILLEROO_DIR, "killeroo-simple-ref.pfm")),
+                    reason="oracle/_ref/scenes is staged by `make -C oracle ref` where /root/reference exists")
+def test_killeroo_as_shipped_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    """BASELINE configs[0], scenes/killeroo-simple.pbrt as the reference ships it (700x700, 8 spp)."""
+    monkeypatch.setattr(P, "PLUGIN", HC_PLUGIN)
+    P.test_killeroo_matches_reference(scenes, tmp_path, "simple", 700)
