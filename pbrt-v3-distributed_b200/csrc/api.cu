@@ -111,7 +111,7 @@ static float host_spectrum_y(const b200pt_scene *sc, const std::vector<float> &c
     const float *Y = sc->cie_xyz.data() + sc->nspec;
     float yy = 0.f;
     for (int i = 0; i < sc->nspec; ++i) yy += Y[i] * c[i];
-    return yy * (float(700 - 400) / float(106.856895f * sc->nspec));
+    return yy * float(700 - 400) / float(106.856895f * sc->nspec);  // (yy * range) / (integral * n), in this order
 }
 // Lemit / I / L of light i as the host holds it
 static std::vector<float> host_light_spectrum(const b200pt_scene *sc, int i) {

@@ -216,11 +216,12 @@ static float h_cie_xyz[3][B200PT_NSPEC];
 #define PT_CIE(k, i) PT_CIE_TABLE[k][i]
 // CIE_Y_integral = 106.856895 and sampledLambdaStart / End = 400 / 700 (spectrum.h:49-53)
 #define PT_SPECTRAL_SCALE (float(700 - 400) / float(106.856895f * B200PT_NSPEC))
-// spectrum.h:393-398
+// spectrum.h:393-398.  Unlike ToXYZ (which multiplies by the precomputed quotient, spectrum.h:388-391) y() multiplies
+// by the wavelength range first and divides afterwards -- the two round differently.
 B200_HD float lum(const Spec &a) {
     float yy = 0.f;
     SPEC_FOR yy += PT_CIE(1, i_) * a.c[i_];
-    return yy * PT_SPECTRAL_SCALE;
+    return yy * float(700 - 400) / float(106.856895f * B200PT_NSPEC);
 }
 #endif
 

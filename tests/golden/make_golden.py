@@ -61,9 +61,13 @@ def filter_fixtures():
     json.dump(out, open(os.path.join(HERE, "filter_tables.json"), "w"), indent=0)
 
 
-SPECTRAL_RGB = [(0.5, 0.5, 0.5), (0.0, 0.0, 0.0), (40.0, 40.0, 40.0)]  # "rgb" parameters of the spectral golden scenes
+# "rgb" parameters of the spectral golden scenes (materials, area lights, sphere lights, point / spot / distant lights)
+SPECTRAL_RGB = [(0.5, 0.5, 0.5), (0.0, 0.0, 0.0), (40.0, 40.0, 40.0), (60.0, 60.0, 60.0), (90.0, 90.0, 90.0), (6.0, 6.0, 6.0),
+                (30.0, 24.0, 18.0), (0.8, 0.8, 0.8)]
 SPECTRAL_CONST = [0.25, 1.0, 0.9]                                      # float-default spectra (plastic, glass, mirror)
-SPECTRAL_RENDERS = {"spectral_four": "four", "spectral_rough": "rough"}  # rendered by the SampledSpectrum reference
+# rendered by the SampledSpectrum reference; instances + SampledSpectrum together are BASELINE configs[4]'s features
+SPECTRAL_RENDERS = {"spectral_four": "four", "spectral_rough": "rough", "spectral_instances": "instances",
+                    "spectral_spheres": "spheres", "spectral_delta_lights": "delta_lights"}
 
 
 def spectral_fixtures():

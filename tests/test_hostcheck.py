@@ -52,7 +52,8 @@ def test_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, name):
     G.test_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, name)
 
 
-@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
+@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough"), ("spectral_instances", "instances"),
+                                        ("spectral_spheres", "spheres"), ("spectral_delta_lights", "delta_lights")])
 def test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, base):
     GS.test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, base)
 

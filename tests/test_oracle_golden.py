@@ -133,7 +133,8 @@ def test_render_matches_reference_pfm(abi, scenes, ob, probe_json, name):
     o.close()
 
 
-@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
+@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough"), ("spectral_instances", "instances"),
+                                        ("spectral_spheres", "spheres"), ("spectral_delta_lights", "delta_lights")])
 def test_spectral_oracle_matches_sampled_spectrum_reference(abi, scenes, ob, gname, base):
     """SURVEY 8(f) row 3, second half (groundwork for the device path): the oracle compiled with 60 spectral bins
     (oracle/Makefile liboracle_spectral.so) against the reference compiled with `typedef SampledSpectrum Spectrum`

@@ -22,7 +22,8 @@ def _spectral_tables():
     return json.load(open(os.path.join(GOLDEN, "spectral_tables.json")))
 
 
-@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough")])
+@pytest.mark.parametrize("gname,base", [("spectral_four", "four"), ("spectral_rough", "rough"), ("spectral_instances", "instances"),
+                                        ("spectral_spheres", "spheres"), ("spectral_delta_lights", "delta_lights")])
 def test_spectral_render_vs_sampled_spectrum_reference(pkg, abi, scenes, ob, ctx, gname, base):
     """a SampledSpectrum host (60-bin spectra in the descriptor) -- the image of the reference compiled
     with `typedef SampledSpectrum Spectrum` (tests/golden/render_spectral_*.pfm), bit for bit."""
