@@ -38,6 +38,9 @@ WORKLOADS = {
     # 3840x2160 x 4096 spp job is sized for 8 GPUs): 50 M instanced triangles = 1000 instances of one 50k-triangle object
     "cfg5rgb": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
                 "synthetic 50M triangles instanced (1000 x 50k, RGB spectrum), maxdepth 16, 64spp, 1920x1080"),
+    # the same with the reference's SampledSpectrum build (60 bins): both halves of BASELINE configs[4]'s feature set
+    "cfg5": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
+             "synthetic 50M triangles instanced (1000 x 50k), SampledSpectrum (60 bins), maxdepth 16, 64spp, 1920x1080"),
     "small": (100000, ("matte", "glass", "metal", "plastic"), 256, 256, 16, 5, None,
               "smoke-sized: 100k triangles, 4 BSDF types, 16spp, 256x256"),
 }
@@ -45,7 +48,7 @@ WORKLOADS = {
 
 def workload_scene_kwargs(name):
     """Extra SceneArrays arguments of a workload (object instancing for cfg5rgb)."""
-    if name != "cfg5rgb":
+    if name not in ("cfg5rgb", "cfg5"):
         return {}
     inst = []
     for k in range(1000):  # 10 x 10 x 10 lattice through the soup's volume, every third one mirrored / stretched
@@ -53,6 +56,14 @@ def workload_scene_kwargs(name):
         sc = (1.0, 1.0, 1.0) if k % 3 == 0 else ((1.2, 0.8, 1.0) if k % 3 == 1 else (1.0, 1.0, -1.1))
         inst.append(dict(object=0, center=c, scale=sc))
     return dict(objects=(dict(n_tris=50000, seed=77, material="plastic", size=0.09),), instances=tuple(inst))
+
+
+SPECTRAL_WORKLOADS = ("cfg5",)
+
+
+def spectral_tables():
+    """The 60-bin spectra of the harness's materials and lights as the SampledSpectrum reference holds them (fixtures)."""
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "spectral_tables.json")))
 
 
 def rank_env():
@@ -120,13 +131,13 @@ def parse_pbrt_output(out):
             "shadow": num(r"Shadow ray intersection tests\s+(\d+)")}
 
 
-def reference_step(ob, scenes, abi, arr, wl, setup_small, sample_spp, tmp, pbrt_path):
+def reference_step(ob, scenes, abi, arr, wl, setup_small, sample_spp, tmp, pbrt_path, spectral=False):
     """One bounded sample of the workload on the host cores: the unmodified
     reference when oracle/_ref exists (kind 'reference'), else the oracle port."""
     cores = os.cpu_count() or 1
-    if ob.have_reference():
+    if pbrt_path is not None:
         t0 = time.time()
-        out = ob.run_pbrt_ref(pbrt_path, threads=cores)
+        out = ob.run_pbrt_ref(pbrt_path, threads=cores, spectral=spectral)
         wall = time.time() - t0
         st = parse_pbrt_output(out)
         secs = st["render_s"] or wall
@@ -175,13 +186,17 @@ def main():
             return 0
         ob = graft.load_oracle()
         arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **workload_scene_kwargs(args.workload))
+        spectral = args.workload in SPECTRAL_WORKLOADS
+        if spectral:
+            arr.attach_spectral(spectral_tables())  # the oracle port reads the tables; the reference binary has its own
         setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
         tmp = tempfile.mkdtemp(prefix="b200pt_ref_")
-        pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if ob.have_reference() else None
+        have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
+        pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None
         rays = secs = samples = 0.0
         last = None
         for i in range(args.warmup + args.steps):
-            last = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path)
+            last = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path, spectral)
             if i >= args.warmup:
                 rays += last["rays"]
                 secs += last["seconds"]
@@ -193,7 +208,7 @@ def main():
             "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "f32 x 60 spectral bins" if args.workload in SPECTRAL_WORKLOADS else "f32", "data": "synthetic", "config": config,
             "msamples_per_s": samples / secs / 1e6,
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"],
                              "sample": sample},
@@ -212,6 +227,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **workload_scene_kwargs(args.workload))
+    if args.workload in SPECTRAL_WORKLOADS:
+        arr.attach_spectral(spectral_tables())
     setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=args.pixel_filter)
     if args.pixel_filter:
         config["pixel_filter"] = args.pixel_filter
@@ -332,8 +349,10 @@ def main():
             ob = graft.load_oracle()
             tmp = tempfile.mkdtemp(prefix="b200pt_cpu_")
             setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
-            pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if ob.have_reference() else None
-            c = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path)
+            spectral = args.workload in SPECTRAL_WORKLOADS
+            have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
+            pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None
+            c = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path, spectral)
             cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"],
                    "sample": "%dx%d film, %d spp of %d, all tiles (%.1f s render)" %
                              (xres, yres, args.cpu_sample_spp, spp, c["seconds"]),
@@ -341,7 +360,7 @@ def main():
         out = {
             "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 x 60 spectral bins" if args.workload in SPECTRAL_WORKLOADS else "f32", "data": "synthetic", "config": config,
             "msamples_per_s": samples / (ms * 1e-3) / 1e6,
             "rays_per_sample": rays / max(samples, 1),
             "roofline": {"bound": "hbm", "kernel": "k_trace<closest-hit> (8-wide BVH traversal)",
