@@ -125,3 +125,138 @@ def test_killeroo_as_shipped_on_the_check_library(hc_plugins, scenes, tmp_path, 
     """BASELINE configs[0], scenes/killeroo-simple.pbrt as the reference ships it (700x700, 8 spp)."""
     monkeypatch.setattr(P, "PLUGIN", HC_PLUGIN)
     P.test_killeroo_matches_reference(scenes, tmp_path, "simple", 700)
+
+
+# ---- error behaviour of the C ABI: bad descriptors are refused with B200PT_ERR_INVALID and a message, never a crash ------
+def _expect(hostcheck, what, fn):
+    with pytest.raises(hostcheck.B200ptError) as e:
+        fn()
+    assert what in str(e.value), (what, str(e.value))
+
+
+def test_bad_scene_descriptors_are_refused(hostcheck, abi, scenes, hctx):
+    import ctypes as C
+
+    def scene_with(mutate, **kw):
+        arr = scenes.SceneArrays(300, materials=("matte", "plastic"), soup_version=1, **kw)
+        d = arr.desc()
+        keep = mutate(arr, d)
+        try:
+            hostcheck.Scene(hctx, d, keepalive=(arr, keep)).close()
+        finally:
+            del keep
+
+    def bad_material_id(arr, d):
+        arr.material_id[7] = 9
+    _expect(hostcheck, "has material 9", lambda: scene_with(bad_material_id))
+
+    def bad_light_id(arr, d):
+        arr.light_id[3] = 1000
+    _expect(hostcheck, "has light 1000", lambda: scene_with(bad_light_id))
+
+    def no_materials(arr, d):
+        d.n_materials = 0
+    _expect(hostcheck, "no materials", lambda: scene_with(no_materials))
+
+    def bad_material_type(arr, d):
+        arr._materials[1].type = 17
+    _expect(hostcheck, "unsupported type 17", lambda: scene_with(bad_material_type))
+
+    def no_vertices(arr, d):
+        d.vertices = None
+    _expect(hostcheck, "vertices / material_id missing", lambda: scene_with(no_vertices))
+
+    def bad_light_kind(arr, d):
+        arr._lights[0].kind = 9
+    _expect(hostcheck, "unknown kind 9", lambda: scene_with(bad_light_kind))
+
+    def light_disagrees(arr, d):
+        arr._lights[0].triangle = 5  # triangle 5 does not name light 0 in light_id[]
+    _expect(hostcheck, "disagree", lambda: scene_with(light_disagrees))
+
+    def bad_bins(arr, d):
+        d.n_spectrum_samples = 30
+    _expect(hostcheck, "n_spectrum_samples is 30", lambda: scene_with(bad_bins))
+
+    def bins_without_tables(arr, d):
+        d.n_spectrum_samples = abi.SPECTRUM_SAMPLES
+    _expect(hostcheck, "must pass material_spectra", lambda: scene_with(bins_without_tables))
+
+    def bad_sphere(arr, d):
+        arr._spheres[0].radius = -1.0
+    _expect(hostcheck, "bad radius", lambda: scene_with(bad_sphere, spheres=(dict(center=(0, 0, 0), radius=0.3, material="matte"),)))
+
+    inst = dict(objects=(dict(n_tris=50, seed=5, material="plastic", size=0.3),), instances=(dict(object=0, center=(0, 0, 0)),))
+
+    def bad_instance_range(arr, d):
+        arr._instances[0].n_triangles = 10 ** 6
+    _expect(hostcheck, "outside the object range", lambda: scene_with(bad_instance_range, **inst))
+
+    def bad_toplevel(arr, d):
+        d.n_toplevel_triangles = d.n_triangles + 1
+    _expect(hostcheck, "bad n_toplevel_triangles", lambda: scene_with(bad_toplevel, **inst))
+
+    # NULL handles
+    with pytest.raises(hostcheck.B200ptError):
+        hostcheck._check(hostcheck.lib.b200pt_scene_create(hctx.h, None, C.byref(C.c_void_p())))
+    # a scene without any geometry is legal (an empty world renders black, like the reference)
+    arr = scenes.SceneArrays(0, materials=("matte",), soup_version=1, n_lights=0)
+    s = hostcheck.Scene(hctx, arr.desc(), keepalive=arr)
+    r = hostcheck.Render(s, scenes.RenderSetup(16, 16, 2))
+    r.render_tiles()
+    raw = r.read_raw()
+    assert np.all(raw[..., :3] == 0) and np.all(raw[..., 3] >= 2)
+    r.close()
+    s.close()
+
+
+def test_bad_render_descriptors_are_refused(hostcheck, abi, scenes, hctx):
+    arr = scenes.SceneArrays(300, materials=("matte",), soup_version=1)
+    scene = hostcheck.Scene(hctx, arr.desc(), keepalive=arr)
+
+    def render_with(mutate, **kw):
+        setup = scenes.RenderSetup(32, 32, 4, **kw)
+        mutate(setup)
+        hostcheck.Render(scene, setup).close()
+
+    def spp3(s):
+        s.sampler.samples_per_pixel = 3
+    _expect(hostcheck, "power of two", lambda: render_with(spp3))
+
+    def depth(s):
+        s.integrator.max_depth = -1
+    _expect(hostcheck, "bad max_depth", lambda: render_with(depth))
+
+    def deep(s):
+        s.integrator.max_depth = 100  # more bounces than the Sobol' tables of this set-up have dimensions for
+        s.sampler.n_dimensions = 200
+    _expect(hostcheck, "sampler dimensions", lambda: render_with(deep))
+
+    def strategy(s):
+        s.integrator.light_strategy = 11
+    _expect(hostcheck, "unsupported light sample strategy", lambda: render_with(strategy))
+
+    def sampler_type(s):
+        s.sampler.type = 5
+    _expect(hostcheck, "unknown sampler type 5", lambda: render_with(sampler_type))
+
+    def empty_bounds(s):
+        s.sampler.sample_bounds[2] = s.sampler.sample_bounds[0]
+    _expect(hostcheck, "empty sample bounds", lambda: render_with(empty_bounds))
+
+    def wide_filter(s):
+        s.film.filter_radius[0] = 9.0
+    _expect(hostcheck, "pixel filter radius", lambda: render_with(wide_filter))
+
+    def no_tables(s):
+        s.sampler.matrices32 = None
+    _expect(hostcheck, "tables missing", lambda: render_with(no_tables))
+
+    r = hostcheck.Render(scene, scenes.RenderSetup(32, 32, 4))
+    _expect(hostcheck, "out of range", lambda: r.render_tiles(np.array([0, 99], np.int32)))
+    _expect(hostcheck, "more tiles than the film has", lambda: r.render_tiles(None, n=50))
+    _expect(hostcheck, "outside the sample bounds", lambda: r.debug_pixel_samples(40, 3))
+    r.render_tiles(np.zeros(0, np.int32))  # an empty shard is legal (a rank without tiles)
+    assert np.all(r.read_raw() == 0)
+    r.close()
+    scene.close()
