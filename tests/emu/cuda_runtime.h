@@ -118,10 +118,15 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     p->multiProcessorCount = 1;
     return cudaSuccess;
 }
+// B200PT_EMU_POISON=<byte>: fresh "device" memory is filled with that byte (0xff: NaNs / huge indices), so a kernel
+// that reads memory nothing wrote shows up as a changed image or a crash instead of passing by luck
 template <class T>
 inline cudaError_t cudaMalloc(T **p, size_t n) {
     *p = static_cast<T *>(malloc(n ? n : 1));
-    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (!*p) return cudaErrorMemoryAllocation;
+    static const char *poison = getenv("B200PT_EMU_POISON");
+    if (poison) memset(*p, (int)strtol(poison, nullptr, 0), n ? n : 1);
+    return cudaSuccess;
 }
 template <class T>
 inline cudaError_t cudaMallocHost(T **p, size_t n) {
