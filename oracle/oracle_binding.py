@@ -48,7 +48,18 @@ def load(abi, spectral=False):
     lib.oracle_libm_sinf.argtypes = [C.c_float]
     lib.oracle_libm_cosf.restype = C.c_float
     lib.oracle_libm_cosf.argtypes = [C.c_float]
+    lib.oracle_set_volpath.restype = None
+    lib.oracle_set_volpath.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float]
     return lib
+
+
+def set_volpath(lib, enabled, medium=None):
+    """VolPathIntegrator instead of PathIntegrator for the renders that follow (process-wide switch of the oracle library);
+    medium = dict(sigma_a=(r, g, b), sigma_s=(r, g, b), g=...) is a homogeneous medium around the whole scene."""
+    f3 = C.c_float * 3
+    m = medium or {}
+    lib.oracle_set_volpath(int(bool(enabled)), int(medium is not None), f3(*m.get("sigma_a", (0, 0, 0))),
+                           f3(*m.get("sigma_s", (0, 0, 0))), float(m.get("g", 0.0)))
 
 
 class Oracle:

@@ -1983,6 +1983,60 @@ inline S3 DeltaLightPower(const oracle_scene &s, const b200pt_area_light &l) {
     return SP(l.lemit) * Pi * r * r;
 }
 
+// ---- participating media (groundwork for SURVEY 8(f) row 4, last item): HomogeneousMedium (media/homogeneous.{h,cpp})
+// filling the whole scene -- the camera ray starts in it and no surface is a medium transition, so every ray carries it
+// (primitive.cpp:121-126) -- and the Henyey-Greenstein phase function (core/medium.{h,cpp}).
+struct HomogeneousMedium {
+    S3 sigma_a, sigma_s, sigma_t;  // homogeneous.h:50-54: sigma_t(sigma_s + sigma_a)
+    float g;
+};
+struct VolPathSetting {  // set through oracle_set_volpath (test infrastructure; the product ABI has no media yet)
+    bool volpath = false, haveMedium = false;
+    HomogeneousMedium medium;
+};
+inline VolPathSetting &VolPath() {
+    static VolPathSetting v;
+    return v;
+}
+inline S3 ExpS(const S3 &a) {  // spectrum.h:222-227
+    S3 r;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = std::exp(a.c[i]);
+    return r;
+}
+inline S3 NegS(const S3 &a) {  // spectrum.h:217-221
+    S3 r;
+    for (int i = 0; i < ORACLE_NSPEC; ++i) r.c[i] = -a.c[i];
+    return r;
+}
+const float MaxFloat = std::numeric_limits<float>::max();
+const float Inv4Pi = 0.07957747154594766788f;  // pbrt.h:203
+// HomogeneousMedium::Tr, homogeneous.cpp:44-47
+inline S3 MediumTr(const HomogeneousMedium &m, const V3 &d, float tMax) {
+    return ExpS(NegS(m.sigma_t) * std::min(tMax * Length(d), MaxFloat));
+}
+// medium.h:69-72
+inline float PhaseHG(float cosTheta, float g) {
+    float denom = 1 + g * g + 2 * g * cosTheta;
+    return Inv4Pi * (1 - g * g) / (denom * std::sqrt(denom));
+}
+// HenyeyGreenstein::Sample_p, medium.cpp:194-213
+inline float HGSample_p(float g, const V3 &wo, V3 *wi, const float u[2]) {
+    float cosTheta;
+    if (std::abs(g) < 1e-3)
+        cosTheta = 1 - 2 * u[0];
+    else {
+        float sqrTerm = (1 - g * g) / (1 - g + 2 * g * u[0]);
+        cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+    }
+    float sinTheta = std::sqrt(std::max((float)0, 1 - cosTheta * cosTheta));
+    float phi = 2 * Pi * u[1];
+    V3 v1, v2;
+    CoordinateSystem(wo, &v1, &v2);
+    // SphericalDirection(sinTheta, cosTheta, phi, v1, v2, -wo), geometry.h:1467-1472
+    *wi = sinTheta * std::cos(phi) * v1 + sinTheta * std::sin(phi) * v2 + cosTheta * (-wo);
+    return PhaseHG(-cosTheta, g);
+}
+
 struct RenderCtx {
     const oracle_scene *s;
     const b200pt_camera_desc *cam;
@@ -2116,8 +2170,11 @@ const Distribution1D *LookupLightDistribution(RenderCtx &rc, const V3 &p) {
 }
 
 // core/integrator.cpp:108-215 (handleMedia = false, specular = false)
+// `med` != nullptr is handleMedia = true (VolPathIntegrator): visibility becomes VisibilityTester::Tr / Scene::IntersectTr
+// through the homogeneous medium every ray is in; `inMedium`: `it` is a MediumInteraction (p, wo; no normal, no error
+// bounds) and the phase function takes the BSDF's place (integrator.cpp:131-137, :178-186).
 S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float uScattering[2], int lightNum,
-                  const float uLight[2]) {
+                  const float uLight[2], const HomogeneousMedium *med = nullptr, bool inMedium = false) {
     const oracle_scene &s = *rc.s;
     const b200pt_area_light &light = s.lights[lightNum];
     int bsdfFlags = BSDF_ALL & ~BSDF_SPECULAR;
@@ -2129,13 +2186,23 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
         V3 pTarget;
         S3 Li = DeltaLightSample(s, light, it.p, &wi, &lightPdf, &pTarget);
         if (lightPdf > 0 && !Li.IsBlack()) {
-            S3 f = bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
+            S3 f = inMedium ? S3(PhaseHG(Dot(it.wo, wi), med->g)) : bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
             if (!f.IsBlack()) {
                 // SpawnRayTo(Interaction) with a target that has neither normal nor error bounds: target = its p
                 V3 origin = OffsetRayOrigin(it.p, it.pError, it.n, pTarget - it.p);
                 V3 d = pTarget - origin;
-                ++rc.shadowRays;
-                if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
+                if (med) {  // VisibilityTester::Tr, light.cpp:63-81 (every surface here has a material)
+                    TriHit hh;
+                    Isect ii;
+                    ++rc.regularRays;
+                    if (SceneIntersect(s, origin, d, 1 - ShadowEpsilon, &hh, &ii) >= 0)
+                        Li = S3(0.f);
+                    else
+                        Li = Li * MediumTr(*med, d, 1 - ShadowEpsilon);
+                } else {
+                    ++rc.shadowRays;
+                    if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
+                }
                 if (!Li.IsBlack()) Ld += f * Li / lightPdf;
             }
         }
@@ -2170,8 +2237,15 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
         Li = AreaLightL(light, pShape.n, -wi);
     }
     if (lightPdf > 0 && !Li.IsBlack()) {
-        S3 f = bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
-        scatteringPdf = bsdf.Pdf(it.wo, wi, bsdfFlags);
+        S3 f;
+        if (inMedium) {  // integrator.cpp:131-137
+            float p = PhaseHG(Dot(it.wo, wi), med->g);
+            f = S3(p);
+            scatteringPdf = p;
+        } else {
+            f = bsdf.f(it.wo, wi, bsdfFlags) * AbsDot(wi, bsdf.ns);
+            scatteringPdf = bsdf.Pdf(it.wo, wi, bsdfFlags);
+        }
         if (!f.IsBlack()) {
             // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
             V3 origin = OffsetRayOrigin(it.p, it.pError, it.n, pShape.p - it.p);
@@ -2186,7 +2260,17 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                         pShape.p.x, pShape.p.y, pShape.p.z, pShape.n.x, pShape.n.y, pShape.n.z, lightPdf, Li.c[0], f.c[0],
                         origin.x, origin.y, origin.z, d.x, d.y, d.z, who, who >= 0 ? hh.t : 0.f, (int)BvhIntersectP(s, s.top, origin, d, 1 - ShadowEpsilon));
             }
-            if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon)) Li = S3(0.f);
+            if (med) {  // Li *= visibility.Tr(scene, sampler), integrator.cpp:141-144
+                --rc.shadowRays;
+                ++rc.regularRays;
+                TriHit hh;
+                Isect ii;
+                if (SceneIntersect(s, origin, d, 1 - ShadowEpsilon, &hh, &ii) >= 0)
+                    Li = S3(0.f);
+                else
+                    Li = Li * MediumTr(*med, d, 1 - ShadowEpsilon);
+            } else if (SceneIntersectP(s, origin, d, 1 - ShadowEpsilon))
+                Li = S3(0.f);
             if (!Li.IsBlack()) {
                 float weight = (lightPdf * lightPdf) / (lightPdf * lightPdf + scatteringPdf * scatteringPdf);
                 Ld += f * Li * weight / lightPdf;
@@ -2198,9 +2282,15 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
         S3 f;
         bool sampledSpecular = false;
         int sampledType = 0;
-        f = bsdf.Sample_f(it.wo, &wi, uScattering, &scatteringPdf, bsdfFlags, &sampledType);
-        f = f * AbsDot(wi, bsdf.ns);
-        sampledSpecular = (sampledType & BSDF_SPECULAR) != 0;
+        if (inMedium) {  // integrator.cpp:178-186
+            float p = HGSample_p(med->g, it.wo, &wi, uScattering);
+            f = S3(p);
+            scatteringPdf = p;
+        } else {
+            f = bsdf.Sample_f(it.wo, &wi, uScattering, &scatteringPdf, bsdfFlags, &sampledType);
+            f = f * AbsDot(wi, bsdf.ns);
+            sampledSpecular = (sampledType & BSDF_SPECULAR) != 0;
+        }
         if (!f.IsBlack() && scatteringPdf > 0) {
             float weight = 1;
             if (!sampledSpecular) {
@@ -2233,7 +2323,9 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                     Li2 = IsectLe(s, li, -wi);
                 }
             }
-            if (!Li2.IsBlack()) Ld += f * Li2 * S3(1.f) * weight / scatteringPdf;
+            // Scene::IntersectTr, scene.cpp:57-70: the transmittance up to the hit (ray.tMax = tHit after Intersect)
+            S3 Tr = med ? MediumTr(*med, wi, hitTri >= 0 ? h.t : Infinity) : S3(1.f);
+            if (!Li2.IsBlack()) Ld += f * Li2 * Tr * weight / scatteringPdf;
         }
     }
     return Ld;
@@ -2310,6 +2402,113 @@ S3 PathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
     return L;
 }
 
+// integrators/volpath.cpp:60-188 for scenes whose media are at most one homogeneous medium around everything (no
+// medium transitions, hence no null-material surfaces to skip; BSSRDFs are out of scope like in PathLi).
+S3 VolPathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
+    const oracle_scene &s = *rc.s;
+    const int maxDepth = rc.integ->max_depth;
+    const float rrThreshold = rc.integ->rr_threshold;
+    const HomogeneousMedium *med = VolPath().haveMedium ? &VolPath().medium : nullptr;
+    S3 L(0.f), beta(1.f);
+    bool specularBounce = false;
+    int bounces;
+    float etaScale = 1;
+    for (bounces = 0;; ++bounces) {
+        TriHit h;
+        ++rc.regularRays;
+        Isect isect;
+        int tri = SceneIntersect(s, ray.o, ray.d, ray.tMax, &h, &isect);
+        bool foundIntersection = tri >= 0;
+        if (foundIntersection) ray.tMax = h.t;  // Intersect shortens the ray
+        // ray.medium->Sample(ray, sampler, arena, &mi), homogeneous.cpp:49-76
+        bool sampledMedium = false;
+        Isect mi;  // the MediumInteraction: p, wo = -ray.d (not normalised), no normal, no error bounds
+        if (med) {
+            int channel = std::min((int)(sampler.Get1D() * ORACLE_NSPEC), ORACLE_NSPEC - 1);
+            float dist = -std::log(1 - sampler.Get1D()) / med->sigma_t.c[channel];
+            float t = std::min(dist / Length(ray.d), ray.tMax);
+            sampledMedium = t < ray.tMax;
+            if (sampledMedium) {
+                mi = Isect();
+                mi.p = ray.o + ray.d * t;
+                mi.wo = -ray.d;
+                mi.n = mi.ns = V3(0, 0, 0);
+                mi.pError = V3(0, 0, 0);
+            }
+            S3 Tr = ExpS(NegS(med->sigma_t) * std::min(t, MaxFloat) * Length(ray.d));
+            S3 density = sampledMedium ? (med->sigma_t * Tr) : Tr;
+            float pdf = 0;
+            for (int i = 0; i < ORACLE_NSPEC; ++i) pdf += density.c[i];
+            pdf *= 1 / (float)ORACLE_NSPEC;
+            if (pdf == 0) pdf = 1;
+            beta = beta * (sampledMedium ? (Tr * med->sigma_s / pdf) : (Tr / pdf));
+        }
+        if (beta.IsBlack()) break;
+        auto sampleOneLight = [&](const Isect &it, const BSDF &bsdf, bool inMedium) {
+            // UniformSampleOneLight(it, ..., handleMedia = true), integrator.cpp:85-106
+            S3 Ld(0.f);
+            int nLights = (int)s.lights.size();
+            if (nLights == 0) return Ld;
+            float lightPdf;
+            const Distribution1D *distrib = LookupLightDistribution(rc, it.p);
+            int lightNum = distrib->SampleDiscrete(sampler.Get1D(), &lightPdf);
+            if (lightPdf == 0) return Ld;
+            float uLight[2], uScattering[2];
+            sampler.Get2D(uLight);
+            sampler.Get2D(uScattering);
+            // handleMedia is true whether or not the ray is in a medium; without one Tr is 1 but the shadow ray is still
+            // a closest-hit query (VisibilityTester::Tr)
+            static const HomogeneousMedium vacuum = {S3(0.f), S3(0.f), S3(0.f), 0.f};
+            return EstimateDirect(rc, it, bsdf, uScattering, lightNum, uLight, med ? med : &vacuum, inMedium) / lightPdf;
+        };
+        if (sampledMedium) {
+            if (bounces >= maxDepth) break;
+            BSDF none;
+            L += beta * sampleOneLight(mi, none, true);
+            V3 wo = -ray.d, wi;
+            float u2[2];
+            sampler.Get2D(u2);
+            HGSample_p(med->g, wo, &wi, u2);
+            ray.o = OffsetRayOrigin(mi.p, mi.pError, mi.n, wi);  // mi.SpawnRay(wi): the point itself
+            ray.d = wi;
+            ray.tMax = Infinity;
+            specularBounce = false;
+        } else {
+            if (bounces == 0 || specularBounce) {
+                if (foundIntersection) L += beta * IsectLe(s, isect, -ray.d);
+            }
+            if (!foundIntersection || bounces >= maxDepth) break;
+            BSDF bsdf;
+            MakeBSDF(s, isect, &bsdf);
+            // unlike PathIntegrator (path.cpp:119) there is no test for non-specular components here (volpath.cpp:124-128)
+            L += beta * sampleOneLight(isect, bsdf, false);
+            V3 wo = -ray.d, wi;
+            float pdf = 0;
+            int flags = 0;
+            float u2[2];
+            sampler.Get2D(u2);
+            S3 f = bsdf.Sample_f(wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+            if (f.IsBlack() || pdf == 0.f) break;
+            beta = beta * (f * AbsDot(wi, bsdf.ns) / pdf);
+            specularBounce = (flags & BSDF_SPECULAR) != 0;
+            if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+                float eta = bsdf.eta;
+                etaScale *= (Dot(wo, isect.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+            }
+            ray.o = OffsetRayOrigin(isect.p, isect.pError, isect.n, wi);
+            ray.d = wi;
+            ray.tMax = Infinity;
+        }
+        S3 rrBeta = beta * etaScale;
+        if (rrBeta.MaxComponentValue() < rrThreshold && bounces > 3) {
+            float q = std::max((float).05, 1 - rrBeta.MaxComponentValue());
+            if (sampler.Get1D() < q) break;
+            beta = beta / (1 - q);
+        }
+    }
+    return L;
+}
+
 // One camera sample: integrator.cpp:276-316.  Returns guarded L and pFilm.
 S3 RenderSample(RenderCtx &rc, Sobol &sampler, int px, int py, int64_t sampleNum, float pFilm[2]) {
     sampler.StartPixelSample(px, py, sampleNum);
@@ -2322,7 +2521,7 @@ S3 RenderSample(RenderCtx &rc, Sobol &sampler, int px, int py, int64_t sampleNum
     sampler.Get2D(pLens);
     Ray ray = GenerateCameraRay(*rc.cam, pFilm, pLens);
     ++rc.cameraRays;
-    S3 L = PathLi(rc, ray, sampler);
+    S3 L = VolPath().volpath ? VolPathLi(rc, ray, sampler) : PathLi(rc, ray, sampler);
     if (L.HasNaNs())
         L = S3(0.f);
     else if (L.y() < -1e-5)
@@ -2840,6 +3039,19 @@ float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const
 }
 
 int oracle_spectrum_samples(void) { return ORACLE_NSPEC; }
+// VolPathIntegrator instead of PathIntegrator for the renders that follow; has_medium: a homogeneous medium around the
+// whole scene (sigma_a / sigma_s through the same RGB -> spectrum route as every other colour)
+void oracle_set_volpath(int enabled, int has_medium, const float sigma_a[3], const float sigma_s[3], float g) {
+    VolPathSetting &v = VolPath();
+    v.volpath = enabled != 0;
+    v.haveMedium = enabled != 0 && has_medium != 0;
+    if (v.haveMedium) {
+        v.medium.sigma_a = SP(sigma_a);
+        v.medium.sigma_s = SP(sigma_s);
+        v.medium.sigma_t = v.medium.sigma_s + v.medium.sigma_a;
+        v.medium.g = g;
+    }
+}
 int oracle_spectral_register(const float rgb[3], const float *spectrum) {
 #if ORACLE_NSPEC != 3
     std::array<uint32_t, 3> key;

@@ -66,6 +66,9 @@ float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const
  * passes SampledSpectrum::X, Y, Z.  Both come from fixtures dumped by the spectral probe.  Return the bin count. */
 int oracle_spectral_register(const float rgb[3], const float *spectrum);
 int oracle_spectral_set_cie(const float *X, const float *Y, const float *Z);
+/* VolPathIntegrator (integrators/volpath.cpp) with at most one homogeneous medium around the whole scene; groundwork,
+ * the product ABI has no media yet */
+void oracle_set_volpath(int enabled, int has_medium, const float sigma_a[3], const float sigma_s[3], float g);
 int oracle_spectrum_samples(void);
 
 /* The host libm's sinf/cosf (what the reference calls through std::sin/cos). */

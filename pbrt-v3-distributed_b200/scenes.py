@@ -392,10 +392,18 @@ def write_ply(path, tris, normals=None, uvs=None):
 
 def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uniform", pixel_bounds=None,
                eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, lens_radius=0.0, focal_distance=1e6,
-               crop_window=None, film_scale=1.0, max_sample_luminance=None, sampler="sobol", pixel_filter=None):
-    """Appendix A.4 wrapper: the reference-readable twin of `scene`."""
+               crop_window=None, film_scale=1.0, max_sample_luminance=None, sampler="sobol", pixel_filter=None,
+               integrator="path", medium=None):
+    """Appendix A.4 wrapper: the reference-readable twin of `scene`.  medium = dict(sigma_a=(r, g, b), sigma_s=(r, g, b),
+    g=...): a homogeneous medium that fills the scene -- the camera starts in it and no surface is a medium transition
+    (media/homogeneous.cpp, api.cpp:763-800, :892-898); meant for integrator="volpath"."""
     os.makedirs(dirname, exist_ok=True)
-    lines = ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
+    lines = []
+    if medium:
+        lines += ['MakeNamedMedium "fog" "string type" "homogeneous" "rgb sigma_a" [%.9g %.9g %.9g] "rgb sigma_s" [%.9g %.9g %.9g] '
+                  '"float g" [%.9g] "float scale" [1]' % (tuple(medium["sigma_a"]) + tuple(medium["sigma_s"]) + (medium.get("g", 0.0),)),
+                  'MediumInterface "" "fog"']
+    lines += ["LookAt %g %g %g  %g %g %g  %g %g %g" % (*eye, *look, *up),
              'Camera "perspective" "float fov" [%g]' % fov +
              (' "float lensradius" [%.9g] "float focaldistance" [%.9g]' % (lens_radius, focal_distance)
               if lens_radius > 0 else ""),
@@ -407,11 +415,13 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
              'Sampler "%s" "integer pixelsamples" [%d]' % (sampler, spp)]
     if pixel_filter:
         lines.append(FilterTables().get(pixel_filter)[0])
-    integ = 'Integrator "path" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (max_depth, strategy)
+    integ = 'Integrator "%s" "integer maxdepth" [%d] "string lightsamplestrategy" "%s"' % (integrator, max_depth, strategy)
     if pixel_bounds is not None:
         integ += ' "integer pixelbounds" [%d %d %d %d]' % (pixel_bounds[0], pixel_bounds[2], pixel_bounds[1],
                                                           pixel_bounds[3])
     lines += [integ, "WorldBegin"]
+    if medium:
+        lines.append('MediumInterface "fog" "fog"')
     for q in scene.light_quads:
         # quad() stores (p0 p1 p2)(p0 p2 p3); recover the 4 corners
         pts = [q[0][0], q[0][1], q[0][2], q[1][2]]

@@ -103,10 +103,24 @@ def spectral_fixtures():
         os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
 
 
+def volpath_goldens():
+    """Images of the reference's VolPathIntegrator (tests/render_cases.py VOLPATH)."""
+    from render_cases import VOLPATH
+    for gname, (base, medium, strat) in VOLPATH.items():
+        nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+        ex = EXTRA.get(base, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+        path = scenes.write_pbrt("/tmp/golden_render", "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
+                                 integrator="volpath", medium=medium, **ex.get("camera", {}))
+        ob.run_pbrt_ref(path)
+        os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
+
+
 def main():
     ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
     filter_fixtures()
     halton_fixtures()
+    volpath_goldens()
     if os.path.exists(ob.PBRT_REF_SPECTRAL):
         spectral_fixtures()
     out = {"cameras": {}, "sobol": [], "camrays": []}

@@ -105,3 +105,12 @@ EXTRA = {"lens_flip": dict(scene=dict(two_sided=True, reverse_orientation=(1, 3)
                                                   dict(center=(2.2, -1.0, 0.0), radius=0.6, emit=30.0,
                                                        reverse_orientation=True),
                                                   dict(center=(-0.7, 0.5, -1.9), radius=0.35, material="glass_rough"))))}
+
+# VolPathIntegrator (integrators/volpath.cpp) renders of the reference, groundwork for media (last item):
+# golden name -> (base case above, homogeneous medium around the whole scene or None, light sample strategy)
+VOLPATH = {
+    "volpath_four": ("four", None, "uniform"),  # no medium: still differs from "path" (light sampling at specular vertices)
+    "volpath_fog": ("four", dict(sigma_a=(0.05, 0.08, 0.12), sigma_s=(0.3, 0.25, 0.2), g=0.4), "uniform"),
+    "volpath_fog_delta": ("delta_lights", dict(sigma_a=(0.02, 0.02, 0.02), sigma_s=(0.5, 0.5, 0.5), g=-0.3), "spatial"),
+    "volpath_fog_spheres": ("spheres", dict(sigma_a=(0.1, 0.05, 0.02), sigma_s=(0.15, 0.2, 0.3), g=0.0), "power"),
+}

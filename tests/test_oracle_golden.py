@@ -168,6 +168,33 @@ def test_spectral_oracle_matches_sampled_spectrum_reference(abi, scenes, ob, gna
     o.close()
 
 
+def test_volpath_oracle_matches_reference_volpath(abi, scenes, ob):
+    """Groundwork for media (SURVEY 8(f) row 4, last item): the oracle's VolPathIntegrator::Li (volpath.cpp:60-188) with a
+    homogeneous medium around the whole scene -- free-flight sampling, Henyey-Greenstein phase function, transmittance
+    along shadow and MIS rays, light sampling at every vertex -- against the reference's images, bit for bit."""
+    from render_cases import VOLPATH
+    for gname, (base, medium, strat) in sorted(VOLPATH.items()):
+        nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+        ex = EXTRA.get(base, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+        setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                                   strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
+                                   **ex.get("camera", {}))
+        o = ob.Oracle(abi, arr)
+        ob.set_volpath(o.lib, True, medium)
+        try:
+            film, _ = o.render(setup, threads=4)
+            rgb = o.film_rgb(setup, film)
+        finally:
+            ob.set_volpath(o.lib, False)
+        ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+        assert np.array_equal(bits(rgb), bits(ref)), gname
+        o.close()
+    # without a medium VolPathIntegrator still is not PathIntegrator (it samples a light at purely specular vertices too)
+    assert not np.array_equal(bits(scenes.read_pfm(os.path.join(GOLDEN, "render_volpath_four.pfm"))),
+                              bits(scenes.read_pfm(os.path.join(GOLDEN, "render_four.pfm"))))
+
+
 @pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
 def test_analytic_scenes_known_answer(abi, scenes, ob, name):
     """The reference's own known-answer test (src/tests/analytic_scenes.cpp:54-66, CheckSceneAverage): the mean of the
