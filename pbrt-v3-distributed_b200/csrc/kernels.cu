@@ -233,8 +233,8 @@ void k_trace(const TraceArgs a) {
         }
     }
     if (COUNT) {
-        a.stats[ANY_HIT ? 5 : 3] += ctr.nodes;
-        a.stats[ANY_HIT ? 6 : 4] += ctr.tris;
+        atomicAdd(&a.stats[ANY_HIT ? 5 : 3], (unsigned long long)ctr.nodes);
+        atomicAdd(&a.stats[ANY_HIT ? 6 : 4], (unsigned long long)ctr.tris);
     }
 }
 #else

@@ -2,8 +2,8 @@
 //
 // A stand-in for <cuda_runtime.h> that lets g++ compile the product's api.cu and kernels.cu as plain C++
 // (tests/emu/Makefile, -DB200PT_HOST_EMU): "device" memory is host memory, a kernel launch runs the kernel
-// function once per thread index, sequentially, and the warp-aggregated helpers of kernels.cu take their
-// one-lane form.  The resulting libb200pt_hostcheck.so exports the C ABI of include/b200pt.h so that the
+// function once per thread index (blocks concurrently on a few host threads, the threads of a block one after the
+// other; atomics are real), and the warp-aggregated helpers of kernels.cu take their one-lane form.  The resulting libb200pt_hostcheck.so exports the C ABI of include/b200pt.h so that the
 // parity tests can pre-flight the host logic (scene / render set-up, wavefront sequencing) and the scalar logic
 // of every kernel against the oracle on a box without a GPU, the way tests/host_preflight.cpp pre-flights the
 // math headers.  It is a checker of the sources, not a renderer: the package never loads it, nothing ships it,
@@ -21,6 +21,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -49,20 +52,44 @@ inline float4 make_float4(float x, float y, float z, float w) { return float4{x,
 namespace b200pt_emu {
 inline thread_local uint3 thread_idx = {0, 0, 0}, block_idx = {0, 0, 0};
 inline thread_local dim3 block_dim, grid_dim;
+inline int worker_count() {
+    static const int n = []() {
+        const char *e = getenv("B200PT_EMU_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::max(1, e ? atoi(e) : std::min(hw > 0 ? hw : 1, 16));
+    }();
+    return n;
+}
+// One kernel launch: the blocks are dealt to a few host threads (like CTAs to SMs: any order, concurrently -- the
+// kernels' atomics are real atomics here), the threads of a block run one after the other.
 template <class F>
 inline void launch(dim3 grid, dim3 block, F &&body) {
-    grid_dim = grid;
-    block_dim = block;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx)
-                for (unsigned tz = 0; tz < block.z; ++tz)
-                    for (unsigned ty = 0; ty < block.y; ++ty)
-                        for (unsigned tx = 0; tx < block.x; ++tx) {
-                            block_idx = uint3{bx, by, bz};
-                            thread_idx = uint3{tx, ty, tz};
-                            body();
-                        }
+    const unsigned long long n_blocks = (unsigned long long)grid.x * grid.y * grid.z;
+    std::atomic<unsigned long long> next{0};
+    auto worker = [&]() {
+        grid_dim = grid;
+        block_dim = block;
+        for (;;) {
+            const unsigned long long b = next.fetch_add(1);
+            if (b >= n_blocks) break;
+            block_idx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+            for (unsigned tz = 0; tz < block.z; ++tz)
+                for (unsigned ty = 0; ty < block.y; ++ty)
+                    for (unsigned tx = 0; tx < block.x; ++tx) {
+                        thread_idx = uint3{tx, ty, tz};
+                        body();
+                    }
+        }
+    };
+    const int n_workers = (int)std::min<unsigned long long>((unsigned long long)worker_count(), n_blocks);
+    if (n_workers <= 1) {
+        worker();
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int i = 1; i < n_workers; ++i) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
 }
 }  // namespace b200pt_emu
 #define threadIdx (::b200pt_emu::thread_idx)
@@ -82,11 +109,23 @@ inline float __uint_as_float(uint32_t u) {
 }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
-template <class T>
-inline T atomicAdd(T *p, T v) {
-    T old = *p;
-    *p = old + v;
-    return old;
+inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float *p, float v) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(p);
+    uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED);
+    for (;;) {
+        float f;
+        memcpy(&f, &old, 4);
+        f += v;
+        uint32_t want;
+        memcpy(&want, &f, 4);
+        if (__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+    }
+    float r;
+    memcpy(&r, &old, 4);
+    return r;
 }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
@@ -115,7 +154,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof(*p));
     strcpy(p->name, "host check build (no GPU)");
     p->major = 10;
-    p->multiProcessorCount = 1;
+    p->multiProcessorCount = 8;  // the persistent kernels size their grids from this: enough blocks for the host threads
     return cudaSuccess;
 }
 // B200PT_EMU_POISON=<byte>: fresh "device" memory is filled with that byte (0xff: NaNs / huge indices), so a kernel
