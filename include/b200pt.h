@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 3
+#define B200PT_ABI_VERSION 4
 #define B200PT_SPECTRUM_SAMPLES 60  /* nSpectralSamples, core/spectrum.h:52 */
 #define B200PT_MATERIAL_SPECTRA 5
 
@@ -247,11 +247,24 @@ typedef enum b200pt_light_strategy {
                                       computed up front on the device instead of lazily */
 } b200pt_light_strategy;
 
+typedef struct b200pt_medium {     /* HomogeneousMedium(sigma_a, sigma_s, g), homogeneous.h:50-54; RGBSpectrum hosts only */
+    int32_t present;
+    float sigma_a[3];              /* already multiplied by "scale" (api.cpp:697-700) */
+    float sigma_s[3];
+    float g;                       /* Henyey-Greenstein asymmetry (core/medium.h:69-72) */
+} b200pt_medium;
+
 typedef struct b200pt_integrator_desc {
     int32_t max_depth;             /* "maxdepth", default 5          */
     float rr_threshold;            /* "rrthreshold", default 1       */
     int32_t light_strategy;        /* b200pt_light_strategy          */
     int32_t pixel_bounds[4];       /* "pixelbounds" ∩ sample bounds, x0 y0 x1 y1 (path.cpp:195-207) */
+    /* VolPathIntegrator (integrators/volpath.cpp:60-188) instead of PathIntegrator: a light is sampled at every vertex
+     * (also purely specular ones, :124-128) and, with `medium.present`, every ray travels through one
+     * HomogeneousMedium (media/homogeneous.cpp) that surrounds the whole scene -- the camera is in it and no surface is
+     * a medium transition.  Media bounded by surfaces and heterogeneous media are not supported. */
+    int32_t volumetric;
+    b200pt_medium medium;
 } b200pt_integrator_desc;
 
 /* ---- per-ray records for the kernel-level entry points ------------------ */

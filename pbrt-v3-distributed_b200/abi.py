@@ -74,9 +74,13 @@ class SamplerDesc(C.Structure):
                 ("halton_permutations", C.c_void_p)]
 
 
+class Medium(C.Structure):
+    _fields_ = [("present", C.c_int32), ("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("g", C.c_float)]
+
+
 class IntegratorDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("pixel_bounds", C.c_int32 * 4)]
+                ("pixel_bounds", C.c_int32 * 4), ("volumetric", C.c_int32), ("medium", Medium)]
 
 
 class Stats(C.Structure):

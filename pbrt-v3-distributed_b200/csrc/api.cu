@@ -752,9 +752,23 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: Halton permutation table missing");
     if (integ->max_depth < 0 || integ->max_depth > 200) return b200pt_fail(B200PT_ERR_INVALID, "render_create: bad max_depth");
     // 5 camera dims + per bounce: light pick 1 + uLight 2 + uScattering 2 + BSDF 2 + roulette 1
-    if (5 + 8 * integ->max_depth > smp->n_dimensions)
+    // ... + medium channel 1 + free-flight distance 1 with VolPathIntegrator inside a medium
+    const int dims_per_bounce = integ->volumetric && integ->medium.present ? 10 : 8;
+    if (5 + dims_per_bounce * integ->max_depth > smp->n_dimensions)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d sampler dimensions, %d provided",
-                           integ->max_depth, 5 + 8 * integ->max_depth, smp->n_dimensions);
+                           integ->max_depth, 5 + dims_per_bounce * integ->max_depth, smp->n_dimensions);
+    if (integ->medium.present && !integ->volumetric)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: a medium needs the volumetric integrator (PathIntegrator ignores media)");
+    if (integ->medium.present && scene->nspec)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: media are not built for SampledSpectrum hosts yet");
+    if (integ->medium.present) {
+        for (int c = 0; c < 3; ++c)
+            if (!(integ->medium.sigma_a[c] >= 0.f) || !(integ->medium.sigma_s[c] >= 0.f) ||
+                !(integ->medium.sigma_a[c] + integ->medium.sigma_s[c] > 0.f))
+                return b200pt_fail(B200PT_ERR_INVALID, "render_create: the medium needs sigma_a, sigma_s >= 0 and sigma_t > 0 in every channel");
+        if (!(integ->medium.g > -1.f && integ->medium.g < 1.f))
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: Henyey-Greenstein g must lie in (-1, 1)");
+    }
     if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER &&
         integ->light_strategy != B200PT_LIGHTS_SPATIAL)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: unsupported light sample strategy");
@@ -856,6 +870,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.max_sample_luminance = film->max_sample_luminance;
     H.max_depth = integ->max_depth;
     H.rr_threshold = integ->rr_threshold;
+    H.volpath = integ->volumetric ? 1 : 0;
+    H.has_medium = integ->volumetric && integ->medium.present ? 1 : 0;
+    for (int c = 0; c < 3 && H.has_medium; ++c) {
+        H.med_sigma_s[c] = integ->medium.sigma_s[c];
+        H.med_sigma_t[c] = integ->medium.sigma_s[c] + integ->medium.sigma_a[c];  // homogeneous.h:53
+    }
+    H.med_g = integ->medium.g;
     H.tiles_x = (sbw + 15) / 16;
     H.tiles_y = (sbh + 15) / 16;
 
@@ -1228,10 +1249,11 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         //   closest(b) -> shade(b) -> { any(b), MIS-closest(b) } || closest(b+1) -> resolve(b) -> shade(b+1) ...
         // The shadow / MIS rays of bounce b and the path rays of bounce b+1 are independent, so they run on
         // two streams: as the persistent CTAs of one launch drain, the other launch fills the freed SMs.
-        const bool overlap = r->overlap && r->sort_from_bounce < 0;
+        const bool medium = H.has_medium != 0;  // k_medium also queues direct-lighting rays: no overlap of bounces then
+        const bool overlap = r->overlap && r->sort_from_bounce < 0 && !medium;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
         const bool has_spheres = H.scene.n_spheres > 0 || H.scene.n_instances > 0;  // "extra shapes" pass needed
-        const bool full_shade = has_spheres || H.has_delta_lights || H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr;
+        const bool full_shade = has_spheres || H.has_delta_lights || H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr || H.volpath;
         auto sphere_args = [&](TraceArgs &a, uint32_t *work) {
             a.spheres = H.scene.spheres;
             a.n_spheres = H.scene.n_spheres;
@@ -1272,12 +1294,17 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             for (int m = 0; m < 4; ++m) a.q_mat[m] = H.q_mat[m];
             a.qcount_mat = qc + Q_MAT0;
             LaunchTimer lt(r, st, 0);
-            // with spheres in the scene the sphere pass decides the final hit, so it does the classification
-            launch_trace(a, false, !has_spheres, r->instrumented, r->grid_trace, st);
+            // with spheres in the scene the sphere pass decides the final hit, so it does the classification;
+            // inside a medium the medium pass does (only paths that reach their surface are shaded)
+            launch_trace(a, false, !has_spheres && !medium, r->instrumented, r->grid_trace, st);
             if (has_spheres) {
                 sphere_args(a, wk + 8);
-                launch_spheres(a, false, true, r->grid_shade, st);
+                launch_spheres(a, false, !medium, r->grid_shade, st);
                 r->launches++;
+            }
+            if (medium) {
+                LaunchTimer lt2(r, st, 2);
+                launch_medium(r->d_dev, b, wk + 11, r->grid_shade, st);
             }
         };
         auto trace_direct = [&](int b) {
@@ -1343,7 +1370,15 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                     else
                         launch_shade(r->d_dev, m, full_shade, b, wk + 1 + m, r->grid_shade, st);
                 }
-            if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
+            if (b < maxDepth && medium) {
+                // the medium pass of bounce b+1 writes the same per-slot direct-lighting records: finish bounce b's first
+                trace_direct(b);
+                {
+                    LaunchTimer lt(r, st, 2);
+                    launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
+                }
+                trace_path(b + 1);
+            } else if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)
                 if (overlap) {
                     CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
                     CUDA_TRY(cudaStreamWaitEvent(st2, ctx->ev_fork, 0));

@@ -582,9 +582,26 @@ struct DirectOut {
 // specular = false, for a DiffuseAreaLight on one triangle.  The two rays it
 // needs are not traced here: the shadow ray and the BSDF-sampled ("MIS") ray
 // are queued with the terms they gate (A and B).
+// With R->has_medium (VolPathIntegrator, handleMedia = true, every ray inside one homogeneous medium) the two rays also
+// carry a transmittance: an unoccluded shadow ray's is known here (VisibilityTester::Tr, light.cpp:63-81, every surface
+// is opaque), and the MIS ray can only contribute if its closest hit is the light's own shape, whose distance Pdf_Li
+// computes anyway (Scene::IntersectTr, scene.cpp:57-70).  `inMedium`: `is` is a MediumInteraction (p, wo; zero normal
+// and error bounds) and the Henyey-Greenstein phase function takes the BSDF's place (integrator.cpp:131-137, :178-186).
 template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
-                                int lightNum, const float uLight[2], DirectOut *out) {
+                                int lightNum, const float uLight[2], DirectOut *out, bool inMedium = false) {
+#if B200PT_NSPEC == 3
+    // (VolPathIntegrator renders always run the general variant, so the lean one carries none of this)
+    const bool medium = VTX && R->has_medium != 0;
+    const Spec sigmaT = VTX ? rgbp(R->med_sigma_t) : rgb1(0.f);
+    const float hgG = R->med_g;
+    if (!VTX) inMedium = false;
+#else
+    const bool medium = false;
+    const Spec sigmaT = rgb1(0.f);
+    const float hgG = 0.f;
+    inMedium = false;
+#endif
     const DevLight &lightRef = R->lights[lightNum];
     if (VTX && lightRef.kind != 0) {
         // delta light (scenes with delta lights always run the VTX variant): Sample_Li has pdf 1, there is no MIS weight
@@ -596,13 +613,15 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         V3 wiD, pTarget;
         const Spec LiD = delta_light_sample(dl, is.p, &wiD, &pTarget);
         if (!is_black(LiD)) {
-            const Spec fD = bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
+            const Spec fD = inMedium ? rgb1(phase_hg(dot(is.wo, wiD), hgG))
+                                     : bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
             if (!is_black(fD)) {
                 // SpawnRayTo(Interaction) towards a point without normal or error bounds (interaction.h:73-78)
                 const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
                 out->sh_o = origin;
                 out->sh_d = pTarget - origin;
-                out->A = fD * LiD / 1.f;
+                const Spec LiT = medium ? LiD * medium_tr(sigmaT, out->sh_d, PT_SHADOW_TMAX) : LiD;  // Li *= Tr
+                out->A = fD * LiT / 1.f;
                 out->pend |= PEND_LIGHT;
             }
         }
@@ -654,14 +673,22 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         Li = (light.two_sided || dot(ps.n, -wi) > 0) ? lemit : rgb1(0.f);  // diffuse.h:56-58
     }
     if (lightPdf > 0 && !is_black(Li)) {
-        Spec f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
-        scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+        Spec f;
+        if (inMedium) {
+            const float p = phase_hg(dot(is.wo, wi), hgG);
+            f = rgb1(p);
+            scatteringPdf = p;
+        } else {
+            f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
+            scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+        }
         if (!is_black(f)) {
             // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
             const V3 origin = offset_ray_origin(is.p, is.pError, is.n, ps.p - is.p);
             const V3 target = offset_ray_origin(ps.p, ps.pError, ps.n, origin - ps.p);
             out->sh_o = origin;
             out->sh_d = target - origin;
+            if (medium) Li = Li * medium_tr(sigmaT, out->sh_d, PT_SHADOW_TMAX);  // Li *= visibility.Tr(scene, sampler)
             const float weight = power_heuristic(lightPdf, scatteringPdf);
             out->A = f * Li * weight / lightPdf;
             out->pend |= PEND_LIGHT;
@@ -669,12 +696,19 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
     }
     // BSDF sampling with MIS (integrator.cpp:166-213)
     int sampledType = 0;
-    Spec f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
-    f = f * absdot(wi, bsdf.ns);
+    Spec f;
+    if (inMedium) {
+        const float p = hg_sample_p(hgG, is.wo, &wi, uScattering);
+        f = rgb1(p);
+        scatteringPdf = p;
+    } else {
+        f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+        f = f * absdot(wi, bsdf.ns);
+    }
     if (!is_black(f) && scatteringPdf > 0) {
         // light.Pdf_Li -> Shape::Pdf (shape.cpp:72-87): intersect the light's own triangle
         const V3 ro = offset_ray_origin(is.p, is.pError, is.n, wi);
-        float lpdf = 0.f;
+        float lpdf = 0.f, tLight = 0.f;  // tLight: distance along the MIS ray to the light's own shape
         V3 ln = mk(0.f, 0.f, 0.f);
         TriHit h;
         if (onSphere) {
@@ -683,12 +717,14 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
             Isect li;
             if (sphere_intersect(*lsp, ro, wi, pt_inf(), &th, &li)) {
                 ln = li.n;
+                tLight = th;
                 lpdf = sphere_pdf(*lsp, is.p, is.pError, is.n, wi);
             }
         } else if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
             Isect li;
             fill_isect(p0, p1, p2, lflip, lsh, h, wi, &li);
             ln = li.n;
+            tLight = h.t;
             lpdf = len2(is.p - li.p) / (absdot(ln, -wi) * light.area);
             if (pt_isinf(lpdf)) lpdf = 0.f;
         }
@@ -696,7 +732,9 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
             const float weight = power_heuristic(scatteringPdf, lpdf);
             // lightIsect.Le(-wi) if the closest hit along the ray is this light (integrator.cpp:205-209)
             const Spec Le = (light.two_sided || dot(ln, -wi) > 0) ? lemit : rgb1(0.f);
-            out->B = is_black(Le) ? rgb1(0.f) : f * Le * 1.f * weight / scatteringPdf;
+            // ... attenuated by the medium up to that hit (Scene::IntersectTr: ray.tMax is the hit distance by then)
+            const Spec Tr = medium ? medium_tr(sigmaT, wi, tLight) : rgb1(1.f);
+            out->B = is_black(Le) ? rgb1(0.f) : f * Le * Tr * weight / scatteringPdf;
             out->mi_o = ro;
             out->mi_d = wi;
             out->pend |= PEND_BSDF;
@@ -789,7 +827,8 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                     st.px = st.py = 0;  // only dimensions 0/1 depend on the pixel
                     const SamplerParams &sp = R->sampler;
                     // path.cpp:119-128 -> UniformSampleOneLight (integrator.cpp:85-106)
-                    if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0 && R->n_lights > 0) {
+                    // (VolPathIntegrator samples a light at every surface vertex, volpath.cpp:124-128)
+                    if (((VTX && R->volpath) || bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0) && R->n_lights > 0) {
                         float pickPdf;
                         const float *cdf = R->light_cdf, *func = R->light_func;
                         float funcInt = R->light_func_int;
@@ -866,6 +905,163 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
         if (cont) q_next[pn] = slot;
     }
 }
+
+#if B200PT_NSPEC == 3
+// Medium pass of a bounce (VolPathIntegrator with every ray inside one homogeneous medium, volpath.cpp:77-103): runs over
+// the bounce's path rays after the closest-hit launch (which then does not classify).  It draws the channel and the
+// free-flight distance (HomogeneousMedium::Sample, homogeneous.cpp:49-76) against the distance of the hit.  A path that
+// scatters in the medium gets its whole vertex here -- light sample with the phase function, phase-sampled MIS ray and
+// next direction, Russian roulette -- and skips the shading kernels; the others have beta scaled by Tr / pdf and are
+// appended to their BSDF family's queue (rays that left the scene end here, like in the reference).
+__global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounce, uint32_t *work) {
+    const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_PATH];
+    const uint32_t *queue = R->q_path[bounce & 1];
+    uint32_t *qc = &R->qcount[bounce * Q_PER_BOUNCE];
+    uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
+    uint32_t *q_next = R->q_path[(bounce + 1) & 1];
+    const Spec sigmaT = rgbp(R->med_sigma_t), sigmaS = rgbp(R->med_sigma_s);
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        const bool active = i < n;
+        bool cont = false;
+        int family = -1;
+        uint32_t pend = 0, slot = 0;
+        if (active) {
+            slot = queue[i];
+            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
+            float betaW;
+            Spec beta = ld_spec(R->beta, R->s_beta, R->capacity, slot, &betaW);
+            const V3 ro = v3(o4), rd = v3(d4);
+            const float etaScale = o4.w;
+            const uint32_t meta = __float_as_uint(d4.w);
+            const int bounces = (int)((meta >> 16) & 0xffu);
+            // distance of the closest hit (ray.tMax after Scene::Intersect) and its material
+            const uint32_t ti = R->hit[slot];
+            float tHit = pt_inf();
+            uint32_t mflags = 0;
+            if (ti != B200PT_MISS) {
+                if (is_sphere_hit(ti)) {
+                    const DevSphere *sp = R->scene.spheres + (ti & SPHERE_HIT_MASK);
+                    float th;
+                    if (sphere_intersect(*sp, ro, rd, pt_inf(), &th, nullptr)) tHit = th;
+                    mflags = sp->mat_flags;
+                } else {
+                    const F4 *tp = R->scene.tris + (size_t)ti * 3;
+                    const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+                    mflags = __float_as_uint(t1.w);
+                    V3 o2 = ro, d2 = rd;
+                    if (mflags & 0x100000u) {  // a triangle of an instanced object: same ray parameter in the object's space
+                        float tm2;
+                        instance_ray(R->scene.instances[R->hit_inst[slot]], ro, rd, pt_inf(), &o2, &d2, &tm2);
+                    }
+                    TriHit h;
+                    if (triangle_test(v3(t0), v3(t1), v3(t2), o2, make_shear(d2), pt_inf(), &h)) tHit = h.t;
+                }
+            }
+            SobolStream st;
+            st.index = R->sobol[slot];
+            st.dim = (int)(meta & 0xffffu);
+            st.px = st.py = 0;
+            const SamplerParams &sp = R->sampler;
+            // HomogeneousMedium::Sample
+            const int channel = pt_mini((int)(get1d(sp, st) * B200PT_NSPEC), B200PT_NSPEC - 1);
+            const float dist = -pt_logf(1 - get1d(sp, st)) / sigmaT.c[channel];
+            const float rdLen = len(rd);
+            const float t = pt_min(dist / rdLen, tHit);
+            const bool sampledMedium = t < tHit;
+            Spec Tr;
+            PT_UNROLL SPEC_FOR Tr.c[i_] = pt_expf((-sigmaT.c[i_]) * pt_min(t, PT_MAX_FLOAT) * rdLen);
+            const Spec density = sampledMedium ? (sigmaT * Tr) : Tr;
+            float pdf = 0.f;
+            SPEC_FOR pdf += density.c[i_];
+            pdf *= 1 / (float)B200PT_NSPEC;
+            if (pdf == 0) pdf = 1;
+            beta = beta * (sampledMedium ? (Tr * sigmaS / pdf) : (Tr / pdf));
+            if (!is_black(beta)) {
+                if (!sampledMedium) {
+                    // on to the surface vertex (or out of the scene)
+                    st_spec(R->beta, R->s_beta, R->capacity, slot, beta, betaW);
+                    R->ray_d[slot] = f4(rd, __uint_as_float((meta & 0xffff0000u) | ((uint32_t)st.dim & 0xffffu)));
+                    if (ti != B200PT_MISS) family = R->scene.materials[mflags & 0xffffu].type;
+                } else if (bounces < R->max_depth) {  // volpath.cpp:84-85
+                    Isect mi;  // MediumInteraction(ray(t), -ray.d, ...): no normal, no error bounds
+                    mi.p = ro + rd * t;
+                    mi.wo = -rd;
+                    mi.n = mi.ns = mk(0.f, 0.f, 0.f);
+                    mi.pError = mk(0.f, 0.f, 0.f);
+                    if (R->n_lights > 0) {
+                        // UniformSampleOneLight(mi, ..., handleMedia = true), integrator.cpp:85-106
+                        float pickPdf;
+                        const float *cdf = R->light_cdf, *func = R->light_func;
+                        float funcInt = R->light_func_int;
+                        if (R->grid.enabled) {
+                            const int vox = spatial_voxel(R->grid, mi.p);
+                            cdf = R->sp_cdf + (size_t)vox * (R->n_lights + 1);
+                            func = R->sp_func + (size_t)vox * R->n_lights;
+                            funcInt = R->sp_func_int[vox];
+                        }
+                        const int lightNum = sample_discrete(cdf, func, funcInt, R->n_lights, get1d(sp, st), &pickPdf);
+                        if (pickPdf != 0) {
+                            float uLight[2], uScattering[2];
+                            get2d(sp, st, uLight);
+                            get2d(sp, st, uScattering);
+                            DirectOut dout;
+                            Bsdf none;
+                            none.n = 0;
+                            estimate_direct<true>(R, mi, none, uScattering, lightNum, uLight, &dout, true);
+                            pend = dout.pend;
+                            if (pend) {
+                                st_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, beta, pickPdf);
+                                R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
+                                if (pend & PEND_LIGHT) st_spec(R->A, R->s_A, R->capacity, slot, dout.A, 0.f);
+                                if (pend & PEND_BSDF) {
+                                    R->mi_o[slot] = f4(dout.mi_o, 0.f);
+                                    R->mi_d[slot] = f4(dout.mi_d, 0.f);
+                                    st_spec(R->B, R->s_B, R->capacity, slot, dout.B, 0.f);
+                                }
+                            }
+                            R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
+                        }
+                    }
+                    // mi.phase->Sample_p(wo, &wi, sampler.Get2D()); ray = mi.SpawnRay(wi) (volpath.cpp:95-98)
+                    V3 wi;
+                    float u2[2];
+                    get2d(sp, st, u2);
+                    hg_sample_p(R->med_g, mi.wo, &wi, u2);
+                    const V3 no = offset_ray_origin(mi.p, mi.pError, mi.n, wi);
+                    cont = true;
+                    const Spec rrBeta = beta * etaScale;  // volpath.cpp:176-184
+                    if (max_comp(rrBeta) < R->rr_threshold && bounces > 3) {
+                        const float q = pt_max(.05f, 1 - max_comp(rrBeta));
+                        if (get1d(sp, st) < q)
+                            cont = false;
+                        else
+                            beta = beta / (1 - q);
+                    }
+                    if (cont) {
+                        const uint32_t nmeta = ((uint32_t)st.dim & 0xffffu) | ((uint32_t)(bounces + 1) << 16);  // specularBounce = false
+                        R->ray_o[slot] = f4(no, etaScale);
+                        R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
+                        st_spec(R->beta, R->s_beta, R->capacity, slot, beta, 0.f);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const bool mine = family == m;
+            const uint32_t pos = warp_append(&qc[Q_MAT0 + m], mine);
+            if (mine) R->q_mat[m][pos] = slot;
+        }
+        const uint32_t ps = warp_append(&qc[Q_SHADOW], (pend & PEND_LIGHT) != 0);
+        if (pend & PEND_LIGHT) R->q_shadow[ps] = slot;
+        const uint32_t pm = warp_append(&qc[Q_MIS], (pend & PEND_BSDF) != 0);
+        if (pend & PEND_BSDF) R->q_mis[pm] = slot;
+        const uint32_t pn = warp_append(qc_next, cont);
+        if (cont) q_next[pn] = slot;
+    }
+}
+#endif  // B200PT_NSPEC == 3
 
 // L += beta * (EstimateDirect(...) / lightPdf)   (path.cpp:122-127, integrator.cpp:104-105)
 __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce, uint32_t *work) {
@@ -1347,6 +1543,12 @@ void launch_shade(const RenderDev *dev, int material, bool vertex_data, int boun
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
     B200PT_LAUNCH(B200PT_KERNEL(k_resolve), grid, 256, s, dev, bounce, work);
 }
+
+#if B200PT_NSPEC == 3
+void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
+    B200PT_LAUNCH(B200PT_KERNEL(k_medium), grid, 128, s, dev, bounce, work);
+}
+#endif
 
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s) {
     const long long nvox = (long long)host.grid.nv[0] * host.grid.nv[1] * host.grid.nv[2];

@@ -123,6 +123,10 @@ struct RenderDev {
     uint32_t *qcount;          // [(max_depth + 2) * Q_PER_BOUNCE]
     uint32_t *work;            // persistent-fetch counters, one per launch of a batch
     unsigned long long *stats; // camera, regular, shadow, nodes, tris
+    // VolPathIntegrator (b200pt_integrator_desc::volumetric / medium): light sampling at every vertex; with has_medium
+    // every ray is inside one homogeneous medium (RGB build only)
+    int volpath, has_medium;
+    float med_sigma_s[3], med_sigma_t[3], med_g;
 };
 
 struct TraceArgs {
@@ -168,6 +172,8 @@ void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, c
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid,
                   cudaStream_t s);
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+// Medium pass of a bounce (scenes inside a homogeneous medium): after the closest-hit launch, before the shading kernels.
+void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
 #define SORT_BUCKETS (1u << 18)  // 3 octant bits + 15 Morton bits
 // Counting sort of a queue of slots by the coherence key of the rays they refer to; `out` receives
 // the permuted queue (order inside a bucket is arbitrary -- it never affects a path's arithmetic).

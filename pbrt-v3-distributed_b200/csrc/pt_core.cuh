@@ -15,6 +15,7 @@
 #include "../../include/b200pt.h"
 #include "pt_platform.h"
 #include "pt_sincos.cuh"
+#include "pt_explog.cuh"
 
 namespace B200PT_NS {
 
@@ -1267,6 +1268,40 @@ B200_HD int spatial_voxel(const SpatialGrid &g, const V3 &p) {
 // One (voxel, light) term of SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:230-275):
 // sum over 128 Halton points of Li.y()/pdf for a DiffuseAreaLight on the triangle (p0,p1,p2).
 // spatial_light_contrib: see pt_sphere.cuh (it samples triangle and sphere lights)
+
+// --------------------------------------------------------------------- media
+#define PT_MAX_FLOAT 3.402823466e+38f
+#define PT_INV_4PI ((float)0.07957747154594766788)
+// Exp(-sigma_t * x) per bin (spectrum.h:217-227 with the host's expf, pt_explog.cuh)
+B200_HD Spec spec_exp_neg(const Spec &sigma_t, float x) {
+    Spec r;
+    PT_UNROLL SPEC_FOR r.c[i_] = pt_expf((-sigma_t.c[i_]) * x);
+    return r;
+}
+// HomogeneousMedium::Tr (homogeneous.cpp:44-47) of a ray (d, tMax)
+B200_HD Spec medium_tr(const Spec &sigma_t, const V3 &d, float tMax) { return spec_exp_neg(sigma_t, pt_min(tMax * len(d), PT_MAX_FLOAT)); }
+// medium.h:69-72
+B200_HD float phase_hg(float cosTheta, float g) {
+    float denom = 1 + g * g + 2 * g * cosTheta;
+    return PT_INV_4PI * (1 - g * g) / (denom * sqrtf(denom));
+}
+// HenyeyGreenstein::Sample_p, medium.cpp:194-213
+B200_HD float hg_sample_p(float g, const V3 &wo, V3 *wi, const float u[2]) {
+    float cosTheta;
+    if (pt_abs(g) < 1e-3)
+        cosTheta = 1 - 2 * u[0];
+    else {
+        float sqrTerm = (1 - g * g) / (1 - g + 2 * g * u[0]);
+        cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+    }
+    float sinTheta = sqrtf(pt_max(0.f, 1 - cosTheta * cosTheta));
+    float phi = 2 * PT_PI * u[1];
+    V3 v1, v2;
+    coordinate_system(wo, &v1, &v2);
+    // SphericalDirection(sinTheta, cosTheta, phi, v1, v2, -wo), geometry.h:1467-1472
+    *wi = v1 * (sinTheta * pt_cosf(phi)) + v2 * (sinTheta * pt_sinf(phi)) + (-wo) * cosTheta;
+    return phase_hg(-cosTheta, g);
+}
 
 // ----------------------------------------------------------------------- film
 // Spectrum::ToXYZ: RGBSpectrum (spectrum.h:455 -> :62-66) or SampledSpectrum (spectrum.h:380-392)

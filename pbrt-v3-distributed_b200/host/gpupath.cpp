@@ -44,6 +44,7 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 #include <glog/logging.h>
@@ -54,6 +55,8 @@
 #include "cameras/perspective.h"
 #include "core/film.h"
 #include "core/integrator.h"
+#include "integrators/volpath.h"
+#include "media/homogeneous.h"
 #include "core/light.h"
 #include "core/paramset.h"
 #include "core/primitive.h"
@@ -238,7 +241,8 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, float *rows, std::
     return false;
 }
 
-bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
+// `volumetric`: VolPathIntegrator looks at the primitives' MediumInterfaces; surfaces that bound a medium are not supported
+bool FlattenScene(const Scene &scene, Flattened *f, std::string *why, bool volumetric) {
     auto bvh = dynamic_cast<const BVHAccel *>(scene.aggregate.get());
     if (!bvh) return *why = "an aggregate other than BVHAccel", false;
     // BVHAccel reorders its vector (orderedPrims, bvh.cpp:208); any order works as long as it is
@@ -246,6 +250,11 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
     const auto &prims = bvh->primitives;
     std::unordered_map<const Material *, int> matIndex;
     std::unordered_map<const Shape *, int> triOfShape, sphereOfShape;
+    auto noTransition = [&](const GeometricPrimitive *gp) {
+        if (volumetric && gp->mediumInterface.IsMediumTransition())
+            return *why = "surfaces that separate two media (MediumInterface with different inside / outside)", false;
+        return true;
+    };
     auto materialOf = [&](const Material *m, int *id) {
         if (!m) return *why = "primitives without a material (medium boundaries)", false;
         auto it = matIndex.find(m);
@@ -263,7 +272,8 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
     auto appendTriangle = [&](const GeometricPrimitive *gp) {
         auto tri = dynamic_cast<const Triangle *>(gp->shape.get());
         if (!tri) return *why = "a shape other than Triangle and Sphere", false;
-        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
+        if (!volumetric && (gp->mediumInterface.inside || gp->mediumInterface.outside)) return *why = "participating media", false;
+        if (!noTransition(gp)) return false;
         const TriangleMesh &mesh = *tri->mesh;
         if (mesh.s || mesh.alphaMask || mesh.shadowAlphaMask)
             return *why = "meshes with per-vertex tangents / alpha masks", false;
@@ -300,7 +310,8 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
         }
         auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
         if (!gp) return *why = "a primitive other than GeometricPrimitive / TransformedPrimitive", false;
-        if (gp->mediumInterface.inside || gp->mediumInterface.outside) return *why = "participating media", false;
+        if (!volumetric && (gp->mediumInterface.inside || gp->mediumInterface.outside)) return *why = "participating media", false;
+        if (!noTransition(gp)) return false;
         if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
             b200pt_sphere bs;
             memset(&bs, 0, sizeof(bs));
@@ -449,11 +460,16 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why) {
 
 }  // namespace
 
-class GpuPathIntegrator : public PathIntegrator {
+// Base = PathIntegrator (integrators/path.h:48-66) or VolPathIntegrator (integrators/volpath.h:49-66): the same members
+// (maxDepth, rrThreshold, lightSampleStrategy), the same constructor signature, Render() replaced.
+template <class Base>
+class GpuIntegrator : public Base {
+    static constexpr bool kVolumetric = std::is_same<Base, VolPathIntegrator>::value;
+
   public:
-    GpuPathIntegrator(int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler,
-                      const Bounds2i &pixelBounds, Float rrThreshold, const std::string &lightSampleStrategy)
-        : PathIntegrator(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightSampleStrategy),
+    GpuIntegrator(int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler,
+                  const Bounds2i &pixelBounds, Float rrThreshold, const std::string &lightSampleStrategy)
+        : Base(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightSampleStrategy),
           cam(camera),
           smp(sampler),
           bounds(pixelBounds) {}
@@ -479,6 +495,9 @@ class GpuPathIntegrator : public PathIntegrator {
         if (film->filter->radius.x > 8 || film->filter->radius.y > 8)
             return Error("gpupath: pixel filters wider than 8 pixels are not supported");
         int strategy;
+        const std::string &lightSampleStrategy = this->lightSampleStrategy;
+        const int maxDepth = this->maxDepth;
+        const Float rrThreshold = this->rrThreshold;
         if (lightSampleStrategy == "uniform" || scene.lights.size() == 1)
             strategy = B200PT_LIGHTS_UNIFORM;
         else if (lightSampleStrategy == "power")
@@ -486,7 +505,7 @@ class GpuPathIntegrator : public PathIntegrator {
         else  // "spatial" and, like the reference (lightdistrib.cpp:59-65), any unknown name
             strategy = B200PT_LIGHTS_SPATIAL;
         Flattened flat;
-        if (!FlattenScene(scene, &flat, &why)) return Error("gpupath: the scene uses %s", why.c_str());
+        if (!FlattenScene(scene, &flat, &why, kVolumetric)) return Error("gpupath: the scene uses %s", why.c_str());
 
         b200pt_scene_desc sd;
         memset(&sd, 0, sizeof(sd));
@@ -566,6 +585,21 @@ class GpuPathIntegrator : public PathIntegrator {
         }
 
         b200pt_integrator_desc id;
+        memset(&id, 0, sizeof(id));
+        if (kVolumetric) {
+            // VolPathIntegrator: the camera ray's medium (camera.h:76) is every ray's medium when no surface is a medium
+            // transition (checked while flattening); only HomogeneousMedium is supported
+            id.volumetric = 1;
+            if (const Medium *m = cam->medium) {
+                auto hm = dynamic_cast<const HomogeneousMedium *>(m);
+                if (!hm) return Error("gpupath: only homogeneous media are supported");
+                if (kSampledHost) return Error("gpupath: media are not supported with SampledSpectrum hosts yet");
+                id.medium.present = 1;
+                ToRGB(hm->sigma_a, id.medium.sigma_a);
+                ToRGB(hm->sigma_s, id.medium.sigma_s);
+                id.medium.g = hm->g;
+            }
+        }
         id.max_depth = maxDepth;
         id.rr_threshold = rrThreshold;
         id.light_strategy = strategy;
@@ -707,7 +741,28 @@ PathIntegrator *CreatePathIntegrator(const ParamSet &params, std::shared_ptr<Sam
     }
     Float rrThreshold = params.FindOneFloat("rrthreshold", 1.);
     std::string lightStrategy = params.FindOneString("lightsamplestrategy", "spatial");
-    return new GpuPathIntegrator(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightStrategy);
+    return new GpuIntegrator<PathIntegrator>(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightStrategy);
+}
+
+// integrators/volpath.cpp:190-214 -- same parameters, same defaults.  `Integrator "volpath"` renders on the GPU when the
+// scene's media are at most one homogeneous medium around everything (the camera's medium, no medium transitions).
+VolPathIntegrator *CreateVolPathIntegrator(const ParamSet &params, std::shared_ptr<Sampler> sampler,
+                                           std::shared_ptr<const Camera> camera) {
+    int maxDepth = params.FindOneInt("maxdepth", 5);
+    int np;
+    const int *pb = params.FindInt("pixelbounds", &np);
+    Bounds2i pixelBounds = camera->film->GetSampleBounds();
+    if (pb) {
+        if (np != 4)
+            Error("Expected four values for \"pixelbounds\" parameter. Got %d.", np);
+        else {
+            pixelBounds = Intersect(pixelBounds, Bounds2i{{pb[0], pb[2]}, {pb[1], pb[3]}});
+            if (pixelBounds.Area() == 0) Error("Degenerate \"pixelbounds\" specified.");
+        }
+    }
+    Float rrThreshold = params.FindOneFloat("rrthreshold", 1.);
+    std::string lightStrategy = params.FindOneString("lightsamplestrategy", "spatial");
+    return new GpuIntegrator<VolPathIntegrator>(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightStrategy);
 }
 
 }  // namespace pbrt

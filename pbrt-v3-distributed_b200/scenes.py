@@ -577,7 +577,7 @@ class RenderSetup:
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
                  lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None,
-                 sampler="sobol", pixel_filter=None):
+                 sampler="sobol", pixel_filter=None, integrator="path", medium=None):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.sampler_name = sampler
@@ -626,6 +626,13 @@ class RenderSetup:
         self.integrator.rr_threshold = 1.0
         self.integrator.light_strategy = strategy
         self.integrator.pixel_bounds[:] = pixel_bounds or sb
+        # integrator="volpath": VolPathIntegrator; medium = dict(sigma_a=, sigma_s=, g=): homogeneous, around everything
+        self.integrator.volumetric = 1 if integrator == "volpath" else 0
+        if medium:
+            self.integrator.medium.present = 1
+            self.integrator.medium.sigma_a[:] = list(medium["sigma_a"])
+            self.integrator.medium.sigma_s[:] = list(medium["sigma_s"])
+            self.integrator.medium.g = medium.get("g", 0.0)
 
     def _sobol_tables(self, cb):
         res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))

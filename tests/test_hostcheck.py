@@ -12,6 +12,7 @@ import pytest
 
 import test_gpu_parity as G
 import test_zz_spectral_gpu as GS
+import test_zz_volpath_gpu as GV
 from conftest import GOLDEN, bits
 from render_cases import EXTRA, RENDERS
 
@@ -61,6 +62,21 @@ def test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, o
 def test_spectral_counters_power_and_filter(hostcheck, abi, scenes, ob, hctx):
     GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 8, "power", None)
     GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "metal"), 5, "uniform", "gaussian")
+
+
+@pytest.mark.parametrize("gname", sorted(GV.VOLPATH))
+def test_volpath_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, gname):
+    GV.test_volpath_render_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, gname)
+
+
+def test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx):
+    thin = dict(sigma_a=(0.01, 0.02, 0.03), sigma_s=(0.4, 0.35, 0.3), g=0.6)
+    thick = dict(sigma_a=(0.2, 0.2, 0.2), sigma_s=(1.5, 1.2, 0.9), g=-0.5)
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 8, "power", thin, {})
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "plastic"), 12, "uniform", thick, {})
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "metal"), 5, "uniform",
+                                     dict(sigma_a=(0.05, 0.05, 0.05), sigma_s=(0.1, 0.1, 0.1), g=0.0), {"pixel_filter": "gaussian"})
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass"), 6, "uniform", None, {})
 
 
 def test_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx):
@@ -117,6 +133,12 @@ def test_spectral_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_pat
     built with `typedef SampledSpectrum Spectrum`."""
     monkeypatch.setattr(GS, "PLUGIN_SPECTRAL", HC_PLUGIN_SPECTRAL)
     GS.test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path)
+
+
+def test_volpath_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    """`Integrator "volpath"` with a named homogeneous medium through the drop-in binary."""
+    monkeypatch.setattr(GV, "PLUGIN", HC_PLUGIN)
+    GV.test_volpath_dropin_binary_matches_reference(scenes, tmp_path)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(P.KILLEROO_DIR, "killeroo-simple-ref.pfm")),
@@ -251,6 +273,21 @@ def test_bad_render_descriptors_are_refused(hostcheck, abi, scenes, hctx):
     def no_tables(s):
         s.sampler.matrices32 = None
     _expect(hostcheck, "tables missing", lambda: render_with(no_tables))
+
+    fog = dict(sigma_a=(0.1, 0.1, 0.1), sigma_s=(0.2, 0.2, 0.2), g=0.2)
+
+    def medium_without_volpath(s):
+        s.integrator.volumetric = 0
+    _expect(hostcheck, "needs the volumetric integrator", lambda: render_with(medium_without_volpath, integrator="volpath", medium=fog))
+
+    def empty_medium(s):
+        s.integrator.medium.sigma_a[1] = 0.0
+        s.integrator.medium.sigma_s[1] = 0.0
+    _expect(hostcheck, "sigma_t > 0", lambda: render_with(empty_medium, integrator="volpath", medium=fog))
+
+    def bad_g(s):
+        s.integrator.medium.g = 1.0
+    _expect(hostcheck, "must lie in (-1, 1)", lambda: render_with(bad_g, integrator="volpath", medium=fog))
 
     r = hostcheck.Render(scene, scenes.RenderSetup(32, 32, 4))
     _expect(hostcheck, "out of range", lambda: r.render_tiles(np.array([0, 99], np.int32)))

@@ -1,0 +1,98 @@
+"""GPU parity tests of VolPathIntegrator with a homogeneous medium around the scene (last item): the
+images of the reference's `Integrator "volpath"` (tests/golden/render_volpath_*.pfm) bit for bit, and larger renders
+against the oracle's VolPathLi.  Like the SampledSpectrum tests this path was written after the round's GPU time was
+spent: collected last, first GPU run pending; tests/test_hostcheck.py replays the same functions against the CPU check
+build of the sources."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bits
+from render_cases import EXTRA, RENDERS, VOLPATH
+from test_gpu_parity import ctx  # noqa: F401  (module-scoped context fixture)
+
+pytestmark = pytest.mark.gpu
+
+STRATEGY = {"uniform": "LIGHTS_UNIFORM", "power": "LIGHTS_POWER", "spatial": "LIGHTS_SPATIAL"}
+
+
+@pytest.mark.parametrize("gname", sorted(VOLPATH))
+def test_volpath_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, gname):
+    base, medium, strat = VOLPATH[gname]
+    nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+    ex = EXTRA.get(base, {})
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=getattr(abi, STRATEGY[strat]), integrator="volpath",
+                               medium=medium, **ex.get("camera", {}))
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    rgb = r.read_rgb()
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+    nbad = int((bits(rgb) != bits(ref)).sum())
+    if nbad:
+        o = ob.Oracle(abi, arr)
+        ob.set_volpath(o.lib, True, medium)
+        ys, xs, _ = np.nonzero(bits(rgb) != bits(ref))
+        y, x = int(ys[0]), int(xs[0])
+        print("first differing pixel", x, y, rgb[y, x], ref[y, x])
+        print("gpu samples", r.debug_pixel_samples(x, y))
+        print("oracle samples", o.pixel_samples(setup, x, y))
+        ob.set_volpath(o.lib, False)
+    assert nbad == 0, "%d of %d components differ from the reference's volpath render" % (nbad, rgb.size)
+    r.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("mats,depth,strat,medium,kw", [
+    (("matte", "glass", "metal", "plastic"), 8, "power", dict(sigma_a=(0.01, 0.02, 0.03), sigma_s=(0.4, 0.35, 0.3), g=0.6), {}),
+    (("matte", "plastic"), 12, "spatial", dict(sigma_a=(0.2, 0.2, 0.2), sigma_s=(1.5, 1.2, 0.9), g=-0.5), {}),   # thick: long chains
+    (("matte", "metal"), 5, "uniform", dict(sigma_a=(0.05, 0.05, 0.05), sigma_s=(0.1, 0.1, 0.1), g=0.0), {"pixel_filter": "gaussian"}),
+    (("matte", "glass"), 6, "uniform", None, {})])                                                                   # volpath without a medium
+def test_volpath_render_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat, medium, kw):
+    """Larger renders (several batches of work per bounce, Russian roulette in the medium, the general film path) against
+    the oracle's VolPathLi: raw film sums bit for bit; every ray the reference traces as a closest-hit query is counted."""
+    arr = scenes.SceneArrays(20000, materials=mats, soup_version=1)
+    setup = scenes.RenderSetup(64, 48, 8, max_depth=depth, strategy=getattr(abi, STRATEGY[strat]), integrator="volpath",
+                               medium=medium, **kw)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    o = ob.Oracle(abi, arr)
+    ob.set_volpath(o.lib, True, medium)
+    try:
+        film, ostats = o.render(setup)
+    finally:
+        ob.set_volpath(o.lib, False)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    raw = r.read_raw()
+    assert int((bits(raw) != bits(film)).sum()) == 0
+    st = r.stats()
+    assert st["camera_rays"] == ostats["camera_rays"]
+    # VisibilityTester::Tr uses Scene::Intersect, so the reference (and the oracle) count shadow rays as regular ones
+    assert st["regular_rays"] + st["shadow_rays"] == ostats["regular_rays"] + ostats["shadow_rays"]
+    r.close()
+    scene.close()
+    o.close()
+
+
+from test_dropin_plugin import PLUGIN, needs_plugin  # noqa: E402
+
+
+@needs_plugin
+def test_volpath_dropin_binary_matches_reference(scenes, tmp_path):
+    """`Integrator "volpath"`, `MakeNamedMedium` / `MediumInterface` parsed by the reference's own code and flattened by
+    gpupath.cpp (GpuIntegrator<VolPathIntegrator>): bit-identical to the reference's image."""
+    import subprocess
+    for gname in ("volpath_fog", "volpath_fog_spheres", "volpath_four"):
+        base, medium, strat = VOLPATH[gname]
+        nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+        ex = EXTRA.get(base, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+        path = scenes.write_pbrt(str(tmp_path), "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
+                                 integrator="volpath", medium=medium, **ex.get("camera", {}))
+        r = subprocess.run([PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = scenes.read_pfm(os.path.join(str(tmp_path), "render_%s.pfm" % gname))
+        ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+        assert np.array_equal(bits(got), bits(ref)), "drop-in volpath render (%s) differs from the reference" % gname
