@@ -41,6 +41,9 @@ WORKLOADS = {
     # the same with the reference's SampledSpectrum build (60 bins): both halves of BASELINE configs[4]'s feature set
     "cfg5": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
              "synthetic 50M triangles instanced (1000 x 50k), SampledSpectrum (60 bins), maxdepth 16, 64spp, 1920x1080"),
+    # cfg2's scene inside a thin homogeneous medium, VolPathIntegrator
+    "cfg2fog": (1000000, ("matte",), 1024, 1024, 256, 5, None,
+                "synthetic 1M triangles in a homogeneous medium (sigma_t ~0.3, g 0.4), volpath, maxdepth 5, 256spp, 1024x1024"),
     "small": (100000, ("matte", "glass", "metal", "plastic"), 256, 256, 16, 5, None,
               "smoke-sized: 100k triangles, 4 BSDF types, 16spp, 256x256"),
 }
@@ -59,6 +62,8 @@ def workload_scene_kwargs(name):
 
 
 SPECTRAL_WORKLOADS = ("cfg5",)
+# workload -> keyword arguments for RenderSetup / write_pbrt: VolPathIntegrator and its medium
+VOLUMETRIC_WORKLOADS = {"cfg2fog": dict(integrator="volpath", medium=dict(sigma_a=(0.05, 0.08, 0.12), sigma_s=(0.3, 0.25, 0.2), g=0.4))}
 
 
 def spectral_tables():
@@ -117,7 +122,7 @@ def measured_peaks():
 
 def write_reference_scene(scenes, arr, wl, spp, tmp):
     n_tris, mats, xres, yres, _, depth, n_lights, _ = wl
-    return scenes.write_pbrt(tmp, "bench", arr, xres, yres, spp, max_depth=depth, strategy="uniform")
+    return scenes.write_pbrt(tmp, "bench", arr, xres, yres, spp, max_depth=depth, strategy="uniform", **getattr(arr, "bench_integrator", {}))
 
 
 def parse_pbrt_output(out):
@@ -189,7 +194,8 @@ def main():
         spectral = args.workload in SPECTRAL_WORKLOADS
         if spectral:
             arr.attach_spectral(spectral_tables())  # the oracle port reads the tables; the reference binary has its own
-        setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
+        arr.bench_integrator = VOLUMETRIC_WORKLOADS.get(args.workload, {})
+        setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth, **arr.bench_integrator)
         tmp = tempfile.mkdtemp(prefix="b200pt_ref_")
         have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
         pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None
@@ -229,7 +235,8 @@ def main():
     arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **workload_scene_kwargs(args.workload))
     if args.workload in SPECTRAL_WORKLOADS:
         arr.attach_spectral(spectral_tables())
-    setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=args.pixel_filter)
+    arr.bench_integrator = VOLUMETRIC_WORKLOADS.get(args.workload, {})
+    setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=args.pixel_filter, **arr.bench_integrator)
     if args.pixel_filter:
         config["pixel_filter"] = args.pixel_filter
     ctx = pkg.Context(local_rank)
@@ -348,7 +355,7 @@ def main():
         if not args.no_cpu_baseline:
             ob = graft.load_oracle()
             tmp = tempfile.mkdtemp(prefix="b200pt_cpu_")
-            setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth)
+            setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth, **arr.bench_integrator)
             spectral = args.workload in SPECTRAL_WORKLOADS
             have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
             pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None

@@ -79,6 +79,10 @@ def test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass"), 6, "uniform", None, {})
 
 
+def test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx):
+    GV.test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx)
+
+
 def test_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     G.test_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 16, "power")
 

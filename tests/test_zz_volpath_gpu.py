@@ -96,3 +96,26 @@ def test_volpath_dropin_binary_matches_reference(scenes, tmp_path):
         got = scenes.read_pfm(os.path.join(str(tmp_path), "render_%s.pfm" % gname))
         ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
         assert np.array_equal(bits(got), bits(ref)), "drop-in volpath render (%s) differs from the reference" % gname
+
+
+def test_volpath_instances_and_partial_spheres_vs_oracle(pkg, abi, scenes, ob, ctx):
+    """The medium pass re-derives the hit distance for every kind of hit: top-level triangles, triangles of instanced
+    objects (ray taken into the object's space), full and partial spheres."""
+    medium = dict(sigma_a=(0.03, 0.04, 0.05), sigma_s=(0.25, 0.2, 0.3), g=0.3)
+    scene_kw = dict(EXTRA["instances"]["scene"])
+    scene_kw["spheres"] = EXTRA["sphere_partial"]["scene"]["spheres"]
+    arr = scenes.SceneArrays(2000, materials=("matte", "glass", "metal", "plastic"), soup_version=1, **scene_kw)
+    setup = scenes.RenderSetup(48, 40, 8, max_depth=6, strategy=abi.LIGHTS_POWER, integrator="volpath", medium=medium)
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    o = ob.Oracle(abi, arr)
+    ob.set_volpath(o.lib, True, medium)
+    try:
+        film, _ = o.render(setup)
+    finally:
+        ob.set_volpath(o.lib, False)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    assert int((bits(r.read_raw()) != bits(film)).sum()) == 0
+    r.close()
+    scene.close()
+    o.close()
