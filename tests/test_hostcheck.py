@@ -43,9 +43,8 @@ def test_trace_entry_points_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     G.test_trace_instances_vs_oracle(hostcheck, abi, scenes, ob, hctx)
 
 
-# every golden render of the reference whose light distribution is not the (slow to emulate) 64^3-voxel one, plus two
-# that are
-FAST = sorted(n for n in RENDERS if RENDERS[n][6] != "spatial") + ["spatial", "spheres"]
+# every golden render of the reference (tests/render_cases.py)
+FAST = sorted(RENDERS)
 
 
 @pytest.mark.parametrize("name", FAST)
