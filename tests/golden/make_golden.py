@@ -63,11 +63,14 @@ def filter_fixtures():
 
 # "rgb" parameters of the spectral golden scenes (materials, area lights, sphere lights, point / spot / distant lights)
 SPECTRAL_RGB = [(0.5, 0.5, 0.5), (0.0, 0.0, 0.0), (40.0, 40.0, 40.0), (60.0, 60.0, 60.0), (90.0, 90.0, 90.0), (6.0, 6.0, 6.0),
-                (30.0, 24.0, 18.0), (0.8, 0.8, 0.8)]
+                (30.0, 24.0, 18.0), (0.8, 0.8, 0.8),
+                (0.05, 0.08, 0.12), (0.3, 0.25, 0.2), (0.1, 0.05, 0.02), (0.15, 0.2, 0.3)]  # sigma_a / sigma_s of the media
 SPECTRAL_CONST = [0.25, 1.0, 0.9]                                      # float-default spectra (plastic, glass, mirror)
 # rendered by the SampledSpectrum reference; instances + SampledSpectrum together are BASELINE configs[4]'s features
 SPECTRAL_RENDERS = {"spectral_four": "four", "spectral_rough": "rough", "spectral_instances": "instances",
                     "spectral_spheres": "spheres", "spectral_delta_lights": "delta_lights"}
+# VolPathIntegrator under the SampledSpectrum reference: golden name -> key of render_cases.VOLPATH
+SPECTRAL_VOLPATH = {"spectral_volpath_fog": "volpath_fog", "spectral_volpath_fog_spheres": "volpath_fog_spheres"}
 
 
 def spectral_fixtures():
@@ -99,6 +102,16 @@ def spectral_fixtures():
         arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
         path = scenes.write_pbrt("/tmp/golden_render", "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
                                  **ex.get("camera", {}))
+        ob.run_pbrt_ref(path, spectral=True)
+        os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
+    from render_cases import VOLPATH
+    for gname, vname in SPECTRAL_VOLPATH.items():
+        base, medium, strat = VOLPATH[vname]
+        nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+        ex = EXTRA.get(base, {})
+        arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+        path = scenes.write_pbrt("/tmp/golden_render", "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
+                                 integrator="volpath", medium=medium, **ex.get("camera", {}))
         ob.run_pbrt_ref(path, spectral=True)
         os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
 
