@@ -247,11 +247,13 @@ typedef enum b200pt_light_strategy {
                                       computed up front on the device instead of lazily */
 } b200pt_light_strategy;
 
-typedef struct b200pt_medium {     /* HomogeneousMedium(sigma_a, sigma_s, g), homogeneous.h:50-54; RGBSpectrum hosts only */
+typedef struct b200pt_medium {     /* HomogeneousMedium(sigma_a, sigma_s, g), homogeneous.h:50-54 */
     int32_t present;
     float sigma_a[3];              /* already multiplied by "scale" (api.cpp:697-700) */
     float sigma_s[3];
     float g;                       /* Henyey-Greenstein asymmetry (core/medium.h:69-72) */
+    const float *spectra;          /* SampledSpectrum hosts (scene n_spectrum_samples == 60): [2][60] = sigma_a, sigma_s
+                                      as the host holds them; the RGB triples are then ignored.  NULL otherwise */
 } b200pt_medium;
 
 typedef struct b200pt_integrator_desc {

@@ -75,7 +75,8 @@ class SamplerDesc(C.Structure):
 
 
 class Medium(C.Structure):
-    _fields_ = [("present", C.c_int32), ("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("g", C.c_float)]
+    _fields_ = [("present", C.c_int32), ("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("g", C.c_float),
+                ("spectra", C.c_void_p)]
 
 
 class IntegratorDesc(C.Structure):

@@ -42,6 +42,7 @@ struct RenderDev;
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots, cudaStream_t s);
 void launch_shade(const RenderDev *dev, int material, bool vertex_data, int bounce, uint32_t *work, int grid, cudaStream_t s);
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s);
 void launch_film(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, cudaStream_t s);
 void launch_film_general(const RenderDev *dev, const RenderDev &host, uint32_t batch_first_tile, uint32_t n_batch_tiles,
@@ -759,13 +760,16 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
                            integ->max_depth, 5 + dims_per_bounce * integ->max_depth, smp->n_dimensions);
     if (integ->medium.present && !integ->volumetric)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: a medium needs the volumetric integrator (PathIntegrator ignores media)");
-    if (integ->medium.present && scene->nspec)
-        return b200pt_fail(B200PT_ERR_INVALID, "render_create: media are not built for SampledSpectrum hosts yet");
+    if (integ->medium.present && scene->nspec && !integ->medium.spectra)
+        return b200pt_fail(B200PT_ERR_INVALID, "render_create: a SampledSpectrum host must pass the medium's spectra");
     if (integ->medium.present) {
-        for (int c = 0; c < 3; ++c)
-            if (!(integ->medium.sigma_a[c] >= 0.f) || !(integ->medium.sigma_s[c] >= 0.f) ||
-                !(integ->medium.sigma_a[c] + integ->medium.sigma_s[c] > 0.f))
+        const int nb = scene->nspec ? scene->nspec : 3;
+        for (int c = 0; c < nb; ++c) {
+            const float sa = scene->nspec ? integ->medium.spectra[c] : integ->medium.sigma_a[c];
+            const float ss = scene->nspec ? integ->medium.spectra[nb + c] : integ->medium.sigma_s[c];
+            if (!(sa >= 0.f) || !(ss >= 0.f) || !(ss + sa > 0.f))
                 return b200pt_fail(B200PT_ERR_INVALID, "render_create: the medium needs sigma_a, sigma_s >= 0 and sigma_t > 0 in every channel");
+        }
         if (!(integ->medium.g > -1.f && integ->medium.g < 1.f))
             return b200pt_fail(B200PT_ERR_INVALID, "render_create: Henyey-Greenstein g must lie in (-1, 1)");
     }
@@ -1038,6 +1042,17 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         ALLOC(H.s_beta_ld, planar);
         ALLOC(d_light_spectra, std::max<size_t>(1, scene->light_spectra.size()));
     }
+    float *d_med_spectra = nullptr;
+    std::vector<float> med_spectra;  // [sigma_s, sigma_t] of a SampledSpectrum host's medium
+    if (scene->nspec && H.has_medium) {
+        const int nb = scene->nspec;
+        med_spectra.resize(2 * (size_t)nb);
+        for (int c = 0; c < nb; ++c) {
+            med_spectra[c] = integ->medium.spectra[nb + c];
+            med_spectra[nb + c] = integ->medium.spectra[nb + c] + integ->medium.spectra[c];  // sigma_t(sigma_s + sigma_a)
+        }
+        ALLOC(d_med_spectra, med_spectra.size());
+    }
     float *d_filter_table = nullptr;
     if (filter_general) {
         ALLOC(d_filter_table, 256);
@@ -1066,6 +1081,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.sampler.table = getenv("B200PT_NO_SOBOL_TABLE") ? nullptr : sobol_table;
     H.lights = d_lights;
     H.light_spectra = d_light_spectra;
+    H.med_spectra = d_med_spectra;
     H.has_delta_lights = has_delta ? 1 : 0;
     H.light_cdf = d_cdf;
     H.light_func = d_func;
@@ -1087,6 +1103,10 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         if (b200pt_s60::render_dev_size() != sizeof(RenderDev)) {
             b200pt_render_destroy(r);
             return b200pt_fail(B200PT_ERR_INVALID, "render_create: the SampledSpectrum kernels were built with another RenderDev layout");
+        }
+        if (d_med_spectra) {
+            CUDA_TRY(cudaMemcpyAsync(d_med_spectra, med_spectra.data(), med_spectra.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));  // med_spectra is a local
         }
         if (!scene->light_spectra.empty())
             CUDA_TRY(cudaMemcpyAsync(d_light_spectra, scene->light_spectra.data(), scene->light_spectra.size() * sizeof(float),
@@ -1304,7 +1324,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             }
             if (medium) {
                 LaunchTimer lt2(r, st, 2);
-                launch_medium(r->d_dev, b, wk + 11, r->grid_shade, st);
+                if (spectral)
+                    b200pt_s60::launch_medium(s60(r->d_dev), b, wk + 11, r->grid_shade, st);
+                else
+                    launch_medium(r->d_dev, b, wk + 11, r->grid_shade, st);
             }
         };
         auto trace_direct = [&](int b) {
@@ -1375,7 +1398,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                 trace_direct(b);
                 {
                     LaunchTimer lt(r, st, 2);
-                    launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
+                    if (spectral)
+                        b200pt_s60::launch_resolve(s60(r->d_dev), b, wk + 7, r->grid_shade, st);
+                    else
+                        launch_resolve(r->d_dev, b, wk + 7, r->grid_shade, st);
                 }
                 trace_path(b + 1);
             } else if (b < maxDepth) {  // no direct lighting is estimated at the last vertex (path.cpp:104)

@@ -60,6 +60,22 @@ __device__ __forceinline__ Spec light_emit(const RenderDev *R, int lightNum, con
 #endif
 }
 
+// sigma_s / sigma_t of the medium around the scene (RenderDev::med_*)
+__device__ __forceinline__ Spec medium_sigma_s(const RenderDev *R) {
+#if B200PT_NSPEC == 3
+    return rgbp(R->med_sigma_s);
+#else
+    return rgbp(R->med_spectra);
+#endif
+}
+__device__ __forceinline__ Spec medium_sigma_t(const RenderDev *R) {
+#if B200PT_NSPEC == 3
+    return rgbp(R->med_sigma_t);
+#else
+    return rgbp(R->med_spectra + B200PT_NSPEC);
+#endif
+}
+
 #ifdef B200PT_HOST_EMU
 // CPU check build (tests/emu): threads run one after the other, so a "warp" is one lane
 __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) { return pred ? atomicAdd(counter, 1u) : 0u; }
@@ -590,18 +606,11 @@ struct DirectOut {
 template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                 int lightNum, const float uLight[2], DirectOut *out, bool inMedium = false) {
-#if B200PT_NSPEC == 3
     // (VolPathIntegrator renders always run the general variant, so the lean one carries none of this)
     const bool medium = VTX && R->has_medium != 0;
-    const Spec sigmaT = VTX ? rgbp(R->med_sigma_t) : rgb1(0.f);
+    const Spec sigmaT = medium ? medium_sigma_t(R) : rgb1(0.f);
     const float hgG = R->med_g;
     if (!VTX) inMedium = false;
-#else
-    const bool medium = false;
-    const Spec sigmaT = rgb1(0.f);
-    const float hgG = 0.f;
-    inMedium = false;
-#endif
     const DevLight &lightRef = R->lights[lightNum];
     if (VTX && lightRef.kind != 0) {
         // delta light (scenes with delta lights always run the VTX variant): Sample_Li has pdf 1, there is no MIS weight
@@ -906,7 +915,6 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
     }
 }
 
-#if B200PT_NSPEC == 3
 // Medium pass of a bounce (VolPathIntegrator with every ray inside one homogeneous medium, volpath.cpp:77-103): runs over
 // the bounce's path rays after the closest-hit launch (which then does not classify).  It draws the channel and the
 // free-flight distance (HomogeneousMedium::Sample, homogeneous.cpp:49-76) against the distance of the hit.  A path that
@@ -919,7 +927,7 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
     uint32_t *qc = &R->qcount[bounce * Q_PER_BOUNCE];
     uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
     uint32_t *q_next = R->q_path[(bounce + 1) & 1];
-    const Spec sigmaT = rgbp(R->med_sigma_t), sigmaS = rgbp(R->med_sigma_s);
+    const Spec sigmaT = medium_sigma_t(R), sigmaS = medium_sigma_s(R);
     uint32_t i;
     while (warp_fetch(work, n, &i)) {
         const bool active = i < n;
@@ -1061,7 +1069,6 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
         if (cont) q_next[pn] = slot;
     }
 }
-#endif  // B200PT_NSPEC == 3
 
 // L += beta * (EstimateDirect(...) / lightPdf)   (path.cpp:122-127, integrator.cpp:104-105)
 __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce, uint32_t *work) {
@@ -1544,11 +1551,9 @@ void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, 
     B200PT_LAUNCH(B200PT_KERNEL(k_resolve), grid, 256, s, dev, bounce, work);
 }
 
-#if B200PT_NSPEC == 3
 void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
     B200PT_LAUNCH(B200PT_KERNEL(k_medium), grid, 128, s, dev, bounce, work);
 }
-#endif
 
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s) {
     const long long nvox = (long long)host.grid.nv[0] * host.grid.nv[1] * host.grid.nv[2];

@@ -127,6 +127,7 @@ struct RenderDev {
     // every ray is inside one homogeneous medium (RGB build only)
     int volpath, has_medium;
     float med_sigma_s[3], med_sigma_t[3], med_g;
+    const float *med_spectra;  // SampledSpectrum build: [2][60] = sigma_s, sigma_t (else the two arrays above)
 };
 
 struct TraceArgs {

@@ -586,6 +586,7 @@ class GpuIntegrator : public Base {
 
         b200pt_integrator_desc id;
         memset(&id, 0, sizeof(id));
+        std::vector<float> mediumSpectra;
         if (kVolumetric) {
             // VolPathIntegrator: the camera ray's medium (camera.h:76) is every ray's medium when no surface is a medium
             // transition (checked while flattening); only HomogeneousMedium is supported
@@ -593,10 +594,11 @@ class GpuIntegrator : public Base {
             if (const Medium *m = cam->medium) {
                 auto hm = dynamic_cast<const HomogeneousMedium *>(m);
                 if (!hm) return Error("gpupath: only homogeneous media are supported");
-                if (kSampledHost) return Error("gpupath: media are not supported with SampledSpectrum hosts yet");
                 id.medium.present = 1;
-                ToRGB(hm->sigma_a, id.medium.sigma_a);
-                ToRGB(hm->sigma_s, id.medium.sigma_s);
+                mediumSpectra.assign(2 * (size_t)B200PT_SPECTRUM_SAMPLES, 0.f);
+                ToRGB(hm->sigma_a, id.medium.sigma_a, mediumSpectra.data());
+                ToRGB(hm->sigma_s, id.medium.sigma_s, mediumSpectra.data() + B200PT_SPECTRUM_SAMPLES);
+                if (kSampledHost) id.medium.spectra = mediumSpectra.data();  // the 60 bins of sigma_a, sigma_s
                 id.medium.g = hm->g;
             }
         }

@@ -577,7 +577,7 @@ class RenderSetup:
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
                  lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None,
-                 sampler="sobol", pixel_filter=None, integrator="path", medium=None):
+                 sampler="sobol", pixel_filter=None, integrator="path", medium=None, spectral_tables=None):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.sampler_name = sampler
@@ -633,6 +633,13 @@ class RenderSetup:
             self.integrator.medium.sigma_a[:] = list(medium["sigma_a"])
             self.integrator.medium.sigma_s[:] = list(medium["sigma_s"])
             self.integrator.medium.g = medium.get("g", 0.0)
+            if spectral_tables is not None:  # a SampledSpectrum host: the medium's 60-bin spectra (fixtures of the probe)
+                f32 = np.float32
+                lut = {tuple(np.array([float.fromhex(x) for x in rgb], f32).view(np.uint32).tolist()):
+                       np.array([float.fromhex(x) for x in spec], f32) for rgb, spec in spectral_tables["spectra"]}
+                self._medium_spectra = np.stack([lut[tuple(np.array(list(medium[k]), f32).view(np.uint32).tolist())]
+                                                 for k in ("sigma_a", "sigma_s")])
+                self.integrator.medium.spectra = abi.ptr(self._medium_spectra)
 
     def _sobol_tables(self, cb):
         res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))

@@ -58,6 +58,11 @@ def test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, o
     GS.test_spectral_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, base)
 
 
+@pytest.mark.parametrize("gname,vname", [("spectral_volpath_fog", "volpath_fog"), ("spectral_volpath_fog_spheres", "volpath_fog_spheres")])
+def test_spectral_volpath_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, vname):
+    GS.test_spectral_volpath_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, gname, vname)
+
+
 def test_spectral_counters_power_and_filter(hostcheck, abi, scenes, ob, hctx):
     GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 8, "power", None)
     GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "metal"), 5, "uniform", "gaussian")

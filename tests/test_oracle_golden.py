@@ -190,6 +190,27 @@ def test_volpath_oracle_matches_reference_volpath(abi, scenes, ob):
         ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
         assert np.array_equal(bits(rgb), bits(ref)), gname
         o.close()
+    # the 60-bin build of both (SampledSpectrum reference, `volpath`): the oracle compiled with ORACLE_NSPEC=60
+    if os.path.exists(ob.LIB_SPECTRAL_PATH):
+        import json
+        tables = json.load(open(os.path.join(GOLDEN, "spectral_tables.json")))
+        for gname, vname in (("spectral_volpath_fog", "volpath_fog"), ("spectral_volpath_fog_spheres", "volpath_fog_spheres")):
+            base, medium, strat = VOLPATH[vname]
+            nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+            ex = EXTRA.get(base, {})
+            arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+            setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                                       strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
+                                       **ex.get("camera", {}))
+            o = ob.Oracle(abi, arr, spectral_tables=tables)
+            ob.set_volpath(o.lib, True, medium)
+            try:
+                film, _ = o.render(setup, threads=4)
+                rgb = o.film_rgb(setup, film)
+            finally:
+                ob.set_volpath(o.lib, False)
+            assert np.array_equal(bits(rgb), bits(scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname)))), gname
+            o.close()
     # without a medium VolPathIntegrator still is not PathIntegrator (it samples a light at purely specular vertices too)
     assert not np.array_equal(bits(scenes.read_pfm(os.path.join(GOLDEN, "render_volpath_four.pfm"))),
                               bits(scenes.read_pfm(os.path.join(GOLDEN, "render_four.pfm"))))

@@ -85,3 +85,25 @@ def test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_p
     got = scenes.read_pfm(os.path.join(str(tmp_path), "render_spectral_four.pfm"))
     ref = scenes.read_pfm(os.path.join(GOLDEN, "render_spectral_four.pfm"))
     assert np.array_equal(bits(got), bits(ref)), "spectral drop-in render differs from the SampledSpectrum reference's PFM"
+
+
+@pytest.mark.parametrize("gname,vname", [("spectral_volpath_fog", "volpath_fog"), ("spectral_volpath_fog_spheres", "volpath_fog_spheres")])
+def test_spectral_volpath_render_vs_sampled_spectrum_reference(pkg, abi, scenes, ob, ctx, gname, vname):
+    """Both widenings together: VolPathIntegrator with a homogeneous medium under a SampledSpectrum host (60-channel
+    free-flight sampling and transmittance) against the 60-bin reference's `volpath` image."""
+    from render_cases import VOLPATH
+    base, medium, strat = VOLPATH[vname]
+    nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+    ex = EXTRA.get(base, {})
+    tables = _spectral_tables()
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {})).attach_spectral(tables)
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth,
+                               strategy={"uniform": abi.LIGHTS_UNIFORM, "power": abi.LIGHTS_POWER, "spatial": abi.LIGHTS_SPATIAL}[strat],
+                               integrator="volpath", medium=medium, spectral_tables=tables, **ex.get("camera", {}))
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+    assert np.array_equal(bits(r.read_rgb()), bits(ref))
+    r.close()
+    scene.close()
