@@ -81,6 +81,9 @@ def test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "metal"), 5, "uniform",
                                      dict(sigma_a=(0.05, 0.05, 0.05), sigma_s=(0.1, 0.1, 0.1), g=0.0), {"pixel_filter": "gaussian"})
     GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass"), 6, "uniform", None, {})
+    # the Halton sampler (ten dimensions per bounce inside a medium) and a thin lens
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "plastic"), 7, "spatial", thin,
+                                     {"sampler": "halton", "lens_radius": 0.05, "focal_distance": 4.0})
 
 
 def test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx):
@@ -305,3 +308,13 @@ def test_bad_render_descriptors_are_refused(hostcheck, abi, scenes, hctx):
     assert np.all(r.read_raw() == 0)
     r.close()
     scene.close()
+
+
+def test_new_paths_in_several_batches(hostcheck, abi, scenes, ob, hctx, monkeypatch):
+    """The 60-bin state arrays are planar [bin][capacity] and the medium pass shares the per-slot direct-lighting records
+    with the shading kernels: render with a capacity of three tiles per batch (many batches) and compare as before."""
+    monkeypatch.setenv("B200PT_BATCH_PATHS", str(256 * 8 * 3))
+    GS.test_spectral_render_and_counters_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "glass", "metal", "plastic"), 8, "power", None)
+    GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "plastic"), 12, "uniform",
+                                     dict(sigma_a=(0.2, 0.2, 0.2), sigma_s=(1.5, 1.2, 0.9), g=-0.5), {})
+    GS.test_spectral_volpath_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, "spectral_volpath_fog", "volpath_fog")

@@ -49,7 +49,9 @@ def test_volpath_render_vs_reference_pfm(pkg, abi, scenes, ob, ctx, gname):
     (("matte", "glass", "metal", "plastic"), 8, "power", dict(sigma_a=(0.01, 0.02, 0.03), sigma_s=(0.4, 0.35, 0.3), g=0.6), {}),
     (("matte", "plastic"), 12, "spatial", dict(sigma_a=(0.2, 0.2, 0.2), sigma_s=(1.5, 1.2, 0.9), g=-0.5), {}),   # thick: long chains
     (("matte", "metal"), 5, "uniform", dict(sigma_a=(0.05, 0.05, 0.05), sigma_s=(0.1, 0.1, 0.1), g=0.0), {"pixel_filter": "gaussian"}),
-    (("matte", "glass"), 6, "uniform", None, {})])                                                                   # volpath without a medium
+    (("matte", "glass"), 6, "uniform", None, {}),                                                                    # volpath without a medium
+    (("matte", "plastic"), 7, "spatial", dict(sigma_a=(0.01, 0.02, 0.03), sigma_s=(0.4, 0.35, 0.3), g=0.6),
+     {"sampler": "halton", "lens_radius": 0.05, "focal_distance": 4.0})])                                            # Halton, thin lens
 def test_volpath_render_vs_oracle(pkg, abi, scenes, ob, ctx, mats, depth, strat, medium, kw):
     """Larger renders (several batches of work per bounce, Russian roulette in the medium, the general film path) against
     the oracle's VolPathLi: raw film sums bit for bit; every ray the reference traces as a closest-hit query is counted."""
