@@ -8,12 +8,16 @@
  * the perspective camera (cameras/perspective.cpp:95-144), the four materials
  * matte/plastic/metal/glass, diffuse area lights with MIS direct lighting
  * (core/integrator.cpp:85-215) and the box-filtered film
- * (core/film.h:121-161, core/film.cpp:117-130).
+ * (core/film.h:121-161, core/film.cpp:117-130).  Widened since (each descriptor
+ * says where): the Halton sampler, Sphere shapes and sphere lights, object
+ * instances, the mirror material, point / spot / distant lights, every pixel
+ * filter, SampledSpectrum hosts (60-bin spectra), and VolPathIntegrator
+ * (integrators/volpath.cpp:60-188) with one homogeneous medium around the scene.
  *
  * The reference has no FFI: its "plugins" are C++ subclasses picked by name in
  * RenderOptions::MakeIntegrator (core/api.cpp:1666-1718).  A host integrator
- * (pbrt-v3-distributed_b200/host/gpupath.cpp, class GpuPathIntegrator :
- * public Integrator, integrator.h:53-58) flattens the parsed Scene into the
+ * (pbrt-v3-distributed_b200/host/gpupath.cpp, GpuIntegrator<PathIntegrator> and
+ * GpuIntegrator<VolPathIntegrator>, Integrator::Render integrator.h:53-58) flattens the parsed Scene into the
  * plain-old-data descriptors below and calls these entry points; see
  * INTEGRATION.md for the binding.  Everything is `extern "C"`, plain pointers
  * and sizes; no torch / CUDA types appear in any signature (device pointers

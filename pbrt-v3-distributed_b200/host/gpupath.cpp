@@ -1,7 +1,8 @@
 // gpupath.cpp -- host side of the drop-in: a pbrt Integrator that renders on
 // the B200 through the C ABI (include/b200pt.h).
 //
-//   class GpuPathIntegrator : public PathIntegrator      (integrators/path.h:48-66)
+//   template <class Base> class GpuIntegrator : public Base   (Base = PathIntegrator, integrators/path.h:48-66,
+//                                                          or VolPathIntegrator, integrators/volpath.h:49-66)
 //       void Render(const Scene &) override               (core/integrator.h:53-58, replaces
 //                                                          SamplerIntegrator::Render, integrator.cpp:228-339)
 //   PathIntegrator *CreatePathIntegrator(const ParamSet&, shared_ptr<Sampler>, shared_ptr<const Camera>)
@@ -21,7 +22,7 @@
 // ABI.  The reference keeps the needed members private (Scene::aggregate,
 // BVHAccel::primitives, GeometricPrimitive::shape/material/areaLight,
 // Triangle::mesh/v, the materials' textures, Film::pixels ...); an in-tree
-// integration would add `friend class GpuPathIntegrator;` to those classes.
+// integration would add `template <class> friend class GpuIntegrator;` to those classes.
 // Out of tree, this file widens access for its own includes only -- it reads
 // those members, never changes layout or behaviour.
 //
