@@ -146,6 +146,11 @@ def test_spectral_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_pat
     GS.test_spectral_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path)
 
 
+def test_spectral_volpath_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    monkeypatch.setattr(GS, "PLUGIN_SPECTRAL", HC_PLUGIN_SPECTRAL)
+    GS.test_spectral_volpath_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path)
+
+
 def test_volpath_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
     """`Integrator "volpath"` with a named homogeneous medium through the drop-in binary."""
     monkeypatch.setattr(GV, "PLUGIN", HC_PLUGIN)

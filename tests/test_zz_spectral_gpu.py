@@ -107,3 +107,21 @@ def test_spectral_volpath_render_vs_sampled_spectrum_reference(pkg, abi, scenes,
     assert np.array_equal(bits(r.read_rgb()), bits(ref))
     r.close()
     scene.close()
+
+
+@needs_spectral_plugin
+def test_spectral_volpath_dropin_binary_matches_sampled_spectrum_reference(scenes, tmp_path):
+    """`Integrator "volpath"` + `MakeNamedMedium` through the SampledSpectrum host: gpupath.cpp hands over the medium's
+    60-bin sigma_a / sigma_s (b200pt_medium::spectra)."""
+    from render_cases import VOLPATH
+    gname, vname = "spectral_volpath_fog", "volpath_fog"
+    base, medium, strat = VOLPATH[vname]
+    nt, mats, w, h, spp, depth, _, nl = RENDERS[base]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl)
+    path = scenes.write_pbrt(str(tmp_path), "render_" + gname, arr, w, h, spp, max_depth=depth, strategy=strat,
+                             integrator="volpath", medium=medium)
+    r = subprocess.run([PLUGIN_SPECTRAL, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = scenes.read_pfm(os.path.join(str(tmp_path), "render_%s.pfm" % gname))
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname))
+    assert np.array_equal(bits(got), bits(ref)), "spectral volpath drop-in render differs from the SampledSpectrum reference's PFM"
