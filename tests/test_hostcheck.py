@@ -323,3 +323,31 @@ def test_new_paths_in_several_batches(hostcheck, abi, scenes, ob, hctx, monkeypa
     GV.test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx, ("matte", "plastic"), 12, "uniform",
                                      dict(sigma_a=(0.2, 0.2, 0.2), sigma_s=(1.5, 1.2, 0.9), g=-0.5), {})
     GS.test_spectral_volpath_render_vs_sampled_spectrum_reference(hostcheck, abi, scenes, ob, hctx, "spectral_volpath_fog", "volpath_fog")
+
+
+def test_dropin_refuses_media_it_does_not_support(hc_plugins, scenes, tmp_path):
+    """Error behaviour of the host side: a surface that separates two media, a heterogeneous medium, or a medium under
+    `Integrator "path"`'s stricter flattening produce pbrt's `Error:` line and no image -- never a silently wrong render."""
+    import subprocess
+    fog = dict(sigma_a=(0.05, 0.05, 0.05), sigma_s=(0.2, 0.2, 0.2), g=0.1)
+    arr = scenes.SceneArrays(300, materials=("matte",), soup_version=1)
+
+    def run(name, edit, **kw):
+        path = scenes.write_pbrt(str(tmp_path), name, arr, 16, 16, 2, max_depth=3, strategy="uniform", **kw)
+        text = edit(open(path).read())
+        open(path, "w").write(text)
+        r = subprocess.run([HC_PLUGIN, "--quiet", os.path.basename(path)], cwd=str(tmp_path), capture_output=True, text=True)
+        return r.stdout + r.stderr, os.path.exists(os.path.join(str(tmp_path), name + ".pfm"))
+
+    # a shape whose inside is vacuum while the world outside is fog: a medium transition
+    out, wrote = run("transition", lambda t: t.replace('MediumInterface "fog" "fog"', 'MediumInterface "" "fog"'),
+                     integrator="volpath", medium=fog)
+    assert "separate two media" in out and not wrote, out
+    # a heterogeneous medium around the camera
+    out, wrote = run("grid", lambda t: t.replace('"string type" "homogeneous"', '"string type" "heterogeneous" "integer nx" [1] '
+                                                 '"integer ny" [1] "integer nz" [1] "float density" [1]'),
+                     integrator="volpath", medium=fog)
+    assert "only homogeneous media" in out and not wrote, out
+    # the fine case still renders
+    out, wrote = run("fine", lambda t: t, integrator="volpath", medium=fog)
+    assert wrote, out
