@@ -86,6 +86,11 @@ def test_volpath_render_vs_oracle(hostcheck, abi, scenes, ob, hctx):
                                      {"sampler": "halton", "lens_radius": 0.05, "focal_distance": 4.0})
 
 
+@pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
+def test_analytic_scenes_known_answer_volpath(hostcheck, abi, scenes, ob, hctx, name):
+    GV.test_analytic_scenes_known_answer_volpath(hostcheck, abi, scenes, ob, hctx, name)
+
+
 def test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     GV.test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx)
 

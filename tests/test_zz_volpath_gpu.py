@@ -121,3 +121,29 @@ def test_volpath_instances_and_partial_spheres_vs_oracle(pkg, abi, scenes, ob, c
     r.close()
     scene.close()
     o.close()
+
+
+@pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
+def test_analytic_scenes_known_answer_volpath(pkg, abi, scenes, ob, ctx, name):
+    """The reference's own known-answer test also runs VolPathIntegrator (depth 8) over its analytic scenes
+    (src/tests/analytic_scenes.cpp:326-351, CheckSceneAverage :54-66): the image mean is 1 +- 0.02.  Here the image must
+    in addition equal the oracle's VolPathLi bit for bit."""
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    ex = EXTRA[name]
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex["scene"])
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=abi.LIGHTS_SPATIAL, integrator="volpath", **ex["camera"])
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    r = pkg.Render(scene, setup)
+    r.render_tiles()
+    rgb = r.read_rgb()
+    assert abs(float(rgb.mean()) - 1.0) < 0.02
+    o = ob.Oracle(abi, arr)
+    ob.set_volpath(o.lib, True, None)
+    try:
+        film, _ = o.render(setup, threads=4)
+    finally:
+        ob.set_volpath(o.lib, False)
+    assert np.array_equal(bits(rgb), bits(o.film_rgb(setup, film)))
+    r.close()
+    scene.close()
+    o.close()
