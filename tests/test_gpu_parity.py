@@ -444,3 +444,61 @@ def test_large_scene_properties(pkg, abi, scenes, ctx):
     assert np.isfinite(raw).all() and (raw[..., 3] >= 4).all() and raw[..., 1].mean() > 0
     r.close()
     scene.close()
+
+
+def watertight_mesh(rng, n_theta=16, n_phi=16):
+    """The closed mesh of the reference's Triangle.Watertight test (src/tests/shapes.cpp:28-93): a triangulated sphere whose
+    vertices are pushed out randomly along their normals; pole vertices and the seam coincide exactly."""
+    verts = []
+    for t in range(n_theta):
+        theta = np.float32(np.pi) * np.float32(t) / np.float32(n_theta - 1)
+        for p in range(n_phi):
+            phi = np.float32(2 * np.pi) * np.float32(p) / np.float32(n_phi - 1)
+            if t == 0:
+                verts.append((0.0, 0.0, 1.0))
+            elif t == n_theta - 1:
+                verts.append((0.0, 0.0, -1.0))
+            elif p == n_phi - 1:
+                verts.append(verts[len(verts) - (n_phi - 1)])
+            else:
+                r = 1.0 + 5.0 * rng.random()
+                verts.append((r * np.sin(theta) * np.cos(phi), r * np.sin(theta) * np.sin(phi), r * np.cos(theta)))
+    verts = np.array(verts, np.float32)
+    off = lambda t, p: t * n_phi + p  # noqa: E731
+    idx = []
+    for p in range(n_phi - 1):
+        idx += [off(0, 0), off(1, p), off(1, p + 1)]
+    for t in range(1, n_theta - 2):
+        for p in range(n_phi - 1):
+            idx += [off(t, p), off(t + 1, p), off(t + 1, p + 1), off(t, p), off(t + 1, p + 1), off(t, p + 1)]
+    for p in range(n_phi - 1):
+        idx += [off(n_theta - 1, 0), off(n_theta - 2, p), off(n_theta - 2, p + 1)]
+    return verts, verts[np.array(idx).reshape(-1, 3)]
+
+
+def test_triangle_watertight(pkg, abi, scenes, ctx):
+    """Triangle.Watertight of the reference's test-suite (src/tests/shapes.cpp:28-128) for the traversal kernels: 100 000 rays
+    from inside a closed, randomly perturbed mesh -- in random directions and aimed exactly at mesh vertices -- must all hit
+    (closest-hit and any-hit)."""
+    rng = np.random.default_rng(12111)
+    verts, tris = watertight_mesh(rng)
+    arr = scenes.SceneArrays(len(tris), materials=("matte",), soup_version=1, n_lights=0)
+    assert arr.vertices.shape == tris.shape
+    arr.vertices[:] = tris
+    scene = pkg.Scene(ctx, arr.desc(), keepalive=arr)
+    n = 100000
+
+    def sphere(k):
+        z = 1 - 2 * rng.random(k)
+        r = np.sqrt(np.maximum(0, 1 - z * z))
+        phi = 2 * np.pi * rng.random(k)
+        return np.stack([r * np.cos(phi), r * np.sin(phi), z], 1).astype(np.float32)
+    rays = np.zeros(2 * n, dtype=abi.RAY_DTYPE)
+    rays["o"][:n] = rays["o"][n:] = np.float32(0.5) * sphere(n)
+    rays["d"][:n] = sphere(n)
+    rays["d"][n:] = verts[rng.integers(0, len(verts), n)] - rays["o"][n:]   # tougher: directly at a vertex
+    rays["t_max"] = np.inf
+    hits = scene.trace_closest(rays)
+    assert (hits["triangle"] >= 0).all(), "%d rays leaked through the mesh" % (hits["triangle"] < 0).sum()
+    assert scene.trace_any(rays).all()
+    scene.close()

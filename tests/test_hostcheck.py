@@ -36,6 +36,10 @@ def test_streams_cameras_intersections(hostcheck, abi, scenes, hctx, probe_json)
     G.test_intersections_vs_reference_bvhaccel(hostcheck, abi, scenes, hctx)
 
 
+def test_triangle_watertight(hostcheck, abi, scenes, hctx):
+    G.test_triangle_watertight(hostcheck, abi, scenes, hctx)
+
+
 def test_trace_entry_points_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     G.test_trace_vs_oracle(hostcheck, abi, scenes, ob, hctx, 37, 20000)
     G.test_trace_vs_oracle(hostcheck, abi, scenes, ob, hctx, 20000, 40000)
