@@ -152,3 +152,53 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "BSDF OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_device_sample_discrete_passes_the_references_distribution1d_test(tmp_path):
+    """Distribution1D.Discrete of src/tests/sampling.cpp:231-279 for the device's light-picking routine (sample_discrete over
+    a cdf built the way Distribution1D's constructor builds it, sampling.h:57-71): same known answers, same behaviour
+    around the cross-over at u = 0.25."""
+    src = tmp_path / "d1d.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include "pt_core.cuh"
+using namespace b200pt;
+#define EXPECT(c) do { if (!(c)) { ++fail; printf("line %d: %s\n", __LINE__, #c); } } while (0)
+int main() {
+    int fail = 0;
+    const int n = 4;
+    float func[n] = {0, 1.f, 0.f, 3.f}, cdf[n + 1];
+    cdf[0] = 0;
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+    const float funcInt = cdf[n];
+    for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    float pdf;
+    EXPECT(sample_discrete(cdf, func, funcInt, n, 0.f, &pdf) == 1 && pdf == 0.25f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, 0.125f, &pdf) == 1 && pdf == 0.25f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, .24999f, &pdf) == 1 && pdf == 0.25f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, .250001f, &pdf) == 3 && pdf == 0.75f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, 0.625f, &pdf) == 3 && pdf == 0.75f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, PT_ONE_MINUS_EPS, &pdf) == 3 && pdf == 0.75f);
+    EXPECT(sample_discrete(cdf, func, funcInt, n, 1.f, &pdf) == 3 && pdf == 0.75f);
+    float u = .25f, uMax = .25f;
+    for (int i = 0; i < 20; ++i) {
+        u = next_float_down(u);
+        uMax = next_float_up(uMax);
+    }
+    for (; u < uMax; u = next_float_up(u)) {
+        int interval = sample_discrete(cdf, func, funcInt, n, u, &pdf);
+        if (interval == 3) break;
+        EXPECT(interval == 1);
+    }
+    EXPECT(u < uMax);
+    for (; u <= uMax; u = next_float_up(u)) EXPECT(sample_discrete(cdf, func, funcInt, n, u, &pdf) == 3);
+    printf(fail ? "D1D FAILED\n" : "D1D OK\n");
+    return fail != 0;
+}
+''')
+    exe = str(tmp_path / "d1d")
+    inc = os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "D1D OK" in r.stdout, r.stdout
