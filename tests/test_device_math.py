@@ -202,3 +202,85 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "D1D OK" in r.stdout, r.stdout
+
+
+def test_device_float_utilities_pass_the_references_fp_tests(tmp_path):
+    """src/tests/fp_tests.cpp for the device's versions (host-compiled): FloatingPoint.NextUpDownFloat (== std::nextafter,
+    the signed-zero and infinity cases) and EFloat.Add / Sub / Mul / Div (the exact result of operands chosen anywhere inside
+    -- or at the ends of -- their intervals lies inside the result's interval; the Sphere quadratic relies on it)."""
+    src = tmp_path / "fp.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include "pt_sphere.cuh"
+using namespace b200pt;
+#define EXPECT(c) do { if (!(c)) { if (++fail < 6) printf("line %d: %s\n", __LINE__, #c); } } while (0)
+static std::mt19937 rng(1);
+static float U() { return std::uniform_real_distribution<float>(0.f, 1.f)(rng); }
+static float anyFloat() { float f; do { f = uint_as_float((uint32_t)rng()); } while (std::isnan(f)); return f; }
+static EFloat getFloat() {  // fp_tests.cpp:99-137: a value with no, small, bigger or large relative error
+    float minExp = -6, maxExp = 6;
+    float logu = minExp + (maxExp - minExp) * U();
+    float val = std::pow(10.f, logu), err = 0;
+    switch (rng() % 4) {
+    case 0: break;
+    case 1: err = std::fabs(uint_as_float(float_as_uint(val) + rng() % 1024) - val); break;
+    case 2: err = std::fabs(uint_as_float(float_as_uint(val) + rng() % (1024 * 1024)) - val); break;
+    case 3: err = (4 * U()) * std::fabs(val); break;
+    }
+    return ef((U() < .5f ? -1.f : 1.f) * val, err);
+}
+static double getPrecise(const EFloat &e) {  // :141-161
+    switch (rng() % 3) {
+    case 0: return e.low;
+    case 1: return e.high;
+    default: {
+        float t = U();
+        double p = (1 - t) * e.low + t * e.high;
+        return p > e.high ? e.high : (p < e.low ? e.low : p);
+    }
+    }
+}
+int main() {
+    int fail = 0;
+    const float inf = pt_inf();
+    EXPECT(next_float_up(-0.f) > 0.f);
+    EXPECT(next_float_down(0.f) < 0.f);
+    EXPECT(next_float_up(inf) == inf);
+    EXPECT(next_float_down(inf) < inf);
+    EXPECT(next_float_down(-inf) == -inf);
+    EXPECT(next_float_up(-inf) > -inf);
+    for (int i = 0; i < 100000; ++i) {
+        float f = anyFloat();
+        if (std::isinf(f)) continue;
+        EXPECT(std::nextafter(f, inf) == next_float_up(f));
+        EXPECT(std::nextafter(f, -inf) == next_float_down(f));
+    }
+    for (int trial = 0; trial < 1000000; ++trial) {
+        EFloat a = getFloat(), b = getFloat();
+        double pa = getPrecise(a), pb = getPrecise(b);
+        EFloat r = ef_add(a, b);
+        float p = (float)(pa + pb);
+        EXPECT(p >= r.low && p <= r.high);
+        r = ef_sub(a, b);
+        p = (float)(pa - pb);
+        EXPECT(p >= r.low && p <= r.high);
+        r = ef_mul(a, b);
+        p = (float)(pa * pb);
+        EXPECT(p >= r.low && p <= r.high);
+        const float bErr = (b.high - b.low) / 2;  // GetAbsoluteError
+        if ((double)b.low * b.high < 0. || bErr > .25 * std::fabs(b.low)) continue;
+        r = ef_div(a, b);
+        p = (float)(pa / pb);
+        EXPECT(p >= r.low && p <= r.high);
+    }
+    printf(fail ? "FP FAILED (%d)\n" : "FP OK\n", fail);
+    return fail != 0;
+}
+''')
+    exe = str(tmp_path / "fp")
+    inc = os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "FP OK" in r.stdout, r.stdout
