@@ -284,3 +284,57 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "FP OK" in r.stdout, r.stdout
+
+
+def test_device_triangle_passes_the_references_reintersect_test(tmp_path):
+    """Triangle.Reintersect of src/tests/shapes.cpp:152-203 for the device's triangle code (host-compiled): a ray spawned from
+    an intersection -- in a random direction (SpawnRay) or towards a random point (SpawnRayTo) -- never hits the triangle it
+    left, over triangles and origins whose coordinates span 10^-8 .. 10^8.  Pins fill_isect's error bounds and
+    offset_ray_origin."""
+    src = tmp_path / "re.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include "pt_core.cuh"
+using namespace b200pt;
+int main() {
+    long fail = 0, tested = 0;
+    for (int i = 0; i < 1000; ++i) {
+        std::mt19937 rng(i);
+        auto U = [&]() { return std::uniform_real_distribution<float>(0.f, 1.f)(rng); };
+        auto pExp = [&]() { return std::pow(10.f, -8.f + 16.f * U()); };
+        V3 v[3];
+        for (int j = 0; j < 3; ++j) v[j] = mk(pExp(), pExp(), pExp());
+        if (len2(cross(v[1] - v[0], v[2] - v[0])) < 1e-20f) continue;
+        TriShading sh;
+        default_shading(&sh);
+        float u[2] = {U(), U()}, pdf;
+        LightSample pTri = triangle_sample(v[0], v[1], v[2], false, sh, u, &pdf);
+        V3 o = mk(pExp(), pExp(), pExp());
+        V3 d = pTri.p - o;
+        TriHit h;
+        if (!triangle_test(v[0], v[1], v[2], o, make_shear(d), pt_inf(), &h)) continue;
+        Isect is;
+        fill_isect(v[0], v[1], v[2], false, sh, h, d, &is);
+        for (int j = 0; j < 10000; ++j) {
+            float z = 1 - 2 * U(), r = std::sqrt(std::max(0.f, 1 - z * z)), phi = 2 * PT_PI * U();
+            V3 w = mk(r * std::cos(phi), r * std::sin(phi), z);
+            V3 ro = offset_ray_origin(is.p, is.pError, is.n, w);  // isect.SpawnRay(w)
+            TriHit h2;
+            ++tested;
+            if (triangle_test(v[0], v[1], v[2], ro, make_shear(w), pt_inf(), &h2)) ++fail;
+            V3 p2 = mk(pExp(), pExp(), pExp());
+            ro = offset_ray_origin(is.p, is.pError, is.n, p2 - is.p);  // isect.SpawnRayTo(p2), interaction.h:66-71: d = p2 - p
+            if (triangle_test(v[0], v[1], v[2], ro, make_shear(p2 - is.p), PT_SHADOW_TMAX, &h2)) ++fail;
+        }
+    }
+    printf("%ld spawned ray pairs, %ld re-intersections\n%s\n", tested, fail, fail ? "REINTERSECT FAILED" : "REINTERSECT OK");
+    return fail != 0;
+}
+''')
+    exe = str(tmp_path / "re")
+    inc = os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "REINTERSECT OK" in r.stdout, r.stdout
