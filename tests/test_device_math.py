@@ -338,3 +338,87 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "REINTERSECT OK" in r.stdout, r.stdout
+
+
+def test_device_sphere_passes_the_references_sphere_tests(tmp_path):
+    """FullSphere.Reintersect, PartialSphere.Reintersect and ParialSphere.Normal of src/tests/shapes.cpp:367-497 for the
+    device's Sphere code (host-compiled pt_sphere.cuh): rays spawned from a hit into the normal's hemisphere never hit the
+    sphere again (radii 10^-4 .. 10^4, origins 10^-8 .. 10^8, clipped in z and phi), and the normal is radial."""
+    src = tmp_path / "sph.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include "pt_sphere.cuh"
+using namespace b200pt;
+static DevSphere make(float radius, float zMin, float zMax, float phiMaxDeg) {
+    DevSphere s;
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 4; ++i) s.o2w[5 * i] = s.w2o[5 * i] = 1.f;
+    s.radius = radius;  // Sphere constructor, sphere.h:50-58
+    s.z_min = pt_clamp(pt_min(zMin, zMax), -radius, radius);
+    s.z_max = pt_clamp(pt_max(zMin, zMax), -radius, radius);
+    s.theta_min = pt_acosf(pt_clamp(pt_min(zMin, zMax) / radius, -1.f, 1.f));
+    s.theta_max = pt_acosf(pt_clamp(pt_max(zMin, zMax) / radius, -1.f, 1.f));
+    s.phi_max = (PT_PI / 180) * pt_clamp(phiMaxDeg, 0.f, 360.f);
+    for (int a = 0; a < 3; ++a) {  // no accelerator leaf in this test: a box that never culls
+        s.leaf_lo[a] = -pt_inf();
+        s.leaf_hi[a] = pt_inf();
+    }
+    return s;
+}
+int main() {
+    long fail = 0, tested = 0, normals = 0;
+    for (int partial = 0; partial < 2; ++partial)
+        for (int i = 0; i < 100; ++i) {
+            std::mt19937 rng(1000 * partial + i);
+            auto U = [&]() { return std::uniform_real_distribution<float>(0.f, 1.f)(rng); };
+            auto pExp = [&](float e) { return std::pow(10.f, -e + 2 * e * U()); };
+            auto lerp = [](float t, float a, float b) { return (1 - t) * a + t * b; };
+            const float radius = pExp(4);
+            float zMin = -radius, zMax = radius, phiMax = 360;
+            if (partial) {
+                zMin = U() < 0.5f ? -radius : lerp(U(), -radius, radius);
+                zMax = U() < 0.5f ? radius : lerp(U(), -radius, radius);
+                phiMax = U() < 0.5f ? 360.f : U() * 360.f;
+            }
+            const DevSphere s = make(radius, zMin, zMax, phiMax);
+            V3 o = mk(pExp(8), pExp(8), pExp(8));
+            // destination: a random point in the sphere's bounding box (Sphere::ObjectBound, sphere.cpp:44-47)
+            V3 p2 = mk(lerp(U(), -radius, radius), lerp(U(), -radius, radius), lerp(U(), s.z_min, s.z_max));
+            V3 d = p2 - o;
+            if (U() < .5f) d = normalize(d);
+            float tHit;
+            Isect is;
+            if (!sphere_intersect(s, o, d, pt_inf(), &tHit, &is)) continue;
+            if (partial) {  // ParialSphere.Normal: EXPECT_FLOAT_EQ(1, dot) = within 4 ulps
+                const float dt = dot(normalize(is.n), normalize(is.p));
+                ++normals;
+                if (!(std::fabs(dt - 1.f) <= 4 * 1.1920929e-7f)) { ++fail; printf("normal: dot %a\n", dt); }
+            }
+            for (int j = 0; j < 10000; ++j) {
+                float z = 1 - 2 * U(), r = std::sqrt(std::max(0.f, 1 - z * z)), phi = 2 * PT_PI * U();
+                V3 w = mk(r * std::cos(phi), r * std::sin(phi), z);
+                if (dot(w, is.n) < 0) w = -w;  // Faceforward(w, isect.n)
+                V3 ro = offset_ray_origin(is.p, is.pError, is.n, w);
+                float t2;
+                ++tested;
+                if (sphere_intersect(s, ro, w, pt_inf(), &t2, nullptr)) ++fail;
+                V3 q = mk(pExp(8), pExp(8), pExp(8));
+                w = q - is.p;
+                if (dot(w, is.n) < 0) w = -w;
+                q = is.p + w;
+                ro = offset_ray_origin(is.p, is.pError, is.n, q - is.p);  // SpawnRayTo(Point3f): d = p2 - p
+                if (sphere_intersect(s, ro, q - is.p, PT_SHADOW_TMAX, &t2, nullptr)) ++fail;
+            }
+        }
+    printf("%ld spawned ray pairs, %ld normals, %ld failures\n%s\n", tested, normals, fail, fail ? "SPHERE FAILED" : "SPHERE OK");
+    return fail != 0;
+}
+''')
+    exe = str(tmp_path / "sph")
+    inc = os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "SPHERE OK" in r.stdout, r.stdout[-1500:]
