@@ -362,49 +362,10 @@ def test_dropin_refuses_media_it_does_not_support(hc_plugins, scenes, tmp_path):
     assert wrote, out
 
 
-COMBOS = [
-    # spectral, integrator, medium, sampler, pixel filter, strategy, scene extras, materials
-    (True, "path", None, "halton", "mitchell", "spatial", "spheres", ("matte", "glass", "metal", "plastic")),
-    (True, "volpath", "thin", "sobol", None, "power", "instances", ("matte", "glass", "metal", "plastic")),
-    (False, "volpath", "thick", "halton", "gaussian", "spatial", "delta_lights", ("matte", "plastic")),
-    (False, "volpath", "thin", "halton", None, "uniform", "sphere_partial", ("matte", "mirror", "glass", "plastic")),
-    (False, "volpath", None, "sobol", "sinc", "power", "instances", ("matte_rough", "glass", "metal", "plastic")),
-    (True, "path", None, "sobol", None, "power", "delta_lights", ("matte", "glass", "metal", "plastic")),
-]
+
+import test_zz_combos_gpu as GC  # noqa: E402
 
 
-@pytest.mark.parametrize("combo", range(len(COMBOS)))
+@pytest.mark.parametrize("combo", range(len(GC.COMBOS)))
 def test_feature_combinations_vs_oracle(hostcheck, abi, scenes, ob, hctx, combo):
-    """The widenings were each pinned on their own scenes; here they meet: spectrum type x integrator x medium x sampler x
-    pixel filter x light distribution x shape / light kinds, device (check build) against the oracle, raw film sums."""
-    import json
-    spectral, integrator, med, sampler, pfilter, strat, extra, mats = COMBOS[combo]
-    media = {"thin": dict(sigma_a=(0.05, 0.08, 0.12), sigma_s=(0.3, 0.25, 0.2), g=0.4),
-             "thick": dict(sigma_a=(0.1, 0.05, 0.02), sigma_s=(0.15, 0.2, 0.3), g=0.0)}
-    medium = media.get(med)
-    tables = json.load(open(os.path.join(GOLDEN, "spectral_tables.json"))) if spectral else None
-    nl = RENDERS[extra][7]
-    arr = scenes.SceneArrays(1500, materials=mats, soup_version=1, n_lights=nl, seed=100 + combo, **EXTRA[extra]["scene"])
-    if spectral:
-        arr.attach_spectral(tables)
-    kw = dict(sampler=sampler, integrator=integrator, medium=medium)
-    if pfilter:
-        kw["pixel_filter"] = pfilter
-    if spectral and medium:
-        kw["spectral_tables"] = tables
-    setup = scenes.RenderSetup(40, 24, 4 if sampler == "sobol" else 3, max_depth=6,
-                               strategy=getattr(abi, GV.STRATEGY[strat]), **kw)
-    o = ob.Oracle(abi, arr, spectral_tables=tables)
-    ob.set_volpath(o.lib, integrator == "volpath", medium)
-    try:
-        film, _ = o.render(setup, threads=4)
-    finally:
-        ob.set_volpath(o.lib, False)
-    scene = hostcheck.Scene(hctx, arr.desc(), keepalive=arr)
-    r = hostcheck.Render(scene, setup)
-    r.render_tiles()
-    raw = r.read_raw()
-    assert np.array_equal(bits(raw), bits(film))
-    r.close()
-    scene.close()
-    o.close()
+    GC.test_feature_combinations_vs_oracle(hostcheck, abi, scenes, ob, hctx, combo)
