@@ -2,13 +2,13 @@
 # The first GPU call after this round, in the order that spends the least budget on the most uncertainty
 # (everything below has only run in the CPU check build of the sources, tests/emu):
 #   gpurun --timeout 1500 -- 'bash profiles/next_gpu_run.sh'
-# 1. the 18 parity tests of the 60-bin kernels and of the homogeneous-medium volpath (seconds)
+# 1. the parity tests of the 60-bin kernels, of the homogeneous-medium volpath and of their combinations (seconds)
 # 2. the whole -m gpu suite (the general k_shade variants changed by 1.6 %; everything else is byte-identical SASS)
 # 3. numbers: cfg5 (instancing + SampledSpectrum), cfg2fog (volpath), and cfg2 again as the control
 # 4. launch lists of the two new workloads (shares only) and one --set full capture each of k_shade (60 bins) and k_medium
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_zz_spectral_gpu.py tests/test_zz_volpath_gpu.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/new_paths_tests.txt
+python -m pytest tests/test_zz_spectral_gpu.py tests/test_zz_volpath_gpu.py tests/test_zz_combos_gpu.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/new_paths_tests.txt
 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/gpu_tests.txt
 python bench.py --no-cpu-baseline > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err
 python bench.py --workload cfg5 --steps 2 --warmup 3 > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err
