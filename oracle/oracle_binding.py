@@ -53,6 +53,19 @@ def load(abi, spectral=False):
     return lib
 
 
+def set_medium_boundaries(lib, scene_arrays):
+    """Groundwork: spheres of the scene with a `boundary` spec are null-material surfaces around a homogeneous medium."""
+    specs = [(k, sp["boundary"]) for k, sp in enumerate(getattr(scene_arrays, "sphere_specs", ())) if sp.get("boundary")]
+    n = len(specs)
+    idx = (C.c_int * max(n, 1))(*[k for k, _ in specs])
+    sa = (C.c_float * max(3 * n, 1))(*[v for _, b_ in specs for v in b_["sigma_a"]])
+    ss = (C.c_float * max(3 * n, 1))(*[v for _, b_ in specs for v in b_["sigma_s"]])
+    g = (C.c_float * max(n, 1))(*[b_.get("g", 0.0) for _, b_ in specs])
+    lib.oracle_set_medium_boundaries.restype = None
+    lib.oracle_set_medium_boundaries.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_set_medium_boundaries(n, idx, sa, ss, g)
+
+
 def set_volpath(lib, enabled, medium=None):
     """VolPathIntegrator instead of PathIntegrator for the renders that follow (process-wide switch of the oracle library);
     medium = dict(sigma_a=(r, g, b), sigma_s=(r, g, b), g=...) is a homogeneous medium around the whole scene."""

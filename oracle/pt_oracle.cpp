@@ -1990,13 +1990,25 @@ struct HomogeneousMedium {
     S3 sigma_a, sigma_s, sigma_t;  // homogeneous.h:50-54: sigma_t(sigma_s + sigma_a)
     float g;
 };
-struct VolPathSetting {  // set through oracle_set_volpath (test infrastructure; the product ABI has no media yet)
+struct VolPathSetting {  // set through oracle_set_volpath / oracle_set_medium_boundaries (test infrastructure)
     bool volpath = false, haveMedium = false;
-    HomogeneousMedium medium;
+    HomogeneousMedium medium;  // medium 0: around the whole scene (camera medium)
+    // Media bounded by surfaces (groundwork): sphere k of the scene is a null-material boundary (Material "" under
+    // `MediumInterface "cloud" ""`) whose inside is media[boundaryMedium[k]]; its outside is the medium around the scene
+    std::vector<HomogeneousMedium> media;  // [0] = `medium` when haveMedium
+    std::vector<int> boundaryOfSphere;     // per sphere: index into media, or -1 for an ordinary sphere
+    bool haveBoundaries = false;
+    int outsideMedium() const { return haveMedium ? 0 : -1; }
+    int boundaryMedium(const oracle_scene &s, int prim) const;
 };
 inline VolPathSetting &VolPath() {
     static VolPathSetting v;
     return v;
+}
+inline int VolPathSetting::boundaryMedium(const oracle_scene &s, int prim) const {
+    if (!haveBoundaries || prim < (int)s.nTris) return -1;
+    size_t k = (size_t)(prim - (int)s.nTris);
+    return k < boundaryOfSphere.size() ? boundaryOfSphere[k] : -1;
 }
 inline S3 ExpS(const S3 &a) {  // spectrum.h:222-227
     S3 r;
@@ -2174,8 +2186,34 @@ const Distribution1D *LookupLightDistribution(RenderCtx &rc, const V3 &p) {
 // through the homogeneous medium every ray is in; `inMedium`: `it` is a MediumInteraction (p, wo; no normal, no error
 // bounds) and the phase function takes the BSDF's place (integrator.cpp:131-137, :178-186).
 S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float uScattering[2], int lightNum,
-                  const float uLight[2], const HomogeneousMedium *med = nullptr, bool inMedium = false) {
+                  const float uLight[2], const HomogeneousMedium *med = nullptr, bool inMedium = false, int curMedium = -2) {
     const oracle_scene &s = *rc.s;
+    // curMedium != -2: the scene has media bounded by null-material surfaces; `curMedium` (index into VolPath().media or
+    // -1) is the medium around `it`, and both visibility queries walk through the boundaries they meet
+    const VolPathSetting &vp = VolPath();
+    const bool general = curMedium != -2;
+    // VisibilityTester::Tr (light.cpp:63-81): p0 = it, p1 = the light sample (point, error bounds, normal)
+    auto visibilityTr = [&](V3 origin, V3 d, const V3 &p1, const V3 &p1Err, const V3 &p1n) {
+        S3 Tr(1.f);
+        int m = curMedium;
+        while (true) {
+            TriHit hh;
+            Isect ii;
+            ++rc.regularRays;
+            int hit = SceneIntersect(s, origin, d, 1 - ShadowEpsilon, &hh, &ii);
+            const int bm = hit >= 0 ? vp.boundaryMedium(s, hit) : -1;
+            if (hit >= 0 && bm < 0) return S3(0.f);  // an opaque surface
+            if (m >= 0) Tr = Tr * MediumTr(vp.media[m], d, hit >= 0 ? hh.t : 1 - ShadowEpsilon);
+            if (hit < 0) break;
+            // ray = isect.SpawnRayTo(p1) (interaction.h:73-78); its medium: GetMedium(d), interaction.h:80-82
+            V3 o2 = OffsetRayOrigin(ii.p, ii.pError, ii.n, p1 - ii.p);
+            V3 target = OffsetRayOrigin(p1, p1Err, p1n, o2 - p1);
+            origin = o2;
+            d = target - o2;
+            m = Dot(d, ii.n) > 0 ? vp.outsideMedium() : bm;
+        }
+        return Tr;
+    };
     const b200pt_area_light &light = s.lights[lightNum];
     int bsdfFlags = BSDF_ALL & ~BSDF_SPECULAR;
     S3 Ld(0.f);
@@ -2191,7 +2229,9 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                 // SpawnRayTo(Interaction) with a target that has neither normal nor error bounds: target = its p
                 V3 origin = OffsetRayOrigin(it.p, it.pError, it.n, pTarget - it.p);
                 V3 d = pTarget - origin;
-                if (med) {  // VisibilityTester::Tr, light.cpp:63-81 (every surface here has a material)
+                if (general) {
+                    Li = Li * visibilityTr(origin, d, pTarget, V3(0, 0, 0), V3(0, 0, 0));
+                } else if (med) {  // VisibilityTester::Tr, light.cpp:63-81 (every surface here has a material)
                     TriHit hh;
                     Isect ii;
                     ++rc.regularRays;
@@ -2260,7 +2300,10 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                         pShape.p.x, pShape.p.y, pShape.p.z, pShape.n.x, pShape.n.y, pShape.n.z, lightPdf, Li.c[0], f.c[0],
                         origin.x, origin.y, origin.z, d.x, d.y, d.z, who, who >= 0 ? hh.t : 0.f, (int)BvhIntersectP(s, s.top, origin, d, 1 - ShadowEpsilon));
             }
-            if (med) {  // Li *= visibility.Tr(scene, sampler), integrator.cpp:141-144
+            if (general) {
+                --rc.shadowRays;
+                Li = Li * visibilityTr(origin, d, pShape.p, pShape.pError, pShape.n);
+            } else if (med) {  // Li *= visibility.Tr(scene, sampler), integrator.cpp:141-144
                 --rc.shadowRays;
                 ++rc.regularRays;
                 TriHit hh;
@@ -2317,6 +2360,21 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
             ++rc.regularRays;
             Isect li;
             int hitTri = SceneIntersect(s, ro, wi, Infinity, &h, &li);
+            S3 TrGeneral(1.f);
+            if (general) {  // Scene::IntersectTr, scene.cpp:57-70: through the boundaries up to the first opaque surface
+                int m = curMedium;
+                V3 o2 = ro;
+                while (true) {
+                    if (m >= 0) TrGeneral = TrGeneral * MediumTr(vp.media[m], wi, hitTri >= 0 ? h.t : Infinity);
+                    if (hitTri < 0) break;
+                    const int bm = vp.boundaryMedium(s, hitTri);
+                    if (bm < 0) break;
+                    o2 = OffsetRayOrigin(li.p, li.pError, li.n, wi);  // isect->SpawnRay(ray.d)
+                    m = Dot(wi, li.n) > 0 ? vp.outsideMedium() : bm;
+                    ++rc.regularRays;
+                    hitTri = SceneIntersect(s, o2, wi, Infinity, &h, &li);
+                }
+            }
             S3 Li2(0.f);
             if (hitTri >= 0) {
                 if (s.PrimLight(hitTri) == lightNum) {
@@ -2324,7 +2382,7 @@ S3 EstimateDirect(RenderCtx &rc, const Isect &it, const BSDF &bsdf, const float 
                 }
             }
             // Scene::IntersectTr, scene.cpp:57-70: the transmittance up to the hit (ray.tMax = tHit after Intersect)
-            S3 Tr = med ? MediumTr(*med, wi, hitTri >= 0 ? h.t : Infinity) : S3(1.f);
+            S3 Tr = general ? TrGeneral : med ? MediumTr(*med, wi, hitTri >= 0 ? h.t : Infinity) : S3(1.f);
             if (!Li2.IsBlack()) Ld += f * Li2 * Tr * weight / scatteringPdf;
         }
     }
@@ -2408,12 +2466,16 @@ S3 VolPathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
     const oracle_scene &s = *rc.s;
     const int maxDepth = rc.integ->max_depth;
     const float rrThreshold = rc.integ->rr_threshold;
-    const HomogeneousMedium *med = VolPath().haveMedium ? &VolPath().medium : nullptr;
+    const VolPathSetting &vp = VolPath();
+    const bool general = vp.haveBoundaries;  // media bounded by null-material spheres: the ray's medium changes along the path
+    int curMed = vp.outsideMedium();         // the camera ray starts in the medium around the scene
+    const HomogeneousMedium *med = vp.haveMedium ? &vp.medium : nullptr;
     S3 L(0.f), beta(1.f);
     bool specularBounce = false;
     int bounces;
     float etaScale = 1;
     for (bounces = 0;; ++bounces) {
+        if (general) med = curMed >= 0 ? &vp.media[curMed] : nullptr;
         TriHit h;
         ++rc.regularRays;
         Isect isect;
@@ -2459,7 +2521,8 @@ S3 VolPathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
             // handleMedia is true whether or not the ray is in a medium; without one Tr is 1 but the shadow ray is still
             // a closest-hit query (VisibilityTester::Tr)
             static const HomogeneousMedium vacuum = {S3(0.f), S3(0.f), S3(0.f), 0.f};
-            return EstimateDirect(rc, it, bsdf, uScattering, lightNum, uLight, med ? med : &vacuum, inMedium) / lightPdf;
+            return EstimateDirect(rc, it, bsdf, uScattering, lightNum, uLight, med ? med : &vacuum, inMedium, general ? curMed : -2) /
+                   lightPdf;
         };
         if (sampledMedium) {
             if (bounces >= maxDepth) break;
@@ -2478,6 +2541,15 @@ S3 VolPathLi(RenderCtx &rc, Ray ray, Sobol &sampler) {
                 if (foundIntersection) L += beta * IsectLe(s, isect, -ray.d);
             }
             if (!foundIntersection || bounces >= maxDepth) break;
+            // isect.ComputeScatteringFunctions: no BSDF on a medium boundary -> skip over it (volpath.cpp:115-121)
+            const int bm = vp.boundaryMedium(s, tri);
+            if (bm >= 0) {
+                curMed = Dot(ray.d, isect.n) > 0 ? vp.outsideMedium() : bm;  // GetMedium(ray.d), interaction.h:80-82
+                ray.o = OffsetRayOrigin(isect.p, isect.pError, isect.n, ray.d);  // isect.SpawnRay(ray.d)
+                ray.tMax = Infinity;
+                bounces--;
+                continue;
+            }
             BSDF bsdf;
             MakeBSDF(s, isect, &bsdf);
             // unlike PathIntegrator (path.cpp:119) there is no test for non-specular components here (volpath.cpp:124-128)
@@ -3041,9 +3113,30 @@ float oracle_sphere_pdf(const b200pt_sphere *sphere, const float ref_p[3], const
 int oracle_spectrum_samples(void) { return ORACLE_NSPEC; }
 // VolPathIntegrator instead of PathIntegrator for the renders that follow; has_medium: a homogeneous medium around the
 // whole scene (sigma_a / sigma_s through the same RGB -> spectrum route as every other colour)
+// Spheres of the scene that are null-material medium boundaries (n = 0 clears): sphere_index[i] bounds a homogeneous medium
+// sigma_a / sigma_s [3 i .. 3 i + 2], g[i]; outside them is the medium of oracle_set_volpath (or none).  Call after
+// oracle_set_volpath.
+void oracle_set_medium_boundaries(int n, const int *sphere_index, const float *sigma_a, const float *sigma_s, const float *g) {
+    VolPathSetting &v = VolPath();
+    v.media.clear();
+    v.boundaryOfSphere.clear();
+    v.media.push_back(v.medium);  // slot 0: the medium around the scene (only used when haveMedium)
+    v.haveBoundaries = n > 0;
+    for (int i = 0; i < n; ++i) {
+        HomogeneousMedium m;
+        m.sigma_a = SP(sigma_a + 3 * i);
+        m.sigma_s = SP(sigma_s + 3 * i);
+        m.sigma_t = m.sigma_s + m.sigma_a;
+        m.g = g[i];
+        v.media.push_back(m);
+        if ((size_t)sphere_index[i] >= v.boundaryOfSphere.size()) v.boundaryOfSphere.resize((size_t)sphere_index[i] + 1, -1);
+        v.boundaryOfSphere[(size_t)sphere_index[i]] = (int)v.media.size() - 1;
+    }
+}
 void oracle_set_volpath(int enabled, int has_medium, const float sigma_a[3], const float sigma_s[3], float g) {
     VolPathSetting &v = VolPath();
     v.volpath = enabled != 0;
+    v.haveBoundaries = false;
     v.haveMedium = enabled != 0 && has_medium != 0;
     if (v.haveMedium) {
         v.medium.sigma_a = SP(sigma_a);

@@ -69,6 +69,8 @@ int oracle_spectral_set_cie(const float *X, const float *Y, const float *Z);
 /* VolPathIntegrator (integrators/volpath.cpp) with at most one homogeneous medium around the whole scene; groundwork,
  * the product ABI has no media yet */
 void oracle_set_volpath(int enabled, int has_medium, const float sigma_a[3], const float sigma_s[3], float g);
+/* groundwork: media bounded by null-material spheres (`Material ""` under `MediumInterface "cloud" ""`) */
+void oracle_set_medium_boundaries(int n, const int *sphere_index, const float *sigma_a, const float *sigma_s, const float *g);
 int oracle_spectrum_samples(void);
 
 /* The host libm's sinf/cosf (what the reference calls through std::sin/cos). */

@@ -476,7 +476,13 @@ def write_pbrt(dirname, name, scene, xres, yres, spp, max_depth=5, strategy="uni
             lines.append('  AreaLightSource "diffuse" "rgb L" [%g %g %g]%s' %
                          (sp["emit"], sp["emit"], sp["emit"], ' "bool twosided" "true"' if sp.get("two_sided") else ""))
         mat = sp.get("material", "black")
-        lines.append("  " + ('Material "matte" "rgb Kd" [0 0 0]' if mat == "black" else PBRT_MATERIAL[mat]))
+        if sp.get("boundary"):  # a null-material sphere that bounds a homogeneous medium (oracle groundwork only)
+            b = sp["boundary"]
+            lines += ['  MakeNamedMedium "cloud%d" "string type" "homogeneous" "rgb sigma_a" [%.9g %.9g %.9g] "rgb sigma_s" '
+                      '[%.9g %.9g %.9g] "float g" [%.9g] "float scale" [1]' % ((len(lines),) + tuple(b["sigma_a"]) + tuple(b["sigma_s"]) + (b.get("g", 0.0),)),
+                      '  MediumInterface "cloud%d" "%s"' % (len(lines), "fog" if medium else ""), '  Material ""']
+        else:
+            lines.append("  " + ('Material "matte" "rgb Kd" [0 0 0]' if mat == "black" else PBRT_MATERIAL[mat]))
         lines.append("  Translate %.9g %.9g %.9g" % tuple(sp["center"]))
         if sp.get("scale"):
             lines.append("  Scale %.9g %.9g %.9g" % tuple(sp["scale"]))

@@ -129,11 +129,23 @@ def volpath_goldens():
         os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
 
 
+def volpath_bounded_goldens():
+    """The reference's volpath images of scenes with media bounded by null-material spheres (render_cases.VOLPATH_BOUNDED)."""
+    from render_cases import VOLPATH_BOUNDED
+    for gname, (fog, spheres) in VOLPATH_BOUNDED.items():
+        arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1, spheres=spheres)
+        path = scenes.write_pbrt("/tmp/golden_render", "render_" + gname, arr, 40, 32, 8, max_depth=6, strategy="uniform",
+                                 integrator="volpath", medium=fog)
+        ob.run_pbrt_ref(path)
+        os.replace(os.path.join("/tmp/golden_render", "render_%s.pfm" % gname), os.path.join(HERE, "render_%s.pfm" % gname))
+
+
 def main():
     ob.probe("tables", os.path.join(HERE, "sobol_tables.bin"), 256)
     filter_fixtures()
     halton_fixtures()
     volpath_goldens()
+    volpath_bounded_goldens()
     if os.path.exists(ob.PBRT_REF_SPECTRAL):
         spectral_fixtures()
     out = {"cameras": {}, "sobol": [], "camrays": []}

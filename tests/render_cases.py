@@ -114,3 +114,14 @@ VOLPATH = {
     "volpath_fog_delta": ("delta_lights", dict(sigma_a=(0.02, 0.02, 0.02), sigma_s=(0.5, 0.5, 0.5), g=-0.3), "spatial"),
     "volpath_fog_spheres": ("spheres", dict(sigma_a=(0.1, 0.05, 0.02), sigma_s=(0.15, 0.2, 0.3), g=0.0), "power"),
 }
+
+# Media bounded by surfaces (oracle groundwork: the device does not support them yet): null-material spheres around a
+# homogeneous medium -- golden name -> (medium around the scene or None, sphere specs); 3000-triangle "four" scene
+_CLOUD = dict(sigma_a=(0.3, 0.2, 0.1), sigma_s=(2.0, 2.5, 3.0), g=0.5)
+VOLPATH_BOUNDED = {
+    "volpath_cloud": (None, (dict(center=(0.1, 0.0, -2.2), radius=0.7, boundary=_CLOUD),)),
+    "volpath_cloud_fog": (dict(sigma_a=(0.02, 0.02, 0.02), sigma_s=(0.1, 0.1, 0.1), g=0.2),
+                          (dict(center=(0.1, 0.0, -2.2), radius=0.7, boundary=_CLOUD),
+                           dict(center=(-1.0, 0.6, -1.8), radius=0.4, boundary=dict(sigma_a=(1, 1, 1), sigma_s=(0.5, 0.5, 0.5), g=-0.2)),
+                           dict(center=(1.2, 1.8, -1.5), radius=0.35, emit=60.0))),
+}

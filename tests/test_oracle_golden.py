@@ -216,6 +216,27 @@ def test_volpath_oracle_matches_reference_volpath(abi, scenes, ob):
                               bits(scenes.read_pfm(os.path.join(GOLDEN, "render_four.pfm"))))
 
 
+def test_volpath_oracle_with_bounded_media_matches_reference(abi, scenes, ob):
+    """Groundwork for the next widening of media: null-material spheres around a homogeneous medium (a cloud in vacuum; two
+    clouds and a sphere light inside a global fog).  The path skips the boundaries without spending a bounce
+    (volpath.cpp:115-121), the ray's medium switches by the side it leaves on (interaction.h:80-82), shadow and MIS rays
+    accumulate transmittance segment by segment (light.cpp:63-81, scene.cpp:57-70): bit-identical to the reference."""
+    from render_cases import VOLPATH_BOUNDED
+    for gname, (fog, spheres) in sorted(VOLPATH_BOUNDED.items()):
+        arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1, spheres=spheres)
+        setup = scenes.RenderSetup(40, 32, 8, max_depth=6, strategy=abi.LIGHTS_UNIFORM)
+        o = ob.Oracle(abi, arr)
+        ob.set_volpath(o.lib, True, fog)
+        ob.set_medium_boundaries(o.lib, arr)
+        try:
+            film, _ = o.render(setup, threads=4)
+            rgb = o.film_rgb(setup, film)
+        finally:
+            ob.set_volpath(o.lib, False)
+        assert np.array_equal(bits(rgb), bits(scenes.read_pfm(os.path.join(GOLDEN, "render_%s.pfm" % gname)))), gname
+        o.close()
+
+
 @pytest.mark.parametrize("name", ["analytic_point", "analytic_4points", "analytic_area"])
 def test_analytic_scenes_known_answer(abi, scenes, ob, name):
     """The reference's own known-answer test (src/tests/analytic_scenes.cpp:54-66, CheckSceneAverage): the mean of the
