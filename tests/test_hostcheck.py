@@ -369,3 +369,33 @@ import test_zz_combos_gpu as GC  # noqa: E402
 @pytest.mark.parametrize("combo", range(len(GC.COMBOS)))
 def test_feature_combinations_vs_oracle(hostcheck, abi, scenes, ob, hctx, combo):
     GC.test_feature_combinations_vs_oracle(hostcheck, abi, scenes, ob, hctx, combo)
+
+
+@pytest.mark.parametrize("spectral", [False, True])
+def test_sample_clamp_crop_and_scale_vs_oracle(hostcheck, abi, scenes, ob, hctx, spectral):
+    """Film options that look at the sample's luminance -- "maxsampleluminance" (film.h:124-125, y() of the sample: the
+    60-bin y() rounds differently from ToXYZ's Y) --, a crop window and the film scale, box and Gaussian filter."""
+    import json
+    tables = json.load(open(os.path.join(GOLDEN, "spectral_tables.json"))) if spectral else None
+    arr = scenes.SceneArrays(3000, materials=("matte", "glass", "metal", "plastic"), soup_version=1)
+    if spectral:
+        arr.attach_spectral(tables)
+    scene = hostcheck.Scene(hctx, arr.desc(), keepalive=arr)
+    o = ob.Oracle(abi, arr, spectral_tables=tables)
+    for kw in (dict(max_sample_luminance=3.0, film_scale=0.5, crop_window=(0.1, 0.9, 0.2, 0.8)),
+               dict(max_sample_luminance=1.5, pixel_filter="gaussian")):
+        setup = scenes.RenderSetup(48, 32, 8, max_depth=5, strategy=abi.LIGHTS_UNIFORM, **kw)
+        film, _ = o.render(setup, threads=4)
+        r = hostcheck.Render(scene, setup)
+        r.render_tiles()
+        assert np.array_equal(bits(r.read_raw()), bits(film))
+        assert np.array_equal(bits(r.read_rgb()), bits(o.film_rgb(setup, film)))
+        clamped = float(np.nan_to_num(r.read_rgb()).max())
+        r.close()
+        r2 = hostcheck.Render(scene, scenes.RenderSetup(48, 32, 8, max_depth=5, strategy=abi.LIGHTS_UNIFORM,
+                                                         **{k: v for k, v in kw.items() if k != "max_sample_luminance"}))
+        r2.render_tiles()
+        assert float(np.nan_to_num(r2.read_rgb()).max()) > clamped  # the clamp really was active
+        r2.close()
+    scene.close()
+    o.close()
