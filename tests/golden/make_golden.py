@@ -64,7 +64,10 @@ def filter_fixtures():
 # "rgb" parameters of the spectral golden scenes (materials, area lights, sphere lights, point / spot / distant lights)
 SPECTRAL_RGB = [(0.5, 0.5, 0.5), (0.0, 0.0, 0.0), (40.0, 40.0, 40.0), (60.0, 60.0, 60.0), (90.0, 90.0, 90.0), (6.0, 6.0, 6.0),
                 (30.0, 24.0, 18.0), (0.8, 0.8, 0.8),
-                (0.05, 0.08, 0.12), (0.3, 0.25, 0.2), (0.1, 0.05, 0.02), (0.15, 0.2, 0.3)]  # sigma_a / sigma_s of the media
+                (0.05, 0.08, 0.12), (0.3, 0.25, 0.2), (0.1, 0.05, 0.02), (0.15, 0.2, 0.3),  # sigma_a / sigma_s of the media
+                # the remaining light intensities of tests/render_cases.py, so that every golden scene has 60-bin fixtures
+                (3.14159265358979323846,) * 3, (3.14159265358979323846 / 4,) * 3, (9.0,) * 3, (400.0,) * 3, (80.0,) * 3,
+                (150.0,) * 3, (1.0, 0.9, 0.8), (30.0,) * 3, (40.0,) * 3]
 SPECTRAL_CONST = [0.25, 1.0, 0.9]                                      # float-default spectra (plastic, glass, mirror)
 # rendered by the SampledSpectrum reference; instances + SampledSpectrum together are BASELINE configs[4]'s features
 SPECTRAL_RENDERS = {"spectral_four": "four", "spectral_rough": "rough", "spectral_instances": "instances",
