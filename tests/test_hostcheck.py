@@ -429,3 +429,30 @@ def test_every_golden_scene_under_sampled_spectrum_vs_oracle(hostcheck, abi, sce
     r.close()
     scene.close()
     o.close()
+
+
+@pytest.mark.parametrize("name", sorted(RENDERS))
+def test_every_golden_scene_in_fog_under_volpath_vs_oracle(hostcheck, abi, scenes, ob, hctx, name):
+    """Every scene of the golden set again with `Integrator "volpath"` inside a homogeneous medium: the medium pass meets
+    every shape, light, sampler, filter and camera option of the set; device (check build) against the oracle's VolPathLi
+    (itself pinned against the reference's volpath on four of these scenes)."""
+    fog = dict(sigma_a=(0.04, 0.06, 0.08), sigma_s=(0.25, 0.2, 0.3), g=0.35)
+    nt, mats, w, h, spp, depth, strat, nl = RENDERS[name]
+    ex = EXTRA.get(name, {})
+    arr = scenes.SceneArrays(nt, materials=mats, soup_version=1, n_lights=nl, **ex.get("scene", {}))
+    setup = scenes.RenderSetup(w, h, spp, max_depth=depth, strategy=getattr(abi, GV.STRATEGY[strat]), integrator="volpath",
+                               medium=fog, **ex.get("camera", {}))
+    o = ob.Oracle(abi, arr)
+    ob.set_volpath(o.lib, True, fog)
+    try:
+        film, ostats = o.render(setup, threads=4)
+    finally:
+        ob.set_volpath(o.lib, False)
+    scene = hostcheck.Scene(hctx, arr.desc(), keepalive=arr)
+    r = hostcheck.Render(scene, setup)
+    r.render_tiles()
+    assert np.array_equal(bits(r.read_raw()), bits(film))
+    assert r.stats()["camera_rays"] == ostats["camera_rays"]
+    r.close()
+    scene.close()
+    o.close()
