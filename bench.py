@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (see DESIGN.md "Measurement").
 
-  python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg4|small] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload cfg4|cfg3|cfg2|small] [--impl reference]
+
+Default workload (round 2): cfg4 = BASELINE configs[3], the 10 M-triangle soup with four BSDF families and 16
+area lights at 1920x1080 x 1024 spp -- configs[2]'s scene (the one the north-star target is quoted on) under
+configs[3]'s lights -- at every N, so that the N=1 line and the scaling lines describe the same job.
 
 One "step" = one complete pass of the hot path over the workload: every 16x16
 tile of the film rendered with all its samples per pixel (SamplerIntegrator::
@@ -162,7 +166,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=None, help="timed steps of the end-to-end leg (default: min(steps, 5))")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the reference's image")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-spp", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -175,15 +181,19 @@ def main():
     wl = WORKLOADS[args.workload]
     n_tris, mats, xres, yres, spp, depth, n_lights, desc = wl
 
-    pkg = graft.load_package()
-    from pbrt_v3_distributed_b200 import abi, scenes
+    if args.impl == "reference":
+        abi, scenes = graft.load_harness()  # descriptor helpers only: the reference arm maps none of the repo's CUDA code
+    else:
+        pkg = graft.load_package()
+        from pbrt_v3_distributed_b200 import abi, scenes
     config = {"workload": "%s: %s, maxdepth %d, Sobol, box filter, lightsamplestrategy uniform" %
               (args.workload, desc, depth),
               "n_triangles": n_tris, "resolution": [xres, yres], "spp": spp,
               "scene": "soup v1 (s=0.5*N^-1/3, seed 1234) + %s" %
                        ("%d emissive triangles at y=+3" % n_lights if n_lights else "5 inward emissive quads (10 lights), L=40"),
               "parallelism": "tiles i mod %d over %d GPU(s), one film reduce" % (world, world) if world > 1 else "1 GPU",
-              "l2_policy": "inputs larger than L2 (BVH+triangles %s MB, path state > 0.5 GB); no flush needed"}
+              "l2_policy": "inputs larger than L2 (BVH+triangles %s MB, path state > 0.5 GB); no flush needed",
+              "excluded_from_timing": "scene_create (host BVH build + first upload), like the reference arm's parse + BVH build"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -249,7 +259,8 @@ def main():
     config["l2_policy"] = config["l2_policy"] % ("%.0f" % ((info["node_bytes"] + info["tri_bytes"]) / 1e6))
     config["bvh"] = {"nodes": info["n_nodes"], "node_bytes": info["node_bytes"], "tri_bytes": info["tri_bytes"],
                      "host_build_s": round(build_s, 2),
-                     "builder": "device (Morton order -> radix tree -> 8-wide collapse)" if args.bvh == "gpu" else "host SAH"}
+                     "builder": "device (Morton order -> radix tree -> 7-wide collapse)" if args.bvh == "gpu" else "host SAH",
+                     "layout": "7-wide, 64-byte nodes + 4-byte triangle base per node, 48-byte triangles"}
     render = pkg.Render(scene, setup)
     my_tiles = scenes.rank_tiles(render.n_tiles, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
@@ -317,7 +328,8 @@ def main():
         return ms, float(t[1]), float(t[2]), st, clocks, h2d
 
     ms, rays, samples, st, clocks, _ = timed(False, args.steps, args.warmup)
-    ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, args.steps, 2)
+    e2e_steps = args.e2e_steps if args.e2e_steps else min(args.steps, 5)
+    ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, e2e_steps, 1)
     # one more end-to-end step with events between its three parts (reported, not part of any timed figure)
     breakdown = None
     if world == 1:
@@ -344,7 +356,7 @@ def main():
         value = rays / (ms * 1e-3) / 1e6
         # roofline of the dominant kernel: closest-hit traversal (k_trace<false,...>)
         n_reg = st_i["regular_rays"]
-        bytes_per_closest_ray = 32 + 4 + (st_i["nodes_visited"] * 80.0 + st_i["tris_tested"] * 48.0) / max(n_reg, 1)
+        bytes_per_closest_ray = 32 + 4 + (st_i["nodes_visited"] * 64.0 + st_i["tris_tested"] * 48.0) / max(n_reg, 1)
         closest_bytes = bytes_per_closest_ray * st["regular_rays"]
         achieved = closest_bytes / (st["closest_ms"] * 1e-3) / 1e9 if st["closest_ms"] > 0 else 0.0
         traffic = None
@@ -352,6 +364,7 @@ def main():
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
         cpu = None
+        parity = None
         if not args.no_cpu_baseline:
             ob = graft.load_oracle()
             tmp = tempfile.mkdtemp(prefix="b200pt_cpu_")
@@ -360,6 +373,26 @@ def main():
             have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
             pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None
             c = reference_step(ob, scenes, abi, arr, wl, setup_small, args.cpu_sample_spp, tmp, pbrt_path, spectral)
+            if pbrt_path is not None and not args.no_parity and world == 1:
+                # full-size parity (SURVEY 8d protocol): the image the reference just rendered (same scene, same film,
+                # cpu_sample_spp samples per pixel) against the GPU render of the same job
+                ref_img = scenes.read_pfm(os.path.join(tmp, "bench.pfm"))
+                r2 = pkg.Render(scene, setup_small)
+                r2.clear()
+                r2.render_tiles()
+                got = r2.read_rgb()
+                st2 = r2.stats()
+                r2.close()
+                a, b = got.astype(np.float64), ref_img.astype(np.float64)
+                eps = 1e-3 * float(b.mean())
+                rel = np.abs(a - b) / np.maximum(np.abs(b), eps)
+                parity = {"against": "oracle/_ref/pbrt_ref PFM of the same scene, %dx%d, %d spp" % (xres, yres, args.cpu_sample_spp),
+                          "max_rel": float(rel.max()), "p99_9_rel": float(np.percentile(rel, 99.9)),
+                          "components_over_1e-4": int((rel > 1e-4).sum()),
+                          "components_bits_differ": int((got.view(np.uint32) != ref_img.view(np.uint32)).sum()),
+                          "components": int(got.size),
+                          "ray_counters_equal": bool(st2["regular_rays"] + st2["shadow_rays"] == c["rays"] and st2["camera_rays"] == c["samples"]),
+                          "stack_overflows": int(st2.get("stack_overflows", 0))}
             cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"],
                    "sample": "%dx%d film, %d spp of %d, all tiles (%.1f s render)" %
                              (xres, yres, args.cpu_sample_spp, spp, c["seconds"]),
@@ -370,9 +403,14 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 x 60 spectral bins" if args.workload in SPECTRAL_WORKLOADS else "f32", "data": "synthetic", "config": config,
             "msamples_per_s": samples / (ms * 1e-3) / 1e6,
             "rays_per_sample": rays / max(samples, 1),
-            "roofline": {"bound": "hbm", "kernel": "k_trace<closest-hit> (8-wide BVH traversal)",
+            # frac = ALGORITHMIC bytes (nodes fetched + triangles tested + ray in / hit out) / time / HBM peak.  Those bytes
+            # are mostly served by L2 (the BVH's hot part is cache resident), so frac is NOT DRAM utilisation: dram_frac is,
+            # from the ncu capture of the same kernel and workload under profiles/ (traffic.source).
+            "roofline": {"bound": "hbm (north_star's roofline; ncu: the kernel is issue / L2->SM bound, see dram_frac and profiles/README.md)",
+                         "kernel": "k_trace<closest-hit> (7-wide BVH traversal)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind, "traffic": traffic,
+                         "dram_frac": (traffic or {}).get("dram_frac"),
                          "algorithmic_bytes_per_ray": bytes_per_closest_ray,
                          "nodes_per_ray": st_i["nodes_visited"] / max(n_reg, 1),
                          "tris_per_ray": st_i["tris_tested"] / max(n_reg, 1),
@@ -382,9 +420,11 @@ def main():
             "kernel_ms_per_step": {"closest_hit": st["closest_ms"] / args.steps, "any_hit": st["any_ms"] / args.steps,
                                    "shade_raygen_film": st["shade_ms"] / args.steps},
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": {"value": rays_e / (ms_e * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / args.steps,
-                    "breakdown_ms": breakdown},
+                    "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
+                    "excludes": "scene_create", "breakdown_ms": breakdown},
+            "stack_overflows": int(st.get("stack_overflows", 0)),
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 4
+#define B200PT_ABI_VERSION 5
 #define B200PT_SPECTRUM_SAMPLES 60  /* nSpectralSamples, core/spectrum.h:52 */
 #define B200PT_MATERIAL_SPECTRA 5
 
@@ -302,6 +302,9 @@ typedef struct b200pt_stats {
     uint64_t launches;             /* kernels launched by the library                 */
     uint64_t closest_launches;     /* of which closest-hit traversal                  */
     uint64_t any_launches;         /* of which any-hit traversal                      */
+    uint64_t stack_overflows;      /* child groups a full traversal stack had to drop (must be 0: a non-zero
+                                      count means hits may have been missed; scene_create rejects trees whose
+                                      depth could overflow, so this is a tripwire, not an expected event)   */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;      /* device + stream                          */

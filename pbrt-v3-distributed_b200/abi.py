@@ -89,7 +89,7 @@ class Stats(C.Structure):
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("any_nodes_visited", C.c_uint64),
                 ("any_tris_tested", C.c_uint64), ("closest_ms", C.c_double),
                 ("any_ms", C.c_double), ("shade_ms", C.c_double), ("launches", C.c_uint64),
-                ("closest_launches", C.c_uint64), ("any_launches", C.c_uint64)]
+                ("closest_launches", C.c_uint64), ("any_launches", C.c_uint64), ("stack_overflows", C.c_uint64)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("t_max", np.float32), ("d", np.float32, 3),

@@ -11,8 +11,8 @@
 #include <vector>
 
 #include "b200pt_internal.h"
-#include "bvh8.h"
-#include "bvh8_gpu.h"
+#include "wbvh.h"
+#include "wbvh_gpu.h"
 #include "kernels.cuh"
 
 using namespace b200pt;
@@ -55,7 +55,10 @@ static inline const b200pt_s60::RenderDev &s60(const RenderDev &p) { return rein
 
 struct b200pt_scene {
     b200pt_ctx *ctx = nullptr;
-    U4 *d_nodes = nullptr;
+    U4 *d_nodes = nullptr;       // WbvhNode[n_nodes] (wbvh.h), the top-level tree first, then the objects' trees, then the tree over the instances
+    uint32_t *d_tri_base = nullptr;  // per node: first triangle of its leaf children
+    uint8_t *d_lut = nullptr;    // permute_slots table of the node test (wbvh_traverse.cuh)
+    TravBounds trav_bounds, tlas_bounds;  // padded bounds of the top-level tree / of the tree over the instances
     F4 *d_tris = nullptr;
     b200pt_material *d_materials = nullptr;
     F4 *d_tri_n = nullptr, *d_tri_uv = nullptr;
@@ -72,7 +75,7 @@ struct b200pt_scene {
     uint32_t tlas_node_off = 0, tlas_tri_off = 0;  // tree over the instances' leaf boxes inside the node / triangle arrays
     uint64_t n_prims = 0;            // triangles of the descriptor (sphere k is reported as primitive n_prims + k)
     uint32_t *d_work = nullptr;  // fetch counter for the ray-batch entry points
-    void *h_nodes = nullptr, *h_tris = nullptr;  // pinned host copies (b200pt_scene_upload)
+    void *h_nodes = nullptr, *h_tris = nullptr, *h_tri_base = nullptr;  // pinned host copies (b200pt_scene_upload)
     // SampledSpectrum hosts (b200pt_scene_desc::n_spectrum_samples == 60): host copies of the tables
     int nspec = 0;
     std::vector<float> material_spectra, light_spectra, cie_xyz;
@@ -118,6 +121,37 @@ static float host_spectrum_y(const b200pt_scene *sc, const std::vector<float> &c
 static std::vector<float> host_light_spectrum(const b200pt_scene *sc, int i) {
     if (!sc->nspec) return std::vector<float>(sc->lights[i].lemit, sc->lights[i].lemit + 3);
     return std::vector<float>(sc->light_spectra.begin() + (size_t)i * sc->nspec, sc->light_spectra.begin() + (size_t)(i + 1) * sc->nspec);
+}
+
+// Bounds a ray is clipped to before it walks a tree (trav_init): the tree's own bounds padded by a few of its
+// smallest cells, so that no triangle on the boundary is lost to the rounding of that clip.
+static TravBounds make_trav_bounds(const float *lo, const float *hi) {
+    TravBounds b;
+    float absmax = 0.f, ext = 0.f;
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) ok = ok && lo[a] <= hi[a];
+    for (int a = 0; a < 3; ++a) {
+        const float l = ok ? lo[a] : 0.f, h = ok ? hi[a] : 0.f;
+        absmax = std::max(absmax, std::max(std::fabs(l), std::fabs(h)));
+        ext = std::max(ext, h - l);
+    }
+    const float pad = 0x1p-14f * absmax + 1e-30f;
+    for (int a = 0; a < 3; ++a) {
+        b.lo[a] = (ok ? lo[a] : 0.f) - pad;
+        b.hi[a] = (ok ? hi[a] : 0.f) + pad;
+    }
+    b.scale = std::max(absmax, ext);
+    return b;
+}
+// the tree-related members of a traversal launch
+static void trace_args_scene(TraceArgs &a, const b200pt_scene *s) {
+    a.nodes = s->d_nodes;
+    a.tri_base = s->d_tri_base;
+    a.lut = s->d_lut;
+    a.bounds = s->trav_bounds;
+    a.tlas_bounds = s->tlas_bounds;
+    a.tris = s->d_tris;
+    a.magic = 0x47000000u;
 }
 
 extern "C" {
@@ -249,10 +283,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         inst_object[i] = (int)oi;
     }
     std::vector<uint32_t> obj_node_off(obj_ranges.size()), obj_tri_off(obj_ranges.size());
-    Bvh8 bvh;
+    std::vector<TravBounds> obj_bounds(obj_ranges.size());
+    Wbvh bvh;
     GpuBuildOutput gout;
     if (gpu_build) {
-        // ---- on-device build (bvh8_gpu.cu): Morton order -> binary radix tree -> 8-wide collapse
+        // ---- on-device build (wbvh_gpu.cu): Morton order -> binary radix tree -> 7-wide collapse
         GpuBuildInput gin;
         gin.vertices = d->vertices;
         gin.n_tris = d->n_triangles;
@@ -265,10 +300,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         char msg[256] = "";
         auto drop = [&]() {
             cudaFree(gout.d_nodes);
+            cudaFree(gout.d_tri_base);
             cudaFree(gout.d_tris);
             cudaFree(gout.d_prim_to_tri);
         };
-        if (!build_bvh8_gpu(gin, ctx->stream, &gout, msg, sizeof(msg))) {
+        if (!build_wbvh_gpu(gin, ctx->stream, &gout, msg, sizeof(msg))) {
             drop();
             return b200pt_fail(B200PT_ERR_CUDA, "scene_create: device BVH build failed: %s", msg);
         }
@@ -299,11 +335,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     }
     int threads = (int)std::thread::hardware_concurrency();
     if (const char *e = getenv("B200PT_BUILD_THREADS")) threads = atoi(e);
-    build_bvh8(d->vertices, n_top, d->material_id, d->light_id, d->flip_normal, degenerate.data(), std::max(1, threads), &bvh);
+    build_wbvh(d->vertices, n_top, d->material_id, d->light_id, d->flip_normal, degenerate.data(), std::max(1, threads), &bvh);
     if (bvh.max_depth > B200PT_STACK - 4)
         return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d exceeds the traversal stack", bvh.max_depth);
     {
-        int64_t bad = validate_bvh8(bvh);
+        int64_t bad = validate_wbvh(bvh);
         if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
     }
     // one tree per object, appended behind the top-level one; k_spheres traverses them through offset pointers,
@@ -311,16 +347,18 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     bvh.prim_to_tri.resize((size_t)d->n_triangles, 0xffffffffu);
     for (size_t o = 0; o < obj_ranges.size(); ++o) {
         const int64_t first = obj_ranges[o].first, count = obj_ranges[o].second;
-        Bvh8 ob;
-        build_bvh8(d->vertices + 9 * first, count, d->material_id + first, d->light_id ? d->light_id + first : nullptr,
+        Wbvh ob;
+        build_wbvh(d->vertices + 9 * first, count, d->material_id + first, d->light_id ? d->light_id + first : nullptr,
                    d->flip_normal ? d->flip_normal + first : nullptr, degenerate.data() + first, std::max(1, threads), &ob);
         if (ob.max_depth > B200PT_STACK - 4)
             return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH depth %d of an object exceeds the traversal stack", ob.max_depth);
-        const int64_t bad = validate_bvh8(ob);
+        const int64_t bad = validate_wbvh(ob);
         if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: object BVH validation found %lld violations", (long long)bad);
         obj_node_off[o] = (uint32_t)bvh.nodes.size();
         obj_tri_off[o] = (uint32_t)bvh.tris.size();
         bvh.nodes.insert(bvh.nodes.end(), ob.nodes.begin(), ob.nodes.end());
+        bvh.tri_base.insert(bvh.tri_base.end(), ob.tri_base.begin(), ob.tri_base.end());
+        obj_bounds[o] = make_trav_bounds(ob.bounds_lo, ob.bounds_hi);
         for (TriRecord t : ob.tris) {
             t.prim += (uint32_t)first;      // back to the scene's triangle numbering
             t.mat_flags |= 0x100000u;       // object-space triangle: shading goes through the instance transform
@@ -353,6 +391,11 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         di.is_identity = in.is_identity != 0;
         di.node_off = obj_node_off[inst_object[i]];
         di.tri_off = obj_tri_off[inst_object[i]];
+        for (int a = 0; a < 3; ++a) {
+            di.obj_lo[a] = obj_bounds[inst_object[i]].lo[a];
+            di.obj_hi[a] = obj_bounds[inst_object[i]].hi[a];
+        }
+        di.obj_scale = obj_bounds[inst_object[i]].scale;
         // TransformedPrimitive::WorldBound (primitive.h:104-106): InstanceToWorld(bounds of the object), 8 corners
         float olo[3] = {INFINITY, INFINITY, INFINITY}, ohi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int64_t v = 3 * in.first_triangle; v < 3 * (in.first_triangle + in.n_triangles); ++v)
@@ -380,6 +423,8 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     // a tree over the instances' leaf boxes (each box enters the builder as a triangle spanning it; the leaf
     // "triangles" of this tree carry instance numbers and are only ever read by k_spheres): scenes with many instances
     uint32_t tlas_node_off = 0, tlas_tri_off = 0;
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    TravBounds tlas_bounds = make_trav_bounds(zero3, zero3);
     if (d->n_instances > 8 && !gpu_build) {
         std::vector<float> boxes((size_t)d->n_instances * 9);
         std::vector<int32_t> zeros((size_t)d->n_instances, 0);
@@ -390,13 +435,15 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
             v[3] = di.leaf_hi[0], v[4] = di.leaf_hi[1], v[5] = di.leaf_hi[2];
             v[6] = di.leaf_lo[0], v[7] = di.leaf_hi[1], v[8] = di.leaf_lo[2];
         }
-        Bvh8 tl;
-        build_bvh8(boxes.data(), d->n_instances, zeros.data(), nullptr, nullptr, nullptr, 1, &tl);
-        if (tl.max_depth <= B200PT_STACK - 4 && validate_bvh8(tl) == 0 && tl.n_in_leaves == (uint32_t)d->n_instances) {
+        Wbvh tl;
+        build_wbvh(boxes.data(), d->n_instances, zeros.data(), nullptr, nullptr, nullptr, 1, &tl);
+        if (tl.max_depth <= B200PT_STACK - 4 && validate_wbvh(tl) == 0 && tl.n_in_leaves == (uint32_t)d->n_instances) {
             tlas_node_off = (uint32_t)bvh.nodes.size();
             tlas_tri_off = (uint32_t)bvh.tris.size();
             bvh.nodes.insert(bvh.nodes.end(), tl.nodes.begin(), tl.nodes.end());
+            bvh.tri_base.insert(bvh.tri_base.end(), tl.tri_base.begin(), tl.tri_base.end());
             bvh.tris.insert(bvh.tris.end(), tl.tris.begin(), tl.tris.end());
+            tlas_bounds = make_trav_bounds(tl.bounds_lo, tl.bounds_hi);
         }
     }
 
@@ -498,6 +545,8 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     s->instances = dinst;
     s->tlas_node_off = tlas_node_off;
     s->tlas_tri_off = tlas_tri_off;
+    s->tlas_bounds = tlas_bounds;
+    s->trav_bounds = gpu_build ? make_trav_bounds(gout.bounds_lo, gout.bounds_hi) : make_trav_bounds(bvh.bounds_lo, bvh.bounds_hi);
     for (const DevInstance &di : dinst)  // TransformedPrimitive::WorldBound joins Scene::WorldBound()
         for (int a = 0; a < 3; ++a) {
             s->bounds_lo[a] = std::min(s->bounds_lo[a], di.world_lo[a]);
@@ -519,19 +568,23 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     cudaError_t e;
     if (gpu_build) {
         s->d_nodes = static_cast<U4 *>(gout.d_nodes);
+        s->d_tri_base = static_cast<uint32_t *>(gout.d_tri_base);
         s->d_tris = static_cast<F4 *>(gout.d_tris);
     }
-    if ((!gpu_build && ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_node_records) * sizeof(Bvh8Node))) != cudaSuccess ||
+    if ((!gpu_build && ((e = cudaMalloc(&s->d_nodes, std::max<size_t>(1, n_node_records) * sizeof(WbvhNode))) != cudaSuccess ||
+                        (e = cudaMalloc(&s->d_tri_base, std::max<size_t>(1, n_node_records) * sizeof(uint32_t))) != cudaSuccess ||
                         (e = cudaMalloc(&s->d_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess)) ||
         (e = cudaMalloc(&s->d_materials, s->materials.size() * sizeof(b200pt_material))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_material_spectra, std::max<size_t>(1, s->material_spectra.size()) * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_spheres, std::max<size_t>(1, s->spheres.size()) * sizeof(DevSphere))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_instances, std::max<size_t>(1, s->instances.size()) * sizeof(DevInstance))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_lut, B200PT_LUT_BYTES)) != cudaSuccess ||
         (e = cudaMalloc(&s->d_work, 64)) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    if ((e = cudaMallocHost(&s->h_nodes, std::max<size_t>(1, n_node_records) * sizeof(Bvh8Node))) != cudaSuccess ||
+    if ((e = cudaMallocHost(&s->h_nodes, std::max<size_t>(1, n_node_records) * sizeof(WbvhNode))) != cudaSuccess ||
+        (e = cudaMallocHost(&s->h_tri_base, std::max<size_t>(1, n_node_records) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMallocHost(&s->h_tris, std::max<size_t>(1, n_tri_records) * sizeof(TriRecord))) != cudaSuccess) {
         b200pt_scene_destroy(s);
         return b200pt_fail(B200PT_ERR_OOM, "scene_create: cudaMallocHost failed: %s", cudaGetErrorString(e));
@@ -552,26 +605,29 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     }
     if (gpu_build) {
         // keep host copies like the host path does (b200pt_scene_upload re-sends them; B200PT_VALIDATE_BVH checks them)
-        if ((e = cudaMemcpy(s->h_nodes, s->d_nodes, n_node_records * sizeof(Bvh8Node), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        if ((e = cudaMemcpy(s->h_nodes, s->d_nodes, n_node_records * sizeof(WbvhNode), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (e = cudaMemcpy(s->h_tri_base, s->d_tri_base, n_node_records * sizeof(uint32_t), cudaMemcpyDeviceToHost)) != cudaSuccess ||
             (e = cudaMemcpy(s->h_tris, s->d_tris, n_tri_records * sizeof(TriRecord), cudaMemcpyDeviceToHost)) != cudaSuccess) {
             b200pt_scene_destroy(s);
             return b200pt_fail(B200PT_ERR_CUDA, "scene_create: BVH download failed: %s", cudaGetErrorString(e));
         }
         if (getenv("B200PT_VALIDATE_BVH")) {
-            Bvh8 chk;
-            chk.nodes.assign(static_cast<Bvh8Node *>(s->h_nodes), static_cast<Bvh8Node *>(s->h_nodes) + n_node_records);
+            Wbvh chk;
+            chk.nodes.assign(static_cast<WbvhNode *>(s->h_nodes), static_cast<WbvhNode *>(s->h_nodes) + n_node_records);
+            chk.tri_base.assign(static_cast<uint32_t *>(s->h_tri_base), static_cast<uint32_t *>(s->h_tri_base) + n_node_records);
             chk.tris.assign(static_cast<TriRecord *>(s->h_tris), static_cast<TriRecord *>(s->h_tris) + n_tri_records);
             chk.prim_to_tri = s->prim_to_tri;
             chk.n_in_leaves = gout.n_in_leaves;
             chk.max_depth = gout.max_depth;
-            const int64_t bad = validate_bvh8(chk);
+            const int64_t bad = validate_wbvh(chk);
             if (bad) {
                 b200pt_scene_destroy(s);
                 return b200pt_fail(B200PT_ERR_INVALID, "scene_create: device-built BVH failed validation (%lld violations)", (long long)bad);
             }
         }
     } else {
-        memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Bvh8Node));
+        memcpy(s->h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(WbvhNode));
+        memcpy(s->h_tri_base, bvh.tri_base.data(), bvh.tri_base.size() * sizeof(uint32_t));
         memcpy(s->h_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord));
     }
     int rc = b200pt_scene_upload(s, nullptr);
@@ -588,9 +644,16 @@ int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
     if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
     CUDA_TRY(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
-    const size_t nb = s->n_nodes * sizeof(Bvh8Node), tb = s->n_tris * sizeof(TriRecord),
-                 mb = s->materials.size() * sizeof(b200pt_material);
+    const size_t nb = s->n_nodes * sizeof(WbvhNode), tb = s->n_tris * sizeof(TriRecord),
+                 mb = s->materials.size() * sizeof(b200pt_material), bb = s->n_nodes * sizeof(uint32_t);
     CUDA_TRY(cudaMemcpyAsync(s->d_nodes, s->h_nodes, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_tri_base, s->h_tri_base, bb, cudaMemcpyHostToDevice, st));
+    {
+        static uint8_t lut[B200PT_LUT_BYTES];  // the same table for every scene
+        for (uint32_t o = 0; o < 8; ++o)
+            for (uint32_t m = 0; m < 256; ++m) lut[o << 8 | m] = (uint8_t)permute_slots(m, o);
+        CUDA_TRY(cudaMemcpyAsync(s->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(s->d_tris, s->h_tris, tb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_materials, s->materials.data(), mb, cudaMemcpyHostToDevice, st));
     const size_t msb = s->material_spectra.size() * sizeof(float);
@@ -599,7 +662,7 @@ int b200pt_scene_upload(b200pt_scene *s, uint64_t *bytes) {
     if (sb) CUDA_TRY(cudaMemcpyAsync(s->d_spheres, s->spheres.data(), sb, cudaMemcpyHostToDevice, st));
     const size_t ib = s->instances.size() * sizeof(DevInstance);
     if (ib) CUDA_TRY(cudaMemcpyAsync(s->d_instances, s->instances.data(), ib, cudaMemcpyHostToDevice, st));
-    if (bytes) *bytes = nb + tb + mb + sb + ib + msb;
+    if (bytes) *bytes = nb + bb + tb + mb + sb + ib + msb + B200PT_LUT_BYTES;
     return B200PT_OK;
 }
 
@@ -607,6 +670,8 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_nodes);
+    cudaFree(s->d_tri_base);
+    cudaFree(s->d_lut);
     cudaFree(s->d_tris);
     cudaFree(s->d_materials);
     cudaFree(s->d_material_spectra);
@@ -616,20 +681,21 @@ void b200pt_scene_destroy(b200pt_scene *s) {
     cudaFree(s->d_instances);
     cudaFree(s->d_work);
     cudaFreeHost(s->h_nodes);
+    cudaFreeHost(s->h_tri_base);
     cudaFreeHost(s->h_tris);
     delete s;
 }
 
 int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri_bytes, uint64_t *n_nodes) {
     if (!s) return b200pt_fail(B200PT_ERR_INVALID, "scene is NULL");
-    if (node_bytes) *node_bytes = s->n_nodes * sizeof(Bvh8Node);
+    if (node_bytes) *node_bytes = s->n_nodes * (sizeof(WbvhNode) + sizeof(uint32_t));
     if (tri_bytes) *tri_bytes = s->n_tris * sizeof(TriRecord);
     if (n_nodes) *n_nodes = s->n_nodes;
     return B200PT_OK;
 }
 
 // ------------------------------------------------- ray-batch entry points
-static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * 8; }
+static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * B200PT_TRACE_CTAS; }
 static int postpone_pct() {
     static int v = getenv("B200PT_POSTPONE_PCT") ? atoi(getenv("B200PT_POSTPONE_PCT")) : 40;
     return v;
@@ -649,8 +715,7 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     CUDA_TRY(cudaMemcpyAsync(s->d_work, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
     TraceArgs a;
     memset(&a, 0, sizeof(a));
-    a.nodes = s->d_nodes;
-    a.tris = s->d_tris;
+    trace_args_scene(a, s);
     a.ray_o = reinterpret_cast<const float4 *>(rays_dev);
     a.ray_d = reinterpret_cast<const float4 *>(rays_dev) + 1;
     a.stride = 2;
@@ -660,7 +725,6 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     a.materials = s->d_materials;
     a.refill_lanes = refill_lanes();
     a.postpone_pct = postpone_pct();
-    a.magic = 0x4B000000u;
     if (any_hit)
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
@@ -790,6 +854,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     RenderDev &H = r->host;
     memset(&H, 0, sizeof(H));
     H.scene.nodes = scene->d_nodes;
+    H.scene.tri_base = scene->d_tri_base;
+    H.scene.lut = scene->d_lut;
+    H.scene.bounds = scene->trav_bounds;
     H.scene.tris = scene->d_tris;
     H.scene.materials = scene->d_materials;
     H.scene.material_spectra = scene->nspec ? scene->d_material_spectra : nullptr;
@@ -1134,7 +1201,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(st));
-    r->grid_trace = ctx->sm_count * 8;
+    r->grid_trace = ctx->sm_count * B200PT_TRACE_CTAS;
     r->grid_shade = ctx->sm_count * 8;
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
@@ -1290,14 +1357,12 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             uint32_t *wk = H.work + (size_t)b * 16;
             TraceArgs a;
             memset(&a, 0, sizeof(a));
-            a.nodes = H.scene.nodes;
-            a.tris = H.scene.tris;
+            trace_args_scene(a, r->scene);
             a.materials = H.scene.materials;
             a.stats = H.stats;
             a.stride = 1;
             a.refill_lanes = refill_lanes();
             a.postpone_pct = postpone_pct();
-            a.magic = 0x4B000000u;
             // closest hit of the path rays + classification by BSDF family
             const bool sorted = r->sort_from_bounce >= 0 && b >= r->sort_from_bounce;
             if (sorted) {
@@ -1335,14 +1400,12 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             uint32_t *wk = H.work + (size_t)b * 16;
             TraceArgs a;
             memset(&a, 0, sizeof(a));
-            a.nodes = H.scene.nodes;
-            a.tris = H.scene.tris;
+            trace_args_scene(a, r->scene);
             a.materials = H.scene.materials;
             a.stats = H.stats;
             a.stride = 1;
             a.refill_lanes = refill_lanes();
             a.postpone_pct = postpone_pct();
-            a.magic = 0x4B000000u;
             // shadow rays (any hit), tMax = 1 - ShadowEpsilon
             const bool sorted_sh = r->sort_from_bounce >= 0;
             if (sorted_sh) {
@@ -1585,6 +1648,7 @@ int b200pt_get_stats(b200pt_render *r, b200pt_stats *out) {
     out->any_ms = r->ms[1];
     out->shade_ms = r->ms[2];
     out->launches = r->launches;
+    out->stack_overflows = h[7];
     return B200PT_OK;
 }
 

@@ -1,7 +1,7 @@
 // kernels.cu -- the sm_100a kernels of the wavefront path tracer.
 //
 //   k_raygen   K1  Sobol' camera samples -> camera rays (GetCameraSample + GenerateRayDifferential)
-//   k_trace    K2/K3  persistent-thread closest-hit / any-hit traversal of the 8-wide BVH; the
+//   k_trace    K2/K3  persistent-thread closest-hit / any-hit traversal of the 7-wide BVH (wbvh.h); the
 //              closest-hit epilogue classifies hits into per-material-family queues
 //              (warp-ballot aggregated appends)
 //   k_shade<M> K4  one kernel per BSDF family: surface reconstruction, emission, light
@@ -212,14 +212,25 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
 // (+ classified by BSDF family with warp-aggregated appends) and idle lanes
 // fetch new rays -- so one long ray never keeps 31 lanes idle.
 
+__device__ __forceinline__ TravBounds instance_bounds(const DevInstance &in) {
+    TravBounds b;
+    for (int a = 0; a < 3; ++a) {
+        b.lo[a] = in.obj_lo[a];
+        b.hi[a] = in.obj_hi[a];
+    }
+    b.scale = in.obj_scale;
+    return b;
+}
+
 #ifdef B200PT_HOST_EMU
 // CPU check build: the warp-synchronous kernel below cannot run one lane at a time; every ray takes the per-ray
-// routine the kernel's lanes step through (traverse_bvh8 = trav_step until done) and retires like a lane does.
+// routine the kernel's lanes step through (traverse_wbvh = trav_step until done) and retires like a lane does.
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
 void k_trace(const TraceArgs a) {
     const uint32_t n = *a.count;
     TraceCounters ctr;
     ctr.nodes = ctr.tris = 0;
+    uint32_t overflow = 0;
     uint32_t i;
     while (warp_fetch(a.work, n, &i)) {
         const uint32_t slot = a.queue ? a.queue[i] : i;
@@ -227,8 +238,8 @@ void k_trace(const TraceArgs a) {
         const float4 d4 = a.ray_d[(size_t)slot * a.stride];
         TriHit hit;
         hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
-        const uint32_t best = traverse_bvh8<ANY_HIT, COUNT>(a.nodes, a.tris, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max,
-                                                            &hit, &ctr);
+        const uint32_t best = traverse_wbvh<ANY_HIT, COUNT>(a.nodes, a.tri_base, a.tris, a.bounds, a.lut, v3(o4), v3(d4),
+                                                            a.t_max_from_w ? o4.w : a.fixed_t_max, &hit, &ctr, &overflow);
         if (ANY_HIT) {
             a.occ_out[slot] = best != B200PT_MISS ? 1 : 0;
             continue;
@@ -252,10 +263,64 @@ void k_trace(const TraceArgs a) {
         atomicAdd(&a.stats[ANY_HIT ? 5 : 3], (unsigned long long)ctr.nodes);
         atomicAdd(&a.stats[ANY_HIT ? 6 : 4], (unsigned long long)ctr.tris);
     }
+    if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
 }
 #else
+// The ray as the triangle test sees it and the result so far (TravRay) live in shared memory, one column per
+// thread (conflict-free): the node loop -- where a lane spends its time -- keeps only the box-test state in
+// registers, the much rarer triangle phase fetches what it needs.
+#define B200PT_RAY_WORDS 15
+__device__ __forceinline__ void ray_store(float *col, const TravRay &R) {
+    col[0 * 128] = R.o.x;
+    col[1 * 128] = R.o.y;
+    col[2 * 128] = R.o.z;
+    col[3 * 128] = R.sh.Sx;
+    col[4 * 128] = R.sh.Sy;
+    col[5 * 128] = R.sh.Sz;
+    col[6 * 128] = __int_as_float(R.sh.kz);
+    col[7 * 128] = R.tmax;
+    col[8 * 128] = __uint_as_float(R.best);
+    col[9 * 128] = R.hit.t;
+    col[10 * 128] = R.hit.b0;
+    col[11 * 128] = R.hit.b1;
+    col[12 * 128] = R.hit.b2;
+    col[13 * 128] = R.t0;
+    col[14 * 128] = R.inv;
+}
+__device__ __forceinline__ void ray_load(const float *col, TravRay &R) {
+    R.o = mk(col[0 * 128], col[1 * 128], col[2 * 128]);
+    R.sh.Sx = col[3 * 128];
+    R.sh.Sy = col[4 * 128];
+    R.sh.Sz = col[5 * 128];
+    R.sh.kz = __float_as_int(col[6 * 128]);
+    R.sh.kx = R.sh.kz == 2 ? 0 : R.sh.kz + 1;
+    R.sh.ky = R.sh.kx == 2 ? 0 : R.sh.kx + 1;
+    R.tmax = col[7 * 128];
+    R.best = __float_as_uint(col[8 * 128]);
+    R.hit.t = col[9 * 128];
+    R.hit.b0 = col[10 * 128];
+    R.hit.b1 = col[11 * 128];
+    R.hit.b2 = col[12 * 128];
+    R.t0 = col[13 * 128];
+    R.inv = col[14 * 128];
+}
+__device__ __forceinline__ void ray_store_hit(float *col, const TravRay &R) {
+    col[7 * 128] = R.tmax;
+    col[8 * 128] = __uint_as_float(R.best);
+    col[9 * 128] = R.hit.t;
+    col[10 * 128] = R.hit.b0;
+    col[11 * 128] = R.hit.b1;
+    col[12 * 128] = R.hit.b2;
+}
+
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
-__global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
+__global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArgs a) {
+    // the slot-permutation table of the node test (wbvh_traverse.cuh), one copy per CTA
+    __shared__ __align__(16) uint8_t s_lut[B200PT_LUT_BYTES];
+    __shared__ float s_ray[B200PT_RAY_WORDS * 128];
+    reinterpret_cast<uint4 *>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + threadIdx.x);
+    __syncthreads();
+    float *const my_ray = s_ray + threadIdx.x;
     const uint32_t n = *a.count;
     const int lane = threadIdx.x & 31;
     TraceCounters ctr;
@@ -269,23 +334,25 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
         {
             int family = -1;
             if (fin) {
+                const uint32_t best = __float_as_uint(my_ray[8 * 128]);
                 if (ANY_HIT) {
-                    a.occ_out[slot] = T.best != B200PT_MISS ? 1 : 0;
+                    a.occ_out[slot] = best != B200PT_MISS ? 1 : 0;
                 } else {
-                    if (a.hit_out) a.hit_out[slot] = T.best;
+                    if (a.hit_out) a.hit_out[slot] = best;
                     if (a.full_out) {
                         b200pt_hit r;
-                        r.triangle = T.best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)T.best * 3).w) : -1;
-                        r.t = T.hit.t;
-                        r.b0 = T.hit.b0;
-                        r.b1 = T.hit.b1;
+                        r.triangle = best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w) : -1;
+                        r.t = my_ray[9 * 128];
+                        r.b0 = my_ray[10 * 128];
+                        r.b1 = my_ray[11 * 128];
                         a.full_out[slot] = r;
                     }
-                    if (CLASSIFY && T.best != B200PT_MISS) {
-                        const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)T.best * 3 + 1).w);
+                    if (CLASSIFY && best != B200PT_MISS) {
+                        const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
                         family = a.materials[mf & 0xffffu].type;
                     }
                 }
+                if (T.overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)T.overflow);
             }
             if (CLASSIFY) {
 #pragma unroll
@@ -312,9 +379,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
                         slot = a.queue ? a.queue[i] : i;
                         const float4 o4 = a.ray_o[(size_t)slot * a.stride];
                         const float4 d4 = a.ray_d[(size_t)slot * a.stride];
-                        trav_init(T, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max);
+                        TravRay R;
+                        trav_init(T, R, v3(o4), v3(d4), a.t_max_from_w ? o4.w : a.fixed_t_max, a.bounds);
+                        ray_store(my_ray, R);
                         pend_y = 0;
-                        T.magic = a.magic;
                         has = true;
                     } else {
                         exhausted = true;
@@ -332,7 +400,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
         while (has) {
             uint32_t ng_x = 0, ng_y = 0;
             const bool node_work = (T.cur_y & 0xff000000u) != 0;
-            if (node_work) trav_node_phase<COUNT>(T, S, a.nodes, &ng_x, &ng_y, &ctr);
+            if (node_work) trav_node_phase<!ANY_HIT, COUNT>(T, S, a.nodes, a.tri_base, s_lut, &ng_x, &ng_y, &ctr);
             bool must = false;
             if (ng_y) {
                 if (pend_y) {
@@ -355,7 +423,13 @@ __global__ void __launch_bounds__(128, 8) k_trace(const TraceArgs a) {
             // only waiting for it that the node phase itself would run half empty
             if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_starving * 4 >= n_act) {
                 bool done = false;
-                if (pend_y) done = trav_tri_phase<ANY_HIT, COUNT>(T, a.tris, pend_x, pend_y, &ctr);
+                if (pend_y) {
+                    TravRay R;
+                    ray_load(my_ray, R);
+                    const uint32_t before = R.best;
+                    done = trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, a.tris, pend_x, pend_y, &ctr);
+                    if (R.best != before) ray_store_hit(my_ray, R);
+                }
                 pend_x = ng_x;
                 pend_y = ng_y;
                 if (done) {
@@ -392,8 +466,11 @@ __device__ uint32_t instance_test(const TraceArgs &a, uint32_t k, const V3 &ro, 
     float tm2;
     instance_ray(in, ro, rd, tmax, &o2, &d2, &tm2);
     TraceCounters ctr;
-    const uint32_t ti = traverse_bvh8<ANY_HIT, false>(a.nodes + (size_t)in.node_off * 5, a.tris + (size_t)in.tri_off * 3, o2, d2,
-                                                      tm2, h, &ctr);
+    uint32_t overflow = 0;
+    const uint32_t ti = traverse_wbvh<ANY_HIT, false>(a.nodes + (size_t)in.node_off * 4, a.tri_base + in.node_off,
+                                                      a.tris + (size_t)in.tri_off * 3, instance_bounds(in), a.lut, o2, d2, tm2, h, &ctr,
+                                                      &overflow);
+    if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
     return ti == B200PT_MISS ? B200PT_MISS : in.tri_off + ti;
 }
 // All instances against one ray: through the tree over their leaf boxes when there is one (its leaf "triangles" carry
@@ -418,25 +495,34 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
     // over the instances' boxes, picking the next candidate instance, or taking ONE step inside that instance's tree --
     // so that the lanes of a warp meet again after every step instead of after whole nested traversals (measured with
     // the nested loops: 2.4 of 32 lanes active per instruction).
-    const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 5;
+    const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 4;
+    const uint32_t *tb1 = a.tri_base + a.tlas_node_off;
     const F4 *tt = a.tris + (size_t)a.tlas_tri_off * 3;
     Trav T1, T2;
+    TravRay R1, R2;
     TravStack S1, S2;
     TraceCounters ctr;
-    trav_init(T1, ro, rd, *tmax);
-    trav_init(T2, ro, rd, *tmax);
+    uint32_t overflow = 0;
+    trav_init(T1, R1, ro, rd, *tmax, a.tlas_bounds);
+    T2 = T1;
+    R2 = R1;
+    T2.cur_y = 0u;
     uint32_t pend_x = 0, pend_y = 0, cur_inst = 0, cur_tri_off = 0;
     const U4 *bn = tn;
+    const uint32_t *bb = tb1;
     const F4 *bt = tt;
     int state = 0;  // 0: instance tree, 1: next candidate, 2: inside an instance
     while (true) {
         if (state == 2) {
-            if (trav_step<ANY_HIT, false>(T2, S2, bn, bt, &ctr)) {
-                if (T2.best != B200PT_MISS) {
-                    best = cur_tri_off + T2.best;
+            if (!(T2.cur_y & 0xff000000u) || trav_step<ANY_HIT, false>(T2, R2, S2, bn, bb, bt, a.lut, &ctr)) {
+                overflow += T2.overflow;
+                T2.overflow = 0;
+                if (R2.best != B200PT_MISS) {
+                    best = cur_tri_off + R2.best;
                     *inst = cur_inst;
-                    *hit = T2.hit;
-                    T1.tmax = T2.hit.t;  // r.tMax = ray.tMax
+                    *hit = R2.hit;
+                    R1.tmax = R2.hit.t;  // r.tMax = ray.tMax
+                    T1.tmaxp = trav_param_of(R1, R1.tmax);
                     if (ANY_HIT) break;
                 }
                 state = 1;
@@ -447,12 +533,13 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
                 pend_y &= ~(1u << j);
                 const uint32_t k = __float_as_uint(ld_f4(tt + (size_t)(pend_x + (uint32_t)j) * 3).w);  // TriRecord::prim
                 const DevInstance &in = a.instances[k];
-                if (instance_leaf_test(in, ro, rd, T1.tmax)) {
+                if (instance_leaf_test(in, ro, rd, R1.tmax)) {
                     V3 o2, d2;
                     float tm2;
-                    instance_ray(in, ro, rd, T1.tmax, &o2, &d2, &tm2);
-                    trav_init(T2, o2, d2, tm2);
-                    bn = a.nodes + (size_t)in.node_off * 5;
+                    instance_ray(in, ro, rd, R1.tmax, &o2, &d2, &tm2);
+                    trav_init(T2, R2, o2, d2, tm2, instance_bounds(in));
+                    bn = a.nodes + (size_t)in.node_off * 4;
+                    bb = a.tri_base + in.node_off;
                     bt = a.tris + (size_t)in.tri_off * 3;
                     cur_inst = k;
                     cur_tri_off = in.tri_off;
@@ -463,14 +550,16 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
             }
         } else {
             if (T1.cur_y & 0xff000000u) {
-                trav_node_phase<false>(T1, S1, tn, &pend_x, &pend_y, &ctr);
+                trav_node_phase<!ANY_HIT, false>(T1, S1, tn, tb1, a.lut, &pend_x, &pend_y, &ctr);
                 state = 1;
             } else if (!trav_next_group(T1, S1)) {
                 break;
             }
         }
     }
-    *tmax = T1.tmax;
+    overflow += T1.overflow;
+    if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
+    *tmax = R1.tmax;
     return best;
 }
 

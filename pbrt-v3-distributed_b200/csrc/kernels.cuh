@@ -13,7 +13,7 @@
 
 #include <cuda_runtime.h>
 
-#include "bvh8_traverse.cuh"
+#include "wbvh_traverse.cuh"
 #include "pt_core.cuh"
 #include "pt_sphere.cuh"
 
@@ -35,6 +35,9 @@ struct DevLight {
 
 struct DevScene {
     const U4 *nodes;
+    const uint32_t *tri_base;  // per node: first triangle of its leaf children (wbvh.h)
+    const uint8_t *lut;        // permute_slots table (B200PT_LUT_BYTES)
+    TravBounds bounds;         // padded bounds of the top-level tree
     const F4 *tris;
     const b200pt_material *materials;
     const float *material_spectra;  // SampledSpectrum build: [n_materials][5][60] (kd, ks, kt, eta, k), else nullptr
@@ -130,8 +133,18 @@ struct RenderDev {
     const float *med_spectra;  // SampledSpectrum build: [2][60] = sigma_s, sigma_t (else the two arrays above)
 };
 
+// resident CTAs of k_trace per SM (128 threads each): 6 leaves 78 registers per thread, which the node test needs
+// without spilling (8 selectors + 9 slab constants per ray next to the 16 node words in flight)
+#ifndef B200PT_TRACE_CTAS
+#define B200PT_TRACE_CTAS 6
+#endif
+
 struct TraceArgs {
     const U4 *nodes;
+    const uint32_t *tri_base;  // parallel to nodes
+    const uint8_t *lut;        // permute_slots table in global memory (k_trace stages it in shared memory)
+    TravBounds bounds;         // padded bounds of the top-level tree
+    TravBounds tlas_bounds;    // ... of the tree over the instances' leaf boxes
     const F4 *tris;
     const float4 *ray_o;   // o.xyz (+ t_max in .w when t_max_from_w)
     const float4 *ray_d;
@@ -151,7 +164,7 @@ struct TraceArgs {
     unsigned long long *stats;  // nodes/tris counters when instrumented
     int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
     int postpone_pct;           // triangle postponing threshold (% of converged lanes), 0 = off
-    uint32_t magic;             // 0x4B000000 as a run-time value (see byte_plus_2p23)
+    uint32_t magic;             // 0x47000000 as a run-time value (PRMT's second source stays in a register, see plane_2p15)
     // sphere pass (launch_spheres): same rays, after the traversal launch
     const DevSphere *spheres;
     uint32_t n_spheres;

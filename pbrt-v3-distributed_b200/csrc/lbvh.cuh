@@ -1,5 +1,5 @@
-// lbvh.cuh -- the per-element steps of the on-device builder of the 8-wide BVH
-// (replaces the host SAH build of bvh8_build.cpp, and with it
+// lbvh.cuh -- the per-element steps of the on-device builder of the 7-wide BVH (wbvh.h)
+// (replaces the host SAH build of wbvh_build.cpp, and with it
 // BVHAccel's constructor accelerators/bvh.cpp:183-225, when build time matters
 // more than tree quality).  The reference's own parallel design is HLBVH
 // (bvh.cpp:404-638: Morton codes -> radix sort -> treelets -> SAH over
@@ -12,20 +12,20 @@
 //                       one thread per internal node, no synchronisation)
 //   4. lbvh_fit_*       bottom-up bounds (second arrival at a node continues)
 //   5. lbvh_collapse    top-down, one thread per wide node: open the child with
-//                       the largest surface area until 8 slots are used,
+//                       the largest surface area until 7 slots are used,
 //                       subtrees of <= 3 triangles become leaf children;
 //                       octant-ordered slots + quantisation exactly like the
 //                       host builder; triangle records written in leaf order
 //
 // Every step is a B200_HD function of an element index so that
 // tests/host_preflight.cpp can run the identical code on the CPU (sequentially)
-// and check the result with validate_bvh8 and against the oracle before GPU
+// and check the result with validate_wbvh and against the oracle before GPU
 // time is spent.  The tree's topology is not part of the parity contract:
 // closest hits are decided by the exact triangle test.
 #ifndef B200PT_LBVH_CUH
 #define B200PT_LBVH_CUH
 
-#include "bvh8.h"
+#include "wbvh.h"
 #include "pt_core.cuh"
 
 namespace b200pt {
@@ -36,7 +36,7 @@ namespace b200pt {
 
 struct LbvhItem {
     int32_t node2;   // binary node to expand (internal id, or ~leaf for a single-triangle root)
-    uint32_t wide;   // index of the 8-wide node to fill
+    uint32_t wide;   // index of the wide node to fill
 };
 
 struct LbvhCtx {
@@ -50,7 +50,8 @@ struct LbvhCtx {
     // ---- pass 1/2
     uint32_t *valid_idx;          // triangles that enter the tree
     uint32_t *n_valid;            // counter
-    int32_t *cbounds;             // centroid bounds as ordered ints: min xyz, max xyz
+    int32_t *cbounds;             // centroid bounds as ordered ints: min xyz, max xyz; then the triangles' bounds [6..11]
+    float cell_floor;             // smallest cell of the quantisation grids (set by the host before the collapse)
     uint64_t *keys;               // Morton keys (sorted in place with `sorted`)
     uint32_t *sorted;             // triangle ids in key order
     int64_t m;                    // = *n_valid, set by the host before pass 3
@@ -61,7 +62,8 @@ struct LbvhCtx {
     float *nbox;                  // [m-1][6]
     uint32_t *arrivals;           // [m-1]
     // ---- output
-    Bvh8Node *nodes;
+    WbvhNode *nodes;
+    uint32_t *tri_base;           // parallel to nodes
     uint64_t node_cap;            // allocated wide nodes (writes beyond it are dropped; the driver reports the overflow)
     TriRecord *tris;
     uint32_t *prim_to_tri;        // [n], 0xffffffff until placed
@@ -155,6 +157,8 @@ B200_HD void lbvh_prep(const LbvhCtx &c, int64_t i) {
         const float cen = 0.5f * b.lo[a] + 0.5f * b.hi[a];
         lb_atomic_min(c.cbounds + a, lb_float_to_ordered(cen));
         lb_atomic_max(c.cbounds + 3 + a, lb_float_to_ordered(cen));
+        lb_atomic_min(c.cbounds + 6 + a, lb_float_to_ordered(b.lo[a]));
+        lb_atomic_max(c.cbounds + 9 + a, lb_float_to_ordered(b.hi[a]));
     }
 }
 
@@ -260,8 +264,9 @@ B200_HD int32_t lb_count(const LbvhCtx &c, int32_t child) { return child < 0 ? 1
 
 // ---- 5. one wide node: choose its children, place them, quantise, write triangles, queue inner children
 B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
-    int32_t ch[8];
-    LbBox box[8];
+    constexpr int W = B200PT_WIDTH;
+    int32_t ch[W];
+    LbBox box[W];
     int k = 0;
     if (it.node2 < 0) {
         ch[k] = it.node2;  // a single triangle: one leaf child of the root
@@ -273,7 +278,7 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
         lb_child_box(c, ch[0], &box[0]);
         lb_child_box(c, ch[1], &box[1]);
         k = 2;
-        while (k < 8) {
+        while (k < W) {
             int best = -1;
             float bestArea = -1.f;
             for (int i = 0; i < k; ++i) {
@@ -301,54 +306,12 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
             ++k;
         }
     }
-    // node bounds, octant-ordered slots (greedy assignment on dot(centroid offset, octant direction))
-    LbBox nb;
-    for (int a = 0; a < 3; ++a) {
-        nb.lo[a] = box[0].lo[a];
-        nb.hi[a] = box[0].hi[a];
-    }
-    for (int i = 1; i < k; ++i)
-        for (int a = 0; a < 3; ++a) {
-            nb.lo[a] = pt_min(nb.lo[a], box[i].lo[a]);
-            nb.hi[a] = pt_max(nb.hi[a], box[i].hi[a]);
-        }
-    float nc[3];
-    for (int a = 0; a < 3; ++a) nc[a] = 0.5f * nb.lo[a] + 0.5f * nb.hi[a];
-    float cost[8][8];
-    for (int i = 0; i < k; ++i) {
-        float cc[3];
-        for (int a = 0; a < 3; ++a) cc[a] = 0.5f * box[i].lo[a] + 0.5f * box[i].hi[a] - nc[a];
-        for (int s = 0; s < 8; ++s)
-            cost[i][s] = ((s & 1) ? cc[0] : -cc[0]) + ((s & 2) ? cc[1] : -cc[1]) + ((s & 4) ? cc[2] : -cc[2]);
-    }
-    int childAt[8];
-    bool slotUsed[8], childDone[8];
-    for (int s = 0; s < 8; ++s) {
-        childAt[s] = -1;
-        slotUsed[s] = childDone[s] = false;
-    }
-    for (int round = 0; round < k; ++round) {
-        int bi = -1, bs = -1;
-        float bc = 0.f;
-        for (int i = 0; i < k; ++i) {
-            if (childDone[i]) continue;
-            for (int s = 0; s < 8; ++s)
-                if (!slotUsed[s] && (bi < 0 || cost[i][s] > bc)) {
-                    bc = cost[i][s];
-                    bi = i;
-                    bs = s;
-                }
-        }
-        childDone[bi] = true;
-        slotUsed[bs] = true;
-        childAt[bs] = bi;
-    }
     // A subtree of 2-3 triangles that found no free slots is either a leaf child (every ray entering its box tests
     // all its triangles: A*n) or a small wide node of its own (A for the node + the triangles' own boxes).
-    bool isLeaf[8];
+    uint8_t ntri[W];
     for (int i = 0; i < k; ++i) {
         const int32_t cnt = lb_count(c, ch[i]);
-        isLeaf[i] = ch[i] < 0;
+        bool isLeaf = ch[i] < 0;
         if (ch[i] >= 0 && cnt <= 3) {
             float triAreas = 0.f;
             for (int32_t t = 0; t < cnt; ++t) {
@@ -357,16 +320,26 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
                 triAreas += lb_half_area(tb);
             }
             const float A = lb_half_area(box[i]);
-            isLeaf[i] = LBVH_OPEN_SMALL == 0 || A * (float)cnt <= A + triAreas;
+            isLeaf = LBVH_OPEN_SMALL == 0 || A * (float)cnt <= A + triAreas;
         }
+        ntri[i] = isLeaf ? (uint8_t)cnt : 0;
     }
+    // octant-ordered slots + quantisation, identical to the host builder (wbvh.h)
+    WbBox wb[W];
+    for (int i = 0; i < k; ++i)
+        for (int a = 0; a < 3; ++a) {
+            wb[i].lo[a] = box[i].lo[a];
+            wb[i].hi[a] = box[i].hi[a];
+        }
+    int childAt[W];
+    wbvh_assign_slots(wb, k, childAt);
     // allocation: inner children contiguous in slot order, leaf triangles contiguous in slot order
     uint32_t nInner = 0, nTri = 0;
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < W; ++s) {
         const int i = childAt[s];
         if (i < 0) continue;
-        if (isLeaf[i])
-            nTri += (uint32_t)lb_count(c, ch[i]);
+        if (ntri[i])
+            nTri += (uint32_t)ntri[i];
         else
             ++nInner;
     }
@@ -374,45 +347,15 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
     const uint32_t triBase = nTri ? lb_atomic_add(c.n_tris, nTri) : 0u;
     const uint32_t qBase = nInner ? lb_atomic_add(c.q_out_count, nInner) : 0u;
 
-    Bvh8Node node;
-    node.imask = 0;
-    for (int s = 0; s < 8; ++s) {
-        node.meta[s] = 0;
-        for (int a = 0; a < 3; ++a) node.qlo[a][s] = node.qhi[a][s] = 0;
-    }
-    float scale[3];
-    for (int a = 0; a < 3; ++a) {  // quantisation grid, identical to the host builder (bvh8_build.cpp)
-        const float ext = nb.hi[a] - nb.lo[a];
-        const float mag = pt_max(pt_abs(nb.lo[a]), pt_abs(nb.hi[a]));
-        const float need = pt_max(ext / 253.f, pt_max(mag * 0x1p-18f, 1e-30f));
-        int e;
-        const float mant = frexpf(need, &e);  // need = mant * 2^e, mant in [0.5, 1)
-        if (mant == 0.5f) e -= 1;
-        const int be = pt_mini(254, pt_maxi(1, e + 127));
-        node.e[a] = (uint8_t)be;
-        scale[a] = uint_as_float((uint32_t)be << 23);
-        node.p[a] = nb.lo[a] - scale[a];
-    }
+    WbvhNode node;
+    wbvh_encode_node(wb, childAt, ntri, c.cell_floor, &node);
     node.child_base = childBase;
-    node.tri_base = triBase;
     uint32_t triOffset = 0, innerRank = 0;
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < W; ++s) {
         const int i = childAt[s];
         if (i < 0) continue;
-        for (int a = 0; a < 3; ++a) {
-            const float lo = floorf((box[i].lo[a] - node.p[a]) / scale[a]) - 1.f;
-            const float hi = ceilf((box[i].hi[a] - node.p[a]) / scale[a]) + 1.f;
-            int qlo = (int)pt_min(255.f, pt_max(0.f, lo));
-            int qhi = (int)pt_min(255.f, pt_max(0.f, hi));
-            while (qlo > 0 && node.p[a] + (float)qlo * scale[a] > box[i].lo[a]) --qlo;
-            while (qhi < 255 && node.p[a] + (float)qhi * scale[a] < box[i].hi[a]) ++qhi;
-            node.qlo[a][s] = (uint8_t)qlo;
-            node.qhi[a][s] = (uint8_t)qhi;
-        }
         const int32_t cnt = lb_count(c, ch[i]);
-        if (isLeaf[i]) {
-            const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
-            node.meta[s] = (uint8_t)((unary << 5) | triOffset);
+        if (ntri[i]) {
             const int64_t f0 = ch[i] < 0 ? (int64_t)(~ch[i]) : (int64_t)c.first[ch[i]];
             for (int32_t t = 0; t < cnt; ++t) {
                 const uint32_t tri = c.sorted[f0 + t];
@@ -434,8 +377,6 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
             }
             triOffset += (uint32_t)cnt;
         } else {
-            node.imask |= (uint8_t)(1u << s);
-            node.meta[s] = (uint8_t)((1u << 5) | (24 + s));
             LbvhItem next;
             next.node2 = ch[i];
             next.wide = childBase + innerRank;
@@ -443,7 +384,10 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
             ++innerRank;
         }
     }
-    if (it.wide < c.node_cap) c.nodes[it.wide] = node;
+    if (it.wide < c.node_cap) {
+        c.nodes[it.wide] = node;
+        c.tri_base[it.wide] = triBase;
+    }
 }
 
 // ---- 6. triangles that never enter the tree still need records (an area light may sit on one)

@@ -452,6 +452,7 @@ struct DevInstance {
     float leaf_lo[3], leaf_hi[3];  // bounds of the host accelerator's leaf holding the instance
     float world_lo[3], world_hi[3];  // TransformedPrimitive::WorldBound()
     uint32_t node_off, tri_off;    // the object's BVH inside the scene's node / triangle arrays
+    float obj_lo[3], obj_hi[3], obj_scale;  // padded object-space bounds of that BVH (TravBounds of wbvh_traverse.cuh)
 };
 // Transform::operator()(const Ray &) with WorldToInstance (transform.h:251-264): origin pushed to the edge of its
 // error bounds, tMax shortened by the same step

@@ -1,4 +1,4 @@
-// bvh8_build.cpp -- host builder of the 8-wide compressed BVH (see bvh8.h).
+// wbvh_build.cpp -- host builder of the 7-wide compressed BVH (see wbvh.h).
 //
 // Replaces BVHAccel's constructor (accelerators/bvh.cpp:183-225: SAH
 // recursiveBuild :236-402, flattenBVHTree :640-658).  The tree topology is
@@ -6,17 +6,16 @@
 // watertight triangle test and are topology independent (DESIGN.md,
 // "Traversal order and ties") -- so the build is designed for the GPU
 // traversal kernel, not to mimic the reference's binary tree:
-//   1. binary BVH by binned SAH (16 bins), leaves of <= 3 triangles, built
+//   1. binary BVH by binned SAH (16 bins) down to single triangles, built
 //      top-down with one std::thread per large subtree;
-//   2. greedy collapse to 8 children per node (open the child with the
-//      largest surface area until 8 slots are used);
-//   3. children placed in octant-ordered slots (greedy assignment on
-//      dot(centroid offset, octant direction)) so that visiting slots by
-//      (slot XOR ray octant) approximates front-to-back order;
+//   2. SAH-optimal collapse to 7 children per node (dynamic programme of
+//      Ylitie et al. 2017, section 3.1; leaves of <= 3 triangles);
+//   3. children placed in octant-ordered slots (wbvh_assign_slots) so that
+//      visiting slots by (slot XOR ray octant) approximates front-to-back order;
 //   4. child boxes quantised to 8 bits per coordinate on a power-of-two grid
-//      anchored one cell below the node's min corner, rounded outward by one
-//      extra cell on every side (the traversal kernel's fused slab arithmetic may be
-//      off by up to half a cell; a second cell of slack costs 7 % more node visits).
+//      anchored at the node's min corner, rounded outward in exact arithmetic
+//      (wbvh_encode_node); the traversal kernel decodes the bytes exactly and
+//      adds its own fraction-of-a-cell slack for float rounding.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -26,7 +25,7 @@
 #include <chrono>
 #include <thread>
 
-#include "bvh8.h"
+#include "wbvh.h"
 
 namespace b200pt {
 namespace {
@@ -176,9 +175,10 @@ struct Child {
 
 }  // namespace
 
-void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_id, const int32_t *light_id,
-                const uint8_t *flip, const uint8_t *degenerate, int n_threads, Bvh8 *out) {
+void build_wbvh(const float *vertices, int64_t n_tris, const int32_t *material_id, const int32_t *light_id,
+                const uint8_t *flip, const uint8_t *degenerate, int n_threads, Wbvh *out) {
     out->nodes.clear();
+    out->tri_base.clear();
     out->tris.clear();
     out->prim_to_tri.assign((size_t)n_tris, 0xffffffffu);
     out->n_in_leaves = 0;
@@ -231,36 +231,37 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
         auto tp1 = tnow();
 
         // ---- SAH-optimal collapse (Ylitie et al. 2017, section 3.1): cost[n][i-1] is the cheapest
-        // way to represent the binary subtree n with at most i roots (i = 1..7); a single root is
-        // either a leaf child (<= 3 triangles) or an 8-wide node whose children come from
-        // distributing the two binary children over 8 slots.
+        // way to represent the binary subtree n with at most i roots (i = 1..W-1); a single root is
+        // either a leaf child (<= 3 triangles) or a W-wide node whose children come from
+        // distributing the two binary children over W slots.
+        constexpr int W = B200PT_WIDTH, R = W - 1;
         const int32_t nNodes2 = b2.next_node.load();
         float cNode = 1.0f, cPrim = 1.0f;  // a watertight triangle test costs about as many instructions as a node
         if (const char *e = getenv("B200PT_SAH_CNODE")) cNode = (float)atof(e);
         if (const char *e = getenv("B200PT_SAH_CPRIM")) cPrim = (float)atof(e);
-        std::vector<float> cost((size_t)nNodes2 * 7);
-        std::vector<uint8_t> dec((size_t)nNodes2 * 7);   // i=1: 0 leaf / 1 inner ; i>=2: 0 = reuse i-1, k = left gets k roots
-        std::vector<uint8_t> split8((size_t)nNodes2);    // left share when the node becomes an 8-wide node
+        std::vector<float> cost((size_t)nNodes2 * R);
+        std::vector<uint8_t> dec((size_t)nNodes2 * R);   // i=1: 0 leaf / 1 inner ; i>=2: 0 = reuse i-1, k = left gets k roots
+        std::vector<uint8_t> splitW((size_t)nNodes2);    // left share when the node becomes a wide node
         for (int32_t n = nNodes2 - 1; n >= 0; --n) {
             const Node2 &nd = b2.nodes[n];
-            float *c = &cost[(size_t)n * 7];
-            uint8_t *d = &dec[(size_t)n * 7];
+            float *c = &cost[(size_t)n * R];
+            uint8_t *d = &dec[(size_t)n * R];
             const float A = nd.box.half_area();
             const float leafCost = nd.ntri <= 3 ? A * nd.ntri * cPrim : INFINITY;
             if (nd.count > 0) {  // single triangle
-                for (int i = 0; i < 7; ++i) {
+                for (int i = 0; i < R; ++i) {
                     c[i] = leafCost;
                     d[i] = 0;
                 }
-                split8[n] = 0;
+                splitW[n] = 0;
                 continue;
             }
-            const float *cl = &cost[(size_t)nd.left * 7], *cr = &cost[(size_t)nd.right * 7];
+            const float *cl = &cost[(size_t)nd.left * R], *cr = &cost[(size_t)nd.right * R];
             auto distribute = [&](int j, int *bestK) {
                 float best = INFINITY;
                 *bestK = 1;
                 for (int k = 1; k < j; ++k) {
-                    if (k > 7 || j - k > 7) continue;
+                    if (k > R || j - k > R) continue;
                     float v = cl[k - 1] + cr[j - k - 1];
                     if (v < best) {
                         best = v;
@@ -269,9 +270,9 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
                 }
                 return best;
             };
-            int k8;
-            const float innerCost = distribute(8, &k8) + A * cNode;
-            split8[n] = (uint8_t)k8;
+            int kW;
+            const float innerCost = distribute(W, &kW) + A * cNode;
+            splitW[n] = (uint8_t)kW;
             if (leafCost <= innerCost) {
                 c[0] = leafCost;
                 d[0] = 0;
@@ -279,7 +280,7 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
                 c[0] = innerCost;
                 d[0] = 1;
             }
-            for (int i = 2; i <= 7; ++i) {
+            for (int i = 2; i <= R; ++i) {
                 int k;
                 float v = distribute(i, &k);
                 if (v < c[i - 2]) {
@@ -301,143 +302,98 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
             void collect(int32_t n, int budget) {
                 const Node2 &nd = b2.nodes[n];
                 int i = budget;
-                while (i >= 2 && dec[(size_t)n * 7 + i - 1] == 0) --i;  // reuse the (i-1)-root solution
+                while (i >= 2 && dec[(size_t)n * R + i - 1] == 0) --i;  // reuse the (i-1)-root solution
                 if (i == 1 || nd.count > 0) {
                     ch[k++] = {n, nd.box};
                     return;
                 }
-                const int kl = dec[(size_t)n * 7 + i - 1];
+                const int kl = dec[(size_t)n * R + i - 1];
                 collect(nd.left, kl);
                 collect(nd.right, i - kl);
             }
         };
 
-        // ---- emit 8-wide nodes breadth-first so siblings are contiguous
+        // ---- emit the wide nodes breadth-first so siblings are contiguous
         struct Pending {
             int32_t node2;
             uint32_t wide;
             int depth;
         };
+        float absmax = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            const Box &rb = b2.nodes[root].box;
+            out->bounds_lo[a] = rb.lo[a];
+            out->bounds_hi[a] = rb.hi[a];
+            absmax = std::max(absmax, std::max(std::fabs(rb.lo[a]), std::fabs(rb.hi[a])));
+        }
+        const float cell_floor = B200PT_CELL_FLOOR * absmax;
         std::vector<Pending> queue;
         out->nodes.reserve((size_t)nLeafTris / 3 + 16);
-        out->nodes.push_back(Bvh8Node());
+        out->nodes.push_back(WbvhNode());
         queue.push_back({root, 0u, 1});
         for (size_t qi = 0; qi < queue.size(); ++qi) {
             Pending cur = queue[qi];
             out->max_depth = std::max(out->max_depth, cur.depth);
-            Child ch[8];
+            Child ch[W];
             int k = 0;
             const Node2 &rn = b2.nodes[cur.node2];
-            if (rn.count > 0 || (cur.node2 == root && dec[(size_t)root * 7] == 0)) {
+            if (rn.count > 0 || (cur.node2 == root && dec[(size_t)root * R] == 0)) {
                 ch[k++] = {cur.node2, rn.box};  // the whole scene is one leaf child of the root
             } else {
                 Collector col{b2, dec, ch, 0};
-                col.collect(rn.left, split8[cur.node2]);
-                col.collect(rn.right, 8 - split8[cur.node2]);
+                col.collect(rn.left, splitW[cur.node2]);
+                col.collect(rn.right, W - splitW[cur.node2]);
                 k = col.k;
             }
-            // node bounds and centroid
-            Box nb;
-            nb.reset();
-            for (int i = 0; i < k; ++i) nb.grow(ch[i].box);
-            float nc[3];
-            for (int a = 0; a < 3; ++a) nc[a] = 0.5f * nb.lo[a] + 0.5f * nb.hi[a];
-            // octant-ordered slot assignment (greedy)
-            int slotOf[8];
-            bool slotUsed[8] = {false, false, false, false, false, false, false, false};
-            bool childDone[8] = {false, false, false, false, false, false, false, false};
-            float cost[8][8];
+            WbBox box[W];
+            uint8_t ntri[W];
             for (int i = 0; i < k; ++i) {
-                float cc[3];
-                for (int a = 0; a < 3; ++a) cc[a] = 0.5f * ch[i].box.lo[a] + 0.5f * ch[i].box.hi[a] - nc[a];
-                for (int s = 0; s < 8; ++s)
-                    cost[i][s] = ((s & 1) ? cc[0] : -cc[0]) + ((s & 2) ? cc[1] : -cc[1]) + ((s & 4) ? cc[2] : -cc[2]);
+                memcpy(box[i].lo, ch[i].box.lo, 12);
+                memcpy(box[i].hi, ch[i].box.hi, 12);
+                const Node2 &c = b2.nodes[ch[i].node2];
+                const bool isLeaf = c.count > 0 || dec[(size_t)ch[i].node2 * R] == 0;
+                ntri[i] = isLeaf ? (uint8_t)c.ntri : 0;
             }
-            for (int it = 0; it < k; ++it) {
-                int bi = -1, bs = -1;
-                float bc = -INFINITY;
-                for (int i = 0; i < k; ++i) {
-                    if (childDone[i]) continue;
-                    for (int s = 0; s < 8; ++s)
-                        if (!slotUsed[s] && (cost[i][s] > bc || bi < 0)) {
-                            bc = cost[i][s];
-                            bi = i;
-                            bs = s;
-                        }
-                }
-                childDone[bi] = true;
-                slotUsed[bs] = true;
-                slotOf[bi] = bs;
-            }
-            int childAt[8];
-            for (int s = 0; s < 8; ++s) childAt[s] = -1;
-            for (int i = 0; i < k; ++i) childAt[slotOf[i]] = i;
-
-            Bvh8Node node;
+            int childAt[W];
+            wbvh_assign_slots(box, k, childAt);
+            WbvhNode node;
             memset(&node, 0, sizeof(node));
-            // quantisation grid
-            float scale[3];
-            for (int a = 0; a < 3; ++a) {
-                float ext = nb.hi[a] - nb.lo[a];
-                float mag = std::max(std::fabs(nb.lo[a]), std::fabs(nb.hi[a]));
-                float need = std::max(ext / 253.f, std::max(mag * 0x1p-18f, 1e-30f));
-                int e;
-                float m = std::frexp(need, &e);  // need = m * 2^e, m in [0.5,1)
-                if (m == 0.5f) e -= 1;           // exact power of two
-                int be = std::min(254, std::max(1, e + 127));
-                node.e[a] = (uint8_t)be;
-                uint32_t bits = (uint32_t)be << 23;
-                memcpy(&scale[a], &bits, 4);
-                node.p[a] = nb.lo[a] - scale[a];
-            }
+            wbvh_encode_node(box, childAt, ntri, cell_floor, &node);
             node.child_base = (uint32_t)out->nodes.size();
-            node.tri_base = (uint32_t)out->tris.size();
-            int triOffset = 0;
-            for (int s = 0; s < 8; ++s) {
-                int i = childAt[s];
+            const uint32_t triBase = (uint32_t)out->tris.size();
+            for (int s = 0; s < W; ++s) {
+                const int i = childAt[s];
                 if (i < 0) continue;
                 const Node2 &c = b2.nodes[ch[i].node2];
-                const bool isLeaf = c.count > 0 || dec[(size_t)ch[i].node2 * 7] == 0;
-                for (int a = 0; a < 3; ++a) {
-                    float lo = std::floor((ch[i].box.lo[a] - node.p[a]) / scale[a]) - 1.f;
-                    float hi = std::ceil((ch[i].box.hi[a] - node.p[a]) / scale[a]) + 1.f;
-                    int qlo = (int)std::min(255.f, std::max(0.f, lo));
-                    int qhi = (int)std::min(255.f, std::max(0.f, hi));
-                    // make sure the decode the kernel performs (p + q*scale in float) is conservative
-                    while (qlo > 0 && node.p[a] + (float)qlo * scale[a] > ch[i].box.lo[a]) --qlo;
-                    while (qhi < 255 && node.p[a] + (float)qhi * scale[a] < ch[i].box.hi[a]) ++qhi;
-                    node.qlo[a][s] = (uint8_t)qlo;
-                    node.qhi[a][s] = (uint8_t)qhi;
-                }
-                if (isLeaf) {
-                    const uint8_t unary[4] = {0, 1, 3, 7};
-                    node.meta[s] = (uint8_t)((unary[c.ntri] << 5) | triOffset);
+                if (ntri[i]) {
                     for (int t = 0; t < c.ntri; ++t) {
                         int32_t tri = b2.idx[c.first + t];
                         out->prim_to_tri[tri] = (uint32_t)out->tris.size();
                         out->tris.push_back(make_tri(tri));
                     }
-                    triOffset += c.ntri;
                 } else {
-                    node.imask |= (uint8_t)(1u << s);
-                    node.meta[s] = (uint8_t)((1u << 5) | (24 + s));
                     queue.push_back({ch[i].node2, (uint32_t)out->nodes.size(), cur.depth + 1});
-                    out->nodes.push_back(Bvh8Node());
+                    out->nodes.push_back(WbvhNode());
                 }
             }
             out->nodes[cur.wide] = node;
+            if (out->tri_base.size() < out->nodes.size()) out->tri_base.resize(out->nodes.size(), 0u);
+            out->tri_base[cur.wide] = triBase;
         }
+        out->tri_base.resize(out->nodes.size(), 0u);
         out->n_in_leaves = (uint32_t)out->tris.size();
         if (trace)
-            fprintf(stderr, "bvh8 build: binary SAH %.3f s, collapse DP %.3f s, emit %.3f s\n",
+            fprintf(stderr, "wbvh build: binary SAH %.3f s, collapse DP %.3f s, emit %.3f s\n",
                     std::chrono::duration<double>(tp1 - tp0).count(), std::chrono::duration<double>(tp2 - tp1).count(),
                     std::chrono::duration<double>(tnow() - tp2).count());
     } else {
         // empty scene: a root with no children
-        Bvh8Node node;
+        WbvhNode node;
         memset(&node, 0, sizeof(node));
-        node.e[0] = node.e[1] = node.e[2] = 127;
+        const int none[B200PT_WIDTH] = {-1, -1, -1, -1, -1, -1, -1};
+        wbvh_encode_node(nullptr, none, nullptr, 1.f, &node);
         out->nodes.push_back(node);
+        out->tri_base.push_back(0u);
         out->max_depth = 1;
     }
     // triangles that can never be hit still need records (an area light may sit on one)
@@ -448,36 +404,44 @@ void build_bvh8(const float *vertices, int64_t n_tris, const int32_t *material_i
         }
 }
 
-int64_t validate_bvh8(const Bvh8 &bvh) {
+int64_t validate_wbvh(const Wbvh &bvh) {
     int64_t bad = 0;
-    std::vector<Box> nodeBox(bvh.nodes.size());
-    // decoded slot boxes must contain what they refer to
-    auto slot_box = [](const Bvh8Node &n, int s) {
-        Box b;
+    if (bvh.tri_base.size() != bvh.nodes.size()) ++bad;
+    // decoded slot boxes must contain what they refer to (p + q * cell is exact in double)
+    struct BoxD {
+        double lo[3], hi[3];
+    };
+    auto slot_box = [](const WbvhNode &n, int s) {
+        BoxD b;
         for (int a = 0; a < 3; ++a) {
-            uint32_t bits = (uint32_t)n.e[a] << 23;
-            float sc;
-            memcpy(&sc, &bits, 4);
-            b.lo[a] = n.p[a] + (float)n.qlo[a][s] * sc;
-            b.hi[a] = n.p[a] + (float)n.qhi[a][s] * sc;
+            const double c = wb_cell(n.e[a]);
+            const int lo = a == 2 ? n.zq[s][0] : n.xyq[s][2 * a], hi = a == 2 ? n.zq[s][1] : n.xyq[s][2 * a + 1];
+            b.lo[a] = (double)n.p[a] + lo * c;
+            b.hi[a] = (double)n.p[a] + hi * c;
         }
         return b;
     };
-    // exact box of each wide node = union of decoded slots is an over-estimate; compute true
-    // content bounds bottom-up (children have larger indices than their parents)
+    // true content bounds bottom-up (children have larger indices than their parents)
     std::vector<Box> content(bvh.nodes.size());
     for (int64_t ni = (int64_t)bvh.nodes.size() - 1; ni >= 0; --ni) {
-        const Bvh8Node &n = bvh.nodes[ni];
+        const WbvhNode &n = bvh.nodes[ni];
         Box cb;
         cb.reset();
-        uint32_t inner = 0;
-        for (int s = 0; s < 8; ++s) {
-            uint8_t m = n.meta[s];
-            if (m == 0) continue;
-            Box sb = slot_box(n, s);
+        uint32_t inner = 0, triOff = 0;
+        for (int s = 0; s < B200PT_WIDTH; ++s) {
+            const int cnt = (n.lcount >> (2 * s)) & 3;
+            const bool isInner = (n.imask >> s) & 1;
+            if (isInner && cnt) ++bad;
+            if (!isInner && !cnt) {
+                if (n.xyq[s][0] != B200PT_EMPTY_LO || n.xyq[s][1] != 0 || n.xyq[s][2] != B200PT_EMPTY_LO || n.xyq[s][3] != 0 ||
+                    n.zq[s][0] != B200PT_EMPTY_LO || n.zq[s][1] != 0)
+                    ++bad;
+                continue;
+            }
+            const BoxD sb = slot_box(n, s);
             Box got;
             got.reset();
-            if (n.imask & (1u << s)) {
+            if (isInner) {
                 uint32_t child = n.child_base + inner++;
                 if (child >= bvh.nodes.size() || child <= (uint32_t)ni) {
                     ++bad;
@@ -485,16 +449,21 @@ int64_t validate_bvh8(const Bvh8 &bvh) {
                 }
                 got = content[child];
             } else {
-                int cnt = __builtin_popcount(m >> 5), off = m & 31;
                 for (int t = 0; t < cnt; ++t) {
-                    const TriRecord &tr = bvh.tris[n.tri_base + off + t];
+                    const size_t ti = (size_t)bvh.tri_base[ni] + triOff + t;
+                    if (ti >= bvh.tris.size()) {
+                        ++bad;
+                        continue;
+                    }
+                    const TriRecord &tr = bvh.tris[ti];
                     got.grow(tr.p0);
                     got.grow(tr.p1);
                     got.grow(tr.p2);
                 }
+                triOff += cnt;
             }
             for (int a = 0; a < 3; ++a)
-                if (!(sb.lo[a] <= got.lo[a]) || !(sb.hi[a] >= got.hi[a])) ++bad;
+                if (!(sb.lo[a] <= (double)got.lo[a]) || !(sb.hi[a] >= (double)got.hi[a])) ++bad;
             cb.grow(got);
         }
         content[ni] = cb;

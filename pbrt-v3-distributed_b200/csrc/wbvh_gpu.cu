@@ -1,7 +1,7 @@
-// bvh8_gpu.cu -- on-device build of the 8-wide BVH (lbvh.cuh has the per-element
+// wbvh_gpu.cu -- on-device build of the 7-wide BVH (lbvh.cuh has the per-element
 // steps and the rationale).  Selected with b200pt_ctx_set_option(ctx,
 // "gpu_bvh_build", 1) or B200PT_BVH_BUILD=gpu; the default stays the host SAH
-// builder (bvh8_build.cpp), whose trees traverse faster.  The only library call
+// builder (wbvh_build.cpp), whose trees traverse faster.  The only library call
 // is the radix sort of the (Morton key, triangle) pairs (CUB); everything else
 // is kernels over lbvh.cuh.
 #include <cub/device/device_radix_sort.cuh>
@@ -9,10 +9,11 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
-#include "bvh8_gpu.h"
+#include "wbvh_gpu.h"
 #include "lbvh.cuh"
 
 namespace b200pt {
@@ -71,7 +72,7 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)std::max<int64_t>(
         }                                             \
     } while (0)
 
-bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *out, char *err, size_t err_len) {
+bool build_wbvh_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *out, char *err, size_t err_len) {
     const int64_t n = in.n_tris;
     Scratch tmp;
     LbvhCtx c;
@@ -85,7 +86,7 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
     float *d_uvs = in.uvs ? tmp.alloc<float>((size_t)n * 6) : nullptr;
     c.valid_idx = tmp.alloc<uint32_t>((size_t)n);
     uint32_t *d_counters = tmp.alloc<uint32_t>(8);  // n_valid, n_nodes, n_tris, q_out_count
-    c.cbounds = tmp.alloc<int32_t>(6);
+    c.cbounds = tmp.alloc<int32_t>(12);
     if (tmp.err != cudaSuccess) GB_TRY(tmp.err);
     if (n) {
         GB_TRY(cudaMemcpyAsync(d_vertices, in.vertices, (size_t)n * 36, cudaMemcpyHostToDevice, st));
@@ -108,7 +109,7 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
     c.n_tris = d_counters + 2;
     c.q_out_count = d_counters + 3;
     const uint32_t counters0[8] = {0, 1, 0, 0, 0, 0, 0, 0};  // node 0 = root
-    const int32_t bounds0[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    const int32_t bounds0[12] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     GB_TRY(cudaMemcpyAsync(d_counters, counters0, sizeof(counters0), cudaMemcpyHostToDevice, st));
     GB_TRY(cudaMemcpyAsync(c.cbounds, bounds0, sizeof(bounds0), cudaMemcpyHostToDevice, st));
     // outputs (final size of the triangle array is known: every triangle gets a record)
@@ -124,11 +125,24 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
     GB_TRY(cudaStreamSynchronize(st));
     const int64_t m = m32;
     c.m = m;
+    {   // bounds of the triangles in the tree -> smallest cell of the quantisation grids (wbvh.h)
+        int32_t tb[6];
+        GB_TRY(cudaMemcpy(tb, c.cbounds + 6, sizeof(tb), cudaMemcpyDeviceToHost));
+        float absmax = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            out->bounds_lo[a] = m ? lb_ordered_to_float(tb[a]) : 0.f;
+            out->bounds_hi[a] = m ? lb_ordered_to_float(tb[3 + a]) : 0.f;
+            absmax = std::max(absmax, std::max(std::fabs(out->bounds_lo[a]), std::fabs(out->bounds_hi[a])));
+        }
+        c.cell_floor = B200PT_CELL_FLOOR * absmax;
+    }
     // wide nodes: every node other than the root holds at least two triangles and a node with a large inner child
-    // always has 8 children, hence fewer than m nodes (lbvh.cuh)
+    // always has 7 children, hence fewer than m nodes (lbvh.cuh)
     const size_t node_cap = (size_t)m + 16;
-    Bvh8Node *d_nodes_tmp = tmp.alloc<Bvh8Node>(node_cap);
+    WbvhNode *d_nodes_tmp = tmp.alloc<WbvhNode>(node_cap);
+    uint32_t *d_tri_base_tmp = tmp.alloc<uint32_t>(node_cap);
     c.nodes = d_nodes_tmp;
+    c.tri_base = d_tri_base_tmp;
     c.node_cap = node_cap;
     int depth = 1;
     if (m > 0) {
@@ -184,10 +198,13 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
         }
     } else {
         // empty scene: a root with no children (same record as the host builder)
-        Bvh8Node node;
+        WbvhNode node;
         memset(&node, 0, sizeof(node));
-        node.e[0] = node.e[1] = node.e[2] = 127;
+        const int none[B200PT_WIDTH] = {-1, -1, -1, -1, -1, -1, -1};
+        wbvh_encode_node(nullptr, none, nullptr, 1.f, &node);
         GB_TRY(cudaMemcpyAsync(d_nodes_tmp, &node, sizeof(node), cudaMemcpyHostToDevice, st));
+        GB_TRY(cudaMemsetAsync(d_tri_base_tmp, 0, 4, st));
+        GB_TRY(cudaStreamSynchronize(st));
     }
     uint32_t counts[3];
     GB_TRY(cudaMemcpyAsync(counts, d_counters, sizeof(counts), cudaMemcpyDeviceToHost, st));
@@ -202,8 +219,10 @@ bool build_bvh8_gpu(const GpuBuildInput &in, cudaStream_t st, GpuBuildOutput *ou
         snprintf(err, err_len, "gpu bvh build: node estimate exceeded (%u > %zu)", counts[1], node_cap);
         return false;
     }
-    GB_TRY(cudaMalloc(&out->d_nodes, std::max<size_t>(1, out->n_nodes) * sizeof(Bvh8Node)));
-    GB_TRY(cudaMemcpyAsync(out->d_nodes, d_nodes_tmp, out->n_nodes * sizeof(Bvh8Node), cudaMemcpyDeviceToDevice, st));
+    GB_TRY(cudaMalloc(&out->d_nodes, std::max<size_t>(1, out->n_nodes) * sizeof(WbvhNode)));
+    GB_TRY(cudaMalloc(&out->d_tri_base, std::max<size_t>(1, out->n_nodes) * sizeof(uint32_t)));
+    GB_TRY(cudaMemcpyAsync(out->d_nodes, d_nodes_tmp, out->n_nodes * sizeof(WbvhNode), cudaMemcpyDeviceToDevice, st));
+    GB_TRY(cudaMemcpyAsync(out->d_tri_base, d_tri_base_tmp, out->n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     GB_TRY(cudaStreamSynchronize(st));
     GB_TRY(cudaGetLastError());
     return true;

@@ -8,7 +8,7 @@
 // of every kernel against the oracle on a box without a GPU, the way tests/host_preflight.cpp pre-flights the
 // math headers.  It is a checker of the sources, not a renderer: the package never loads it, nothing ships it,
 // and it is ~1000x slower than the reference it is checked against.  The warp-synchronous traversal kernel
-// k_trace is the one piece it cannot execute; its rays go through traverse_bvh8 (bvh8_traverse.cuh), the same
+// k_trace is the one piece it cannot execute; its rays go through traverse_wbvh (wbvh_traverse.cuh), the same
 // per-ray routine the kernel's lanes step through.
 #ifndef B200PT_EMU_CUDA_RUNTIME_H
 #define B200PT_EMU_CUDA_RUNTIME_H

@@ -3,10 +3,10 @@
 // unavailable, so `gpu_bvh_build` scenes fail loudly instead of silently taking the host builder.
 #include <cstdio>
 
-#include "bvh8_gpu.h"
+#include "wbvh_gpu.h"
 
 namespace b200pt {
-bool build_bvh8_gpu(const GpuBuildInput &, cudaStream_t, GpuBuildOutput *, char *err, size_t err_len) {
+bool build_wbvh_gpu(const GpuBuildInput &, cudaStream_t, GpuBuildOutput *, char *err, size_t err_len) {
     snprintf(err, err_len, "the device BVH builder is not part of the CPU check build");
     return false;
 }

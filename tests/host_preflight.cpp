@@ -1,9 +1,9 @@
 // tests/host_preflight.cpp -- CPU pre-flight of the product's device arithmetic.
 //
-// Compiles the product's host+device headers (pt_core.cuh, bvh8_traverse.cuh)
+// Compiles the product's host+device headers (pt_core.cuh, wbvh_traverse.cuh)
 // and the host BVH builder as plain C++ and checks them against the oracle
 // (oracle/liboracle.so) BEFORE GPU time is spent:
-//   * 8-wide BVH build + traversal vs the oracle's closest / any hit answers (bit-exact t)
+//   * 7-wide BVH build + traversal vs the oracle's closest / any hit answers (bit-exact t)
 //   * Sobol' sample stream and camera rays vs the oracle
 //   * the on-device BVH builder's per-element steps (lbvh.cuh) run sequentially: structure check + traversal vs the oracle
 //   * Sphere::Intersect / IntersectP arithmetic (EFloat quadratic, error-tracking transforms) vs the oracle,
@@ -18,8 +18,8 @@
 #include <vector>
 
 #include "../oracle/pt_oracle.h"
-#include "../pbrt-v3-distributed_b200/csrc/bvh8.h"
-#include "../pbrt-v3-distributed_b200/csrc/bvh8_traverse.cuh"
+#include "../pbrt-v3-distributed_b200/csrc/wbvh.h"
+#include "../pbrt-v3-distributed_b200/csrc/wbvh_traverse.cuh"
 #include "../pbrt-v3-distributed_b200/csrc/lbvh.cuh"
 #include "../pbrt-v3-distributed_b200/csrc/pt_sphere.cuh"
 #include <algorithm>
@@ -27,6 +27,26 @@
 #include <numeric>
 
 using namespace b200pt;
+
+// bounds a ray is clipped to before traversal: the same padding rule as the library (api.cu make_trav_bounds)
+static TravBounds trav_bounds_of(const float *lo, const float *hi) {
+    TravBounds b;
+    float absmax = 0.f, ext = 0.f;
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) ok = ok && lo[a] <= hi[a];
+    for (int a = 0; a < 3; ++a) {
+        const float l = ok ? lo[a] : 0.f, h = ok ? hi[a] : 0.f;
+        absmax = std::max(absmax, std::max(std::fabs(l), std::fabs(h)));
+        ext = std::max(ext, h - l);
+    }
+    const float pad = 0x1p-14f * absmax + 1e-30f;
+    for (int a = 0; a < 3; ++a) {
+        b.lo[a] = (ok ? lo[a] : 0.f) - pad;
+        b.hi[a] = (ok ? hi[a] : 0.f) + pad;
+    }
+    b.scale = std::max(absmax, ext);
+    return b;
+}
 
 static uint32_t bits(float f) {
     uint32_t u;
@@ -75,10 +95,11 @@ int main(int argc, char **argv) {
         default_shading(&sh);
         degenerate[i] = !triangle_partials(mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), sh.uv, &a, &b);
     }
-    Bvh8 bvh;
-    build_bvh8(verts.data(), nTris, mat.data(), light.data(), nullptr, degenerate.data(), 8, &bvh);
-    int64_t bad = validate_bvh8(bvh);
-    printf("bvh8: %zu nodes, %zu tris (%u in leaves), depth %d, validation violations %lld\n", bvh.nodes.size(),
+    Wbvh bvh;
+    build_wbvh(verts.data(), nTris, mat.data(), light.data(), nullptr, degenerate.data(), 8, &bvh);
+    int64_t bad = validate_wbvh(bvh);
+    const TravBounds tb = trav_bounds_of(bvh.bounds_lo, bvh.bounds_hi);
+    printf("wbvh: %zu nodes, %zu tris (%u in leaves), depth %d, validation violations %lld\n", bvh.nodes.size(),
            bvh.tris.size(), bvh.n_in_leaves, bvh.max_depth, (long long)bad);
     int fail = bad != 0;
 
@@ -106,10 +127,11 @@ int main(int argc, char **argv) {
     const F4 *tris = reinterpret_cast<const F4 *>(bvh.tris.data());
     int64_t nHit = 0, badTri = 0, badT = 0, badOcc = 0, tieOk = 0;
     TraceCounters ctr = {0, 0};
+    uint32_t overflow = 0;
     for (int64_t i = 0; i < nRays; ++i) {
         V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
         TriHit h = {0, 0, 0, 0};
-        uint32_t ti = traverse_bvh8<false, true>(nodes, tris, o, d, rays[i].t_max, &h, &ctr);
+        uint32_t ti = traverse_wbvh<false, true>(nodes, bvh.tri_base.data(), tris, tb, nullptr, o, d, rays[i].t_max, &h, &ctr, &overflow);
         int32_t prim = ti == B200PT_MISS ? -1 : (int32_t)bvh.tris[ti].prim;
         if (prim >= 0) ++nHit;
         if (prim != want[i].triangle) {
@@ -122,14 +144,15 @@ int main(int argc, char **argv) {
                                  bits(h.b1) != bits(want[i].b1)))
             ++badT;
         TriHit h2;
-        uint32_t occ = traverse_bvh8<true, false>(nodes, tris, o, d, rays[i].t_max, &h2, &ctr);
+        uint32_t occ = traverse_wbvh<true, false>(nodes, bvh.tri_base.data(), tris, tb, nullptr, o, d, rays[i].t_max, &h2, &ctr, &overflow);
         if ((occ != B200PT_MISS) != (wantOcc[i] != 0)) ++badOcc;
     }
     printf("rays %lld: hits %lld, wrong triangle %lld (ties resolved differently: %lld), wrong t/b %lld, wrong any-hit %lld; "
            "%.2f nodes/ray %.2f tris/ray (closest)\n",
            (long long)nRays, (long long)nHit, (long long)badTri, (long long)tieOk, (long long)badT, (long long)badOcc,
            (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
-    fail |= (badTri || badT || badOcc);
+    if (overflow) printf("traversal stack overflows: %u\n", overflow);
+    fail |= (badTri || badT || badOcc || overflow);
     // ---- the on-device builder (lbvh.cuh), emulated: same tree checks, same traversal answers
     {
         LbvhCtx c;
@@ -141,7 +164,7 @@ int main(int argc, char **argv) {
         std::vector<uint32_t> validIdx(nTris), sortedV(nTris), p2t(nTris);
         std::vector<uint64_t> keys(nTris);
         uint32_t counters[4] = {0, 1, 0, 0};
-        int32_t cb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        int32_t cb[12] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
         c.valid_idx = validIdx.data();
         c.n_valid = &counters[0];
         c.n_nodes = &counters[1];
@@ -151,15 +174,26 @@ int main(int argc, char **argv) {
         c.keys = keys.data();
         c.sorted = sortedV.data();
         c.prim_to_tri = p2t.data();
-        Bvh8 g;
+        Wbvh g;
         g.tris.resize(nTris);
         c.tris = g.tris.data();
         for (int64_t i = 0; i < nTris; ++i) lbvh_prep(c, i);
         const int64_t m = counters[0];
         c.m = m;
         g.nodes.resize((size_t)m + 16);
+        g.tri_base.assign((size_t)m + 16, 0u);
         c.nodes = g.nodes.data();
+        c.tri_base = g.tri_base.data();
         c.node_cap = g.nodes.size();
+        {
+            float absmax = 0.f;
+            for (int a = 0; a < 3; ++a) {
+                g.bounds_lo[a] = m ? lb_ordered_to_float(cb[6 + a]) : 0.f;
+                g.bounds_hi[a] = m ? lb_ordered_to_float(cb[9 + a]) : 0.f;
+                absmax = std::max(absmax, std::max(std::fabs(g.bounds_lo[a]), std::fabs(g.bounds_hi[a])));
+            }
+            c.cell_floor = B200PT_CELL_FLOOR * absmax;
+        }
         for (int64_t k = 0; k < m; ++k) lbvh_key(c, k);
         std::vector<uint32_t> order(m);
         std::iota(order.begin(), order.end(), 0u);
@@ -216,15 +250,18 @@ int main(int argc, char **argv) {
             if (nItems) ++depth;
         }
         if (m == 0) {
-            memset(&g.nodes[0], 0, sizeof(Bvh8Node));
-            g.nodes[0].e[0] = g.nodes[0].e[1] = g.nodes[0].e[2] = 127;
+            memset(&g.nodes[0], 0, sizeof(WbvhNode));
+            const int none[B200PT_WIDTH] = {-1, -1, -1, -1, -1, -1, -1};
+            wbvh_encode_node(nullptr, none, nullptr, 1.f, &g.nodes[0]);
         }
         g.n_in_leaves = counters[2];
         for (int64_t i = 0; i < nTris; ++i) lbvh_leftover(c, i);
         g.nodes.resize(counters[1]);
+        g.tri_base.resize(counters[1]);
         g.max_depth = depth;
         g.prim_to_tri = p2t;
-        const int64_t badG = validate_bvh8(g);
+        const int64_t badG = validate_wbvh(g);
+        const TravBounds gb = trav_bounds_of(g.bounds_lo, g.bounds_hi);
         const U4 *gn = reinterpret_cast<const U4 *>(g.nodes.data());
         const F4 *gt = reinterpret_cast<const F4 *>(g.tris.data());
         int64_t wrong = 0, wrongOcc = 0;
@@ -232,20 +269,20 @@ int main(int argc, char **argv) {
         for (int64_t i = 0; i < nRays; ++i) {
             V3 o = mk(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = mk(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
             TriHit h = {0, 0, 0, 0};
-            uint32_t ti = traverse_bvh8<false, true>(gn, gt, o, d, rays[i].t_max, &h, &gc);
+            uint32_t ti = traverse_wbvh<false, true>(gn, g.tri_base.data(), gt, gb, nullptr, o, d, rays[i].t_max, &h, &gc, &overflow);
             int32_t prim = ti == B200PT_MISS ? -1 : (int32_t)g.tris[ti].prim;
             const bool tie = prim >= 0 && want[i].triangle >= 0 && bits(h.t) == bits(want[i].t);
             if (prim != want[i].triangle && !tie) ++wrong;
             if (prim == want[i].triangle && prim >= 0 && bits(h.t) != bits(want[i].t)) ++wrong;
             TriHit h2;
-            uint32_t occ = traverse_bvh8<true, false>(gn, gt, o, d, rays[i].t_max, &h2, &gc);
+            uint32_t occ = traverse_wbvh<true, false>(gn, g.tri_base.data(), gt, gb, nullptr, o, d, rays[i].t_max, &h2, &gc, &overflow);
             if ((occ != B200PT_MISS) != (wantOcc[i] != 0)) ++wrongOcc;
         }
         printf("lbvh builder (emulated): %lld of %lld triangles in the tree, %zu nodes, depth %d, violations %lld, wrong hits %lld, "
                "wrong any-hit %lld, %.2f nodes/ray %.2f tris/ray (host SAH tree: %.2f, %.2f)\n",
                (long long)m, (long long)nTris, g.nodes.size(), depth, (long long)badG, (long long)wrong, (long long)wrongOcc,
                (double)gc.nodes / nRays, (double)gc.tris / nRays, (double)ctr.nodes / nRays, (double)ctr.tris / nRays);
-        fail |= (badG || wrong || wrongOcc || depth > B200PT_STACK - 4);
+        fail |= (badG || wrong || wrongOcc || overflow || depth > B200PT_STACK - 4);
     }
     oracle_scene_destroy(os);
 
@@ -396,9 +433,10 @@ int main(int argc, char **argv) {
         const int64_t nObj = std::min<int64_t>(nTris, 3000);
         std::vector<float> ov(verts.begin(), verts.begin() + 9 * nObj);
         for (float &v : ov) v *= 0.3f;
-        Bvh8 ob;
+        Wbvh ob;
         std::vector<uint8_t> degO(degenerate.begin(), degenerate.begin() + nObj);
-        build_bvh8(ov.data(), nObj, mat.data(), light.data(), nullptr, degO.data(), 4, &ob);
+        build_wbvh(ov.data(), nObj, mat.data(), light.data(), nullptr, degO.data(), 4, &ob);
+        const TravBounds obb = trav_bounds_of(ob.bounds_lo, ob.bounds_hi);
         const int nInst = 4;
         std::vector<b200pt_instance> insts(nInst);
         std::vector<DevInstance> dev(nInst);
@@ -473,18 +511,18 @@ int main(int argc, char **argv) {
                 TriHit h;
                 if (instance_leaf_test(dev[k], o, d, rays[i].t_max)) {
                     instance_ray(dev[k], o, d, rays[i].t_max, &o2, &d2, &tm2);
-                    if (traverse_bvh8<true, false>(on, ot, o2, d2, tm2, &h, &ic) != B200PT_MISS) occ = true;
+                    if (traverse_wbvh<true, false>(on, ob.tri_base.data(), ot, obb, nullptr, o2, d2, tm2, &h, &ic, &overflow) != B200PT_MISS) occ = true;
                 }
                 if (getenv("PREFLIGHT_VERBOSE") && (i == 4505 || i == 15674)) {
                     instance_ray(dev[k], o, d, tmax, &o2, &d2, &tm2);
                     TriHit hb = {0, 0, 0, 0};
-                    uint32_t tb = traverse_bvh8<false, false>(on, ot, o2, d2, tm2, &hb, &ic);
+                    uint32_t tb = traverse_wbvh<false, false>(on, ob.tri_base.data(), ot, obb, nullptr, o2, d2, tm2, &hb, &ic, &overflow);
                     printf("   ray %lld inst %d: leaf %d o2=(%g %g %g) d2=(%g %g %g) tm2=%g hit %u t=%g\n", (long long)i, k,
                            (int)instance_leaf_test(dev[k], o, d, tmax), o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, tm2, tb, hb.t);
                 }
                 if (!instance_leaf_test(dev[k], o, d, tmax)) continue;
                 instance_ray(dev[k], o, d, tmax, &o2, &d2, &tm2);
-                const uint32_t ti = traverse_bvh8<false, false>(on, ot, o2, d2, tm2, &h, &ic);
+                const uint32_t ti = traverse_wbvh<false, false>(on, ob.tri_base.data(), ot, obb, nullptr, o2, d2, tm2, &h, &ic, &overflow);
                 if (ti == B200PT_MISS) continue;
                 tmax = h.t;
                 tBest = h.t;

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert declared <= exported, "missing: %s" % sorted(declared - exported)
     assert not pkg.MISSING_SYMBOLS
     assert set(pkg.EXPORTED_SYMBOLS) == declared
-    assert pkg.lib.b200pt_abi_version() == 4
+    assert pkg.lib.b200pt_abi_version() == 5
 
 
 def test_struct_sizes_match_header(abi):
@@ -52,7 +52,7 @@ def test_host_preflight_traversal_matches_oracle(tmp_path):
     """The product's BVH build + traversal arithmetic, compiled for the host, against the oracle."""
     exe = str(tmp_path / "host_preflight")
     src = [os.path.join(ROOT, "tests", "host_preflight.cpp"),
-           os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc", "bvh8_build.cpp")]
+           os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc", "wbvh_build.cpp")]
     r = subprocess.run(["g++", "-O2", "-std=gnu++17", "-ffp-contract=off", "-pthread", *src, "-o", exe,
                         "-L" + os.path.join(ROOT, "oracle"), "-loracle",
                         "-Wl,-rpath," + os.path.join(ROOT, "oracle")], capture_output=True, text=True)

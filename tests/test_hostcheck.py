@@ -2,7 +2,7 @@
 compiles into libb200pt.so -- as plain C++ against a stand-in <cuda_runtime.h> in which a kernel launch runs the kernel
 function once per thread index.  The GPU parity tests are then replayed against that library: the host logic (scene and
 render set-up, batching, wavefront sequencing, film read-back) and the scalar logic of every kernel except the
-warp-synchronous k_trace (its rays take traverse_bvh8, the per-ray routine the kernel's lanes step through) are checked
+warp-synchronous k_trace (its rays take traverse_wbvh, the per-ray routine the kernel's lanes step through) are checked
 against the reference's golden images and the oracle before any GPU time is spent.  What this cannot show -- nvcc's
 code generation, the real warp-level execution, performance -- is what the `-m gpu` run of the same tests is for."""
 import os
