@@ -262,6 +262,13 @@ def main():
                      "builder": "device (Morton order -> radix tree -> 7-wide collapse)" if args.bvh == "gpu" else "host SAH",
                      "layout": "7-wide, 64-byte nodes + 4-byte triangle base per node, 48-byte triangles"}
     render = pkg.Render(scene, setup)
+    comm = None
+    if world > 1:
+        # the library's own communicator for the film merge (b200pt_comm_create: NCCL id through a file); torch.distributed
+        # stays the launcher's plumbing (rendezvous of this file name, barriers, the max / sum of the timing scalars)
+        token = [os.path.join(tempfile.gettempdir(), "b200pt_nccl_%d_%d.id" % (os.getpid(), int(time.time() * 1e3)))]
+        dist.broadcast_object_list(token, src=0)
+        comm = pkg.Comm(ctx, rank, world, token[0])
     my_tiles = scenes.rank_tiles(render.n_tiles, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     film_ptr, film_n = render.film_device_buffer()
@@ -283,8 +290,7 @@ def main():
         render.clear()
         render.render_tiles(my_tiles)
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            render.film_reduce(comm, 0)               # one ncclReduce of the raw film sums, behind the C ABI
         if e2e and rank == 0:
             pkg._check(pkg.lib.b200pt_film_read_rgb(render.h, host_rgb.data_ptr()))
         return h2d
@@ -429,6 +435,8 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(out))
+    if comm is not None:
+        comm.close()
     render.close()
     scene.close()
     ctx.close()

@@ -376,6 +376,23 @@ int b200pt_film_device_buffer(b200pt_render *r, uint64_t *dev_ptr, uint64_t *n_f
 
 /* Copies the raw film (X,Y,Z,weight per pixel) to the host (synchronises). */
 int b200pt_film_read_raw(b200pt_render *r, float *xyzw);
+
+/* ---- multi-GPU film merge ------------------------------------------------
+ * One process per GPU renders a disjoint set of tiles of the SAME film (full-film sampler); the raw
+ * (X,Y,Z,weight) sums are then added on `root` with one ncclReduce over NVLink.  This replaces what the reference's
+ * distributed runs do with files afterwards (imgtool assemble, tools/imgtool.cpp:190-285) and the MergeFilmTile
+ * mutex inside one process (film.cpp:117-130).  NCCL is loaded at run time (libnccl.so.2; B200PT_NCCL_LIB overrides).
+ *
+ * b200pt_comm_create: bootstraps a communicator of `world_size` processes through a file every rank can reach:
+ * rank 0 writes the NCCL unique id to `id_file`, the others wait for it (up to 120 s).  b200pt_comm_from_nccl wraps
+ * a communicator the host application already owns (an ncclComm_t passed as void *; it is not destroyed). */
+typedef struct b200pt_comm b200pt_comm;
+int b200pt_comm_create(b200pt_ctx *ctx, int rank, int world_size, const char *id_file, b200pt_comm **out);
+int b200pt_comm_from_nccl(b200pt_ctx *ctx, void *nccl_comm, int rank, int world_size, b200pt_comm **out);
+void b200pt_comm_destroy(b200pt_comm *comm);
+/* Adds the raw film sums of all ranks into `root`'s film buffer (in place, on the context's stream; the other
+ * ranks' buffers keep their own partial sums).  Every rank of the communicator must call it. */
+int b200pt_film_reduce(b200pt_render *r, b200pt_comm *comm, int root);
 /* Film::WriteImage's pixel pipeline (film.cpp:174-203): XYZ->RGB, divide by
  * weight, clamp >=0, *scale; rgb is [h][w][3] over the cropped bounds. */
 int b200pt_film_read_rgb(b200pt_render *r, float *rgb);

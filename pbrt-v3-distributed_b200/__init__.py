@@ -18,6 +18,9 @@ from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+# profiles/ A/B runs load an experimental build of the same sources (make VARIANT=<name> EXTRA=-D...) instead
+if os.environ.get("B200PT_LIB_VARIANT"):
+    LIB_PATH = os.path.join(_HERE, "_variants", os.environ["B200PT_LIB_VARIANT"], "libb200pt.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("libb200pt.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
@@ -52,6 +55,10 @@ _SIGNATURES = {
     "b200pt_film_device_buffer": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "b200pt_film_read_raw": (C.c_int, [_vp, _vp]),
     "b200pt_film_read_rgb": (C.c_int, [_vp, _vp]),
+    "b200pt_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    "b200pt_comm_from_nccl": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "b200pt_comm_destroy": (None, [_vp]),
+    "b200pt_film_reduce": (C.c_int, [_vp, _vp, C.c_int]),
     "b200pt_debug_sobol": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _i32, _vp]),
     "b200pt_debug_camera_rays": (C.c_int, [_vp, _i32, _i32, _i32, _vp]),
     "b200pt_debug_pixel_samples": (C.c_int, [_vp, _i32, _i32, _vp]),
@@ -188,6 +195,20 @@ class Scene:
             self.h = _vp()
 
 
+class Comm:
+    """NCCL communicator for the film merge of a multi-process render (b200pt_comm_create: rank 0 publishes the
+    NCCL id through `id_file`, a path every rank can reach)."""
+
+    def __init__(self, ctx, rank, world_size, id_file):
+        self.h = _vp()
+        _check(lib.b200pt_comm_create(ctx.h, rank, world_size, os.fsencode(id_file), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib.b200pt_comm_destroy(self.h)
+            self.h = _vp()
+
+
 class Render:
     """SamplerIntegrator::Render replacement bound to a scene (b200pt_render_create)."""
 
@@ -221,6 +242,10 @@ class Render:
         p, n = _u64(), _u64()
         _check(lib.b200pt_film_device_buffer(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def film_reduce(self, comm, root=0):
+        """Adds every rank's raw film sums into `root`'s film (one ncclReduce, b200pt_film_reduce)."""
+        _check(lib.b200pt_film_reduce(self.h, comm.h, root))
 
     def read_raw(self):
         out = np.zeros((self.height, self.width, 4), np.float32)

@@ -2,8 +2,11 @@
 // upload (+ host BVH build), the wavefront batch driver and film read-back.
 // Host code only orchestrates; all arithmetic of the path runs in kernels.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <string>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -63,6 +66,7 @@ struct b200pt_scene {
     b200pt_material *d_materials = nullptr;
     F4 *d_tri_n = nullptr, *d_tri_uv = nullptr;
     uint64_t n_nodes = 0, n_tris = 0;
+    uint64_t n_top_nodes = 0;  // nodes of the top-level tree (the first ones of d_nodes)
     std::vector<b200pt_material> materials;
     std::vector<b200pt_area_light> lights;  // host copy, triangle = original index
     std::vector<uint32_t> prim_to_tri;
@@ -100,6 +104,7 @@ struct b200pt_render {
     float *d_rgb = nullptr;  // b200pt_film_read_rgb staging (lazily allocated, freed with the render object)
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
+    int refill_lanes = 26, postpone_pct = 40, trace_ctas = 0, stage_nodes = 0;  // k_trace knobs (b200pt_render_set_option)
     bool overlap = true;  // run shadow/MIS rays of bounce b concurrently with the path rays of bounce b+1
     int sort_from_bounce = -1;  // coherence-sort the path / shadow queues from this bounce on (<0: never; measured: no gain on the soups)
     std::vector<TimedLaunch> timed;
@@ -286,6 +291,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     std::vector<TravBounds> obj_bounds(obj_ranges.size());
     Wbvh bvh;
     GpuBuildOutput gout;
+    uint64_t n_top_nodes = 0;
     if (gpu_build) {
         // ---- on-device build (wbvh_gpu.cu): Morton order -> binary radix tree -> 7-wide collapse
         GpuBuildInput gin;
@@ -342,6 +348,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
         int64_t bad = validate_wbvh(bvh);
         if (bad) return b200pt_fail(B200PT_ERR_INVALID, "scene_create: BVH validation found %lld violations", (long long)bad);
     }
+    n_top_nodes = bvh.nodes.size();
     // one tree per object, appended behind the top-level one; k_spheres traverses them through offset pointers,
     // so their node / triangle indices stay relative to the object's own arrays
     bvh.prim_to_tri.resize((size_t)d->n_triangles, 0xffffffffu);
@@ -472,6 +479,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     b200pt_scene *s = new b200pt_scene;
     s->ctx = ctx;
     s->n_nodes = n_node_records;
+    s->n_top_nodes = gpu_build ? (uint64_t)gout.n_nodes : n_top_nodes;
     s->n_tris = n_tri_records;
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
@@ -695,13 +703,21 @@ int b200pt_scene_info(const b200pt_scene *s, uint64_t *node_bytes, uint64_t *tri
 }
 
 // ------------------------------------------------- ray-batch entry points
-static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count * B200PT_TRACE_CTAS; }
+static int trace_grid(const b200pt_ctx *ctx) { return ctx->sm_count; }  // launch_trace multiplies by its CTAs per SM
 static int postpone_pct() {
     static int v = getenv("B200PT_POSTPONE_PCT") ? atoi(getenv("B200PT_POSTPONE_PCT")) : 40;
     return v;
 }
 static int refill_lanes() {
     static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 26;
+    return v;
+}
+static int trace_ctas_default() {
+    static int v = getenv("B200PT_TRACE_CTAS_RT") ? atoi(getenv("B200PT_TRACE_CTAS_RT")) : 0;
+    return v;
+}
+static int stage_nodes_default() {
+    static int v = getenv("B200PT_STAGE_NODES") ? atoi(getenv("B200PT_STAGE_NODES")) : 0;
     return v;
 }
 
@@ -725,6 +741,8 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
     a.materials = s->d_materials;
     a.refill_lanes = refill_lanes();
     a.postpone_pct = postpone_pct();
+    a.ctas = trace_ctas_default();
+    a.n_staged = (uint32_t)std::min<uint64_t>((uint64_t)std::max(0, stage_nodes_default()), s->n_top_nodes);
     if (any_hit)
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
@@ -1201,12 +1219,16 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(st));
-    r->grid_trace = ctx->sm_count * B200PT_TRACE_CTAS;
+    r->grid_trace = ctx->sm_count;  // launch_trace multiplies by its CTAs per SM
     r->grid_shade = ctx->sm_count * 8;
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
     if (getenv("B200PT_SORT_FROM")) r->sort_from_bounce = atoi(getenv("B200PT_SORT_FROM"));
     if (getenv("B200PT_OVERLAP")) r->overlap = atoi(getenv("B200PT_OVERLAP")) != 0;
+    r->refill_lanes = refill_lanes();
+    r->postpone_pct = postpone_pct();
+    r->trace_ctas = trace_ctas_default();
+    r->stage_nodes = stage_nodes_default();
     *out = r;
     return B200PT_OK;
 }
@@ -1361,8 +1383,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.materials = H.scene.materials;
             a.stats = H.stats;
             a.stride = 1;
-            a.refill_lanes = refill_lanes();
-            a.postpone_pct = postpone_pct();
+            a.refill_lanes = r->refill_lanes;
+            a.postpone_pct = r->postpone_pct;
+            a.ctas = r->trace_ctas;
+            a.n_staged = (uint32_t)std::min<uint64_t>((uint64_t)std::max(0, r->stage_nodes), r->scene->n_top_nodes);
             // closest hit of the path rays + classification by BSDF family
             const bool sorted = r->sort_from_bounce >= 0 && b >= r->sort_from_bounce;
             if (sorted) {
@@ -1404,8 +1428,10 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.materials = H.scene.materials;
             a.stats = H.stats;
             a.stride = 1;
-            a.refill_lanes = refill_lanes();
-            a.postpone_pct = postpone_pct();
+            a.refill_lanes = r->refill_lanes;
+            a.postpone_pct = r->postpone_pct;
+            a.ctas = r->trace_ctas;
+            a.n_staged = (uint32_t)std::min<uint64_t>((uint64_t)std::max(0, r->stage_nodes), r->scene->n_top_nodes);
             // shadow rays (any hit), tMax = 1 - ShadowEpsilon
             const bool sorted_sh = r->sort_from_bounce >= 0;
             if (sorted_sh) {
@@ -1515,6 +1541,126 @@ int b200pt_film_read_raw(b200pt_render *r, float *xyzw) {
     cudaStream_t st = r->scene->ctx->stream;
     CUDA_TRY(cudaMemcpyAsync(xyzw, r->host.film, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return B200PT_OK;
+}
+
+// ---- multi-GPU film merge: NCCL through dlopen (no link-time dependency; the library is usable without it)
+namespace {
+struct NcclUniqueId {
+    char internal[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char *names[] = {getenv("B200PT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm) continue;
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return &api;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.Reduce = reinterpret_cast<decltype(api.Reduce)>(dlsym(api.lib, "ncclReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.GetErrorString;
+    return &api;
+}
+}  // namespace
+
+struct b200pt_comm {
+    b200pt_ctx *ctx = nullptr;
+    void *nccl = nullptr;
+    int rank = 0, world = 1;
+    bool owned = false;
+};
+
+int b200pt_comm_from_nccl(b200pt_ctx *ctx, void *nccl_comm, int rank, int world_size, b200pt_comm **out) {
+    if (!ctx || !nccl_comm || !out || world_size < 1 || rank < 0 || rank >= world_size)
+        return b200pt_fail(B200PT_ERR_INVALID, "comm_from_nccl: bad argument");
+    if (!nccl_api()->ok) return b200pt_fail(B200PT_ERR_INVALID, "comm: libnccl.so.2 could not be loaded (set B200PT_NCCL_LIB)");
+    b200pt_comm *c = new b200pt_comm;
+    c->ctx = ctx;
+    c->nccl = nccl_comm;
+    c->rank = rank;
+    c->world = world_size;
+    *out = c;
+    return B200PT_OK;
+}
+
+int b200pt_comm_create(b200pt_ctx *ctx, int rank, int world_size, const char *id_file, b200pt_comm **out) {
+    if (!ctx || !out || !id_file || world_size < 1 || rank < 0 || rank >= world_size)
+        return b200pt_fail(B200PT_ERR_INVALID, "comm_create: bad argument");
+    NcclApi *api = nccl_api();
+    if (!api->ok) return b200pt_fail(B200PT_ERR_INVALID, "comm_create: libnccl.so.2 could not be loaded (set B200PT_NCCL_LIB)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    NcclUniqueId id;
+    memset(&id, 0, sizeof(id));
+    if (rank == 0) {
+        int rc = api->GetUniqueId(&id);
+        if (rc != 0) return b200pt_fail(B200PT_ERR_CUDA, "comm_create: ncclGetUniqueId: %s", api->GetErrorString(rc));
+        const std::string tmp = std::string(id_file) + ".tmp";
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(&id, 1, sizeof(id), f) != sizeof(id)) {
+            if (f) fclose(f);
+            return b200pt_fail(B200PT_ERR_INVALID, "comm_create: cannot write %s", tmp.c_str());
+        }
+        fclose(f);
+        if (rename(tmp.c_str(), id_file) != 0) return b200pt_fail(B200PT_ERR_INVALID, "comm_create: cannot publish %s", id_file);
+    } else {
+        bool got = false;
+        for (int tries = 0; tries < 2400 && !got; ++tries) {  // up to 120 s
+            if (FILE *f = fopen(id_file, "rb")) {
+                got = fread(&id, 1, sizeof(id), f) == sizeof(id);
+                fclose(f);
+            }
+            if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        }
+        if (!got) return b200pt_fail(B200PT_ERR_INVALID, "comm_create: rank %d never saw the NCCL id in %s", rank, id_file);
+    }
+    void *comm = nullptr;
+    int rc = api->CommInitRank(&comm, world_size, id, rank);
+    if (rc != 0) return b200pt_fail(B200PT_ERR_CUDA, "comm_create: ncclCommInitRank: %s", api->GetErrorString(rc));
+    b200pt_comm *c = new b200pt_comm;
+    c->ctx = ctx;
+    c->nccl = comm;
+    c->rank = rank;
+    c->world = world_size;
+    c->owned = true;
+    *out = c;
+    return B200PT_OK;
+}
+
+void b200pt_comm_destroy(b200pt_comm *c) {
+    if (!c) return;
+    if (c->owned && c->nccl && nccl_api()->ok) {
+        cudaSetDevice(c->ctx->device);
+        nccl_api()->CommDestroy(c->nccl);
+    }
+    delete c;
+}
+
+int b200pt_film_reduce(b200pt_render *r, b200pt_comm *c, int root) {
+    if (!r || !c) return b200pt_fail(B200PT_ERR_INVALID, "film_reduce: NULL argument");
+    if (root < 0 || root >= c->world) return b200pt_fail(B200PT_ERR_INVALID, "film_reduce: root %d out of range", root);
+    if (c->ctx != r->scene->ctx) return b200pt_fail(B200PT_ERR_INVALID, "film_reduce: communicator and render belong to different contexts");
+    CUDA_TRY(cudaSetDevice(c->ctx->device));
+    const size_t n = 4 * (size_t)(r->host.crop[2] - r->host.crop[0]) * (r->host.crop[3] - r->host.crop[1]);
+    // ncclFloat = 7, ncclSum = 0 (nccl.h); in place: send == recv
+    const int rc = nccl_api()->Reduce(r->host.film, r->host.film, n, 7, 0, root, c->nccl, c->ctx->stream);
+    if (rc != 0) return b200pt_fail(B200PT_ERR_CUDA, "film_reduce: ncclReduce: %s", nccl_api()->GetErrorString(rc));
     return B200PT_OK;
 }
 
@@ -1671,6 +1817,16 @@ int b200pt_render_set_option(b200pt_render *r, const char *name, int value) {
         r->instrumented = value != 0;
     else if (!strcmp(name, "profile"))
         r->profiling = value != 0;
+    else if (!strcmp(name, "refill_lanes"))
+        r->refill_lanes = value;
+    else if (!strcmp(name, "postpone_pct"))
+        r->postpone_pct = value;
+    else if (!strcmp(name, "trace_ctas"))
+        r->trace_ctas = value;
+    else if (!strcmp(name, "stage_nodes"))
+        r->stage_nodes = value < 0 ? 0 : (value > 512 ? 512 : value);
+    else if (!strcmp(name, "overlap"))
+        r->overlap = value != 0;
     else
         return b200pt_fail(B200PT_ERR_INVALID, "set_option: unknown option %s", name);
     return B200PT_OK;

@@ -297,10 +297,7 @@ __device__ __forceinline__ void ray_load(const float *col, TravRay &R) {
     R.sh.ky = R.sh.kx == 2 ? 0 : R.sh.kx + 1;
     R.tmax = col[7 * 128];
     R.best = __float_as_uint(col[8 * 128]);
-    R.hit.t = col[9 * 128];
-    R.hit.b0 = col[10 * 128];
-    R.hit.b1 = col[11 * 128];
-    R.hit.b2 = col[12 * 128];
+    R.hit.t = R.hit.b0 = R.hit.b1 = R.hit.b2 = 0.f;  // outputs of the triangle phase (stored again only after a hit)
     R.t0 = col[13 * 128];
     R.inv = col[14 * 128];
 }
@@ -313,12 +310,38 @@ __device__ __forceinline__ void ray_store_hit(float *col, const TravRay &R) {
     col[12 * 128] = R.hit.b2;
 }
 
-template <bool ANY_HIT, bool CLASSIFY, bool COUNT>
-__global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArgs a) {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// CTAS: resident CTAs per SM the kernel is compiled for (register budget); STAGE: the top of the tree is staged in
+// shared memory by TMA (north_star's variant; measured against the plain one in profiles/README.md).
+template <bool ANY_HIT, bool CLASSIFY, bool COUNT, int CTAS, bool STAGE>
+__global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     // the slot-permutation table of the node test (wbvh_traverse.cuh), one copy per CTA
     __shared__ __align__(16) uint8_t s_lut[B200PT_LUT_BYTES];
     __shared__ float s_ray[B200PT_RAY_WORDS * 128];
+    __shared__ __align__(8) unsigned long long s_bar;
+    extern __shared__ __align__(128) uint8_t s_top[];  // STAGE: WbvhNode[a.n_staged]
     reinterpret_cast<uint4 *>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + threadIdx.x);
+    if (STAGE) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = a.n_staged * 64u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_top)),
+                         "l"(a.nodes), "r"(bytes), "r"(smem_u32(&s_bar))
+                         : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(smem_u32(&s_bar)), "r"(0u)
+                         : "memory");
+    }
     __syncthreads();
     float *const my_ray = s_ray + threadIdx.x;
     const uint32_t n = *a.count;
@@ -352,7 +375,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArg
                         family = a.materials[mf & 0xffffu].type;
                     }
                 }
-                if (T.overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)T.overflow);
+                if ((T.sp & B200PT_SP_OVERFLOW) && a.stats) atomicAdd(&a.stats[7], 1ull);
             }
             if (CLASSIFY) {
 #pragma unroll
@@ -400,7 +423,9 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArg
         while (has) {
             uint32_t ng_x = 0, ng_y = 0;
             const bool node_work = (T.cur_y & 0xff000000u) != 0;
-            if (node_work) trav_node_phase<!ANY_HIT, COUNT>(T, S, a.nodes, a.tri_base, s_lut, &ng_x, &ng_y, &ctr);
+            if (node_work)
+                trav_node_phase<!ANY_HIT, COUNT, STAGE>(T, S, a.nodes, a.tri_base, s_lut, &ng_x, &ng_y, &ctr,
+                                                        reinterpret_cast<const U4 *>(s_top), a.n_staged);
             bool must = false;
             if (ng_y) {
                 if (pend_y) {
@@ -411,7 +436,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArg
                     ng_y = 0;
                 }
             }
-            const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0 && T.sp == 0;
+            const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0 && (T.sp & B200PT_SP_MASK) == 0;
             // one warp reduction instead of three votes: byte 0 counts parked lanes, byte 1 urgent, byte 2 starving
             const unsigned act = __activemask();
             const bool starving_me = out_of_nodes && pend_y != 0;
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(128, B200PT_TRACE_CTAS) k_trace(const TraceArg
                     TravRay R;
                     ray_load(my_ray, R);
                     const uint32_t before = R.best;
-                    done = trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, a.tris, pend_x, pend_y, &ctr);
+                    done = trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, a.tri_base, a.tris, pend_x, pend_y, &ctr);
                     if (R.best != before) ray_store_hit(my_ray, R);
                 }
                 pend_x = ng_x;
@@ -515,8 +540,8 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
     while (true) {
         if (state == 2) {
             if (!(T2.cur_y & 0xff000000u) || trav_step<ANY_HIT, false>(T2, R2, S2, bn, bb, bt, a.lut, &ctr)) {
-                overflow += T2.overflow;
-                T2.overflow = 0;
+                overflow += (T2.sp & B200PT_SP_OVERFLOW) ? 1u : 0u;
+                T2.sp &= B200PT_SP_MASK;
                 if (R2.best != B200PT_MISS) {
                     best = cur_tri_off + R2.best;
                     *inst = cur_inst;
@@ -550,14 +575,16 @@ __device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &r
             }
         } else {
             if (T1.cur_y & 0xff000000u) {
-                trav_node_phase<!ANY_HIT, false>(T1, S1, tn, tb1, a.lut, &pend_x, &pend_y, &ctr);
+                uint32_t lg_x = 0, lg_y = 0;
+                trav_node_phase<!ANY_HIT, false>(T1, S1, tn, tb1, a.lut, &lg_x, &lg_y, &ctr);
+                leaf_group_triangles(tb1, lg_x, lg_y, &pend_x, &pend_y);
                 state = 1;
             } else if (!trav_next_group(T1, S1)) {
                 break;
             }
         }
     }
-    overflow += T1.overflow;
+    overflow += (T1.sp & B200PT_SP_OVERFLOW) ? 1u : 0u;
     if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
     *tmax = R1.tmax;
     return best;
@@ -1579,7 +1606,9 @@ void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_b
 }
 
 #if B200PT_NSPEC == 3  // spectrum-independent: compiled once, in the RGBSpectrum translation unit
-void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s) {
+#ifdef B200PT_HOST_EMU
+void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int n_sm, cudaStream_t s) {
+    const int grid = n_sm;
     if (any_hit) {
         if (count)
             B200PT_LAUNCH(B200PT_KERNEL(k_trace<true, false, true>), grid, 128, s, a);
@@ -1597,6 +1626,36 @@ void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, i
             B200PT_LAUNCH(B200PT_KERNEL(k_trace<false, false, false>), grid, 128, s, a);
     }
 }
+#else
+template <bool ANY_HIT, bool CLASSIFY>
+static void launch_trace_variant(const TraceArgs &a, bool count, int n_sm, cudaStream_t s) {
+    const bool stage = a.n_staged > 0;
+    const size_t smem = stage ? (size_t)a.n_staged * 64 : 0;
+    if (count) {  // instrumented pass: the default build only
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, true, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
+    } else if (a.ctas == 8) {
+        if (stage)
+            B200PT_LAUNCH_SMEM(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 8, true>), n_sm * 8, 128, smem, s, a);
+        else
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 8, false>), n_sm * 8, 128, s, a);
+    } else if (a.ctas == 7 && !stage) {
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 7, false>), n_sm * 7, 128, s, a);
+    } else {
+        if (stage)
+            B200PT_LAUNCH_SMEM(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, B200PT_TRACE_CTAS, true>), n_sm * B200PT_TRACE_CTAS, 128, smem, s, a);
+        else
+            B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
+    }
+}
+void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int n_sm, cudaStream_t s) {
+    if (any_hit)
+        launch_trace_variant<true, false>(a, count, n_sm, s);
+    else if (classify)
+        launch_trace_variant<false, true>(a, count, n_sm, s);
+    else
+        launch_trace_variant<false, false>(a, count, n_sm, s);
+}
+#endif
 
 void launch_spheres(const TraceArgs &a, bool any_hit, bool classify, int grid, cudaStream_t s) {
     if (any_hit)

@@ -162,6 +162,9 @@ struct TraceArgs {
     uint32_t *qcount_mat;  // &qcount[bounce*Q_PER_BOUNCE + Q_MAT0]
     const b200pt_material *materials;
     unsigned long long *stats;  // nodes/tris counters when instrumented
+    int ctas;                   // resident CTAs per SM the launch is compiled for (B200PT_TRACE_CTAS or 8), 0 = default
+    uint32_t n_staged;          // > 0: k_trace copies nodes [0, n_staged) -- the top of the breadth-first tree -- into shared
+                                // memory with one TMA bulk copy (cp.async.bulk + mbarrier) and reads them there
     int refill_lanes;           // refill the warp when fewer lanes than this are still traversing
     int postpone_pct;           // triangle postponing threshold (% of converged lanes), 0 = off
     uint32_t magic;             // 0x47000000 as a run-time value (PRMT's second source stays in a register, see plane_2p15)
@@ -178,7 +181,8 @@ struct TraceArgs {
 
 void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_batch_tiles, uint32_t n_slots,
                    cudaStream_t s);
-void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int grid, cudaStream_t s);
+// grid = SMs of the device (the launcher multiplies by the CTAs per SM of the chosen variant)
+void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int n_sm, cudaStream_t s);
 // Tests the spheres against the rays of a finished traversal launch (tMax shortened by the triangle hit),
 // updates hit_out / full_out / occ_out and, with `classify`, appends the slots to the BSDF-family queues
 // (the traversal launch then runs without classification).

@@ -385,7 +385,7 @@ B200_HD void lbvh_collapse(const LbvhCtx &c, const LbvhItem &it) {
         }
     }
     if (it.wide < c.node_cap) {
-        c.nodes[it.wide] = node;
+        wbvh_store_node(c.nodes, it.wide, node);
         c.tri_base[it.wide] = triBase;
     }
 }

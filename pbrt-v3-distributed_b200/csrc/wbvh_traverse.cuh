@@ -38,6 +38,7 @@
 #define B200PT_WBVH_TRAVERSE_CUH
 
 #include "pt_core.cuh"
+#include "wbvh.h"
 
 namespace B200PT_NS {
 
@@ -71,14 +72,29 @@ B200_D F4 ld_f4(const F4 *p) {
     return r;
 }
 // one 64-byte node = two 256-bit loads (LDG.E.ENL2.256, sm_100)
+// (the first load fetches the record's logical first half wherever the storage order put it, see wbvh.h)
 B200_D void ld_node(const U4 *nodes, uint32_t index, NodeWords *n) {
-    const U4 *p = nodes + (size_t)index * 4;
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(nodes) + (size_t)index * 64;
+    const uint32_t r = b200pt::wb_swapped(index) << 5;
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(n->w[0]), "=r"(n->w[1]), "=r"(n->w[2]), "=r"(n->w[3]), "=r"(n->w[4]), "=r"(n->w[5]), "=r"(n->w[6]), "=r"(n->w[7])
-                 : "l"(p));
+                 : "l"(p + r));
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(n->w[8]), "=r"(n->w[9]), "=r"(n->w[10]), "=r"(n->w[11]), "=r"(n->w[12]), "=r"(n->w[13]), "=r"(n->w[14]), "=r"(n->w[15])
-                 : "l"(p + 2));
+                 : "l"(p + (r ^ 32u)));
+}
+// the same record from the CTA's shared-memory copy of the top of the tree (k_trace's TMA-staged variant)
+B200_D void ld_node_smem(const U4 *staged, uint32_t index, NodeWords *n) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(staged) + (size_t)index * 4;
+    const uint32_t r = b200pt::wb_swapped(index) << 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 v = p[j ^ r];
+        n->w[4 * j] = v.x;
+        n->w[4 * j + 1] = v.y;
+        n->w[4 * j + 2] = v.z;
+        n->w[4 * j + 3] = v.w;
+    }
 }
 B200_D float fma_any(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 B200_D float fma_sat(float a, float b, float c) {
@@ -94,12 +110,20 @@ B200_D float plane_2p15(uint32_t w, uint32_t sel) {
 }
 B200_D float box_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 B200_D float box_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// the word with the bytes of each 16-bit half swapped: (lo, hi) pairs become (hi, lo)
+B200_D uint32_t swap_pairs(uint32_t w) { return __byte_perm(w, 0u, 0x2301u); }
+// B200PT_BOX_SLACK with the sign of x
+B200_D float slack_signed(float x) { return __uint_as_float(0x3e99999au | (__float_as_uint(x) & 0x80000000u)); }
 B200_D int msb32(uint32_t v) { return 31 - __clz((int)v); }
 B200_D int popc32(uint32_t v) { return __popc(v); }
 #else
 inline U4 ld_u4(const U4 *p) { return *p; }
 inline F4 ld_f4(const F4 *p) { return *p; }
-inline void ld_node(const U4 *nodes, uint32_t index, NodeWords *n) { memcpy(n->w, nodes + (size_t)index * 4, 64); }
+inline void ld_node(const U4 *nodes, uint32_t index, NodeWords *n) {
+    const b200pt::WbvhNode rec = b200pt::wbvh_load_node(reinterpret_cast<const b200pt::WbvhNode *>(nodes), index);
+    memcpy(n->w, &rec, 64);
+}
+inline void ld_node_smem(const U4 *staged, uint32_t index, NodeWords *n) { ld_node(staged, index, n); }
 inline float fma_any(float a, float b, float c) { return fmaf(a, b, c); }
 inline float fma_sat(float a, float b, float c) {
     const float r = fmaf(a, b, c);
@@ -110,13 +134,15 @@ inline float plane_2p15(uint32_t w, uint32_t sel) {
 }
 inline float box_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 inline float box_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+inline uint32_t swap_pairs(uint32_t w) { return ((w & 0x00ff00ffu) << 8) | ((w >> 8) & 0x00ff00ffu); }
+inline float slack_signed(float x) { return uint_as_float(0x3e99999au | (float_as_uint(x) & 0x80000000u)); }
 inline int msb32(uint32_t v) { return 31 - __builtin_clz(v); }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 #endif
 
 #define B200PT_STACK 48
 #define B200PT_MISS 0xffffffffu
-#define B200PT_BOX_SLACK 0.3f  // cells, see the header
+#define B200PT_BOX_SLACK 0.3f  // cells, see the header (0x3e99999a, slack_signed)
 
 struct TraceCounters {
     uint32_t nodes, tris;
@@ -152,15 +178,17 @@ struct Trav {
     // ---- box test
     float idx, idy, idz;   // 1 / d, per unit of the box parameter
     float oix, oiy, oiz;   // (o + t0 d) * (idx, idy, idz)
-    float snx, sny, snz;   // -B200PT_BOX_SLACK * sign(d): the slack of the near planes in units of a = cell / d
-    uint32_t sel[8];       // PRMT selectors of the near / far byte: x, y (bytes 0-1 / 2-3 of a slot's xy word), z pair at bytes 0-1, at bytes 2-3
+    uint32_t sel[4];       // PRMT selectors of the NEAR byte: x, y (bytes 0-1 / 2-3 of a slot's xy word), z pair at bytes 0-1, at
+                           // bytes 2-3; the far byte is fetched with the same selector from the word with its byte pairs swapped
     uint32_t octinv;       // 7 - ray octant
     float tmaxp;           // the ray's current tMax as a box parameter (closest hit shrinks it)
     // ---- position in the tree
     uint32_t cur_x, cur_y;
-    int sp;
-    uint32_t overflow;     // pushes dropped because the stack was full (reported, never silent)
+    int sp;                // stack pointer; bit 30 is set when a push was dropped because the stack was full (reported,
+                           // never silent: B200PT_SP_OVERFLOW)
 };
+#define B200PT_SP_OVERFLOW 0x40000000
+#define B200PT_SP_MASK 0x3fffffff
 struct TravRay {
     V3 o;
     RayShear sh;
@@ -183,7 +211,6 @@ B200_HD void trav_init(Trav &T, TravRay &R, const V3 &o, const V3 &d, float rayT
     R.best = B200PT_MISS;
     R.hit.t = R.hit.b0 = R.hit.b1 = R.hit.b2 = 0.f;
     T.sp = 0;
-    T.overflow = 0u;
     T.cur_x = 0u;
     T.cur_y = 0u;  // nothing to do unless the ray meets the bounds
     const float ix = safe_rcp_dir(d.x), iy = safe_rcp_dir(d.y), iz = safe_rcp_dir(d.z);
@@ -194,16 +221,9 @@ B200_HD void trav_init(Trav &T, TravRay &R, const V3 &o, const V3 &d, float rayT
     T.octinv = 7u - oct;
     // PRMT selector 0x74B4: result bytes (3..0) = (0x47, 0x00, byte B of the node word, 0x00) = the float 32768 + byte
     T.sel[0] = 0x7404u | (nx << 4);
-    T.sel[1] = 0x7404u | ((nx ^ 1u) << 4);
-    T.sel[2] = 0x7424u | (ny << 4);
-    T.sel[3] = 0x7424u | ((ny ^ 1u) << 4);
-    T.sel[4] = 0x7404u | (nz << 4);
-    T.sel[5] = 0x7404u | ((nz ^ 1u) << 4);
-    T.sel[6] = 0x7424u | (nz << 4);
-    T.sel[7] = 0x7424u | ((nz ^ 1u) << 4);
-    T.snx = nx ? B200PT_BOX_SLACK : -B200PT_BOX_SLACK;
-    T.sny = ny ? B200PT_BOX_SLACK : -B200PT_BOX_SLACK;
-    T.snz = nz ? B200PT_BOX_SLACK : -B200PT_BOX_SLACK;
+    T.sel[1] = 0x7424u | (ny << 4);
+    T.sel[2] = 0x7404u | (nz << 4);
+    T.sel[3] = 0x7424u | (nz << 4);
     // the part of the ray inside the bounds: [t0, t1] (the clip itself widened by its own rounding)
     const float ax0 = (B.lo[0] - o.x) * ix, ax1 = (B.hi[0] - o.x) * ix;
     const float ay0 = (B.lo[1] - o.y) * iy, ay1 = (B.hi[1] - o.y) * iy;
@@ -241,39 +261,45 @@ B200_HD float trav_param_of(const TravRay &R, float t) {
     return p < 1.f ? p : 1.f;
 }
 
-#define B200PT_SLOT(S, WXY, WZ, ZN, ZF)                                                                              \
+#define B200PT_SLOT(S, WXY, WXYS, WZ, WZS, ZSEL)                                                                     \
     {                                                                                                                \
-        const float tn = box_max3(fma_sat(plane_2p15(WXY, T.sel[0]), ax, cnx), fma_sat(plane_2p15(WXY, T.sel[2]), ay, cny), \
-                                  fma_sat(plane_2p15(WZ, T.sel[ZN]), az, cnz));                                      \
-        const float tf = box_min3(fma_sat(plane_2p15(WXY, T.sel[1]), ax, cfx), fma_sat(plane_2p15(WXY, T.sel[3]), ay, cfy), \
-                                  fma_sat(plane_2p15(WZ, T.sel[ZF]), az, cfz));                                      \
+        const float tn = box_max3(fma_sat(plane_2p15(WXY, T.sel[0]), ax, cnx), fma_sat(plane_2p15(WXY, T.sel[1]), ay, cny), \
+                                  fma_sat(plane_2p15(WZ, T.sel[ZSEL]), az, cnz));                                    \
+        const float tf = box_min3(fma_sat(plane_2p15(WXYS, T.sel[0]), ax, cfx), fma_sat(plane_2p15(WXYS, T.sel[1]), ay, cfy), \
+                                  fma_sat(plane_2p15(WZS, T.sel[ZSEL]), az, cfz));                                   \
         if (CLOSEST ? (tn < tf && tn < T.tmaxp) : (tn < tf)) m |= (1u << S);                                         \
     }
 
 // Node phase: take the next inner child of the current group, fetch its node, test the seven
-// children.  Leaves the hit inner children in T.cur and returns the hit leaf triangles as a
-// triangle group (*tg_x = first triangle, *tg_y = bit per triangle).  Requires T.cur to be a node group.
+// children.  Leaves the hit inner children in T.cur and returns the hit leaf children as a
+// leaf group (*tg_x = the node, *tg_y = hit leaf slots | lcount << 8, 0 if none).  Requires T.cur to be a node group.
 // CLOSEST: the ray's tMax shrinks during traversal (closest hit); any-hit rays keep the span they started with.
-template <bool CLOSEST, bool COUNT>
-B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const uint32_t *__restrict__ tri_base,
-                             const uint8_t *lut, uint32_t *tg_x, uint32_t *tg_y, TraceCounters *ctr) {
+// STAGE: nodes [0, n_staged) -- the top of the tree, which is stored breadth-first -- are read from `staged`, a copy in
+// shared memory, instead of global memory.
+template <bool CLOSEST, bool COUNT, bool STAGE = false>
+B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const uint32_t *__restrict__ /*tri_base*/,
+                             const uint8_t *lut, uint32_t *tg_x, uint32_t *tg_y, TraceCounters *ctr, const U4 *staged = nullptr,
+                             uint32_t n_staged = 0) {
     const uint32_t hits = T.cur_y;
     const int bit = msb32(hits);
     T.cur_y &= ~(1u << bit);
     if (T.cur_y & 0xff000000u) {
-        if (T.sp < B200PT_STACK) {
-            S.x[T.sp] = T.cur_x;
-            S.y[T.sp] = T.cur_y;
+        if ((T.sp & B200PT_SP_MASK) < B200PT_STACK) {
+            S.x[T.sp & B200PT_SP_MASK] = T.cur_x;
+            S.y[T.sp & B200PT_SP_MASK] = T.cur_y;
             ++T.sp;
         } else {
-            T.overflow++;
+            T.sp |= B200PT_SP_OVERFLOW;
         }
     }
     const uint32_t slot = ((uint32_t)(bit - 24)) ^ T.octinv;
     const uint32_t rel = (uint32_t)popc32(hits & 0xffu & ((1u << slot) - 1u));
     const uint32_t ni = T.cur_x + rel;
     NodeWords n;
-    ld_node(nodes, ni, &n);
+    if (STAGE && ni < n_staged)
+        ld_node_smem(staged, ni, &n);
+    else
+        ld_node(nodes, ni, &n);
     if (COUNT) ctr->nodes++;
     // w0-2: p   w3: e.x e.y e.z imask   w4: child_base   w5: lcount | z pair of slot 0   w6-8: z pairs of slots 1..6
     // w9+s: (lo.x hi.x lo.y hi.y) of slot s.  plane(q) = p + q*cell, in box-parameter units q*a + k with a = cell/d,
@@ -285,16 +311,19 @@ B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes
     const float c0x = fma_any(-32768.0f, ax, fma_any(uint_as_float(n.w[0]), T.idx, -T.oix));
     const float c0y = fma_any(-32768.0f, ay, fma_any(uint_as_float(n.w[1]), T.idy, -T.oiy));
     const float c0z = fma_any(-32768.0f, az, fma_any(uint_as_float(n.w[2]), T.idz, -T.oiz));
-    const float cnx = fma_any(T.snx, ax, c0x), cny = fma_any(T.sny, ay, c0y), cnz = fma_any(T.snz, az, c0z);
-    const float cfx = fma_any(-T.snx, ax, c0x), cfy = fma_any(-T.sny, ay, c0y), cfz = fma_any(-T.snz, az, c0z);
+    // slack: 0.3 |a| towards the ray for the near planes, away from it for the far ones (a has the sign of the direction)
+    const float sx = slack_signed(T.idx), sy = slack_signed(T.idy), sz = slack_signed(T.idz);
+    const float cnx = fma_any(-sx, ax, c0x), cny = fma_any(-sy, ay, c0y), cnz = fma_any(-sz, az, c0z);
+    const float cfx = fma_any(sx, ax, c0x), cfy = fma_any(sy, ay, c0y), cfz = fma_any(sz, az, c0z);
+    const uint32_t z0 = swap_pairs(n.w[5]), z1 = swap_pairs(n.w[6]), z2 = swap_pairs(n.w[7]), z3 = swap_pairs(n.w[8]);
     uint32_t m = 0;
-    B200PT_SLOT(0, n.w[9], n.w[5], 6, 7)
-    B200PT_SLOT(1, n.w[10], n.w[6], 4, 5)
-    B200PT_SLOT(2, n.w[11], n.w[6], 6, 7)
-    B200PT_SLOT(3, n.w[12], n.w[7], 4, 5)
-    B200PT_SLOT(4, n.w[13], n.w[7], 6, 7)
-    B200PT_SLOT(5, n.w[14], n.w[8], 4, 5)
-    B200PT_SLOT(6, n.w[15], n.w[8], 6, 7)
+    B200PT_SLOT(0, n.w[9], swap_pairs(n.w[9]), n.w[5], z0, 3)
+    B200PT_SLOT(1, n.w[10], swap_pairs(n.w[10]), n.w[6], z1, 2)
+    B200PT_SLOT(2, n.w[11], swap_pairs(n.w[11]), n.w[6], z1, 3)
+    B200PT_SLOT(3, n.w[12], swap_pairs(n.w[12]), n.w[7], z2, 2)
+    B200PT_SLOT(4, n.w[13], swap_pairs(n.w[13]), n.w[7], z2, 3)
+    B200PT_SLOT(5, n.w[14], swap_pairs(n.w[14]), n.w[8], z3, 2)
+    B200PT_SLOT(6, n.w[15], swap_pairs(n.w[15]), n.w[8], z3, 3)
     const uint32_t imask = n.w[3] >> 24;
     const uint32_t mi = m & imask;
 #ifdef __CUDA_ARCH__
@@ -305,27 +334,51 @@ B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes
 #endif
     T.cur_x = n.w[4];
     T.cur_y = (pm << 24) | imask;
-    uint32_t ml = m & ~imask, tb = 0, bits = 0;
-    if (ml) {
-        // leaf children that were hit: their triangles follow each other in slot order behind tri_base[node]
-        tb = tri_base[ni];
-        const uint32_t lc = n.w[5] & 0xffffu;
-        do {
-            const int s = msb32(ml);
-            ml &= ~(1u << s);
-            const uint32_t below = lc & ((1u << (2 * s)) - 1u);
-            const uint32_t off = (uint32_t)popc32(below & 0x5555u) + 2u * (uint32_t)popc32(below & 0xaaaau);
-            bits |= ((1u << ((lc >> (2 * s)) & 3u)) - 1u) << off;
-        } while (ml);
+#if defined(__CUDA_ARCH__) && defined(B200PT_PREFETCH_CHILDREN)
+    {   // experiment: the hit children that will wait on the stack (all but the first in traversal order) are pulled
+        // into L2 now, so that their fetch -- many steps later -- does not go to DRAM
+        uint32_t rest = pm & (pm - 1u) ? pm & ~(1u << msb32(pm)) : 0u;
+        while (rest) {
+            const int b = msb32(rest);
+            rest &= ~(1u << b);
+            const uint32_t sl = (uint32_t)b ^ T.octinv;
+            const uint32_t ci = n.w[4] + (uint32_t)popc32(imask & ((1u << sl) - 1u));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(nodes) + (size_t)ci * 64));
+        }
     }
-    *tg_x = tb;
-    *tg_y = bits;
+#endif
+    // leaf children that were hit: the node's number and (slot bits | lcount << 8); trav_tri_phase turns them into triangles
+    const uint32_t ml = m & ~imask;
+    *tg_x = ni;
+    *tg_y = ml ? (ml | ((n.w[5] & 0xffffu) << 8)) : 0u;
 }
 #undef B200PT_SLOT
 
 // Triangle phase: exact watertight tests of a triangle group.  Returns true if ANY_HIT found a hit.
+// A leaf group of the node phase (node, hit leaf slots | lcount << 8) as a triangle group: *tg_x = first triangle of the
+// node's leaf children, *tg_y = bit per triangle (the triangles of the leaf slots follow each other in slot order).
+B200_HD void leaf_group_triangles(const uint32_t *__restrict__ tri_base, uint32_t lg_x, uint32_t lg_y, uint32_t *tg_x, uint32_t *tg_y) {
+    *tg_x = 0;
+    *tg_y = 0;
+    if (!lg_y) return;
+    *tg_x = tri_base[lg_x];
+    const uint32_t lc = lg_y >> 8;
+    uint32_t ml = lg_y & 0x7fu, bits = 0;
+    do {
+        const int s = msb32(ml);
+        ml &= ~(1u << s);
+        const uint32_t below = lc & ((1u << (2 * s)) - 1u);
+        const uint32_t off = (uint32_t)popc32(below & 0x5555u) + 2u * (uint32_t)popc32(below & 0xaaaau);
+        bits |= ((1u << ((lc >> (2 * s)) & 3u)) - 1u) << off;
+    } while (ml);
+    *tg_y = bits;
+}
+
 template <bool ANY_HIT, bool COUNT>
-B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const F4 *__restrict__ tris, uint32_t tg_x, uint32_t tg_y, TraceCounters *ctr) {
+B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const uint32_t *__restrict__ tri_base, const F4 *__restrict__ tris, uint32_t lg_x,
+                            uint32_t lg_y, TraceCounters *ctr) {
+    uint32_t tg_x, tg_y;
+    leaf_group_triangles(tri_base, lg_x, lg_y, &tg_x, &tg_y);
     while (tg_y) {
         const int j = msb32(tg_y);
         tg_y &= ~(1u << j);
@@ -348,10 +401,10 @@ B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const F4 *__restrict__ tri
 // Pops the next node group if the current one is exhausted; false when nothing is left.
 B200_HD bool trav_next_group(Trav &T, TravStack &S) {
     if ((T.cur_y & 0xff000000u) == 0) {
-        if (T.sp == 0) return false;
+        if ((T.sp & B200PT_SP_MASK) == 0) return false;
         --T.sp;
-        T.cur_x = S.x[T.sp];
-        T.cur_y = S.y[T.sp];
+        T.cur_x = S.x[T.sp & B200PT_SP_MASK];
+        T.cur_y = S.y[T.sp & B200PT_SP_MASK];
     }
     return true;
 }
@@ -363,7 +416,7 @@ B200_HD bool trav_step(Trav &T, TravRay &R, TravStack &S, const U4 *__restrict__
                         const F4 *__restrict__ tris, const uint8_t *lut, TraceCounters *ctr) {
     uint32_t tg_x = 0, tg_y = 0;
     if (T.cur_y & 0xff000000u) trav_node_phase<!ANY_HIT, COUNT>(T, S, nodes, tri_base, lut, &tg_x, &tg_y, ctr);
-    if (trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, tris, tg_x, tg_y, ctr)) return true;
+    if (trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, tri_base, tris, tg_x, tg_y, ctr)) return true;
     return !trav_next_group(T, S);
 }
 
@@ -382,7 +435,7 @@ B200_HD uint32_t traverse_wbvh(const U4 *__restrict__ nodes, const uint32_t *__r
         while (!trav_step<ANY_HIT, COUNT>(T, R, S, nodes, tri_base, tris, lut, ctr)) {
         }
     *hit = R.hit;
-    if (overflow) *overflow += T.overflow;
+    if (overflow && (T.sp & B200PT_SP_OVERFLOW)) *overflow += 1;
     return R.best;
 }
 

@@ -649,6 +649,17 @@ class GpuIntegrator : public Base {
         b200pt_ctx *ctx = nullptr;
         b200pt_scene *gscene = nullptr;
         b200pt_render *render = nullptr;
+        // whatever way this function is left (B200_CHECK returns on the first failing call), the device objects go with it
+        struct Handles {
+            b200pt_ctx *&c;
+            b200pt_scene *&s;
+            b200pt_render *&r;
+            ~Handles() {
+                if (r) b200pt_render_destroy(r);
+                if (s) b200pt_scene_destroy(s);
+                if (c) b200pt_ctx_destroy(c);
+            }
+        } handles{ctx, gscene, render};
         auto now = []() { return std::chrono::steady_clock::now(); };
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
             return std::chrono::duration<double, std::milli>(b - a).count();
@@ -687,7 +698,57 @@ class GpuIntegrator : public Base {
         // raw film sums -> Film::pixels (film.h:83-89), then the reference's own WriteImage
         const int w = cb.pMax.x - cb.pMin.x, h = cb.pMax.y - cb.pMin.y;
         std::vector<float> raw((size_t)w * h * 4);
+        // Several processes (B200PT_RANK / B200PT_WORLD_SIZE, one per GPU) rendered disjoint tile sets of this film:
+        // their raw sums meet on rank 0, the only rank that writes the image.  With B200PT_NCCL_ID_FILE (a fresh path
+        // every rank can reach, chosen by the launcher) it is one ncclReduce over NVLink behind the C ABI
+        // (b200pt_film_reduce); otherwise -- or if NCCL cannot start, e.g. two ranks on one GPU -- the ranks hand their
+        // raw films to rank 0 through files next to the image.  The reference's equivalent is `imgtool assemble`
+        // (tools/imgtool.cpp:190-285) after independent crop-window runs.
+        bool merged = world == 1;
+        if (!merged && getenv("B200PT_NCCL_ID_FILE")) {
+            b200pt_comm *comm = nullptr;
+            if (b200pt_comm_create(ctx, rank, world, getenv("B200PT_NCCL_ID_FILE"), &comm) == B200PT_OK) {
+                B200_CHECK(b200pt_film_reduce(render, comm, 0));
+                B200_CHECK(b200pt_ctx_synchronize(ctx));
+                b200pt_comm_destroy(comm);
+                merged = true;
+            } else {
+                Warning("gpupath: NCCL film reduce unavailable (%s); merging through files", b200pt_last_error());
+            }
+        }
         B200_CHECK(b200pt_film_read_raw(render, raw.data()));
+        if (!merged) {
+            auto part = [&](int k) { return film->filename + ".rank" + std::to_string(k) + ".raw"; };
+            if (rank != 0) {
+                const std::string tmp = part(rank) + ".tmp";
+                FILE *f = fopen(tmp.c_str(), "wb");
+                if (!f || fwrite(raw.data(), sizeof(float), raw.size(), f) != raw.size()) {
+                    Error("gpupath: cannot write %s", tmp.c_str());
+                    if (f) fclose(f);
+                } else {
+                    fclose(f);
+                    rename(tmp.c_str(), part(rank).c_str());
+                }
+            } else {
+                std::vector<float> other(raw.size());
+                for (int k = 1; k < world; ++k) {  // rank order: the sum is reproducible
+                    bool got = false;
+                    for (int tries = 0; tries < 72000 && !got; ++tries) {  // up to an hour for the slowest rank
+                        if (FILE *f = fopen(part(k).c_str(), "rb")) {
+                            got = fread(other.data(), sizeof(float), other.size(), f) == other.size();
+                            fclose(f);
+                        }
+                        if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+                    }
+                    if (!got) {
+                        Error("gpupath: rank %d's film %s never arrived; the image holds the other ranks' tiles only", k, part(k).c_str());
+                        continue;
+                    }
+                    for (size_t i = 0; i < raw.size(); ++i) raw[i] += other[i];
+                    remove(part(k).c_str());
+                }
+            }
+        }
         for (size_t i = 0; i < (size_t)w * h; ++i) {
             Film::Pixel &p = film->pixels[i];
             p.xyz[0] = raw[4 * i];
@@ -715,9 +776,12 @@ class GpuIntegrator : public Base {
             }
         }
         b200pt_render_destroy(render);
+        render = nullptr;
         b200pt_scene_destroy(gscene);
+        gscene = nullptr;
         b200pt_ctx_destroy(ctx);
-        film->WriteImage();
+        ctx = nullptr;
+        if (rank == 0) film->WriteImage();  // the other ranks' tiles are part of rank 0's image
 #undef B200_CHECK
     }
 

@@ -32,6 +32,33 @@ def test_plugin_fails_loudly_without_gpu(scenes, tmp_path):
     assert not os.path.exists(os.path.join(str(tmp_path), "render_four.pfm")), "no image may be produced without a GPU"
 
 
+def run_ranks(plugin, scenes, tmp_path, world, extra_env=None):
+    """pbrt_b200 as `world` processes (B200PT_RANK / B200PT_WORLD_SIZE, tiles i mod world each): the ranks' raw film sums
+    meet on rank 0, which alone writes the image; returns that image."""
+    path = _scene(scenes, tmp_path)
+    out = os.path.join(str(tmp_path), "render_four.pfm")
+    procs = []
+    for k in range(world):
+        env = dict(os.environ, B200PT_RANK=str(k), B200PT_WORLD_SIZE=str(world), **(extra_env or {}))
+        procs.append(subprocess.Popen([plugin, "--quiet", os.path.basename(path)], cwd=str(tmp_path), env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    assert not [f for f in os.listdir(str(tmp_path)) if ".rank" in f], "the ranks' partial films must be consumed by rank 0"
+    return scenes.read_pfm(out), logs
+
+
+@needs_plugin
+@pytest.mark.gpu
+def test_dropin_two_ranks_one_image(scenes, tmp_path):
+    """ADVICE r1 / SURVEY 8e: two pbrt_b200 processes shard the tiles of one film; rank 0 writes the one image, equal to
+    the reference's.  (Both ranks share this box's GPU, so the merge goes through the file hand-over; with one GPU per
+    rank and B200PT_NCCL_ID_FILE it is b200pt_film_reduce = one ncclReduce.)"""
+    got, _ = run_ranks(PLUGIN, scenes, tmp_path, 2)
+    ref = scenes.read_pfm(os.path.join(GOLDEN, "render_four.pfm"))
+    assert np.array_equal(bits(got), bits(ref)), "the two ranks' merged image differs from the reference PFM"
+
+
 @needs_plugin
 @pytest.mark.gpu
 def test_dropin_binary_matches_reference(scenes, tmp_path):

@@ -148,6 +148,14 @@ def test_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkey
     P.test_dropin_binary_matches_reference(scenes, tmp_path)
 
 
+def test_dropin_three_ranks_one_image_on_the_check_library(hc_plugins, scenes, tmp_path):
+    """Multi-process drop-in (B200PT_RANK / B200PT_WORLD_SIZE): three processes render tiles i mod 3 of one film, the
+    partial films meet on rank 0, one image comes out and it is the reference's, bit for bit."""
+    got, logs = P.run_ranks(HC_PLUGIN, scenes, tmp_path, 3)
+    ref = scenes.read_pfm(os.path.join(P.GOLDEN, "render_four.pfm"))
+    assert np.array_equal(P.bits(got), P.bits(ref)), "merged image of three ranks differs from the reference PFM"
+
+
 def test_spectral_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
     """The same through the SampledSpectrum host: the 60-bin tables gpupath.cpp extracts give the image of the reference
     built with `typedef SampledSpectrum Spectrum`."""
