@@ -205,10 +205,16 @@ def main():
         if spectral:
             arr.attach_spectral(spectral_tables())  # the oracle port reads the tables; the reference binary has its own
         arr.bench_integrator = VOLUMETRIC_WORKLOADS.get(args.workload, {})
-        setup_small = scenes.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth, **arr.bench_integrator)
         tmp = tempfile.mkdtemp(prefix="b200pt_ref_")
         have_ref = os.path.exists(ob.PBRT_REF_SPECTRAL) if spectral else ob.have_reference()
         pbrt_path = write_reference_scene(scenes, arr, wl, args.cpu_sample_spp, tmp) if have_ref else None
+        setup_small = None
+        if not have_ref:
+            # no reference binary on this box: the oracle port renders the sample; its camera descriptor comes from the
+            # library's host helper (no kernel of the repo runs in this arm either way)
+            graft.load_package()
+            from pbrt_v3_distributed_b200 import scenes as scenes_full
+            setup_small = scenes_full.RenderSetup(xres, yres, args.cpu_sample_spp, max_depth=depth, **arr.bench_integrator)
         rays = secs = samples = 0.0
         last = None
         for i in range(args.warmup + args.steps):

@@ -432,7 +432,7 @@ int b200pt_scene_create(b200pt_ctx *ctx, const b200pt_scene_desc *d, b200pt_scen
     uint32_t tlas_node_off = 0, tlas_tri_off = 0;
     const float zero3[3] = {0.f, 0.f, 0.f};
     TravBounds tlas_bounds = make_trav_bounds(zero3, zero3);
-    if (d->n_instances > 8 && !gpu_build) {
+    if (d->n_instances > 0 && !gpu_build) {
         std::vector<float> boxes((size_t)d->n_instances * 9);
         std::vector<int32_t> zeros((size_t)d->n_instances, 0);
         for (int i = 0; i < d->n_instances; ++i) {
@@ -712,6 +712,10 @@ static int refill_lanes() {
     static int v = getenv("B200PT_REFILL_LANES") ? atoi(getenv("B200PT_REFILL_LANES")) : 26;
     return v;
 }
+static int sphere_refill_lanes() {
+    static int v = getenv("B200PT_SPHERE_REFILL") ? atoi(getenv("B200PT_SPHERE_REFILL")) : 8;
+    return v;
+}
 static int trace_ctas_default() {
     static int v = getenv("B200PT_TRACE_CTAS_RT") ? atoi(getenv("B200PT_TRACE_CTAS_RT")) : 0;
     return v;
@@ -719,6 +723,19 @@ static int trace_ctas_default() {
 static int stage_nodes_default() {
     static int v = getenv("B200PT_STAGE_NODES") ? atoi(getenv("B200PT_STAGE_NODES")) : 0;
     return v;
+}
+
+// Scenes with object instances: the persistent two-level kernel (k_trace2) walks top-level triangles and instances in
+// one launch.  Scenes that also hold Sphere shapes (tested by the separate pass k_spheres, which needs every earlier hit's
+// distance), the CPU check build and scenes without a tree over the instances keep the separate pass for both.
+static bool two_level(const b200pt_scene *s) {
+#ifdef B200PT_HOST_EMU
+    (void)s;
+    return false;
+#else
+    static const bool off = getenv("B200PT_NO_TRACE2") != nullptr;
+    return !off && !s->instances.empty() && s->tlas_node_off != 0 && s->spheres.empty();
+#endif
 }
 
 static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64_t n, bool any_hit) {
@@ -747,16 +764,24 @@ static int trace_dev(b200pt_scene *s, uint64_t rays_dev, uint64_t out_dev, int64
         a.occ_out = reinterpret_cast<uint8_t *>(out_dev);
     else
         a.full_out = reinterpret_cast<b200pt_hit *>(out_dev);
-    launch_trace(a, any_hit, false, false, trace_grid(s->ctx), st);
-    if (!s->spheres.empty() || !s->instances.empty()) {
-        a.spheres = s->d_spheres;
-        a.n_spheres = (uint32_t)s->spheres.size();
-        a.instances = s->d_instances;
-        a.n_instances = (uint32_t)s->instances.size();
-        a.tlas_node_off = s->tlas_node_off;
-        a.tlas_tri_off = s->tlas_tri_off;
-        a.n_tris = (uint32_t)s->n_prims;
-        a.sphere_work = s->d_work + 2;
+    const bool tl = two_level(s);
+    a.spheres = s->d_spheres;
+    a.n_spheres = (uint32_t)s->spheres.size();
+    a.instances = s->d_instances;
+    a.n_instances = (uint32_t)s->instances.size();
+    a.tlas_node_off = s->tlas_node_off;
+    a.tlas_tri_off = s->tlas_tri_off;
+    a.n_tris = (uint32_t)s->n_prims;
+    a.sphere_work = s->d_work + 2;
+    a.sphere_refill_lanes = sphere_refill_lanes();
+#ifndef B200PT_HOST_EMU
+    if (tl)
+        launch_trace2(a, any_hit, false, trace_grid(s->ctx), st);
+    else
+#endif
+        launch_trace(a, any_hit, false, false, trace_grid(s->ctx), st);
+    if (!s->spheres.empty() || (!s->instances.empty() && !tl)) {
+        if (tl) a.n_instances = 0;  // already walked
         launch_spheres(a, any_hit, false, trace_grid(s->ctx), st);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1361,13 +1386,31 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         const bool medium = H.has_medium != 0;  // k_medium also queues direct-lighting rays: no overlap of bounces then
         const bool overlap = r->overlap && r->sort_from_bounce < 0 && !medium;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
-        const bool has_spheres = H.scene.n_spheres > 0 || H.scene.n_instances > 0;  // "extra shapes" pass needed
-        const bool full_shade = has_spheres || H.has_delta_lights || H.scene.tri_n != nullptr || H.scene.tri_uv != nullptr || H.volpath;
+        const bool tl = two_level(r->scene) && !r->instrumented;  // instances inside the traversal kernel
+        const bool has_spheres = H.scene.n_spheres > 0 || (H.scene.n_instances > 0 && !tl);  // "extra shapes" pass needed
+        const bool full_shade = has_spheres || H.scene.n_instances > 0 || H.has_delta_lights || H.scene.tri_n != nullptr ||
+                                H.scene.tri_uv != nullptr || H.volpath;
+        // traversal of one ray queue: the plain kernel, or the two-level one when the scene has instances
+        auto trace = [&](TraceArgs &a, bool any_hit, bool classify, cudaStream_t s_) {
+#ifndef B200PT_HOST_EMU
+            if (tl) {
+                a.instances = H.scene.instances;
+                a.n_instances = H.scene.n_instances;
+                a.tlas_node_off = H.scene.tlas_node_off;
+                a.tlas_tri_off = H.scene.tlas_tri_off;
+                a.hit_inst_out = a.hit_out == H.hit ? H.hit_inst : nullptr;
+                launch_trace2(a, any_hit, classify, r->grid_trace, s_);
+                return;
+            }
+#endif
+            launch_trace(a, any_hit, classify, r->instrumented, r->grid_trace, s_);
+        };
         auto sphere_args = [&](TraceArgs &a, uint32_t *work) {
+            a.sphere_refill_lanes = sphere_refill_lanes();
             a.spheres = H.scene.spheres;
             a.n_spheres = H.scene.n_spheres;
             a.instances = H.scene.instances;
-            a.n_instances = H.scene.n_instances;
+            a.n_instances = tl ? 0u : H.scene.n_instances;
             a.tlas_node_off = H.scene.tlas_node_off;
             a.tlas_tri_off = H.scene.tlas_tri_off;
             a.hit_inst_out = a.hit_out == H.hit ? H.hit_inst : nullptr;
@@ -1405,7 +1448,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             LaunchTimer lt(r, st, 0);
             // with spheres in the scene the sphere pass decides the final hit, so it does the classification;
             // inside a medium the medium pass does (only paths that reach their surface are shaded)
-            launch_trace(a, false, !has_spheres && !medium, r->instrumented, r->grid_trace, st);
+            trace(a, false, !has_spheres && !medium, st);
             if (has_spheres) {
                 sphere_args(a, wk + 8);
                 launch_spheres(a, false, !medium, r->grid_shade, st);
@@ -1447,7 +1490,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.occ_out = H.occluded;
             {
                 LaunchTimer lt(r, st2, 1);
-                launch_trace(a, true, false, r->instrumented, r->grid_trace, st2);
+                trace(a, true, false, st2);
                 if (has_spheres) {
                     sphere_args(a, wk + 9);
                     launch_spheres(a, true, false, r->grid_shade, st2);
@@ -1464,7 +1507,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.hit_out = H.mis_hit;
             a.occ_out = nullptr;
             LaunchTimer lt(r, st2, 0);
-            launch_trace(a, false, false, r->instrumented, r->grid_trace, st2);
+            trace(a, false, false, st2);
             if (has_spheres) {
                 sphere_args(a, wk + 10);
                 launch_spheres(a, false, false, r->grid_shade, st2);

@@ -314,11 +314,45 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 // CTAS: resident CTAs per SM the kernel is compiled for (register budget); STAGE: the top of the tree is staged in
 // shared memory by TMA (north_star's variant; measured against the plain one in profiles/README.md).
+// Experiment (off): with B200PT_SMEM_STACK = n the first n entries of a lane's traversal stack live in shared memory, one
+// column per thread (lanes at different depths hit different rows but their own bank: a push or pop of the whole warp is
+// two conflict-free wavefronts instead of one L1 tag lookup per distinct depth in local memory); deeper entries go to local
+// memory.  Measured on cfg3 (profiles/README.md, "stack in shared memory"): 730 Mrays/s with 0 or 8 entries, 699 with 4 --
+// no gain for 8 KB of shared memory per CTA, so the stack stays in local memory.
+#ifndef B200PT_SMEM_STACK
+#define B200PT_SMEM_STACK 0
+#endif
+struct LaneStack {
+    uint32_t *sx, *sy;  // this thread's column of the shared part: entry e at [e * 128]
+    uint32_t x[B200PT_STACK - B200PT_SMEM_STACK], y[B200PT_STACK - B200PT_SMEM_STACK];
+    __device__ __forceinline__ void push(int sp, uint32_t gx, uint32_t gy) {
+        if (sp < B200PT_SMEM_STACK) {
+            sx[sp * 128] = gx;
+            sy[sp * 128] = gy;
+        } else {
+            x[sp - B200PT_SMEM_STACK] = gx;
+            y[sp - B200PT_SMEM_STACK] = gy;
+        }
+    }
+    __device__ __forceinline__ void pop(int sp, uint32_t *gx, uint32_t *gy) const {
+        if (sp < B200PT_SMEM_STACK) {
+            *gx = sx[sp * 128];
+            *gy = sy[sp * 128];
+        } else {
+            *gx = x[sp - B200PT_SMEM_STACK];
+            *gy = y[sp - B200PT_SMEM_STACK];
+        }
+    }
+};
+
 template <bool ANY_HIT, bool CLASSIFY, bool COUNT, int CTAS, bool STAGE>
 __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     // the slot-permutation table of the node test (wbvh_traverse.cuh), one copy per CTA
     __shared__ __align__(16) uint8_t s_lut[B200PT_LUT_BYTES];
     __shared__ float s_ray[B200PT_RAY_WORDS * 128];
+#if B200PT_SMEM_STACK > 0
+    __shared__ uint32_t s_stack[2 * B200PT_SMEM_STACK * 128];
+#endif
     __shared__ __align__(8) unsigned long long s_bar;
     extern __shared__ __align__(128) uint8_t s_top[];  // STAGE: WbvhNode[a.n_staged]
     reinterpret_cast<uint4 *>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + threadIdx.x);
@@ -349,7 +383,13 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     TraceCounters ctr;
     ctr.nodes = ctr.tris = 0;
     Trav T;
+#if B200PT_SMEM_STACK > 0
+    LaneStack S;
+    S.sx = s_stack + threadIdx.x;
+    S.sy = s_stack + B200PT_SMEM_STACK * 128 + threadIdx.x;
+#else
     TravStack S;
+#endif
     uint32_t slot = 0, pend_x = 0, pend_y = 0;
     bool has = false, fin = false, exhausted = false;
     while (true) {
@@ -477,6 +517,273 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- two-level traversal (scenes with object instances)
+// TransformedPrimitive::Intersect / IntersectP (core/primitive.cpp:70-106) inside the persistent kernel: a lane walks
+// the top-level tree (triangles outside objects), then the tree over the instances' leaf boxes; a leaf of that tree
+// names instances, and each candidate that passes its leaf-box gate takes the lane -- with the ray transformed into the
+// object's space -- through that object's own tree, after which the walk over the instances resumes.  One set of
+// box-test constants lives in registers (re-derived when the lane changes space: once per instance entered, not per
+// node); what the lane must come back to waits on the same traversal stack behind a marked entry.  Replaces the
+// one-batch-of-32-rays walk of k_spheres for the instances (measured in profiles/README.md, "instances").
+#define B200PT_RAY_WORDS2 18  // k_trace's record + instance of the hit, world tMax, current instance
+#define B200PT_MARK 0x80000000u  // stack entry x: "what follows is what the lane left behind when it entered an instance"
+template <bool ANY_HIT, bool CLASSIFY>
+__global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
+    __shared__ __align__(16) uint8_t s_lut[B200PT_LUT_BYTES];
+    __shared__ float s_ray[B200PT_RAY_WORDS2 * 128];
+    reinterpret_cast<uint4 *>(s_lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + threadIdx.x);
+    __syncthreads();
+    float *const my_ray = s_ray + threadIdx.x;
+    const uint32_t n = *a.count;
+    const int lane = threadIdx.x & 31;
+    TraceCounters ctr;
+    ctr.nodes = ctr.tris = 0;
+    Trav T;
+    TravStack S;
+    uint32_t slot = 0, pend_x = 0, pend_y = 0;
+    uint32_t noff = 0, toff = 0;  // the tree the lane is in: offsets of its nodes / triangles inside the scene's arrays
+    int phase = 0;                // 0: top-level tree, 1: tree over the instances, 2: inside an instance
+    bool has = false, fin = false, exhausted = false;
+    // (re)derives the box-test constants and the triangle-test record for a ray in the space the lane enters;
+    // the position on the stack and the result so far are the lane's own and stay
+    auto enter_space = [&](const V3 &o, const V3 &d, float tmax, const TravBounds &B) {
+        TravRay R;
+        const int sp = T.sp;
+        trav_init(T, R, o, d, tmax, B);
+        T.sp = sp;
+        my_ray[0 * 128] = R.o.x;
+        my_ray[1 * 128] = R.o.y;
+        my_ray[2 * 128] = R.o.z;
+        my_ray[3 * 128] = R.sh.Sx;
+        my_ray[4 * 128] = R.sh.Sy;
+        my_ray[5 * 128] = R.sh.Sz;
+        my_ray[6 * 128] = __int_as_float(R.sh.kz);
+        my_ray[7 * 128] = R.tmax;
+        my_ray[13 * 128] = R.t0;
+        my_ray[14 * 128] = R.inv;
+    };
+    auto world_ray = [&](V3 *o, V3 *d) {
+        const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+        const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+        *o = v3(o4);
+        *d = v3(d4);
+    };
+    while (true) {
+        // ---- converged: retire finished rays
+        {
+            int family = -1;
+            if (fin) {
+                const uint32_t best = __float_as_uint(my_ray[8 * 128]);
+                if (ANY_HIT) {
+                    a.occ_out[slot] = best != B200PT_MISS ? 1 : 0;
+                } else {
+                    if (a.hit_out) a.hit_out[slot] = best;
+                    if (a.hit_inst_out && best != B200PT_MISS) a.hit_inst_out[slot] = __float_as_uint(my_ray[15 * 128]);
+                    if (a.full_out) {
+                        b200pt_hit r;
+                        r.triangle = best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w) : -1;
+                        r.t = my_ray[9 * 128];
+                        r.b0 = my_ray[10 * 128];
+                        r.b1 = my_ray[11 * 128];
+                        a.full_out[slot] = r;
+                    }
+                    if (CLASSIFY && best != B200PT_MISS) {
+                        const uint32_t mf = __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
+                        family = a.materials[mf & 0xffffu].type;
+                    }
+                }
+                if ((T.sp & B200PT_SP_OVERFLOW) && a.stats) atomicAdd(&a.stats[7], 1ull);
+            }
+            if (CLASSIFY) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const bool mine = family == m;
+                    const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
+                    if (mine) a.q_mat[m][pos] = slot;
+                }
+            }
+            fin = false;
+        }
+        // ---- converged: idle lanes fetch new rays
+        {
+            const bool want = !has && !exhausted;
+            const uint32_t mask = __ballot_sync(FULL_MASK, want);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(a.work, (uint32_t)__popc(mask));
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if (want) {
+                    const uint32_t i = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    if (i < n) {
+                        slot = a.queue ? a.queue[i] : i;
+                        const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+                        const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+                        const float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
+                        T.sp = 0;
+                        phase = 0;
+                        noff = toff = 0;
+                        enter_space(v3(o4), v3(d4), tmax, a.bounds);
+                        my_ray[8 * 128] = __uint_as_float(B200PT_MISS);
+                        my_ray[9 * 128] = my_ray[10 * 128] = my_ray[11 * 128] = my_ray[12 * 128] = 0.f;
+                        my_ray[15 * 128] = __uint_as_float(0u);
+                        my_ray[16 * 128] = tmax;  // the world ray's tMax
+                        pend_y = 0;
+                        has = true;
+                    } else {
+                        exhausted = true;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL_MASK, has) == 0) break;
+        while (has) {
+            uint32_t ng_x = 0, ng_y = 0;
+            // in the tree over the instances a leaf group is dealt with before the walk goes on: entering an instance
+            // leaves ONE group of untried candidates behind, so the lane must never hold two
+            const bool hold = phase == 1 && pend_y != 0;
+            const bool node_work = !hold && (T.cur_y & 0xff000000u) != 0;
+            if (node_work)
+                trav_node_phase<!ANY_HIT, false>(T, S, a.nodes + (size_t)noff * 4, a.tri_base + noff, s_lut, &ng_x, &ng_y, &ctr);
+            bool must = hold;
+            if (ng_y) {
+                if (pend_y) {
+                    must = true;  // two groups: flush the parked one now, park the new one after
+                } else {
+                    pend_x = ng_x;
+                    pend_y = ng_y;
+                    ng_y = 0;
+                    if (phase == 1) must = true;
+                }
+            }
+            const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0;  // (what is left on the stack waits behind the parked group)
+            const unsigned act = __activemask();
+            const bool starving_me = out_of_nodes && pend_y != 0;
+            const unsigned counts = __reduce_add_sync(
+                act, (pend_y != 0 ? 1u : 0u) | ((must || (starving_me && a.postpone_pct <= 0)) ? 0x100u : 0u) |
+                         (starving_me ? 0x10000u : 0u));
+            const int n_act = __popc(act), n_parked = (int)(counts & 0xffu), n_starving = (int)((counts >> 16) & 0xffu);
+            if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_starving * 4 >= n_act) {
+                bool done = false;
+                if (pend_y && phase == 1) {
+                    // leaf of the tree over the instances: its "triangles" name instances; the first candidate whose
+                    // leaf box the ray (with its current tMax) enters takes the lane into that object's tree
+                    uint32_t tg_x, tg_y;
+                    if (pend_x & B200PT_MARK) {  // candidates left over from before an instance was entered: already triangles
+                        tg_x = pend_x & ~B200PT_MARK;
+                        tg_y = pend_y;
+                    } else {
+                        leaf_group_triangles(a.tri_base + noff, pend_x, pend_y, &tg_x, &tg_y);
+                    }
+                    V3 ro, rd;
+                    world_ray(&ro, &rd);
+                    const float wtmax = my_ray[16 * 128];
+                    while (tg_y) {
+                        const int j = msb32(tg_y);
+                        tg_y &= ~(1u << j);
+                        const uint32_t k = __float_as_uint(ld_f4(a.tris + (size_t)(toff + tg_x + (uint32_t)j) * 3).w);  // TriRecord::prim
+                        const DevInstance &in = a.instances[k];
+                        if (!instance_leaf_test(in, ro, rd, wtmax)) continue;
+                        // left behind: the group being walked and the candidates not tried yet
+                        if ((T.sp & B200PT_SP_MASK) + 2 > B200PT_STACK) {
+                            T.sp |= B200PT_SP_OVERFLOW;
+                            break;
+                        }
+                        S.push(T.sp & B200PT_SP_MASK, T.cur_x, T.cur_y);
+                        S.push((T.sp & B200PT_SP_MASK) + 1, tg_x | B200PT_MARK, tg_y);
+                        T.sp += 2;
+                        V3 o2, d2;
+                        float tm2;
+                        instance_ray(in, ro, rd, wtmax, &o2, &d2, &tm2);
+                        enter_space(o2, d2, tm2, instance_bounds(in));
+                        noff = in.node_off;
+                        toff = in.tri_off;
+                        my_ray[17 * 128] = __uint_as_float(k);
+                        phase = 2;
+                        break;
+                    }
+                } else if (pend_y) {
+                    TravRay R;
+                    ray_load(my_ray, R);
+                    R.best = B200PT_MISS;  // (an index inside this tree; the record keeps scene-wide ones)
+                    done = trav_tri_phase<ANY_HIT, false>(R, &T.tmaxp, a.tri_base + noff, a.tris + (size_t)toff * 3, pend_x, pend_y, &ctr);
+                    if (R.best != B200PT_MISS) {
+                        R.best += toff;
+                        ray_store_hit(my_ray, R);
+                        if (phase == 2) my_ray[15 * 128] = my_ray[17 * 128];  // the instance of the hit
+                        my_ray[16 * 128] = R.tmax;                            // r.tMax = ray.tMax (primitive.cpp:91 / :120)
+                    }
+                }
+                pend_x = ng_x;
+                pend_y = ng_y;
+                if (done) {
+                    has = false;
+                    fin = true;
+                    pend_y = 0;
+                }
+            }
+            // ---- the next group of the current tree, or back out of an instance, or on to the next tree, or done
+            if (has && (T.cur_y & 0xff000000u) == 0) {
+                bool more = false, blocked = false;
+                while (!more && !blocked) {
+                    if ((T.sp & B200PT_SP_MASK) == 0) break;
+                    uint32_t ex, ey;
+                    S.pop((T.sp & B200PT_SP_MASK) - 1, &ex, &ey);
+                    if (!(ex & B200PT_MARK)) {
+                        --T.sp;
+                        T.cur_x = ex;
+                        T.cur_y = ey;
+                        more = (ey & 0xff000000u) != 0;
+                    } else if (pend_y != 0) {
+                        blocked = true;  // triangles of the object are still parked: they are tested in its space first
+                    } else {
+                        // the object's tree is done: back to the world ray (its tMax is the hit's, if there was one) and
+                        // to the walk over the instances -- first the candidates of the same leaf that were not tried
+                        T.sp -= 2;
+                        uint32_t gx, gy;
+                        S.pop(T.sp & B200PT_SP_MASK, &gx, &gy);
+                        V3 ro, rd;
+                        world_ray(&ro, &rd);
+                        noff = a.tlas_node_off;
+                        toff = a.tlas_tri_off;
+                        phase = 1;
+                        enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
+                        T.cur_x = gx;
+                        T.cur_y = gy;
+                        if (ey) {
+                            pend_x = ex;  // marked: already a triangle group
+                            pend_y = ey;
+                            more = true;
+                        } else {
+                            more = (gy & 0xff000000u) != 0;
+                        }
+                    }
+                }
+                if (!more && !blocked && pend_y == 0) {
+                    if (phase == 0 && a.n_instances > 0) {
+                        // the top-level triangles are done: on to the instances, with the ray's tMax so far
+                        V3 ro, rd;
+                        world_ray(&ro, &rd);
+                        noff = a.tlas_node_off;
+                        toff = a.tlas_tri_off;
+                        phase = 1;
+                        enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
+                        if ((T.cur_y & 0xff000000u) == 0) {
+                            has = false;
+                            fin = true;
+                        }
+                    } else {
+                        has = false;
+                        fin = true;
+                    }
+                }
+            }
+            if (__popc(__activemask()) < a.refill_lanes) break;
+        }
+        __syncwarp();
+    }
+}
+
 #endif  // B200PT_HOST_EMU
 
 // ---------------------------------------------------------------------- instances
@@ -498,195 +805,282 @@ __device__ uint32_t instance_test(const TraceArgs &a, uint32_t k, const V3 &ro, 
     if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
     return ti == B200PT_MISS ? B200PT_MISS : in.tri_off + ti;
 }
-// All instances against one ray: through the tree over their leaf boxes when there is one (its leaf "triangles" carry
-// instance numbers), else one by one.  Returns the closest object triangle (and *inst) or B200PT_MISS; *tmax is updated.
+// All instances against one ray, as a resumable state machine: through the tree over their leaf boxes when there is
+// one (its leaf "triangles" carry instance numbers), else one by one.  Each lane walks the tree over the instances'
+// boxes, picks the next candidate instance, or takes ONE step inside that instance's tree per call of step(), so that
+// the lanes of a warp meet again after every step instead of after whole nested traversals (measured with nested loops:
+// 2.4 of 32 lanes active per instruction) and a lane whose ray is done can take the next ray (k_spheres).
 template <bool ANY_HIT>
-__device__ uint32_t instances_test(const TraceArgs &a, const V3 &ro, const V3 &rd, float *tmax, TriHit *hit, uint32_t *inst) {
-    uint32_t best = B200PT_MISS;
-    if (a.tlas_node_off == 0u) {
-        for (uint32_t k = 0; k < a.n_instances; ++k) {
-            TriHit h;
-            const uint32_t ti = instance_test<ANY_HIT>(a, k, ro, rd, *tmax, &h);
-            if (ti == B200PT_MISS) continue;
-            best = ti;
-            *inst = k;
-            *hit = h;
-            *tmax = h.t;  // r.tMax = ray.tMax
-            if (ANY_HIT) return best;
-        }
-        return best;
-    }
-    // Step-synchronous two-level traversal.  Each lane is a small state machine over its own ray -- walking the tree
-    // over the instances' boxes, picking the next candidate instance, or taking ONE step inside that instance's tree --
-    // so that the lanes of a warp meet again after every step instead of after whole nested traversals (measured with
-    // the nested loops: 2.4 of 32 lanes active per instruction).
-    const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 4;
-    const uint32_t *tb1 = a.tri_base + a.tlas_node_off;
-    const F4 *tt = a.tris + (size_t)a.tlas_tri_off * 3;
+struct InstanceWalk {
     Trav T1, T2;
     TravRay R1, R2;
     TravStack S1, S2;
-    TraceCounters ctr;
-    uint32_t overflow = 0;
-    trav_init(T1, R1, ro, rd, *tmax, a.tlas_bounds);
-    T2 = T1;
-    R2 = R1;
-    T2.cur_y = 0u;
-    uint32_t pend_x = 0, pend_y = 0, cur_inst = 0, cur_tri_off = 0;
-    const U4 *bn = tn;
-    const uint32_t *bb = tb1;
-    const F4 *bt = tt;
-    int state = 0;  // 0: instance tree, 1: next candidate, 2: inside an instance
-    while (true) {
+    V3 ro, rd;
+    uint32_t pend_x, pend_y, cur_inst, cur_tri_off, overflow;
+    const U4 *bn;
+    const uint32_t *bb;
+    const F4 *bt;
+    int state;  // 0: instance tree, 1: next candidate, 2: inside an instance, 3: done
+    uint32_t next_linear;  // scenes without a tree over the instances: the next instance to try
+    // results
+    uint32_t best, inst;
+    TriHit hit;
+
+    __device__ void init(const TraceArgs &a, const V3 &o, const V3 &d, float tmax) {
+        ro = o;
+        rd = d;
+        best = B200PT_MISS;
+        inst = 0;
+        hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
+        pend_x = pend_y = cur_inst = cur_tri_off = overflow = 0;
+        next_linear = 0;
+        bn = nullptr;
+        bb = nullptr;
+        bt = nullptr;
+        state = 0;
+        trav_init(T1, R1, o, d, tmax, a.tlas_bounds);
+        if (a.tlas_node_off == 0u) {  // no tree: T1 only carries the ray's tMax
+            T1.cur_y = 0u;
+            R1.tmax = tmax;
+            state = 1;
+        }
+        T2 = T1;
+        R2 = R1;
+        T2.cur_y = 0u;
+    }
+    __device__ float tmax() const { return R1.tmax; }
+    __device__ bool enter(const TraceArgs &a, uint32_t k) {
+        const DevInstance &in = a.instances[k];
+        if (!instance_leaf_test(in, ro, rd, R1.tmax)) return false;
+        V3 o2, d2;
+        float tm2;
+        instance_ray(in, ro, rd, R1.tmax, &o2, &d2, &tm2);
+        trav_init(T2, R2, o2, d2, tm2, instance_bounds(in));
+        bn = a.nodes + (size_t)in.node_off * 4;
+        bb = a.tri_base + in.node_off;
+        bt = a.tris + (size_t)in.tri_off * 3;
+        cur_inst = k;
+        cur_tri_off = in.tri_off;
+        return true;
+    }
+    // one step; true when the walk is complete
+    __device__ bool step(const TraceArgs &a) {
+        TraceCounters ctr;
         if (state == 2) {
             if (!(T2.cur_y & 0xff000000u) || trav_step<ANY_HIT, false>(T2, R2, S2, bn, bb, bt, a.lut, &ctr)) {
                 overflow += (T2.sp & B200PT_SP_OVERFLOW) ? 1u : 0u;
                 T2.sp &= B200PT_SP_MASK;
+                state = 1;
                 if (R2.best != B200PT_MISS) {
                     best = cur_tri_off + R2.best;
-                    *inst = cur_inst;
-                    *hit = R2.hit;
-                    R1.tmax = R2.hit.t;  // r.tMax = ray.tMax
+                    inst = cur_inst;
+                    hit = R2.hit;
+                    R1.tmax = R2.hit.t;  // r.tMax = ray.tMax (primitive.cpp:91)
                     T1.tmaxp = trav_param_of(R1, R1.tmax);
-                    if (ANY_HIT) break;
+                    if (ANY_HIT) state = 3;
                 }
-                state = 1;
             }
         } else if (state == 1) {
-            if (pend_y) {
+            if (a.tlas_node_off == 0u) {
+                if (next_linear < a.n_instances) {
+                    if (enter(a, next_linear)) state = 2;
+                    ++next_linear;
+                } else {
+                    state = 3;
+                }
+            } else if (pend_y) {
                 const int j = msb32(pend_y);
                 pend_y &= ~(1u << j);
+                const F4 *tt = a.tris + (size_t)a.tlas_tri_off * 3;
                 const uint32_t k = __float_as_uint(ld_f4(tt + (size_t)(pend_x + (uint32_t)j) * 3).w);  // TriRecord::prim
-                const DevInstance &in = a.instances[k];
-                if (instance_leaf_test(in, ro, rd, R1.tmax)) {
-                    V3 o2, d2;
-                    float tm2;
-                    instance_ray(in, ro, rd, R1.tmax, &o2, &d2, &tm2);
-                    trav_init(T2, R2, o2, d2, tm2, instance_bounds(in));
-                    bn = a.nodes + (size_t)in.node_off * 4;
-                    bb = a.tri_base + in.node_off;
-                    bt = a.tris + (size_t)in.tri_off * 3;
-                    cur_inst = k;
-                    cur_tri_off = in.tri_off;
-                    state = 2;
-                }
+                if (enter(a, k)) state = 2;
             } else {
                 state = 0;
             }
-        } else {
+        } else if (state == 0) {
+            const U4 *tn = a.nodes + (size_t)a.tlas_node_off * 4;
+            const uint32_t *tb1 = a.tri_base + a.tlas_node_off;
             if (T1.cur_y & 0xff000000u) {
                 uint32_t lg_x = 0, lg_y = 0;
                 trav_node_phase<!ANY_HIT, false>(T1, S1, tn, tb1, a.lut, &lg_x, &lg_y, &ctr);
                 leaf_group_triangles(tb1, lg_x, lg_y, &pend_x, &pend_y);
                 state = 1;
             } else if (!trav_next_group(T1, S1)) {
-                break;
+                state = 3;
             }
         }
+        if (state == 3) {
+            overflow += (T1.sp & B200PT_SP_OVERFLOW) ? 1u : 0u;
+            T1.sp &= B200PT_SP_MASK;
+            if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
+            overflow = 0;
+            return true;
+        }
+        return false;
     }
-    overflow += (T1.sp & B200PT_SP_OVERFLOW) ? 1u : 0u;
-    if (overflow && a.stats) atomicAdd(&a.stats[7], (unsigned long long)overflow);
-    *tmax = R1.tmax;
-    return best;
-}
+};
 
-// ---------------------------------------------------------------------- spheres
-// Scene::Intersect / IntersectP for the Sphere shapes (not part of the BVH): one thread per ray of the
-// traversal launch that just finished.
+// ---------------------------------------------------------------------- spheres + instances
+// Scene::Intersect / IntersectP for the Sphere shapes (not part of the BVH) and the object instances: the rays of
+// the traversal launch that just finished (tMax shortened by its triangle hit).  Persistent warps; a lane that finished
+// its ray takes the next one as soon as fewer than refill_lanes lanes of the warp are still walking (like k_trace).
 template <bool ANY_HIT, bool CLASSIFY>
 __global__ void __launch_bounds__(128) k_spheres(const TraceArgs a) {
     const uint32_t n = *a.count;
-    uint32_t i;
-    while (warp_fetch(a.sphere_work, n, &i)) {
-        int family = -1;
-        uint32_t slot = 0;
-        if (i < n) {
-            slot = a.queue ? a.queue[i] : i;
-            const float4 o4 = a.ray_o[(size_t)slot * a.stride];
-            const float4 d4 = a.ray_d[(size_t)slot * a.stride];
-            const V3 ro = v3(o4), rd = v3(d4);
-            float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
-            if (ANY_HIT) {
-                if (!a.occ_out[slot]) {
-                    for (uint32_t k = 0; k < a.n_spheres; ++k) {
-                        float t;
-                        if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
-                            a.occ_out[slot] = 1;
-                            break;
-                        }
-                    }
-                }
-                if (!a.occ_out[slot] && a.n_instances) {
-                    TriHit h;
-                    uint32_t inst = 0;
-                    float tm = tmax;
-                    if (instances_test<true>(a, ro, rd, &tm, &h, &inst) != B200PT_MISS) a.occ_out[slot] = 1;
-                }
-            } else {
-                uint32_t best = B200PT_MISS;
-                if (a.hit_out) {
-                    best = a.hit_out[slot];
-                    if (best != B200PT_MISS) {  // ray.tMax after the triangle hit: Triangle::Intersect's t
-                        const F4 *tp = a.tris + (size_t)best * 3;
-                        TriHit h;
-                        if (triangle_test(v3(ld_f4(tp)), v3(ld_f4(tp + 1)), v3(ld_f4(tp + 2)), ro, make_shear(rd), pt_inf(), &h))
-                            tmax = h.t;
-                    }
-                } else if (a.full_out[slot].triangle >= 0) {
-                    tmax = a.full_out[slot].t;
-                }
-                uint32_t sph = B200PT_MISS;
-                for (uint32_t k = 0; k < a.n_spheres; ++k) {
-                    float t;
-                    if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
-                        tmax = t;
-                        sph = k;
-                    }
-                }
-                if (sph != B200PT_MISS) {
-                    best = SPHERE_HIT_BASE | sph;
-                    if (a.hit_out) a.hit_out[slot] = best;
-                    if (a.full_out) {
-                        b200pt_hit r;
-                        r.triangle = (int32_t)(a.n_tris + sph);
-                        r.t = tmax;
-                        r.b0 = r.b1 = 0.f;
-                        a.full_out[slot] = r;
-                    }
-                }
-                if (a.n_instances) {
-                    TriHit h;
-                    uint32_t inst = 0;
-                    const uint32_t ti = instances_test<false>(a, ro, rd, &tmax, &h, &inst);
-                    if (ti != B200PT_MISS) {
-                        best = ti;
+#ifndef B200PT_HOST_EMU
+    const int lane = threadIdx.x & 31;
+#endif
+    InstanceWalk<ANY_HIT> W;
+    uint32_t slot = 0, best = B200PT_MISS;
+    bool has = false, fin = false, exhausted = false, occluded = false;
+    while (true) {
+        // ---- converged: retire finished rays
+        {
+            int family = -1;
+            if (fin) {
+                if (ANY_HIT) {
+                    if (occluded || W.best != B200PT_MISS) a.occ_out[slot] = 1;
+                } else {
+                    if (W.best != B200PT_MISS) {
+                        best = W.best;
                         if (a.hit_out) a.hit_out[slot] = best;
-                        if (a.hit_inst_out) a.hit_inst_out[slot] = inst;
+                        if (a.hit_inst_out) a.hit_inst_out[slot] = W.inst;
                         if (a.full_out) {
                             b200pt_hit r;
                             r.triangle = (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w);
-                            r.t = h.t;
-                            r.b0 = h.b0;
-                            r.b1 = h.b1;
+                            r.t = W.hit.t;
+                            r.b0 = W.hit.b0;
+                            r.b1 = W.hit.b1;
+                            a.full_out[slot] = r;
+                        }
+                    }
+                    if (CLASSIFY && best != B200PT_MISS) {
+                        const uint32_t mf = is_sphere_hit(best) ? a.spheres[best & SPHERE_HIT_MASK].mat_flags
+                                                                : __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
+                        family = a.materials[mf & 0xffffu].type;
+                    }
+                }
+            }
+            if (CLASSIFY) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const bool mine = family == m;
+                    const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
+                    if (mine) a.q_mat[m][pos] = slot;
+                }
+            }
+            fin = false;
+        }
+        // ---- converged: idle lanes fetch new rays, test the spheres, set up the walk over the instances
+        {
+            const bool want = !has && !exhausted;
+            uint32_t i = 0;
+            bool got = false;
+#ifdef B200PT_HOST_EMU
+            if (want) {
+                i = atomicAdd(a.sphere_work, 1u);
+                got = i < n;
+                exhausted = !got;
+            }
+#else
+            const uint32_t mask = __ballot_sync(FULL_MASK, want);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(a.sphere_work, (uint32_t)__popc(mask));
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if (want) {
+                    i = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    got = i < n;
+                    exhausted = !got;
+                }
+            }
+#endif
+            if (got) {
+                slot = a.queue ? a.queue[i] : i;
+                const float4 o4 = a.ray_o[(size_t)slot * a.stride];
+                const float4 d4 = a.ray_d[(size_t)slot * a.stride];
+                const V3 ro = v3(o4), rd = v3(d4);
+                float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
+                best = B200PT_MISS;
+                occluded = false;
+                if (ANY_HIT) {
+                    occluded = a.occ_out[slot] != 0;
+                    for (uint32_t k = 0; k < a.n_spheres && !occluded; ++k) {
+                        float t;
+                        if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                            a.occ_out[slot] = 1;
+                            occluded = true;
+                        }
+                    }
+                } else {
+                    if (a.hit_out) {
+                        best = a.hit_out[slot];
+                        if (best != B200PT_MISS) {  // ray.tMax after the triangle hit: Triangle::Intersect's t
+                            const F4 *tp = a.tris + (size_t)best * 3;
+                            const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+                            V3 o2 = ro, d2 = rd;
+                            if ((__float_as_uint(t1.w) & 0x100000u) && a.hit_inst_out) {
+                                // a triangle of an instanced object (found by the two-level kernel): the same ray parameter in
+                                // the object's space (primitive.cpp:91)
+                                float tm2;
+                                instance_ray(a.instances[a.hit_inst_out[slot]], ro, rd, pt_inf(), &o2, &d2, &tm2);
+                            }
+                            TriHit h;
+                            if (triangle_test(v3(t0), v3(t1), v3(t2), o2, make_shear(d2), pt_inf(), &h)) tmax = h.t;
+                        }
+                    } else if (a.full_out[slot].triangle >= 0) {
+                        tmax = a.full_out[slot].t;
+                        best = 0u;  // some top-level triangle (only its presence matters below: full_out keeps the record)
+                    }
+                    uint32_t sph = B200PT_MISS;
+                    for (uint32_t k = 0; k < a.n_spheres; ++k) {
+                        float t;
+                        if (sphere_leaf_test(a.spheres[k], ro, rd, tmax) && sphere_intersect(a.spheres[k], ro, rd, tmax, &t, nullptr)) {
+                            tmax = t;
+                            sph = k;
+                        }
+                    }
+                    if (sph != B200PT_MISS) {
+                        best = SPHERE_HIT_BASE | sph;
+                        if (a.hit_out) a.hit_out[slot] = best;
+                        if (a.full_out) {
+                            b200pt_hit r;
+                            r.triangle = (int32_t)(a.n_tris + sph);
+                            r.t = tmax;
+                            r.b0 = r.b1 = 0.f;
                             a.full_out[slot] = r;
                         }
                     }
                 }
-                if (CLASSIFY && best != B200PT_MISS) {
-                    const uint32_t mf = is_sphere_hit(best) ? a.spheres[best & SPHERE_HIT_MASK].mat_flags
-                                                            : __float_as_uint(ld_f4(a.tris + (size_t)best * 3 + 1).w);
-                    family = a.materials[mf & 0xffffu].type;
+                W.best = B200PT_MISS;
+                if (a.n_instances && !(ANY_HIT && occluded)) {
+                    W.init(a, ro, rd, tmax);
+                    has = true;
+                } else {
+                    fin = true;  // nothing to walk: retire in the next round
                 }
             }
         }
-        if (CLASSIFY) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const bool mine = family == m;
-                const uint32_t pos = warp_append(&a.qcount_mat[m], mine);
-                if (mine) a.q_mat[m][pos] = slot;
+#ifdef B200PT_HOST_EMU
+        while (has) {
+            if (W.step(a)) {
+                has = false;
+                fin = true;
             }
         }
+        if (!fin && exhausted) break;
+#else
+        if (__ballot_sync(FULL_MASK, has || fin) == 0) break;
+        while (has) {
+            if (W.step(a)) {
+                has = false;
+                fin = true;
+            }
+            if (__popc(__activemask()) < a.sphere_refill_lanes) break;
+        }
+        __syncwarp();
+#endif
     }
 }
 
@@ -1627,25 +2021,34 @@ void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, i
     }
 }
 #else
+// B200PT_TRACE_VARIANTS (experiment builds): also instantiate the 6- and 7-CTA register budgets and the TMA-staged
+// variant, selectable at run time (TraceArgs::ctas, ::n_staged); the product builds the one configuration that measured best.
 template <bool ANY_HIT, bool CLASSIFY>
 static void launch_trace_variant(const TraceArgs &a, bool count, int n_sm, cudaStream_t s) {
+    if (count) {  // instrumented pass
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, true, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
+        return;
+    }
+#ifdef B200PT_TRACE_VARIANTS
     const bool stage = a.n_staged > 0;
     const size_t smem = stage ? (size_t)a.n_staged * 64 : 0;
-    if (count) {  // instrumented pass: the default build only
-        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, true, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
-    } else if (a.ctas == 8) {
-        if (stage)
+    if (stage) {
+        if (a.ctas == 6)
+            B200PT_LAUNCH_SMEM(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 6, true>), n_sm * 6, 128, smem, s, a);
+        else
             B200PT_LAUNCH_SMEM(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 8, true>), n_sm * 8, 128, smem, s, a);
-        else
-            B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 8, false>), n_sm * 8, 128, s, a);
-    } else if (a.ctas == 7 && !stage) {
-        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 7, false>), n_sm * 7, 128, s, a);
-    } else {
-        if (stage)
-            B200PT_LAUNCH_SMEM(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, B200PT_TRACE_CTAS, true>), n_sm * B200PT_TRACE_CTAS, 128, smem, s, a);
-        else
-            B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
+        return;
     }
+    if (a.ctas == 6) {
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 6, false>), n_sm * 6, 128, s, a);
+        return;
+    }
+    if (a.ctas == 7) {
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, 7, false>), n_sm * 7, 128, s, a);
+        return;
+    }
+#endif
+    B200PT_LAUNCH(B200PT_KERNEL(k_trace<ANY_HIT, CLASSIFY, false, B200PT_TRACE_CTAS, false>), n_sm * B200PT_TRACE_CTAS, 128, s, a);
 }
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int n_sm, cudaStream_t s) {
     if (any_hit)
@@ -1654,6 +2057,17 @@ void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, i
         launch_trace_variant<false, true>(a, count, n_sm, s);
     else
         launch_trace_variant<false, false>(a, count, n_sm, s);
+}
+#endif
+
+#ifndef B200PT_HOST_EMU
+void launch_trace2(const TraceArgs &a, bool any_hit, bool classify, int n_sm, cudaStream_t s) {
+    if (any_hit)
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace2<true, false>), n_sm * 6, 128, s, a);
+    else if (classify)
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace2<false, true>), n_sm * 6, 128, s, a);
+    else
+        B200PT_LAUNCH(B200PT_KERNEL(k_trace2<false, false>), n_sm * 6, 128, s, a);
 }
 #endif
 

@@ -133,10 +133,10 @@ struct RenderDev {
     const float *med_spectra;  // SampledSpectrum build: [2][60] = sigma_s, sigma_t (else the two arrays above)
 };
 
-// resident CTAs of k_trace per SM (128 threads each): 6 leaves 78 registers per thread, which the node test needs
-// without spilling (8 selectors + 9 slab constants per ray next to the 16 node words in flight)
+// resident CTAs of k_trace per SM (128 threads each).  8 (64 registers, two spilled per-ray constants re-read next to the
+// node loads) measured fastest: 703 Mrays/s against 699 with 7 (72 registers, no spills) and 658 with 6 (profiles/README.md)
 #ifndef B200PT_TRACE_CTAS
-#define B200PT_TRACE_CTAS 6
+#define B200PT_TRACE_CTAS 8
 #endif
 
 struct TraceArgs {
@@ -173,6 +173,7 @@ struct TraceArgs {
     uint32_t n_spheres;
     uint32_t n_tris;            // sphere k is reported as primitive n_tris + k in full_out
     uint32_t *sphere_work;      // persistent fetch counter of the sphere pass (zeroed)
+    int sphere_refill_lanes;    // the sphere / instance pass refills a warp when fewer lanes than this are still walking
     const DevInstance *instances;
     uint32_t n_instances;
     uint32_t tlas_node_off, tlas_tri_off;  // see DevScene
@@ -183,6 +184,9 @@ void launch_raygen(const RenderDev *dev, uint32_t batch_first_tile, uint32_t n_b
                    cudaStream_t s);
 // grid = SMs of the device (the launcher multiplies by the CTAs per SM of the chosen variant)
 void launch_trace(const TraceArgs &a, bool any_hit, bool classify, bool count, int n_sm, cudaStream_t s);
+// Scenes with object instances (and a tree over them): top-level triangles + instances in one persistent two-level
+// traversal (k_trace2); launch_spheres is then only needed for Sphere shapes.  Not part of the CPU check build.
+void launch_trace2(const TraceArgs &a, bool any_hit, bool classify, int n_sm, cudaStream_t s);
 // Tests the spheres against the rays of a finished traversal launch (tMax shortened by the triangle hit),
 // updates hit_out / full_out / occ_out and, with `classify`, appends the slots to the BSDF-family queues
 // (the traversal launch then runs without classification).

@@ -202,6 +202,14 @@ struct TravRay {
 // placed in local memory as a whole).
 struct TravStack {
     uint32_t x[B200PT_STACK], y[B200PT_STACK];
+    B200_HD void push(int sp, uint32_t gx, uint32_t gy) {
+        x[sp] = gx;
+        y[sp] = gy;
+    }
+    B200_HD void pop(int sp, uint32_t *gx, uint32_t *gy) const {
+        *gx = x[sp];
+        *gy = y[sp];
+    }
 };
 
 B200_HD void trav_init(Trav &T, TravRay &R, const V3 &o, const V3 &d, float rayTMax, const TravBounds &B) {
@@ -276,8 +284,8 @@ B200_HD float trav_param_of(const TravRay &R, float t) {
 // CLOSEST: the ray's tMax shrinks during traversal (closest hit); any-hit rays keep the span they started with.
 // STAGE: nodes [0, n_staged) -- the top of the tree, which is stored breadth-first -- are read from `staged`, a copy in
 // shared memory, instead of global memory.
-template <bool CLOSEST, bool COUNT, bool STAGE = false>
-B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes, const uint32_t *__restrict__ /*tri_base*/,
+template <bool CLOSEST, bool COUNT, bool STAGE = false, class Stack = TravStack>
+B200_HD void trav_node_phase(Trav &T, Stack &S, const U4 *__restrict__ nodes, const uint32_t *__restrict__ /*tri_base*/,
                              const uint8_t *lut, uint32_t *tg_x, uint32_t *tg_y, TraceCounters *ctr, const U4 *staged = nullptr,
                              uint32_t n_staged = 0) {
     const uint32_t hits = T.cur_y;
@@ -285,8 +293,7 @@ B200_HD void trav_node_phase(Trav &T, TravStack &S, const U4 *__restrict__ nodes
     T.cur_y &= ~(1u << bit);
     if (T.cur_y & 0xff000000u) {
         if ((T.sp & B200PT_SP_MASK) < B200PT_STACK) {
-            S.x[T.sp & B200PT_SP_MASK] = T.cur_x;
-            S.y[T.sp & B200PT_SP_MASK] = T.cur_y;
+            S.push(T.sp & B200PT_SP_MASK, T.cur_x, T.cur_y);
             ++T.sp;
         } else {
             T.sp |= B200PT_SP_OVERFLOW;
@@ -399,12 +406,12 @@ B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const uint32_t *__restrict
 }
 
 // Pops the next node group if the current one is exhausted; false when nothing is left.
-B200_HD bool trav_next_group(Trav &T, TravStack &S) {
+template <class Stack>
+B200_HD bool trav_next_group(Trav &T, Stack &S) {
     if ((T.cur_y & 0xff000000u) == 0) {
         if ((T.sp & B200PT_SP_MASK) == 0) return false;
         --T.sp;
-        T.cur_x = S.x[T.sp & B200PT_SP_MASK];
-        T.cur_y = S.y[T.sp & B200PT_SP_MASK];
+        S.pop(T.sp & B200PT_SP_MASK, &T.cur_x, &T.cur_y);
     }
     return true;
 }
