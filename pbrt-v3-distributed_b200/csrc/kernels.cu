@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
     uint32_t noff = 0, toff = 0;  // the tree the lane is in: offsets of its nodes / triangles inside the scene's arrays
     int phase = 0;                // 0: top-level tree, 1: tree over the instances, 2: inside an instance
     bool has = false, fin = false, exhausted = false;
+    bool want_exit = false;       // the object's tree is exhausted: the lane waits to go back to the world ray
     // (re)derives the box-test constants and the triangle-test record for a ray in the space the lane enters;
     // the position on the stack and the result so far are the lane's own and stay
     auto enter_space = [&](const V3 &o, const V3 &d, float tmax, const TravBounds &B) {
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         const float tmax = a.t_max_from_w ? o4.w : a.fixed_t_max;
                         T.sp = 0;
                         phase = 0;
+                        want_exit = false;
                         noff = toff = 0;
                         enter_space(v3(o4), v3(d4), tmax, a.bounds);
                         my_ray[8 * 128] = __uint_as_float(B200PT_MISS);
@@ -639,13 +641,15 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
         if (__ballot_sync(FULL_MASK, has) == 0) break;
         while (has) {
             uint32_t ng_x = 0, ng_y = 0;
-            // in the tree over the instances a leaf group is dealt with before the walk goes on: entering an instance
-            // leaves ONE group of untried candidates behind, so the lane must never hold two
-            const bool hold = phase == 1 && pend_y != 0;
+            // Entering an instance leaves ONE group of untried candidates behind, so in the tree over the instances a lane
+            // holds (takes no node step) while it has a leaf group; a lane that is done with an object's tree waits the
+            // same way.  Both wait for company: changing space is ~900 instructions and runs once the usual share of the
+            // warp's lanes has something parked (triangles, candidates, a way back), not one lane at a time.
+            const bool hold = (phase == 1 && pend_y != 0) || want_exit;
             const bool node_work = !hold && (T.cur_y & 0xff000000u) != 0;
             if (node_work)
                 trav_node_phase<!ANY_HIT, false>(T, S, a.nodes + (size_t)noff * 4, a.tri_base + noff, s_lut, &ng_x, &ng_y, &ctr);
-            bool must = hold;
+            bool must = false;
             if (ng_y) {
                 if (pend_y) {
                     must = true;  // two groups: flush the parked one now, park the new one after
@@ -653,19 +657,38 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     pend_x = ng_x;
                     pend_y = ng_y;
                     ng_y = 0;
-                    if (phase == 1) must = true;
                 }
             }
             const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0;  // (what is left on the stack waits behind the parked group)
             const unsigned act = __activemask();
-            const bool starving_me = out_of_nodes && pend_y != 0;
+            const bool parked_me = pend_y != 0 || want_exit;
+            const bool idle_me = hold || (phase == 1 && pend_y != 0) || (out_of_nodes && pend_y != 0);
             const unsigned counts = __reduce_add_sync(
-                act, (pend_y != 0 ? 1u : 0u) | ((must || (starving_me && a.postpone_pct <= 0)) ? 0x100u : 0u) |
-                         (starving_me ? 0x10000u : 0u));
-            const int n_act = __popc(act), n_parked = (int)(counts & 0xffu), n_starving = (int)((counts >> 16) & 0xffu);
-            if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_starving * 4 >= n_act) {
+                act, (parked_me ? 1u : 0u) | ((must || (idle_me && a.postpone_pct <= 0)) ? 0x100u : 0u) | (idle_me ? 0x10000u : 0u));
+            const int n_act = __popc(act), n_parked = (int)(counts & 0xffu), n_idle = (int)((counts >> 16) & 0xffu);
+            if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_idle * 4 >= n_act) {
                 bool done = false;
-                if (pend_y && phase == 1) {
+                if (want_exit) {
+                    // the object's tree is done: back to the world ray (its tMax is the hit's, if there was one) and to
+                    // the walk over the instances -- first the candidates of the same leaf that were not tried
+                    want_exit = false;
+                    uint32_t ex, ey, gx, gy;
+                    T.sp -= 2;
+                    S.pop((T.sp & B200PT_SP_MASK) + 1, &ex, &ey);
+                    S.pop(T.sp & B200PT_SP_MASK, &gx, &gy);
+                    V3 ro, rd;
+                    world_ray(&ro, &rd);
+                    noff = a.tlas_node_off;
+                    toff = a.tlas_tri_off;
+                    phase = 1;
+                    enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
+                    T.cur_x = gx;
+                    T.cur_y = gy;
+                    if (ey) {
+                        pend_x = ex;  // marked: already a triangle group
+                        pend_y = ey;
+                    }
+                } else if (pend_y && phase == 1) {
                     // leaf of the tree over the instances: its "triangles" name instances; the first candidate whose
                     // leaf box the ray (with its current tMax) enters takes the lane into that object's tree
                     uint32_t tg_x, tg_y;
@@ -675,6 +698,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     } else {
                         leaf_group_triangles(a.tri_base + noff, pend_x, pend_y, &tg_x, &tg_y);
                     }
+                    pend_y = 0;
                     V3 ro, rd;
                     world_ray(&ro, &rd);
                     const float wtmax = my_ray[16 * 128];
@@ -713,17 +737,20 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         if (phase == 2) my_ray[15 * 128] = my_ray[17 * 128];  // the instance of the hit
                         my_ray[16 * 128] = R.tmax;                            // r.tMax = ray.tMax (primitive.cpp:91 / :120)
                     }
+                    pend_y = 0;
                 }
-                pend_x = ng_x;
-                pend_y = ng_y;
+                if (ng_y) {  // the second group found in this step (only outside the tree over the instances)
+                    pend_x = ng_x;
+                    pend_y = ng_y;
+                }
                 if (done) {
                     has = false;
                     fin = true;
                     pend_y = 0;
                 }
             }
-            // ---- the next group of the current tree, or back out of an instance, or on to the next tree, or done
-            if (has && (T.cur_y & 0xff000000u) == 0) {
+            // ---- the next group of the current tree, or (later, in company) back out of an instance, or on to the next tree, or done
+            if (has && !want_exit && (T.cur_y & 0xff000000u) == 0) {
                 bool more = false, blocked = false;
                 while (!more && !blocked) {
                     if ((T.sp & B200PT_SP_MASK) == 0) break;
@@ -734,29 +761,9 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         T.cur_x = ex;
                         T.cur_y = ey;
                         more = (ey & 0xff000000u) != 0;
-                    } else if (pend_y != 0) {
-                        blocked = true;  // triangles of the object are still parked: they are tested in its space first
                     } else {
-                        // the object's tree is done: back to the world ray (its tMax is the hit's, if there was one) and
-                        // to the walk over the instances -- first the candidates of the same leaf that were not tried
-                        T.sp -= 2;
-                        uint32_t gx, gy;
-                        S.pop(T.sp & B200PT_SP_MASK, &gx, &gy);
-                        V3 ro, rd;
-                        world_ray(&ro, &rd);
-                        noff = a.tlas_node_off;
-                        toff = a.tlas_tri_off;
-                        phase = 1;
-                        enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
-                        T.cur_x = gx;
-                        T.cur_y = gy;
-                        if (ey) {
-                            pend_x = ex;  // marked: already a triangle group
-                            pend_y = ey;
-                            more = true;
-                        } else {
-                            more = (gy & 0xff000000u) != 0;
-                        }
+                        blocked = true;  // an object's tree is exhausted: leave it once its parked triangles are tested
+                        if (pend_y == 0) want_exit = true;
                     }
                 }
                 if (!more && !blocked && pend_y == 0) {
