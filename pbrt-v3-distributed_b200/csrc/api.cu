@@ -891,6 +891,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     b200pt_ctx *ctx = scene->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     b200pt_render *r = new b200pt_render;
+    // every failure below leaves through a return: the guard frees what was allocated so far (released on success)
+    struct RenderGuard {
+        b200pt_render *p;
+        ~RenderGuard() {
+            if (p) b200pt_render_destroy(p);
+        }
+    } render_guard{r};
     r->scene = scene;
     r->film = *film;
     r->spp = smp->samples_per_pixel;
@@ -1076,7 +1083,6 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         }
         nvox = (long long)H.grid.nv[0] * H.grid.nv[1] * H.grid.nv[2];
         if (nvox * (2ll * nl + 2) * 4 > (8ll << 30)) {
-            delete r;
             return b200pt_fail(B200PT_ERR_INVALID,
                                "render_create: spatial light distribution needs %lld voxels x %d lights; use \"uniform\" or \"power\"",
                                nvox, nl);
@@ -1097,7 +1103,6 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     r->tiles_per_batch = std::min<uint32_t>(r->tiles_per_batch, (uint32_t)(H.tiles_x * H.tiles_y));
     const size_t cap = (size_t)r->tiles_per_batch * per_tile;
     if (cap >= (1ull << 31)) {
-        delete r;
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: one tile needs %zu path slots (too many samples)", per_tile);
     }
     H.capacity = (uint32_t)cap;
@@ -1184,7 +1189,6 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(r->d_dev, 1);
 #undef ALLOC
     if (e != cudaSuccess) {
-        b200pt_render_destroy(r);
         return b200pt_fail(B200PT_ERR_OOM, "render_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
     H.sampler.mat32 = mat32;
@@ -1211,7 +1215,6 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     if (nl) CUDA_TRY(cudaMemcpyAsync(d_lights, dl.data(), nl * sizeof(DevLight), cudaMemcpyHostToDevice, st));
     if (scene->nspec) {
         if (b200pt_s60::render_dev_size() != sizeof(RenderDev)) {
-            b200pt_render_destroy(r);
             return b200pt_fail(B200PT_ERR_INVALID, "render_create: the SampledSpectrum kernels were built with another RenderDev layout");
         }
         if (d_med_spectra) {
@@ -1254,6 +1257,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     r->postpone_pct = postpone_pct();
     r->trace_ctas = trace_ctas_default();
     r->stage_nodes = stage_nodes_default();
+    render_guard.p = nullptr;
     *out = r;
     return B200PT_OK;
 }
@@ -1445,14 +1449,18 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
             a.hit_out = H.hit;
             for (int m = 0; m < 4; ++m) a.q_mat[m] = H.q_mat[m];
             a.qcount_mat = qc + Q_MAT0;
-            LaunchTimer lt(r, st, 0);
-            // with spheres in the scene the sphere pass decides the final hit, so it does the classification;
-            // inside a medium the medium pass does (only paths that reach their surface are shaded)
-            trace(a, false, !has_spheres && !medium, st);
-            if (has_spheres) {
-                sphere_args(a, wk + 8);
-                launch_spheres(a, false, !medium, r->grid_shade, st);
-                r->launches++;
+            {
+                // closest_ms = the traversal launch and, for scenes with spheres, the pass that completes Scene::Intersect;
+                // the medium pass below is timed on its own (category 2)
+                LaunchTimer lt(r, st, 0);
+                // with spheres in the scene the sphere pass decides the final hit, so it does the classification;
+                // inside a medium the medium pass does (only paths that reach their surface are shaded)
+                trace(a, false, !has_spheres && !medium, st);
+                if (has_spheres) {
+                    sphere_args(a, wk + 8);
+                    launch_spheres(a, false, !medium, r->grid_shade, st);
+                    r->launches++;
+                }
             }
             if (medium) {
                 LaunchTimer lt2(r, st, 2);

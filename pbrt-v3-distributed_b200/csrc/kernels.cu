@@ -269,7 +269,7 @@ void k_trace(const TraceArgs a) {
 // The ray as the triangle test sees it and the result so far (TravRay) live in shared memory, one column per
 // thread (conflict-free): the node loop -- where a lane spends its time -- keeps only the box-test state in
 // registers, the much rarer triangle phase fetches what it needs.
-#define B200PT_RAY_WORDS 15
+#define B200PT_RAY_WORDS 21  // 0-2 o, 3-5 shear, 6 kz, 7 tMax, 8 best, 9-12 hit, 13 t0, 14-16 1/d, 17-19 origin/d, 20 span floor
 __device__ __forceinline__ void ray_store(float *col, const TravRay &R) {
     col[0 * 128] = R.o.x;
     col[1 * 128] = R.o.y;
@@ -285,7 +285,24 @@ __device__ __forceinline__ void ray_store(float *col, const TravRay &R) {
     col[11 * 128] = R.hit.b1;
     col[12 * 128] = R.hit.b2;
     col[13 * 128] = R.t0;
-    col[14 * 128] = R.inv;
+    col[14 * 128] = R.iu[0];
+    col[15 * 128] = R.iu[1];
+    col[16 * 128] = R.iu[2];
+    col[17 * 128] = R.ou[0];
+    col[18 * 128] = R.ou[1];
+    col[19 * 128] = R.ou[2];
+    col[20 * 128] = R.span_floor;
+}
+// what trav_rescale reads (fetched only after a closest hit shortened the ray)
+__device__ __forceinline__ void ray_load_scale(const float *col, TravRay &R) {
+    R.t0 = col[13 * 128];
+    R.iu[0] = col[14 * 128];
+    R.iu[1] = col[15 * 128];
+    R.iu[2] = col[16 * 128];
+    R.ou[0] = col[17 * 128];
+    R.ou[1] = col[18 * 128];
+    R.ou[2] = col[19 * 128];
+    R.span_floor = col[20 * 128];
 }
 __device__ __forceinline__ void ray_load(const float *col, TravRay &R) {
     R.o = mk(col[0 * 128], col[1 * 128], col[2 * 128]);
@@ -298,8 +315,6 @@ __device__ __forceinline__ void ray_load(const float *col, TravRay &R) {
     R.tmax = col[7 * 128];
     R.best = __float_as_uint(col[8 * 128]);
     R.hit.t = R.hit.b0 = R.hit.b1 = R.hit.b2 = 0.f;  // outputs of the triangle phase (stored again only after a hit)
-    R.t0 = col[13 * 128];
-    R.inv = col[14 * 128];
 }
 __device__ __forceinline__ void ray_store_hit(float *col, const TravRay &R) {
     col[7 * 128] = R.tmax;
@@ -492,8 +507,14 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
                     TravRay R;
                     ray_load(my_ray, R);
                     const uint32_t before = R.best;
-                    done = trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, a.tri_base, a.tris, pend_x, pend_y, &ctr);
-                    if (R.best != before) ray_store_hit(my_ray, R);
+                    done = trav_tri_phase<ANY_HIT, COUNT>(R, a.tri_base, a.tris, pend_x, pend_y, &ctr);
+                    if (R.best != before) {
+                        ray_store_hit(my_ray, R);
+                        if (!ANY_HIT) {  // the ray got shorter: the box parameter ends at the hit from now on
+                            ray_load_scale(my_ray, R);
+                            trav_rescale(T, R, R.tmax);
+                        }
+                    }
                 }
                 pend_x = ng_x;
                 pend_y = ng_y;
@@ -525,7 +546,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
 // box-test constants lives in registers (re-derived when the lane changes space: once per instance entered, not per
 // node); what the lane must come back to waits on the same traversal stack behind a marked entry.  Replaces the
 // one-batch-of-32-rays walk of k_spheres for the instances (measured in profiles/README.md, "instances").
-#define B200PT_RAY_WORDS2 18  // k_trace's record + instance of the hit, world tMax, current instance
+#define B200PT_RAY_WORDS2 24  // k_trace's record + 21 instance of the hit, 22 world tMax, 23 current instance
 #define B200PT_MARK 0x80000000u  // stack entry x: "what follows is what the lane left behind when it entered an instance"
 template <bool ANY_HIT, bool CLASSIFY>
 __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
@@ -561,7 +582,13 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
         my_ray[6 * 128] = __int_as_float(R.sh.kz);
         my_ray[7 * 128] = R.tmax;
         my_ray[13 * 128] = R.t0;
-        my_ray[14 * 128] = R.inv;
+        my_ray[14 * 128] = R.iu[0];
+        my_ray[15 * 128] = R.iu[1];
+        my_ray[16 * 128] = R.iu[2];
+        my_ray[17 * 128] = R.ou[0];
+        my_ray[18 * 128] = R.ou[1];
+        my_ray[19 * 128] = R.ou[2];
+        my_ray[20 * 128] = R.span_floor;
     };
     auto world_ray = [&](V3 *o, V3 *d) {
         const float4 o4 = a.ray_o[(size_t)slot * a.stride];
@@ -579,7 +606,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     a.occ_out[slot] = best != B200PT_MISS ? 1 : 0;
                 } else {
                     if (a.hit_out) a.hit_out[slot] = best;
-                    if (a.hit_inst_out && best != B200PT_MISS) a.hit_inst_out[slot] = __float_as_uint(my_ray[15 * 128]);
+                    if (a.hit_inst_out && best != B200PT_MISS) a.hit_inst_out[slot] = __float_as_uint(my_ray[21 * 128]);
                     if (a.full_out) {
                         b200pt_hit r;
                         r.triangle = best != B200PT_MISS ? (int32_t)__float_as_uint(ld_f4(a.tris + (size_t)best * 3).w) : -1;
@@ -628,8 +655,8 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         enter_space(v3(o4), v3(d4), tmax, a.bounds);
                         my_ray[8 * 128] = __uint_as_float(B200PT_MISS);
                         my_ray[9 * 128] = my_ray[10 * 128] = my_ray[11 * 128] = my_ray[12 * 128] = 0.f;
-                        my_ray[15 * 128] = __uint_as_float(0u);
-                        my_ray[16 * 128] = tmax;  // the world ray's tMax
+                        my_ray[21 * 128] = __uint_as_float(0u);
+                        my_ray[22 * 128] = tmax;  // the world ray's tMax
                         pend_y = 0;
                         has = true;
                     } else {
@@ -681,7 +708,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     noff = a.tlas_node_off;
                     toff = a.tlas_tri_off;
                     phase = 1;
-                    enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
+                    enter_space(ro, rd, my_ray[22 * 128], a.tlas_bounds);
                     T.cur_x = gx;
                     T.cur_y = gy;
                     if (ey) {
@@ -701,7 +728,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     pend_y = 0;
                     V3 ro, rd;
                     world_ray(&ro, &rd);
-                    const float wtmax = my_ray[16 * 128];
+                    const float wtmax = my_ray[22 * 128];
                     while (tg_y) {
                         const int j = msb32(tg_y);
                         tg_y &= ~(1u << j);
@@ -722,7 +749,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         enter_space(o2, d2, tm2, instance_bounds(in));
                         noff = in.node_off;
                         toff = in.tri_off;
-                        my_ray[17 * 128] = __uint_as_float(k);
+                        my_ray[23 * 128] = __uint_as_float(k);
                         phase = 2;
                         break;
                     }
@@ -730,12 +757,16 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     TravRay R;
                     ray_load(my_ray, R);
                     R.best = B200PT_MISS;  // (an index inside this tree; the record keeps scene-wide ones)
-                    done = trav_tri_phase<ANY_HIT, false>(R, &T.tmaxp, a.tri_base + noff, a.tris + (size_t)toff * 3, pend_x, pend_y, &ctr);
+                    done = trav_tri_phase<ANY_HIT, false>(R, a.tri_base + noff, a.tris + (size_t)toff * 3, pend_x, pend_y, &ctr);
                     if (R.best != B200PT_MISS) {
                         R.best += toff;
                         ray_store_hit(my_ray, R);
-                        if (phase == 2) my_ray[15 * 128] = my_ray[17 * 128];  // the instance of the hit
-                        my_ray[16 * 128] = R.tmax;                            // r.tMax = ray.tMax (primitive.cpp:91 / :120)
+                        if (!ANY_HIT) {
+                            ray_load_scale(my_ray, R);
+                            trav_rescale(T, R, R.tmax);
+                        }
+                        if (phase == 2) my_ray[21 * 128] = my_ray[23 * 128];  // the instance of the hit
+                        my_ray[22 * 128] = R.tmax;                            // r.tMax = ray.tMax (primitive.cpp:91 / :120)
                     }
                     pend_y = 0;
                 }
@@ -774,7 +805,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         noff = a.tlas_node_off;
                         toff = a.tlas_tri_off;
                         phase = 1;
-                        enter_space(ro, rd, my_ray[16 * 128], a.tlas_bounds);
+                        enter_space(ro, rd, my_ray[22 * 128], a.tlas_bounds);
                         if ((T.cur_y & 0xff000000u) == 0) {
                             has = false;
                             fin = true;
@@ -883,7 +914,7 @@ struct InstanceWalk {
                     inst = cur_inst;
                     hit = R2.hit;
                     R1.tmax = R2.hit.t;  // r.tMax = ray.tMax (primitive.cpp:91)
-                    T1.tmaxp = trav_param_of(R1, R1.tmax);
+                    trav_rescale(T1, R1, R1.tmax);
                     if (ANY_HIT) state = 3;
                 }
             }
@@ -1933,6 +1964,12 @@ __global__ void k_accumulate_stats(const RenderDev *R) {
     for (int b = 0; b <= R->max_depth; ++b) {
         regular += R->qcount[b * Q_PER_BOUNCE + Q_PATH] + R->qcount[b * Q_PER_BOUNCE + Q_MIS];
         shadow += R->qcount[b * Q_PER_BOUNCE + Q_SHADOW];
+    }
+    if (R->volpath) {
+        // VolPathIntegrator's direct-lighting rays go through VisibilityTester::Tr -> Scene::Intersect (light.cpp:63-81):
+        // the reference counts them as regular intersection tests, its shadow-ray counter stays 0
+        regular += shadow;
+        shadow = 0;
     }
     R->stats[0] += R->qcount[Q_PATH];
     R->stats[1] += regular;

@@ -112,6 +112,11 @@ B200_D float box_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c);
 B200_D float box_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 // the word with the bytes of each 16-bit half swapped: (lo, hi) pairs become (hi, lo)
 B200_D uint32_t swap_pairs(uint32_t w) { return __byte_perm(w, 0u, 0x2301u); }
+// m |= bit if a < b, as one compare and one predicated OR
+template <uint32_t BIT>
+B200_D void or_if_less(uint32_t &m, float a, float b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(a), "f"(b), "n"(BIT));
+}
 // B200PT_BOX_SLACK with the sign of x
 B200_D float slack_signed(float x) { return __uint_as_float(0x3e99999au | (__float_as_uint(x) & 0x80000000u)); }
 B200_D int msb32(uint32_t v) { return 31 - __clz((int)v); }
@@ -134,6 +139,10 @@ inline float plane_2p15(uint32_t w, uint32_t sel) {
 }
 inline float box_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 inline float box_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+template <uint32_t BIT>
+inline void or_if_less(uint32_t &m, float a, float b) {
+    if (a < b) m |= BIT;
+}
 inline uint32_t swap_pairs(uint32_t w) { return ((w & 0x00ff00ffu) << 8) | ((w >> 8) & 0x00ff00ffu); }
 inline float slack_signed(float x) { return uint_as_float(0x3e99999au | (float_as_uint(x) & 0x80000000u)); }
 inline int msb32(uint32_t v) { return 31 - __builtin_clz(v); }
@@ -181,7 +190,6 @@ struct Trav {
     uint32_t sel[4];       // PRMT selectors of the NEAR byte: x, y (bytes 0-1 / 2-3 of a slot's xy word), z pair at bytes 0-1, at
                            // bytes 2-3; the far byte is fetched with the same selector from the word with its byte pairs swapped
     uint32_t octinv;       // 7 - ray octant
-    float tmaxp;           // the ray's current tMax as a box parameter (closest hit shrinks it)
     // ---- position in the tree
     uint32_t cur_x, cur_y;
     int sp;                // stack pointer; bit 30 is set when a push was dropped because the stack was full (reported,
@@ -195,7 +203,10 @@ struct TravRay {
     float tmax;
     uint32_t best;
     TriHit hit;
-    float t0, inv;         // box parameter = (t - t0) * inv
+    float t0;              // box parameter = (t - t0) / span
+    // what trav_rescale needs when a closest hit shortens the ray: the unscaled reciprocal direction, the advanced
+    // origin times it, and the floor of the span
+    float iu[3], ou[3], span_floor;
 };
 // The stack of postponed child groups lives in its own object so that the scalar
 // state above stays in registers (a struct with a dynamically indexed array is
@@ -211,6 +222,22 @@ struct TravStack {
         *gy = y[sp];
     }
 };
+
+// The box parameter ends (s = 1) a little beyond `tEnd`, the ray's current tMax (or where it leaves the bounds): the span
+// is a little longer than tEnd - t0 and never shorter than 2^-30 of the tree's extent (keeps every product finite).
+// Called once per ray and again whenever a closest hit shortens the ray -- from the unscaled values, so nothing drifts.
+B200_HD void trav_rescale(Trav &T, const TravRay &R, float tEnd) {
+    float span = (tEnd - R.t0) * 1.001f + 0x1p-20f * tEnd;
+    if (!(span > R.span_floor)) span = R.span_floor;
+    if (!(span > 1e-30f)) span = 1e-30f;
+    const float inv = 1.0f / span;
+    T.idx = R.iu[0] * inv;
+    T.idy = R.iu[1] * inv;
+    T.idz = R.iu[2] * inv;
+    T.oix = R.ou[0] * inv;
+    T.oiy = R.ou[1] * inv;
+    T.oiz = R.ou[2] * inv;
+}
 
 B200_HD void trav_init(Trav &T, TravRay &R, const V3 &o, const V3 &d, float rayTMax, const TravBounds &B) {
     R.o = o;
@@ -241,32 +268,20 @@ B200_HD void trav_init(Trav &T, TravRay &R, const V3 &o, const V3 &d, float rayT
     const float t0 = tEnter > 0.f ? tEnter : 0.f;
     const float t1 = tExit < rayTMax ? tExit : rayTMax;
     R.t0 = t0;
-    R.inv = 0.f;
-    T.tmaxp = 1.f;
+    R.iu[0] = ix;
+    R.iu[1] = iy;
+    R.iu[2] = iz;
+    R.ou[0] = R.ou[1] = R.ou[2] = 0.f;
+    R.span_floor = 0x1p-30f * B.scale;
     T.idx = T.idy = T.idz = T.oix = T.oiy = T.oiz = 0.f;
     if (!(t0 <= t1)) return;  // misses the bounds (or NaN): no traversal at all
-    // span: a little longer than t1 - t0, never shorter than 2^-30 of the tree's extent (keeps every product finite)
-    float span = (t1 - t0) * 1.001f + 0x1p-20f * t1;
-    const float floorSpan = 0x1p-30f * B.scale;
-    if (!(span > floorSpan)) span = floorSpan;
-    if (!(span > 1e-30f)) span = 1e-30f;
-    const float inv = 1.0f / span;
-    R.inv = inv;
-    T.idx = ix * inv;
-    T.idy = iy * inv;
-    T.idz = iz * inv;
     const float obx = t0 > 0.f ? fma_any(d.x, t0, o.x) : o.x, oby = t0 > 0.f ? fma_any(d.y, t0, o.y) : o.y,
                 obz = t0 > 0.f ? fma_any(d.z, t0, o.z) : o.z;
-    T.oix = obx * T.idx;
-    T.oiy = oby * T.idy;
-    T.oiz = obz * T.idz;
+    R.ou[0] = obx * ix;
+    R.ou[1] = oby * iy;
+    R.ou[2] = obz * iz;
+    trav_rescale(T, R, t1);
     T.cur_y = 0x80000000u;  // the root as a one-child group
-}
-
-// the box parameter of a hit at distance t, rounded up
-B200_HD float trav_param_of(const TravRay &R, float t) {
-    const float p = ((t - R.t0) + 0x1p-21f * t) * R.inv * 1.000001f;
-    return p < 1.f ? p : 1.f;
 }
 
 #define B200PT_SLOT(S, WXY, WXYS, WZ, WZS, ZSEL)                                                                     \
@@ -275,13 +290,14 @@ B200_HD float trav_param_of(const TravRay &R, float t) {
                                   fma_sat(plane_2p15(WZ, T.sel[ZSEL]), az, cnz));                                    \
         const float tf = box_min3(fma_sat(plane_2p15(WXYS, T.sel[0]), ax, cfx), fma_sat(plane_2p15(WXYS, T.sel[1]), ay, cfy), \
                                   fma_sat(plane_2p15(WZS, T.sel[ZSEL]), az, cfz));                                   \
-        if (CLOSEST ? (tn < tf && tn < T.tmaxp) : (tn < tf)) m |= (1u << S);                                         \
+        or_if_less<(1u << S)>(m, tn, tf);                                                                            \
     }
 
 // Node phase: take the next inner child of the current group, fetch its node, test the seven
 // children.  Leaves the hit inner children in T.cur and returns the hit leaf children as a
 // leaf group (*tg_x = the node, *tg_y = hit leaf slots | lcount << 8, 0 if none).  Requires T.cur to be a node group.
-// CLOSEST: the ray's tMax shrinks during traversal (closest hit); any-hit rays keep the span they started with.
+// (CLOSEST is kept for the callers' sake: a closest hit rescales the box parameter, trav_rescale, so the test itself is
+// the same for both kinds of ray.)
 // STAGE: nodes [0, n_staged) -- the top of the tree, which is stored breadth-first -- are read from `staged`, a copy in
 // shared memory, instead of global memory.
 template <bool CLOSEST, bool COUNT, bool STAGE = false, class Stack = TravStack>
@@ -382,7 +398,7 @@ B200_HD void leaf_group_triangles(const uint32_t *__restrict__ tri_base, uint32_
 }
 
 template <bool ANY_HIT, bool COUNT>
-B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const uint32_t *__restrict__ tri_base, const F4 *__restrict__ tris, uint32_t lg_x,
+B200_HD bool trav_tri_phase(TravRay &R, const uint32_t *__restrict__ tri_base, const F4 *__restrict__ tris, uint32_t lg_x,
                             uint32_t lg_y, TraceCounters *ctr) {
     uint32_t tg_x, tg_y;
     leaf_group_triangles(tri_base, lg_x, lg_y, &tg_x, &tg_y);
@@ -395,8 +411,7 @@ B200_HD bool trav_tri_phase(TravRay &R, float *tmaxp, const uint32_t *__restrict
         if (COUNT) ctr->tris++;
         TriHit h;
         if (triangle_test(mk(v0.x, v0.y, v0.z), mk(v1.x, v1.y, v1.z), mk(v2.x, v2.y, v2.z), R.o, R.sh, R.tmax, &h)) {
-            R.tmax = h.t;  // primitive.cpp:120
-            *tmaxp = trav_param_of(R, h.t);
+            R.tmax = h.t;  // primitive.cpp:120 (the caller rescales the box parameter: trav_rescale)
             R.best = ti;
             R.hit = h;
             if (ANY_HIT) return true;
@@ -423,7 +438,9 @@ B200_HD bool trav_step(Trav &T, TravRay &R, TravStack &S, const U4 *__restrict__
                         const F4 *__restrict__ tris, const uint8_t *lut, TraceCounters *ctr) {
     uint32_t tg_x = 0, tg_y = 0;
     if (T.cur_y & 0xff000000u) trav_node_phase<!ANY_HIT, COUNT>(T, S, nodes, tri_base, lut, &tg_x, &tg_y, ctr);
-    if (trav_tri_phase<ANY_HIT, COUNT>(R, &T.tmaxp, tri_base, tris, tg_x, tg_y, ctr)) return true;
+    const float before = R.tmax;
+    if (trav_tri_phase<ANY_HIT, COUNT>(R, tri_base, tris, tg_x, tg_y, ctr)) return true;
+    if (R.tmax != before) trav_rescale(T, R, R.tmax);
     return !trav_next_group(T, S);
 }
 
