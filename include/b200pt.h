@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 5
+#define B200PT_ABI_VERSION 6
 #define B200PT_SPECTRUM_SAMPLES 60  /* nSpectralSamples, core/spectrum.h:52 */
 #define B200PT_MATERIAL_SPECTRA 5
 
@@ -268,9 +268,19 @@ typedef struct b200pt_integrator_desc {
     /* VolPathIntegrator (integrators/volpath.cpp:60-188) instead of PathIntegrator: a light is sampled at every vertex
      * (also purely specular ones, :124-128) and, with `medium.present`, every ray travels through one
      * HomogeneousMedium (media/homogeneous.cpp) that surrounds the whole scene -- the camera is in it and no surface is
-     * a medium transition.  Media bounded by surfaces and heterogeneous media are not supported. */
+     * a medium transition.  Heterogeneous media are not supported. */
     int32_t volumetric;
     b200pt_medium medium;
+    /* Media bounded by surfaces (ABI 6): Sphere shapes with `Material ""` under `MediumInterface "inside" "outside"`
+     * (api.cpp:1032-1045, primitive.cpp:106-127).  sphere_medium[k] >= 0 makes sphere k of the scene such a boundary:
+     * no BSDF (the path steps over it without spending a bounce, volpath.cpp:115-121), inside it is
+     * bounded_media[sphere_medium[k]], outside it the medium above (or vacuum); a ray's medium switches by the side it
+     * leaves on (interaction.h:80-82), shadow and MIS rays accumulate transmittance segment by segment
+     * (light.cpp:63-81, scene.cpp:57-70).  Such a sphere must not be a light.  n_bounded_media == 0: none. */
+    int32_t n_bounded_media;
+    int32_t reserved;
+    const b200pt_medium *bounded_media;  /* [n_bounded_media]; `present` is ignored */
+    const int32_t *sphere_medium;        /* [scene n_spheres]: index into bounded_media, or -1 for an ordinary sphere */
 } b200pt_integrator_desc;
 
 /* ---- per-ray records for the kernel-level entry points ------------------ */
@@ -305,6 +315,9 @@ typedef struct b200pt_stats {
     uint64_t stack_overflows;      /* child groups a full traversal stack had to drop (must be 0: a non-zero
                                       count means hits may have been missed; scene_create rejects trees whose
                                       depth could overflow, so this is a tripwire, not an expected event)   */
+    uint64_t dimension_overflows;  /* paths ended because their sampler dimension ran past n_dimensions (only
+                                      possible with bounded media: every boundary crossed inside a medium spends
+                                      two dimensions without spending a bounce; the reference aborts there)    */
 } b200pt_stats;
 
 typedef struct b200pt_ctx b200pt_ctx;      /* device + stream                          */

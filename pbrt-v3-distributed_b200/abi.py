@@ -81,7 +81,9 @@ class Medium(C.Structure):
 
 class IntegratorDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32),
-                ("pixel_bounds", C.c_int32 * 4), ("volumetric", C.c_int32), ("medium", Medium)]
+                ("pixel_bounds", C.c_int32 * 4), ("volumetric", C.c_int32), ("medium", Medium),
+                ("n_bounded_media", C.c_int32), ("reserved", C.c_int32), ("bounded_media", C.c_void_p),
+                ("sphere_medium", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -89,7 +91,8 @@ class Stats(C.Structure):
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("any_nodes_visited", C.c_uint64),
                 ("any_tris_tested", C.c_uint64), ("closest_ms", C.c_double),
                 ("any_ms", C.c_double), ("shade_ms", C.c_double), ("launches", C.c_uint64),
-                ("closest_launches", C.c_uint64), ("any_launches", C.c_uint64), ("stack_overflows", C.c_uint64)]
+                ("closest_launches", C.c_uint64), ("any_launches", C.c_uint64), ("stack_overflows", C.c_uint64),
+                ("dimension_overflows", C.c_uint64)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("t_max", np.float32), ("d", np.float32, 3),

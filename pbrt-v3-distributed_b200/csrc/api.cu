@@ -102,6 +102,7 @@ struct b200pt_render {
     int32_t *d_tile_list = nullptr;
     size_t tile_list_capacity = 0;
     float *d_rgb = nullptr;  // b200pt_film_read_rgb staging (lazily allocated, freed with the render object)
+    uint32_t *d_walk_counts = nullptr;  // bounded media: [16] queue counters / fetch counters of the boundary passes
     int grid_trace = 0, grid_shade = 0;
     bool instrumented = false, profiling = false;
     int refill_lanes = 26, postpone_pct = 40, trace_ctas = 0, stage_nodes = 0;  // k_trace knobs (b200pt_render_set_option)
@@ -861,7 +862,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     if (integ->max_depth < 0 || integ->max_depth > 200) return b200pt_fail(B200PT_ERR_INVALID, "render_create: bad max_depth");
     // 5 camera dims + per bounce: light pick 1 + uLight 2 + uScattering 2 + BSDF 2 + roulette 1
     // ... + medium channel 1 + free-flight distance 1 with VolPathIntegrator inside a medium
-    const int dims_per_bounce = integ->volumetric && integ->medium.present ? 10 : 8;
+    const int dims_per_bounce = integ->volumetric && (integ->medium.present || integ->n_bounded_media > 0) ? 10 : 8;
     if (5 + dims_per_bounce * integ->max_depth > smp->n_dimensions)
         return b200pt_fail(B200PT_ERR_INVALID, "render_create: max_depth %d needs %d sampler dimensions, %d provided",
                            integ->max_depth, 5 + dims_per_bounce * integ->max_depth, smp->n_dimensions);
@@ -879,6 +880,34 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         }
         if (!(integ->medium.g > -1.f && integ->medium.g < 1.f))
             return b200pt_fail(B200PT_ERR_INVALID, "render_create: Henyey-Greenstein g must lie in (-1, 1)");
+    }
+    // media bounded by null-material spheres (ABI 6)
+    const int n_bounded = integ->n_bounded_media;
+    if (n_bounded < 0 || n_bounded > 4096) return b200pt_fail(B200PT_ERR_INVALID, "render_create: bad n_bounded_media");
+    if (n_bounded > 0) {
+        if (!integ->volumetric)
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded media need the volumetric integrator (PathIntegrator ignores media)");
+        if (!integ->bounded_media || !integ->sphere_medium)
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded_media / sphere_medium missing");
+        if (scene->nspec)
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded media are not supported for SampledSpectrum hosts");
+        if (!scene->instances.empty())
+            return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded media are not supported in scenes with object instances");
+        for (int k = 0; k < n_bounded; ++k) {
+            const b200pt_medium &m = integ->bounded_media[k];
+            for (int c = 0; c < 3; ++c)
+                if (!(m.sigma_a[c] >= 0.f) || !(m.sigma_s[c] >= 0.f) || !(m.sigma_a[c] + m.sigma_s[c] > 0.f))
+                    return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded medium %d needs sigma_a, sigma_s >= 0 and sigma_t > 0 in every channel", k);
+            if (!(m.g > -1.f && m.g < 1.f))
+                return b200pt_fail(B200PT_ERR_INVALID, "render_create: bounded medium %d: Henyey-Greenstein g must lie in (-1, 1)", k);
+        }
+        for (size_t k = 0; k < scene->spheres.size(); ++k) {
+            const int32_t mk_ = integ->sphere_medium[k];
+            if (mk_ < -1 || mk_ >= n_bounded)
+                return b200pt_fail(B200PT_ERR_INVALID, "render_create: sphere_medium[%zu] = %d is not a bounded medium", k, mk_);
+            if (mk_ >= 0 && scene->spheres[k].light_id >= 0)
+                return b200pt_fail(B200PT_ERR_INVALID, "render_create: sphere %zu bounds a medium and is an area light", k);
+        }
     }
     if (integ->light_strategy != B200PT_LIGHTS_UNIFORM && integ->light_strategy != B200PT_LIGHTS_POWER &&
         integ->light_strategy != B200PT_LIGHTS_SPATIAL)
@@ -998,6 +1027,7 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         H.med_sigma_t[c] = integ->medium.sigma_s[c] + integ->medium.sigma_a[c];  // homogeneous.h:53
     }
     H.med_g = integ->medium.g;
+    H.med_general = n_bounded > 0 ? 1 : 0;
     H.tiles_x = (sbw + 15) / 16;
     H.tiles_y = (sbh + 15) / 16;
 
@@ -1185,7 +1215,44 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.q_mis, cap);
     ALLOC(H.qcount, (size_t)(H.max_depth + 2) * Q_PER_BOUNCE);
     ALLOC(H.work, (size_t)(H.max_depth + 2) * 16);
-    ALLOC(H.stats, 8);
+    ALLOC(H.stats, 9);
+    // media bounded by surfaces: medium table, per-sphere medium ids, the walkers' per-slot state
+    float *d_media_tab = nullptr, *d_media_g = nullptr;
+    int32_t *d_sphere_med = nullptr;
+    std::vector<float> media_tab, media_g;
+    std::vector<int32_t> sphere_med;
+    if (H.med_general) {
+        media_tab.assign((size_t)(1 + n_bounded) * 6, 0.f);
+        media_g.assign((size_t)(1 + n_bounded), 0.f);
+        for (int k = 0; k <= n_bounded; ++k) {
+            if (k == 0 && !H.has_medium) continue;  // id 0 = the medium around the scene (never used when there is none)
+            const b200pt_medium &m = k == 0 ? integ->medium : integ->bounded_media[k - 1];
+            for (int c = 0; c < 3; ++c) {
+                media_tab[(size_t)k * 6 + c] = m.sigma_s[c];
+                media_tab[(size_t)k * 6 + 3 + c] = m.sigma_s[c] + m.sigma_a[c];  // homogeneous.h:53
+            }
+            media_g[(size_t)k] = m.g;
+        }
+        sphere_med.resize(std::max<size_t>(1, scene->spheres.size()), -1);
+        for (size_t k = 0; k < scene->spheres.size(); ++k)
+            sphere_med[k] = integ->sphere_medium[k] >= 0 ? integ->sphere_medium[k] + 1 : -1;
+        ALLOC(d_media_tab, media_tab.size());
+        ALLOC(d_media_g, media_g.size());
+        ALLOC(d_sphere_med, sphere_med.size());
+        ALLOC(H.cur_med, cap);
+        ALLOC(H.q_cross[0], cap);
+        ALLOC(H.q_cross[1], cap);
+        ALLOC(H.q_walk[0], cap);
+        ALLOC(H.q_walk[1], cap);
+        ALLOC(H.sh_hit, cap);
+        ALLOC(H.A2, cap);
+        ALLOC(H.sh_tr, cap);
+        ALLOC(H.mi_tr, cap);
+        ALLOC(H.sh_p1, cap);
+        ALLOC(H.sh_p1e, cap);
+        ALLOC(H.sh_p1n, cap);
+        ALLOC(r->d_walk_counts, 16);
+    }
     ALLOC(r->d_dev, 1);
 #undef ALLOC
     if (e != cudaSuccess) {
@@ -1196,6 +1263,10 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     H.lights = d_lights;
     H.light_spectra = d_light_spectra;
     H.med_spectra = d_med_spectra;
+    H.media_tab = d_media_tab;
+    H.media_g = d_media_g;
+    H.sphere_med = d_sphere_med;
+    H.dim_overflows = H.stats + 8;
     H.has_delta_lights = has_delta ? 1 : 0;
     H.light_cdf = d_cdf;
     H.light_func = d_func;
@@ -1237,7 +1308,13 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
         CUDA_TRY(cudaMemsetAsync(H.tile_slot, 0xff, (size_t)H.tiles_x * H.tiles_y * sizeof(int32_t), st));
         CUDA_TRY(cudaStreamSynchronize(st));  // `table` is a local
     }
-    CUDA_TRY(cudaMemsetAsync(H.stats, 0, 8 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(H.stats, 0, 9 * sizeof(unsigned long long), st));
+    if (H.med_general) {
+        CUDA_TRY(cudaMemcpyAsync(d_media_tab, media_tab.data(), media_tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_media_g, media_g.data(), media_g.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_sphere_med, sphere_med.data(), sphere_med.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // locals
+    }
     CUDA_TRY(cudaMemcpyAsync(r->d_dev, &H, sizeof(H), cudaMemcpyHostToDevice, st));
     if (H.grid.enabled) {
         if (scene->nspec)
@@ -1387,7 +1464,15 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
         //   closest(b) -> shade(b) -> { any(b), MIS-closest(b) } || closest(b+1) -> resolve(b) -> shade(b+1) ...
         // The shadow / MIS rays of bounce b and the path rays of bounce b+1 are independent, so they run on
         // two streams: as the persistent CTAs of one launch drain, the other launch fills the freed SMs.
-        const bool medium = H.has_medium != 0;  // k_medium also queues direct-lighting rays: no overlap of bounces then
+        const bool general = H.med_general != 0;  // media bounded by surfaces: boundary passes inside a bounce (see RenderDev)
+        const bool medium = H.has_medium != 0 || general;  // k_medium also queues direct-lighting rays: no overlap of bounces then
+        uint32_t *const wc = r->d_walk_counts;  // [0], [1] crossers of a pass (ping-pong), [2] walk kernel, [3] trace, [4] sphere pass
+        auto device_count = [&](const uint32_t *d, cudaStream_t s_) {
+            uint32_t v = 0;
+            if (cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, s_) != cudaSuccess) return 0u;
+            if (cudaStreamSynchronize(s_) != cudaSuccess) return 0u;
+            return v;
+        };
         const bool overlap = r->overlap && r->sort_from_bounce < 0 && !medium;
         cudaStream_t st2 = overlap ? ctx->stream_aux : st;
         const bool tl = two_level(r->scene) && !r->instrumented;  // instances inside the traversal kernel
@@ -1462,7 +1547,31 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                     r->launches++;
                 }
             }
-            if (medium) {
+            if (general) {
+                // the medium pass, then -- while some rays reached a medium boundary -- the same two steps again for those
+                // rays from behind the boundary (volpath.cpp:115-121: no bounce is spent)
+                cudaMemsetAsync(wc, 0, 16 * sizeof(uint32_t), st);
+                {
+                    LaunchTimer lt2(r, st, 2);
+                    launch_medium_general(r->d_dev, H, b, a.queue, qc + Q_PATH, 0, wc + 0, wk + 11, false, r->grid_shade, st);
+                }
+                for (int cur = 0; device_count(wc + cur, st) != 0; cur ^= 1) {
+                    cudaMemsetAsync(wc + (cur ^ 1), 0, sizeof(uint32_t), st);
+                    cudaMemsetAsync(wc + 2, 0, 3 * sizeof(uint32_t), st);
+                    a.queue = H.q_cross[cur];
+                    a.count = wc + cur;
+                    a.work = wc + 3;
+                    {
+                        LaunchTimer lt(r, st, 0);
+                        trace(a, false, false, st);
+                        sphere_args(a, wc + 4);
+                        launch_spheres(a, false, false, r->grid_shade, st);
+                        r->launches++;
+                    }
+                    LaunchTimer lt2(r, st, 2);
+                    launch_medium_general(r->d_dev, H, b, H.q_cross[cur], wc + cur, cur ^ 1, wc + (cur ^ 1), wc + 2, true, r->grid_shade, st);
+                }
+            } else if (medium) {
                 LaunchTimer lt2(r, st, 2);
                 if (spectral)
                     b200pt_s60::launch_medium(s60(r->d_dev), b, wk + 11, r->grid_shade, st);
@@ -1470,7 +1579,62 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                     launch_medium(r->d_dev, b, wk + 11, r->grid_shade, st);
             }
         };
+        // Bounded media: the shadow (VisibilityTester::Tr) or MIS (Scene::IntersectTr) rays of bounce b walk from boundary to
+        // boundary -- a closest-hit launch per segment, then k_direct_walk ends each ray or sends it on
+        auto walk_direct = [&](int b, bool shadow) {
+            uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
+            uint32_t *wk = H.work + (size_t)b * 16;
+            TraceArgs a;
+            memset(&a, 0, sizeof(a));
+            trace_args_scene(a, r->scene);
+            a.materials = H.scene.materials;
+            a.stats = H.stats;
+            a.stride = 1;
+            a.refill_lanes = r->refill_lanes;
+            a.postpone_pct = r->postpone_pct;
+            a.ctas = r->trace_ctas;
+            a.ray_o = shadow ? H.sh_o : H.mi_o;
+            a.ray_d = shadow ? H.sh_d : H.mi_d;
+            a.fixed_t_max = shadow ? PT_SHADOW_TMAX : INFINITY;
+            a.hit_out = shadow ? H.sh_hit : H.mis_hit;
+            const uint32_t *queue = shadow ? H.q_shadow : H.q_mis;
+            const uint32_t *count = qc + (shadow ? Q_SHADOW : Q_MIS);
+            uint32_t *trace_work = wk + (shadow ? 5 : 6), *sphere_work = wk + (shadow ? 9 : 10);
+            cudaMemsetAsync(wc, 0, 16 * sizeof(uint32_t), st);
+            bool first = true;
+            for (int cur = 0;; cur ^= 1) {
+                if (!first) {
+                    if (device_count(count, st) == 0) break;
+                    cudaMemsetAsync(wc + cur, 0, sizeof(uint32_t), st);
+                    cudaMemsetAsync(wc + 2, 0, 3 * sizeof(uint32_t), st);
+                    trace_work = wc + 3;
+                    sphere_work = wc + 4;
+                }
+                a.queue = queue;
+                a.count = count;
+                a.work = trace_work;
+                {
+                    LaunchTimer lt(r, st, 0);
+                    trace(a, false, false, st);
+                    sphere_args(a, sphere_work);
+                    launch_spheres(a, false, false, r->grid_shade, st);
+                    r->launches++;
+                }
+                {
+                    LaunchTimer lt2(r, st, 2);
+                    launch_direct_walk(r->d_dev, H, shadow, queue, count, cur, wc + cur, wc + 2, !first, r->grid_shade, st);
+                }
+                queue = H.q_walk[cur];
+                count = wc + cur;
+                first = false;
+            }
+        };
         auto trace_direct = [&](int b) {
+            if (general) {
+                walk_direct(b, true);
+                walk_direct(b, false);
+                return;
+            }
             uint32_t *qc = H.qcount + (size_t)b * Q_PER_BOUNCE;
             uint32_t *wk = H.work + (size_t)b * 16;
             TraceArgs a;
@@ -1827,7 +1991,7 @@ int b200pt_get_stats(b200pt_render *r, b200pt_stats *out) {
     if (!r || !out) return b200pt_fail(B200PT_ERR_INVALID, "get_stats: NULL argument");
     CUDA_TRY(cudaSetDevice(r->scene->ctx->device));
     cudaStream_t st = r->scene->ctx->stream;
-    unsigned long long h[8];
+    unsigned long long h[9];
     CUDA_TRY(cudaMemcpyAsync(h, r->host.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     drain_timers(r);
@@ -1846,6 +2010,7 @@ int b200pt_get_stats(b200pt_render *r, b200pt_stats *out) {
     out->shade_ms = r->ms[2];
     out->launches = r->launches;
     out->stack_overflows = h[7];
+    out->dimension_overflows = h[8];
     return B200PT_OK;
 }
 
@@ -1855,7 +2020,7 @@ int b200pt_reset_stats(b200pt_render *r) {
     cudaStream_t st = r->scene->ctx->stream;
     CUDA_TRY(cudaStreamSynchronize(st));
     drain_timers(r);
-    CUDA_TRY(cudaMemsetAsync(r->host.stats, 0, 8 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(r->host.stats, 0, 9 * sizeof(unsigned long long), st));
     r->ms[0] = r->ms[1] = r->ms[2] = 0;
     r->launches = 0;
     r->launches_cat[0] = r->launches_cat[1] = r->launches_cat[2] = 0;

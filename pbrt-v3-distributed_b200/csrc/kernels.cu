@@ -68,6 +68,9 @@ __device__ __forceinline__ Spec medium_sigma_s(const RenderDev *R) {
     return rgbp(R->med_spectra);
 #endif
 }
+// media bounded by surfaces (RGB build): coefficients of medium id k (RenderDev::media_tab)
+__device__ __forceinline__ Spec media_sigma_s(const RenderDev *R, int k) { return rgbp(R->media_tab + (size_t)k * 2 * B200PT_NSPEC); }
+__device__ __forceinline__ Spec media_sigma_t(const RenderDev *R, int k) { return rgbp(R->media_tab + ((size_t)k * 2 + 1) * B200PT_NSPEC); }
 __device__ __forceinline__ Spec medium_sigma_t(const RenderDev *R) {
 #if B200PT_NSPEC == 3
     return rgbp(R->med_sigma_t);
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderDev *R, uint32_t fir
             st_spec(R->beta, R->s_beta, R->capacity, slot, rgb1(1.f), 0.f);
             st_spec(R->L, R->s_L, R->capacity, slot, rgb1(0.f), __uint_as_float(code));
             R->sh_d[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (R->med_general) R->cur_med[slot] = R->has_medium ? 0 : -1;  // the camera's medium (camera.h:76)
         }
     }
     const uint32_t pos = warp_append(&R->qcount[Q_PATH], valid);
@@ -337,6 +341,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 #ifndef B200PT_SMEM_STACK
 #define B200PT_SMEM_STACK 0
 #endif
+// Parked triangle groups per lane (see the traversal loop of k_trace): 1 = one group in registers; 2 = a second one in
+// shared memory, so that the triangle phase starts with more lanes on board.
+#ifndef B200PT_PARK_DEPTH
+#define B200PT_PARK_DEPTH 1
+#endif
+// Triangle phase as a warp-wide work list (1) or per lane (0).  Per lane, a lane with three triangles loops three times
+// while lanes without any wait: ncu counted 5 of 32 lanes active over the phase's instructions (29 % of all instructions
+// issued, profiles/r02/ncu_trace_cfg4.json).  With the list, the lanes that parked a group publish (lane, triangle)
+// pairs in shared memory and every converged lane takes one pair: the ray is read from its owner's column of s_ray, the
+// closest candidate per owner is settled with a 64-bit shared-memory atomicMin on (t, position in the list), the winner
+// writes the hit into the owner's column.
+#ifndef B200PT_TRI_SHARE
+#define B200PT_TRI_SHARE 0
+#endif
+#define B200PT_PAIR_CAP 64
 struct LaneStack {
     uint32_t *sx, *sy;  // this thread's column of the shared part: entry e at [e * 128]
     uint32_t x[B200PT_STACK - B200PT_SMEM_STACK], y[B200PT_STACK - B200PT_SMEM_STACK];
@@ -367,6 +386,14 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     __shared__ float s_ray[B200PT_RAY_WORDS * 128];
 #if B200PT_SMEM_STACK > 0
     __shared__ uint32_t s_stack[2 * B200PT_SMEM_STACK * 128];
+#endif
+#if B200PT_PARK_DEPTH > 1
+    __shared__ uint32_t s_park[2 * 128];  // a lane's second parked triangle group (x, y)
+#endif
+#if B200PT_TRI_SHARE
+    __shared__ uint32_t s_pairs[4 * B200PT_PAIR_CAP];  // per warp: owner lane << 27 | triangle
+    __shared__ unsigned long long s_key[128];          // per owner: min over its pairs of (t bits << 32 | list position)
+    __shared__ uint32_t s_cnt[4];
 #endif
     __shared__ __align__(8) unsigned long long s_bar;
     extern __shared__ __align__(128) uint8_t s_top[];  // STAGE: WbvhNode[a.n_staged]
@@ -406,6 +433,10 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
     TravStack S;
 #endif
     uint32_t slot = 0, pend_x = 0, pend_y = 0;
+#if B200PT_PARK_DEPTH > 1
+    uint32_t *const my_park = s_park + threadIdx.x;
+    my_park[128] = 0;
+#endif
     bool has = false, fin = false, exhausted = false;
     while (true) {
         // ---- converged: retire finished rays
@@ -484,7 +515,15 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
             bool must = false;
             if (ng_y) {
                 if (pend_y) {
-                    must = true;  // two groups: flush the parked one now, park the new one after
+#if B200PT_PARK_DEPTH > 1
+                    // a second group waits in shared memory; only a third one forces the triangle phase
+                    if (my_park[128] == 0) {
+                        my_park[0] = ng_x;
+                        my_park[128] = ng_y;
+                        ng_y = 0;
+                    } else
+#endif
+                        must = true;  // no room: flush the oldest parked group now, park the new one after
                 } else {
                     pend_x = ng_x;
                     pend_y = ng_y;
@@ -503,6 +542,94 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
             // only waiting for it that the node phase itself would run half empty
             if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_starving * 4 >= n_act) {
                 bool done = false;
+#if B200PT_TRI_SHARE
+                {
+                    const int warp = threadIdx.x >> 5;
+                    uint32_t *const wp = s_pairs + warp * B200PT_PAIR_CAP;
+                    float *const warp_rays = s_ray + (threadIdx.x & ~31);
+                    uint32_t tg_x = 0, tg_y = 0;
+                    if (pend_y) leaf_group_triangles(a.tri_base, pend_x, pend_y, &tg_x, &tg_y);
+                    const uint32_t cnt = (uint32_t)__popc(tg_y);
+                    if (COUNT) ctr.tris += cnt;
+                    if (lane == __ffs(act) - 1) s_cnt[warp] = 0;
+                    __syncwarp(act);
+                    uint32_t pos = 0;
+                    if (cnt) {
+                        pos = atomicAdd(&s_cnt[warp], cnt);
+                        s_key[threadIdx.x] = ~0ull;
+                    }
+                    // a group that does not fit the list (or a triangle index too large for the pair word) stays with its lane
+                    const bool own = cnt && (pos + cnt > B200PT_PAIR_CAP || tg_x + 32u >= (1u << 27));
+                    if (cnt) {
+                        uint32_t bits = tg_y, k = pos;
+                        while (bits && k < B200PT_PAIR_CAP) {
+                            const int j = msb32(bits);
+                            bits &= ~(1u << j);
+                            wp[k++] = own ? 0xffffffffu : (((uint32_t)lane << 27) | (tg_x + (uint32_t)j));
+                        }
+                    }
+                    __syncwarp(act);
+                    const uint32_t total = min(s_cnt[warp], (uint32_t)B200PT_PAIR_CAP);
+                    const uint32_t rank = (uint32_t)__popc(act & ((1u << lane) - 1u)), nact = (uint32_t)__popc(act);
+                    for (uint32_t base = 0; base < total; base += nact) {
+                        const uint32_t k = base + rank;
+                        const uint32_t pr = k < total ? wp[k] : 0xffffffffu;
+                        bool hit = false;
+                        unsigned long long key = 0;
+                        TriHit h;
+                        float *col = warp_rays;
+                        uint32_t ti = 0;
+                        if (pr != 0xffffffffu) {
+                            col = warp_rays + (pr >> 27);
+                            ti = pr & 0x7ffffffu;
+                            RayShear sh;
+                            sh.Sx = col[3 * 128];
+                            sh.Sy = col[4 * 128];
+                            sh.Sz = col[5 * 128];
+                            sh.kz = __float_as_int(col[6 * 128]);
+                            sh.kx = sh.kz == 2 ? 0 : sh.kz + 1;
+                            sh.ky = sh.kx == 2 ? 0 : sh.kx + 1;
+                            const F4 *tp = a.tris + (size_t)ti * 3;
+                            const F4 v0 = ld_f4(tp), v1 = ld_f4(tp + 1), v2 = ld_f4(tp + 2);
+                            hit = triangle_test(mk(v0.x, v0.y, v0.z), mk(v1.x, v1.y, v1.z), mk(v2.x, v2.y, v2.z),
+                                                mk(col[0 * 128], col[1 * 128], col[2 * 128]), sh, col[7 * 128], &h);
+                            if (hit) {
+                                key = ((unsigned long long)__float_as_uint(h.t) << 32) | k;
+                                atomicMin(&s_key[(threadIdx.x & ~31) + (pr >> 27)], key);
+                            }
+                        }
+                        __syncwarp(act);
+                        if (hit && s_key[(threadIdx.x & ~31) + (pr >> 27)] == key) {
+                            col[7 * 128] = h.t;  // primitive.cpp:120
+                            col[8 * 128] = __uint_as_float(ti);
+                            col[9 * 128] = h.t;
+                            col[10 * 128] = h.b0;
+                            col[11 * 128] = h.b1;
+                            col[12 * 128] = h.b2;
+                        }
+                        __syncwarp(act);
+                    }
+                    bool was_hit = cnt && !own && s_key[threadIdx.x] != ~0ull;
+                    if (own) {
+                        TravRay R;
+                        ray_load(my_ray, R);
+                        const uint32_t before = R.best;
+                        trav_tri_phase<ANY_HIT, false>(R, a.tri_base, a.tris, pend_x, pend_y, &ctr);
+                        was_hit = R.best != before;
+                        if (was_hit) ray_store_hit(my_ray, R);
+                    }
+                    if (was_hit) {
+                        if (ANY_HIT) {
+                            done = true;
+                        } else {  // the ray got shorter: the box parameter ends at the hit from now on
+                            TravRay R;
+                            ray_load_scale(my_ray, R);
+                            R.tmax = my_ray[7 * 128];
+                            trav_rescale(T, R, R.tmax);
+                        }
+                    }
+                }
+#else
                 if (pend_y) {
                     TravRay R;
                     ray_load(my_ray, R);
@@ -516,6 +643,25 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
                         }
                     }
                 }
+#endif
+#if B200PT_PARK_DEPTH > 1
+                // the queue moves up: second -> first, a group found in this step -> second
+                pend_x = my_park[0];
+                pend_y = my_park[128];
+                my_park[0] = ng_x;
+                my_park[128] = ng_y;
+                if (pend_y == 0) {
+                    pend_x = ng_x;
+                    pend_y = ng_y;
+                    my_park[128] = 0;
+                }
+                if (done) {
+                    has = false;
+                    fin = true;
+                    pend_y = 0;
+                    my_park[128] = 0;
+                }
+#else
                 pend_x = ng_x;
                 pend_y = ng_y;
                 if (done) {
@@ -523,6 +669,7 @@ __global__ void __launch_bounds__(128, CTAS) k_trace(const TraceArgs a) {
                     fin = true;
                     pend_y = 0;
                 }
+#endif
             }
             if (has && !trav_next_group(T, S) && pend_y == 0) {
                 has = false;
@@ -1140,7 +1287,15 @@ struct DirectOut {
     uint32_t pend;
     V3 sh_o, sh_d, mi_o, mi_d;
     Spec A, B;
+    // scenes with bounded media: the transmittance of the two rays is only known after they have walked through the
+    // boundaries, so the factors stay apart: A = f, A2 = Li, wA = MIS weight (< 0: delta light, none), pdfA = lightPdf, and
+    // the point the shadow ray is re-aimed at (p1 + error bounds + normal); B = f, wB = weight, pdfB = scatteringPdf
+    Spec A2;
+    float wA, pdfA, wB, pdfB;
+    V3 p1, p1e, p1n;
 };
+// whether this translation unit carries the bounded-media code (the RGBSpectrum one)
+#define B200PT_MEDIA_GENERAL (B200PT_NSPEC == 3)
 
 // EstimateDirect (core/integrator.cpp:108-215), handleMedia = false,
 // specular = false, for a DiffuseAreaLight on one triangle.  The two rays it
@@ -1153,12 +1308,18 @@ struct DirectOut {
 // and error bounds) and the Henyey-Greenstein phase function takes the BSDF's place (integrator.cpp:131-137, :178-186).
 template <bool VTX>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
-                                int lightNum, const float uLight[2], DirectOut *out, bool inMedium = false) {
+                                int lightNum, const float uLight[2], DirectOut *out, bool inMedium = false, int med = 0) {
     // (VolPathIntegrator renders always run the general variant, so the lean one carries none of this)
-    const bool medium = VTX && R->has_medium != 0;
+    // `general`: media bounded by surfaces; `med` is the medium id around `is` and the rays' transmittance is left to
+    // the walk kernels
+    const bool general = B200PT_MEDIA_GENERAL && VTX && R->med_general != 0;
+    const bool medium = VTX && R->has_medium != 0 && !general;
     const Spec sigmaT = medium ? medium_sigma_t(R) : rgb1(0.f);
-    const float hgG = R->med_g;
+    const float hgG = general ? (med >= 0 ? R->media_g[med] : 0.f) : R->med_g;
     if (!VTX) inMedium = false;
+    out->A2 = rgb1(0.f);
+    out->wA = out->pdfA = out->wB = out->pdfB = 0.f;
+    out->p1 = out->p1e = out->p1n = mk(0.f, 0.f, 0.f);
     const DevLight &lightRef = R->lights[lightNum];
     if (VTX && lightRef.kind != 0) {
         // delta light (scenes with delta lights always run the VTX variant): Sample_Li has pdf 1, there is no MIS weight
@@ -1179,6 +1340,13 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
                 out->sh_d = pTarget - origin;
                 const Spec LiT = medium ? LiD * medium_tr(sigmaT, out->sh_d, PT_SHADOW_TMAX) : LiD;  // Li *= Tr
                 out->A = fD * LiT / 1.f;
+                if (general) {
+                    out->A = fD;
+                    out->A2 = LiD;
+                    out->wA = -1.f;
+                    out->pdfA = 1.f;
+                    out->p1 = pTarget;
+                }
                 out->pend |= PEND_LIGHT;
             }
         }
@@ -1248,6 +1416,15 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
             if (medium) Li = Li * medium_tr(sigmaT, out->sh_d, PT_SHADOW_TMAX);  // Li *= visibility.Tr(scene, sampler)
             const float weight = power_heuristic(lightPdf, scatteringPdf);
             out->A = f * Li * weight / lightPdf;
+            if (general) {
+                out->A = f;
+                out->A2 = Li;
+                out->wA = weight;
+                out->pdfA = lightPdf;
+                out->p1 = ps.p;
+                out->p1e = ps.pError;
+                out->p1n = ps.n;
+            }
             out->pend |= PEND_LIGHT;
         }
     }
@@ -1276,6 +1453,10 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
                 ln = li.n;
                 tLight = th;
                 lpdf = sphere_pdf(*lsp, is.p, is.pError, is.n, wi);
+            } else if (general) {
+                // from outside, Sphere::Pdf is the cone's density whether or not wi points into the cone: the reference
+                // traces the ray (it finds no light); with bounded media its segments are counted, so it is traced here too
+                lpdf = sphere_pdf(*lsp, is.p, is.pError, is.n, wi);
             }
         } else if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
             Isect li;
@@ -1292,11 +1473,31 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
             // ... attenuated by the medium up to that hit (Scene::IntersectTr: ray.tMax is the hit distance by then)
             const Spec Tr = medium ? medium_tr(sigmaT, wi, tLight) : rgb1(1.f);
             out->B = is_black(Le) ? rgb1(0.f) : f * Le * Tr * weight / scatteringPdf;
+            if (general) {  // Le and Tr belong to the hit the walk ends on
+                out->B = f;
+                out->wB = weight;
+                out->pdfB = scatteringPdf;
+            }
             out->mi_o = ro;
             out->mi_d = wi;
             out->pend |= PEND_BSDF;
         }
     }
+}
+
+// bounded media: the start of the two rays' walks (transmittance 1, the medium around the vertex) and the light sample
+__device__ __forceinline__ void store_direct_general(const RenderDev *R, uint32_t slot, const DirectOut &d, int med) {
+#if B200PT_MEDIA_GENERAL
+    const float mbits = __uint_as_float((uint32_t)med);
+    if (d.pend & PEND_LIGHT) {
+        R->A2[slot] = make_float4(d.A2.c[0], d.A2.c[1], d.A2.c[2], d.pdfA);
+        R->sh_tr[slot] = make_float4(1.f, 1.f, 1.f, mbits);
+        R->sh_p1[slot] = f4(d.p1, 0.f);
+        R->sh_p1e[slot] = f4(d.p1e, 0.f);
+        R->sh_p1n[slot] = f4(d.p1n, 0.f);
+    }
+    if (d.pend & PEND_BSDF) R->mi_tr[slot] = make_float4(1.f, 1.f, 1.f, mbits);
+#endif
 }
 
 template <int MAT, bool VTX>
@@ -1401,17 +1602,19 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                             get2d(sp, st, uLight);
                             get2d(sp, st, uScattering);
                             DirectOut dout;
-                            estimate_direct<VTX>(R, is, bsdf, uScattering, lightNum, uLight, &dout);
+                            const int med = (B200PT_MEDIA_GENERAL && VTX && R->med_general) ? R->cur_med[slot] : 0;
+                            estimate_direct<VTX>(R, is, bsdf, uScattering, lightNum, uLight, &dout, false, med);
                             pend = dout.pend;
                             if (pend) {
                                 st_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, beta, pickPdf);
                                 R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
-                                if (pend & PEND_LIGHT) st_spec(R->A, R->s_A, R->capacity, slot, dout.A, 0.f);
+                                if (pend & PEND_LIGHT) st_spec(R->A, R->s_A, R->capacity, slot, dout.A, dout.wA);
                                 if (pend & PEND_BSDF) {
-                                    R->mi_o[slot] = f4(dout.mi_o, 0.f);
+                                    R->mi_o[slot] = f4(dout.mi_o, dout.pdfB);
                                     R->mi_d[slot] = f4(dout.mi_d, 0.f);
-                                    st_spec(R->B, R->s_B, R->capacity, slot, dout.B, 0.f);
+                                    st_spec(R->B, R->s_B, R->capacity, slot, dout.B, dout.wB);
                                 }
+                                if (B200PT_MEDIA_GENERAL && VTX && R->med_general) store_direct_general(R, slot, dout, med);
                             }
                             R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
                         }
@@ -1617,6 +1820,311 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
         if (cont) q_next[pn] = slot;
     }
 }
+
+#if B200PT_MEDIA_GENERAL
+// ---- media bounded by null-material spheres (b200pt_integrator_desc::bounded_media) ------------------------------------
+// distance of the closest hit `ti` along (ro, rd) -- ray.tMax after Scene::Intersect -- and the hit's material word
+// (render_create refuses bounded media in scenes with object instances)
+__device__ __forceinline__ float hit_distance(const RenderDev *R, uint32_t ti, const V3 &ro, const V3 &rd, uint32_t *mflags) {
+    float tHit = pt_inf();
+    *mflags = 0;
+    if (ti == B200PT_MISS) return tHit;
+    if (is_sphere_hit(ti)) {
+        const DevSphere *sp = R->scene.spheres + (ti & SPHERE_HIT_MASK);
+        float th;
+        if (sphere_intersect(*sp, ro, rd, pt_inf(), &th, nullptr)) tHit = th;
+        *mflags = sp->mat_flags;
+    } else {
+        const F4 *tp = R->scene.tris + (size_t)ti * 3;
+        const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+        *mflags = __float_as_uint(t1.w);
+        TriHit h;
+        if (triangle_test(v3(t0), v3(t1), v3(t2), ro, make_shear(rd), pt_inf(), &h)) tHit = h.t;
+    }
+    return tHit;
+}
+// medium id inside the boundary sphere that hit `ti` names, -1 when the hit is an ordinary surface (or a miss)
+__device__ __forceinline__ int boundary_medium(const RenderDev *R, uint32_t ti) {
+    return (ti != B200PT_MISS && is_sphere_hit(ti)) ? R->sphere_med[ti & SPHERE_HIT_MASK] : -1;
+}
+
+// The medium pass of k_medium for scenes whose media are bounded by surfaces (volpath.cpp:77-121).  Differences: the ray's
+// medium is per-path state (cur_med; vacuum samples nothing and spends no sampler dimension), and a ray that reaches a
+// boundary -- a surface without a BSDF -- continues behind it in the medium of the side it leaves on (interaction.h:80-82)
+// without spending a bounce: it goes to q_cross and is traced again before the bounce's shading kernels run.
+__global__ void __launch_bounds__(128, 4) k_medium_general(const RenderDev *R, int bounce, const uint32_t *queue, const uint32_t *count,
+                                                           uint32_t *q_cross, uint32_t *cross_count, uint32_t *work, int count_rays) {
+    const uint32_t n = *count;
+    if (count_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&R->stats[1], (unsigned long long)n);
+    uint32_t *qc = &R->qcount[bounce * Q_PER_BOUNCE];
+    uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
+    uint32_t *q_next = R->q_path[(bounce + 1) & 1];
+    const int outside = R->has_medium ? 0 : -1;
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        const bool active = i < n;
+        bool cont = false, cross = false;
+        int family = -1;
+        uint32_t pend = 0, slot = 0;
+        if (active) {
+            slot = queue[i];
+            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
+            float betaW;
+            Spec beta = ld_spec(R->beta, R->s_beta, R->capacity, slot, &betaW);
+            const V3 ro = v3(o4), rd = v3(d4);
+            const float etaScale = o4.w;
+            const uint32_t meta = __float_as_uint(d4.w);
+            const int bounces = (int)((meta >> 16) & 0xffu);
+            const int med = R->cur_med[slot];
+            const uint32_t ti = R->hit[slot];
+            uint32_t mflags;
+            const float tHit = hit_distance(R, ti, ro, rd, &mflags);
+            const int bm = boundary_medium(R, ti);
+            SobolStream st;
+            st.index = R->sobol[slot];
+            st.dim = (int)(meta & 0xffffu);
+            st.px = st.py = 0;
+            const SamplerParams &sp = R->sampler;
+            // every boundary crossed inside a medium spends two dimensions, so a path can run past the host's tables (the
+            // reference aborts there, sobol.cpp / lowdiscrepancy.h:229); such a path ends here and is counted
+            bool alive = true;
+            if (st.dim + 10 > sp.n_dims) {
+                alive = false;
+                atomicAdd(R->dim_overflows, 1ull);
+            }
+            bool sampledMedium = false;
+            float t = tHit;
+            if (alive && med >= 0) {  // ray.medium->Sample (homogeneous.cpp:49-76)
+                const Spec sigmaT = media_sigma_t(R, med), sigmaS = media_sigma_s(R, med);
+                const int channel = pt_mini((int)(get1d(sp, st) * B200PT_NSPEC), B200PT_NSPEC - 1);
+                const float dist = -pt_logf(1 - get1d(sp, st)) / sigmaT.c[channel];
+                const float rdLen = len(rd);
+                t = pt_min(dist / rdLen, tHit);
+                sampledMedium = t < tHit;
+                Spec Tr;
+                PT_UNROLL SPEC_FOR Tr.c[i_] = pt_expf((-sigmaT.c[i_]) * pt_min(t, PT_MAX_FLOAT) * rdLen);
+                const Spec density = sampledMedium ? (sigmaT * Tr) : Tr;
+                float pdf = 0.f;
+                SPEC_FOR pdf += density.c[i_];
+                pdf *= 1 / (float)B200PT_NSPEC;
+                if (pdf == 0) pdf = 1;
+                beta = beta * (sampledMedium ? (Tr * sigmaS / pdf) : (Tr / pdf));
+            }
+            if (alive && !is_black(beta)) {
+                if (!sampledMedium) {
+                    if (bm >= 0) {
+                        // a medium boundary: nothing is emitted or scattered there; volpath.cpp:112 ends the path at maxDepth
+                        if (bounces < R->max_depth) {
+                            const DevSphere *bs = R->scene.spheres + (ti & SPHERE_HIT_MASK);
+                            float th;
+                            Isect is;
+                            if (sphere_intersect(*bs, ro, rd, pt_inf(), &th, &is)) {
+                                R->cur_med[slot] = dot(rd, is.n) > 0 ? outside : bm;          // GetMedium(ray.d)
+                                const V3 no = offset_ray_origin(is.p, is.pError, is.n, rd);  // isect.SpawnRay(ray.d)
+                                R->ray_o[slot] = f4(no, etaScale);
+                                R->ray_d[slot] = f4(rd, __uint_as_float((meta & 0xffff0000u) | ((uint32_t)st.dim & 0xffffu)));
+                                st_spec(R->beta, R->s_beta, R->capacity, slot, beta, betaW);
+                                cross = true;
+                            }
+                        }
+                    } else {
+                        // on to the surface vertex (or out of the scene)
+                        st_spec(R->beta, R->s_beta, R->capacity, slot, beta, betaW);
+                        R->ray_d[slot] = f4(rd, __uint_as_float((meta & 0xffff0000u) | ((uint32_t)st.dim & 0xffffu)));
+                        if (ti != B200PT_MISS) family = R->scene.materials[mflags & 0xffffu].type;
+                    }
+                } else if (bounces < R->max_depth) {  // volpath.cpp:84-85
+                    Isect mi;  // MediumInteraction(ray(t), -ray.d, ...): no normal, no error bounds
+                    mi.p = ro + rd * t;
+                    mi.wo = -rd;
+                    mi.n = mi.ns = mk(0.f, 0.f, 0.f);
+                    mi.pError = mk(0.f, 0.f, 0.f);
+                    if (R->n_lights > 0) {
+                        float pickPdf;
+                        const float *cdf = R->light_cdf, *func = R->light_func;
+                        float funcInt = R->light_func_int;
+                        if (R->grid.enabled) {
+                            const int vox = spatial_voxel(R->grid, mi.p);
+                            cdf = R->sp_cdf + (size_t)vox * (R->n_lights + 1);
+                            func = R->sp_func + (size_t)vox * R->n_lights;
+                            funcInt = R->sp_func_int[vox];
+                        }
+                        const int lightNum = sample_discrete(cdf, func, funcInt, R->n_lights, get1d(sp, st), &pickPdf);
+                        if (pickPdf != 0) {
+                            float uLight[2], uScattering[2];
+                            get2d(sp, st, uLight);
+                            get2d(sp, st, uScattering);
+                            DirectOut dout;
+                            Bsdf none;
+                            none.n = 0;
+                            estimate_direct<true>(R, mi, none, uScattering, lightNum, uLight, &dout, true, med);
+                            pend = dout.pend;
+                            if (pend) {
+                                st_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, beta, pickPdf);
+                                R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
+                                if (pend & PEND_LIGHT) st_spec(R->A, R->s_A, R->capacity, slot, dout.A, dout.wA);
+                                if (pend & PEND_BSDF) {
+                                    R->mi_o[slot] = f4(dout.mi_o, dout.pdfB);
+                                    R->mi_d[slot] = f4(dout.mi_d, 0.f);
+                                    st_spec(R->B, R->s_B, R->capacity, slot, dout.B, dout.wB);
+                                }
+                                store_direct_general(R, slot, dout, med);
+                            }
+                            R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
+                        }
+                    }
+                    V3 wi;
+                    float u2[2];
+                    get2d(sp, st, u2);
+                    hg_sample_p(R->media_g[med], mi.wo, &wi, u2);
+                    const V3 no = offset_ray_origin(mi.p, mi.pError, mi.n, wi);
+                    cont = true;
+                    const Spec rrBeta = beta * etaScale;  // volpath.cpp:176-184
+                    if (max_comp(rrBeta) < R->rr_threshold && bounces > 3) {
+                        const float q = pt_max(.05f, 1 - max_comp(rrBeta));
+                        if (get1d(sp, st) < q)
+                            cont = false;
+                        else
+                            beta = beta / (1 - q);
+                    }
+                    if (cont) {
+                        const uint32_t nmeta = ((uint32_t)st.dim & 0xffffu) | ((uint32_t)(bounces + 1) << 16);  // specularBounce = false
+                        R->ray_o[slot] = f4(no, etaScale);
+                        R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
+                        st_spec(R->beta, R->s_beta, R->capacity, slot, beta, 0.f);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const bool mine = family == m;
+            const uint32_t pos = warp_append(&qc[Q_MAT0 + m], mine);
+            if (mine) R->q_mat[m][pos] = slot;
+        }
+        const uint32_t ps = warp_append(&qc[Q_SHADOW], (pend & PEND_LIGHT) != 0);
+        if (pend & PEND_LIGHT) R->q_shadow[ps] = slot;
+        const uint32_t pm = warp_append(&qc[Q_MIS], (pend & PEND_BSDF) != 0);
+        if (pend & PEND_BSDF) R->q_mis[pm] = slot;
+        const uint32_t pn = warp_append(qc_next, cont);
+        if (cont) q_next[pn] = slot;
+        const uint32_t pc = warp_append(cross_count, cross);
+        if (cross) q_cross[pc] = slot;
+    }
+}
+
+// One segment of the direct-lighting rays' walk through the boundaries, after the segment's closest-hit launch.
+// SHADOW: VisibilityTester::Tr (light.cpp:63-81) -- an opaque hit ends the ray occluded; otherwise the transmittance of
+// the segment's medium is multiplied in and the ray is re-aimed at the light sample from behind the boundary
+// (SpawnRayTo, interaction.h:73-78), or it arrived: A = f * (Li * Tr) * weight / lightPdf (integrator.cpp:141-158).
+// !SHADOW: Scene::IntersectTr (scene.cpp:57-70) for the BSDF-sampled ray -- same direction behind a boundary; the walk
+// ends on the first opaque hit: B = f * Le * Tr * weight / scatteringPdf if that is the sampled light (integrator.cpp:192-212).
+template <bool SHADOW>
+__global__ void __launch_bounds__(128, 4) k_direct_walk(const RenderDev *R, const uint32_t *queue, const uint32_t *count, uint32_t *q_out,
+                                                        uint32_t *out_count, uint32_t *work, int count_rays) {
+    const uint32_t n = *count;
+    if (count_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&R->stats[1], (unsigned long long)n);
+    const int outside = R->has_medium ? 0 : -1;
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        bool again = false;
+        uint32_t slot = 0;
+        if (i < n) {
+            slot = queue[i];
+            if (SHADOW) {
+                const float4 o4 = R->sh_o[slot], d4 = R->sh_d[slot], tr4 = R->sh_tr[slot];
+                const V3 o = v3(o4), d = v3(d4);
+                int m = (int)__float_as_uint(tr4.w);
+                Spec Tr = rgb(tr4.x, tr4.y, tr4.z);
+                const uint32_t ti = R->sh_hit[slot];
+                const int bm = boundary_medium(R, ti);
+                if (ti != B200PT_MISS && bm < 0) {
+                    R->occluded[slot] = 1;  // an opaque surface between the point and the light
+                } else {
+                    float th = PT_SHADOW_TMAX;
+                    Isect ii;
+                    bool crossed = false;
+                    if (ti != B200PT_MISS) crossed = sphere_intersect(R->scene.spheres[ti & SPHERE_HIT_MASK], o, d, PT_SHADOW_TMAX, &th, &ii);
+                    if (!crossed) th = PT_SHADOW_TMAX;
+                    if (m >= 0) Tr = Tr * medium_tr(media_sigma_t(R, m), d, th);
+                    if (!crossed) {
+                        float wA;
+                        const Spec f = ld_spec(R->A, R->s_A, R->capacity, slot, &wA);
+                        const float4 l4 = R->A2[slot];
+                        const Spec Li = rgb(l4.x, l4.y, l4.z) * Tr;
+                        const Spec A = wA < 0.f ? f * Li / 1.f : f * Li * wA / l4.w;
+                        st_spec(R->A, R->s_A, R->capacity, slot, A, 0.f);
+                        R->occluded[slot] = 0;
+                    } else {
+                        const V3 p1 = v3(R->sh_p1[slot]), p1e = v3(R->sh_p1e[slot]), p1n = v3(R->sh_p1n[slot]);
+                        const V3 o2 = offset_ray_origin(ii.p, ii.pError, ii.n, p1 - ii.p);
+                        const V3 target = offset_ray_origin(p1, p1e, p1n, o2 - p1);
+                        const V3 d2 = target - o2;
+                        m = dot(d2, ii.n) > 0 ? outside : bm;  // GetMedium(d)
+                        R->sh_o[slot] = f4(o2, o4.w);
+                        R->sh_d[slot] = f4(d2, d4.w);
+                        R->sh_tr[slot] = make_float4(Tr.c[0], Tr.c[1], Tr.c[2], __uint_as_float((uint32_t)m));
+                        again = true;
+                    }
+                }
+            } else {
+                const float4 o4 = R->mi_o[slot], d4 = R->mi_d[slot], tr4 = R->mi_tr[slot];
+                const V3 o = v3(o4), wi = v3(d4);
+                int m = (int)__float_as_uint(tr4.w);
+                Spec Tr = rgb(tr4.x, tr4.y, tr4.z);
+                const uint32_t ti = R->mis_hit[slot];
+                const int bm = boundary_medium(R, ti);
+                float th = pt_inf();
+                Isect ii;
+                if (bm >= 0 && sphere_intersect(R->scene.spheres[ti & SPHERE_HIT_MASK], o, wi, pt_inf(), &th, &ii)) {
+                    if (m >= 0) Tr = Tr * medium_tr(media_sigma_t(R, m), wi, th);
+                    const V3 o2 = offset_ray_origin(ii.p, ii.pError, ii.n, wi);  // isect->SpawnRay(ray.d)
+                    m = dot(wi, ii.n) > 0 ? outside : bm;
+                    R->mi_o[slot] = f4(o2, o4.w);
+                    R->mi_tr[slot] = make_float4(Tr.c[0], Tr.c[1], Tr.c[2], __uint_as_float((uint32_t)m));
+                    again = true;
+                } else {
+                    const int lightNum = (int)__float_as_uint(R->sh_o[slot].w);
+                    const DevLight light = R->lights[lightNum];
+                    Spec B = rgb1(0.f);
+                    if (ti != B200PT_MISS && ti == light.tri) {
+                        // distance and normal of the light's shape as this segment meets it
+                        float t = pt_inf();
+                        V3 ln = mk(0.f, 0.f, 0.f);
+                        if (is_sphere_hit(ti)) {
+                            Isect li;
+                            if (sphere_intersect(R->scene.spheres[ti & SPHERE_HIT_MASK], o, wi, pt_inf(), &t, &li)) ln = li.n;
+                        } else {
+                            const F4 *tp = R->scene.tris + (size_t)ti * 3;
+                            const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+                            const uint32_t lflags = __float_as_uint(t1.w);
+                            TriHit h;
+                            if (triangle_test(v3(t0), v3(t1), v3(t2), o, make_shear(wi), pt_inf(), &h)) {
+                                TriShading lsh;
+                                load_shading<true>(R->scene, ti, lflags, &lsh);
+                                Isect li;
+                                fill_isect(v3(t0), v3(t1), v3(t2), (lflags & 0x10000u) != 0, lsh, h, wi, &li);
+                                ln = li.n;
+                                t = h.t;
+                            }
+                        }
+                        if (m >= 0) Tr = Tr * medium_tr(media_sigma_t(R, m), wi, t);
+                        const Spec Le = (light.two_sided || dot(ln, -wi) > 0) ? light_emit(R, lightNum, light) : rgb1(0.f);
+                        if (!is_black(Le)) {
+                            float wB;
+                            const Spec f = ld_spec(R->B, R->s_B, R->capacity, slot, &wB);
+                            B = f * Le * Tr * wB / o4.w;
+                        }
+                    }
+                    st_spec(R->B, R->s_B, R->capacity, slot, B, 0.f);
+                }
+            }
+        }
+        const uint32_t pos = warp_append(out_count, again);
+        if (again) q_out[pos] = slot;
+    }
+}
+#endif  // B200PT_MEDIA_GENERAL
 
 // L += beta * (EstimateDirect(...) / lightPdf)   (path.cpp:122-127, integrator.cpp:104-105)
 __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce, uint32_t *work) {
@@ -2160,6 +2668,22 @@ void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, 
 void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s) {
     B200PT_LAUNCH(B200PT_KERNEL(k_medium), grid, 128, s, dev, bounce, work);
 }
+#if B200PT_MEDIA_GENERAL
+void launch_medium_general(const RenderDev *dev, const RenderDev &host, int bounce, const uint32_t *queue, const uint32_t *count,
+                           int out, uint32_t *cross_count, uint32_t *work, bool count_rays, int grid, cudaStream_t s) {
+    B200PT_LAUNCH(B200PT_KERNEL(k_medium_general), grid, 128, s, dev, bounce, queue, count, host.q_cross[out], cross_count, work,
+                  count_rays ? 1 : 0);
+}
+void launch_direct_walk(const RenderDev *dev, const RenderDev &host, bool shadow, const uint32_t *queue, const uint32_t *count,
+                        int out, uint32_t *walk_count, uint32_t *work, bool count_rays, int grid, cudaStream_t s) {
+    if (shadow)
+        B200PT_LAUNCH(B200PT_KERNEL(k_direct_walk<true>), grid, 128, s, dev, queue, count, host.q_walk[out], walk_count, work,
+                      count_rays ? 1 : 0);
+    else
+        B200PT_LAUNCH(B200PT_KERNEL(k_direct_walk<false>), grid, 128, s, dev, queue, count, host.q_walk[out], walk_count, work,
+                      count_rays ? 1 : 0);
+}
+#endif
 
 void launch_spatial_build(const RenderDev *dev, const RenderDev &host, cudaStream_t s) {
     const long long nvox = (long long)host.grid.nv[0] * host.grid.nv[1] * host.grid.nv[2];

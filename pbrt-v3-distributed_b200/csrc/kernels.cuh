@@ -131,6 +131,22 @@ struct RenderDev {
     int volpath, has_medium;
     float med_sigma_s[3], med_sigma_t[3], med_g;
     const float *med_spectra;  // SampledSpectrum build: [2][60] = sigma_s, sigma_t (else the two arrays above)
+    // Media bounded by null-material spheres (b200pt_integrator_desc::bounded_media, RGB build): medium ids are -1 = vacuum,
+    // 0 = the medium around the scene, k >= 1 = bounded_media[k - 1].  The path ray's medium is per-slot state; rays that
+    // reach a boundary are traced again from the far side within the same bounce (q_cross), shadow and MIS rays walk from
+    // boundary to boundary while their transmittance accumulates (k_shadow_walk / k_mis_walk).
+    int med_general;
+    const float *media_tab;    // [1 + n_bounded][2][3] = sigma_s, sigma_t of medium id k
+    const float *media_g;      // [1 + n_bounded]
+    const int32_t *sphere_med; // [n_spheres] medium id inside a boundary sphere, -1 for an ordinary sphere
+    int32_t *cur_med;          // per slot: medium of the path ray
+    uint32_t *q_cross[2];      // path rays that crossed a boundary (ping-pong between passes of one bounce)
+    uint32_t *q_walk[2];       // shadow / MIS rays that crossed a boundary
+    uint32_t *sh_hit;          // closest hit of the shadow ray's current segment
+    float4 *A2;                // pending light sample: Li, lightPdf   (A then holds f, MIS weight; weight < 0: delta light)
+    float4 *sh_tr, *mi_tr;     // transmittance so far along the shadow / MIS ray, medium id of the current segment (bits)
+    float4 *sh_p1, *sh_p1e, *sh_p1n;  // the light sample the shadow ray is re-aimed at after each boundary (SpawnRayTo)
+    unsigned long long *dim_overflows;  // paths ended because their sampler dimension ran past the host's tables
 };
 
 // resident CTAs of k_trace per SM (128 threads each).  8 (64 registers, two spilled per-ray constants re-read next to the
@@ -196,6 +212,15 @@ void launch_shade(const RenderDev *dev, int material, bool vertex_data, int boun
 void launch_resolve(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
 // Medium pass of a bounce (scenes inside a homogeneous medium): after the closest-hit launch, before the shading kernels.
 void launch_medium(const RenderDev *dev, int bounce, uint32_t *work, int grid, cudaStream_t s);
+// Scenes with bounded media: one pass of the medium kernel over `queue` (the bounce's path queue, then the rays that crossed
+// a boundary); crossers of this pass are appended to q_cross[out] / *cross_count.  count_rays: add the pass's rays to the
+// regular-ray counter (every pass but a bounce's first, which the queue counters already cover).
+void launch_medium_general(const RenderDev *dev, const RenderDev &host, int bounce, const uint32_t *queue, const uint32_t *count,
+                           int out, uint32_t *cross_count, uint32_t *work, bool count_rays, int grid, cudaStream_t s);
+// One segment of the shadow (any = false: MIS) rays' walk through the boundaries: reads the segment's closest hit, ends the
+// ray (occluded / A or mis_hit / B final) or re-queues it behind the boundary into q_walk[out] / *walk_count.
+void launch_direct_walk(const RenderDev *dev, const RenderDev &host, bool shadow, const uint32_t *queue, const uint32_t *count,
+                        int out, uint32_t *walk_count, uint32_t *work, bool count_rays, int grid, cudaStream_t s);
 #define SORT_BUCKETS (1u << 18)  // 3 octant bits + 15 Morton bits
 // Counting sort of a queue of slots by the coherence key of the rays they refer to; `out` receives
 // the permuted queue (order inside a bucket is arbitrary -- it never affects a path's arithmetic).

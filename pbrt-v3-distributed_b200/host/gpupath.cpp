@@ -154,6 +154,10 @@ struct Flattened {
     std::vector<b200pt_instance> instances;
     int64_t nTopLevel = 0;
     std::vector<float> materialSpectra, lightSpectra;  // SampledSpectrum hosts: [material][5][60], [light][60]
+    // VolPathIntegrator: spheres without a material whose MediumInterface is a transition (clouds): per sphere the index
+    // into boundedMedia (the medium inside) or -1; boundaryOutside[k] is what the scene declares outside boundary medium k
+    std::vector<int32_t> sphereMedium;
+    std::vector<const Medium *> boundedMedia, boundaryOutside;
 };
 
 // materials/{matte,plastic,metal,glass}.cpp ComputeScatteringFunctions with constant textures
@@ -242,7 +246,8 @@ bool ConvertMaterial(const Material *m, b200pt_material *out, float *rows, std::
     return false;
 }
 
-// `volumetric`: VolPathIntegrator looks at the primitives' MediumInterfaces; surfaces that bound a medium are not supported
+// `volumetric`: VolPathIntegrator looks at the primitives' MediumInterfaces; of the surfaces that separate two media only
+// spheres without a material are supported (the path steps over them, volpath.cpp:115-121)
 bool FlattenScene(const Scene &scene, Flattened *f, std::string *why, bool volumetric) {
     auto bvh = dynamic_cast<const BVHAccel *>(scene.aggregate.get());
     if (!bvh) return *why = "an aggregate other than BVHAccel", false;
@@ -312,8 +317,10 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why, bool volum
         auto gp = dynamic_cast<const GeometricPrimitive *>(prims[i].get());
         if (!gp) return *why = "a primitive other than GeometricPrimitive / TransformedPrimitive", false;
         if (!volumetric && (gp->mediumInterface.inside || gp->mediumInterface.outside)) return *why = "participating media", false;
-        if (!noTransition(gp)) return false;
-        if (auto sph = dynamic_cast<const Sphere *>(gp->shape.get())) {
+        auto sph = dynamic_cast<const Sphere *>(gp->shape.get());
+        const bool boundary = volumetric && sph && gp->mediumInterface.IsMediumTransition() && !gp->material;
+        if (!boundary && !noTransition(gp)) return false;
+        if (sph) {
             b200pt_sphere bs;
             memset(&bs, 0, sizeof(bs));
             memcpy(bs.object_to_world, sph->ObjectToWorld->m.m, sizeof(float) * 16);
@@ -325,7 +332,18 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why, bool volum
             bs.theta_max = sph->thetaMax;
             bs.phi_max = sph->phiMax;
             if (!(sph->phiMax > 0)) return *why = "a sphere with phimax 0", false;
-            if (!materialOf(gp->material.get(), &bs.material_id)) return false;
+            if (boundary) {
+                // `Material ""` under `MediumInterface "inside" "outside"`: no BSDF, the ray changes medium there
+                if (gp->areaLight) return *why = "a medium boundary that is also an area light", false;
+                if (!gp->mediumInterface.inside) return *why = "a medium boundary with vacuum inside", false;
+                if (kSampledHost) return *why = "media bounded by surfaces in a SampledSpectrum build", false;
+                bs.material_id = 0;  // never looked at; the scene gets a material 0 below if it has none
+                f->sphereMedium.resize(f->spheres.size(), -1);
+                f->sphereMedium.push_back((int32_t)f->boundedMedia.size());
+                f->boundedMedia.push_back(gp->mediumInterface.inside);
+                f->boundaryOutside.push_back(gp->mediumInterface.outside);
+            } else if (!materialOf(gp->material.get(), &bs.material_id))
+                return false;
             bs.light_id = -1;
             bs.reverse_orientation = sph->reverseOrientation ? 1 : 0;
             bs.transform_swaps_handedness = sph->transformSwapsHandedness ? 1 : 0;
@@ -336,6 +354,16 @@ bool FlattenScene(const Scene &scene, Flattened *f, std::string *why, bool volum
         if (!appendTriangle(gp)) return false;
     }
     f->nTopLevel = (int64_t)f->materialId.size();
+    if (!f->boundedMedia.empty()) {
+        f->sphereMedium.resize(f->spheres.size(), -1);
+        if (!transformed.empty()) return *why = "media bounded by surfaces together with object instances", false;
+        if (f->materials.empty()) {  // only boundaries: material id 0 must exist for the descriptor to validate
+            b200pt_material bm;
+            memset(&bm, 0, sizeof(bm));
+            bm.type = B200PT_MAT_MATTE;
+            f->materials.push_back(bm);
+        }
+    }
     // object instances (TransformedPrimitive, primitive.cpp:70-98): the triangles of every distinct object are appended
     // behind the top-level ones, in the object's own space
     std::unordered_map<const Primitive *, std::pair<int64_t, int64_t>> objectRange;
@@ -602,6 +630,24 @@ class GpuIntegrator : public Base {
                 if (kSampledHost) id.medium.spectra = mediumSpectra.data();  // the 60 bins of sigma_a, sigma_s
                 id.medium.g = hm->g;
             }
+        }
+        // media bounded by null-material spheres: the medium inside each, all of them inside the camera's medium (or vacuum)
+        std::vector<b200pt_medium> boundedMedia(flat.boundedMedia.size());
+        for (size_t k = 0; k < flat.boundedMedia.size(); ++k) {
+            auto hm = dynamic_cast<const HomogeneousMedium *>(flat.boundedMedia[k]);
+            if (!hm) return Error("gpupath: only homogeneous media are supported");
+            if (flat.boundaryOutside[k] != cam->medium)
+                return Error("gpupath: a medium boundary whose outside is not the camera's medium");
+            memset(&boundedMedia[k], 0, sizeof(b200pt_medium));
+            boundedMedia[k].present = 1;
+            ToRGB(hm->sigma_a, boundedMedia[k].sigma_a);
+            ToRGB(hm->sigma_s, boundedMedia[k].sigma_s);
+            boundedMedia[k].g = hm->g;
+        }
+        if (!boundedMedia.empty()) {
+            id.n_bounded_media = (int32_t)boundedMedia.size();
+            id.bounded_media = boundedMedia.data();
+            id.sphere_medium = flat.sphereMedium.data();
         }
         id.max_depth = maxDepth;
         id.rr_threshold = rrThreshold;

@@ -583,7 +583,8 @@ class RenderSetup:
     def __init__(self, xres, yres, spp, max_depth=5, strategy=abi.LIGHTS_UNIFORM, pixel_bounds=None,
                  eye=(0, 0, -4.5), look=(0, 0, 0), up=(0, 1, 0), fov=35.0, tables=None, camera=None,
                  lens_radius=0.0, focal_distance=1e6, crop_window=None, film_scale=1.0, max_sample_luminance=None,
-                 sampler="sobol", pixel_filter=None, integrator="path", medium=None, spectral_tables=None):
+                 sampler="sobol", pixel_filter=None, integrator="path", medium=None, spectral_tables=None,
+                 boundaries=None):
         from . import host_perspective_camera
         self.xres, self.yres = xres, yres
         self.sampler_name = sampler
@@ -646,6 +647,21 @@ class RenderSetup:
                 self._medium_spectra = np.stack([lut[tuple(np.array(list(medium[k]), f32).view(np.uint32).tolist())]
                                                  for k in ("sigma_a", "sigma_s")])
                 self.integrator.medium.spectra = abi.ptr(self._medium_spectra)
+        # boundaries = the scene's sphere specs (SceneArrays.sphere_specs): those with a `boundary` entry are null-material
+        # surfaces around a homogeneous medium (MediumInterface "inside" "outside" + Material "")
+        specs = [(k, sp["boundary"]) for k, sp in enumerate(boundaries or ()) if sp.get("boundary")]
+        if specs:
+            self._bounded = (abi.Medium * len(specs))()
+            self._sphere_medium = np.full(len(boundaries), -1, np.int32)
+            for j, (k, b) in enumerate(specs):
+                self._bounded[j].present = 1
+                self._bounded[j].sigma_a[:] = list(b["sigma_a"])
+                self._bounded[j].sigma_s[:] = list(b["sigma_s"])
+                self._bounded[j].g = b.get("g", 0.0)
+                self._sphere_medium[k] = j
+            self.integrator.n_bounded_media = len(specs)
+            self.integrator.bounded_media = C.cast(self._bounded, C.c_void_p)
+            self.integrator.sphere_medium = abi.ptr(self._sphere_medium)
 
     def _sobol_tables(self, cb):
         res = round_up_pow2(max(cb[2] - cb[0], cb[3] - cb[1]))

@@ -49,6 +49,9 @@ class DumpScene:
         self.film = abi.FilmDesc.from_buffer_copy(raw, off)
         off += C.sizeof(abi.FilmDesc)
         self.integrator = abi.IntegratorDesc.from_buffer_copy(raw, off)
+        self.integrator.n_bounded_media = 0  # the dump carries the host's pointers, not the tables behind them
+        self.integrator.bounded_media = None
+        self.integrator.sphere_medium = None
         off += C.sizeof(abi.IntegratorDesc)
         sm = struct.unpack_from("<6i", raw, off)
         self.n_triangles, self.n_lights, self.n_spheres, self.n_materials = nt, nl, ns, nm

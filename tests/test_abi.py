@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert declared <= exported, "missing: %s" % sorted(declared - exported)
     assert not pkg.MISSING_SYMBOLS
     assert set(pkg.EXPORTED_SYMBOLS) == declared
-    assert pkg.lib.b200pt_abi_version() == 5
+    assert pkg.lib.b200pt_abi_version() == 6
 
 
 def test_struct_sizes_match_header(abi):
@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(abi):
     assert C.sizeof(abi.CameraDesc) == 144
     assert C.sizeof(abi.FilmDesc) == 48
     assert C.sizeof(abi.SamplerDesc) == 64
-    assert C.sizeof(abi.IntegratorDesc) == 72 and C.sizeof(abi.Medium) == 40
+    assert C.sizeof(abi.IntegratorDesc) == 96 and C.sizeof(abi.Medium) == 40
     assert C.sizeof(abi.SceneDesc) == 168
     assert C.sizeof(abi.Instance) == 176
     assert abi.RAY_DTYPE.itemsize == 32 and abi.HIT_DTYPE.itemsize == 16

@@ -95,6 +95,15 @@ def test_analytic_scenes_known_answer_volpath(hostcheck, abi, scenes, ob, hctx, 
     GV.test_analytic_scenes_known_answer_volpath(hostcheck, abi, scenes, ob, hctx, name)
 
 
+@pytest.mark.parametrize("gname", ["volpath_cloud", "volpath_cloud_fog"])
+def test_volpath_bounded_media_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, gname):
+    GV.test_volpath_bounded_media_vs_reference_pfm(hostcheck, abi, scenes, ob, hctx, gname)
+
+
+def test_bounded_media_larger_render_vs_oracle(hostcheck, abi, scenes, ob, hctx):
+    GV.test_bounded_media_larger_render_vs_oracle(hostcheck, abi, scenes, ob, hctx)
+
+
 def test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx):
     GV.test_volpath_instances_and_partial_spheres_vs_oracle(hostcheck, abi, scenes, ob, hctx)
 
@@ -172,6 +181,12 @@ def test_volpath_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path
     """`Integrator "volpath"` with a named homogeneous medium through the drop-in binary."""
     monkeypatch.setattr(GV, "PLUGIN", HC_PLUGIN)
     GV.test_volpath_dropin_binary_matches_reference(scenes, tmp_path)
+
+
+def test_bounded_media_dropin_binary_on_the_check_library(hc_plugins, scenes, tmp_path, monkeypatch):
+    """Null-material spheres around named media through the drop-in binary (medium transitions)."""
+    monkeypatch.setattr(GV, "PLUGIN", HC_PLUGIN)
+    GV.test_bounded_media_dropin_binary_matches_reference(scenes, tmp_path)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(P.KILLEROO_DIR, "killeroo-simple-ref.pfm")),
