@@ -45,6 +45,10 @@ WORKLOADS = {
     # the same with the reference's SampledSpectrum build (60 bins): both halves of BASELINE configs[4]'s feature set
     "cfg5": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
              "synthetic 50M triangles instanced (1000 x 50k), SampledSpectrum (60 bins), maxdepth 16, 64spp, 1920x1080"),
+    # the instanced scene as SURVEY 8(d) words it: 50 ObjectInstances of one 1 M-triangle soup under distinct transforms
+    # (= 50 M instanced triangles) around a 100 k-triangle top-level soup
+    "cfg5s": (100000, ("matte", "glass", "metal", "plastic"), 1920, 1080, 64, 16, None,
+              "synthetic 50M triangles instanced (50 x 1M, RGB spectrum), maxdepth 16, 64spp, 1920x1080"),
     # cfg2's scene inside a thin homogeneous medium, VolPathIntegrator
     "cfg2fog": (1000000, ("matte",), 1024, 1024, 256, 5, None,
                 "synthetic 1M triangles in a homogeneous medium (sigma_t ~0.3, g 0.4), volpath, maxdepth 5, 256spp, 1024x1024"),
@@ -55,6 +59,13 @@ WORKLOADS = {
 
 def workload_scene_kwargs(name):
     """Extra SceneArrays arguments of a workload (object instancing for cfg5rgb)."""
+    if name == "cfg5s":
+        inst = []
+        for k in range(50):  # 5 x 5 x 2 lattice, every third instance mirrored / stretched
+            c = (-0.8 + 0.4 * (k % 5), -0.8 + 0.4 * ((k // 5) % 5), -0.4 + 0.8 * (k // 25))
+            sc = (1.0, 1.0, 1.0) if k % 3 == 0 else ((1.2, 0.8, 1.0) if k % 3 == 1 else (1.0, 1.0, -1.1))
+            inst.append(dict(object=0, center=c, scale=sc))
+        return dict(objects=(dict(n_tris=1000000, seed=77, material="plastic", size=0.25),), instances=tuple(inst))
     if name not in ("cfg5rgb", "cfg5"):
         return {}
     inst = []
@@ -404,6 +415,8 @@ def main():
                           "components_bits_differ": int((got.view(np.uint32) != ref_img.view(np.uint32)).sum()),
                           "components": int(got.size),
                           "ray_counters_equal": bool(st2["regular_rays"] + st2["shadow_rays"] == c["rays"] and st2["camera_rays"] == c["samples"]),
+                          "rays_gpu_reference": [int(st2["regular_rays"] + st2["shadow_rays"]), int(c["rays"])],
+                          "samples_gpu_reference": [int(st2["camera_rays"]), int(c["samples"])],
                           "stack_overflows": int(st2.get("stack_overflows", 0))}
             cpu = {"value": c["rays"] / c["seconds"] / 1e6, "unit": "Mrays/s", "cores": c["cores"], "kind": c["kind"],
                    "sample": "%dx%d film, %d spp of %d, all tiles (%.1f s render)" %
@@ -415,6 +428,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 x 60 spectral bins" if args.workload in SPECTRAL_WORKLOADS else "f32", "data": "synthetic", "config": config,
             "msamples_per_s": samples / (ms * 1e-3) / 1e6,
             "rays_per_sample": rays / max(samples, 1),
+            "ray_mix_per_step": {"camera": int(st["camera_rays"] // args.steps), "regular": int(st["regular_rays"] // args.steps),
+                                 "shadow": int(st["shadow_rays"] // args.steps)},
             # frac = ALGORITHMIC bytes (nodes fetched + triangles tested + ray in / hit out) / time / HBM peak.  Those bytes
             # are mostly served by L2 (the BVH's hot part is cache resident), so frac is NOT DRAM utilisation: dram_frac is,
             # from the ncu capture of the same kernel and workload under profiles/ (traffic.source).
