@@ -103,7 +103,7 @@ struct b200pt_render {
     size_t tile_list_capacity = 0;
     float *d_rgb = nullptr;  // b200pt_film_read_rgb staging (lazily allocated, freed with the render object)
     uint32_t *d_walk_counts = nullptr;  // bounded media: [16] queue counters / fetch counters of the boundary passes
-    int grid_trace = 0, grid_shade = 0;
+    int grid_trace = 0, grid_shade = 0, grid_shade_s60 = 0;
     bool instrumented = false, profiling = false;
     int refill_lanes = 26, postpone_pct = 40, trace_ctas = 0, stage_nodes = 0;  // k_trace knobs (b200pt_render_set_option)
     bool overlap = true;  // run shadow/MIS rays of bounce b concurrently with the path rays of bounce b+1
@@ -1326,6 +1326,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     CUDA_TRY(cudaStreamSynchronize(st));
     r->grid_trace = ctx->sm_count;  // launch_trace multiplies by its CTAs per SM
     r->grid_shade = ctx->sm_count * 8;
+    // 60-bin shading kernels keep their spectra in local memory (6.4 KB per thread): the number of resident CTAs decides
+    // whether that working set stays in L2 (B200PT_S60_SHADE_CTAS per SM; measured in profiles/README.md)
+    r->grid_shade_s60 = ctx->sm_count * (getenv("B200PT_S60_SHADE_CTAS") ? std::max(1, atoi(getenv("B200PT_S60_SHADE_CTAS"))) : 8);
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;
     if (getenv("B200PT_SORT_FROM")) r->sort_from_bounce = atoi(getenv("B200PT_SORT_FROM"));
@@ -1693,7 +1696,7 @@ int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles)
                 if (families[m]) {
                     LaunchTimer lt(r, st, 2);
                     if (spectral)
-                        b200pt_s60::launch_shade(s60(r->d_dev), m, full_shade, b, wk + 1 + m, r->grid_shade, st);
+                        b200pt_s60::launch_shade(s60(r->d_dev), m, full_shade, b, wk + 1 + m, r->grid_shade_s60, st);
                     else
                         launch_shade(r->d_dev, m, full_shade, b, wk + 1 + m, r->grid_shade, st);
                 }

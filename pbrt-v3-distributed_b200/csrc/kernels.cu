@@ -713,7 +713,6 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
     int phase = 0;                // 0: top-level tree, 1: tree over the instances, 2: inside an instance
     bool has = false, fin = false, exhausted = false;
     bool want_exit = false;       // the object's tree is exhausted: the lane waits to go back to the world ray
-    bool want_tlas = false;       // the top-level tree is exhausted: the lane waits to start on the tree over the instances
     // (re)derives the box-test constants and the triangle-test record for a ray in the space the lane enters;
     // the position on the stack and the result so far are the lane's own and stay
     auto enter_space = [&](const V3 &o, const V3 &d, float tmax, const TravBounds &B) {
@@ -799,7 +798,6 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         T.sp = 0;
                         phase = 0;
                         want_exit = false;
-                        want_tlas = false;
                         noff = toff = 0;
                         enter_space(v3(o4), v3(d4), tmax, a.bounds);
                         my_ray[8 * 128] = __uint_as_float(B200PT_MISS);
@@ -821,7 +819,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
             // holds (takes no node step) while it has a leaf group; a lane that is done with an object's tree waits the
             // same way.  Both wait for company: changing space is ~900 instructions and runs once the usual share of the
             // warp's lanes has something parked (triangles, candidates, a way back), not one lane at a time.
-            const bool hold = (phase == 1 && pend_y != 0) || want_exit || want_tlas;
+            const bool hold = (phase == 1 && pend_y != 0) || want_exit;
             const bool node_work = !hold && (T.cur_y & 0xff000000u) != 0;
             if (node_work)
                 trav_node_phase<!ANY_HIT, false>(T, S, a.nodes + (size_t)noff * 4, a.tri_base + noff, s_lut, &ng_x, &ng_y, &ctr);
@@ -837,48 +835,33 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
             }
             const bool out_of_nodes = (T.cur_y & 0xff000000u) == 0;  // (what is left on the stack waits behind the parked group)
             const unsigned act = __activemask();
-            const bool parked_me = pend_y != 0 || want_exit || want_tlas;
+            const bool parked_me = pend_y != 0 || want_exit;
             const bool idle_me = hold || (phase == 1 && pend_y != 0) || (out_of_nodes && pend_y != 0);
             const unsigned counts = __reduce_add_sync(
                 act, (parked_me ? 1u : 0u) | ((must || (idle_me && a.postpone_pct <= 0)) ? 0x100u : 0u) | (idle_me ? 0x10000u : 0u));
             const int n_act = __popc(act), n_parked = (int)(counts & 0xffu), n_idle = (int)((counts >> 16) & 0xffu);
             if ((counts & 0xff00u) || n_parked * 100 >= n_act * a.postpone_pct || n_idle * 4 >= n_act) {
                 bool done = false;
-                // The three ways a lane changes space -- out of an object, on to the tree over the instances, into an
-                // object -- only prepare the ray here; the box-test constants are re-derived once, below, by all of
-                // them together (ncu: a change of space used to run with two lanes active)
-                bool need_enter = false, resume = false;
-                V3 eo = mk(0.f, 0.f, 0.f), ed = eo;
-                float etm = 0.f;
-                TravBounds eb = a.tlas_bounds;
-                uint32_t gx = 0, gy = 0;
                 if (want_exit) {
                     // the object's tree is done: back to the world ray (its tMax is the hit's, if there was one) and to
                     // the walk over the instances -- first the candidates of the same leaf that were not tried
                     want_exit = false;
-                    uint32_t ex, ey;
+                    uint32_t ex, ey, gx, gy;
                     T.sp -= 2;
                     S.pop((T.sp & B200PT_SP_MASK) + 1, &ex, &ey);
                     S.pop(T.sp & B200PT_SP_MASK, &gx, &gy);
-                    world_ray(&eo, &ed);
-                    etm = my_ray[22 * 128];
+                    V3 ro, rd;
+                    world_ray(&ro, &rd);
                     noff = a.tlas_node_off;
                     toff = a.tlas_tri_off;
                     phase = 1;
-                    need_enter = resume = true;
+                    enter_space(ro, rd, my_ray[22 * 128], a.tlas_bounds);
+                    T.cur_x = gx;
+                    T.cur_y = gy;
                     if (ey) {
                         pend_x = ex;  // marked: already a triangle group
                         pend_y = ey;
                     }
-                } else if (want_tlas) {
-                    // the top-level triangles are done: on to the instances, with the ray's tMax so far
-                    want_tlas = false;
-                    world_ray(&eo, &ed);
-                    etm = my_ray[22 * 128];
-                    noff = a.tlas_node_off;
-                    toff = a.tlas_tri_off;
-                    phase = 1;
-                    need_enter = true;
                 } else if (pend_y && phase == 1) {
                     // leaf of the tree over the instances: its "triangles" name instances; the first candidate whose
                     // leaf box the ray (with its current tMax) enters takes the lane into that object's tree
@@ -907,9 +890,10 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                         S.push(T.sp & B200PT_SP_MASK, T.cur_x, T.cur_y);
                         S.push((T.sp & B200PT_SP_MASK) + 1, tg_x | B200PT_MARK, tg_y);
                         T.sp += 2;
-                        instance_ray(in, ro, rd, wtmax, &eo, &ed, &etm);
-                        eb = instance_bounds(in);
-                        need_enter = true;
+                        V3 o2, d2;
+                        float tm2;
+                        instance_ray(in, ro, rd, wtmax, &o2, &d2, &tm2);
+                        enter_space(o2, d2, tm2, instance_bounds(in));
                         noff = in.node_off;
                         toff = in.tri_off;
                         my_ray[23 * 128] = __uint_as_float(k);
@@ -933,16 +917,6 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                     }
                     pend_y = 0;
                 }
-                if (need_enter) {
-                    enter_space(eo, ed, etm, eb);
-                    if (resume) {  // back in the tree over the instances: the group the lane was walking
-                        T.cur_x = gx;
-                        T.cur_y = gy;
-                    } else if (phase == 1 && (T.cur_y & 0xff000000u) == 0) {  // the ray misses the instances' bounds altogether
-                        has = false;
-                        fin = true;
-                    }
-                }
                 if (ng_y) {  // the second group found in this step (only outside the tree over the instances)
                     pend_x = ng_x;
                     pend_y = ng_y;
@@ -954,7 +928,7 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                 }
             }
             // ---- the next group of the current tree, or (later, in company) back out of an instance, or on to the next tree, or done
-            if (has && !want_exit && !want_tlas && (T.cur_y & 0xff000000u) == 0) {
+            if (has && !want_exit && (T.cur_y & 0xff000000u) == 0) {
                 bool more = false, blocked = false;
                 while (!more && !blocked) {
                     if ((T.sp & B200PT_SP_MASK) == 0) break;
@@ -972,7 +946,17 @@ __global__ void __launch_bounds__(128, 6) k_trace2(const TraceArgs a) {
                 }
                 if (!more && !blocked && pend_y == 0) {
                     if (phase == 0 && a.n_instances > 0) {
-                        want_tlas = true;  // the top-level triangles are done: on to the instances, in company (above)
+                        // the top-level triangles are done: on to the instances, with the ray's tMax so far
+                        V3 ro, rd;
+                        world_ray(&ro, &rd);
+                        noff = a.tlas_node_off;
+                        toff = a.tlas_tri_off;
+                        phase = 1;
+                        enter_space(ro, rd, my_ray[22 * 128], a.tlas_bounds);
+                        if ((T.cur_y & 0xff000000u) == 0) {
+                            has = false;
+                            fin = true;
+                        }
                     } else {
                         has = false;
                         fin = true;
