@@ -834,23 +834,43 @@ B200_HD V3 cosine_sample_hemisphere(const float u[2]) {
 // 4 MicrofacetTransmission (TR)
 enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR = 3, BX_MICROFACET_TRANS = 4,
        BX_SPECULAR_REFLECTION = 5 };
+// A lobe's spectra are rows of the material table (or the constant 1).  The RGBSpectrum build keeps them by value in
+// registers; the SampledSpectrum build keeps a pointer to the row -- 60 floats per spectrum copied into every thread's
+// Bsdf were a third of k_shade's 6.4 KB local-memory frame, and the rows are shared by all threads (L1 hits).
+#if B200PT_NSPEC == 3
+typedef Spec SpecRef;
+B200_HD SpecRef sref(const float *p) { return rgbp(p); }
+B200_HD SpecRef sref_one() { return rgb1(1.f); }
+B200_HD const Spec &sval(const SpecRef &r) { return r; }
+#else
+struct SpecRef {
+    const float *p;  // nullptr: the constant spectrum 1
+};
+B200_HD SpecRef sref(const float *p) {
+    SpecRef r;
+    r.p = p;
+    return r;
+}
+B200_HD SpecRef sref_one() { return sref(nullptr); }
+B200_HD Spec sval(const SpecRef &r) { return r.p ? rgbp(r.p) : rgb1(1.f); }
+#endif
 struct Lobe {
     int kind, type;
-    Spec R, T;
+    SpecRef R, T;
     TRDist dist;
     int conductor;      // Fresnel of the microfacet lobe: 0 dielectric(etaI, etaT), 1 conductor(1, cEta, cK)
     float frEtaI, frEtaT;
-    Spec cEta, cK;
+    SpecRef cEta, cK;
     float etaA, etaB;   // FresnelSpecular, MicrofacetTransmission
     float onA, onB;     // OrenNayar
 };
 B200_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
 B200_HD Spec lobe_fresnel(const Lobe &l, float cosThetaI) {
     if (!l.conductor) return rgb1(fr_dielectric(cosThetaI, l.frEtaI, l.frEtaT));  // reflection.cpp:128-130
-    return fr_conductor(pt_abs(cosThetaI), rgb1(1.f), l.cEta, l.cK);               // reflection.cpp:117-119
+    return fr_conductor(pt_abs(cosThetaI), rgb1(1.f), sval(l.cEta), sval(l.cK));               // reflection.cpp:117-119
 }
 B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
-    if (l.kind == BX_LAMBERT) return l.R * PT_INV_PI;  // reflection.cpp:178-180
+    if (l.kind == BX_LAMBERT) return sval(l.R) * PT_INV_PI;  // reflection.cpp:178-180
     if (l.kind == BX_MICROFACET) {                     // reflection.cpp:226-236
         float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
         V3 wh = wi + wo;
@@ -858,7 +878,7 @@ B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         if (wh.x == 0 && wh.y == 0 && wh.z == 0) return rgb1(0.f);
         wh = normalize(wh);
         Spec F = lobe_fresnel(l, dot(wi, wh));
-        return l.R * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
+        return sval(l.R) * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
     if (l.kind == BX_OREN_NAYAR) {  // reflection.cpp:197-219
         float sinThetaI = sin_theta(wi);
@@ -878,7 +898,7 @@ B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
             sinAlpha = sinThetaI;
             tanBeta = sinThetaO / abs_cos_theta(wo);
         }
-        return l.R * PT_INV_PI * (l.onA + l.onB * maxCos * sinAlpha * tanBeta);
+        return sval(l.R) * PT_INV_PI * (l.onA + l.onB * maxCos * sinAlpha * tanBeta);
     }
     if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:244-266 (TransportMode::Radiance)
         if (same_hemisphere(wo, wi)) return rgb1(0.f);
@@ -891,7 +911,7 @@ B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         Spec F = rgb1(fr_dielectric(dot(wo, wh), l.etaA, l.etaB));
         float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
         float factor = 1 / eta;
-        return (rgb1(1.f) - F) * l.T *
+        return (rgb1(1.f) - F) * sval(l.T) *
                pt_abs(tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor *
                       factor / (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
     }
@@ -942,7 +962,7 @@ B200_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2]
     if (l.kind == BX_SPECULAR_REFLECTION) {  // reflection.cpp:136-143 with FresnelNoOp (mirror.cpp:45-56)
         *wi = mk(-wo.x, -wo.y, wo.z);
         *pdf = 1.f;
-        return rgb1(1.f) * l.R / abs_cos_theta(*wi);
+        return rgb1(1.f) * sval(l.R) / abs_cos_theta(*wi);
     }
     // FresnelSpecular::Sample_f, reflection.cpp:477-511 (TransportMode::Radiance)
     float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
@@ -950,7 +970,7 @@ B200_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2]
         *wi = mk(-wo.x, -wo.y, wo.z);
         *sampledType = BSDF_SPECULAR | BSDF_REFLECTION;
         *pdf = F;
-        return F * l.R / abs_cos_theta(*wi);
+        return F * sval(l.R) / abs_cos_theta(*wi);
     }
     bool entering = cos_theta(wo) > 0;
     float etaI = entering ? l.etaA : l.etaB;
@@ -958,7 +978,7 @@ B200_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2]
     V3 nn = mk(0.f, 0.f, 1.f);
     if (dot(nn, wo) < 0.f) nn = -nn;  // Faceforward, geometry.h:1213-1216
     if (!refract(wo, nn, etaI / etaT, wi)) return rgb1(0.f);
-    Spec ft = l.T * (1 - F);
+    Spec ft = sval(l.T) * (1 - F);
     ft = ft * ((etaI * etaI) / (etaT * etaT));
     *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
     *pdf = 1 - F;
@@ -1056,7 +1076,7 @@ B200_HD void add_lambert(Bsdf *b, const float *kd) {
     Lobe &l = b->lobes[b->n++];
     l.kind = BX_LAMBERT;
     l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
-    l.R = rgbp(kd);
+    l.R = sref(kd);
 }
 // Material::ComputeScatteringFunctions with constant textures
 // (allowMultipleLobes = true, TransportMode::Radiance; path.cpp:107).
@@ -1111,7 +1131,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_MICROFACET;
             l.type = BSDF_REFLECTION | BSDF_GLOSSY;
-            l.R = rgbp(ms.ks);
+            l.R = sref(ms.ks);
             l.dist.ax = m.alpha_x;
             l.dist.ay = m.alpha_x;
             l.conductor = 0;
@@ -1122,19 +1142,19 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
         Lobe &l = b->lobes[b->n++];
         l.kind = BX_MICROFACET;
         l.type = BSDF_REFLECTION | BSDF_GLOSSY;
-        l.R = rgb1(1.f);
+        l.R = sref_one();
         l.dist.ax = m.alpha_x;
         l.dist.ay = m.alpha_y;
         l.conductor = 1;
-        l.cEta = rgbp(ms.eta);
-        l.cK = rgbp(ms.k);
+        l.cEta = sref(ms.eta);
+        l.cK = sref(ms.k);
     } else if (type == B200PT_MAT_GLASS && m.variant == 2) {  // MirrorMaterial, mirror.cpp:45-56 (BSDF eta stays 1)
         const Spec R = rgbp(ms.ks);
         if (!is_black(R)) {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_SPECULAR_REFLECTION;
             l.type = BSDF_REFLECTION | BSDF_SPECULAR;
-            l.R = R;
+            l.R = sref(ms.ks);
         }
     } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
         b->eta = m.index;
@@ -1145,7 +1165,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
                 Lobe &l = b->lobes[b->n++];
                 l.kind = BX_MICROFACET;
                 l.type = BSDF_REFLECTION | BSDF_GLOSSY;
-                l.R = R;
+                l.R = sref(ms.ks);
                 l.dist.ax = m.alpha_x;
                 l.dist.ay = m.alpha_y;
                 l.conductor = 0;
@@ -1156,7 +1176,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
                 Lobe &l = b->lobes[b->n++];
                 l.kind = BX_MICROFACET_TRANS;
                 l.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
-                l.T = T;
+                l.T = sref(ms.kt);
                 l.dist.ax = m.alpha_x;
                 l.dist.ay = m.alpha_y;
                 l.etaA = 1.f;
@@ -1166,8 +1186,8 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_FRESNEL_SPECULAR;
             l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
-            l.R = R;
-            l.T = T;
+            l.R = sref(ms.ks);
+            l.T = sref(ms.kt);
             l.etaA = 1.f;
             l.etaB = m.index;
         }
