@@ -1500,6 +1500,7 @@ __device__ __forceinline__ void store_direct_general(const RenderDev *R, uint32_
 #endif
 }
 
+#if B200PT_NSPEC == 3
 template <int MAT, bool VTX>
 __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
     const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
@@ -1665,6 +1666,421 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
         if (cont) q_next[pn] = slot;
     }
 }
+
+#else
+// ---- SampledSpectrum build: the same vertex with lazy spectra (pt_core.cuh "Lazy spectra").  No Spec by value: the
+// BSDF value is a recipe (FSpec), the light's radiance a row of the light table with a few scalars (LiTerm), and beta,
+// beta_ld, A, B and L are streamed bin by bin between the planar per-slot arrays -- the arithmetic per bin is that of the
+// eager kernel above / estimate_direct, operation for operation.
+struct LiTerm {
+    const float *row;  // nullptr: black
+    int op;            // 1: row   2: row / s0   3: (row * s0) / s1
+    float s0, s1;
+    const float *sigma_t;  // != nullptr: times Exp(-sigma_t * x) (homogeneous medium around the scene)
+    float x;
+};
+__device__ __forceinline__ void li_eval4(const LiTerm &t, int b0, float v[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float r = t.row[b0 + j];
+        float li = t.op == 1 ? r : (t.op == 2 ? r / t.s0 : (r * t.s0) / t.s1);
+        if (t.sigma_t) li = li * pt_expf((-t.sigma_t[b0 + j]) * t.x);
+        v[j] = li;
+    }
+}
+__device__ __forceinline__ bool li_is_black(const LiTerm &t) {
+    if (!t.row) return true;
+    for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+        float v[4];
+        LiTerm u = t;
+        u.sigma_t = nullptr;  // callers test Li before the transmittance is applied
+        li_eval4(u, b0, v);
+        if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) return false;
+    }
+    return true;
+}
+struct DirectLazy {
+    uint32_t pend;
+    V3 sh_o, sh_d, mi_o, mi_d;
+};
+// estimate_direct with the two terms written straight into the slot's planar A / B arrays
+__device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
+                                     int lightNum, const float uLight[2], DirectLazy *out) {
+    const bool medium = R->has_medium != 0;
+    const float *sigmaT = medium ? R->med_spectra + B200PT_NSPEC : nullptr;
+    const uint32_t cap = R->capacity;
+    float *sA = R->s_A + slot, *sB = R->s_B + slot;
+    out->pend = 0;
+    out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
+    const DevLight &lightRef = R->lights[lightNum];
+    const float *lrow = R->light_spectra + (size_t)lightNum * B200PT_NSPEC;
+    if (lightRef.kind != 0) {
+        // delta light: delta_light_sample (pt_sphere.cuh) as a recipe
+        const V3 lpos = mk(lightRef.position[0], lightRef.position[1], lightRef.position[2]);
+        V3 wiD, pTarget;
+        LiTerm Li;
+        Li.row = lrow;
+        Li.sigma_t = nullptr;
+        Li.x = 0.f;
+        Li.s0 = Li.s1 = 0.f;
+        if (lightRef.kind == 3) {
+            wiD = lpos;
+            pTarget = is.p + lpos * lightRef.two_world_radius;
+            Li.op = 1;
+        } else {
+            wiD = normalize(lpos - is.p);
+            pTarget = lpos;
+            const float d2 = len2(lpos - is.p);
+            if (lightRef.kind == 1) {
+                Li.op = 2;
+                Li.s0 = d2;
+            } else {
+                const V3 wl = normalize(xform_vector(lightRef.world_to_light, -wiD));
+                const float cosTheta = wl.z;
+                float falloff;
+                if (cosTheta < lightRef.cos_total_width)
+                    falloff = 0.f;
+                else if (cosTheta >= lightRef.cos_falloff_start)
+                    falloff = 1.f;
+                else {
+                    const float delta = (cosTheta - lightRef.cos_total_width) / (lightRef.cos_falloff_start - lightRef.cos_total_width);
+                    falloff = (delta * delta) * (delta * delta);
+                }
+                Li.op = 3;
+                Li.s0 = falloff;
+                Li.s1 = d2;
+            }
+        }
+        if (!li_is_black(Li)) {
+            const FSpec fD = bsdf_f_lazy(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR);
+            const float ad = absdot(wiD, bsdf.ns);
+            if (!fspec_is_black(fD, ad)) {
+                const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
+                out->sh_o = origin;
+                out->sh_d = pTarget - origin;
+                if (medium) {
+                    Li.sigma_t = sigmaT;
+                    Li.x = pt_min(PT_SHADOW_TMAX * len(out->sh_d), PT_MAX_FLOAT);
+                }
+#pragma unroll 1
+                for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+                    float fv[4], lv[4];
+                    fspec_eval4(fD, b0, fv);
+                    li_eval4(Li, b0, lv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = ((fv[j] * ad) * lv[j]) / 1.f;
+                }
+                out->pend |= PEND_LIGHT;
+            }
+        }
+        return;
+    }
+    const DevLight light = lightRef;
+    const bool onSphere = is_sphere_hit(light.tri);
+    const DevSphere *lsp = onSphere ? R->scene.spheres + (light.tri & SPHERE_HIT_MASK) : nullptr;
+    const F4 *tp = R->scene.tris + (size_t)(onSphere ? 0u : light.tri) * 3;
+    F4 t0 = {0.f, 0.f, 0.f, 0.f}, t1 = t0, t2 = t0;
+    if (!onSphere) {
+        t0 = ld_f4(tp);
+        t1 = ld_f4(tp + 1);
+        t2 = ld_f4(tp + 2);
+    }
+    const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
+    const uint32_t lflags = __float_as_uint(t1.w);
+    const bool lflip = (lflags & 0x10000u) != 0, ldegenerate = (lflags & 0x20000u) != 0;
+    TriShading lsh;
+    load_shading<true>(R->scene, light.tri, lflags, &lsh);
+    const int flagsNS = BSDF_ALL & ~BSDF_SPECULAR;
+    V3 wi = mk(0.f, 0.f, 0.f);
+    float lightPdf = 0.f, scatteringPdf = 0.f;
+    LiTerm Li;
+    Li.row = nullptr;
+    Li.op = 1;
+    Li.s0 = Li.s1 = Li.x = 0.f;
+    Li.sigma_t = nullptr;
+    LightSample ps;
+    if (onSphere) {
+        ps = sphere_sample(*lsp, is.p, is.pError, is.n, uLight, &lightPdf);
+    } else {
+        ps = triangle_sample(p0, p1, p2, lflip, lsh, uLight, &lightPdf);
+        V3 w = ps.p - is.p;
+        if (len2(w) == 0)
+            lightPdf = 0;
+        else {
+            w = normalize(w);
+            lightPdf *= len2(is.p - ps.p) / absdot(ps.n, -w);
+            if (pt_isinf(lightPdf)) lightPdf = 0.f;
+        }
+    }
+    if (lightPdf == 0 || len2(ps.p - is.p) == 0) {
+        lightPdf = 0;
+    } else {
+        wi = normalize(ps.p - is.p);
+        Li.row = (light.two_sided || dot(ps.n, -wi) > 0) ? lrow : nullptr;
+    }
+    if (lightPdf > 0 && !li_is_black(Li)) {
+        const FSpec f = bsdf_f_lazy(bsdf, is.wo, wi, flagsNS);
+        const float ad = absdot(wi, bsdf.ns);
+        scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+        if (!fspec_is_black(f, ad)) {
+            const V3 origin = offset_ray_origin(is.p, is.pError, is.n, ps.p - is.p);
+            const V3 target = offset_ray_origin(ps.p, ps.pError, ps.n, origin - ps.p);
+            out->sh_o = origin;
+            out->sh_d = target - origin;
+            if (medium) {
+                Li.sigma_t = sigmaT;
+                Li.x = pt_min(PT_SHADOW_TMAX * len(out->sh_d), PT_MAX_FLOAT);
+            }
+            const float weight = power_heuristic(lightPdf, scatteringPdf);
+#pragma unroll 1
+            for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+                float fv[4], lv[4];
+                fspec_eval4(f, b0, fv);
+                li_eval4(Li, b0, lv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = (((fv[j] * ad) * lv[j]) * weight) / lightPdf;
+            }
+            out->pend |= PEND_LIGHT;
+        }
+    }
+    // BSDF sampling with MIS
+    int sampledType = 0;
+    const FSpec f = bsdf_sample_f_lazy(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+    const float ad = absdot(wi, bsdf.ns);
+    if (!fspec_is_black(f, ad) && scatteringPdf > 0) {
+        const V3 ro = offset_ray_origin(is.p, is.pError, is.n, wi);
+        float lpdf = 0.f, tLight = 0.f;
+        V3 ln = mk(0.f, 0.f, 0.f);
+        TriHit h;
+        if (onSphere) {
+            float th;
+            Isect li;
+            if (sphere_intersect(*lsp, ro, wi, pt_inf(), &th, &li)) {
+                ln = li.n;
+                tLight = th;
+                lpdf = sphere_pdf(*lsp, is.p, is.pError, is.n, wi);
+            }
+        } else if (!ldegenerate && triangle_test(p0, p1, p2, ro, make_shear(wi), pt_inf(), &h)) {
+            Isect li;
+            fill_isect(p0, p1, p2, lflip, lsh, h, wi, &li);
+            ln = li.n;
+            tLight = h.t;
+            lpdf = len2(is.p - li.p) / (absdot(ln, -wi) * light.area);
+            if (pt_isinf(lpdf)) lpdf = 0.f;
+        }
+        if (lpdf != 0) {
+            const float weight = power_heuristic(scatteringPdf, lpdf);
+            LiTerm Le;
+            Le.row = (light.two_sided || dot(ln, -wi) > 0) ? lrow : nullptr;
+            Le.op = 1;
+            Le.s0 = Le.s1 = 0.f;
+            Le.sigma_t = nullptr;
+            Le.x = 0.f;
+            const bool black = li_is_black(Le);
+            const float xTr = medium ? pt_min(tLight * len(wi), PT_MAX_FLOAT) : 0.f;
+#pragma unroll 1
+            for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+                float fv[4], lv[4];
+                if (!black) {
+                    fspec_eval4(f, b0, fv);
+                    li_eval4(Le, b0, lv);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float bval = 0.f;
+                    if (!black) {
+                        const float tr = medium ? pt_expf((-sigmaT[b0 + j]) * xTr) : 1.f;
+                        bval = ((((fv[j] * ad) * lv[j]) * tr) * weight) / scatteringPdf;
+                    }
+                    sB[(size_t)(b0 + j) * cap] = bval;
+                }
+            }
+            out->mi_o = ro;
+            out->mi_d = wi;
+            out->pend |= PEND_BSDF;
+        }
+    }
+}
+
+template <int MAT, bool VTX>
+__global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
+    const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
+    const uint32_t *queue = R->q_mat[MAT];
+    uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
+    uint32_t *qc_shadow = &R->qcount[bounce * Q_PER_BOUNCE + Q_SHADOW];
+    uint32_t *qc_mis = &R->qcount[bounce * Q_PER_BOUNCE + Q_MIS];
+    uint32_t *q_next = R->q_path[(bounce + 1) & 1];
+    const uint32_t cap = R->capacity;
+    uint32_t i;
+    while (warp_fetch(work, n, &i)) {
+        const bool active = i < n;
+        bool cont = false;
+        uint32_t pend = 0, slot = 0;
+        if (active) {
+            slot = queue[i];
+            const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
+            float *sBeta = R->s_beta + slot, *sL = R->s_L + slot;
+            const V3 ro = v3(o4), rd = v3(d4);
+            float etaScale = o4.w;
+            const uint32_t meta = __float_as_uint(d4.w);
+            const int bounces = (int)((meta >> 16) & 0xffu);
+            const bool specularBounce = ((meta >> 24) & PF_SPECULAR) != 0;
+            const uint32_t ti = R->hit[slot];
+            Isect is;
+            uint32_t mflags;
+            int lightId;
+            bool found;
+            if (is_sphere_hit(ti)) {
+                const DevSphere *sp = R->scene.spheres + (ti & SPHERE_HIT_MASK);
+                float th;
+                found = sphere_intersect(*sp, ro, rd, pt_inf(), &th, &is);
+                mflags = sp->mat_flags;
+                lightId = sp->light_id;
+            } else {
+                const F4 *tp = R->scene.tris + (size_t)ti * 3;
+                const F4 t0 = ld_f4(tp), t1 = ld_f4(tp + 1), t2 = ld_f4(tp + 2);
+                const V3 p0 = v3(t0), p1 = v3(t1), p2 = v3(t2);
+                mflags = __float_as_uint(t1.w);
+                lightId = (int)__float_as_uint(t2.w);
+                TriHit h;
+                if (mflags & 0x100000u) {
+                    const DevInstance *in = R->scene.instances + R->hit_inst[slot];
+                    V3 o2, d2;
+                    float tm2;
+                    instance_ray(*in, ro, rd, pt_inf(), &o2, &d2, &tm2);
+                    found = triangle_test(p0, p1, p2, o2, make_shear(d2), pt_inf(), &h);
+                    if (found) {
+                        TriShading tsh;
+                        load_shading<true>(R->scene, ti, mflags, &tsh);
+                        fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, d2, &is);
+                        instance_isect_to_world(*in, &is);
+                    }
+                } else {
+                    found = triangle_test(p0, p1, p2, ro, make_shear(rd), pt_inf(), &h);
+                    if (found) {
+                        TriShading tsh;
+                        load_shading<true>(R->scene, ti, mflags, &tsh);
+                        fill_isect(p0, p1, p2, (mflags & 0x10000u) != 0, tsh, h, rd, &is);
+                    }
+                }
+            }
+            if (found) {
+                // path.cpp:91-101: L += beta * Le at the first vertex or after a specular bounce
+                if ((bounces == 0 || specularBounce) && lightId >= 0) {
+                    const DevLight &lt = R->lights[lightId];
+                    if (lt.two_sided || dot(is.n, -rd) > 0) {
+                        const float *le = R->light_spectra + (size_t)lightId * B200PT_NSPEC;
+#pragma unroll 4
+                        for (int b = 0; b < B200PT_NSPEC; ++b) sL[(size_t)b * cap] = sL[(size_t)b * cap] + sBeta[(size_t)b * cap] * le[b];
+                    } else {
+                        // L + beta * 0: only a -0 would change, and L never holds one (it starts at +0 and only sums)
+                    }
+                }
+                if (bounces < R->max_depth) {
+                    Bsdf bsdf;
+                    const uint32_t mi = mflags & 0xffffu;
+                    make_bsdf<MAT>(R->scene.materials[mi], R->scene.material_spectra + (size_t)mi * (5 * B200PT_NSPEC), is, &bsdf);
+                    SobolStream st;
+                    st.index = R->sobol[slot];
+                    st.dim = (int)(meta & 0xffffu);
+                    st.px = st.py = 0;
+                    const SamplerParams &sp = R->sampler;
+                    if ((R->volpath || bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0) && R->n_lights > 0) {
+                        float pickPdf;
+                        const float *cdf = R->light_cdf, *func = R->light_func;
+                        float funcInt = R->light_func_int;
+                        if (R->grid.enabled) {
+                            const int vox = spatial_voxel(R->grid, is.p);
+                            cdf = R->sp_cdf + (size_t)vox * (R->n_lights + 1);
+                            func = R->sp_func + (size_t)vox * R->n_lights;
+                            funcInt = R->sp_func_int[vox];
+                        }
+                        const int lightNum = sample_discrete(cdf, func, funcInt, R->n_lights, get1d(sp, st), &pickPdf);
+                        if (pickPdf != 0) {
+                            float uLight[2], uScattering[2];
+                            get2d(sp, st, uLight);
+                            get2d(sp, st, uScattering);
+                            DirectLazy dout;
+                            estimate_direct_lazy(R, slot, is, bsdf, uScattering, lightNum, uLight, &dout);
+                            pend = dout.pend;
+                            if (pend) {
+                                // beta as it is before this vertex's BSDF sample scales it
+                                float *sBl = R->s_beta_ld + slot;
+#pragma unroll 4
+                                for (int b = 0; b < B200PT_NSPEC; ++b) sBl[(size_t)b * cap] = sBeta[(size_t)b * cap];
+                                R->beta_ld[slot] = make_float4(0.f, 0.f, 0.f, pickPdf);
+                                R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
+                                if (pend & PEND_LIGHT) R->A[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (pend & PEND_BSDF) {
+                                    R->mi_o[slot] = f4(dout.mi_o, 0.f);
+                                    R->mi_d[slot] = f4(dout.mi_d, 0.f);
+                                    R->B[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+                            R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
+                        }
+                    }
+                    // path.cpp:131-150
+                    const V3 wo = -rd;
+                    V3 wi = mk(0.f, 0.f, 0.f);
+                    float pdf = 0.f;
+                    int flags = 0;
+                    float u2[2];
+                    get2d(sp, st, u2);
+                    const FSpec f = bsdf_sample_f_lazy(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+                    if (!(fspec_is_black(f, 1.f) || pdf == 0.f)) {
+                        const float ad = absdot(wi, bsdf.ns);
+                        const bool spec = (flags & BSDF_SPECULAR) != 0;
+                        if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+                            const float eta = bsdf.eta;
+                            etaScale *= (dot(wo, is.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+                        }
+                        const V3 no = offset_ray_origin(is.p, is.pError, is.n, wi);
+                        cont = true;
+                        // beta *= f * |cos| / pdf, and max(beta * etaScale) for the roulette (path.cpp:176-184)
+                        float mx = 0.f;
+#pragma unroll 1
+                        for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+                            float fv[4];
+                            fspec_eval4(f, b0, fv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float nb = sBeta[(size_t)(b0 + j) * cap] * ((fv[j] * ad) / pdf);
+                                sBeta[(size_t)(b0 + j) * cap] = nb;
+                                const float rr = nb * etaScale;
+                                mx = (b0 + j == 0) ? rr : pt_max(mx, rr);
+                            }
+                        }
+                        if (mx < R->rr_threshold && bounces > 3) {
+                            const float q = pt_max(.05f, 1 - mx);
+                            if (get1d(sp, st) < q)
+                                cont = false;
+                            else {
+                                const float dq = 1 - q;
+#pragma unroll 4
+                                for (int b = 0; b < B200PT_NSPEC; ++b) sBeta[(size_t)b * cap] = sBeta[(size_t)b * cap] / dq;
+                            }
+                        }
+                        if (cont) {
+                            const uint32_t nmeta = ((uint32_t)st.dim & 0xffffu) | ((uint32_t)(bounces + 1) << 16) |
+                                                   ((spec ? (uint32_t)PF_SPECULAR : 0u) << 24);
+                            R->ray_o[slot] = f4(no, etaScale);
+                            R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
+                            R->beta[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+            }
+        }
+        const uint32_t ps = warp_append(qc_shadow, (pend & PEND_LIGHT) != 0);
+        if (pend & PEND_LIGHT) R->q_shadow[ps] = slot;
+        const uint32_t pm = warp_append(qc_mis, (pend & PEND_BSDF) != 0);
+        if (pend & PEND_BSDF) R->q_mis[pm] = slot;
+        const uint32_t pn = warp_append(qc_next, cont);
+        if (cont) q_next[pn] = slot;
+    }
+}
+#endif  // B200PT_NSPEC == 3 (k_shade)
 
 // Medium pass of a bounce (VolPathIntegrator with every ray inside one homogeneous medium, volpath.cpp:77-103): runs over
 // the bounce's path rays after the closest-hit launch (which then does not classify).  It draws the channel and the
@@ -2137,6 +2553,7 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
         const float4 sd = R->sh_d[slot];
         const uint32_t pend = __float_as_uint(sd.w);
         if (!pend) continue;
+#if B200PT_NSPEC == 3
         Spec Ld = rgb1(0.f);
         bool any = false;
         if ((pend & PEND_LIGHT) && !R->occluded[slot]) {
@@ -2159,6 +2576,31 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
             const Spec L = ld_spec(R->L, R->s_L, R->capacity, slot, &LW) + betaLd * (Ld / pickPdf);
             st_spec(R->L, R->s_L, R->capacity, slot, L, LW);
         }
+#else
+        // 60 bins: streamed through the planar arrays, bin by bin (Ld = 0 + A + B; L += beta_ld * (Ld / pickPdf))
+        const uint32_t cap = R->capacity;
+        const bool takeA = (pend & PEND_LIGHT) && !R->occluded[slot];
+        bool takeB = false;
+        if (pend & PEND_BSDF) {
+            const uint32_t lightNum = __float_as_uint(R->sh_o[slot].w);
+            if (R->mis_hit[slot] == R->lights[lightNum].tri) {
+                const float *sB = R->s_B + slot;
+                for (int b = 0; b < B200PT_NSPEC && !takeB; ++b) takeB = sB[(size_t)b * cap] != 0.f;
+            }
+        }
+        if (takeA || takeB) {
+            const float pickPdf = R->beta_ld[slot].w;
+            const float *sA = R->s_A + slot, *sB = R->s_B + slot, *sBl = R->s_beta_ld + slot;
+            float *sL = R->s_L + slot;
+#pragma unroll 4
+            for (int b = 0; b < B200PT_NSPEC; ++b) {
+                float Ld = 0.f;
+                if (takeA) Ld = Ld + sA[(size_t)b * cap];
+                if (takeB) Ld = Ld + sB[(size_t)b * cap];
+                sL[(size_t)b * cap] = sL[(size_t)b * cap] + sBl[(size_t)b * cap] * (Ld / pickPdf);
+            }
+        }
+#endif
         R->sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.f);
     }
 }

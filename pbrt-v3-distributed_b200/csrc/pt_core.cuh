@@ -1072,6 +1072,330 @@ B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[
     return f;
 }
 
+#if B200PT_NSPEC != 3
+// ----------------------------------------------------------------------------------------------------------------
+// Lazy spectra (SampledSpectrum build).  A 60-bin Spec by value is 240 bytes: the shading kernel that held beta, L,
+// f, Li, A and B that way ran out of a 4.5-6.4 KB local-memory frame per thread (profiles/README.md).  Every spectrum
+// of the path is a per-bin function of table rows and a few scalars, so the kernel keeps the *recipe* (LTerm: which
+// rows, which scalars, which BxDF formula) in registers and evaluates it bin by bin, four bins at a time, straight
+// from / to the planar per-slot arrays.  The per-bin arithmetic is the eager code's, operation for operation
+// (lobe_f / lobe_sample_f / bsdf_f / bsdf_sample_f above, which follow core/reflection.cpp), so results are bit-identical.
+enum { LT_ZERO = 0, LT_ROW_S, LT_ROW_S2, LT_MF_DIEL, LT_MF_COND, LT_MFT, LT_SPEC_R, LT_FS_R, LT_FS_T };
+struct LTerm {
+    int op;
+    const float *r;        // the lobe's R / T row; nullptr = the constant spectrum 1
+    const float *eta, *k;  // LT_MF_COND: the conductor's rows
+    float s0, s1, s2, s3, s4, s5;
+};
+B200_HD LTerm lterm_zero() {
+    LTerm t;
+    t.op = LT_ZERO;
+    t.r = t.eta = t.k = nullptr;
+    t.s0 = t.s1 = t.s2 = t.s3 = t.s4 = t.s5 = 0.f;
+    return t;
+}
+// FrConductor (reflection.cpp:71-94) of one bin with etaI = 1; c = the clamped cosine, c2 = c*c, s2 = 1 - c2 (fr_conductor)
+B200_HD float fr_conductor_bin(float c, float c2, float s2, float etat, float kk) {
+    const float eta = etat / 1.f;
+    const float etak = kk / 1.f;
+    const float eta2 = eta * eta;
+    const float etak2 = etak * etak;
+    const float t0 = eta2 - etak2 - s2;
+    const float a2plusb2 = sqrtf(t0 * t0 + (eta2 * 4.f) * etak2);
+    const float t1 = a2plusb2 + c2;
+    const float a = sqrtf((a2plusb2 + t0) * 0.5f);
+    const float t2 = a * (2.f * c);
+    const float Rs = (t1 - t2) / (t1 + t2);
+    const float t3 = a2plusb2 * c2 + s2 * s2;
+    const float t4 = t2 * s2;
+    const float Rp = Rs * (t3 - t4) / (t3 + t4);
+    return (Rp + Rs) * 0.5f;
+}
+// bins [b0, b0 + 4) of a term
+B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
+    float x[4];
+    PT_UNROLL
+    for (int j = 0; j < 4; ++j) x[j] = t.r ? t.r[b0 + j] : 1.f;
+    switch (t.op) {
+    case LT_ROW_S:  // LambertianReflection::f
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = x[j] * t.s0;
+        break;
+    case LT_ROW_S2:  // OrenNayar::f
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = (x[j] * t.s0) * t.s1;
+        break;
+    case LT_MF_DIEL:  // MicrofacetReflection::f with FresnelDielectric: R * D * G * F / (4 cosI cosO)
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = (((x[j] * t.s0) * t.s1) * t.s2) / t.s3;
+        break;
+    case LT_MF_COND:  // ... with FresnelConductor
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j)
+            v[j] = (((x[j] * t.s0) * t.s1) * fr_conductor_bin(t.s2, t.s4, t.s5, t.eta[b0 + j], t.k[b0 + j])) / t.s3;
+        break;
+    case LT_MFT:  // MicrofacetTransmission::f: (1 - F) * T * scalar
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = ((1.f - t.s0) * x[j]) * t.s1;
+        break;
+    case LT_SPEC_R:  // SpecularReflection::Sample_f with FresnelNoOp: 1 * R / |cos|
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = (1.f * x[j]) / t.s0;
+        break;
+    case LT_FS_R:  // FresnelSpecular::Sample_f, reflection: F * R / |cos|
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = (x[j] * t.s0) / t.s1;
+        break;
+    case LT_FS_T:  // ... transmission: T * (1 - F) * (etaI^2 / etaT^2) / |cos|
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = ((x[j] * t.s0) * t.s1) / t.s2;
+        break;
+    default:
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = 0.f;
+        break;
+    }
+}
+// lobe_f as a recipe
+B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
+    LTerm t = lterm_zero();
+    if (l.kind == BX_LAMBERT) {
+        t.op = LT_ROW_S;
+        t.r = l.R.p;
+        t.s0 = PT_INV_PI;
+        return t;
+    }
+    if (l.kind == BX_MICROFACET) {
+        float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
+        V3 wh = wi + wo;
+        if (cosThetaI == 0 || cosThetaO == 0) return t;
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return t;
+        wh = normalize(wh);
+        t.r = l.R.p;
+        t.s0 = tr_D(l.dist, wh);
+        t.s1 = tr_G(l.dist, wo, wi);
+        t.s3 = 4 * cosThetaI * cosThetaO;
+        const float cosF = dot(wi, wh);
+        if (!l.conductor) {
+            t.op = LT_MF_DIEL;
+            t.s2 = fr_dielectric(cosF, l.frEtaI, l.frEtaT);
+        } else {
+            t.op = LT_MF_COND;
+            t.eta = l.cEta.p;
+            t.k = l.cK.p;
+            const float c = pt_clamp(pt_abs(cosF), -1.f, 1.f);
+            t.s2 = c;
+            t.s4 = c * c;
+            t.s5 = (float)(1. - (double)t.s4);
+        }
+        return t;
+    }
+    if (l.kind == BX_OREN_NAYAR) {
+        float sinThetaI = sin_theta(wi);
+        float sinThetaO = sin_theta(wo);
+        float maxCos = 0;
+        if ((double)sinThetaI > 1e-4 && (double)sinThetaO > 1e-4) {
+            float sinPhiI = sin_phi(wi), cosPhiI = cos_phi(wi);
+            float sinPhiO = sin_phi(wo), cosPhiO = cos_phi(wo);
+            float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+            maxCos = pt_max(0.f, dCos);
+        }
+        float sinAlpha, tanBeta;
+        if (abs_cos_theta(wi) > abs_cos_theta(wo)) {
+            sinAlpha = sinThetaO;
+            tanBeta = sinThetaI / abs_cos_theta(wi);
+        } else {
+            sinAlpha = sinThetaI;
+            tanBeta = sinThetaO / abs_cos_theta(wo);
+        }
+        t.op = LT_ROW_S2;
+        t.r = l.R.p;
+        t.s0 = PT_INV_PI;
+        t.s1 = l.onA + l.onB * maxCos * sinAlpha * tanBeta;
+        return t;
+    }
+    if (l.kind == BX_MICROFACET_TRANS) {
+        if (same_hemisphere(wo, wi)) return t;
+        float cosThetaO = cos_theta(wo);
+        float cosThetaI = cos_theta(wi);
+        if (cosThetaI == 0 || cosThetaO == 0) return t;
+        float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3 wh = normalize(wo + wi * eta);
+        if (wh.z < 0) wh = -wh;
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float factor = 1 / eta;
+        t.op = LT_MFT;
+        t.r = l.T.p;
+        t.s0 = fr_dielectric(dot(wo, wh), l.etaA, l.etaB);
+        t.s1 = pt_abs(tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
+                      (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
+        return t;
+    }
+    return t;  // FresnelSpecular::f, SpecularReflection::f
+}
+// lobe_sample_f as a recipe
+B200_HD LTerm lobe_sample_term(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
+    LTerm t = lterm_zero();
+    if (l.kind == BX_MICROFACET_TRANS) {
+        if (wo.z == 0) return t;
+        V3 wh = tr_sample_wh(l.dist, wo, u);
+        float eta = cos_theta(wo) > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
+        if (!refract(wo, wh, eta, wi)) return t;
+        *pdf = lobe_pdf(l, wo, *wi);
+        return lobe_term(l, wo, *wi);
+    }
+    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR) {
+        *wi = cosine_sample_hemisphere(u);
+        if (wo.z < 0) wi->z *= -1;
+        *pdf = lobe_pdf(l, wo, *wi);
+        return lobe_term(l, wo, *wi);
+    }
+    if (l.kind == BX_MICROFACET) {
+        if (wo.z == 0) return t;
+        V3 wh = tr_sample_wh(l.dist, wo, u);
+        *wi = reflect(wo, wh);
+        if (!same_hemisphere(wo, *wi)) return t;
+        *pdf = tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
+        return lobe_term(l, wo, *wi);
+    }
+    if (l.kind == BX_SPECULAR_REFLECTION) {
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *pdf = 1.f;
+        t.op = LT_SPEC_R;
+        t.r = l.R.p;
+        t.s0 = abs_cos_theta(*wi);
+        return t;
+    }
+    float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
+    if (u[0] < F) {
+        *wi = mk(-wo.x, -wo.y, wo.z);
+        *sampledType = BSDF_SPECULAR | BSDF_REFLECTION;
+        *pdf = F;
+        t.op = LT_FS_R;
+        t.r = l.R.p;
+        t.s0 = F;
+        t.s1 = abs_cos_theta(*wi);
+        return t;
+    }
+    bool entering = cos_theta(wo) > 0;
+    float etaI = entering ? l.etaA : l.etaB;
+    float etaT = entering ? l.etaB : l.etaA;
+    V3 nn = mk(0.f, 0.f, 1.f);
+    if (dot(nn, wo) < 0.f) nn = -nn;
+    if (!refract(wo, nn, etaI / etaT, wi)) return t;
+    *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
+    *pdf = 1 - F;
+    t.op = LT_FS_T;
+    t.r = l.T.p;
+    t.s0 = 1 - F;
+    t.s1 = (etaI * etaI) / (etaT * etaT);
+    t.s2 = abs_cos_theta(*wi);
+    return t;
+}
+// A BSDF value: the sum (in lobe order, starting from 0 like `Spectrum f(0.f); f += ...` when from_zero) of up to two terms
+struct FSpec {
+    int n;
+    int from_zero;
+    LTerm t[2];
+};
+B200_HD FSpec fspec_zero() {
+    FSpec f;
+    f.n = 0;
+    f.from_zero = 1;
+    f.t[0] = f.t[1] = lterm_zero();
+    return f;
+}
+B200_HD void fspec_eval4(const FSpec &f, int b0, float v[4]) {
+    if (f.n == 0) {
+        v[0] = v[1] = v[2] = v[3] = 0.f;
+        return;
+    }
+    lterm_eval4(f.t[0], b0, v);
+    if (f.from_zero) {
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = 0.f + v[j];
+    }
+    if (f.n > 1) {
+        float w[4];
+        lterm_eval4(f.t[1], b0, w);
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = v[j] + w[j];
+    }
+}
+// is_black(f * s) without materialising it
+B200_HD bool fspec_is_black(const FSpec &f, float s) {
+    if (f.n == 0) return true;
+    for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
+        float v[4];
+        fspec_eval4(f, b0, v);
+        if (v[0] * s != 0.f || v[1] * s != 0.f || v[2] * s != 0.f || v[3] * s != 0.f) return false;
+    }
+    return true;
+}
+B200_HD bool row_is_black(const float *p) {
+    for (int i = 0; i < B200PT_NSPEC; ++i)
+        if (p[i] != 0.f) return false;
+    return true;
+}
+// bsdf_f (reflection.cpp:670-683) as a recipe
+B200_HD FSpec bsdf_f_lazy(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+    FSpec f = fspec_zero();
+    V3 wi = world_to_local(b, wiW), wo = world_to_local(b, woW);
+    if (wo.z == 0) return f;
+    bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], flags) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
+                                                (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
+            f.t[f.n++] = lobe_term(b.lobes[i], wo, wi);
+    return f;
+}
+// bsdf_sample_f (reflection.cpp:703-768) as a recipe
+B200_HD FSpec bsdf_sample_f_lazy(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type, int *sampledType) {
+    FSpec f = fspec_zero();
+    int matching = bsdf_num_components(b, type);
+    if (matching == 0) {
+        *pdf = 0;
+        *sampledType = 0;
+        return f;
+    }
+    int comp_ = pt_mini((int)floorf(u[0] * matching), matching - 1);
+    int which = 0, count = comp_;
+    for (int i = 0; i < b.n; ++i)
+        if (lobe_matches(b.lobes[i], type) && count-- == 0) {
+            which = i;
+            break;
+        }
+    const Lobe &lobe = b.lobes[which];
+    float ur[2] = {pt_min(u[0] * matching - comp_, PT_ONE_MINUS_EPS), u[1]};
+    V3 wi = mk(0.f, 0.f, 0.f), wo = world_to_local(b, woW);
+    if (wo.z == 0) return f;
+    *pdf = 0;
+    *sampledType = lobe.type;
+    const LTerm ts = lobe_sample_term(lobe, wo, &wi, ur, pdf, sampledType);
+    if (*pdf == 0) {
+        *sampledType = 0;
+        return f;
+    }
+    *wiW = local_to_world(b, wi);
+    if (!(lobe.type & BSDF_SPECULAR) && matching > 1)
+        for (int i = 0; i < b.n; ++i)
+            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    if (matching > 1) *pdf /= matching;
+    if (!(lobe.type & BSDF_SPECULAR)) {
+        bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        for (int i = 0; i < b.n; ++i)
+            if (lobe_matches(b.lobes[i], type) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
+                                                   (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
+                f.t[f.n++] = lobe_term(b.lobes[i], wo, wi);
+    } else {
+        f.n = 1;
+        f.from_zero = 0;
+        f.t[0] = ts;
+    }
+    return f;
+}
+#endif  // B200PT_NSPEC != 3
+
 B200_HD void add_lambert(Bsdf *b, const float *kd) {
     Lobe &l = b->lobes[b->n++];
     l.kind = BX_LAMBERT;
@@ -1105,6 +1429,12 @@ B200_HD MatSpec mat_spec(const b200pt_material &m, const float *rows) {
 #endif
     return s;
 }
+// is_black of a material row (the 60-bin build tests the row in place instead of copying it)
+#if B200PT_NSPEC == 3
+#define PT_ROW_BLACK(p) is_black(rgbp(p))
+#else
+#define PT_ROW_BLACK(p) row_is_black(p)
+#endif
 template <int MATERIAL>
 B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, const Isect &is, Bsdf *b) {
     const MatSpec ms = mat_spec(m, spectra_rows);
@@ -1116,7 +1446,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
     b->n = 0;
     const int type = MATERIAL >= 0 ? MATERIAL : m.type;
     if (type == B200PT_MAT_MATTE) {  // matte.cpp:45-62
-        if (!is_black(rgbp(ms.kd))) {
+        if (!PT_ROW_BLACK(ms.kd)) {
             add_lambert(b, ms.kd);
             if (m.variant == 1) {  // sigma != 0: OrenNayar(r, sig)
                 Lobe &l = b->lobes[b->n - 1];
@@ -1126,8 +1456,8 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
             }
         }
     } else if (type == B200PT_MAT_PLASTIC) {  // plastic.cpp:45-70
-        if (!is_black(rgbp(ms.kd))) add_lambert(b, ms.kd);
-        if (!is_black(rgbp(ms.ks))) {
+        if (!PT_ROW_BLACK(ms.kd)) add_lambert(b, ms.kd);
+        if (!PT_ROW_BLACK(ms.ks)) {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_MICROFACET;
             l.type = BSDF_REFLECTION | BSDF_GLOSSY;
@@ -1149,8 +1479,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
         l.cEta = sref(ms.eta);
         l.cK = sref(ms.k);
     } else if (type == B200PT_MAT_GLASS && m.variant == 2) {  // MirrorMaterial, mirror.cpp:45-56 (BSDF eta stays 1)
-        const Spec R = rgbp(ms.ks);
-        if (!is_black(R)) {
+        if (!PT_ROW_BLACK(ms.ks)) {
             Lobe &l = b->lobes[b->n++];
             l.kind = BX_SPECULAR_REFLECTION;
             l.type = BSDF_REFLECTION | BSDF_SPECULAR;
@@ -1158,10 +1487,10 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
         }
     } else if (type == B200PT_MAT_GLASS) {  // glass.cpp:45-64
         b->eta = m.index;
-        Spec R = rgbp(ms.ks), T = rgbp(ms.kt);
-        if (is_black(R) && is_black(T)) {
+        const bool blackR = PT_ROW_BLACK(ms.ks), blackT = PT_ROW_BLACK(ms.kt);
+        if (blackR && blackT) {
         } else if (m.variant == 1) {  // rough glass, glass.cpp:65-90
-            if (!is_black(R)) {
+            if (!blackR) {
                 Lobe &l = b->lobes[b->n++];
                 l.kind = BX_MICROFACET;
                 l.type = BSDF_REFLECTION | BSDF_GLOSSY;
@@ -1172,7 +1501,7 @@ B200_HD void make_bsdf(const b200pt_material &m, const float *spectra_rows, cons
                 l.frEtaI = 1.f;
                 l.frEtaT = m.index;
             }
-            if (!is_black(T)) {
+            if (!blackT) {
                 Lobe &l = b->lobes[b->n++];
                 l.kind = BX_MICROFACET_TRANS;
                 l.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
