@@ -321,12 +321,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(e2e):
+    def step(e2e, marks=None):
         h2d = 0
         if e2e:
             h2d = scene.upload()                      # pinned host -> device: BVH nodes + triangle records
         render.clear()
+        if marks is not None and world > 1:
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                m0.record()
         render.render_tiles(my_tiles)
+        if marks is not None and world > 1:
+            with torch.cuda.stream(stream):
+                m1.record()
+            marks.append((m0, m1))
         if world > 1:
             render.film_reduce(comm, 0)               # one ncclReduce of the raw film sums, behind the C ABI
         if e2e and rank == 0:
@@ -353,25 +361,35 @@ def main():
         with torch.cuda.stream(stream):
             ev0.record()
         h2d = 0
+        marks = []
         for _ in range(steps):
-            h2d = step(e2e)
+            h2d = step(e2e, marks)
         with torch.cuda.stream(stream):
             ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
+        busy_ms = sum(a.elapsed_time(b) for a, b in marks) if marks else ms
         clocks = sampler.summary()
         st = render.stats()
         render.set_option("profile", 0)
         t = torch.tensor([ms, float(st["regular_rays"] + st["shadow_rays"]), float(st["camera_rays"])],
                          dtype=torch.float64, device="cuda")
+        rank_ms = [ms]
         if world > 1:
+            # every rank's device time for rendering its own tiles in the same K steps (before the film reduce, which makes
+            # the fast ranks wait): the load balance of the static tile split shows as the spread of these
+            every = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(every, torch.tensor([busy_ms], dtype=torch.float64, device="cuda"))
+            rank_ms = [float(x[0]) for x in every]
             mx = t.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ms = float(mx[0])
+        timed.rank_ms = rank_ms
         return ms, float(t[1]), float(t[2]), st, clocks, h2d
 
     ms, rays, samples, st, clocks, _ = timed(False, args.steps, args.warmup)
+    rank_ms = list(timed.rank_ms)
     e2e_steps = args.e2e_steps if args.e2e_steps else min(args.steps, 5)
     ms_e, rays_e, samples_e, st_e, _, h2d = timed(True, e2e_steps, 1)
     # one more end-to-end step with events between its three parts (reported, not part of any timed figure)
@@ -473,6 +491,7 @@ def main():
                     "d2h_bytes_per_step": int(host_rgb.numel() * 4), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps,
                     "excludes": "scene_create", "breakdown_ms": breakdown},
             "stack_overflows": int(st.get("stack_overflows", 0)),
+            "per_rank_render_ms_per_step": [x / args.steps for x in rank_ms],
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }

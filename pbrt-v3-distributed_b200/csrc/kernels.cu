@@ -1306,7 +1306,7 @@ struct DirectOut {
 // is opaque), and the MIS ray can only contribute if its closest hit is the light's own shape, whose distance Pdf_Li
 // computes anyway (Scene::IntersectTr, scene.cpp:57-70).  `inMedium`: `is` is a MediumInteraction (p, wo; zero normal
 // and error bounds) and the Henyey-Greenstein phase function takes the BSDF's place (integrator.cpp:131-137, :178-186).
-template <bool VTX>
+template <bool VTX, int KINDS = KM_ALL>
 __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                 int lightNum, const float uLight[2], DirectOut *out, bool inMedium = false, int med = 0) {
     // (VolPathIntegrator renders always run the general variant, so the lean one carries none of this)
@@ -1332,7 +1332,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         const Spec LiD = delta_light_sample(dl, is.p, &wiD, &pTarget);
         if (!is_black(LiD)) {
             const Spec fD = inMedium ? rgb1(phase_hg(dot(is.wo, wiD), hgG))
-                                     : bsdf_f(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
+                                     : bsdf_f<KINDS>(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR) * absdot(wiD, bsdf.ns);
             if (!is_black(fD)) {
                 // SpawnRayTo(Interaction) towards a point without normal or error bounds (interaction.h:73-78)
                 const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
@@ -1404,8 +1404,8 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
             f = rgb1(p);
             scatteringPdf = p;
         } else {
-            f = bsdf_f(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
-            scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+            f = bsdf_f<KINDS>(bsdf, is.wo, wi, flagsNS) * absdot(wi, bsdf.ns);
+            scatteringPdf = bsdf_pdf<KINDS>(bsdf, is.wo, wi, flagsNS);
         }
         if (!is_black(f)) {
             // VisibilityTester::Unoccluded -> SpawnRayTo(Interaction), interaction.h:73-78
@@ -1436,7 +1436,7 @@ __device__ void estimate_direct(const RenderDev *R, const Isect &is, const Bsdf 
         f = rgb1(p);
         scatteringPdf = p;
     } else {
-        f = bsdf_sample_f(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+        f = bsdf_sample_f<KINDS>(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
         f = f * absdot(wi, bsdf.ns);
     }
     if (!is_black(f) && scatteringPdf > 0) {
@@ -1501,8 +1501,12 @@ __device__ __forceinline__ void store_direct_general(const RenderDev *R, uint32_
 }
 
 #if B200PT_NSPEC == 3
+// resident CTAs per SM the shading kernels are compiled for (4 -> 128 registers; A/B builds: 5 -> 96, 6 -> 80)
+#ifndef B200PT_SHADE_MINCTAS
+#define B200PT_SHADE_MINCTAS 4
+#endif
 template <int MAT, bool VTX>
-__global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
+__global__ void __launch_bounds__(128, B200PT_SHADE_MINCTAS) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
     const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
     const uint32_t *queue = R->q_mat[MAT];
     uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
@@ -1604,7 +1608,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                             get2d(sp, st, uScattering);
                             DirectOut dout;
                             const int med = (B200PT_MEDIA_GENERAL && VTX && R->med_general) ? R->cur_med[slot] : 0;
-                            estimate_direct<VTX>(R, is, bsdf, uScattering, lightNum, uLight, &dout, false, med);
+                            estimate_direct<VTX, mat_kinds(MAT)>(R, is, bsdf, uScattering, lightNum, uLight, &dout, false, med);
                             pend = dout.pend;
                             if (pend) {
                                 st_spec(R->beta_ld, R->s_beta_ld, R->capacity, slot, beta, pickPdf);
@@ -1627,7 +1631,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                     int flags = 0;
                     float u2[2];
                     get2d(sp, st, u2);
-                    const Spec f = bsdf_sample_f(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+                    const Spec f = bsdf_sample_f<mat_kinds(MAT)>(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
                     if (!(is_black(f) || pdf == 0.f)) {
                         beta = beta * (f * absdot(wi, bsdf.ns) / pdf);
                         const bool spec = (flags & BSDF_SPECULAR) != 0;
@@ -1704,6 +1708,7 @@ struct DirectLazy {
     V3 sh_o, sh_d, mi_o, mi_d;
 };
 // estimate_direct with the two terms written straight into the slot's planar A / B arrays
+template <int KINDS>
 __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                      int lightNum, const float uLight[2], DirectLazy *out) {
     const bool medium = R->has_medium != 0;
@@ -1752,9 +1757,9 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
             }
         }
         if (!li_is_black(Li)) {
-            const FSpec fD = bsdf_f_lazy(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR);
+            const FSpec fD = bsdf_f_lazy<KINDS>(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR);
             const float ad = absdot(wiD, bsdf.ns);
-            if (!fspec_is_black(fD, ad)) {
+            if (!fspec_is_black<KINDS>(fD, ad)) {
                 const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
                 out->sh_o = origin;
                 out->sh_d = pTarget - origin;
@@ -1765,7 +1770,7 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
 #pragma unroll 1
                 for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
                     float fv[4], lv[4];
-                    fspec_eval4(fD, b0, fv);
+                    fspec_eval4<KINDS>(fD, b0, fv);
                     li_eval4(Li, b0, lv);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = ((fv[j] * ad) * lv[j]) / 1.f;
@@ -1819,10 +1824,10 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
         Li.row = (light.two_sided || dot(ps.n, -wi) > 0) ? lrow : nullptr;
     }
     if (lightPdf > 0 && !li_is_black(Li)) {
-        const FSpec f = bsdf_f_lazy(bsdf, is.wo, wi, flagsNS);
+        const FSpec f = bsdf_f_lazy<KINDS>(bsdf, is.wo, wi, flagsNS);
         const float ad = absdot(wi, bsdf.ns);
         scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
-        if (!fspec_is_black(f, ad)) {
+        if (!fspec_is_black<KINDS>(f, ad)) {
             const V3 origin = offset_ray_origin(is.p, is.pError, is.n, ps.p - is.p);
             const V3 target = offset_ray_origin(ps.p, ps.pError, ps.n, origin - ps.p);
             out->sh_o = origin;
@@ -1835,7 +1840,7 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
 #pragma unroll 1
             for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
                 float fv[4], lv[4];
-                fspec_eval4(f, b0, fv);
+                fspec_eval4<KINDS>(f, b0, fv);
                 li_eval4(Li, b0, lv);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = (((fv[j] * ad) * lv[j]) * weight) / lightPdf;
@@ -1845,9 +1850,9 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
     }
     // BSDF sampling with MIS
     int sampledType = 0;
-    const FSpec f = bsdf_sample_f_lazy(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+    const FSpec f = bsdf_sample_f_lazy<KINDS>(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
     const float ad = absdot(wi, bsdf.ns);
-    if (!fspec_is_black(f, ad) && scatteringPdf > 0) {
+    if (!fspec_is_black<KINDS>(f, ad) && scatteringPdf > 0) {
         const V3 ro = offset_ray_origin(is.p, is.pError, is.n, wi);
         float lpdf = 0.f, tLight = 0.f;
         V3 ln = mk(0.f, 0.f, 0.f);
@@ -1882,7 +1887,7 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
             for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
                 float fv[4], lv[4];
                 if (!black) {
-                    fspec_eval4(f, b0, fv);
+                    fspec_eval4<KINDS>(f, b0, fv);
                     li_eval4(Le, b0, lv);
                 }
 #pragma unroll
@@ -1902,8 +1907,12 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
     }
 }
 
+// resident CTAs per SM the 60-bin shading kernel is compiled for (register budget: 4 -> 128, 3 -> 168, 2 -> 255)
+#ifndef B200PT_S60_SHADE_MINCTAS
+#define B200PT_S60_SHADE_MINCTAS 4
+#endif
 template <int MAT, bool VTX>
-__global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
+__global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const RenderDev *R, int bounce, uint32_t *work) {
     const uint32_t n = R->qcount[bounce * Q_PER_BOUNCE + Q_MAT0 + MAT];
     const uint32_t *queue = R->q_mat[MAT];
     uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
@@ -2001,7 +2010,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                             get2d(sp, st, uLight);
                             get2d(sp, st, uScattering);
                             DirectLazy dout;
-                            estimate_direct_lazy(R, slot, is, bsdf, uScattering, lightNum, uLight, &dout);
+                            estimate_direct_lazy<mat_kinds(MAT)>(R, slot, is, bsdf, uScattering, lightNum, uLight, &dout);
                             pend = dout.pend;
                             if (pend) {
                                 // beta as it is before this vertex's BSDF sample scales it
@@ -2027,8 +2036,8 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
                     int flags = 0;
                     float u2[2];
                     get2d(sp, st, u2);
-                    const FSpec f = bsdf_sample_f_lazy(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
-                    if (!(fspec_is_black(f, 1.f) || pdf == 0.f)) {
+                    const FSpec f = bsdf_sample_f_lazy<mat_kinds(MAT)>(bsdf, wo, &wi, u2, &pdf, BSDF_ALL, &flags);
+                    if (!(fspec_is_black<mat_kinds(MAT)>(f, 1.f) || pdf == 0.f)) {
                         const float ad = absdot(wi, bsdf.ns);
                         const bool spec = (flags & BSDF_SPECULAR) != 0;
                         if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
@@ -2042,7 +2051,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(const RenderDev *R, int bounce
 #pragma unroll 1
                         for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
                             float fv[4];
-                            fspec_eval4(f, b0, fv);
+                            fspec_eval4<mat_kinds(MAT)>(f, b0, fv);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float nb = sBeta[(size_t)(b0 + j) * cap] * ((fv[j] * ad) / pdf);

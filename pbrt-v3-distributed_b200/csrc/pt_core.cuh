@@ -771,7 +771,7 @@ B200_HD float tr_pdf(const TRDist &d, const V3 &wo, const V3 &wh) {
 }
 // microfacet.cpp:238-283.  The normal-incidence branch calls the C `cos`/`sin`
 // on a float (promoted to double) and multiplies in double.
-B200_HD void tr_sample11(float cosTheta, float U1, float U2, float *slope_x, float *slope_y) {
+B200_HD_L2 void tr_sample11(float cosTheta, float U1, float U2, float *slope_x, float *slope_y) {
     if ((double)cosTheta > .9999) {
         float r = sqrtf(U1 / (1 - U1));
         float phi = (float)(6.28318530718 * (double)U2);
@@ -834,6 +834,22 @@ B200_HD V3 cosine_sample_hemisphere(const float u[2]) {
 // 4 MicrofacetTransmission (TR)
 enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR = 3, BX_MICROFACET_TRANS = 4,
        BX_SPECULAR_REFLECTION = 5 };
+// The lobe kinds a material family can produce (make_bsdf): the per-family shading kernels pass this mask down as a
+// template argument, so each carries only its own BxDFs' code (the lobes themselves stay run-time data).  ncu showed
+// the shading kernels' warps waiting for instruction fetches; the plastic kernel does not need the conductor's
+// Fresnel term, rough-glass transmission or Oren-Nayar.
+#define KM(k) (1 << (k))
+#define KM_DIEL 0x100  // microfacet reflection with FresnelDielectric
+#define KM_COND 0x200  // ... with FresnelConductor
+#define KM_ALL 0x3ff
+B200_HD constexpr int mat_kinds(int material) {
+    return material == 0   ? (KM(BX_LAMBERT) | KM(BX_OREN_NAYAR))                  // B200PT_MAT_MATTE
+           : material == 1 ? (KM(BX_LAMBERT) | KM(BX_MICROFACET) | KM_DIEL)        // B200PT_MAT_PLASTIC
+           : material == 2 ? (KM(BX_MICROFACET) | KM_COND)                         // B200PT_MAT_METAL
+           : material == 3 ? (KM(BX_MICROFACET) | KM_DIEL | KM(BX_MICROFACET_TRANS) | KM(BX_FRESNEL_SPECULAR) |
+                              KM(BX_SPECULAR_REFLECTION))                          // B200PT_MAT_GLASS (smooth, rough, mirror)
+                           : KM_ALL;
+}
 // A lobe's spectra are rows of the material table (or the constant 1).  The RGBSpectrum build keeps them by value in
 // registers; the SampledSpectrum build keeps a pointer to the row -- 60 floats per spectrum copied into every thread's
 // Bsdf were a third of k_shade's 6.4 KB local-memory frame, and the rows are shared by all threads (L1 hits).
@@ -865,22 +881,25 @@ struct Lobe {
     float onA, onB;     // OrenNayar
 };
 B200_HD bool lobe_matches(const Lobe &l, int flags) { return (l.type & flags) == l.type; }
+template <int KINDS = KM_ALL>
 B200_HD Spec lobe_fresnel(const Lobe &l, float cosThetaI) {
-    if (!l.conductor) return rgb1(fr_dielectric(cosThetaI, l.frEtaI, l.frEtaT));  // reflection.cpp:128-130
+    if (!(KINDS & KM_COND) || ((KINDS & KM_DIEL) && !l.conductor))
+        return rgb1(fr_dielectric(cosThetaI, l.frEtaI, l.frEtaT));  // reflection.cpp:128-130
     return fr_conductor(pt_abs(cosThetaI), rgb1(1.f), sval(l.cEta), sval(l.cK));               // reflection.cpp:117-119
 }
-B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
-    if (l.kind == BX_LAMBERT) return sval(l.R) * PT_INV_PI;  // reflection.cpp:178-180
-    if (l.kind == BX_MICROFACET) {                     // reflection.cpp:226-236
+template <int KINDS = KM_ALL>
+B200_HD_L2 Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
+    if ((KINDS & KM(BX_LAMBERT)) && l.kind == BX_LAMBERT) return sval(l.R) * PT_INV_PI;  // reflection.cpp:178-180
+    if ((KINDS & KM(BX_MICROFACET)) && l.kind == BX_MICROFACET) {                     // reflection.cpp:226-236
         float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
         V3 wh = wi + wo;
         if (cosThetaI == 0 || cosThetaO == 0) return rgb1(0.f);
         if (wh.x == 0 && wh.y == 0 && wh.z == 0) return rgb1(0.f);
         wh = normalize(wh);
-        Spec F = lobe_fresnel(l, dot(wi, wh));
+        Spec F = lobe_fresnel<KINDS>(l, dot(wi, wh));
         return sval(l.R) * tr_D(l.dist, wh) * tr_G(l.dist, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
-    if (l.kind == BX_OREN_NAYAR) {  // reflection.cpp:197-219
+    if ((KINDS & KM(BX_OREN_NAYAR)) && l.kind == BX_OREN_NAYAR) {  // reflection.cpp:197-219
         float sinThetaI = sin_theta(wi);
         float sinThetaO = sin_theta(wo);
         float maxCos = 0;
@@ -900,7 +919,7 @@ B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
         }
         return sval(l.R) * PT_INV_PI * (l.onA + l.onB * maxCos * sinAlpha * tanBeta);
     }
-    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:244-266 (TransportMode::Radiance)
+    if ((KINDS & KM(BX_MICROFACET_TRANS)) && l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:244-266 (TransportMode::Radiance)
         if (same_hemisphere(wo, wi)) return rgb1(0.f);
         float cosThetaO = cos_theta(wo);
         float cosThetaI = cos_theta(wi);
@@ -917,10 +936,11 @@ B200_HD Spec lobe_f(const Lobe &l, const V3 &wo, const V3 &wi) {
     }
     return rgb1(0.f);  // FresnelSpecular::f, reflection.h:363-365
 }
-B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
-    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR)
+template <int KINDS = KM_ALL>
+B200_HD_L2 float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
+    if ((KINDS & (KM(BX_LAMBERT) | KM(BX_OREN_NAYAR))) && (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR))
         return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PT_INV_PI : 0.f;  // reflection.cpp:387-389
-    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:436-448
+    if ((KINDS & KM(BX_MICROFACET_TRANS)) && l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:436-448
         if (same_hemisphere(wo, wi)) return 0.f;
         float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
         V3 wh = normalize(wo + wi * eta);
@@ -928,7 +948,7 @@ B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
         float dwh_dwi = pt_abs((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
         return tr_pdf(l.dist, wo, wh) * dwh_dwi;
     }
-    if (l.kind == BX_MICROFACET) {                                                                   // reflection.cpp:419-423
+    if ((KINDS & KM(BX_MICROFACET)) && l.kind == BX_MICROFACET) {                                    // reflection.cpp:419-423
         if (!same_hemisphere(wo, wi)) return 0.f;
         V3 wh = normalize(wo + wi);
         return tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
@@ -936,34 +956,36 @@ B200_HD float lobe_pdf(const Lobe &l, const V3 &wo, const V3 &wi) {
     return 0.f;
 }
 // BxDF::Sample_f; *pdf is written only where the reference writes it.
-B200_HD Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
-    if (l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:425-434
+template <int KINDS = KM_ALL>
+B200_HD_L2 Spec lobe_sample_f(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
+    if ((KINDS & KM(BX_MICROFACET_TRANS)) && l.kind == BX_MICROFACET_TRANS) {  // reflection.cpp:425-434
         if (wo.z == 0) return rgb1(0.f);
         V3 wh = tr_sample_wh(l.dist, wo, u);
         float eta = cos_theta(wo) > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
         if (!refract(wo, wh, eta, wi)) return rgb1(0.f);
-        *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        *pdf = lobe_pdf<KINDS>(l, wo, *wi);
+        return lobe_f<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR) {  // BxDF::Sample_f, reflection.cpp:378-385
+    if ((KINDS & (KM(BX_LAMBERT) | KM(BX_OREN_NAYAR))) && (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR)) {  // BxDF::Sample_f, reflection.cpp:378-385
         *wi = cosine_sample_hemisphere(u);
         if (wo.z < 0) wi->z *= -1;
-        *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_f(l, wo, *wi);
+        *pdf = lobe_pdf<KINDS>(l, wo, *wi);
+        return lobe_f<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_MICROFACET) {  // reflection.cpp:405-417
+    if ((KINDS & KM(BX_MICROFACET)) && l.kind == BX_MICROFACET) {  // reflection.cpp:405-417
         if (wo.z == 0) return rgb1(0.f);
         V3 wh = tr_sample_wh(l.dist, wo, u);
         *wi = reflect(wo, wh);
         if (!same_hemisphere(wo, *wi)) return rgb1(0.f);
         *pdf = tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
-        return lobe_f(l, wo, *wi);
+        return lobe_f<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_SPECULAR_REFLECTION) {  // reflection.cpp:136-143 with FresnelNoOp (mirror.cpp:45-56)
+    if ((KINDS & KM(BX_SPECULAR_REFLECTION)) && l.kind == BX_SPECULAR_REFLECTION) {  // reflection.cpp:136-143 with FresnelNoOp (mirror.cpp:45-56)
         *wi = mk(-wo.x, -wo.y, wo.z);
         *pdf = 1.f;
         return rgb1(1.f) * sval(l.R) / abs_cos_theta(*wi);
     }
+    if (!(KINDS & KM(BX_FRESNEL_SPECULAR))) return rgb1(0.f);  // (no such lobe in this family)
     // FresnelSpecular::Sample_f, reflection.cpp:477-511 (TransportMode::Radiance)
     float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
     if (u[0] < F) {
@@ -1004,7 +1026,8 @@ B200_HD int bsdf_num_components(const Bsdf &b, int flags) {
     return num;
 }
 // reflection.cpp:670-683
-B200_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+template <int KINDS = KM_ALL>
+B200_HD_L1 Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     V3 wi = world_to_local(b, wiW), wo = world_to_local(b, woW);
     if (wo.z == 0) return rgb1(0.f);
     bool refl = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
@@ -1012,11 +1035,12 @@ B200_HD Spec bsdf_f(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     for (int i = 0; i < b.n; ++i)
         if (lobe_matches(b.lobes[i], flags) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
                                                 (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
-            f = f + lobe_f(b.lobes[i], wo, wi);
+            f = f + lobe_f<KINDS>(b.lobes[i], wo, wi);
     return f;
 }
 // reflection.cpp:770-785
-B200_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+template <int KINDS = KM_ALL>
+B200_HD_L1 float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     if (b.n == 0) return 0.f;
     V3 wo = world_to_local(b, woW), wi = world_to_local(b, wiW);
     if (wo.z == 0) return 0.f;
@@ -1025,12 +1049,13 @@ B200_HD float bsdf_pdf(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     for (int i = 0; i < b.n; ++i)
         if (lobe_matches(b.lobes[i], flags)) {
             ++matching;
-            pdf += lobe_pdf(b.lobes[i], wo, wi);
+            pdf += lobe_pdf<KINDS>(b.lobes[i], wo, wi);
         }
     return matching > 0 ? pdf / matching : 0.f;
 }
 // reflection.cpp:703-768
-B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type,
+template <int KINDS = KM_ALL>
+B200_HD_L1 Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type,
                           int *sampledType) {
     int matching = bsdf_num_components(b, type);
     if (matching == 0) {
@@ -1051,7 +1076,7 @@ B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[
     if (wo.z == 0) return rgb1(0.f);
     *pdf = 0;
     *sampledType = lobe.type;
-    Spec f = lobe_sample_f(lobe, wo, &wi, ur, pdf, sampledType);
+    Spec f = lobe_sample_f<KINDS>(lobe, wo, &wi, ur, pdf, sampledType);
     if (*pdf == 0) {
         *sampledType = 0;
         return rgb1(0.f);
@@ -1059,7 +1084,7 @@ B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[
     *wiW = local_to_world(b, wi);
     if (!(lobe.type & BSDF_SPECULAR) && matching > 1)
         for (int i = 0; i < b.n; ++i)
-            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf<KINDS>(b.lobes[i], wo, wi);
     if (matching > 1) *pdf /= matching;
     if (!(lobe.type & BSDF_SPECULAR)) {
         bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
@@ -1067,7 +1092,7 @@ B200_HD Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[
         for (int i = 0; i < b.n; ++i)
             if (lobe_matches(b.lobes[i], type) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
                                                    (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
-                f = f + lobe_f(b.lobes[i], wo, wi);
+                f = f + lobe_f<KINDS>(b.lobes[i], wo, wi);
     }
     return f;
 }
@@ -1112,41 +1137,58 @@ B200_HD float fr_conductor_bin(float c, float c2, float s2, float etat, float kk
     return (Rp + Rs) * 0.5f;
 }
 // bins [b0, b0 + 4) of a term
+template <int KINDS = KM_ALL>
 B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
     float x[4];
     PT_UNROLL
     for (int j = 0; j < 4; ++j) x[j] = t.r ? t.r[b0 + j] : 1.f;
-    switch (t.op) {
+    // (cases of BxDFs this family cannot have are compiled out)
+    const int op = ((t.op == LT_ROW_S && !(KINDS & KM(BX_LAMBERT))) || (t.op == LT_ROW_S2 && !(KINDS & KM(BX_OREN_NAYAR))) ||
+                    (t.op == LT_MF_DIEL && !(KINDS & KM_DIEL)) || (t.op == LT_MF_COND && !(KINDS & KM_COND)) ||
+                    (t.op == LT_MFT && !(KINDS & KM(BX_MICROFACET_TRANS))) ||
+                    (t.op == LT_SPEC_R && !(KINDS & KM(BX_SPECULAR_REFLECTION))) ||
+                    ((t.op == LT_FS_R || t.op == LT_FS_T) && !(KINDS & KM(BX_FRESNEL_SPECULAR))))
+                       ? LT_ZERO
+                       : t.op;
+    switch (op) {
     case LT_ROW_S:  // LambertianReflection::f
+        if (!(KINDS & KM(BX_LAMBERT))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = x[j] * t.s0;
         break;
     case LT_ROW_S2:  // OrenNayar::f
+        if (!(KINDS & KM(BX_OREN_NAYAR))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = (x[j] * t.s0) * t.s1;
         break;
     case LT_MF_DIEL:  // MicrofacetReflection::f with FresnelDielectric: R * D * G * F / (4 cosI cosO)
+        if (!(KINDS & KM_DIEL)) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = (((x[j] * t.s0) * t.s1) * t.s2) / t.s3;
         break;
     case LT_MF_COND:  // ... with FresnelConductor
+        if (!(KINDS & KM_COND)) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j)
             v[j] = (((x[j] * t.s0) * t.s1) * fr_conductor_bin(t.s2, t.s4, t.s5, t.eta[b0 + j], t.k[b0 + j])) / t.s3;
         break;
     case LT_MFT:  // MicrofacetTransmission::f: (1 - F) * T * scalar
+        if (!(KINDS & KM(BX_MICROFACET_TRANS))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = ((1.f - t.s0) * x[j]) * t.s1;
         break;
     case LT_SPEC_R:  // SpecularReflection::Sample_f with FresnelNoOp: 1 * R / |cos|
+        if (!(KINDS & KM(BX_SPECULAR_REFLECTION))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = (1.f * x[j]) / t.s0;
         break;
     case LT_FS_R:  // FresnelSpecular::Sample_f, reflection: F * R / |cos|
+        if (!(KINDS & KM(BX_FRESNEL_SPECULAR))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = (x[j] * t.s0) / t.s1;
         break;
     case LT_FS_T:  // ... transmission: T * (1 - F) * (etaI^2 / etaT^2) / |cos|
+        if (!(KINDS & KM(BX_FRESNEL_SPECULAR))) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = ((x[j] * t.s0) * t.s1) / t.s2;
         break;
@@ -1157,15 +1199,16 @@ B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
     }
 }
 // lobe_f as a recipe
+template <int KINDS = KM_ALL>
 B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
     LTerm t = lterm_zero();
-    if (l.kind == BX_LAMBERT) {
+    if ((KINDS & KM(BX_LAMBERT)) && l.kind == BX_LAMBERT) {
         t.op = LT_ROW_S;
         t.r = l.R.p;
         t.s0 = PT_INV_PI;
         return t;
     }
-    if (l.kind == BX_MICROFACET) {
+    if ((KINDS & KM(BX_MICROFACET)) && l.kind == BX_MICROFACET) {
         float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
         V3 wh = wi + wo;
         if (cosThetaI == 0 || cosThetaO == 0) return t;
@@ -1176,7 +1219,7 @@ B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
         t.s1 = tr_G(l.dist, wo, wi);
         t.s3 = 4 * cosThetaI * cosThetaO;
         const float cosF = dot(wi, wh);
-        if (!l.conductor) {
+        if (!(KINDS & KM_COND) || ((KINDS & KM_DIEL) && !l.conductor)) {
             t.op = LT_MF_DIEL;
             t.s2 = fr_dielectric(cosF, l.frEtaI, l.frEtaT);
         } else {
@@ -1190,7 +1233,7 @@ B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
         }
         return t;
     }
-    if (l.kind == BX_OREN_NAYAR) {
+    if ((KINDS & KM(BX_OREN_NAYAR)) && l.kind == BX_OREN_NAYAR) {
         float sinThetaI = sin_theta(wi);
         float sinThetaO = sin_theta(wo);
         float maxCos = 0;
@@ -1214,7 +1257,7 @@ B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
         t.s1 = l.onA + l.onB * maxCos * sinAlpha * tanBeta;
         return t;
     }
-    if (l.kind == BX_MICROFACET_TRANS) {
+    if ((KINDS & KM(BX_MICROFACET_TRANS)) && l.kind == BX_MICROFACET_TRANS) {
         if (same_hemisphere(wo, wi)) return t;
         float cosThetaO = cos_theta(wo);
         float cosThetaI = cos_theta(wi);
@@ -1234,31 +1277,32 @@ B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
     return t;  // FresnelSpecular::f, SpecularReflection::f
 }
 // lobe_sample_f as a recipe
+template <int KINDS = KM_ALL>
 B200_HD LTerm lobe_sample_term(const Lobe &l, const V3 &wo, V3 *wi, const float u[2], float *pdf, int *sampledType) {
     LTerm t = lterm_zero();
-    if (l.kind == BX_MICROFACET_TRANS) {
+    if ((KINDS & KM(BX_MICROFACET_TRANS)) && l.kind == BX_MICROFACET_TRANS) {
         if (wo.z == 0) return t;
         V3 wh = tr_sample_wh(l.dist, wo, u);
         float eta = cos_theta(wo) > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
         if (!refract(wo, wh, eta, wi)) return t;
-        *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_term(l, wo, *wi);
+        *pdf = lobe_pdf<KINDS>(l, wo, *wi);
+        return lobe_term<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR) {
+    if ((KINDS & (KM(BX_LAMBERT) | KM(BX_OREN_NAYAR))) && (l.kind == BX_LAMBERT || l.kind == BX_OREN_NAYAR)) {
         *wi = cosine_sample_hemisphere(u);
         if (wo.z < 0) wi->z *= -1;
-        *pdf = lobe_pdf(l, wo, *wi);
-        return lobe_term(l, wo, *wi);
+        *pdf = lobe_pdf<KINDS>(l, wo, *wi);
+        return lobe_term<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_MICROFACET) {
+    if ((KINDS & KM(BX_MICROFACET)) && l.kind == BX_MICROFACET) {
         if (wo.z == 0) return t;
         V3 wh = tr_sample_wh(l.dist, wo, u);
         *wi = reflect(wo, wh);
         if (!same_hemisphere(wo, *wi)) return t;
         *pdf = tr_pdf(l.dist, wo, wh) / (4 * dot(wo, wh));
-        return lobe_term(l, wo, *wi);
+        return lobe_term<KINDS>(l, wo, *wi);
     }
-    if (l.kind == BX_SPECULAR_REFLECTION) {
+    if ((KINDS & KM(BX_SPECULAR_REFLECTION)) && l.kind == BX_SPECULAR_REFLECTION) {
         *wi = mk(-wo.x, -wo.y, wo.z);
         *pdf = 1.f;
         t.op = LT_SPEC_R;
@@ -1266,6 +1310,7 @@ B200_HD LTerm lobe_sample_term(const Lobe &l, const V3 &wo, V3 *wi, const float 
         t.s0 = abs_cos_theta(*wi);
         return t;
     }
+    if (!(KINDS & KM(BX_FRESNEL_SPECULAR))) return t;
     float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
     if (u[0] < F) {
         *wi = mk(-wo.x, -wo.y, wo.z);
@@ -1305,29 +1350,31 @@ B200_HD FSpec fspec_zero() {
     f.t[0] = f.t[1] = lterm_zero();
     return f;
 }
-B200_HD void fspec_eval4(const FSpec &f, int b0, float v[4]) {
+template <int KINDS = KM_ALL>
+B200_HD_S60 void fspec_eval4(const FSpec &f, int b0, float v[4]) {
     if (f.n == 0) {
         v[0] = v[1] = v[2] = v[3] = 0.f;
         return;
     }
-    lterm_eval4(f.t[0], b0, v);
+    lterm_eval4<KINDS>(f.t[0], b0, v);
     if (f.from_zero) {
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = 0.f + v[j];
     }
     if (f.n > 1) {
         float w[4];
-        lterm_eval4(f.t[1], b0, w);
+        lterm_eval4<KINDS>(f.t[1], b0, w);
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = v[j] + w[j];
     }
 }
 // is_black(f * s) without materialising it
+template <int KINDS = KM_ALL>
 B200_HD bool fspec_is_black(const FSpec &f, float s) {
     if (f.n == 0) return true;
     for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
         float v[4];
-        fspec_eval4(f, b0, v);
+        fspec_eval4<KINDS>(f, b0, v);
         if (v[0] * s != 0.f || v[1] * s != 0.f || v[2] * s != 0.f || v[3] * s != 0.f) return false;
     }
     return true;
@@ -1338,7 +1385,8 @@ B200_HD bool row_is_black(const float *p) {
     return true;
 }
 // bsdf_f (reflection.cpp:670-683) as a recipe
-B200_HD FSpec bsdf_f_lazy(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
+template <int KINDS = KM_ALL>
+B200_HD_L1 FSpec bsdf_f_lazy(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags) {
     FSpec f = fspec_zero();
     V3 wi = world_to_local(b, wiW), wo = world_to_local(b, woW);
     if (wo.z == 0) return f;
@@ -1346,11 +1394,12 @@ B200_HD FSpec bsdf_f_lazy(const Bsdf &b, const V3 &woW, const V3 &wiW, int flags
     for (int i = 0; i < b.n; ++i)
         if (lobe_matches(b.lobes[i], flags) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
                                                 (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
-            f.t[f.n++] = lobe_term(b.lobes[i], wo, wi);
+            f.t[f.n++] = lobe_term<KINDS>(b.lobes[i], wo, wi);
     return f;
 }
 // bsdf_sample_f (reflection.cpp:703-768) as a recipe
-B200_HD FSpec bsdf_sample_f_lazy(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type, int *sampledType) {
+template <int KINDS = KM_ALL>
+B200_HD_L1 FSpec bsdf_sample_f_lazy(const Bsdf &b, const V3 &woW, V3 *wiW, const float u[2], float *pdf, int type, int *sampledType) {
     FSpec f = fspec_zero();
     int matching = bsdf_num_components(b, type);
     if (matching == 0) {
@@ -1371,7 +1420,7 @@ B200_HD FSpec bsdf_sample_f_lazy(const Bsdf &b, const V3 &woW, V3 *wiW, const fl
     if (wo.z == 0) return f;
     *pdf = 0;
     *sampledType = lobe.type;
-    const LTerm ts = lobe_sample_term(lobe, wo, &wi, ur, pdf, sampledType);
+    const LTerm ts = lobe_sample_term<KINDS>(lobe, wo, &wi, ur, pdf, sampledType);
     if (*pdf == 0) {
         *sampledType = 0;
         return f;
@@ -1379,14 +1428,14 @@ B200_HD FSpec bsdf_sample_f_lazy(const Bsdf &b, const V3 &woW, V3 *wiW, const fl
     *wiW = local_to_world(b, wi);
     if (!(lobe.type & BSDF_SPECULAR) && matching > 1)
         for (int i = 0; i < b.n; ++i)
-            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+            if (i != which && lobe_matches(b.lobes[i], type)) *pdf += lobe_pdf<KINDS>(b.lobes[i], wo, wi);
     if (matching > 1) *pdf /= matching;
     if (!(lobe.type & BSDF_SPECULAR)) {
         bool refl = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
         for (int i = 0; i < b.n; ++i)
             if (lobe_matches(b.lobes[i], type) && ((refl && (b.lobes[i].type & BSDF_REFLECTION)) ||
                                                    (!refl && (b.lobes[i].type & BSDF_TRANSMISSION))))
-                f.t[f.n++] = lobe_term(b.lobes[i], wo, wi);
+                f.t[f.n++] = lobe_term<KINDS>(b.lobes[i], wo, wi);
     } else {
         f.n = 1;
         f.from_zero = 0;

@@ -36,6 +36,27 @@
 #define B200_HD inline
 #define B200_D inline
 #endif
+// Everything above is force-inlined, which made the shading kernels 18-55 k instructions long; ncu showed their warps
+// waiting for instruction fetches (profiles/README.md).  B200PT_OUTLINE >= 1 keeps one copy of the BSDF entry points
+// (bsdf_f / bsdf_pdf / bsdf_sample_f), >= 2 also of the lobe functions and the microfacet sampling routine.  Inlining never changes a result bit (no contraction, no fast math).
+#ifndef B200PT_OUTLINE
+#define B200PT_OUTLINE 0
+#endif
+#if defined(__CUDACC__) && B200PT_OUTLINE >= 1
+#define B200_HD_L1 inline __host__ __device__ __noinline__
+#else
+#define B200_HD_L1 B200_HD
+#endif
+#if defined(__CUDACC__) && B200PT_OUTLINE >= 2
+#define B200_HD_L2 inline __host__ __device__ __noinline__
+#else
+#define B200_HD_L2 B200_HD
+#endif
+#if defined(__CUDACC__) && defined(B200PT_S60_OUTLINE)
+#define B200_HD_S60 inline __host__ __device__ __noinline__
+#else
+#define B200_HD_S60 B200_HD
+#endif
 
 namespace B200PT_NS {
 
