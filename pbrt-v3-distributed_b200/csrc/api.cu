@@ -1125,8 +1125,9 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     }
 
     // batch sizing: whole tiles, about B200PT_BATCH_PATHS path slots
-    // path slots per batch: ~200 B each, plus 5 x 60 floats with a SampledSpectrum host
-    size_t target = scene->nspec ? (4u << 20) : (16u << 20);
+    // path slots per batch: ~200 B each, plus 5 x 60 floats with a SampledSpectrum host (16 Mi slots = 23 GB there; with
+    // 4 Mi-slot batches the traversal launches of cfg5 took 45 % longer: 1149 against 793 ms per step, call S)
+    size_t target = 16u << 20;
     if (const char *e = getenv("B200PT_BATCH_PATHS")) target = (size_t)atoll(e);
     const size_t per_tile = 256u * (size_t)r->spp;
     r->tiles_per_batch = (uint32_t)std::max<size_t>(1, target / per_tile);
@@ -1326,8 +1327,8 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     CUDA_TRY(cudaStreamSynchronize(st));
     r->grid_trace = ctx->sm_count;  // launch_trace multiplies by its CTAs per SM
     r->grid_shade = ctx->sm_count * 8;
-    // 60-bin shading kernels keep their spectra in local memory (6.4 KB per thread): the number of resident CTAs decides
-    // whether that working set stays in L2 (B200PT_S60_SHADE_CTAS per SM; measured in profiles/README.md)
+    // grid of the 60-bin shading kernels in CTAs per SM (B200PT_S60_SHADE_CTAS; a knob from the time they kept their
+    // spectra in 6.4 KB local-memory frames, profiles/README.md -- with lazy spectra the frame is 1.1 KB)
     r->grid_shade_s60 = ctx->sm_count * (getenv("B200PT_S60_SHADE_CTAS") ? std::max(1, atoi(getenv("B200PT_S60_SHADE_CTAS"))) : 8);
     if (getenv("B200PT_INSTRUMENT")) r->instrumented = atoi(getenv("B200PT_INSTRUMENT")) != 0;
     if (getenv("B200PT_PROFILE")) r->profiling = atoi(getenv("B200PT_PROFILE")) != 0;

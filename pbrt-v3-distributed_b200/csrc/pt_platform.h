@@ -39,8 +39,10 @@
 // Everything above is force-inlined, which made the shading kernels 18-55 k instructions long; ncu showed their warps
 // waiting for instruction fetches (profiles/README.md).  B200PT_OUTLINE >= 1 keeps one copy of the BSDF entry points
 // (bsdf_f / bsdf_pdf / bsdf_sample_f), >= 2 also of the lobe functions and the microfacet sampling routine.  Inlining never changes a result bit (no contraction, no fast math).
+// Measured on cfg4 (profiles/README.md, call S): shading + raygen + film of three batches 63.6 ms all inlined, 53.4-55.2 ms
+// at level 1, 54.7 ms at level 2 -> level 1 is the default.
 #ifndef B200PT_OUTLINE
-#define B200PT_OUTLINE 0
+#define B200PT_OUTLINE 1
 #endif
 #if defined(__CUDACC__) && B200PT_OUTLINE >= 1
 #define B200_HD_L1 inline __host__ __device__ __noinline__

@@ -22,6 +22,8 @@ from pbrt_v3_distributed_b200 import scenes  # noqa: E402
 
 n_tris, mats, xres, yres, spp, depth, n_lights, _ = bench.WORKLOADS[name]
 arr = scenes.SceneArrays(n_tris, materials=mats, soup_version=1, n_lights=n_lights, **bench.workload_scene_kwargs(name))
+if name in bench.SPECTRAL_WORKLOADS:
+    arr.attach_spectral(bench.spectral_tables())  # 60-bin host: the SampledSpectrum kernels
 # PROFILE_PIXEL_FILTER=gaussian profiles the general film path, PROFILE_BVH=gpu the on-device builder
 setup = scenes.RenderSetup(xres, yres, spp, max_depth=depth, pixel_filter=os.environ.get("PROFILE_PIXEL_FILTER"))
 ctx = pkg.Context(0)
