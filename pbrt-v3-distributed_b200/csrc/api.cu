@@ -1951,9 +1951,9 @@ int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *
         std::vector<float> bins((size_t)r->spp * (size_t)std::max(ns, 1));
         cudaError_t e = cudaMemcpyAsync(tmp.data(), H.L + (size_t)pix * r->spp, (size_t)r->spp * sizeof(float4),
                                         cudaMemcpyDeviceToHost, st);
-        for (int b = 0; b < ns && e == cudaSuccess; ++b)  // planar [bin][capacity]
-            e = cudaMemcpyAsync(bins.data() + (size_t)b * r->spp, H.s_L + (size_t)b * H.capacity + (size_t)pix * r->spp,
-                                (size_t)r->spp * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (ns && e == cudaSuccess)  // slot-major [capacity][bins]: the pixel's samples are consecutive slots
+            e = cudaMemcpyAsync(bins.data(), H.s_L + (size_t)pix * r->spp * ns, (size_t)r->spp * ns * sizeof(float),
+                                cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(H.film, saved, npx * sizeof(float4), cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = b200pt_fail(B200PT_ERR_CUDA, "debug_pixel_samples: %s", cudaGetErrorString(e));
@@ -1970,7 +1970,7 @@ int b200pt_debug_pixel_samples(b200pt_render *r, int32_t px, int32_t py, float *
             std::vector<float> L((size_t)ns);
             bool nan = false;
             for (int b = 0; b < ns; ++b) {
-                L[b] = bins[(size_t)b * r->spp + i];
+                L[b] = bins[(size_t)i * ns + b];
                 nan = nan || pt_isnan(L[b]);
             }
             const float y = host_spectrum_y(r->scene, L);

@@ -22,7 +22,10 @@ __device__ __forceinline__ V3 v3(const float4 &f) { return mk(f.x, f.y, f.z); }
 __device__ __forceinline__ V3 v3(const F4 &f) { return mk(f.x, f.y, f.z); }
 __device__ __forceinline__ float4 f4(const V3 &v, float w) { return make_float4(v.x, v.y, v.z, w); }
 // A per-slot spectrum travels with one packed scalar.  RGBSpectrum build: one float4 (r, g, b, w).  SampledSpectrum
-// build: the float4 keeps only w and the 60 bins live in a planar array [bin][capacity] (coalesced across slots).
+// build: the float4 keeps only w and the 60 bins live slot-major in a second array, [capacity][60] (240 contiguous bytes
+// per slot, read and written as float4s).  A [bin][capacity] layout would coalesce only if a warp's slots were neighbours;
+// the slots of a BSDF family's queue are scattered, every 4-byte access then cost a 32-byte sector, and ncu showed the
+// 60-bin shading kernels waiting on 2.1-3.1 TB/s of DRAM traffic (profiles/README.md, call T).
 __device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *planar, uint32_t cap, uint32_t slot, float *w) {
     const float4 f = a4[slot];
     *w = f.w;
@@ -31,9 +34,17 @@ __device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *planar, u
     (void)cap;
     return rgb(f.x, f.y, f.z);
 #else
+    (void)cap;
     Spec s;
+    const float4 *p4 = reinterpret_cast<const float4 *>(planar + (size_t)slot * B200PT_NSPEC);
 #pragma unroll
-    SPEC_FOR s.c[i_] = planar[(size_t)i_ * cap + slot];
+    for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
+        const float4 v = p4[q];
+        s.c[4 * q] = v.x;
+        s.c[4 * q + 1] = v.y;
+        s.c[4 * q + 2] = v.z;
+        s.c[4 * q + 3] = v.w;
+    }
     return s;
 #endif
 }
@@ -43,9 +54,11 @@ __device__ __forceinline__ void st_spec(float4 *a4, float *planar, uint32_t cap,
     (void)cap;
     a4[slot] = make_float4(s.c[0], s.c[1], s.c[2], w);
 #else
+    (void)cap;
     a4[slot] = make_float4(0.f, 0.f, 0.f, w);
+    float4 *p4 = reinterpret_cast<float4 *>(planar + (size_t)slot * B200PT_NSPEC);
 #pragma unroll
-    SPEC_FOR planar[(size_t)i_ * cap + slot] = s.c[i_];
+    for (int q = 0; q < B200PT_NSPEC / 4; ++q) p4[q] = make_float4(s.c[4 * q], s.c[4 * q + 1], s.c[4 * q + 2], s.c[4 * q + 3]);
 #endif
 }
 // Lemit / I / L of light `lightNum` (b200pt_area_light::lemit, or its row of b200pt_scene_desc::light_spectra)
@@ -1514,12 +1527,43 @@ __global__ void __launch_bounds__(128, B200PT_SHADE_MINCTAS) k_shade(const Rende
     uint32_t *qc_mis = &R->qcount[bounce * Q_PER_BOUNCE + Q_MIS];
     uint32_t *q_next = R->q_path[(bounce + 1) & 1];
     uint32_t i;
+#if defined(B200PT_SHADE_PREFETCH) && !defined(B200PT_HOST_EMU)
+    // A/B build: the next work item is fetched one iteration ahead and its state (slot record, hit triangle) is pulled
+    // towards the SM while the current vertex is shaded -- the chain queue -> slot -> hit -> triangle is four dependent
+    // DRAM accesses otherwise
+    uint32_t i_next = 0, slot_next = 0, hit_next = B200PT_MISS;
+    bool have = warp_fetch(work, n, &i_next);
+    if (have && i_next < n) {
+        slot_next = queue[i_next];
+        hit_next = R->hit[slot_next];
+    }
+    while (have) {
+        i = i_next;
+        const uint32_t slot_cur = slot_next;
+        have = warp_fetch(work, n, &i_next);
+        slot_next = 0;
+        hit_next = B200PT_MISS;
+        if (have && i_next < n) {
+            slot_next = queue[i_next];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(R->ray_o + slot_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(R->ray_d + slot_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(R->beta + slot_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(R->L + slot_next));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(R->sobol + slot_next));
+            hit_next = R->hit[slot_next];
+        }
+#else
     while (warp_fetch(work, n, &i)) {
+#endif
         const bool active = i < n;
         bool cont = false;
         uint32_t pend = 0, slot = 0;
         if (active) {
+#if defined(B200PT_SHADE_PREFETCH) && !defined(B200PT_HOST_EMU)
+            slot = slot_cur;
+#else
             slot = queue[i];
+#endif
             const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
             float betaW, LW;
             Spec beta = ld_spec(R->beta, R->s_beta, R->capacity, slot, &betaW);
@@ -1668,6 +1712,13 @@ __global__ void __launch_bounds__(128, B200PT_SHADE_MINCTAS) k_shade(const Rende
         if (pend & PEND_BSDF) R->q_mis[pm] = slot;
         const uint32_t pn = warp_append(qc_next, cont);
         if (cont) q_next[pn] = slot;
+#if defined(B200PT_SHADE_PREFETCH) && !defined(B200PT_HOST_EMU)
+        if (hit_next != B200PT_MISS && !is_sphere_hit(hit_next)) {
+            const F4 *tp = R->scene.tris + (size_t)hit_next * 3;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + 2));
+        }
+#endif
     }
 }
 
@@ -1713,8 +1764,8 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
                                      int lightNum, const float uLight[2], DirectLazy *out) {
     const bool medium = R->has_medium != 0;
     const float *sigmaT = medium ? R->med_spectra + B200PT_NSPEC : nullptr;
-    const uint32_t cap = R->capacity;
-    float *sA = R->s_A + slot, *sB = R->s_B + slot;
+    float4 *sA = reinterpret_cast<float4 *>(R->s_A + (size_t)slot * B200PT_NSPEC);
+    float4 *sB = reinterpret_cast<float4 *>(R->s_B + (size_t)slot * B200PT_NSPEC);
     out->pend = 0;
     out->sh_o = out->sh_d = out->mi_o = out->mi_d = mk(0.f, 0.f, 0.f);
     const DevLight &lightRef = R->lights[lightNum];
@@ -1772,8 +1823,8 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
                     float fv[4], lv[4];
                     fspec_eval4<KINDS>(fD, b0, fv);
                     li_eval4(Li, b0, lv);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = ((fv[j] * ad) * lv[j]) / 1.f;
+                    sA[b0 >> 2] = make_float4(((fv[0] * ad) * lv[0]) / 1.f, ((fv[1] * ad) * lv[1]) / 1.f, ((fv[2] * ad) * lv[2]) / 1.f,
+                                              ((fv[3] * ad) * lv[3]) / 1.f);
                 }
                 out->pend |= PEND_LIGHT;
             }
@@ -1842,8 +1893,10 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
                 float fv[4], lv[4];
                 fspec_eval4<KINDS>(f, b0, fv);
                 li_eval4(Li, b0, lv);
+                float av[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sA[(size_t)(b0 + j) * cap] = (((fv[j] * ad) * lv[j]) * weight) / lightPdf;
+                for (int j = 0; j < 4; ++j) av[j] = (((fv[j] * ad) * lv[j]) * weight) / lightPdf;
+                sA[b0 >> 2] = make_float4(av[0], av[1], av[2], av[3]);
             }
             out->pend |= PEND_LIGHT;
         }
@@ -1890,6 +1943,7 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
                     fspec_eval4<KINDS>(f, b0, fv);
                     li_eval4(Le, b0, lv);
                 }
+                float bv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float bval = 0.f;
@@ -1897,8 +1951,9 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
                         const float tr = medium ? pt_expf((-sigmaT[b0 + j]) * xTr) : 1.f;
                         bval = ((((fv[j] * ad) * lv[j]) * tr) * weight) / scatteringPdf;
                     }
-                    sB[(size_t)(b0 + j) * cap] = bval;
+                    bv[j] = bval;
                 }
+                sB[b0 >> 2] = make_float4(bv[0], bv[1], bv[2], bv[3]);
             }
             out->mi_o = ro;
             out->mi_d = wi;
@@ -1919,7 +1974,6 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
     uint32_t *qc_shadow = &R->qcount[bounce * Q_PER_BOUNCE + Q_SHADOW];
     uint32_t *qc_mis = &R->qcount[bounce * Q_PER_BOUNCE + Q_MIS];
     uint32_t *q_next = R->q_path[(bounce + 1) & 1];
-    const uint32_t cap = R->capacity;
     uint32_t i;
     while (warp_fetch(work, n, &i)) {
         const bool active = i < n;
@@ -1928,7 +1982,8 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
         if (active) {
             slot = queue[i];
             const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
-            float *sBeta = R->s_beta + slot, *sL = R->s_L + slot;
+            float4 *sBeta = reinterpret_cast<float4 *>(R->s_beta + (size_t)slot * B200PT_NSPEC);
+            float4 *sL = reinterpret_cast<float4 *>(R->s_L + (size_t)slot * B200PT_NSPEC);
             const V3 ro = v3(o4), rd = v3(d4);
             float etaScale = o4.w;
             const uint32_t meta = __float_as_uint(d4.w);
@@ -1979,8 +2034,12 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
                     const DevLight &lt = R->lights[lightId];
                     if (lt.two_sided || dot(is.n, -rd) > 0) {
                         const float *le = R->light_spectra + (size_t)lightId * B200PT_NSPEC;
-#pragma unroll 4
-                        for (int b = 0; b < B200PT_NSPEC; ++b) sL[(size_t)b * cap] = sL[(size_t)b * cap] + sBeta[(size_t)b * cap] * le[b];
+#pragma unroll 3
+                        for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
+                            const float4 l = sL[q], bt = sBeta[q];
+                            sL[q] = make_float4(l.x + bt.x * le[4 * q], l.y + bt.y * le[4 * q + 1], l.z + bt.z * le[4 * q + 2],
+                                                l.w + bt.w * le[4 * q + 3]);
+                        }
                     } else {
                         // L + beta * 0: only a -0 would change, and L never holds one (it starts at +0 and only sums)
                     }
@@ -2014,9 +2073,9 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
                             pend = dout.pend;
                             if (pend) {
                                 // beta as it is before this vertex's BSDF sample scales it
-                                float *sBl = R->s_beta_ld + slot;
-#pragma unroll 4
-                                for (int b = 0; b < B200PT_NSPEC; ++b) sBl[(size_t)b * cap] = sBeta[(size_t)b * cap];
+                                float4 *sBl = reinterpret_cast<float4 *>(R->s_beta_ld + (size_t)slot * B200PT_NSPEC);
+#pragma unroll 5
+                                for (int q = 0; q < B200PT_NSPEC / 4; ++q) sBl[q] = sBeta[q];
                                 R->beta_ld[slot] = make_float4(0.f, 0.f, 0.f, pickPdf);
                                 R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
                                 if (pend & PEND_LIGHT) R->A[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2052,13 +2111,17 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
                         for (int b0 = 0; b0 < B200PT_NSPEC; b0 += 4) {
                             float fv[4];
                             fspec_eval4<mat_kinds(MAT)>(f, b0, fv);
+                            const float4 bo = sBeta[b0 >> 2];
+                            const float bold[4] = {bo.x, bo.y, bo.z, bo.w};
+                            float nbv[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float nb = sBeta[(size_t)(b0 + j) * cap] * ((fv[j] * ad) / pdf);
-                                sBeta[(size_t)(b0 + j) * cap] = nb;
+                                const float nb = bold[j] * ((fv[j] * ad) / pdf);
+                                nbv[j] = nb;
                                 const float rr = nb * etaScale;
                                 mx = (b0 + j == 0) ? rr : pt_max(mx, rr);
                             }
+                            sBeta[b0 >> 2] = make_float4(nbv[0], nbv[1], nbv[2], nbv[3]);
                         }
                         if (mx < R->rr_threshold && bounces > 3) {
                             const float q = pt_max(.05f, 1 - mx);
@@ -2066,8 +2129,11 @@ __global__ void __launch_bounds__(128, B200PT_S60_SHADE_MINCTAS) k_shade(const R
                                 cont = false;
                             else {
                                 const float dq = 1 - q;
-#pragma unroll 4
-                                for (int b = 0; b < B200PT_NSPEC; ++b) sBeta[(size_t)b * cap] = sBeta[(size_t)b * cap] / dq;
+#pragma unroll 5
+                                for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
+                                    const float4 v = sBeta[q];
+                                    sBeta[q] = make_float4(v.x / dq, v.y / dq, v.z / dq, v.w / dq);
+                                }
                             }
                         }
                         if (cont) {
@@ -2586,27 +2652,36 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderDev *R, int bounce,
             st_spec(R->L, R->s_L, R->capacity, slot, L, LW);
         }
 #else
-        // 60 bins: streamed through the planar arrays, bin by bin (Ld = 0 + A + B; L += beta_ld * (Ld / pickPdf))
-        const uint32_t cap = R->capacity;
+        // 60 bins: streamed through the slot's rows, bin by bin (Ld = 0 + A + B; L += beta_ld * (Ld / pickPdf))
         const bool takeA = (pend & PEND_LIGHT) && !R->occluded[slot];
         bool takeB = false;
         if (pend & PEND_BSDF) {
             const uint32_t lightNum = __float_as_uint(R->sh_o[slot].w);
             if (R->mis_hit[slot] == R->lights[lightNum].tri) {
-                const float *sB = R->s_B + slot;
-                for (int b = 0; b < B200PT_NSPEC && !takeB; ++b) takeB = sB[(size_t)b * cap] != 0.f;
+                const float *sB = R->s_B + (size_t)slot * B200PT_NSPEC;
+                for (int b = 0; b < B200PT_NSPEC && !takeB; ++b) takeB = sB[b] != 0.f;
             }
         }
         if (takeA || takeB) {
             const float pickPdf = R->beta_ld[slot].w;
-            const float *sA = R->s_A + slot, *sB = R->s_B + slot, *sBl = R->s_beta_ld + slot;
-            float *sL = R->s_L + slot;
-#pragma unroll 4
-            for (int b = 0; b < B200PT_NSPEC; ++b) {
-                float Ld = 0.f;
-                if (takeA) Ld = Ld + sA[(size_t)b * cap];
-                if (takeB) Ld = Ld + sB[(size_t)b * cap];
-                sL[(size_t)b * cap] = sL[(size_t)b * cap] + sBl[(size_t)b * cap] * (Ld / pickPdf);
+            const float4 *sA = reinterpret_cast<const float4 *>(R->s_A + (size_t)slot * B200PT_NSPEC);
+            const float4 *sB = reinterpret_cast<const float4 *>(R->s_B + (size_t)slot * B200PT_NSPEC);
+            const float4 *sBl = reinterpret_cast<const float4 *>(R->s_beta_ld + (size_t)slot * B200PT_NSPEC);
+            float4 *sL = reinterpret_cast<float4 *>(R->s_L + (size_t)slot * B200PT_NSPEC);
+#pragma unroll 3
+            for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
+                float4 Ld = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (takeA) {
+                    const float4 a = sA[q];
+                    Ld = make_float4(Ld.x + a.x, Ld.y + a.y, Ld.z + a.z, Ld.w + a.w);
+                }
+                if (takeB) {
+                    const float4 b = sB[q];
+                    Ld = make_float4(Ld.x + b.x, Ld.y + b.y, Ld.z + b.z, Ld.w + b.w);
+                }
+                const float4 l = sL[q], bl = sBl[q];
+                sL[q] = make_float4(l.x + bl.x * (Ld.x / pickPdf), l.y + bl.y * (Ld.y / pickPdf), l.z + bl.z * (Ld.z / pickPdf),
+                                    l.w + bl.w * (Ld.w / pickPdf));
             }
         }
 #endif

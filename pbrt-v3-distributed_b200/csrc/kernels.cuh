@@ -109,8 +109,8 @@ struct RenderDev {
     float4 *beta_ld;   // beta at the time of the direct-lighting estimate
     uint8_t *occluded; // any-hit result of the shadow ray
     uint32_t *mis_hit; // closest-hit triangle of the MIS ray
-    // SampledSpectrum build only (nullptr otherwise): the bins of beta, L, A, B and beta_ld as planar arrays
-    // [60][capacity]; the float4 arrays above then keep just their fourth component
+    // SampledSpectrum build only (nullptr otherwise): the bins of beta, L, A, B and beta_ld, slot-major [capacity][60]
+    // (240 contiguous bytes per slot, see ld_spec); the float4 arrays above then keep just their fourth component
     float *s_beta, *s_L, *s_A, *s_B, *s_beta_ld;
     const float *light_spectra;  // [n_lights][60]: Lemit / I / L of each light
     uint8_t *pix_bleed;  // [tiles_per_batch*256] pixel has a sample whose box-filter footprint leaves the pixel

@@ -474,3 +474,109 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, str(src), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "LD OK" in r.stdout, r.stdout
+
+
+def test_lazy_spectra_equal_the_eager_bsdf_code_bit_for_bit(tmp_path):
+    """The 60-bin shading kernel evaluates BSDF values from recipes (pt_core.cuh "Lazy spectra": FSpec / LTerm) instead of
+    holding 60-float spectra.  Compiled for the host with B200PT_NSPEC=60: for every material family (smooth / rough glass
+    and the mirror included, random 60-bin rows), bsdf_f_lazy / bsdf_sample_f_lazy -- with the family's lobe-kind mask and
+    with the full mask -- give, bin by bin, exactly the bits of bsdf_f / bsdf_sample_f (and the same pdf, direction, sampled
+    type and is_black decision)."""
+    src = tmp_path / "lazy.cpp"
+    src.write_text(r'''
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#define B200PT_NSPEC 60
+#define B200PT_NS b200pt_s60
+#include "pt_core.cuh"
+using namespace b200pt_s60;
+static std::mt19937 rng(23);
+static float U() { return std::uniform_real_distribution<float>(0.f, 1.f)(rng); }
+static V3 uniformSphere() {
+    float z = 1 - 2 * U(), r = std::sqrt(std::max(0.f, 1 - z * z)), phi = 2 * PT_PI * U();
+    return mk(r * std::cos(phi), r * std::sin(phi), z);
+}
+static int fail = 0;
+template <int KINDS>
+static void compare(const char *name, const Spec &f, const FSpec &l, float s) {
+    bool black = true;
+    for (int b0 = 0; b0 < 60; b0 += 4) {
+        float v[4];
+        fspec_eval4<KINDS>(l, b0, v);
+        for (int j = 0; j < 4; ++j) {
+            if (float_as_uint(v[j]) != float_as_uint(f.c[b0 + j])) {
+                if (++fail < 6) printf("%s: bin %d lazy %a eager %a\n", name, b0 + j, v[j], f.c[b0 + j]);
+            }
+            if (f.c[b0 + j] * s != 0.f) black = false;
+        }
+    }
+    if (fspec_is_black<KINDS>(l, s) != black) { ++fail; printf("%s: is_black differs\n", name); }
+}
+template <int M>
+static void check(const b200pt_material &m, const char *name) {
+    constexpr int K = mat_kinds(M);
+    float rows[5 * 60];
+    for (int i = 0; i < 5 * 60; ++i) rows[i] = 0.05f + 3.5f * U();
+    if (M == B200PT_MAT_PLASTIC || M == B200PT_MAT_MATTE || M == B200PT_MAT_GLASS)
+        for (int i = 0; i < 3 * 60; ++i) rows[i] = U();
+    for (int trial = 0; trial < 40; ++trial) {
+        Isect is;
+        is.n = is.ns = normalize(uniformSphere());
+        V3 a, b;
+        coordinate_system(is.ns, &a, &b);
+        is.sdpdu = a;
+        is.p = is.pError = mk(0.f, 0.f, 0.f);
+        Bsdf bsdf;
+        make_bsdf<M>(m, rows, is, &bsdf);
+        V3 wo = uniformSphere();
+        for (int i = 0; i < 100; ++i) {
+            const V3 wi = uniformSphere();
+            for (int flags : {(int)BSDF_ALL, (int)(BSDF_ALL & ~BSDF_SPECULAR)}) {
+                const Spec f = bsdf_f(bsdf, wo, wi, flags);
+                compare<K>(name, f, bsdf_f_lazy<K>(bsdf, wo, wi, flags), absdot(wi, bsdf.ns));
+                compare<KM_ALL>(name, f, bsdf_f_lazy<KM_ALL>(bsdf, wo, wi, flags), 1.f);
+                float u[2] = {U(), U()};
+                V3 w1 = mk(0.f, 0.f, 0.f), w2 = w1, w3 = w1;
+                float p1 = 0, p2 = 0, p3 = 0;
+                int t1 = 0, t2 = 0, t3 = 0;
+                const Spec fs = bsdf_sample_f(bsdf, wo, &w1, u, &p1, flags, &t1);
+                const FSpec ls = bsdf_sample_f_lazy<K>(bsdf, wo, &w2, u, &p2, flags, &t2);
+                const FSpec la = bsdf_sample_f_lazy<KM_ALL>(bsdf, wo, &w3, u, &p3, flags, &t3);
+                compare<K>(name, fs, ls, 1.f);
+                compare<KM_ALL>(name, fs, la, 1.f);
+                const bool same = float_as_uint(p1) == float_as_uint(p2) && float_as_uint(p1) == float_as_uint(p3) && t1 == t2 && t1 == t3 &&
+                                  (is_black(fs) || (memcmp(&w1, &w2, sizeof(V3)) == 0 && memcmp(&w1, &w3, sizeof(V3)) == 0));
+                if (!same) { if (++fail < 6) printf("%s: sample pdf %a/%a/%a type %d/%d/%d\n", name, p1, p2, p3, t1, t2, t3); }
+            }
+        }
+    }
+}
+int main() {
+    b200pt_material m;
+    memset(&m, 0, sizeof(m)); m.type = B200PT_MAT_MATTE;
+    check<B200PT_MAT_MATTE>(m, "matte");
+    m.variant = 1; m.alpha_x = 0.7f; m.alpha_y = 0.4f;  // OrenNayar A, B
+    check<B200PT_MAT_MATTE>(m, "oren-nayar");
+    memset(&m, 0, sizeof(m)); m.type = B200PT_MAT_PLASTIC; m.alpha_x = m.alpha_y = 0.3f;
+    check<B200PT_MAT_PLASTIC>(m, "plastic");
+    memset(&m, 0, sizeof(m)); m.type = B200PT_MAT_METAL; m.alpha_x = 0.25f; m.alpha_y = 0.4f;
+    check<B200PT_MAT_METAL>(m, "metal");
+    memset(&m, 0, sizeof(m)); m.type = B200PT_MAT_GLASS; m.index = 1.5f;
+    check<B200PT_MAT_GLASS>(m, "glass");
+    m.variant = 1; m.alpha_x = 0.3f; m.alpha_y = 0.2f;
+    check<B200PT_MAT_GLASS>(m, "rough glass");
+    m.variant = 2;
+    check<B200PT_MAT_GLASS>(m, "mirror");
+    check<-1>(m, "run-time family");
+    printf(fail ? "LAZY FAILED (%d)\n" : "LAZY OK\n", fail);
+    return fail != 0;
+}
+''')
+    exe = str(tmp_path / "lazy")
+    inc = os.path.join(ROOT, "pbrt-v3-distributed_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + inc, "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "LAZY OK" in r.stdout, r.stdout[-2000:]
