@@ -1761,7 +1761,10 @@ struct DirectLazy {
 // estimate_direct with the two terms written straight into the slot's planar A / B arrays
 template <int KINDS>
 __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
-                                     int lightNum, const float uLight[2], DirectLazy *out) {
+                                     int lightNum, const float uLight[2], DirectLazy *out, bool inMedium = false) {
+    // inMedium: `is` is a MediumInteraction and the Henyey-Greenstein phase function takes the BSDF's place (its value p is
+    // the constant spectrum Spectrum(p) and there is no cosine: |cos| = 1 multiplies exactly)
+    const float hgG = R->med_g;
     const bool medium = R->has_medium != 0;
     const float *sigmaT = medium ? R->med_spectra + B200PT_NSPEC : nullptr;
     float4 *sA = reinterpret_cast<float4 *>(R->s_A + (size_t)slot * B200PT_NSPEC);
@@ -1808,8 +1811,9 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
             }
         }
         if (!li_is_black(Li)) {
-            const FSpec fD = bsdf_f_lazy<KINDS>(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR);
-            const float ad = absdot(wiD, bsdf.ns);
+            const FSpec fD = inMedium ? fspec_const(phase_hg(dot(is.wo, wiD), hgG))
+                                      : bsdf_f_lazy<KINDS>(bsdf, is.wo, wiD, BSDF_ALL & ~BSDF_SPECULAR);
+            const float ad = inMedium ? 1.f : absdot(wiD, bsdf.ns);
             if (!fspec_is_black<KINDS>(fD, ad)) {
                 const V3 origin = offset_ray_origin(is.p, is.pError, is.n, pTarget - is.p);
                 out->sh_o = origin;
@@ -1875,9 +1879,17 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
         Li.row = (light.two_sided || dot(ps.n, -wi) > 0) ? lrow : nullptr;
     }
     if (lightPdf > 0 && !li_is_black(Li)) {
-        const FSpec f = bsdf_f_lazy<KINDS>(bsdf, is.wo, wi, flagsNS);
-        const float ad = absdot(wi, bsdf.ns);
-        scatteringPdf = bsdf_pdf(bsdf, is.wo, wi, flagsNS);
+        FSpec f;
+        float ad = 1.f;
+        if (inMedium) {
+            const float p = phase_hg(dot(is.wo, wi), hgG);
+            f = fspec_const(p);
+            scatteringPdf = p;
+        } else {
+            f = bsdf_f_lazy<KINDS>(bsdf, is.wo, wi, flagsNS);
+            ad = absdot(wi, bsdf.ns);
+            scatteringPdf = bsdf_pdf<KINDS>(bsdf, is.wo, wi, flagsNS);
+        }
         if (!fspec_is_black<KINDS>(f, ad)) {
             const V3 origin = offset_ray_origin(is.p, is.pError, is.n, ps.p - is.p);
             const V3 target = offset_ray_origin(ps.p, ps.pError, ps.n, origin - ps.p);
@@ -1903,8 +1915,16 @@ __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Is
     }
     // BSDF sampling with MIS
     int sampledType = 0;
-    const FSpec f = bsdf_sample_f_lazy<KINDS>(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
-    const float ad = absdot(wi, bsdf.ns);
+    FSpec f;
+    float ad = 1.f;
+    if (inMedium) {
+        const float p = hg_sample_p(hgG, is.wo, &wi, uScattering);
+        f = fspec_const(p);
+        scatteringPdf = p;
+    } else {
+        f = bsdf_sample_f_lazy<KINDS>(bsdf, is.wo, &wi, uScattering, &scatteringPdf, flagsNS, &sampledType);
+        ad = absdot(wi, bsdf.ns);
+    }
     if (!fspec_is_black<KINDS>(f, ad) && scatteringPdf > 0) {
         const V3 ro = offset_ray_origin(is.p, is.pError, is.n, wi);
         float lpdf = 0.f, tLight = 0.f;
@@ -2169,7 +2189,14 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
     uint32_t *qc = &R->qcount[bounce * Q_PER_BOUNCE];
     uint32_t *qc_next = &R->qcount[(bounce + 1) * Q_PER_BOUNCE + Q_PATH];
     uint32_t *q_next = R->q_path[(bounce + 1) & 1];
+#if B200PT_NSPEC == 3
     const Spec sigmaT = medium_sigma_t(R), sigmaS = medium_sigma_s(R);
+#define PT_SIGMA_T(ch_) sigmaT.c[ch_]
+#else
+    // 60 bins: the medium's rows are read in place and beta is streamed through the slot's row (lazy spectra, see k_shade)
+    const float *sigmaSrow = R->med_spectra, *sigmaTrow = R->med_spectra + B200PT_NSPEC;
+#define PT_SIGMA_T(ch_) sigmaTrow[ch_]
+#endif
     uint32_t i;
     while (warp_fetch(work, n, &i)) {
         const bool active = i < n;
@@ -2179,8 +2206,13 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
         if (active) {
             slot = queue[i];
             const float4 o4 = R->ray_o[slot], d4 = R->ray_d[slot];
+#if B200PT_NSPEC == 3
             float betaW;
             Spec beta = ld_spec(R->beta, R->s_beta, R->capacity, slot, &betaW);
+#else
+            const float betaW = R->beta[slot].w;
+            float4 *sBeta = reinterpret_cast<float4 *>(R->s_beta + (size_t)slot * B200PT_NSPEC);
+#endif
             const V3 ro = v3(o4), rd = v3(d4);
             const float etaScale = o4.w;
             const uint32_t meta = __float_as_uint(d4.w);
@@ -2215,10 +2247,11 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
             const SamplerParams &sp = R->sampler;
             // HomogeneousMedium::Sample
             const int channel = pt_mini((int)(get1d(sp, st) * B200PT_NSPEC), B200PT_NSPEC - 1);
-            const float dist = -pt_logf(1 - get1d(sp, st)) / sigmaT.c[channel];
+            const float dist = -pt_logf(1 - get1d(sp, st)) / PT_SIGMA_T(channel);
             const float rdLen = len(rd);
             const float t = pt_min(dist / rdLen, tHit);
             const bool sampledMedium = t < tHit;
+#if B200PT_NSPEC == 3
             Spec Tr;
             PT_UNROLL SPEC_FOR Tr.c[i_] = pt_expf((-sigmaT.c[i_]) * pt_min(t, PT_MAX_FLOAT) * rdLen);
             const Spec density = sampledMedium ? (sigmaT * Tr) : Tr;
@@ -2227,10 +2260,42 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
             pdf *= 1 / (float)B200PT_NSPEC;
             if (pdf == 0) pdf = 1;
             beta = beta * (sampledMedium ? (Tr * sigmaS / pdf) : (Tr / pdf));
-            if (!is_black(beta)) {
+            const bool alive = !is_black(beta);
+#else
+            // two passes over the bins: the pdf (mean density), then beta *= Tr [* sigma_s] / pdf with the is_black test
+            const float tClamped = pt_min(t, PT_MAX_FLOAT);
+            float pdf = 0.f;
+#pragma unroll 4
+            for (int b = 0; b < B200PT_NSPEC; ++b) {
+                const float tr = pt_expf((-sigmaTrow[b]) * tClamped * rdLen);
+                pdf += sampledMedium ? (sigmaTrow[b] * tr) : tr;
+            }
+            pdf *= 1 / (float)B200PT_NSPEC;
+            if (pdf == 0) pdf = 1;
+            bool alive = false;
+#pragma unroll 1
+            for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
+                const float4 bo = sBeta[q];
+                const float bold[4] = {bo.x, bo.y, bo.z, bo.w};
+                float nb[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int b = 4 * q + j;
+                    const float tr = pt_expf((-sigmaTrow[b]) * tClamped * rdLen);
+                    nb[j] = bold[j] * (sampledMedium ? ((tr * sigmaSrow[b]) / pdf) : (tr / pdf));
+                    alive = alive || nb[j] != 0.f;
+                }
+                sBeta[q] = make_float4(nb[0], nb[1], nb[2], nb[3]);
+            }
+#endif
+            if (alive) {
                 if (!sampledMedium) {
                     // on to the surface vertex (or out of the scene)
+#if B200PT_NSPEC == 3
                     st_spec(R->beta, R->s_beta, R->capacity, slot, beta, betaW);
+#else
+                    R->beta[slot] = make_float4(0.f, 0.f, 0.f, betaW);
+#endif
                     R->ray_d[slot] = f4(rd, __uint_as_float((meta & 0xffff0000u) | ((uint32_t)st.dim & 0xffffu)));
                     if (ti != B200PT_MISS) family = R->scene.materials[mflags & 0xffffu].type;
                 } else if (bounces < R->max_depth) {  // volpath.cpp:84-85
@@ -2255,9 +2320,10 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
                             float uLight[2], uScattering[2];
                             get2d(sp, st, uLight);
                             get2d(sp, st, uScattering);
-                            DirectOut dout;
                             Bsdf none;
                             none.n = 0;
+#if B200PT_NSPEC == 3
+                            DirectOut dout;
                             estimate_direct<true>(R, mi, none, uScattering, lightNum, uLight, &dout, true);
                             pend = dout.pend;
                             if (pend) {
@@ -2270,6 +2336,24 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
                                     st_spec(R->B, R->s_B, R->capacity, slot, dout.B, 0.f);
                                 }
                             }
+#else
+                            DirectLazy dout;
+                            estimate_direct_lazy<KM_ALL>(R, slot, mi, none, uScattering, lightNum, uLight, &dout, true);
+                            pend = dout.pend;
+                            if (pend) {
+                                float4 *sBl = reinterpret_cast<float4 *>(R->s_beta_ld + (size_t)slot * B200PT_NSPEC);
+#pragma unroll 5
+                                for (int q = 0; q < B200PT_NSPEC / 4; ++q) sBl[q] = sBeta[q];
+                                R->beta_ld[slot] = make_float4(0.f, 0.f, 0.f, pickPdf);
+                                R->sh_o[slot] = f4(dout.sh_o, __uint_as_float((uint32_t)lightNum));
+                                if (pend & PEND_LIGHT) R->A[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (pend & PEND_BSDF) {
+                                    R->mi_o[slot] = f4(dout.mi_o, 0.f);
+                                    R->mi_d[slot] = f4(dout.mi_d, 0.f);
+                                    R->B[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#endif
                             R->sh_d[slot] = f4(dout.sh_d, __uint_as_float(pend));
                         }
                     }
@@ -2280,6 +2364,7 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
                     hg_sample_p(R->med_g, mi.wo, &wi, u2);
                     const V3 no = offset_ray_origin(mi.p, mi.pError, mi.n, wi);
                     cont = true;
+#if B200PT_NSPEC == 3
                     const Spec rrBeta = beta * etaScale;  // volpath.cpp:176-184
                     if (max_comp(rrBeta) < R->rr_threshold && bounces > 3) {
                         const float q = pt_max(.05f, 1 - max_comp(rrBeta));
@@ -2288,11 +2373,40 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
                         else
                             beta = beta / (1 - q);
                     }
+#else
+                    if (bounces > 3) {  // volpath.cpp:176-184 (the maximum is only needed then)
+                        float mx = 0.f;
+#pragma unroll 3
+                        for (int q4 = 0; q4 < B200PT_NSPEC / 4; ++q4) {
+                            const float4 v = sBeta[q4];
+                            const float r0 = v.x * etaScale, r1 = v.y * etaScale, r2 = v.z * etaScale, r3 = v.w * etaScale;
+                            mx = q4 == 0 ? r0 : pt_max(mx, r0);
+                            mx = pt_max(pt_max(pt_max(mx, r1), r2), r3);
+                        }
+                        if (mx < R->rr_threshold) {
+                            const float q = pt_max(.05f, 1 - mx);
+                            if (get1d(sp, st) < q)
+                                cont = false;
+                            else {
+                                const float dq = 1 - q;
+#pragma unroll 5
+                                for (int q4 = 0; q4 < B200PT_NSPEC / 4; ++q4) {
+                                    const float4 v = sBeta[q4];
+                                    sBeta[q4] = make_float4(v.x / dq, v.y / dq, v.z / dq, v.w / dq);
+                                }
+                            }
+                        }
+                    }
+#endif
                     if (cont) {
                         const uint32_t nmeta = ((uint32_t)st.dim & 0xffffu) | ((uint32_t)(bounces + 1) << 16);  // specularBounce = false
                         R->ray_o[slot] = f4(no, etaScale);
                         R->ray_d[slot] = f4(wi, __uint_as_float(nmeta));
+#if B200PT_NSPEC == 3
                         st_spec(R->beta, R->s_beta, R->capacity, slot, beta, 0.f);
+#else
+                        R->beta[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
                     }
                 }
             }
@@ -2311,6 +2425,7 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
         if (cont) q_next[pn] = slot;
     }
 }
+#undef PT_SIGMA_T
 
 #if B200PT_MEDIA_GENERAL
 // ---- media bounded by null-material spheres (b200pt_integrator_desc::bounded_media) ------------------------------------

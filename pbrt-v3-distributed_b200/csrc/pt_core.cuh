@@ -1105,7 +1105,7 @@ B200_HD_L1 Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float
 // rows, which scalars, which BxDF formula) in registers and evaluates it bin by bin, four bins at a time, straight
 // from / to the planar per-slot arrays.  The per-bin arithmetic is the eager code's, operation for operation
 // (lobe_f / lobe_sample_f / bsdf_f / bsdf_sample_f above, which follow core/reflection.cpp), so results are bit-identical.
-enum { LT_ZERO = 0, LT_ROW_S, LT_ROW_S2, LT_MF_DIEL, LT_MF_COND, LT_MFT, LT_SPEC_R, LT_FS_R, LT_FS_T };
+enum { LT_ZERO = 0, LT_ROW_S, LT_ROW_S2, LT_MF_DIEL, LT_MF_COND, LT_MFT, LT_SPEC_R, LT_FS_R, LT_FS_T, LT_CONST };
 struct LTerm {
     int op;
     const float *r;        // the lobe's R / T row; nullptr = the constant spectrum 1
@@ -1192,12 +1192,17 @@ B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = ((x[j] * t.s0) * t.s1) / t.s2;
         break;
+    case LT_CONST:  // Spectrum(p): the phase function's value at a medium vertex
+        PT_UNROLL
+        for (int j = 0; j < 4; ++j) v[j] = t.s0;
+        break;
     default:
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = 0.f;
         break;
     }
 }
+
 // lobe_f as a recipe
 template <int KINDS = KM_ALL>
 B200_HD LTerm lobe_term(const Lobe &l, const V3 &wo, const V3 &wi) {
@@ -1348,6 +1353,14 @@ B200_HD FSpec fspec_zero() {
     f.n = 0;
     f.from_zero = 1;
     f.t[0] = f.t[1] = lterm_zero();
+    return f;
+}
+B200_HD FSpec fspec_const(float p) {
+    FSpec f = fspec_zero();
+    f.n = 1;
+    f.from_zero = 0;
+    f.t[0].op = LT_CONST;
+    f.t[0].s0 = p;
     return f;
 }
 template <int KINDS = KM_ALL>
