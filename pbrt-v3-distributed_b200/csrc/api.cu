@@ -1180,12 +1180,12 @@ int b200pt_render_create(b200pt_scene *scene, const b200pt_camera_desc *cam, con
     ALLOC(H.pix_bleed, (size_t)r->tiles_per_batch * 256);
     float *d_light_spectra = nullptr;
     if (scene->nspec) {
-        const size_t planar = cap * (size_t)scene->nspec;
-        ALLOC(H.s_beta, planar);
-        ALLOC(H.s_L, planar);
-        ALLOC(H.s_A, planar);
-        ALLOC(H.s_B, planar);
-        ALLOC(H.s_beta_ld, planar);
+        const size_t spectra = cap * (size_t)scene->nspec;  // slot-major [capacity][60]
+        ALLOC(H.s_beta, spectra);
+        ALLOC(H.s_L, spectra);
+        ALLOC(H.s_A, spectra);
+        ALLOC(H.s_B, spectra);
+        ALLOC(H.s_beta_ld, spectra);
         ALLOC(d_light_spectra, std::max<size_t>(1, scene->light_spectra.size()));
     }
     float *d_med_spectra = nullptr;

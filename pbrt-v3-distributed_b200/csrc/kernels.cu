@@ -26,17 +26,17 @@ __device__ __forceinline__ float4 f4(const V3 &v, float w) { return make_float4(
 // per slot, read and written as float4s).  A [bin][capacity] layout would coalesce only if a warp's slots were neighbours;
 // the slots of a BSDF family's queue are scattered, every 4-byte access then cost a 32-byte sector, and ncu showed the
 // 60-bin shading kernels waiting on 2.1-3.1 TB/s of DRAM traffic (profiles/README.md, call T).
-__device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *planar, uint32_t cap, uint32_t slot, float *w) {
+__device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *bins, uint32_t cap, uint32_t slot, float *w) {
     const float4 f = a4[slot];
     *w = f.w;
 #if B200PT_NSPEC == 3
-    (void)planar;
+    (void)bins;
     (void)cap;
     return rgb(f.x, f.y, f.z);
 #else
     (void)cap;
     Spec s;
-    const float4 *p4 = reinterpret_cast<const float4 *>(planar + (size_t)slot * B200PT_NSPEC);
+    const float4 *p4 = reinterpret_cast<const float4 *>(bins + (size_t)slot * B200PT_NSPEC);
 #pragma unroll
     for (int q = 0; q < B200PT_NSPEC / 4; ++q) {
         const float4 v = p4[q];
@@ -48,15 +48,15 @@ __device__ __forceinline__ Spec ld_spec(const float4 *a4, const float *planar, u
     return s;
 #endif
 }
-__device__ __forceinline__ void st_spec(float4 *a4, float *planar, uint32_t cap, uint32_t slot, const Spec &s, float w) {
+__device__ __forceinline__ void st_spec(float4 *a4, float *bins, uint32_t cap, uint32_t slot, const Spec &s, float w) {
 #if B200PT_NSPEC == 3
-    (void)planar;
+    (void)bins;
     (void)cap;
     a4[slot] = make_float4(s.c[0], s.c[1], s.c[2], w);
 #else
     (void)cap;
     a4[slot] = make_float4(0.f, 0.f, 0.f, w);
-    float4 *p4 = reinterpret_cast<float4 *>(planar + (size_t)slot * B200PT_NSPEC);
+    float4 *p4 = reinterpret_cast<float4 *>(bins + (size_t)slot * B200PT_NSPEC);
 #pragma unroll
     for (int q = 0; q < B200PT_NSPEC / 4; ++q) p4[q] = make_float4(s.c[4 * q], s.c[4 * q + 1], s.c[4 * q + 2], s.c[4 * q + 3]);
 #endif
@@ -1725,7 +1725,7 @@ __global__ void __launch_bounds__(128, B200PT_SHADE_MINCTAS) k_shade(const Rende
 #else
 // ---- SampledSpectrum build: the same vertex with lazy spectra (pt_core.cuh "Lazy spectra").  No Spec by value: the
 // BSDF value is a recipe (FSpec), the light's radiance a row of the light table with a few scalars (LiTerm), and beta,
-// beta_ld, A, B and L are streamed bin by bin between the planar per-slot arrays -- the arithmetic per bin is that of the
+// beta_ld, A, B and L are streamed bin by bin between the slot-major per-slot arrays -- the arithmetic per bin is that of the
 // eager kernel above / estimate_direct, operation for operation.
 struct LiTerm {
     const float *row;  // nullptr: black
@@ -1758,7 +1758,7 @@ struct DirectLazy {
     uint32_t pend;
     V3 sh_o, sh_d, mi_o, mi_d;
 };
-// estimate_direct with the two terms written straight into the slot's planar A / B arrays
+// estimate_direct with the two terms written straight into the slot's A / B rows
 template <int KINDS>
 __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
                                      int lightNum, const float uLight[2], DirectLazy *out, bool inMedium = false) {

@@ -1103,7 +1103,7 @@ B200_HD_L1 Spec bsdf_sample_f(const Bsdf &b, const V3 &woW, V3 *wiW, const float
 // f, Li, A and B that way ran out of a 4.5-6.4 KB local-memory frame per thread (profiles/README.md).  Every spectrum
 // of the path is a per-bin function of table rows and a few scalars, so the kernel keeps the *recipe* (LTerm: which
 // rows, which scalars, which BxDF formula) in registers and evaluates it bin by bin, four bins at a time, straight
-// from / to the planar per-slot arrays.  The per-bin arithmetic is the eager code's, operation for operation
+// from / to the per-slot arrays (slot-major, 60 floats per slot).  The per-bin arithmetic is the eager code's, operation for operation
 // (lobe_f / lobe_sample_f / bsdf_f / bsdf_sample_f above, which follow core/reflection.cpp), so results are bit-identical.
 enum { LT_ZERO = 0, LT_ROW_S, LT_ROW_S2, LT_MF_DIEL, LT_MF_COND, LT_MFT, LT_SPEC_R, LT_FS_R, LT_FS_T, LT_CONST };
 struct LTerm {
