@@ -481,7 +481,8 @@ def test_lazy_spectra_equal_the_eager_bsdf_code_bit_for_bit(tmp_path):
     holding 60-float spectra.  Compiled for the host with B200PT_NSPEC=60: for every material family (smooth / rough glass
     and the mirror included, random 60-bin rows), bsdf_f_lazy / bsdf_sample_f_lazy -- with the family's lobe-kind mask and
     with the full mask -- give, bin by bin, exactly the bits of bsdf_f / bsdf_sample_f (and the same pdf, direction, sampled
-    type and is_black decision)."""
+    type and is_black decision); and the eager functions instantiated with the family's mask (the RGB kernels) equal the
+    unmasked ones."""
     src = tmp_path / "lazy.cpp"
     src.write_text(r'''
 #include <cmath>
@@ -535,6 +536,12 @@ static void check(const b200pt_material &m, const char *name) {
             const V3 wi = uniformSphere();
             for (int flags : {(int)BSDF_ALL, (int)(BSDF_ALL & ~BSDF_SPECULAR)}) {
                 const Spec f = bsdf_f(bsdf, wo, wi, flags);
+                // the eager code under the family's lobe-kind mask (what the RGB shading kernels instantiate) against the full mask
+                const Spec fk = bsdf_f<K>(bsdf, wo, wi, flags);
+                if (memcmp(&f, &fk, sizeof(Spec)) != 0 ||
+                    float_as_uint(bsdf_pdf<K>(bsdf, wo, wi, flags)) != float_as_uint(bsdf_pdf(bsdf, wo, wi, flags))) {
+                    if (++fail < 6) printf("%s: masked eager bsdf_f / bsdf_pdf differ from the unmasked ones\n", name);
+                }
                 compare<K>(name, f, bsdf_f_lazy<K>(bsdf, wo, wi, flags), absdot(wi, bsdf.ns));
                 compare<KM_ALL>(name, f, bsdf_f_lazy<KM_ALL>(bsdf, wo, wi, flags), 1.f);
                 float u[2] = {U(), U()};
@@ -542,6 +549,16 @@ static void check(const b200pt_material &m, const char *name) {
                 float p1 = 0, p2 = 0, p3 = 0;
                 int t1 = 0, t2 = 0, t3 = 0;
                 const Spec fs = bsdf_sample_f(bsdf, wo, &w1, u, &p1, flags, &t1);
+                {
+                    V3 wk = mk(0.f, 0.f, 0.f);
+                    float pk = 0;
+                    int tk = 0;
+                    const Spec fsk = bsdf_sample_f<K>(bsdf, wo, &wk, u, &pk, flags, &tk);
+                    if (memcmp(&fs, &fsk, sizeof(Spec)) != 0 || float_as_uint(pk) != float_as_uint(p1) || tk != t1 ||
+                        (!is_black(fs) && memcmp(&wk, &w1, sizeof(V3)) != 0)) {
+                        if (++fail < 6) printf("%s: masked eager bsdf_sample_f differs from the unmasked one\n", name);
+                    }
+                }
                 const FSpec ls = bsdf_sample_f_lazy<K>(bsdf, wo, &w2, u, &p2, flags, &t2);
                 const FSpec la = bsdf_sample_f_lazy<KM_ALL>(bsdf, wo, &w3, u, &p3, flags, &t3);
                 compare<K>(name, fs, ls, 1.f);
