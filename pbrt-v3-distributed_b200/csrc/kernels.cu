@@ -1759,9 +1759,9 @@ struct DirectLazy {
     V3 sh_o, sh_d, mi_o, mi_d;
 };
 // estimate_direct with the two terms written straight into the slot's A / B rows
-template <int KINDS>
+template <int KINDS, bool inMedium = false>
 __device__ void estimate_direct_lazy(const RenderDev *R, uint32_t slot, const Isect &is, const Bsdf &bsdf, const float uScattering[2],
-                                     int lightNum, const float uLight[2], DirectLazy *out, bool inMedium = false) {
+                                     int lightNum, const float uLight[2], DirectLazy *out) {
     // inMedium: `is` is a MediumInteraction and the Henyey-Greenstein phase function takes the BSDF's place (its value p is
     // the constant spectrum Spectrum(p) and there is no cosine: |cos| = 1 multiplies exactly)
     const float hgG = R->med_g;
@@ -2338,7 +2338,7 @@ __global__ void __launch_bounds__(128, 4) k_medium(const RenderDev *R, int bounc
                             }
 #else
                             DirectLazy dout;
-                            estimate_direct_lazy<KM_ALL>(R, slot, mi, none, uScattering, lightNum, uLight, &dout, true);
+                            estimate_direct_lazy<KM_CONST, true>(R, slot, mi, none, uScattering, lightNum, uLight, &dout);
                             pend = dout.pend;
                             if (pend) {
                                 float4 *sBl = reinterpret_cast<float4 *>(R->s_beta_ld + (size_t)slot * B200PT_NSPEC);

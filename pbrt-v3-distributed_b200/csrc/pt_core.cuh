@@ -842,6 +842,7 @@ enum { BX_LAMBERT = 0, BX_MICROFACET = 1, BX_FRESNEL_SPECULAR = 2, BX_OREN_NAYAR
 #define KM_DIEL 0x100  // microfacet reflection with FresnelDielectric
 #define KM_COND 0x200  // ... with FresnelConductor
 #define KM_ALL 0x3ff
+#define KM_CONST 0x400  // (lazy spectra) the constant recipe LT_CONST: only the medium vertex asks for it
 B200_HD constexpr int mat_kinds(int material) {
     return material == 0   ? (KM(BX_LAMBERT) | KM(BX_OREN_NAYAR))                  // B200PT_MAT_MATTE
            : material == 1 ? (KM(BX_LAMBERT) | KM(BX_MICROFACET) | KM_DIEL)        // B200PT_MAT_PLASTIC
@@ -1147,7 +1148,8 @@ B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
                     (t.op == LT_MF_DIEL && !(KINDS & KM_DIEL)) || (t.op == LT_MF_COND && !(KINDS & KM_COND)) ||
                     (t.op == LT_MFT && !(KINDS & KM(BX_MICROFACET_TRANS))) ||
                     (t.op == LT_SPEC_R && !(KINDS & KM(BX_SPECULAR_REFLECTION))) ||
-                    ((t.op == LT_FS_R || t.op == LT_FS_T) && !(KINDS & KM(BX_FRESNEL_SPECULAR))))
+                    ((t.op == LT_FS_R || t.op == LT_FS_T) && !(KINDS & KM(BX_FRESNEL_SPECULAR))) ||
+                    (t.op == LT_CONST && !(KINDS & KM_CONST)))
                        ? LT_ZERO
                        : t.op;
     switch (op) {
@@ -1193,6 +1195,7 @@ B200_HD void lterm_eval4(const LTerm &t, int b0, float v[4]) {
         for (int j = 0; j < 4; ++j) v[j] = ((x[j] * t.s0) * t.s1) / t.s2;
         break;
     case LT_CONST:  // Spectrum(p): the phase function's value at a medium vertex
+        if (!(KINDS & KM_CONST)) break;
         PT_UNROLL
         for (int j = 0; j < 4; ++j) v[j] = t.s0;
         break;
