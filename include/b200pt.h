@@ -379,7 +379,12 @@ int b200pt_film_clear(b200pt_render *r);
  * integrator.cpp:247) with ALL samples per pixel and merges them into the
  * device film (raw XYZ sums + filter weight sums, film.cpp:117-130).
  * tiles == NULL renders tiles [0, n_tiles) in order.  Asynchronous on the
- * context's stream. */
+ * context's stream: argument errors are returned here, a failure of the
+ * device work itself (a CUDA error inside a launch) is reported by the next
+ * call that synchronises -- b200pt_ctx_synchronize, b200pt_film_read_*,
+ * b200pt_get_stats -- as B200PT_ERR_CUDA with b200pt_last_error() naming it.
+ * Dropped traversal-stack pushes and sampler-dimension overruns are counted,
+ * never silent (b200pt_stats::stack_overflows / dimension_overflows). */
 int b200pt_render_tiles(b200pt_render *r, const int32_t *tiles, int64_t n_tiles);
 
 /* Device address and size of the film accumulation buffer: float4 per cropped
